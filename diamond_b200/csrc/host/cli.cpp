@@ -1,0 +1,163 @@
+// cli.cpp -- `dmnd-b200 blastp`: the reference's command-line surface for the hot path (run/main.cpp:73-209,
+// basic/config.cpp:216-648) reduced to the flags the path understands; everything else is rejected, not ignored.
+// FASTA in (data/fasta/fasta_file.cpp), block images as data/string_set.h:26-78, BLAST tabular out
+// (output/blast_tab_format.cpp:234-293,652,694; util/text_buffer.h:224-246; util/string/string.h:87-92).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../../include/dmnd_b200.h"
+
+namespace {
+
+struct SeqBlock {
+	std::vector<int8_t> letters;
+	std::vector<int64_t> limits;
+	std::vector<std::string> ids;
+	SeqBlock() : letters(DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER) { limits.push_back(DMND_PERIMETER_PADDING); }
+	void finish() { letters.insert(letters.end(), DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER); }
+	uint32_t size() const { return (uint32_t)ids.size(); }
+};
+
+int8_t encode(char c) {  // basic/value.cpp:26-41 with amino_acid_traits (stats/stats.cpp:41): "UO-" -> mask
+	static int8_t table[256];
+	static bool init = false;
+	if (!init) {
+		std::memset(table, -1, sizeof table);
+		const char* a = "ARNDCQEGHILKMFPSTWYVBJZX*_";
+		for (int i = 0; a[i]; ++i) { table[(unsigned char)a[i]] = (int8_t)i; table[(unsigned char)tolower(a[i])] = (int8_t)i; }
+		for (const char* m = "UO-"; *m; ++m) { table[(unsigned char)*m] = 23; table[(unsigned char)tolower(*m)] = 23; }
+		init = true;
+	}
+	const int8_t v = table[(unsigned char)c];
+	if (v < 0) throw std::runtime_error(std::string("Invalid character in sequence: '") + c + "'");
+	return v;
+}
+
+void read_fasta(const std::string& path, SeqBlock& b) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::string line;
+	bool open = false;
+	auto close_seq = [&] {
+		if (!open) return;
+		b.letters.push_back((int8_t)DMND_DELIMITER);
+		b.limits.push_back((int64_t)b.letters.size());
+		open = false;
+	};
+	while (std::getline(f, line)) {
+		if (!line.empty() && line.back() == '\r') line.pop_back();
+		if (line.empty()) continue;
+		if (line[0] == '>') {
+			close_seq();
+			size_t e = 1;
+			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;  // Util::Seq::id_delimiters
+			b.ids.push_back(line.substr(1, e - 1));
+			open = true;
+		}
+		else {
+			if (!open) throw std::runtime_error("FASTA format error: sequence data before the first header in " + path);
+			for (char c : line) b.letters.push_back(encode(c));
+		}
+	}
+	close_seq();
+	b.finish();
+}
+
+int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
+	if (x >= 100.0) return snprintf(p, n, "%lli", (long long)std::floor(x));
+	const long long i = std::llround(x * 10.0);
+	return snprintf(p, n, "%lli.%lli", i / 10, i % 10);
+}
+
+[[noreturn]] void usage(const char* msg) {
+	fprintf(stderr, "Error: %s\nusage: dmnd-b200 blastp -q QUERY.faa -d DB.faa -o OUT [--fast] [-p N] [-c N] [-k N] [-e X] "
+	                "[--comp-based-stats 0|1] [--masking 0] [--motif-masking 0] [-f 6] [--log]\n", msg);
+	exit(1);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+	try {
+		if (argc < 2) usage("missing command");
+		const std::string cmd = argv[1];
+		if (cmd == "version") { printf("dmnd-b200 (%s) for diamond 2.2.2 blastp hot path\n", dmnd_backend()); return 0; }
+		if (cmd != "blastp") usage("only the blastp hot path is implemented (makedb/blastx are 'next' rows, see DESIGN.md)");
+		dmnd_search_opts o;
+		dmnd_search_opts_default(&o);
+		std::string qf, df, of;
+		bool log = false, masking_off = false, motif_off = false;
+		for (int i = 2; i < argc; ++i) {
+			const std::string a = argv[i];
+			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
+			if (a == "-q" || a == "--query") qf = val();
+			else if (a == "-d" || a == "--db") df = val();
+			else if (a == "-o" || a == "--out") of = val();
+			else if (a == "--fast") o.sensitivity = 0;
+			else if (a == "-p" || a == "--threads") o.threads = atoi(val());
+			else if (a == "-c" || a == "--index-chunks") o.index_chunks = atoi(val());
+			else if (a == "-k" || a == "--max-target-seqs") o.max_target_seqs = atoi(val());
+			else if (a == "-e" || a == "--evalue") o.max_evalue = atof(val());
+			else if (a == "--comp-based-stats") o.comp_based_stats = atoi(val());
+			else if (a == "--masking") { const std::string v = val(); if (v != "0" && v != "none") usage("only --masking 0 is implemented (tantan is a 'next' row)"); masking_off = true; }
+			else if (a == "--motif-masking") { if (std::string(val()) != "0") usage("only --motif-masking 0 is implemented"); motif_off = true; }
+			else if (a == "-f" || a == "--outfmt") { if (std::string(val()) != "6") usage("only -f 6 is implemented"); }
+			else if (a == "--log") log = true;
+			else if (a == "--quiet") {}
+			else usage(("unsupported option " + a).c_str());
+		}
+		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (!masking_off || !motif_off) usage("this build requires --masking 0 --motif-masking 0 (masking parity is a 'next' row)");
+		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
+		SeqBlock q, r;
+		read_fasta(qf, q);
+		read_fasta(df, r);
+		dmnd_params params;
+		if (dmnd_params_init(&o, &params)) throw std::runtime_error(dmnd_last_error());
+		dmnd_ctx* ctx = nullptr;
+		if (dmnd_create(0, &params, &ctx)) throw std::runtime_error(dmnd_last_error());
+		dmnd_result* res = nullptr;
+		if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), q.size(), r.letters.data(), r.letters.size(),
+		                r.limits.data(), r.size(), &o, &res))
+			throw std::runtime_error(dmnd_last_error());
+		size_t n = 0;
+		const dmnd_match* m = dmnd_result_matches(res, &n);
+		FILE* out = fopen(of.c_str(), "wb");
+		if (!out) throw std::runtime_error("Error opening file " + of);
+		char pid[32], bits[32], ev[32];
+		for (size_t i = 0; i < n; ++i) {
+			format_double((double)m[i].identities * 100.0 / (double)m[i].length, pid, sizeof pid);
+			format_double(m[i].bit_score, bits, sizeof bits);
+			if (m[i].evalue == 0.0) snprintf(ev, sizeof ev, "0.0"); else snprintf(ev, sizeof ev, "%.2e", m[i].evalue);
+			fprintf(out, "%s\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s\n", q.ids[m[i].query].c_str(), r.ids[m[i].target].c_str(), pid,
+			        m[i].length, m[i].mismatches, m[i].gap_openings, m[i].q_begin + 1, m[i].q_end, m[i].t_begin + 1, m[i].t_end, ev, bits);
+		}
+		fclose(out);
+		if (log) {
+			const dmnd_run_stats* s = dmnd_result_stats(res);
+			fprintf(stderr, "Seed partition bits = %d\n", params.seedp_bits);
+			fprintf(stderr, "Seeds hit             = %llu\n", (unsigned long long)s->seed.seeds_hit);
+			fprintf(stderr, "Hits (filter stage 0) = %llu\n", (unsigned long long)s->seed.seed_hits);
+			fprintf(stderr, "Hits (filter stage 1) = %llu\n", (unsigned long long)s->seed.tentative_matches1);
+			fprintf(stderr, "Hits (filter stage 2) = %llu\n", (unsigned long long)s->seed.tentative_matches2);
+			fprintf(stderr, "Hits (filter stage 3) = %llu\n", (unsigned long long)s->seed.tentative_matches3);
+			fprintf(stderr, "Target hits (stage 0) = %llu\n", (unsigned long long)s->targets);
+			fprintf(stderr, "DP problems round 1/2 = %llu / %llu\n", (unsigned long long)s->dp_problems_round1, (unsigned long long)s->dp_problems_round2);
+			fprintf(stderr, "DP cells round 1/2    = %llu / %llu\n", (unsigned long long)s->cells_round1, (unsigned long long)s->cells_round2);
+			fprintf(stderr, "Time seed/bridge/dp1/dp2/total (ms) = %.2f / %.2f / %.2f / %.2f / %.2f\n", s->seed_ms, s->host_bridge_ms, s->dp1_ms, s->dp2_ms, s->total_ms);
+			fprintf(stderr, "%llu queries aligned.\n", (unsigned long long)s->queries_aligned);
+		}
+		dmnd_result_free(res);
+		dmnd_destroy(ctx);
+		return 0;
+	}
+	catch (const std::exception& e) {
+		fprintf(stderr, "Error: %s\n", e.what());
+		return 1;
+	}
+}

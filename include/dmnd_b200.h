@@ -1,0 +1,204 @@
+/* dmnd_b200.h -- C ABI of the B200-native DIAMOND seed-and-extend hot path.
+ *
+ * Two layers, both plain C (pointers + sizes, no C++/torch types, no exceptions across the boundary):
+ *
+ *  K layer ("kernel ABI")   batch-oriented replacements for the reference's three SIMD dispatch seams
+ *                           (util/simd/dispatch.h:46-116):
+ *                             Search::search_shape          search/search.h:80,   search/stage0.cpp:101-228
+ *                             DP::BandedSwipe::swipe        dp/dp.h:287,          dp/swipe/swipe_wrapper.cpp:446-470
+ *                           plus block residency (data/string_set.h:26-275 layout, re-used byte for byte).
+ *                           Implemented by hand-written sm_100a CUDA in libdmnd_b200.so.  The CPU restatement under
+ *                           oracle/ implements the SAME symbols and is linked in their place only by tests/.
+ *
+ *  P layer ("pipeline ABI") host C++ restating run_ref_chunk -> search_shape -> align_queries
+ *                           (run/double_indexed.cpp:102-252, align/align.cpp:203-269, align/extend.cpp:226-387)
+ *                           on top of the K layer: what a `diamond blastp` maintainer would call instead of
+ *                           Search::run for one (query block, reference block) pair.
+ *
+ * Every function returns 0 on success, non-zero on failure; the message is available from dmnd_last_error().
+ * Caller owns all host buffers; the library owns device memory behind the opaque handles.  Calls on one
+ * dmnd_ctx must be serialised by the caller.  There is NO CPU fallback: dmnd_create fails without a CUDA device.
+ */
+#ifndef DMND_B200_H
+#define DMND_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMND_MAX_SHAPES 16
+#define DMND_MAX_WEIGHT 12
+#define DMND_PERIMETER_PADDING 256 /* data/string_set.h:34 */
+#define DMND_DELIMITER 31          /* basic/value.h:62 */
+#define DMND_LETTER_MASK 31        /* basic/value.h:63 */
+#define DMND_SEED_MASK 0x80        /* basic/value.h:64 (bit 7 of a query letter) */
+
+typedef struct dmnd_ctx dmnd_ctx;
+typedef struct dmnd_block dmnd_block;
+typedef struct dmnd_hits dmnd_hits;
+
+/* Everything the kernels need that the reference keeps in globals (`config`, `score_matrix`, `shapes`,
+ * Reduction::instance): filled by dmnd_params_init() from the host restatement of search/setup.cpp:338-402. */
+typedef struct dmnd_params {
+	int8_t score[32 * 32];            /* matrix8 layout [a*32+b], out-of-alphabet = -128 (stats/score_matrix.h:35-44) */
+	int32_t gap_open, gap_extend;     /* 11 / 1 */
+	uint8_t reduction[32];            /* Reduction::map_  (basic/basic.cpp:267-296): letter -> class, MASK/STOP -> 23 */
+	uint8_t map8[32], map8b[32];      /* Reduction::map8_/map8b_: distinct sentinels for masked letters */
+	int32_t reduction_size;           /* 10 (murphy10) */
+	int32_t n_shapes, shape_weight;
+	int32_t shape_len[DMND_MAX_SHAPES];
+	uint32_t shape_mask[DMND_MAX_SHAPES];                 /* Shape::mask_  bit i = position i is a '1' */
+	int32_t shape_pos[DMND_MAX_SHAPES][DMND_MAX_WEIGHT];  /* Shape::positions_ */
+	int32_t hamming_id;               /* Search::Config::hamming_filter_id (11; 9 very-sensitive) */
+	int32_t seedp_bits, index_chunks; /* search/setup.cpp:306-309, :42-53 */
+	double seed_cut;                  /* seed_complexity_cut = cut * ln2 * weight (search/setup.cpp:369-370) */
+	int32_t left_most_interval;       /* config.left_most_interval = 32 */
+	int32_t ungapped_window;          /* config.ungapped_window = 48 */
+	double ungapped_evalue;           /* 0 => stage-2 ungapped filter skipped (fast); >0 not implemented yet */
+} dmnd_params;
+
+/* Search::Hit (search/hit.h:30-48) as a fixed 16-byte record. */
+typedef struct dmnd_hit {
+	uint32_t query;       /* frame-level query id */
+	int32_t seed_offset;  /* offset of the seed in the query sequence */
+	uint64_t subject_score; /* bits 0..47 = global offset of the seed in the reference block (PackedLoc),
+	                           bits 48..63 = score_ (0xFFFF when the ungapped stage is skipped) */
+} dmnd_hit;
+#define DMND_HIT_SUBJECT(h) ((h).subject_score & 0xFFFFFFFFFFFFull)
+#define DMND_HIT_SCORE(h) ((uint32_t)((h).subject_score >> 48))
+
+/* Counters printed by the reference under --log (basic/basic.cpp:186-190). */
+typedef struct dmnd_stage_counters {
+	uint64_t seeds_hit;          /* shared keys                      "Seeds hit" */
+	uint64_t seed_hits;          /* sum nq*ns                        "Hits (filter stage 0)" */
+	uint64_t tentative_matches1; /* passed Hamming                   "Hits (filter stage 1)" */
+	uint64_t tentative_matches2; /* passed ungapped (== 1 for fast)  "Hits (filter stage 2)" */
+	uint64_t tentative_matches3; /* passed left-most                 "Hits (filter stage 3)" */
+	uint64_t masked_seeds;       /* keys erased by the entropy cut */
+} dmnd_stage_counters;
+
+/* One banded DP problem == one DpTarget (dp/dp.h:34-146) of one (query, frame). */
+typedef struct dmnd_dp_problem {
+	uint32_t query;   /* sequence index in the query block */
+	uint32_t target;  /* sequence index in the reference block */
+	int32_t d_begin;  /* band = diagonals [d_begin, d_end), diagonal = i - j */
+	int32_t d_end;
+} dmnd_dp_problem;
+
+enum { DMND_DP_SCORE_ONLY = 0, /* round 1: HspValues::NONE, banded_swipe.h:189-351 with DummyRowCounter */
+       DMND_DP_TRACEBACK = 1   /* round 2: TracebackVectorMatrix kernel + walk, banded_swipe.h:127-187 */ };
+
+typedef struct dmnd_dp_result {
+	int32_t score;
+	int32_t q_begin, q_end, t_begin, t_end; /* half-open, 0-based (Hsp::query_range / subject_range) */
+	int32_t identities, mismatches, gap_openings, length, gaps, positives; /* basic/hssp.cpp:260-290 */
+	uint32_t transcript_off, transcript_len; /* into the transcript buffer; 0/0 if not requested */
+	int32_t status; /* 0 ok; 1 = transcript buffer too small */
+} dmnd_dp_result;
+
+/* Transcript bytes (forward order): one byte per edit operation.
+ *   0x00 | n  (n=1)  is not used; encoding is: high 2 bits = op (0 match, 1 insertion(gap in subject),
+ *   2 deletion(gap in query), 3 substitution), low 6 bits = letter of the subject for deletion/substitution,
+ *   0 for match/insertion.  One byte per alignment column (insertions of length n are n bytes). */
+enum { DMND_OP_MATCH = 0, DMND_OP_INSERTION = 1, DMND_OP_DELETION = 2, DMND_OP_SUBSTITUTION = 3 };
+
+const char* dmnd_last_error(void);
+void dmnd_set_last_error(const char* msg);
+/* "cuda-sm100a" for the product library, "oracle-cpu" for the test stand-in under oracle/. */
+const char* dmnd_backend(void);
+
+/* ---- K layer ---------------------------------------------------------------------------------------------- */
+int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out);
+void dmnd_destroy(dmnd_ctx* ctx);
+
+/* `letters` is the reference's block image (256 B delimiter padding + sum(seq + 1 delimiter) + 256 B padding),
+ * raw_len bytes long; limits[0..nseq] are the sequence start offsets into it (limits[0] == 256).  Copies to HBM. */
+int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq,
+                      dmnd_block** out);
+void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b);
+/* Per-position int8 composition bias (HauserCorrection::int8, stats/hauser_correction.cpp:53-109), laid out at the
+ * same offsets as the block's letters.  NULL => all zero (--comp-based-stats 0). */
+int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t raw_len);
+/* Reads back the block's letters (query letters carry SEED_MASK bits set by dmnd_search_shape). */
+int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
+/* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
+int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
+
+/* Stages 0-2 for shape `sid`, all index chunks in reference order; hits are grouped by query (ascending),
+ * order inside a query unspecified (the reference's is thread-dependent; consumers sort, align/load_hits.h:45).
+ * Sets SEED_MASK bits in the query block exactly like Search::mask_seeds (search/seed_complexity.cpp:77-127). */
+int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out,
+                      dmnd_stage_counters* counters);
+size_t dmnd_hits_count(const dmnd_hits* h);
+int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap);
+void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
+
+/* Banded affine-gap local alignment of n problems.  `transcripts` may be NULL (no edit transcript wanted). */
+int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems,
+                      size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
+
+/* Device time (ms) spent in the library's own kernels since the last call, and the number of kernel launches:
+ * filled from CUDA events recorded on the library's stream. */
+typedef struct dmnd_timing {
+	double seed_ms, dp_score_ms, dp_trace_ms, h2d_ms, d2h_ms;
+	uint64_t launches;
+	uint64_t h2d_bytes, d2h_bytes;
+} dmnd_timing;
+int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset);
+
+/* ---- P layer ---------------------------------------------------------------------------------------------- */
+typedef struct dmnd_search_opts {
+	int32_t sensitivity;       /* 0 = --fast (the only mode wired so far) */
+	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
+	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
+	int32_t comp_based_stats;  /* 0 or 1 (Hauser) */
+	int32_t max_target_seqs;   /* -k, default 25 */
+	double max_evalue;         /* -e, default 0.001 */
+	uint64_t db_letters;       /* 0 = letters of the reference block */
+	int32_t want_transcript;   /* 1 = keep edit transcripts (fmt 0) */
+} dmnd_search_opts;
+
+typedef struct dmnd_match {
+	uint32_t query, target;
+	int32_t score;
+	double evalue, bit_score;
+	int32_t q_begin, q_end, t_begin, t_end;
+	int32_t identities, mismatches, gap_openings, length, gaps, positives;
+	uint64_t transcript_off;
+	uint32_t transcript_len;
+	uint32_t reserved;
+} dmnd_match;
+
+typedef struct dmnd_run_stats {
+	dmnd_stage_counters seed;
+	uint64_t hits, targets, dp_problems_round1, dp_problems_round2;
+	uint64_t cells_round1, cells_round2; /* algorithmic cells = sum (d_end-d_begin)*cols, dp/dp.h:121-124 */
+	uint64_t queries_aligned, matches;
+	double seed_ms, host_bridge_ms, dp1_ms, dp2_ms, total_ms; /* wall clock, host */
+	dmnd_timing device;
+} dmnd_run_stats;
+
+typedef struct dmnd_result dmnd_result;
+
+void dmnd_search_opts_default(dmnd_search_opts* o);
+/* Fills a dmnd_params for BLOSUM62 11/1 and the given options (host restatement of setup_search). */
+int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* out);
+/* One (query block, reference block) pass of blastp: seed search, extension rounds, culling.
+ * Matches come back grouped by query in ascending query order, inside a query in the reference's report order. */
+int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const int64_t* q_limits, uint32_t nq,
+                const int8_t* r_letters, size_t r_raw_len, const int64_t* r_limits, uint32_t nr,
+                const dmnd_search_opts* opts, dmnd_result** out);
+/* Same, with both blocks already resident (used by the bench's device-resident timing and by multi-GPU shards). */
+int dmnd_blastp_resident(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, const int8_t* q_letters,
+                         const int64_t* q_limits, uint32_t nq, const int8_t* r_letters, const int64_t* r_limits,
+                         uint32_t nr, const dmnd_search_opts* opts, dmnd_result** out);
+const dmnd_match* dmnd_result_matches(const dmnd_result* r, size_t* n);
+const uint8_t* dmnd_result_transcripts(const dmnd_result* r, size_t* n);
+const dmnd_run_stats* dmnd_result_stats(const dmnd_result* r);
+void dmnd_result_free(dmnd_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
