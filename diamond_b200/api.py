@@ -1,0 +1,295 @@
+"""ctypes binding of the C ABI in include/dmnd_b200.h (the product library diamond_b200/libdmnd_b200.so).
+
+This is a thin harness for tests, bench.py and multi-GPU launch: block images are built with numpy, everything else
+happens behind the C ABI.  There is no Python/torch compute path and no CPU fallback: `load()` raises if the CUDA
+library is missing, and `Context()` raises if it cannot open a CUDA device.
+
+`load(path)` can also open the test-only oracle build (oracle/_build/libdmnd_oracle.so); only tests/, smoke() and
+bench.py's cpu_baseline leg do that.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(HERE, "libdmnd_b200.so")
+PADDING = 256
+DELIMITER = 31
+MAX_SHAPES, MAX_WEIGHT = 16, 12
+
+
+class Params(C.Structure):
+    _fields_ = [("score", C.c_int8 * 1024), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
+                ("reduction", C.c_uint8 * 32), ("map8", C.c_uint8 * 32), ("map8b", C.c_uint8 * 32),
+                ("reduction_size", C.c_int32), ("n_shapes", C.c_int32), ("shape_weight", C.c_int32),
+                ("shape_len", C.c_int32 * MAX_SHAPES), ("shape_mask", C.c_uint32 * MAX_SHAPES),
+                ("shape_pos", (C.c_int32 * MAX_WEIGHT) * MAX_SHAPES), ("hamming_id", C.c_int32),
+                ("seedp_bits", C.c_int32), ("index_chunks", C.c_int32), ("seed_cut", C.c_double),
+                ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("seed_offset", C.c_int32), ("subject_score", C.c_uint64)]
+
+
+class StageCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2",
+                                          "tentative_matches3", "masked_seeds")]
+
+
+class DpProblem(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("d_begin", C.c_int32), ("d_end", C.c_int32)]
+
+
+class DpResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches",
+                                         "gap_openings", "length", "gaps", "positives")] + \
+               [("transcript_off", C.c_uint32), ("transcript_len", C.c_uint32), ("status", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("seed_ms", "dp_score_ms", "dp_trace_ms", "h2d_ms", "d2h_ms")] + \
+               [(n, C.c_uint64) for n in ("launches", "h2d_bytes", "d2h_bytes")]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("sensitivity", C.c_int32), ("threads", C.c_int32), ("index_chunks", C.c_int32),
+                ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
+                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32)]
+
+
+class Match(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("score", C.c_int32), ("evalue", C.c_double),
+                ("bit_score", C.c_double)] + \
+               [(n, C.c_int32) for n in ("q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches",
+                                         "gap_openings", "length", "gaps", "positives")] + \
+               [("transcript_off", C.c_uint64), ("transcript_len", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("seed", StageCounters)] + \
+               [(n, C.c_uint64) for n in ("hits", "targets", "dp_problems_round1", "dp_problems_round2", "cells_round1",
+                                          "cells_round2", "queries_aligned", "matches")] + \
+               [(n, C.c_double) for n in ("seed_ms", "host_bridge_ms", "dp1_ms", "dp2_ms", "total_ms")] + \
+               [("device", Timing)]
+
+
+MATCH_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("_pad", "<i4"), ("evalue", "<f8"),
+                        ("bit_score", "<f8"), ("q_begin", "<i4"), ("q_end", "<i4"), ("t_begin", "<i4"), ("t_end", "<i4"),
+                        ("identities", "<i4"), ("mismatches", "<i4"), ("gap_openings", "<i4"), ("length", "<i4"),
+                        ("gaps", "<i4"), ("positives", "<i4"), ("transcript_off", "<u8"), ("transcript_len", "<u4"),
+                        ("reserved", "<u4")])
+assert MATCH_DTYPE.itemsize == C.sizeof(Match), (MATCH_DTYPE.itemsize, C.sizeof(Match))
+HIT_DTYPE = np.dtype([("query", "<u4"), ("seed_offset", "<i4"), ("subject_score", "<u8")])
+RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches",
+                                               "gap_openings", "length", "gaps", "positives")] +
+                        [("transcript_off", "<u4"), ("transcript_len", "<u4"), ("status", "<i4")])
+PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"), ("d_end", "<i4")])
+
+# every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
+SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_block_upload",
+           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_clear_seed_mask",
+           "dmnd_search_shape", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
+           "dmnd_timing_fetch", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
+           "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
+
+
+def load(path: str | None = None) -> C.CDLL:
+    path = path or PRODUCT_LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `make lib` (there is no fallback implementation)")
+    lib = C.CDLL(path)
+    vp, i8p, i64p = C.c_void_p, C.POINTER(C.c_int8), C.POINTER(C.c_int64)
+    lib.dmnd_last_error.restype = C.c_char_p
+    lib.dmnd_backend.restype = C.c_char_p
+    lib.dmnd_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(vp)]
+    lib.dmnd_destroy.argtypes = [vp]
+    lib.dmnd_destroy.restype = None
+    lib.dmnd_block_upload.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.POINTER(vp)]
+    lib.dmnd_block_free.argtypes = [vp, vp]
+    lib.dmnd_block_free.restype = None
+    lib.dmnd_block_set_bias.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_block_download_letters.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
+    lib.dmnd_search_shape.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(StageCounters)]
+    lib.dmnd_hits_count.argtypes = [vp]
+    lib.dmnd_hits_count.restype = C.c_size_t
+    lib.dmnd_hits_download.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_hits_free.argtypes = [vp, vp]
+    lib.dmnd_hits_free.restype = None
+    lib.dmnd_banded_swipe.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
+    lib.dmnd_timing_fetch.argtypes = [vp, C.POINTER(Timing), C.c_int]
+    lib.dmnd_search_opts_default.argtypes = [C.POINTER(SearchOpts)]
+    lib.dmnd_search_opts_default.restype = None
+    lib.dmnd_params_init.argtypes = [C.POINTER(SearchOpts), C.POINTER(Params)]
+    lib.dmnd_blastp.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, vp, C.c_size_t, vp, C.c_uint32, C.POINTER(SearchOpts),
+                                C.POINTER(vp)]
+    lib.dmnd_blastp_resident.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(SearchOpts),
+                                         C.POINTER(vp)]
+    lib.dmnd_result_matches.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.dmnd_result_matches.restype = vp
+    lib.dmnd_result_transcripts.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.dmnd_result_transcripts.restype = vp
+    lib.dmnd_result_stats.argtypes = [vp]
+    lib.dmnd_result_stats.restype = C.POINTER(RunStats)
+    lib.dmnd_result_free.argtypes = [vp]
+    lib.dmnd_result_free.restype = None
+    return lib
+
+
+class DmndError(RuntimeError):
+    pass
+
+
+def block_image(letters: np.ndarray, offsets: np.ndarray):
+    """Flat encoded letters + offsets (n+1) -> the reference's block image (data/string_set.h:26-78):
+    256 B of delimiter, each sequence followed by one delimiter, 256 B of delimiter; limits[i] = start of seq i."""
+    letters = np.ascontiguousarray(letters, dtype=np.int8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    lens = np.diff(offsets)
+    limits = np.empty(n + 1, dtype=np.int64)
+    limits[0] = PADDING
+    np.cumsum(lens + 1, out=limits[1:])
+    limits[1:] += PADDING
+    raw = np.full(int(limits[-1]) + PADDING, DELIMITER, dtype=np.int8)
+    dst = np.arange(len(letters), dtype=np.int64) + np.repeat(limits[:-1] - offsets[:-1], lens)
+    raw[dst] = letters
+    return raw, limits
+
+
+class Context:
+    """One dmnd_ctx on one device."""
+
+    def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
+                 comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False):
+        self.lib = lib or load()
+        self.opts = SearchOpts()
+        self.lib.dmnd_search_opts_default(C.byref(self.opts))
+        self.opts.threads = threads
+        self.opts.index_chunks = index_chunks
+        self.opts.comp_based_stats = comp_based_stats
+        self.opts.max_target_seqs = max_target_seqs
+        self.opts.max_evalue = max_evalue
+        self.opts.want_transcript = int(want_transcript)
+        self.params = Params()
+        self._check(self.lib.dmnd_params_init(C.byref(self.opts), C.byref(self.params)))
+        self.ctx = C.c_void_p()
+        self._check(self.lib.dmnd_create(device, C.byref(self.params), C.byref(self.ctx)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DmndError(self.lib.dmnd_last_error().decode())
+
+    def backend(self) -> str:
+        return self.lib.dmnd_backend().decode()
+
+    def close(self):
+        if self.ctx:
+            self.lib.dmnd_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    # ---- K layer
+    def upload(self, raw: np.ndarray, limits: np.ndarray):
+        b = C.c_void_p()
+        self._check(self.lib.dmnd_block_upload(self.ctx, raw.ctypes.data, raw.size, limits.ctypes.data, len(limits) - 1, C.byref(b)))
+        return b
+
+    def free_block(self, b):
+        self.lib.dmnd_block_free(self.ctx, b)
+
+    def set_bias(self, b, bias: np.ndarray | None, raw_len: int):
+        self._check(self.lib.dmnd_block_set_bias(self.ctx, b, bias.ctypes.data if bias is not None else None, raw_len))
+
+    def download_letters(self, b, raw_len: int) -> np.ndarray:
+        out = np.empty(raw_len, dtype=np.int8)
+        self._check(self.lib.dmnd_block_download_letters(self.ctx, b, out.ctypes.data, raw_len))
+        return out
+
+    def clear_seed_mask(self, b):
+        self._check(self.lib.dmnd_block_clear_seed_mask(self.ctx, b))
+
+    def search_shape(self, qb, rb, sid: int = 0):
+        h = C.c_void_p()
+        cn = StageCounters()
+        self._check(self.lib.dmnd_search_shape(self.ctx, qb, rb, sid, C.byref(h), C.byref(cn)))
+        n = self.lib.dmnd_hits_count(h)
+        hits = np.zeros(n, dtype=HIT_DTYPE)
+        if n:
+            self._check(self.lib.dmnd_hits_download(self.ctx, h, hits.ctypes.data, n))
+        self.lib.dmnd_hits_free(self.ctx, h)
+        return hits, {k: getattr(cn, k) for k, _ in StageCounters._fields_}
+
+    def banded_swipe(self, qb, rb, problems: np.ndarray, traceback: bool, transcript_cap: int = 0):
+        problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)
+        res = np.zeros(len(problems), dtype=RESULT_DTYPE)
+        tr = np.zeros(transcript_cap, dtype=np.uint8) if transcript_cap else None
+        self._check(self.lib.dmnd_banded_swipe(self.ctx, qb, rb, problems.ctypes.data, len(problems), 1 if traceback else 0,
+                                               res.ctypes.data, tr.ctypes.data if tr is not None else None, transcript_cap))
+        return res, tr
+
+    def timing(self, reset: bool = False) -> dict:
+        t = Timing()
+        self.lib.dmnd_timing_fetch(self.ctx, C.byref(t), int(reset))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    # ---- P layer
+    def _collect(self, res):
+        n = C.c_size_t()
+        p = self.lib.dmnd_result_matches(res, C.byref(n))
+        m = np.zeros(n.value, dtype=MATCH_DTYPE)
+        if n.value:
+            C.memmove(m.ctypes.data, p, n.value * MATCH_DTYPE.itemsize)
+        nt = C.c_size_t()
+        tp = self.lib.dmnd_result_transcripts(res, C.byref(nt))
+        tr = np.zeros(nt.value, dtype=np.uint8)
+        if nt.value:
+            C.memmove(tr.ctypes.data, tp, nt.value)
+        st = self.lib.dmnd_result_stats(res).contents
+        stats = {}
+        for k, _ in RunStats._fields_:
+            v = getattr(st, k)
+            if isinstance(v, C.Structure):
+                stats[k] = {kk: getattr(v, kk) for kk, _ in v._fields_}
+            else:
+                stats[k] = v
+        self.lib.dmnd_result_free(res)
+        return m, tr, stats
+
+    def blastp(self, q_raw, q_limits, r_raw, r_limits):
+        """Host buffers in, matches out (host<->device copies inside the call)."""
+        res = C.c_void_p()
+        self._check(self.lib.dmnd_blastp(self.ctx, q_raw.ctypes.data, q_raw.size, q_limits.ctypes.data, len(q_limits) - 1,
+                                         r_raw.ctypes.data, r_raw.size, r_limits.ctypes.data, len(r_limits) - 1,
+                                         C.byref(self.opts), C.byref(res)))
+        return self._collect(res)
+
+    def blastp_resident(self, qb, rb, q_raw, q_limits, r_raw, r_limits):
+        """Blocks already resident in HBM (uploaded with `upload`)."""
+        res = C.c_void_p()
+        self._check(self.lib.dmnd_blastp_resident(self.ctx, qb, rb, q_raw.ctypes.data, q_limits.ctypes.data, len(q_limits) - 1,
+                                                  r_raw.ctypes.data, r_limits.ctypes.data, len(r_limits) - 1,
+                                                  C.byref(self.opts), C.byref(res)))
+        return self._collect(res)
+
+
+def format_double(x: float) -> str:
+    """util/string/string.h:87-92"""
+    import math
+    if x >= 100.0:
+        return str(int(math.floor(x)))
+    i = int(math.floor(abs(x) * 10.0 + 0.5)) * (1 if x >= 0 else -1)  # llround
+    return f"{i // 10}.{i % 10}"
+
+
+def fmt6(matches: np.ndarray, q_prefix: str = "q", d_prefix: str = "d") -> str:
+    """BLAST tabular lines for synthetic ids (>qI / >dI), output/blast_tab_format.cpp:234-293,652."""
+    out = []
+    for m in matches:
+        ev = "0.0" if m["evalue"] == 0.0 else "%.2e" % m["evalue"]
+        out.append("%s%d\t%s%d\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
+            q_prefix, m["query"], d_prefix, m["target"], format_double(float(m["identities"]) * 100.0 / float(m["length"])),
+            m["length"], m["mismatches"], m["gap_openings"], m["q_begin"] + 1, m["q_end"], m["t_begin"] + 1, m["t_end"],
+            ev, format_double(float(m["bit_score"]))))
+    return "\n".join(out) + ("\n" if out else "")

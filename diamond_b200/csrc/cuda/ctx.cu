@@ -1,0 +1,215 @@
+// ctx.cu -- context, block residency and the extern "C" K-layer entry points of libdmnd_b200.so.
+#include "ctx.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace dmnd_cuda {
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+}  // namespace dmnd_cuda
+using namespace dmnd_cuda;
+
+static __global__ void clear_seed_mask_kernel(int8_t* letters, size_t n) {
+	// 16 B per thread; every byte keeps its low 7 bits (delimiter 31 is unaffected)
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint4* p = reinterpret_cast<uint4*>(letters);
+	if (i * 16 + 16 <= n) {
+		uint4 v = p[i];
+		v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
+		p[i] = v;
+	}
+	else
+		for (size_t k = i * 16; k < n; ++k) letters[k] &= 0x7f;
+}
+
+extern "C" {
+
+const char* dmnd_last_error(void) { return g_err.c_str(); }
+void dmnd_set_last_error(const char* m) { g_err = m ? m : ""; }
+const char* dmnd_backend(void) { return "cuda-sm100a"; }
+
+int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		set_error("dmnd_create: no CUDA device visible -- libdmnd_b200.so has no CPU path");
+		return 1;
+	}
+	if (device < 0 || device >= ndev) { set_error("dmnd_create: bad device index"); return 1; }
+	DMND_CUDA_CHECK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	DMND_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) { set_error(std::string("dmnd_create: device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only"); return 1; }
+	dmnd_ctx* c = new dmnd_ctx();
+	c->device = device;
+	c->params = *params;
+	c->sm_count = prop.multiProcessorCount;
+	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_a));
+	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_b));
+	DevParams& d = c->h_dev_params;
+	std::memset(&d, 0, sizeof d);
+	std::memcpy(d.score, params->score, 1024);
+	std::memcpy(d.reduction, params->reduction, 32);
+	std::memcpy(d.map8, params->map8, 32);
+	std::memcpy(d.map8b, params->map8b, 32);
+	std::memcpy(d.shape_pos, params->shape_pos, sizeof d.shape_pos);
+	std::memcpy(d.shape_mask, params->shape_mask, sizeof d.shape_mask);
+	std::memcpy(d.shape_len, params->shape_len, sizeof d.shape_len);
+	d.n_shapes = params->n_shapes; d.shape_weight = params->shape_weight; d.reduction_size = params->reduction_size;
+	d.hamming_id = params->hamming_id; d.seedp_bits = params->seedp_bits; d.index_chunks = params->index_chunks;
+	d.left_most_interval = params->left_most_interval; d.ungapped_window = params->ungapped_window;
+	d.gap_open = params->gap_open; d.gap_extend = params->gap_extend; d.seed_cut = params->seed_cut;
+	{
+		unsigned long long pw = 1;
+		for (int i = 0; i < params->shape_weight; ++i) pw *= (unsigned long long)params->reduction_size;
+		int bits = 0;
+		for (unsigned long long x = pw - 1; x > 0; x >>= 1) ++bits;
+		d.seed_bits = bits;
+	}
+	// ln(n!) rounded to 6 decimals, as tabulated by the reference (lib/blast/blast_seg.cpp:54-58)
+	static const double LNFACT[13] = { 0.000000, 0.000000, 0.693147, 1.791759, 3.178054, 4.787492, 6.579251, 8.525161,
+		10.604603, 12.801827, 15.104413, 17.502308, 19.987214 };
+	std::memcpy(d.lnfact, LNFACT, sizeof LNFACT);
+	DMND_CUDA_CHECK(cudaMalloc(&c->d_params, sizeof(DevParams)));
+	DMND_CUDA_CHECK(cudaMemcpy(c->d_params, &d, sizeof d, cudaMemcpyHostToDevice));
+	// PatternMatcher tables (util/algo/pattern_matcher.h:25-45): matcher[k] over shapes [0,k)
+	for (int k = 0; k <= params->n_shapes; ++k) {
+		uint32_t minl = 32, maxl = 0;
+		for (int i = 0; i < k; ++i) {
+			const uint32_t len = 32 - (uint32_t)__builtin_clz(params->shape_mask[i]);
+			maxl = len > maxl ? len : maxl;
+			minl = len < minl ? len : minl;
+		}
+		c->matcher_minlen[k] = minl;
+		c->matcher_suffix[k] = (1u << maxl) - 1;
+		std::vector<uint8_t> t((size_t)c->matcher_suffix[k] + 1, 0);
+		for (uint32_t s = 0; s <= c->matcher_suffix[k]; ++s)
+			for (int i = 0; i < k; ++i)
+				if ((s & params->shape_mask[i]) == params->shape_mask[i]) t[s] = 1;
+		DMND_CUDA_CHECK(cudaMalloc(&c->d_matcher[k], t.size()));
+		DMND_CUDA_CHECK(cudaMemcpy(c->d_matcher[k], t.data(), t.size(), cudaMemcpyHostToDevice));
+	}
+	c->h_pinned_cap = 1 << 16;
+	DMND_CUDA_CHECK(cudaMallocHost(&c->h_pinned, c->h_pinned_cap));
+	*out = c;
+	return 0;
+}
+
+void dmnd_destroy(dmnd_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
+		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work };
+	for (DevBuf* b : bufs) b->release();
+	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
+	if (c->d_params) cudaFree(c->d_params);
+	if (c->h_pinned) cudaFreeHost(c->h_pinned);
+	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq, dmnd_block** out) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len < 2 * DMND_PERIMETER_PADDING || limits[0] != DMND_PERIMETER_PADDING || (size_t)limits[nseq] + DMND_PERIMETER_PADDING != raw_len) {
+		set_error("dmnd_block_upload: not a block image (256 B padding + sequences + 256 B padding)");
+		return 1;
+	}
+	dmnd_block* b = new dmnd_block();
+	b->raw_len = raw_len; b->nseq = nseq;
+	b->h_limits.assign(limits, limits + nseq + 1);
+	const size_t padded = (raw_len + 63) & ~(size_t)63;  // 16 B vector loads may touch the tail
+	DMND_CUDA_CHECK(cudaMalloc(&b->letters, padded + 64));
+	DMND_CUDA_CHECK(cudaMalloc(&b->bias, padded + 64));
+	DMND_CUDA_CHECK(cudaMalloc(&b->limits, sizeof(int64_t) * ((size_t)nseq + 1)));
+	PhaseTimer t(ctx, PH_H2D);
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(b->letters, letters, raw_len, cudaMemcpyHostToDevice, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(b->limits, limits, sizeof(int64_t) * ((size_t)nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, ctx->stream));
+	t.stop();
+	ctx->h2d_bytes += raw_len + sizeof(int64_t) * ((size_t)nseq + 1);
+	*out = b;
+	return 0;
+}
+
+void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
+	if (!b) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits);
+	delete b;
+}
+
+int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t raw_len) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len != b->raw_len) { set_error("dmnd_block_set_bias: length mismatch"); return 1; }
+	PhaseTimer t(ctx, PH_H2D);
+	if (bias) { DMND_CUDA_CHECK(cudaMemcpyAsync(b->bias, bias, raw_len, cudaMemcpyHostToDevice, ctx->stream)); ctx->h2d_bytes += raw_len; }
+	else DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, raw_len, ctx->stream));
+	t.stop();
+	return 0;
+}
+
+int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len != b->raw_len) { set_error("dmnd_block_download_letters: length mismatch"); return 1; }
+	DMND_CUDA_CHECK(cudaMemcpyAsync(letters, b->letters, raw_len, cudaMemcpyDeviceToHost, ctx->stream));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	ctx->d2h_bytes += raw_len;
+	return 0;
+}
+
+int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	const size_t n = b->raw_len, threads = (n + 15) / 16;
+	clear_seed_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(b->letters, n);
+	++ctx->launches;
+	DMND_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return search_shape_impl(ctx, query, ref, sid, out, counters);
+}
+
+size_t dmnd_hits_count(const dmnd_hits* h) { return h->n; }
+
+int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (cap < h->n) { set_error("dmnd_hits_download: buffer too small"); return 1; }
+	if (h->n == 0) return 0;
+	PhaseTimer t(ctx, PH_D2H);
+	DMND_CUDA_CHECK(cudaMemcpyAsync(host, h->d, h->n * sizeof(dmnd_hit), cudaMemcpyDeviceToHost, ctx->stream));
+	t.stop();
+	ctx->d2h_bytes += h->n * sizeof(dmnd_hit);
+	return 0;
+}
+
+void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) {
+	if (!h) return;
+	cudaSetDevice(ctx->device);
+	if (h->d) cudaFree(h->d);
+	delete h;
+}
+
+int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
+                      dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+}
+
+int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset) {
+	out->seed_ms = ctx->phase_ms[PH_SEED]; out->dp_score_ms = ctx->phase_ms[PH_DP_SCORE]; out->dp_trace_ms = ctx->phase_ms[PH_DP_TRACE];
+	out->h2d_ms = ctx->phase_ms[PH_H2D]; out->d2h_ms = ctx->phase_ms[PH_D2H];
+	out->launches = ctx->launches; out->h2d_bytes = ctx->h2d_bytes; out->d2h_bytes = ctx->d2h_bytes;
+	if (reset) {
+		for (double& x : ctx->phase_ms) x = 0;
+		ctx->launches = 0; ctx->h2d_bytes = 0; ctx->d2h_bytes = 0;
+	}
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// ctx.cuh -- shared definitions of the CUDA K layer (libdmnd_b200.so): context, block residency, scratch arena,
+// event-based phase timing.  sm_100a only; no fallback of any kind.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../../include/dmnd_b200.h"
+
+namespace dmnd_cuda {
+
+void set_error(const std::string& m);
+
+#define DMND_CUDA_CHECK(expr)                                                                             \
+	do {                                                                                                  \
+		cudaError_t _e = (expr);                                                                          \
+		if (_e != cudaSuccess) {                                                                          \
+			dmnd_cuda::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+			return 1;                                                                                     \
+		}                                                                                                 \
+	} while (0)
+
+// Grow-only device buffer (the library owns all device memory; nothing is allocated per launch in steady state).
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		const size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { set_error(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); return 1; }
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template<typename T> T* as() const { return (T*)p; }
+};
+
+// Device-side copy of what the kernels need from dmnd_params (constant-memory sized).
+struct DevParams {
+	int8_t score[1024];
+	uint8_t reduction[32], map8[32], map8b[32];
+	int32_t shape_pos[DMND_MAX_SHAPES][DMND_MAX_WEIGHT];
+	uint32_t shape_mask[DMND_MAX_SHAPES];
+	int32_t shape_len[DMND_MAX_SHAPES];
+	int32_t n_shapes, shape_weight, reduction_size;
+	int32_t hamming_id, seedp_bits, index_chunks, left_most_interval, ungapped_window;
+	int32_t gap_open, gap_extend;
+	int32_t seed_bits;     // bit length of reduction_size^weight - 1
+	double seed_cut;
+	double lnfact[DMND_MAX_WEIGHT + 1];
+};
+
+enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
+
+}  // namespace dmnd_cuda
+
+struct dmnd_block {
+	int8_t* letters = nullptr;  // device
+	int8_t* bias = nullptr;     // device, same offsets as letters
+	int64_t* limits = nullptr;  // device
+	size_t raw_len = 0;
+	uint32_t nseq = 0;
+	std::vector<int64_t> h_limits;  // host copy (problem binning needs lengths)
+};
+
+struct dmnd_hits {
+	dmnd_hit* d = nullptr;  // device, grouped by query
+	size_t n = 0;
+};
+
+struct dmnd_ctx {
+	int device = 0;
+	dmnd_params params;
+	dmnd_cuda::DevParams h_dev_params;
+	dmnd_cuda::DevParams* d_params = nullptr;
+	uint8_t* d_matcher[DMND_MAX_SHAPES + 1] = {};  // PatternMatcher tables
+	uint32_t matcher_minlen[DMND_MAX_SHAPES + 1] = {}, matcher_suffix[DMND_MAX_SHAPES + 1] = {};
+	cudaStream_t stream = nullptr;
+	int sm_count = 148;
+	// scratch
+	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
+	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work;
+	void* h_pinned = nullptr;  // small pinned staging for counters
+	size_t h_pinned_cap = 0;
+	// timing
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+	double phase_ms[dmnd_cuda::PH_COUNT] = {};
+	uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+namespace dmnd_cuda {
+
+struct PhaseTimer {  // CUDA events on the library's stream, accumulated per phase
+	dmnd_ctx* c; Phase ph;
+	PhaseTimer(dmnd_ctx* c, Phase ph) : c(c), ph(ph) { cudaEventRecord(c->ev_a, c->stream); }
+	void stop() {
+		cudaEventRecord(c->ev_b, c->stream);
+		cudaEventSynchronize(c->ev_b);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+		c->phase_ms[ph] += ms;
+	}
+};
+
+int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters);
+int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
+                      dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
+
+}  // namespace dmnd_cuda

@@ -1,0 +1,406 @@
+// seed.cu -- stages 0-2 of the double-indexed seed search (Search::search_shape, search/stage0.cpp:101-228) for sm_100a.
+//
+// The reference materialises both seed arrays per index chunk, radix-partitions them and hash-joins each partition
+// on the CPU.  Here only the REFERENCE side is indexed (reduced-alphabet seed -> bijective 40-bit mix -> device radix
+// sort -> 2^24-entry bucket directory that stays L2 resident); every QUERY position probes that directory directly, so
+// the 10x larger query side is never sorted or written out.  A probe that finds a shared key becomes a compact
+// "entry" (query loc, run begin, run length, seed partition); the rest of the stage works on entries only:
+//   per index chunk, in the reference's order (search/stage0.cpp:109-121: masking of ALL keys of the chunk first, then
+//   the search): entropy masking (seed_complexity.cpp:37-51,77-127) -> pair expansion -> 48-byte Hamming fingerprint
+//   (hamming/finger_print.h:180-215, kernel.h:29-50) -> left-most filter (stage2.h:73-154, left_most.h:30-110,
+//   sse_dist.h:105-190 SSE branch, pattern_matcher.h:23-65) -> Hit append (hit.h:30-48).
+// Chunk order matters and is reproduced: SEED_MASK bits set while processing chunk k are visible to the left-most
+// filter of chunks >= k, and verify_hit compares seed partitions against the current chunk's range (left_most.h:32-41).
+#include "ctx.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+
+namespace dmnd_cuda {
+
+struct Entry { uint32_t qloc, lo, cnt, part; };
+
+__device__ __forceinline__ uint64_t mix40(uint64_t seed) { return (seed * 0x9E3779B97F4A7C15ull) & 0xFFFFFFFFFFull; }
+
+// basic/shape.h:113-171 on the reduced sequence; a window that contains a delimiter is past the end of its sequence
+// (search/seed_array/seed_iterator.h:30-33).
+__device__ __forceinline__ bool seed_at(const DevParams* P, int sid, const int8_t* s, uint64_t& out) {
+	const int span = P->shape_len[sid];
+	bool ok = true;
+	for (int k = 0; k < span; ++k) ok &= (s[k] != DMND_DELIMITER);
+	if (!ok) return false;
+	uint64_t v = 0;
+	for (int k = 0; k < P->shape_weight; ++k) {
+		const unsigned r = P->reduction[s[P->shape_pos[sid][k]] & 31];
+		if (r == 23) return false;
+		v = v * (uint64_t)P->reduction_size + r;
+	}
+	out = v;
+	return true;
+}
+
+__global__ void ref_enum_kernel(const int8_t* __restrict__ letters, size_t raw_len, const DevParams* __restrict__ P, int sid,
+                                uint64_t* keys, uint32_t* vals, unsigned long long* count) {
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + DMND_PERIMETER_PADDING;
+	uint64_t seed = 0;
+	const bool ok = p + DMND_PERIMETER_PADDING < raw_len && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
+	const unsigned m = __ballot_sync(0xffffffffu, ok);
+	if (m == 0) return;
+	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (ok) {
+		const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
+		keys[idx] = mix40(seed);
+		vals[idx] = (uint32_t)p;
+	}
+}
+
+__global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int shift, uint32_t* hist) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift)], 1u);
+}
+
+__global__ void probe_kernel(const int8_t* __restrict__ letters, size_t raw_len, const DevParams* __restrict__ P, int sid,
+                             const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
+                             Entry* entries, unsigned long long* count, unsigned long long cap) {
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + DMND_PERIMETER_PADDING;
+	uint64_t seed = 0;
+	bool ok = p + DMND_PERIMETER_PADDING < raw_len && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
+	uint32_t lo = 0, cnt = 0;
+	if (ok) {
+		const uint64_t key = mix40(seed);
+		const uint32_t b = (uint32_t)(key >> shift);
+		uint32_t i = bucket[b];
+		const uint32_t e = bucket[b + 1];
+		while (i < e && keys[i] < key) ++i;
+		lo = i;
+		while (i < e && keys[i] == key) ++i;
+		cnt = i - lo;
+		ok = cnt > 0;
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, ok);
+	if (m == 0) return;
+	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+	unsigned long long base = 0;
+	if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (ok) {
+		const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
+		if (idx < cap) entries[idx] = Entry{ (uint32_t)p, lo, cnt, (uint32_t)(seed & (((uint64_t)1 << P->seedp_bits) - 1)) };
+		atomicAdd(count + 1, (unsigned long long)cnt);  // upper bound on (q,s) pairs over all chunks
+	}
+}
+
+// search/seed_complexity.cpp:37-51
+__device__ __forceinline__ bool seed_is_complex(const DevParams* P, int sid, const int8_t* seq) {
+	unsigned count[20];
+#pragma unroll
+	for (int i = 0; i < 20; ++i) count[i] = 0;
+	for (int k = 0; k < P->shape_weight; ++k) {
+		const int l = seq[P->shape_pos[sid][k]] & 31;
+		if (l >= 20) return false;
+		++count[P->reduction[l]];
+	}
+	double entropy = P->lnfact[P->shape_weight];
+	for (int c = 0; c < P->reduction_size; ++c) entropy -= P->lnfact[count[c]];
+	return entropy >= P->seed_cut;
+}
+
+// Chunk pass 1: entropy masking.  pairs[e] = number of (q,s) pairs entry e contributes to THIS chunk's search.
+__global__ void mask_kernel(int8_t* q_letters, const DevParams* __restrict__ P, int sid, Entry* entries, size_t n, uint32_t pb, uint32_t pe,
+                            uint64_t* pairs, uint32_t* key_seen /* bitmap over reference run starts */, unsigned long long* counters) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Entry e = entries[i];
+	uint64_t np = 0;
+	if (e.part >= pb && e.part < pe) {
+		const bool first = (atomicOr(&key_seen[e.lo >> 5], 1u << (e.lo & 31)) & (1u << (e.lo & 31))) == 0;  // one per shared key
+		if (!seed_is_complex(P, sid, q_letters + e.qloc)) {
+			q_letters[e.qloc] = (int8_t)(q_letters[e.qloc] | DMND_SEED_MASK);  // one writer per byte
+			entries[i].cnt = 0;
+			if (first) atomicAdd(&counters[7], 1ull);
+		}
+		else { np = e.cnt; if (first) atomicAdd(&counters[0], 1ull); }
+	}
+	pairs[i] = np;
+}
+
+__device__ __forceinline__ unsigned fingerprint_match(const int8_t* q, const int8_t* s) {
+	unsigned n = 0;
+#pragma unroll 8
+	for (int k = -16; k < 32; ++k) n += ((q[k] ^ s[k]) & 31) == 0;
+	return n;
+}
+
+struct LmCtx {
+	const DevParams* P;
+	const uint8_t* cur_matcher; uint32_t cur_minlen, cur_suffix;
+	const uint8_t* prev_matcher; uint32_t prev_minlen, prev_suffix;
+	int sid, chunked;
+	uint32_t range_begin, range_end;
+};
+
+__device__ __forceinline__ uint32_t matcher_hit(const uint8_t* table, uint32_t minlen, uint32_t suffix, uint32_t h, uint32_t len) {
+	if (len < minlen) return 0;
+	const uint32_t end = len - minlen + 1;
+	uint32_t r = 0;
+	for (uint32_t i = 0; i < end; ++i) { r |= (uint32_t)table[h & suffix] << i; h >>= 1; }
+	return r;
+}
+
+// search/left_most.h:30-49
+__device__ bool verify_hit(const LmCtx& x, const int8_t* q, const int8_t* s, bool left, uint32_t match_mask) {
+	const DevParams* P = x.P;
+	if (x.chunked) {
+		const uint32_t sm = P->shape_mask[x.sid];
+		if ((sm & match_mask) == sm) {
+			uint64_t seed = 0;
+			for (int k = 0; k < P->shape_weight; ++k) {  // Shape::set_seed, basic/shape.h:73-96
+				const int l = s[P->shape_pos[x.sid][k]] & 31;
+				if (l == 23 || l == 31 || l == 24) return false;
+				seed = seed * (uint64_t)P->reduction_size + P->reduction[l];
+			}
+			const uint32_t part = (uint32_t)(seed & (((uint64_t)1 << P->seedp_bits) - 1));
+			if (left && !(part < x.range_end)) return false;
+			if (!left && !(part < x.range_begin)) return false;
+		}
+	}
+	return fingerprint_match(q, s) >= (unsigned)P->hamming_id;
+}
+// search/left_most.h:51-60
+__device__ bool verify_hits(const LmCtx& x, uint32_t mask, const int8_t* q, const int8_t* s, bool left, uint32_t match_mask) {
+	int shift = 0;
+	while (mask != 0) {
+		const int i = __ffs(mask) - 1;
+		if (verify_hit(x, q + i + shift, s + i + shift, left, (i + shift) < 32 ? match_mask >> (i + shift) : 0u)) return true;
+		mask = (i + 1) < 32 ? mask >> (i + 1) : 0u;
+		shift += i + 1;
+	}
+	return false;
+}
+// util/sequence/sequence.h:30-40 on [seq, seq+len) around seq+anchor
+__device__ __forceinline__ void clip(const int8_t* seq, int len, int anchor, int& b, int& e) {
+	b = 0; e = len;
+	for (int k = 0; k < len; ++k)
+		if (seq[k] == DMND_DELIMITER) {
+			if (k >= anchor) { e = k; return; }
+			b = k + 1;
+		}
+}
+// search/left_most.h:62-110
+__device__ bool left_most_filter(const LmCtx& x, const int8_t* query, int query_len, const int8_t* subject, int seed_offset, int seed_len) {
+	const DevParams* P = x.P;
+	int d = max(seed_offset - 16, 0), window_left = min(16, seed_offset);
+	const int8_t *q = query + d, *s = subject + d;
+	int window = min(query_len - d, window_left + 1 + 32);
+	int cb, ce;
+	clip(s, window, window_left, cb, ce);
+	window = ce;
+	d = cb;
+	q += d; s += d; window_left -= d; window -= d;
+	uint64_t match_mask = 0, seed_bits = 0;
+	for (int k = 0; k < window && k < 64; ++k) {
+		if (P->map8[q[k] & 31] == P->map8b[s[k] & 31]) match_mask |= (uint64_t)1 << k;
+		if (q[k] & DMND_SEED_MASK) seed_bits |= (uint64_t)1 << k;
+	}
+	const uint64_t query_seed_mask = ~seed_bits;
+	const uint32_t len_left = (uint32_t)(window_left + seed_len - 1),
+		match_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & match_mask),
+		query_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & query_seed_mask);
+	const uint32_t left_hit = matcher_hit(x.cur_matcher, x.cur_minlen, x.cur_suffix, match_mask_left, len_left) & query_mask_left;
+	if (x.sid == 0 && !x.chunked) return left_hit == 0 || !verify_hits(x, left_hit, q, s, true, match_mask_left);
+	const uint32_t len_right = (uint32_t)(window - window_left - 1),
+		match_mask_right = (uint32_t)(match_mask >> (window_left + 1)),
+		query_mask_right = (uint32_t)(query_seed_mask >> (window_left + 1));
+	const uint32_t right_hit = (x.chunked ? matcher_hit(x.cur_matcher, x.cur_minlen, x.cur_suffix, match_mask_right, len_right)
+	                                      : matcher_hit(x.prev_matcher, x.prev_minlen, x.prev_suffix, match_mask_right, len_right)) & query_mask_right;
+	return (left_hit == 0 || !verify_hits(x, left_hit, q, s, true, match_mask_left))
+		&& (right_hit == 0 || !verify_hits(x, right_hit, q + window_left + 1, s + window_left + 1, false, match_mask_right));
+}
+
+// Chunk pass 2: one thread per (query loc, reference loc) pair of the chunk's surviving keys.
+__global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                               const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
+                               const uint64_t* __restrict__ pair_off /* exclusive scan, n_entries + 1 */, uint64_t total_pairs,
+                               const uint32_t* __restrict__ ref_locs, LmCtx x, dmnd_hit* hits, unsigned long long* hit_count,
+                               unsigned long long* counters) {
+	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (pid >= total_pairs) return;
+	// entry = last e with pair_off[e] <= pid
+	size_t lo = 0, hi = n_entries;
+	while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+	const Entry e = entries[lo];
+	const uint32_t k = (uint32_t)(pid - pair_off[lo]);
+	const uint32_t sloc = ref_locs[e.lo + k];
+	const int8_t *qp = q_letters + e.qloc, *sp = r_letters + sloc;
+	if (fingerprint_match(qp, sp) < (unsigned)x.P->hamming_id) return;
+	atomicAdd(&counters[2], 1ull);
+	// query id / seed offset (SequenceSet::local_position)
+	uint32_t a = 0, b = nq;
+	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)q_limits[mid] <= (uint64_t)e.qloc) a = mid; else b = mid; }
+	const int seed_offset = (int)((int64_t)e.qloc - q_limits[a]);
+	// search/stage2.h:92-103
+	const int window = x.P->ungapped_window;
+	int cb, ce;
+	clip(qp - window, 2 * window, window, cb, ce);
+	const int window_left = window - cb, window_clipped = ce - cb;
+	const int interval_mod = x.P->left_most_interval > 0 ? seed_offset % x.P->left_most_interval : window_left;
+	const int overhang = max(window_left - interval_mod, 0);
+	const int8_t* qc = qp - window + cb;
+	if (!left_most_filter(x, qc + overhang, window_clipped - overhang, sp - window_left + overhang, window_left - overhang, x.P->shape_len[x.sid])) return;
+	const unsigned long long idx = atomicAdd(hit_count, 1ull);
+	dmnd_hit h;
+	h.query = a; h.seed_offset = seed_offset; h.subject_score = (uint64_t)sloc | ((uint64_t)0xFFFF << 48);
+	hits[idx] = h;
+}
+
+__global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, uint32_t* keys) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) keys[i] = h[i].query;
+}
+
+static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long long* h) {
+	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	*h = *(unsigned long long*)ctx->h_pinned;
+	return 0;
+}
+
+int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters) {
+	const dmnd_params& hp = ctx->params;
+	if (hp.ungapped_evalue != 0.0) { set_error("dmnd_search_shape: stage-2 ungapped window filter (sensitive modes) is not built yet"); return 1; }
+	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
+	if (sid < 0 || sid >= hp.n_shapes) { set_error("dmnd_search_shape: bad shape id"); return 1; }
+	cudaStream_t st = ctx->stream;
+	const DevParams* P = ctx->d_params;
+	const int seed_bits = ctx->h_dev_params.seed_bits;  // 40 for 10^12
+	const int bucket_bits = std::min(24, seed_bits), shift = 40 - bucket_bits;  // keys are 40-bit mixes
+	const size_t nbuckets = (size_t)1 << bucket_bits;
+	PhaseTimer timer(ctx, PH_SEED);
+
+	// counters: [0] seeds_hit (filled on host) [1] seed_hits [2] tm1 [3] tm3 [4] ref count [5] entry count [6] hit count [7] masked
+	if (ctx->b_counters.ensure(16 * sizeof(unsigned long long))) return 1;
+	unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
+
+	// ---- reference index
+	const size_t rpos = ref->raw_len - 2 * DMND_PERIMETER_PADDING, qpos = query->raw_len - 2 * DMND_PERIMETER_PADDING;
+	if (ctx->b_keys.ensure(rpos * 8) || ctx->b_keys2.ensure(rpos * 8) || ctx->b_vals.ensure(rpos * 4) || ctx->b_vals2.ensure(rpos * 4)
+	    || ctx->b_bucket.ensure((nbuckets + 1) * 4 * 2))
+		return 1;
+	ref_enum_kernel<<<(unsigned)((rpos + 255) / 256), 256, 0, st>>>(ref->letters, ref->raw_len, P, sid, ctx->b_keys.as<uint64_t>(), ctx->b_vals.as<uint32_t>(), d_cnt + 4);
+	++ctx->launches;
+	unsigned long long nref = 0;
+	if (fetch_u64(ctx, d_cnt + 4, &nref)) return 1;
+	uint64_t* d_keys = ctx->b_keys2.as<uint64_t>();
+	uint32_t* d_locs = ctx->b_vals2.as<uint32_t>();
+	uint32_t* d_bucket = ctx->b_bucket.as<uint32_t>();
+	uint32_t* d_hist = d_bucket + nbuckets + 1;
+	{
+		size_t tmp = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->b_keys.as<uint64_t>(), d_keys, ctx->b_vals.as<uint32_t>(), d_locs, (size_t)nref, 0, 40, st);
+		size_t tmp2 = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_hist, d_bucket, nbuckets + 1, st);
+		if (ctx->b_cub.ensure(std::max(tmp, tmp2))) return 1;
+		if (nref) {
+			DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp, ctx->b_keys.as<uint64_t>(), d_keys, ctx->b_vals.as<uint32_t>(), d_locs, (size_t)nref, 0, 40, st));
+			ctx->launches += 6;
+		}
+		DMND_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, (nbuckets + 1) * 4, st));
+		if (nref) { bucket_hist_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, shift, d_hist); ++ctx->launches; }
+		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_hist, d_bucket, nbuckets + 1, st));
+		ctx->launches += 2;
+	}
+
+	// ---- probe every query position
+	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
+	unsigned long long nent = 0;
+	for (;;) {
+		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
+		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
+		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, query->raw_len, P, sid, d_keys, d_bucket, shift, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		++ctx->launches;
+		if (fetch_u64(ctx, d_cnt + 5, &nent)) return 1;
+		if (nent <= ecap) break;
+		ecap = (size_t)nent + 1024;  // rare: rerun with an exact capacity
+	}
+	Entry* d_entries = ctx->b_entries.as<Entry>();
+	unsigned long long pairs_bound = 0;
+	if (fetch_u64(ctx, d_cnt + 6, &pairs_bound)) return 1;  // written by the last probe pass (count + 1 == d_cnt + 6)
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
+	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
+	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;
+	if (ctx->b_vals.ensure(bm_words * 4)) return 1;  // b_vals (unsorted reference locs) is dead after the sort
+	uint32_t* d_key_seen = ctx->b_vals.as<uint32_t>();
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_key_seen, 0, bm_words * 4, st));
+
+	// ---- chunks, in the reference's order
+	const uint32_t parts_total = 1u << hp.seedp_bits;
+	const uint32_t nchunks = std::min<uint32_t>((uint32_t)hp.index_chunks, parts_total);
+	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
+	if (ctx->b_pairs.ensure((nent + 2) * 8 * 2)) return 1;
+	uint64_t* d_pairs = ctx->b_pairs.as<uint64_t>();
+	uint64_t* d_pair_off = d_pairs + nent + 1;
+	size_t scan_tmp = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st);
+	if (ctx->b_cub.ensure(scan_tmp)) return 1;
+	size_t hits_total = 0;
+	uint64_t seed_hits_total = 0;
+	for (uint32_t chunk = 0; chunk < nchunks && nent > 0; ++chunk) {
+		const uint32_t bsel = std::min(chunk, prem);
+		const uint32_t pb = bsel * (psize + 1) + (chunk - bsel) * psize, pe = pb + (chunk < prem ? psize + 1 : psize);
+		DMND_CUDA_CHECK(cudaMemsetAsync(d_pairs + nent, 0, 8, st));
+		mask_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(query->letters, P, sid, d_entries, (size_t)nent, pb, pe, d_pairs, d_key_seen, d_cnt);
+		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st));
+		ctx->launches += 3;
+		unsigned long long total_pairs = 0;
+		if (fetch_u64(ctx, (const unsigned long long*)(d_pair_off + nent), &total_pairs)) return 1;
+		seed_hits_total += total_pairs;
+		if (total_pairs == 0) continue;
+		LmCtx x;
+		x.P = P; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
+		x.cur_matcher = ctx->d_matcher[sid + 1]; x.cur_minlen = ctx->matcher_minlen[sid + 1]; x.cur_suffix = ctx->matcher_suffix[sid + 1];
+		x.prev_matcher = ctx->d_matcher[sid]; x.prev_minlen = ctx->matcher_minlen[sid]; x.prev_suffix = ctx->matcher_suffix[sid];
+		stage12_kernel<<<(unsigned)((total_pairs + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
+			d_pair_off, total_pairs, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+		++ctx->launches;
+		unsigned long long nh = 0;
+		if (fetch_u64(ctx, d_cnt + 6, &nh)) return 1;
+		hits_total = (size_t)nh;
+	}
+
+	// ---- group hits by query (stable order inside a query is not required)
+	dmnd_hits* h = new dmnd_hits();
+	h->n = hits_total;
+	if (hits_total) {
+		DMND_CUDA_CHECK(cudaMalloc(&h->d, hits_total * sizeof(dmnd_hit)));
+		if (ctx->b_keys.ensure(hits_total * 4) || ctx->b_vals.ensure(hits_total * 4)) return 1;
+		uint32_t* k_in = ctx->b_keys.as<uint32_t>();
+		uint32_t* k_out = ctx->b_vals.as<uint32_t>();
+		extract_query_kernel<<<(unsigned)((hits_total + 255) / 256), 256, 0, st>>>(ctx->b_hits.as<dmnd_hit>(), hits_total, k_in);
+		size_t tmp = 0;
+		int end_bit = 1;
+		while (((uint64_t)1 << end_bit) < (uint64_t)query->nseq) ++end_bit;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h->d, hits_total, 0, end_bit, st);
+		if (ctx->b_cub.ensure(tmp)) return 1;
+		DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h->d, hits_total, 0, end_bit, st));
+		ctx->launches += 4;
+	}
+	unsigned long long hc[16];
+	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+	timer.stop();
+	std::memcpy(hc, ctx->h_pinned, sizeof hc);
+	if (counters) {
+		counters->seeds_hit = hc[0];
+		counters->seed_hits = seed_hits_total;
+		counters->tentative_matches1 = hc[2];
+		counters->tentative_matches2 = hc[2];
+		counters->tentative_matches3 = hits_total;
+		counters->masked_seeds = hc[7];
+	}
+	*out = h;
+	return 0;
+}
+
+}  // namespace dmnd_cuda

@@ -1,0 +1,383 @@
+// swipe.cu -- banded affine-gap local alignment (DP::BandedSwipe::swipe, dp/swipe/banded_swipe.h:189-351) for sm_100a.
+//
+// Mapping.  The reference fills SIMD lanes with <= 32 targets of ONE query and walks band rows serially.  Here every
+// DP problem (one DpTarget) gets one warp, and the lanes split the BAND: lane t owns R consecutive diagonals
+// (band rows r = t*R .. t*R+R-1, diagonal d = d_begin + r) and keeps their H / hgap / vgap state in registers.
+// Cell (r, c) [c = column index into the banded target range] depends on
+//     (r, c-1) diagonal predecessor, (r+1, c-1) horizontal gap source, (r-1, c) vertical gap source,
+// so with the wavefront time s = 2c + r all three are exactly one or two steps old: at step s the rows with
+// r == s (mod 2) are active, every lane updates R/2 cells per step and exchanges ONE boundary value with a
+// neighbour lane by warp shuffle (vgap from the lane above on even steps, hgap from the lane below on odd steps).
+// The recurrence is (max,+): DPX three-input instructions (VIADDMNMX / VIMNMX3 with fused relu) carry it; it is
+// not a contraction, so tensor cores do not apply.
+//
+// Semantics are the reference's int8/int16 lane semantics (every H, hgap, vgap floored at 0; cell_update.h:103-141),
+// evaluated in exact int32, so no overflow cascade is needed.  Traceback mode stores the reference's two mask pairs
+// per cell (gap: cur==vgap / cur==hgap, open: vgap'==open / hgap'==open) and a second kernel walks them
+// (banded_swipe.h:127-187, banded_matrix.h:357-402, basic/hssp.cpp:260-290), one problem per thread.
+#include "ctx.cuh"
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace dmnd_cuda {
+
+struct ProbGeom {  // derived on the device from the problem + block limits
+	const int8_t *q, *cb, *t;
+	int qlen, tlen, d_begin, B, j0, cols;
+};
+
+struct SwipeArgs {
+	const int8_t *q_letters, *q_bias, *r_letters;
+	const int64_t *q_limits, *r_limits;
+	const dmnd_dp_problem* probs;
+	const uint32_t* order;  // problem indices of this launch, heaviest first
+	uint32_t n;
+	int32_t* score;         // [problem]
+	int32_t* end_cell;      // [problem][2] = (column, band row) of the end cell, traceback only
+	uint8_t* trace;         // traceback masks, one byte per cell, column-major [c * B + r]
+	const uint64_t* trace_off;  // [problem]
+	unsigned int* work;     // atomic work counter
+};
+
+__device__ __forceinline__ ProbGeom geom(const SwipeArgs& a, const dmnd_dp_problem& pr) {
+	ProbGeom g;
+	const int64_t qo = a.q_limits[pr.query], to = a.r_limits[pr.target];
+	g.qlen = (int)(a.q_limits[pr.query + 1] - qo - 1);
+	g.tlen = (int)(a.r_limits[pr.target + 1] - to - 1);
+	g.q = a.q_letters + qo; g.cb = a.q_bias + qo; g.t = a.r_letters + to;
+	g.d_begin = pr.d_begin;
+	g.B = pr.d_end - pr.d_begin;
+	const int i1 = max(pr.d_end - 1, 0);
+	g.j0 = i1 - (pr.d_end - 1);
+	g.cols = min(g.qlen - 1 - pr.d_begin, g.tlen - 1) + 1 - g.j0;  // dp/dp.h:47-52
+	return g;
+}
+
+template<int R, bool TRACE>
+__global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const DevParams* __restrict__ P) {
+	__shared__ int8_t s_score[1024];
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_score[i] = P->score[i];
+	__syncthreads();
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int go = P->gap_open + P->gap_extend, ge = P->gap_extend;
+	const int r0 = lane * R;
+
+	for (;;) {
+		unsigned int w = 0;
+		if (lane == 0) w = atomicAdd(a.work, 1u);
+		w = __shfl_sync(FULL, w, 0);
+		if (w >= a.n) break;
+		const uint32_t pi = a.order[w];
+		const dmnd_dp_problem pr = a.probs[pi];
+		const ProbGeom g = geom(a, pr);
+		int H[R], E[R], F[R], bestv[R], bestc[R];
+#pragma unroll
+		for (int k = 0; k < R; ++k) { H[k] = 0; E[k] = 0; F[k] = 0; bestv[k] = 0; bestc[k] = 0; }
+		int best = 0;
+		uint8_t* tr = TRACE ? a.trace + a.trace_off[pi] : nullptr;
+		if (g.B > 0 && g.cols > 0) {
+			const int ibase = g.j0 + g.d_begin;  // i = ibase + c + r
+			const int nsteps = 2 * (g.cols - 1) + g.B;
+			const int nmacro = (nsteps + 1) >> 1;
+			for (int m = 0; m < nmacro; ++m) {
+				// ---- even step s = 2m : rows k = 0,2,.. ; column c = m - (r0 + k)/2
+				{
+					int f_up = __shfl_up_sync(FULL, F[R - 1], 1);
+					if (lane == 0) f_up = 0;
+#pragma unroll
+					for (int k = 0; k < R; k += 2) {
+						const int r = r0 + k, c = m - ((r0 + k) >> 1), i = ibase + c + r;
+						if (r < g.B && (unsigned)c < (unsigned)g.cols && (unsigned)i < (unsigned)g.qlen) {
+							const int sc = (int)s_score[((g.q[i] & 31) << 5) | (g.t[g.j0 + c] & 31)] + (int)g.cb[i];
+							const int e_in = E[k + 1], f_in = k > 0 ? F[k > 0 ? k - 1 : 0] : f_up;
+							const int h = __vimax3_s32_relu(H[k] + sc, e_in, f_in);
+							const int open = max(h - go, 0);
+							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
+							if (TRACE) {
+								tr[(size_t)c * g.B + r] = (uint8_t)((h == f_in ? 1 : 0) | (h == e_in ? 2 : 0) | (f == open ? 4 : 0) | (e == open ? 8 : 0));
+								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
+							}
+							else best = max(best, h);
+							H[k] = h; E[k] = e; F[k] = f;
+						}
+					}
+				}
+				// ---- odd step s = 2m + 1 : rows k = 1,3,.. ; column c = m - (r0 + k - 1)/2
+				{
+					int e_dn = __shfl_down_sync(FULL, E[0], 1);
+					if (lane == 31) e_dn = 0;
+#pragma unroll
+					for (int k = 1; k < R; k += 2) {
+						const int r = r0 + k, c = m - ((r0 + k - 1) >> 1), i = ibase + c + r;
+						if (r < g.B && (unsigned)c < (unsigned)g.cols && (unsigned)i < (unsigned)g.qlen) {
+							const int sc = (int)s_score[((g.q[i] & 31) << 5) | (g.t[g.j0 + c] & 31)] + (int)g.cb[i];
+							const int e_in = k + 1 < R ? E[k + 1 < R ? k + 1 : 0] : e_dn, f_in = F[k - 1];
+							const int h = __vimax3_s32_relu(H[k] + sc, e_in, f_in);
+							const int open = max(h - go, 0);
+							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
+							if (TRACE) {
+								tr[(size_t)c * g.B + r] = (uint8_t)((h == f_in ? 1 : 0) | (h == e_in ? 2 : 0) | (f == open ? 4 : 0) | (e == open ? 8 : 0));
+								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
+							}
+							else best = max(best, h);
+							H[k] = h; E[k] = e; F[k] = f;
+						}
+					}
+				}
+			}
+		}
+		if (TRACE) {
+			// end cell = maximal H; ties: smallest column, then largest band row (banded_swipe.h:312-328, cell_update.h:43-46)
+			int bv = 0, bc = 0, br = 0;
+#pragma unroll
+			for (int k = 0; k < R; ++k) {
+				const int r = r0 + k;
+				if (bestv[k] > bv || (bestv[k] == bv && bv > 0 && (bestc[k] < bc || (bestc[k] == bc && r > br)))) { bv = bestv[k]; bc = bestc[k]; br = r; }
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const int ov = __shfl_xor_sync(FULL, bv, o), oc = __shfl_xor_sync(FULL, bc, o), orr = __shfl_xor_sync(FULL, br, o);
+				if (ov > bv || (ov == bv && ov > 0 && (oc < bc || (oc == bc && orr > br)))) { bv = ov; bc = oc; br = orr; }
+			}
+			if (lane == 0) { a.score[pi] = bv; a.end_cell[2 * (size_t)pi] = bc; a.end_cell[2 * (size_t)pi + 1] = br; }
+		}
+		else {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+			if (lane == 0) a.score[pi] = best;
+		}
+	}
+}
+
+struct WalkArgs {
+	const int8_t *q_letters, *q_bias, *r_letters;
+	const int64_t *q_limits, *r_limits;
+	const dmnd_dp_problem* probs;
+	const uint32_t* order;
+	uint32_t n;
+	const int32_t* score;
+	const int32_t* end_cell;
+	const uint8_t* trace;
+	const uint64_t* trace_off;
+	dmnd_dp_result* res;
+	uint8_t* transcripts;           // may be null
+	const uint64_t* transcript_off; // [problem], capacity qlen + tlen each
+};
+
+__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevParams* __restrict__ P) {
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= a.n) return;
+	const uint32_t pi = a.order[w];
+	const dmnd_dp_problem pr = a.probs[pi];
+	SwipeArgs sa;
+	sa.q_letters = a.q_letters; sa.q_bias = a.q_bias; sa.r_letters = a.r_letters; sa.q_limits = a.q_limits; sa.r_limits = a.r_limits;
+	const ProbGeom g = geom(sa, pr);
+	dmnd_dp_result res;
+	res.score = a.score[pi];
+	res.q_begin = res.q_end = res.t_begin = res.t_end = 0;
+	res.identities = res.mismatches = res.gap_openings = res.length = res.gaps = res.positives = 0;
+	res.transcript_off = 0; res.transcript_len = 0; res.status = 0;
+	const int best = res.score;
+	if (best > 0) {
+		const uint8_t* tr = a.trace + a.trace_off[pi];
+		int c = a.end_cell[2 * (size_t)pi], r = a.end_cell[2 * (size_t)pi + 1];
+		int i = g.j0 + g.d_begin + c + r, j = g.j0 + c;
+		res.q_end = i + 1; res.t_end = j + 1;
+		uint8_t* out = a.transcripts ? a.transcripts + a.transcript_off[pi] : nullptr;
+		const uint32_t cap = (uint32_t)(g.qlen + g.tlen);
+		uint32_t n = 0;
+		int sc = 0;
+		const int gopen = P->gap_open, gext = P->gap_extend;
+		bool bad = false;
+		while (i >= 0 && j >= 0 && sc < best) {
+			if (c < 0 || r < 0 || r >= g.B) { bad = true; break; }
+			const uint8_t nib = tr[(size_t)c * g.B + r];
+			if ((nib & 3) == 0) {
+				const int ql = g.q[i] & 31, sl = g.t[j] & 31;
+				const int m = P->score[(ql << 5) | sl];
+				sc += m + (int)g.cb[i];
+				if (ql == sl) { ++res.identities; ++res.positives; if (out && n < cap) out[n] = (uint8_t)(DMND_OP_MATCH << 6); }
+				else { ++res.mismatches; if (m > 0) ++res.positives; if (out && n < cap) out[n] = (uint8_t)((DMND_OP_SUBSTITUTION << 6) | sl); }
+				++n; ++res.length;
+				--i; --j; --c;
+			}
+			else if (nib & 1) {
+				int l = 0;
+				do { ++l; --i; --r; } while (r >= 0 && (tr[(size_t)c * g.B + r] & 4) == 0 && i > 0);
+				if (r < 0) { bad = true; break; }
+				++res.gap_openings; res.length += l; res.gaps += l;
+				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)(DMND_OP_INSERTION << 6); ++n; }
+				sc -= gopen + l * gext;
+			}
+			else {
+				int l = 0;
+				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && (tr[(size_t)c * g.B + r] & 8) == 0 && j > 0);
+				if (c < 0 || r >= g.B) { bad = true; break; }
+				++res.gap_openings; res.length += l; res.gaps += l;
+				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)((DMND_OP_DELETION << 6) | (g.t[j + l - k] & 31)); ++n; }
+				sc -= gopen + l * gext;
+			}
+		}
+		if (bad || sc != best) res.status = 2;  // "Traceback error." (banded_swipe.h:176-177)
+		res.q_begin = i + 1; res.t_begin = j + 1;
+		if (out) {
+			if (n > cap) res.status = 1;
+			else {
+				for (uint32_t x = 0, y = n; x + 1 < y; ++x, --y) { const uint8_t tmp = out[x]; out[x] = out[y - 1]; out[y - 1] = tmp; }
+				res.transcript_off = (uint32_t)a.transcript_off[pi];
+				res.transcript_len = n;
+			}
+		}
+	}
+	a.res[pi] = res;
+}
+
+static __global__ void fill_score_results(const int32_t* score, dmnd_dp_result* res, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	dmnd_dp_result r;
+	r.score = score[i];
+	r.q_begin = r.q_end = r.t_begin = r.t_end = 0;
+	r.identities = r.mismatches = r.gap_openings = r.length = r.gaps = r.positives = 0;
+	r.transcript_off = r.transcript_len = 0; r.status = 0;
+	res[i] = r;
+}
+
+template<bool TRACE>
+static void launch_bin(int R, const SwipeArgs& a, const DevParams* P, int grid, cudaStream_t st) {
+	switch (R) {
+	case 2: swipe_kernel<2, TRACE><<<grid, 128, 0, st>>>(a, P); break;
+	case 4: swipe_kernel<4, TRACE><<<grid, 128, 0, st>>>(a, P); break;
+	case 8: swipe_kernel<8, TRACE><<<grid, 128, 0, st>>>(a, P); break;
+	case 16: swipe_kernel<16, TRACE><<<grid, 128, 0, st>>>(a, P); break;
+	default: swipe_kernel<32, TRACE><<<grid, 128, 0, st>>>(a, P); break;
+	}
+}
+
+int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
+                      dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
+	if (n == 0) return 0;
+	if (n > 0xfffffff0ull) { set_error("dmnd_banded_swipe: too many problems in one call"); return 1; }
+	const bool trace = mode == DMND_DP_TRACEBACK;
+	cudaStream_t st = ctx->stream;
+	// ---- host-side geometry: band, cols, cost, register-tile bin
+	static const int RS[5] = { 2, 4, 8, 16, 32 };
+	std::vector<uint64_t> cost(n), troff(trace ? n : 0), tsoff((trace && transcripts) ? n : 0);
+	std::vector<uint8_t> bin(n);
+	uint64_t ts_total = 0;
+	for (size_t k = 0; k < n; ++k) {
+		const dmnd_dp_problem& p = problems[k];
+		if (p.query >= query->nseq || p.target >= ref->nseq) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
+		const int qlen = (int)(query->h_limits[p.query + 1] - query->h_limits[p.query] - 1), tlen = (int)(ref->h_limits[p.target + 1] - ref->h_limits[p.target] - 1);
+		const int B = p.d_end - p.d_begin;
+		const int i1 = std::max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
+		const int cols = std::min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
+		cost[k] = (B > 0 && cols > 0) ? (uint64_t)B * (uint64_t)cols : 0;
+		if (B > 1024) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
+		int b = 0;
+		while (RS[b] * 32 < B) ++b;
+		bin[k] = (uint8_t)b;
+		if (trace && transcripts) { tsoff[k] = ts_total; ts_total += (uint64_t)qlen + (uint64_t)tlen; }
+	}
+	if (trace && transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
+	if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
+	// order: by bin, heaviest first inside a bin
+	std::vector<uint32_t> order(n);
+	std::iota(order.begin(), order.end(), 0u);
+	std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return bin[x] != bin[y] ? bin[x] < bin[y] : (cost[x] != cost[y] ? cost[x] > cost[y] : x < y); });
+
+	// ---- device buffers
+	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
+	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 64 * sizeof(unsigned int)))
+		return 1;
+	int32_t* d_score = ctx->b_work.as<int32_t>();
+	int32_t* d_end = d_score + n;
+	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);
+	{
+		PhaseTimer t(ctx, PH_H2D);
+		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_probs.p, problems, n * sizeof(dmnd_dp_problem), cudaMemcpyHostToDevice, st));
+		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_order.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+		t.stop();
+		ctx->h2d_bytes += n * (sizeof(dmnd_dp_problem) + sizeof(uint32_t));
+	}
+	SwipeArgs a;
+	a.q_letters = query->letters; a.q_bias = query->bias; a.r_letters = ref->letters; a.q_limits = query->limits; a.r_limits = ref->limits;
+	a.probs = ctx->b_probs.as<dmnd_dp_problem>();
+	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_off = nullptr;
+
+	if (!trace) {
+		PhaseTimer t(ctx, PH_DP_SCORE);
+		DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
+		size_t pos = 0;
+		for (int b = 0; b < 5; ++b) {
+			size_t e = pos;
+			while (e < n && bin[order[e]] == b) ++e;
+			if (e > pos) {
+				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters + b;
+				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
+				launch_bin<false>(RS[b], a, ctx->d_params, grid, st);
+				++ctx->launches;
+			}
+			pos = e;
+		}
+		fill_score_results<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_score, ctx->b_results.as<dmnd_dp_result>(), (uint32_t)n);
+		++ctx->launches;
+		DMND_CUDA_CHECK(cudaGetLastError());
+		t.stop();
+	}
+	else {
+		// trace memory is bounded: process the ordered list in slices that fit the budget
+		size_t free_b = 0, total_b = 0;
+		DMND_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+		const uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)(free_b + ctx->b_trace.cap) / 2);
+		if (ctx->b_trace_off.ensure(n * sizeof(uint64_t))) return 1;
+		if (transcripts) {
+			if (ctx->b_tr.ensure(ts_total + 16) || ctx->b_hits2.ensure(n * sizeof(uint64_t))) return 1;
+			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_hits2.p, tsoff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		}
+		size_t pos = 0;
+		while (pos < n) {
+			// slice [pos, e): same bin, total trace <= budget
+			const int b = bin[order[pos]];
+			size_t e = pos;
+			uint64_t bytes = 0;
+			while (e < n && bin[order[e]] == b && (e == pos || bytes + cost[order[e]] <= budget)) { troff[order[e]] = bytes; bytes += cost[order[e]]; ++e; }
+			if (bytes > ctx->b_trace.cap && ctx->b_trace.ensure((size_t)std::min<uint64_t>(std::max<uint64_t>(bytes, budget), (uint64_t)free_b + ctx->b_trace.cap - ((uint64_t)256 << 20)))) return 1;
+			if (bytes > ctx->b_trace.cap) { set_error("dmnd_banded_swipe: a single traceback matrix exceeds free device memory"); return 1; }
+			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_trace_off.p, troff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+			PhaseTimer t(ctx, PH_DP_TRACE);
+			DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
+			a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters;
+			a.trace = ctx->b_trace.as<uint8_t>(); a.trace_off = ctx->b_trace_off.as<uint64_t>();
+			const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
+			launch_bin<true>(RS[b], a, ctx->d_params, grid, st);
+			WalkArgs wa;
+			wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
+			wa.probs = a.probs; wa.order = a.order; wa.n = a.n; wa.score = d_score; wa.end_cell = d_end;
+			wa.trace = a.trace; wa.trace_off = a.trace_off; wa.res = ctx->b_results.as<dmnd_dp_result>();
+			wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
+			wa.transcript_off = transcripts ? ctx->b_hits2.as<uint64_t>() : nullptr;
+			walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
+			ctx->launches += 2;
+			DMND_CUDA_CHECK(cudaGetLastError());
+			t.stop();  // synchronises: troff may be rewritten for the next slice
+			pos = e;
+		}
+	}
+	{
+		PhaseTimer t(ctx, PH_D2H);
+		DMND_CUDA_CHECK(cudaMemcpyAsync(results, ctx->b_results.p, n * sizeof(dmnd_dp_result), cudaMemcpyDeviceToHost, st));
+		if (trace && transcripts && ts_total) DMND_CUDA_CHECK(cudaMemcpyAsync(transcripts, ctx->b_tr.p, ts_total, cudaMemcpyDeviceToHost, st));
+		t.stop();
+		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
+	}
+	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (trace)
+		for (size_t k = 0; k < n; ++k)
+			if (results[k].status == 2) { set_error("dmnd_banded_swipe: Traceback error."); return 1; }
+	return 0;
+}
+
+}  // namespace dmnd_cuda

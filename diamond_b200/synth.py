@@ -27,13 +27,14 @@ def make_db(n_db: int, rng: np.random.Generator):
     return letters, off
 
 
-def make_queries(n_q: int, db_letters: np.ndarray, db_off: np.ndarray, rng: np.random.Generator, qlen: int = 300):
+def make_queries(n_q: int, db_letters: np.ndarray, db_off: np.ndarray, rng: np.random.Generator, qlen: int = 300,
+                 rate_range=(0.1, 0.6)):
     n_db = len(db_off) - 1
     src = rng.integers(0, n_db, n_q)
     slen = db_off[src + 1] - db_off[src]
     wlen = np.minimum(slen, qlen)
     start = (rng.random(n_q) * (slen - wlen + 1)).astype(np.int64)
-    rate = rng.uniform(0.1, 0.6, n_q)
+    rate = rng.uniform(rate_range[0], rate_range[1], n_q)
     woff = np.zeros(n_q + 1, dtype=np.int64)
     np.cumsum(wlen, out=woff[1:])
     total = int(woff[-1])
@@ -67,7 +68,7 @@ def workload(n_q: int, n_db: int, seed: int, qlen: int = 300):
 
 
 def write_fasta(path: str, letters: np.ndarray, off: np.ndarray, prefix: str) -> None:
-    lut = np.frombuffer(ALPHABET.encode(), dtype=np.uint8)
+    lut = np.frombuffer(b"ARNDCQEGHILKMFPSTWYVBJZX*_", dtype=np.uint8)
     text = lut[letters]
     with open(path, "wb") as f:
         chunks = []
@@ -78,6 +79,75 @@ def write_fasta(path: str, letters: np.ndarray, off: np.ndarray, prefix: str) ->
             if len(chunks) >= 30000:
                 f.write(b"".join(chunks)); chunks = []
         f.write(b"".join(chunks))
+
+
+def edge_workload(seed: int, n_db: int = 2000, n_q: int = 300):
+    """Short / ragged queries (25..150 letters, some shorter than the 16-letter seed span), masked letters (X) and stop
+    codons (*) inside queries, queries without any homolog -- the edge cases the reference's own goldens cover with
+    data.faa (short sequences) and nanopore reads (stops)."""
+    rng = np.random.default_rng(seed)
+    dbl, dbo = make_db(n_db, rng)
+    qs = []
+    for k in range(n_q):
+        if k % 29 == 0:  # no homolog at all
+            L = int(rng.integers(10, 150))
+            qs.append(rng.choice(20, size=L, p=RR_FREQ).astype(np.int8))
+            continue
+        s = int(rng.integers(0, n_db))
+        slen = int(dbo[s + 1] - dbo[s])
+        L = int(min(slen, rng.integers(12, 150)))
+        st = int(rng.integers(0, slen - L + 1))
+        q = dbl[dbo[s] + st: dbo[s] + st + L].copy()
+        sub = rng.random(L) < rng.uniform(0.05, 0.4)
+        q[sub] = rng.choice(20, size=int(sub.sum()), p=RR_FREQ)
+        if k % 10 == 3:
+            q[rng.integers(0, L, size=min(3, L))] = 23  # X
+        if k % 17 == 5:
+            q[int(rng.integers(0, L))] = 24  # *
+        qs.append(q)
+    qo = np.zeros(n_q + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in qs], out=qo[1:])
+    return {"q_letters": np.concatenate(qs).astype(np.int8), "q_off": qo, "db_letters": dbl, "db_off": dbo, "src": None}
+
+
+def family_workload(n_fam: int, fam_size: int, n_q: int, seed: int, base_len: int = 350, member_div=(0.10, 0.35),
+                    query_div=(0.1, 0.6)):
+    """DB of `n_fam` families, each `fam_size` diverged copies (10-35 % substitutions, 1 % indels) of a random base
+    protein; queries are further-mutated windows of family members.  Gives queries with hundreds of targets, which
+    exercises the ranking-chunk loop (align/extend.cpp:259-336) and -k culling."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for f in range(n_fam):
+        L = int(rng.integers(base_len // 2, base_len * 2))
+        base = rng.choice(20, size=L, p=RR_FREQ).astype(np.int8)
+        for m in range(fam_size):
+            r = rng.uniform(member_div[0], member_div[1])
+            s = base.copy()
+            sub = rng.random(L) < r
+            s[sub] = rng.choice(20, size=int(sub.sum()), p=RR_FREQ)
+            keep = rng.random(L) >= 0.01
+            s = s[keep]
+            seqs.append(s)
+    perm = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in perm]
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    dbl = np.concatenate(seqs).astype(np.int8)
+    ql, qo, src = make_queries(n_q, dbl, off, rng, 400, query_div)
+    return {"q_letters": ql, "q_off": qo, "db_letters": dbl, "db_off": off, "src": src}
+
+
+WORKLOADS = {
+    # name: (factory, kwargs)  -- the committed golden fixtures under tests/golden/ are keyed by these names
+    "c1": (workload, dict(n_q=1000, n_db=10000, seed=1)),
+    "fam2": (family_workload, dict(n_fam=4, fam_size=400, n_q=120, seed=12, member_div=(0.02, 0.12), query_div=(0.03, 0.3))),
+    "edge": (edge_workload, dict(seed=21)),
+}
+
+
+def named(name: str):
+    f, kw = WORKLOADS[name]
+    return f(**kw)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,46 @@
+"""Regenerates the golden fixtures in this directory by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref/diamond, built from
+/root/reference by oracle/ref_build/Makefile) on the seeded synthetic workloads of diamond_b200/synth.py.
+
+    python tests/golden/make_golden.py            # needs oracle/_ref/diamond (make ref)
+
+For every workload W and parity-ladder level L:
+    L0 = --masking 0 --motif-masking 0 --comp-based-stats 0      L1 = --masking 0 --motif-masking 0 (Hauser CBS on)
+it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
+The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
+"""
+import json, os, re, subprocess, sys, tempfile
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from diamond_b200 import synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "diamond")
+LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats", "0"],
+          "l1": ["--masking", "0", "--motif-masking", "0"]}
+COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
+            "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
+            "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
+            "targets_round2": r"Target hits \(stage 5\) = (\d+)", "seedp_bits": r"Seed partition bits = (\d+)"}
+
+
+def main():
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/diamond missing: run `make ref` where /root/reference is available")
+    for name in synth.WORKLOADS:
+        w = synth.named(name)
+        with tempfile.TemporaryDirectory() as td:
+            q, d = os.path.join(td, "q.faa"), os.path.join(td, "d.faa")
+            synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+            synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+            for lvl, flags in LEVELS.items():
+                out = os.path.join(HERE, f"{name}.{lvl}.tsv")
+                r = subprocess.run([REF, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", out, "-p", "8", "--log"] + flags,
+                                   capture_output=True, text=True, check=True)
+                log = r.stderr + r.stdout
+                cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
+                json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)
+                print(name, lvl, sum(1 for _ in open(out)), cn)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+"""Parity of the CUDA K layer and of the GPU pipeline against the oracle and the reference goldens.  Every call goes
+through the C ABI (ctypes).  Integer results must be bit-exact; e-values are compared to 1e-6 relative as north_star
+states (they are computed by the same host code on both sides, so they are in fact identical)."""
+import json, os
+import numpy as np
+import pytest
+from conftest import GOLDEN, workload_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def both(oracle_lib, product_lib, **kw):
+    from diamond_b200 import api
+    o = api.Context(oracle_lib, **kw)
+    g = api.Context(product_lib, **kw)
+    assert g.backend() == "cuda-sm100a" and o.backend() == "oracle-cpu"
+    return o, g
+
+
+def sorted_hits(h):
+    return np.sort(h, order=["query", "subject_score", "seed_offset"])
+
+
+@pytest.mark.parametrize("name", ["c1", "edge", "fam2"])
+def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name):
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    res = []
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        hits, cn = c.search_shape(qb, rb, 0)
+        letters = c.download_letters(qb, q_raw.size)
+        c.clear_seed_mask(qb)
+        cleared = c.download_letters(qb, q_raw.size)
+        res.append((hits, cn, letters, cleared))
+        c.free_block(qb); c.free_block(rb)
+    (ho, co, lo, clo), (hg, cg, lg, clg) = res
+    assert np.all(np.diff(hg["query"].astype(np.int64)) >= 0), "ABI promise: hits grouped by ascending query"
+    assert len(ho) == len(hg)
+    assert np.array_equal(sorted_hits(ho), sorted_hits(hg))
+    assert co == cg
+    assert np.array_equal(lo, lg), "SEED_MASK bits (search/seed_complexity.cpp:77-127)"
+    assert np.array_equal(clg, q_raw) and np.array_equal(clo, q_raw)
+    o.close(); g.close()
+
+
+def random_problems(w, q_lim, r_lim, rng, n):
+    """Bands around the planted diagonal of (query, source target) pairs plus unrelated pairs and degenerate bands."""
+    nq, nr = len(q_lim) - 1, len(r_lim) - 1
+    P = []
+    src = w["src"]
+    for _ in range(n):
+        q = int(rng.integers(0, nq))
+        qlen = int(q_lim[q + 1] - q_lim[q] - 1)
+        kind = rng.integers(0, 10)
+        t = int(src[q]) if (src is not None and kind < 7) else int(rng.integers(0, nr))
+        tlen = int(r_lim[t + 1] - r_lim[t] - 1)
+        lo, hi = -(tlen - 1), qlen  # valid diagonal range [lo, hi)
+        if kind < 7:
+            c = int(rng.integers(lo, hi))
+            wdt = int(rng.choice([1, 2, 7, 25, 33, 64, 65, 100, 129, 200, 300, 513, 700]))
+            d0 = max(lo, c - wdt // 2); d1 = min(hi, d0 + wdt)
+        elif kind == 7:
+            d0, d1 = lo, min(hi, lo + 1000)  # widest supported band from the lower corner
+        elif kind == 8:
+            d1 = hi; d0 = max(lo, hi - int(rng.integers(1, 40)))  # upper corner
+        else:
+            d0 = int(rng.integers(lo, hi)); d1 = d0 + 1
+        if d1 <= d0:
+            d1 = d0 + 1
+        P.append((q, t, d0, d1))
+    return P
+
+
+@pytest.mark.parametrize("name,cbs", [("c1", 0), ("c1", 1), ("edge", 1), ("fam2", 1)])
+def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    rng = np.random.default_rng(7)
+    P = random_problems(w, q_lim, r_lim, rng, 1500)
+    # true pipeline bands too: diagonal of the planted window +- the reference's padding
+    probs = np.array(P, dtype=api.PROBLEM_DTYPE)
+    bias = None
+    if cbs:
+        bias = rng.integers(-3, 2, size=q_raw.size).astype(np.int8)  # any int8 bias exercises the code path
+    o, g = both(oracle_lib, product_lib, threads=8)
+    out = []
+    cap = int(sum((q_lim[p[0] + 1] - q_lim[p[0]] - 1) + (r_lim[p[1] + 1] - r_lim[p[1]] - 1) for p in P))
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.set_bias(qb, bias, q_raw.size)
+        s, _ = c.banded_swipe(qb, rb, probs, traceback=False)
+        t, tr = c.banded_swipe(qb, rb, probs, traceback=True, transcript_cap=cap)
+        out.append((s, t, tr))
+        c.free_block(qb); c.free_block(rb)
+    (so, to, tro), (sg, tg, trg) = out
+    assert np.array_equal(so["score"], sg["score"])
+    assert np.array_equal(to["score"], so["score"]) and np.array_equal(tg["score"], sg["score"])
+    for f in ("q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length", "gaps", "positives", "transcript_len", "status"):
+        assert np.array_equal(to[f], tg[f]), f
+    assert (so["score"] > 0).sum() > 300, "workload must contain real alignments"
+    for k in range(len(P)):
+        a = tro[to["transcript_off"][k]: to["transcript_off"][k] + to["transcript_len"][k]]
+        b = trg[tg["transcript_off"][k]: tg["transcript_off"][k] + tg["transcript_len"][k]]
+        assert np.array_equal(a, b), k
+    o.close(); g.close()
+
+
+def test_banded_swipe_empty_and_errors(product_lib):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("edge")
+    g = api.Context(product_lib)
+    qb, rb = g.upload(q_raw, q_lim), g.upload(r_raw, r_lim)
+    res, _ = g.banded_swipe(qb, rb, np.zeros(0, dtype=api.PROBLEM_DTYPE), traceback=False)
+    assert len(res) == 0
+    bad = np.array([(10**6, 0, 0, 10)], dtype=api.PROBLEM_DTYPE)
+    with pytest.raises(api.DmndError, match="out of range"):
+        g.banded_swipe(qb, rb, bad, traceback=False)
+    g.free_block(qb); g.free_block(rb); g.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "fam2", "edge"])
+@pytest.mark.parametrize("level,cbs", [("l0", 0), ("l1", 1)])
+def test_blastp_pipeline_matches_reference_golden(oracle_lib, product_lib, name, level, cbs):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    g = api.Context(product_lib, threads=8, comp_based_stats=cbs, want_transcript=True)
+    m, tr, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.{level}.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["device"]["launches"] > 0
+    o = api.Context(oracle_lib, threads=8, comp_based_stats=cbs, want_transcript=True)
+    mo, tro, sto = o.blastp(q_raw, q_lim, r_raw, r_lim)
+    o.close()
+    for f in m.dtype.names:
+        if f in ("transcript_off", "_pad", "reserved"):
+            continue
+        if f in ("evalue", "bit_score"):
+            assert np.allclose(m[f], mo[f], rtol=1e-6, atol=0), f
+        else:
+            assert np.array_equal(m[f], mo[f]), f
+    for a, b in zip(m, mo):
+        assert np.array_equal(tr[a["transcript_off"]: a["transcript_off"] + a["transcript_len"]],
+                              tro[b["transcript_off"]: b["transcript_off"] + b["transcript_len"]])
+    assert st["cells_round1"] == sto["cells_round1"] and st["cells_round2"] == sto["cells_round2"]
+
+
+def test_transcript_is_consistent_with_coordinates(product_lib):
+    """Size-independent property: walking the edit transcript reproduces the reported coordinates, counts and score."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("c1")
+    g = api.Context(product_lib, threads=8, comp_based_stats=0, want_transcript=True)
+    m, tr, _ = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    S = np.ctypeslib.as_array(g.params.score).reshape(32, 32).astype(np.int64)
+    g.close()
+    for x in m[:200]:
+        ops = tr[x["transcript_off"]: x["transcript_off"] + x["transcript_len"]]
+        i, j = int(x["q_begin"]), int(x["t_begin"])
+        q0, t0 = int(q_lim[x["query"]]), int(r_lim[x["target"]])
+        score = ident = mism = 0
+        gap_open = 0
+        prev = -1
+        for b in ops:
+            op = int(b) >> 6
+            if op in (0, 3):
+                a, c = int(q_raw[q0 + i]) & 31, int(r_raw[t0 + j]) & 31
+                score += S[a, c]; ident += a == c; mism += a != c
+                assert (op == 0) == (a == c)
+                i += 1; j += 1
+            elif op == 1:
+                if prev != 1: score -= 11; gap_open += 1
+                score -= 1; i += 1
+            else:
+                if prev != 2: score -= 11; gap_open += 1
+                score -= 1; assert (int(b) & 63) == (int(r_raw[t0 + j]) & 31); j += 1
+            prev = op
+        assert (i, j) == (x["q_end"], x["t_end"])
+        assert score == x["score"] and ident == x["identities"] and mism == x["mismatches"]
+        assert len(ops) == x["length"] and gap_open == x["gap_openings"]

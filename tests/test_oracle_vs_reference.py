@@ -1,0 +1,74 @@
+"""Pins the oracle (oracle/dmnd_oracle.c under the host pipeline) against the REFERENCE ITSELF:
+ * byte-identical fmt-6 output and equal --log stage counters with the committed golden fixtures, which were produced
+   by running the unmodified reference (tests/golden/make_golden.py);
+ * when oracle/_ref/diamond is present (this container), a live run of the reference on a fresh seed as well.
+CPU only."""
+import json, os, subprocess, tempfile
+import numpy as np
+import pytest
+from conftest import GOLDEN, REF_BIN, workload_blocks
+
+
+@pytest.mark.parametrize("name", ["c1", "fam2", "edge"])
+@pytest.mark.parametrize("level,cbs", [("l0", 0), ("l1", 1)])
+def test_fmt6_and_counters_match_reference_golden(oracle_lib, name, level, cbs):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=cbs)
+    assert ctx.backend() == "oracle-cpu"
+    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    gold = open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
+    assert api.fmt6(m) == gold
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.{level}.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"]
+    assert st["dp_problems_round2"] == cn["targets_round2"]
+    assert ctx.params.seedp_bits == cn["seedp_bits"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/diamond not built here")
+@pytest.mark.parametrize("seed", [101])
+def test_live_reference_run(oracle_lib, seed):
+    from diamond_b200 import api, synth
+    w = synth.workload(300, 3000, seed)
+    q_raw, q_lim = api.block_image(w["q_letters"], w["q_off"])
+    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+    with tempfile.TemporaryDirectory() as td:
+        q, d, o = (os.path.join(td, x) for x in ("q.faa", "d.faa", "o.tsv"))
+        synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+        synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+        subprocess.run([REF_BIN, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", o, "-p", "8", "--masking", "0",
+                        "--motif-masking", "0", "--quiet"], check=True, capture_output=True)
+        gold = open(o).read()
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1)
+    m, _, _ = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == gold
+
+
+def test_evalue_within_tolerance_of_printed_reference_values(oracle_lib):
+    """north_star: e-values within 1e-6 relative.  The reference prints %.2e, so compare at that precision and make
+    sure no value sits on a rounding edge by also checking the raw double against the printed one to 0.5 % (3 digits)."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("c1")
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1)
+    m, _, _ = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    gold = [l.split("\t") for l in open(os.path.join(GOLDEN, "c1.l1.tsv")).read().splitlines()]
+    assert len(gold) == len(m)
+    for g, x in zip(gold, m):
+        ref = float(g[10])
+        if ref > 0:
+            assert abs(x["evalue"] - ref) / ref < 5.1e-3
+        assert ("0.0" if x["evalue"] == 0 else "%.2e" % x["evalue"]) == g[10]
+
+
+def test_cli_rejects_what_it_does_not_implement(oracle_lib):
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z"], capture_output=True, text=True)
+    assert r.returncode != 0 and "masking" in r.stderr
+    r = subprocess.run([cli, "blastx"], capture_output=True, text=True)
+    assert r.returncode != 0
