@@ -17,13 +17,19 @@ ALPHABET = "ARNDCQEGHILKMFPSTWYV"
 RR_FREQ = np.array([0.07805, 0.05129, 0.04487, 0.05364, 0.01925, 0.04264, 0.06295, 0.07377, 0.02199, 0.05142,
                     0.09019, 0.05744, 0.02243, 0.03856, 0.05203, 0.07120, 0.05841, 0.01330, 0.03216, 0.06441])
 RR_FREQ = RR_FREQ / RR_FREQ.sum()
+# 16-bit inverse-CDF table: letter = _LUT[u16] draws from RR_FREQ quantised to 1/65536 (fast enough for 3e8 letters)
+_LUT = np.searchsorted(np.cumsum(RR_FREQ), (np.arange(65536) + 0.5) / 65536.0).clip(0, 19).astype(np.int8)
+
+
+def draw_letters(rng: np.random.Generator, n: int) -> np.ndarray:
+    return _LUT[rng.integers(0, 65536, size=n, dtype=np.uint16)]
 
 
 def make_db(n_db: int, rng: np.random.Generator):
     lens = np.clip(rng.gamma(4.0, 75.0, n_db), 50, 2000).astype(np.int64)
     off = np.zeros(n_db + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
-    letters = rng.choice(20, size=int(off[-1]), p=RR_FREQ).astype(np.int8)
+    letters = draw_letters(rng, int(off[-1]))
     return letters, off
 
 
@@ -41,12 +47,12 @@ def make_queries(n_q: int, db_letters: np.ndarray, db_off: np.ndarray, rng: np.r
     qid = np.repeat(np.arange(n_q), wlen)
     pos_in_w = np.arange(total, dtype=np.int64) - woff[qid]
     base = db_letters[db_off[src][qid] + start[qid] + pos_in_w]
-    sub = rng.random(total) < rate[qid]
-    bg = rng.choice(20, size=total, p=RR_FREQ).astype(np.int8)
+    sub = rng.random(total, dtype=np.float32) < rate[qid].astype(np.float32)
+    bg = draw_letters(rng, total)
     base = np.where(sub, bg, base)
-    keep = rng.random(total) >= 0.01
-    ins = rng.random(total) < 0.01
-    ins_letter = rng.choice(20, size=total, p=RR_FREQ).astype(np.int8)
+    keep = rng.random(total, dtype=np.float32) >= np.float32(0.01)
+    ins = rng.random(total, dtype=np.float32) < np.float32(0.01)
+    ins_letter = draw_letters(rng, total)
     # emit: kept letter (0/1) followed by inserted letter (0/1)
     cnt = keep.astype(np.int64) + ins.astype(np.int64)
     out_off_flat = np.zeros(total + 1, dtype=np.int64)
@@ -60,10 +66,31 @@ def make_queries(n_q: int, db_letters: np.ndarray, db_off: np.ndarray, rng: np.r
     return out, q_off.astype(np.int64), src
 
 
-def workload(n_q: int, n_db: int, seed: int, qlen: int = 300):
+def workload(n_q: int, n_db: int, seed: int, qlen: int = 300, chunk: int = 8192, threads: int | None = None,
+             q_stream: int = 0):
+    """DB from default_rng(seed); queries in fixed chunks of `chunk`, chunk k drawn from default_rng([seed, 1 + q_stream, k]) so the
+    result does not depend on the number of worker threads (numpy releases the GIL in the heavy passes)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
     rng = np.random.default_rng(seed)
     dbl, dbo = make_db(n_db, rng)
-    ql, qo, src = make_queries(n_q, dbl, dbo, rng, qlen)
+    starts = list(range(0, n_q, chunk))
+
+    def job(k):
+        n = min(chunk, n_q - starts[k])
+        return make_queries(n, dbl, dbo, np.random.default_rng([seed, 1 + q_stream, k]), qlen)
+
+    threads = threads or min(64, os.cpu_count() or 1)
+    if len(starts) == 1 or threads == 1:
+        parts = [job(k) for k in range(len(starts))]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(job, range(len(starts))))
+    ql = np.concatenate([p[0] for p in parts])
+    lens = np.concatenate([np.diff(p[1]) for p in parts])
+    qo = np.zeros(n_q + 1, dtype=np.int64)
+    np.cumsum(lens, out=qo[1:])
+    src = np.concatenate([p[2] for p in parts])
     return {"q_letters": ql, "q_off": qo, "db_letters": dbl, "db_off": dbo, "src": src}
 
 
@@ -91,7 +118,7 @@ def edge_workload(seed: int, n_db: int = 2000, n_q: int = 300):
     for k in range(n_q):
         if k % 29 == 0:  # no homolog at all
             L = int(rng.integers(10, 150))
-            qs.append(rng.choice(20, size=L, p=RR_FREQ).astype(np.int8))
+            qs.append(draw_letters(rng, L))
             continue
         s = int(rng.integers(0, n_db))
         slen = int(dbo[s + 1] - dbo[s])
@@ -99,7 +126,7 @@ def edge_workload(seed: int, n_db: int = 2000, n_q: int = 300):
         st = int(rng.integers(0, slen - L + 1))
         q = dbl[dbo[s] + st: dbo[s] + st + L].copy()
         sub = rng.random(L) < rng.uniform(0.05, 0.4)
-        q[sub] = rng.choice(20, size=int(sub.sum()), p=RR_FREQ)
+        q[sub] = draw_letters(rng, int(sub.sum()))
         if k % 10 == 3:
             q[rng.integers(0, L, size=min(3, L))] = 23  # X
         if k % 17 == 5:
@@ -119,12 +146,12 @@ def family_workload(n_fam: int, fam_size: int, n_q: int, seed: int, base_len: in
     seqs = []
     for f in range(n_fam):
         L = int(rng.integers(base_len // 2, base_len * 2))
-        base = rng.choice(20, size=L, p=RR_FREQ).astype(np.int8)
+        base = draw_letters(rng, L)
         for m in range(fam_size):
             r = rng.uniform(member_div[0], member_div[1])
             s = base.copy()
             sub = rng.random(L) < r
-            s[sub] = rng.choice(20, size=int(sub.sum()), p=RR_FREQ)
+            s[sub] = draw_letters(rng, int(sub.sum()))
             keep = rng.random(L) >= 0.01
             s = s[keep]
             seqs.append(s)
