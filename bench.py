@@ -219,7 +219,8 @@ def main():
         # roofline of the dominant kernels (banded SWIPE, both rounds): integer-ALU bound, see DESIGN.md
         dp_ms = (tm["dp_score_ms"] + tm["dp_trace_ms"]) / args.steps
         laneops = st["cells_round1"] * 9 + st["cells_round2"] * 13  # 9 lane-ops / score cell, +4 for the trace masks
-        peak = ctx.int_peak() if hasattr(ctx, "int_peak") else None
+        # peak: every DPX instruction (VIADDMNMX / VIMNMX3) retires two of those lane-ops; its issue rate is measured live
+        peak = 2.0 * ctx.int_peak()
         ach = laneops / (dp_ms / 1e3) / 1e12 if dp_ms > 0 else None
         roofline = {"bound": "int-alu", "kernel": "swipe_kernel<R,*> (banded SWIPE rounds 1+2)", "achieved": ach, "peak": peak, "unit": "Tlaneop/s",
                     "frac": (ach / peak) if (ach and peak) else None, "traffic": None, "kernel_ms_per_step": dp_ms,

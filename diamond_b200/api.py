@@ -26,7 +26,8 @@ class Params(C.Structure):
                 ("shape_len", C.c_int32 * MAX_SHAPES), ("shape_mask", C.c_uint32 * MAX_SHAPES),
                 ("shape_pos", (C.c_int32 * MAX_WEIGHT) * MAX_SHAPES), ("hamming_id", C.c_int32),
                 ("seedp_bits", C.c_int32), ("index_chunks", C.c_int32), ("seed_cut", C.c_double),
-                ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double)]
+                ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double),
+                ("background_scores_f32", C.c_float * 20)]
 
 
 class Hit(C.Structure):
@@ -89,9 +90,9 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_block_upload",
-           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_clear_seed_mask",
+           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_clear_seed_mask",
            "dmnd_search_shape", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
-           "dmnd_timing_fetch", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
+           "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
 
 
@@ -112,6 +113,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_block_set_bias.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_block_download_letters.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
+    lib.dmnd_block_compute_bias.argtypes = [vp, vp, C.c_int]
+    lib.dmnd_block_download_bias.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_search_shape.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(StageCounters)]
     lib.dmnd_hits_count.argtypes = [vp]
     lib.dmnd_hits_count.restype = C.c_size_t
@@ -120,6 +123,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_hits_free.restype = None
     lib.dmnd_banded_swipe.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
     lib.dmnd_timing_fetch.argtypes = [vp, C.POINTER(Timing), C.c_int]
+    lib.dmnd_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.dmnd_search_opts_default.argtypes = [C.POINTER(SearchOpts)]
     lib.dmnd_search_opts_default.restype = None
     lib.dmnd_params_init.argtypes = [C.POINTER(SearchOpts), C.POINTER(Params)]
@@ -207,6 +211,14 @@ class Context:
         self._check(self.lib.dmnd_block_download_letters(self.ctx, b, out.ctypes.data, raw_len))
         return out
 
+    def compute_bias(self, b, mode: int = 1):
+        self._check(self.lib.dmnd_block_compute_bias(self.ctx, b, mode))
+
+    def download_bias(self, b, raw_len: int) -> np.ndarray:
+        out = np.empty(raw_len, dtype=np.int8)
+        self._check(self.lib.dmnd_block_download_bias(self.ctx, b, out.ctypes.data, raw_len))
+        return out
+
     def clear_seed_mask(self, b):
         self._check(self.lib.dmnd_block_clear_seed_mask(self.ctx, b))
 
@@ -233,6 +245,12 @@ class Context:
         t = Timing()
         self.lib.dmnd_timing_fetch(self.ctx, C.byref(t), int(reset))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def int_peak(self) -> float:
+        """Measured DPX issue rate in T lane-instructions / s (roofline denominator of the DP kernels)."""
+        v = C.c_double()
+        self._check(self.lib.dmnd_measure_int_peak(self.ctx, C.byref(v)))
+        return v.value / 1e12
 
     # ---- P layer
     def _collect(self, res):

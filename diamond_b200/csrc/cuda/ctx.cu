@@ -22,7 +22,85 @@ static __global__ void clear_seed_mask_kernel(int8_t* letters, size_t n) {
 		for (size_t k = i * 16; k < n; ++k) letters[k] &= 0x7f;
 }
 
+// HauserCorrection (stats/hauser_correction.cpp:53-109), one thread per sequence running the reference's own five-phase
+// sliding-window loop.  The window sums are integers; the three float operations per position (int->float, divide,
+// subtract) and the half-away-from-zero rounding use the explicit round-to-nearest intrinsics, so the int8 results are
+// bit-identical to the host's scalar code (no FMA contraction, IEEE division).
+static __global__ void hauser_kernel(const int8_t* __restrict__ letters, const int64_t* __restrict__ limits, uint32_t nseq,
+                                     const DevParams* __restrict__ P, int8_t* __restrict__ bias) {
+	__shared__ int8_t s_score[32 * 20];
+	__shared__ float s_bg[20];
+	for (int i = threadIdx.x; i < 32 * 20; i += blockDim.x) s_score[i] = P->score[(i / 20) * 32 + (i % 20)];
+	if (threadIdx.x < 20) s_bg[threadIdx.x] = P->background_scores_f32[threadIdx.x];
+	__syncthreads();
+	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (sidx >= nseq) return;
+	const int64_t beg = limits[sidx];
+	const int len = (int)(limits[sidx + 1] - beg - 1);
+	if (len <= 0) return;
+	const int8_t* seq = letters + beg;
+	int8_t* out = bias + beg;
+	int scores[20];
+#pragma unroll
+	for (int i = 0; i < 20; ++i) scores[i] = 0;
+	const unsigned window = 40, l = (unsigned)len, window_half = min(window / 2, l - 1);
+	unsigned n = 0, h = 0, m = 0, t = 0;
+	auto add = [&](unsigned pos) { const int8_t* row = s_score + (seq[pos] & 31) * 20;
+#pragma unroll
+		for (int i = 0; i < 20; ++i) scores[i] += row[i]; };
+	auto sub = [&](unsigned pos) { const int8_t* row = s_score + (seq[pos] & 31) * 20;
+#pragma unroll
+		for (int i = 0; i < 20; ++i) scores[i] -= row[i]; };
+	auto emit = [&](unsigned pos) {
+		const int r = seq[pos] & 31;
+		int8_t v = 0;
+		if (r < 20) {
+			int sr = 0;
+#pragma unroll
+			for (int i = 0; i < 20; ++i) if (i == r) sr = scores[i];
+			const float f = __fsub_rn(s_bg[r], __fdiv_rn(__int2float_rn(sr - (int)s_score[r * 20 + r]), __uint2float_rn(n - 1)));
+			v = (int8_t)(f < 0.0f ? __fsub_rn(f, 0.5f) : __fadd_rn(f, 0.5f));
+		}
+		out[pos] = v;
+	};
+	while (n < window_half && h < l) { ++n; add(h); ++h; }
+	while (n < (window + 1) && h < l) { ++n; add(h); emit(m); ++h; ++m; }
+	while (h < l) { add(h); sub(t); emit(m); ++h; ++t; ++m; }
+	while (m < l && n > (window_half + 1)) { --n; sub(t); emit(m); ++t; ++m; }
+	while (m < l) { emit(m); ++m; }
+}
+
+// Issue-rate micro-benchmark: 8 independent chains of VIADDMNMX per thread, enough warps to fill every SMSP.
+static __global__ void __launch_bounds__(256) int_peak_kernel(int* out, int iters, int b) {
+	int a[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) a[k] = threadIdx.x + k;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 8; ++k) a[k] = __viaddmax_s32(a[k], b, k - i);
+	}
+	int s = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) s += a[k];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 extern "C" {
+
+int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 15;
+	if (ctx->b_work.ensure((size_t)blocks * threads * sizeof(int))) return 1;
+	int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), 1024, -1);  // warm-up
+	cudaEventRecord(ctx->ev_a, ctx->stream);
+	int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), iters, -1);
+	cudaEventRecord(ctx->ev_b, ctx->stream);
+	DMND_CUDA_CHECK(cudaEventSynchronize(ctx->ev_b));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+	*lane_instr_per_s = (double)blocks * threads * (double)iters * 8.0 / (ms * 1e-3);
+	return 0;
+}
 
 const char* dmnd_last_error(void) { return g_err.c_str(); }
 void dmnd_set_last_error(const char* m) { g_err = m ? m : ""; }
@@ -59,6 +137,7 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	d.hamming_id = params->hamming_id; d.seedp_bits = params->seedp_bits; d.index_chunks = params->index_chunks;
 	d.left_most_interval = params->left_most_interval; d.ungapped_window = params->ungapped_window;
 	d.gap_open = params->gap_open; d.gap_extend = params->gap_extend; d.seed_cut = params->seed_cut;
+	std::memcpy(d.background_scores_f32, params->background_scores_f32, sizeof d.background_scores_f32);
 	{
 		unsigned long long pw = 1;
 		for (int i = 0; i < params->shape_weight; ++i) pw *= (unsigned long long)params->reduction_size;
@@ -100,7 +179,7 @@ void dmnd_destroy(dmnd_ctx* c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
-		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work };
+		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep };
 	for (DevBuf* b : bufs) b->release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
 	if (c->d_params) cudaFree(c->d_params);
@@ -149,6 +228,29 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 	if (bias) { DMND_CUDA_CHECK(cudaMemcpyAsync(b->bias, bias, raw_len, cudaMemcpyHostToDevice, ctx->stream)); ctx->h2d_bytes += raw_len; }
 	else DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, raw_len, ctx->stream));
 	t.stop();
+	return 0;
+}
+
+int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (mode != 0 && mode != 1) { set_error("dmnd_block_compute_bias: unknown mode"); return 1; }
+	PhaseTimer t(ctx, PH_SEED);
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, b->raw_len, ctx->stream));
+	if (mode == 1 && b->nseq) {
+		hauser_kernel<<<(b->nseq + 127) / 128, 128, 0, ctx->stream>>>(b->letters, b->limits, b->nseq, ctx->d_params, b->bias);
+		++ctx->launches;
+		DMND_CUDA_CHECK(cudaGetLastError());
+	}
+	t.stop();
+	return 0;
+}
+
+int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len != b->raw_len) { set_error("dmnd_block_download_bias: length mismatch"); return 1; }
+	DMND_CUDA_CHECK(cudaMemcpyAsync(bias, b->bias, raw_len, cudaMemcpyDeviceToHost, ctx->stream));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	ctx->d2h_bytes += raw_len;
 	return 0;
 }
 

@@ -52,6 +52,7 @@ struct DevParams {
 	int32_t seed_bits;     // bit length of reduction_size^weight - 1
 	double seed_cut;
 	double lnfact[DMND_MAX_WEIGHT + 1];
+	float background_scores_f32[20];
 };
 
 enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
@@ -83,7 +84,8 @@ struct dmnd_ctx {
 	int sm_count = 148;
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
-	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work;
+	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work, b_prep;
+	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	void* h_pinned = nullptr;  // small pinned staging for counters
 	size_t h_pinned_cap = 0;
 	// timing

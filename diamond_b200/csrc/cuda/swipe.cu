@@ -16,10 +16,12 @@
 // per cell (gap: cur==vgap / cur==hgap, open: vgap'==open / hgap'==open) and a second kernel walks them
 // (banded_swipe.h:127-187, banded_matrix.h:357-402, basic/hssp.cpp:260-290), one problem per thread.
 #include "ctx.cuh"
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <cstring>
 #include <numeric>
 #include <cstdlib>
+#include <chrono>
 
 namespace dmnd_cuda {
 
@@ -36,8 +38,10 @@ struct SwipeArgs {
 	uint32_t n;
 	int32_t* score;         // [problem]
 	int32_t* end_cell;      // [problem][2] = (column, band row) of the end cell, traceback only
-	uint8_t* trace;         // traceback masks, one byte per cell, column-major [c * B + r]
-	const uint64_t* trace_off;  // [problem]
+	uint8_t* trace;         // traceback masks, wavefront-major nibbles: byte [(m * 32 + lane) * R/2 + k/2], see trace_store()
+	const uint64_t* trace_excl; // exclusive prefix of trace bytes over the ORDER sequence (global order position)
+	uint64_t trace_base;    // prefix value at the first position of the slice in flight
+	uint32_t order_pos0;    // global order position of order[0]
 	unsigned int* work;     // atomic work counter
 };
 
@@ -67,6 +71,21 @@ __device__ __forceinline__ uint8_t trace_flags(int hd, int e_in, int f_in, int o
 	return (uint8_t)(b0 | (b1 << 1) | (b2 << 2) | (b3 << 3));
 }
 
+template<int R>
+__device__ __forceinline__ void trace_store(uint8_t* p, const uint32_t* pk) {
+	if (R == 2) *p = (uint8_t)pk[0];
+	else if (R == 4) *reinterpret_cast<uint16_t*>(p) = (uint16_t)pk[0];
+	else if (R == 8) *reinterpret_cast<uint32_t*>(p) = pk[0];
+	else if (R == 16) *reinterpret_cast<uint2*>(p) = make_uint2(pk[0], pk[1]);
+	else *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+__host__ __device__ __forceinline__ int tile_rows(int B) { return B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 32; }
+// nibble of cell (column c, band row r) in the wavefront-major layout
+__device__ __forceinline__ unsigned trace_nibble(const uint8_t* tr, int R, int c, int r) {
+	const int m = c + (r >> 1), lane = r / R, k = r - lane * R;
+	return (tr[((size_t)m * 32 + lane) * (R >> 1) + (k >> 1)] >> ((k & 1) * 4)) & 15u;
+}
+
 template<int R, bool TRACE>
 __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const DevParams* __restrict__ P) {
 	__shared__ int8_t s_score[1024];
@@ -89,12 +108,17 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 #pragma unroll
 		for (int k = 0; k < R; ++k) { H[k] = 0; E[k] = 0; F[k] = 0; bestv[k] = 0; bestc[k] = 0; }
 		int best = 0;
-		uint8_t* tr = TRACE ? a.trace + a.trace_off[pi] : nullptr;
+		// lane t stores its R nibbles of one macro step as R/2 consecutive bytes: the warp writes 16*R contiguous bytes
+		uint8_t* tr = TRACE ? a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base) + (size_t)lane * (R / 2) : nullptr;
+		constexpr int PKW = (R + 7) / 8;
 		if (g.B > 0 && g.cols > 0) {
 			const int ibase = g.j0 + g.d_begin;  // i = ibase + c + r
 			const int nsteps = 2 * (g.cols - 1) + g.B;
 			const int nmacro = (nsteps + 1) >> 1;
 			for (int m = 0; m < nmacro; ++m) {
+				uint32_t pk[PKW];
+#pragma unroll
+				for (int x = 0; x < PKW; ++x) pk[x] = 0;
 				// ---- even step s = 2m : rows k = 0,2,.. ; column c = m - (r0 + k)/2
 				{
 					int f_up = __shfl_up_sync(FULL, F[R - 1], 1);
@@ -110,7 +134,7 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 							const int open = max(h - go, 0);
 							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
 							if (TRACE) {
-								tr[(size_t)c * g.B + r] = trace_flags(hd, e_in, f_in, open, ge);
+								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
 							}
 							else best = max(best, h);
@@ -133,7 +157,7 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 							const int open = max(h - go, 0);
 							const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
 							if (TRACE) {
-								tr[(size_t)c * g.B + r] = trace_flags(hd, e_in, f_in, open, ge);
+								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = c; }
 							}
 							else best = max(best, h);
@@ -141,6 +165,7 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 						}
 					}
 				}
+				if (TRACE) trace_store<R>(tr + (size_t)m * (16 * R), pk);
 			}
 		}
 		if (TRACE) {
@@ -175,7 +200,9 @@ struct WalkArgs {
 	const int32_t* score;
 	const int32_t* end_cell;
 	const uint8_t* trace;
-	const uint64_t* trace_off;
+	const uint64_t* trace_excl;
+	uint64_t trace_base;
+	uint32_t order_pos0;
 	dmnd_dp_result* res;
 	uint8_t* transcripts;           // may be null
 	const uint64_t* transcript_off; // [problem], capacity qlen + tlen each
@@ -196,7 +223,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 	res.transcript_off = 0; res.transcript_len = 0; res.status = 0;
 	const int best = res.score;
 	if (best > 0) {
-		const uint8_t* tr = a.trace + a.trace_off[pi];
+		const uint8_t* tr = a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base);
+		const int R = tile_rows(g.B);
 		int c = a.end_cell[2 * (size_t)pi], r = a.end_cell[2 * (size_t)pi + 1];
 		int i = g.j0 + g.d_begin + c + r, j = g.j0 + c;
 		res.q_end = i + 1; res.t_end = j + 1;
@@ -208,7 +236,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 		bool bad = false;
 		while (i >= 0 && j >= 0 && sc < best) {
 			if (c < 0 || r < 0 || r >= g.B) { bad = true; break; }
-			const uint8_t nib = tr[(size_t)c * g.B + r];
+			const unsigned nib = trace_nibble(tr, R, c, r);
 			if ((nib & 3) == 0) {
 				const int ql = g.q[i] & 31, sl = g.t[j] & 31;
 				const int m = P->score[(ql << 5) | sl];
@@ -220,7 +248,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 			}
 			else if (nib & 1) {
 				int l = 0;
-				do { ++l; --i; --r; } while (r >= 0 && (tr[(size_t)c * g.B + r] & 4) == 0 && i > 0);
+				do { ++l; --i; --r; } while (r >= 0 && (trace_nibble(tr, R, c, r) & 4) == 0 && i > 0);
 				if (r < 0) { bad = true; break; }
 				++res.gap_openings; res.length += l; res.gaps += l;
 				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)(DMND_OP_INSERTION << 6); ++n; }
@@ -228,7 +256,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 			}
 			else {
 				int l = 0;
-				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && (tr[(size_t)c * g.B + r] & 8) == 0 && j > 0);
+				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && (trace_nibble(tr, R, c, r) & 8) == 0 && j > 0);
 				if (c < 0 || r >= g.B) { bad = true; break; }
 				++res.gap_openings; res.length += l; res.gaps += l;
 				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)((DMND_OP_DELETION << 6) | (g.t[j + l - k] & 31)); ++n; }
@@ -271,116 +299,188 @@ static void launch_bin(int R, const SwipeArgs& a, const DevParams* P, int grid, 
 	}
 }
 
+// ---- device-side preparation: geometry, register-tile bin, cost class, bucket histogram ------------------------------
+struct PrepOut {
+	uint8_t* key;        // [n] bucket = bin * 32 + (31 - log2 class of the cell count): heavy problems first inside a bin
+	uint64_t* cost;      // [n] trace bytes (traceback) or cells (score only)
+	uint64_t* tslen;     // [n] qlen + tlen (transcript capacity)
+	unsigned int* hist;  // [256]
+	unsigned int* flag;  // error flag
+};
+__global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t n, const int64_t* __restrict__ ql, uint32_t nq,
+                            const int64_t* __restrict__ rl, uint32_t nr, int trace, PrepOut o) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	const dmnd_dp_problem p = probs[k];
+	if (p.query >= nq || p.target >= nr) { atomicMax(o.flag, 1u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
+	const int qlen = (int)(ql[p.query + 1] - ql[p.query] - 1), tlen = (int)(rl[p.target + 1] - rl[p.target] - 1);
+	const int B = p.d_end - p.d_begin;
+	const int i1 = max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
+	const int cols = min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
+	if (B > 1024) { atomicMax(o.flag, 2u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
+	const bool live = B > 0 && cols > 0;
+	const int R = tile_rows(B);
+	const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : 4;
+	const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
+	const int cls = 31 - min(31, 63 - __clzll(cells + 1));
+	const uint8_t key = (uint8_t)(b * 32 + cls);
+	o.key[k] = key;
+	const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
+	o.cost[k] = trace ? nmacro * 16ull * (unsigned long long)R : cells;
+	o.tslen[k] = (uint64_t)qlen + (uint64_t)tlen;
+	atomicAdd(&o.hist[key], 1u);
+}
+__global__ void scatter_kernel(const uint8_t* __restrict__ key, uint32_t n, const unsigned int* __restrict__ off, unsigned int* fill, uint32_t* order) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	const unsigned b = key[k];
+	order[off[b] + atomicAdd(&fill[b], 1u)] = k;
+}
+__global__ void gather_cost_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ cost, uint32_t n, uint64_t* out) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) out[k] = cost[order[k]];
+}
+
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
 	if (n == 0) return 0;
 	if (n > 0xfffffff0ull) { set_error("dmnd_banded_swipe: too many problems in one call"); return 1; }
 	const bool trace = mode == DMND_DP_TRACEBACK;
 	cudaStream_t st = ctx->stream;
-	// ---- host-side geometry: band, cols, cost, register-tile bin
+	const bool prof = getenv("DMND_PROFILE") != nullptr;
+	auto tp = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!prof) return;
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[dmnd profile]     swipe %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+		tp = now;
+	};
 	static const int RS[5] = { 2, 4, 8, 16, 32 };
-	std::vector<uint64_t> cost(n), troff(trace ? n : 0), tsoff((trace && transcripts) ? n : 0);
-	std::vector<uint8_t> bin(n);
-	uint64_t ts_total = 0;
-	for (size_t k = 0; k < n; ++k) {
-		const dmnd_dp_problem& p = problems[k];
-		if (p.query >= query->nseq || p.target >= ref->nseq) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
-		const int qlen = (int)(query->h_limits[p.query + 1] - query->h_limits[p.query] - 1), tlen = (int)(ref->h_limits[p.target + 1] - ref->h_limits[p.target] - 1);
-		const int B = p.d_end - p.d_begin;
-		const int i1 = std::max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
-		const int cols = std::min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
-		cost[k] = (B > 0 && cols > 0) ? (uint64_t)B * (uint64_t)cols : 0;
-		if (B > 1024) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
-		int b = 0;
-		while (RS[b] * 32 < B) ++b;
-		bin[k] = (uint8_t)b;
-		if (trace && transcripts) { tsoff[k] = ts_total; ts_total += (uint64_t)qlen + (uint64_t)tlen; }
-	}
-	if (trace && transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
-	if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
-	// order: by bin, heaviest first inside a bin
-	std::vector<uint32_t> order(n);
-	std::iota(order.begin(), order.end(), 0u);
-	std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return bin[x] != bin[y] ? bin[x] < bin[y] : (cost[x] != cost[y] ? cost[x] > cost[y] : x < y); });
-
+	const unsigned nb = (unsigned)((n + 255) / 256);
 	// ---- device buffers
 	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
-	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 64 * sizeof(unsigned int)))
+	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1024 * sizeof(unsigned int))
+	    || ctx->b_prep.ensure(n * (1 + 8 + 8 + 8 + 8) + 64))
 		return 1;
 	int32_t* d_score = ctx->b_work.as<int32_t>();
 	int32_t* d_end = d_score + n;
-	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);
+	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);  // [0..63] work counters, [256..511] hist, [512..767] offsets, [768..1023] fill, [64] flag
+	uint64_t* d_cost = ctx->b_prep.as<uint64_t>();
+	uint64_t* d_tslen = d_cost + n;
+	uint64_t* d_cum = d_tslen + n;    // exclusive prefix of cost in order sequence (n entries) -- reused as gather buffer
+	uint64_t* d_tsoff = d_cum + n;    // exclusive prefix of tslen in problem order
+	uint8_t* d_key = (uint8_t*)(d_tsoff + n);
 	{
 		PhaseTimer t(ctx, PH_H2D);
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_probs.p, problems, n * sizeof(dmnd_dp_problem), cudaMemcpyHostToDevice, st));
-		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_order.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 		t.stop();
-		ctx->h2d_bytes += n * (sizeof(dmnd_dp_problem) + sizeof(uint32_t));
+		ctx->h2d_bytes += n * sizeof(dmnd_dp_problem);
 	}
+	lap("upload problems");
+	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1024 * sizeof(unsigned int), st));
+	PrepOut po{ d_key, d_cost, d_tslen, d_counters + 256, d_counters + 64 };
+	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? 1 : 0, po);
+	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
+	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
+	unsigned int off[257];
+	off[0] = 0;
+	for (int k = 0; k < 256; ++k) off[k + 1] = off[k] + hp[k];
+	size_t bin_begin[6];
+	for (int b = 0; b <= 5; ++b) bin_begin[b] = off[std::min(b * 32, 256)];
+	std::memcpy(hp + 512, off, 256 * sizeof(unsigned int));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(d_counters + 512, hp + 512, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+	scatter_kernel<<<nb, 256, 0, st>>>(d_key, (uint32_t)n, d_counters + 512, d_counters + 768, ctx->b_order.as<uint32_t>());
+	ctx->launches += 2;
+	lap("device prep");
+
 	SwipeArgs a;
 	a.q_letters = query->letters; a.q_bias = query->bias; a.r_letters = ref->letters; a.q_limits = query->limits; a.r_limits = ref->limits;
 	a.probs = ctx->b_probs.as<dmnd_dp_problem>();
-	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_off = nullptr;
+	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_excl = nullptr; a.trace_base = 0; a.order_pos0 = 0;
+	uint64_t ts_total = 0;
 
 	if (!trace) {
-		PhaseTimer t(ctx, PH_DP_SCORE);
-		DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
-		size_t pos = 0;
 		for (int b = 0; b < 5; ++b) {
-			size_t e = pos;
-			while (e < n && bin[order[e]] == b) ++e;
+			const size_t pos = bin_begin[b], e = bin_begin[b + 1];
 			if (e > pos) {
-				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters + b;
+				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters + b; a.order_pos0 = (uint32_t)pos;
 				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
 				launch_bin<false>(RS[b], a, ctx->d_params, grid, st);
 				++ctx->launches;
 			}
-			pos = e;
 		}
-		fill_score_results<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_score, ctx->b_results.as<dmnd_dp_result>(), (uint32_t)n);
+		fill_score_results<<<nb, 256, 0, st>>>(d_score, ctx->b_results.as<dmnd_dp_result>(), (uint32_t)n);
 		++ctx->launches;
 		DMND_CUDA_CHECK(cudaGetLastError());
-		t.stop();
+		t_dp.stop();
 	}
 	else {
-		// trace memory is bounded: process the ordered list in slices that fit the budget
+		// exclusive prefix of the trace bytes along the order sequence; its host copy drives the slicing
+		size_t tmp1 = 0, tmp2 = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp1, d_cum, d_cum, n, st);
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_tslen, d_tsoff, n, st);
+		if (ctx->b_cub.ensure(std::max(tmp1, tmp2)) || ctx->b_trace_off.ensure((n + 1) * sizeof(uint64_t))) return 1;
+		uint64_t* d_excl = ctx->b_trace_off.as<uint64_t>();
+		gather_cost_kernel<<<nb, 256, 0, st>>>(ctx->b_order.as<uint32_t>(), d_cost, (uint32_t)n, d_cum);
+		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp1, d_cum, d_excl, n, st));
+		ctx->launches += 2;
+		std::vector<uint64_t>& excl = ctx->h_excl;
+		excl.resize(n + 1);
+		DMND_CUDA_CHECK(cudaMemcpyAsync(excl.data(), d_excl, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		uint64_t last_cost = 0, ts_last[2] = { 0, 0 };
+		DMND_CUDA_CHECK(cudaMemcpyAsync(&last_cost, d_cum + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		if (transcripts) {
+			DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_tslen, d_tsoff, n, st));
+			++ctx->launches;
+			DMND_CUDA_CHECK(cudaMemcpyAsync(&ts_last[0], d_tsoff + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			DMND_CUDA_CHECK(cudaMemcpyAsync(&ts_last[1], d_tslen + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		}
+		DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+		excl[n] = excl[n - 1] + last_cost;
+		ts_total = ts_last[0] + ts_last[1];
+		if (transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
+		if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
+		if (transcripts && ctx->b_tr.ensure(ts_total + 16)) return 1;
 		size_t free_b = 0, total_b = 0;
 		DMND_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-		const uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)(free_b + ctx->b_trace.cap) / 2);
-		if (ctx->b_trace_off.ensure(n * sizeof(uint64_t))) return 1;
-		if (transcripts) {
-			if (ctx->b_tr.ensure(ts_total + 16) || ctx->b_hits2.ensure(n * sizeof(uint64_t))) return 1;
-			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_hits2.p, tsoff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		const uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)((free_b + ctx->b_trace.cap) / 5) * 2);  // <= 40 % of what is free
+		lap("trace prefix");
+		for (int b = 0; b < 5; ++b) {
+			size_t pos = bin_begin[b];
+			const size_t bend = bin_begin[b + 1];
+			while (pos < bend) {
+				// slice [pos, e) of this bin whose trace fits the budget (at least one problem)
+				size_t e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + bend + 1, excl[pos] + budget) - excl.begin()) - 1;
+				e = std::max(e, pos + 1);
+				const uint64_t bytes = excl[e] - excl[pos];
+				if (ctx->b_trace.ensure((size_t)bytes + 64)) return 1;
+				DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
+				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters; a.order_pos0 = (uint32_t)pos;
+				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = excl[pos];
+				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
+				launch_bin<true>(RS[b], a, ctx->d_params, grid, st);
+				WalkArgs wa;
+				wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
+				wa.probs = a.probs; wa.order = a.order; wa.n = a.n; wa.score = d_score; wa.end_cell = d_end;
+				wa.trace = a.trace; wa.trace_excl = d_excl; wa.trace_base = a.trace_base; wa.order_pos0 = a.order_pos0;
+				wa.res = ctx->b_results.as<dmnd_dp_result>();
+				wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
+				wa.transcript_off = transcripts ? d_tsoff : nullptr;
+				walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
+				ctx->launches += 2;
+				DMND_CUDA_CHECK(cudaGetLastError());
+				if (e < bend || bytes > ctx->b_trace.cap / 2) DMND_CUDA_CHECK(cudaStreamSynchronize(st));  // the arena is reused by the next slice
+				pos = e;
+			}
 		}
-		size_t pos = 0;
-		while (pos < n) {
-			// slice [pos, e): same bin, total trace <= budget
-			const int b = bin[order[pos]];
-			size_t e = pos;
-			uint64_t bytes = 0;
-			while (e < n && bin[order[e]] == b && (e == pos || bytes + cost[order[e]] <= budget)) { troff[order[e]] = bytes; bytes += cost[order[e]]; ++e; }
-			if (bytes > ctx->b_trace.cap && ctx->b_trace.ensure((size_t)std::min<uint64_t>(std::max<uint64_t>(bytes, budget), (uint64_t)free_b + ctx->b_trace.cap - ((uint64_t)256 << 20)))) return 1;
-			if (bytes > ctx->b_trace.cap) { set_error("dmnd_banded_swipe: a single traceback matrix exceeds free device memory"); return 1; }
-			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_trace_off.p, troff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-			PhaseTimer t(ctx, PH_DP_TRACE);
-			DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
-			a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters;
-			a.trace = ctx->b_trace.as<uint8_t>(); a.trace_off = ctx->b_trace_off.as<uint64_t>();
-			const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
-			launch_bin<true>(RS[b], a, ctx->d_params, grid, st);
-			WalkArgs wa;
-			wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
-			wa.probs = a.probs; wa.order = a.order; wa.n = a.n; wa.score = d_score; wa.end_cell = d_end;
-			wa.trace = a.trace; wa.trace_off = a.trace_off; wa.res = ctx->b_results.as<dmnd_dp_result>();
-			wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
-			wa.transcript_off = transcripts ? ctx->b_hits2.as<uint64_t>() : nullptr;
-			walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
-			ctx->launches += 2;
-			DMND_CUDA_CHECK(cudaGetLastError());
-			t.stop();  // synchronises: troff may be rewritten for the next slice
-			pos = e;
-		}
+		t_dp.stop();
 	}
+	lap("kernels");
 	{
 		PhaseTimer t(ctx, PH_D2H);
 		DMND_CUDA_CHECK(cudaMemcpyAsync(results, ctx->b_results.p, n * sizeof(dmnd_dp_result), cudaMemcpyDeviceToHost, st));
@@ -389,6 +489,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
 	}
 	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	lap("download results");
 	if (trace && !getenv("DMND_NO_TRACE_CHECK"))
 		for (size_t k = 0; k < n; ++k)
 			if (results[k].status == 2) { set_error("dmnd_banded_swipe: Traceback error."); return 1; }

@@ -14,15 +14,23 @@
 //   dp/dp.h:47-52,121-124                  banded_cols, cells
 // Every per-query extend() is a small state machine (produce DP problems -> wait -> consume results), so the chunked
 // ranking loop of the reference is replayed exactly while the DP itself runs in device-wide waves.
+//
+// Memory: a query's state is plain data; its variable-length lists live in the bump arena of the worker thread that
+// owns the query (static block partition, so no list is ever touched by two threads), and every large buffer is kept
+// in a process-wide workspace between calls -- a steady-state step performs no heap allocation and no page faults.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -36,24 +44,103 @@ using namespace dmnd;
 using Clock = std::chrono::steady_clock;
 static double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
 
+// DMND_PROFILE=1: wall-clock of the host phases on stderr (development aid)
+struct Prof {
+	bool on = std::getenv("DMND_PROFILE") != nullptr;
+	Clock::time_point t = Clock::now();
+	void lap(const char* what) {
+		if (!on) return;
+		std::fprintf(stderr, "[dmnd profile] %-34s %8.2f ms\n", what, ms_since(t));
+		t = Clock::now();
+	}
+};
 
-template<typename F>
-void parallel_for(size_t n, int threads, size_t grain, F&& f) {
-	if (n == 0) return;
-	threads = std::max(1, std::min<int>(threads, (int)((n + grain - 1) / grain)));
-	if (threads == 1) { f(0, n, 0); return; }
-	std::atomic<size_t> next(0);
-	std::vector<std::thread> pool;
-	for (int t = 0; t < threads; ++t)
-		pool.emplace_back([&, t] {
-			for (;;) {
-				const size_t b = next.fetch_add(grain);
-				if (b >= n) break;
-				f(b, std::min(n, b + grain), t);
+// ---- fork-join pool: threads persist between calls, run(f) executes f(t) for t in [0, T) ---------------------------
+class Pool {
+public:
+	explicit Pool(int n) : n_(n) {
+		for (int t = 1; t < n; ++t) th_.emplace_back([this, t] { loop(t); });
+	}
+	~Pool() {
+		{ std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+		cv_.notify_all();
+		for (auto& t : th_) t.join();
+	}
+	int size() const { return n_; }
+	void run(const std::function<void(int)>& f) {
+		if (n_ == 1) { f(0); return; }
+		{ std::lock_guard<std::mutex> l(m_); fn_ = &f; pending_ = n_ - 1; ++gen_; }
+		cv_.notify_all();
+		f(0);
+		std::unique_lock<std::mutex> l(m_);
+		done_.wait(l, [this] { return pending_ == 0; });
+	}
+private:
+	void loop(int t) {
+		uint64_t seen = 0;
+		for (;;) {
+			const std::function<void(int)>* f;
+			{
+				std::unique_lock<std::mutex> l(m_);
+				cv_.wait(l, [&] { return gen_ != seen; });
+				seen = gen_;
+				if (stop_) return;
+				f = fn_;
 			}
-		});
-	for (auto& th : pool) th.join();
-}
+			(*f)(t);
+			{ std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+		}
+	}
+	int n_;
+	std::vector<std::thread> th_;
+	std::mutex m_;
+	std::condition_variable cv_, done_;
+	const std::function<void(int)>* fn_ = nullptr;
+	int pending_ = 0;
+	uint64_t gen_ = 0;
+	bool stop_ = false;
+};
+
+// ---- bump arena ---------------------------------------------------------------------------------------------------
+class Arena {
+public:
+	void reset() { cur_ = 0; used_ = 0; }
+	void* alloc(size_t bytes) {
+		bytes = (bytes + 15) & ~(size_t)15;
+		while (cur_ < blocks_.size() && used_ + bytes > sizes_[cur_]) { ++cur_; used_ = 0; }
+		if (cur_ == blocks_.size()) {
+			const size_t sz = std::max<size_t>(bytes, (size_t)4 << 20);
+			blocks_.emplace_back(new char[sz]);
+			sizes_.push_back(sz);
+		}
+		void* p = blocks_[cur_].get() + used_;
+		used_ += bytes;
+		return p;
+	}
+private:
+	std::vector<std::unique_ptr<char[]>> blocks_;
+	std::vector<size_t> sizes_;
+	size_t cur_ = 0, used_ = 0;
+};
+
+template<typename T>
+struct List {  // trivially-copyable elements only
+	T* p = nullptr;
+	uint32_t n = 0, cap = 0;
+	void reserve(Arena& a, uint32_t c) {
+		if (c <= cap) return;
+		T* np = (T*)a.alloc(sizeof(T) * c);
+		if (n) std::memcpy(np, p, sizeof(T) * n);
+		p = np; cap = c;
+	}
+	void push(Arena& a, const T& v) {
+		if (n == cap) reserve(a, cap ? cap * 2 : 4);
+		p[n++] = v;
+	}
+	T* begin() const { return p; }
+	T* end() const { return p + n; }
+	void clear() { n = 0; }
+};
 
 struct SeedHit { int i, j, score; bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
 struct TargetScore { uint32_t target; uint16_t score; bool operator<(const TargetScore& x) const { return score > x.score || (score == x.score && target < x.target); } };
@@ -62,15 +149,15 @@ struct HspLite { int score; double evalue; int d_begin, d_end; };
 inline bool hsp_less(const HspLite& a, const HspLite& b) {  // basic/match.h:199-202 (query_source_range.begin_ is 0 in round 1)
 	return a.score > b.score || (a.score == b.score && a.d_begin < b.d_begin);
 }
-struct Target {  // align/target.h:83-144
-	uint32_t block_id; int tlen; int filter_score; double filter_evalue; std::vector<HspLite> hsp;
+struct Target {  // align/target.h:83-144 after inner_culling (max_hsps == 1): only the best HSP is kept
+	uint32_t block_id; int tlen; int filter_score; double filter_evalue; HspLite hsp; bool has_hsp;
 	static bool comp_evalue(const Target& t, const Target& u) {
 		return t.filter_evalue < u.filter_evalue || (t.filter_evalue == u.filter_evalue && (t.filter_score > u.filter_score || (t.filter_score == u.filter_score && t.block_id < u.block_id)));
 	}
 };
 struct Match {  // align/extend.h:36-70
 	uint32_t target_block_id; int tlen; int filter_score; double filter_evalue; bool has_hsp; HspLite h; dmnd_dp_result r;
-	std::vector<uint8_t> tr;
+	uint64_t tr_off; uint32_t tr_len;  // into the owner thread's transcript buffer
 	static bool cmp_evalue(const Match& m, const Match& n) {
 		return m.filter_evalue < n.filter_evalue || (m.filter_evalue == n.filter_evalue && (m.filter_score > n.filter_score || (m.filter_score == n.filter_score && m.target_block_id < n.target_block_id)));
 	}
@@ -101,131 +188,195 @@ inline int banded_cols(int qlen, int tlen, int d_begin, int d_end) {  // dp/dp.h
 
 struct Env {
 	const Scoring* sc;
-	const int8_t *q_letters, *r_letters, *bias;  // bias may be null
+	const int8_t *q_letters, *r_letters;
 	const int64_t *q_limits, *r_limits;
 	uint32_t nq, nr;
 	int64_t ref_letters;
 	int max_target_seqs;
 	double max_evalue;
+	bool hauser, want_transcript;
 	int qlen(uint32_t q) const { return (int)(q_limits[q + 1] - q_limits[q] - 1); }
 	int tlen(uint32_t t) const { return (int)(r_limits[t + 1] - r_limits[t] - 1); }
 };
 
-enum Phase { PH_ROUND1_PRODUCE, PH_ROUND1_CONSUME, PH_ROUND2_CONSUME, PH_DONE };
+enum Phase : uint8_t { PH_ROUND1_PRODUCE, PH_ROUND1_CONSUME, PH_ROUND2_PRODUCE, PH_ROUND2_CONSUME, PH_DONE };
 
 struct QueryState {
-	uint32_t qid = 0;
-	int qlen = 0;
-	Phase phase = PH_ROUND1_PRODUCE;
-	// SeedHitList (align/target.h:160-165)
-	std::vector<SeedHit> seed_hits;
-	std::vector<uint32_t> hit_begin;  // per target, into seed_hits (size targets+1)
-	std::vector<uint32_t> target_block_ids;
-	std::vector<TargetScore> target_scores;
+	uint32_t qid;
+	int qlen;
+	Phase phase;
+	bool new_hits_ev;
+	// SeedHitList (align/target.h:160-165): slices of the owner thread's flat arrays
+	uint32_t sh_off, tgt_off, n_targets;  // hit_begin[tgt_off + k] (n_targets + 1 entries), block ids / scores [ts_off..]
+	uint32_t ts_off;
 	// extend() loop state (align/extend.cpp:259-336)
-	int64_t chunk_size = 0, i0 = 0, i1 = 0;
-	bool new_hits_ev = false;
-	int tail_score = 0, previous_tail_score = 0;
-	std::vector<Target> aligned_targets;
-	std::vector<Match> matches;
-	// in-flight
-	std::vector<Target> r1;            // targets of the chunk in flight (the `r` of gapped_score.cpp:182)
-	std::vector<uint32_t> prob_target; // per DP problem of this query: index into r1 / r2
-	std::vector<Match> r2;
-	size_t prob_begin = 0, prob_count = 0;  // slice of the wave's problem array
-	uint64_t stat_targets = 0;
-
-	void load_hits(const Env& e, dmnd_hit* begin, dmnd_hit* end);
-	void start(const Env& e);
-	void produce_round1(const Env& e, std::vector<dmnd_dp_problem>& out, uint64_t& cells);
-	void consume_round1(const Env& e, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
-	void produce_round2(const Env& e, std::vector<dmnd_dp_problem>& out, uint64_t& cells);
-	void consume_round2(const Env& e, const dmnd_dp_result* res);
-	void finish_outer(const Env& e);
+	int64_t chunk_size, i0, i1;
+	int tail_score, previous_tail_score;
+	List<Target> aligned_targets, r1;
+	List<Match> matches, r2;
+	List<uint32_t> prob_target;  // per DP problem in flight: index into r1 / r2
+	size_t prob_begin;           // offset in the owner thread's problem list of this wave
+	uint32_t prob_count;
 };
 
-void QueryState::load_hits(const Env& e, dmnd_hit* begin, dmnd_hit* end) {
+struct ThreadCtx {
+	Arena arena;
+	std::vector<SeedHit> seed_hits;
+	std::vector<uint32_t> hit_begin, target_block_ids;
+	std::vector<TargetScore> target_scores;
+	std::vector<dmnd_dp_problem> p1, p2;
+	std::vector<uint8_t> trbuf;
+	// scratch
+	std::vector<SeedHit> hits;
+	std::vector<Segment> segs;
+	std::vector<Chain> chains;
+	std::vector<int8_t> cbs;
+	std::vector<Target> tmp_targets;
+	uint64_t cells1 = 0, cells2 = 0, n_targets = 0, n_matches = 0, n_aligned = 0;
+	void reset() {
+		arena.reset(); seed_hits.clear(); hit_begin.clear(); target_block_ids.clear(); target_scores.clear();
+		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = 0;
+	}
+};
+
+// Everything that survives between calls (buffers keep their capacity: no page faults in steady state).
+struct Workspace {
+	std::mutex mtx;
+	std::unique_ptr<Pool> pool;
+	std::vector<ThreadCtx> tc;
+	std::vector<dmnd_hit> hv;
+	std::vector<size_t> qstart;
+	std::vector<QueryState> qs;
+	std::vector<dmnd_dp_problem> p1, p2;
+	std::vector<dmnd_dp_result> res1, res2;
+	std::vector<uint8_t> tr;
+	void ensure_pool(int threads) {
+		if (!pool || pool->size() != threads) { pool.reset(new Pool(threads)); tc.clear(); tc.resize((size_t)threads); }
+	}
+};
+Workspace& workspace() { static Workspace w; return w; }
+
+struct Driver {
+	dmnd_ctx* ctx;
+	dmnd_block* qb;
+	const dmnd_block* rb;
+	Env env;
+	Workspace* ws;
+	int T;
+	dmnd_run_stats stats;
+
+	size_t nq_hit = 0;
+	size_t block_begin(int t) const { return nq_hit * (size_t)t / (size_t)T; }
+
+	void load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* end);
+	void start(QueryState& q, ThreadCtx& tc);
+	void produce_round1(QueryState& q, ThreadCtx& tc);
+	void produce_round2(QueryState& q, ThreadCtx& tc);
+	void consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
+	void consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
+	void finish_outer(QueryState& q);
+	int run_waves();
+};
+
+void Driver::load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* end) {
 	// align/load_hits.h:44-122
+	const Env& e = env;
 	std::sort(begin, end, [](const dmnd_hit& a, const dmnd_hit& b) {
 		const uint64_t sa = DMND_HIT_SUBJECT(a), sb = DMND_HIT_SUBJECT(b);
 		return sa < sb || (sa == sb && (a.query < b.query || (a.query == b.query && a.seed_offset < b.seed_offset)));
 	});
-	uint32_t target = UINT32_MAX;
+	q.sh_off = (uint32_t)tc.seed_hits.size();
+	q.tgt_off = (uint32_t)tc.hit_begin.size();
+	q.ts_off = (uint32_t)tc.target_scores.size();
+	uint32_t target = UINT32_MAX, ntg = 0;
 	uint16_t score = 0;
 	for (dmnd_hit* h = begin; h < end; ++h) {
 		const uint64_t subj = DMND_HIT_SUBJECT(*h);
 		// SequenceSet::local_position: sequence whose [limits[t], limits[t+1]) holds subj
 		const uint32_t t = (uint32_t)(std::upper_bound(e.r_limits, e.r_limits + e.nr + 1, (int64_t)subj) - e.r_limits) - 1;
 		if (t != target) {
-			if (target != UINT32_MAX) { target_scores.push_back({ (uint32_t)target_block_ids.size() - 1, score }); score = 0; }
-			hit_begin.push_back((uint32_t)seed_hits.size());
+			if (target != UINT32_MAX) { tc.target_scores.push_back({ ntg - 1, score }); score = 0; }
+			tc.hit_begin.push_back((uint32_t)tc.seed_hits.size());
 			target = t;
-			target_block_ids.push_back(t);
+			tc.target_block_ids.push_back(t);
+			++ntg;
 		}
 		const uint16_t hs = (uint16_t)DMND_HIT_SCORE(*h);
-		seed_hits.push_back({ h->seed_offset, (int)((int64_t)subj - e.r_limits[t]), (int)hs });
+		tc.seed_hits.push_back({ h->seed_offset, (int)((int64_t)subj - e.r_limits[t]), (int)hs });
 		score = std::max(score, hs);
 	}
-	if (target != UINT32_MAX) target_scores.push_back({ (uint32_t)target_block_ids.size() - 1, score });
-	hit_begin.push_back((uint32_t)seed_hits.size());
+	if (target != UINT32_MAX) tc.target_scores.push_back({ ntg - 1, score });
+	tc.hit_begin.push_back((uint32_t)tc.seed_hits.size());
+	q.n_targets = ntg;
 }
 
-void QueryState::start(const Env& e) {
+void Driver::start(QueryState& q, ThreadCtx& tc) {
 	// align/extend.cpp:346-387 then :226-258
-	qlen = e.qlen(qid);
-	const int64_t target_count = (int64_t)target_block_ids.size();
-	stat_targets = (uint64_t)target_count;
-	if (target_count == 0) { phase = PH_DONE; return; }
+	const Env& e = env;
+	q.qlen = e.qlen(q.qid);
+	q.new_hits_ev = false; q.tail_score = q.previous_tail_score = 0;
+	q.aligned_targets = {}; q.r1 = {}; q.matches = {}; q.r2 = {}; q.prob_target = {};
+	q.prob_begin = 0; q.prob_count = 0;
+	const int64_t target_count = q.n_targets;
+	tc.n_targets += (uint64_t)target_count;
+	if (target_count == 0) { q.phase = PH_DONE; return; }
 	const int64_t block_mult = std::max<int64_t>((int64_t)std::round((double)e.ref_letters / 2e9), 1);
 	const int64_t mm = ((int64_t)e.max_target_seqs + 31) / 32 * 32;  // make_multiple(max_target_seqs, 32)
-	chunk_size = std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;
-	if (chunk_size < target_count) std::sort(target_scores.begin(), target_scores.end());
-	i0 = 0;
-	i1 = std::min<int64_t>(chunk_size, target_count);
-	if ((i1 - i0) < e.max_target_seqs)
-		while (i1 < target_count && e.sc->evalue(target_scores[(size_t)i1].score, (unsigned)qlen, 50) <= e.max_evalue)
-			i1 += std::min<int64_t>(16, target_count - i1);
-	phase = PH_ROUND1_PRODUCE;
+	q.chunk_size = std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;
+	TargetScore* ts = tc.target_scores.data() + q.ts_off;
+	if (q.chunk_size < target_count) std::sort(ts, ts + target_count);
+	q.i0 = 0;
+	q.i1 = std::min<int64_t>(q.chunk_size, target_count);
+	if ((q.i1 - q.i0) < e.max_target_seqs)
+		while (q.i1 < target_count && e.sc->evalue(ts[q.i1].score, (unsigned)q.qlen, 50) <= e.max_evalue)
+			q.i1 += std::min<int64_t>(16, target_count - q.i1);
+	q.phase = PH_ROUND1_PRODUCE;
 }
 
-void QueryState::produce_round1(const Env& e, std::vector<dmnd_dp_problem>& out, uint64_t& cells) {
+void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	// extend_chunk -> ungapped_stage -> align (round 1)
-	r1.clear();
-	prob_target.clear();
-	prob_begin = out.size();
-	const int8_t* query = e.q_letters + e.q_limits[qid];
-	const int8_t* cbs = e.bias ? e.bias + e.q_limits[qid] : nullptr;
-	const int band = band_for(qlen);
-	std::vector<SeedHit> hits;
-	std::vector<Segment> segs;
-	std::vector<Chain> chains;
-	for (int64_t k = i0; k < i1; ++k) {
-		const uint32_t tix = target_scores[(size_t)k].target;
-		const uint32_t block_id = target_block_ids[tix];
+	const Env& e = env;
+	q.r1.clear();
+	q.r1.reserve(tc.arena, (uint32_t)(q.i1 - q.i0));
+	q.prob_target.clear();
+	q.prob_begin = tc.p1.size();
+	const int8_t* query = e.q_letters + e.q_limits[q.qid];
+	const int8_t* cbs = nullptr;
+	if (e.hauser) {  // HauserCorrection per query, align/extend.cpp:247-250
+		hauser_correction(*e.sc, query, q.qlen, tc.cbs);
+		cbs = tc.cbs.data();
+	}
+	const int band = band_for(q.qlen);
+	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
+	const uint32_t* hb = tc.hit_begin.data() + q.tgt_off;
+	const uint32_t* ids = tc.target_block_ids.data() + q.ts_off;
+	for (int64_t k = q.i0; k < q.i1; ++k) {
+		const uint32_t tix = ts[k].target;
+		const uint32_t block_id = ids[tix];
 		const int slen = e.tlen(block_id);
 		const int8_t* subject = e.r_letters + e.r_limits[block_id];
-		r1.push_back(Target{ block_id, slen, 0, DBL_MAX, {} });
-		hits.assign(seed_hits.begin() + hit_begin[tix], seed_hits.begin() + hit_begin[tix + 1]);
-		std::sort(hits.begin(), hits.end());
-		segs.clear();
-		for (const SeedHit& h : hits) {  // align/ungapped.cpp:81-91
-			if (!segs.empty() && segs.back().diag() == h.i - h.j && segs.back().subject_end() >= h.j) continue;
+		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false });
+		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
+		std::sort(tc.hits.begin(), tc.hits.end());
+		tc.segs.clear();
+		for (const SeedHit& h : tc.hits) {  // align/ungapped.cpp:81-91
+			if (!tc.segs.empty() && tc.segs.back().diag() == h.i - h.j && tc.segs.back().subject_end() >= h.j) continue;
 			const Segment d = xdrop_ungapped(*e.sc, query, cbs, subject, h.i, h.j);
-			if (d.score > 0) segs.push_back(d);
+			if (d.score > 0) tc.segs.push_back(d);
 		}
-		if (segs.empty()) continue;
-		std::stable_sort(segs.begin(), segs.end(), [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
-		chain_segments(*e.sc, query, qlen, subject, slen, segs, chains);
-		std::stable_sort(chains.begin(), chains.end(), [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
+		if (tc.segs.empty()) continue;
+		std::stable_sort(tc.segs.begin(), tc.segs.end(), [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
+		chain_segments(*e.sc, query, q.qlen, subject, slen, tc.segs, tc.chains);
+		std::stable_sort(tc.chains.begin(), tc.chains.end(), [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
 		// add_dp_targets, align/gapped_score.cpp:107-180
 		int d0 = INT_MAX, d1 = INT_MIN;
 		auto emit = [&] {
-			out.push_back(dmnd_dp_problem{ qid, block_id, d0, d1 });
-			prob_target.push_back((uint32_t)r1.size() - 1);
-			cells += (uint64_t)(d1 - d0) * (uint64_t)banded_cols(qlen, slen, d0, d1);
+			tc.p1.push_back(dmnd_dp_problem{ q.qid, block_id, d0, d1 });
+			q.prob_target.push(tc.arena, q.r1.n - 1);
+			tc.cells1 += (uint64_t)(d1 - d0) * (uint64_t)banded_cols(q.qlen, slen, d0, d1);
 		};
-		for (const Chain& h : chains) {
-			const int b0 = std::max(h.d_min - band, -(slen - 1)), b1 = std::min(h.d_max + 1 + band, qlen);
+		for (const Chain& h : tc.chains) {
+			const int b0 = std::max(h.d_min - band, -(slen - 1)), b1 = std::min(h.d_max + 1 + band, q.qlen);
 			bool merge = false;
 			if (d0 != INT_MAX) {
 				const int ib = std::max(d0, b0), ie = std::min(d1, b1);
@@ -238,238 +389,199 @@ void QueryState::produce_round1(const Env& e, std::vector<dmnd_dp_problem>& out,
 				d0 = b0; d1 = b1;
 			}
 		}
-		if (!chains.empty()) emit();
+		if (!tc.chains.empty()) emit();
 	}
-	prob_count = out.size() - prob_begin;
-	phase = PH_ROUND1_CONSUME;
+	q.prob_count = (uint32_t)(tc.p1.size() - q.prob_begin);
+	q.phase = PH_ROUND1_CONSUME;
 }
 
-static void culling_targets(std::vector<Target>& targets, bool sort_only, int max_target_seqs) {  // align/culling.cpp:187-191
+static void culling_targets(List<Target>& targets, bool sort_only, int max_target_seqs) {  // align/culling.cpp:187-191
 	std::sort(targets.begin(), targets.end(), Target::comp_evalue);
-	if (!sort_only) targets.erase(output_range(targets.begin(), targets.end(), max_target_seqs), targets.end());
+	if (!sort_only) targets.n = (uint32_t)(output_range(targets.begin(), targets.end(), max_target_seqs) - targets.begin());
 }
 
-void QueryState::consume_round1(const Env& e, const dmnd_dp_problem* probs, const dmnd_dp_result* res) {
-	// tail of align() round 1 (gapped_score.cpp:231-246): add_hit, inner_culling, drop targets without hits
-	for (size_t k = 0; k < prob_count; ++k) {
-		const int score = res[prob_begin + k].score;
-		Target& t = r1[prob_target[k]];
-		const double ev = e.sc->evalue(score, (unsigned)qlen, (unsigned)t.tlen);
+void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res) {
+	const Env& e = env;
+	// tail of align() round 1 (gapped_score.cpp:231-246): add_hit + inner_culling (max_hsps == 1 keeps the first HSP in
+	// Hsp::operator< order; list::sort is stable, so among equal keys the earliest-added wins)
+	for (uint32_t k = 0; k < q.prob_count; ++k) {
+		const int score = res[k].score;
+		Target& t = q.r1.p[q.prob_target.p[k]];
+		const double ev = e.sc->evalue(score, (unsigned)q.qlen, (unsigned)t.tlen);
 		if (score > 0 && ev <= e.max_evalue) {  // banded_swipe.h:341-342, ScoreMatrix::report_cutoff
-			const dmnd_dp_problem& pr = probs[prob_begin + k];
-			t.hsp.push_back(HspLite{ score, ev, pr.d_begin, pr.d_end });  // Hsp::d_begin/d_end = the DpTarget's band
+			const HspLite h{ score, ev, probs[k].d_begin, probs[k].d_end };
+			if (!t.has_hsp || hsp_less(h, t.hsp)) t.hsp = h;
+			t.has_hsp = true;
 			if (score > t.filter_score) { t.filter_evalue = ev; t.filter_score = score; }  // Target::add_hit(list,it), target.h:104-112
 		}
 	}
+	// keep targets with hits (gapped_score.cpp:236-243)
+	tc.tmp_targets.clear();
+	for (const Target& t : q.r1) if (t.filter_evalue != DBL_MAX) tc.tmp_targets.push_back(t);
+	q.r1.clear();
+	std::vector<Target>& v = tc.tmp_targets;
+	// align/extend.cpp:307-320
+	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
+	const int64_t n_targets = q.n_targets;
+	const bool multi_chunk = (q.i1 - q.i0) < n_targets;
+	bool new_hits = q.new_hits_ev = !v.empty();
+	if (multi_chunk) {
+		// append_hits, align/culling.cpp:111-141 (with_culling = first_round_culling = true)
+		if (v.empty()) new_hits = false;
+		else {
+			new_hits = (int64_t)q.aligned_targets.n < e.max_target_seqs;
+			bool append = new_hits;
+			culling_targets(q.aligned_targets, append, e.max_target_seqs);
+			double min_evalue = DBL_MAX;
+			for (const Target& t : v) min_evalue = std::min(min_evalue, t.filter_evalue);
+			Target* range_end = output_range(q.aligned_targets.begin(), q.aligned_targets.end(), e.max_target_seqs);
+			if (q.aligned_targets.n == 0 || min_evalue <= (range_end - 1)->filter_evalue) { append = true; new_hits = true; }
+			if (append) for (const Target& t : v) q.aligned_targets.push(tc.arena, t);
+		}
+	}
+	else {
+		q.aligned_targets.clear();
+		q.aligned_targets.reserve(tc.arena, (uint32_t)v.size());
+		for (const Target& t : v) q.aligned_targets.push(tc.arena, t);
+	}
+	q.i0 = q.i1;
+	q.i1 += std::min<int64_t>(q.chunk_size, n_targets - q.i1);
+	q.previous_tail_score = q.tail_score;
+	if (new_hits) q.tail_score = ts[q.i1 - 1].score;
+	bool terminate = false;
+	if (q.i0 < n_targets) {  // ranking_terminate, align/extend.cpp:111-119
+		const int tscore = ts[q.i1 - 1].score;
+		terminate = !new_hits && (q.previous_tail_score == 0 || double(tscore) / (double)q.previous_tail_score <= 0.95 || e.sc->bitscore(tscore) < 25.0);
+	}
+	if (q.i0 < n_targets && !terminate) { q.phase = PH_ROUND1_PRODUCE; return; }
+	culling_targets(q.aligned_targets, false, e.max_target_seqs);  // extend.cpp:331
+	if (q.aligned_targets.n == 0) finish_outer(q);  // round 2 over nothing returns no matches
+	else q.phase = PH_ROUND2_PRODUCE;
 }
 
-}  // namespace
+void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
+	// round-2 problems (gapped_final.cpp:64-78,118-124): one per kept HSP of every culled target
+	q.prob_begin = tc.p2.size();
+	q.prob_target.clear();
+	q.r2.clear();
+	q.r2.reserve(tc.arena, q.aligned_targets.n);
+	for (const Target& tg : q.aligned_targets) {
+		if (tg.has_hsp) {
+			tc.p2.push_back(dmnd_dp_problem{ q.qid, tg.block_id, tg.hsp.d_begin, tg.hsp.d_end });
+			q.prob_target.push(tc.arena, q.r2.n);
+			tc.cells2 += (uint64_t)(tg.hsp.d_end - tg.hsp.d_begin) * (uint64_t)banded_cols(q.qlen, tg.tlen, tg.hsp.d_begin, tg.hsp.d_end);
+		}
+		Match m;
+		std::memset(&m, 0, sizeof m);
+		m.target_block_id = tg.block_id; m.tlen = tg.tlen; m.filter_score = 0; m.filter_evalue = DBL_MAX; m.has_hsp = false;
+		q.r2.push(tc.arena, m);
+	}
+	q.prob_count = (uint32_t)(tc.p2.size() - q.prob_begin);
+	q.phase = PH_ROUND2_CONSUME;
+}
 
-// The remaining state-machine steps need the wave's problem array, so they live in the driver below.
-namespace {
-
-struct Driver {
-	dmnd_ctx* ctx;
-	dmnd_block *qb;
-	const dmnd_block* rb;
-	Env env;
-	dmnd_search_opts opts;
-	int host_threads;
-	dmnd_run_stats stats;
-
-	std::vector<QueryState> qs;
-
-	int run_waves(std::vector<dmnd_match>& out_matches, std::vector<uint8_t>& out_tr);
-};
-
-int Driver::run_waves(std::vector<dmnd_match>& out_matches, std::vector<uint8_t>& out_tr) {
+void Driver::consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr) {
 	const Env& e = env;
-	std::vector<size_t> active(qs.size());
-	for (size_t i = 0; i < qs.size(); ++i) active[i] = i;
-	const int T = host_threads;
-	std::vector<std::vector<dmnd_dp_problem>> tl_p1((size_t)T), tl_p2((size_t)T);
-	std::vector<uint64_t> tl_c1((size_t)T), tl_c2((size_t)T);
-	std::vector<dmnd_dp_problem> p1, p2;
-	std::vector<dmnd_dp_result> res1, res2;
-	std::vector<uint8_t> tr;
-
-	while (!active.empty()) {
-		auto t0 = Clock::now();
-		for (auto& v : tl_p1) v.clear();
-		for (auto& v : tl_p2) v.clear();
-		std::fill(tl_c1.begin(), tl_c1.end(), 0);
-		std::fill(tl_c2.begin(), tl_c2.end(), 0);
-		// ---- produce: every active query emits the DP problems of its next step into a per-thread list
-		std::vector<int> owner(active.size());
-		parallel_for(active.size(), T, 64, [&](size_t b, size_t en, int t) {
-			for (size_t a = b; a < en; ++a) {
-				QueryState& q = qs[active[a]];
-				owner[a] = t;
-				if (q.phase == PH_ROUND1_PRODUCE) q.produce_round1(e, tl_p1[(size_t)t], tl_c1[(size_t)t]);
-				else if (q.phase == PH_ROUND2_CONSUME) {
-					// round-2 problems (gapped_final.cpp:64-78,118-124): one per kept HSP of every culled target
-					q.prob_begin = tl_p2[(size_t)t].size();
-					q.prob_target.clear();
-					q.r2.clear();
-					for (const Target& tg : q.aligned_targets) {
-						for (const HspLite& h : tg.hsp) {
-							tl_p2[(size_t)t].push_back(dmnd_dp_problem{ q.qid, tg.block_id, h.d_begin, h.d_end });
-							q.prob_target.push_back((uint32_t)q.r2.size());
-							tl_c2[(size_t)t] += (uint64_t)(h.d_end - h.d_begin) * (uint64_t)banded_cols(q.qlen, tg.tlen, h.d_begin, h.d_end);
-						}
-						Match m{};
-						m.target_block_id = tg.block_id; m.tlen = tg.tlen; m.filter_score = 0; m.filter_evalue = DBL_MAX; m.has_hsp = false;
-						q.r2.push_back(m);
-					}
-					q.prob_count = tl_p2[(size_t)t].size() - q.prob_begin;
+	// gapped_final.cpp:140-149
+	for (uint32_t k = 0; k < q.prob_count; ++k) {
+		const dmnd_dp_result& r = res[k];
+		Match& m = q.r2.p[q.prob_target.p[k]];
+		const double ev = e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
+		if (r.score > 0 && ev <= e.max_evalue) {
+			const HspLite h{ r.score, ev, probs[k].d_begin, probs[k].d_end };
+			if (!m.has_hsp || hsp_less(h, m.h)) {
+				m.h = h; m.r = r;
+				m.tr_off = 0; m.tr_len = 0;
+				if (e.want_transcript && r.status == 0 && tr) {
+					m.tr_off = tc.trbuf.size(); m.tr_len = r.transcript_len;
+					tc.trbuf.insert(tc.trbuf.end(), tr + r.transcript_off, tr + r.transcript_off + r.transcript_len);
 				}
 			}
+			m.has_hsp = true;
+		}
+	}
+	for (Match& m : q.r2) if (m.has_hsp) { m.filter_evalue = m.h.evalue; m.filter_score = m.h.score; }  // Match::inner_culling
+	std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
+	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e.max_target_seqs) - q.r2.begin());
+	for (const Match& m : q.r2) q.matches.push(tc.arena, m);
+	q.r2.clear();
+	q.aligned_targets.clear();
+	finish_outer(q);
+}
+
+void Driver::finish_outer(QueryState& q) {
+	// outer do-while of extend(), align/extend.cpp:336, then the final culling (:341)
+	const Env& e = env;
+	if ((int64_t)q.matches.n < e.max_target_seqs && q.i0 < (int64_t)q.n_targets && q.new_hits_ev) { q.phase = PH_ROUND1_PRODUCE; return; }
+	std::sort(q.matches.begin(), q.matches.end(), Match::cmp_evalue);
+	q.matches.n = (uint32_t)(output_range(q.matches.begin(), q.matches.end(), e.max_target_seqs) - q.matches.begin());
+	q.phase = PH_DONE;
+}
+
+int Driver::run_waves() {
+	Workspace& w = *ws;
+	Prof prof;
+	std::vector<size_t> off1((size_t)T + 1), off2((size_t)T + 1);
+	for (;;) {
+		auto t0 = Clock::now();
+		// ---- produce: every active query emits the DP problems of its next step into its owner's list
+		ws->pool->run([&](int t) {
+			ThreadCtx& tc = w.tc[(size_t)t];
+			tc.p1.clear(); tc.p2.clear();
+			for (size_t k = block_begin(t), en = block_begin(t + 1); k < en; ++k) {
+				QueryState& q = w.qs[k];
+				if (q.phase == PH_ROUND1_PRODUCE) produce_round1(q, tc);
+				else if (q.phase == PH_ROUND2_PRODUCE) produce_round2(q, tc);
+			}
 		});
-		// ---- concatenate (per-thread offsets)
-		std::vector<size_t> off1((size_t)T + 1, 0), off2((size_t)T + 1, 0);
-		for (int t = 0; t < T; ++t) { off1[(size_t)t + 1] = off1[(size_t)t] + tl_p1[(size_t)t].size(); off2[(size_t)t + 1] = off2[(size_t)t] + tl_p2[(size_t)t].size(); }
-		p1.resize(off1[(size_t)T]); p2.resize(off2[(size_t)T]);
-		for (int t = 0; t < T; ++t) {
-			if (!tl_p1[(size_t)t].empty()) std::memcpy(p1.data() + off1[(size_t)t], tl_p1[(size_t)t].data(), tl_p1[(size_t)t].size() * sizeof(dmnd_dp_problem));
-			if (!tl_p2[(size_t)t].empty()) std::memcpy(p2.data() + off2[(size_t)t], tl_p2[(size_t)t].data(), tl_p2[(size_t)t].size() * sizeof(dmnd_dp_problem));
-			stats.cells_round1 += tl_c1[(size_t)t]; stats.cells_round2 += tl_c2[(size_t)t];
-		}
-		for (size_t a = 0; a < active.size(); ++a) {
-			QueryState& q = qs[active[a]];
-			if (q.phase == PH_ROUND1_CONSUME) q.prob_begin += off1[(size_t)owner[a]];
-			else if (q.phase == PH_ROUND2_CONSUME) q.prob_begin += off2[(size_t)owner[a]];
-		}
-		stats.dp_problems_round1 += p1.size(); stats.dp_problems_round2 += p2.size();
+		off1[0] = off2[0] = 0;
+		for (int t = 0; t < T; ++t) { off1[(size_t)t + 1] = off1[(size_t)t] + w.tc[(size_t)t].p1.size(); off2[(size_t)t + 1] = off2[(size_t)t] + w.tc[(size_t)t].p2.size(); }
+		if (off1[(size_t)T] + off2[(size_t)T] == 0) break;  // nothing in flight: every query is done
+		w.p1.resize(off1[(size_t)T]); w.p2.resize(off2[(size_t)T]);
+		w.res1.resize(w.p1.size()); w.res2.resize(w.p2.size());
+		ws->pool->run([&](int t) {
+			const ThreadCtx& tc = w.tc[(size_t)t];
+			if (!tc.p1.empty()) std::memcpy(w.p1.data() + off1[(size_t)t], tc.p1.data(), tc.p1.size() * sizeof(dmnd_dp_problem));
+			if (!tc.p2.empty()) std::memcpy(w.p2.data() + off2[(size_t)t], tc.p2.data(), tc.p2.size() * sizeof(dmnd_dp_problem));
+		});
+		stats.dp_problems_round1 += w.p1.size(); stats.dp_problems_round2 += w.p2.size();
 		stats.host_bridge_ms += ms_since(t0);
+		prof.lap("  wave: produce + concat");
 		// ---- device waves
-		res1.resize(p1.size()); res2.resize(p2.size());
 		t0 = Clock::now();
-		if (!p1.empty() && dmnd_banded_swipe(ctx, qb, rb, p1.data(), p1.size(), DMND_DP_SCORE_ONLY, res1.data(), nullptr, 0)) return 1;
+		if (!w.p1.empty() && dmnd_banded_swipe(ctx, qb, rb, w.p1.data(), w.p1.size(), DMND_DP_SCORE_ONLY, w.res1.data(), nullptr, 0)) return 1;
 		stats.dp1_ms += ms_since(t0);
 		t0 = Clock::now();
-		if (!p2.empty()) {
-			uint8_t* trp = nullptr; size_t cap = 0;
-			if (opts.want_transcript) {
-				for (const dmnd_dp_problem& pr : p2) cap += (size_t)e.qlen(pr.query) + (size_t)e.tlen(pr.target);
-				tr.resize(cap); trp = tr.data();
+		uint8_t* trp = nullptr;
+		if (!w.p2.empty()) {
+			size_t cap = 0;
+			if (env.want_transcript) {
+				for (const dmnd_dp_problem& pr : w.p2) cap += (size_t)env.qlen(pr.query) + (size_t)env.tlen(pr.target);
+				w.tr.resize(cap); trp = w.tr.data();
 			}
-			if (dmnd_banded_swipe(ctx, qb, rb, p2.data(), p2.size(), DMND_DP_TRACEBACK, res2.data(), trp, cap)) return 1;
+			if (dmnd_banded_swipe(ctx, qb, rb, w.p2.data(), w.p2.size(), DMND_DP_TRACEBACK, w.res2.data(), trp, cap)) return 1;
 		}
 		stats.dp2_ms += ms_since(t0);
+		prof.lap("  wave: banded_swipe x2");
 		t0 = Clock::now();
 		// ---- consume
-		parallel_for(active.size(), T, 64, [&](size_t b, size_t en, int) {
-			for (size_t a = b; a < en; ++a) {
-				QueryState& q = qs[active[a]];
-				if (q.phase == PH_ROUND1_CONSUME) {
-					q.consume_round1(e, p1.data(), res1.data());
-					// inner_culling (max_hsps == 1), keep targets with hits
-					std::vector<Target> v;
-					for (Target& t : q.r1) {
-						if (t.filter_evalue == DBL_MAX) continue;
-						std::stable_sort(t.hsp.begin(), t.hsp.end(), hsp_less);  // Target::inner_culling, culling.cpp:60-70
-						t.hsp.resize(1);
-						v.push_back(std::move(t));
-					}
-					q.r1.clear();
-					// align/extend.cpp:307-320
-					const int64_t n_targets = (int64_t)q.target_scores.size();
-					const bool multi_chunk = (q.i1 - q.i0) < n_targets;
-					bool new_hits = q.new_hits_ev = !v.empty();
-					if (multi_chunk) {
-						// append_hits, align/culling.cpp:111-141 (with_culling = first_round_culling = true)
-						if (v.empty()) new_hits = false;
-						else {
-							new_hits = (int64_t)q.aligned_targets.size() < e.max_target_seqs;
-							bool append = new_hits;
-							culling_targets(q.aligned_targets, append, e.max_target_seqs);
-							double min_evalue = DBL_MAX;
-							for (const Target& t : v) min_evalue = std::min(min_evalue, t.filter_evalue);
-							auto range_end = output_range(q.aligned_targets.begin(), q.aligned_targets.end(), e.max_target_seqs);
-							if (q.aligned_targets.empty() || min_evalue <= (range_end - 1)->filter_evalue) { append = true; new_hits = true; }
-							if (append) for (Target& t : v) q.aligned_targets.push_back(std::move(t));
-						}
-					}
-					else q.aligned_targets = std::move(v);
-					q.i0 = q.i1;
-					q.i1 += std::min<int64_t>(q.chunk_size, n_targets - q.i1);
-					q.previous_tail_score = q.tail_score;
-					if (new_hits) q.tail_score = q.target_scores[(size_t)(q.i1 - 1)].score;
-					bool terminate = false;
-					if (q.i0 < n_targets) {  // ranking_terminate, align/extend.cpp:111-119
-						const int ts = q.target_scores[(size_t)(q.i1 - 1)].score;
-						terminate = !new_hits && (q.previous_tail_score == 0 || double(ts) / (double)q.previous_tail_score <= 0.95 || e.sc->bitscore(ts) < 25.0);
-					}
-					if (q.i0 < n_targets && !terminate) { q.phase = PH_ROUND1_PRODUCE; continue; }
-					culling_targets(q.aligned_targets, false, e.max_target_seqs);  // extend.cpp:331
-					if (q.aligned_targets.empty()) {
-						// round 2 over nothing: align() returns no matches; evaluate the outer loop condition
-						q.finish_outer(e);
-					}
-					else q.phase = PH_ROUND2_CONSUME;  // problems are produced at the top of the next wave
-				}
-				else if (q.phase == PH_ROUND2_CONSUME && q.prob_target.size() == q.prob_count && !q.r2.empty()) {
-					// gapped_final.cpp:140-149
-					for (size_t k = 0; k < q.prob_count; ++k) {
-						const dmnd_dp_result& r = res2[q.prob_begin + k];
-						Match& m = q.r2[q.prob_target[k]];
-						const double ev = e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
-						if (r.score > 0 && ev <= e.max_evalue) {
-							const dmnd_dp_problem& pr = p2[q.prob_begin + k];
-							const HspLite h{ r.score, ev, pr.d_begin, pr.d_end };
-							if (!m.has_hsp || hsp_less(h, m.h)) {
-								m.h = h; m.r = r;
-								if (opts.want_transcript && r.status == 0) m.tr.assign(tr.begin() + r.transcript_off, tr.begin() + r.transcript_off + r.transcript_len);
-							}
-							m.has_hsp = true;
-							if (r.score > m.filter_score) { m.filter_evalue = ev; m.filter_score = r.score; }
-						}
-					}
-					for (Match& m : q.r2) if (m.has_hsp) { m.filter_evalue = m.h.evalue; m.filter_score = m.h.score; }  // Match::inner_culling
-					std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
-					q.r2.erase(output_range(q.r2.begin(), q.r2.end(), e.max_target_seqs), q.r2.end());
-					for (Match& m : q.r2) q.matches.push_back(m);
-					q.r2.clear();
-					q.aligned_targets.clear();
-					q.finish_outer(e);
-				}
+		ws->pool->run([&](int t) {
+			ThreadCtx& tc = w.tc[(size_t)t];
+			const dmnd_dp_problem *P1 = w.p1.data() + off1[(size_t)t], *P2 = w.p2.data() + off2[(size_t)t];
+			const dmnd_dp_result *R1 = w.res1.data() + off1[(size_t)t], *R2 = w.res2.data() + off2[(size_t)t];
+			for (size_t k = block_begin(t), en = block_begin(t + 1); k < en; ++k) {
+				QueryState& q = w.qs[k];
+				if (q.phase == PH_ROUND1_CONSUME) consume_round1(q, tc, P1 + q.prob_begin, R1 + q.prob_begin);
+				else if (q.phase == PH_ROUND2_CONSUME) consume_round2(q, tc, P2 + q.prob_begin, R2 + q.prob_begin, trp);
 			}
 		});
-		std::vector<size_t> next_active;
-		for (size_t a : active) if (qs[a].phase != PH_DONE) next_active.push_back(a);
-		active.swap(next_active);
 		stats.host_bridge_ms += ms_since(t0);
+		prof.lap("  wave: consume");
 	}
-	// ---- emit
-	for (QueryState& q : qs) {
-		if (q.matches.empty()) continue;
-		++stats.queries_aligned;
-		for (const Match& m : q.matches) {
-			dmnd_match o{};
-			o.query = q.qid; o.target = m.target_block_id; o.score = m.h.score; o.evalue = m.h.evalue;
-			o.bit_score = e.sc->bitscore(m.h.score);
-			o.q_begin = m.r.q_begin; o.q_end = m.r.q_end; o.t_begin = m.r.t_begin; o.t_end = m.r.t_end;
-			o.identities = m.r.identities; o.mismatches = m.r.mismatches; o.gap_openings = m.r.gap_openings;
-			o.length = m.r.length; o.gaps = m.r.gaps; o.positives = m.r.positives;
-			o.transcript_off = out_tr.size(); o.transcript_len = (uint32_t)m.tr.size();
-			out_tr.insert(out_tr.end(), m.tr.begin(), m.tr.end());
-			out_matches.push_back(o);
-		}
-	}
-	stats.matches = out_matches.size();
 	return 0;
 }
 
 }  // namespace
-
-void QueryState::finish_outer(const Env& e) {
-	// outer do-while of extend(), align/extend.cpp:336, then the final culling (:341)
-	const int64_t n_targets = (int64_t)target_scores.size();
-	if ((int64_t)matches.size() < e.max_target_seqs && i0 < n_targets && new_hits_ev) { phase = PH_ROUND1_PRODUCE; return; }
-	std::sort(matches.begin(), matches.end(), Match::cmp_evalue);
-	matches.erase(output_range(matches.begin(), matches.end(), e.max_target_seqs), matches.end());
-	phase = PH_DONE;
-}
 
 // ------------------------------------------------------------------------------------------------------------
 struct dmnd_result {
@@ -491,6 +603,7 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	Scoring sc;
 	std::memcpy(p->score, sc.m8, sizeof p->score);
 	p->gap_open = sc.gap_open; p->gap_extend = sc.gap_extend;
+	for (int i = 0; i < 20; ++i) p->background_scores_f32[i] = (float)sc.background_scores[i];
 	// Reduction("A KR EDNQ C G H ILVM FYW P ST"), stats/stats.cpp:48, basic/basic.cpp:267-296
 	static const char* groups[10] = { "A", "KR", "EDNQ", "C", "G", "H", "ILVM", "FYW", "P", "ST" };
 	const char* alph = letter_alphabet();
@@ -530,6 +643,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
                        uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
                        dmnd_result** out) {
 	auto t_total = Clock::now();
+	Workspace& w = workspace();
+	std::lock_guard<std::mutex> guard(w.mtx);
 	std::unique_ptr<dmnd_result> res(new dmnd_result());
 	std::memset(&res->stats, 0, sizeof res->stats);
 	Scoring sc;
@@ -539,61 +654,105 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	int host_threads = (int)std::thread::hardware_concurrency();
 	if (host_threads < 1) host_threads = 1;
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
+	w.ensure_pool(host_threads);
 
 	Driver d;
-	d.ctx = ctx; d.qb = qb; d.rb = rb; d.opts = *opts; d.host_threads = host_threads;
+	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads;
 	std::memset(&d.stats, 0, sizeof d.stats);
 	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, 1);
+	Env& e = d.env;
+	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
+	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
+	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
+	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 
 	// ---- seed stage (run_ref_chunk: one search_shape per shape; FAST has one shape)
+	Prof prof;
 	auto t0 = Clock::now();
+	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
+	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;
 	dmnd_hits* hits = nullptr;
 	if (dmnd_search_shape(ctx, qb, rb, 0, &hits, &d.stats.seed)) return 1;
+	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
-	std::vector<dmnd_hit> hv(nh);
-	if (nh && dmnd_hits_download(ctx, hits, hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
+	w.hv.resize(nh);
+	if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	dmnd_hits_free(ctx, hits);
 	if (dmnd_block_clear_seed_mask(ctx, qb)) return 1;  // run/double_indexed.cpp:211-212
+	prof.lap("hits download");
 	d.stats.seed_ms = ms_since(t0);
 	d.stats.hits = nh;
 
 	// ---- group by query (hits arrive grouped by ascending query id)
 	t0 = Clock::now();
-	std::vector<size_t> qstart;
+	w.qstart.clear();
 	for (size_t i = 0; i < nh; ++i)
-		if (i == 0 || hv[i].query != hv[i - 1].query) {
-			if (i > 0 && hv[i].query < hv[i - 1].query) { dmnd_set_last_error("dmnd_blastp: hits not grouped by ascending query"); return 1; }
-			qstart.push_back(i);
+		if (i == 0 || w.hv[i].query != w.hv[i - 1].query) {
+			if (i > 0 && w.hv[i].query < w.hv[i - 1].query) { dmnd_set_last_error("dmnd_blastp: hits not grouped by ascending query"); return 1; }
+			w.qstart.push_back(i);
 		}
-	qstart.push_back(nh);
-	const size_t nqh = qstart.size() - 1;
-	d.qs.resize(nqh);
+	w.qstart.push_back(nh);
+	const size_t nqh = w.qstart.size() - 1;
+	d.nq_hit = nqh;
+	w.qs.resize(nqh);
+	prof.lap("group queries");
+	w.pool->run([&](int t) {
+		ThreadCtx& tc = w.tc[(size_t)t];
+		tc.reset();
+		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
+			QueryState& q = w.qs[k];
+			q.qid = w.hv[w.qstart[k]].query;
+			d.load_hits(q, tc, w.hv.data() + w.qstart[k], w.hv.data() + w.qstart[k + 1]);
+			d.start(q, tc);
+		}
+	});
+	for (const ThreadCtx& tc : w.tc) d.stats.targets += tc.n_targets;
+	d.stats.host_bridge_ms += ms_since(t0);
+	prof.lap("load_hits (parallel)");
 
-	std::vector<int8_t> bias;
-	if (opts->comp_based_stats == 1) bias.assign((size_t)(q_limits[nq] + DMND_PERIMETER_PADDING), 0);
-	Env& e = d.env;
-	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters; e.bias = bias.empty() ? nullptr : bias.data();
-	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
-	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
+	if (d.run_waves()) return 1;
+	prof.lap("run_waves");
 
-	parallel_for(nqh, host_threads, 64, [&](size_t b, size_t en, int) {
-		std::vector<int8_t> hc;
-		for (size_t k = b; k < en; ++k) {
-			QueryState& q = d.qs[k];
-			q.qid = hv[qstart[k]].query;
-			q.load_hits(e, hv.data() + qstart[k], hv.data() + qstart[k + 1]);
-			q.start(e);
-			if (!bias.empty()) {  // HauserCorrection per query, align/extend.cpp:247-250
-				hauser_correction(sc, q_letters + q_limits[q.qid], q.qlen, hc);
-				std::memcpy(bias.data() + q_limits[q.qid], hc.data(), (size_t)q.qlen);
+	// ---- emit: per-thread counts -> offsets -> parallel fill (matches grouped by ascending query)
+	t0 = Clock::now();
+	const int T = host_threads;
+	std::vector<size_t> moff((size_t)T + 1, 0), troff((size_t)T + 1, 0);
+	w.pool->run([&](int t) {
+		ThreadCtx& tc = w.tc[(size_t)t];
+		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
+			tc.n_matches += w.qs[k].matches.n;
+			if (w.qs[k].matches.n) ++tc.n_aligned;
+		}
+	});
+	for (int t = 0; t < T; ++t) {
+		moff[(size_t)t + 1] = moff[(size_t)t] + w.tc[(size_t)t].n_matches;
+		troff[(size_t)t + 1] = troff[(size_t)t] + w.tc[(size_t)t].trbuf.size();
+		d.stats.queries_aligned += w.tc[(size_t)t].n_aligned;
+		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
+	}
+	res->matches.resize(moff[(size_t)T]);
+	res->transcripts.resize(troff[(size_t)T]);
+	w.pool->run([&](int t) {
+		const ThreadCtx& tc = w.tc[(size_t)t];
+		dmnd_match* o = res->matches.data() + moff[(size_t)t];
+		if (!tc.trbuf.empty()) std::memcpy(res->transcripts.data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
+		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
+			const QueryState& q = w.qs[k];
+			for (const Match& m : q.matches) {
+				std::memset(o, 0, sizeof *o);
+				o->query = q.qid; o->target = m.target_block_id; o->score = m.h.score; o->evalue = m.h.evalue;
+				o->bit_score = sc.bitscore(m.h.score);
+				o->q_begin = m.r.q_begin; o->q_end = m.r.q_end; o->t_begin = m.r.t_begin; o->t_end = m.r.t_end;
+				o->identities = m.r.identities; o->mismatches = m.r.mismatches; o->gap_openings = m.r.gap_openings;
+				o->length = m.r.length; o->gaps = m.r.gaps; o->positives = m.r.positives;
+				o->transcript_off = troff[(size_t)t] + m.tr_off; o->transcript_len = m.tr_len;
+				++o;
 			}
 		}
 	});
-	for (const QueryState& q : d.qs) d.stats.targets += q.stat_targets;
-	if (dmnd_block_set_bias(ctx, qb, bias.empty() ? nullptr : bias.data(), (size_t)(q_limits[nq] + DMND_PERIMETER_PADDING))) return 1;
+	d.stats.matches = res->matches.size();
 	d.stats.host_bridge_ms += ms_since(t0);
-
-	if (d.run_waves(res->matches, res->transcripts)) return 1;
+	prof.lap("emit matches");
 	d.stats.total_ms = ms_since(t_total);
 	dmnd_timing_fetch(ctx, &d.stats.device, 0);
 	res->stats = d.stats;

@@ -56,6 +56,7 @@ typedef struct dmnd_params {
 	int32_t left_most_interval;       /* config.left_most_interval = 32 */
 	int32_t ungapped_window;          /* config.ungapped_window = 48 */
 	double ungapped_evalue;           /* 0 => stage-2 ungapped filter skipped (fast); >0 not implemented yet */
+	float background_scores_f32[20];  /* (float)ScoreMatrix::background_scores_ (stats/score_matrix.cpp:241-248), for Hauser */
 } dmnd_params;
 
 /* Search::Hit (search/hit.h:30-48) as a fixed 16-byte record. */
@@ -120,6 +121,11 @@ void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b);
 /* Per-position int8 composition bias (HauserCorrection::int8, stats/hauser_correction.cpp:53-109), laid out at the
  * same offsets as the block's letters.  NULL => all zero (--comp-based-stats 0). */
 int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t raw_len);
+/* Fills the block's bias array on the device: mode 1 = HauserCorrection of every sequence (stats/hauser_correction.cpp:
+ * 53-109, window 40, fp32, rounded half away from zero), mode 0 = zeros (--comp-based-stats 0). */
+int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode);
+/* Reads back the block's bias array (tests). */
+int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len);
 /* Reads back the block's letters (query letters carry SEED_MASK bits set by dmnd_search_shape). */
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
 /* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
@@ -146,6 +152,9 @@ typedef struct dmnd_timing {
 	uint64_t h2d_bytes, d2h_bytes;
 } dmnd_timing;
 int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset);
+/* Roofline denominator for the DP kernels: measured issue rate (lane-instructions / s, whole GPU) of the three-input
+ * integer DPX instructions (VIADDMNMX / VIMNMX3) the recurrence is built from.  Runs a ~20 ms micro-benchmark. */
+int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {

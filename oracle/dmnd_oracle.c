@@ -114,6 +114,45 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 	if (bias) memcpy(b->bias, bias, raw_len); else memset(b->bias, 0, raw_len);
 	return 0;
 }
+/* stats/hauser_correction.cpp:53-109 (same loop structure: five phases of the sliding 40-letter window) */
+static void hauser_one(const dmnd_params* p, const int8_t* seq, int len, int8_t* out) {
+	int scores[20];
+	memset(scores, 0, sizeof scores);
+	const unsigned window = 40, l = (unsigned)len, window_half = (window / 2 < l - 1) ? window / 2 : l - 1;
+	unsigned n = 0, h = 0, m = 0, t = 0;
+	memset(out, 0, (size_t)len);
+#define SC(a, b) ((int)p->score[(a) * 32 + (b)])
+#define ADD(pos) do { const int _l = seq[pos] & 31; for (int _i = 0; _i < 20; ++_i) scores[_i] += SC(_l, _i); } while (0)
+#define SUB(pos) do { const int _l = seq[pos] & 31; for (int _i = 0; _i < 20; ++_i) scores[_i] -= SC(_l, _i); } while (0)
+#define EMIT(pos) do { const int _r = seq[pos] & 31; if (_r < 20) { const float _f = p->background_scores_f32[_r] - (float)(scores[_r] - SC(_r, _r)) / (float)(n - 1); \
+		out[pos] = (int8_t)(_f < 0.0f ? _f - 0.5f : _f + 0.5f); } } while (0)
+	while (n < window_half && h < l) { ++n; ADD(h); ++h; }
+	while (n < (window + 1) && h < l) { ++n; ADD(h); EMIT(m); ++h; ++m; }
+	while (h < l) { ADD(h); SUB(t); EMIT(m); ++h; ++t; ++m; }
+	while (m < l && n > (window_half + 1)) { --n; SUB(t); EMIT(m); ++t; ++m; }
+	while (m < l) { EMIT(m); ++m; }
+#undef SC
+#undef ADD
+#undef SUB
+#undef EMIT
+}
+int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
+	memset(b->bias, 0, b->raw_len);
+	if (mode == 0) return 0;
+	if (mode != 1) return fail("dmnd_block_compute_bias: unknown mode");
+	for (uint32_t i = 0; i < b->nseq; ++i) {
+		const int64_t beg = b->limits[i];
+		const int len = (int)(b->limits[i + 1] - beg - 1);
+		if (len > 0) hauser_one(&ctx->p, b->letters + beg, len, b->bias + beg);
+	}
+	return 0;
+}
+int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) {
+	(void)ctx;
+	if (raw_len != b->raw_len) return fail("dmnd_block_download_bias: length mismatch");
+	memcpy(bias, b->bias, raw_len);
+	return 0;
+}
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {
 	(void)ctx;
 	if (raw_len != b->raw_len) return fail("dmnd_block_download_letters: length mismatch");
@@ -126,6 +165,7 @@ int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
 		if (b->letters[i] != DMND_DELIMITER) b->letters[i] &= 0x7f; /* only bit 7 is ever added */
 	return 0;
 }
+int dmnd_measure_int_peak(dmnd_ctx* ctx, double* v) { (void)ctx; *v = 0; return fail("oracle: no device to measure"); }
 int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset) {
 	(void)ctx; (void)reset;
 	memset(out, 0, sizeof *out);

@@ -44,6 +44,25 @@ def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name
     o.close(); g.close()
 
 
+@pytest.mark.parametrize("name", ["c1", "edge"])
+def test_device_hauser_bias_matches_oracle(oracle_lib, product_lib, name):
+    """HauserCorrection (fp32 -> int8) computed on the device is bit-identical to the scalar restatement."""
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    out = []
+    for c in (o, g):
+        qb = c.upload(q_raw, q_lim)
+        c.compute_bias(qb, 1)
+        b1 = c.download_bias(qb, q_raw.size)
+        c.compute_bias(qb, 0)
+        b0 = c.download_bias(qb, q_raw.size)
+        out.append((b1, b0))
+        c.free_block(qb)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.any(out[1][0] != 0) and not np.any(out[1][1])
+    o.close(); g.close()
+
+
 def random_problems(w, q_lim, r_lim, rng, n):
     """Bands around the planted diagonal of (query, source target) pairs plus unrelated pairs and degenerate bands."""
     nq, nr = len(q_lim) - 1, len(r_lim) - 1
