@@ -86,11 +86,12 @@ HIT_DTYPE = np.dtype([("query", "<u4"), ("seed_offset", "<i4"), ("subject_score"
 RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches",
                                                "gap_openings", "length", "gaps", "positives")] +
                         [("transcript_off", "<u4"), ("transcript_len", "<u4"), ("status", "<i4")])
+SEGMENT_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("len", "<i4"), ("score", "<i4")])
 PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"), ("d_end", "<i4")])
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_block_upload",
-           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_clear_seed_mask",
+           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_block_clear_seed_mask",
            "dmnd_search_shape", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
@@ -119,6 +120,13 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_hits_count.argtypes = [vp]
     lib.dmnd_hits_count.restype = C.c_size_t
     lib.dmnd_hits_download.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_hits_xdrop.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_size_t]
+    lib.dmnd_block_download_bias_async.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_copy_wait.argtypes = [vp]
+    lib.dmnd_host_alloc.argtypes = [vp, C.c_size_t]
+    lib.dmnd_host_alloc.restype = vp
+    lib.dmnd_host_free.argtypes = [vp, vp]
+    lib.dmnd_host_free.restype = None
     lib.dmnd_hits_free.argtypes = [vp, vp]
     lib.dmnd_hits_free.restype = None
     lib.dmnd_banded_swipe.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
@@ -222,7 +230,8 @@ class Context:
     def clear_seed_mask(self, b):
         self._check(self.lib.dmnd_block_clear_seed_mask(self.ctx, b))
 
-    def search_shape(self, qb, rb, sid: int = 0):
+    def search_shape(self, qb, rb, sid: int = 0, xdrop: int | None = None):
+        """Hits (+ per-hit x-drop segments when `xdrop` is given) and the stage counters."""
         h = C.c_void_p()
         cn = StageCounters()
         self._check(self.lib.dmnd_search_shape(self.ctx, qb, rb, sid, C.byref(h), C.byref(cn)))
@@ -230,8 +239,13 @@ class Context:
         hits = np.zeros(n, dtype=HIT_DTYPE)
         if n:
             self._check(self.lib.dmnd_hits_download(self.ctx, h, hits.ctypes.data, n))
+        segs = None
+        if xdrop is not None:
+            segs = np.zeros(n, dtype=SEGMENT_DTYPE)
+            self._check(self.lib.dmnd_hits_xdrop(self.ctx, qb, rb, h, xdrop, segs.ctypes.data, n))
         self.lib.dmnd_hits_free(self.ctx, h)
-        return hits, {k: getattr(cn, k) for k, _ in StageCounters._fields_}
+        cnd = {k: getattr(cn, k) for k, _ in StageCounters._fields_}
+        return (hits, cnd) if xdrop is None else (hits, cnd, segs)
 
     def banded_swipe(self, qb, rb, problems: np.ndarray, traceback: bool, transcript_cap: int = 0):
         problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)

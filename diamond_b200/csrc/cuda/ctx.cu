@@ -122,6 +122,8 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	c->params = *params;
 	c->sm_count = prop.multiProcessorCount;
 	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_a));
 	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_b));
 	DevParams& d = c->h_dev_params;
@@ -186,6 +188,8 @@ void dmnd_destroy(dmnd_ctx* c) {
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
 	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->copy_stream);
+	cudaEventDestroy(c->ev_copy);
 	delete c;
 }
 
@@ -252,6 +256,40 @@ int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, s
 	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	ctx->d2h_bytes += raw_len;
 	return 0;
+}
+
+int dmnd_block_download_bias_async(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len != b->raw_len) { set_error("dmnd_block_download_bias_async: length mismatch"); return 1; }
+	// the copy stream waits for everything issued so far on the compute stream (the bias kernel), then runs beside it
+	DMND_CUDA_CHECK(cudaEventRecord(ctx->ev_copy, ctx->stream));
+	DMND_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(bias, b->bias, raw_len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	ctx->d2h_bytes += raw_len;
+	return 0;
+}
+
+int dmnd_copy_wait(dmnd_ctx* ctx) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+	return 0;
+}
+
+void* dmnd_host_alloc(dmnd_ctx* ctx, size_t bytes) {
+	cudaSetDevice(ctx->device);
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("dmnd_host_alloc: cudaMallocHost failed"); return nullptr; }
+	return p;
+}
+
+void dmnd_host_free(dmnd_ctx* ctx, void* p) {
+	cudaSetDevice(ctx->device);
+	if (p) cudaFreeHost(p);
+}
+
+int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return hits_xdrop_impl(ctx, query, ref, h, raw_xdrop, host, cap);
 }
 
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {

@@ -80,7 +80,8 @@ struct dmnd_ctx {
 	dmnd_cuda::DevParams* d_params = nullptr;
 	uint8_t* d_matcher[DMND_MAX_SHAPES + 1] = {};  // PatternMatcher tables
 	uint32_t matcher_minlen[DMND_MAX_SHAPES + 1] = {}, matcher_suffix[DMND_MAX_SHAPES + 1] = {};
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaEvent_t ev_copy = nullptr;
 	int sm_count = 148;
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
@@ -109,6 +110,7 @@ struct PhaseTimer {  // CUDA events on the library's stream, accumulated per pha
 };
 
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters);
+int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap);
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 

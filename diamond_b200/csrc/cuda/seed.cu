@@ -260,6 +260,59 @@ __global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, u
 	if (i < n) keys[i] = h[i].query;
 }
 
+// xdrop_ungapped (dp/ungapped_align.cpp:150-214, ScoreOnly + bias): one thread per hit
+__global__ void xdrop_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ q_bias, const int64_t* __restrict__ q_limits,
+                             const int8_t* __restrict__ r_letters, const int64_t* __restrict__ r_limits, uint32_t nr,
+                             const dmnd_hit* __restrict__ hits, size_t n, const DevParams* __restrict__ P, int xdrop, dmnd_segment* out) {
+	__shared__ int8_t s_score[1024];
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_score[i] = P->score[i];
+	__syncthreads();
+	const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	const dmnd_hit hit = hits[k];
+	const uint64_t sloc = hit.subject_score & 0xFFFFFFFFFFFFull;
+	uint32_t a = 0, b = nr;
+	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)r_limits[mid] <= sloc) a = mid; else b = mid; }
+	const int64_t qo = q_limits[hit.query];
+	const int8_t *qs = q_letters + qo, *cb = q_bias + qo, *ss = r_letters + r_limits[a];
+	const int qa = hit.seed_offset, sa = (int)((int64_t)sloc - r_limits[a]);
+	int score = 0, st = 0, n1 = 1, delta = 0, len = 0;
+	int q = qa - 1, s = sa - 1;
+	for (;;) {
+		if (!(score - st < xdrop)) break;
+		const int ql = qs[q] & 31, sl = ss[s] & 31;
+		if (ql == DMND_DELIMITER || sl == DMND_DELIMITER) break;
+		st += (int)s_score[(ql << 5) | sl] + (int)cb[q];
+		if (st > score) { score = st; delta = n1; }
+		--q; --s; ++n1;
+	}
+	q = qa; s = sa; st = score; n1 = 1;
+	for (;;) {
+		if (!(score - st < xdrop)) break;
+		const int ql = qs[q] & 31, sl = ss[s] & 31;
+		if (ql == DMND_DELIMITER || sl == DMND_DELIMITER) break;
+		st += (int)s_score[(ql << 5) | sl] + (int)cb[q];
+		if (st > score) { score = st; len = n1; }
+		++q; ++s; ++n1;
+	}
+	out[k] = dmnd_segment{ qa - delta, sa - delta, len + delta, score };
+}
+
+int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap) {
+	if (cap < h->n) { set_error("dmnd_hits_xdrop: buffer too small"); return 1; }
+	if (h->n == 0) return 0;
+	if (ctx->b_pairs.ensure(h->n * sizeof(dmnd_segment))) return 1;
+	PhaseTimer t(ctx, PH_SEED);
+	xdrop_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, ctx->stream>>>(query->letters, query->bias, query->limits, ref->letters, ref->limits, ref->nseq,
+		h->d, h->n, ctx->d_params, raw_xdrop, ctx->b_pairs.as<dmnd_segment>());
+	++ctx->launches;
+	DMND_CUDA_CHECK(cudaGetLastError());
+	DMND_CUDA_CHECK(cudaMemcpyAsync(host, ctx->b_pairs.p, h->n * sizeof(dmnd_segment), cudaMemcpyDeviceToHost, ctx->stream));
+	t.stop();
+	ctx->d2h_bytes += h->n * sizeof(dmnd_segment);
+	return 0;
+}
+
 static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long long* h) {
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -142,7 +142,7 @@ struct List {  // trivially-copyable elements only
 	void clear() { n = 0; }
 };
 
-struct SeedHit { int i, j, score; bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
+struct SeedHit { int i, j, score; dmnd_segment seg; bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
 struct TargetScore { uint32_t target; uint16_t score; bool operator<(const TargetScore& x) const { return score > x.score || (score == x.score && target < x.target); } };
 
 struct HspLite { int score; double evalue; int d_begin, d_end; };
@@ -245,6 +245,9 @@ struct Workspace {
 	std::unique_ptr<Pool> pool;
 	std::vector<ThreadCtx> tc;
 	std::vector<dmnd_hit> hv;
+	std::vector<dmnd_segment> segv;
+	struct HitSeg { dmnd_hit h; dmnd_segment s; };
+	std::vector<HitSeg> hs;
 	std::vector<size_t> qstart;
 	std::vector<QueryState> qs;
 	std::vector<dmnd_dp_problem> p1, p2;
@@ -268,7 +271,7 @@ struct Driver {
 	size_t nq_hit = 0;
 	size_t block_begin(int t) const { return nq_hit * (size_t)t / (size_t)T; }
 
-	void load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* end);
+	void load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end);
 	void start(QueryState& q, ThreadCtx& tc);
 	void produce_round1(QueryState& q, ThreadCtx& tc);
 	void produce_round2(QueryState& q, ThreadCtx& tc);
@@ -278,10 +281,11 @@ struct Driver {
 	int run_waves();
 };
 
-void Driver::load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* end) {
-	// align/load_hits.h:44-122
+void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end) {
+	// align/load_hits.h:44-122 (each hit carries its precomputed x-drop segment along)
 	const Env& e = env;
-	std::sort(begin, end, [](const dmnd_hit& a, const dmnd_hit& b) {
+	std::sort(begin, end, [](const Workspace::HitSeg& x, const Workspace::HitSeg& y) {
+		const dmnd_hit &a = x.h, &b = y.h;
 		const uint64_t sa = DMND_HIT_SUBJECT(a), sb = DMND_HIT_SUBJECT(b);
 		return sa < sb || (sa == sb && (a.query < b.query || (a.query == b.query && a.seed_offset < b.seed_offset)));
 	});
@@ -290,7 +294,8 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* 
 	q.ts_off = (uint32_t)tc.target_scores.size();
 	uint32_t target = UINT32_MAX, ntg = 0;
 	uint16_t score = 0;
-	for (dmnd_hit* h = begin; h < end; ++h) {
+	for (Workspace::HitSeg* hsp = begin; hsp < end; ++hsp) {
+		const dmnd_hit* h = &hsp->h;
 		const uint64_t subj = DMND_HIT_SUBJECT(*h);
 		// SequenceSet::local_position: sequence whose [limits[t], limits[t+1]) holds subj
 		const uint32_t t = (uint32_t)(std::upper_bound(e.r_limits, e.r_limits + e.nr + 1, (int64_t)subj) - e.r_limits) - 1;
@@ -302,7 +307,7 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, dmnd_hit* begin, dmnd_hit* 
 			++ntg;
 		}
 		const uint16_t hs = (uint16_t)DMND_HIT_SCORE(*h);
-		tc.seed_hits.push_back({ h->seed_offset, (int)((int64_t)subj - e.r_limits[t]), (int)hs });
+		tc.seed_hits.push_back({ h->seed_offset, (int)((int64_t)subj - e.r_limits[t]), (int)hs, hsp->s });
 		score = std::max(score, hs);
 	}
 	if (target != UINT32_MAX) tc.target_scores.push_back({ ntg - 1, score });
@@ -341,11 +346,6 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	q.prob_target.clear();
 	q.prob_begin = tc.p1.size();
 	const int8_t* query = e.q_letters + e.q_limits[q.qid];
-	const int8_t* cbs = nullptr;
-	if (e.hauser) {  // HauserCorrection per query, align/extend.cpp:247-250
-		hauser_correction(*e.sc, query, q.qlen, tc.cbs);
-		cbs = tc.cbs.data();
-	}
 	const int band = band_for(q.qlen);
 	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
 	const uint32_t* hb = tc.hit_begin.data() + q.tgt_off;
@@ -361,7 +361,8 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		tc.segs.clear();
 		for (const SeedHit& h : tc.hits) {  // align/ungapped.cpp:81-91
 			if (!tc.segs.empty() && tc.segs.back().diag() == h.i - h.j && tc.segs.back().subject_end() >= h.j) continue;
-			const Segment d = xdrop_ungapped(*e.sc, query, cbs, subject, h.i, h.j);
+			// xdrop_ungapped(query, cbs, target, hit.i, hit.j) was evaluated for every hit on the device (dmnd_hits_xdrop)
+			const Segment d{ h.seg.i, h.seg.j, h.seg.len, h.seg.score };
 			if (d.score > 0) tc.segs.push_back(d);
 		}
 		if (tc.segs.empty()) continue;
@@ -659,7 +660,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	Driver d;
 	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads;
 	std::memset(&d.stats, 0, sizeof d.stats);
-	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, 1);
+	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, 0);  // snapshot: the device counters of this call are reported as a delta
 	Env& e = d.env;
 	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
 	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
@@ -676,7 +677,10 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
 	w.hv.resize(nh);
+	w.segv.resize(nh);
 	if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
+	// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
+	if (nh && dmnd_hits_xdrop(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	dmnd_hits_free(ctx, hits);
 	if (dmnd_block_clear_seed_mask(ctx, qb)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
@@ -695,6 +699,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	const size_t nqh = w.qstart.size() - 1;
 	d.nq_hit = nqh;
 	w.qs.resize(nqh);
+	w.hs.resize(nh);
 	prof.lap("group queries");
 	w.pool->run([&](int t) {
 		ThreadCtx& tc = w.tc[(size_t)t];
@@ -702,7 +707,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			QueryState& q = w.qs[k];
 			q.qid = w.hv[w.qstart[k]].query;
-			d.load_hits(q, tc, w.hv.data() + w.qstart[k], w.hv.data() + w.qstart[k + 1]);
+			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; }
+			d.load_hits(q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]);
 			d.start(q, tc);
 		}
 	});
@@ -754,7 +760,13 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	d.stats.host_bridge_ms += ms_since(t0);
 	prof.lap("emit matches");
 	d.stats.total_ms = ms_since(t_total);
-	dmnd_timing_fetch(ctx, &d.stats.device, 0);
+	{
+		dmnd_timing tm1; dmnd_timing_fetch(ctx, &tm1, 0);
+		dmnd_timing& dv = d.stats.device;
+		dv.seed_ms = tm1.seed_ms - tm0.seed_ms; dv.dp_score_ms = tm1.dp_score_ms - tm0.dp_score_ms; dv.dp_trace_ms = tm1.dp_trace_ms - tm0.dp_trace_ms;
+		dv.h2d_ms = tm1.h2d_ms - tm0.h2d_ms; dv.d2h_ms = tm1.d2h_ms - tm0.d2h_ms;
+		dv.launches = tm1.launches - tm0.launches; dv.h2d_bytes = tm1.h2d_bytes - tm0.h2d_bytes; dv.d2h_bytes = tm1.d2h_bytes - tm0.d2h_bytes;
+	}
 	res->stats = d.stats;
 	*out = res.release();
 	return 0;

@@ -124,8 +124,15 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 /* Fills the block's bias array on the device: mode 1 = HauserCorrection of every sequence (stats/hauser_correction.cpp:
  * 53-109, window 40, fp32, rounded half away from zero), mode 0 = zeros (--comp-based-stats 0). */
 int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode);
-/* Reads back the block's bias array (tests). */
+/* Reads back the block's bias array. */
 int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len);
+/* Same, on the library's copy stream: returns at once, dmnd_copy_wait() blocks until `bias` is complete.  Overlaps with
+ * kernels issued afterwards (the bias must have been computed before).  `bias` should come from dmnd_host_alloc(). */
+int dmnd_block_download_bias_async(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len);
+int dmnd_copy_wait(dmnd_ctx* ctx);
+/* Page-locked host memory for buffers that cross the bus every step. */
+void* dmnd_host_alloc(dmnd_ctx* ctx, size_t bytes);
+void dmnd_host_free(dmnd_ctx* ctx, void* p);
 /* Reads back the block's letters (query letters carry SEED_MASK bits set by dmnd_search_shape). */
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
 /* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
@@ -137,6 +144,13 @@ int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out,
                       dmnd_stage_counters* counters);
 size_t dmnd_hits_count(const dmnd_hits* h);
+/* x-drop ungapped extension of every hit (xdrop_ungapped, dp/ungapped_align.cpp:150-214, score-only variant with the
+ * query block's bias): out[k] belongs to hit k of dmnd_hits_download().  `raw_xdrop` = config.raw_ungapped_xdrop.
+ * The caller applies the reference's "covered by the previous segment on this diagonal" skip (align/ungapped.cpp:84)
+ * itself; the extension of one hit does not depend on any other hit. */
+typedef struct dmnd_segment { int32_t i, j, len, score; } dmnd_segment; /* DiagonalSegment, util/geo/diagonal_segment.h */
+int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
+                    dmnd_segment* host, size_t cap);
 int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap);
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
 

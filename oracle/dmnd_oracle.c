@@ -153,6 +153,10 @@ int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, s
 	memcpy(bias, b->bias, raw_len);
 	return 0;
 }
+int dmnd_block_download_bias_async(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) { return dmnd_block_download_bias(ctx, b, bias, raw_len); }
+int dmnd_copy_wait(dmnd_ctx* ctx) { (void)ctx; return 0; }
+void* dmnd_host_alloc(dmnd_ctx* ctx, size_t bytes) { (void)ctx; return malloc(bytes ? bytes : 1); }
+void dmnd_host_free(dmnd_ctx* ctx, void* p) { (void)ctx; free(p); }
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {
 	(void)ctx;
 	if (raw_len != b->raw_len) return fail("dmnd_block_download_letters: length mismatch");
@@ -434,6 +438,34 @@ int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t
 	(void)ctx;
 	if (cap < h->n) return fail("dmnd_hits_download: buffer too small");
 	memcpy(host, h->h, h->n * sizeof(dmnd_hit));
+	return 0;
+}
+/* dp/ungapped_align.cpp:150-214 (ScoreOnly) */
+int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
+                    dmnd_segment* host, size_t cap) {
+	const dmnd_params* p = &ctx->p;
+	if (cap < h->n) return fail("dmnd_hits_xdrop: buffer too small");
+	for (size_t k = 0; k < h->n; ++k) {
+		const dmnd_hit* hit = &h->h[k];
+		const uint64_t sloc = DMND_HIT_SUBJECT(*hit);
+		const uint32_t t = seq_of(ref, sloc);
+		const int8_t *qs = query->letters + query->limits[hit->query], *cb = query->bias + query->limits[hit->query], *ss = ref->letters + ref->limits[t];
+		const int qa = hit->seed_offset, sa = (int)((int64_t)sloc - ref->limits[t]);
+		int score = 0, st = 0, n = 1, delta = 0, len = 0, ql, sl;
+		int q = qa - 1, s = sa - 1;
+		while (score - st < raw_xdrop && (ql = qs[q] & 31) != DMND_DELIMITER && (sl = ss[s] & 31) != DMND_DELIMITER) {
+			st += p->score[ql * 32 + sl] + cb[q];
+			if (st > score) { score = st; delta = n; }
+			--q; --s; ++n;
+		}
+		q = qa; s = sa; st = score; n = 1;
+		while (score - st < raw_xdrop && (ql = qs[q] & 31) != DMND_DELIMITER && (sl = ss[s] & 31) != DMND_DELIMITER) {
+			st += p->score[ql * 32 + sl] + cb[q];
+			if (st > score) { score = st; len = n; }
+			++q; ++s; ++n;
+		}
+		host[k].i = qa - delta; host[k].j = sa - delta; host[k].len = len + delta; host[k].score = score;
+	}
 	return 0;
 }
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) { (void)ctx; if (h) { free(h->h); free(h); } }

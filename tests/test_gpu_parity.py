@@ -44,6 +44,25 @@ def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name
     o.close(); g.close()
 
 
+@pytest.mark.parametrize("name", ["c1", "edge", "fam2"])
+def test_hits_xdrop_segments_match_oracle(oracle_lib, product_lib, name):
+    """Per-hit x-drop ungapped extension (dp/ungapped_align.cpp:150-214) with the Hauser bias, oracle vs device."""
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    out = []
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.compute_bias(qb, 1)
+        hits, _, segs = c.search_shape(qb, rb, 0, xdrop=20)
+        order = np.argsort(hits, order=["query", "subject_score", "seed_offset"])
+        out.append((hits[order], segs[order]))
+        c.free_block(qb); c.free_block(rb)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert (out[1][1]["score"] > 0).mean() > 0.5
+    o.close(); g.close()
+
+
 @pytest.mark.parametrize("name", ["c1", "edge"])
 def test_device_hauser_bias_matches_oracle(oracle_lib, product_lib, name):
     """HauserCorrection (fp32 -> int8) computed on the device is bit-identical to the scalar restatement."""
