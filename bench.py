@@ -72,6 +72,23 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def effective_cpus():
+    """min(visible CPUs, cgroup CFS quota): what 'all the host threads it can use' means inside a quota-limited container."""
+    n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, -(-int(q) // int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, -(-q // per)))
+        except Exception:
+            pass
+    return n
+
+
 def make_workload(args, rank):
     from diamond_b200 import api, synth
     w = synth.workload(args.queries, args.db, args.seed, q_stream=rank)
@@ -113,11 +130,11 @@ def sample_cells_and_tsv(args, w, threads, device):
 def main():
     args = parse()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    ncpu = os.cpu_count() or 1
+    ncpu = effective_cpus()
     ref_threads = ncpu  # the reference arm uses every host thread; our seedp_bits must follow the same -p (setup.cpp:306-309)
     config = {"workload": f"blastp --fast, {args.queries} synthetic queries (len<=300) per GPU x {args.db}-protein DB (BASELINE configs[1])",
               "queries_per_gpu": args.queries, "db_seqs": args.db, "parallelism": f"query-sharded x{world}", "seed": args.seed,
-              "flags": "--fast --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001", "reference_threads": ref_threads,
+              "flags": "--fast --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001", "reference_threads": ref_threads, "visible_cpus": os.cpu_count(),
               "l2": "inputs (242 MB queries + 30 MB reference per GPU) larger than the 126 MB L2"}
 
     if args.impl == "reference":

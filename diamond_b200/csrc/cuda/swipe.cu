@@ -191,6 +191,170 @@ __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const Dev
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// v2: query-profile kernel.  Same wavefront mapping and the same results as swipe_kernel, with the per-cell work cut to
+// the recurrence itself:
+//  * the warp first builds the problem's score profile in shared memory, prof[a][i + HALO] = S[a][q_i] + bias_i for the
+//    27 target-letter rows a (row 26 = delimiter / out-of-alphabet) -- one LDS per cell replaces three global byte loads,
+//    the 32x32 table lookup and the bias add;
+//  * validity tests disappear: query positions outside [0, qlen) read -128 from the profile halo (HALO = 16 R columns on
+//    each side covers every lane of every executed step), target positions are clamped to the delimiters at -1 / tlen,
+//    and cells before the first column are zero by induction.  Cells past the query or target end can become positive
+//    but only feed other out-of-matrix cells and stay strictly below a real cell's score, so neither the recurrence nor
+//    the end-cell choice sees them (CPU emulation against the oracle: tests/test_swipe_emulation.py);
+//  * each lane keeps the R/2 target letters it needs as premultiplied profile-row offsets in registers and shifts the
+//    window by one letter per macro step; the band's lower edge is a per-lane row count kb (cells with k > kb are
+//    predicated off, so their registers stay 0 exactly like the reference's hgap_[band] sentinel).
+struct ProfArgs {
+	int w4;              // profile row stride in bytes (multiple of 4), >= max(qlen) + 32 R + 4 of the launch
+	unsigned int* overflow;  // set when S + bias does not fit int8: the host re-runs the call on the generic kernel
+};
+
+template<int R, bool TRACE>
+__global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, const DevParams* __restrict__ P, const ProfArgs pa) {
+	extern __shared__ int8_t smem[];
+	__shared__ int8_t s_score[1024];
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_score[i] = P->score[i];
+	__syncthreads();
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int go = P->gap_open + P->gap_extend, ge = P->gap_extend;
+	const int W4 = pa.w4;
+	int8_t* prof = smem + (size_t)warp * 27 * W4;
+	constexpr int HALO = 16 * R, U = R / 2;
+	constexpr int PKW = (R + 7) / 8;
+
+	for (;;) {
+		unsigned int w = 0;
+		if (lane == 0) w = atomicAdd(a.work, 1u);
+		w = __shfl_sync(FULL, w, 0);
+		if (w >= a.n) break;
+		const uint32_t pi = a.order[w];
+		const dmnd_dp_problem pr = a.probs[pi];
+		const ProbGeom g = geom(a, pr);
+		int H[R], E[R], F[R], bestv[R], bestc[R];
+#pragma unroll
+		for (int k = 0; k < R; ++k) { H[k] = 0; E[k] = 0; F[k] = 0; bestv[k] = 0; bestc[k] = 0; }
+		int best = 0;
+		if (g.B > 0 && g.cols > 0) {
+			// ---- profile
+			const int W = g.qlen + 32 * R + 4;
+			bool ok = true;
+			__syncwarp();
+			for (int idx = lane; idx < W; idx += 32) {
+				const int i = idx - HALO;
+				if (i >= 0 && i < g.qlen) {
+					const int ql = g.q[i] & 31, cb = g.cb[i];
+#pragma unroll 9
+					for (int al = 0; al < 27; ++al) {
+						int v = al < 26 ? (int)s_score[(al << 5) | ql] + cb : -128;
+						if (al < 26 && (v > 127 || v < -127)) { ok = false; v = max(min(v, 127), -127); }
+						prof[al * W4 + idx] = (int8_t)v;
+					}
+				}
+				else {
+#pragma unroll 9
+					for (int al = 0; al < 27; ++al) prof[al * W4 + idx] = (int8_t)-128;
+				}
+			}
+			if (!__all_sync(FULL, ok) && lane == 0) atomicExch(pa.overflow, 1u);
+			__syncwarp();
+			// ---- wavefront
+			const int ibase = g.j0 + g.d_begin;
+			const int nsteps = 2 * (g.cols - 1) + g.B, nmacro = (nsteps + 1) >> 1;
+			const int m_lo = max(0, -ibase - 16 * R), m_hi = min(nmacro, g.qlen - ibase);
+			const int kb = min(R - 1, g.B - 1 - lane * R);
+			const int lofs = lane * U;
+			auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return min((int)(g.t[jj] & 31), 26) * W4; };
+			int trow[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) trow[u] = trow_of(g.j0 + m_lo - lofs - u);
+			int I0 = ibase + m_lo + lofs + HALO;  // profile column of (even row u = 0); +u, +u+1 for the others
+			uint8_t* tr = TRACE ? a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base) + (size_t)lane * U : nullptr;
+			for (int m = m_lo; m < m_hi; ++m) {
+				const int tnext = trow_of(g.j0 + m + 1 - lofs);  // issued early: consumed after the two half steps
+				uint32_t pk[PKW];
+#pragma unroll
+				for (int x = 0; x < PKW; ++x) pk[x] = 0;
+				{
+					int f_up = __shfl_up_sync(FULL, F[R - 1], 1);
+					if (lane == 0) f_up = 0;
+#pragma unroll
+					for (int k = 0; k < R; k += 2) {
+						{
+							// rows past the band's lower edge (k > kb) are kept at H = E = 0 by a select on h: their F is never
+							// read by a live row, so the reference's hgap_[band] = 0 sentinel holds without a branch
+							const int u = k >> 1;
+							const int sc = (int)prof[trow[u] + I0 + u];
+							const int e_in = E[k + 1], f_in = k > 0 ? F[k > 0 ? k - 1 : 0] : f_up;
+							const int hd = H[k] + sc;
+							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
+							const int t2 = h - go;
+							if (TRACE) {
+								const int open = max(t2, 0);
+								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
+								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
+							}
+							else best = max(best, h);
+							H[k] = h;
+							E[k] = __viaddmax_s32_relu(e_in, -ge, t2);
+							F[k] = __viaddmax_s32_relu(f_in, -ge, t2);
+						}
+					}
+				}
+				{
+					int e_dn = __shfl_down_sync(FULL, E[0], 1);
+					if (lane == 31) e_dn = 0;
+#pragma unroll
+					for (int k = 1; k < R; k += 2) {
+						{
+							const int u = k >> 1;
+							const int sc = (int)prof[trow[u] + I0 + u + 1];
+							const int e_in = k + 1 < R ? E[k + 1 < R ? k + 1 : 0] : e_dn, f_in = F[k - 1];
+							const int hd = H[k] + sc;
+							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
+							const int t2 = h - go;
+							if (TRACE) {
+								const int open = max(t2, 0);
+								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
+								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
+							}
+							else best = max(best, h);
+							H[k] = h;
+							E[k] = __viaddmax_s32_relu(e_in, -ge, t2);
+							F[k] = __viaddmax_s32_relu(f_in, -ge, t2);
+						}
+					}
+				}
+				if (TRACE) trace_store<R>(tr + (size_t)m * (16 * R), pk);
+#pragma unroll
+				for (int u = U - 1; u > 0; --u) trow[u] = trow[u - 1];
+				trow[0] = tnext;
+				++I0;
+			}
+		}
+		if (TRACE) {
+			int bv = 0, bc = 0, br = 0;
+#pragma unroll
+			for (int k = 0; k < R; ++k) {
+				const int r = lane * R + k;
+				if (bestv[k] > bv || (bestv[k] == bv && bv > 0 && (bestc[k] < bc || (bestc[k] == bc && r > br)))) { bv = bestv[k]; bc = bestc[k]; br = r; }
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const int ov = __shfl_xor_sync(FULL, bv, o), oc = __shfl_xor_sync(FULL, bc, o), orr = __shfl_xor_sync(FULL, br, o);
+				if (ov > bv || (ov == bv && ov > 0 && (oc < bc || (oc == bc && orr > br)))) { bv = ov; bc = oc; br = orr; }
+			}
+			if (lane == 0) { a.score[pi] = bv; a.end_cell[2 * (size_t)pi] = bc; a.end_cell[2 * (size_t)pi + 1] = br; }
+		}
+		else {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+			if (lane == 0) a.score[pi] = best;
+		}
+	}
+}
+
 struct WalkArgs {
 	const int8_t *q_letters, *q_bias, *r_letters;
 	const int64_t *q_limits, *r_limits;
@@ -299,9 +463,28 @@ static void launch_bin(int R, const SwipeArgs& a, const DevParams* P, int grid, 
 	}
 }
 
+template<bool TRACE>
+static int launch_prof_bin(int R, const SwipeArgs& a, const DevParams* P, const ProfArgs& pa, int grid, int threads, size_t smem, cudaStream_t st) {
+#define DMND_LAUNCH_PROF(RR)                                                                                            \
+	do {                                                                                                                 \
+		if (smem > 48 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_prof_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		swipe_prof_kernel<RR, TRACE><<<grid, threads, smem, st>>>(a, P, pa);                                             \
+	} while (0)
+	switch (R) {
+	case 2: DMND_LAUNCH_PROF(2); break;
+	case 4: DMND_LAUNCH_PROF(4); break;
+	case 8: DMND_LAUNCH_PROF(8); break;
+	case 16: DMND_LAUNCH_PROF(16); break;
+	default: DMND_LAUNCH_PROF(32); break;
+	}
+#undef DMND_LAUNCH_PROF
+	return 0;
+}
+
 // ---- device-side preparation: geometry, register-tile bin, cost class, bucket histogram ------------------------------
 struct PrepOut {
-	uint8_t* key;        // [n] bucket = bin * 32 + (31 - log2 class of the cell count): heavy problems first inside a bin
+	uint8_t* key;        // [n] bucket = (bin * 2 + long) * 16 + cost class (heavy problems first inside a bucket group)
+	unsigned int* maxq;  // [256] longest query per bucket (sizes the shared-memory profile of the launch)
 	uint64_t* cost;      // [n] trace bytes (traceback) or cells (score only)
 	uint64_t* tslen;     // [n] qlen + tlen (transcript capacity)
 	unsigned int* hist;  // [256]
@@ -322,8 +505,10 @@ __global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t 
 	const int R = tile_rows(B);
 	const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : 4;
 	const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
-	const int cls = 31 - min(31, 63 - __clzll(cells + 1));
-	const uint8_t key = (uint8_t)(b * 32 + cls);
+	const int cls = 15 - min(15, (63 - __clzll(cells + 1)) >> 1);
+	const int lng = (qlen + 32 * R + 4) > 768 ? 1 : 0;
+	const uint8_t key = (uint8_t)((b * 2 + lng) * 16 + cls);
+	atomicMax(&o.maxq[key], (unsigned)qlen);
 	o.key[k] = key;
 	const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
 	o.cost[k] = trace ? nmacro * 16ull * (unsigned long long)R : cells;
@@ -359,12 +544,12 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	const unsigned nb = (unsigned)((n + 255) / 256);
 	// ---- device buffers
 	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
-	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1024 * sizeof(unsigned int))
+	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1280 * sizeof(unsigned int))
 	    || ctx->b_prep.ensure(n * (1 + 8 + 8 + 8 + 8) + 64))
 		return 1;
 	int32_t* d_score = ctx->b_work.as<int32_t>();
 	int32_t* d_end = d_score + n;
-	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);  // [0..63] work counters, [256..511] hist, [512..767] offsets, [768..1023] fill, [64] flag
+	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);  // [0..63] work counters, [64] error flag, [65] profile overflow, [256..511] hist, [512..767] offsets, [768..1023] fill, [1024..1279] max qlen
 	uint64_t* d_cost = ctx->b_prep.as<uint64_t>();
 	uint64_t* d_tslen = d_cost + n;
 	uint64_t* d_cum = d_tslen + n;    // exclusive prefix of cost in order sequence (n entries) -- reused as gather buffer
@@ -378,11 +563,12 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	}
 	lap("upload problems");
 	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1024 * sizeof(unsigned int), st));
-	PrepOut po{ d_key, d_cost, d_tslen, d_counters + 256, d_counters + 64 };
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1280 * sizeof(unsigned int), st));
+	PrepOut po{ d_key, d_counters + 1024, d_cost, d_tslen, d_counters + 256, d_counters + 64 };
 	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? 1 : 0, po);
-	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag
+	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag, [512..767] offsets (upload), [1024..1279] max qlen
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
 	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
@@ -390,8 +576,9 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	unsigned int off[257];
 	off[0] = 0;
 	for (int k = 0; k < 256; ++k) off[k + 1] = off[k] + hp[k];
-	size_t bin_begin[6];
-	for (int b = 0; b <= 5; ++b) bin_begin[b] = off[std::min(b * 32, 256)];
+	// launch groups: g = bin * 2 + long-query flag; inside a group the buckets are ordered heavy -> light
+	size_t grp_begin[11];
+	for (int g = 0; g <= 10; ++g) grp_begin[g] = off[std::min(g * 16, 256)];
 	std::memcpy(hp + 512, off, 256 * sizeof(unsigned int));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(d_counters + 512, hp + 512, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
 	scatter_kernel<<<nb, 256, 0, st>>>(d_key, (uint32_t)n, d_counters + 512, d_counters + 768, ctx->b_order.as<uint32_t>());
@@ -403,16 +590,35 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	a.probs = ctx->b_probs.as<dmnd_dp_problem>();
 	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_excl = nullptr; a.trace_base = 0; a.order_pos0 = 0;
 	uint64_t ts_total = 0;
+	const bool force_generic = ctx->force_generic_dp || getenv("DMND_GENERIC_DP") != nullptr;
+	// one DP launch over order[pos, e) of group g: profile kernel when the profile fits shared memory, else the generic one
+	auto launch_dp = [&](int g, size_t pos, size_t e, bool tr_mode) -> int {
+		const int R = RS[g >> 1];
+		unsigned maxq = 0;
+		for (int k = 0; k < 16; ++k) maxq = std::max(maxq, hp[1024 + g * 16 + k]);
+		const int w4 = ((int)maxq + 32 * R + 4 + 3) & ~3;
+		const size_t per_warp = (size_t)27 * (size_t)w4;
+		const int warps = (int)std::min<size_t>(4, ((size_t)200 << 10) / per_warp);
+		a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.order_pos0 = (uint32_t)pos;
+		if (force_generic || warps == 0) {
+			const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
+			if (tr_mode) launch_bin<true>(R, a, ctx->d_params, grid, st); else launch_bin<false>(R, a, ctx->d_params, grid, st);
+		}
+		else {
+			const size_t smem = per_warp * (size_t)warps;
+			const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)220 << 10) / (smem + 2048)));
+			const int grid = (int)std::min<size_t>((e - pos + warps - 1) / warps, (size_t)ctx->sm_count * ctas_per_sm);
+			ProfArgs pa{ w4, d_counters + 65 };
+			if (tr_mode ? launch_prof_bin<true>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st) : launch_prof_bin<false>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st)) return 1;
+		}
+		++ctx->launches;
+		return 0;
+	};
 
 	if (!trace) {
-		for (int b = 0; b < 5; ++b) {
-			const size_t pos = bin_begin[b], e = bin_begin[b + 1];
-			if (e > pos) {
-				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters + b; a.order_pos0 = (uint32_t)pos;
-				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
-				launch_bin<false>(RS[b], a, ctx->d_params, grid, st);
-				++ctx->launches;
-			}
+		for (int g = 0; g < 10; ++g) {
+			const size_t pos = grp_begin[g], e = grp_begin[g + 1];
+			if (e > pos) { a.work = d_counters + g; if (launch_dp(g, pos, e, false)) return 1; }
 		}
 		fill_score_results<<<nb, 256, 0, st>>>(d_score, ctx->b_results.as<dmnd_dp_result>(), (uint32_t)n);
 		++ctx->launches;
@@ -449,21 +655,22 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		size_t free_b = 0, total_b = 0;
 		DMND_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
 		const uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)((free_b + ctx->b_trace.cap) / 5) * 2);  // <= 40 % of what is free
+		if (ctx->b_trace.ensure((size_t)std::min<uint64_t>(excl[n], budget) + 64)) return 1;
 		lap("trace prefix");
-		for (int b = 0; b < 5; ++b) {
-			size_t pos = bin_begin[b];
-			const size_t bend = bin_begin[b + 1];
-			while (pos < bend) {
-				// slice [pos, e) of this bin whose trace fits the budget (at least one problem)
-				size_t e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + bend + 1, excl[pos] + budget) - excl.begin()) - 1;
+		for (int g = 0; g < 10; ++g) {
+			size_t pos = grp_begin[g];
+			const size_t gend = grp_begin[g + 1];
+			while (pos < gend) {
+				// slice [pos, e) of this group whose trace fits the budget (at least one problem); launches are stream-ordered,
+				// so the arena can be reused by the next slice without a host synchronisation
+				size_t e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + gend + 1, excl[pos] + budget) - excl.begin()) - 1;
 				e = std::max(e, pos + 1);
 				const uint64_t bytes = excl[e] - excl[pos];
 				if (ctx->b_trace.ensure((size_t)bytes + 64)) return 1;
 				DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
-				a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.work = d_counters; a.order_pos0 = (uint32_t)pos;
+				a.work = d_counters;
 				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = excl[pos];
-				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
-				launch_bin<true>(RS[b], a, ctx->d_params, grid, st);
+				if (launch_dp(g, pos, e, true)) return 1;
 				WalkArgs wa;
 				wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
 				wa.probs = a.probs; wa.order = a.order; wa.n = a.n; wa.score = d_score; wa.end_cell = d_end;
@@ -472,9 +679,8 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
 				wa.transcript_off = transcripts ? d_tsoff : nullptr;
 				walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
-				ctx->launches += 2;
+				++ctx->launches;
 				DMND_CUDA_CHECK(cudaGetLastError());
-				if (e < bend || bytes > ctx->b_trace.cap / 2) DMND_CUDA_CHECK(cudaStreamSynchronize(st));  // the arena is reused by the next slice
 				pos = e;
 			}
 		}
@@ -488,8 +694,16 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		t.stop();
 		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
 	}
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 257, d_counters + 65, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
 	lap("download results");
+	if (hp[257] != 0 && !force_generic) {
+		// S + bias left the int8 range of the shared-memory profile somewhere: redo the whole call on the generic kernel
+		ctx->force_generic_dp = true;
+		const int rc = banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+		ctx->force_generic_dp = false;
+		return rc;
+	}
 	if (trace && !getenv("DMND_NO_TRACE_CHECK"))
 		for (size_t k = 0; k < n; ++k)
 			if (results[k].status == 2) { set_error("dmnd_banded_swipe: Traceback error."); return 1; }

@@ -55,6 +55,31 @@ struct Prof {
 	}
 };
 
+// CPUs this process may actually use: min(hardware threads, cgroup v2/v1 CFS quota).  Oversubscribing a quota-limited
+// container (128 visible CPUs, 16 allowed) throttles every worker, so the pool is sized to the quota.
+int effective_cpus() {
+	int n = (int)std::thread::hardware_concurrency();
+	if (n < 1) n = 1;
+	auto read2 = [](const char* path, long long& a, long long& b) {
+		FILE* f = std::fopen(path, "r");
+		if (!f) return false;
+		char s1[64] = { 0 }, s2[64] = { 0 };
+		const int k = std::fscanf(f, "%63s %63s", s1, s2);
+		std::fclose(f);
+		if (k < 1 || std::strcmp(s1, "max") == 0) return false;
+		a = std::atoll(s1); b = k > 1 ? std::atoll(s2) : 0;
+		return true;
+	};
+	long long q = 0, per = 0;
+	if (read2("/sys/fs/cgroup/cpu.max", q, per) && q > 0 && per > 0) n = std::min<long long>(n, std::max<long long>(1, (q + per - 1) / per));
+	else {
+		long long q1 = 0, p1 = 0, d = 0;
+		if (read2("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", q1, d) && q1 > 0 && read2("/sys/fs/cgroup/cpu/cpu.cfs_period_us", p1, d) && p1 > 0)
+			n = std::min<long long>(n, std::max<long long>(1, (q1 + p1 - 1) / p1));
+	}
+	return n;
+}
+
 // ---- fork-join pool: threads persist between calls, run(f) executes f(t) for t in [0, T) ---------------------------
 class Pool {
 public:
@@ -652,8 +677,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	int64_t ref_letters = 0;
 	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
-	int host_threads = (int)std::thread::hardware_concurrency();
-	if (host_threads < 1) host_threads = 1;
+	int host_threads = effective_cpus();
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
 	w.ensure_pool(host_threads);
 

@@ -80,7 +80,7 @@ def workload(n_q: int, n_db: int, seed: int, qlen: int = 300, chunk: int = 8192,
         n = min(chunk, n_q - starts[k])
         return make_queries(n, dbl, dbo, np.random.default_rng([seed, 1 + q_stream, k]), qlen)
 
-    threads = threads or min(64, os.cpu_count() or 1)
+    threads = threads or min(32, os.cpu_count() or 1)
     if len(starts) == 1 or threads == 1:
         parts = [job(k) for k in range(len(starts))]
     else:

@@ -110,9 +110,14 @@ def random_problems(w, q_lim, r_lim, rng, n):
     return P
 
 
+@pytest.mark.parametrize("kernel", ["profile", "generic"])
 @pytest.mark.parametrize("name,cbs", [("c1", 0), ("c1", 1), ("edge", 1), ("fam2", 1)])
-def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs):
+def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs, kernel, monkeypatch):
     from diamond_b200 import api
+    if kernel == "generic":
+        monkeypatch.setenv("DMND_GENERIC_DP", "1")  # the fallback for profiles that do not fit shared memory
+    else:
+        monkeypatch.delenv("DMND_GENERIC_DP", raising=False)
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
     rng = np.random.default_rng(7)
     P = random_problems(w, q_lim, r_lim, rng, 1500)
@@ -141,6 +146,25 @@ def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs):
         a = tro[to["transcript_off"][k]: to["transcript_off"][k] + to["transcript_len"][k]]
         b = trg[tg["transcript_off"][k]: tg["transcript_off"][k] + tg["transcript_len"][k]]
         assert np.array_equal(a, b), k
+    o.close(); g.close()
+
+
+def test_banded_swipe_bias_outside_int8_profile_falls_back(oracle_lib, product_lib):
+    """S + bias beyond int8 cannot live in the shared-memory profile: the library must notice and redo the call generically."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("edge")
+    rng = np.random.default_rng(5)
+    probs = np.array(random_problems(w, q_lim, r_lim, rng, 300), dtype=api.PROBLEM_DTYPE)
+    bias = rng.integers(-127, 128, size=q_raw.size).astype(np.int8)
+    o, g = both(oracle_lib, product_lib)
+    out = []
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.set_bias(qb, bias, q_raw.size)
+        out.append(c.banded_swipe(qb, rb, probs, traceback=True)[0])
+        c.free_block(qb); c.free_block(rb)
+    for f in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "length"):
+        assert np.array_equal(out[0][f], out[1][f]), f
     o.close(); g.close()
 
 
