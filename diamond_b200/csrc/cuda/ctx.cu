@@ -26,48 +26,74 @@ static __global__ void clear_seed_mask_kernel(int8_t* letters, size_t n) {
 // sliding-window loop.  The window sums are integers; the three float operations per position (int->float, divide,
 // subtract) and the half-away-from-zero rounding use the explicit round-to-nearest intrinsics, so the int8 results are
 // bit-identical to the host's scalar code (no FMA contraction, IEEE division).
-static __global__ void hauser_kernel(const int8_t* __restrict__ letters, const int64_t* __restrict__ limits, uint32_t nseq,
+// Memory: the 128 sequences of a block are contiguous in the block image, so the block stages their letters through
+// shared memory with coalesced 16-byte loads, works on the staged copy in place (letter -> bias) and writes the range
+// back coalesced; a range that does not fit (long sequences) is processed straight from global memory.
+#define HAUSER_STAGE_BYTES (40 * 1024)
+static __global__ void __launch_bounds__(128) hauser_kernel(const int8_t* __restrict__ letters, const int64_t* __restrict__ limits, uint32_t nseq,
                                      const DevParams* __restrict__ P, int8_t* __restrict__ bias) {
 	__shared__ int8_t s_score[32 * 20];
 	__shared__ float s_bg[20];
+	__shared__ __align__(16) int8_t s_stage[HAUSER_STAGE_BYTES];
 	for (int i = threadIdx.x; i < 32 * 20; i += blockDim.x) s_score[i] = P->score[(i / 20) * 32 + (i % 20)];
 	if (threadIdx.x < 20) s_bg[threadIdx.x] = P->background_scores_f32[threadIdx.x];
+	const uint32_t s0 = blockIdx.x * blockDim.x, s1 = min(nseq, s0 + blockDim.x);
+	const int64_t rbeg = limits[s0] & ~(int64_t)15, rend = limits[s1];  // [rbeg, rend) covers the block's sequences (+ delimiters)
+	const bool staged = (rend - rbeg) <= HAUSER_STAGE_BYTES;
+	if (staged)
+		for (int64_t x = (int64_t)threadIdx.x * 16; x < rend - rbeg; x += (int64_t)blockDim.x * 16)
+			*reinterpret_cast<uint4*>(s_stage + x) = *reinterpret_cast<const uint4*>(letters + rbeg + x);  // block images are 16 B aligned and padded
 	__syncthreads();
-	const uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (sidx >= nseq) return;
-	const int64_t beg = limits[sidx];
-	const int len = (int)(limits[sidx + 1] - beg - 1);
-	if (len <= 0) return;
-	const int8_t* seq = letters + beg;
-	int8_t* out = bias + beg;
-	int scores[20];
+	const uint32_t sidx = s0 + threadIdx.x;
+	if (sidx < nseq) {
+		const int64_t beg = limits[sidx];
+		const int len = (int)(limits[sidx + 1] - beg - 1);
+		if (len > 0) {
+			const int8_t* seq = staged ? s_stage + (beg - rbeg) : letters + beg;
+			int8_t* out = staged ? s_stage + (beg - rbeg) : bias + beg;  // in place when staged: position m is read before it is overwritten
+			int scores[20];
 #pragma unroll
-	for (int i = 0; i < 20; ++i) scores[i] = 0;
-	const unsigned window = 40, l = (unsigned)len, window_half = min(window / 2, l - 1);
-	unsigned n = 0, h = 0, m = 0, t = 0;
-	auto add = [&](unsigned pos) { const int8_t* row = s_score + (seq[pos] & 31) * 20;
+			for (int i = 0; i < 20; ++i) scores[i] = 0;
+			const unsigned window = 40, l = (unsigned)len, window_half = min(window / 2, l - 1);
+			unsigned n = 0, h = 0, m = 0, t = 0;
+			auto add = [&](int letter) { const int8_t* row = s_score + letter * 20;
 #pragma unroll
-		for (int i = 0; i < 20; ++i) scores[i] += row[i]; };
-	auto sub = [&](unsigned pos) { const int8_t* row = s_score + (seq[pos] & 31) * 20;
+				for (int i = 0; i < 20; ++i) scores[i] += row[i]; };
+			auto sub = [&](int letter) { const int8_t* row = s_score + letter * 20;
 #pragma unroll
-		for (int i = 0; i < 20; ++i) scores[i] -= row[i]; };
-	auto emit = [&](unsigned pos) {
-		const int r = seq[pos] & 31;
-		int8_t v = 0;
-		if (r < 20) {
-			int sr = 0;
+				for (int i = 0; i < 20; ++i) scores[i] -= row[i]; };
+			// the in-place update destroys letters behind m, but the trailing edge t <= m - 20 still needs them: keep the last
+			// 41 letters in a small ring (registers / local) -- simpler: a ring buffer of the window's letters
+			uint8_t ring[64];
+			auto letter_at = [&](unsigned pos) -> int { return staged ? (int)ring[pos & 63] : (int)(seq[pos] & 31); };
+			auto emit = [&](unsigned pos) {
+				const int r = letter_at(pos);
+				int8_t v = 0;
+				if (r < 20) {
+					int sr = 0;
 #pragma unroll
-			for (int i = 0; i < 20; ++i) if (i == r) sr = scores[i];
-			const float f = __fsub_rn(s_bg[r], __fdiv_rn(__int2float_rn(sr - (int)s_score[r * 20 + r]), __uint2float_rn(n - 1)));
-			v = (int8_t)(f < 0.0f ? __fsub_rn(f, 0.5f) : __fadd_rn(f, 0.5f));
+					for (int i = 0; i < 20; ++i) if (i == r) sr = scores[i];
+					const float f = __fsub_rn(s_bg[r], __fdiv_rn(__int2float_rn(sr - (int)s_score[r * 20 + r]), __uint2float_rn(n - 1)));
+					v = (int8_t)(f < 0.0f ? __fsub_rn(f, 0.5f) : __fadd_rn(f, 0.5f));
+				}
+				out[pos] = v;
+			};
+			auto take = [&](unsigned pos) -> int { const int L = seq[pos] & 31; if (staged) ring[pos & 63] = (uint8_t)L; return L; };  // h runs ahead of m and t
+			while (n < window_half && h < l) { ++n; add(take(h)); ++h; }
+			while (n < (window + 1) && h < l) { ++n; add(take(h)); emit(m); ++h; ++m; }
+			while (h < l) { add(take(h)); sub(letter_at(t)); emit(m); ++h; ++t; ++m; }
+			while (m < l && n > (window_half + 1)) { --n; sub(letter_at(t)); emit(m); ++t; ++m; }
+			while (m < l) { emit(m); ++m; }
 		}
-		out[pos] = v;
-	};
-	while (n < window_half && h < l) { ++n; add(h); ++h; }
-	while (n < (window + 1) && h < l) { ++n; add(h); emit(m); ++h; ++m; }
-	while (h < l) { add(h); sub(t); emit(m); ++h; ++t; ++m; }
-	while (m < l && n > (window_half + 1)) { --n; sub(t); emit(m); ++t; ++m; }
-	while (m < l) { emit(m); ++m; }
+	}
+	__syncthreads();
+	if (staged) {
+		// delimiters (and the 0..15 leading bytes of the previous block's tail) must stay 0 in the bias array
+		for (int64_t x = threadIdx.x; x < rend - rbeg; x += blockDim.x) {
+			const int64_t g = rbeg + x;
+			if (g >= limits[s0]) bias[g] = (letters[g] == DMND_DELIMITER) ? (int8_t)0 : s_stage[x];
+		}
+	}
 }
 
 // Issue-rate micro-benchmark: 8 independent chains of VIADDMNMX per thread, enough warps to fill every SMSP.

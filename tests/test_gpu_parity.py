@@ -75,9 +75,13 @@ def test_device_hauser_bias_matches_oracle(oracle_lib, product_lib, name):
         b1 = c.download_bias(qb, q_raw.size)
         c.compute_bias(qb, 0)
         b0 = c.download_bias(qb, q_raw.size)
-        out.append((b1, b0))
-        c.free_block(qb)
+        rb = c.upload(r_raw, r_lim)  # longer sequences: exercises the unstaged path of the kernel as well
+        c.compute_bias(rb, 1)
+        b2 = c.download_bias(rb, r_raw.size)
+        out.append((b1, b0, b2))
+        c.free_block(qb); c.free_block(rb)
     assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][2], out[1][2])
     assert np.any(out[1][0] != 0) and not np.any(out[1][1])
     o.close(); g.close()
 
