@@ -90,9 +90,9 @@ SEGMENT_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("len", "<i4"), ("score", 
 PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"), ("d_end", "<i4")])
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
-SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_block_upload",
-           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_block_clear_seed_mask",
-           "dmnd_search_shape", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
+SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
+           "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range",
+           "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
 
@@ -117,6 +117,9 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_block_compute_bias.argtypes = [vp, vp, C.c_int]
     lib.dmnd_block_download_bias.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_search_shape.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(StageCounters)]
+    lib.dmnd_search_shape_range.argtypes = [vp, vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(StageCounters)]
+    lib.dmnd_block_clear_seed_mask_range.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    lib.dmnd_ctx_lane.argtypes = [vp, C.c_int, C.POINTER(vp)]
     lib.dmnd_hits_count.argtypes = [vp]
     lib.dmnd_hits_count.restype = C.c_size_t
     lib.dmnd_hits_download.argtypes = [vp, vp, vp, C.c_size_t]

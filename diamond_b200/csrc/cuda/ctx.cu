@@ -9,17 +9,19 @@ void set_error(const std::string& m) { g_err = m; }
 }  // namespace dmnd_cuda
 using namespace dmnd_cuda;
 
-static __global__ void clear_seed_mask_kernel(int8_t* letters, size_t n) {
-	// 16 B per thread; every byte keeps its low 7 bits (delimiter 31 is unaffected)
-	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	uint4* p = reinterpret_cast<uint4*>(letters);
-	if (i * 16 + 16 <= n) {
-		uint4 v = p[i];
+static __global__ void clear_seed_mask_kernel(int8_t* letters, size_t begin, size_t end) {
+	// 16 B per thread over [begin, end); every byte keeps its low 7 bits (delimiter 31 is unaffected).  Chunks that
+	// straddle the range ends are handled byte by byte so that bytes of a neighbouring query range are never rewritten.
+	const size_t c0 = (begin / 16) * 16 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+	if (c0 >= end) return;
+	if (c0 >= begin && c0 + 16 <= end) {
+		uint4* p = reinterpret_cast<uint4*>(letters + c0);
+		uint4 v = *p;
 		v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
-		p[i] = v;
+		*p = v;
 	}
 	else
-		for (size_t k = i * 16; k < n; ++k) letters[k] &= 0x7f;
+		for (size_t k = (c0 > begin ? c0 : begin); k < c0 + 16 && k < end; ++k) letters[k] &= 0x7f;
 }
 
 // HauserCorrection (stats/hauser_correction.cpp:53-109), one thread per sequence running the reference's own five-phase
@@ -202,8 +204,21 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	return 0;
 }
 
+int dmnd_ctx_lane(dmnd_ctx* ctx, int lane, dmnd_ctx** out) {
+	if (lane < 0 || lane > 15) { set_error("dmnd_ctx_lane: lane index out of range"); return 1; }
+	while ((int)ctx->lanes.size() <= lane) {
+		dmnd_ctx* c = nullptr;
+		if (dmnd_create(ctx->device, &ctx->params, &c)) return 1;
+		ctx->lanes.push_back(c);
+	}
+	*out = ctx->lanes[(size_t)lane];
+	return 0;
+}
+
 void dmnd_destroy(dmnd_ctx* c) {
 	if (!c) return;
+	for (dmnd_ctx* l : c->lanes) dmnd_destroy(l);
+	c->lanes.clear();
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
@@ -327,18 +342,36 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 	return 0;
 }
 
-int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
-	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
-	const size_t n = b->raw_len, threads = (n + 15) / 16;
-	clear_seed_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(b->letters, n);
+static int clear_range(dmnd_ctx* ctx, dmnd_block* b, size_t begin, size_t end) {
+	if (end <= begin) return 0;
+	const size_t threads = (end - (begin / 16) * 16 + 15) / 16;
+	clear_seed_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(b->letters, begin, end);
 	++ctx->launches;
 	DMND_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
 
+int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return clear_range(ctx, b, 0, b->raw_len);
+}
+
+int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (q_begin > q_end || q_end > b->nseq) { set_error("dmnd_block_clear_seed_mask_range: bad range"); return 1; }
+	return clear_range(ctx, b, (size_t)b->h_limits[q_begin], (size_t)b->h_limits[q_end]);
+}
+
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
-	return search_shape_impl(ctx, query, ref, sid, out, counters);
+	return search_shape_impl(ctx, query, ref, sid, 0, query->nseq, out, counters);
+}
+
+int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end,
+                            dmnd_hits** out, dmnd_stage_counters* counters) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (q_begin > q_end || q_end > query->nseq) { set_error("dmnd_search_shape_range: bad query range"); return 1; }
+	return search_shape_impl(ctx, query, ref, sid, q_begin, q_end, out, counters);
 }
 
 size_t dmnd_hits_count(const dmnd_hits* h) { return h->n; }

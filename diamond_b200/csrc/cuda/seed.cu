@@ -61,12 +61,12 @@ __global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, size_t n, 
 	if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift)], 1u);
 }
 
-__global__ void probe_kernel(const int8_t* __restrict__ letters, size_t raw_len, const DevParams* __restrict__ P, int sid,
+__global__ void probe_kernel(const int8_t* __restrict__ letters, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, int sid,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
-	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + DMND_PERIMETER_PADDING;
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + p_begin;
 	uint64_t seed = 0;
-	bool ok = p + DMND_PERIMETER_PADDING < raw_len && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
+	bool ok = p < p_end && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
 	uint32_t lo = 0, cnt = 0;
 	if (ok) {
 		const uint64_t key = mix40(seed);
@@ -320,7 +320,7 @@ static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long l
 	return 0;
 }
 
-int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters) {
+int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
 	const dmnd_params& hp = ctx->params;
 	if (hp.ungapped_evalue != 0.0) { set_error("dmnd_search_shape: stage-2 ungapped window filter (sensitive modes) is not built yet"); return 1; }
 	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
@@ -338,7 +338,8 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
 
 	// ---- reference index
-	const size_t rpos = ref->raw_len - 2 * DMND_PERIMETER_PADDING, qpos = query->raw_len - 2 * DMND_PERIMETER_PADDING;
+	const size_t rpos = ref->raw_len - 2 * DMND_PERIMETER_PADDING;
+	const size_t qp_begin = (size_t)query->h_limits[q_begin], qp_end = (size_t)query->h_limits[q_end], qpos = qp_end - qp_begin;
 	if (ctx->b_keys.ensure(rpos * 8) || ctx->b_keys2.ensure(rpos * 8) || ctx->b_vals.ensure(rpos * 4) || ctx->b_vals2.ensure(rpos * 4)
 	    || ctx->b_bucket.ensure((nbuckets + 1) * 4 * 2))
 		return 1;
@@ -369,10 +370,10 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	// ---- probe every query position
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
 	unsigned long long nent = 0;
-	for (;;) {
+	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, query->raw_len, P, sid, d_keys, d_bucket, shift, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, sid, d_keys, d_bucket, shift, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
 		if (fetch_u64(ctx, d_cnt + 5, &nent)) return 1;
 		if (nent <= ecap) break;

@@ -93,6 +93,7 @@ public:
 	}
 	int size() const { return n_; }
 	void run(const std::function<void(int)>& f) {
+		std::lock_guard<std::mutex> turn(run_mtx_);  // lanes take turns: whoever has host work gets every worker
 		if (n_ == 1) { f(0); return; }
 		{ std::lock_guard<std::mutex> l(m_); fn_ = &f; pending_ = n_ - 1; ++gen_; }
 		cv_.notify_all();
@@ -118,7 +119,7 @@ private:
 	}
 	int n_;
 	std::vector<std::thread> th_;
-	std::mutex m_;
+	std::mutex m_, run_mtx_;
 	std::condition_variable cv_, done_;
 	const std::function<void(int)>* fn_ = nullptr;
 	int pending_ = 0;
@@ -266,8 +267,7 @@ struct ThreadCtx {
 
 // Everything that survives between calls (buffers keep their capacity: no page faults in steady state).
 struct Workspace {
-	std::mutex mtx;
-	std::unique_ptr<Pool> pool;
+	Pool* pool = nullptr;
 	std::vector<ThreadCtx> tc;
 	std::vector<dmnd_hit> hv;
 	std::vector<dmnd_segment> segv;
@@ -278,11 +278,19 @@ struct Workspace {
 	std::vector<dmnd_dp_problem> p1, p2;
 	std::vector<dmnd_dp_result> res1, res2;
 	std::vector<uint8_t> tr;
-	void ensure_pool(int threads) {
-		if (!pool || pool->size() != threads) { pool.reset(new Pool(threads)); tc.clear(); tc.resize((size_t)threads); }
+};
+// Process-wide: the worker pool and one workspace per lane.
+struct Shared {
+	std::mutex mtx;
+	std::unique_ptr<Pool> pool;
+	std::vector<std::unique_ptr<Workspace>> lanes;
+	void ensure(int threads, int nlanes) {
+		if (!pool || pool->size() != threads) { pool.reset(new Pool(threads)); lanes.clear(); }
+		while ((int)lanes.size() < nlanes) lanes.emplace_back(new Workspace());
+		for (auto& w : lanes) { w->pool = pool.get(); if ((int)w->tc.size() != threads) { w->tc.clear(); w->tc.resize((size_t)threads); } }
 	}
 };
-Workspace& workspace() { static Workspace w; return w; }
+Shared& shared() { static Shared s; return s; }
 
 struct Driver {
 	dmnd_ctx* ctx;
@@ -665,39 +673,31 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	return 0;
 }
 
-static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const int8_t* q_letters, const int64_t* q_limits,
-                       uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
-                       dmnd_result** out) {
-	auto t_total = Clock::now();
-	Workspace& w = workspace();
-	std::lock_guard<std::mutex> guard(w.mtx);
-	std::unique_ptr<dmnd_result> res(new dmnd_result());
-	std::memset(&res->stats, 0, sizeof res->stats);
-	Scoring sc;
-	int64_t ref_letters = 0;
-	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
-	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
-	int host_threads = effective_cpus();
-	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
-	w.ensure_pool(host_threads);
+// One lane: the whole pipeline for the queries [q_begin, q_end) on its own lane context (stream + scratch).  Lanes run
+// on their own host threads; while one lane waits for its kernels the other one owns the worker pool, so the host
+// bridge of one query range overlaps the device work of the other.
+struct LaneOut {
+	std::vector<dmnd_match> matches;
+	std::vector<uint8_t> transcripts;
+	dmnd_run_stats stats;
+	std::string error;
+	int rc = 0;
+};
 
+static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const Env& env, const Scoring& sc, uint32_t q_begin, uint32_t q_end,
+                    Workspace& w, int host_threads, LaneOut& lo) {
+	auto t_total = Clock::now();
 	Driver d;
-	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads;
+	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads; d.env = env;
 	std::memset(&d.stats, 0, sizeof d.stats);
 	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, 0);  // snapshot: the device counters of this call are reported as a delta
-	Env& e = d.env;
-	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
-	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
-	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
-	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
+	const Env& e = d.env;
 
 	// ---- seed stage (run_ref_chunk: one search_shape per shape; FAST has one shape)
 	Prof prof;
 	auto t0 = Clock::now();
-	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
-	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;
 	dmnd_hits* hits = nullptr;
-	if (dmnd_search_shape(ctx, qb, rb, 0, &hits, &d.stats.seed)) return 1;
+	if (dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed)) return 1;
 	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
 	w.hv.resize(nh);
@@ -706,19 +706,28 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
 	if (nh && dmnd_hits_xdrop(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	dmnd_hits_free(ctx, hits);
-	if (dmnd_block_clear_seed_mask(ctx, qb)) return 1;  // run/double_indexed.cpp:211-212
+	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
 	d.stats.seed_ms = ms_since(t0);
 	d.stats.hits = nh;
 
-	// ---- group by query (hits arrive grouped by ascending query id)
+	// ---- group by query (hits arrive grouped by ascending query id): boundaries found in parallel
 	t0 = Clock::now();
+	const int T = host_threads;
+	std::vector<std::vector<size_t>> tl_bounds((size_t)T);
+	std::atomic<int> bad(0);
+	w.pool->run([&](int t) {
+		auto& v = tl_bounds[(size_t)t];
+		v.clear();
+		for (size_t i = nh * (size_t)t / (size_t)T, en = nh * (size_t)(t + 1) / (size_t)T; i < en; ++i)
+			if (i == 0 || w.hv[i].query != w.hv[i - 1].query) {
+				if (i > 0 && w.hv[i].query < w.hv[i - 1].query) bad = 1;
+				v.push_back(i);
+			}
+	});
+	if (bad) { dmnd_set_last_error("dmnd_blastp: hits not grouped by ascending query"); return 1; }
 	w.qstart.clear();
-	for (size_t i = 0; i < nh; ++i)
-		if (i == 0 || w.hv[i].query != w.hv[i - 1].query) {
-			if (i > 0 && w.hv[i].query < w.hv[i - 1].query) { dmnd_set_last_error("dmnd_blastp: hits not grouped by ascending query"); return 1; }
-			w.qstart.push_back(i);
-		}
+	for (const auto& v : tl_bounds) w.qstart.insert(w.qstart.end(), v.begin(), v.end());
 	w.qstart.push_back(nh);
 	const size_t nqh = w.qstart.size() - 1;
 	d.nq_hit = nqh;
@@ -745,7 +754,6 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 
 	// ---- emit: per-thread counts -> offsets -> parallel fill (matches grouped by ascending query)
 	t0 = Clock::now();
-	const int T = host_threads;
 	std::vector<size_t> moff((size_t)T + 1, 0), troff((size_t)T + 1, 0);
 	w.pool->run([&](int t) {
 		ThreadCtx& tc = w.tc[(size_t)t];
@@ -760,12 +768,12 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		d.stats.queries_aligned += w.tc[(size_t)t].n_aligned;
 		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
 	}
-	res->matches.resize(moff[(size_t)T]);
-	res->transcripts.resize(troff[(size_t)T]);
+	lo.matches.resize(moff[(size_t)T]);
+	lo.transcripts.resize(troff[(size_t)T]);
 	w.pool->run([&](int t) {
 		const ThreadCtx& tc = w.tc[(size_t)t];
-		dmnd_match* o = res->matches.data() + moff[(size_t)t];
-		if (!tc.trbuf.empty()) std::memcpy(res->transcripts.data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
+		dmnd_match* o = lo.matches.data() + moff[(size_t)t];
+		if (!tc.trbuf.empty()) std::memcpy(lo.transcripts.data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			const QueryState& q = w.qs[k];
 			for (const Match& m : q.matches) {
@@ -780,7 +788,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 			}
 		}
 	});
-	d.stats.matches = res->matches.size();
+	d.stats.matches = lo.matches.size();
 	d.stats.host_bridge_ms += ms_since(t0);
 	prof.lap("emit matches");
 	d.stats.total_ms = ms_since(t_total);
@@ -791,7 +799,87 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		dv.h2d_ms = tm1.h2d_ms - tm0.h2d_ms; dv.d2h_ms = tm1.d2h_ms - tm0.d2h_ms;
 		dv.launches = tm1.launches - tm0.launches; dv.h2d_bytes = tm1.h2d_bytes - tm0.h2d_bytes; dv.d2h_bytes = tm1.d2h_bytes - tm0.d2h_bytes;
 	}
-	res->stats = d.stats;
+	lo.stats = d.stats;
+	return 0;
+}
+
+static void add_stats(dmnd_run_stats& a, const dmnd_run_stats& b) {
+	a.seed.seeds_hit += b.seed.seeds_hit; a.seed.seed_hits += b.seed.seed_hits; a.seed.tentative_matches1 += b.seed.tentative_matches1;
+	a.seed.tentative_matches2 += b.seed.tentative_matches2; a.seed.tentative_matches3 += b.seed.tentative_matches3; a.seed.masked_seeds += b.seed.masked_seeds;
+	a.hits += b.hits; a.targets += b.targets; a.dp_problems_round1 += b.dp_problems_round1; a.dp_problems_round2 += b.dp_problems_round2;
+	a.cells_round1 += b.cells_round1; a.cells_round2 += b.cells_round2; a.queries_aligned += b.queries_aligned; a.matches += b.matches;
+	// wall-clock phase times of concurrent lanes overlap: report the longest lane
+	a.seed_ms = std::max(a.seed_ms, b.seed_ms); a.host_bridge_ms = std::max(a.host_bridge_ms, b.host_bridge_ms);
+	a.dp1_ms = std::max(a.dp1_ms, b.dp1_ms); a.dp2_ms = std::max(a.dp2_ms, b.dp2_ms);
+	a.device.seed_ms += b.device.seed_ms; a.device.dp_score_ms += b.device.dp_score_ms; a.device.dp_trace_ms += b.device.dp_trace_ms;
+	a.device.h2d_ms += b.device.h2d_ms; a.device.d2h_ms += b.device.d2h_ms; a.device.launches += b.device.launches;
+	a.device.h2d_bytes += b.device.h2d_bytes; a.device.d2h_bytes += b.device.d2h_bytes;
+}
+
+static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const int8_t* q_letters, const int64_t* q_limits,
+                       uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
+                       dmnd_result** out) {
+	auto t_total = Clock::now();
+	Shared& sh = shared();
+	std::lock_guard<std::mutex> guard(sh.mtx);
+	std::unique_ptr<dmnd_result> res(new dmnd_result());
+	std::memset(&res->stats, 0, sizeof res->stats);
+	Scoring sc;
+	int64_t ref_letters = 0;
+	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
+	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
+	int host_threads = effective_cpus();
+	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
+	int nlanes = nq < 40000u ? 1 : 2;  // small inputs: lane overlap buys nothing
+	if (const char* ev = std::getenv("DMND_LANES")) nlanes = std::max(1, std::min(8, std::atoi(ev)));
+	nlanes = (int)std::min<uint32_t>((uint32_t)nlanes, std::max<uint32_t>(nq, 1));
+	sh.ensure(host_threads, nlanes);
+
+	Env e;
+	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
+	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
+	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
+	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
+
+	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
+	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;
+
+	// contiguous, letter-balanced query ranges (SequenceSet::partition, data/sequence_set.cpp:57-75, is the reference's analogue)
+	std::vector<uint32_t> cut((size_t)nlanes + 1, nq);
+	cut[0] = 0;
+	for (int l = 1; l < nlanes; ++l) {
+		const int64_t want = q_limits[0] + (q_limits[nq] - q_limits[0]) * l / nlanes;
+		cut[(size_t)l] = (uint32_t)(std::lower_bound(q_limits, q_limits + nq + 1, want) - q_limits);
+		cut[(size_t)l] = std::min(std::max(cut[(size_t)l], cut[(size_t)l - 1]), nq);
+	}
+	std::vector<LaneOut> lo((size_t)nlanes);
+	std::vector<dmnd_ctx*> lctx((size_t)nlanes, ctx);
+	for (int l = 1; l < nlanes; ++l)
+		if (dmnd_ctx_lane(ctx, l - 1, &lctx[(size_t)l])) return 1;
+	auto body = [&](int l) {
+		LaneOut& o = lo[(size_t)l];
+		o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o);
+		if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
+	};
+	std::vector<std::thread> th;
+	for (int l = 1; l < nlanes; ++l) th.emplace_back(body, l);
+	body(0);
+	for (auto& t : th) t.join();
+	for (int l = 0; l < nlanes; ++l)
+		if (lo[(size_t)l].rc) { dmnd_set_last_error(lo[(size_t)l].error.c_str()); return 1; }
+
+	// ---- concatenate lanes (ascending query ranges)
+	size_t nm = 0, nt = 0;
+	for (const LaneOut& o : lo) { nm += o.matches.size(); nt += o.transcripts.size(); }
+	res->matches.reserve(nm); res->transcripts.reserve(nt);
+	for (LaneOut& o : lo) {
+		const size_t tbase = res->transcripts.size();
+		if (tbase) for (dmnd_match& m : o.matches) m.transcript_off += tbase;
+		if (res->matches.empty()) res->matches.swap(o.matches); else res->matches.insert(res->matches.end(), o.matches.begin(), o.matches.end());
+		if (res->transcripts.empty()) res->transcripts.swap(o.transcripts); else res->transcripts.insert(res->transcripts.end(), o.transcripts.begin(), o.transcripts.end());
+		add_stats(res->stats, o.stats);
+	}
+	res->stats.total_ms = ms_since(t_total);
 	*out = res.release();
 	return 0;
 }
@@ -806,10 +894,14 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
                 const int8_t* r_letters, size_t r_raw_len, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
                 dmnd_result** out) {
 	dmnd_block *qb = nullptr, *rb = nullptr;
+	Prof prof;
 	if (dmnd_block_upload(ctx, q_letters, q_raw_len, q_limits, nq, &qb)) return 1;
 	if (dmnd_block_upload(ctx, r_letters, r_raw_len, r_limits, nr, &rb)) { dmnd_block_free(ctx, qb); return 1; }
+	prof.lap("e2e: block uploads");
 	const int rc = blastp_impl(ctx, qb, rb, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, out);
+	prof.t = Clock::now();
 	dmnd_block_free(ctx, qb); dmnd_block_free(ctx, rb);
+	prof.lap("e2e: block frees");
 	return rc;
 }
 

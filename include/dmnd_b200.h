@@ -112,6 +112,10 @@ const char* dmnd_backend(void);
 /* ---- K layer ---------------------------------------------------------------------------------------------- */
 int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out);
 void dmnd_destroy(dmnd_ctx* ctx);
+/* Lane contexts: independent stream + scratch memory on the same device and parameters, owned by `ctx` (destroyed with
+ * it).  Blocks uploaded through `ctx` may be used with any of its lanes; calls on DIFFERENT lanes may run concurrently
+ * from different host threads (the P layer overlaps the host bridge of one query range with the kernels of another). */
+int dmnd_ctx_lane(dmnd_ctx* ctx, int lane, dmnd_ctx** out);
 
 /* `letters` is the reference's block image (256 B delimiter padding + sum(seq + 1 delimiter) + 256 B padding),
  * raw_len bytes long; limits[0..nseq] are the sequence start offsets into it (limits[0] == 256).  Copies to HBM. */
@@ -137,12 +141,16 @@ void dmnd_host_free(dmnd_ctx* ctx, void* p);
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
 /* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
 int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
+int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end);
 
 /* Stages 0-2 for shape `sid`, all index chunks in reference order; hits are grouped by query (ascending),
  * order inside a query unspecified (the reference's is thread-dependent; consumers sort, align/load_hits.h:45).
  * Sets SEED_MASK bits in the query block exactly like Search::mask_seeds (search/seed_complexity.cpp:77-127). */
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out,
                       dmnd_stage_counters* counters);
+/* Same for the queries [q_begin, q_end) only (query sharding inside one block); SEED_MASK bits are set in that range only. */
+int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end,
+                            dmnd_hits** out, dmnd_stage_counters* counters);
 size_t dmnd_hits_count(const dmnd_hits* h);
 /* x-drop ungapped extension of every hit (xdrop_ungapped, dp/ungapped_align.cpp:150-214, score-only variant with the
  * query block's bias): out[k] belongs to hit k of dmnd_hits_download().  `raw_xdrop` = config.raw_ungapped_xdrop.

@@ -83,6 +83,7 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	*out = c;
 	return 0;
 }
+int dmnd_ctx_lane(dmnd_ctx* ctx, int lane, dmnd_ctx** out) { (void)lane; *out = ctx; return 0; } /* the CPU restatement is stateless per call */
 void dmnd_destroy(dmnd_ctx* c) {
 	if (!c) return;
 	for (int k = 0; k <= c->p.n_shapes; ++k) free(c->matcher[k]);
@@ -163,6 +164,13 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 	memcpy(letters, b->letters, raw_len);
 	return 0;
 }
+int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end) {
+	(void)ctx;
+	if (q_begin > q_end || q_end > b->nseq) return fail("dmnd_block_clear_seed_mask_range: bad range");
+	for (int64_t i = b->limits[q_begin]; i < b->limits[q_end]; ++i)
+		if (b->letters[i] != DMND_DELIMITER) b->letters[i] &= 0x7f;
+	return 0;
+}
 int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
 	(void)ctx;
 	for (size_t i = 0; i < b->raw_len; ++i)
@@ -208,12 +216,12 @@ static int seed_at_unreduced(const dmnd_params* p, int sid, const int8_t* s, uin
 	return 1;
 }
 
-static size_t enum_seeds(const dmnd_params* p, int sid, const dmnd_block* b, uint32_t pbegin, uint32_t pend, entry** out) {
+static size_t enum_seeds(const dmnd_params* p, int sid, const dmnd_block* b, uint32_t pbegin, uint32_t pend, uint32_t s_begin, uint32_t s_end, entry** out) {
 	const uint64_t mask = ((uint64_t)1 << p->seedp_bits) - 1;
 	const int span = p->shape_len[sid];
 	size_t n = 0, cap = 1024;
 	entry* e = (entry*)malloc(cap * sizeof *e);
-	for (uint32_t i = 0; i < b->nseq; ++i) {
+	for (uint32_t i = s_begin; i < s_end; ++i) {
 		const int64_t beg = b->limits[i], len = b->limits[i + 1] - b->limits[i] - 1;
 		for (int64_t j = 0; j + span <= len; ++j) {
 			uint64_t s;
@@ -344,7 +352,12 @@ static uint32_t seq_of(const dmnd_block* b, uint64_t loc) { /* SequenceSet::loca
 
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out,
                       dmnd_stage_counters* counters) {
+	return dmnd_search_shape_range(ctx, query, ref, sid, 0, query->nseq, out, counters);
+}
+int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end,
+                            dmnd_hits** out, dmnd_stage_counters* counters) {
 	const dmnd_params* p = &ctx->p;
+	if (q_begin > q_end || q_end > query->nseq) return fail("dmnd_search_shape_range: bad query range");
 	if (p->ungapped_evalue != 0.0) return fail("oracle: stage-2 ungapped window filter not restated yet");
 	dmnd_stage_counters cn; memset(&cn, 0, sizeof cn);
 	size_t nh = 0, hcap = 1024;
@@ -357,7 +370,7 @@ int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		const uint32_t bsel = chunk < prem ? chunk : prem;
 		const uint32_t pb = bsel * (psize + 1) + (chunk - bsel) * psize, pe = pb + (chunk < prem ? psize + 1 : psize);
 		entry *re, *qe;
-		const size_t nr = enum_seeds(p, sid, ref, pb, pe, &re), nq = enum_seeds(p, sid, query, pb, pe, &qe);
+		const size_t nr = enum_seeds(p, sid, ref, pb, pe, 0, ref->nseq, &re), nq = enum_seeds(p, sid, query, pb, pe, q_begin, q_end, &qe);
 		/* pass 1: entropy masking of every shared key of this chunk (search/stage0.cpp:173 runs before the search) */
 		size_t i = 0, j = 0;
 		uint8_t* erased = (uint8_t*)calloc(nq + 1, 1); /* marks first entry of an erased query run */

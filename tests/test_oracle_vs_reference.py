@@ -48,6 +48,23 @@ def test_live_reference_run(oracle_lib, seed):
     assert api.fmt6(m) == gold
 
 
+@pytest.mark.parametrize("lanes", ["1", "3"])
+def test_query_lanes_do_not_change_results(oracle_lib, lanes, monkeypatch):
+    """The P layer may split the query block into lanes that run concurrently: output must be independent of it."""
+    from diamond_b200 import api
+    monkeypatch.setenv("DMND_LANES", lanes)
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("fam2")
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, want_transcript=True)
+    m, tr, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, "fam2.l1.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, "fam2.l1.counters.json")))
+    assert st["seed"]["tentative_matches3"] == cn["tentative_matches3"] and st["seed"]["seeds_hit"] >= cn["seeds_hit"]
+    assert np.all(m["transcript_off"] + m["transcript_len"] <= len(tr)) and np.array_equal(m["transcript_len"], m["length"])
+    ops = np.concatenate([tr[a:a + n] for a, n in zip(m["transcript_off"][:50], m["transcript_len"][:50])]) >> 6
+    assert set(np.unique(ops)) <= {0, 1, 2, 3}
+
+
 def test_evalue_within_tolerance_of_printed_reference_values(oracle_lib):
     """north_star: e-values within 1e-6 relative.  The reference prints %.2e, so compare at that precision and make
     sure no value sits on a rounding edge by also checking the raw double against the printed one to 0.5 % (3 digits)."""
