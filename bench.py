@@ -174,12 +174,10 @@ def main():
     w, q_raw, q_lim, r_raw, r_lim = make_workload(args, rank)
     if world > 1:
         # the packed reference block travels once over NVLink (NCCL broadcast from rank 0); every rank then adopts it
-        t = torch.from_numpy(r_raw.view(np.uint8)).cuda()
-        dist.broadcast(t, 0)
-        r_raw = t.cpu().numpy().view(np.int8)
-        lt = torch.from_numpy(r_lim).cuda()
-        dist.broadcast(lt, 0)
-        r_lim = lt.cpu().numpy()
+        from diamond_b200 import shard
+        if rank != 0:
+            r_raw, r_lim = np.zeros(0, np.int8), np.zeros(0, np.int64)
+        r_raw, r_lim = shard.broadcast_reference(r_raw, r_lim, dist, device=torch.device("cuda", local))
     # pinned host copies for the e2e path
     q_pin = torch.from_numpy(q_raw).pin_memory().numpy()
     r_pin = torch.from_numpy(r_raw).pin_memory().numpy()

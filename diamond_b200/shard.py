@@ -1,0 +1,57 @@
+"""Query sharding across the GPUs of one node: one process per GPU, every rank holds the whole packed
+reference block and works on a contiguous, letter-balanced range of the query block.  The ONLY collective is the one-off
+broadcast of the packed reference block (NCCL over NVLink on GPUs, gloo in the CPU tests); there is no collective on the
+data path and results are concatenated in rank order."""
+from __future__ import annotations
+import numpy as np
+
+
+def query_ranges(q_limits: np.ndarray, parts: int):
+    """Contiguous query-id ranges with ~equal letter counts (the reference's SequenceSet::partition,
+    data/sequence_set.cpp:57-75, does the same for threads)."""
+    n = len(q_limits) - 1
+    total = int(q_limits[-1] - q_limits[0])
+    cuts = [0]
+    for k in range(1, parts):
+        want = int(q_limits[0]) + total * k // parts
+        c = int(np.searchsorted(q_limits, want, side="left"))
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(parts)]
+
+
+def sub_block(raw: np.ndarray, limits: np.ndarray, begin: int, end: int):
+    """Block image of sequences [begin, end) cut out of a block image (ids are re-based to 0)."""
+    from .api import PADDING, DELIMITER
+    a, b = int(limits[begin]), int(limits[end])
+    out = np.full(b - a + 2 * PADDING, DELIMITER, dtype=np.int8)
+    out[PADDING:PADDING + (b - a)] = raw[a:b]
+    lim = (limits[begin:end + 1] - a + PADDING).astype(np.int64)
+    return out, lim
+
+
+def broadcast_reference(r_raw, r_limits, dist, device=None):
+    """Rank 0's packed reference block to every rank (one broadcast of the letters, one of the limits)."""
+    import torch
+    rank = dist.get_rank()
+    meta = torch.tensor([len(r_raw) if rank == 0 else 0, len(r_limits) if rank == 0 else 0], dtype=torch.int64)
+    if device is not None:
+        meta = meta.to(device)
+    dist.broadcast(meta, 0)
+    n_raw, n_lim = int(meta[0]), int(meta[1])
+    t = torch.from_numpy(np.ascontiguousarray(r_raw).view(np.uint8)) if rank == 0 else torch.empty(n_raw, dtype=torch.uint8)
+    l = torch.from_numpy(np.ascontiguousarray(r_limits)) if rank == 0 else torch.empty(n_lim, dtype=torch.int64)
+    if device is not None:
+        t, l = t.to(device), l.to(device)
+    dist.broadcast(t, 0)
+    dist.broadcast(l, 0)
+    return t.cpu().numpy().view(np.int8), l.cpu().numpy()
+
+
+def gather_matches(matches: np.ndarray, query_offset: int, dist):
+    """All ranks' match records on rank 0, query ids re-based to the unsharded block, in rank (= query) order."""
+    m = matches.copy()
+    m["query"] += query_offset
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(m, out, dst=0)
+    return np.concatenate(out) if dist.get_rank() == 0 else None
