@@ -224,6 +224,8 @@ void dmnd_destroy(dmnd_ctx* c) {
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
 		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep };
 	for (DevBuf* b : bufs) b->release();
+	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); }
+	c->b_hits_out.release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -244,9 +246,21 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	b->raw_len = raw_len; b->nseq = nseq;
 	b->h_limits.assign(limits, limits + nseq + 1);
 	const size_t padded = (raw_len + 63) & ~(size_t)63;  // 16 B vector loads may touch the tail
-	DMND_CUDA_CHECK(cudaMalloc(&b->letters, padded + 64));
-	DMND_CUDA_CHECK(cudaMalloc(&b->bias, padded + 64));
-	DMND_CUDA_CHECK(cudaMalloc(&b->limits, sizeof(int64_t) * ((size_t)nseq + 1)));
+	// reuse the device memory of a freed block when one is large enough (steady-state uploads allocate nothing)
+	for (size_t k = 0; k < ctx->block_pool.size(); ++k) {
+		const dmnd_ctx::FreeBlock& f = ctx->block_pool[k];
+		if (f.cap_bytes >= padded + 64 && f.cap_seqs >= (size_t)nseq + 1 && f.cap_bytes <= 2 * (padded + 64) + (1 << 20)) {
+			b->letters = f.letters; b->bias = f.bias; b->limits = f.limits; b->cap_bytes = f.cap_bytes; b->cap_seqs = f.cap_seqs;
+			ctx->block_pool.erase(ctx->block_pool.begin() + (ptrdiff_t)k);
+			break;
+		}
+	}
+	if (!b->letters) {
+		b->cap_bytes = padded + 64; b->cap_seqs = (size_t)nseq + 1;
+		DMND_CUDA_CHECK(cudaMalloc(&b->letters, b->cap_bytes));
+		DMND_CUDA_CHECK(cudaMalloc(&b->bias, b->cap_bytes));
+		DMND_CUDA_CHECK(cudaMalloc(&b->limits, sizeof(int64_t) * b->cap_seqs));
+	}
 	PhaseTimer t(ctx, PH_H2D);
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, ctx->stream));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(b->letters, letters, raw_len, cudaMemcpyHostToDevice, ctx->stream));
@@ -262,7 +276,9 @@ void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	if (!b) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits);
+	for (dmnd_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream);
+	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->cap_bytes, b->cap_seqs });
+	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); }
 	delete b;
 }
 
@@ -389,9 +405,8 @@ int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t
 
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) {
 	if (!h) return;
-	cudaSetDevice(ctx->device);
-	if (h->d) cudaFree(h->d);
-	delete h;
+	(void)ctx;
+	delete h;  // the records live in the context's hit arena
 }
 
 int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,

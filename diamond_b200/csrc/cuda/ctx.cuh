@@ -60,6 +60,7 @@ enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
 }  // namespace dmnd_cuda
 
 struct dmnd_block {
+	size_t cap_bytes = 0, cap_seqs = 0;  // allocated sizes (the block pool matches on them)
 	int8_t* letters = nullptr;  // device
 	int8_t* bias = nullptr;     // device, same offsets as letters
 	int64_t* limits = nullptr;  // device
@@ -69,8 +70,8 @@ struct dmnd_block {
 };
 
 struct dmnd_hits {
-	dmnd_hit* d = nullptr;  // device, grouped by query
-	size_t n = 0;
+	dmnd_hit* d = nullptr;  // device, grouped by query; lives in the context's hit arena (no per-call cudaMalloc/cudaFree:
+	size_t n = 0;           // cudaFree synchronises the whole device and would stall the other lanes)
 };
 
 struct dmnd_ctx {
@@ -89,6 +90,9 @@ struct dmnd_ctx {
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	bool force_generic_dp = false;
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
+	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)
+	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; size_t cap_bytes, cap_seqs; };
+	std::vector<FreeBlock> block_pool;  // device memory of freed blocks, reused by dmnd_block_upload
 	void* h_pinned = nullptr;  // small pinned staging for counters
 	size_t h_pinned_cap = 0;
 	// timing

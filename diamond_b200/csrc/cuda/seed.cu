@@ -428,7 +428,8 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	dmnd_hits* h = new dmnd_hits();
 	h->n = hits_total;
 	if (hits_total) {
-		DMND_CUDA_CHECK(cudaMalloc(&h->d, hits_total * sizeof(dmnd_hit)));
+		if (ctx->b_hits_out.ensure(hits_total * sizeof(dmnd_hit))) return 1;
+		h->d = ctx->b_hits_out.as<dmnd_hit>();
 		if (ctx->b_keys.ensure(hits_total * 4) || ctx->b_vals.ensure(hits_total * 4)) return 1;
 		uint32_t* k_in = ctx->b_keys.as<uint32_t>();
 		uint32_t* k_out = ctx->b_vals.as<uint32_t>();
