@@ -86,7 +86,7 @@ struct dmnd_ctx {
 	int sm_count = 148;
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
-	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work, b_prep;
+	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work, b_prep, b_bloom;
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	bool force_generic_dp = false;
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)

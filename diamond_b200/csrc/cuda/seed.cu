@@ -56,6 +56,42 @@ __global__ void ref_enum_kernel(const int8_t* __restrict__ letters, size_t raw_l
 	}
 }
 
+// Blocked Bloom filter over the reference keys: one 32-byte block (= one L2 sector) per key, 4 bits set.  99 % of the query
+// positions have no partner in the reference; the filter answers them from a 64 MB structure that stays L2 resident instead
+// of touching the bucket directory and the 228 MB key array in HBM.
+__device__ __forceinline__ void bloom_slots(uint64_t key, uint32_t block_mask, uint32_t& block, uint32_t& bits) {
+	const uint64_t h = key * 0xD6E8FEB86659FD93ull;
+	block = (uint32_t)(h >> 40) & block_mask;
+	bits = (uint32_t)(h >> 8);  // four 8-bit positions inside the 256-bit block
+}
+__global__ void bloom_build_kernel(const uint64_t* __restrict__ keys, size_t n, uint32_t* bloom, uint32_t block_mask) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (i > 0 && keys[i] == keys[i - 1]) return;  // sorted: one insert per distinct key
+	uint32_t block, bits;
+	bloom_slots(keys[i], block_mask, block, bits);
+	uint32_t* w = bloom + (size_t)block * 8;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) { const uint32_t p = (bits >> (8 * k)) & 255u; atomicOr(&w[p >> 5], 1u << (p & 31)); }
+}
+__device__ __forceinline__ bool bloom_test(const uint32_t* __restrict__ bloom, uint32_t block_mask, uint64_t key) {
+	uint32_t block, bits;
+	bloom_slots(key, block_mask, block, bits);
+	const uint4* w4 = reinterpret_cast<const uint4*>(bloom + (size_t)block * 8);
+	const uint4 a = w4[0], b = w4[1];
+	const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+	bool ok = true;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t p = (bits >> (8 * k)) & 255u;
+		uint32_t word = 0;
+#pragma unroll
+		for (int x = 0; x < 8; ++x) if ((p >> 5) == (uint32_t)x) word = w[x];
+		ok &= (word >> (p & 31)) & 1u;
+	}
+	return ok;
+}
+
 __global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int shift, uint32_t* hist) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift)], 1u);
@@ -63,11 +99,13 @@ __global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, size_t n, 
 
 __global__ void probe_kernel(const int8_t* __restrict__ letters, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, int sid,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
+                             const uint32_t* __restrict__ bloom, uint32_t bloom_mask,
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
 	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + p_begin;
 	uint64_t seed = 0;
 	bool ok = p < p_end && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
 	uint32_t lo = 0, cnt = 0;
+	if (ok) ok = bloom_test(bloom, bloom_mask, mix40(seed));
 	if (ok) {
 		const uint64_t key = mix40(seed);
 		const uint32_t b = (uint32_t)(key >> shift);
@@ -366,6 +404,13 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_hist, d_bucket, nbuckets + 1, st));
 		ctx->launches += 2;
 	}
+	// Bloom filter: >= 12 keys' worth of 256-bit blocks per 12 keys, i.e. >= 21 bits per key (false positives < 1 %)
+	uint32_t bloom_blocks = 1024;
+	while ((unsigned long long)bloom_blocks * 12ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
+	if (ctx->b_bloom.ensure((size_t)bloom_blocks * 32)) return 1;
+	uint32_t* d_bloom = ctx->b_bloom.as<uint32_t>();
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_bloom, 0, (size_t)bloom_blocks * 32, st));
+	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, d_bloom, bloom_blocks - 1); ++ctx->launches; }
 
 	// ---- probe every query position
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
@@ -373,7 +418,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, sid, d_keys, d_bucket, shift, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, sid, d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
 		if (fetch_u64(ctx, d_cnt + 5, &nent)) return 1;
 		if (nent <= ecap) break;
