@@ -224,8 +224,9 @@ void dmnd_destroy(dmnd_ctx* c) {
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
 		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep, &c->b_bloom };
 	for (DevBuf* b : bufs) b->release();
-	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); }
+	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); f.idx.release(); }
 	c->b_hits_out.release();
+	c->own_index.release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -251,6 +252,7 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 		const dmnd_ctx::FreeBlock& f = ctx->block_pool[k];
 		if (f.cap_bytes >= padded + 64 && f.cap_seqs >= (size_t)nseq + 1 && f.cap_bytes <= 2 * (padded + 64) + (1 << 20)) {
 			b->letters = f.letters; b->bias = f.bias; b->limits = f.limits; b->cap_bytes = f.cap_bytes; b->cap_seqs = f.cap_seqs;
+			b->idx = f.idx; b->idx.valid = false;  // keeps the index buffers' capacity, not their contents
 			ctx->block_pool.erase(ctx->block_pool.begin() + (ptrdiff_t)k);
 			break;
 		}
@@ -277,8 +279,8 @@ void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (dmnd_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream);
-	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->cap_bytes, b->cap_seqs });
-	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); }
+	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->cap_bytes, b->cap_seqs, b->idx });
+	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); b->idx.release(); }
 	delete b;
 }
 
@@ -290,6 +292,15 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 	else DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, raw_len, ctx->stream));
 	t.stop();
 	return 0;
+}
+
+int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (sid < 0 || sid >= ctx->params.n_shapes) { set_error("dmnd_block_build_index: bad shape id"); return 1; }
+	PhaseTimer t(ctx, PH_SEED);
+	const int rc = build_ref_index(ctx, b, sid, b->idx);
+	t.stop();
+	return rc;
 }
 
 int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {

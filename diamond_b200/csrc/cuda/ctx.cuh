@@ -59,7 +59,20 @@ enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
 
 }  // namespace dmnd_cuda
 
+namespace dmnd_cuda {
+// Seed index of a reference block for one shape: sorted 40-bit key mixes + locations, bucket directory, Bloom filter.
+struct RefIndex {
+	DevBuf keys, locs, bucket, bloom;
+	unsigned long long nref = 0;
+	int sid = -1, shift = 0;
+	uint32_t bloom_blocks = 0;
+	bool valid = false;
+	void release() { keys.release(); locs.release(); bucket.release(); bloom.release(); valid = false; }
+};
+}  // namespace dmnd_cuda
+
 struct dmnd_block {
+	dmnd_cuda::RefIndex idx;             // built by dmnd_block_build_index (reference side), reused by every lane
 	size_t cap_bytes = 0, cap_seqs = 0;  // allocated sizes (the block pool matches on them)
 	int8_t* letters = nullptr;  // device
 	int8_t* bias = nullptr;     // device, same offsets as letters
@@ -90,8 +103,9 @@ struct dmnd_ctx {
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	bool force_generic_dp = false;
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
+	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
 	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)
-	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; size_t cap_bytes, cap_seqs; };
+	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; size_t cap_bytes, cap_seqs; dmnd_cuda::RefIndex idx; };
 	std::vector<FreeBlock> block_pool;  // device memory of freed blocks, reused by dmnd_block_upload
 	void* h_pinned = nullptr;  // small pinned staging for counters
 	size_t h_pinned_cap = 0;
@@ -116,6 +130,7 @@ struct PhaseTimer {  // CUDA events on the library's stream, accumulated per pha
 };
 
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters);
+int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix);
 int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap);
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);

@@ -358,36 +358,29 @@ static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long l
 	return 0;
 }
 
-int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
-	const dmnd_params& hp = ctx->params;
-	if (hp.ungapped_evalue != 0.0) { set_error("dmnd_search_shape: stage-2 ungapped window filter (sensitive modes) is not built yet"); return 1; }
-	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
-	if (sid < 0 || sid >= hp.n_shapes) { set_error("dmnd_search_shape: bad shape id"); return 1; }
+int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix) {
 	cudaStream_t st = ctx->stream;
 	const DevParams* P = ctx->d_params;
 	const int seed_bits = ctx->h_dev_params.seed_bits;  // 40 for 10^12
 	const int bucket_bits = std::min(24, seed_bits), shift = 40 - bucket_bits;  // keys are 40-bit mixes
 	const size_t nbuckets = (size_t)1 << bucket_bits;
-	PhaseTimer timer(ctx, PH_SEED);
-
-	// counters: [0] seeds_hit (filled on host) [1] seed_hits [2] tm1 [3] tm3 [4] ref count [5] entry count [6] hit count [7] masked
+	const size_t rpos = ref->raw_len - 2 * DMND_PERIMETER_PADDING;
+	ix.valid = false;
 	if (ctx->b_counters.ensure(16 * sizeof(unsigned long long))) return 1;
 	unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
-
-	// ---- reference index
-	const size_t rpos = ref->raw_len - 2 * DMND_PERIMETER_PADDING;
-	const size_t qp_begin = (size_t)query->h_limits[q_begin], qp_end = (size_t)query->h_limits[q_end], qpos = qp_end - qp_begin;
-	if (ctx->b_keys.ensure(rpos * 8) || ctx->b_keys2.ensure(rpos * 8) || ctx->b_vals.ensure(rpos * 4) || ctx->b_vals2.ensure(rpos * 4)
-	    || ctx->b_bucket.ensure((nbuckets + 1) * 4 * 2))
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 4, 0, sizeof(unsigned long long), st));
+	if (ctx->b_keys.ensure(rpos * 8) || ix.keys.ensure(rpos * 8) || ctx->b_vals.ensure(rpos * 4) || ix.locs.ensure(rpos * 4)
+	    || ix.bucket.ensure((nbuckets + 1) * 4 * 2))
 		return 1;
 	ref_enum_kernel<<<(unsigned)((rpos + 255) / 256), 256, 0, st>>>(ref->letters, ref->raw_len, P, sid, ctx->b_keys.as<uint64_t>(), ctx->b_vals.as<uint32_t>(), d_cnt + 4);
 	++ctx->launches;
 	unsigned long long nref = 0;
-	if (fetch_u64(ctx, d_cnt + 4, &nref)) return 1;
-	uint64_t* d_keys = ctx->b_keys2.as<uint64_t>();
-	uint32_t* d_locs = ctx->b_vals2.as<uint32_t>();
-	uint32_t* d_bucket = ctx->b_bucket.as<uint32_t>();
+	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	nref = *(unsigned long long*)ctx->h_pinned;
+	uint64_t* d_keys = ix.keys.as<uint64_t>();
+	uint32_t* d_locs = ix.locs.as<uint32_t>();
+	uint32_t* d_bucket = ix.bucket.as<uint32_t>();
 	uint32_t* d_hist = d_bucket + nbuckets + 1;
 	{
 		size_t tmp = 0;
@@ -407,10 +400,44 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	// Bloom filter: >= 12 keys' worth of 256-bit blocks per 12 keys, i.e. >= 21 bits per key (false positives < 1 %)
 	uint32_t bloom_blocks = 1024;
 	while ((unsigned long long)bloom_blocks * 12ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
-	if (ctx->b_bloom.ensure((size_t)bloom_blocks * 32)) return 1;
-	uint32_t* d_bloom = ctx->b_bloom.as<uint32_t>();
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_bloom, 0, (size_t)bloom_blocks * 32, st));
-	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, d_bloom, bloom_blocks - 1); ++ctx->launches; }
+	if (ix.bloom.ensure((size_t)bloom_blocks * 32)) return 1;
+	DMND_CUDA_CHECK(cudaMemsetAsync(ix.bloom.p, 0, (size_t)bloom_blocks * 32, st));
+	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, ix.bloom.as<uint32_t>(), bloom_blocks - 1); ++ctx->launches; }
+	DMND_CUDA_CHECK(cudaStreamSynchronize(st));  // other lanes may use the index from their own streams
+	ix.nref = nref; ix.sid = sid; ix.shift = shift; ix.bloom_blocks = bloom_blocks; ix.valid = true;
+	return 0;
+}
+
+int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
+	const dmnd_params& hp = ctx->params;
+	if (hp.ungapped_evalue != 0.0) { set_error("dmnd_search_shape: stage-2 ungapped window filter (sensitive modes) is not built yet"); return 1; }
+	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
+	if (sid < 0 || sid >= hp.n_shapes) { set_error("dmnd_search_shape: bad shape id"); return 1; }
+	cudaStream_t st = ctx->stream;
+	const DevParams* P = ctx->d_params;
+	PhaseTimer timer(ctx, PH_SEED);
+
+	// counters: [0] seeds_hit (filled on host) [1] seed_hits [2] tm1 [3] tm3 [4] ref count [5] entry count [6] hit count [7] masked
+	if (ctx->b_counters.ensure(16 * sizeof(unsigned long long))) return 1;
+	unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
+
+	// ---- reference index: the block's own (dmnd_block_build_index, shared by all lanes) or a private one built now
+	RefIndex& own = ctx->own_index;
+	const RefIndex* ixp = &ref->idx;
+	if (!(ref->idx.valid && ref->idx.sid == sid)) {
+		if (build_ref_index(ctx, ref, sid, own)) return 1;
+		ixp = &own;
+	}
+	const RefIndex& ix = *ixp;
+	const unsigned long long nref = ix.nref;
+	const int shift = ix.shift;
+	const uint64_t* d_keys = ix.keys.as<uint64_t>();
+	const uint32_t* d_locs = ix.locs.as<uint32_t>();
+	const uint32_t* d_bucket = ix.bucket.as<uint32_t>();
+	const uint32_t* d_bloom = ix.bloom.as<uint32_t>();
+	const uint32_t bloom_blocks = ix.bloom_blocks;
+	const size_t qp_begin = (size_t)query->h_limits[q_begin], qp_end = (size_t)query->h_limits[q_end], qpos = qp_end - qp_begin;
 
 	// ---- probe every query position
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);

@@ -843,6 +843,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 
 	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
 	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;
+	// reference side of the seed join, once per call, shared by the lanes (the reference rebuilds it per run as well)
+	if (dmnd_block_build_index(ctx, const_cast<dmnd_block*>(rb), 0)) return 1;
 
 	// contiguous, letter-balanced query ranges (SequenceSet::partition, data/sequence_set.cpp:57-75, is the reference's analogue)
 	std::vector<uint32_t> cut((size_t)nlanes + 1, nq);

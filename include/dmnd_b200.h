@@ -125,6 +125,10 @@ void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b);
 /* Per-position int8 composition bias (HauserCorrection::int8, stats/hauser_correction.cpp:53-109), laid out at the
  * same offsets as the block's letters.  NULL => all zero (--comp-based-stats 0). */
 int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t raw_len);
+/* Builds (or rebuilds) the block's seed index for shape `sid` (reference side of the join: packed seeds, sorted, with a
+ * bucket directory and a Bloom filter).  dmnd_search_shape[_range] uses it when present -- every lane shares it -- and
+ * builds a private one otherwise.  The index is a cache: it does not change any result. */
+int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid);
 /* Fills the block's bias array on the device: mode 1 = HauserCorrection of every sequence (stats/hauser_correction.cpp:
  * 53-109, window 40, fp32, rounded half away from zero), mode 0 = zeros (--comp-based-stats 0). */
 int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode);

@@ -28,6 +28,8 @@ def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name
     res = []
     for c in (o, g):
         qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        if name == "edge":
+            c.build_index(rb, 0)  # shared block index path; the other workloads take the private-index path
         hits, cn = c.search_shape(qb, rb, 0)
         letters = c.download_letters(qb, q_raw.size)
         c.clear_seed_mask(qb)
