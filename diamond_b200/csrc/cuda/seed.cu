@@ -97,36 +97,75 @@ __global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, size_t n, 
 	if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift)], 1u);
 }
 
-__global__ void probe_kernel(const int8_t* __restrict__ letters, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, int sid,
+// Shape of the seed, passed by value (kernel parameters live in the constant bank: uniform, no memory traffic).
+struct ShapeArg {
+	int8_t pos[DMND_MAX_WEIGHT];
+	int weight, span, rsize, seedp_bits;
+};
+
+// Tile loader shared by the enumeration kernels: TILE consecutive letters (+ 32 halo) become "codes" in shared memory:
+// reduced class 0..9, 0x40 for MASK/STOP (reduction 23), 0x80 for the delimiter.  One global byte per letter, coalesced.
+#define SEED_TILE 1024
+__device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, size_t p0, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut) {
+	if (threadIdx.x < 32) {
+		const unsigned r = P->reduction[threadIdx.x];
+		s_lut[threadIdx.x] = threadIdx.x == DMND_DELIMITER ? 0x80 : (r == 23 ? 0x40 : (uint8_t)r);
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) s_code[x] = s_lut[letters[p0 + x] & 31];
+	__syncthreads();
+}
+// Packed seed at tile offset `o` (basic/shape.h:113-171: base-`rsize` number of the reduced classes at the shape's '1'
+// positions; invalid if a MASK class is among them or the window runs into a delimiter).
+__device__ __forceinline__ bool seed_from_codes(const uint8_t* s_code, int o, const ShapeArg& sh, uint64_t& seed) {
+	unsigned flags = 0;
+	for (int k = 0; k < sh.span; ++k) flags |= s_code[o + k] & 0x80u;
+	uint32_t hi = 0, lo = 0;
+	const int wh = sh.weight / 2;
+	for (int k = 0; k < wh; ++k) { const unsigned c = s_code[o + sh.pos[k]]; flags |= c & 0x40u; hi = hi * (uint32_t)sh.rsize + (c & 15u); }
+	uint32_t pw = 1;
+	for (int k = wh; k < sh.weight; ++k) { const unsigned c = s_code[o + sh.pos[k]]; flags |= c & 0x40u; lo = lo * (uint32_t)sh.rsize + (c & 15u); pw *= (uint32_t)sh.rsize; }
+	seed = (uint64_t)hi * pw + lo;
+	return flags == 0;
+}
+
+__global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ letters, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, const ShapeArg sh,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
                              const uint32_t* __restrict__ bloom, uint32_t bloom_mask,
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
-	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + p_begin;
-	uint64_t seed = 0;
-	bool ok = p < p_end && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
-	uint32_t lo = 0, cnt = 0;
-	if (ok) ok = bloom_test(bloom, bloom_mask, mix40(seed));
-	if (ok) {
-		const uint64_t key = mix40(seed);
-		const uint32_t b = (uint32_t)(key >> shift);
-		uint32_t i = bucket[b];
-		const uint32_t e = bucket[b + 1];
-		while (i < e && keys[i] < key) ++i;
-		lo = i;
-		while (i < e && keys[i] == key) ++i;
-		cnt = i - lo;
-		ok = cnt > 0;
-	}
-	const unsigned m = __ballot_sync(0xffffffffu, ok);
-	if (m == 0) return;
-	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-	unsigned long long base = 0;
-	if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	if (ok) {
-		const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
-		if (idx < cap) entries[idx] = Entry{ (uint32_t)p, lo, cnt, (uint32_t)(seed & (((uint64_t)1 << P->seedp_bits) - 1)) };
-		atomicAdd(count + 1, (unsigned long long)cnt);  // upper bound on (q,s) pairs over all chunks
+	__shared__ uint8_t s_code[SEED_TILE + 32];
+	__shared__ uint8_t s_lut[32];
+	const size_t p0 = p_begin + (size_t)blockIdx.x * SEED_TILE;
+	load_code_tile(letters, p0, P, s_code, s_lut);
+	for (int it = 0; it < SEED_TILE / 256; ++it) {
+		const int o = it * 256 + threadIdx.x;
+		const size_t p = p0 + o;
+		uint64_t seed = 0;
+		bool ok = p < p_end && seed_from_codes(s_code, o, sh, seed);
+		uint64_t key = 0;
+		if (ok) { key = mix40(seed); ok = bloom_test(bloom, bloom_mask, key); }
+		uint32_t lo = 0, cnt = 0;
+		if (ok) {
+			const uint32_t b = (uint32_t)(key >> shift);
+			uint32_t i = bucket[b];
+			const uint32_t e = bucket[b + 1];
+			while (i < e && keys[i] < key) ++i;
+			lo = i;
+			while (i < e && keys[i] == key) ++i;
+			cnt = i - lo;
+			ok = cnt > 0;
+		}
+		const unsigned m = __ballot_sync(0xffffffffu, ok);
+		if (m == 0) continue;
+		const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+		unsigned long long base = 0;
+		if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if (ok) {
+			const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
+			if (idx < cap) entries[idx] = Entry{ (uint32_t)p, lo, cnt, (uint32_t)(seed & (((uint64_t)1 << sh.seedp_bits) - 1)) };
+			atomicAdd(count + 1, (unsigned long long)cnt);  // upper bound on (q,s) pairs over all chunks
+		}
 	}
 }
 
@@ -351,6 +390,13 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 	return 0;
 }
 
+static ShapeArg shape_arg(const dmnd_params& hp, int sid) {
+	ShapeArg s;
+	for (int k = 0; k < DMND_MAX_WEIGHT; ++k) s.pos[k] = (int8_t)hp.shape_pos[sid][k];
+	s.weight = hp.shape_weight; s.span = hp.shape_len[sid]; s.rsize = hp.reduction_size; s.seedp_bits = hp.seedp_bits;
+	return s;
+}
+
 static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long long* h) {
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -445,7 +491,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, sid, d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
 		if (fetch_u64(ctx, d_cnt + 5, &nent)) return 1;
 		if (nent <= ecap) break;
