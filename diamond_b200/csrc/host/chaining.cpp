@@ -15,7 +15,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
-#include <map>
+#include <utility>
 
 namespace dmnd {
 
@@ -100,12 +100,28 @@ struct Graph {
 	}
 };
 
+// Ordered diagonal -> node window of Aligner::forward_pass (a std::map<int, unsigned> in the reference).  A sorted
+// vector reproduces its ordered iteration and erase-while-iterating behaviour with indices instead of node iterators.
+struct Window {
+	std::vector<std::pair<int, unsigned>> v;
+	void clear() { v.clear(); }
+	size_t size() const { return v.size(); }
+	// index of `key`, inserting (key, val) when absent (std::map::find + insert)
+	size_t find_or_insert(int key, unsigned val) {
+		size_t lo = 0, hi = v.size();
+		while (lo < hi) { const size_t mid = (lo + hi) / 2; if (v[mid].first < key) lo = mid + 1; else hi = mid; }
+		if (lo == v.size() || v[lo].first != key) v.insert(v.begin() + (ptrdiff_t)lo, std::make_pair(key, val));
+		return lo;
+	}
+	void erase(size_t i) { v.erase(v.begin() + (ptrdiff_t)i); }
+};
+
 struct Chainer {
 	const Scoring& sc;
 	Seq query, subject;
 	int qlen, slen;
-	Graph g;
-	std::map<int, unsigned> window;
+	Graph& g;
+	Window& window;
 
 	int score_range(Seq q, Seq s, int i, int j, int j_end) const {
 		int v = 0;
@@ -198,24 +214,24 @@ struct Chainer {
 		for (unsigned node = 0; node < g.nodes.size(); ++node) {
 			g.nodes[node].link_idx = (int)g.edges.size();
 			const int dd = g.nodes[node].diag();
-			auto i = window.find(dd);
-			if (i == window.end()) i = window.insert(std::make_pair(dd, node)).first;
-			auto j = i;
+			size_t i = window.find_or_insert(dd, node);  // the map entry of this diagonal (value = last node seen on it)
+			size_t j = i;
 			int max_j = 0;
-			if (i != window.begin()) {
+			if (i != 0) {
 				do {
 					--j;
 					const Node& d = g.nodes[node];
-					const Node& e = g.nodes[j->second];
+					const Node& e = g.nodes[window.v[j].second];
 					if (e.prefix_score - int(space_penalty * (std::max(d.j - e.subject_end(), 0))) <= 0) {
-						if (j == window.begin()) { window.erase(j); break; }
-						auto k = j; ++k;
+						// std::map::erase(j): the successor keeps its position in the order; with indices it slides into slot j
+						const bool was_first = j == 0;
 						window.erase(j);
-						j = k;
-						continue;
+						--i;
+						if (was_first) break;
+						continue;  // `j = k; continue;` of the reference: the loop test holds (j > 0) and --j steps before the erased slot
 					}
 					if (e.subject_end() < max_j) continue;
-					const unsigned e_idx = j->second;
+					const unsigned e_idx = window.v[j].second;
 					approximate_link((int)node, (int)e_idx, space_penalty);
 					{
 						const Node& d2 = g.nodes[node];
@@ -224,22 +240,20 @@ struct Chainer {
 						if (e2.subject_end() - (d2.subject_end() - std::min(e2.diag() - d2.diag(), 0)) >= REVERSE_LINK_MIN_OVERHANG)
 							approximate_link((int)e_idx, (int)node, space_penalty);
 					}
-				} while (j != window.begin());
+				} while (j != 0);
 			}
 			j = i;
-			if (j->second == node) ++j;
+			if (window.v[j].second == node) ++j;
 			int max_i = 0;
-			while (j != window.end()) {
+			while (j != window.size()) {
 				const Node& d = g.nodes[node];
-				const Node& e = g.nodes[j->second];
+				const Node& e = g.nodes[window.v[j].second];
 				if (e.prefix_score - int(space_penalty * (std::max(d.j - e.subject_end(), 0))) <= 0 && j != i) {
-					auto k = j; ++k;
-					window.erase(j);
-					j = k;
+					window.erase(j);  // the successor slides into slot j
 					continue;
 				}
 				if (e.query_end() < max_i) { ++j; continue; }
-				const unsigned e_idx = j->second;
+				const unsigned e_idx = window.v[j].second;
 				approximate_link((int)node, (int)e_idx, space_penalty);
 				{
 					const Node& d2 = g.nodes[node];
@@ -250,7 +264,7 @@ struct Chainer {
 				}
 				++j;
 			}
-			i->second = node;
+			window.v[i].second = node;
 		}
 	}
 
@@ -394,7 +408,10 @@ void chain_segments(const Scoring& sc, const int8_t* query, int qlen, const int8
 		out.push_back(c);
 		return;
 	}
-	Chainer ch{ sc, Seq{ query }, Seq{ subject }, qlen, slen, {}, {} };
+	static thread_local Graph graph;    // storage reused across calls (the reference keeps them thread_local as well,
+	static thread_local Window window;  // chaining/greedy_align.cpp:418-419)
+	graph.nodes.clear(); graph.edges.clear();
+	Chainer ch{ sc, Seq{ query }, Seq{ subject }, qlen, slen, graph, window };
 	// DiagGraph::load, greedy_align.cpp:58-74
 	int d = INT_MIN, max_j_end = INT_MIN;
 	for (const Segment& s : segs) {
