@@ -275,17 +275,34 @@ class Context:
 
     # ---- P layer
     def _collect(self, res):
+        """Zero-copy views of the result arrays; the dmnd_result is freed when the last view dies."""
+        lib = self.lib
+
+        class _Owner:
+            def __init__(self, h):
+                self.h = h
+
+            def __del__(self):
+                lib.dmnd_result_free(self.h)
+
+        owner = _Owner(res)
         n = C.c_size_t()
-        p = self.lib.dmnd_result_matches(res, C.byref(n))
-        m = np.zeros(n.value, dtype=MATCH_DTYPE)
+        p = lib.dmnd_result_matches(res, C.byref(n))
         if n.value:
-            C.memmove(m.ctypes.data, p, n.value * MATCH_DTYPE.itemsize)
+            buf = (C.c_char * (n.value * MATCH_DTYPE.itemsize)).from_address(p)
+            buf._owner = owner
+            m = np.frombuffer(buf, dtype=MATCH_DTYPE)
+        else:
+            m = np.zeros(0, dtype=MATCH_DTYPE)
         nt = C.c_size_t()
-        tp = self.lib.dmnd_result_transcripts(res, C.byref(nt))
-        tr = np.zeros(nt.value, dtype=np.uint8)
+        tp = lib.dmnd_result_transcripts(res, C.byref(nt))
         if nt.value:
-            C.memmove(tr.ctypes.data, tp, nt.value)
-        st = self.lib.dmnd_result_stats(res).contents
+            tbuf = (C.c_char * nt.value).from_address(tp)
+            tbuf._owner = owner
+            tr = np.frombuffer(tbuf, dtype=np.uint8)
+        else:
+            tr = np.zeros(0, dtype=np.uint8)
+        st = lib.dmnd_result_stats(res).contents
         stats = {}
         for k, _ in RunStats._fields_:
             v = getattr(st, k)
@@ -293,7 +310,6 @@ class Context:
                 stats[k] = {kk: getattr(v, kk) for kk, _ in v._fields_}
             else:
                 stats[k] = v
-        self.lib.dmnd_result_free(res)
         return m, tr, stats
 
     def blastp(self, q_raw, q_limits, r_raw, r_limits):

@@ -70,6 +70,13 @@ __device__ __forceinline__ uint8_t trace_flags(int hd, int e_in, int f_in, int o
 	const int b2 = open >= f_in - ge, b3 = open >= e_in - ge;
 	return (uint8_t)(b0 | (b1 << 1) | (b2 << 2) | (b3 << 3));
 }
+// Same four masks from differences instead of compares (h >= e_in, f_in and E', F' >= open always hold, so each
+// difference is >= 0 and min(diff, 1) is the negated mask bit): 4 VIADDMNMX + 3 IMAD per cell.  Returns the nibble.
+__device__ __forceinline__ unsigned trace_flags_arith(int h, int e_in, int f_in, int e_new, int f_new, int open) {
+	const int n0 = __viaddmin_s32(h, -f_in, 1), n1 = __viaddmin_s32(h, -e_in, 1);
+	const int n2 = __viaddmin_s32(f_new, -open, 1), n3 = __viaddmin_s32(e_new, -open, 1);
+	return 15u ^ (unsigned)((n0 + 2 * n1) + 4 * (n2 + 2 * n3));
+}
 
 template<int R>
 __device__ __forceinline__ void trace_store(uint8_t* p, const uint32_t* pk) {
@@ -290,15 +297,15 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 							const int hd = H[k] + sc;
 							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
 							const int t2 = h - go;
+							const int e_new = __viaddmax_s32_relu(e_in, -ge, t2), f_new = __viaddmax_s32_relu(f_in, -ge, t2);
 							if (TRACE) {
-								const int open = max(t2, 0);
-								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
+								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, max(t2, 0)) << ((k & 7) * 4);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
 							}
 							else best = max(best, h);
 							H[k] = h;
-							E[k] = __viaddmax_s32_relu(e_in, -ge, t2);
-							F[k] = __viaddmax_s32_relu(f_in, -ge, t2);
+							E[k] = e_new;
+							F[k] = f_new;
 						}
 					}
 				}
@@ -314,15 +321,15 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 							const int hd = H[k] + sc;
 							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
 							const int t2 = h - go;
+							const int e_new = __viaddmax_s32_relu(e_in, -ge, t2), f_new = __viaddmax_s32_relu(f_in, -ge, t2);
 							if (TRACE) {
-								const int open = max(t2, 0);
-								pk[k >> 3] |= (uint32_t)trace_flags(hd, e_in, f_in, open, ge) << ((k & 7) * 4);
+								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, max(t2, 0)) << ((k & 7) * 4);
 								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
 							}
 							else best = max(best, h);
 							H[k] = h;
-							E[k] = __viaddmax_s32_relu(e_in, -ge, t2);
-							F[k] = __viaddmax_s32_relu(f_in, -ge, t2);
+							E[k] = e_new;
+							F[k] = f_new;
 						}
 					}
 				}

@@ -870,16 +870,28 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	for (int l = 0; l < nlanes; ++l)
 		if (lo[(size_t)l].rc) { dmnd_set_last_error(lo[(size_t)l].error.c_str()); return 1; }
 
-	// ---- concatenate lanes (ascending query ranges)
-	size_t nm = 0, nt = 0;
-	for (const LaneOut& o : lo) { nm += o.matches.size(); nt += o.transcripts.size(); }
-	res->matches.reserve(nm); res->transcripts.reserve(nt);
-	for (LaneOut& o : lo) {
-		const size_t tbase = res->transcripts.size();
-		if (tbase) for (dmnd_match& m : o.matches) m.transcript_off += tbase;
-		if (res->matches.empty()) res->matches.swap(o.matches); else res->matches.insert(res->matches.end(), o.matches.begin(), o.matches.end());
-		if (res->transcripts.empty()) res->transcripts.swap(o.transcripts); else res->transcripts.insert(res->transcripts.end(), o.transcripts.begin(), o.transcripts.end());
-		add_stats(res->stats, o.stats);
+	// ---- concatenate lanes (ascending query ranges); a single lane hands its vectors over, several are copied in parallel
+	if (nlanes == 1) {
+		res->matches.swap(lo[0].matches); res->transcripts.swap(lo[0].transcripts);
+		add_stats(res->stats, lo[0].stats);
+	}
+	else {
+		std::vector<size_t> mo((size_t)nlanes + 1, 0), to((size_t)nlanes + 1, 0);
+		for (int l = 0; l < nlanes; ++l) { mo[(size_t)l + 1] = mo[(size_t)l] + lo[(size_t)l].matches.size(); to[(size_t)l + 1] = to[(size_t)l] + lo[(size_t)l].transcripts.size(); }
+		res->matches.resize(mo[(size_t)nlanes]);
+		res->transcripts.resize(to[(size_t)nlanes]);
+		const int T = host_threads;
+		sh.pool->run([&](int t) {
+			for (int l = 0; l < nlanes; ++l) {
+				const LaneOut& o = lo[(size_t)l];
+				const size_t n = o.matches.size(), b = n * (size_t)t / (size_t)T, e = n * (size_t)(t + 1) / (size_t)T;
+				dmnd_match* dst = res->matches.data() + mo[(size_t)l];
+				for (size_t k = b; k < e; ++k) { dst[k] = o.matches[k]; dst[k].transcript_off += to[(size_t)l]; }
+				const size_t nt = o.transcripts.size(), tb = nt * (size_t)t / (size_t)T, te = nt * (size_t)(t + 1) / (size_t)T;
+				if (te > tb) std::memcpy(res->transcripts.data() + to[(size_t)l] + tb, o.transcripts.data() + tb, te - tb);
+			}
+		});
+		for (int l = 0; l < nlanes; ++l) add_stats(res->stats, lo[(size_t)l].stats);
 	}
 	res->stats.total_ms = ms_since(t_total);
 	*out = res.release();
