@@ -153,7 +153,8 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_a));
-	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_b));
+	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_b, cudaEventBlockingSync));
+	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
 	DevParams& d = c->h_dev_params;
 	std::memset(&d, 0, sizeof d);
 	std::memcpy(d.score, params->score, 1024);
@@ -230,7 +231,7 @@ void dmnd_destroy(dmnd_ctx* c) {
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
-	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
+	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_sync);
 	cudaStreamDestroy(c->stream);
 	cudaStreamDestroy(c->copy_stream);
 	cudaEventDestroy(c->ev_copy);
@@ -321,7 +322,7 @@ int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, s
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (raw_len != b->raw_len) { set_error("dmnd_block_download_bias: length mismatch"); return 1; }
 	DMND_CUDA_CHECK(cudaMemcpyAsync(bias, b->bias, raw_len, cudaMemcpyDeviceToHost, ctx->stream));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
 	ctx->d2h_bytes += raw_len;
 	return 0;
 }
@@ -339,7 +340,7 @@ int dmnd_block_download_bias_async(dmnd_ctx* ctx, const dmnd_block* b, int8_t* b
 
 int dmnd_copy_wait(dmnd_ctx* ctx) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->copy_stream));
 	return 0;
 }
 
@@ -364,7 +365,7 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (raw_len != b->raw_len) { set_error("dmnd_block_download_letters: length mismatch"); return 1; }
 	DMND_CUDA_CHECK(cudaMemcpyAsync(letters, b->letters, raw_len, cudaMemcpyDeviceToHost, ctx->stream));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
 	ctx->d2h_bytes += raw_len;
 	return 0;
 }

@@ -111,11 +111,20 @@ struct dmnd_ctx {
 	size_t h_pinned_cap = 0;
 	// timing
 	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+	cudaEvent_t ev_sync = nullptr;  // cudaEventBlockingSync: host waits sleep instead of spinning (the host pool owns the CPU quota)
 	double phase_ms[dmnd_cuda::PH_COUNT] = {};
 	uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 namespace dmnd_cuda {
+
+// Host wait for everything queued on `st`: sleeps on a blocking event.  cudaStreamSynchronize spins under the default
+// schedule flags, and a spinning lane thread burns one CPU of the container's quota that the worker pool needs.
+inline cudaError_t stream_wait(dmnd_ctx* c, cudaStream_t st) {
+	cudaError_t e = cudaEventRecord(c->ev_sync, st);
+	if (e != cudaSuccess) return e;
+	return cudaEventSynchronize(c->ev_sync);
+}
 
 struct PhaseTimer {  // CUDA events on the library's stream, accumulated per phase
 	dmnd_ctx* c; Phase ph;

@@ -399,7 +399,7 @@ static ShapeArg shape_arg(const dmnd_params& hp, int sid) {
 
 static int fetch_u64(dmnd_ctx* ctx, const unsigned long long* d, unsigned long long* h) {
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
 	*h = *(unsigned long long*)ctx->h_pinned;
 	return 0;
 }
@@ -422,7 +422,7 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	++ctx->launches;
 	unsigned long long nref = 0;
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	nref = *(unsigned long long*)ctx->h_pinned;
 	uint64_t* d_keys = ix.keys.as<uint64_t>();
 	uint32_t* d_locs = ix.locs.as<uint32_t>();
@@ -449,7 +449,7 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	if (ix.bloom.ensure((size_t)bloom_blocks * 32)) return 1;
 	DMND_CUDA_CHECK(cudaMemsetAsync(ix.bloom.p, 0, (size_t)bloom_blocks * 32, st));
 	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, ix.bloom.as<uint32_t>(), bloom_blocks - 1); ++ctx->launches; }
-	DMND_CUDA_CHECK(cudaStreamSynchronize(st));  // other lanes may use the index from their own streams
+	DMND_CUDA_CHECK(stream_wait(ctx, st));  // other lanes may use the index from their own streams
 	ix.nref = nref; ix.sid = sid; ix.shift = shift; ix.bloom_blocks = bloom_blocks; ix.valid = true;
 	return 0;
 }

@@ -577,7 +577,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
 	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
 	unsigned int off[257];
@@ -642,27 +642,40 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		gather_cost_kernel<<<nb, 256, 0, st>>>(ctx->b_order.as<uint32_t>(), d_cost, (uint32_t)n, d_cum);
 		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp1, d_cum, d_excl, n, st));
 		ctx->launches += 2;
-		std::vector<uint64_t>& excl = ctx->h_excl;
-		excl.resize(n + 1);
-		DMND_CUDA_CHECK(cudaMemcpyAsync(excl.data(), d_excl, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		uint64_t last_cost = 0, ts_last[2] = { 0, 0 };
-		DMND_CUDA_CHECK(cudaMemcpyAsync(&last_cost, d_cum + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		// host copies (pinned): the prefix at the 11 group boundaries, the last cost and the transcript total
+		uint64_t* hq = (uint64_t*)(hp + 1536);  // [0..10] excl at grp_begin[g], [11] cost of the last problem, [12..13] transcript tail
+		for (int g = 0; g <= 10; ++g)
+			if (grp_begin[g] < n) DMND_CUDA_CHECK(cudaMemcpyAsync(hq + g, d_excl + grp_begin[g], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 11, d_cum + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 14, d_excl + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		hq[12] = hq[13] = 0;
 		if (transcripts) {
 			DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_tslen, d_tsoff, n, st));
 			++ctx->launches;
-			DMND_CUDA_CHECK(cudaMemcpyAsync(&ts_last[0], d_tsoff + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			DMND_CUDA_CHECK(cudaMemcpyAsync(&ts_last[1], d_tslen + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 12, d_tsoff + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 13, d_tslen + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		}
-		DMND_CUDA_CHECK(cudaStreamSynchronize(st));
-		excl[n] = excl[n - 1] + last_cost;
-		ts_total = ts_last[0] + ts_last[1];
+		DMND_CUDA_CHECK(stream_wait(ctx, st));
+		const uint64_t trace_total = hq[14] + hq[11];
+		for (int g = 0; g <= 10; ++g) if (grp_begin[g] >= n) hq[g] = trace_total;
+		ts_total = hq[12] + hq[13];
 		if (transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
 		if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
 		if (transcripts && ctx->b_tr.ensure(ts_total + 16)) return 1;
 		size_t free_b = 0, total_b = 0;
 		DMND_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-		const uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)((free_b + ctx->b_trace.cap) / 5) * 2);  // <= 40 % of what is free
-		if (ctx->b_trace.ensure((size_t)std::min<uint64_t>(excl[n], budget) + 64)) return 1;
+		uint64_t budget = std::max<uint64_t>((uint64_t)1 << 30, (uint64_t)((free_b + ctx->b_trace.cap) / 5) * 2);  // <= 40 % of what is free
+		if (const char* ev = getenv("DMND_TRACE_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(ev, nullptr, 10));  // tests: force slicing
+		if (ctx->b_trace.ensure((size_t)std::min<uint64_t>(trace_total, budget) + 64)) return 1;
+		// the whole prefix is only needed on the host when the trace has to be cut into slices
+		const bool sliced = trace_total > budget;
+		std::vector<uint64_t>& excl = ctx->h_excl;
+		if (sliced) {
+			excl.resize(n + 1);
+			DMND_CUDA_CHECK(cudaMemcpyAsync(excl.data(), d_excl, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			DMND_CUDA_CHECK(stream_wait(ctx, st));
+			excl[n] = trace_total;
+		}
 		lap("trace prefix");
 		for (int g = 0; g < 10; ++g) {
 			size_t pos = grp_begin[g];
@@ -670,13 +683,17 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			while (pos < gend) {
 				// slice [pos, e) of this group whose trace fits the budget (at least one problem); launches are stream-ordered,
 				// so the arena can be reused by the next slice without a host synchronisation
-				size_t e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + gend + 1, excl[pos] + budget) - excl.begin()) - 1;
-				e = std::max(e, pos + 1);
-				const uint64_t bytes = excl[e] - excl[pos];
+				size_t e = gend;
+				uint64_t base = hq[g], bytes = hq[g + 1] - hq[g];
+				if (sliced) {
+					e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + gend + 1, excl[pos] + budget) - excl.begin()) - 1;
+					e = std::max(e, pos + 1);
+					base = excl[pos]; bytes = excl[e] - excl[pos];
+				}
 				if (ctx->b_trace.ensure((size_t)bytes + 64)) return 1;
 				DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
 				a.work = d_counters;
-				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = excl[pos];
+				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = base;
 				if (launch_dp(g, pos, e, true)) return 1;
 				WalkArgs wa;
 				wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
@@ -702,7 +719,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
 	}
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 257, d_counters + 65, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-	DMND_CUDA_CHECK(cudaStreamSynchronize(st));
+	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	lap("download results");
 	if (hp[257] != 0 && !force_generic) {
 		// S + bias left the int8 range of the shared-memory profile somewhere: redo the whole call on the generic kernel

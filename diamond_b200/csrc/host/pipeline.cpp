@@ -265,19 +265,44 @@ struct ThreadCtx {
 	}
 };
 
+// Grow-only page-locked host buffer (dmnd_host_alloc): device<->host copies of hits, DP problems, results and
+// transcripts run as real DMA at link speed instead of staged pageable copies.  Contents are not preserved by resize().
+template<typename T> struct HostBuf {
+	T* p = nullptr;
+	size_t n = 0, cap = 0;
+	int resize(dmnd_ctx* ctx, size_t count) {
+		if (count > cap) {
+			if (p) dmnd_host_free(ctx, p);
+			cap = count + count / 4 + 1024;
+			p = static_cast<T*>(dmnd_host_alloc(ctx, cap * sizeof(T)));
+			if (!p) { cap = n = 0; return 1; }
+		}
+		n = count;
+		return 0;
+	}
+	T* data() { return p; }
+	const T* data() const { return p; }
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	T& operator[](size_t i) { return p[i]; }
+	const T& operator[](size_t i) const { return p[i]; }
+	const T* begin() const { return p; }
+	const T* end() const { return p + n; }
+};
+
 // Everything that survives between calls (buffers keep their capacity: no page faults in steady state).
 struct Workspace {
 	Pool* pool = nullptr;
 	std::vector<ThreadCtx> tc;
-	std::vector<dmnd_hit> hv;
-	std::vector<dmnd_segment> segv;
+	HostBuf<dmnd_hit> hv;
+	HostBuf<dmnd_segment> segv;
 	struct HitSeg { dmnd_hit h; dmnd_segment s; };
 	std::vector<HitSeg> hs;
 	std::vector<size_t> qstart;
 	std::vector<QueryState> qs;
-	std::vector<dmnd_dp_problem> p1, p2;
-	std::vector<dmnd_dp_result> res1, res2;
-	std::vector<uint8_t> tr;
+	HostBuf<dmnd_dp_problem> p1, p2;
+	HostBuf<dmnd_dp_result> res1, res2;
+	HostBuf<uint8_t> tr;
 };
 // Process-wide: the worker pool and one workspace per lane.
 struct Shared {
@@ -571,8 +596,7 @@ int Driver::run_waves() {
 		off1[0] = off2[0] = 0;
 		for (int t = 0; t < T; ++t) { off1[(size_t)t + 1] = off1[(size_t)t] + w.tc[(size_t)t].p1.size(); off2[(size_t)t + 1] = off2[(size_t)t] + w.tc[(size_t)t].p2.size(); }
 		if (off1[(size_t)T] + off2[(size_t)T] == 0) break;  // nothing in flight: every query is done
-		w.p1.resize(off1[(size_t)T]); w.p2.resize(off2[(size_t)T]);
-		w.res1.resize(w.p1.size()); w.res2.resize(w.p2.size());
+		if (w.p1.resize(ctx, off1[(size_t)T]) || w.p2.resize(ctx, off2[(size_t)T]) || w.res1.resize(ctx, off1[(size_t)T]) || w.res2.resize(ctx, off2[(size_t)T])) return 1;
 		ws->pool->run([&](int t) {
 			const ThreadCtx& tc = w.tc[(size_t)t];
 			if (!tc.p1.empty()) std::memcpy(w.p1.data() + off1[(size_t)t], tc.p1.data(), tc.p1.size() * sizeof(dmnd_dp_problem));
@@ -591,7 +615,8 @@ int Driver::run_waves() {
 			size_t cap = 0;
 			if (env.want_transcript) {
 				for (const dmnd_dp_problem& pr : w.p2) cap += (size_t)env.qlen(pr.query) + (size_t)env.tlen(pr.target);
-				w.tr.resize(cap); trp = w.tr.data();
+				if (w.tr.resize(ctx, cap)) return 1;
+				trp = w.tr.data();
 			}
 			if (dmnd_banded_swipe(ctx, qb, rb, w.p2.data(), w.p2.size(), DMND_DP_TRACEBACK, w.res2.data(), trp, cap)) return 1;
 		}
@@ -700,8 +725,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	if (dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed)) return 1;
 	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
-	w.hv.resize(nh);
-	w.segv.resize(nh);
+	if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
 	if (nh && dmnd_hits_xdrop(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }

@@ -116,7 +116,7 @@ def random_problems(w, q_lim, r_lim, rng, n):
     return P
 
 
-@pytest.mark.parametrize("kernel", ["profile", "generic"])
+@pytest.mark.parametrize("kernel", ["profile", "generic", "profile-sliced"])
 @pytest.mark.parametrize("name,cbs", [("c1", 0), ("c1", 1), ("edge", 1), ("fam2", 1)])
 def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs, kernel, monkeypatch):
     from diamond_b200 import api
@@ -124,6 +124,10 @@ def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs, 
         monkeypatch.setenv("DMND_GENERIC_DP", "1")  # the fallback for profiles that do not fit shared memory
     else:
         monkeypatch.delenv("DMND_GENERIC_DP", raising=False)
+    if kernel == "profile-sliced":
+        monkeypatch.setenv("DMND_TRACE_BUDGET", "300000")  # trace arena far smaller than the batch: many slices per group
+    else:
+        monkeypatch.delenv("DMND_TRACE_BUDGET", raising=False)
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
     rng = np.random.default_rng(7)
     P = random_problems(w, q_lim, r_lim, rng, 1500)
