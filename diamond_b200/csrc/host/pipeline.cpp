@@ -339,6 +339,18 @@ struct Driver {
 	int run_waves();
 };
 
+// std::stable_sort without its temporary-buffer allocation for the short lists that dominate (insertion sort is stable)
+template<typename T, typename Cmp> static void stable_small_sort(std::vector<T>& v, Cmp cmp) {
+	if (v.size() > 24) { std::stable_sort(v.begin(), v.end(), cmp); return; }
+	for (size_t i = 1; i < v.size(); ++i) {
+		size_t j = i;
+		if (!cmp(v[i], v[i - 1])) continue;
+		const T x = v[i];
+		while (j > 0 && cmp(x, v[j - 1])) { v[j] = v[j - 1]; --j; }
+		v[j] = x;
+	}
+}
+
 void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end) {
 	// align/load_hits.h:44-122 (each hit carries its precomputed x-drop segment along)
 	const Env& e = env;
@@ -356,7 +368,9 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, W
 		const dmnd_hit* h = &hsp->h;
 		const uint64_t subj = DMND_HIT_SUBJECT(*h);
 		// SequenceSet::local_position: sequence whose [limits[t], limits[t+1]) holds subj
-		const uint32_t t = (uint32_t)(std::upper_bound(e.r_limits, e.r_limits + e.nr + 1, (int64_t)subj) - e.r_limits) - 1;
+		// (hits are sorted by subject position: most of them fall into the target of their predecessor)
+		const uint32_t t = (target != UINT32_MAX && (int64_t)subj < e.r_limits[target + 1]) ? target
+			: (uint32_t)(std::upper_bound(e.r_limits, e.r_limits + e.nr + 1, (int64_t)subj) - e.r_limits) - 1;
 		if (t != target) {
 			if (target != UINT32_MAX) { tc.target_scores.push_back({ ntg - 1, score }); score = 0; }
 			tc.hit_begin.push_back((uint32_t)tc.seed_hits.size());
@@ -424,9 +438,9 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 			if (d.score > 0) tc.segs.push_back(d);
 		}
 		if (tc.segs.empty()) continue;
-		std::stable_sort(tc.segs.begin(), tc.segs.end(), [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
+		stable_small_sort(tc.segs, [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
 		chain_segments(*e.sc, query, q.qlen, subject, slen, tc.segs, tc.chains);
-		std::stable_sort(tc.chains.begin(), tc.chains.end(), [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
+		stable_small_sort(tc.chains, [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
 		// add_dp_targets, align/gapped_score.cpp:107-180
 		int d0 = INT_MAX, d1 = INT_MIN;
 		auto emit = [&] {
