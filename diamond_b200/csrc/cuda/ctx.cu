@@ -149,7 +149,11 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	c->device = device;
 	c->params = *params;
 	c->sm_count = prop.multiProcessorCount;
-	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	{
+		int least = 0, greatest = 0;
+		DMND_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		DMND_CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
+	}
 	DMND_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
 	DMND_CUDA_CHECK(cudaEventCreate(&c->ev_a));
@@ -210,6 +214,11 @@ int dmnd_ctx_lane(dmnd_ctx* ctx, int lane, dmnd_ctx** out) {
 	while ((int)ctx->lanes.size() <= lane) {
 		dmnd_ctx* c = nullptr;
 		if (dmnd_create(ctx->device, &ctx->params, &c)) return 1;
+		// lanes run staggered: an earlier lane is further along, so its kernels go first (lower lane = higher priority)
+		int least = 0, greatest = 0;
+		DMND_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		cudaStreamDestroy(c->stream);
+		DMND_CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, std::min(least, greatest + 1 + (int)ctx->lanes.size())));
 		ctx->lanes.push_back(c);
 	}
 	*out = ctx->lanes[(size_t)lane];

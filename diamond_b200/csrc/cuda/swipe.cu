@@ -474,7 +474,7 @@ template<bool TRACE>
 static int launch_prof_bin(int R, const SwipeArgs& a, const DevParams* P, const ProfArgs& pa, int grid, int threads, size_t smem, cudaStream_t st) {
 #define DMND_LAUNCH_PROF(RR)                                                                                            \
 	do {                                                                                                                 \
-		if (smem > 48 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_prof_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		if (smem > 40 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_prof_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* the 48 KB default covers static + dynamic */ \
 		swipe_prof_kernel<RR, TRACE><<<grid, threads, smem, st>>>(a, P, pa);                                             \
 	} while (0)
 	switch (R) {
@@ -486,6 +486,123 @@ static int launch_prof_bin(int R, const SwipeArgs& a, const DevParams* P, const 
 	}
 #undef DMND_LAUNCH_PROF
 	return 0;
+}
+
+// ---- statistics passes for problems above max_swipe_dp (no transcript requested) ---------------------------------------
+// Reference: swipe_wrapper.cpp:89-96 bins such targets into the statistics kernels, dispatch_swipe :177-199 runs
+// ForwardCell (ident, len) forwards and BackwardCell (mismatch, gapopen) over the reversed query x reversed target prefix
+// (recompute_reversed :364-444); cell rules stat_cell.h:225-272 + cell_update.h:100-139.  These problems are rare (a band
+// of some hundred diagonals over thousands of columns), so the kernel favours clarity: one CTA per problem, one thread
+// per band row, wavefront time s = 2c + r with one barrier per step; a cell is {v, a, b} and ties copy the statistics of
+// the max() argument exactly like set_max does.
+struct SCell { int v, a, b; };
+__device__ __forceinline__ void scell_max(SCell& x, const SCell& y) {
+	x.v = max(x.v, y.v);
+	if (x.v == y.v) { x.a = y.a; x.b = y.b; }
+}
+struct StatsArgs {
+	const int8_t *q_letters, *q_bias, *r_letters;
+	const int64_t *q_limits, *r_limits;
+	const dmnd_dp_problem* probs;
+	const uint32_t* order;
+	uint32_t n;
+	dmnd_dp_result* res;
+};
+struct StatsOut { int best, col, row, a, b; };
+
+template<bool BACKWARD>
+__device__ void stats_pass(const int8_t* __restrict__ q, const int8_t* __restrict__ cbs, int qlen, const int8_t* __restrict__ t, int tlen,
+                           int d_begin, int d_end, const int8_t* __restrict__ score, int go, int ge, int* sm, StatsOut& out) {
+	// BACKWARD reads q, cbs and t mirrored: q'[i] = q[qlen-1-i], t'[j] = t[tlen-1-j]
+	const int band = d_end - d_begin, r = (int)threadIdx.x;
+	const int i1 = max(d_end - 1, 0), i0 = i1 + 1 - band, j0 = i1 - (d_end - 1);
+	const int cols = min(qlen - 1 - d_begin, tlen - 1) + 1 - j0;
+	int *hg_v = sm, *hg_a = sm + 1025, *hg_b = sm + 2050, *vg_v = sm + 3075, *vg_a = sm + 4100, *vg_b = sm + 5125;
+	for (int k = r; k < 1025; k += (int)blockDim.x) { hg_v[k] = hg_a[k] = hg_b[k] = 0; vg_v[k] = vg_a[k] = vg_b[k] = 0; }
+	__syncthreads();
+	SCell h{ 0, 0, 0 };
+	int my_best = 0, my_col = 0, my_a = 0, my_b = 0;
+	const int steps = cols > 0 ? 2 * (cols - 1) + band : 0;
+	for (int s = 0; s < steps; ++s) {
+		const int c2 = s - r;
+		if (r < band && c2 >= 0 && !(c2 & 1) && (c2 >> 1) < cols) {
+			const int c = c2 >> 1, i = i0 + c + r, j = j0 + c;
+			if (i >= 0 && i < qlen) {
+				const int qi = BACKWARD ? qlen - 1 - i : i, tj = BACKWARD ? tlen - 1 - j : j;
+				const int ql = q[qi] & DMND_LETTER_MASK, tl = t[tj] & DMND_LETTER_MASK;
+				SCell hg{ hg_v[r + 1], hg_a[r + 1], hg_b[r + 1] };
+				SCell vg{ 0, 0, 0 };
+				if (r > 0 && i > 0) vg = SCell{ vg_v[r], vg_a[r], vg_b[r] };
+				SCell cur = h;
+				cur.v += (int)score[ql * 32 + tl] + (int)cbs[qi];
+				const int id = ql == tl;
+				if (!BACKWARD) { cur.a += id; cur.b += 1; hg.b += 1; vg.b += 1; }
+				else cur.a += 1 - id;
+				scell_max(cur, hg); scell_max(cur, vg);
+				cur.v = max(cur.v, 0);
+				if (cur.v > my_best) { my_best = cur.v; my_col = c; my_a = cur.a; my_b = cur.b; }
+				vg.v = max(vg.v - ge, 0); hg.v = max(hg.v - ge, 0);
+				SCell open = cur;
+				open.v = max(cur.v - go, 0);
+				if (BACKWARD) open.b += 1;
+				if (cur.v == 0) { cur.a = 0; cur.b = 0; }
+				scell_max(hg, open); scell_max(vg, open);
+				hg_v[r] = hg.v; hg_a[r] = hg.a; hg_b[r] = hg.b;
+				vg_v[r + 1] = vg.v; vg_a[r + 1] = vg.a; vg_b[r + 1] = vg.b;
+				h = cur;
+			}
+		}
+		__syncthreads();
+	}
+	// end cell: highest value, then the first column, then the last band row (banded_swipe.h:321-326, VectorRowCounter)
+	__syncthreads();
+	if (r < band) { hg_v[r] = my_best; hg_a[r] = my_col; hg_b[r] = my_a; vg_v[r] = my_b; }
+	__syncthreads();
+	if (r == 0) {
+		StatsOut o{ 0, 0, 0, 0, 0 };
+		for (int k = 0; k < band; ++k) {
+			const int v = hg_v[k], c = hg_a[k];
+			if (v > o.best || (v == o.best && v > 0 && c <= o.col)) { o.best = v; o.col = c; o.row = k; o.a = hg_b[k]; o.b = vg_v[k]; }
+		}
+		vg_a[0] = o.best; vg_a[1] = o.col; vg_a[2] = o.row; vg_a[3] = o.a; vg_a[4] = o.b;
+	}
+	__syncthreads();
+	out.best = vg_a[0]; out.col = vg_a[1]; out.row = vg_a[2]; out.a = vg_a[3]; out.b = vg_a[4];
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) swipe_stats_kernel(const StatsArgs a, const DevParams* __restrict__ P) {
+	__shared__ int sm[6 * 1025];
+	const uint32_t pi = a.order[blockIdx.x];
+	const dmnd_dp_problem pr = a.probs[pi];
+	const int64_t qo = a.q_limits[pr.query], to = a.r_limits[pr.target];
+	const int qlen = (int)(a.q_limits[pr.query + 1] - qo - 1), tlen = (int)(a.r_limits[pr.target + 1] - to - 1);
+	const int8_t *q = a.q_letters + qo, *cbs = a.q_bias + qo, *t = a.r_letters + to;
+	const int go = P->gap_open + P->gap_extend, ge = P->gap_extend;
+	const int band = pr.d_end - pr.d_begin;
+	dmnd_dp_result res;
+	res.score = 0; res.q_begin = res.q_end = res.t_begin = res.t_end = 0;
+	res.identities = res.mismatches = res.gap_openings = res.length = res.gaps = res.positives = 0;
+	res.transcript_off = 0; res.transcript_len = 0; res.status = 0;
+	StatsOut f, b;
+	stats_pass<false>(q, cbs, qlen, t, tlen, pr.d_begin, pr.d_end, P->score, go, ge, sm, f);
+	if (f.best > 0) {
+		const int i1 = max(pr.d_end - 1, 0), i0 = i1 + 1 - band, j0 = i1 - (pr.d_end - 1);
+		const int q_end = i0 + f.col + f.row + 1, t_end = j0 + f.col + 1;
+		const int rd0 = -(pr.d_end - 1) + qlen - t_end, rd1 = -pr.d_begin + qlen - t_end + 1;  // Geo::rev_diag
+		stats_pass<true>(q, cbs, qlen, t, t_end, rd0, rd1, P->score, go, ge, sm, b);
+		if (b.best > 0) {
+			const int ri1 = max(rd1 - 1, 0), ri0 = ri1 + 1 - band, rj0 = ri1 - (rd1 - 1);
+			res.score = b.best;
+			res.q_end = q_end; res.t_end = t_end;
+			res.q_begin = qlen - (ri0 + b.col + b.row + 1);
+			res.t_begin = t_end - (rj0 + b.col + 1);
+			res.identities = f.a; res.length = f.b;
+			res.mismatches = b.a; res.gap_openings = b.b;
+			res.gaps = res.length - res.identities - res.mismatches;  // assign_stats, stat_cell.h:215-219
+		}
+	}
+	if (threadIdx.x == 0) a.res[pi] = res;
 }
 
 // ---- device-side preparation: geometry, register-tile bin, cost class, bucket histogram ------------------------------
@@ -514,11 +631,13 @@ __global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t 
 	const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
 	const int cls = 15 - min(15, (63 - __clzll(cells + 1)) >> 1);
 	const int lng = (qlen + 32 * R + 4) > 768 ? 1 : 0;
-	const uint8_t key = (uint8_t)((b * 2 + lng) * 16 + cls);
+	// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (bucket 160, no trace bytes)
+	const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
+	const uint8_t key = stats ? (uint8_t)160 : (uint8_t)((b * 2 + lng) * 16 + cls);
 	atomicMax(&o.maxq[key], (unsigned)qlen);
 	o.key[k] = key;
 	const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
-	o.cost[k] = trace ? nmacro * 16ull * (unsigned long long)R : cells;
+	o.cost[k] = stats ? 0ull : trace ? nmacro * 16ull * (unsigned long long)R : cells;
 	o.tslen[k] = (uint64_t)qlen + (uint64_t)tlen;
 	atomicAdd(&o.hist[key], 1u);
 }
@@ -572,7 +691,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1280 * sizeof(unsigned int), st));
 	PrepOut po{ d_key, d_counters + 1024, d_cost, d_tslen, d_counters + 256, d_counters + 64 };
-	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? 1 : 0, po);
+	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, po);
 	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag, [512..767] offsets (upload), [1024..1279] max qlen
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -619,6 +738,12 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			if (tr_mode ? launch_prof_bin<true>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st) : launch_prof_bin<false>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st)) return 1;
 		}
 		++ctx->launches;
+		if (cudaError_t le = cudaGetLastError()) {
+			char msg[256];
+			snprintf(msg, sizeof msg, "dmnd_banded_swipe: DP launch failed (%s): group %d, %zu problems, R %d, max query %u, %d warps", cudaGetErrorString(le), g, e - pos, R, maxq, warps);
+			set_error(msg);
+			return 1;
+		}
 		return 0;
 	};
 
@@ -707,6 +832,15 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				DMND_CUDA_CHECK(cudaGetLastError());
 				pos = e;
 			}
+		}
+		if (hp[160]) {  // statistics passes, one CTA per problem
+			StatsArgs sa;
+			sa.q_letters = a.q_letters; sa.q_bias = a.q_bias; sa.r_letters = a.r_letters; sa.q_limits = a.q_limits; sa.r_limits = a.r_limits;
+			sa.probs = a.probs; sa.order = ctx->b_order.as<uint32_t>() + off[160]; sa.n = hp[160];
+			sa.res = ctx->b_results.as<dmnd_dp_result>();
+			swipe_stats_kernel<<<hp[160], 1024, 0, st>>>(sa, ctx->d_params);
+			++ctx->launches;
+			DMND_CUDA_CHECK(cudaGetLastError());
 		}
 		t_dp.stop();
 	}

@@ -92,14 +92,26 @@ public:
 		for (auto& t : th_) t.join();
 	}
 	int size() const { return n_; }
-	void run(const std::function<void(int)>& f) {
-		std::lock_guard<std::mutex> turn(run_mtx_);  // lanes take turns: whoever has host work gets every worker
-		if (n_ == 1) { f(0); return; }
-		{ std::lock_guard<std::mutex> l(m_); fn_ = &f; pending_ = n_ - 1; ++gen_; }
-		cv_.notify_all();
-		f(0);
-		std::unique_lock<std::mutex> l(m_);
-		done_.wait(l, [this] { return pending_ == 0; });
+	// Lanes take turns: whoever has host work gets every worker; among waiting lanes the lowest id (the one furthest
+	// along in the staggered pipeline) goes first.
+	void run(const std::function<void(int)>& f, int prio = 0) {
+		{
+			std::unique_lock<std::mutex> l(turn_m_);
+			waiting_.push_back(prio);
+			turn_cv_.wait(l, [&] { return !busy_ && *std::min_element(waiting_.begin(), waiting_.end()) == prio; });
+			busy_ = true;
+			waiting_.erase(std::find(waiting_.begin(), waiting_.end(), prio));
+		}
+		if (n_ == 1) f(0);
+		else {
+			{ std::lock_guard<std::mutex> l(m_); fn_ = &f; pending_ = n_ - 1; ++gen_; }
+			cv_.notify_all();
+			f(0);
+			std::unique_lock<std::mutex> l(m_);
+			done_.wait(l, [this] { return pending_ == 0; });
+		}
+		{ std::lock_guard<std::mutex> l(turn_m_); busy_ = false; }
+		turn_cv_.notify_all();
 	}
 private:
 	void loop(int t) {
@@ -119,8 +131,10 @@ private:
 	}
 	int n_;
 	std::vector<std::thread> th_;
-	std::mutex m_, run_mtx_;
-	std::condition_variable cv_, done_;
+	std::mutex m_, turn_m_;
+	std::condition_variable cv_, done_, turn_cv_;
+	std::vector<int> waiting_;
+	bool busy_ = false;
 	const std::function<void(int)>* fn_ = nullptr;
 	int pending_ = 0;
 	uint64_t gen_ = 0;
@@ -293,6 +307,8 @@ template<typename T> struct HostBuf {
 // Everything that survives between calls (buffers keep their capacity: no page faults in steady state).
 struct Workspace {
 	Pool* pool = nullptr;
+	int lane = 0;  // turn priority on the shared pool
+	void run(const std::function<void(int)>& f) { pool->run(f, lane); }
 	std::vector<ThreadCtx> tc;
 	HostBuf<dmnd_hit> hv;
 	HostBuf<dmnd_segment> segv;
@@ -598,7 +614,7 @@ int Driver::run_waves() {
 	for (;;) {
 		auto t0 = Clock::now();
 		// ---- produce: every active query emits the DP problems of its next step into its owner's list
-		ws->pool->run([&](int t) {
+		ws->run([&](int t) {
 			ThreadCtx& tc = w.tc[(size_t)t];
 			tc.p1.clear(); tc.p2.clear();
 			for (size_t k = block_begin(t), en = block_begin(t + 1); k < en; ++k) {
@@ -611,7 +627,7 @@ int Driver::run_waves() {
 		for (int t = 0; t < T; ++t) { off1[(size_t)t + 1] = off1[(size_t)t] + w.tc[(size_t)t].p1.size(); off2[(size_t)t + 1] = off2[(size_t)t] + w.tc[(size_t)t].p2.size(); }
 		if (off1[(size_t)T] + off2[(size_t)T] == 0) break;  // nothing in flight: every query is done
 		if (w.p1.resize(ctx, off1[(size_t)T]) || w.p2.resize(ctx, off2[(size_t)T]) || w.res1.resize(ctx, off1[(size_t)T]) || w.res2.resize(ctx, off2[(size_t)T])) return 1;
-		ws->pool->run([&](int t) {
+		ws->run([&](int t) {
 			const ThreadCtx& tc = w.tc[(size_t)t];
 			if (!tc.p1.empty()) std::memcpy(w.p1.data() + off1[(size_t)t], tc.p1.data(), tc.p1.size() * sizeof(dmnd_dp_problem));
 			if (!tc.p2.empty()) std::memcpy(w.p2.data() + off2[(size_t)t], tc.p2.data(), tc.p2.size() * sizeof(dmnd_dp_problem));
@@ -638,7 +654,7 @@ int Driver::run_waves() {
 		prof.lap("  wave: banded_swipe x2");
 		t0 = Clock::now();
 		// ---- consume
-		ws->pool->run([&](int t) {
+		ws->run([&](int t) {
 			ThreadCtx& tc = w.tc[(size_t)t];
 			const dmnd_dp_problem *P1 = w.p1.data() + off1[(size_t)t], *P2 = w.p2.data() + off2[(size_t)t];
 			const dmnd_dp_result *R1 = w.res1.data() + off1[(size_t)t], *R2 = w.res2.data() + off2[(size_t)t];
@@ -723,8 +739,19 @@ struct LaneOut {
 	int rc = 0;
 };
 
+// Seed stages of the lanes are issued one after the other, in lane order: lane 0 gets its hits after 1/nlanes of the
+// seed time instead of sharing the device with everybody, which staggers the lanes into a pipeline (host bridge of
+// lane k overlaps the seed stage of lane k+1 and the DP kernels of lane k-1).
+struct SeedTurn {
+	std::mutex m;
+	std::condition_variable cv;
+	int turn = 0;
+	void wait_for(int lane) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return turn >= lane; }); }
+	void pass(int lane) { { std::lock_guard<std::mutex> l(m); turn = std::max(turn, lane + 1); } cv.notify_all(); }
+};
+
 static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const Env& env, const Scoring& sc, uint32_t q_begin, uint32_t q_end,
-                    Workspace& w, int host_threads, LaneOut& lo) {
+                    Workspace& w, int host_threads, LaneOut& lo, int lane, SeedTurn& seed_turn) {
 	auto t_total = Clock::now();
 	Driver d;
 	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads; d.env = env;
@@ -736,7 +763,11 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	Prof prof;
 	auto t0 = Clock::now();
 	dmnd_hits* hits = nullptr;
-	if (dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed)) return 1;
+	w.lane = lane;
+	seed_turn.wait_for(lane);
+	const int seed_rc = dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
+	seed_turn.pass(lane);
+	if (seed_rc) return 1;
 	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
 	if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
@@ -754,7 +785,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	const int T = host_threads;
 	std::vector<std::vector<size_t>> tl_bounds((size_t)T);
 	std::atomic<int> bad(0);
-	w.pool->run([&](int t) {
+	w.run([&](int t) {
 		auto& v = tl_bounds[(size_t)t];
 		v.clear();
 		for (size_t i = nh * (size_t)t / (size_t)T, en = nh * (size_t)(t + 1) / (size_t)T; i < en; ++i)
@@ -772,7 +803,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	w.qs.resize(nqh);
 	w.hs.resize(nh);
 	prof.lap("group queries");
-	w.pool->run([&](int t) {
+	w.run([&](int t) {
 		ThreadCtx& tc = w.tc[(size_t)t];
 		tc.reset();
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
@@ -793,7 +824,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	// ---- emit: per-thread counts -> offsets -> parallel fill (matches grouped by ascending query)
 	t0 = Clock::now();
 	std::vector<size_t> moff((size_t)T + 1, 0), troff((size_t)T + 1, 0);
-	w.pool->run([&](int t) {
+	w.run([&](int t) {
 		ThreadCtx& tc = w.tc[(size_t)t];
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			tc.n_matches += w.qs[k].matches.n;
@@ -808,7 +839,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	}
 	lo.matches.resize(moff[(size_t)T]);
 	lo.transcripts.resize(troff[(size_t)T]);
-	w.pool->run([&](int t) {
+	w.run([&](int t) {
 		const ThreadCtx& tc = w.tc[(size_t)t];
 		dmnd_match* o = lo.matches.data() + moff[(size_t)t];
 		if (!tc.trbuf.empty()) std::memcpy(lo.transcripts.data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
@@ -896,9 +927,10 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	std::vector<dmnd_ctx*> lctx((size_t)nlanes, ctx);
 	for (int l = 1; l < nlanes; ++l)
 		if (dmnd_ctx_lane(ctx, l - 1, &lctx[(size_t)l])) return 1;
+	SeedTurn seed_turn;
 	auto body = [&](int l) {
 		LaneOut& o = lo[(size_t)l];
-		o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o);
+		o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn);
 		if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
 	};
 	std::vector<std::thread> th;

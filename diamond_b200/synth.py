@@ -164,11 +164,56 @@ def family_workload(n_fam: int, fam_size: int, n_q: int, seed: int, base_len: in
     return {"q_letters": ql, "q_off": qo, "db_letters": dbl, "db_off": off, "src": src}
 
 
+def long_workload(seed: int, n_db: int = 300, n_long: int = 5, n_short_q: int = 20):
+    """A few very long proteins (7 000..12 000 letters) with diverged, indel-carrying query copies among ordinary
+    sequences: their round-2 problems exceed max_swipe_dp (band x columns > 10^6), so the reference aligns them with
+    the statistics passes instead of a traceback (dp/swipe/swipe_wrapper.cpp:89-96)."""
+    rng = np.random.default_rng(seed)
+    dbl, dbo = make_db(n_db, rng)
+    seqs = [dbl[dbo[i]:dbo[i + 1]] for i in range(n_db)]
+    qs = []
+    for k in range(n_long):
+        L = int(rng.integers(7000, 12000))
+        base = draw_letters(rng, L)
+        seqs.append(base)
+        # query: substitutions + a handful of indels that widen the chain's diagonal range
+        q = base.copy()
+        sub = rng.random(L) < rng.uniform(0.45, 0.7)
+        q[sub] = draw_letters(rng, int(sub.sum()))
+        parts, pos = [], 0
+        for cut in sorted(rng.integers(200, L - 200, size=int(rng.integers(3, 9)))):
+            parts.append(q[pos:cut])
+            if rng.random() < 0.5:
+                parts.append(draw_letters(rng, int(rng.integers(3, 30))))  # insertion
+                pos = cut
+            else:
+                pos = min(L, cut + int(rng.integers(3, 30)))  # deletion
+        parts.append(q[pos:])
+        qs.append(np.concatenate(parts))
+        if k % 2 == 0:  # a long fragment as well (different length ratio, band clipped by the query end)
+            st = int(rng.integers(0, L // 3))
+            qs.append(qs[-1][st: st + int(rng.integers(3000, 6000))].copy())
+    for k in range(n_short_q):
+        s = int(rng.integers(0, n_db))
+        q = seqs[s].copy()
+        sub = rng.random(len(q)) < 0.2
+        q[sub] = draw_letters(rng, int(sub.sum()))
+        qs.append(q)
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    dbo2 = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in seqs], out=dbo2[1:])
+    qo = np.zeros(len(qs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in qs], out=qo[1:])
+    return {"q_letters": np.concatenate(qs).astype(np.int8), "q_off": qo, "db_letters": np.concatenate(seqs).astype(np.int8), "db_off": dbo2, "src": None}
+
+
 WORKLOADS = {
     # name: (factory, kwargs)  -- the committed golden fixtures under tests/golden/ are keyed by these names
     "c1": (workload, dict(n_q=1000, n_db=10000, seed=1)),
     "fam2": (family_workload, dict(n_fam=4, fam_size=400, n_q=120, seed=12, member_div=(0.02, 0.12), query_div=(0.03, 0.3))),
     "edge": (edge_workload, dict(seed=21)),
+    "long": (long_workload, dict(seed=33)),
 }
 
 

@@ -87,6 +87,9 @@ typedef struct dmnd_dp_problem {
 	int32_t d_end;
 } dmnd_dp_problem;
 
+/* config.max_swipe_dp (basic/config.cpp:595): a round-2 problem with band * cols above this is not traced back unless
+ * a transcript is requested; its coordinates and counts come from two statistics passes (swipe_wrapper.cpp:89-96). */
+#define DMND_MAX_SWIPE_DP 1000000
 enum { DMND_DP_SCORE_ONLY = 0, /* round 1: HspValues::NONE, banded_swipe.h:189-351 with DummyRowCounter */
        DMND_DP_TRACEBACK = 1   /* round 2: TracebackVectorMatrix kernel + walk, banded_swipe.h:127-187 */ };
 

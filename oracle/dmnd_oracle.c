@@ -489,6 +489,64 @@ void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) { (void)ctx; if (h) { free(h->h
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
 
+/* Stats-only passes (round 2 when band*cols > max_swipe_dp and no transcript is requested: swipe_wrapper.cpp:89-96 puts
+ * such targets into bins 3..5, dispatch_swipe :177-199 runs ForwardCell in round 0 and BackwardCell in the reversed
+ * round 1).  A cell is {v, a, b}: ForwardCell a = ident, b = len; BackwardCell a = mismatch, b = gapopen
+ * (stat_cell.h:46-160).  Ties copy the statistics of the max() argument (set_max, stat_cell.h:258-272), in the order
+ * hgap, vgap for the current cell and `open` for the gaps (cell_update.h:113-136). */
+typedef struct { int v, a, b; } scell;
+static inline void scell_max(scell* x, const scell* y) { /* set_max: v = max; if (v == y.v) take y's statistics */
+	if (y->v > x->v) x->v = y->v;
+	if (x->v == y->v) { x->a = y->a; x->b = y->b; }
+}
+typedef struct { int best, max_col, max_band_row, a, b; } stats_out;
+static void stats_pass(const dmnd_params* p, const int8_t* q, const int8_t* cbs, int qlen, const int8_t* t, int tlen, int d_begin, int d_end,
+                       int backward, stats_out* o) {
+	const int band = d_end - d_begin;
+	const int i1 = imax(d_end - 1, 0), i0 = i1 + 1 - band, j0 = i1 - (d_end - 1);
+	const int cols = imin(qlen - 1 - d_begin, tlen - 1) + 1 - j0;
+	memset(o, 0, sizeof *o);
+	if (band <= 0 || cols <= 0) return;
+	const int go = p->gap_open + p->gap_extend, ge = p->gap_extend;
+	scell* score = (scell*)calloc((size_t)band, sizeof(scell));
+	scell* hgap = (scell*)calloc((size_t)band + 1, sizeof(scell));
+	for (int c = 0; c < cols; ++c) {
+		const int j = j0 + c;
+		const int r_begin = imax(i0 + c, 0) - (i0 + c), r_end = imin(i1 + c, qlen - 1) + 1 - (i0 + c);
+		if (r_begin >= r_end) break;
+		const int tl = t[j] & DMND_LETTER_MASK;
+		scell vgap = { 0, 0, 0 };
+		int col_best = 0, i_max = 0;
+		for (int r = r_begin; r < r_end; ++r) {
+			const int i = i0 + c + r;
+			scell hg = hgap[r + 1];
+			const int ql = q[i] & DMND_LETTER_MASK;
+			scell cur = score[r];
+			cur.v += p->score[ql * 32 + tl] + cbs[i];
+			const int id = ql == tl; /* VectorIdMask, stat_cell.h:38-44 */
+			if (!backward) { cur.a += id; cur.b += 1; hg.b += 1; vgap.b += 1; } /* update_stats, :225-232 */
+			else cur.a += 1 - id;                                                /* :234-237 */
+			scell_max(&cur, &hg); scell_max(&cur, &vgap);
+			if (cur.v < 0) cur.v = 0;
+			col_best = imax(col_best, cur.v);
+			if (col_best == cur.v) i_max = r;
+			vgap.v = imax(vgap.v - ge, 0); hg.v = imax(hg.v - ge, 0);
+			scell open = cur;
+			open.v = imax(cur.v - go, 0);
+			if (backward) open.b += 1;                /* update_open, :250-257 */
+			if (cur.v == 0) { cur.a = 0; cur.b = 0; } /* :243-257 */
+			scell_max(&hg, &open); scell_max(&vgap, &open);
+			hgap[r] = hg;
+			score[r] = cur;
+		}
+		if (col_best > o->best) { /* banded_swipe.h:321-326 */
+			o->best = col_best; o->max_col = c; o->max_band_row = i_max;
+			o->a = score[i_max].a; o->b = score[i_max].b;
+		}
+	}
+	free(score); free(hgap);
+}
+
 /* One problem; values use the reference's int8/int16 lane semantics: every score, hgap and vgap is floored at 0
  * (saturating arithmetic around DELTA, dp/score_vector_int8.h:263-346,421-436).  trace nibble per cell:
  * bit0 cur==vgap, bit1 cur==hgap (cell_update.h:76-79), bit2 vgap'==open, bit3 hgap'==open (:85-88). */
@@ -500,6 +558,30 @@ static int swipe_one(const dmnd_ctx* ctx, const int8_t* q, const int8_t* cbs, in
 	const int cols = imin(qlen - 1 - d_begin, tlen - 1) + 1 - j0; /* dp/dp.h:47-52 */
 	memset(res, 0, sizeof *res);
 	if (band <= 0 || cols <= 0) return 0;
+	if (mode == DMND_DP_TRACEBACK && tr == NULL && (int64_t)band * (int64_t)cols > DMND_MAX_SWIPE_DP) {
+		/* forward statistics, then the reversed pass over (reversed query) x (reversed target prefix [0, t_end)) in the
+		 * mirrored band: recompute_reversed, swipe_wrapper.cpp:364-444; result assembly banded_swipe.h:86-122 */
+		stats_out f, b;
+		stats_pass(p, q, cbs, qlen, t, tlen, d_begin, d_end, 0, &f);
+		if (f.best <= 0) return 0;
+		const int q_end = i0 + f.max_col + f.max_band_row + 1, t_end = j0 + f.max_col + 1;
+		int8_t* rq = (int8_t*)malloc((size_t)qlen), *rc = (int8_t*)malloc((size_t)qlen), *rt = (int8_t*)malloc((size_t)t_end);
+		for (int i = 0; i < qlen; ++i) { rq[i] = q[qlen - 1 - i]; rc[i] = cbs[qlen - 1 - i]; }
+		for (int j = 0; j < t_end; ++j) rt[j] = t[t_end - 1 - j];
+		const int rd0 = -(d_end - 1) + qlen - t_end, rd1 = -d_begin + qlen - t_end + 1; /* Geo::rev_diag */
+		stats_pass(p, rq, rc, qlen, rt, t_end, rd0, rd1, 1, &b);
+		free(rq); free(rc); free(rt);
+		if (b.best <= 0) return 0;
+		const int ri1 = imax(rd1 - 1, 0), ri0 = ri1 + 1 - band, rj0 = ri1 - (rd1 - 1);
+		res->score = b.best;
+		res->q_end = q_end; res->t_end = t_end;
+		res->q_begin = qlen - (ri0 + b.max_col + b.max_band_row + 1);
+		res->t_begin = t_end - (rj0 + b.max_col + 1);
+		res->identities = f.a; res->length = f.b;
+		res->mismatches = b.a; res->gap_openings = b.b;
+		res->gaps = res->length - res->identities - res->mismatches; /* assign_stats, stat_cell.h:215-219 */
+		return 0;
+	}
 	const int go = p->gap_open + p->gap_extend, ge = p->gap_extend;
 	int* score = (int*)calloc((size_t)band, sizeof(int));
 	int* hgap = (int*)calloc((size_t)band + 1, sizeof(int));

@@ -21,7 +21,7 @@ def sorted_hits(h):
     return np.sort(h, order=["query", "subject_score", "seed_offset"])
 
 
-@pytest.mark.parametrize("name", ["c1", "edge", "fam2"])
+@pytest.mark.parametrize("name", ["c1", "edge", "fam2", "long"])
 def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name):
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
     o, g = both(oracle_lib, product_lib, threads=8)
@@ -46,7 +46,7 @@ def test_search_shape_hits_counters_and_seed_masks(oracle_lib, product_lib, name
     o.close(); g.close()
 
 
-@pytest.mark.parametrize("name", ["c1", "edge", "fam2"])
+@pytest.mark.parametrize("name", ["c1", "edge", "fam2", "long"])
 def test_hits_xdrop_segments_match_oracle(oracle_lib, product_lib, name):
     """Per-hit x-drop ungapped extension (dp/ungapped_align.cpp:150-214) with the Hauser bias, oracle vs device."""
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
@@ -65,7 +65,7 @@ def test_hits_xdrop_segments_match_oracle(oracle_lib, product_lib, name):
     o.close(); g.close()
 
 
-@pytest.mark.parametrize("name", ["c1", "edge"])
+@pytest.mark.parametrize("name", ["c1", "edge", "long"])
 def test_device_hauser_bias_matches_oracle(oracle_lib, product_lib, name):
     """HauserCorrection (fp32 -> int8) computed on the device is bit-identical to the scalar restatement."""
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
@@ -159,6 +159,88 @@ def test_banded_swipe_scores_and_tracebacks(oracle_lib, product_lib, name, cbs, 
     o.close(); g.close()
 
 
+def test_banded_swipe_statistics_passes_above_max_swipe_dp(oracle_lib, product_lib):
+    """Traceback mode WITHOUT a transcript buffer: problems with band x columns > 10^6 take the forward/backward statistics
+    passes of the reference (swipe_wrapper.cpp:89-96, stat_cell.h) -- same coordinates and counts as the oracle, and the
+    same score as the traceback kernel gives when a transcript is requested."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("long")
+    rng = np.random.default_rng(5)
+    nq, nr = len(q_lim) - 1, len(r_lim) - 1
+    qlen = np.diff(q_lim) - 1
+    tlen = np.diff(r_lim) - 1
+    longq = np.flatnonzero(qlen > 2500)
+    longt = np.flatnonzero(tlen > 2500)
+    P = []
+    for q in longq:
+        for t in longt:
+            for _ in range(2):
+                lo, hi = -(int(tlen[t]) - 1), int(qlen[q])
+                c = int(rng.integers(-400, 400))
+                wdt = int(rng.choice([130, 257, 400, 640, 1000]))
+                d0 = max(lo, c - wdt // 2); d1 = min(hi, d0 + wdt)
+                P.append((int(q), int(t), d0, d1))
+    P += random_problems(w, q_lim, r_lim, rng, 200)  # ordinary problems in the same call
+    probs = np.array(P, dtype=api.PROBLEM_DTYPE)
+    bias = rng.integers(-2, 2, size=q_raw.size).astype(np.int8)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    out = []
+    cap = int(sum(qlen[p[0]] + tlen[p[1]] for p in P))
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.set_bias(qb, bias, q_raw.size)
+        st, _ = c.banded_swipe(qb, rb, probs, traceback=True)                      # statistics passes where dp_size > 10^6
+        tb, _ = c.banded_swipe(qb, rb, probs, traceback=True, transcript_cap=cap)  # traceback everywhere
+        out.append((st, tb))
+        c.free_block(qb); c.free_block(rb)
+    (so, to), (sg, tg) = out
+    for f in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length", "gaps"):
+        assert np.array_equal(so[f], sg[f]), f
+        assert np.array_equal(to[f], tg[f]), f
+    assert np.array_equal(so["score"], to["score"])  # both routes find the same optimum
+    big = np.array([(p[3] - p[2]) * min(qlen[p[0]], tlen[p[1]]) > 2_000_000 for p in P])
+    assert (so["score"][big] > 1000).sum() >= 5, "the workload must contain real long alignments"
+    o.close(); g.close()
+
+
+def test_banded_swipe_profile_sizes_around_the_48k_shared_memory_default(oracle_lib, product_lib):
+    """The per-warp profile is 27 x (max query + 32 R + 4) bytes; launches whose dynamic shared memory lands just below
+    48 KB (where static + dynamic crosses the default limit) must still run: one call per maximum query length."""
+    from diamond_b200 import api, synth
+    rng = np.random.default_rng(11)
+    lens = list(range(372, 388)) + list(range(308, 324))
+    qs = [synth.draw_letters(rng, L) for L in lens]
+    ts = []
+    for q in qs:  # target: the query with substitutions and one deletion
+        t = q.copy()
+        sub = rng.random(len(t)) < 0.25
+        t[sub] = synth.draw_letters(rng, int(sub.sum()))
+        ts.append(np.concatenate([t[:100], t[104:]]))
+    q_off = np.zeros(len(qs) + 1, np.int64); np.cumsum([len(x) for x in qs], out=q_off[1:])
+    t_off = np.zeros(len(ts) + 1, np.int64); np.cumsum([len(x) for x in ts], out=t_off[1:])
+    q_raw, q_lim = api.block_image(np.concatenate(qs).astype(np.int8), q_off)
+    r_raw, r_lim = api.block_image(np.concatenate(ts).astype(np.int8), t_off)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    blocks = [(c, c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)) for c in (o, g)]
+    for c, qb, rb in blocks:
+        c.compute_bias(qb, 1)
+    for k in range(len(lens)):
+        for band in (40, 100):  # R = 2 and R = 4 register tiles
+            probs = np.array([(k, k, -band // 2, band - band // 2)] * 5, dtype=api.PROBLEM_DTYPE)
+            out = []
+            for c, qb, rb in blocks:
+                s, _ = c.banded_swipe(qb, rb, probs, traceback=False)
+                t, _ = c.banded_swipe(qb, rb, probs, traceback=True)
+                out.append((s, t))
+            assert np.array_equal(out[0][0]["score"], out[1][0]["score"]), (lens[k], band)
+            for f in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length"):
+                assert np.array_equal(out[0][1][f], out[1][1][f]), (lens[k], band, f)
+            assert out[0][0]["score"][0] > 200
+    for c, qb, rb in blocks:
+        c.free_block(qb); c.free_block(rb)
+    o.close(); g.close()
+
+
 def test_banded_swipe_bias_outside_int8_profile_falls_back(oracle_lib, product_lib):
     """S + bias beyond int8 cannot live in the shared-memory profile: the library must notice and redo the call generically."""
     from diamond_b200 import api
@@ -191,12 +273,15 @@ def test_banded_swipe_empty_and_errors(product_lib):
     g.free_block(qb); g.free_block(rb); g.close()
 
 
-@pytest.mark.parametrize("name", ["c1", "fam2", "edge"])
+@pytest.mark.parametrize("name", ["c1", "fam2", "edge", "long"])
 @pytest.mark.parametrize("level,cbs", [("l0", 0), ("l1", 1)])
 def test_blastp_pipeline_matches_reference_golden(oracle_lib, product_lib, name, level, cbs):
     from diamond_b200 import api
     w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
-    g = api.Context(product_lib, threads=8, comp_based_stats=cbs, want_transcript=True)
+    # fmt 6 asks the reference for no transcript, which sends the > 10^6-cell problems of "long" through the statistics
+    # passes; with a transcript requested they are traced back instead (same optimum, ties may resolve differently)
+    wt = name != "long"
+    g = api.Context(product_lib, threads=8, comp_based_stats=cbs, want_transcript=wt)
     m, tr, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
     g.close()
     assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
@@ -204,7 +289,7 @@ def test_blastp_pipeline_matches_reference_golden(oracle_lib, product_lib, name,
     for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
         assert st["seed"][k] == cn[k], k
     assert st["device"]["launches"] > 0
-    o = api.Context(oracle_lib, threads=8, comp_based_stats=cbs, want_transcript=True)
+    o = api.Context(oracle_lib, threads=8, comp_based_stats=cbs, want_transcript=wt)
     mo, tro, sto = o.blastp(q_raw, q_lim, r_raw, r_lim)
     o.close()
     for f in m.dtype.names:

@@ -9,7 +9,7 @@ import pytest
 from conftest import GOLDEN, REF_BIN, workload_blocks
 
 
-@pytest.mark.parametrize("name", ["c1", "fam2", "edge"])
+@pytest.mark.parametrize("name", ["c1", "fam2", "edge", "long"])  # "long": round-2 problems above max_swipe_dp (statistics passes)
 @pytest.mark.parametrize("level,cbs", [("l0", 0), ("l1", 1)])
 def test_fmt6_and_counters_match_reference_golden(oracle_lib, name, level, cbs):
     from diamond_b200 import api
