@@ -436,14 +436,20 @@ int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	return banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
 }
 
-int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset) {
-	out->seed_ms = ctx->phase_ms[PH_SEED]; out->dp_score_ms = ctx->phase_ms[PH_DP_SCORE]; out->dp_trace_ms = ctx->phase_ms[PH_DP_TRACE];
-	out->h2d_ms = ctx->phase_ms[PH_H2D]; out->d2h_ms = ctx->phase_ms[PH_D2H];
-	out->launches = ctx->launches; out->h2d_bytes = ctx->h2d_bytes; out->d2h_bytes = ctx->d2h_bytes;
-	if (reset) {
-		for (double& x : ctx->phase_ms) x = 0;
-		ctx->launches = 0; ctx->h2d_bytes = 0; ctx->d2h_bytes = 0;
-	}
+int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int flags) {
+	std::memset(out, 0, sizeof *out);
+	auto take = [&](dmnd_ctx* c) {
+		out->seed_ms += c->phase_ms[PH_SEED]; out->dp_score_ms += c->phase_ms[PH_DP_SCORE]; out->dp_trace_ms += c->phase_ms[PH_DP_TRACE];
+		out->h2d_ms += c->phase_ms[PH_H2D]; out->d2h_ms += c->phase_ms[PH_D2H];
+		out->launches += c->launches; out->h2d_bytes += c->h2d_bytes; out->d2h_bytes += c->d2h_bytes;
+		if (flags & DMND_TIMING_RESET) {
+			for (double& x : c->phase_ms) x = 0;
+			c->launches = 0; c->h2d_bytes = 0; c->d2h_bytes = 0;
+		}
+	};
+	take(ctx);
+	if (!(flags & DMND_TIMING_THIS_CONTEXT))
+		for (dmnd_ctx* l : ctx->lanes) take(l);
 	return 0;
 }
 

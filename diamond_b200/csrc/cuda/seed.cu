@@ -57,8 +57,10 @@ __global__ void ref_enum_kernel(const int8_t* __restrict__ letters, size_t raw_l
 }
 
 // Blocked Bloom filter over the reference keys: one 32-byte block (= one L2 sector) per key, 4 bits set.  99 % of the query
-// positions have no partner in the reference; the filter answers them from a 64 MB structure that stays L2 resident instead
-// of touching the bucket directory and the 228 MB key array in HBM.
+// positions have no partner in the reference; the filter answers them from a structure sized to stay L2 resident
+// (<= 32 reference keys per 256-bit block: 34 MB for the 3*10^7 keys of a 100 k-protein block, ~2 % false positives)
+// instead of touching the bucket directory and the key array in HBM.  At 6.8 keys per block (134 MB) the filter itself
+// missed L2 and the probe ran at DRAM random-sector speed (ncu: 62 B of DRAM traffic per query position).
 __device__ __forceinline__ void bloom_slots(uint64_t key, uint32_t block_mask, uint32_t& block, uint32_t& bits) {
 	const uint64_t h = key * 0xD6E8FEB86659FD93ull;
 	block = (uint32_t)(h >> 40) & block_mask;
@@ -135,7 +137,13 @@ __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ l
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
 	__shared__ uint8_t s_code[SEED_TILE + 32];
 	__shared__ uint8_t s_lut[32];
+	// matches of the tile are staged in shared memory: ONE pair of global atomics per CTA (returning atomics on a single
+	// hot address cost microseconds each and stalled every warp that found a match) and a coalesced copy-out
+	__shared__ Entry s_ent[SEED_TILE];
+	__shared__ unsigned s_n;
+	__shared__ unsigned long long s_pairs, s_base;
 	const size_t p0 = p_begin + (size_t)blockIdx.x * SEED_TILE;
+	if (threadIdx.x == 0) { s_n = 0; s_pairs = 0; }
 	load_code_tile(letters, p0, P, s_code, s_lut);
 	for (int it = 0; it < SEED_TILE / 256; ++it) {
 		const int o = it * 256 + threadIdx.x;
@@ -144,29 +152,31 @@ __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ l
 		bool ok = p < p_end && seed_from_codes(s_code, o, sh, seed);
 		uint64_t key = 0;
 		if (ok) { key = mix40(seed); ok = bloom_test(bloom, bloom_mask, key); }
-		uint32_t lo = 0, cnt = 0;
 		if (ok) {
 			const uint32_t b = (uint32_t)(key >> shift);
 			uint32_t i = bucket[b];
 			const uint32_t e = bucket[b + 1];
 			while (i < e && keys[i] < key) ++i;
-			lo = i;
+			const uint32_t lo = i;
 			while (i < e && keys[i] == key) ++i;
-			cnt = i - lo;
-			ok = cnt > 0;
-		}
-		const unsigned m = __ballot_sync(0xffffffffu, ok);
-		if (m == 0) continue;
-		const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-		unsigned long long base = 0;
-		if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-		base = __shfl_sync(0xffffffffu, base, leader);
-		if (ok) {
-			const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
-			if (idx < cap) entries[idx] = Entry{ (uint32_t)p, lo, cnt, (uint32_t)(seed & (((uint64_t)1 << sh.seedp_bits) - 1)) };
-			atomicAdd(count + 1, (unsigned long long)cnt);  // upper bound on (q,s) pairs over all chunks
+			const uint32_t cnt = i - lo;
+			if (cnt > 0) {
+				s_ent[atomicAdd(&s_n, 1u)] = Entry{ (uint32_t)p, lo, cnt, (uint32_t)(seed & (((uint64_t)1 << sh.seedp_bits) - 1)) };
+				atomicAdd(&s_pairs, (unsigned long long)cnt);  // upper bound on (q,s) pairs over all chunks
+			}
 		}
 	}
+	__syncthreads();
+	const unsigned n = s_n;
+	if (n == 0) return;
+	if (threadIdx.x == 0) {
+		s_base = atomicAdd(count, (unsigned long long)n);
+		atomicAdd(count + 1, s_pairs);
+	}
+	__syncthreads();
+	const unsigned long long base = s_base;
+	for (unsigned k = threadIdx.x; k < n; k += blockDim.x)
+		if (base + k < cap) entries[base + k] = s_ent[k];
 }
 
 // search/seed_complexity.cpp:37-51
@@ -445,7 +455,7 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	}
 	// Bloom filter: >= 12 keys' worth of 256-bit blocks per 12 keys, i.e. >= 21 bits per key (false positives < 1 %)
 	uint32_t bloom_blocks = 1024;
-	while ((unsigned long long)bloom_blocks * 12ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
+	while ((unsigned long long)bloom_blocks * 32ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
 	if (ix.bloom.ensure((size_t)bloom_blocks * 32)) return 1;
 	DMND_CUDA_CHECK(cudaMemsetAsync(ix.bloom.p, 0, (size_t)bloom_blocks * 32, st));
 	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, ix.bloom.as<uint32_t>(), bloom_blocks - 1); ++ctx->launches; }

@@ -279,6 +279,31 @@ struct ThreadCtx {
 	}
 };
 
+// Grow-only plain host buffer WITHOUT value initialisation (std::vector::resize would memset tens of MB on one thread);
+// kept alive between calls so that steady-state steps touch no fresh pages.
+template<typename T> struct RawBuf {
+	T* p = nullptr;
+	size_t n = 0, cap = 0;
+	RawBuf() = default;
+	RawBuf(const RawBuf&) = delete;
+	RawBuf& operator=(const RawBuf&) = delete;
+	~RawBuf() { std::free(p); }
+	void resize(size_t count) {
+		if (count > cap) {
+			std::free(p);
+			cap = count + count / 8 + 4096;
+			p = static_cast<T*>(std::malloc(cap * sizeof(T)));
+			if (!p) { cap = n = 0; throw std::bad_alloc(); }
+		}
+		n = count;
+	}
+	T* data() { return p; }
+	const T* data() const { return p; }
+	size_t size() const { return n; }
+	T& operator[](size_t i) { return p[i]; }
+	const T& operator[](size_t i) const { return p[i]; }
+};
+
 // Grow-only page-locked host buffer (dmnd_host_alloc): device<->host copies of hits, DP problems, results and
 // transcripts run as real DMA at link speed instead of staged pageable copies.  Contents are not preserved by resize().
 template<typename T> struct HostBuf {
@@ -319,6 +344,8 @@ struct Workspace {
 	HostBuf<dmnd_dp_problem> p1, p2;
 	HostBuf<dmnd_dp_result> res1, res2;
 	HostBuf<uint8_t> tr;
+	RawBuf<dmnd_match> out_matches;   // lane output when several lanes run (copied into the result afterwards)
+	RawBuf<uint8_t> out_transcripts;
 };
 // Process-wide: the worker pool and one workspace per lane.
 struct Shared {
@@ -674,10 +701,29 @@ int Driver::run_waves() {
 
 // ------------------------------------------------------------------------------------------------------------
 struct dmnd_result {
-	std::vector<dmnd_match> matches;
-	std::vector<uint8_t> transcripts;
+	RawBuf<dmnd_match> matches;
+	RawBuf<uint8_t> transcripts;
 	dmnd_run_stats stats;
 };
+// dmnd_result_free parks up to two results here; the next call reuses their (already touched) memory.
+struct ResultPool {
+	std::mutex m;
+	std::vector<dmnd_result*> free_list;
+	dmnd_result* take() {
+		std::lock_guard<std::mutex> l(m);
+		if (free_list.empty()) return new dmnd_result();
+		dmnd_result* r = free_list.back(); free_list.pop_back();
+		return r;
+	}
+	void give(dmnd_result* r) {
+		{
+			std::lock_guard<std::mutex> l(m);
+			if (free_list.size() < 2) { free_list.push_back(r); return; }
+		}
+		delete r;
+	}
+};
+static ResultPool& result_pool() { static ResultPool p; return p; }
 
 extern "C" {
 
@@ -732,8 +778,8 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 // on their own host threads; while one lane waits for its kernels the other one owns the worker pool, so the host
 // bridge of one query range overlaps the device work of the other.
 struct LaneOut {
-	std::vector<dmnd_match> matches;
-	std::vector<uint8_t> transcripts;
+	RawBuf<dmnd_match>* matches = nullptr;  // the result's buffers (one lane) or the lane workspace's (several)
+	RawBuf<uint8_t>* transcripts = nullptr;
 	dmnd_run_stats stats;
 	std::string error;
 	int rc = 0;
@@ -756,8 +802,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	Driver d;
 	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads; d.env = env;
 	std::memset(&d.stats, 0, sizeof d.stats);
-	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, 0);  // snapshot: the device counters of this call are reported as a delta
-	const Env& e = d.env;
+	dmnd_timing tm0; dmnd_timing_fetch(ctx, &tm0, DMND_TIMING_THIS_CONTEXT);  // snapshot: the device counters of this call are reported as a delta
 
 	// ---- seed stage (run_ref_chunk: one search_shape per shape; FAST has one shape)
 	Prof prof;
@@ -837,12 +882,12 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		d.stats.queries_aligned += w.tc[(size_t)t].n_aligned;
 		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
 	}
-	lo.matches.resize(moff[(size_t)T]);
-	lo.transcripts.resize(troff[(size_t)T]);
+	lo.matches->resize(moff[(size_t)T]);
+	lo.transcripts->resize(troff[(size_t)T]);
 	w.run([&](int t) {
 		const ThreadCtx& tc = w.tc[(size_t)t];
-		dmnd_match* o = lo.matches.data() + moff[(size_t)t];
-		if (!tc.trbuf.empty()) std::memcpy(lo.transcripts.data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
+		dmnd_match* o = lo.matches->data() + moff[(size_t)t];
+		if (!tc.trbuf.empty()) std::memcpy(lo.transcripts->data() + troff[(size_t)t], tc.trbuf.data(), tc.trbuf.size());
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			const QueryState& q = w.qs[k];
 			for (const Match& m : q.matches) {
@@ -857,12 +902,12 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 			}
 		}
 	});
-	d.stats.matches = lo.matches.size();
+	d.stats.matches = lo.matches->size();
 	d.stats.host_bridge_ms += ms_since(t0);
 	prof.lap("emit matches");
 	d.stats.total_ms = ms_since(t_total);
 	{
-		dmnd_timing tm1; dmnd_timing_fetch(ctx, &tm1, 0);
+		dmnd_timing tm1; dmnd_timing_fetch(ctx, &tm1, DMND_TIMING_THIS_CONTEXT);
 		dmnd_timing& dv = d.stats.device;
 		dv.seed_ms = tm1.seed_ms - tm0.seed_ms; dv.dp_score_ms = tm1.dp_score_ms - tm0.dp_score_ms; dv.dp_trace_ms = tm1.dp_trace_ms - tm0.dp_trace_ms;
 		dv.h2d_ms = tm1.h2d_ms - tm0.h2d_ms; dv.d2h_ms = tm1.d2h_ms - tm0.d2h_ms;
@@ -891,7 +936,9 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	auto t_total = Clock::now();
 	Shared& sh = shared();
 	std::lock_guard<std::mutex> guard(sh.mtx);
-	std::unique_ptr<dmnd_result> res(new dmnd_result());
+	struct PoolReturn { void operator()(dmnd_result* r) const { result_pool().give(r); } };
+	std::unique_ptr<dmnd_result, PoolReturn> res(result_pool().take());
+	res->matches.resize(0); res->transcripts.resize(0);
 	std::memset(&res->stats, 0, sizeof res->stats);
 	Scoring sc;
 	int64_t ref_letters = 0;
@@ -899,7 +946,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
 	int host_threads = effective_cpus();
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
-	int nlanes = nq < 40000u ? 1 : 2;  // small inputs: lane overlap buys nothing
+	// staggered query lanes (see SeedTurn): small inputs gain nothing, 4 lanes measured best at 10^6 queries on 16 host CPUs
+	int nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(4u, std::max<uint32_t>(2u, nq / 200000u));
 	if (const char* ev = std::getenv("DMND_LANES")) nlanes = std::max(1, std::min(8, std::atoi(ev)));
 	nlanes = (int)std::min<uint32_t>((uint32_t)nlanes, std::max<uint32_t>(nq, 1));
 	sh.ensure(host_threads, nlanes);
@@ -924,14 +972,21 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		cut[(size_t)l] = std::min(std::max(cut[(size_t)l], cut[(size_t)l - 1]), nq);
 	}
 	std::vector<LaneOut> lo((size_t)nlanes);
+	for (int l = 0; l < nlanes; ++l) {
+		lo[(size_t)l].matches = nlanes == 1 ? &res->matches : &sh.lanes[(size_t)l]->out_matches;
+		lo[(size_t)l].transcripts = nlanes == 1 ? &res->transcripts : &sh.lanes[(size_t)l]->out_transcripts;
+	}
 	std::vector<dmnd_ctx*> lctx((size_t)nlanes, ctx);
 	for (int l = 1; l < nlanes; ++l)
 		if (dmnd_ctx_lane(ctx, l - 1, &lctx[(size_t)l])) return 1;
 	SeedTurn seed_turn;
 	auto body = [&](int l) {
 		LaneOut& o = lo[(size_t)l];
-		o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn);
-		if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
+		try {
+			o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn);
+			if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
+		}
+		catch (const std::exception& ex) { o.rc = 1; o.error = std::string("dmnd_blastp: ") + ex.what(); seed_turn.pass(l); }
 	};
 	std::vector<std::thread> th;
 	for (int l = 1; l < nlanes; ++l) th.emplace_back(body, l);
@@ -941,24 +996,21 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		if (lo[(size_t)l].rc) { dmnd_set_last_error(lo[(size_t)l].error.c_str()); return 1; }
 
 	// ---- concatenate lanes (ascending query ranges); a single lane hands its vectors over, several are copied in parallel
-	if (nlanes == 1) {
-		res->matches.swap(lo[0].matches); res->transcripts.swap(lo[0].transcripts);
-		add_stats(res->stats, lo[0].stats);
-	}
+	if (nlanes == 1) add_stats(res->stats, lo[0].stats);  // the lane wrote straight into the result
 	else {
 		std::vector<size_t> mo((size_t)nlanes + 1, 0), to((size_t)nlanes + 1, 0);
-		for (int l = 0; l < nlanes; ++l) { mo[(size_t)l + 1] = mo[(size_t)l] + lo[(size_t)l].matches.size(); to[(size_t)l + 1] = to[(size_t)l] + lo[(size_t)l].transcripts.size(); }
+		for (int l = 0; l < nlanes; ++l) { mo[(size_t)l + 1] = mo[(size_t)l] + lo[(size_t)l].matches->size(); to[(size_t)l + 1] = to[(size_t)l] + lo[(size_t)l].transcripts->size(); }
 		res->matches.resize(mo[(size_t)nlanes]);
 		res->transcripts.resize(to[(size_t)nlanes]);
 		const int T = host_threads;
 		sh.pool->run([&](int t) {
 			for (int l = 0; l < nlanes; ++l) {
 				const LaneOut& o = lo[(size_t)l];
-				const size_t n = o.matches.size(), b = n * (size_t)t / (size_t)T, e = n * (size_t)(t + 1) / (size_t)T;
+				const size_t n = o.matches->size(), b = n * (size_t)t / (size_t)T, e = n * (size_t)(t + 1) / (size_t)T;
 				dmnd_match* dst = res->matches.data() + mo[(size_t)l];
-				for (size_t k = b; k < e; ++k) { dst[k] = o.matches[k]; dst[k].transcript_off += to[(size_t)l]; }
-				const size_t nt = o.transcripts.size(), tb = nt * (size_t)t / (size_t)T, te = nt * (size_t)(t + 1) / (size_t)T;
-				if (te > tb) std::memcpy(res->transcripts.data() + to[(size_t)l] + tb, o.transcripts.data() + tb, te - tb);
+				for (size_t k = b; k < e; ++k) { dst[k] = (*o.matches)[k]; dst[k].transcript_off += to[(size_t)l]; }
+				const size_t nt = o.transcripts->size(), tb = nt * (size_t)t / (size_t)T, te = nt * (size_t)(t + 1) / (size_t)T;
+				if (te > tb) std::memcpy(res->transcripts.data() + to[(size_t)l] + tb, o.transcripts->data() + tb, te - tb);
 			}
 		});
 		for (int l = 0; l < nlanes; ++l) add_stats(res->stats, lo[(size_t)l].stats);
@@ -992,6 +1044,6 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
 const dmnd_match* dmnd_result_matches(const dmnd_result* r, size_t* n) { *n = r->matches.size(); return r->matches.data(); }
 const uint8_t* dmnd_result_transcripts(const dmnd_result* r, size_t* n) { *n = r->transcripts.size(); return r->transcripts.data(); }
 const dmnd_run_stats* dmnd_result_stats(const dmnd_result* r) { return &r->stats; }
-void dmnd_result_free(dmnd_result* r) { delete r; }
+void dmnd_result_free(dmnd_result* r) { if (r) result_pool().give(r); }
 
 }  // extern "C"

@@ -173,14 +173,16 @@ void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
 int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems,
                       size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 
-/* Device time (ms) spent in the library's own kernels since the last call, and the number of kernel launches:
- * filled from CUDA events recorded on the library's stream. */
+/* Device time (ms) spent in the library's own kernels since the last reset, and the number of kernel launches: filled
+ * from CUDA events recorded on the context's stream.  A root context reports itself plus its lanes; lanes run
+ * concurrently, so their stream times overlap (a serial kernel time needs a single-lane run). */
 typedef struct dmnd_timing {
 	double seed_ms, dp_score_ms, dp_trace_ms, h2d_ms, d2h_ms;
 	uint64_t launches;
 	uint64_t h2d_bytes, d2h_bytes;
 } dmnd_timing;
-int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset);
+enum { DMND_TIMING_RESET = 1, DMND_TIMING_THIS_CONTEXT = 2 /* do not add the lanes */ };
+int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int flags);
 /* Roofline denominator for the DP kernels: measured issue rate (lane-instructions / s, whole GPU) of the three-input
  * integer DPX instructions (VIADDMNMX / VIMNMX3) the recurrence is built from.  Runs a ~20 ms micro-benchmark. */
 int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
