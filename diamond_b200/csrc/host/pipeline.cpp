@@ -946,8 +946,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
 	int host_threads = effective_cpus();
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
-	// staggered query lanes (see SeedTurn): small inputs gain nothing, 4 lanes measured best at 10^6 queries on 16 host CPUs
-	int nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(4u, std::max<uint32_t>(2u, nq / 200000u));
+	// staggered query lanes (see SeedTurn): small inputs gain nothing, 3 lanes measured best at 10^6 queries on 16 host CPUs
+	int nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(3u, std::max<uint32_t>(2u, nq / 300000u));
 	if (const char* ev = std::getenv("DMND_LANES")) nlanes = std::max(1, std::min(8, std::atoi(ev)));
 	nlanes = (int)std::min<uint32_t>((uint32_t)nlanes, std::max<uint32_t>(nq, 1));
 	sh.ensure(host_threads, nlanes);
