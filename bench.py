@@ -270,7 +270,10 @@ def main():
                        "d2h_bytes_per_step": tm2["d2h_bytes"] // args.steps},
                "gpu_launches": int(tm["launches"]), "roofline": roofline, "cpu_baseline": cpu,
                "breakdown_ms_per_step": {"seed_stage": st["seed_ms"], "host_bridge": st["host_bridge_ms"], "dp_round1": st["dp1_ms"], "dp_round2": st["dp2_ms"], "total": st["total_ms"]},
-               "work": {"cells_per_gpu": cells, "dp_problems_round1": st["dp_problems_round1"], "dp_problems_round2": st["dp_problems_round2"], "alignments": int(len(m)), "hits": st["hits"]}}
+               "work": {"cells_per_gpu": cells, "dp_problems_round1": st["dp_problems_round1"], "dp_problems_round2": st["dp_problems_round2"], "dp_problems_fused": st["dp_problems_fused"],
+                        "note": "cells = sum band x cols over the reference's round-1 and round-2 problem lists (dp/dp.h:121-124): a property of the workload, "
+                                "the same for both arms; fused queries evaluate a surviving problem's matrix once (with traceback) instead of twice",
+                        "alignments": int(len(m)), "hits": st["hits"]}}
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -71,7 +71,7 @@ class Match(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("seed", StageCounters)] + \
                [(n, C.c_uint64) for n in ("hits", "targets", "dp_problems_round1", "dp_problems_round2", "cells_round1",
-                                          "cells_round2", "queries_aligned", "matches")] + \
+                                          "cells_round2", "queries_aligned", "matches", "dp_problems_fused")] + \
                [(n, C.c_double) for n in ("seed_ms", "host_bridge_ms", "dp1_ms", "dp2_ms", "total_ms")] + \
                [("device", Timing)]
 

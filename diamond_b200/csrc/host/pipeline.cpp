@@ -191,6 +191,7 @@ inline bool hsp_less(const HspLite& a, const HspLite& b) {  // basic/match.h:199
 }
 struct Target {  // align/target.h:83-144 after inner_culling (max_hsps == 1): only the best HSP is kept
 	uint32_t block_id; int tlen; int filter_score; double filter_evalue; HspLite hsp; bool has_hsp;
+	uint32_t hsp_prob;  // fused queries: index (within the query's problem slice) of the problem that produced `hsp`
 	static bool comp_evalue(const Target& t, const Target& u) {
 		return t.filter_evalue < u.filter_evalue || (t.filter_evalue == u.filter_evalue && (t.filter_score > u.filter_score || (t.filter_score == u.filter_score && t.block_id < u.block_id)));
 	}
@@ -235,6 +236,7 @@ struct Env {
 	int max_target_seqs;
 	double max_evalue;
 	bool hauser, want_transcript;
+	bool fuse;  // see Driver::start
 	int qlen(uint32_t q) const { return (int)(q_limits[q + 1] - q_limits[q] - 1); }
 	int tlen(uint32_t t) const { return (int)(r_limits[t + 1] - r_limits[t] - 1); }
 };
@@ -246,6 +248,7 @@ struct QueryState {
 	int qlen;
 	Phase phase;
 	bool new_hits_ev;
+	bool fused;
 	// SeedHitList (align/target.h:160-165): slices of the owner thread's flat arrays
 	uint32_t sh_off, tgt_off, n_targets;  // hit_begin[tgt_off + k] (n_targets + 1 entries), block ids / scores [ts_off..]
 	uint32_t ts_off;
@@ -273,9 +276,10 @@ struct ThreadCtx {
 	std::vector<int8_t> cbs;
 	std::vector<Target> tmp_targets;
 	uint64_t cells1 = 0, cells2 = 0, n_targets = 0, n_matches = 0, n_aligned = 0;
+	uint64_t fused_r1 = 0, fused_r2 = 0, fused_r1_wave = 0;  // fused queries: round-1 problems traced, round-2 problems answered from them
 	void reset() {
 		arena.reset(); seed_hits.clear(); hit_begin.clear(); target_block_ids.clear(); target_scores.clear();
-		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = 0;
+		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = 0; fused_r1 = fused_r2 = fused_r1_wave = 0;
 	}
 };
 
@@ -378,6 +382,9 @@ struct Driver {
 	void produce_round2(QueryState& q, ThreadCtx& tc);
 	void consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
 	void consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
+	void consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
+	void take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr);
+	void finish_round2(QueryState& q, ThreadCtx& tc);
 	void finish_outer(QueryState& q);
 	int run_waves();
 };
@@ -450,6 +457,12 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	if ((q.i1 - q.i0) < e.max_target_seqs)
 		while (q.i1 < target_count && e.sc->evalue(ts[q.i1].score, (unsigned)q.qlen, 50) <= e.max_evalue)
 			q.i1 += std::min<int64_t>(16, target_count - q.i1);
+	// Fused rounds: round 2 re-evaluates, with traceback, exactly the (query, target, band) problem of round 1 that gave
+	// each surviving target its HSP (gapped_final.cpp:64-78 takes hsp.d_begin/d_end).  With 180 GB of HBM the trace of
+	// round 1 can simply be kept: a query whose targets mostly survive culling (<= 64 targets, one ranking chunk, at most
+	// max_target_seqs = 25 culled away) sends its round-1 problems through the traceback kernel once and answers round 2
+	// from those results -- one device round trip instead of two, 13 instead of 9 + 13 lane-ops per surviving cell.
+	q.fused = e.fuse && target_count <= 64 && target_count <= q.chunk_size;
 	q.phase = PH_ROUND1_PRODUCE;
 }
 
@@ -459,7 +472,8 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	q.r1.clear();
 	q.r1.reserve(tc.arena, (uint32_t)(q.i1 - q.i0));
 	q.prob_target.clear();
-	q.prob_begin = tc.p1.size();
+	std::vector<dmnd_dp_problem>& plist = q.fused ? tc.p2 : tc.p1;  // fused: straight into the traceback batch
+	q.prob_begin = plist.size();
 	const int8_t* query = e.q_letters + e.q_limits[q.qid];
 	const int band = band_for(q.qlen);
 	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
@@ -470,7 +484,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		const uint32_t block_id = ids[tix];
 		const int slen = e.tlen(block_id);
 		const int8_t* subject = e.r_letters + e.r_limits[block_id];
-		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false });
+		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false, 0 });
 		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
 		std::sort(tc.hits.begin(), tc.hits.end());
 		tc.segs.clear();
@@ -487,7 +501,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		// add_dp_targets, align/gapped_score.cpp:107-180
 		int d0 = INT_MAX, d1 = INT_MIN;
 		auto emit = [&] {
-			tc.p1.push_back(dmnd_dp_problem{ q.qid, block_id, d0, d1 });
+			plist.push_back(dmnd_dp_problem{ q.qid, block_id, d0, d1 });
 			q.prob_target.push(tc.arena, q.r1.n - 1);
 			tc.cells1 += (uint64_t)(d1 - d0) * (uint64_t)banded_cols(q.qlen, slen, d0, d1);
 		};
@@ -507,7 +521,8 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		}
 		if (!tc.chains.empty()) emit();
 	}
-	q.prob_count = (uint32_t)(tc.p1.size() - q.prob_begin);
+	q.prob_count = (uint32_t)(plist.size() - q.prob_begin);
+	if (q.fused) { tc.fused_r1 += q.prob_count; tc.fused_r1_wave += q.prob_count; }
 	q.phase = PH_ROUND1_CONSUME;
 }
 
@@ -526,7 +541,7 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		const double ev = e.sc->evalue(score, (unsigned)q.qlen, (unsigned)t.tlen);
 		if (score > 0 && ev <= e.max_evalue) {  // banded_swipe.h:341-342, ScoreMatrix::report_cutoff
 			const HspLite h{ score, ev, probs[k].d_begin, probs[k].d_end };
-			if (!t.has_hsp || hsp_less(h, t.hsp)) t.hsp = h;
+			if (!t.has_hsp || hsp_less(h, t.hsp)) { t.hsp = h; t.hsp_prob = k; }
 			t.has_hsp = true;
 			if (score > t.filter_score) { t.filter_evalue = ev; t.filter_score = score; }  // Target::add_hit(list,it), target.h:104-112
 		}
@@ -596,26 +611,26 @@ void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
 	q.phase = PH_ROUND2_CONSUME;
 }
 
-void Driver::consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr) {
-	const Env& e = env;
+void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr) {
 	// gapped_final.cpp:140-149
-	for (uint32_t k = 0; k < q.prob_count; ++k) {
-		const dmnd_dp_result& r = res[k];
-		Match& m = q.r2.p[q.prob_target.p[k]];
-		const double ev = e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
-		if (r.score > 0 && ev <= e.max_evalue) {
-			const HspLite h{ r.score, ev, probs[k].d_begin, probs[k].d_end };
-			if (!m.has_hsp || hsp_less(h, m.h)) {
-				m.h = h; m.r = r;
-				m.tr_off = 0; m.tr_len = 0;
-				if (e.want_transcript && r.status == 0 && tr) {
-					m.tr_off = tc.trbuf.size(); m.tr_len = r.transcript_len;
-					tc.trbuf.insert(tc.trbuf.end(), tr + r.transcript_off, tr + r.transcript_off + r.transcript_len);
-				}
+	const Env& e = env;
+	const double ev = e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
+	if (r.score > 0 && ev <= e.max_evalue) {
+		const HspLite h{ r.score, ev, pr.d_begin, pr.d_end };
+		if (!m.has_hsp || hsp_less(h, m.h)) {
+			m.h = h; m.r = r;
+			m.tr_off = 0; m.tr_len = 0;
+			if (e.want_transcript && r.status == 0 && tr) {
+				m.tr_off = tc.trbuf.size(); m.tr_len = r.transcript_len;
+				tc.trbuf.insert(tc.trbuf.end(), tr + r.transcript_off, tr + r.transcript_off + r.transcript_len);
 			}
-			m.has_hsp = true;
 		}
+		m.has_hsp = true;
 	}
+}
+
+void Driver::finish_round2(QueryState& q, ThreadCtx& tc) {
+	const Env& e = env;
 	for (Match& m : q.r2) if (m.has_hsp) { m.filter_evalue = m.h.evalue; m.filter_score = m.h.score; }  // Match::inner_culling
 	std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
 	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e.max_target_seqs) - q.r2.begin());
@@ -623,6 +638,32 @@ void Driver::consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 	q.r2.clear();
 	q.aligned_targets.clear();
 	finish_outer(q);
+}
+
+void Driver::consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr) {
+	for (uint32_t k = 0; k < q.prob_count; ++k) take_round2_result(q, tc, q.r2.p[q.prob_target.p[k]], probs[k], res[k], tr);
+	finish_round2(q, tc);
+}
+
+void Driver::consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr) {
+	// round 1 over the traceback results (their scores are the score-only kernel's), then round 2 answered from them
+	consume_round1(q, tc, probs, res);
+	if (q.phase != PH_ROUND2_PRODUCE) return;  // nothing survived, or (never for a fused query) another ranking chunk
+	q.r2.clear();
+	q.r2.reserve(tc.arena, q.aligned_targets.n);
+	for (const Target& tg : q.aligned_targets) {
+		Match m;
+		std::memset(&m, 0, sizeof m);
+		m.target_block_id = tg.block_id; m.tlen = tg.tlen; m.filter_score = 0; m.filter_evalue = DBL_MAX; m.has_hsp = false;
+		if (tg.has_hsp) {  // the round-2 problem of this target IS round-1 problem hsp_prob (gapped_final.cpp:64-78)
+			const dmnd_dp_problem& pr = probs[tg.hsp_prob];
+			tc.cells2 += (uint64_t)(pr.d_end - pr.d_begin) * (uint64_t)banded_cols(q.qlen, tg.tlen, pr.d_begin, pr.d_end);
+			++tc.fused_r2;
+			take_round2_result(q, tc, m, pr, res[tg.hsp_prob], tr);
+		}
+		q.r2.push(tc.arena, m);
+	}
+	finish_round2(q, tc);
 }
 
 void Driver::finish_outer(QueryState& q) {
@@ -659,7 +700,11 @@ int Driver::run_waves() {
 			if (!tc.p1.empty()) std::memcpy(w.p1.data() + off1[(size_t)t], tc.p1.data(), tc.p1.size() * sizeof(dmnd_dp_problem));
 			if (!tc.p2.empty()) std::memcpy(w.p2.data() + off2[(size_t)t], tc.p2.data(), tc.p2.size() * sizeof(dmnd_dp_problem));
 		});
-		stats.dp_problems_round1 += w.p1.size(); stats.dp_problems_round2 += w.p2.size();
+		// problem counts in the reference's terms: a fused query's round-1 problems sit in the traceback batch, its round-2
+		// problems are answered from their results (counted in consume_fused)
+		uint64_t fused_wave = 0;
+		for (ThreadCtx& tc : w.tc) { fused_wave += tc.fused_r1_wave; tc.fused_r1_wave = 0; }
+		stats.dp_problems_round1 += w.p1.size() + fused_wave; stats.dp_problems_round2 += w.p2.size() - fused_wave;
 		stats.host_bridge_ms += ms_since(t0);
 		prof.lap("  wave: produce + concat");
 		// ---- device waves
@@ -687,7 +732,10 @@ int Driver::run_waves() {
 			const dmnd_dp_result *R1 = w.res1.data() + off1[(size_t)t], *R2 = w.res2.data() + off2[(size_t)t];
 			for (size_t k = block_begin(t), en = block_begin(t + 1); k < en; ++k) {
 				QueryState& q = w.qs[k];
-				if (q.phase == PH_ROUND1_CONSUME) consume_round1(q, tc, P1 + q.prob_begin, R1 + q.prob_begin);
+				if (q.phase == PH_ROUND1_CONSUME) {
+					if (q.fused) consume_fused(q, tc, P2 + q.prob_begin, R2 + q.prob_begin, trp);
+					else consume_round1(q, tc, P1 + q.prob_begin, R1 + q.prob_begin);
+				}
 				else if (q.phase == PH_ROUND2_CONSUME) consume_round2(q, tc, P2 + q.prob_begin, R2 + q.prob_begin, trp);
 			}
 		});
@@ -881,6 +929,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		troff[(size_t)t + 1] = troff[(size_t)t] + w.tc[(size_t)t].trbuf.size();
 		d.stats.queries_aligned += w.tc[(size_t)t].n_aligned;
 		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
+		d.stats.dp_problems_round2 += w.tc[(size_t)t].fused_r2; d.stats.dp_problems_fused += w.tc[(size_t)t].fused_r1;
 	}
 	lo.matches->resize(moff[(size_t)T]);
 	lo.transcripts->resize(troff[(size_t)T]);
@@ -922,6 +971,7 @@ static void add_stats(dmnd_run_stats& a, const dmnd_run_stats& b) {
 	a.seed.tentative_matches2 += b.seed.tentative_matches2; a.seed.tentative_matches3 += b.seed.tentative_matches3; a.seed.masked_seeds += b.seed.masked_seeds;
 	a.hits += b.hits; a.targets += b.targets; a.dp_problems_round1 += b.dp_problems_round1; a.dp_problems_round2 += b.dp_problems_round2;
 	a.cells_round1 += b.cells_round1; a.cells_round2 += b.cells_round2; a.queries_aligned += b.queries_aligned; a.matches += b.matches;
+	a.dp_problems_fused += b.dp_problems_fused;
 	// wall-clock phase times of concurrent lanes overlap: report the longest lane
 	a.seed_ms = std::max(a.seed_ms, b.seed_ms); a.host_bridge_ms = std::max(a.host_bridge_ms, b.host_bridge_ms);
 	a.dp1_ms = std::max(a.dp1_ms, b.dp1_ms); a.dp2_ms = std::max(a.dp2_ms, b.dp2_ms);
@@ -957,6 +1007,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
 	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
+	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 
 	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
 	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;

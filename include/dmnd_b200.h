@@ -215,6 +215,8 @@ typedef struct dmnd_run_stats {
 	uint64_t hits, targets, dp_problems_round1, dp_problems_round2;
 	uint64_t cells_round1, cells_round2; /* algorithmic cells = sum (d_end-d_begin)*cols, dp/dp.h:121-124 */
 	uint64_t queries_aligned, matches;
+	uint64_t dp_problems_fused; /* round-1 problems evaluated once WITH traceback; their queries' round-2 problems were
+	                               answered from those results (counted in dp_problems_round2 / cells_round2 all the same) */
 	double seed_ms, host_bridge_ms, dp1_ms, dp2_ms, total_ms; /* wall clock, host */
 	dmnd_timing device;
 } dmnd_run_stats;

@@ -89,3 +89,27 @@ def test_cli_rejects_what_it_does_not_implement(oracle_lib):
     assert r.returncode != 0 and "masking" in r.stderr
     r = subprocess.run([cli, "blastx"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+@pytest.mark.parametrize("name", ["c1", "edge", "long"])
+def test_fused_rounds_equal_two_round_execution(oracle_lib, name, monkeypatch):
+    """Queries with few targets answer round 2 from the traceback results of their round-1 problems (pipeline.cpp,
+    Driver::start); DMND_NO_FUSE=1 runs the reference's two separate rounds.  Same matches, same problem and cell counts."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    out = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            monkeypatch.setenv("DMND_NO_FUSE", "1")
+        else:
+            monkeypatch.delenv("DMND_NO_FUSE", raising=False)
+        ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, want_transcript=(name != "long"))
+        m, tr, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+        ctx.close()
+        out.append((api.fmt6(m), m.copy(), tr.copy(), st))
+    assert out[0][0] == out[1][0]
+    for f in ("dp_problems_round1", "dp_problems_round2", "cells_round1", "cells_round2", "matches", "queries_aligned"):
+        assert out[0][3][f] == out[1][3][f], f
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(out[0][2][a["transcript_off"]: a["transcript_off"] + a["transcript_len"]],
+                              out[1][2][b["transcript_off"]: b["transcript_off"] + b["transcript_len"]])
