@@ -328,7 +328,8 @@ struct Chainer {
 		prune();
 		forward_pass(space_penalty);
 		// backtrace.cpp:327-356
-		std::vector<const Node*> top;
+		static thread_local std::vector<const Node*> top;  // scratch reused across calls (no allocation in steady state)
+		top.clear();
 		for (const Node& d : g.nodes)
 			if (d.rel_score() >= cutoff) top.push_back(&d);
 		std::sort(top.begin(), top.end(), [](const Node* x, const Node* y) { return x->rel_score() > y->rel_score(); });
@@ -358,7 +359,8 @@ struct Chainer {
 
 	// greedy_align.cpp:106-127
 	void prune() {
-		std::vector<Node> finished, win;
+		static thread_local std::vector<Node> finished, win;  // scratch reused across calls
+		finished.clear(); win.clear();
 		finished.reserve(g.nodes.size());
 		for (const Node& d : g.nodes) {
 			size_t n = 0;
@@ -372,7 +374,7 @@ struct Chainer {
 			if (n <= 8) win.push_back(d);  // config.chaining_range_cover
 		}
 		for (const Node& d : win) finished.push_back(d);
-		g.nodes = std::move(finished);
+		g.nodes.swap(finished);  // both buffers stay alive for the next call
 	}
 };
 

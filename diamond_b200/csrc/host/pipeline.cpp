@@ -383,7 +383,7 @@ struct Driver {
 	void consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
 	void consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
 	void consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
-	void take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr);
+	void take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr, double known_evalue = -1.0);
 	void finish_round2(QueryState& q, ThreadCtx& tc);
 	void finish_outer(QueryState& q);
 	int run_waves();
@@ -611,10 +611,10 @@ void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
 	q.phase = PH_ROUND2_CONSUME;
 }
 
-void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr) {
-	// gapped_final.cpp:140-149
+void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr, double known_evalue) {
+	// gapped_final.cpp:140-149; known_evalue >= 0: the e-value of (r.score, qlen, tlen) was already computed in round 1
 	const Env& e = env;
-	const double ev = e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
+	const double ev = known_evalue >= 0.0 ? known_evalue : e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
 	if (r.score > 0 && ev <= e.max_evalue) {
 		const HspLite h{ r.score, ev, pr.d_begin, pr.d_end };
 		if (!m.has_hsp || hsp_less(h, m.h)) {
@@ -659,7 +659,8 @@ void Driver::consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* 
 			const dmnd_dp_problem& pr = probs[tg.hsp_prob];
 			tc.cells2 += (uint64_t)(pr.d_end - pr.d_begin) * (uint64_t)banded_cols(q.qlen, tg.tlen, pr.d_begin, pr.d_end);
 			++tc.fused_r2;
-			take_round2_result(q, tc, m, pr, res[tg.hsp_prob], tr);
+			// same problem, same score: the e-value of round 1 (tg.hsp) is the e-value of round 2
+			take_round2_result(q, tc, m, pr, res[tg.hsp_prob], tr, res[tg.hsp_prob].score == tg.hsp.score ? tg.hsp.evalue : -1.0);
 		}
 		q.r2.push(tc.arena, m);
 	}
