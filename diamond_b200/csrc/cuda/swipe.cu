@@ -239,9 +239,14 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 		const uint32_t pi = a.order[w];
 		const dmnd_dp_problem pr = a.probs[pi];
 		const ProbGeom g = geom(a, pr);
-		int H[R], E[R], F[R], bestv[R], bestc[R];
+		// per row: best cell as ONE key = score * 2^15 + (31743 - macro step + lane offset): an unsigned max keeps the highest
+		// score and, among equals, the first column (1 IMAD on the FMA pipe + 1 VIMNMX instead of compare + select + max).
+		// Fits: the profile lives in <= 200 KB of shared memory, so qlen < 7.6 k, macro steps < 31743 and scores < 2^17
+		// (checked below; an out-of-range score raises the overflow flag and the call is redone on the generic kernel).
+		int H[R], E[R], F[R];
+		unsigned bestk[R];
 #pragma unroll
-		for (int k = 0; k < R; ++k) { H[k] = 0; E[k] = 0; F[k] = 0; bestv[k] = 0; bestc[k] = 0; }
+		for (int k = 0; k < R; ++k) { H[k] = 0; E[k] = 0; F[k] = 0; bestk[k] = 0; }
 		int best = 0;
 		if (g.B > 0 && g.cols > 0) {
 			// ---- profile
@@ -280,6 +285,7 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 			uint8_t* tr = TRACE ? a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base) + (size_t)lane * U : nullptr;
 			for (int m = m_lo; m < m_hi; ++m) {
 				const int tnext = trow_of(g.j0 + m + 1 - lofs);  // issued early: consumed after the two half steps
+				const unsigned ckey = (unsigned)(31743 - m + lofs);
 				uint32_t pk[PKW];
 #pragma unroll
 				for (int x = 0; x < PKW; ++x) pk[x] = 0;
@@ -296,11 +302,11 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 							const int e_in = E[k + 1], f_in = k > 0 ? F[k > 0 ? k - 1 : 0] : f_up;
 							const int hd = H[k] + sc;
 							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
-							const int t2 = h - go;
-							const int e_new = __viaddmax_s32_relu(e_in, -ge, t2), f_new = __viaddmax_s32_relu(f_in, -ge, t2);
+							const int open = __viaddmax_s32_relu(h, -go, 0);  // relu(h - go), cell_update.h:129-131
+							const int e_new = __viaddmax_s32_relu(e_in, -ge, open), f_new = __viaddmax_s32_relu(f_in, -ge, open);
 							if (TRACE) {
-								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, max(t2, 0)) << ((k & 7) * 4);
-								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
+								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, open) << ((k & 7) * 4);
+								bestk[k] = max(bestk[k], (unsigned)h * 32768u + ckey);
 							}
 							else best = max(best, h);
 							H[k] = h;
@@ -320,11 +326,11 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 							const int e_in = k + 1 < R ? E[k + 1 < R ? k + 1 : 0] : e_dn, f_in = F[k - 1];
 							const int hd = H[k] + sc;
 							const int h = k <= kb ? __vimax3_s32_relu(hd, e_in, f_in) : 0;
-							const int t2 = h - go;
-							const int e_new = __viaddmax_s32_relu(e_in, -ge, t2), f_new = __viaddmax_s32_relu(f_in, -ge, t2);
+							const int open = __viaddmax_s32_relu(h, -go, 0);  // relu(h - go), cell_update.h:129-131
+							const int e_new = __viaddmax_s32_relu(e_in, -ge, open), f_new = __viaddmax_s32_relu(f_in, -ge, open);
 							if (TRACE) {
-								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, max(t2, 0)) << ((k & 7) * 4);
-								if (h > bestv[k]) { bestv[k] = h; bestc[k] = m - lofs - u; }
+								pk[k >> 3] |= trace_flags_arith(h, e_in, f_in, e_new, f_new, open) << ((k & 7) * 4);
+								bestk[k] = max(bestk[k], (unsigned)h * 32768u + ckey);
 							}
 							else best = max(best, h);
 							H[k] = h;
@@ -342,11 +348,16 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 		}
 		if (TRACE) {
 			int bv = 0, bc = 0, br = 0;
+			const int lofs = lane * U;
+			bool wide = false;
 #pragma unroll
 			for (int k = 0; k < R; ++k) {
 				const int r = lane * R + k;
-				if (bestv[k] > bv || (bestv[k] == bv && bv > 0 && (bestc[k] < bc || (bestc[k] == bc && r > br)))) { bv = bestv[k]; bc = bestc[k]; br = r; }
+				const int v = (int)(bestk[k] >> 15), c = 31743 + lofs - (int)(bestk[k] & 32767u) - lofs - (k >> 1);
+				wide |= v >= 131072 - 256;
+				if (v > bv || (v == bv && bv > 0 && (c < bc || (c == bc && r > br)))) { bv = v; bc = c; br = r; }
 			}
+			if (__any_sync(FULL, wide) && lane == 0) atomicExch(pa.overflow, 1u);
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) {
 				const int ov = __shfl_xor_sync(FULL, bv, o), oc = __shfl_xor_sync(FULL, bc, o), orr = __shfl_xor_sync(FULL, br, o);
