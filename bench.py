@@ -24,7 +24,7 @@ LADDER = ["--masking", "0", "--motif-masking", "0"]  # masking parity is a 'next
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=1_000_000, help="queries per GPU")

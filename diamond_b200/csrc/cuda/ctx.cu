@@ -247,10 +247,9 @@ void dmnd_destroy(dmnd_ctx* c) {
 	delete c;
 }
 
-int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq, dmnd_block** out) {
-	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+static int block_alloc(dmnd_ctx* ctx, size_t raw_len, const int64_t* limits, uint32_t nseq, const char* who, dmnd_block** out, size_t* padded_out) {
 	if (raw_len < 2 * DMND_PERIMETER_PADDING || limits[0] != DMND_PERIMETER_PADDING || (size_t)limits[nseq] + DMND_PERIMETER_PADDING != raw_len) {
-		set_error("dmnd_block_upload: not a block image (256 B padding + sequences + 256 B padding)");
+		set_error((std::string(who) + ": not a block image (256 B padding + sequences + 256 B padding)").c_str());
 		return 1;
 	}
 	dmnd_block* b = new dmnd_block();
@@ -269,10 +268,22 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	}
 	if (!b->letters) {
 		b->cap_bytes = padded + 64; b->cap_seqs = (size_t)nseq + 1;
-		DMND_CUDA_CHECK(cudaMalloc(&b->letters, b->cap_bytes));
-		DMND_CUDA_CHECK(cudaMalloc(&b->bias, b->cap_bytes));
-		DMND_CUDA_CHECK(cudaMalloc(&b->limits, sizeof(int64_t) * b->cap_seqs));
+		if (cudaMalloc(&b->letters, b->cap_bytes) != cudaSuccess || cudaMalloc(&b->bias, b->cap_bytes) != cudaSuccess
+		    || cudaMalloc(&b->limits, sizeof(int64_t) * b->cap_seqs) != cudaSuccess) {
+			cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); delete b;
+			set_error((std::string(who) + ": cudaMalloc failed").c_str());
+			return 1;
+		}
 	}
+	*out = b; *padded_out = padded;
+	return 0;
+}
+
+int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq, dmnd_block** out) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	dmnd_block* b = nullptr;
+	size_t padded = 0;
+	if (block_alloc(ctx, raw_len, limits, nseq, "dmnd_block_upload", &b, &padded)) return 1;
 	PhaseTimer t(ctx, PH_H2D);
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, ctx->stream));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(b->letters, letters, raw_len, cudaMemcpyHostToDevice, ctx->stream));
@@ -284,11 +295,51 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	return 0;
 }
 
+int dmnd_block_upload_ranges(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq,
+                             const uint32_t* cuts, int nranges, dmnd_block** out) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (nranges < 1 || nranges > 64 || cuts[0] != 0 || cuts[nranges] != nseq) { set_error("dmnd_block_upload_ranges: cuts must run from 0 to nseq in 1..64 ranges"); return 1; }
+	for (int k = 0; k < nranges; ++k) if (cuts[k] > cuts[k + 1]) { set_error("dmnd_block_upload_ranges: cuts not ascending"); return 1; }
+	dmnd_block* b = nullptr;
+	size_t padded = 0;
+	if (block_alloc(ctx, raw_len, limits, nseq, "dmnd_block_upload_ranges", &b, &padded)) return 1;
+	cudaStream_t cs = ctx->copy_stream;
+	// order the copy stream behind whatever the compute streams still do with a recycled buffer: block_free synchronised them
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, cs));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, cs));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(b->limits, limits, sizeof(int64_t) * ((size_t)nseq + 1), cudaMemcpyHostToDevice, cs));
+	b->range_ready.resize((size_t)nranges, nullptr);
+	b->range_cuts.assign(cuts, cuts + nranges + 1);
+	for (int k = 0; k < nranges; ++k) {
+		// range k: from its first sequence (the head padding with range 0) to 256 bytes past its last one: the seed windows,
+		// fingerprints and left-most filter of a range read a little beyond its end (into the next range's first letters)
+		const size_t lo = k == 0 ? 0 : (size_t)limits[cuts[k]];
+		const size_t hi = std::min(raw_len, (size_t)limits[cuts[k + 1]] + DMND_PERIMETER_PADDING);
+		if (hi > lo) DMND_CUDA_CHECK(cudaMemcpyAsync(b->letters + lo, letters + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+		DMND_CUDA_CHECK(cudaEventCreateWithFlags(&b->range_ready[(size_t)k], cudaEventDisableTiming));
+		DMND_CUDA_CHECK(cudaEventRecord(b->range_ready[(size_t)k], cs));
+	}
+	ctx->h2d_bytes += raw_len + sizeof(int64_t) * ((size_t)nseq + 1);
+	*out = b;
+	return 0;
+}
+
+int dmnd_block_range_wait(dmnd_ctx* ctx, const dmnd_block* b, uint32_t s_begin, uint32_t s_end) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (b->range_ready.empty() || s_begin >= s_end) return 0;  // uploaded synchronously: everything is there
+	for (size_t k = 0; k < b->range_ready.size(); ++k)
+		if (b->range_cuts[k] < s_end && b->range_cuts[k + 1] > s_begin)  // range k holds some of the sequences
+			DMND_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, b->range_ready[k], 0));
+	return 0;
+}
+
 void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	if (!b) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (dmnd_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream);
+	cudaStreamSynchronize(ctx->copy_stream);
+	for (cudaEvent_t e : b->range_ready) if (e) cudaEventDestroy(e);
 	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->cap_bytes, b->cap_seqs, b->idx });
 	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); b->idx.release(); }
 	delete b;
@@ -313,18 +364,29 @@ int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid) {
 	return rc;
 }
 
-int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
+int dmnd_block_compute_bias_range(dmnd_ctx* ctx, dmnd_block* b, int mode, uint32_t s_begin, uint32_t s_end) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (mode != 0 && mode != 1) { set_error("dmnd_block_compute_bias: unknown mode"); return 1; }
+	if (s_begin > s_end || s_end > b->nseq) { set_error("dmnd_block_compute_bias_range: sequence range out of bounds"); return 1; }
+	if (s_begin == s_end) return 0;
 	PhaseTimer t(ctx, PH_SEED);
-	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, b->raw_len, ctx->stream));
-	if (mode == 1 && b->nseq) {
-		hauser_kernel<<<(b->nseq + 127) / 128, 128, 0, ctx->stream>>>(b->letters, b->limits, b->nseq, ctx->d_params, b->bias);
+	const size_t lo = (size_t)b->h_limits[s_begin], hi = (size_t)b->h_limits[s_end];
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias + lo, 0, hi - lo, ctx->stream));
+	if (mode == 1) {
+		const uint32_t n = s_end - s_begin;
+		hauser_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(b->letters, b->limits + s_begin, n, ctx->d_params, b->bias);
 		++ctx->launches;
 		DMND_CUDA_CHECK(cudaGetLastError());
 	}
 	t.stop();
 	return 0;
+}
+
+int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (mode != 0 && mode != 1) { set_error("dmnd_block_compute_bias: unknown mode"); return 1; }
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, b->raw_len, ctx->stream));  // padding included
+	return dmnd_block_compute_bias_range(ctx, b, mode, 0, b->nseq);
 }
 
 int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) {

@@ -80,6 +80,8 @@ struct dmnd_block {
 	size_t raw_len = 0;
 	uint32_t nseq = 0;
 	std::vector<int64_t> h_limits;  // host copy (problem binning needs lengths)
+	std::vector<cudaEvent_t> range_ready;  // dmnd_block_upload_ranges: one event per uploaded sequence range
+	std::vector<uint32_t> range_cuts;      // [nranges + 1] sequence boundaries of those ranges
 };
 
 struct dmnd_hits {

@@ -858,8 +858,11 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	auto t0 = Clock::now();
 	dmnd_hits* hits = nullptr;
 	w.lane = lane;
+	// this lane's query range may still be on its way (dmnd_block_upload_ranges); its composition bias is computed here, on
+	// the lane's stream, as soon as the letters are there
+	const int prep_rc = dmnd_block_range_wait(ctx, qb, q_begin, q_end) || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
 	seed_turn.wait_for(lane);
-	const int seed_rc = dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
+	const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
 	seed_turn.pass(lane);
 	if (seed_rc) return 1;
 	prof.lap("search_shape");
@@ -981,6 +984,30 @@ static void add_stats(dmnd_run_stats& a, const dmnd_run_stats& b) {
 	a.device.h2d_bytes += b.device.h2d_bytes; a.device.d2h_bytes += b.device.d2h_bytes;
 }
 
+// Host threads, number of staggered query lanes and their contiguous, letter-balanced query ranges
+// (SequenceSet::partition, data/sequence_set.cpp:57-75, is the reference's analogue for its threads).
+struct LanePlan {
+	int host_threads = 1, nlanes = 1;
+	std::vector<uint32_t> cut;
+};
+static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits) {
+	LanePlan p;
+	p.host_threads = effective_cpus();
+	if (const char* ev = std::getenv("DMND_HOST_THREADS")) p.host_threads = std::max(1, std::atoi(ev));
+	// staggered query lanes (see SeedTurn): small inputs gain nothing, 3 lanes measured best at 10^6 queries on 16 host CPUs
+	p.nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(3u, std::max<uint32_t>(2u, nq / 300000u));
+	if (const char* ev = std::getenv("DMND_LANES")) p.nlanes = std::max(1, std::min(8, std::atoi(ev)));
+	p.nlanes = (int)std::min<uint32_t>((uint32_t)p.nlanes, std::max<uint32_t>(nq, 1));
+	p.cut.assign((size_t)p.nlanes + 1, nq);
+	p.cut[0] = 0;
+	for (int l = 1; l < p.nlanes; ++l) {
+		const int64_t want = q_limits[0] + (q_limits[nq] - q_limits[0]) * l / p.nlanes;
+		p.cut[(size_t)l] = (uint32_t)(std::lower_bound(q_limits, q_limits + nq + 1, want) - q_limits);
+		p.cut[(size_t)l] = std::min(std::max(p.cut[(size_t)l], p.cut[(size_t)l - 1]), nq);
+	}
+	return p;
+}
+
 static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const int8_t* q_letters, const int64_t* q_limits,
                        uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
                        dmnd_result** out) {
@@ -995,12 +1022,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	int64_t ref_letters = 0;
 	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
-	int host_threads = effective_cpus();
-	if (const char* ev = std::getenv("DMND_HOST_THREADS")) host_threads = std::max(1, std::atoi(ev));
-	// staggered query lanes (see SeedTurn): small inputs gain nothing, 3 lanes measured best at 10^6 queries on 16 host CPUs
-	int nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(3u, std::max<uint32_t>(2u, nq / 300000u));
-	if (const char* ev = std::getenv("DMND_LANES")) nlanes = std::max(1, std::min(8, std::atoi(ev)));
-	nlanes = (int)std::min<uint32_t>((uint32_t)nlanes, std::max<uint32_t>(nq, 1));
+	const LanePlan plan = plan_lanes(nq, q_limits);
+	const int host_threads = plan.host_threads, nlanes = plan.nlanes;
 	sh.ensure(host_threads, nlanes);
 
 	Env e;
@@ -1010,19 +1033,11 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 
-	// the device computes its own copy of the per-position composition bias (identical arithmetic, see hauser_kernel)
-	if (dmnd_block_compute_bias(ctx, qb, e.hauser ? 1 : 0)) return 1;
+	// (the per-position composition bias of the queries is computed on the device by each lane for its own range)
 	// reference side of the seed join, once per call, shared by the lanes (the reference rebuilds it per run as well)
 	if (dmnd_block_build_index(ctx, const_cast<dmnd_block*>(rb), 0)) return 1;
 
-	// contiguous, letter-balanced query ranges (SequenceSet::partition, data/sequence_set.cpp:57-75, is the reference's analogue)
-	std::vector<uint32_t> cut((size_t)nlanes + 1, nq);
-	cut[0] = 0;
-	for (int l = 1; l < nlanes; ++l) {
-		const int64_t want = q_limits[0] + (q_limits[nq] - q_limits[0]) * l / nlanes;
-		cut[(size_t)l] = (uint32_t)(std::lower_bound(q_limits, q_limits + nq + 1, want) - q_limits);
-		cut[(size_t)l] = std::min(std::max(cut[(size_t)l], cut[(size_t)l - 1]), nq);
-	}
+	const std::vector<uint32_t>& cut = plan.cut;
 	std::vector<LaneOut> lo((size_t)nlanes);
 	for (int l = 0; l < nlanes; ++l) {
 		lo[(size_t)l].matches = nlanes == 1 ? &res->matches : &sh.lanes[(size_t)l]->out_matches;
@@ -1083,9 +1098,12 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
                 dmnd_result** out) {
 	dmnd_block *qb = nullptr, *rb = nullptr;
 	Prof prof;
-	if (dmnd_block_upload(ctx, q_letters, q_raw_len, q_limits, nq, &qb)) return 1;
-	if (dmnd_block_upload(ctx, r_letters, r_raw_len, r_limits, nr, &rb)) { dmnd_block_free(ctx, qb); return 1; }
-	prof.lap("e2e: block uploads");
+	// the reference block first (the index build needs it), then the query block range by range on the copy stream: lane 0
+	// starts as soon as ITS range is there, the other ranges travel while it already searches
+	if (dmnd_block_upload(ctx, r_letters, r_raw_len, r_limits, nr, &rb)) return 1;
+	const LanePlan plan = plan_lanes(nq, q_limits);
+	if (dmnd_block_upload_ranges(ctx, q_letters, q_raw_len, q_limits, nq, plan.cut.data(), plan.nlanes, &qb)) { dmnd_block_free(ctx, rb); return 1; }
+	prof.lap("e2e: block uploads (queries in flight)");
 	const int rc = blastp_impl(ctx, qb, rb, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, out);
 	prof.t = Clock::now();
 	dmnd_block_free(ctx, qb); dmnd_block_free(ctx, rb);

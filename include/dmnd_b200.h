@@ -124,6 +124,15 @@ int dmnd_ctx_lane(dmnd_ctx* ctx, int lane, dmnd_ctx** out);
  * raw_len bytes long; limits[0..nseq] are the sequence start offsets into it (limits[0] == 256).  Copies to HBM. */
 int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq,
                       dmnd_block** out);
+/* Same, but the letters travel asynchronously on the library's copy stream in `nranges` consecutive sequence ranges
+ * [cuts[k], cuts[k+1]) (cuts[0] == 0, cuts[nranges] == nseq); the call returns while the copies are in flight.
+ * dmnd_block_range_wait(ctx_or_lane, b, s_begin, s_end) makes that context's stream wait until the sequences
+ * [s_begin, s_end) (and the 256 bytes after them, which their seed windows may read) have arrived -- the P layer starts
+ * lane 0 while the other ranges are still uploading.  A no-op for blocks uploaded with dmnd_block_upload.
+ * `letters` must stay valid (and should be page-locked) until every range has been waited for or the block is freed. */
+int dmnd_block_upload_ranges(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq,
+                             const uint32_t* cuts, int nranges, dmnd_block** out);
+int dmnd_block_range_wait(dmnd_ctx* ctx, const dmnd_block* b, uint32_t s_begin, uint32_t s_end);
 void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b);
 /* Per-position int8 composition bias (HauserCorrection::int8, stats/hauser_correction.cpp:53-109), laid out at the
  * same offsets as the block's letters.  NULL => all zero (--comp-based-stats 0). */
@@ -135,6 +144,8 @@ int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid);
 /* Fills the block's bias array on the device: mode 1 = HauserCorrection of every sequence (stats/hauser_correction.cpp:
  * 53-109, window 40, fp32, rounded half away from zero), mode 0 = zeros (--comp-based-stats 0). */
 int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode);
+/* Same for the sequences [s_begin, s_end) only, on `ctx`'s stream (a lane computes the bias of its own query range). */
+int dmnd_block_compute_bias_range(dmnd_ctx* ctx, dmnd_block* b, int mode, uint32_t s_begin, uint32_t s_end);
 /* Reads back the block's bias array. */
 int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len);
 /* Same, on the library's copy stream: returns at once, dmnd_copy_wait() blocks until `bias` is complete.  Overlaps with

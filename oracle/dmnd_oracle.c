@@ -104,6 +104,12 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	*out = b;
 	return 0;
 }
+int dmnd_block_upload_ranges(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, const int64_t* limits, uint32_t nseq,
+                             const uint32_t* cuts, int nranges, dmnd_block** out) {
+	if (nranges < 1 || nranges > 64 || cuts[0] != 0 || cuts[nranges] != nseq) return fail("dmnd_block_upload_ranges: cuts must run from 0 to nseq in 1..64 ranges");
+	return dmnd_block_upload(ctx, letters, raw_len, limits, nseq, out); /* nothing to overlap on the CPU */
+}
+int dmnd_block_range_wait(dmnd_ctx* ctx, const dmnd_block* b, uint32_t s_begin, uint32_t s_end) { (void)ctx; (void)b; (void)s_begin; (void)s_end; return 0; }
 void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	(void)ctx;
 	if (!b) return;
@@ -138,16 +144,23 @@ static void hauser_one(const dmnd_params* p, const int8_t* seq, int len, int8_t*
 #undef EMIT
 }
 int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid) { (void)ctx; (void)b; (void)sid; return 0; } /* the restatement joins per call */
-int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
-	memset(b->bias, 0, b->raw_len);
+int dmnd_block_compute_bias_range(dmnd_ctx* ctx, dmnd_block* b, int mode, uint32_t s_begin, uint32_t s_end) {
+	if (mode != 0 && mode != 1) return fail("dmnd_block_compute_bias: unknown mode");
+	if (s_begin > s_end || s_end > b->nseq) return fail("dmnd_block_compute_bias_range: sequence range out of bounds");
+	if (s_begin == s_end) return 0;
+	memset(b->bias + b->limits[s_begin], 0, (size_t)(b->limits[s_end] - b->limits[s_begin]));
 	if (mode == 0) return 0;
-	if (mode != 1) return fail("dmnd_block_compute_bias: unknown mode");
-	for (uint32_t i = 0; i < b->nseq; ++i) {
+	for (uint32_t i = s_begin; i < s_end; ++i) {
 		const int64_t beg = b->limits[i];
 		const int len = (int)(b->limits[i + 1] - beg - 1);
 		if (len > 0) hauser_one(&ctx->p, b->letters + beg, len, b->bias + beg);
 	}
 	return 0;
+}
+int dmnd_block_compute_bias(dmnd_ctx* ctx, dmnd_block* b, int mode) {
+	if (mode != 0 && mode != 1) return fail("dmnd_block_compute_bias: unknown mode");
+	memset(b->bias, 0, b->raw_len);
+	return dmnd_block_compute_bias_range(ctx, b, mode, 0, b->nseq);
 }
 int dmnd_block_download_bias(dmnd_ctx* ctx, const dmnd_block* b, int8_t* bias, size_t raw_len) {
 	(void)ctx;
