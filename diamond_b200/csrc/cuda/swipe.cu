@@ -624,6 +624,7 @@ struct PrepOut {
 	uint64_t* tslen;     // [n] qlen + tlen (transcript capacity)
 	unsigned int* hist;  // [256]
 	unsigned int* flag;  // error flag
+	unsigned long long* cost_hist;  // [256] cost per bucket, [256] sum of tslen: the host derives group bases and totals without a second sync
 };
 __global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t n, const int64_t* __restrict__ ql, uint32_t nq,
                             const int64_t* __restrict__ rl, uint32_t nr, int trace, PrepOut o) {
@@ -651,6 +652,8 @@ __global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t 
 	o.cost[k] = stats ? 0ull : trace ? nmacro * 16ull * (unsigned long long)R : cells;
 	o.tslen[k] = (uint64_t)qlen + (uint64_t)tlen;
 	atomicAdd(&o.hist[key], 1u);
+	atomicAdd(&o.cost_hist[key], o.cost[k]);
+	atomicAdd(&o.cost_hist[256], (unsigned long long)qlen + (unsigned long long)tlen);
 }
 __global__ void scatter_kernel(const uint8_t* __restrict__ key, uint32_t n, const unsigned int* __restrict__ off, unsigned int* fill, uint32_t* order) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,7 +684,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	const unsigned nb = (unsigned)((n + 255) / 256);
 	// ---- device buffers
 	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
-	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1280 * sizeof(unsigned int))
+	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1280 * sizeof(unsigned int) + 8 + 258 * sizeof(unsigned long long))
 	    || ctx->b_prep.ensure(n * (1 + 8 + 8 + 8 + 8) + 64))
 		return 1;
 	int32_t* d_score = ctx->b_work.as<int32_t>();
@@ -701,12 +704,16 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	lap("upload problems");
 	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1280 * sizeof(unsigned int), st));
-	PrepOut po{ d_key, d_counters + 1024, d_cost, d_tslen, d_counters + 256, d_counters + 64 };
+	unsigned long long* d_cost_hist = (unsigned long long*)(((uintptr_t)(d_counters + 1280) + 7) & ~(uintptr_t)7);  // [0..255] cost per bucket, [256] sum of tslen
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cost_hist, 0, 258 * sizeof(unsigned long long), st));
+	PrepOut po{ d_key, d_counters + 1024, d_cost, d_tslen, d_counters + 256, d_counters + 64, d_cost_hist };
 	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, po);
 	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag, [512..767] offsets (upload), [1024..1279] max qlen
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	uint64_t* hq = (uint64_t*)(hp + 1536);  // [0..255] cost per bucket, [256] sum of tslen, then [260..270] group bases
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, 257 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
 	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
@@ -778,23 +785,21 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		gather_cost_kernel<<<nb, 256, 0, st>>>(ctx->b_order.as<uint32_t>(), d_cost, (uint32_t)n, d_cum);
 		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp1, d_cum, d_excl, n, st));
 		ctx->launches += 2;
-		// host copies (pinned): the prefix at the 11 group boundaries, the last cost and the transcript total
-		uint64_t* hq = (uint64_t*)(hp + 1536);  // [0..10] excl at grp_begin[g], [11] cost of the last problem, [12..13] transcript tail
-		for (int g = 0; g <= 10; ++g)
-			if (grp_begin[g] < n) DMND_CUDA_CHECK(cudaMemcpyAsync(hq + g, d_excl + grp_begin[g], sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 11, d_cum + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 14, d_excl + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		hq[12] = hq[13] = 0;
 		if (transcripts) {
 			DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_tslen, d_tsoff, n, st));
 			++ctx->launches;
-			DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 12, d_tsoff + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			DMND_CUDA_CHECK(cudaMemcpyAsync(hq + 13, d_tslen + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		}
-		DMND_CUDA_CHECK(stream_wait(ctx, st));
-		const uint64_t trace_total = hq[14] + hq[11];
-		for (int g = 0; g <= 10; ++g) if (grp_begin[g] >= n) hq[g] = trace_total;
-		ts_total = hq[12] + hq[13];
+		// group bases and totals come from the per-bucket cost histogram of the prep kernel (already on the host): the scans
+		// above stay on the device, no second synchronisation
+		uint64_t* gbase = hq + 260;  // [0..10] trace bytes before group g
+		gbase[0] = 0;
+		for (int g = 0; g < 10; ++g) {
+			uint64_t c = 0;
+			for (int k = 0; k < 16; ++k) c += hq[g * 16 + k];
+			gbase[g + 1] = gbase[g] + c;
+		}
+		const uint64_t trace_total = gbase[10];  // (the statistics bucket 160 carries no trace)
+		ts_total = hq[256];
 		if (transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
 		if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
 		if (transcripts && ctx->b_tr.ensure(ts_total + 16)) return 1;
@@ -820,7 +825,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				// slice [pos, e) of this group whose trace fits the budget (at least one problem); launches are stream-ordered,
 				// so the arena can be reused by the next slice without a host synchronisation
 				size_t e = gend;
-				uint64_t base = hq[g], bytes = hq[g + 1] - hq[g];
+				uint64_t base = gbase[g], bytes = gbase[g + 1] - gbase[g];
 				if (sliced) {
 					e = (size_t)(std::upper_bound(excl.begin() + pos + 1, excl.begin() + gend + 1, excl[pos] + budget) - excl.begin()) - 1;
 					e = std::max(e, pos + 1);
