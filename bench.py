@@ -251,7 +251,10 @@ def main():
         peak = 2.0 * ctx.int_peak()
         ach = laneops / (dp_ms / 1e3) / 1e12 if dp_ms > 0 else None
         roofline = {"bound": "int-alu", "kernel": "swipe_kernel<R,*> (banded SWIPE rounds 1+2)", "achieved": ach, "peak": peak, "unit": "Tlaneop/s",
-                    "frac": (ach / peak) if (ach and peak) else None, "traffic": None, "kernel_ms_per_step": dp_ms,
+                    "frac": (ach / peak) if (ach and peak) else None,
+                    # dram__bytes_read + dram__bytes_write of swipe_prof_kernel<4,1>, one launch over 200 k queries (ncu --set full,
+                    # profiles/ncu_summary_r1.txt); 1.70e9 of it is the algorithmic trace (16 R bytes per macro step and problem)
+                    "traffic": 1.825e9, "traffic_note": "ncu capture of the dominant launch at 200 k queries; the kernel is ALU-pipe bound (89.5 % busy), not HBM bound", "kernel_ms_per_step": dp_ms,
                     "kernel_gcups": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None,
                     "seed_stage_ms_per_step": tm1["seed_ms"] / rsteps, "timed": f"CUDA events on the library stream, {rsteps} single-lane step(s) after the timed region"}
         cpu = None

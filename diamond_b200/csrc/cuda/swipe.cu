@@ -86,7 +86,10 @@ __device__ __forceinline__ void trace_store(uint8_t* p, const uint32_t* pk) {
 	else if (R == 16) *reinterpret_cast<uint2*>(p) = make_uint2(pk[0], pk[1]);
 	else *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
-__host__ __device__ __forceinline__ int tile_rows(int B) { return B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 32; }
+// register tile per lane of the warp kernels (32 R >= B); bands beyond 1024 diagonals use the same trace layout with R = 64 / 128
+// and are evaluated by swipe_wide_kernel (one CTA per problem)
+#define DMND_MAX_BAND 4096
+__host__ __device__ __forceinline__ int tile_rows(int B) { return B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : B <= 2048 ? 64 : 128; }
 // nibble of cell (column c, band row r) in the wavefront-major layout
 __device__ __forceinline__ unsigned trace_nibble(const uint8_t* tr, int R, int c, int r) {
 	const int m = c + (r >> 1), lane = r / R, k = r - lane * R;
@@ -521,55 +524,67 @@ struct StatsArgs {
 };
 struct StatsOut { int best, col, row, a, b; };
 
+constexpr int WIDE_THREADS = 1024, WIDE_RPT = DMND_MAX_BAND / WIDE_THREADS;  // band rows per thread: r = tid + x * 1024
+
 template<bool BACKWARD>
 __device__ void stats_pass(const int8_t* __restrict__ q, const int8_t* __restrict__ cbs, int qlen, const int8_t* __restrict__ t, int tlen,
                            int d_begin, int d_end, const int8_t* __restrict__ score, int go, int ge, int* sm, StatsOut& out) {
 	// BACKWARD reads q, cbs and t mirrored: q'[i] = q[qlen-1-i], t'[j] = t[tlen-1-j]
-	const int band = d_end - d_begin, r = (int)threadIdx.x;
+	const int band = d_end - d_begin, tid = (int)threadIdx.x;
 	const int i1 = max(d_end - 1, 0), i0 = i1 + 1 - band, j0 = i1 - (d_end - 1);
 	const int cols = min(qlen - 1 - d_begin, tlen - 1) + 1 - j0;
-	int *hg_v = sm, *hg_a = sm + 1025, *hg_b = sm + 2050, *vg_v = sm + 3075, *vg_a = sm + 4100, *vg_b = sm + 5125;
-	for (int k = r; k < 1025; k += (int)blockDim.x) { hg_v[k] = hg_a[k] = hg_b[k] = 0; vg_v[k] = vg_a[k] = vg_b[k] = 0; }
+	constexpr int S = DMND_MAX_BAND + 1;
+	int *hg_v = sm, *hg_a = sm + S, *hg_b = sm + 2 * S, *vg_v = sm + 3 * S, *vg_a = sm + 4 * S, *vg_b = sm + 5 * S;
+	for (int k = tid; k <= band; k += WIDE_THREADS) { hg_v[k] = hg_a[k] = hg_b[k] = 0; vg_v[k] = vg_a[k] = vg_b[k] = 0; }
 	__syncthreads();
-	SCell h{ 0, 0, 0 };
-	int my_best = 0, my_col = 0, my_a = 0, my_b = 0;
+	SCell h[WIDE_RPT];
+	int my_best[WIDE_RPT], my_col[WIDE_RPT], my_a[WIDE_RPT], my_b[WIDE_RPT];
+#pragma unroll
+	for (int x = 0; x < WIDE_RPT; ++x) { h[x] = SCell{ 0, 0, 0 }; my_best[x] = my_col[x] = my_a[x] = my_b[x] = 0; }
 	const int steps = cols > 0 ? 2 * (cols - 1) + band : 0;
 	for (int s = 0; s < steps; ++s) {
-		const int c2 = s - r;
-		if (r < band && c2 >= 0 && !(c2 & 1) && (c2 >> 1) < cols) {
-			const int c = c2 >> 1, i = i0 + c + r, j = j0 + c;
-			if (i >= 0 && i < qlen) {
-				const int qi = BACKWARD ? qlen - 1 - i : i, tj = BACKWARD ? tlen - 1 - j : j;
-				const int ql = q[qi] & DMND_LETTER_MASK, tl = t[tj] & DMND_LETTER_MASK;
-				SCell hg{ hg_v[r + 1], hg_a[r + 1], hg_b[r + 1] };
-				SCell vg{ 0, 0, 0 };
-				if (r > 0 && i > 0) vg = SCell{ vg_v[r], vg_a[r], vg_b[r] };
-				SCell cur = h;
-				cur.v += (int)score[ql * 32 + tl] + (int)cbs[qi];
-				const int id = ql == tl;
-				if (!BACKWARD) { cur.a += id; cur.b += 1; hg.b += 1; vg.b += 1; }
-				else cur.a += 1 - id;
-				scell_max(cur, hg); scell_max(cur, vg);
-				cur.v = max(cur.v, 0);
-				if (cur.v > my_best) { my_best = cur.v; my_col = c; my_a = cur.a; my_b = cur.b; }
-				vg.v = max(vg.v - ge, 0); hg.v = max(hg.v - ge, 0);
-				SCell open = cur;
-				open.v = max(cur.v - go, 0);
-				if (BACKWARD) open.b += 1;
-				if (cur.v == 0) { cur.a = 0; cur.b = 0; }
-				scell_max(hg, open); scell_max(vg, open);
-				hg_v[r] = hg.v; hg_a[r] = hg.a; hg_b[r] = hg.b;
-				vg_v[r + 1] = vg.v; vg_a[r + 1] = vg.a; vg_b[r + 1] = vg.b;
-				h = cur;
+#pragma unroll
+		for (int x = 0; x < WIDE_RPT; ++x) {
+			const int r = tid + x * WIDE_THREADS, c2 = s - r;
+			if (r < band && c2 >= 0 && !(c2 & 1) && (c2 >> 1) < cols) {
+				const int c = c2 >> 1, i = i0 + c + r, j = j0 + c;
+				if (i >= 0 && i < qlen) {
+					const int qi = BACKWARD ? qlen - 1 - i : i, tj = BACKWARD ? tlen - 1 - j : j;
+					const int ql = q[qi] & DMND_LETTER_MASK, tl = t[tj] & DMND_LETTER_MASK;
+					SCell hg{ hg_v[r + 1], hg_a[r + 1], hg_b[r + 1] };
+					SCell vg{ 0, 0, 0 };
+					if (r > 0 && i > 0) vg = SCell{ vg_v[r], vg_a[r], vg_b[r] };
+					SCell cur = h[x];
+					cur.v += (int)score[ql * 32 + tl] + (int)cbs[qi];
+					const int id = ql == tl;
+					if (!BACKWARD) { cur.a += id; cur.b += 1; hg.b += 1; vg.b += 1; }
+					else cur.a += 1 - id;
+					scell_max(cur, hg); scell_max(cur, vg);
+					cur.v = max(cur.v, 0);
+					if (cur.v > my_best[x]) { my_best[x] = cur.v; my_col[x] = c; my_a[x] = cur.a; my_b[x] = cur.b; }
+					vg.v = max(vg.v - ge, 0); hg.v = max(hg.v - ge, 0);
+					SCell open = cur;
+					open.v = max(cur.v - go, 0);
+					if (BACKWARD) open.b += 1;
+					if (cur.v == 0) { cur.a = 0; cur.b = 0; }
+					scell_max(hg, open); scell_max(vg, open);
+					hg_v[r] = hg.v; hg_a[r] = hg.a; hg_b[r] = hg.b;
+					vg_v[r + 1] = vg.v; vg_a[r + 1] = vg.a; vg_b[r + 1] = vg.b;
+					h[x] = cur;
+				}
 			}
 		}
-		__syncthreads();
+		__syncthreads();  // rows r and r +- 1 never act in the same step (parity of s - r), so one barrier per step orders all exchanges
 	}
 	// end cell: highest value, then the first column, then the last band row (banded_swipe.h:321-326, VectorRowCounter)
 	__syncthreads();
-	if (r < band) { hg_v[r] = my_best; hg_a[r] = my_col; hg_b[r] = my_a; vg_v[r] = my_b; }
+#pragma unroll
+	for (int x = 0; x < WIDE_RPT; ++x) {
+		const int r = tid + x * WIDE_THREADS;
+		if (r < band) { hg_v[r] = my_best[x]; hg_a[r] = my_col[x]; hg_b[r] = my_a[x]; vg_v[r] = my_b[x]; }
+	}
 	__syncthreads();
-	if (r == 0) {
+	if (tid == 0) {
 		StatsOut o{ 0, 0, 0, 0, 0 };
 		for (int k = 0; k < band; ++k) {
 			const int v = hg_v[k], c = hg_a[k];
@@ -582,8 +597,9 @@ __device__ void stats_pass(const int8_t* __restrict__ q, const int8_t* __restric
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) swipe_stats_kernel(const StatsArgs a, const DevParams* __restrict__ P) {
-	__shared__ int sm[6 * 1025];
+#define DMND_STATS_SMEM (6 * (DMND_MAX_BAND + 1) * sizeof(int))
+__global__ void __launch_bounds__(WIDE_THREADS) swipe_stats_kernel(const StatsArgs a, const DevParams* __restrict__ P) {
+	extern __shared__ int sm[];
 	const uint32_t pi = a.order[blockIdx.x];
 	const dmnd_dp_problem pr = a.probs[pi];
 	const int64_t qo = a.q_limits[pr.query], to = a.r_limits[pr.target];
@@ -616,6 +632,78 @@ __global__ void __launch_bounds__(1024) swipe_stats_kernel(const StatsArgs a, co
 	if (threadIdx.x == 0) a.res[pi] = res;
 }
 
+// ---- bands wider than 1024 diagonals (chains with far-apart diagonals on very long sequences; rare) ---------------------
+// Same recurrence, masks, end-cell rule and trace layout as the warp kernels (tile_rows() = 64 / 128 fixes the nibble
+// addresses the walk kernel reads), evaluated like the statistics passes: one CTA per problem, thread t owns the band rows
+// t, t + 1024, ..., wavefront time s = 2c + r, one barrier per step, H in registers, E / F exchanged through shared memory.
+// The two nibbles of a trace byte belong to rows 2x and 2x + 1, which act in consecutive steps: the slice is zeroed
+// beforehand and each cell ORs its nibble in (the barrier orders the two read-modify-writes).
+#define DMND_WIDE_SMEM (2 * (DMND_MAX_BAND + 1) * sizeof(int))
+template<bool TRACE>
+__global__ void __launch_bounds__(WIDE_THREADS) swipe_wide_kernel(const SwipeArgs a, const DevParams* __restrict__ P) {
+	extern __shared__ int sm[];
+	const uint32_t w = blockIdx.x;
+	const uint32_t pi = a.order[w];
+	const dmnd_dp_problem pr = a.probs[pi];
+	const ProbGeom g = geom(a, pr);
+	const int tid = (int)threadIdx.x;
+	const int go = P->gap_open + P->gap_extend, ge = P->gap_extend;
+	constexpr int S = DMND_MAX_BAND + 1;
+	int *hg = sm, *vg = sm + S;
+	const int band = g.B, R = tile_rows(band);
+	for (int k = tid; k <= band; k += WIDE_THREADS) { hg[k] = 0; vg[k] = 0; }
+	__syncthreads();
+	int h[WIDE_RPT], my_best[WIDE_RPT], my_col[WIDE_RPT];
+#pragma unroll
+	for (int x = 0; x < WIDE_RPT; ++x) { h[x] = 0; my_best[x] = 0; my_col[x] = 0; }
+	uint8_t* tr = TRACE ? a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base) : nullptr;
+	const int ibase = g.j0 + g.d_begin;
+	const int steps = (band > 0 && g.cols > 0) ? 2 * (g.cols - 1) + band : 0;
+	for (int s = 0; s < steps; ++s) {
+#pragma unroll
+		for (int x = 0; x < WIDE_RPT; ++x) {
+			const int r = tid + x * WIDE_THREADS, c2 = s - r;
+			if (r < band && c2 >= 0 && !(c2 & 1) && (c2 >> 1) < g.cols) {
+				const int c = c2 >> 1, i = ibase + c + r;
+				if (i >= 0 && i < g.qlen) {
+					const int sc = (int)P->score[((g.q[i] & 31) << 5) | (g.t[g.j0 + c] & 31)] + (int)g.cb[i];
+					const int e_in = hg[r + 1], f_in = (r > 0 && i > 0) ? vg[r] : 0;
+					const int hd = h[x] + sc;
+					const int cur = max(max(max(hd, e_in), f_in), 0);
+					const int open = max(cur - go, 0);
+					const int e = max(max(e_in - ge, 0), open), f = max(max(f_in - ge, 0), open);
+					if (TRACE) {
+						const unsigned nib = trace_flags(hd, e_in, f_in, open, ge);
+						const int m = c + (r >> 1), lane = r / R, k = r - lane * R;
+						uint8_t* p = tr + ((size_t)m * 32 + lane) * (size_t)(R >> 1) + (k >> 1);
+						*p = (uint8_t)(*p | (nib << ((k & 1) * 4)));
+					}
+					if (cur > my_best[x]) { my_best[x] = cur; my_col[x] = c; }
+					hg[r] = e; vg[r + 1] = f;
+					h[x] = cur;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	__syncthreads();
+#pragma unroll
+	for (int x = 0; x < WIDE_RPT; ++x) {
+		const int r = tid + x * WIDE_THREADS;
+		if (r < band) { hg[r] = my_best[x]; vg[r] = my_col[x]; }
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int bv = 0, bc = 0, br = 0;
+		for (int k = 0; k < band; ++k) {
+			const int v = hg[k], c = vg[k];
+			if (v > bv || (v == bv && v > 0 && c <= bc)) { bv = v; bc = c; br = k; }
+		}
+		a.score[pi] = bv;
+		if (TRACE) { a.end_cell[2 * (size_t)pi] = bc; a.end_cell[2 * (size_t)pi + 1] = br; }
+	}
+}
+
 // ---- device-side preparation: geometry, register-tile bin, cost class, bucket histogram ------------------------------
 struct PrepOut {
 	uint8_t* key;        // [n] bucket = (bin * 2 + long) * 16 + cost class (heavy problems first inside a bucket group)
@@ -636,16 +724,16 @@ __global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t 
 	const int B = p.d_end - p.d_begin;
 	const int i1 = max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
 	const int cols = min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
-	if (B > 1024) { atomicMax(o.flag, 2u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
+	if (B > DMND_MAX_BAND) { atomicMax(o.flag, 2u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
 	const bool live = B > 0 && cols > 0;
 	const int R = tile_rows(B);
-	const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : 4;
+	const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : R == 32 ? 4 : R == 64 ? 5 : 6;
 	const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
 	const int cls = 15 - min(15, (63 - __clzll(cells + 1)) >> 1);
 	const int lng = (qlen + 32 * R + 4) > 768 ? 1 : 0;
-	// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (bucket 160, no trace bytes)
+	// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (bucket 240, no trace bytes)
 	const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
-	const uint8_t key = stats ? (uint8_t)160 : (uint8_t)((b * 2 + lng) * 16 + cls);
+	const uint8_t key = stats ? (uint8_t)240 : (uint8_t)((b * 2 + lng) * 16 + cls);
 	atomicMax(&o.maxq[key], (unsigned)qlen);
 	o.key[k] = key;
 	const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
@@ -680,7 +768,8 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		fprintf(stderr, "[dmnd profile]     swipe %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
 		tp = now;
 	};
-	static const int RS[5] = { 2, 4, 8, 16, 32 };
+	static const int RS[7] = { 2, 4, 8, 16, 32, 64, 128 };
+	constexpr int NG = 14;  // launch groups g = bin * 2 + long-query flag; bucket 240 = statistics passes
 	const unsigned nb = (unsigned)((n + 255) / 256);
 	// ---- device buffers
 	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
@@ -716,13 +805,13 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, 257 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
-	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 1024 diagonals is not supported by this build"); return 1; }
+	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 4096 diagonals is not supported by this build"); return 1; }
 	unsigned int off[257];
 	off[0] = 0;
 	for (int k = 0; k < 256; ++k) off[k + 1] = off[k] + hp[k];
 	// launch groups: g = bin * 2 + long-query flag; inside a group the buckets are ordered heavy -> light
-	size_t grp_begin[11];
-	for (int g = 0; g <= 10; ++g) grp_begin[g] = off[std::min(g * 16, 256)];
+	size_t grp_begin[NG + 1];
+	for (int g = 0; g <= NG; ++g) grp_begin[g] = off[std::min(g * 16, 256)];
 	std::memcpy(hp + 512, off, 256 * sizeof(unsigned int));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(d_counters + 512, hp + 512, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
 	scatter_kernel<<<nb, 256, 0, st>>>(d_key, (uint32_t)n, d_counters + 512, d_counters + 768, ctx->b_order.as<uint32_t>());
@@ -744,7 +833,11 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		const size_t per_warp = (size_t)27 * (size_t)w4;
 		const int warps = (int)std::min<size_t>(4, ((size_t)200 << 10) / per_warp);
 		a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.order_pos0 = (uint32_t)pos;
-		if (force_generic || warps == 0) {
+		if (R > 32) {  // bands beyond 1024 diagonals: one CTA per problem
+			if (tr_mode) swipe_wide_kernel<true><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
+			else swipe_wide_kernel<false><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
+		}
+		else if (force_generic || warps == 0) {
 			const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
 			if (tr_mode) launch_bin<true>(R, a, ctx->d_params, grid, st); else launch_bin<false>(R, a, ctx->d_params, grid, st);
 		}
@@ -766,7 +859,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	};
 
 	if (!trace) {
-		for (int g = 0; g < 10; ++g) {
+		for (int g = 0; g < NG; ++g) {
 			const size_t pos = grp_begin[g], e = grp_begin[g + 1];
 			if (e > pos) { a.work = d_counters + g; if (launch_dp(g, pos, e, false)) return 1; }
 		}
@@ -791,14 +884,14 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		}
 		// group bases and totals come from the per-bucket cost histogram of the prep kernel (already on the host): the scans
 		// above stay on the device, no second synchronisation
-		uint64_t* gbase = hq + 260;  // [0..10] trace bytes before group g
+		uint64_t* gbase = hq + 260;  // [0..NG] trace bytes before group g
 		gbase[0] = 0;
-		for (int g = 0; g < 10; ++g) {
+		for (int g = 0; g < NG; ++g) {
 			uint64_t c = 0;
 			for (int k = 0; k < 16; ++k) c += hq[g * 16 + k];
 			gbase[g + 1] = gbase[g] + c;
 		}
-		const uint64_t trace_total = gbase[10];  // (the statistics bucket 160 carries no trace)
+		const uint64_t trace_total = gbase[NG];  // (the statistics bucket 240 carries no trace)
 		ts_total = hq[256];
 		if (transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
 		if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
@@ -818,7 +911,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			excl[n] = trace_total;
 		}
 		lap("trace prefix");
-		for (int g = 0; g < 10; ++g) {
+		for (int g = 0; g < NG; ++g) {
 			size_t pos = grp_begin[g];
 			const size_t gend = grp_begin[g + 1];
 			while (pos < gend) {
@@ -835,6 +928,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
 				a.work = d_counters;
 				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = base;
+				if (RS[g >> 1] > 32) DMND_CUDA_CHECK(cudaMemsetAsync(ctx->b_trace.p, 0, (size_t)bytes, st));  // the wide kernel ORs nibbles in
 				if (launch_dp(g, pos, e, true)) return 1;
 				WalkArgs wa;
 				wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
@@ -849,12 +943,13 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				pos = e;
 			}
 		}
-		if (hp[160]) {  // statistics passes, one CTA per problem
+		if (hp[240]) {  // statistics passes, one CTA per problem
 			StatsArgs sa;
 			sa.q_letters = a.q_letters; sa.q_bias = a.q_bias; sa.r_letters = a.r_letters; sa.q_limits = a.q_limits; sa.r_limits = a.r_limits;
-			sa.probs = a.probs; sa.order = ctx->b_order.as<uint32_t>() + off[160]; sa.n = hp[160];
+			sa.probs = a.probs; sa.order = ctx->b_order.as<uint32_t>() + off[240]; sa.n = hp[240];
 			sa.res = ctx->b_results.as<dmnd_dp_result>();
-			swipe_stats_kernel<<<hp[160], 1024, 0, st>>>(sa, ctx->d_params);
+			DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMND_STATS_SMEM));
+			swipe_stats_kernel<<<hp[240], WIDE_THREADS, DMND_STATS_SMEM, st>>>(sa, ctx->d_params);
 			++ctx->launches;
 			DMND_CUDA_CHECK(cudaGetLastError());
 		}

@@ -203,6 +203,54 @@ def test_banded_swipe_statistics_passes_above_max_swipe_dp(oracle_lib, product_l
     o.close(); g.close()
 
 
+def test_banded_swipe_bands_wider_than_1024_diagonals(oracle_lib, product_lib):
+    """Bands of 1025..4096 diagonals (chains with far-apart diagonals on very long sequences) run on the one-CTA-per-problem
+    kernels: same scores, end cells, tracebacks, transcripts and statistics passes as the oracle; > 4096 is an error."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("long")
+    qlen = np.diff(q_lim) - 1
+    tlen = np.diff(r_lim) - 1
+    longq = np.flatnonzero(qlen > 6000)[:3]
+    longt = np.flatnonzero(tlen > 6000)[:3]
+    P = []
+    for k, (q, t) in enumerate(zip(longq, longt)):
+        for wdt, c in ((1025, 0), (1800, -300), (2049, 200), (4096, 0)):
+            lo, hi = -(int(tlen[t]) - 1), int(qlen[q])
+            d0 = max(lo, c - wdt // 2); d1 = min(hi, d0 + wdt)
+            P.append((int(q), int(t), d0, d1))
+    # every long query against every long protein (one of them is its source): real alignments cross wide bands too
+    P += [(int(q), int(t), -700, 700) for q in longq for t in np.flatnonzero(tlen > 6000)]
+    P += random_problems(w, q_lim, r_lim, np.random.default_rng(3), 50)
+    probs = np.array(P, dtype=api.PROBLEM_DTYPE)
+    bias = np.random.default_rng(4).integers(-2, 2, size=q_raw.size).astype(np.int8)
+    o, g = both(oracle_lib, product_lib, threads=8)
+    cap = int(sum(qlen[p[0]] + tlen[p[1]] for p in P))
+    out = []
+    for c in (o, g):
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.set_bias(qb, bias, q_raw.size)
+        s, _ = c.banded_swipe(qb, rb, probs, traceback=False)
+        t, tr = c.banded_swipe(qb, rb, probs, traceback=True, transcript_cap=cap)
+        st, _ = c.banded_swipe(qb, rb, probs, traceback=True)  # statistics passes for the big ones
+        out.append((s, t, tr, st))
+        if c is g:
+            with pytest.raises(api.DmndError, match="4096"):
+                c.banded_swipe(qb, rb, np.array([(int(longq[0]), int(longt[0]), -2500, 2500)], dtype=api.PROBLEM_DTYPE), traceback=False)
+        c.free_block(qb); c.free_block(rb)
+    (so, to, tro, sto), (sg, tg, trg, stg) = out
+    assert np.array_equal(so["score"], sg["score"])
+    for f in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length", "gaps", "positives", "transcript_len"):
+        assert np.array_equal(to[f], tg[f]), f
+    for f in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length", "gaps"):
+        assert np.array_equal(sto[f], stg[f]), f
+    for k in range(len(P)):
+        assert np.array_equal(tro[to["transcript_off"][k]: to["transcript_off"][k] + to["transcript_len"][k]],
+                              trg[tg["transcript_off"][k]: tg["transcript_off"][k] + tg["transcript_len"][k]]), k
+    wide = np.array([p[3] - p[2] > 1024 for p in P])
+    assert (so["score"][wide] > 1000).sum() >= 2, "real alignments must cross the wide bands"
+    o.close(); g.close()
+
+
 def test_banded_swipe_profile_sizes_around_the_48k_shared_memory_default(oracle_lib, product_lib):
     """The per-warp profile is 27 x (max query + 32 R + 4) bytes; launches whose dynamic shared memory lands just below
     48 KB (where static + dynamic crosses the default limit) must still run: one call per maximum query length."""
@@ -337,3 +385,20 @@ def test_transcript_is_consistent_with_coordinates(product_lib):
         assert (i, j) == (x["q_end"], x["t_end"])
         assert score == x["score"] and ident == x["identities"] and mism == x["mismatches"]
         assert len(ops) == x["length"] and gap_open == x["gap_openings"]
+
+
+@pytest.mark.parametrize("name,level,extra", [("edge", "l1", []), ("c1", "l0", ["--comp-based-stats", "0"]), ("long", "l1", [])])
+def test_cli_binary_reproduces_reference_fmt6(product_lib, name, level, extra, tmp_path):
+    """The C++ command line (host/cli.cpp over the C ABI): FASTA in, fmt 6 out, byte-identical to the reference's file."""
+    import subprocess
+    from diamond_b200 import synth
+    from conftest import ROOT
+    w, *_ = workload_blocks(name)
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    cli = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+    r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-o", o, "-p", "8", "--masking", "0", "--motif-masking", "0"] + extra,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
