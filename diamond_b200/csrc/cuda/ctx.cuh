@@ -138,6 +138,15 @@ struct PhaseTimer {  // CUDA events on the library's stream, accumulated per pha
 		cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
 		c->phase_ms[ph] += ms;
 	}
+	// split form for phases with a host decision in the middle: mark_end() closes the interval on the stream without
+	// waiting, collect() adds it up once the stream is known to have passed the mark, restart() opens the next interval --
+	// the host gap between the two intervals is not counted as device time
+	void mark_end() { cudaEventRecord(c->ev_b, c->stream); }
+	void collect() {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->phase_ms[ph] += ms;
+	}
+	void restart() { cudaEventRecord(c->ev_a, c->stream); }
 };
 
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters);

@@ -802,8 +802,10 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	uint64_t* hq = (uint64_t*)(hp + 1536);  // [0..255] cost per bucket, [256] sum of tslen, then [260..270] group bases
+	t_dp.mark_end();  // device time of the prep kernel; the host's binning decisions below are not device time
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, 257 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
+	t_dp.collect();
 	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
 	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 4096 diagonals is not supported by this build"); return 1; }
 	unsigned int off[257];
@@ -813,6 +815,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	size_t grp_begin[NG + 1];
 	for (int g = 0; g <= NG; ++g) grp_begin[g] = off[std::min(g * 16, 256)];
 	std::memcpy(hp + 512, off, 256 * sizeof(unsigned int));
+	t_dp.restart();
 	DMND_CUDA_CHECK(cudaMemcpyAsync(d_counters + 512, hp + 512, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
 	scatter_kernel<<<nb, 256, 0, st>>>(d_key, (uint32_t)n, d_counters + 512, d_counters + 768, ctx->b_order.as<uint32_t>());
 	ctx->launches += 2;
