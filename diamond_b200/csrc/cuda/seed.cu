@@ -309,11 +309,12 @@ __device__ bool left_most_filter(const LmCtx& x, const int8_t* query, int query_
 // Chunk pass 2: one thread per (query loc, reference loc) pair of the chunk's surviving keys.
 __global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
                                const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
-                               const uint64_t* __restrict__ pair_off /* exclusive scan, n_entries + 1 */, uint64_t total_pairs,
+                               const uint64_t* __restrict__ pair_off /* exclusive scan, n_entries + 1: pair_off[n_entries] = pairs of this chunk */,
                                const uint32_t* __restrict__ ref_locs, LmCtx x, dmnd_hit* hits, unsigned long long* hit_count,
                                unsigned long long* counters) {
+	// the grid is sized from an upper bound known on the host (pairs over all chunks): the chunk's own total stays on the device
 	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (pid >= total_pairs) return;
+	if (pid >= pair_off[n_entries]) return;
 	// entry = last e with pair_off[e] <= pid
 	size_t lo = 0, hi = n_entries;
 	while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
@@ -474,9 +475,11 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	PhaseTimer timer(ctx, PH_SEED);
 
 	// counters: [0] seeds_hit (filled on host) [1] seed_hits [2] tm1 [3] tm3 [4] ref count [5] entry count [6] hit count [7] masked
-	if (ctx->b_counters.ensure(16 * sizeof(unsigned long long))) return 1;
+	// ... [16 + chunk] (q,s) pairs of each chunk
+	constexpr int NCNT = 16 + 64;
+	if (ctx->b_counters.ensure(NCNT * sizeof(unsigned long long))) return 1;
 	unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), st));
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, NCNT * sizeof(unsigned long long), st));
 
 	// ---- reference index: the block's own (dmnd_block_build_index, shared by all lanes) or a private one built now
 	RefIndex& own = ctx->own_index;
@@ -497,19 +500,20 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 
 	// ---- probe every query position
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
-	unsigned long long nent = 0;
+	unsigned long long nent = 0, pairs_bound = 0;
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
 		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
-		if (fetch_u64(ctx, d_cnt + 5, &nent)) return 1;
+		// entry count and the (q,s) pair bound of this pass (count + 1 == d_cnt + 6) in one round trip
+		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 5, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		DMND_CUDA_CHECK(stream_wait(ctx, st));
+		nent = ((unsigned long long*)ctx->h_pinned)[0]; pairs_bound = ((unsigned long long*)ctx->h_pinned)[1];
 		if (nent <= ecap) break;
 		ecap = (size_t)nent + 1024;  // rare: rerun with an exact capacity
 	}
 	Entry* d_entries = ctx->b_entries.as<Entry>();
-	unsigned long long pairs_bound = 0;
-	if (fetch_u64(ctx, d_cnt + 6, &pairs_bound)) return 1;  // written by the last probe pass (count + 1 == d_cnt + 6)
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
 	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
 	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;
@@ -520,6 +524,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	// ---- chunks, in the reference's order
 	const uint32_t parts_total = 1u << hp.seedp_bits;
 	const uint32_t nchunks = std::min<uint32_t>((uint32_t)hp.index_chunks, parts_total);
+	if (nchunks > 64) { set_error("dmnd_search_shape: more than 64 index chunks are not supported"); return 1; }
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
 	if (ctx->b_pairs.ensure((nent + 2) * 8 * 2)) return 1;
 	uint64_t* d_pairs = ctx->b_pairs.as<uint64_t>();
@@ -536,20 +541,24 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		mask_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(query->letters, P, sid, d_entries, (size_t)nent, pb, pe, d_pairs, d_key_seen, d_cnt);
 		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st));
 		ctx->launches += 3;
-		unsigned long long total_pairs = 0;
-		if (fetch_u64(ctx, (const unsigned long long*)(d_pair_off + nent), &total_pairs)) return 1;
-		seed_hits_total += total_pairs;
-		if (total_pairs == 0) continue;
+		// no host round trip inside the chunk loop: the chunk's pair total stays on the device (stage12 reads it, a copy goes
+		// to the counters), the grid covers the bound over all chunks and surplus CTAs leave at once
+		DMND_CUDA_CHECK(cudaMemcpyAsync(d_cnt + 16 + chunk, d_pair_off + nent, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+		if (pairs_bound == 0) continue;
 		LmCtx x;
 		x.P = P; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
 		x.cur_matcher = ctx->d_matcher[sid + 1]; x.cur_minlen = ctx->matcher_minlen[sid + 1]; x.cur_suffix = ctx->matcher_suffix[sid + 1];
 		x.prev_matcher = ctx->d_matcher[sid]; x.prev_minlen = ctx->matcher_minlen[sid]; x.prev_suffix = ctx->matcher_suffix[sid];
-		stage12_kernel<<<(unsigned)((total_pairs + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
-			d_pair_off, total_pairs, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+		stage12_kernel<<<(unsigned)((pairs_bound + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
+			d_pair_off, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
 		++ctx->launches;
-		unsigned long long nh = 0;
-		if (fetch_u64(ctx, d_cnt + 6, &nh)) return 1;
-		hits_total = (size_t)nh;
+	}
+	{
+		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt, NCNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		DMND_CUDA_CHECK(stream_wait(ctx, st));
+		const unsigned long long* hcn = (const unsigned long long*)ctx->h_pinned;
+		hits_total = (size_t)hcn[6];
+		for (uint32_t chunk = 0; chunk < nchunks; ++chunk) seed_hits_total += hcn[16 + chunk];
 	}
 
 	// ---- group hits by query (stable order inside a query is not required)
