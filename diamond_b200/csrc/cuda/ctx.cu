@@ -429,7 +429,13 @@ void dmnd_host_free(dmnd_ctx* ctx, void* p) {
 
 int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
-	return hits_xdrop_impl(ctx, query, ref, h, raw_xdrop, host, cap);
+	return hits_xdrop_impl(ctx, query, ref, h, raw_xdrop, host, nullptr, cap);
+}
+
+int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host,
+                          dmnd_hit_site* sites, size_t cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return hits_xdrop_impl(ctx, query, ref, h, raw_xdrop, host, sites, cap);
 }
 
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {

@@ -351,7 +351,7 @@ __global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, u
 // xdrop_ungapped (dp/ungapped_align.cpp:150-214, ScoreOnly + bias): one thread per hit
 __global__ void xdrop_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ q_bias, const int64_t* __restrict__ q_limits,
                              const int8_t* __restrict__ r_letters, const int64_t* __restrict__ r_limits, uint32_t nr,
-                             const dmnd_hit* __restrict__ hits, size_t n, const DevParams* __restrict__ P, int xdrop, dmnd_segment* out) {
+                             const dmnd_hit* __restrict__ hits, size_t n, const DevParams* __restrict__ P, int xdrop, dmnd_segment* out, dmnd_hit_site* sites) {
 	__shared__ int8_t s_score[1024];
 	for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_score[i] = P->score[i];
 	__syncthreads();
@@ -384,20 +384,23 @@ __global__ void xdrop_kernel(const int8_t* __restrict__ q_letters, const int8_t*
 		++q; ++s; ++n1;
 	}
 	out[k] = dmnd_segment{ qa - delta, sa - delta, len + delta, score };
+	if (sites) sites[k] = dmnd_hit_site{ a, sa };
 }
 
-int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, size_t cap) {
+int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, dmnd_hit_site* sites, size_t cap) {
 	if (cap < h->n) { set_error("dmnd_hits_xdrop: buffer too small"); return 1; }
 	if (h->n == 0) return 0;
-	if (ctx->b_pairs.ensure(h->n * sizeof(dmnd_segment))) return 1;
+	if (ctx->b_pairs.ensure(h->n * (sizeof(dmnd_segment) + sizeof(dmnd_hit_site)))) return 1;
+	dmnd_hit_site* d_sites = sites ? reinterpret_cast<dmnd_hit_site*>(ctx->b_pairs.as<dmnd_segment>() + h->n) : nullptr;
 	PhaseTimer t(ctx, PH_SEED);
 	xdrop_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, ctx->stream>>>(query->letters, query->bias, query->limits, ref->letters, ref->limits, ref->nseq,
-		h->d, h->n, ctx->d_params, raw_xdrop, ctx->b_pairs.as<dmnd_segment>());
+		h->d, h->n, ctx->d_params, raw_xdrop, ctx->b_pairs.as<dmnd_segment>(), d_sites);
 	++ctx->launches;
 	DMND_CUDA_CHECK(cudaGetLastError());
 	DMND_CUDA_CHECK(cudaMemcpyAsync(host, ctx->b_pairs.p, h->n * sizeof(dmnd_segment), cudaMemcpyDeviceToHost, ctx->stream));
+	if (sites) DMND_CUDA_CHECK(cudaMemcpyAsync(sites, d_sites, h->n * sizeof(dmnd_hit_site), cudaMemcpyDeviceToHost, ctx->stream));
 	t.stop();
-	ctx->d2h_bytes += h->n * sizeof(dmnd_segment);
+	ctx->d2h_bytes += h->n * (sizeof(dmnd_segment) + (sites ? sizeof(dmnd_hit_site) : 0));
 	return 0;
 }
 

@@ -341,7 +341,8 @@ struct Workspace {
 	std::vector<ThreadCtx> tc;
 	HostBuf<dmnd_hit> hv;
 	HostBuf<dmnd_segment> segv;
-	struct HitSeg { dmnd_hit h; dmnd_segment s; };
+	HostBuf<dmnd_hit_site> sitev;
+	struct HitSeg { dmnd_hit h; dmnd_segment s; dmnd_hit_site site; };
 	std::vector<HitSeg> hs;
 	std::vector<size_t> qstart;
 	std::vector<QueryState> qs;
@@ -402,7 +403,6 @@ template<typename T, typename Cmp> static void stable_small_sort(std::vector<T>&
 }
 
 void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end) {
-	// align/load_hits.h:44-122 (each hit carries its precomputed x-drop segment along)
 	const Env& e = env;
 	std::sort(begin, end, [](const Workspace::HitSeg& x, const Workspace::HitSeg& y) {
 		const dmnd_hit &a = x.h, &b = y.h;
@@ -416,11 +416,8 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, W
 	uint16_t score = 0;
 	for (Workspace::HitSeg* hsp = begin; hsp < end; ++hsp) {
 		const dmnd_hit* h = &hsp->h;
-		const uint64_t subj = DMND_HIT_SUBJECT(*h);
-		// SequenceSet::local_position: sequence whose [limits[t], limits[t+1]) holds subj
-		// (hits are sorted by subject position: most of them fall into the target of their predecessor)
-		const uint32_t t = (target != UINT32_MAX && (int64_t)subj < e.r_limits[target + 1]) ? target
-			: (uint32_t)(std::upper_bound(e.r_limits, e.r_limits + e.nr + 1, (int64_t)subj) - e.r_limits) - 1;
+		// SequenceSet::local_position of the subject position: delivered with the hit (dmnd_hits_xdrop_sites)
+		const uint32_t t = hsp->site.target;
 		if (t != target) {
 			if (target != UINT32_MAX) { tc.target_scores.push_back({ ntg - 1, score }); score = 0; }
 			tc.hit_begin.push_back((uint32_t)tc.seed_hits.size());
@@ -429,7 +426,7 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, W
 			++ntg;
 		}
 		const uint16_t hs = (uint16_t)DMND_HIT_SCORE(*h);
-		tc.seed_hits.push_back({ h->seed_offset, (int)((int64_t)subj - e.r_limits[t]), (int)hs, hsp->s });
+		tc.seed_hits.push_back({ h->seed_offset, hsp->site.j, (int)hs, hsp->s });
 		score = std::max(score, hs);
 	}
 	if (target != UINT32_MAX) tc.target_scores.push_back({ ntg - 1, score });
@@ -867,10 +864,11 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	if (seed_rc) return 1;
 	prof.lap("search_shape");
 	const size_t nh = dmnd_hits_count(hits);
-	if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
+	if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
-	if (nh && dmnd_hits_xdrop(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
+	// ... together with the sequence and local position of every hit (what load_hits would otherwise search for)
+	if (nh && dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 	dmnd_hits_free(ctx, hits);
 	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
@@ -906,7 +904,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			QueryState& q = w.qs[k];
 			q.qid = w.hv[w.qstart[k]].query;
-			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; }
+			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; }
 			d.load_hits(q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]);
 			d.start(q, tc);
 		}

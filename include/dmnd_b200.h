@@ -177,6 +177,12 @@ size_t dmnd_hits_count(const dmnd_hits* h);
 typedef struct dmnd_segment { int32_t i, j, len, score; } dmnd_segment; /* DiagonalSegment, util/geo/diagonal_segment.h */
 int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
                     dmnd_segment* host, size_t cap);
+/* Same, and also where each hit lies in the reference block: the sequence holding its subject position
+ * (SequenceSet::local_position, data/string_set.h) and the position inside that sequence -- load_hits (align/load_hits.h:
+ * 44-122) needs exactly this per hit, and the extension kernel has it at hand.  `sites` may be NULL. */
+typedef struct dmnd_hit_site { uint32_t target; int32_t j; } dmnd_hit_site;
+int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
+                          dmnd_segment* host, dmnd_hit_site* sites, size_t cap);
 int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap);
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
 

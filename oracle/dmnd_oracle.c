@@ -468,8 +468,8 @@ int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t
 	return 0;
 }
 /* dp/ungapped_align.cpp:150-214 (ScoreOnly) */
-int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
-                    dmnd_segment* host, size_t cap) {
+int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
+                          dmnd_segment* host, dmnd_hit_site* sites, size_t cap) {
 	const dmnd_params* p = &ctx->p;
 	if (cap < h->n) return fail("dmnd_hits_xdrop: buffer too small");
 	for (size_t k = 0; k < h->n; ++k) {
@@ -492,8 +492,13 @@ int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 			++q; ++s; ++n;
 		}
 		host[k].i = qa - delta; host[k].j = sa - delta; host[k].len = len + delta; host[k].score = score;
+		if (sites) { sites[k].target = t; sites[k].j = sa; }
 	}
 	return 0;
+}
+int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
+                    dmnd_segment* host, size_t cap) {
+	return dmnd_hits_xdrop_sites(ctx, query, ref, h, raw_xdrop, host, NULL, cap);
 }
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) { (void)ctx; if (h) { free(h->h); free(h); } }
 
