@@ -189,6 +189,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = []  # host wall time of every step of the last timed() call (each step ends with a device->host read)
+
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -196,8 +198,11 @@ def main():
         t0 = time.perf_counter()
         e0.record()
         last = None
+        step_ms.clear()
         for _ in range(n):
+            ts = time.perf_counter()
             last = fn()
+            step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -218,10 +223,12 @@ def main():
     if rank == 0:
         clocks.start()
     ms, (m, _, st), tm = timed(step_res, args.steps)
+    step_ms_res = list(step_ms)
     clk = clocks.stop() if rank == 0 else None
     for _ in range(min(args.warmup, 2)):  # the e2e path has its own first-call allocations (block pool, staging)
         step_e2e()
     ms_e2e, (m2, _, st2), tm2 = timed(step_e2e, args.steps)
+    step_ms_e2e = list(step_ms)
     cells = st["cells_round1"] + st["cells_round2"]
     tot = torch.tensor([float(cells), float(st2["cells_round1"] + st2["cells_round2"])], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -272,6 +279,7 @@ def main():
                "e2e": {"value": e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": tm2["h2d_bytes"] // args.steps,
                        "d2h_bytes_per_step": tm2["d2h_bytes"] // args.steps},
                "gpu_launches": int(tm["launches"]), "roofline": roofline, "cpu_baseline": cpu,
+               "step_ms": {"resident": step_ms_res, "e2e": step_ms_e2e},
                "breakdown_ms_per_step": {"seed_stage": st["seed_ms"], "host_bridge": st["host_bridge_ms"], "dp_round1": st["dp1_ms"], "dp_round2": st["dp2_ms"], "total": st["total_ms"]},
                "work": {"cells_per_gpu": cells, "dp_problems_round1": st["dp_problems_round1"], "dp_problems_round2": st["dp_problems_round2"], "dp_problems_fused": st["dp_problems_fused"],
                         "note": "cells = sum band x cols over the reference's round-1 and round-2 problem lists (dp/dp.h:121-124): a property of the workload, "

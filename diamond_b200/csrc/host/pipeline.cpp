@@ -403,7 +403,7 @@ template<typename T, typename Cmp> static void stable_small_sort(std::vector<T>&
 }
 
 void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end) {
-	const Env& e = env;
+	// align/load_hits.h:44-122 (each hit carries its precomputed x-drop segment and its site in the reference block along)
 	std::sort(begin, end, [](const Workspace::HitSeg& x, const Workspace::HitSeg& y) {
 		const dmnd_hit &a = x.h, &b = y.h;
 		const uint64_t sa = DMND_HIT_SUBJECT(a), sb = DMND_HIT_SUBJECT(b);
