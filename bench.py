@@ -129,6 +129,10 @@ def sample_cells_and_tsv(args, w, threads, device):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # launched plainly with --gpus N: re-launch as one rank per GPU (what the driver does itself with torch.distributed.run)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:])
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     ncpu = effective_cpus()
     ref_threads = ncpu  # the reference arm uses every host thread; our seedp_bits must follow the same -p (setup.cpp:306-309)
