@@ -11,10 +11,10 @@ CUDA := diamond_b200/csrc/cuda
 OBJ  := build/obj
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
-CXXFLAGS := -O2 -std=c++17 -fPIC -pthread -Wall -Wextra
+CXXFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -pthread -Wall -Wextra
 
 HOST_SRC := pipeline.cpp chaining.cpp scoring.cpp
-CUDA_SRC := ctx.cu swipe.cu seed.cu
+CUDA_SRC := ctx.cu swipe.cu seed.cu mask.cu
 HOST_OBJ := $(patsubst %.cpp,$(OBJ)/host/%.o,$(HOST_SRC))
 CUDA_OBJ := $(patsubst %.cu,$(OBJ)/cuda/%.o,$(CUDA_SRC))
 
@@ -26,7 +26,7 @@ oracle: oracle/_build/libdmnd_oracle.so oracle/_build/dmnd-oracle-cli
 $(OBJ)/host/%.o: $(HOST)/%.cpp $(wildcard $(HOST)/*.h) include/dmnd_b200.h
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
-$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh include/dmnd_b200.h
+$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh include/dmnd_b200.h $(HOST)/motif_table.h
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/cuda/$*.ptxas.log || (cat $(OBJ)/cuda/$*.ptxas.log; false)
 
@@ -37,9 +37,9 @@ diamond_b200/bin/dmnd-b200: $(HOST)/cli.cpp diamond_b200/libdmnd_b200.so
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) $< -o $@ -Ldiamond_b200 -ldmnd_b200 -Wl,-rpath,'$$ORIGIN/..'
 
-$(OBJ)/oracle/dmnd_oracle.o: oracle/dmnd_oracle.c include/dmnd_b200.h
+$(OBJ)/oracle/dmnd_oracle.o: oracle/dmnd_oracle.c include/dmnd_b200.h $(HOST)/motif_table.h
 	@mkdir -p $(dir $@)
-	gcc -O2 -fPIC -Wall -Wextra -c $< -o $@
+	gcc -O2 -ffp-contract=off -fPIC -Wall -Wextra -c $< -o $@
 oracle/_build/libdmnd_oracle.so: $(HOST_OBJ) $(OBJ)/oracle/dmnd_oracle.o
 	@mkdir -p $(dir $@)
 	$(CXX) -shared -pthread -o $@ $^

@@ -27,7 +27,9 @@ class Params(C.Structure):
                 ("shape_pos", (C.c_int32 * MAX_WEIGHT) * MAX_SHAPES), ("hamming_id", C.c_int32),
                 ("seedp_bits", C.c_int32), ("index_chunks", C.c_int32), ("seed_cut", C.c_double),
                 ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double),
-                ("background_scores_f32", C.c_float * 20)]
+                ("background_scores_f32", C.c_float * 20),
+                ("tantan_lr", C.c_float * 1024), ("tantan_d", C.c_float * 50), ("tantan_b2b", C.c_float), ("tantan_f2f", C.c_float),
+                ("tantan_p_repeat_end", C.c_float), ("tantan_p_mask", C.c_float), ("max_motif_len", C.c_int32)]
 
 
 class Hit(C.Structure):
@@ -57,7 +59,7 @@ class Timing(C.Structure):
 class SearchOpts(C.Structure):
     _fields_ = [("sensitivity", C.c_int32), ("threads", C.c_int32), ("index_chunks", C.c_int32),
                 ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
-                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32)]
+                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32)]
 
 
 class Match(C.Structure):
@@ -91,7 +93,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
-           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range",
+           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
@@ -113,6 +115,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_block_free.restype = None
     lib.dmnd_block_set_bias.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_block_download_letters.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.dmnd_block_mask.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.dmnd_block_mask_fetch.argtypes = [vp, vp, C.c_size_t]
     lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
     lib.dmnd_block_build_index.argtypes = [vp, vp, C.c_int]
     lib.dmnd_block_compute_bias.argtypes = [vp, vp, C.c_int]
@@ -179,7 +183,11 @@ class Context:
     """One dmnd_ctx on one device."""
 
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
-                 comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False):
+                 comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
+                 masking: int = 0, motif_masking: int = 0):
+        """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
+        wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
+        default to the reference's own defaults (1, 1)."""
         self.lib = lib or load()
         self.opts = SearchOpts()
         self.lib.dmnd_search_opts_default(C.byref(self.opts))
@@ -189,6 +197,8 @@ class Context:
         self.opts.max_target_seqs = max_target_seqs
         self.opts.max_evalue = max_evalue
         self.opts.want_transcript = int(want_transcript)
+        self.opts.masking = int(masking)
+        self.opts.motif_masking = int(motif_masking)
         self.params = Params()
         self._check(self.lib.dmnd_params_init(C.byref(self.opts), C.byref(self.params)))
         self.ctx = C.c_void_p()
@@ -211,6 +221,17 @@ class Context:
         b = C.c_void_p()
         self._check(self.lib.dmnd_block_upload(self.ctx, raw.ctypes.data, raw.size, limits.ctypes.data, len(limits) - 1, C.byref(b)))
         return b
+
+    def mask_block(self, b, algo: int, s_begin: int, s_end: int) -> np.ndarray:
+        """dmnd_block_mask + dmnd_block_mask_fetch: masks sequences [s_begin, s_end) of the resident block in place
+        (algo: 1 = tantan hard masking, 4 = motif soft-masking table, 5 = both) and returns the ascending offsets of
+        the letters that became X."""
+        n = C.c_uint64()
+        self._check(self.lib.dmnd_block_mask(self.ctx, b, algo, s_begin, s_end, C.byref(n)))
+        pos = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self.lib.dmnd_block_mask_fetch(self.ctx, pos.ctypes.data, pos.size))
+        return pos
 
     def free_block(self, b):
         self.lib.dmnd_block_free(self.ctx, b)

@@ -173,6 +173,10 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	d.left_most_interval = params->left_most_interval; d.ungapped_window = params->ungapped_window;
 	d.gap_open = params->gap_open; d.gap_extend = params->gap_extend; d.seed_cut = params->seed_cut;
 	std::memcpy(d.background_scores_f32, params->background_scores_f32, sizeof d.background_scores_f32);
+	std::memcpy(d.tantan_lr, params->tantan_lr, sizeof d.tantan_lr);
+	std::memcpy(d.tantan_d, params->tantan_d, sizeof d.tantan_d);
+	d.tantan_b2b = params->tantan_b2b; d.tantan_f2f = params->tantan_f2f; d.tantan_p_repeat_end = params->tantan_p_repeat_end;
+	d.tantan_p_mask = params->tantan_p_mask; d.max_motif_len = params->max_motif_len;
 	{
 		unsigned long long pw = 1;
 		for (int i = 0; i < params->shape_weight; ++i) pw *= (unsigned long long)params->reduction_size;
@@ -232,9 +236,10 @@ void dmnd_destroy(dmnd_ctx* c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
-		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep, &c->b_bloom };
+		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep, &c->b_bloom,
+		&c->b_mask_pb, &c->b_mask_scale, &c->b_mask_pos, &c->b_mask_pos2, &c->b_mask_cov, &c->b_mask_flag, &c->b_mask_seqs };
 	for (DevBuf* b : bufs) b->release();
-	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); f.idx.release(); }
+	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); cudaFree(f.soft); f.idx.release(); }
 	c->b_hits_out.release();
 	c->own_index.release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
@@ -260,7 +265,7 @@ static int block_alloc(dmnd_ctx* ctx, size_t raw_len, const int64_t* limits, uin
 	for (size_t k = 0; k < ctx->block_pool.size(); ++k) {
 		const dmnd_ctx::FreeBlock& f = ctx->block_pool[k];
 		if (f.cap_bytes >= padded + 64 && f.cap_seqs >= (size_t)nseq + 1 && f.cap_bytes <= 2 * (padded + 64) + (1 << 20)) {
-			b->letters = f.letters; b->bias = f.bias; b->limits = f.limits; b->cap_bytes = f.cap_bytes; b->cap_seqs = f.cap_seqs;
+			b->letters = f.letters; b->bias = f.bias; b->limits = f.limits; b->soft = f.soft; b->cap_bytes = f.cap_bytes; b->cap_seqs = f.cap_seqs;
 			b->idx = f.idx; b->idx.valid = false;  // keeps the index buffers' capacity, not their contents
 			ctx->block_pool.erase(ctx->block_pool.begin() + (ptrdiff_t)k);
 			break;
@@ -269,8 +274,9 @@ static int block_alloc(dmnd_ctx* ctx, size_t raw_len, const int64_t* limits, uin
 	if (!b->letters) {
 		b->cap_bytes = padded + 64; b->cap_seqs = (size_t)nseq + 1;
 		if (cudaMalloc(&b->letters, b->cap_bytes) != cudaSuccess || cudaMalloc(&b->bias, b->cap_bytes) != cudaSuccess
-		    || cudaMalloc(&b->limits, sizeof(int64_t) * b->cap_seqs) != cudaSuccess) {
-			cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); delete b;
+		    || cudaMalloc(&b->limits, sizeof(int64_t) * b->cap_seqs) != cudaSuccess
+		    || cudaMalloc(&b->soft, b->cap_bytes / 8 + 16) != cudaSuccess) {
+			cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); cudaFree(b->soft); delete b;
 			set_error((std::string(who) + ": cudaMalloc failed").c_str());
 			return 1;
 		}
@@ -289,6 +295,7 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	DMND_CUDA_CHECK(cudaMemcpyAsync(b->letters, letters, raw_len, cudaMemcpyHostToDevice, ctx->stream));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(b->limits, limits, sizeof(int64_t) * ((size_t)nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->soft, 0, b->cap_bytes / 8 + 16, ctx->stream));
 	t.stop();
 	ctx->h2d_bytes += raw_len + sizeof(int64_t) * ((size_t)nseq + 1);
 	*out = b;
@@ -307,6 +314,7 @@ int dmnd_block_upload_ranges(dmnd_ctx* ctx, const int8_t* letters, size_t raw_le
 	// order the copy stream behind whatever the compute streams still do with a recycled buffer: block_free synchronised them
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, cs));
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, cs));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->soft, 0, b->cap_bytes / 8 + 16, cs));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(b->limits, limits, sizeof(int64_t) * ((size_t)nseq + 1), cudaMemcpyHostToDevice, cs));
 	b->range_ready.resize((size_t)nranges, nullptr);
 	b->range_cuts.assign(cuts, cuts + nranges + 1);
@@ -340,8 +348,8 @@ void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	for (dmnd_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream);
 	cudaStreamSynchronize(ctx->copy_stream);
 	for (cudaEvent_t e : b->range_ready) if (e) cudaEventDestroy(e);
-	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->cap_bytes, b->cap_seqs, b->idx });
-	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); b->idx.release(); }
+	if (ctx->block_pool.size() < 4) ctx->block_pool.push_back(dmnd_ctx::FreeBlock{ b->letters, b->bias, b->limits, b->soft, b->cap_bytes, b->cap_seqs, b->idx });
+	else { cudaFree(b->letters); cudaFree(b->bias); cudaFree(b->limits); cudaFree(b->soft); b->idx.release(); }
 	delete b;
 }
 
@@ -465,6 +473,15 @@ int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_be
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (q_begin > q_end || q_end > b->nseq) { set_error("dmnd_block_clear_seed_mask_range: bad range"); return 1; }
 	return clear_range(ctx, b, (size_t)b->h_limits[q_begin], (size_t)b->h_limits[q_end]);
+}
+
+int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return block_mask_impl(ctx, b, algo, s_begin, s_end, n_hard);
+}
+int dmnd_block_mask_fetch(dmnd_ctx* ctx, uint64_t* positions, size_t cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return block_mask_fetch_impl(ctx, positions, cap);
 }
 
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out, dmnd_stage_counters* counters) {

@@ -53,6 +53,11 @@ struct DevParams {
 	double seed_cut;
 	double lnfact[DMND_MAX_WEIGHT + 1];
 	float background_scores_f32[20];
+	// tantan (masking/tantan.cpp:121-214): likelihood ratios [a*32+b], per-offset repeat start probabilities, transition constants
+	float tantan_lr[1024];
+	float tantan_d[50];
+	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
+	int32_t max_motif_len;
 };
 
 enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
@@ -77,6 +82,8 @@ struct dmnd_block {
 	int8_t* letters = nullptr;  // device
 	int8_t* bias = nullptr;     // device, same offsets as letters
 	int64_t* limits = nullptr;  // device
+	uint32_t* soft = nullptr;   // device, one bit per letter: inside a MaskingTable entry (abundant motif), see dmnd_block_mask
+	bool has_soft = false;      // dmnd_block_mask(MOTIF) has run: dmnd_search_shape reads `soft`
 	size_t raw_len = 0;
 	uint32_t nseq = 0;
 	std::vector<int64_t> h_limits;  // host copy (problem binning needs lengths)
@@ -102,12 +109,14 @@ struct dmnd_ctx {
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
 	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work, b_prep, b_bloom;
+	dmnd_cuda::DevBuf b_mask_pb, b_mask_scale, b_mask_pos, b_mask_pos2, b_mask_cov, b_mask_flag, b_mask_seqs;  // dmnd_block_mask scratch
+	uint64_t mask_n = 0;  // letters hard-masked by the last dmnd_block_mask on this context (sorted offsets in b_mask_pos)
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	bool force_generic_dp = false;
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
 	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
 	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)
-	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; size_t cap_bytes, cap_seqs; dmnd_cuda::RefIndex idx; };
+	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; uint32_t* soft; size_t cap_bytes, cap_seqs; dmnd_cuda::RefIndex idx; };
 	std::vector<FreeBlock> block_pool;  // device memory of freed blocks, reused by dmnd_block_upload
 	void* h_pinned = nullptr;  // small pinned staging for counters
 	size_t h_pinned_cap = 0;
@@ -152,6 +161,8 @@ struct PhaseTimer {  // CUDA events on the library's stream, accumulated per pha
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters);
 int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix);
 int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, dmnd_hit_site* sites, size_t cap);
+int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard);
+int block_mask_fetch_impl(dmnd_ctx* ctx, uint64_t* positions, size_t cap);
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 

@@ -23,13 +23,18 @@ __device__ __forceinline__ uint64_t mix40(uint64_t seed) { return (seed * 0x9E37
 
 // basic/shape.h:113-171 on the reduced sequence; a window that contains a delimiter is past the end of its sequence
 // (search/seed_array/seed_iterator.h:30-33).
-__device__ __forceinline__ bool seed_at(const DevParams* P, int sid, const int8_t* s, uint64_t& out) {
+// One bit per letter: inside a MaskingTable entry (abundant motif, dmnd_block_mask).  While seeds are enumerated such a
+// letter reads as MASK_LETTER (Block::soft_mask, data/block/block.cpp:162-171, search/seed_array/enum_seeds.h:262-270).
+__device__ __forceinline__ bool soft_bit(const uint32_t* __restrict__ soft, size_t p) { return (soft[p >> 5] >> (p & 31)) & 1u; }
+
+__device__ __forceinline__ bool seed_at(const DevParams* P, int sid, const int8_t* s, const uint32_t* __restrict__ soft, size_t p, uint64_t& out) {
 	const int span = P->shape_len[sid];
 	bool ok = true;
 	for (int k = 0; k < span; ++k) ok &= (s[k] != DMND_DELIMITER);
 	if (!ok) return false;
 	uint64_t v = 0;
 	for (int k = 0; k < P->shape_weight; ++k) {
+		if (soft && soft_bit(soft, p + (size_t)P->shape_pos[sid][k])) return false;
 		const unsigned r = P->reduction[s[P->shape_pos[sid][k]] & 31];
 		if (r == 23) return false;
 		v = v * (uint64_t)P->reduction_size + r;
@@ -39,10 +44,10 @@ __device__ __forceinline__ bool seed_at(const DevParams* P, int sid, const int8_
 }
 
 __global__ void ref_enum_kernel(const int8_t* __restrict__ letters, size_t raw_len, const DevParams* __restrict__ P, int sid,
-                                uint64_t* keys, uint32_t* vals, unsigned long long* count) {
+                                const uint32_t* __restrict__ soft, uint64_t* keys, uint32_t* vals, unsigned long long* count) {
 	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x + DMND_PERIMETER_PADDING;
 	uint64_t seed = 0;
-	const bool ok = p + DMND_PERIMETER_PADDING < raw_len && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, seed);
+	const bool ok = p + DMND_PERIMETER_PADDING < raw_len && letters[p] != DMND_DELIMITER && seed_at(P, sid, letters + p, soft, p, seed);
 	const unsigned m = __ballot_sync(0xffffffffu, ok);
 	if (m == 0) return;
 	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
@@ -108,13 +113,20 @@ struct ShapeArg {
 // Tile loader shared by the enumeration kernels: TILE consecutive letters (+ 32 halo) become "codes" in shared memory:
 // reduced class 0..9, 0x40 for MASK/STOP (reduction 23), 0x80 for the delimiter.  One global byte per letter, coalesced.
 #define SEED_TILE 1024
-__device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, size_t p0, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut) {
+__device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p0, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut) {
 	if (threadIdx.x < 32) {
 		const unsigned r = P->reduction[threadIdx.x];
 		s_lut[threadIdx.x] = threadIdx.x == DMND_DELIMITER ? 0x80 : (r == 23 ? 0x40 : (uint8_t)r);
 	}
 	__syncthreads();
-	for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) s_code[x] = s_lut[letters[p0 + x] & 31];
+	if (soft) {  // soft-masked letters read as MASK_LETTER (class flag 0x40); they are never delimiters
+		for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) {
+			const uint8_t c = s_lut[letters[p0 + x] & 31];
+			s_code[x] = (soft_bit(soft, p0 + x) && !(c & 0x80)) ? (uint8_t)0x40 : c;
+		}
+	}
+	else
+		for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) s_code[x] = s_lut[letters[p0 + x] & 31];
 	__syncthreads();
 }
 // Packed seed at tile offset `o` (basic/shape.h:113-171: base-`rsize` number of the reduced classes at the shape's '1'
@@ -131,7 +143,7 @@ __device__ __forceinline__ bool seed_from_codes(const uint8_t* s_code, int o, co
 	return flags == 0;
 }
 
-__global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ letters, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, const ShapeArg sh,
+__global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, const ShapeArg sh,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
                              const uint32_t* __restrict__ bloom, uint32_t bloom_mask,
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ l
 	__shared__ unsigned long long s_pairs, s_base;
 	const size_t p0 = p_begin + (size_t)blockIdx.x * SEED_TILE;
 	if (threadIdx.x == 0) { s_n = 0; s_pairs = 0; }
-	load_code_tile(letters, p0, P, s_code, s_lut);
+	load_code_tile(letters, soft, p0, P, s_code, s_lut);
 	for (int it = 0; it < SEED_TILE / 256; ++it) {
 		const int o = it * 256 + threadIdx.x;
 		const size_t p = p0 + o;
@@ -192,6 +204,22 @@ __device__ __forceinline__ bool seed_is_complex(const DevParams* P, int sid, con
 	double entropy = P->lnfact[P->shape_weight];
 	for (int c = 0; c < P->reduction_size; ++c) entropy -= P->lnfact[count[c]];
 	return entropy >= P->seed_cut;
+}
+
+// MaskingTable::remove(template_len, add_bit_mask = true) after the query enumeration (masking/masking.cpp:96-107 through
+// search/seed_array/enum_seeds.h:255-260, EnumCfg::mask_seeds of the query side, search/stage0.cpp:139-142): an entry [b, e)
+// leaves SEED_MASK on [max(b - span + 1, 0), e) of its sequence, i.e. on every position j that sees a soft-masked letter of
+// its own sequence within [j, j + span).  One thread per position; each writes only its own byte.
+__global__ void motif_seedmask_kernel(int8_t* q_letters, const uint32_t* __restrict__ soft, size_t p_begin, size_t p_end, int span) {
+	const size_t j = p_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= p_end) return;
+	const uint32_t w0 = soft[j >> 5], w1 = soft[(j >> 5) + 1];
+	const uint32_t v = __funnelshift_r(w0, w1, (unsigned)(j & 31)) & ((1u << span) - 1u);
+	if (v == 0) return;
+	for (int k = 0; k < span; ++k) {
+		if ((q_letters[j + k] & 31) == DMND_DELIMITER) return;
+		if ((v >> k) & 1u) { q_letters[j] = (int8_t)(q_letters[j] | DMND_SEED_MASK); return; }
+	}
 }
 
 // Chunk pass 1: entropy masking.  pairs[e] = number of (q,s) pairs entry e contributes to THIS chunk's search.
@@ -432,7 +460,7 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	if (ctx->b_keys.ensure(rpos * 8) || ix.keys.ensure(rpos * 8) || ctx->b_vals.ensure(rpos * 4) || ix.locs.ensure(rpos * 4)
 	    || ix.bucket.ensure((nbuckets + 1) * 4 * 2))
 		return 1;
-	ref_enum_kernel<<<(unsigned)((rpos + 255) / 256), 256, 0, st>>>(ref->letters, ref->raw_len, P, sid, ctx->b_keys.as<uint64_t>(), ctx->b_vals.as<uint32_t>(), d_cnt + 4);
+	ref_enum_kernel<<<(unsigned)((rpos + 255) / 256), 256, 0, st>>>(ref->letters, ref->raw_len, P, sid, ref->has_soft ? ref->soft : nullptr, ctx->b_keys.as<uint64_t>(), ctx->b_vals.as<uint32_t>(), d_cnt + 4);
 	++ctx->launches;
 	unsigned long long nref = 0;
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -507,7 +535,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, query->has_soft ? query->soft : nullptr, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
 		// entry count and the (q,s) pair bound of this pass (count + 1 == d_cnt + 6) in one round trip
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 5, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -517,6 +545,10 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		ecap = (size_t)nent + 1024;  // rare: rerun with an exact capacity
 	}
 	Entry* d_entries = ctx->b_entries.as<Entry>();
+	if (query->has_soft && qpos > 0) {  // before any chunk's left-most filter looks at SEED_MASK bits
+		motif_seedmask_kernel<<<(unsigned)((qpos + 255) / 256), 256, 0, st>>>(query->letters, query->soft, qp_begin, qp_end, hp.shape_len[sid]);
+		++ctx->launches;
+	}
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
 	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
 	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;

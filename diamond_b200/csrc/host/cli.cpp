@@ -76,7 +76,7 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 
 [[noreturn]] void usage(const char* msg) {
 	fprintf(stderr, "Error: %s\nusage: dmnd-b200 blastp -q QUERY.faa -d DB.faa -o OUT [--fast] [-p N] [-c N] [-k N] [-e X] "
-	                "[--comp-based-stats 0|1] [--masking 0] [--motif-masking 0] [-f 6] [--log]\n", msg);
+	                "[--comp-based-stats 0|1] [--masking 0|none|1|tantan] [--motif-masking 0|1] [-f 6] [--log]\n", msg);
 	exit(1);
 }
 
@@ -91,7 +91,7 @@ int main(int argc, char** argv) {
 		dmnd_search_opts o;
 		dmnd_search_opts_default(&o);
 		std::string qf, df, of;
-		bool log = false, masking_off = false, motif_off = false;
+		bool log = false;
 		for (int i = 2; i < argc; ++i) {
 			const std::string a = argv[i];
 			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
@@ -104,15 +104,20 @@ int main(int argc, char** argv) {
 			else if (a == "-k" || a == "--max-target-seqs") o.max_target_seqs = atoi(val());
 			else if (a == "-e" || a == "--evalue") o.max_evalue = atof(val());
 			else if (a == "--comp-based-stats") o.comp_based_stats = atoi(val());
-			else if (a == "--masking") { const std::string v = val(); if (v != "0" && v != "none") usage("only --masking 0 is implemented (tantan is a 'next' row)"); masking_off = true; }
-			else if (a == "--motif-masking") { if (std::string(val()) != "0") usage("only --motif-masking 0 is implemented"); motif_off = true; }
+			else if (a == "--masking") {  // masking/masking.cpp:42-48: 0/none, 1/tantan (seg is not part of this build)
+				const std::string v = val();
+				if (v == "0" || v == "none") o.masking = 0; else if (v == "1" || v == "tantan") o.masking = 1; else usage("--masking must be 0, none, 1 or tantan (seg is not implemented)");
+			}
+			else if (a == "--motif-masking") {  // search/setup.cpp:322-336
+				const std::string v = val();
+				if (v == "0") o.motif_masking = 0; else if (v == "1") o.motif_masking = 1; else usage("Permitted values for --motif-masking: 0, 1");
+			}
 			else if (a == "-f" || a == "--outfmt") { if (std::string(val()) != "6") usage("only -f 6 is implemented"); }
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
-		if (!masking_off || !motif_off) usage("this build requires --masking 0 --motif-masking 0 (masking parity is a 'next' row)");
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
 		read_fasta(qf, q);

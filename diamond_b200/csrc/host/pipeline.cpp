@@ -227,9 +227,45 @@ inline int banded_cols(int qlen, int tlen, int d_begin, int d_end) {  // dp/dp.h
 	return std::min(qlen - 1 - d_begin, tlen - 1) + 1 - pos;
 }
 
+// Host view of a block whose letters were hard-masked on the device (dmnd_block_mask): the caller's letter image stays
+// const; sequences that contain masked letters get a patched private copy (with the delimiter on either side, as the
+// x-drop and chaining loops expect), every other sequence is read in place.  Read-only after build().
+struct PatchSet {
+	std::vector<uint64_t> bits;      // one bit per sequence: has a patched copy
+	std::vector<uint32_t> ids;       // ascending sequence ids with a copy
+	std::vector<size_t> off;         // start of the copy (its leading delimiter) in `arena`
+	std::vector<int8_t> arena;
+	bool empty() const { return ids.empty(); }
+	// pos[0..n): ascending offsets of masked letters in the block image; [s_begin, s_end) = the sequences they can lie in
+	void build(const int8_t* letters, const int64_t* limits, uint32_t nseq, uint32_t s_begin, uint32_t s_end, const uint64_t* pos, size_t n) {
+		bits.assign(((size_t)nseq + 63) / 64, 0); ids.clear(); off.clear(); arena.clear();
+		const int64_t* lb = limits + s_begin;
+		for (size_t k = 0; k < n;) {
+			const uint32_t sid = (uint32_t)(std::upper_bound(lb, limits + s_end + 1, (int64_t)pos[k]) - limits) - 1;
+			const int64_t b = limits[sid], e = limits[sid + 1];  // [b, e - 1) letters, e - 1 = delimiter
+			const size_t o = arena.size();
+			arena.resize(o + (size_t)(e - b) + 1);
+			std::memcpy(arena.data() + o, letters + b - 1, (size_t)(e - b) + 1);
+			for (; k < n && (int64_t)pos[k] < e; ++k) arena[o + 1 + (size_t)((int64_t)pos[k] - b)] = MASK_LETTER;
+			bits[sid >> 6] |= (uint64_t)1 << (sid & 63);
+			ids.push_back(sid); off.push_back(o);
+			lb = limits + sid + 1;
+		}
+	}
+	const int8_t* find(uint32_t sid) const {  // patched copy of the sequence, or nullptr
+		if (bits.empty() || !((bits[sid >> 6] >> (sid & 63)) & 1)) return nullptr;
+		const size_t k = (size_t)(std::lower_bound(ids.begin(), ids.end(), sid) - ids.begin());
+		return arena.data() + off[k] + 1;
+	}
+};
+
 struct Env {
 	const Scoring* sc;
 	const int8_t *q_letters, *r_letters;
+	const PatchSet *q_patch = nullptr, *r_patch = nullptr;  // hard-masked sequences (dmnd_blastp with masking); null = read in place
+	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
+	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
+	const int8_t* rseq(uint32_t t) const { const int8_t* p = r_patch ? r_patch->find(t) : nullptr; return p ? p : r_letters + r_limits[t]; }
 	const int64_t *q_limits, *r_limits;
 	uint32_t nq, nr;
 	int64_t ref_letters;
@@ -351,12 +387,16 @@ struct Workspace {
 	HostBuf<uint8_t> tr;
 	RawBuf<dmnd_match> out_matches;   // lane output when several lanes run (copied into the result afterwards)
 	RawBuf<uint8_t> out_transcripts;
+	std::vector<uint64_t> mask_pos;   // letters of this lane's query range that dmnd_block_mask turned into X
+	PatchSet q_patch;
 };
 // Process-wide: the worker pool and one workspace per lane.
 struct Shared {
 	std::mutex mtx;
 	std::unique_ptr<Pool> pool;
 	std::vector<std::unique_ptr<Workspace>> lanes;
+	std::vector<uint64_t> r_mask_pos;  // reference-block counterpart of Workspace::mask_pos / q_patch
+	PatchSet r_patch;
 	void ensure(int threads, int nlanes) {
 		if (!pool || pool->size() != threads) { pool.reset(new Pool(threads)); lanes.clear(); }
 		while ((int)lanes.size() < nlanes) lanes.emplace_back(new Workspace());
@@ -471,7 +511,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	q.prob_target.clear();
 	std::vector<dmnd_dp_problem>& plist = q.fused ? tc.p2 : tc.p1;  // fused: straight into the traceback batch
 	q.prob_begin = plist.size();
-	const int8_t* query = e.q_letters + e.q_limits[q.qid];
+	const int8_t* query = e.qseq(q.qid);
 	const int band = band_for(q.qlen);
 	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
 	const uint32_t* hb = tc.hit_begin.data() + q.tgt_off;
@@ -480,7 +520,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		const uint32_t tix = ts[k].target;
 		const uint32_t block_id = ids[tix];
 		const int slen = e.tlen(block_id);
-		const int8_t* subject = e.r_letters + e.r_limits[block_id];
+		const int8_t* subject = e.rseq(block_id);
 		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false, 0 });
 		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
 		std::sort(tc.hits.begin(), tc.hits.end());
@@ -777,6 +817,7 @@ void dmnd_search_opts_default(dmnd_search_opts* o) {
 	std::memset(o, 0, sizeof *o);
 	o->sensitivity = 0; o->threads = 8; o->index_chunks = 0; o->comp_based_stats = 1; o->max_target_seqs = 25;
 	o->max_evalue = 0.001; o->db_letters = 0; o->want_transcript = 0;
+	o->masking = 1; o->motif_masking = 1;  // the reference's defaults for blastp --fast (run/config.cpp:126-135, search/setup.cpp:43)
 }
 
 int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
@@ -817,6 +858,25 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	}
 	p->seed_cut = 0.9 * std::log(2.0) * p->shape_weight;
 	p->left_most_interval = 32; p->ungapped_window = 48; p->ungapped_evalue = 0.0;
+	{	// tantan constants, masking/masking.cpp:133-153 and masking/tantan.cpp:131-142, evaluated in the reference's types.
+		// lambda is what cbrc::LambdaCalculator (lib/tantan, a randomised root search seeded by the C library's default
+		// rand() state) returns for BLOSUM62's 20 x 20 core; tests/test_masking.py re-derives it from the reference's own
+		// LambdaCalculator.cc (oracle/ref_build lambda probe) and requires this exact double.
+		const double lambda = 0x1.4bcf16a672882p-2;  // 0.32403216734804385
+		// masking.cpp:146-151 fills the ratio for the whole 26-letter alphabet (value_traits.alphabet_size), X * _ included
+		for (int a = 0; a < 26; ++a)
+			for (int b = 0; b < 26; ++b) p->tantan_lr[a * 32 + b] = (float)std::exp(lambda * (double)sc.m8[a * 32 + b]);
+		const float p_repeat = 0.005f, p_repeat_end = 0.05f;
+		volatile float growth_rt = 1.0f / 0.9f;  // run-time value: powf below must be the C library's, as in the reference,
+		const float repeat_growth = growth_rt;   // not a compile-time folding of it
+		const int W = 50;
+		const float b2f0 = p_repeat * (1.0f - repeat_growth) / (1.0f - std::pow(repeat_growth, (float)W));
+		p->tantan_d[W - 1] = b2f0;
+		for (int i = W - 2; i >= 0; --i) p->tantan_d[i] = p->tantan_d[i + 1] * repeat_growth;
+		p->tantan_b2b = 1.0f - p_repeat; p->tantan_f2f = 1.0f - p_repeat_end; p->tantan_p_repeat_end = p_repeat_end;
+		p->tantan_p_mask = (float)0.9;  // config.tantan_minMaskProb (basic/config.cpp:402)
+		p->max_motif_len = 30;
+	}
 	return 0;
 }
 
@@ -857,7 +917,17 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	w.lane = lane;
 	// this lane's query range may still be on its way (dmnd_block_upload_ranges); its composition bias is computed here, on
 	// the lane's stream, as soon as the letters are there
-	const int prep_rc = dmnd_block_range_wait(ctx, qb, q_begin, q_end) || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
+	int prep_rc = dmnd_block_range_wait(ctx, qb, q_begin, q_end);
+	if (!prep_rc && env.mask_algo) {
+		// "Masking queries" (run/double_indexed.cpp:737-741) + the query block's motif table, for this lane's range; the host
+		// only learns WHICH letters became X and patches private copies of those sequences
+		uint64_t n_hard = 0;
+		prep_rc = dmnd_block_mask(ctx, qb, env.mask_algo, q_begin, q_end, &n_hard);
+		w.mask_pos.resize((size_t)n_hard);
+		if (!prep_rc && n_hard) prep_rc = dmnd_block_mask_fetch(ctx, w.mask_pos.data(), w.mask_pos.size());
+		if (!prep_rc) { w.q_patch.build(env.q_letters, env.q_limits, env.nq, q_begin, q_end, w.mask_pos.data(), w.mask_pos.size()); d.env.q_patch = &w.q_patch; }
+	}
+	prep_rc = prep_rc || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
 	seed_turn.wait_for(lane);
 	const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
 	seed_turn.pass(lane);
@@ -1006,10 +1076,18 @@ static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits) {
 	return p;
 }
 
+static int mask_bits(const dmnd_search_opts* o) { return (o->masking ? DMND_MASK_TANTAN : 0) | (o->motif_masking ? DMND_MASK_MOTIF : 0); }
+
+// mask_algo != 0: the blocks arrive unmasked (dmnd_blastp); the reference block is masked here, every lane masks its own
+// query range.  mask_algo == 0: resident blocks, already in their searched state.
 static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const int8_t* q_letters, const int64_t* q_limits,
                        uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
-                       dmnd_result** out) {
+                       int mask_algo, dmnd_result** out) {
 	auto t_total = Clock::now();
+	if (opts->masking < 0 || opts->masking > 1 || opts->motif_masking < 0 || opts->motif_masking > 1) {
+		dmnd_set_last_error("dmnd_blastp: masking / motif_masking must be 0 or 1 (SEG masking is not part of this build)");
+		return 1;
+	}
 	Shared& sh = shared();
 	std::lock_guard<std::mutex> guard(sh.mtx);
 	struct PoolReturn { void operator()(dmnd_result* r) const { result_pool().give(r); } };
@@ -1030,6 +1108,16 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
+	e.mask_algo = mask_algo;
+	if (mask_algo) {
+		// "Masking reference" (run/double_indexed.cpp:122-127) and the reference block's motif table, before its seed index
+		uint64_t n_hard = 0;
+		if (dmnd_block_mask(ctx, const_cast<dmnd_block*>(rb), mask_algo, 0, nr, &n_hard)) return 1;
+		sh.r_mask_pos.resize((size_t)n_hard);
+		if (n_hard && dmnd_block_mask_fetch(ctx, sh.r_mask_pos.data(), sh.r_mask_pos.size())) return 1;
+		sh.r_patch.build(r_letters, r_limits, nr, 0, nr, sh.r_mask_pos.data(), sh.r_mask_pos.size());
+		e.r_patch = &sh.r_patch;
+	}
 
 	// (the per-position composition bias of the queries is computed on the device by each lane for its own range)
 	// reference side of the seed join, once per call, shared by the lanes (the reference rebuilds it per run as well)
@@ -1088,7 +1176,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 int dmnd_blastp_resident(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, const int8_t* q_letters, const int64_t* q_limits,
                          uint32_t nq, const int8_t* r_letters, const int64_t* r_limits, uint32_t nr, const dmnd_search_opts* opts,
                          dmnd_result** out) {
-	return blastp_impl(ctx, query, ref, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, out);
+	return blastp_impl(ctx, query, ref, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, 0, out);
 }
 
 int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const int64_t* q_limits, uint32_t nq,
@@ -1102,7 +1190,7 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
 	const LanePlan plan = plan_lanes(nq, q_limits);
 	if (dmnd_block_upload_ranges(ctx, q_letters, q_raw_len, q_limits, nq, plan.cut.data(), plan.nlanes, &qb)) { dmnd_block_free(ctx, rb); return 1; }
 	prof.lap("e2e: block uploads (queries in flight)");
-	const int rc = blastp_impl(ctx, qb, rb, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, out);
+	const int rc = blastp_impl(ctx, qb, rb, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, mask_bits(opts), out);
 	prof.t = Clock::now();
 	dmnd_block_free(ctx, qb); dmnd_block_free(ctx, rb);
 	prof.lap("e2e: block frees");

@@ -208,12 +208,91 @@ def long_workload(seed: int, n_db: int = 300, n_long: int = 5, n_short_q: int = 
     return {"q_letters": np.concatenate(qs).astype(np.int8), "q_off": qo, "db_letters": np.concatenate(seqs).astype(np.int8), "db_off": dbo2, "src": None}
 
 
+def motif_codes():
+    """The reference's abundant-motif 8-mers (diamond_b200/csrc/host/motif_table.h) as letter arrays."""
+    import os, re
+    h = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "host", "motif_table.h")).read()
+    out = []
+    for c in re.findall(r"0x([0-9a-f]+)ull", h):
+        v, m = int(c, 16), []
+        for _ in range(8):
+            m.append(v % 20); v //= 20
+        out.append(np.array(m[::-1], dtype=np.int8))
+    return out
+
+
+def repeat_workload(seed: int, n_db: int = 1500, n_q: int = 400):
+    """Sequences that the masking stages act on (masking/tantan.cpp, masking/masking.cpp:110-131): tandem repeats of
+    period 1..40 with diverged copies, homopolymer / two-letter low-complexity runs, abundant-motif 8-mers (single, adjacent
+    pairs that merge into one range, chains longer than max_motif_len, at the very start and end of a sequence, covering more
+    than half of a short sequence), X letters next to repeats, sequences shorter than a motif.  Queries are mutated windows of
+    those sequences, so seeds, x-drop extensions and alignments run across masked letters."""
+    rng = np.random.default_rng(seed)
+    motifs = motif_codes()
+    seqs = []
+    for k in range(n_db):
+        L = int(np.clip(rng.gamma(4.0, 75.0), 30, 1500))
+        s = draw_letters(rng, L)
+        kind = k % 8
+        if kind in (0, 1, 2):  # tandem repeat
+            period = int(rng.integers(1, 41)) if kind != 2 else int(rng.integers(1, 4))
+            copies = int(rng.integers(3, 30))
+            unit = draw_letters(rng, period)
+            rep = np.tile(unit, copies)
+            mut = rng.random(len(rep)) < rng.uniform(0.0, 0.25)
+            rep[mut] = draw_letters(rng, int(mut.sum()))
+            at = int(rng.integers(0, max(1, L - 1)))
+            s = np.concatenate([s[:at], rep, s[at:]])
+        elif kind == 3:  # motifs
+            mode = (k // 8) % 6
+            pick = lambda: motifs[int(rng.integers(0, len(motifs)))]
+            if mode == 0: ins = [pick()]
+            elif mode == 1: ins = [pick(), pick()]                      # adjacent: merges into one 16-letter range
+            elif mode == 2: ins = [pick() for _ in range(5)]            # 40 letters > max_motif_len: not masked
+            elif mode == 3: ins = [pick(), draw_letters(rng, 3), pick()]
+            else: ins = [pick()]
+            piece = np.concatenate(ins)
+            if mode == 4: s = np.concatenate([piece, s])               # at the very start (SEED_MASK range clipped at 0)
+            elif mode == 5: s = np.concatenate([s, piece])             # at the very end
+            else:
+                at = int(rng.integers(0, L))
+                s = np.concatenate([s[:at], piece, s[at:]])
+        elif kind == 4 and (k // 8) % 5 == 0:  # short sequence, motifs cover more than half of it: nothing is masked
+            s = np.concatenate([motifs[int(rng.integers(0, len(motifs)))], draw_letters(rng, 5), motifs[int(rng.integers(0, len(motifs)))], draw_letters(rng, 4)])
+        elif kind == 4 and (k // 8) % 5 == 1:  # shorter than a motif
+            s = draw_letters(rng, int(rng.integers(1, 8)))
+        elif kind == 5:  # low complexity: two-letter run + X letters around it
+            a, b = draw_letters(rng, 2)
+            run = np.where(rng.random(int(rng.integers(10, 80))) < 0.7, a, b).astype(np.int8)
+            at = int(rng.integers(0, L))
+            s = np.concatenate([s[:at], run, s[at:]])
+            s[rng.integers(0, len(s), size=3)] = 23
+        seqs.append(s.astype(np.int8))
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in seqs], out=off[1:])
+    dbl = np.concatenate(seqs).astype(np.int8)
+    qs = []
+    for k in range(n_q):
+        sid = int(rng.integers(0, n_db))
+        src = seqs[sid]
+        L = int(min(len(src), rng.integers(20, 400)))
+        st = int(rng.integers(0, len(src) - L + 1))
+        q = src[st:st + L].copy()
+        sub = rng.random(L) < rng.uniform(0.0, 0.35)
+        q[sub] = draw_letters(rng, int(sub.sum()))
+        qs.append(q)
+    qo = np.zeros(n_q + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in qs], out=qo[1:])
+    return {"q_letters": np.concatenate(qs).astype(np.int8), "q_off": qo, "db_letters": dbl, "db_off": off, "src": None}
+
+
 WORKLOADS = {
     # name: (factory, kwargs)  -- the committed golden fixtures under tests/golden/ are keyed by these names
     "c1": (workload, dict(n_q=1000, n_db=10000, seed=1)),
     "fam2": (family_workload, dict(n_fam=4, fam_size=400, n_q=120, seed=12, member_div=(0.02, 0.12), query_div=(0.03, 0.3))),
     "edge": (edge_workload, dict(seed=21)),
     "long": (long_workload, dict(seed=33)),
+    "rep": (repeat_workload, dict(seed=44)),
 }
 
 

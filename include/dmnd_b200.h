@@ -57,6 +57,13 @@ typedef struct dmnd_params {
 	int32_t ungapped_window;          /* config.ungapped_window = 48 */
 	double ungapped_evalue;           /* 0 => stage-2 ungapped filter skipped (fast); >0 not implemented yet */
 	float background_scores_f32[20];  /* (float)ScoreMatrix::background_scores_ (stats/score_matrix.cpp:241-248), for Hauser */
+	/* tantan repeat masking (masking/tantan.cpp:121-214, called from masking/masking.cpp:162 with p_repeat 0.005,
+	 * p_repeat_end 0.05, growth 1/0.9, min. mask probability config.tantan_minMaskProb 0.9): every constant the
+	 * forward-backward pass uses, evaluated once on the host exactly as the reference evaluates it (fp32). */
+	float tantan_lr[32 * 32];         /* Masking::likelihoodRatioMatrixf_ [a*32+b] = (float)exp(lambda * score(a,b)), a,b < 26 (whole alphabet, X * _ included); 0 elsewhere (masking.cpp:133-153) */
+	float tantan_d[50];               /* d[49] = b2f0, d[i] = d[i+1] * growth (tantan.cpp:136-142) */
+	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
+	int32_t max_motif_len;            /* config.max_motif_len = 30 (basic/config.cpp:602) */
 } dmnd_params;
 
 /* Search::Hit (search/hit.h:30-48) as a fixed 16-byte record. */
@@ -161,6 +168,24 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
 int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end);
 
+/* Sequence masking, a property of the resident block (MaskingAlgo bits, masking/def.h:27).
+ *   DMND_MASK_TANTAN  hard masking: every letter whose tantan repeat probability is >= params.tantan_p_mask becomes
+ *                     MASK_LETTER (X = 23) in place, as mask_seqs(seqs, Masking::get(), true, TANTAN) does when the
+ *                     reference loads a query or reference block (run/double_indexed.cpp:122-127, :737-741;
+ *                     masking/tantan.cpp:113-214, AVX2 dispatch: the fp32 evaluation order of that path is kept).
+ *   DMND_MASK_MOTIF   soft masking: builds the block's MaskingTable of abundant 8-mer motifs (masking/masking.cpp:110-131:
+ *                     merged ranges of table hits, none if they cover >= half of the sequence, only ranges of
+ *                     <= params.max_motif_len letters).  dmnd_search_shape then enumerates seeds of either side with those
+ *                     letters read as X (Block::soft_mask, search/seed_array/enum_seeds.h:262-270) and sets SEED_MASK on
+ *                     the query positions MaskingTable::remove(template_len, add_bit_mask) marks (masking.cpp:96-107).
+ * Sequences [s_begin, s_end) are processed on `ctx`'s stream (a lane masks its own query range).  TANTAN runs before
+ * MOTIF when both bits are given (the reference builds the motif table from the hard-masked letters).  *n_hard receives
+ * the number of letters hard-masked by this call; dmnd_block_mask_fetch() then copies their offsets into the block image
+ * (ascending) so that the caller can keep its host copy of the letters in step. */
+enum { DMND_MASK_NONE = 0, DMND_MASK_TANTAN = 1, DMND_MASK_MOTIF = 4 };
+int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard);
+int dmnd_block_mask_fetch(dmnd_ctx* ctx, uint64_t* positions, size_t cap);
+
 /* Stages 0-2 for shape `sid`, all index chunks in reference order; hits are grouped by query (ascending),
  * order inside a query unspecified (the reference's is thread-dependent; consumers sort, align/load_hits.h:45).
  * Sets SEED_MASK bits in the query block exactly like Search::mask_seeds (search/seed_complexity.cpp:77-127). */
@@ -214,6 +239,8 @@ typedef struct dmnd_search_opts {
 	double max_evalue;         /* -e, default 0.001 */
 	uint64_t db_letters;       /* 0 = letters of the reference block */
 	int32_t want_transcript;   /* 1 = keep edit transcripts (fmt 0) */
+	int32_t masking;           /* --masking: 1 = tantan (reference default), 0 = none */
+	int32_t motif_masking;     /* --motif-masking: 1 = soft-mask abundant motifs (reference default for --fast), 0 = off */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {
@@ -248,7 +275,10 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* out);
 int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const int64_t* q_limits, uint32_t nq,
                 const int8_t* r_letters, size_t r_raw_len, const int64_t* r_limits, uint32_t nr,
                 const dmnd_search_opts* opts, dmnd_result** out);
-/* Same, with both blocks already resident (used by the bench's device-resident timing and by multi-GPU shards). */
+/* Same, with both blocks already resident (used by the bench's device-resident timing and by multi-GPU shards).
+ * Resident blocks are in the state the reference holds a loaded block in: with opts->masking / motif_masking set the
+ * caller has already run dmnd_block_mask() on both, and q_letters / r_letters are the equally masked host images
+ * (dmnd_block_download_letters); dmnd_blastp() does all of that itself inside the call. */
 int dmnd_blastp_resident(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, const int8_t* q_letters,
                          const int64_t* q_limits, uint32_t nq, const int8_t* r_letters, const int64_t* r_limits,
                          uint32_t nr, const dmnd_search_opts* opts, dmnd_result** out);

@@ -25,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include "../diamond_b200/csrc/host/motif_table.h"
 
 static char g_err[512];
 const char* dmnd_last_error(void) { return g_err; }
@@ -35,6 +36,8 @@ static int fail(const char* m) { snprintf(g_err, sizeof g_err, "%s", m); return 
 struct dmnd_block {
 	int8_t* letters;
 	int8_t* bias;
+	uint8_t* soft_buf; /* 1 = letter inside a MaskingTable entry (abundant motif) */
+	uint8_t* soft;     /* == soft_buf once dmnd_block_mask(MOTIF) has run, NULL before */
 	size_t raw_len;
 	int64_t* limits;
 	uint32_t nseq;
@@ -45,6 +48,8 @@ struct dmnd_ctx {
 	uint32_t m_minlen[DMND_MAX_SHAPES + 1], m_suffix[DMND_MAX_SHAPES + 1];
 };
 struct dmnd_hits { dmnd_hit* h; size_t n; };
+/* letters hard-masked by the calling thread's last dmnd_block_mask (lanes share one oracle context but run on their own threads) */
+static __thread uint64_t* t_mask_pos; static __thread size_t t_mask_n, t_mask_cap;
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* util/algo/pattern_matcher.h:25-45 */
@@ -97,6 +102,7 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	b->letters = (int8_t*)malloc(raw_len);
 	memcpy(b->letters, letters, raw_len);
 	b->bias = (int8_t*)calloc(raw_len, 1);
+	b->soft_buf = (uint8_t*)calloc(raw_len, 1);
 	b->raw_len = raw_len;
 	b->limits = (int64_t*)malloc(sizeof(int64_t) * ((size_t)nseq + 1));
 	memcpy(b->limits, limits, sizeof(int64_t) * ((size_t)nseq + 1));
@@ -113,7 +119,7 @@ int dmnd_block_range_wait(dmnd_ctx* ctx, const dmnd_block* b, uint32_t s_begin, 
 void dmnd_block_free(dmnd_ctx* ctx, dmnd_block* b) {
 	(void)ctx;
 	if (!b) return;
-	free(b->letters); free(b->bias); free(b->limits); free(b);
+	free(b->letters); free(b->bias); free(b->soft_buf); free(b->limits); free(b);
 }
 int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t raw_len) {
 	(void)ctx;
@@ -178,6 +184,166 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 	memcpy(letters, b->letters, raw_len);
 	return 0;
 }
+/* ---------------------------------------------------------------------------------------------------------- */
+/* Masking.  masking/tantan.cpp:43-214 as the AVX2 dispatch object evaluates it (oracle/ref_build compiles that object
+ * with -mavx2 and without -mfma, so Traits<float>::LANES == 8 and fmadd(a,b,c) == add(mul(a,b),c),
+ * util/simd/vector8_avx2.h:124-139): every product and sum is a separate IEEE fp32 operation, horizontal sums go
+ * through hsum's ((a0+a4)+(a1+a5)) + ((a2+a6)+(a3+a7)) tree, register sums are accumulated left to right, the two tail
+ * elements 48 and 49 last.  Compile with -ffp-contract=off (Makefile). */
+#define TT_W 50
+static float tt_hsum8(const float* a) { const float s0 = a[0] + a[4], s1 = a[1] + a[5], s2 = a[2] + a[6], s3 = a[3] + a[7]; return (s0 + s1) + (s2 + s3); }
+/* util/simd/vector.h:37-48 sum(x, 50) */
+static float tt_sum50(const float* x) {
+	float acc[8];
+	for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+	for (int r = 0; r < 6; ++r) for (int k = 0; k < 8; ++k) acc[k] = acc[k] + x[8 * r + k];
+	float sum = tt_hsum8(acc);
+	sum += x[48]; sum += x[49];
+	return sum;
+}
+/* e_seg[off] of tantan.cpp:163-171,181: the likelihood ratio of letter i against the letter off+1 positions before it */
+static float tt_e(const dmnd_params* p, const int8_t* seq, int i, int ltr, int off) {
+	const int j = i - 1 - off;
+	return j >= 0 ? p->tantan_lr[ltr * 32 + (seq[j] & DMND_LETTER_MASK)] : 0.0f;
+}
+/* Util::tantan::mask(seq, len, ..., mask_mode 1): returns the number of letters set to MASK_LETTER, their offsets
+ * (base + i) are appended to ctx->mask_pos. */
+static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t base) {
+	if (len == 0) return 0;
+	const float* d = p->tantan_d;
+	const float b2b = p->tantan_b2b, f2f = p->tantan_f2f, p_repeat_end = p->tantan_p_repeat_end, p_mask = p->tantan_p_mask;
+	float f[TT_W];
+	float* pb = (float*)malloc(sizeof(float) * (size_t)len);
+	float* scale = (float*)malloc(sizeof(float) * (size_t)((len - 1) / 16 + 1));
+	for (int k = 0; k < TT_W; ++k) f[k] = 0.0f;
+	float b = 1.0f, f_sum = 0.0f;
+	for (int i = 0; i < len; ++i) {
+		const int ltr = seq[i] & DMND_LETTER_MASK;
+		/* forward_step, tantan.cpp:43-76 */
+		const float b_old = b;
+		float f_sum_new = 0.0f;
+		for (int r = 0; r < 6; ++r) {
+			for (int k = 0; k < 8; ++k) {
+				const int off = 8 * r + k;
+				const float tmp = f[off] * f2f + b_old * d[off];
+				f[off] = tmp * tt_e(p, seq, i, ltr, off);
+			}
+			f_sum_new += tt_hsum8(f + 8 * r);
+		}
+		for (int off = 48; off < 50; ++off) {
+			float vf = f[off];
+			vf = (vf * f2f + b_old * d[off]) * tt_e(p, seq, i, ltr, off);
+			f[off] = vf;
+			f_sum_new += vf;
+		}
+		b = b_old * b2b + f_sum * p_repeat_end;
+		f_sum = f_sum_new;
+		if ((i & 15) == 15) {
+			const float s = 1.0f / b;
+			scale[i / 16] = s;
+			b *= s;
+			for (int k = 0; k < TT_W; ++k) f[k] = f[k] * s;
+			f_sum *= s;
+		}
+		pb[i] = b;
+	}
+	const float z = b * b2b + tt_sum50(f) * p_repeat_end;
+	const float zinv = 1.0f / z;
+	b = b2b;
+	for (int k = 0; k < TT_W; ++k) f[k] = p_repeat_end;
+	size_t n = 0;
+	for (int i = len - 1; i >= 0; --i) {
+		const float pf = 1.0f - (pb[i] * b * zinv);
+		if ((i & 15) == 15) {
+			const float s = scale[i / 16];
+			b *= s;
+			for (int k = 0; k < TT_W; ++k) f[k] = f[k] * s;
+		}
+		const int ltr = seq[i] & DMND_LETTER_MASK;
+		/* backward_step, tantan.cpp:78-111 */
+		const float vC = p_repeat_end * b;
+		float tsum = 0.0f;
+		for (int r = 0; r < 6; ++r) {
+			float vt[8];
+			for (int k = 0; k < 8; ++k) {
+				const int off = 8 * r + k;
+				const float vf = f[off] * tt_e(p, seq, i, ltr, off);
+				vt[k] = vf * d[off];
+				f[off] = vf * f2f + vC;
+			}
+			tsum += tt_hsum8(vt);
+		}
+		for (int off = 48; off < 50; ++off) {
+			float vf = f[off] * tt_e(p, seq, i, ltr, off);
+			tsum += vf * d[off];
+			vf = vf * f2f + p_repeat_end * b;
+			f[off] = vf;
+		}
+		b = b2b * b + tsum;
+		if (pf >= p_mask) {
+			seq[i] = 23; /* value_traits.mask_char: MASK_LETTER */
+			if (t_mask_n == t_mask_cap) { t_mask_cap = t_mask_cap ? t_mask_cap * 2 : 1024; t_mask_pos = (uint64_t*)realloc(t_mask_pos, t_mask_cap * sizeof(uint64_t)); }
+			t_mask_pos[t_mask_n++] = base + (uint64_t)i;
+			++n;
+		}
+	}
+	free(pb); free(scale);
+	return n;
+}
+static int cmp_u64(const void* a, const void* b) { const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : x > y; }
+/* masking/masking.cpp:110-131 mask_motifs: util/kmer/kmer.h:62-117 KmerIterator<8> (letters >= 20 restart the k-mer),
+ * Mask::Ranges::push_back merging (masking/def.h:73-79), the >= 50 % rule and config.max_motif_len. */
+static void motifs_one(const dmnd_params* p, const int8_t* seq, int len, uint8_t* soft) {
+	if (len < DMND_MOTIF_LEN) return;
+	uint8_t* cov = (uint8_t*)calloc((size_t)len, 1);
+	long n = 0;
+	for (int i = 0; i + DMND_MOTIF_LEN <= len; ++i) {
+		uint64_t code = 0;
+		int ok = 1;
+		for (int k = 0; k < DMND_MOTIF_LEN; ++k) {
+			const int l = seq[i + k] & DMND_LETTER_MASK;
+			if (l >= 20) { ok = 0; break; }
+			code = code * 20 + (uint64_t)l;
+		}
+		if (!ok || !bsearch(&code, DMND_MOTIF_CODES, DMND_MOTIF_COUNT, sizeof(uint64_t), cmp_u64)) continue;
+		for (int k = 0; k < DMND_MOTIF_LEN; ++k) cov[i + k] = 1;
+	}
+	for (int i = 0; i < len; ++i) n += cov[i];
+	if ((double)n / len < 0.5)
+		for (int i = 0; i < len;) {
+			if (!cov[i]) { ++i; continue; }
+			int e = i;
+			while (e < len && cov[e]) ++e;
+			if (e - i <= p->max_motif_len) memset(soft + i, 1, (size_t)(e - i));
+			i = e;
+		}
+	free(cov);
+}
+int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard) {
+	if (s_begin > s_end || s_end > b->nseq) return fail("dmnd_block_mask: bad sequence range");
+	if (algo & ~(DMND_MASK_TANTAN | DMND_MASK_MOTIF)) return fail("dmnd_block_mask: unknown masking algorithm");
+	t_mask_n = 0;
+	if (algo & DMND_MASK_TANTAN)
+		for (uint32_t i = s_begin; i < s_end; ++i)
+			tantan_one(&ctx->p, b->letters + b->limits[i], (int)(b->limits[i + 1] - b->limits[i] - 1), (uint64_t)b->limits[i]);
+	if (t_mask_n) qsort(t_mask_pos, t_mask_n, sizeof(uint64_t), cmp_u64);
+	if (algo & DMND_MASK_MOTIF) {
+		b->soft = b->soft_buf;
+		for (uint32_t i = s_begin; i < s_end; ++i) {
+			const int len = (int)(b->limits[i + 1] - b->limits[i] - 1);
+			memset(b->soft + b->limits[i], 0, (size_t)len);
+			motifs_one(&ctx->p, b->letters + b->limits[i], len, b->soft + b->limits[i]);
+		}
+	}
+	if (n_hard) *n_hard = t_mask_n;
+	return 0;
+}
+int dmnd_block_mask_fetch(dmnd_ctx* ctx, uint64_t* positions, size_t cap) {
+	(void)ctx;
+	if (cap < t_mask_n) return fail("dmnd_block_mask_fetch: buffer too small");
+	if (t_mask_n) memcpy(positions, t_mask_pos, t_mask_n * sizeof(uint64_t));
+	return 0;
+}
 int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end) {
 	(void)ctx;
 	if (q_begin > q_end || q_end > b->nseq) return fail("dmnd_block_clear_seed_mask_range: bad range");
@@ -208,10 +374,12 @@ static int cmp_entry(const void* a, const void* b) {
 }
 
 /* basic/shape.h:113-171 on a sequence reduced by basic/reduction.h:98-105: invalid iff any class == MASK (23). */
-static int seed_at(const dmnd_params* p, int sid, const int8_t* s, uint64_t* out) {
+static int seed_at(const dmnd_params* p, int sid, const int8_t* s, const uint8_t* soft, uint64_t* out) {
 	uint64_t v = 0;
 	for (int k = 0; k < p->shape_weight; ++k) {
-		const unsigned r = p->reduction[s[p->shape_pos[sid][k]] & DMND_LETTER_MASK];
+		const int pos = p->shape_pos[sid][k];
+		/* a soft-masked letter reads as MASK_LETTER while the seeds are enumerated (Block::soft_mask, data/block/block.cpp:162-171) */
+		const unsigned r = (soft && soft[pos]) ? 23u : p->reduction[s[pos] & DMND_LETTER_MASK];
 		if (r == 23) return 0;
 		v = v * (uint64_t)p->reduction_size + r;
 	}
@@ -239,7 +407,7 @@ static size_t enum_seeds(const dmnd_params* p, int sid, const dmnd_block* b, uin
 		const int64_t beg = b->limits[i], len = b->limits[i + 1] - b->limits[i] - 1;
 		for (int64_t j = 0; j + span <= len; ++j) {
 			uint64_t s;
-			if (!seed_at(p, sid, b->letters + beg + j, &s)) continue;
+			if (!seed_at(p, sid, b->letters + beg + j, b->soft ? b->soft + beg + j : NULL, &s)) continue;
 			const uint32_t part = (uint32_t)(s & mask);
 			if (part < pbegin || part >= pend) continue;
 			if (n == cap) { cap *= 2; e = (entry*)realloc(e, cap * sizeof *e); }
@@ -380,6 +548,23 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
 	const uint32_t nchunks = (uint32_t)p->index_chunks < parts_total ? (uint32_t)p->index_chunks : parts_total;
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
 	const int window = p->ungapped_window;
+	if (query->soft) {
+		/* MaskingTable::remove(template_len, add_bit_mask = true) after the query enumeration (masking/masking.cpp:96-107,
+		 * search/seed_array/enum_seeds.h:255-260 with EnumCfg::mask_seeds of the query side, search/stage0.cpp:139-142):
+		 * every table entry [b, e) leaves SEED_MASK on [max(b - shape_len + 1, 0), e).  Entries are the maximal runs of `soft`. */
+		const int tl = p->shape_len[sid];
+		for (uint32_t qi = q_begin; qi < q_end; ++qi) {
+			const int64_t beg = query->limits[qi];
+			const int len = (int)(query->limits[qi + 1] - beg - 1);
+			for (int i = 0; i < len;) {
+				if (!query->soft[beg + i]) { ++i; continue; }
+				int e = i;
+				while (e < len && query->soft[beg + e]) ++e;
+				for (int j = (i - tl + 1 > 0 ? i - tl + 1 : 0); j < e; ++j) query->letters[beg + j] |= (int8_t)DMND_SEED_MASK;
+				i = e;
+			}
+		}
+	}
 	for (uint32_t chunk = 0; chunk < nchunks; ++chunk) {
 		const uint32_t bsel = chunk < prem ? chunk : prem;
 		const uint32_t pb = bsel * (psize + 1) + (chunk - bsel) * psize, pe = pb + (chunk < prem ? psize + 1 : psize);

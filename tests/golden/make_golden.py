@@ -5,6 +5,7 @@
 
 For every workload W and parity-ladder level L:
     L0 = --masking 0 --motif-masking 0 --comp-based-stats 0      L1 = --masking 0 --motif-masking 0 (Hauser CBS on)
+    L2 = the reference's default flags (tantan masking of both blocks, motif soft-masking, Hauser CBS)
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -16,7 +17,8 @@ from diamond_b200 import synth  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "diamond")
 LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats", "0"],
-          "l1": ["--masking", "0", "--motif-masking", "0"]}
+          "l1": ["--masking", "0", "--motif-masking", "0"],
+          "l2": []}
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",

@@ -1,0 +1,118 @@
+"""Masking parity (SURVEY 8f rank 2 -> the reference's DEFAULT flags): tantan hard masking of both blocks
+(masking/tantan.cpp) and motif soft masking (masking/masking.cpp:110-131) in the oracle, pinned against the reference:
+ * fmt-6 + --log counters of the L2 goldens (tests/golden/*.l2.*: the reference run with its default flags);
+ * the tantan lambda constant against the reference's own LambdaCalculator.cc (compiled here when /root/reference exists);
+ * a live default-flag run of the reference on real proteins (src/test/nr_10k.faa, X/B/J letters) when it is present.
+CPU only."""
+import ctypes as C, json, os, re, subprocess, tempfile
+import numpy as np
+import pytest
+from conftest import GOLDEN, REF_BIN, ROOT, workload_blocks
+
+WORKLOADS = ["c1", "fam2", "edge", "long", "rep"]
+
+
+@pytest.mark.parametrize("name", WORKLOADS)
+def test_default_flags_match_reference_golden(oracle_lib, name):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1)
+    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.l2.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.l2.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
+
+
+def test_repeat_workload_is_actually_masked(oracle_lib):
+    """The fixture must exercise the code: tantan masks thousands of letters, the motif table marks ranges, and both change the output."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("rep")
+    ctx = api.Context(oracle_lib, threads=8)
+    rb = ctx.upload(r_raw, r_lim)
+    pos = ctx.mask_block(rb, 5, 0, len(r_lim) - 1)
+    after = ctx.download_letters(rb, r_raw.size)
+    ctx.free_block(rb); ctx.close()
+    assert len(pos) > 2000 and np.all(np.diff(pos.astype(np.int64)) > 0)
+    changed = np.flatnonzero(after != r_raw)
+    p64 = pos.astype(np.int64)
+    assert np.all(after[p64] == 23) and np.all(np.isin(changed, p64))   # (a letter that already was X may be reported as well)
+    assert np.all(r_raw[np.setdiff1d(p64, changed)] == 23)
+    assert open(os.path.join(GOLDEN, "rep.l2.tsv")).read() != open(os.path.join(GOLDEN, "rep.l1.tsv")).read()
+
+
+def test_resident_blocks_masked_by_the_caller_equal_the_e2e_call(oracle_lib):
+    """dmnd_blastp masks inside the call; dmnd_blastp_resident expects masked blocks + equally masked host letters."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("rep")
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1)
+    qb, rb = ctx.upload(q_raw, q_lim), ctx.upload(r_raw, r_lim)
+    ctx.mask_block(qb, 5, 0, len(q_lim) - 1); ctx.mask_block(rb, 5, 0, len(r_lim) - 1)
+    qm, rm = ctx.download_letters(qb, q_raw.size), ctx.download_letters(rb, r_raw.size)
+    m, _, _ = ctx.blastp_resident(qb, rb, qm, q_lim, rm, r_lim)
+    out = api.fmt6(m)
+    ctx.free_block(qb); ctx.free_block(rb); ctx.close()
+    assert out == open(os.path.join(GOLDEN, "rep.l2.tsv")).read()
+
+
+@pytest.mark.parametrize("lanes", ["3"])
+def test_query_lanes_mask_their_own_ranges(oracle_lib, lanes, monkeypatch):
+    from diamond_b200 import api
+    monkeypatch.setenv("DMND_LANES", lanes)
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("rep")
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1)
+    m, _, _ = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, "rep.l2.tsv")).read()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/lib/tantan"), reason="reference sources not present")
+def test_tantan_lambda_equals_the_reference_lambda_calculator(oracle_lib, tmp_path):
+    """dmnd_params_init hard-codes lambda(BLOSUM62 20x20) = 0x1.4bcf16a672882p-2; re-derive it with the reference's own
+    lib/tantan/LambdaCalculator.cc (compiled from where it lies) and compare the likelihood-ratio table bit for bit."""
+    from diamond_b200 import api
+    src = tmp_path / "probe.cpp"
+    src.write_text('#include "LambdaCalculator.hh"\n#include <cstdio>\nint main(){int m[20][20];const int*p[20];for(int i=0;i<20;++i){p[i]=m[i];'
+                   'for(int j=0;j<20;++j)if(scanf("%d",&m[i][j])!=1)return 2;}cbrc::LambdaCalculator lc;lc.calculate(p,20);printf("%a\\n",lc.lambda());return 0;}\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["g++", "-O2", "-I/root/reference/src/lib/tantan", str(src), "/root/reference/src/lib/tantan/LambdaCalculator.cc", "-o", str(exe)], check=True)
+    o = api.SearchOpts(); oracle_lib.dmnd_search_opts_default(C.byref(o))
+    p = api.Params(); assert oracle_lib.dmnd_params_init(C.byref(o), C.byref(p)) == 0
+    s = list(p.score)
+    txt = "\n".join(" ".join(str(s[a * 32 + b]) for b in range(20)) for a in range(20))
+    lam = float.fromhex(subprocess.run([str(exe)], input=txt, capture_output=True, text=True, check=True).stdout.strip())
+    assert lam == float.fromhex("0x1.4bcf16a672882p-2")
+    lr = np.array(list(p.tantan_lr), dtype=np.float32).reshape(32, 32)
+    want = np.zeros((32, 32), dtype=np.float32)
+    for a in range(26):
+        for b in range(26):
+            want[a, b] = np.float32(np.exp(lam * s[a * 32 + b]))
+    assert np.array_equal(lr.view(np.uint32), want.view(np.uint32))
+    assert o.masking == 1 and o.motif_masking == 1  # the C defaults are the reference's defaults
+
+
+NR10K = "/root/reference/src/test/nr_10k.faa"
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(NR10K)), reason="reference binary / nr_10k.faa not present")
+def test_live_reference_default_flags_on_real_proteins(tmp_path):
+    """2 000 real proteins (X, B, J letters, long viral polyproteins that are > 50 % motif-covered) against themselves with
+    the reference's default flags: fmt-6 byte-identical and the --log stage counters equal."""
+    cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+    sub = tmp_path / "nr2k.faa"
+    n = 0
+    with open(NR10K) as f, open(sub, "w") as g:
+        for line in f:
+            if line.startswith(">"):
+                n += 1
+                if n > 2000:
+                    break
+            g.write(line)
+    ref_out, our_out = tmp_path / "ref.tsv", tmp_path / "our.tsv"
+    r = subprocess.run([REF_BIN, "blastp", "--fast", "-q", str(sub), "-d", str(sub), "-f", "6", "-o", str(ref_out), "-p", "8", "--log"], capture_output=True, text=True, check=True)
+    o = subprocess.run([cli, "blastp", "--fast", "-q", str(sub), "-d", str(sub), "-o", str(our_out), "-p", "8", "--log"], capture_output=True, text=True, check=True)
+    assert open(ref_out).read() == open(our_out).read() and os.path.getsize(ref_out) > 10000
+    for pat in (r"Seeds hit\s+= (\d+)", r"Hits \(filter stage 0\) = (\d+)", r"Hits \(filter stage 1\) = (\d+)", r"Hits \(filter stage 3\) = (\d+)", r"Target hits \(stage 0\) = (\d+)"):
+        assert re.search(pat, r.stdout + r.stderr).group(1) == re.search(pat, o.stdout + o.stderr).group(1), pat

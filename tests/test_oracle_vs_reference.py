@@ -85,8 +85,10 @@ def test_evalue_within_tolerance_of_printed_reference_values(oracle_lib):
 def test_cli_rejects_what_it_does_not_implement(oracle_lib):
     from conftest import ROOT
     cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
-    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z"], capture_output=True, text=True)
+    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z", "--masking", "seg"], capture_output=True, text=True)
     assert r.returncode != 0 and "masking" in r.stderr
+    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z", "--sensitive"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unsupported option" in r.stderr
     r = subprocess.run([cli, "blastx"], capture_output=True, text=True)
     assert r.returncode != 0
 
