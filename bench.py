@@ -12,13 +12,17 @@ GCUPS numerator = algorithmic DP cells = sum over every banded DP problem of rou
 (dp/dp.h:121-124); it is a property of the workload (the DP target list is parity-checked against the reference).
 `value` times steps with both blocks already resident in HBM; `e2e` times dmnd_blastp() with pinned HOST buffers
 (block upload, problem lists, hit/result downloads inside).  Inputs (242 MB + 30 MB) exceed the 126 MB L2.
+Flags: the reference's DEFAULTS (tantan masking of both blocks, motif soft masking, Hauser composition bias) on both arms.
+Masking belongs to loading a block (run/double_indexed.cpp:122-127, :737-741): resident blocks are masked when they are
+made resident (outside the `value` region, like the upload); `e2e` and the reference arm mask inside the timed region.
+`--masking 0` runs both arms on the parity-ladder rung without masking (--masking 0 --motif-masking 0).
 """
 import argparse, json, os, subprocess, sys, tempfile, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "diamond")
-LADDER = ["--masking", "0", "--motif-masking", "0"]  # masking parity is a 'next' row: both arms run without it
+NO_MASKING = ["--masking", "0", "--motif-masking", "0"]  # parity-ladder rung L1 (SURVEY 8c); [] = the reference's default flags
 
 
 def parse():
@@ -32,6 +36,7 @@ def parse():
     ap.add_argument("--sample", type=int, default=100_000, help="queries of the bounded CPU-baseline sample")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--masking", type=int, default=1, choices=[0, 1], help="1 = reference default flags (tantan + motif masking), 0 = --masking 0 --motif-masking 0 on both arms")
     return ap.parse_args()
 
 
@@ -105,9 +110,9 @@ def write_sample_fasta(w, n, td):
     return q, d
 
 
-def run_reference(q, d, out, threads):
+def run_reference(q, d, out, threads, masking=1):
     t0 = time.perf_counter()
-    r = subprocess.run([REF_BIN, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", out, "-p", str(threads), "--log"] + LADDER,
+    r = subprocess.run([REF_BIN, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", out, "-p", str(threads), "--log"] + ([] if masking else NO_MASKING),
                        capture_output=True, text=True)
     dt = time.perf_counter() - t0
     if r.returncode != 0:
@@ -121,7 +126,7 @@ def sample_cells_and_tsv(args, w, threads, device):
     n = min(args.sample, args.queries)
     q_raw, q_lim = api.block_image(w["q_letters"][: w["q_off"][n]], w["q_off"][: n + 1])
     r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
-    ctx = api.Context(device=device, threads=threads)
+    ctx = api.Context(device=device, threads=threads, masking=args.masking, motif_masking=args.masking)
     m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
     ctx.close()
     return st["cells_round1"] + st["cells_round2"], api.fmt6(m), n
@@ -138,7 +143,9 @@ def main():
     ref_threads = ncpu  # the reference arm uses every host thread; our seedp_bits must follow the same -p (setup.cpp:306-309)
     config = {"workload": f"blastp --fast, {args.queries} synthetic queries (len<=300) per GPU x {args.db}-protein DB (BASELINE configs[1])",
               "queries_per_gpu": args.queries, "db_seqs": args.db, "parallelism": f"query-sharded x{world}", "seed": args.seed,
-              "flags": "--fast --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001", "reference_threads": ref_threads, "visible_cpus": os.cpu_count(),
+              "flags": "--fast (reference defaults: tantan masking, motif masking, comp-based-stats 1) -k 25 -e 0.001" if args.masking else "--fast --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001",
+              "masking": "resident blocks are masked when made resident (block load); e2e and the reference arm mask inside the timed region" if args.masking else "off on both arms",
+              "reference_threads": ref_threads, "visible_cpus": os.cpu_count(),
               "l2": "inputs (242 MB queries + 30 MB reference per GPU) larger than the 126 MB L2"}
 
     if args.impl == "reference":
@@ -154,7 +161,7 @@ def main():
             q, d = write_sample_fasta(w, n, td)
             times = []
             for s in range(args.warmup + args.steps):
-                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads)
+                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads, args.masking)
                 if s >= args.warmup:
                     times.append(dt)
         T = sum(times)
@@ -185,7 +192,7 @@ def main():
     # pinned host copies for the e2e path
     q_pin = torch.from_numpy(q_raw).pin_memory().numpy()
     r_pin = torch.from_numpy(r_raw).pin_memory().numpy()
-    ctx = api.Context(device=local, threads=ref_threads)
+    ctx = api.Context(device=local, threads=ref_threads, masking=args.masking, motif_masking=args.masking)
 
     def barrier():
         torch.cuda.synchronize()
@@ -219,7 +226,13 @@ def main():
         return ms, last, ctx.timing()
 
     qb, rb = ctx.upload(q_raw, q_lim), ctx.upload(r_raw, r_lim)
-    step_res = lambda: ctx.blastp_resident(qb, rb, q_raw, q_lim, r_raw, r_lim)
+    q_res, r_res = q_raw, r_raw
+    if args.masking:
+        # making the blocks resident includes masking them (what the reference does when it loads a block); the host images
+        # the resident call reads (chaining link scores) are the equally masked letters
+        ctx.mask_block(qb, 5, 0, len(q_lim) - 1); ctx.mask_block(rb, 5, 0, len(r_lim) - 1)
+        q_res, r_res = ctx.download_letters(qb, q_raw.size), ctx.download_letters(rb, r_raw.size)
+    step_res = lambda: ctx.blastp_resident(qb, rb, q_res, q_lim, r_res, r_lim)
     step_e2e = lambda: ctx.blastp(q_pin, q_lim, r_pin, r_lim)
     for _ in range(args.warmup):
         step_res()
@@ -273,7 +286,7 @@ def main():
             scells, tsv, n = sample_cells_and_tsv(args, w, ref_threads, local)
             with tempfile.TemporaryDirectory() as td:
                 q, d = write_sample_fasta(w, n, td)
-                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads)
+                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads, args.masking)
                 same = open(os.path.join(td, "o.tsv")).read() == tsv
             cpu = {"value": scells / dt / 1e9, "unit": "GCUPS", "cores": ref_threads, "kind": "reference",
                    "sample": f"first {n} queries x full DB, one reference run (FASTA in, fmt 6 out), wall {dt:.2f} s; fmt-6 identical to ours: {same}"}

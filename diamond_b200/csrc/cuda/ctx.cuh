@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "../../../include/dmnd_b200.h"
+#include "dev_params.h"
 
 namespace dmnd_cuda {
 
@@ -37,27 +38,6 @@ struct DevBuf {
 	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 	template<typename T> T* as() const { return (T*)p; }
-};
-
-// Device-side copy of what the kernels need from dmnd_params (constant-memory sized).
-struct DevParams {
-	int8_t score[1024];
-	uint8_t reduction[32], map8[32], map8b[32];
-	int32_t shape_pos[DMND_MAX_SHAPES][DMND_MAX_WEIGHT];
-	uint32_t shape_mask[DMND_MAX_SHAPES];
-	int32_t shape_len[DMND_MAX_SHAPES];
-	int32_t n_shapes, shape_weight, reduction_size;
-	int32_t hamming_id, seedp_bits, index_chunks, left_most_interval, ungapped_window;
-	int32_t gap_open, gap_extend;
-	int32_t seed_bits;     // bit length of reduction_size^weight - 1
-	double seed_cut;
-	double lnfact[DMND_MAX_WEIGHT + 1];
-	float background_scores_f32[20];
-	// tantan (masking/tantan.cpp:121-214): likelihood ratios [a*32+b], per-offset repeat start probabilities, transition constants
-	float tantan_lr[1024];
-	float tantan_d[50];
-	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
-	int32_t max_motif_len;
 };
 
 enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };

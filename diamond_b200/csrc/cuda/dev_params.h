@@ -1,0 +1,30 @@
+// dev_params.h -- device-side copy of what the kernels need from dmnd_params.  Plain C++ (no CUDA headers) so that the
+// CPU emulation of the kernels under tests/ can include the kernel sources unchanged.
+#pragma once
+#include <cstdint>
+#include "../../../include/dmnd_b200.h"
+
+namespace dmnd_cuda {
+
+// Device-side copy of what the kernels need from dmnd_params (constant-memory sized).
+struct DevParams {
+	int8_t score[1024];
+	uint8_t reduction[32], map8[32], map8b[32];
+	int32_t shape_pos[DMND_MAX_SHAPES][DMND_MAX_WEIGHT];
+	uint32_t shape_mask[DMND_MAX_SHAPES];
+	int32_t shape_len[DMND_MAX_SHAPES];
+	int32_t n_shapes, shape_weight, reduction_size;
+	int32_t hamming_id, seedp_bits, index_chunks, left_most_interval, ungapped_window;
+	int32_t gap_open, gap_extend;
+	int32_t seed_bits;     // bit length of reduction_size^weight - 1
+	double seed_cut;
+	double lnfact[DMND_MAX_WEIGHT + 1];
+	float background_scores_f32[20];
+	// tantan (masking/tantan.cpp:121-214): likelihood ratios [a*32+b], per-offset repeat start probabilities, transition constants
+	float tantan_lr[1024];
+	float tantan_d[50];
+	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
+	int32_t max_motif_len;
+};
+
+}  // namespace dmnd_cuda

@@ -1,256 +1,10 @@
-// mask.cu -- sequence masking of a resident block (dmnd_block_mask) for sm_100a.
-//
-//   tantan hard masking   masking/tantan.cpp:113-214 (Util::tantan::mask, mask_mode 1), called for every sequence of a loaded
-//                         query / reference block (masking/masking.cpp:155-166, run/double_indexed.cpp:122-127, :737-741)
-//   motif soft masking    masking/masking.cpp:110-131 (mask_motifs), MaskingTable (:76-107), Block::soft_mask (data/block/block.cpp:162-178)
-//
-// tantan is a forward-backward pass over a 50-state repeat HMM, sequential along the sequence and 50-wide across it.  The
-// reference's AVX2 object evaluates it in fp32 with 8-lane registers and no FMA (util/simd/vector8_avx2.h:124-139 without
-// __FMA__), so the result of every letter is fixed by an evaluation ORDER: products and sums are separate roundings, a
-// register's horizontal sum is ((a0+a4)+(a1+a5))+((a2+a6)+(a3+a7)), the six register sums and the two tail states are added
-// left to right.  Here EIGHT LANES own one sequence (lane k holds states 8r+k, r = 0..5, every lane carries the tail states 48
-// and 49 redundantly), four sequences per warp: the xor-shuffle tree 4,1,2 reproduces hsum's association exactly (fp32 add
-// is commutative, so all eight lanes end with the same bits), everything else is lane-local.  All arithmetic goes through
-// __fmul_rn / __fadd_rn / __fdiv_rn: never contracted, never reassociated.  Bound: shuffle + LSU issue (18 shuffles, 8 byte
-// loads and 8 shared-memory ratio look-ups per 4 letters), not HBM -- the pass reads each letter ~100 times from L1 and
-// writes 4 B (the scaled background probability pb[i], tantan.cpp:186) per letter.
-//
-// Motifs: one thread per letter position looks its 8-mer up (base-20 code, util/kmer/kmer.h:38-47) in the 1000-entry table
-// held in shared memory behind a 64 Kbit prefilter; hits set bits in a coverage bitmap; the (rare) sequences with a hit are
-// finished by one thread each: the >= 50 % rule, merged ranges, ranges of <= max_motif_len letters become `soft` bits.
+// mask.cu -- dmnd_block_mask / dmnd_block_mask_fetch: launch sequence of the masking kernels (mask_kernels.cuh).
 #include "ctx.cuh"
-#include "../host/motif_table.h"
+#include "mask_kernels.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 
 namespace dmnd_cuda {
-
-// hsum (util/simd/vector8_avx2.h:132-139) over the 8 lanes of a group; every lane returns the same value
-__device__ __forceinline__ float hsum8(float v, unsigned gmask) {
-	const float x = __fadd_rn(v, __shfl_xor_sync(gmask, v, 4));
-	const float y = __fadd_rn(x, __shfl_xor_sync(gmask, x, 1));
-	return __fadd_rn(y, __shfl_xor_sync(gmask, y, 2));
-}
-
-// e_seg[off] (tantan.cpp:163-171,181): likelihood ratio of letter i (row) against the letter off + 1 positions before it
-__device__ __forceinline__ float tt_e(const float* row, const int8_t* seq, int i, int off) {
-	const int j = i - 1 - off;
-	return j >= 0 ? row[seq[j] & 31] : 0.0f;
-}
-
-__global__ void __launch_bounds__(128) tantan_kernel(int8_t* letters, const int64_t* __restrict__ limits, uint32_t s_begin, uint32_t s_end,
-                                                     const DevParams* __restrict__ P, float* pb, float* scale, int64_t base,
-                                                     unsigned int* next_seq, uint32_t* hard /* bit per letter offset */) {
-	__shared__ float s_lr[1024];
-	for (int x = threadIdx.x; x < 1024; x += blockDim.x) s_lr[x] = P->tantan_lr[x];
-	__syncthreads();
-	const int lane = threadIdx.x & 31, k = lane & 7, lead = lane & 24;
-	const unsigned gmask = 0xffu << lead;
-	float d[6];
-#pragma unroll
-	for (int r = 0; r < 6; ++r) d[r] = P->tantan_d[8 * r + k];
-	const float d48 = P->tantan_d[48], d49 = P->tantan_d[49];
-	const float b2b = P->tantan_b2b, f2f = P->tantan_f2f, p_repeat_end = P->tantan_p_repeat_end, p_mask = P->tantan_p_mask;
-	for (;;) {
-		unsigned int sid = 0;
-		if (k == 0) sid = atomicAdd(next_seq, 1u);
-		sid = __shfl_sync(gmask, sid, lead) + s_begin;
-		if (sid >= s_end) break;
-		const int64_t beg = limits[sid];
-		const int len = (int)(limits[sid + 1] - beg - 1);
-		if (len <= 0) continue;
-		int8_t* seq = letters + beg;
-		float* pbs = pb + (beg - base);
-		float* scs = scale + ((beg - base) >> 4) + (sid - s_begin);
-		float f[6], f48 = 0.0f, f49 = 0.0f;
-#pragma unroll
-		for (int r = 0; r < 6; ++r) f[r] = 0.0f;
-		float b = 1.0f, f_sum = 0.0f;
-		// ---- forward pass, tantan.cpp:173-187 with forward_step :43-76
-		for (int i = 0; i < len; ++i) {
-			const float* row = s_lr + (seq[i] & 31) * 32;
-			const float b_old = b;
-			float f_sum_new = 0.0f;
-#pragma unroll
-			for (int r = 0; r < 6; ++r) {
-				const float tmp = __fadd_rn(__fmul_rn(f[r], f2f), __fmul_rn(b_old, d[r]));
-				f[r] = __fmul_rn(tmp, tt_e(row, seq, i, 8 * r + k));
-				f_sum_new = __fadd_rn(f_sum_new, hsum8(f[r], gmask));
-			}
-			f48 = __fmul_rn(__fadd_rn(__fmul_rn(f48, f2f), __fmul_rn(b_old, d48)), tt_e(row, seq, i, 48));
-			f_sum_new = __fadd_rn(f_sum_new, f48);
-			f49 = __fmul_rn(__fadd_rn(__fmul_rn(f49, f2f), __fmul_rn(b_old, d49)), tt_e(row, seq, i, 49));
-			f_sum_new = __fadd_rn(f_sum_new, f49);
-			b = __fadd_rn(__fmul_rn(b_old, b2b), __fmul_rn(f_sum, p_repeat_end));
-			f_sum = f_sum_new;
-			if ((i & 15) == 15) {
-				const float s = __fdiv_rn(1.0f, b);
-				if (k == 0) scs[i >> 4] = s;
-				b = __fmul_rn(b, s);
-#pragma unroll
-				for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
-				f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
-				f_sum = __fmul_rn(f_sum, s);
-			}
-			if (k == 0) pbs[i] = b;
-		}
-		// z = b * b2b + sum(f, 50) * p_repeat_end, util/simd/vector.h:37-48 for the sum
-		float acc = 0.0f;
-#pragma unroll
-		for (int r = 0; r < 6; ++r) acc = __fadd_rn(acc, f[r]);
-		float fs = hsum8(acc, gmask);
-		fs = __fadd_rn(fs, f48);
-		fs = __fadd_rn(fs, f49);
-		const float z = __fadd_rn(__fmul_rn(b, b2b), __fmul_rn(fs, p_repeat_end));
-		const float zinv = __fdiv_rn(1.0f, z);
-		// ---- backward pass, tantan.cpp:192-212 with backward_step :78-111.  Only the group's first lane reads pb / scale back
-		// (its own stores) and decides; the scale factor is broadcast.
-		b = b2b;
-#pragma unroll
-		for (int r = 0; r < 6; ++r) f[r] = p_repeat_end;
-		f48 = p_repeat_end; f49 = p_repeat_end;
-		for (int i = len - 1; i >= 0; --i) {
-			bool mask_it = false;
-			if (k == 0) {
-				const float pf = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(pbs[i], b), zinv));
-				mask_it = pf >= p_mask;
-			}
-			if ((i & 15) == 15) {
-				float s = 0.0f;
-				if (k == 0) s = scs[i >> 4];
-				s = __shfl_sync(gmask, s, lead);
-				b = __fmul_rn(b, s);
-#pragma unroll
-				for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
-				f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
-			}
-			const float* row = s_lr + (seq[i] & 31) * 32;
-			const float vC = __fmul_rn(p_repeat_end, b);
-			float tsum = 0.0f;
-#pragma unroll
-			for (int r = 0; r < 6; ++r) {
-				const float vf = __fmul_rn(f[r], tt_e(row, seq, i, 8 * r + k));
-				const float vt = __fmul_rn(vf, d[r]);
-				f[r] = __fadd_rn(__fmul_rn(vf, f2f), vC);
-				tsum = __fadd_rn(tsum, hsum8(vt, gmask));
-			}
-			{
-				const float vf = __fmul_rn(f48, tt_e(row, seq, i, 48));
-				tsum = __fadd_rn(tsum, __fmul_rn(vf, d48));
-				f48 = __fadd_rn(__fmul_rn(vf, f2f), vC);
-			}
-			{
-				const float vf = __fmul_rn(f49, tt_e(row, seq, i, 49));
-				tsum = __fadd_rn(tsum, __fmul_rn(vf, d49));
-				f49 = __fadd_rn(__fmul_rn(vf, f2f), vC);
-			}
-			b = __fadd_rn(__fmul_rn(b2b, b), tsum);
-			// position i is never read again (the remaining steps look at letters before i): mask it in place now
-			__syncwarp(gmask);  // every lane of the group has read seq[i] for this step
-			if (mask_it) {
-				seq[i] = 23;  // value_traits.mask_char = MASK_LETTER
-				const uint64_t p = (uint64_t)(beg + i);
-				atomicOr(&hard[p >> 5], 1u << (p & 31));
-			}
-		}
-	}
-}
-
-__global__ void popc_kernel(const uint32_t* __restrict__ bits, size_t w_begin, size_t w_end, unsigned long long* total) {
-	const size_t w = w_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned n = w < w_end ? __popc(bits[w]) : 0u;
-	for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
-	if ((threadIdx.x & 31) == 0 && n) atomicAdd(total, (unsigned long long)n);
-}
-
-struct BitSet {
-	const uint32_t* bits;
-	__host__ __device__ bool operator()(const uint64_t& p) const { return (bits[p >> 5] >> (p & 31)) & 1u; }
-};
-
-// ---- motifs -------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t motif_hash(uint64_t code) { return (uint32_t)((code * 0x9E3779B97F4A7C15ull) >> 48); }
-
-#define MOTIF_TILE 2048
-__global__ void __launch_bounds__(256) motif_hit_kernel(const int8_t* __restrict__ letters, size_t raw_len, size_t p_begin, size_t p_end, const uint64_t* __restrict__ table,
-                                                        uint32_t* cov, const int64_t* __restrict__ limits, uint32_t s_begin, uint32_t s_end,
-                                                        uint32_t* seq_flag, uint32_t* seq_list, unsigned int* n_list) {
-	__shared__ uint64_t s_tab[DMND_MOTIF_COUNT];
-	__shared__ uint32_t s_pre[2048];  // 64 Kbit prefilter over motif_hash
-	__shared__ uint8_t s_let[MOTIF_TILE + DMND_MOTIF_LEN];
-	for (int x = threadIdx.x; x < 2048; x += blockDim.x) s_pre[x] = 0;
-	for (int x = threadIdx.x; x < DMND_MOTIF_COUNT; x += blockDim.x) s_tab[x] = table[x];
-	const size_t p0 = p_begin + (size_t)blockIdx.x * MOTIF_TILE;
-	for (int x = threadIdx.x; x < MOTIF_TILE + DMND_MOTIF_LEN; x += blockDim.x) s_let[x] = p0 + x < raw_len ? (uint8_t)(letters[p0 + x] & 31) : (uint8_t)DMND_DELIMITER;
-	__syncthreads();
-	for (int x = threadIdx.x; x < DMND_MOTIF_COUNT; x += blockDim.x) { const uint32_t h = motif_hash(s_tab[x]); atomicOr(&s_pre[h >> 5], 1u << (h & 31)); }
-	__syncthreads();
-	for (int it = 0; it < MOTIF_TILE / 256; ++it) {
-		const int o = it * 256 + threadIdx.x;
-		const size_t p = p0 + o;
-		if (p >= p_end) continue;
-		// KmerIterator<8> (util/kmer/kmer.h:62-117): a k-mer exists where 8 consecutive letters are < TRUE_AA (the delimiter is 31)
-		uint64_t code = 0;
-		unsigned bad = 0;
-#pragma unroll
-		for (int q = 0; q < DMND_MOTIF_LEN; ++q) { const unsigned l = s_let[o + q]; bad |= l >= 20u; code = code * 20u + l; }
-		if (bad) continue;
-		const uint32_t h = motif_hash(code);
-		if (!((s_pre[h >> 5] >> (h & 31)) & 1u)) continue;
-		int lo = 0, hi = DMND_MOTIF_COUNT;
-		while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tab[mid] < code) lo = mid + 1; else hi = mid; }
-		if (lo == DMND_MOTIF_COUNT || s_tab[lo] != code) continue;
-		// pos.push_back(p, p + 8), masking.cpp:116-119: coverage bits
-		const unsigned sh = (unsigned)(p & 31);
-		atomicOr(&cov[p >> 5], 0xffu << sh);
-		if (sh > 24) atomicOr(&cov[(p >> 5) + 1], 0xffu >> (32 - sh));
-		uint32_t a = s_begin, b = s_end;  // sequence holding p
-		while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)limits[mid] <= (uint64_t)p) a = mid; else b = mid; }
-		const uint32_t bit = 1u << (a & 31);
-		if (!(atomicOr(&seq_flag[a >> 5], bit) & bit)) seq_list[atomicAdd(n_list, 1u)] = a;
-	}
-}
-
-__device__ __forceinline__ bool bit_at(const uint32_t* bits, size_t p) { return (bits[p >> 5] >> (p & 31)) & 1u; }
-__device__ __forceinline__ void set_bits(uint32_t* bits, size_t b, size_t e) {  // [b, e)
-	for (size_t p = b; p < e;) {
-		const unsigned sh = (unsigned)(p & 31);
-		const size_t n = (size_t)(32 - sh) < e - p ? (size_t)(32 - sh) : e - p;
-		const uint32_t m = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << sh;
-		atomicOr(&bits[p >> 5], m);
-		p += n;
-	}
-}
-
-// One thread per sequence with at least one table hit: masking.cpp:120-129
-__global__ void motif_apply_kernel(const int64_t* __restrict__ limits, const uint32_t* __restrict__ seq_list, const unsigned int* __restrict__ n_list,
-                                   const uint32_t* __restrict__ cov, uint32_t* soft, int max_motif_len) {
-	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= *n_list) return;
-	const uint32_t sid = seq_list[t];
-	const size_t beg = (size_t)limits[sid], end = (size_t)limits[sid + 1] - 1;
-	const size_t len = end - beg;
-	size_t n = 0;
-	for (size_t p = beg; p < end; ++p) n += bit_at(cov, p);
-	if ((double)(ptrdiff_t)n / (double)len >= 0.5) return;
-	for (size_t p = beg; p < end;) {
-		if (!bit_at(cov, p)) { ++p; continue; }
-		size_t e = p;
-		while (e < end && bit_at(cov, e)) ++e;
-		if (e - p <= (size_t)max_motif_len) set_bits(soft, p, e);
-		p = e;
-	}
-}
-
-// clears the bits of [p_begin, p_end) in a bitmap other lanes share at the edges
-__global__ void clear_bits_kernel(uint32_t* bits, size_t p_begin, size_t p_end) {
-	const size_t w = (p_begin >> 5) + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (w > ((p_end - 1) >> 5)) return;
-	uint32_t m = 0xffffffffu;
-	if (w == (p_begin >> 5)) m &= 0xffffffffu << (p_begin & 31);
-	if (w == ((p_end - 1) >> 5)) m &= 0xffffffffu >> (31 - ((p_end - 1) & 31));
-	if (m == 0xffffffffu) bits[w] = 0; else atomicAnd(&bits[w], ~m);
-}
 
 int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard) {
 	if (s_begin > s_end || s_end > b->nseq) { set_error("dmnd_block_mask: bad sequence range"); return 1; }

@@ -12,6 +12,7 @@
 // Chunk order matters and is reproduced: SEED_MASK bits set while processing chunk k are visible to the left-most
 // filter of chunks >= k, and verify_hit compares seed partitions against the current chunk's range (left_most.h:32-41).
 #include "ctx.cuh"
+#include "mask_kernels.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 
@@ -23,10 +24,6 @@ __device__ __forceinline__ uint64_t mix40(uint64_t seed) { return (seed * 0x9E37
 
 // basic/shape.h:113-171 on the reduced sequence; a window that contains a delimiter is past the end of its sequence
 // (search/seed_array/seed_iterator.h:30-33).
-// One bit per letter: inside a MaskingTable entry (abundant motif, dmnd_block_mask).  While seeds are enumerated such a
-// letter reads as MASK_LETTER (Block::soft_mask, data/block/block.cpp:162-171, search/seed_array/enum_seeds.h:262-270).
-__device__ __forceinline__ bool soft_bit(const uint32_t* __restrict__ soft, size_t p) { return (soft[p >> 5] >> (p & 31)) & 1u; }
-
 __device__ __forceinline__ bool seed_at(const DevParams* P, int sid, const int8_t* s, const uint32_t* __restrict__ soft, size_t p, uint64_t& out) {
 	const int span = P->shape_len[sid];
 	bool ok = true;
@@ -204,22 +201,6 @@ __device__ __forceinline__ bool seed_is_complex(const DevParams* P, int sid, con
 	double entropy = P->lnfact[P->shape_weight];
 	for (int c = 0; c < P->reduction_size; ++c) entropy -= P->lnfact[count[c]];
 	return entropy >= P->seed_cut;
-}
-
-// MaskingTable::remove(template_len, add_bit_mask = true) after the query enumeration (masking/masking.cpp:96-107 through
-// search/seed_array/enum_seeds.h:255-260, EnumCfg::mask_seeds of the query side, search/stage0.cpp:139-142): an entry [b, e)
-// leaves SEED_MASK on [max(b - span + 1, 0), e) of its sequence, i.e. on every position j that sees a soft-masked letter of
-// its own sequence within [j, j + span).  One thread per position; each writes only its own byte.
-__global__ void motif_seedmask_kernel(int8_t* q_letters, const uint32_t* __restrict__ soft, size_t p_begin, size_t p_end, int span) {
-	const size_t j = p_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= p_end) return;
-	const uint32_t w0 = soft[j >> 5], w1 = soft[(j >> 5) + 1];
-	const uint32_t v = __funnelshift_r(w0, w1, (unsigned)(j & 31)) & ((1u << span) - 1u);
-	if (v == 0) return;
-	for (int k = 0; k < span; ++k) {
-		if ((q_letters[j + k] & 31) == DMND_DELIMITER) return;
-		if ((v >> k) & 1u) { q_letters[j] = (int8_t)(q_letters[j] | DMND_SEED_MASK); return; }
-	}
 }
 
 // Chunk pass 1: entropy masking.  pairs[e] = number of (q,s) pairs entry e contributes to THIS chunk's search.

@@ -532,6 +532,35 @@ static uint32_t seq_of(const dmnd_block* b, uint64_t loc) { /* SequenceSet::loca
 	return lo;
 }
 
+/* MaskingTable::remove(template_len, add_bit_mask = true) after the query enumeration (masking/masking.cpp:96-107,
+ * search/seed_array/enum_seeds.h:255-260 with EnumCfg::mask_seeds of the query side, search/stage0.cpp:139-142):
+ * every table entry [b, e) leaves SEED_MASK on [max(b - shape_len + 1, 0), e).  Entries are the maximal runs of `soft`. */
+static void motif_seed_mask(const dmnd_params* p, dmnd_block* query, int sid, uint32_t q_begin, uint32_t q_end) {
+	const int tl = p->shape_len[sid];
+	for (uint32_t qi = q_begin; qi < q_end; ++qi) {
+		const int64_t beg = query->limits[qi];
+		const int len = (int)(query->limits[qi + 1] - beg - 1);
+		for (int i = 0; i < len;) {
+			if (!query->soft[beg + i]) { ++i; continue; }
+			int e = i;
+			while (e < len && query->soft[beg + e]) ++e;
+			for (int j = (i - tl + 1 > 0 ? i - tl + 1 : 0); j < e; ++j) query->letters[beg + j] |= (int8_t)DMND_SEED_MASK;
+			i = e;
+		}
+	}
+}
+/* Test-only views for tests/emu_mask.cpp (not part of include/dmnd_b200.h): the soft-masking table as one byte per letter,
+ * and the SEED_MASK marking above on its own. */
+int dmnd_oracle_block_soft(const dmnd_block* b, uint8_t* out, size_t raw_len) {
+	if (raw_len != b->raw_len) return fail("dmnd_oracle_block_soft: length mismatch");
+	if (b->soft) memcpy(out, b->soft, raw_len); else memset(out, 0, raw_len);
+	return 0;
+}
+int dmnd_oracle_motif_seed_mask(dmnd_ctx* ctx, dmnd_block* b, int sid, uint32_t q_begin, uint32_t q_end) {
+	if (b->soft) motif_seed_mask(&ctx->p, b, sid, q_begin, q_end);
+	return 0;
+}
+
 int dmnd_search_shape(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, dmnd_hits** out,
                       dmnd_stage_counters* counters) {
 	return dmnd_search_shape_range(ctx, query, ref, sid, 0, query->nseq, out, counters);
@@ -548,23 +577,7 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
 	const uint32_t nchunks = (uint32_t)p->index_chunks < parts_total ? (uint32_t)p->index_chunks : parts_total;
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
 	const int window = p->ungapped_window;
-	if (query->soft) {
-		/* MaskingTable::remove(template_len, add_bit_mask = true) after the query enumeration (masking/masking.cpp:96-107,
-		 * search/seed_array/enum_seeds.h:255-260 with EnumCfg::mask_seeds of the query side, search/stage0.cpp:139-142):
-		 * every table entry [b, e) leaves SEED_MASK on [max(b - shape_len + 1, 0), e).  Entries are the maximal runs of `soft`. */
-		const int tl = p->shape_len[sid];
-		for (uint32_t qi = q_begin; qi < q_end; ++qi) {
-			const int64_t beg = query->limits[qi];
-			const int len = (int)(query->limits[qi + 1] - beg - 1);
-			for (int i = 0; i < len;) {
-				if (!query->soft[beg + i]) { ++i; continue; }
-				int e = i;
-				while (e < len && query->soft[beg + e]) ++e;
-				for (int j = (i - tl + 1 > 0 ? i - tl + 1 : 0); j < e; ++j) query->letters[beg + j] |= (int8_t)DMND_SEED_MASK;
-				i = e;
-			}
-		}
-	}
+	if (query->soft) motif_seed_mask(p, query, sid, q_begin, q_end);
 	for (uint32_t chunk = 0; chunk < nchunks; ++chunk) {
 		const uint32_t bsel = chunk < prem ? chunk : prem;
 		const uint32_t pb = bsel * (psize + 1) + (chunk - bsel) * psize, pe = pb + (chunk < prem ? psize + 1 : psize);
