@@ -42,7 +42,7 @@ $(OBJ)/oracle/dmnd_oracle.o: oracle/dmnd_oracle.c include/dmnd_b200.h $(HOST)/mo
 	gcc -O2 -ffp-contract=off -fPIC -Wall -Wextra -c $< -o $@
 oracle/_build/libdmnd_oracle.so: $(HOST_OBJ) $(OBJ)/oracle/dmnd_oracle.o
 	@mkdir -p $(dir $@)
-	$(CXX) -shared -pthread -o $@ $^
+	$(CXX) -shared -pthread -o $@ $^ -lm
 oracle/_build/dmnd-oracle-cli: $(HOST)/cli.cpp oracle/_build/libdmnd_oracle.so
 	$(CXX) $(CXXFLAGS) $< -o $@ -Loracle/_build -ldmnd_oracle -Wl,-rpath,'$$ORIGIN'
 

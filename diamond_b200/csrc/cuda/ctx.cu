@@ -237,7 +237,7 @@ void dmnd_destroy(dmnd_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->b_keys, &c->b_keys2, &c->b_vals, &c->b_vals2, &c->b_cub, &c->b_bucket, &c->b_entries, &c->b_pairs, &c->b_hits,
 		&c->b_hits2, &c->b_counters, &c->b_probs, &c->b_results, &c->b_order, &c->b_trace, &c->b_trace_off, &c->b_tr, &c->b_work, &c->b_prep, &c->b_bloom,
-		&c->b_mask_pb, &c->b_mask_scale, &c->b_mask_pos, &c->b_mask_pos2, &c->b_mask_cov, &c->b_mask_flag, &c->b_mask_seqs };
+		&c->b_mask_pb, &c->b_mask_scale, &c->b_mask_pos, &c->b_mask_pos2, &c->b_mask_cov, &c->b_mask_flag, &c->b_mask_seqs, &c->b_mask_zinv, &c->b_mask_need };
 	for (DevBuf* b : bufs) b->release();
 	for (auto& f : c->block_pool) { cudaFree(f.letters); cudaFree(f.bias); cudaFree(f.limits); cudaFree(f.soft); f.idx.release(); }
 	c->b_hits_out.release();

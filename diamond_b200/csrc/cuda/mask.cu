@@ -24,11 +24,32 @@ int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, ui
 	if (algo & DMND_MASK_TANTAN) {
 		if (ctx->b_mask_pb.ensure(nlet * 4) || ctx->b_mask_scale.ensure(((nlet >> 4) + nseq + 2) * 4)) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_bits + w_begin, 0, (w_end - w_begin) * 4, st));
-		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), st));
-		// persistent grid, sequences handed out one at a time to 8-lane groups (lengths vary by orders of magnitude)
-		const unsigned groups = (unsigned)std::min<size_t>((nseq + 15) / 16, (size_t)ctx->sm_count * 8);
-		tantan_kernel<<<std::max(groups, 1u), 128, 0, st>>>(b->letters, b->limits, s_begin, s_end, ctx->d_params, ctx->b_mask_pb.as<float>(),
-			ctx->b_mask_scale.as<float>(), (int64_t)p_begin, (unsigned int*)(d_cnt + 1), d_bits);
+		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 6 * sizeof(unsigned long long), st));
+		// longest-first order of the range's sequences: the four sequences of a warp run in lock step (mask_kernels.cuh), so
+		// neighbours in the order should have the same length; long sequences also start first
+		if (ctx->b_keys.ensure(nseq * 4) || ctx->b_keys2.ensure(nseq * 4) || ctx->b_vals.ensure(nseq * 4) || ctx->b_vals2.ensure(nseq * 4)) return 1;
+		seq_len_kernel<<<(unsigned)((nseq + 255) / 256), 256, 0, st>>>(b->limits, s_begin, (uint32_t)nseq, ctx->b_keys.as<uint32_t>(), ctx->b_vals.as<uint32_t>());
+		{
+			size_t tmp = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, ctx->b_keys.as<uint32_t>(), ctx->b_keys2.as<uint32_t>(), ctx->b_vals.as<uint32_t>(), ctx->b_vals2.as<uint32_t>(), (int)nseq, 0, 32, st);
+			if (ctx->b_cub.ensure(tmp)) return 1;
+			DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ctx->b_cub.p, tmp, ctx->b_keys.as<uint32_t>(), ctx->b_keys2.as<uint32_t>(), ctx->b_vals.as<uint32_t>(), ctx->b_vals2.as<uint32_t>(), (int)nseq, 0, 32, st));
+		}
+		// forward pass of everything; it also decides which sequences need the backward pass at all (mask_kernels.cuh); the
+		// compacted longest-first list of those goes through the backward kernel, whose grid covers the worst case
+		if (ctx->b_mask_zinv.ensure(nseq * 4) || ctx->b_mask_need.ensure(nseq + 16)) return 1;
+		int* d_nneed = (int*)(d_cnt + 2);
+		tantan_forward_kernel<<<(unsigned)((nseq + 15) / 16), 128, 0, st>>>(b->letters, b->limits, ctx->b_vals2.as<uint32_t>(), (uint32_t)nseq, ctx->d_params,
+			ctx->b_mask_pb.as<float>(), ctx->b_mask_scale.as<float>(), (int64_t)p_begin, s_begin, ctx->b_mask_zinv.as<float>(), ctx->b_mask_need.as<uint8_t>());
+		{
+			size_t tmp = 0;
+			cub::DeviceSelect::Flagged(nullptr, tmp, ctx->b_vals2.as<uint32_t>(), ctx->b_mask_need.as<uint8_t>(), ctx->b_keys2.as<uint32_t>(), d_nneed, (int)nseq, st);
+			if (ctx->b_cub.ensure(tmp)) return 1;
+			DMND_CUDA_CHECK(cub::DeviceSelect::Flagged(ctx->b_cub.p, tmp, ctx->b_vals2.as<uint32_t>(), ctx->b_mask_need.as<uint8_t>(), ctx->b_keys2.as<uint32_t>(), d_nneed, (int)nseq, st));
+		}
+		tantan_backward_kernel<<<(unsigned)((nseq + 15) / 16), 128, 0, st>>>(b->letters, b->limits, ctx->b_keys2.as<uint32_t>(), d_nneed, ctx->d_params,
+			ctx->b_mask_pb.as<float>(), ctx->b_mask_scale.as<float>(), (int64_t)p_begin, s_begin, ctx->b_mask_zinv.as<float>(), d_bits);
+		ctx->launches += 8;
 		popc_kernel<<<(unsigned)((w_end - w_begin + 255) / 256), 256, 0, st>>>(d_bits, w_begin, w_end, d_cnt);
 		ctx->launches += 2;
 		DMND_CUDA_CHECK(cudaGetLastError());
@@ -40,7 +61,7 @@ int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, ui
 			if (ctx->b_mask_pos.ensure((size_t)n * 8)) return 1;
 			cub::CountingInputIterator<uint64_t> first((uint64_t)p_begin);
 			size_t tmp = 0;
-			int* d_num = (int*)(d_cnt + 2);
+			int* d_num = (int*)(d_cnt + 4);
 			cub::DeviceSelect::If(nullptr, tmp, first, ctx->b_mask_pos.as<uint64_t>(), d_num, (int)nlet, BitSet{ d_bits }, st);
 			if (ctx->b_cub.ensure(tmp)) return 1;
 			DMND_CUDA_CHECK(cub::DeviceSelect::If(ctx->b_cub.p, tmp, first, ctx->b_mask_pos.as<uint64_t>(), d_num, (int)nlet, BitSet{ d_bits }, st));

@@ -30,134 +30,224 @@ namespace dmnd_cuda {
 // letter reads as MASK_LETTER (Block::soft_mask, data/block/block.cpp:162-171, search/seed_array/enum_seeds.h:262-270).
 __device__ __forceinline__ bool soft_bit(const uint32_t* __restrict__ soft, size_t p) { return (soft[p >> 5] >> (p & 31)) & 1u; }
 
-// hsum (util/simd/vector8_avx2.h:132-139) over the 8 lanes of a group; every lane returns the same value
-__device__ __forceinline__ float hsum8(float v, unsigned gmask) {
-	const float x = __fadd_rn(v, __shfl_xor_sync(gmask, v, 4));
-	const float y = __fadd_rn(x, __shfl_xor_sync(gmask, x, 1));
-	return __fadd_rn(y, __shfl_xor_sync(gmask, y, 2));
+// hsum (util/simd/vector8_avx2.h:132-139) over the 8 lanes of a group; every lane returns the same value.  All four groups
+// of a warp run in lock step (see tantan_kernel), so the shuffles use the full mask: xor 4, 1, 2 never leaves a group.
+__device__ __forceinline__ float hsum8(float v) {
+	const float x = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+	const float y = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 1));
+	return __fadd_rn(y, __shfl_xor_sync(0xffffffffu, y, 2));
 }
 
-// e_seg[off] (tantan.cpp:163-171,181): likelihood ratio of letter i (row) against the letter off + 1 positions before it
-__device__ __forceinline__ float tt_e(const float* row, const int8_t* seq, int i, int off) {
-	const int j = i - 1 - off;
-	return j >= 0 ? row[seq[j] & 31] : 0.0f;
+// (sequence length, sequence id) of the range, input of the longest-first order the tantan kernel walks
+static __global__ void seq_len_kernel(const int64_t* __restrict__ limits, uint32_t s_begin, uint32_t n, uint32_t* len, uint32_t* id) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const uint32_t sid = s_begin + t;
+	len[t] = (uint32_t)(limits[sid + 1] - limits[sid] - 1);
+	id[t] = sid;
 }
 
-static __global__ void __launch_bounds__(128) tantan_kernel(int8_t* letters, const int64_t* __restrict__ limits, uint32_t s_begin, uint32_t s_end,
-                                                     const DevParams* __restrict__ P, float* pb, float* scale, int64_t base,
-                                                     unsigned int* next_seq, uint32_t* hard /* bit per letter offset */) {
+// Eight lanes per sequence, four sequences per warp, `order` = sequence ids sorted by length (longest first), so that the
+// four sequences of a warp have (almost) the same length and the warp can run ONE loop of maxlen steps in lock step:
+//  * forward pass: a shorter sequence starts late (i = t - (maxlen - len)); before its start it is fed delimiters, whose
+//    likelihood ratios are 0, which keeps f == 0 exactly, and b is set to 1 at i == 0 -- all four end together;
+//  * backward pass: all start together at their own last letter (i = len - 1 - t); a sequence that is finished keeps
+//    stepping on delimiters and stores nothing.
+// Lock step makes every shuffle a full-mask shuffle (no per-group convergence barriers) and lets the letters travel in
+// registers: lane k keeps the six letters its states look back at (i-1-8r-k, r = 0..5) packed 5 bits each in W, every lane
+// keeps the two tail letters (i-49, i-50); one step shifts the window by two shuffles instead of eight byte loads.
+// e_seg[off] (tantan.cpp:163-171,181) = ratio(letter i, letter i-1-off) with 0 before the sequence start == ratio row of the
+// delimiter code 31, which dmnd_params_init leaves at 0.
+//
+// The two passes are two kernels, because most sequences never need the second one.  pf(i) = 1 - P(background at i) and
+// every path weight of the HMM is non-negative, so P(background at i) >= W_bg / Z for every i, where Z is the total weight
+// (tantan.cpp:189, what the forward pass ends with) and W_bg = b2b^(len+1) the weight of the all-background path.  A
+// sequence with Z < 8 W_bg therefore has pf(i) <= 0.875 everywhere: nothing reaches p_mask = 0.9 and the backward pass can
+// decide nothing.  (The margin to 0.9, a factor 1.25 in Z, is far beyond the rounding of the fp32 recurrences -- sums of
+// positive terms -- at the lengths the shortcut is allowed for; longer sequences always take the full computation.)  ~98 %
+// of random 300-letter sequences and ~93 % of a synthetic 100 k-protein block are decided by the forward kernel alone; the
+// masked letters are identical either way (tests: emulation + device vs the oracle, which knows no shortcut).
+#define TANTAN_CERT_MAX_LEN 4096
+#define TANTAN_CERT_LOG2_RATIO 3.0f
+
+struct TantanGroup {  // what both passes derive from the slot of an 8-lane group
+	uint32_t sid;
+	int64_t beg;
+	int len, maxlen;
+};
+__device__ __forceinline__ TantanGroup tantan_group(const int64_t* __restrict__ limits, const uint32_t* __restrict__ order, uint32_t n_seq) {
+	TantanGroup g;
+	const uint32_t slot = (uint32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+	g.sid = 0; g.beg = 0; g.len = 0;
+	if (slot < n_seq) { g.sid = order[slot]; g.beg = limits[g.sid]; g.len = (int)(limits[g.sid + 1] - g.beg - 1); }
+	int m = max(g.len, __shfl_xor_sync(0xffffffffu, g.len, 8));
+	g.maxlen = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+	return g;
+}
+
+// Forward pass of every sequence of the range: stores pb[i] (tantan.cpp:186), the scale factors (:181-185), 1/z per sequence
+// and whether the backward pass is needed at all.
+static __global__ void __launch_bounds__(128) tantan_forward_kernel(const int8_t* __restrict__ letters, const int64_t* __restrict__ limits, const uint32_t* __restrict__ order,
+                                                                    uint32_t n_seq, const DevParams* __restrict__ P, float* pb, float* scale, int64_t base, uint32_t s_begin,
+                                                                    float* zinv_out /* by sid - s_begin */, uint8_t* need /* by slot */) {
 	__shared__ float s_lr[1024];
 	for (int x = threadIdx.x; x < 1024; x += blockDim.x) s_lr[x] = P->tantan_lr[x];
 	__syncthreads();
 	const int lane = threadIdx.x & 31, k = lane & 7, lead = lane & 24;
-	const unsigned gmask = 0xffu << lead;
+	const uint32_t slot = (uint32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+	const TantanGroup g = tantan_group(limits, order, n_seq);
+	const int len = g.len, maxlen = g.maxlen;
+	if (maxlen <= 0) {  // warp-uniform: nothing but empty slots / empty sequences
+		if (k == 0 && slot < n_seq) need[slot] = 0;
+		return;
+	}
+	const int8_t* seq = letters + g.beg;
+	float* pbs = pb + (g.beg - base);
+	float* scs = scale + ((g.beg - base) >> 4) + (g.sid - s_begin);
+	float d[6];
+#pragma unroll
+	for (int r = 0; r < 6; ++r) d[r] = P->tantan_d[8 * r + k];
+	const float d48 = P->tantan_d[48], d49 = P->tantan_d[49];
+	const float b2b = P->tantan_b2b, f2f = P->tantan_f2f, p_repeat_end = P->tantan_p_repeat_end;
+	float f[6], f48 = 0.0f, f49 = 0.0f;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) f[r] = 0.0f;
+	float b = 1.0f, f_sum = 0.0f;
+	float log2_unscale = 0.0f;  // log2 of the product of the b's the rescaling divided by: Z = z * 2^log2_unscale
+	uint32_t W = 0x3fffffffu, T48 = 31u, T49 = 31u;  // nothing but delimiters before the sequence
+	// tantan.cpp:173-187 with forward_step :43-76
+	const int shift = maxlen - len;
+	for (int t = 0; t < maxlen; ++t) {
+		const int i = t - shift;
+		const uint32_t s_cur = i >= 0 ? (uint32_t)(seq[i] & 31) : 31u;
+		if (i == 0) b = 1.0f;  // (f and f_sum are still exactly 0)
+		const float* row = s_lr + s_cur * 32;
+		const float b_old = b;
+		float f_sum_new = 0.0f;
+#pragma unroll
+		for (int r = 0; r < 6; ++r) {
+			const float tmp = __fadd_rn(__fmul_rn(f[r], f2f), __fmul_rn(b_old, d[r]));
+			f[r] = __fmul_rn(tmp, row[(W >> (5 * r)) & 31u]);
+			f_sum_new = __fadd_rn(f_sum_new, hsum8(f[r]));
+		}
+		f48 = __fmul_rn(__fadd_rn(__fmul_rn(f48, f2f), __fmul_rn(b_old, d48)), row[T48]);
+		f_sum_new = __fadd_rn(f_sum_new, f48);
+		f49 = __fmul_rn(__fadd_rn(__fmul_rn(f49, f2f), __fmul_rn(b_old, d49)), row[T49]);
+		f_sum_new = __fadd_rn(f_sum_new, f49);
+		b = __fadd_rn(__fmul_rn(b_old, b2b), __fmul_rn(f_sum, p_repeat_end));
+		f_sum = f_sum_new;
+		if ((i & 15) == 15) {  // (also at negative i: there it only renormalises b, f is 0)
+			const float s = __fdiv_rn(1.0f, b);
+			if (i >= 0) { log2_unscale += __log2f(b); if (k == 0) scs[i >> 4] = s; }
+			b = __fmul_rn(b, s);
+#pragma unroll
+			for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
+			f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
+			f_sum = __fmul_rn(f_sum, s);
+		}
+		if (k == 0 && i >= 0) pbs[i] = b;
+		// window of letter i + 1: lane k takes lane k-1's, lane 0 takes lane 7's shifted up with letter i at the bottom
+		const uint32_t Wp = __shfl_sync(0xffffffffu, W, lead + ((k + 7) & 7));
+		const uint32_t W7 = __shfl_sync(0xffffffffu, W, lead + 7);
+		T49 = T48;
+		T48 = (W7 >> 25) & 31u;  // letter i-48
+		W = k ? Wp : (((Wp << 5) | s_cur) & 0x3fffffffu);
+	}
+	// z = b * b2b + sum(f, 50) * p_repeat_end, util/simd/vector.h:37-48 for the sum
+	float acc = 0.0f;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) acc = __fadd_rn(acc, f[r]);
+	float fs = hsum8(acc);
+	fs = __fadd_rn(fs, f48);
+	fs = __fadd_rn(fs, f49);
+	const float z = __fadd_rn(__fmul_rn(b, b2b), __fmul_rn(fs, p_repeat_end));
+	if (k == 0 && slot < n_seq) {
+		zinv_out[g.sid - s_begin] = __fdiv_rn(1.0f, z);
+		// log2(Z / W_bg) < 3: no letter of this sequence can reach the masking threshold (see above); NaN compares false
+		const float log2_ratio = __log2f(z) + log2_unscale - (float)(len + 1) * __log2f(b2b);
+		need[slot] = (len > 0 && !(len <= TANTAN_CERT_MAX_LEN && log2_ratio < TANTAN_CERT_LOG2_RATIO)) ? 1 : 0;
+	}
+}
+
+// Backward pass (tantan.cpp:192-212 with backward_step :78-111) of the sequences the forward kernel could not decide:
+// `order` is the compacted longest-first list, *n_need its length (the grid covers the worst case, surplus warps leave).
+static __global__ void __launch_bounds__(128) tantan_backward_kernel(int8_t* letters, const int64_t* __restrict__ limits, const uint32_t* __restrict__ order,
+                                                                     const int* __restrict__ n_need, const DevParams* __restrict__ P, const float* __restrict__ pb,
+                                                                     const float* __restrict__ scale, int64_t base, uint32_t s_begin, const float* __restrict__ zinv_in,
+                                                                     uint32_t* hard /* bit per letter offset */) {
+	__shared__ float s_lr[1024];
+	for (int x = threadIdx.x; x < 1024; x += blockDim.x) s_lr[x] = P->tantan_lr[x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31, k = lane & 7, lead = lane & 24;
+	const TantanGroup g = tantan_group(limits, order, (uint32_t)*n_need);
+	const int len = g.len, maxlen = g.maxlen;
+	if (maxlen <= 0) return;  // warp-uniform
+	const int8_t* seq = letters + g.beg;
+	const float* pbs = pb + (g.beg - base);
+	const float* scs = scale + ((g.beg - base) >> 4) + (g.sid - s_begin);
 	float d[6];
 #pragma unroll
 	for (int r = 0; r < 6; ++r) d[r] = P->tantan_d[8 * r + k];
 	const float d48 = P->tantan_d[48], d49 = P->tantan_d[49];
 	const float b2b = P->tantan_b2b, f2f = P->tantan_f2f, p_repeat_end = P->tantan_p_repeat_end, p_mask = P->tantan_p_mask;
-	for (;;) {
-		unsigned int sid = 0;
-		if (k == 0) sid = atomicAdd(next_seq, 1u);
-		sid = __shfl_sync(gmask, sid, lead) + s_begin;
-		if (sid >= s_end) break;
-		const int64_t beg = limits[sid];
-		const int len = (int)(limits[sid + 1] - beg - 1);
-		if (len <= 0) continue;
-		int8_t* seq = letters + beg;
-		float* pbs = pb + (beg - base);
-		float* scs = scale + ((beg - base) >> 4) + (sid - s_begin);
-		float f[6], f48 = 0.0f, f49 = 0.0f;
+	const float zinv = len > 0 ? zinv_in[g.sid - s_begin] : 0.0f;
+	// window of the last letter: the letters len-2-8r-k (delimiter code before the start), tails len-50 and len-51
+	uint32_t W = 0;
 #pragma unroll
-		for (int r = 0; r < 6; ++r) f[r] = 0.0f;
-		float b = 1.0f, f_sum = 0.0f;
-		// ---- forward pass, tantan.cpp:173-187 with forward_step :43-76
-		for (int i = 0; i < len; ++i) {
-			const float* row = s_lr + (seq[i] & 31) * 32;
-			const float b_old = b;
-			float f_sum_new = 0.0f;
+	for (int r = 0; r < 6; ++r) { const int j = len - 2 - 8 * r - k; W |= (j >= 0 ? (uint32_t)(seq[j] & 31) : 31u) << (5 * r); }
+	uint32_t T48 = len >= 50 ? (uint32_t)(seq[len - 50] & 31) : 31u, T49 = len >= 51 ? (uint32_t)(seq[len - 51] & 31) : 31u;
+	uint32_t s_cur = len >= 1 ? (uint32_t)(seq[len - 1] & 31) : 31u;
+	float f[6], f48 = p_repeat_end, f49 = p_repeat_end;
 #pragma unroll
-			for (int r = 0; r < 6; ++r) {
-				const float tmp = __fadd_rn(__fmul_rn(f[r], f2f), __fmul_rn(b_old, d[r]));
-				f[r] = __fmul_rn(tmp, tt_e(row, seq, i, 8 * r + k));
-				f_sum_new = __fadd_rn(f_sum_new, hsum8(f[r], gmask));
-			}
-			f48 = __fmul_rn(__fadd_rn(__fmul_rn(f48, f2f), __fmul_rn(b_old, d48)), tt_e(row, seq, i, 48));
-			f_sum_new = __fadd_rn(f_sum_new, f48);
-			f49 = __fmul_rn(__fadd_rn(__fmul_rn(f49, f2f), __fmul_rn(b_old, d49)), tt_e(row, seq, i, 49));
-			f_sum_new = __fadd_rn(f_sum_new, f49);
-			b = __fadd_rn(__fmul_rn(b_old, b2b), __fmul_rn(f_sum, p_repeat_end));
-			f_sum = f_sum_new;
-			if ((i & 15) == 15) {
-				const float s = __fdiv_rn(1.0f, b);
-				if (k == 0) scs[i >> 4] = s;
-				b = __fmul_rn(b, s);
-#pragma unroll
-				for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
-				f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
-				f_sum = __fmul_rn(f_sum, s);
-			}
-			if (k == 0) pbs[i] = b;
+	for (int r = 0; r < 6; ++r) f[r] = p_repeat_end;
+	float b = b2b;
+	for (int t = 0; t < maxlen; ++t) {
+		const int i = len - 1 - t;  // < 0: this sequence is done, the group idles on delimiters
+		bool mask_it = false;
+		if (k == 0 && i >= 0) {
+			const float pf = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(pbs[i], b), zinv));
+			mask_it = pf >= p_mask;
 		}
-		// z = b * b2b + sum(f, 50) * p_repeat_end, util/simd/vector.h:37-48 for the sum
-		float acc = 0.0f;
+		if (i >= 0 && (i & 15) == 15) {
+			const float s = scs[i >> 4];
+			b = __fmul_rn(b, s);
 #pragma unroll
-		for (int r = 0; r < 6; ++r) acc = __fadd_rn(acc, f[r]);
-		float fs = hsum8(acc, gmask);
-		fs = __fadd_rn(fs, f48);
-		fs = __fadd_rn(fs, f49);
-		const float z = __fadd_rn(__fmul_rn(b, b2b), __fmul_rn(fs, p_repeat_end));
-		const float zinv = __fdiv_rn(1.0f, z);
-		// ---- backward pass, tantan.cpp:192-212 with backward_step :78-111.  Only the group's first lane reads pb / scale back
-		// (its own stores) and decides; the scale factor is broadcast.
-		b = b2b;
-#pragma unroll
-		for (int r = 0; r < 6; ++r) f[r] = p_repeat_end;
-		f48 = p_repeat_end; f49 = p_repeat_end;
-		for (int i = len - 1; i >= 0; --i) {
-			bool mask_it = false;
-			if (k == 0) {
-				const float pf = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(pbs[i], b), zinv));
-				mask_it = pf >= p_mask;
-			}
-			if ((i & 15) == 15) {
-				float s = 0.0f;
-				if (k == 0) s = scs[i >> 4];
-				s = __shfl_sync(gmask, s, lead);
-				b = __fmul_rn(b, s);
-#pragma unroll
-				for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
-				f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
-			}
-			const float* row = s_lr + (seq[i] & 31) * 32;
-			const float vC = __fmul_rn(p_repeat_end, b);
-			float tsum = 0.0f;
-#pragma unroll
-			for (int r = 0; r < 6; ++r) {
-				const float vf = __fmul_rn(f[r], tt_e(row, seq, i, 8 * r + k));
-				const float vt = __fmul_rn(vf, d[r]);
-				f[r] = __fadd_rn(__fmul_rn(vf, f2f), vC);
-				tsum = __fadd_rn(tsum, hsum8(vt, gmask));
-			}
-			{
-				const float vf = __fmul_rn(f48, tt_e(row, seq, i, 48));
-				tsum = __fadd_rn(tsum, __fmul_rn(vf, d48));
-				f48 = __fadd_rn(__fmul_rn(vf, f2f), vC);
-			}
-			{
-				const float vf = __fmul_rn(f49, tt_e(row, seq, i, 49));
-				tsum = __fadd_rn(tsum, __fmul_rn(vf, d49));
-				f49 = __fadd_rn(__fmul_rn(vf, f2f), vC);
-			}
-			b = __fadd_rn(__fmul_rn(b2b, b), tsum);
-			// position i is never read again (the remaining steps look at letters before i): mask it in place now
-			__syncwarp(gmask);  // every lane of the group has read seq[i] for this step
-			if (mask_it) {
-				seq[i] = 23;  // value_traits.mask_char = MASK_LETTER
-				const uint64_t p = (uint64_t)(beg + i);
-				atomicOr(&hard[p >> 5], 1u << (p & 31));
-			}
+			for (int r = 0; r < 6; ++r) f[r] = __fmul_rn(f[r], s);
+			f48 = __fmul_rn(f48, s); f49 = __fmul_rn(f49, s);
 		}
+		const float* row = s_lr + s_cur * 32;
+		const float vC = __fmul_rn(p_repeat_end, b);
+		float tsum = 0.0f;
+#pragma unroll
+		for (int r = 0; r < 6; ++r) {
+			const float vf = __fmul_rn(f[r], row[(W >> (5 * r)) & 31u]);
+			const float vt = __fmul_rn(vf, d[r]);
+			f[r] = __fadd_rn(__fmul_rn(vf, f2f), vC);
+			tsum = __fadd_rn(tsum, hsum8(vt));
+		}
+		{
+			const float vf = __fmul_rn(f48, row[T48]);
+			tsum = __fadd_rn(tsum, __fmul_rn(vf, d48));
+			f48 = __fadd_rn(__fmul_rn(vf, f2f), vC);
+		}
+		{
+			const float vf = __fmul_rn(f49, row[T49]);
+			tsum = __fadd_rn(tsum, __fmul_rn(vf, d49));
+			f49 = __fadd_rn(__fmul_rn(vf, f2f), vC);
+		}
+		b = __fadd_rn(__fmul_rn(b2b, b), tsum);
+		if (mask_it) {  // position i is never looked at again (its letter already sits in the registers of the steps that need it)
+			letters[g.beg + i] = 23;  // value_traits.mask_char = MASK_LETTER
+			const uint64_t p = (uint64_t)(g.beg + i);
+			atomicOr(&hard[p >> 5], 1u << (p & 31));
+		}
+		// window of letter i - 1: lane k takes lane k+1's, lane 7 takes lane 0's shifted down with letter i-49 on top
+		const uint32_t Wn = __shfl_sync(0xffffffffu, W, lead + ((k + 1) & 7));
+		const uint32_t W0 = __shfl_sync(0xffffffffu, W, lead);
+		W = k < 7 ? Wn : ((W0 >> 5) | (T48 << 25));
+		s_cur = i >= 1 ? (W0 & 31u) : 31u;  // letter i-1 (lane 0's most recent one)
+		T48 = T49;
+		T49 = i >= 51 ? (uint32_t)(seq[i - 51] & 31) : 31u;
 	}
 }
 

@@ -25,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "../diamond_b200/csrc/host/motif_table.h"
 
 static char g_err[512];
@@ -208,7 +209,7 @@ static float tt_e(const dmnd_params* p, const int8_t* seq, int i, int ltr, int o
 }
 /* Util::tantan::mask(seq, len, ..., mask_mode 1): returns the number of letters set to MASK_LETTER, their offsets
  * (base + i) are appended to ctx->mask_pos. */
-static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t base) {
+static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t base, float* log2_ratio) {
 	if (len == 0) return 0;
 	const float* d = p->tantan_d;
 	const float b2b = p->tantan_b2b, f2f = p->tantan_f2f, p_repeat_end = p->tantan_p_repeat_end, p_mask = p->tantan_p_mask;
@@ -217,6 +218,7 @@ static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t ba
 	float* scale = (float*)malloc(sizeof(float) * (size_t)((len - 1) / 16 + 1));
 	for (int k = 0; k < TT_W; ++k) f[k] = 0.0f;
 	float b = 1.0f, f_sum = 0.0f;
+	float log2_unscale = 0.0f; /* test-only: log2 of the product of the b's the rescaling divided by (see dmnd_oracle_tantan_log2_ratio) */
 	for (int i = 0; i < len; ++i) {
 		const int ltr = seq[i] & DMND_LETTER_MASK;
 		/* forward_step, tantan.cpp:43-76 */
@@ -240,6 +242,7 @@ static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t ba
 		f_sum = f_sum_new;
 		if ((i & 15) == 15) {
 			const float s = 1.0f / b;
+			log2_unscale += log2f(b);
 			scale[i / 16] = s;
 			b *= s;
 			for (int k = 0; k < TT_W; ++k) f[k] = f[k] * s;
@@ -249,6 +252,7 @@ static size_t tantan_one(const dmnd_params* p, int8_t* seq, int len, uint64_t ba
 	}
 	const float z = b * b2b + tt_sum50(f) * p_repeat_end;
 	const float zinv = 1.0f / z;
+	if (log2_ratio) *log2_ratio = log2f(z) + log2_unscale - (float)(len + 1) * log2f(b2b);
 	b = b2b;
 	for (int k = 0; k < TT_W; ++k) f[k] = p_repeat_end;
 	size_t n = 0;
@@ -325,7 +329,7 @@ int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, ui
 	t_mask_n = 0;
 	if (algo & DMND_MASK_TANTAN)
 		for (uint32_t i = s_begin; i < s_end; ++i)
-			tantan_one(&ctx->p, b->letters + b->limits[i], (int)(b->limits[i + 1] - b->limits[i] - 1), (uint64_t)b->limits[i]);
+			tantan_one(&ctx->p, b->letters + b->limits[i], (int)(b->limits[i + 1] - b->limits[i] - 1), (uint64_t)b->limits[i], NULL);
 	if (t_mask_n) qsort(t_mask_pos, t_mask_n, sizeof(uint64_t), cmp_u64);
 	if (algo & DMND_MASK_MOTIF) {
 		b->soft = b->soft_buf;
@@ -548,6 +552,18 @@ static void motif_seed_mask(const dmnd_params* p, dmnd_block* query, int sid, ui
 			i = e;
 		}
 	}
+}
+/* Test-only: tantan on every sequence of the block (letters are masked in place); out_ratio[i] = log2(Z / W_bg) of
+ * sequence i as the device's forward kernel computes it (diamond_b200/csrc/cuda/mask_kernels.cuh: sequences with a ratio
+ * below 3 skip the backward pass there), out_masked[i] = letters tantan masked in it.  tests/test_masking.py checks the
+ * implication "ratio < 3  =>  nothing masked" on real and synthetic proteins. */
+int dmnd_oracle_tantan_log2_ratio(dmnd_ctx* ctx, dmnd_block* b, float* out_ratio, uint32_t* out_masked) {
+	t_mask_n = 0;
+	for (uint32_t i = 0; i < b->nseq; ++i) {
+		out_ratio[i] = 0.0f;
+		out_masked[i] = (uint32_t)tantan_one(&ctx->p, b->letters + b->limits[i], (int)(b->limits[i + 1] - b->limits[i] - 1), (uint64_t)b->limits[i], out_ratio + i);
+	}
+	return 0;
 }
 /* Test-only views for tests/emu_mask.cpp (not part of include/dmnd_b200.h): the soft-masking table as one byte per letter,
  * and the SEED_MASK marking above on its own. */

@@ -22,6 +22,7 @@ template<typename T> static std::vector<T> slurp(const std::string& path) {
 	return v;
 }
 
+static size_t g_forward_seqs = 0, g_backward_seqs = 0;
 struct EmuBlock {
 	std::vector<int8_t> letters;  // with the slack the device allocation has
 	std::vector<int64_t> limits;
@@ -30,7 +31,7 @@ struct EmuBlock {
 };
 
 // mirrors block_mask_impl (diamond_b200/csrc/cuda/mask.cu)
-static void emu_block_mask(const DevParams& P, EmuBlock& b, int algo, uint32_t s_begin, uint32_t s_end, int sm_count, unsigned tantan_block, std::vector<uint64_t>& pos) {
+static void emu_block_mask(const DevParams& P, EmuBlock& b, int algo, uint32_t s_begin, uint32_t s_end, unsigned tantan_block, std::vector<uint64_t>& pos) {
 	pos.clear();
 	const size_t p_begin = (size_t)b.limits[s_begin], p_end = (size_t)b.limits[s_end];
 	const size_t nlet = p_end - p_begin, nseq = s_end - s_begin;
@@ -40,9 +41,21 @@ static void emu_block_mask(const DevParams& P, EmuBlock& b, int algo, uint32_t s
 	if (algo & DMND_MASK_TANTAN) {
 		std::vector<float> pb(nlet, -1.0f), scale((nlet >> 4) + nseq + 2, -1.0f);
 		std::fill(bits.begin() + (ptrdiff_t)w_begin, bits.begin() + (ptrdiff_t)w_end, 0u);
-		unsigned int next_seq = 0;
-		const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((nseq + 15) / 16, (size_t)sm_count * 8));
-		emu::launch(grid, tantan_block, [&] { tantan_kernel(b.letters.data(), b.limits.data(), s_begin, s_end, &P, pb.data(), scale.data(), (int64_t)p_begin, &next_seq, bits.data()); });
+		std::vector<uint32_t> len(nseq), id(nseq);
+		emu::launch((unsigned)((nseq + 255) / 256), 256, [&] { seq_len_kernel(b.limits.data(), s_begin, (uint32_t)nseq, len.data(), id.data()); });
+		std::vector<uint32_t> order(id);  // cub::DeviceRadixSort::SortPairsDescending (stable) on (len, id)
+		std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len[x - s_begin] > len[y - s_begin]; });
+		std::vector<float> zinv(nseq, -1.0f);
+		std::vector<uint8_t> need(nseq + 16, 0xee);
+		emu::launch((unsigned)((nseq + 15) / 16), tantan_block, [&] { tantan_forward_kernel(b.letters.data(), b.limits.data(), order.data(), (uint32_t)nseq, &P, pb.data(), scale.data(),
+			(int64_t)p_begin, s_begin, zinv.data(), need.data()); });
+		std::vector<uint32_t> order2;  // cub::DeviceSelect::Flagged(order, need)
+		for (size_t x = 0; x < nseq; ++x) { if (need[x] > 1) { printf("FAIL need flag of slot %zu not written\n", x); exit(1); } if (need[x]) order2.push_back(order[x]); }
+		int n_need = (int)order2.size();
+		g_backward_seqs += (size_t)n_need; g_forward_seqs += nseq;
+		order2.resize(nseq + 1, 0xffffffffu);
+		emu::launch((unsigned)((nseq + 15) / 16), tantan_block, [&] { tantan_backward_kernel(b.letters.data(), b.limits.data(), order2.data(), &n_need, &P, pb.data(), scale.data(),
+			(int64_t)p_begin, s_begin, zinv.data(), bits.data()); });
 		unsigned long long total = 0;
 		emu::launch((unsigned)((w_end - w_begin + 255) / 256), 256, [&] { popc_kernel(bits.data(), w_begin, w_end, &total); });
 		BitSet sel{ bits.data() };
@@ -107,7 +120,7 @@ int main(int argc, char** argv) {
 		std::vector<uint64_t> pos, all;
 		std::vector<uint32_t> cuts = mode == 0 ? std::vector<uint32_t>{ 0, nseq } : std::vector<uint32_t>{ 0, nseq / 3, nseq / 3, (2 * nseq) / 3 + 1, nseq };
 		for (size_t c = 0; c + 1 < cuts.size(); ++c) {
-			emu_block_mask(P, b, DMND_MASK_TANTAN | DMND_MASK_MOTIF, cuts[c], cuts[c + 1], 148, mode == 0 ? 128u : 32u, pos);
+			emu_block_mask(P, b, DMND_MASK_TANTAN | DMND_MASK_MOTIF, cuts[c], cuts[c + 1], 128u, pos);
 			all.insert(all.end(), pos.begin(), pos.end());
 		}
 		if (all != opos) { ++fails; printf("FAIL mode %d: %zu masked positions, oracle %zu\n", mode, all.size(), opos.size()); }
@@ -122,7 +135,7 @@ int main(int argc, char** argv) {
 		}
 		if (memcmp(b.letters.data(), oseed.data(), raw.size()) != 0) { ++fails; printf("FAIL mode %d: SEED_MASK marking differs\n", mode); }
 	}
-	printf("seqs=%u letters=%zu tantan_masked=%zu soft_letters=%zu seed_mask_positions=%zu context_switches=%llu fails=%d \n", nseq, raw.size() - 512 - nseq, opos.size(),
-	       n_soft, n_bits, (unsigned long long)emu::g_switches, fails);
+	printf("seqs=%u letters=%zu tantan_masked=%zu soft_letters=%zu seed_mask_positions=%zu context_switches=%llu backward_pass_seqs=%zu/%zu fails=%d \n", nseq, raw.size() - 512 - nseq, opos.size(),
+	       n_soft, n_bits, (unsigned long long)emu::g_switches, g_backward_seqs, g_forward_seqs, fails);
 	return fails ? 1 : 0;
 }

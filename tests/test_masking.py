@@ -116,3 +116,54 @@ def test_live_reference_default_flags_on_real_proteins(tmp_path):
     assert open(ref_out).read() == open(our_out).read() and os.path.getsize(ref_out) > 10000
     for pat in (r"Seeds hit\s+= (\d+)", r"Hits \(filter stage 0\) = (\d+)", r"Hits \(filter stage 1\) = (\d+)", r"Hits \(filter stage 3\) = (\d+)", r"Target hits \(stage 0\) = (\d+)"):
         assert re.search(pat, r.stdout + r.stderr).group(1) == re.search(pat, o.stdout + o.stderr).group(1), pat
+
+
+def _fasta_blocks(path, limit):
+    from diamond_b200 import api
+    alph = {c: i for i, c in enumerate("ARNDCQEGHILKMFPSTWYVBJZX*_")}
+    seqs, cur = [], []
+    for line in open(path):
+        if line.startswith(">"):
+            if cur:
+                seqs.append("".join(cur)); cur = []
+            if len(seqs) >= limit:
+                break
+        else:
+            cur.append(line.strip())
+    if cur and len(seqs) < limit:
+        seqs.append("".join(cur))
+    letters = np.array([alph.get(c.upper(), 23) for s in seqs for c in s], dtype=np.int8)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    return api.block_image(letters, off)
+
+
+@pytest.mark.parametrize("source", ["synthetic", "rep", "nr10k"])
+def test_forward_only_certificate_is_sound(oracle_lib, source):
+    """The device skips tantan's backward pass for sequences whose total HMM weight Z stays below 8x the all-background
+    weight (log2 ratio < 3, mask_kernels.cuh): then no letter can reach the 0.9 masking threshold.  Checked against the full
+    computation of the oracle: every sequence below the bound has no masked letter; and the bound is worth having."""
+    from diamond_b200 import api, synth
+    if source == "nr10k":
+        if not os.path.exists(NR10K):
+            pytest.skip("nr_10k.faa not present")
+        raw, lim = _fasta_blocks(NR10K, 4000)
+    elif source == "rep":
+        raw, lim = workload_blocks("rep")[3:5]
+    else:
+        w = synth.workload(100, 20000, 7)
+        raw, lim = api.block_image(w["db_letters"], w["db_off"])
+    n = len(lim) - 1
+    ctx = api.Context(oracle_lib, threads=8)
+    b = ctx.upload(raw, lim)
+    ratio, masked = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.uint32)
+    oracle_lib.dmnd_oracle_tantan_log2_ratio.argtypes = [C.c_void_p] * 4
+    assert oracle_lib.dmnd_oracle_tantan_log2_ratio(ctx.ctx, b, ratio.ctypes.data, masked.ctypes.data) == 0
+    ctx.free_block(b); ctx.close()
+    lens = np.diff(lim) - 1
+    cert = (ratio < 3.0) & (lens <= 4096)
+    assert not np.any(masked[cert] > 0), f"{int((masked[cert] > 0).sum())} certified sequences have masked letters"
+    assert np.all(ratio[lens > 0] > -1e-3)  # Z >= W_bg
+    if source == "synthetic":
+        assert cert.mean() > 0.85
+    print(source, "certified", float(cert.mean()), "masked seqs", int((masked > 0).sum()), "closest call", float(ratio[masked > 0].min()) if (masked > 0).any() else None)
