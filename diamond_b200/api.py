@@ -27,6 +27,7 @@ class Params(C.Structure):
                 ("shape_pos", (C.c_int32 * MAX_WEIGHT) * MAX_SHAPES), ("hamming_id", C.c_int32),
                 ("seedp_bits", C.c_int32), ("index_chunks", C.c_int32), ("seed_cut", C.c_double),
                 ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double),
+                ("ungapped_cutoff", C.c_int32 * 32), ("short_query_ungapped_cutoff", C.c_int32), ("short_query_max_len", C.c_int32),
                 ("background_scores_f32", C.c_float * 20),
                 ("tantan_lr", C.c_float * 1024), ("tantan_d", C.c_float * 50), ("tantan_b2b", C.c_float), ("tantan_f2f", C.c_float),
                 ("tantan_p_repeat_end", C.c_float), ("tantan_p_mask", C.c_float), ("max_motif_len", C.c_int32)]
@@ -184,7 +185,7 @@ class Context:
 
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
                  comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
-                 masking: int = 0, motif_masking: int = 0):
+                 masking: int = 0, motif_masking: int = 0, sensitivity: int = 0):
         """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
         wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
         default to the reference's own defaults (1, 1)."""
@@ -197,6 +198,7 @@ class Context:
         self.opts.max_target_seqs = max_target_seqs
         self.opts.max_evalue = max_evalue
         self.opts.want_transcript = int(want_transcript)
+        self.opts.sensitivity = int(sensitivity)  # 0 = --fast, 1 = the reference's default sensitivity
         self.opts.masking = int(masking)
         self.opts.motif_masking = int(motif_masking)
         self.params = Params()

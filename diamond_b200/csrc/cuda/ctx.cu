@@ -173,6 +173,8 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	d.left_most_interval = params->left_most_interval; d.ungapped_window = params->ungapped_window;
 	d.gap_open = params->gap_open; d.gap_extend = params->gap_extend; d.seed_cut = params->seed_cut;
 	std::memcpy(d.background_scores_f32, params->background_scores_f32, sizeof d.background_scores_f32);
+	std::memcpy(d.ungapped_cutoff, params->ungapped_cutoff, sizeof d.ungapped_cutoff);
+	d.short_query_ungapped_cutoff = params->short_query_ungapped_cutoff; d.short_query_max_len = params->short_query_max_len;
 	std::memcpy(d.tantan_lr, params->tantan_lr, sizeof d.tantan_lr);
 	std::memcpy(d.tantan_d, params->tantan_d, sizeof d.tantan_d);
 	d.tantan_b2b = params->tantan_b2b; d.tantan_f2f = params->tantan_f2f; d.tantan_p_repeat_end = params->tantan_p_repeat_end;

@@ -20,6 +20,7 @@ struct DevParams {
 	double seed_cut;
 	double lnfact[DMND_MAX_WEIGHT + 1];
 	float background_scores_f32[20];
+	int32_t ungapped_cutoff[32], short_query_ungapped_cutoff, short_query_max_len;  // stage-2 ungapped window filter (0 tables: skipped)
 	// tantan (masking/tantan.cpp:121-214): likelihood ratios [a*32+b], per-offset repeat start probabilities, transition constants
 	float tantan_lr[1024];
 	float tantan_d[50];

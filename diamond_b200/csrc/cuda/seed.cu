@@ -315,7 +315,53 @@ __device__ bool left_most_filter(const LmCtx& x, const int8_t* query, int query_
 		&& (right_hit == 0 || !verify_hits(x, right_hit, q + window_left + 1, s + window_left + 1, false, match_mask_right));
 }
 
-// Chunk pass 2: one thread per (query loc, reference loc) pair of the chunk's surviving keys.
+// What follows the Hamming filter for one (query loc, reference loc) pair (search/stage2.h:73-154): the ungapped window
+// filter when the mode has one (batch_size >= 0: number of stage-1 survivors that share this pair's window_ungapped_best call,
+// search/stage2.h:114-120; < 0: stage skipped, score 0xFFFF), the left-most filter, the hit.
+__device__ __forceinline__ void stage2_tail(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                                            const int8_t* __restrict__ r_letters, const Entry& e, uint32_t sloc, const LmCtx& x, int batch_size,
+                                            dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
+	const int8_t *qp = q_letters + e.qloc, *sp = r_letters + sloc;
+	// query id / seed offset (SequenceSet::local_position)
+	uint32_t a = 0, b = nq;
+	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)q_limits[mid] <= (uint64_t)e.qloc) a = mid; else b = mid; }
+	const int seed_offset = (int)((int64_t)e.qloc - q_limits[a]);
+	// search/stage2.h:92-103
+	const int window = x.P->ungapped_window;
+	int cb, ce;
+	clip(qp - window, 2 * window, window, cb, ce);
+	const int window_left = window - cb, window_clipped = ce - cb;
+	const int8_t* qc = qp - window + cb;
+	uint32_t score16 = 0xFFFFu;
+	if (batch_size >= 0) {
+		// ungapped_cutoff (search/stage2.h:41-57) and the window score: scalar ungapped_window (dp/ungapped_align.cpp:244-257) for
+		// calls with < 4 subjects, the int8 kernel (dp/ungapped_simd.cpp:32-88) otherwise -- its biased saturating lanes differ
+		// from the scalar loop only by capping the result at 255
+		const int query_len = (int)(q_limits[a + 1] - q_limits[a] - 1);
+		const int cutoff = query_len <= x.P->short_query_max_len ? x.P->short_query_ungapped_cutoff : x.P->ungapped_cutoff[32 - __clz((unsigned)query_len)];
+		const int8_t* sw = sp - window_left;
+		int st = 0, best = 0;
+		for (int t = 0; t < window_clipped; ++t) {
+			st += (int)x.P->score[((qc[t] & 31) << 5) | (sw[t] & 31)];
+			st = max(st, 0);
+			best = max(best, st);
+		}
+		const int score = (batch_size >= 4 && best > 255) ? 255 : best;
+		if (!(score > cutoff)) return;
+		atomicAdd(&counters[8], 1ull);
+		score16 = (uint32_t)score & 0xFFFFu;
+	}
+	const int interval_mod = x.P->left_most_interval > 0 ? seed_offset % x.P->left_most_interval : window_left;
+	const int overhang = max(window_left - interval_mod, 0);
+	if (!left_most_filter(x, qc + overhang, window_clipped - overhang, sp - window_left + overhang, window_left - overhang, x.P->shape_len[x.sid])) return;
+	const unsigned long long idx = atomicAdd(hit_count, 1ull);
+	dmnd_hit h;
+	h.query = a; h.seed_offset = seed_offset; h.subject_score = (uint64_t)sloc | ((uint64_t)score16 << 48);
+	hits[idx] = h;
+}
+
+// Chunk pass 2 (modes without the ungapped window filter, --fast): one thread per (query loc, reference loc) pair of the
+// chunk's surviving keys.
 __global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
                                const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
                                const uint64_t* __restrict__ pair_off /* exclusive scan, n_entries + 1: pair_off[n_entries] = pairs of this chunk */,
@@ -330,26 +376,60 @@ __global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64
 	const Entry e = entries[lo];
 	const uint32_t k = (uint32_t)(pid - pair_off[lo]);
 	const uint32_t sloc = ref_locs[e.lo + k];
-	const int8_t *qp = q_letters + e.qloc, *sp = r_letters + sloc;
-	if (fingerprint_match(qp, sp) < (unsigned)x.P->hamming_id) return;
+	if (fingerprint_match(q_letters + e.qloc, r_letters + sloc) < (unsigned)x.P->hamming_id) return;
 	atomicAdd(&counters[2], 1ull);
-	// query id / seed offset (SequenceSet::local_position)
-	uint32_t a = 0, b = nq;
-	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)q_limits[mid] <= (uint64_t)e.qloc) a = mid; else b = mid; }
-	const int seed_offset = (int)((int64_t)e.qloc - q_limits[a]);
-	// search/stage2.h:92-103
-	const int window = x.P->ungapped_window;
-	int cb, ce;
-	clip(qp - window, 2 * window, window, cb, ce);
-	const int window_left = window - cb, window_clipped = ce - cb;
-	const int interval_mod = x.P->left_most_interval > 0 ? seed_offset % x.P->left_most_interval : window_left;
-	const int overhang = max(window_left - interval_mod, 0);
-	const int8_t* qc = qp - window + cb;
-	if (!left_most_filter(x, qc + overhang, window_clipped - overhang, sp - window_left + overhang, window_left - overhang, x.P->shape_len[x.sid])) return;
-	const unsigned long long idx = atomicAdd(hit_count, 1ull);
-	dmnd_hit h;
-	h.query = a; h.seed_offset = seed_offset; h.subject_score = (uint64_t)sloc | ((uint64_t)0xFFFF << 48);
-	hits[idx] = h;
+	stage2_tail(q_letters, q_limits, nq, r_letters, e, sloc, x, -1, hits, hit_count, counters);
+}
+
+// Modes WITH the ungapped window filter: the reference scores the stage-1 survivors of one query location in calls of up to 32
+// subjects (per 1024-subject tile of the key, ascending subject order: search/hamming/kernel.h:61-74, hit_field.h:44-57), and
+// the size of a survivor's call decides which window kernel scores it.  Pass A writes one survivor bit per pair (one ballot
+// word per warp, the grid covers the bound so every word is written); pass B counts the survivors of the pair's tile in that
+// bitmap to find the size of its call.
+__global__ void stage1_flags_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
+                                    const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ ref_locs, unsigned hamming_id, uint32_t* flags,
+                                    unsigned long long* counters) {
+	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool pass = false;
+	if (pid < pair_off[n_entries]) {
+		size_t lo = 0, hi = n_entries;
+		while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+		const Entry e = entries[lo];
+		const uint32_t sloc = ref_locs[e.lo + (uint32_t)(pid - pair_off[lo])];
+		pass = fingerprint_match(q_letters + e.qloc, r_letters + sloc) >= hamming_id;
+	}
+	const unsigned word = __ballot_sync(0xffffffffu, pass);
+	if ((threadIdx.x & 31) == 0) {
+		flags[pid >> 5] = word;
+		if (word) atomicAdd(&counters[2], (unsigned long long)__popc(word));
+	}
+}
+__device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits, uint64_t a, uint64_t b) {  // set bits in [a, b)
+	unsigned n = 0;
+	while (a < b) {
+		const unsigned sh = (unsigned)(a & 31);
+		const uint64_t take = min((uint64_t)(32 - sh), b - a);
+		const uint32_t m = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << sh;
+		n += __popc(bits[a >> 5] & m);
+		a += take;
+	}
+	return n;
+}
+__global__ void stage2_window_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                                     const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
+                                     const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
+                                     dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
+	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (pid >= pair_off[n_entries] || !((flags[pid >> 5] >> (pid & 31)) & 1u)) return;
+	size_t lo = 0, hi = n_entries;
+	while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+	const Entry e = entries[lo];
+	const uint64_t first = pair_off[lo];
+	const uint32_t k = (uint32_t)(pid - first);
+	const uint32_t tile_begin = k & ~1023u, tile_end = min(tile_begin + 1024u, e.cnt);
+	const unsigned rank = count_bits(flags, first + tile_begin, pid), total = count_bits(flags, first + tile_begin, first + tile_end);
+	const int batch_size = (int)min(32u, total - (rank & ~31u));
+	stage2_tail(q_letters, q_limits, nq, r_letters, e, ref_locs[e.lo + k], x, batch_size, hits, hit_count, counters);
 }
 
 __global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, uint32_t* keys) {
@@ -479,7 +559,6 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
 	const dmnd_params& hp = ctx->params;
-	if (hp.ungapped_evalue != 0.0) { set_error("dmnd_search_shape: stage-2 ungapped window filter (sensitive modes) is not built yet"); return 1; }
 	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
 	if (sid < 0 || sid >= hp.n_shapes) { set_error("dmnd_search_shape: bad shape id"); return 1; }
 	cudaStream_t st = ctx->stream;
@@ -532,6 +611,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	}
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
 	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
+	if (hp.ungapped_evalue != 0.0 && ctx->b_keys2.ensure(((size_t)pairs_bound / 32 + 8) * 4)) return 1;  // stage-1 survivor bits
 	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;
 	if (ctx->b_vals.ensure(bm_words * 4)) return 1;  // b_vals (unsorted reference locs) is dead after the sort
 	uint32_t* d_key_seen = ctx->b_vals.as<uint32_t>();
@@ -565,8 +645,16 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		x.P = P; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
 		x.cur_matcher = ctx->d_matcher[sid + 1]; x.cur_minlen = ctx->matcher_minlen[sid + 1]; x.cur_suffix = ctx->matcher_suffix[sid + 1];
 		x.prev_matcher = ctx->d_matcher[sid]; x.prev_minlen = ctx->matcher_minlen[sid]; x.prev_suffix = ctx->matcher_suffix[sid];
-		stage12_kernel<<<(unsigned)((pairs_bound + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
-			d_pair_off, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+		if (hp.ungapped_evalue == 0.0)
+			stage12_kernel<<<(unsigned)((pairs_bound + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
+				d_pair_off, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+		else {
+			const unsigned grid = (unsigned)((pairs_bound + 127) / 128);
+			stage1_flags_kernel<<<grid, 128, 0, st>>>(query->letters, ref->letters, d_entries, (size_t)nent, d_pair_off, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(), d_cnt);
+			stage2_window_kernel<<<grid, 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent, d_pair_off, d_locs,
+				ctx->b_keys2.as<uint32_t>(), x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+			++ctx->launches;
+		}
 		++ctx->launches;
 	}
 	{
@@ -603,7 +691,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		counters->seeds_hit = hc[0];
 		counters->seed_hits = seed_hits_total;
 		counters->tentative_matches1 = hc[2];
-		counters->tentative_matches2 = hc[2];
+		counters->tentative_matches2 = hp.ungapped_evalue == 0.0 ? hc[2] : hc[8];
 		counters->tentative_matches3 = hits_total;
 		counters->masked_seeds = hc[7];
 	}

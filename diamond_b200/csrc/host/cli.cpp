@@ -90,6 +90,7 @@ int main(int argc, char** argv) {
 		if (cmd != "blastp") usage("only the blastp hot path is implemented (makedb/blastx are 'next' rows, see DESIGN.md)");
 		dmnd_search_opts o;
 		dmnd_search_opts_default(&o);
+		o.sensitivity = 1;  // like the reference: no sensitivity flag = Sensitivity::DEFAULT, --fast = Sensitivity::FAST
 		std::string qf, df, of;
 		bool log = false;
 		for (int i = 2; i < argc; ++i) {

@@ -263,6 +263,7 @@ struct Env {
 	const Scoring* sc;
 	const int8_t *q_letters, *r_letters;
 	const PatchSet *q_patch = nullptr, *r_patch = nullptr;  // hard-masked sequences (dmnd_blastp with masking); null = read in place
+	int n_shapes = 1;   // shapes of the sensitivity mode (search/setup.cpp:80-304): one dmnd_search_shape per shape
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
 	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
 	const int8_t* rseq(uint32_t t) const { const int8_t* p = r_patch ? r_patch->find(t) : nullptr; return p ? p : r_letters + r_limits[t]; }
@@ -387,6 +388,7 @@ struct Workspace {
 	HostBuf<uint8_t> tr;
 	RawBuf<dmnd_match> out_matches;   // lane output when several lanes run (copied into the result afterwards)
 	RawBuf<uint8_t> out_transcripts;
+	std::vector<dmnd_hit> acc_hits; std::vector<dmnd_segment> acc_segs; std::vector<dmnd_hit_site> acc_sites;  // hits of all shapes (several shapes only)
 	std::vector<uint64_t> mask_pos;   // letters of this lane's query range that dmnd_block_mask turned into X
 	PatchSet q_patch;
 };
@@ -838,10 +840,12 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	p->map8[MASK_LETTER] = p->map8[STOP_LETTER] = p->map8[DMND_DELIMITER] = 10;
 	p->map8b[MASK_LETTER] = p->map8b[STOP_LETTER] = p->map8b[DMND_DELIMITER] = 11;
 	p->reduction_size = 10;
-	if (o->sensitivity != 0) { dmnd_set_last_error("only --fast (sensitivity 0) is wired in this build"); return 1; }
-	// Sensitivity::FAST: shape_codes (search/setup.cpp:211-212), traits (:43)
-	const char* codes[] = { "1101110101101111" };
-	p->n_shapes = 1;
+	if (o->sensitivity != 0 && o->sensitivity != 1) { dmnd_set_last_error("sensitivity must be 0 (--fast) or 1 (default); the sensitive modes are not wired in this build"); return 1; }
+	// shape_codes (search/setup.cpp:211-212 FAST uses the first code of its own list; :90-93 DEFAULT) and traits (:43, :47)
+	static const char* fast_codes[] = { "1101110101101111" };
+	static const char* default_codes[] = { "111101110111", "111011010010111" };
+	const char** codes = o->sensitivity == 0 ? fast_codes : default_codes;
+	p->n_shapes = o->sensitivity == 0 ? 1 : 2;
 	for (int s = 0; s < p->n_shapes; ++s) {
 		int w = 0, len = 0;
 		for (const char* c = codes[s]; *c; ++c, ++len)
@@ -856,8 +860,14 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 		const int threads = o->threads > 0 ? o->threads : 1;
 		p->seedp_bits = std::max(std::max(bit_length(pw - 1) - 32, bit_length((int64_t)threads * 4 * p->index_chunks - 1)), 8);
 	}
-	p->seed_cut = 0.9 * std::log(2.0) * p->shape_weight;
-	p->left_most_interval = 32; p->ungapped_window = 48; p->ungapped_evalue = 0.0;
+	p->seed_cut = (o->sensitivity == 0 ? 0.9 : 0.8) * std::log(2.0) * p->shape_weight;
+	p->left_most_interval = 32; p->ungapped_window = 48;
+	p->ungapped_evalue = o->sensitivity == 0 ? 0.0 : 10000.0;  // traits ug_ev (search/setup.cpp:43,47)
+	p->short_query_max_len = 60;
+	p->short_query_ungapped_cutoff = sc.rawscore(25.0);
+	if (p->ungapped_evalue > 0.0)
+		for (int b = 1; b <= 31; ++b)  // CutoffTable: rawscore(bitscore_norm(evalue, 2^(b-1))), stats/score_matrix.h:133-151
+			p->ungapped_cutoff[b] = sc.rawscore(-std::log(p->ungapped_evalue / 1e9 / (double)(1u << (b - 1))) / std::log(2.0));
 	{	// tantan constants, masking/masking.cpp:133-153 and masking/tantan.cpp:131-142, evaluated in the reference's types.
 		// lambda is what cbrc::LambdaCalculator (lib/tantan, a randomised root search seeded by the C library's default
 		// rand() state) returns for BLOSUM62's 20 x 20 core; tests/test_masking.py re-derives it from the reference's own
@@ -929,17 +939,50 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	}
 	prep_rc = prep_rc || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
 	seed_turn.wait_for(lane);
-	const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
-	seed_turn.pass(lane);
-	if (seed_rc) return 1;
-	prof.lap("search_shape");
-	const size_t nh = dmnd_hits_count(hits);
-	if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
-	if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
-	// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
-	// ... together with the sequence and local position of every hit (what load_hits would otherwise search for)
-	if (nh && dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
-	dmnd_hits_free(ctx, hits);
+	const int n_shapes = env.n_shapes;
+	size_t nh = 0;
+	if (n_shapes == 1) {
+		const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
+		seed_turn.pass(lane);
+		if (seed_rc) return 1;
+		prof.lap("search_shape");
+		nh = dmnd_hits_count(hits);
+		if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
+		if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
+		// ungapped x-drop extension of every seed hit (align/ungapped.cpp:88, dp/ungapped_align.cpp:150-214), batched
+		// ... together with the sequence and local position of every hit (what load_hits would otherwise search for)
+		if (nh && dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
+		dmnd_hits_free(ctx, hits);
+	}
+	else {
+		// run_ref_chunk's loop over the shapes (run/double_indexed.cpp:185-214): SEED_MASK bits set by one shape stay visible
+		// to the next ones, the hits of all shapes feed one extension; every shape's hits arrive grouped by query and are merged
+		// into one query-grouped list (counting sort by query, stable)
+		int rc = prep_rc;
+		std::vector<dmnd_hit>& ah = w.acc_hits; std::vector<dmnd_segment>& as = w.acc_segs; std::vector<dmnd_hit_site>& at = w.acc_sites;
+		ah.clear(); as.clear(); at.clear();
+		for (int sid = 0; sid < n_shapes && !rc; ++sid) {
+			dmnd_stage_counters cn;
+			rc = dmnd_search_shape_range(ctx, qb, rb, sid, q_begin, q_end, &hits, &cn);
+			if (rc) break;
+			d.stats.seed.seeds_hit += cn.seeds_hit; d.stats.seed.seed_hits += cn.seed_hits; d.stats.seed.tentative_matches1 += cn.tentative_matches1;
+			d.stats.seed.tentative_matches2 += cn.tentative_matches2; d.stats.seed.tentative_matches3 += cn.tentative_matches3; d.stats.seed.masked_seeds += cn.masked_seeds;
+			const size_t n = dmnd_hits_count(hits);
+			if (w.hv.resize(ctx, n) || w.segv.resize(ctx, n) || w.sitev.resize(ctx, n)) rc = 1;
+			if (!rc && n) rc = dmnd_hits_download(ctx, hits, w.hv.data(), n) || dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), n);
+			dmnd_hits_free(ctx, hits);
+			if (!rc) { ah.insert(ah.end(), w.hv.begin(), w.hv.end()); as.insert(as.end(), w.segv.begin(), w.segv.end()); at.insert(at.end(), w.sitev.begin(), w.sitev.end()); }
+		}
+		seed_turn.pass(lane);
+		if (rc) return 1;
+		prof.lap("search_shape (all shapes)");
+		nh = ah.size();
+		if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh)) return 1;
+		std::vector<size_t> off((size_t)(q_end - q_begin) + 1, 0);
+		for (const dmnd_hit& h : ah) ++off[(size_t)(h.query - q_begin) + 1];
+		for (size_t k = 1; k < off.size(); ++k) off[k] += off[k - 1];
+		for (size_t k = 0; k < nh; ++k) { const size_t o = off[(size_t)(ah[k].query - q_begin)]++; w.hv[o] = ah[k]; w.segv[o] = as[k]; w.sitev[o] = at[k]; }
+	}
 	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
 	d.stats.seed_ms = ms_since(t0);
@@ -1109,6 +1152,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo;
+	e.n_shapes = opts->sensitivity == 0 ? 1 : 2;
 	if (mask_algo) {
 		// "Masking reference" (run/double_indexed.cpp:122-127) and the reference block's motif table, before its seed index
 		uint64_t n_hard = 0;

@@ -55,7 +55,11 @@ typedef struct dmnd_params {
 	double seed_cut;                  /* seed_complexity_cut = cut * ln2 * weight (search/setup.cpp:369-370) */
 	int32_t left_most_interval;       /* config.left_most_interval = 32 */
 	int32_t ungapped_window;          /* config.ungapped_window = 48 */
-	double ungapped_evalue;           /* 0 => stage-2 ungapped filter skipped (fast); >0 not implemented yet */
+	double ungapped_evalue;           /* 0 => stage-2 ungapped window filter skipped (--fast); > 0: Search::Config::ungapped_evalue */
+	int32_t ungapped_cutoff[32];      /* Util::Scores::CutoffTable(ungapped_evalue) (util/scores/cutoff_table.h:26-47): raw score
+	                                     cutoff by bit length of the query length; all 0 when ungapped_evalue == 0 */
+	int32_t short_query_ungapped_cutoff; /* score_matrix.rawscore(config.short_query_ungapped_bitscore = 25) (search/stage0.cpp:187) */
+	int32_t short_query_max_len;      /* config.short_query_max_len = 60 (basic/config.cpp:566) */
 	float background_scores_f32[20];  /* (float)ScoreMatrix::background_scores_ (stats/score_matrix.cpp:241-248), for Hauser */
 	/* tantan repeat masking (masking/tantan.cpp:121-214, called from masking/masking.cpp:162 with p_repeat 0.005,
 	 * p_repeat_end 0.05, growth 1/0.9, min. mask probability config.tantan_minMaskProb 0.9): every constant the
@@ -231,7 +235,8 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {
-	int32_t sensitivity;       /* 0 = --fast (the only mode wired so far) */
+	int32_t sensitivity;       /* 0 = --fast, 1 = the reference's default sensitivity (2 shapes of weight 10, stage-2 ungapped window
+	                              filter; CPU oracle + host pipeline only so far: the CUDA library rejects it) */
 	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
 	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
 	int32_t comp_based_stats;  /* 0 or 1 (Hauser) */

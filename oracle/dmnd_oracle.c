@@ -585,7 +585,6 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
                             dmnd_hits** out, dmnd_stage_counters* counters) {
 	const dmnd_params* p = &ctx->p;
 	if (q_begin > q_end || q_end > query->nseq) return fail("dmnd_search_shape_range: bad query range");
-	if (p->ungapped_evalue != 0.0) return fail("oracle: stage-2 ungapped window filter not restated yet");
 	dmnd_stage_counters cn; memset(&cn, 0, sizeof cn);
 	size_t nh = 0, hcap = 1024;
 	dmnd_hit* hits = (dmnd_hit*)malloc(hcap * sizeof *hits);
@@ -637,19 +636,53 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
 					const int window_left = (int)(qp - cb), window_clipped = (int)(ce - cb);
 					const int interval_mod = p->left_most_interval > 0 ? seed_offset % p->left_most_interval : window_left;
 					const int overhang = window_left - interval_mod > 0 ? window_left - interval_mod : 0;
-					for (size_t bb = j; bb < j2; ++bb) {
-						const int8_t* sp = ref->letters + re[bb].loc;
-						if (fingerprint_match(qp, sp) < (unsigned)p->hamming_id) continue;
-						++cn.tentative_matches1;
-						++cn.tentative_matches2;
-						if (left_most_filter(&x, cb + overhang, window_clipped - overhang, sp - window_left + overhang,
-						                     window_left - overhang, p->shape_len[sid])) {
-							++cn.tentative_matches3;
-							if (nh == hcap) { hcap *= 2; hits = (dmnd_hit*)realloc(hits, hcap * sizeof *hits); }
-							hits[nh].query = qid;
-							hits[nh].seed_offset = seed_offset;
-							hits[nh].subject_score = re[bb].loc | ((uint64_t)0xFFFF << 48);
-							++nh;
+					/* search/stage2.h:41-57 ungapped_cutoff (blastp: no translated-query branch) */
+					const int query_len = (int)(query->limits[qid + 1] - query->limits[qid] - 1);
+					int score_cutoff = 0;
+					if (p->ungapped_evalue != 0.0) {
+						if (query_len <= p->short_query_max_len) score_cutoff = p->short_query_ungapped_cutoff;
+						else score_cutoff = p->ungapped_cutoff[32 - __builtin_clz((uint32_t)query_len)];
+					}
+					/* search/hamming/kernel.h:61-74: the key's subject locations are visited in tiles of config.tile_size = 1024;
+					 * per query location the stage-1 survivors of a tile (ascending, hit_field.h:44-57) go through
+					 * window_ungapped_best in batches of 32 (search/stage2.h:114-120, AVX2 int8 channels) */
+					for (size_t tile = j; tile < j2; tile += 1024) {
+						const size_t tile_end = tile + 1024 < j2 ? tile + 1024 : j2;
+						size_t surv[1024], ns = 0;
+						for (size_t bb = tile; bb < tile_end; ++bb)
+							if (fingerprint_match(qp, ref->letters + re[bb].loc) >= (unsigned)p->hamming_id) surv[ns++] = bb;
+						cn.tentative_matches1 += ns;
+						for (size_t b0 = 0; b0 < ns; b0 += 32) {
+							const size_t nb = ns - b0 < 32 ? ns - b0 : 32;
+							for (size_t k = 0; k < nb; ++k) {
+								const size_t bb = surv[b0 + k];
+								const int8_t* sp = ref->letters + re[bb].loc;
+								int score = 0x7fffffff; /* INT_MAX when the ungapped stage is skipped: (uint16_t) -> 0xFFFF */
+								if (score_cutoff) {
+									/* dp/ungapped_align.cpp:244-257 ungapped_window over the clipped query window; batches of >= 4
+									 * subjects take the int8 kernel instead (dp/ungapped_simd.cpp:32-88), whose biased saturating
+									 * lanes cap the running score at 255 (score_vector_int8.h) -- same floor at 0, same maximum below it */
+									int st = 0, best = 0;
+									const int8_t* sw = sp - window_left;
+									for (int t = 0; t < window_clipped; ++t) {
+										st += (int)p->score[(cb[t] & DMND_LETTER_MASK) * 32 + (sw[t] & DMND_LETTER_MASK)];
+										if (st < 0) st = 0;
+										if (st > best) best = st;
+									}
+									score = (nb >= 4 && best > 255) ? 255 : best;
+								}
+								if (!(score > score_cutoff)) continue;
+								++cn.tentative_matches2;
+								if (left_most_filter(&x, cb + overhang, window_clipped - overhang, sp - window_left + overhang,
+								                     window_left - overhang, p->shape_len[sid])) {
+									++cn.tentative_matches3;
+									if (nh == hcap) { hcap *= 2; hits = (dmnd_hit*)realloc(hits, hcap * sizeof *hits); }
+									hits[nh].query = qid;
+									hits[nh].seed_offset = seed_offset;
+									hits[nh].subject_score = re[bb].loc | ((uint64_t)(uint16_t)score << 48);
+									++nh;
+								}
+							}
 						}
 					}
 				}

@@ -6,6 +6,8 @@
 For every workload W and parity-ladder level L:
     L0 = --masking 0 --motif-masking 0 --comp-based-stats 0      L1 = --masking 0 --motif-masking 0 (Hauser CBS on)
     L2 = the reference's default flags (tantan masking of both blocks, motif soft-masking, Hauser CBS)
+    S1 = no sensitivity flag at all: the reference's DEFAULT sensitivity (2 shapes of weight 10, stage-2 ungapped window filter)
+         with its default flags -- `diamond blastp -q Q -d DB` as most users run it
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -18,7 +20,9 @@ from diamond_b200 import synth  # noqa: E402
 REF = os.path.join(ROOT, "oracle", "_ref", "diamond")
 LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats", "0"],
           "l1": ["--masking", "0", "--motif-masking", "0"],
-          "l2": []}
+          "l2": [],
+          "s1": []}
+MODE = {"s1": []}  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -36,7 +40,9 @@ def main():
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, flags in LEVELS.items():
                 out = os.path.join(HERE, f"{name}.{lvl}.tsv")
-                r = subprocess.run([REF, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", out, "-p", "8", "--log"] + flags,
+                if os.path.exists(out) and "--missing" in sys.argv:
+                    continue
+                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", "6", "-o", out, "-p", "8", "--log"] + flags,
                                    capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

@@ -1,0 +1,65 @@
+"""The reference's DEFAULT sensitivity on the device: both shapes through dmnd_search_shape (stage-2 ungapped window filter,
+call-size dependent score cap, multi-shape left-most filter) against the oracle, and the GPU pipeline / CLI against the S1
+goldens (the reference run with no sensitivity flag).  Through the C ABI."""
+import json, os, subprocess
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT, workload_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def sorted_hits(h):
+    return np.sort(h, order=["query", "subject_score", "seed_offset"])
+
+
+@pytest.mark.parametrize("name,masking", [("fam2", 0), ("rep", 1), ("edge", 1)])
+def test_search_shapes_match_oracle(oracle_lib, product_lib, name, masking):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    res = []
+    for lib in (oracle_lib, product_lib):
+        c = api.Context(lib, threads=8, sensitivity=1)
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        if masking:
+            c.mask_block(qb, 5, 0, len(q_lim) - 1); c.mask_block(rb, 5, 0, len(r_lim) - 1)
+        out = []
+        for sid in (0, 1):  # SEED_MASK bits of shape 0 stay set for shape 1 (run/double_indexed.cpp:185-214)
+            hits, cn = c.search_shape(qb, rb, sid)
+            out.append((hits, cn, c.download_letters(qb, q_raw.size)))
+        res.append(out)
+        c.free_block(qb); c.free_block(rb); c.close()
+    for sid in (0, 1):
+        (ho, co, lo), (hg, cg, lg) = res[0][sid], res[1][sid]
+        assert len(ho) == len(hg) and np.array_equal(sorted_hits(ho), sorted_hits(hg)), f"shape {sid}: hits incl. ungapped scores"
+        assert co == cg, f"shape {sid}: stage counters"
+        assert np.array_equal(lo, lg), f"shape {sid}: SEED_MASK bits"
+    if name == "fam2":
+        sc = (res[1][0][0]["subject_score"] >> np.uint64(48)).astype(np.int64)
+        assert (sc == 255).sum() > 100 and (sc > 255).sum() > 0
+
+
+@pytest.mark.parametrize("name", ["c1", "fam2", "edge", "long", "rep"])
+def test_blastp_default_sensitivity_matches_reference_golden(product_lib, name):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    g = api.Context(product_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1, sensitivity=1)
+    m, _, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.s1.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.s1.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
+
+
+def test_cli_without_sensitivity_flag(product_lib, tmp_path):
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("c1")
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    cli = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+    r = subprocess.run([cli, "blastp", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, "c1.s1.tsv")).read()
