@@ -536,7 +536,19 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 		cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->b_keys.as<uint64_t>(), d_keys, ctx->b_vals.as<uint32_t>(), d_locs, (size_t)nref, 0, 40, st);
 		size_t tmp2 = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_hist, d_bucket, nbuckets + 1, st);
-		if (ctx->b_cub.ensure(std::max(tmp, tmp2))) return 1;
+		size_t tmp3 = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp3, ctx->b_vals.as<uint32_t>(), d_locs, ctx->b_keys.as<uint64_t>(), d_keys, (size_t)nref, 0, 32, st);
+		if (ctx->b_cub.ensure(std::max(std::max(tmp, tmp2), tmp3))) return 1;
+		if (nref && ctx->params.ungapped_evalue != 0.0) {
+			// Modes with the stage-2 ungapped window filter: the locations of a seed key must come in ASCENDING order, as in the
+			// reference's seed arrays, because the order decides which survivors share a window_ungapped_best call (stage2_window_kernel).
+			// ref_enum_kernel hands out slots warp by warp (unordered); the key sort below is stable, so sorting by location first
+			// yields (key, location) order.  --fast never looks at the order and skips this pass.
+			DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp3, ctx->b_vals.as<uint32_t>(), d_locs, ctx->b_keys.as<uint64_t>(), d_keys, (size_t)nref, 0, 32, st));
+			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_vals.p, d_locs, (size_t)nref * 4, cudaMemcpyDeviceToDevice, st));
+			DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_keys.p, d_keys, (size_t)nref * 8, cudaMemcpyDeviceToDevice, st));
+			ctx->launches += 4;
+		}
 		if (nref) {
 			DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp, ctx->b_keys.as<uint64_t>(), d_keys, ctx->b_vals.as<uint32_t>(), d_locs, (size_t)nref, 0, 40, st));
 			ctx->launches += 6;
