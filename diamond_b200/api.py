@@ -28,6 +28,8 @@ class Params(C.Structure):
                 ("seedp_bits", C.c_int32), ("index_chunks", C.c_int32), ("seed_cut", C.c_double),
                 ("left_most_interval", C.c_int32), ("ungapped_window", C.c_int32), ("ungapped_evalue", C.c_double),
                 ("ungapped_cutoff", C.c_int32 * 32), ("short_query_ungapped_cutoff", C.c_int32), ("short_query_max_len", C.c_int32),
+                ("gapped_filter_evalue", C.c_double), ("gapped_cutoff1", (C.c_int16 * 32) * 32), ("gapped_cutoff2", (C.c_int16 * 32) * 32),
+                ("gapped_filter_diag_score", C.c_int32), ("gapped_filter_window", C.c_int32),
                 ("background_scores_f32", C.c_float * 20),
                 ("tantan_lr", C.c_float * 1024), ("tantan_d", C.c_float * 50), ("tantan_b2b", C.c_float), ("tantan_f2f", C.c_float),
                 ("tantan_p_repeat_end", C.c_float), ("tantan_p_mask", C.c_float), ("max_motif_len", C.c_int32)]
@@ -74,7 +76,7 @@ class Match(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [("seed", StageCounters)] + \
                [(n, C.c_uint64) for n in ("hits", "targets", "dp_problems_round1", "dp_problems_round2", "cells_round1",
-                                          "cells_round2", "queries_aligned", "matches", "dp_problems_fused")] + \
+                                          "cells_round2", "queries_aligned", "matches", "dp_problems_fused", "targets_extended")] + \
                [(n, C.c_double) for n in ("seed_ms", "host_bridge_ms", "dp1_ms", "dp2_ms", "total_ms")] + \
                [("device", Timing)]
 
@@ -94,7 +96,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
-           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch",
+           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_free"]
@@ -118,6 +120,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_block_download_letters.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_block_mask.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.dmnd_block_mask_fetch.argtypes = [vp, vp, C.c_size_t]
+    lib.dmnd_hits_gapped_filter.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
     lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
     lib.dmnd_block_build_index.argtypes = [vp, vp, C.c_int]
     lib.dmnd_block_compute_bias.argtypes = [vp, vp, C.c_int]
@@ -260,8 +263,8 @@ class Context:
     def clear_seed_mask(self, b):
         self._check(self.lib.dmnd_block_clear_seed_mask(self.ctx, b))
 
-    def search_shape(self, qb, rb, sid: int = 0, xdrop: int | None = None):
-        """Hits (+ per-hit x-drop segments when `xdrop` is given) and the stage counters."""
+    def search_shape(self, qb, rb, sid: int = 0, xdrop: int | None = None, gapped_filter: bool = False):
+        """Hits (+ per-hit x-drop segments when `xdrop` is given, + per-hit gapped-filter flags when asked) and the stage counters."""
         h = C.c_void_p()
         cn = StageCounters()
         self._check(self.lib.dmnd_search_shape(self.ctx, qb, rb, sid, C.byref(h), C.byref(cn)))
@@ -273,8 +276,15 @@ class Context:
         if xdrop is not None:
             segs = np.zeros(n, dtype=SEGMENT_DTYPE)
             self._check(self.lib.dmnd_hits_xdrop(self.ctx, qb, rb, h, xdrop, segs.ctypes.data, n))
+        gf = None
+        if gapped_filter:
+            gf = np.zeros(n, dtype=np.uint8)
+            if n:
+                self._check(self.lib.dmnd_hits_gapped_filter(self.ctx, qb, rb, h, gf.ctypes.data, n))
         self.lib.dmnd_hits_free(self.ctx, h)
         cnd = {k: getattr(cn, k) for k, _ in StageCounters._fields_}
+        if gapped_filter:
+            return hits, cnd, gf
         return (hits, cnd) if xdrop is None else (hits, cnd, segs)
 
     def banded_swipe(self, qb, rb, problems: np.ndarray, traceback: bool, transcript_cap: int = 0):

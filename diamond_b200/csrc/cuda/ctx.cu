@@ -175,6 +175,8 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	std::memcpy(d.background_scores_f32, params->background_scores_f32, sizeof d.background_scores_f32);
 	std::memcpy(d.ungapped_cutoff, params->ungapped_cutoff, sizeof d.ungapped_cutoff);
 	d.short_query_ungapped_cutoff = params->short_query_ungapped_cutoff; d.short_query_max_len = params->short_query_max_len;
+	std::memcpy(d.gapped_cutoff1, params->gapped_cutoff1, sizeof d.gapped_cutoff1); std::memcpy(d.gapped_cutoff2, params->gapped_cutoff2, sizeof d.gapped_cutoff2);
+	d.gapped_filter_diag_score = params->gapped_filter_diag_score; d.gapped_filter_window = params->gapped_filter_window;
 	std::memcpy(d.tantan_lr, params->tantan_lr, sizeof d.tantan_lr);
 	std::memcpy(d.tantan_d, params->tantan_d, sizeof d.tantan_d);
 	d.tantan_b2b = params->tantan_b2b; d.tantan_f2f = params->tantan_f2f; d.tantan_p_repeat_end = params->tantan_p_repeat_end;
@@ -446,6 +448,11 @@ int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_blo
                           dmnd_hit_site* sites, size_t cap) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	return hits_xdrop_impl(ctx, query, ref, h, raw_xdrop, host, sites, cap);
+}
+
+int dmnd_hits_gapped_filter(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return hits_gapped_filter_impl(ctx, query, ref, h, pass, cap);
 }
 
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len) {

@@ -13,6 +13,7 @@
 // filter of chunks >= k, and verify_hit compares seed partitions against the current chunk's range (left_most.h:32-41).
 #include "ctx.cuh"
 #include "mask_kernels.cuh"
+#include "gf_kernels.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 
@@ -490,6 +491,22 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 	if (sites) DMND_CUDA_CHECK(cudaMemcpyAsync(sites, d_sites, h->n * sizeof(dmnd_hit_site), cudaMemcpyDeviceToHost, ctx->stream));
 	t.stop();
 	ctx->d2h_bytes += h->n * (sizeof(dmnd_segment) + (sites ? sizeof(dmnd_hit_site) : 0));
+	return 0;
+}
+
+int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap) {
+	if (cap < h->n) { set_error("dmnd_hits_gapped_filter: buffer too small"); return 1; }
+	if (ctx->params.gapped_filter_evalue <= 0.0) { set_error("dmnd_hits_gapped_filter: this sensitivity mode has no gapped filter"); return 1; }
+	if (h->n == 0) return 0;
+	if (ctx->b_pairs.ensure(h->n + 64)) return 1;
+	PhaseTimer t(ctx, PH_SEED);
+	gapped_filter_kernel<<<(unsigned)((h->n + 3) / 4), 128, 0, ctx->stream>>>(query->letters, query->bias, query->limits, ref->letters, ref->limits, ref->nseq,
+		h->d, h->n, ctx->d_params, ctx->b_pairs.as<uint8_t>());
+	++ctx->launches;
+	DMND_CUDA_CHECK(cudaGetLastError());
+	DMND_CUDA_CHECK(cudaMemcpyAsync(pass, ctx->b_pairs.p, h->n, cudaMemcpyDeviceToHost, ctx->stream));
+	t.stop();
+	ctx->d2h_bytes += h->n;
 	return 0;
 }
 

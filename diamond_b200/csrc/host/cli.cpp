@@ -100,6 +100,8 @@ int main(int argc, char** argv) {
 			else if (a == "-d" || a == "--db") df = val();
 			else if (a == "-o" || a == "--out") of = val();
 			else if (a == "--fast") o.sensitivity = 0;
+			else if (a == "--mid-sensitive") o.sensitivity = 2;
+			else if (a == "--sensitive") o.sensitivity = 3;
 			else if (a == "-p" || a == "--threads") o.threads = atoi(val());
 			else if (a == "-c" || a == "--index-chunks") o.index_chunks = atoi(val());
 			else if (a == "-k" || a == "--max-target-seqs") o.max_target_seqs = atoi(val());
@@ -153,6 +155,7 @@ int main(int argc, char** argv) {
 			fprintf(stderr, "Hits (filter stage 2) = %llu\n", (unsigned long long)s->seed.tentative_matches2);
 			fprintf(stderr, "Hits (filter stage 3) = %llu\n", (unsigned long long)s->seed.tentative_matches3);
 			fprintf(stderr, "Target hits (stage 0) = %llu\n", (unsigned long long)s->targets);
+			fprintf(stderr, "Target hits (stage 3) = %llu\n", (unsigned long long)s->targets_extended);
 			fprintf(stderr, "DP problems round 1/2 = %llu / %llu\n", (unsigned long long)s->dp_problems_round1, (unsigned long long)s->dp_problems_round2);
 			fprintf(stderr, "DP cells round 1/2    = %llu / %llu\n", (unsigned long long)s->cells_round1, (unsigned long long)s->cells_round2);
 			fprintf(stderr, "Time seed/bridge/dp1/dp2/total (ms) = %.2f / %.2f / %.2f / %.2f / %.2f\n", s->seed_ms, s->host_bridge_ms, s->dp1_ms, s->dp2_ms, s->total_ms);

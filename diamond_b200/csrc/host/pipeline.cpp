@@ -182,7 +182,7 @@ struct List {  // trivially-copyable elements only
 	void clear() { n = 0; }
 };
 
-struct SeedHit { int i, j, score; dmnd_segment seg; bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
+struct SeedHit { int i, j, score; dmnd_segment seg; uint8_t gf;  /* gf: the hit passes the gapped filter (modes that have one) */ bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
 struct TargetScore { uint32_t target; uint16_t score; bool operator<(const TargetScore& x) const { return score > x.score || (score == x.score && target < x.target); } };
 
 struct HspLite { int score; double evalue; int d_begin, d_end; };
@@ -263,6 +263,7 @@ struct Env {
 	const Scoring* sc;
 	const int8_t *q_letters, *r_letters;
 	const PatchSet *q_patch = nullptr, *r_patch = nullptr;  // hard-masked sequences (dmnd_blastp with masking); null = read in place
+	bool gapped_filter = false;  // Extension::gapped_filter before the ungapped stage (align/extend.cpp:205-214)
 	int n_shapes = 1;   // shapes of the sensitivity mode (search/setup.cpp:80-304): one dmnd_search_shape per shape
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
 	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
@@ -312,11 +313,11 @@ struct ThreadCtx {
 	std::vector<Chain> chains;
 	std::vector<int8_t> cbs;
 	std::vector<Target> tmp_targets;
-	uint64_t cells1 = 0, cells2 = 0, n_targets = 0, n_matches = 0, n_aligned = 0;
+	uint64_t cells1 = 0, cells2 = 0, n_targets = 0, n_matches = 0, n_aligned = 0, n_extended = 0;
 	uint64_t fused_r1 = 0, fused_r2 = 0, fused_r1_wave = 0;  // fused queries: round-1 problems traced, round-2 problems answered from them
 	void reset() {
 		arena.reset(); seed_hits.clear(); hit_begin.clear(); target_block_ids.clear(); target_scores.clear();
-		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = 0; fused_r1 = fused_r2 = fused_r1_wave = 0;
+		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = n_extended = 0; fused_r1 = fused_r2 = fused_r1_wave = 0;
 	}
 };
 
@@ -379,7 +380,7 @@ struct Workspace {
 	HostBuf<dmnd_hit> hv;
 	HostBuf<dmnd_segment> segv;
 	HostBuf<dmnd_hit_site> sitev;
-	struct HitSeg { dmnd_hit h; dmnd_segment s; dmnd_hit_site site; };
+	struct HitSeg { dmnd_hit h; dmnd_segment s; dmnd_hit_site site; uint8_t gf; };
 	std::vector<HitSeg> hs;
 	std::vector<size_t> qstart;
 	std::vector<QueryState> qs;
@@ -388,7 +389,7 @@ struct Workspace {
 	HostBuf<uint8_t> tr;
 	RawBuf<dmnd_match> out_matches;   // lane output when several lanes run (copied into the result afterwards)
 	RawBuf<uint8_t> out_transcripts;
-	std::vector<dmnd_hit> acc_hits; std::vector<dmnd_segment> acc_segs; std::vector<dmnd_hit_site> acc_sites;  // hits of all shapes (several shapes only)
+	std::vector<dmnd_hit> acc_hits; std::vector<dmnd_segment> acc_segs; std::vector<dmnd_hit_site> acc_sites; std::vector<uint8_t> acc_gf, gf_tmp, gfv;  // hits of all shapes (several shapes only)
 	std::vector<uint64_t> mask_pos;   // letters of this lane's query range that dmnd_block_mask turned into X
 	PatchSet q_patch;
 };
@@ -468,7 +469,7 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, W
 			++ntg;
 		}
 		const uint16_t hs = (uint16_t)DMND_HIT_SCORE(*h);
-		tc.seed_hits.push_back({ h->seed_offset, hsp->site.j, (int)hs, hsp->s });
+		tc.seed_hits.push_back({ h->seed_offset, hsp->site.j, (int)hs, hsp->s, hsp->gf });
 		score = std::max(score, hs);
 	}
 	if (target != UINT32_MAX) tc.target_scores.push_back({ ntg - 1, score });
@@ -525,6 +526,12 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		const int8_t* subject = e.rseq(block_id);
 		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false, 0 });
 		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
+		if (e.gapped_filter) {  // Extension::gapped_filter (align/gapped_filter.cpp:41-63): a target stays iff one of its hits passes
+			bool any = false;
+			for (const SeedHit& h : tc.hits) any |= h.gf != 0;
+			if (!any) continue;
+		}
+		++tc.n_extended;
 		std::sort(tc.hits.begin(), tc.hits.end());
 		tc.segs.clear();
 		for (const SeedHit& h : tc.hits) {  // align/ungapped.cpp:81-91
@@ -840,12 +847,17 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	p->map8[MASK_LETTER] = p->map8[STOP_LETTER] = p->map8[DMND_DELIMITER] = 10;
 	p->map8b[MASK_LETTER] = p->map8b[STOP_LETTER] = p->map8b[DMND_DELIMITER] = 11;
 	p->reduction_size = 10;
-	if (o->sensitivity != 0 && o->sensitivity != 1) { dmnd_set_last_error("sensitivity must be 0 (--fast) or 1 (default); the sensitive modes are not wired in this build"); return 1; }
+	if (o->sensitivity < 0 || o->sensitivity > 3) { dmnd_set_last_error("sensitivity must be 0 (--fast), 1 (default), 2 (--mid-sensitive) or 3 (--sensitive); the modes above are not wired in this build"); return 1; }
 	// shape_codes (search/setup.cpp:211-212 FAST uses the first code of its own list; :90-93 DEFAULT) and traits (:43, :47)
 	static const char* fast_codes[] = { "1101110101101111" };
 	static const char* default_codes[] = { "111101110111", "111011010010111" };
-	const char** codes = o->sensitivity == 0 ? fast_codes : default_codes;
-	p->n_shapes = o->sensitivity == 0 ? 1 : 2;
+	static const char* mid_codes[] = { "11110110111", "1101100111101", "1110010101111", "11010101100111", "11101110001011", "1110100100010111",
+		"1101000011010111", "1110011000011011" };  // MID_SENSITIVE 8x9, search/setup.cpp:201-210
+	static const char* sens_codes[] = { "1011110111", "110100100010111", "11001011111", "101110001111", "11011101100001", "1111010010101", "111001001001011",
+		"10101001101011", "111101010011", "1111000010000111", "1100011011011", "1101010000011011", "1110001010101001", "110011000110011", "11011010001101",
+		"1101001100010011" };  // SENSITIVE 16x8, search/setup.cpp:94-110
+	const char** codes = o->sensitivity == 0 ? fast_codes : o->sensitivity == 1 ? default_codes : o->sensitivity == 2 ? mid_codes : sens_codes;
+	p->n_shapes = o->sensitivity == 0 ? 1 : o->sensitivity == 1 ? 2 : o->sensitivity == 2 ? 8 : 16;
 	for (int s = 0; s < p->n_shapes; ++s) {
 		int w = 0, len = 0;
 		for (const char* c = codes[s]; *c; ++c, ++len)
@@ -860,7 +872,7 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 		const int threads = o->threads > 0 ? o->threads : 1;
 		p->seedp_bits = std::max(std::max(bit_length(pw - 1) - 32, bit_length((int64_t)threads * 4 * p->index_chunks - 1)), 8);
 	}
-	p->seed_cut = (o->sensitivity == 0 ? 0.9 : 0.8) * std::log(2.0) * p->shape_weight;
+	p->seed_cut = (o->sensitivity == 0 ? 0.9 : o->sensitivity == 1 ? 0.8 : 1.0) * std::log(2.0) * p->shape_weight;  // traits seed_cut (search/setup.cpp:43-49)
 	p->left_most_interval = 32; p->ungapped_window = 48;
 	p->ungapped_evalue = o->sensitivity == 0 ? 0.0 : 10000.0;  // traits ug_ev (search/setup.cpp:43,47)
 	p->short_query_max_len = 60;
@@ -868,6 +880,23 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	if (p->ungapped_evalue > 0.0)
 		for (int b = 1; b <= 31; ++b)  // CutoffTable: rawscore(bitscore_norm(evalue, 2^(b-1))), stats/score_matrix.h:133-151
 			p->ungapped_cutoff[b] = sc.rawscore(-std::log(p->ungapped_evalue / 1e9 / (double)(1u << (b - 1))) / std::log(2.0));
+	p->gapped_filter_evalue = o->sensitivity >= 3 ? 1.0 : 0.0;  // traits gf_ev (search/setup.cpp:49)
+	p->gapped_filter_window = 200;
+	p->gapped_filter_diag_score = sc.rawscore(12.0);
+	if (p->gapped_filter_evalue > 0.0) {
+		// CutoffTable2D::calc_min_score (util/scores/cutoff_table.h:69-74) over ScoreMatrix::evalue_norm (stats/score_matrix.cpp:222-225:
+		// the e-value against a 10^9-letter database)
+		Scoring norm; norm.db_letters = 1e9;
+		auto min_score = [&](unsigned qlen, unsigned slen, double evalue) {
+			for (int i = 10; i < 1000; ++i) if (norm.evalue(i, qlen, slen) <= evalue) return i;
+			return 1000;
+		};
+		for (int b1 = 1; b1 <= 31; ++b1)
+			for (int b2 = 1; b2 <= 31; ++b2) {
+				p->gapped_cutoff1[b1][b2] = (int16_t)min_score(1u << (b1 - 1), 1u << (b2 - 1), 2000.0);  // config.gapped_filter_evalue1
+				p->gapped_cutoff2[b1][b2] = (int16_t)min_score(1u << (b1 - 1), 1u << (b2 - 1), p->gapped_filter_evalue);
+			}
+	}
 	{	// tantan constants, masking/masking.cpp:133-153 and masking/tantan.cpp:131-142, evaluated in the reference's types.
 		// lambda is what cbrc::LambdaCalculator (lib/tantan, a randomised root search seeded by the C library's default
 		// rand() state) returns for BLOSUM62's 20 x 20 core; tests/test_masking.py re-derives it from the reference's own
@@ -960,7 +989,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		// into one query-grouped list (counting sort by query, stable)
 		int rc = prep_rc;
 		std::vector<dmnd_hit>& ah = w.acc_hits; std::vector<dmnd_segment>& as = w.acc_segs; std::vector<dmnd_hit_site>& at = w.acc_sites;
-		ah.clear(); as.clear(); at.clear();
+		ah.clear(); as.clear(); at.clear(); w.acc_gf.clear();
 		for (int sid = 0; sid < n_shapes && !rc; ++sid) {
 			dmnd_stage_counters cn;
 			rc = dmnd_search_shape_range(ctx, qb, rb, sid, q_begin, q_end, &hits, &cn);
@@ -970,8 +999,11 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 			const size_t n = dmnd_hits_count(hits);
 			if (w.hv.resize(ctx, n) || w.segv.resize(ctx, n) || w.sitev.resize(ctx, n)) rc = 1;
 			if (!rc && n) rc = dmnd_hits_download(ctx, hits, w.hv.data(), n) || dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), n);
+			w.gf_tmp.assign(n, 1);
+			if (!rc && n && env.gapped_filter) rc = dmnd_hits_gapped_filter(ctx, qb, rb, hits, w.gf_tmp.data(), n);  // align/gapped_filter.cpp, per hit
 			dmnd_hits_free(ctx, hits);
-			if (!rc) { ah.insert(ah.end(), w.hv.begin(), w.hv.end()); as.insert(as.end(), w.segv.begin(), w.segv.end()); at.insert(at.end(), w.sitev.begin(), w.sitev.end()); }
+			if (!rc) { ah.insert(ah.end(), w.hv.begin(), w.hv.end()); as.insert(as.end(), w.segv.begin(), w.segv.end()); at.insert(at.end(), w.sitev.begin(), w.sitev.end());
+			           w.acc_gf.insert(w.acc_gf.end(), w.gf_tmp.begin(), w.gf_tmp.end()); }
 		}
 		seed_turn.pass(lane);
 		if (rc) return 1;
@@ -981,8 +1013,10 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		std::vector<size_t> off((size_t)(q_end - q_begin) + 1, 0);
 		for (const dmnd_hit& h : ah) ++off[(size_t)(h.query - q_begin) + 1];
 		for (size_t k = 1; k < off.size(); ++k) off[k] += off[k - 1];
-		for (size_t k = 0; k < nh; ++k) { const size_t o = off[(size_t)(ah[k].query - q_begin)]++; w.hv[o] = ah[k]; w.segv[o] = as[k]; w.sitev[o] = at[k]; }
+		w.gfv.resize(nh);
+		for (size_t k = 0; k < nh; ++k) { const size_t o = off[(size_t)(ah[k].query - q_begin)]++; w.hv[o] = ah[k]; w.segv[o] = as[k]; w.sitev[o] = at[k]; w.gfv[o] = w.acc_gf[k]; }
 	}
+	if (n_shapes == 1) w.gfv.assign(nh, 1);
 	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
 	d.stats.seed_ms = ms_since(t0);
@@ -1017,7 +1051,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			QueryState& q = w.qs[k];
 			q.qid = w.hv[w.qstart[k]].query;
-			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; }
+			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; w.hs[x].gf = w.gfv[x]; }
 			d.load_hits(q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]);
 			d.start(q, tc);
 		}
@@ -1045,6 +1079,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		d.stats.queries_aligned += w.tc[(size_t)t].n_aligned;
 		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
 		d.stats.dp_problems_round2 += w.tc[(size_t)t].fused_r2; d.stats.dp_problems_fused += w.tc[(size_t)t].fused_r1;
+		d.stats.targets_extended += w.tc[(size_t)t].n_extended;
 	}
 	lo.matches->resize(moff[(size_t)T]);
 	lo.transcripts->resize(troff[(size_t)T]);
@@ -1086,7 +1121,7 @@ static void add_stats(dmnd_run_stats& a, const dmnd_run_stats& b) {
 	a.seed.tentative_matches2 += b.seed.tentative_matches2; a.seed.tentative_matches3 += b.seed.tentative_matches3; a.seed.masked_seeds += b.seed.masked_seeds;
 	a.hits += b.hits; a.targets += b.targets; a.dp_problems_round1 += b.dp_problems_round1; a.dp_problems_round2 += b.dp_problems_round2;
 	a.cells_round1 += b.cells_round1; a.cells_round2 += b.cells_round2; a.queries_aligned += b.queries_aligned; a.matches += b.matches;
-	a.dp_problems_fused += b.dp_problems_fused;
+	a.dp_problems_fused += b.dp_problems_fused; a.targets_extended += b.targets_extended;
 	// wall-clock phase times of concurrent lanes overlap: report the longest lane
 	a.seed_ms = std::max(a.seed_ms, b.seed_ms); a.host_bridge_ms = std::max(a.host_bridge_ms, b.host_bridge_ms);
 	a.dp1_ms = std::max(a.dp1_ms, b.dp1_ms); a.dp2_ms = std::max(a.dp2_ms, b.dp2_ms);
@@ -1152,7 +1187,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo;
-	e.n_shapes = opts->sensitivity == 0 ? 1 : 2;
+	e.n_shapes = opts->sensitivity == 0 ? 1 : opts->sensitivity == 1 ? 2 : opts->sensitivity == 2 ? 8 : 16;
+	e.gapped_filter = opts->sensitivity >= 3;
 	if (mask_algo) {
 		// "Masking reference" (run/double_indexed.cpp:122-127) and the reference block's motif table, before its seed index
 		uint64_t n_hard = 0;

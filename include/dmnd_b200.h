@@ -60,6 +60,12 @@ typedef struct dmnd_params {
 	                                     cutoff by bit length of the query length; all 0 when ungapped_evalue == 0 */
 	int32_t short_query_ungapped_cutoff; /* score_matrix.rawscore(config.short_query_ungapped_bitscore = 25) (search/stage0.cpp:187) */
 	int32_t short_query_max_len;      /* config.short_query_max_len = 60 (basic/config.cpp:566) */
+	/* gapped filter of the modes from --sensitive upwards (align/gapped_filter.cpp:33-63, dp/scan_diags.cpp) */
+	double gapped_filter_evalue;      /* 0 => no gapped filter; 1.0 for --sensitive (search/setup.cpp:49) */
+	int16_t gapped_cutoff1[32][32];   /* Util::Scores::CutoffTable2D(config.gapped_filter_evalue1 = 2000) by bit lengths of (query, target) length */
+	int16_t gapped_cutoff2[32][32];   /* CutoffTable2D(gapped_filter_evalue) (run/double_indexed.cpp:302-305) */
+	int32_t gapped_filter_diag_score; /* score_matrix.rawscore(config.gapped_filter_diag_bit_score = 12) (search/setup.cpp:368) */
+	int32_t gapped_filter_window;     /* config.gapped_filter_window = 200 (basic/config.cpp:560) */
 	float background_scores_f32[20];  /* (float)ScoreMatrix::background_scores_ (stats/score_matrix.cpp:241-248), for Hauser */
 	/* tantan repeat masking (masking/tantan.cpp:121-214, called from masking/masking.cpp:162 with p_repeat 0.005,
 	 * p_repeat_end 0.05, growth 1/0.9, min. mask probability config.tantan_minMaskProb 0.9): every constant the
@@ -212,6 +218,12 @@ int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 typedef struct dmnd_hit_site { uint32_t target; int32_t j; } dmnd_hit_site;
 int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
                           dmnd_segment* host, dmnd_hit_site* sites, size_t cap);
+/* Gapped filter of every hit (Extension::gapped_filter, align/gapped_filter.cpp:33-63): pass[k] = 1 iff hit k's 64-diagonal
+ * scan (window 100) scores above gapped_cutoff1 AND its 128-diagonal scan (window gapped_filter_window) above gapped_cutoff2,
+ * both through DP::diag_alignment (dp/scan_diags.cpp:277-297) on the int8 query profile with the block's Hauser bias
+ * (DP::make_profile8, dp/score_profile.cpp:32-65).  The caller keeps a target iff any of its hits passes.  Same order as
+ * dmnd_hits_download(). */
+int dmnd_hits_gapped_filter(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap);
 int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap);
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
 
@@ -235,7 +247,7 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {
-	int32_t sensitivity;       /* 0 = --fast, 1 = the reference's default sensitivity (2 shapes of weight 10, stage-2 ungapped window
+	int32_t sensitivity;       /* 0 = --fast, 1 = default, 2 = --mid-sensitive, 3 = --sensitive (gapped filter: CPU oracle only so far); 1: 2 shapes of weight 10, stage-2 ungapped window
 	                              filter; CPU oracle + host pipeline only so far: the CUDA library rejects it) */
 	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
 	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
@@ -266,6 +278,8 @@ typedef struct dmnd_run_stats {
 	uint64_t queries_aligned, matches;
 	uint64_t dp_problems_fused; /* round-1 problems evaluated once WITH traceback; their queries' round-2 problems were
 	                               answered from those results (counted in dp_problems_round2 / cells_round2 all the same) */
+	uint64_t targets_extended;  /* targets that enter the ungapped stage, i.e. after the gapped filter where the mode has one:
+	                               "Target hits (stage 3)" of the reference's --log (align/extend.cpp:215) */
 	double seed_ms, host_bridge_ms, dp1_ms, dp2_ms, total_ms; /* wall clock, host */
 	dmnd_timing device;
 } dmnd_run_stats;

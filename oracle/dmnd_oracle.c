@@ -743,6 +743,74 @@ int dmnd_hits_xdrop_sites(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_blo
 	}
 	return 0;
 }
+/* ---------------------------------------------------------------------------------------------------------- */
+/* Gapped filter.  DP::make_profile8 (dp/score_profile.cpp:32-65, AVX2 branch): profile(l, i) = sat8(matrix8[l][query[i]] +
+ * bias[i]) for true amino acids l (no bias for l >= 20), -1 in the 128 positions of padding on either side.
+ * DP::scan_diags64/128 (dp/scan_diags.cpp:30-275): per diagonal d_begin + k the running score, floored at 0 and saturating
+ * at 255 (biased int8 lanes), over the target columns [j0, j1); the maximum per diagonal.  DP::diag_alignment (:277-297). */
+static int gf_profile(const dmnd_params* p, const int8_t* q, const int8_t* cbs, int qlen, int l, int i) {
+	if (i < 0 || i >= qlen) return -1;
+	int v = p->score[l * 32 + (q[i] & DMND_LETTER_MASK)];
+	if (l < 20) { v += cbs[i]; if (v > 127) v = 127; if (v < -128) v = -128; }
+	return v;
+}
+static void gf_scan(const dmnd_params* p, const int8_t* q, const int8_t* cbs, int qlen, const int8_t* t, int band, int d_begin, int j_begin, int j_end, int* out) {
+	int v[128];
+	for (int k = 0; k < band; ++k) { v[k] = 0; out[k] = 0; }
+	const int j0 = j_begin > -(d_begin + band - 1) ? j_begin : -(d_begin + band - 1), j1 = (qlen - d_begin) < j_end ? (qlen - d_begin) : j_end;
+	for (int j = j0, i = d_begin + j0; j < j1; ++j, ++i) {
+		const int l = t[j] & DMND_LETTER_MASK;
+		for (int k = 0; k < band; ++k) {
+			int x = v[k] + gf_profile(p, q, cbs, qlen, l, i + k);
+			if (x < 0) x = 0;
+			if (x > 255) x = 255;
+			v[k] = x;
+			if (x > out[k]) out[k] = x;
+		}
+	}
+}
+static int gf_diag_alignment(const dmnd_params* p, const int* s, int count) {
+	int best = 0, best_gap = -p->gap_open, d = -1;
+	for (int i = 0; i < count; ++i) {
+		if (s[i] < p->gapped_filter_diag_score) continue;
+		const int gap_score = -p->gap_extend * (i - d) + best_gap;
+		int n = s[i];
+		if (gap_score + s[i] > best) best = n = gap_score + s[i];
+		if (s[i] > best) best = n = s[i];
+		const int open_score = -p->gap_open + n;
+		if (open_score > gap_score) { best_gap = open_score; d = i; }
+	}
+	return best;
+}
+static int gf_one(const dmnd_params* p, const int8_t* q, const int8_t* cbs, int qlen, const int8_t* t, int slen, int hi, int hj, int band, int window) {
+	const int diag = hi - hj;
+	const int d = diag - band / 2 > -(slen - 1) ? diag - band / 2 : -(slen - 1);
+	const int j0 = hj - window > 0 ? hj - window : 0, j1 = hj + window < slen ? hj + window : slen;
+	int scores[128];
+	gf_scan(p, q, cbs, qlen, t, band, d, j0, j1, scores);
+	return gf_diag_alignment(p, scores, band);
+}
+static int bit_len(int x) { return 32 - __builtin_clz((uint32_t)x); }
+int dmnd_hits_gapped_filter(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap) {
+	const dmnd_params* p = &ctx->p;
+	if (cap < h->n) return fail("dmnd_hits_gapped_filter: buffer too small");
+	for (size_t k = 0; k < h->n; ++k) {
+		const dmnd_hit* hit = &h->h[k];
+		const uint64_t sloc = DMND_HIT_SUBJECT(*hit);
+		const uint32_t t = seq_of(ref, sloc);
+		const int8_t *qs = query->letters + query->limits[hit->query], *cb = query->bias + query->limits[hit->query], *ss = ref->letters + ref->limits[t];
+		const int qlen = (int)(query->limits[hit->query + 1] - query->limits[hit->query] - 1), slen = (int)(ref->limits[t + 1] - ref->limits[t] - 1);
+		const int hi = hit->seed_offset, hj = (int)((int64_t)sloc - ref->limits[t]);
+		pass[k] = 0;
+		/* align/gapped_filter.cpp:44-63 (blastp: no translated-query shortcut) */
+		const int f1 = gf_one(p, qs, cb, qlen, ss, slen, hi, hj, 64, 100);
+		if (f1 > p->gapped_cutoff1[bit_len(qlen)][bit_len(slen)]) {
+			const int f2 = gf_one(p, qs, cb, qlen, ss, slen, hi, hj, 128, p->gapped_filter_window);
+			if (f2 > p->gapped_cutoff2[bit_len(qlen)][bit_len(slen)]) pass[k] = 1;
+		}
+	}
+	return 0;
+}
 int dmnd_hits_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop,
                     dmnd_segment* host, size_t cap) {
 	return dmnd_hits_xdrop_sites(ctx, query, ref, h, raw_xdrop, host, NULL, cap);

@@ -8,6 +8,8 @@ For every workload W and parity-ladder level L:
     L2 = the reference's default flags (tantan masking of both blocks, motif soft-masking, Hauser CBS)
     S1 = no sensitivity flag at all: the reference's DEFAULT sensitivity (2 shapes of weight 10, stage-2 ungapped window filter)
          with its default flags -- `diamond blastp -q Q -d DB` as most users run it
+    S2 = --mid-sensitive (8 shapes of weight 9, same filters) with default flags
+    S3 = --sensitive (16 shapes of weight 8, stage-2 window filter, gapped filter) with default flags
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -21,12 +23,15 @@ REF = os.path.join(ROOT, "oracle", "_ref", "diamond")
 LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats", "0"],
           "l1": ["--masking", "0", "--motif-masking", "0"],
           "l2": [],
-          "s1": []}
-MODE = {"s1": []}  # every other level runs --fast
+          "s1": [],
+          "s2": [],
+          "s3": []}
+MODE = {"s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"]}  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
-            "targets_round2": r"Target hits \(stage 5\) = (\d+)", "seedp_bits": r"Seed partition bits = (\d+)"}
+            "targets_round2": r"Target hits \(stage 5\) = (\d+)", "seedp_bits": r"Seed partition bits = (\d+)",
+            "targets_extended": r"Target hits \(stage 3\) = (\d+)"}
 
 
 def main():

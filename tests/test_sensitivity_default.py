@@ -25,6 +25,44 @@ def test_default_sensitivity_matches_reference_golden(oracle_lib, name):
     assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"] and ctx.params.seedp_bits == cn["seedp_bits"]
 
 
+@pytest.mark.parametrize("name", ["c1", "edge", "rep"])  # (fam2.s2 is pinned too, but takes the scalar oracle half a minute)
+def test_mid_sensitive_matches_reference_golden(oracle_lib, name):
+    """--mid-sensitive: 8 shapes of weight 9 (search/setup.cpp:201-210), entropy cut 1.0, the same stage-2 window filter."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1, sensitivity=2)
+    assert ctx.params.n_shapes == 8 and ctx.params.shape_weight == 9
+    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.s2.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.s2.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
+
+
+@pytest.mark.parametrize("name", ["c1", "edge", "long", "rep"])  # (fam2.s3: 2 x 10^7 stage-0 pairs, two minutes in the scalar oracle; run it by hand)
+def test_sensitive_matches_reference_golden(oracle_lib, name):
+    """--sensitive: 16 shapes of weight 8 (search/setup.cpp:94-110) and the gapped filter (align/gapped_filter.cpp:33-63: 64- and
+    128-diagonal scans of the int8 query profile, dp/scan_diags.cpp, cutoffs from CutoffTable2D at e-values 2000 and 1)."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1, sensitivity=3)
+    p = ctx.params
+    assert p.n_shapes == 16 and p.shape_weight == 8 and p.gapped_filter_evalue == 1.0
+    assert 10 < p.gapped_cutoff1[9][9] < p.gapped_cutoff2[9][9] < 200  # the second stage (e-value 1) is the stricter one
+    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.s3.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.s3.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
+    assert st["targets_extended"] == cn["targets_extended"], "targets that survive the gapped filter (Target hits (stage 3))"
+    if name == "c1":
+        assert st["targets_extended"] < st["targets"]  # the filter does remove targets here
+
+
 def test_ungapped_cutoffs_and_hit_scores(oracle_lib):
     """The hit score is the ungapped window score (search/stage2.h:144-147): above the cutoff of the query's length class,
     at most 255 where the reference's int8 kernel scored the call (>= 4 survivors), unbounded for the scalar calls; the

@@ -59,6 +59,39 @@ def test_blastp_default_sensitivity_matches_reference_golden(product_lib, name):
     assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
 
 
+@pytest.mark.parametrize("name", ["c1", "rep"])
+def test_gapped_filter_flags_match_oracle(oracle_lib, product_lib, name):
+    """dmnd_hits_gapped_filter (--sensitive): per-hit pass flags of the 64/128-diagonal scans, device vs oracle."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    res = []
+    for lib in (oracle_lib, product_lib):
+        c = api.Context(lib, threads=8, sensitivity=3)
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.compute_bias(qb, 1)
+        hits, cn, gf = c.search_shape(qb, rb, 0, gapped_filter=True)
+        order = np.argsort(hits, order=["query", "subject_score", "seed_offset"])
+        res.append((hits[order], gf[order]))
+        c.free_block(qb); c.free_block(rb); c.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert 0 < res[1][1].sum() < len(res[1][1])
+
+
+@pytest.mark.parametrize("sens,level", [(2, "s2"), (3, "s3")])
+@pytest.mark.parametrize("name", ["c1", "edge", "rep"])
+def test_blastp_mid_sensitive_and_sensitive_match_reference_golden(product_lib, name, sens, level):
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    g = api.Context(product_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=1, sensitivity=sens)
+    m, _, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.{level}.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
+
+
 def test_cli_without_sensitivity_flag(product_lib, tmp_path):
     from diamond_b200 import synth
     w, *_ = workload_blocks("c1")
