@@ -26,7 +26,7 @@ oracle: oracle/_build/libdmnd_oracle.so oracle/_build/dmnd-oracle-cli
 $(OBJ)/host/%.o: $(HOST)/%.cpp $(wildcard $(HOST)/*.h) include/dmnd_b200.h
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
-$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh $(CUDA)/dev_params.h $(CUDA)/mask_kernels.cuh $(CUDA)/gf_kernels.cuh include/dmnd_b200.h $(HOST)/motif_table.h
+$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh $(CUDA)/dev_params.h $(CUDA)/mask_kernels.cuh $(CUDA)/gf_kernels.cuh $(CUDA)/seed_kernels.cuh include/dmnd_b200.h $(HOST)/motif_table.h
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/cuda/$*.ptxas.log || (cat $(OBJ)/cuda/$*.ptxas.log; false)
 

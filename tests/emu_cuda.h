@@ -35,7 +35,7 @@ struct Thread {
 	bool done = false;
 	unsigned tid = 0;
 	uint64_t warp_round = 0;   // number of warp-level primitives this thread has entered
-	uint32_t posted[2] = { 0, 0 };  // value posted for round parity
+	uint64_t posted[2] = { 0, 0 };  // value posted for round parity
 	uint64_t block_round = 0;  // __syncthreads count
 };
 static std::vector<Thread> g_threads;
@@ -86,7 +86,7 @@ static void launch(unsigned grid, unsigned block, const std::function<void()>& b
 
 // Posts `v` for this thread's next warp round and waits until every lane in `mask` (of this thread's warp) has posted the
 // same round; returns the round's parity slot to read partners from.
-static int warp_rendezvous(unsigned mask, uint32_t v) {
+static int warp_rendezvous(unsigned mask, uint64_t v) {
 	Thread& me = g_threads[(size_t)g_cur];
 	const unsigned lane = me.tid & 31u, wbase = me.tid & ~31u;
 	if (!((mask >> lane) & 1u)) { fprintf(stderr, "emu: thread %u calls a warp primitive with a mask (%08x) that excludes it\n", me.tid, mask); exit(3); }
@@ -108,7 +108,7 @@ static int warp_rendezvous(unsigned mask, uint32_t v) {
 	}
 	return slot;
 }
-static uint32_t read_lane(unsigned src_lane, int slot) {
+static uint64_t read_lane(unsigned src_lane, int slot) {
 	const Thread& me = g_threads[(size_t)g_cur];
 	return g_threads[(me.tid & ~31u) + src_lane].posted[slot];
 }
@@ -117,8 +117,8 @@ static uint32_t read_lane(unsigned src_lane, int slot) {
 
 // NOTE on round counters: a lane's counter only has to agree with the lanes in its own masks.  Groups use disjoint masks and
 // the full-warp kernels (popc_kernel) use 0xffffffff from the first primitive on, so counters never mix.
-template<typename T> static inline T emu_bits_to(uint32_t u) { T v; static_assert(sizeof(T) == 4, "32-bit shuffles only"); memcpy(&v, &u, 4); return v; }
-template<typename T> static inline uint32_t emu_to_bits(T v) { uint32_t u; static_assert(sizeof(T) == 4, "32-bit shuffles only"); memcpy(&u, &v, 4); return u; }
+template<typename T> static inline T emu_bits_to(uint64_t u) { T v; static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only"); memcpy(&v, &u, sizeof(T)); return v; }
+template<typename T> static inline uint64_t emu_to_bits(T v) { uint64_t u = 0; static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only"); memcpy(&u, &v, sizeof(T)); return u; }
 
 template<typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
 	const int slot = emu::warp_rendezvous(mask, emu_to_bits(v));
@@ -140,6 +140,13 @@ template<typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsign
 	emu::warp_rendezvous(mask, 0);
 	return r;
 }
+static inline unsigned __ballot_sync(unsigned mask, bool pred) {
+	const int slot = emu::warp_rendezvous(mask, pred ? 1u : 0u);
+	unsigned r = 0;
+	for (unsigned l = 0; l < 32; ++l) if (((mask >> l) & 1u) && emu::read_lane(l, slot)) r |= 1u << l;
+	emu::warp_rendezvous(mask, 0);
+	return r;
+}
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_rendezvous(mask, 0); }
 static inline void __syncthreads() {
 	emu::Thread& me = emu::g_threads[(size_t)emu::g_cur];
@@ -153,6 +160,12 @@ static inline void __syncthreads() {
 }
 
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+struct uint4 { unsigned x, y, z, w; };
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }

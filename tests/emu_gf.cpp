@@ -3,8 +3,6 @@
 // (--sensitive parameters, Hauser bias on, SEED_MASK bits still set on the query letters as in the pipeline).
 // usage: emu_gf DIR MAX_HITS      (DIR holds q.i8 q.i64 r.i8 r.i64: the two block images)
 #include "emu_cuda.h"
-static inline int min(int a, int b) { return a < b ? a : b; }
-static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 #include "../diamond_b200/csrc/cuda/gf_kernels.cuh"
 #include <string>
 using namespace dmnd_cuda;

@@ -1,0 +1,18 @@
+"""The seed stage's kernel SOURCE (diamond_b200/csrc/cuda/seed_kernels.cuh: ref_enum, bloom/bucket build, probe, entropy
+masking, stage 1 flags, stage-2 window + left-most filter, motif SEED_MASK marking) compiled for the CPU behind
+tests/emu_cuda.h and driven by a mirror of build_ref_index + search_shape_impl, against the oracle's dmnd_search_shape:
+hits incl. ungapped window scores, stage counters and SEED_MASK bits, for BOTH shapes of the default sensitivity on masked
+blocks (bits of shape 0 stay set for shape 1).  Runs without a GPU.  (`emu_seed DIR 0 0` = --fast, `DIR 1 0` on the fam2
+workload = 339 104 hits incl. the 255-capped scores, 4 minutes: run by hand.)"""
+import os, subprocess
+from conftest import ROOT, workload_blocks
+
+
+def test_seed_stage_emulation_matches_oracle_default_sensitivity(oracle_lib, tmp_path):
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("edge")
+    q_raw.tofile(str(tmp_path / "q.i8")); q_lim.tofile(str(tmp_path / "q.i64")); r_raw.tofile(str(tmp_path / "r.i8")); r_lim.tofile(str(tmp_path / "r.i64"))
+    exe = str(tmp_path / "emu_seed")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "emu_seed.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "oracle", "_build"), "-ldmnd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")], check=True)
+    r = subprocess.run([exe, str(tmp_path), "1", "1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "shapes=2 " in r.stdout and "fails=0 " in r.stdout, r.stdout + r.stderr
