@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
 		dmnd_search_opts_default(&o);
 		o.sensitivity = 1;  // like the reference: no sensitivity flag = Sensitivity::DEFAULT, --fast = Sensitivity::FAST
 		std::string qf, df, of;
-		bool log = false;
+		bool log = false, motif_set = false;
 		for (int i = 2; i < argc; ++i) {
 			const std::string a = argv[i];
 			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
@@ -102,6 +102,9 @@ int main(int argc, char** argv) {
 			else if (a == "--fast") o.sensitivity = 0;
 			else if (a == "--mid-sensitive") o.sensitivity = 2;
 			else if (a == "--sensitive") o.sensitivity = 3;
+			else if (a == "--more-sensitive") o.sensitivity = 4;
+			else if (a == "--very-sensitive") o.sensitivity = 5;
+			else if (a == "--ultra-sensitive") o.sensitivity = 6;
 			else if (a == "-p" || a == "--threads") o.threads = atoi(val());
 			else if (a == "-c" || a == "--index-chunks") o.index_chunks = atoi(val());
 			else if (a == "-k" || a == "--max-target-seqs") o.max_target_seqs = atoi(val());
@@ -114,6 +117,7 @@ int main(int argc, char** argv) {
 			else if (a == "--motif-masking") {  // search/setup.cpp:322-336
 				const std::string v = val();
 				if (v == "0") o.motif_masking = 0; else if (v == "1") o.motif_masking = 1; else usage("Permitted values for --motif-masking: 0, 1");
+				motif_set = true;
 			}
 			else if (a == "-f" || a == "--outfmt") { if (std::string(val()) != "6") usage("only -f 6 is implemented"); }
 			else if (a == "--log") log = true;
@@ -121,6 +125,7 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
 		read_fasta(qf, q);

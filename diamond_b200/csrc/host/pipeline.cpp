@@ -215,12 +215,22 @@ It output_range(It begin, It end, int64_t max_target_seqs) {  // align/culling.c
 	return i;
 }
 
-int band_for(int len) {  // align/gapped_score.cpp:41-72, Mode::BANDED_FAST
-	if (len < 50) return 12;
-	if (len < 100) return 16;
-	if (len < 250) return 30;
-	if (len < 350) return 40;
-	return 64;
+int band_for(int len, bool slow) {  // Extension::band, align/gapped_score.cpp:41-72
+	if (!slow) {  // Mode::BANDED_FAST
+		if (len < 50) return 12;
+		if (len < 100) return 16;
+		if (len < 250) return 30;
+		if (len < 350) return 40;
+		return 64;
+	}
+	if (len < 50) return 15;  // Mode::BANDED_SLOW
+	if (len < 100) return 20;
+	if (len < 150) return 30;
+	if (len < 200) return 50;
+	if (len < 250) return 60;
+	if (len < 350) return 100;
+	if (len < 500) return 120;
+	return 150;
 }
 inline int banded_cols(int qlen, int tlen, int d_begin, int d_end) {  // dp/dp.h:47-52
 	const int pos = std::max(d_end - 1, 0) - (d_end - 1);
@@ -263,6 +273,8 @@ struct Env {
 	const Scoring* sc;
 	const int8_t *q_letters, *r_letters;
 	const PatchSet *q_patch = nullptr, *r_patch = nullptr;  // hard-masked sequences (dmnd_blastp with masking); null = read in place
+	bool band_slow = false;      // Extension::Mode::BANDED_SLOW band table (align/extend.cpp:62-75, gapped_score.cpp:41-72)
+	double ranking_letters = 2e9; // ranking_chunk_size's default_letters (align/extend.cpp:86)
 	bool gapped_filter = false;  // Extension::gapped_filter before the ungapped stage (align/extend.cpp:205-214)
 	int n_shapes = 1;   // shapes of the sensitivity mode (search/setup.cpp:80-304): one dmnd_search_shape per shape
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
@@ -487,7 +499,7 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	const int64_t target_count = q.n_targets;
 	tc.n_targets += (uint64_t)target_count;
 	if (target_count == 0) { q.phase = PH_DONE; return; }
-	const int64_t block_mult = std::max<int64_t>((int64_t)std::round((double)e.ref_letters / 2e9), 1);
+	const int64_t block_mult = std::max<int64_t>((int64_t)std::round((double)e.ref_letters / e.ranking_letters), 1);
 	const int64_t mm = ((int64_t)e.max_target_seqs + 31) / 32 * 32;  // make_multiple(max_target_seqs, 32)
 	q.chunk_size = std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;
 	TargetScore* ts = tc.target_scores.data() + q.ts_off;
@@ -515,7 +527,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	std::vector<dmnd_dp_problem>& plist = q.fused ? tc.p2 : tc.p1;  // fused: straight into the traceback batch
 	q.prob_begin = plist.size();
 	const int8_t* query = e.qseq(q.qid);
-	const int band = band_for(q.qlen);
+	const int band = band_for(q.qlen, e.band_slow);
 	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
 	const uint32_t* hb = tc.hit_begin.data() + q.tgt_off;
 	const uint32_t* ids = tc.target_block_ids.data() + q.ts_off;
@@ -822,6 +834,43 @@ static ResultPool& result_pool() { static ResultPool p; return p; }
 
 extern "C" {
 
+// Sensitivity::{FAST, DEFAULT, MID_SENSITIVE, SENSITIVE, MORE_SENSITIVE, VERY_SENSITIVE, ULTRA_SENSITIVE}: sensitivity_traits
+// (search/setup.cpp:40-54), shape_codes (:80-304), default_ext_mode (align/extend.cpp:62-75), ranking_chunk_size's default_letters
+// (align/extend.cpp:86).  The shape codes are the reference's (spaced-seed patterns are data of the method, like BLOSUM62).
+struct ModeTraits {
+	int n_shapes; const char* const* codes;
+	int min_identities; double ungapped_evalue, gapped_filter_evalue; int index_chunks; double seed_cut;
+	bool motif_masking, band_slow; double ranking_letters;
+};
+static const ModeTraits* mode_traits(int sensitivity) {
+	static const char* const fast[] = { "1101110101101111" };
+	static const char* const dflt[] = { "111101110111", "111011010010111" };
+	static const char* const mid[] = { "11110110111", "1101100111101", "1110010101111", "11010101100111", "11101110001011", "1110100100010111", "1101000011010111", "1110011000011011" };
+	static const char* const sens[] = { "1011110111", "110100100010111", "11001011111", "101110001111", "11011101100001", "1111010010101", "111001001001011", "10101001101011",
+		"111101010011", "1111000010000111", "1100011011011", "1101010000011011", "1110001010101001", "110011000110011", "11011010001101", "1101001100010011" };
+	static const char* const very[] = { "11101111", "110110111", "111111001", "1010111011", "11110001011", "110100101011", "110110001101", "1010101000111", "1100101001011",
+		"1101010101001", "1110010010011", "110110000010011", "111001000100011", "1101000100010011" };
+	static const char* const ultra[] = { "1111111", "11101111", "110011111", "110110111", "111111001", "1010111011", "1011110101", "1111000111", "10011110011", "10101101101",
+		"10111010101", "11001010111", "11001100111", "11010101101", "11110001011", "100111010011", "101100110101", "101110000111", "110100101011", "110110001101", "111000110011",
+		"1010001011011", "1010101000111", "1010110100011", "1100100110011", "1100101001011", "1101001100101", "1101010101001", "1110001010101", "1110010010011", "10100001101101",
+		"11000100010111", "11010000100111", "11010100110001", "11101000011001", "11110000001101", "11110100000011", "101001000001111", "110000100101011", "110010010000111",
+		"110101100001001", "110110000010011", "111001000100011", "111100000100101", "1000110010010101", "1001000100101101", "1001000110011001", "1010001001001011",
+		"1010001010010011", "1010010001010101", "1010010100010011", "1010010101001001", "1010100000101011", "1010100011000101", "1011000010001011", "1100010000111001",
+		"1100010010001011", "1100100001001011", "1100100100100011", "1100110000001101", "1101000100010011", "1101000110000101", "1110000001010011", "1110100000010101" };
+	static const ModeTraits t[7] = {
+		//  shapes        minid ug_ev     gf_ev chunks seed_cut motif  slow   ranking letters
+		{ 1, fast,  11, 0.0,      0.0, 4, 0.9, true,  false, 2e9 },
+		{ 2, dflt,  11, 10000.0,  0.0, 4, 0.8, true,  false, 2e9 },
+		{ 8, mid,   11, 10000.0,  0.0, 4, 1.0, true,  false, 2e9 },
+		{ 16, sens, 11, 10000.0,  1.0, 4, 1.0, true,  false, 2e9 },
+		{ 16, sens, 11, 10000.0,  1.0, 4, 1.0, false, true,  2e9 },   // MORE_SENSITIVE: the shapes of SENSITIVE, no motif masking, BANDED_SLOW
+		{ 14, very,  9, 100000.0, 1.0, 1, 1.0, false, true,  800e6 },
+		{ 64, ultra, 9, 300000.0, 1.0, 1, 1.0, false, true,  800e6 },
+	};
+	return sensitivity >= 0 && sensitivity <= 6 ? &t[sensitivity] : nullptr;
+}
+extern "C" int dmnd_mode_motif_masking(int sensitivity) { const ModeTraits* t = mode_traits(sensitivity); return t ? (int)t->motif_masking : -1; }
+
 void dmnd_search_opts_default(dmnd_search_opts* o) {
 	std::memset(o, 0, sizeof *o);
 	o->sensitivity = 0; o->threads = 8; o->index_chunks = 0; o->comp_based_stats = 1; o->max_target_seqs = 25;
@@ -847,40 +896,32 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	p->map8[MASK_LETTER] = p->map8[STOP_LETTER] = p->map8[DMND_DELIMITER] = 10;
 	p->map8b[MASK_LETTER] = p->map8b[STOP_LETTER] = p->map8b[DMND_DELIMITER] = 11;
 	p->reduction_size = 10;
-	if (o->sensitivity < 0 || o->sensitivity > 3) { dmnd_set_last_error("sensitivity must be 0 (--fast), 1 (default), 2 (--mid-sensitive) or 3 (--sensitive); the modes above are not wired in this build"); return 1; }
-	// shape_codes (search/setup.cpp:211-212 FAST uses the first code of its own list; :90-93 DEFAULT) and traits (:43, :47)
-	static const char* fast_codes[] = { "1101110101101111" };
-	static const char* default_codes[] = { "111101110111", "111011010010111" };
-	static const char* mid_codes[] = { "11110110111", "1101100111101", "1110010101111", "11010101100111", "11101110001011", "1110100100010111",
-		"1101000011010111", "1110011000011011" };  // MID_SENSITIVE 8x9, search/setup.cpp:201-210
-	static const char* sens_codes[] = { "1011110111", "110100100010111", "11001011111", "101110001111", "11011101100001", "1111010010101", "111001001001011",
-		"10101001101011", "111101010011", "1111000010000111", "1100011011011", "1101010000011011", "1110001010101001", "110011000110011", "11011010001101",
-		"1101001100010011" };  // SENSITIVE 16x8, search/setup.cpp:94-110
-	const char** codes = o->sensitivity == 0 ? fast_codes : o->sensitivity == 1 ? default_codes : o->sensitivity == 2 ? mid_codes : sens_codes;
-	p->n_shapes = o->sensitivity == 0 ? 1 : o->sensitivity == 1 ? 2 : o->sensitivity == 2 ? 8 : 16;
+	const ModeTraits* mt = mode_traits(o->sensitivity);
+	if (!mt) { dmnd_set_last_error("sensitivity must be 0 (--fast) .. 6 (--ultra-sensitive)"); return 1; }
+	p->n_shapes = mt->n_shapes;
 	for (int s = 0; s < p->n_shapes; ++s) {
 		int w = 0, len = 0;
-		for (const char* c = codes[s]; *c; ++c, ++len)
+		for (const char* c = mt->codes[s]; *c; ++c, ++len)
 			if (*c == '1') { p->shape_pos[s][w++] = len; p->shape_mask[s] |= 1u << len; }
 		p->shape_len[s] = len; p->shape_weight = w;
 	}
-	p->hamming_id = 11;
-	p->index_chunks = o->index_chunks > 0 ? o->index_chunks : 4;
+	p->hamming_id = mt->min_identities;
+	p->index_chunks = o->index_chunks > 0 ? o->index_chunks : mt->index_chunks;
 	{  // seedp_bits, search/setup.cpp:306-309
 		auto bit_length = [](int64_t x) { int n = 0; while (x > 0) { ++n; x >>= 1; } return n; };
 		int64_t pw = 1; for (int i = 0; i < p->shape_weight; ++i) pw *= p->reduction_size;
 		const int threads = o->threads > 0 ? o->threads : 1;
 		p->seedp_bits = std::max(std::max(bit_length(pw - 1) - 32, bit_length((int64_t)threads * 4 * p->index_chunks - 1)), 8);
 	}
-	p->seed_cut = (o->sensitivity == 0 ? 0.9 : o->sensitivity == 1 ? 0.8 : 1.0) * std::log(2.0) * p->shape_weight;  // traits seed_cut (search/setup.cpp:43-49)
+	p->seed_cut = mt->seed_cut * std::log(2.0) * p->shape_weight;  // traits seed_cut (search/setup.cpp:43-49)
 	p->left_most_interval = 32; p->ungapped_window = 48;
-	p->ungapped_evalue = o->sensitivity == 0 ? 0.0 : 10000.0;  // traits ug_ev (search/setup.cpp:43,47)
+	p->ungapped_evalue = mt->ungapped_evalue;
 	p->short_query_max_len = 60;
 	p->short_query_ungapped_cutoff = sc.rawscore(25.0);
 	if (p->ungapped_evalue > 0.0)
 		for (int b = 1; b <= 31; ++b)  // CutoffTable: rawscore(bitscore_norm(evalue, 2^(b-1))), stats/score_matrix.h:133-151
 			p->ungapped_cutoff[b] = sc.rawscore(-std::log(p->ungapped_evalue / 1e9 / (double)(1u << (b - 1))) / std::log(2.0));
-	p->gapped_filter_evalue = o->sensitivity >= 3 ? 1.0 : 0.0;  // traits gf_ev (search/setup.cpp:49)
+	p->gapped_filter_evalue = mt->gapped_filter_evalue;
 	p->gapped_filter_window = 200;
 	p->gapped_filter_diag_score = sc.rawscore(12.0);
 	if (p->gapped_filter_evalue > 0.0) {
@@ -1187,8 +1228,11 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo;
-	e.n_shapes = opts->sensitivity == 0 ? 1 : opts->sensitivity == 1 ? 2 : opts->sensitivity == 2 ? 8 : 16;
-	e.gapped_filter = opts->sensitivity >= 3;
+	{
+		const ModeTraits* mt = mode_traits(opts->sensitivity);
+		if (!mt) { dmnd_set_last_error("dmnd_blastp: bad sensitivity"); return 1; }
+		e.n_shapes = mt->n_shapes; e.gapped_filter = mt->gapped_filter_evalue > 0.0; e.band_slow = mt->band_slow; e.ranking_letters = mt->ranking_letters;
+	}
 	if (mask_algo) {
 		// "Masking reference" (run/double_indexed.cpp:122-127) and the reference block's motif table, before its seed index
 		uint64_t n_hard = 0;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMND_MAX_SHAPES 16
+#define DMND_MAX_SHAPES 64
 #define DMND_MAX_WEIGHT 12
 #define DMND_PERIMETER_PADDING 256 /* data/string_set.h:34 */
 #define DMND_DELIMITER 31          /* basic/value.h:62 */
@@ -247,7 +247,7 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {
-	int32_t sensitivity;       /* 0 = --fast, 1 = default, 2 = --mid-sensitive, 3 = --sensitive (gapped filter: CPU oracle only so far); 1: 2 shapes of weight 10, stage-2 ungapped window
+	int32_t sensitivity;       /* 0 = --fast, 1 = default, 2 = --mid-sensitive, 3 = --sensitive, 4 = --more-sensitive, 5 = --very-sensitive, 6 = --ultra-sensitive; 1: 2 shapes of weight 10, stage-2 ungapped window
 	                              filter; CPU oracle + host pipeline only so far: the CUDA library rejects it) */
 	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
 	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
@@ -287,6 +287,8 @@ typedef struct dmnd_run_stats {
 typedef struct dmnd_result dmnd_result;
 
 void dmnd_search_opts_default(dmnd_search_opts* o);
+/* The sensitivity mode's default for --motif-masking (SensitivityTraits::motif_masking, search/setup.cpp:40-54): 1, 0, or -1 for a bad mode. */
+int dmnd_mode_motif_masking(int sensitivity);
 /* Fills a dmnd_params for BLOSUM62 11/1 and the given options (host restatement of setup_search). */
 int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* out);
 /* One (query block, reference block) pass of blastp: seed search, extension rounds, culling.

@@ -10,6 +10,8 @@ For every workload W and parity-ladder level L:
          with its default flags -- `diamond blastp -q Q -d DB` as most users run it
     S2 = --mid-sensitive (8 shapes of weight 9, same filters) with default flags
     S3 = --sensitive (16 shapes of weight 8, stage-2 window filter, gapped filter) with default flags
+    S4 / S5 / S6 = --more-sensitive / --very-sensitive / --ultra-sensitive (no motif masking, BANDED_SLOW bands; 14 x 7 and 64 x 7 shapes,
+         Hamming cutoff 9, one index chunk for the last two)
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -25,8 +27,9 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "l2": [],
           "s1": [],
           "s2": [],
-          "s3": []}
-MODE = {"s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"]}  # every other level runs --fast
+          "s3": [], "s4": [], "s5": [], "s6": []}
+MODE = {"s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
+ONLY = {"s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -44,6 +47,8 @@ def main():
             synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, flags in LEVELS.items():
+                if lvl in ONLY and name not in ONLY[lvl]:
+                    continue
                 out = os.path.join(HERE, f"{name}.{lvl}.tsv")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue

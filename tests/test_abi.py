@@ -43,3 +43,18 @@ def test_struct_layouts():
     assert ctypes.sizeof(api.DpProblem) == 16 and api.PROBLEM_DTYPE.itemsize == 16
     assert ctypes.sizeof(api.DpResult) == api.RESULT_DTYPE.itemsize == 56
     assert ctypes.sizeof(api.Match) == api.MATCH_DTYPE.itemsize
+
+
+def test_ctypes_structs_have_the_c_sizes(tmp_path):
+    """diamond_b200/api.py mirrors the structs of include/dmnd_b200.h by hand: a stale mirror corrupts memory silently."""
+    import ctypes as C, subprocess
+    from conftest import ROOT
+    from diamond_b200 import api
+    src = tmp_path / "sz.c"
+    src.write_text('#include "dmnd_b200.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dmnd_params), sizeof(dmnd_search_opts), '
+                   'sizeof(dmnd_run_stats), sizeof(dmnd_match), sizeof(dmnd_hit), sizeof(dmnd_dp_result), sizeof(dmnd_timing));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    want = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    got = [C.sizeof(t) for t in (api.Params, api.SearchOpts, api.RunStats, api.Match, api.Hit, api.DpResult, api.Timing)]
+    assert got == want

@@ -87,7 +87,7 @@ def test_cli_rejects_what_it_does_not_implement(oracle_lib):
     cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
     r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z", "--masking", "seg"], capture_output=True, text=True)
     assert r.returncode != 0 and "masking" in r.stderr
-    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z", "--more-sensitive"], capture_output=True, text=True)
+    r = subprocess.run([cli, "blastp", "-q", "x", "-d", "y", "-o", "z", "--faster"], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported option" in r.stderr
     r = subprocess.run([cli, "blastx"], capture_output=True, text=True)
     assert r.returncode != 0

@@ -63,6 +63,26 @@ def test_sensitive_matches_reference_golden(oracle_lib, name):
         assert st["targets_extended"] < st["targets"]  # the filter does remove targets here
 
 
+@pytest.mark.parametrize("sens,level,name", [(4, "s4", "edge"), (5, "s5", "c1"), (5, "s5", "edge"), (6, "s6", "edge")])  # (c1 / rep goldens of all three exist; the scalar oracle needs a minute for c1.s6)
+def test_more_very_ultra_sensitive_match_reference_golden(oracle_lib, name, sens, level):
+    """--more-sensitive (the 16 shapes of --sensitive, no motif masking, BANDED_SLOW bands), --very-sensitive (14 shapes of weight 7,
+    Hamming cutoff 9, one index chunk, ungapped e-value 10^5) and --ultra-sensitive (64 shapes, 3 x 10^5): sensitivity_traits
+    (search/setup.cpp:40-54), shape_codes (:111-200), Extension::band (align/gapped_score.cpp:41-72)."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks(name)
+    assert oracle_lib.dmnd_mode_motif_masking(sens) == 0 and oracle_lib.dmnd_mode_motif_masking(3) == 1
+    ctx = api.Context(oracle_lib, threads=8, comp_based_stats=1, masking=1, motif_masking=0, sensitivity=sens)
+    p = ctx.params
+    assert (p.n_shapes, p.shape_weight, p.hamming_id, p.index_chunks) == {4: (16, 8, 11, 4), 5: (14, 7, 9, 1), 6: (64, 7, 9, 1)}[sens]
+    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m) == open(os.path.join(GOLDEN, f"{name}.{level}.tsv")).read()
+    cn = json.load(open(os.path.join(GOLDEN, f"{name}.{level}.counters.json")))
+    for k in ("seeds_hit", "seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3"):
+        assert st["seed"][k] == cn[k], k
+    assert st["targets"] == cn["targets"] and st["targets_extended"] == cn["targets_extended"] and st["dp_problems_round2"] == cn["targets_round2"]
+
+
 def test_ungapped_cutoffs_and_hit_scores(oracle_lib):
     """The hit score is the ungapped window score (search/stage2.h:144-147): above the cutoff of the query's length class,
     at most 255 where the reference's int8 kernel scored the call (>= 4 survivors), unbounded for the scalar calls; the
