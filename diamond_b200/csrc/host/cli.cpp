@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <string>
 #include "../../../include/dmnd_b200.h"
 
 namespace {
@@ -93,6 +94,7 @@ int main(int argc, char** argv) {
 		o.sensitivity = 1;  // like the reference: no sensitivity flag = Sensitivity::DEFAULT, --fast = Sensitivity::FAST
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
+		std::vector<std::string> fields;
 		for (int i = 2; i < argc; ++i) {
 			const std::string a = argv[i];
 			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
@@ -119,12 +121,24 @@ int main(int argc, char** argv) {
 				if (v == "0") o.motif_masking = 0; else if (v == "1") o.motif_masking = 1; else usage("Permitted values for --motif-masking: 0, 1");
 				motif_set = true;
 			}
-			else if (a == "-f" || a == "--outfmt") { if (std::string(val()) != "6") usage("only -f 6 is implemented"); }
+			else if (a == "-f" || a == "--outfmt") {  // -f 6 [field ...]  (output/blast_tab_format.cpp:41-118; the 12 default fields + the transcript fields)
+				if (std::string(val()) != "6") usage("only -f 6 is implemented");
+				while (i + 1 < argc && argv[i + 1][0] != '-') {
+					const std::string f = argv[++i];
+					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
+					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen" };
+					bool ok = false;
+					for (const char* k : known) ok |= f == k;
+					if (!ok) usage(("unsupported output field " + f).c_str());
+					fields.push_back(f);
+				}
+			}
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
@@ -140,15 +154,80 @@ int main(int argc, char** argv) {
 			throw std::runtime_error(dmnd_last_error());
 		size_t n = 0;
 		const dmnd_match* m = dmnd_result_matches(res, &n);
+		size_t ntr = 0;
+		const uint8_t* tr = dmnd_result_transcripts(res, &ntr);
+		if (fields.empty()) fields = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore" };
+		// sequence-bearing fields print the MASKED letters, as the reference does (its blocks are masked in place)
+		for (int side = 0; side < 2; ++side) {
+			size_t nm = 0;
+			const uint64_t* mp = dmnd_result_masked_positions(res, side, &nm);
+			std::vector<int8_t>& l = side ? r.letters : q.letters;
+			for (size_t k = 0; k < nm; ++k) l[(size_t)mp[k]] = 23;
+		}
+		static const char* alphabet = "ARNDCQEGHILKMFPSTWYVBJZX*_";
 		FILE* out = fopen(of.c_str(), "wb");
 		if (!out) throw std::runtime_error("Error opening file " + of);
-		char pid[32], bits[32], ev[32];
+		char buf[32];
+		std::string line;
 		for (size_t i = 0; i < n; ++i) {
-			format_double((double)m[i].identities * 100.0 / (double)m[i].length, pid, sizeof pid);
-			format_double(m[i].bit_score, bits, sizeof bits);
-			if (m[i].evalue == 0.0) snprintf(ev, sizeof ev, "0.0"); else snprintf(ev, sizeof ev, "%.2e", m[i].evalue);
-			fprintf(out, "%s\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s\n", q.ids[m[i].query].c_str(), r.ids[m[i].target].c_str(), pid,
-			        m[i].length, m[i].mismatches, m[i].gap_openings, m[i].q_begin + 1, m[i].q_end, m[i].t_begin + 1, m[i].t_end, ev, bits);
+			const dmnd_match& x = m[i];
+			const uint8_t* t = tr + x.transcript_off;
+			const int8_t* qs = q.letters.data() + q.limits[x.query];
+			line.clear();
+			for (size_t fi = 0; fi < fields.size(); ++fi) {
+				const std::string& f = fields[fi];
+				if (fi) line += '\t';
+				if (f == "qseqid") line += q.ids[x.query];
+				else if (f == "sseqid") line += r.ids[x.target];
+				else if (f == "pident") { format_double((double)x.identities * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
+				else if (f == "length") line += std::to_string(x.length);
+				else if (f == "mismatch") line += std::to_string(x.mismatches);
+				else if (f == "gapopen") line += std::to_string(x.gap_openings);
+				else if (f == "qstart") line += std::to_string(x.q_begin + 1);
+				else if (f == "qend") line += std::to_string(x.q_end);
+				else if (f == "sstart") line += std::to_string(x.t_begin + 1);
+				else if (f == "send") line += std::to_string(x.t_end);
+				else if (f == "evalue") { if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; } }
+				else if (f == "bitscore") { format_double(x.bit_score, buf, sizeof buf); line += buf; }
+				else if (f == "score") line += std::to_string(x.score);
+				else if (f == "gaps") line += std::to_string(x.gaps);
+				else if (f == "nident") line += std::to_string(x.identities);
+				else if (f == "qlen") line += std::to_string(q.limits[x.query + 1] - q.limits[x.query] - 1);
+				else if (f == "slen") line += std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1);
+				else if (f == "cigar") {  // print_cigar, output/sam_format.cpp:67-83: match and substitution are both M
+					uint32_t run = 0; int op = -1;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6, c = (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;
+						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID"[op]; } run = 1; op = c; }
+					}
+					if (run) { line += std::to_string(run); line += "MID"[op]; }
+				}
+				else if (f == "btop") {  // output/blast_tab_format.cpp:365-398
+					uint32_t nm = 0; int qi = x.q_begin;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6;
+						if (o2 == DMND_OP_MATCH) { ++nm; ++qi; continue; }
+						if (nm) { line += std::to_string(nm); nm = 0; }
+						if (o2 == DMND_OP_SUBSTITUTION) { line += alphabet[qs[qi++] & 31]; line += alphabet[t[k] & 63]; }
+						else if (o2 == DMND_OP_INSERTION) { line += alphabet[qs[qi++] & 31]; line += '-'; }
+						else { line += '-'; line += alphabet[t[k] & 63]; }
+					}
+					if (nm) line += std::to_string(nm);
+				}
+				else if (f == "qseq_gapped" || f == "sseq_gapped") {
+					const bool query_side = f[0] == 'q';
+					int qi = x.q_begin;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6;
+						const char qc = (o2 == DMND_OP_DELETION) ? '-' : alphabet[qs[qi] & 31];
+						const char sc = (o2 == DMND_OP_INSERTION) ? '-' : (o2 == DMND_OP_MATCH ? alphabet[qs[qi] & 31] : alphabet[t[k] & 63]);
+						if (o2 != DMND_OP_DELETION) ++qi;
+						line += query_side ? qc : sc;
+					}
+				}
+			}
+			line += '\n';
+			fwrite(line.data(), 1, line.size(), out);
 		}
 		fclose(out);
 		if (log) {

@@ -811,6 +811,7 @@ struct dmnd_result {
 	RawBuf<dmnd_match> matches;
 	RawBuf<uint8_t> transcripts;
 	dmnd_run_stats stats;
+	std::vector<uint64_t> masked[2];  // hard-masked letters of the query / reference block (dmnd_blastp with masking)
 };
 // dmnd_result_free parks up to two results here; the next call reuses their (already touched) memory.
 struct ResultPool {
@@ -1212,6 +1213,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	struct PoolReturn { void operator()(dmnd_result* r) const { result_pool().give(r); } };
 	std::unique_ptr<dmnd_result, PoolReturn> res(result_pool().take());
 	res->matches.resize(0); res->transcripts.resize(0);
+	res->masked[0].clear(); res->masked[1].clear();
 	std::memset(&res->stats, 0, sizeof res->stats);
 	Scoring sc;
 	int64_t ref_letters = 0;
@@ -1292,6 +1294,10 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		});
 		for (int l = 0; l < nlanes; ++l) add_stats(res->stats, lo[(size_t)l].stats);
 	}
+	if (mask_algo) {  // lanes cover ascending query ranges and report ascending offsets: concatenation is sorted
+		for (int l = 0; l < nlanes; ++l) res->masked[0].insert(res->masked[0].end(), sh.lanes[(size_t)l]->mask_pos.begin(), sh.lanes[(size_t)l]->mask_pos.end());
+		res->masked[1] = sh.r_mask_pos;
+	}
 	res->stats.total_ms = ms_since(t_total);
 	*out = res.release();
 	return 0;
@@ -1324,6 +1330,11 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
 const dmnd_match* dmnd_result_matches(const dmnd_result* r, size_t* n) { *n = r->matches.size(); return r->matches.data(); }
 const uint8_t* dmnd_result_transcripts(const dmnd_result* r, size_t* n) { *n = r->transcripts.size(); return r->transcripts.data(); }
 const dmnd_run_stats* dmnd_result_stats(const dmnd_result* r) { return &r->stats; }
+const uint64_t* dmnd_result_masked_positions(const dmnd_result* r, int side, size_t* n) {
+	const std::vector<uint64_t>& v = r->masked[side ? 1 : 0];
+	*n = v.size();
+	return v.data();
+}
 void dmnd_result_free(dmnd_result* r) { if (r) result_pool().give(r); }
 
 }  // extern "C"

@@ -306,6 +306,11 @@ int dmnd_blastp_resident(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref
 const dmnd_match* dmnd_result_matches(const dmnd_result* r, size_t* n);
 const uint8_t* dmnd_result_transcripts(const dmnd_result* r, size_t* n);
 const dmnd_run_stats* dmnd_result_stats(const dmnd_result* r);
+/* Offsets (ascending) into the caller's block image of the letters dmnd_blastp hard-masked (tantan, opts->masking): side 0 =
+ * query block, 1 = reference block.  The reference prints MASKED sequences in its sequence-bearing output fields (btop,
+ * qseq_gapped, ...: output/blast_tab_format.cpp:365-398, align/output.cpp:80-90); a caller that formats those patches its copy
+ * with these.  Empty for dmnd_blastp_resident (the caller masked the blocks itself). */
+const uint64_t* dmnd_result_masked_positions(const dmnd_result* r, int side, size_t* n);
 void dmnd_result_free(dmnd_result* r);
 
 #ifdef __cplusplus

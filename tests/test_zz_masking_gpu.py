@@ -92,3 +92,18 @@ def test_cli_default_flags(product_lib, tmp_path):
     r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, "rep.l2.tsv")).read()
+
+
+@pytest.mark.parametrize("name", ["c1", "long", "rep"])
+def test_cli_transcript_fields(product_lib, name, tmp_path):
+    """cigar / btop / gapped sequences from the device's traceback (and the masked letters) against the reference's columns."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks(name)
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    cli = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+    fields = "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()
+    r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "6"] + fields + ["-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, f"{name}.t2.tsv")).read()
