@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <string>
+#include <algorithm>
 #include "../../../include/dmnd_b200.h"
 
 namespace {
@@ -18,7 +19,7 @@ namespace {
 struct SeqBlock {
 	std::vector<int8_t> letters;
 	std::vector<int64_t> limits;
-	std::vector<std::string> ids;
+	std::vector<std::string> ids, titles;  // id = title up to the first blank (Util::Seq::id_delimiters)
 	SeqBlock() : letters(DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER) { limits.push_back(DMND_PERIMETER_PADDING); }
 	void finish() { letters.insert(letters.end(), DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER); }
 	uint32_t size() const { return (uint32_t)ids.size(); }
@@ -58,6 +59,7 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 			size_t e = 1;
 			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;  // Util::Seq::id_delimiters
 			b.ids.push_back(line.substr(1, e - 1));
+			b.titles.push_back(line.substr(1));
 			open = true;
 		}
 		else {
@@ -95,6 +97,7 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
+		bool pairwise = false;
 		for (int i = 2; i < argc; ++i) {
 			const std::string a = argv[i];
 			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
@@ -122,7 +125,9 @@ int main(int argc, char** argv) {
 				motif_set = true;
 			}
 			else if (a == "-f" || a == "--outfmt") {  // -f 6 [field ...]  (output/blast_tab_format.cpp:41-118; the 12 default fields + the transcript fields)
-				if (std::string(val()) != "6") usage("only -f 6 is implemented");
+				const std::string fmt = val();
+				if (fmt == "0") { pairwise = true; continue; }
+				if (fmt != "6") usage("only -f 6 [fields] and -f 0 are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -138,6 +143,7 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (pairwise) o.want_transcript = 1;
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
@@ -169,6 +175,59 @@ int main(int argc, char** argv) {
 		if (!out) throw std::runtime_error("Error opening file " + of);
 		char buf[32];
 		std::string line;
+		if (pairwise) {
+			// PairwiseFormat (output/blast_pairwise_format.cpp:24-101): header once, an intro per aligned query, one record per match in
+			// 60-column blocks; numbers go through TextBuffer::print(i, width), which keeps only `width` characters (util/text_buffer.h:248-254)
+			const dmnd_params* pp = &params;
+			auto put_num = [&](unsigned v, unsigned width) { char nb[24]; snprintf(nb, sizeof nb, "%*u", (int)width, v); line.append(nb, width); };
+			line = "BLASTP 2.3.0+\n\n\n";
+			fwrite(line.data(), 1, line.size(), out);
+			for (size_t i = 0; i < n; ++i) {
+				const dmnd_match& x = m[i];
+				const uint8_t* t = tr + x.transcript_off;
+				const int8_t* qs = q.letters.data() + q.limits[x.query];
+				line.clear();
+				if (i == 0 || m[i - 1].query != x.query)
+					line += "Query= " + q.titles[x.query] + "\n\nLength=" + std::to_string(q.limits[x.query + 1] - q.limits[x.query] - 1) + "\n\n";
+				line += ">";
+				{	// OutputFormat::print_title(out, title, true, true, " "): the titles of a merged record ("\x01" or " >" between them,
+					// util/sequence/sequence.cpp:38) joined by one blank
+					const std::string& tt = r.titles[x.target];
+					for (size_t a = 0; a < tt.size();) {
+						if (tt[a] == '\x01') { line += ' '; ++a; }
+						else if (tt[a] == ' ' && a + 1 < tt.size() && tt[a + 1] == '>') { line += ' '; a += 2; }
+						else line += tt[a++];
+					}
+				}
+				line += "\nLength=" + std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1) + "\n\n";
+				format_double(x.bit_score, buf, sizeof buf);
+				line += " Score = "; line += buf; line += " bits (" + std::to_string(x.score) + "),  Expect = ";
+				if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; }
+				const unsigned len = (unsigned)x.length;
+				line += "\n Identities = " + std::to_string(x.identities) + "/" + std::to_string(len) + " (" + std::to_string((unsigned)x.identities * 100u / len) + "%), Positives = "
+					+ std::to_string(x.positives) + "/" + std::to_string(len) + " (" + std::to_string((unsigned)x.positives * 100u / len) + "%), Gaps = " + std::to_string(x.gaps) + "/"
+					+ std::to_string(len) + " (" + std::to_string((unsigned)x.gaps * 100u / len) + "%)\n\n";
+				const unsigned digits = (unsigned)std::max(std::ceil(std::log10((double)x.t_end)), std::ceil(std::log10((double)x.q_end)));
+				int qi = x.q_begin, si = x.t_begin;
+				for (uint32_t k0 = 0; k0 < x.transcript_len; k0 += 60) {
+					const uint32_t k1 = std::min<uint32_t>(k0 + 60, x.transcript_len);
+					std::string ql, ml, sl;
+					const int q0 = qi, s0 = si;
+					for (uint32_t k = k0; k < k1; ++k) {
+						const int op = t[k] >> 6, sc = t[k] & 63;
+						if (op == DMND_OP_MATCH) { const char c = alphabet[qs[qi] & 31]; ql += c; ml += c; sl += c; ++qi; ++si; }
+						else if (op == DMND_OP_SUBSTITUTION) { const int a = qs[qi] & 31; ql += alphabet[a]; sl += alphabet[sc]; ml += pp->score[a * 32 + sc] > 0 ? '+' : ' '; ++qi; ++si; }
+						else if (op == DMND_OP_INSERTION) { ql += alphabet[qs[qi] & 31]; sl += '-'; ml += ' '; ++qi; }
+						else { ql += '-'; sl += alphabet[sc]; ml += ' '; ++si; }
+					}
+					line += "Query  "; put_num((unsigned)q0 + 1, digits); line += "  " + ql + " " + std::to_string(qi) + "\n";
+					line.append(digits + 9, ' '); line += ml + "\n";
+					line += "Sbjct  "; put_num((unsigned)s0 + 1, digits); line += "  " + sl + " " + std::to_string(si) + "\n\n";
+				}
+				fwrite(line.data(), 1, line.size(), out);
+			}
+			n = 0;  // nothing left for the tabular writer
+		}
 		for (size_t i = 0; i < n; ++i) {
 			const dmnd_match& x = m[i];
 			const uint8_t* t = tr + x.transcript_off;

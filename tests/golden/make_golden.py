@@ -12,6 +12,7 @@ For every workload W and parity-ladder level L:
     S3 = --sensitive (16 shapes of weight 8, stage-2 window filter, gapped filter) with default flags
     S4 / S5 / S6 = --more-sensitive / --very-sensitive / --ultra-sensitive (no motif masking, BANDED_SLOW bands; 14 x 7 and 64 x 7 shapes,
          Hamming cutoff 9, one index chunk for the last two)
+    F0 = L2 in the BLAST pairwise format (-f 0): .txt
     T2 = L2 (--fast, default flags) with the transcript-bearing output fields: cigar, btop, qseq_gapped, sseq_gapped -- pins the
          traceback (and the masked letters the reference prints) byte for byte
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
@@ -30,10 +31,11 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "s1": [],
           "s2": [],
           "s3": [], "s4": [], "s5": [], "s6": [],
-          "t2": []}
+          "t2": [], "f0": []}
+FORMAT = {"f0": "0"}  # BLAST pairwise (-f 0); everything else is tabular (-f 6)
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
 MODE = {"s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-ONLY = {"t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
+ONLY = {"f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -53,10 +55,10 @@ def main():
             for lvl, flags in LEVELS.items():
                 if lvl in ONLY and name not in ONLY[lvl]:
                     continue
-                out = os.path.join(HERE, f"{name}.{lvl}.tsv")
+                out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl not in FORMAT else f"{name}.{lvl}.txt")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", "6"] + FIELDS.get(lvl, []) + ["-o", out, "-p", "8", "--log"] + flags,
+                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", "8", "--log"] + flags,
                                    capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

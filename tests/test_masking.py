@@ -189,3 +189,18 @@ def test_transcript_fields_match_reference_golden(oracle_lib, name, tmp_path):
         assert [l.split("\t")[:12] for l in gold.splitlines()] == [l.split("\t") for l in open(os.path.join(GOLDEN, f"{name}.l2.tsv")).read().splitlines()]
     if name == "rep":
         assert any("X" in l.split("\t")[13] for l in gold.splitlines())  # masked letters do show up in BTOP
+
+
+@pytest.mark.parametrize("name", ["edge", "long"])
+def test_pairwise_format_matches_reference_golden(oracle_lib, name, tmp_path):
+    """-f 0, the BLAST pairwise format (output/blast_pairwise_format.cpp:24-101): header, query intros, 60-column alignment
+    blocks with midline, identities / positives / gaps -- from the library's transcripts; byte-identical to the reference's file."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks(name)
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.txt"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+    r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "0", "-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, f"{name}.f0.txt")).read()

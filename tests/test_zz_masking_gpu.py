@@ -107,3 +107,15 @@ def test_cli_transcript_fields(product_lib, name, tmp_path):
     r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "6"] + fields + ["-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, f"{name}.t2.tsv")).read()
+
+
+def test_cli_pairwise_format(product_lib, tmp_path):
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("edge")
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.txt"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    cli = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+    r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "0", "-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, "edge.f0.txt")).read()
