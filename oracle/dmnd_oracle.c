@@ -7,7 +7,9 @@
  *
  * Pinned against the reference itself: tests/test_oracle_vs_reference.py links this file under the host pipeline
  * (diamond_b200/csrc/host) and requires byte-identical fmt-6 output with oracle/_ref/diamond (the unmodified
- * reference compiled by oracle/ref_build/Makefile) plus equal --log stage counters, on the committed fixtures.
+ * reference compiled by oracle/ref_build/Makefile) plus equal --log stage counters, on the committed fixtures: every
+ * blastp sensitivity mode (--fast .. --ultra-sensitive), with and without the reference's default masking, tabular output
+ * incl. the CIGAR / BTOP / gapped-sequence fields and the pairwise format (tests/golden/make_golden.py lists the levels).
  *
  * Reference sections restated (file:line in /root/reference/src):
  *   seed packing            basic/shape.h:113-171, basic/reduction.h:98-105, search/seed_array/enum_seeds.h:56-89
@@ -17,6 +19,11 @@
  *   stage 1 (Hamming)       search/hamming/kernel.h:29-75, search/hamming/finger_print.h:180-215
  *   stage 2 (left-most)     search/stage2.h:73-154, search/left_most.h:30-110, search/sse_dist.h:105-190 (SSE branch),
  *                           util/algo/pattern_matcher.h:23-65, util/sequence/sequence.h:30-40
+ *   stage 2 (ungapped win.) search/stage2.h:41-57,104-154, dp/ungapped_align.cpp:244-257, dp/ungapped_simd.cpp:32-88 (call size -> 255 cap),
+ *                           search/hamming/kernel.h:61-74 + hit_field.h:44-57 (1024-subject tiles, ascending survivors), util/scores/cutoff_table.h
+ *   masking                 masking/tantan.cpp:43-214 (AVX2 object's fp32 order), masking/masking.cpp:76-166 (motif table, MaskingTable),
+ *                           util/kmer/kmer.h:62-117, data/block/block.cpp:162-178, search/seed_array/enum_seeds.h:255-270
+ *   gapped filter           align/gapped_filter.cpp:33-63, dp/scan_diags.cpp:30-297, dp/score_profile.cpp:32-65
  *   banded SWIPE            dp/swipe/banded_swipe.h:189-351, dp/swipe/cell_update.h:103-141,
  *                           dp/swipe/banded_matrix.h:313-445, dp/swipe/target_iterator.h:59-173, dp/dp.h:47-52
  *   traceback walk          dp/swipe/banded_swipe.h:127-187, basic/hssp.cpp:260-290
