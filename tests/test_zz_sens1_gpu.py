@@ -20,6 +20,21 @@ def sorted_hits(h):
     return np.sort(h, order=["query", "subject_score", "seed_offset"])
 
 
+def hit_diff(ho, hg, r_lim):
+    """Readable difference of two hit lists for the assertion message: hits only one side has (ignoring the score), and hits
+    both have with different scores -- (query, seed offset, target, target position, score)."""
+    def key(h):
+        return {(int(x["query"]), int(x["seed_offset"]), int(x["subject_score"]) & ((1 << 48) - 1)): int(x["subject_score"]) >> 48 for x in h}
+    a, b = key(ho), key(hg)
+    def show(k, sc):
+        t = int(np.searchsorted(r_lim, k[2], side="right")) - 1
+        return f"(q{k[0]} off {k[1]} d{t}+{k[2] - int(r_lim[t])} score {sc})"
+    only_o = [show(k, a[k]) for k in sorted(set(a) - set(b))][:8]
+    only_g = [show(k, b[k]) for k in sorted(set(b) - set(a))][:8]
+    other = [show(k, f"{a[k]} vs {b[k]}") for k in sorted(set(a) & set(b)) if a[k] != b[k]][:8]
+    return f"hits: oracle {len(ho)} device {len(hg)}; only oracle {len(set(a) - set(b))}: {only_o}; only device {len(set(b) - set(a))}: {only_g}; other score {sum(a[k] != b[k] for k in set(a) & set(b))}: {other}"
+
+
 @SEED_STAGE_OPEN
 @pytest.mark.parametrize("name,masking", [("fam2", 0), ("rep", 1), ("edge", 1)])
 def test_search_shapes_match_oracle(oracle_lib, product_lib, name, masking):
@@ -39,9 +54,9 @@ def test_search_shapes_match_oracle(oracle_lib, product_lib, name, masking):
         c.free_block(qb); c.free_block(rb); c.close()
     for sid in (0, 1):
         (ho, co, lo), (hg, cg, lg) = res[0][sid], res[1][sid]
-        assert len(ho) == len(hg) and np.array_equal(sorted_hits(ho), sorted_hits(hg)), f"shape {sid}: hits incl. ungapped scores"
-        assert co == cg, f"shape {sid}: stage counters"
-        assert np.array_equal(lo, lg), f"shape {sid}: SEED_MASK bits"
+        assert co == cg, f"shape {sid}: stage counters oracle {co} device {cg}\n" + hit_diff(ho, hg, r_lim)
+        assert len(ho) == len(hg) and np.array_equal(sorted_hits(ho), sorted_hits(hg)), f"shape {sid}: hits incl. ungapped scores\n" + hit_diff(ho, hg, r_lim)
+        assert np.array_equal(lo, lg), f"shape {sid}: SEED_MASK bits differ at {np.flatnonzero(lo != lg)[:20]}"
     if name == "fam2":
         sc = (res[1][0][0]["subject_score"] >> np.uint64(48)).astype(np.int64)
         assert (sc == 255).sum() > 100 and (sc > 255).sum() > 0
