@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -71,6 +73,139 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 	b.finish();
 }
 
+// ---- DIAMOND database files (legacy/dmnd/dmnd.h:28-66, dmnd.cpp:50-120,224-234,319-327): 40-byte header, a size-prefixed second
+// header with a 128-bit hash, one record per sequence (0xff, letters with bit 7 = tantan soft mask, 0xff, title, 0), then the
+// position array {u64 offset, u32 length, u32 0} with a terminating entry.  Little endian.
+constexpr uint64_t DMND_MAGIC = 0x24af8a415ee186dull;
+constexpr uint32_t DMND_BUILD = 182, DMND_DB_VERSION = 3;  // Const::build_version (basic/const.h:25), ReferenceHeader::current_db_version_prot
+
+bool is_dmnd(const std::string& path) {
+	std::ifstream f(path, std::ios::binary);
+	uint64_t m = 0;
+	return f.read((char*)&m, 8) && m == DMND_MAGIC;
+}
+
+void read_dmnd(const std::string& path, SeqBlock& b) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::vector<char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	auto u64 = [&](size_t o) { uint64_t v; std::memcpy(&v, d.data() + o, 8); return v; };
+	auto u32 = [&](size_t o) { uint32_t v; std::memcpy(&v, d.data() + o, 4); return v; };
+	if (d.size() < 96 || u64(0) != DMND_MAGIC) throw std::runtime_error("Database file is not a DIAMOND database.");
+	if (u32(12) < 2 || u32(12) > 3) throw std::runtime_error("Database was built with an unsupported database format version.");
+	const uint64_t nseq = u64(16), pos_off = u64(32);
+	if (pos_off + 16 * (nseq + 1) > d.size()) throw std::runtime_error("Database file is truncated.");
+	for (uint64_t i = 0; i < nseq; ++i) {
+		const uint64_t pos = u64(pos_off + 16 * i), len = u32(pos_off + 16 * i + 8);
+		if (pos + len + 2 > pos_off || (unsigned char)d[pos] != 0xff || (unsigned char)d[pos + 1 + len] != 0xff) throw std::runtime_error("Database file format error.");
+		for (uint64_t k = 0; k < len; ++k) b.letters.push_back((int8_t)(d[pos + 1 + k] & 0x7f));  // the soft-mask bit is recomputed by the pipeline (same algorithm)
+		b.letters.push_back((int8_t)DMND_DELIMITER);
+		b.limits.push_back((int64_t)b.letters.size());
+		const char* title = d.data() + pos + 2 + len;
+		b.titles.emplace_back(title);
+		size_t e = 0;
+		while (title[e] && !strchr(" \t\x01", title[e])) ++e;
+		b.ids.emplace_back(title, e);
+	}
+	b.finish();
+}
+
+// MurmurHash3_x64_128 (Austin Appleby, public domain) with a 128-bit seed, as lib/murmurhash is called from make_db (dmnd.cpp:304-308)
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t fmix64(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33; return k; }
+void murmur3_x64_128(const void* key, int len, uint64_t h[2]) {
+	const uint8_t* data = (const uint8_t*)key;
+	const int nblocks = len / 16;
+	uint64_t h1 = h[0], h2 = h[1];
+	const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
+	for (int i = 0; i < nblocks; ++i) {
+		uint64_t k1, k2;
+		std::memcpy(&k1, data + 16 * i, 8); std::memcpy(&k2, data + 16 * i + 8, 8);
+		k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+		h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+		k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+		h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+	}
+	const uint8_t* tail = data + nblocks * 16;
+	uint64_t k1 = 0, k2 = 0;
+	switch (len & 15) {
+	case 15: k2 ^= (uint64_t)tail[14] << 48; [[fallthrough]];
+	case 14: k2 ^= (uint64_t)tail[13] << 40; [[fallthrough]];
+	case 13: k2 ^= (uint64_t)tail[12] << 32; [[fallthrough]];
+	case 12: k2 ^= (uint64_t)tail[11] << 24; [[fallthrough]];
+	case 11: k2 ^= (uint64_t)tail[10] << 16; [[fallthrough]];
+	case 10: k2 ^= (uint64_t)tail[9] << 8; [[fallthrough]];
+	case 9: k2 ^= (uint64_t)tail[8]; k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; [[fallthrough]];
+	case 8: k1 ^= (uint64_t)tail[7] << 56; [[fallthrough]];
+	case 7: k1 ^= (uint64_t)tail[6] << 48; [[fallthrough]];
+	case 6: k1 ^= (uint64_t)tail[5] << 40; [[fallthrough]];
+	case 5: k1 ^= (uint64_t)tail[4] << 32; [[fallthrough]];
+	case 4: k1 ^= (uint64_t)tail[3] << 24; [[fallthrough]];
+	case 3: k1 ^= (uint64_t)tail[2] << 16; [[fallthrough]];
+	case 2: k1 ^= (uint64_t)tail[1] << 8; [[fallthrough]];
+	case 1: k1 ^= (uint64_t)tail[0]; k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+	}
+	h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+	h1 += h2; h2 += h1;
+	h1 = fmix64(h1); h2 = fmix64(h2);
+	h1 += h2; h2 += h1;
+	h[0] = h1; h[1] = h2;
+}
+
+// `makedb` (DatabaseFile::make_db, dmnd.cpp:236-370 without taxonomy): FASTA in, .dmnd out; unless --masking 0 the letters carry the
+// tantan soft-mask bit, computed by the library (dmnd_block_mask on the resident block).
+int make_db(const std::string& in, std::string out_path, bool masking) {
+	if (out_path.size() < 5 || out_path.substr(out_path.size() - 5) != ".dmnd") out_path += ".dmnd";
+	SeqBlock b;
+	read_fasta(in, b);
+	for (uint32_t i = 0; i < b.size(); ++i) if (b.limits[i + 1] - b.limits[i] - 1 == 0) throw std::runtime_error("File format error: sequence of length 0");
+	std::vector<uint8_t> soft(b.letters.size(), 0);
+	if (masking && b.size()) {
+		dmnd_search_opts o; dmnd_search_opts_default(&o);
+		dmnd_params params;
+		dmnd_ctx* ctx = nullptr;
+		dmnd_block* blk = nullptr;
+		uint64_t n = 0;
+		if (dmnd_params_init(&o, &params) || dmnd_create(0, &params, &ctx) || dmnd_block_upload(ctx, b.letters.data(), b.letters.size(), b.limits.data(), b.size(), &blk)
+		    || dmnd_block_mask(ctx, blk, DMND_MASK_TANTAN, 0, b.size(), &n))
+			throw std::runtime_error(dmnd_last_error());
+		std::vector<uint64_t> pos((size_t)n);
+		if (n && dmnd_block_mask_fetch(ctx, pos.data(), pos.size())) throw std::runtime_error(dmnd_last_error());
+		for (uint64_t p : pos) soft[(size_t)p] = 0x80;
+		dmnd_block_free(ctx, blk); dmnd_destroy(ctx);
+	}
+	std::string rec;
+	std::vector<std::pair<uint64_t, uint32_t>> pos_array;
+	uint64_t offset = 96, letters = 0, hash[2] = { 0, 0 };
+	for (uint32_t i = 0; i < b.size(); ++i) {
+		const size_t beg = (size_t)b.limits[i], len = (size_t)(b.limits[i + 1] - b.limits[i] - 1);
+		pos_array.emplace_back(offset, (uint32_t)len);
+		const size_t r0 = rec.size();
+		rec += '\xff';
+		for (size_t k = 0; k < len; ++k) rec += (char)((uint8_t)b.letters[beg + k] | soft[beg + k]);
+		rec += '\xff';
+		rec += b.titles[i]; rec += '\0';
+		murmur3_x64_128(rec.data() + r0 + 1, (int)len, hash);
+		murmur3_x64_128(b.titles[i].data(), (int)b.titles[i].size(), hash);
+		letters += len;
+		offset += len + b.titles[i].size() + 3;
+	}
+	pos_array.emplace_back(offset, 0u);
+	FILE* f = fopen(out_path.c_str(), "wb");
+	if (!f) throw std::runtime_error("Error opening file " + out_path);
+	const uint64_t nseq = b.size(), h2size = 48, zero = 0;
+	fwrite(&DMND_MAGIC, 8, 1, f); fwrite(&DMND_BUILD, 4, 1, f); fwrite(&DMND_DB_VERSION, 4, 1, f); fwrite(&nseq, 8, 1, f); fwrite(&letters, 8, 1, f); fwrite(&offset, 8, 1, f);
+	fwrite(&h2size, 8, 1, f); fwrite(hash, 16, 1, f);
+	for (int k = 0; k < 4; ++k) fwrite(&zero, 8, 1, f);
+	fwrite(rec.data(), 1, rec.size(), f);
+	for (const auto& pr : pos_array) { const uint32_t z = 0; fwrite(&pr.first, 8, 1, f); fwrite(&pr.second, 4, 1, f); fwrite(&z, 4, 1, f); }
+	fclose(f);
+	fprintf(stderr, "Database sequences  %llu\nDatabase letters  %llu\nDatabase hash  ", (unsigned long long)nseq, (unsigned long long)letters);
+	for (int k = 0; k < 16; ++k) fprintf(stderr, "%02x", ((const uint8_t*)hash)[k]);
+	fprintf(stderr, "\n");
+	return 0;
+}
+
 int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 	if (x >= 100.0) return snprintf(p, n, "%lli", (long long)std::floor(x));
 	const long long i = std::llround(x * 10.0);
@@ -78,7 +213,7 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 }
 
 [[noreturn]] void usage(const char* msg) {
-	fprintf(stderr, "Error: %s\nusage: dmnd-b200 blastp -q QUERY.faa -d DB.faa -o OUT [--fast] [-p N] [-c N] [-k N] [-e X] "
+	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] [-c N] [-k N] [-e X] "
 	                "[--comp-based-stats 0|1] [--masking 0|none|1|tantan] [--motif-masking 0|1] [-f 6] [--log]\n", msg);
 	exit(1);
 }
@@ -90,7 +225,23 @@ int main(int argc, char** argv) {
 		if (argc < 2) usage("missing command");
 		const std::string cmd = argv[1];
 		if (cmd == "version") { printf("dmnd-b200 (%s) for diamond 2.2.2 blastp hot path\n", dmnd_backend()); return 0; }
-		if (cmd != "blastp") usage("only the blastp hot path is implemented (makedb/blastx are 'next' rows, see DESIGN.md)");
+		if (cmd == "makedb") {  // diamond makedb --in X.faa -d OUT [--masking 0]
+			std::string in, db;
+			const bool masking = true;
+			for (int i = 2; i < argc; ++i) {
+				const std::string a = argv[i];
+				auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
+				if (a == "--in") in = val();
+				else if (a == "-d" || a == "--db") db = val();
+				else if (a == "--masking") usage("Option is not permitted for this workflow: masking");  // as the reference answers
+				else if (a == "-p" || a == "--threads") val();
+				else if (a == "--quiet") {}
+				else usage(("unsupported option " + a).c_str());
+			}
+			if (in.empty() || db.empty()) usage("makedb needs --in and -d");
+			return make_db(in, db, masking);
+		}
+		if (cmd != "blastp") usage("only blastp and makedb are implemented (blastx is a 'next' row, see DESIGN.md)");
 		dmnd_search_opts o;
 		dmnd_search_opts_default(&o);
 		o.sensitivity = 1;  // like the reference: no sensitivity flag = Sensitivity::DEFAULT, --fast = Sensitivity::FAST
@@ -149,7 +300,8 @@ int main(int argc, char** argv) {
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
 		read_fasta(qf, q);
-		read_fasta(df, r);
+		if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
+		else read_fasta(df, r);
 		dmnd_params params;
 		if (dmnd_params_init(&o, &params)) throw std::runtime_error(dmnd_last_error());
 		dmnd_ctx* ctx = nullptr;

@@ -204,3 +204,43 @@ def test_pairwise_format_matches_reference_golden(oracle_lib, name, tmp_path):
     r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "0", "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, f"{name}.f0.txt")).read()
+
+
+def test_makedb_and_dmnd_reader(oracle_lib, tmp_path):
+    """`makedb` writes the reference's database format byte for byte (legacy/dmnd: headers, MurmurHash3 database hash, records
+    with the tantan soft-mask bit from dmnd_block_mask, position array) -- tests/golden/rep100.dmnd is the reference's own
+    makedb output for the first 100 sequences of the `rep` database -- and `blastp -d` reads such a file back: same output as
+    with the FASTA database."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("rep")
+    d100, q = str(tmp_path / "d100.faa"), str(tmp_path / "q.faa")
+    synth.write_fasta(d100, w["db_letters"][: w["db_off"][100]], w["db_off"][:101], "d")
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+    r = subprocess.run([cli, "makedb", "--in", d100, "-d", str(tmp_path / "ours")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ours, gold = open(tmp_path / "ours.dmnd", "rb").read(), open(os.path.join(GOLDEN, "rep100.dmnd"), "rb").read()
+    assert ours == gold and sum(1 for b in gold[96:] if b & 0x80 and b != 0xff) > 100  # (soft-mask bits are present)
+    out = []
+    for db in (d100, str(tmp_path / "ours.dmnd"), str(tmp_path / "ours")):  # FASTA, .dmnd, .dmnd without the extension
+        o = str(tmp_path / "o.tsv")
+        r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", db, "-o", o, "-p", "8"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out.append(open(o).read())
+    assert out[0] == out[1] == out[2] and out[0].count("\n") > 10
+    r = subprocess.run([cli, "makedb", "--in", d100, "-d", str(tmp_path / "x"), "--masking", "0"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not permitted" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not present")
+def test_reference_reads_our_database(oracle_lib, tmp_path):
+    """The unmodified reference searches a database written by our makedb and gives the L2 golden."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("edge")
+    d, q, o = (str(tmp_path / x) for x in ("d.faa", "q.faa", "o.tsv"))
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    cli = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+    subprocess.run([cli, "makedb", "--in", d, "-d", str(tmp_path / "db")], capture_output=True, check=True)
+    subprocess.run([REF_BIN, "blastp", "--fast", "-q", q, "-d", str(tmp_path / "db.dmnd"), "-f", "6", "-o", o, "-p", "8", "--quiet"], capture_output=True, check=True)
+    assert open(o).read() == open(os.path.join(GOLDEN, "edge.l2.tsv")).read()
