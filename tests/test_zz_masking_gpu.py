@@ -119,3 +119,15 @@ def test_cli_pairwise_format(product_lib, tmp_path):
     r = subprocess.run([cli, "blastp", "--fast", "-q", q, "-d", d, "-f", "0", "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, "edge.f0.txt")).read()
+
+
+def test_cli_makedb_matches_reference_database(product_lib, tmp_path):
+    """makedb with the device's tantan: byte-identical to the reference's .dmnd (tests/golden/rep100.dmnd)."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("rep")
+    d100 = str(tmp_path / "d100.faa")
+    synth.write_fasta(d100, w["db_letters"][: w["db_off"][100]], w["db_off"][:101], "d")
+    cli = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+    r = subprocess.run([cli, "makedb", "--in", d100, "-d", str(tmp_path / "ours")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "ours.dmnd", "rb").read() == open(os.path.join(GOLDEN, "rep100.dmnd"), "rb").read()
