@@ -62,7 +62,7 @@ class Timing(C.Structure):
 class SearchOpts(C.Structure):
     _fields_ = [("sensitivity", C.c_int32), ("threads", C.c_int32), ("index_chunks", C.c_int32),
                 ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
-                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32)]
+                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32), ("query_contexts", C.c_int32)]
 
 
 class Match(C.Structure):
@@ -188,7 +188,7 @@ class Context:
 
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
                  comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
-                 masking: int = 0, motif_masking: int = 0, sensitivity: int = 0):
+                 masking: int = 0, motif_masking: int = 0, sensitivity: int = 0, query_contexts: int = 1):
         """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
         wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
         default to the reference's own defaults (1, 1)."""
@@ -204,6 +204,7 @@ class Context:
         self.opts.sensitivity = int(sensitivity)  # 0 = --fast, 1 = the reference's default sensitivity
         self.opts.masking = int(masking)
         self.opts.motif_masking = int(motif_masking)
+        self.opts.query_contexts = int(query_contexts)  # 6 = blastx: six translated frames per query in the query block
         self.params = Params()
         self._check(self.lib.dmnd_params_init(C.byref(self.opts), C.byref(self.params)))
         self.ctx = C.c_void_p()
@@ -379,5 +380,81 @@ def fmt6(matches: np.ndarray, q_prefix: str = "q", d_prefix: str = "d") -> str:
         out.append("%s%d\t%s%d\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
             q_prefix, m["query"], d_prefix, m["target"], format_double(float(m["identities"]) * 100.0 / float(m["length"])),
             m["length"], m["mismatches"], m["gap_openings"], m["q_begin"] + 1, m["q_end"], m["t_begin"] + 1, m["t_end"],
+            ev, format_double(float(m["bit_score"]))))
+    return "\n".join(out) + ("\n" if out else "")
+
+
+# ---- blastx: the six translated contexts of DNA queries ------------------------------------------------------------------------
+_GENCODE1 = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"  # Translator::codes[1], TCAG order (basic/basic.cpp:86-113)
+_AA = "ARNDCQEGHILKMFPSTWYVBJZX*_"
+
+
+def _codon_tables():
+    idx, comp = (2, 1, 3, 0), (3, 2, 1, 0)  # A C G T -> position in TCAG; complement
+    fwd = np.full((5, 5, 5), 23, dtype=np.int8)
+    rev = np.full((5, 5, 5), 23, dtype=np.int8)
+    for i in range(4):
+        for j in range(4):
+            for k in range(4):
+                fwd[i, j, k] = _AA.index(_GENCODE1[idx[i] * 16 + idx[j] * 4 + idx[k]])
+                rev[i, j, k] = _AA.index(_GENCODE1[idx[comp[i]] * 16 + idx[comp[j]] * 4 + idx[comp[k]]])
+            for t in (fwd, rev):  # an N in the last slot is harmless when the other two bases fix the amino acid (basic/basic.cpp:132-138)
+                if len(set(t[i, j, :4].tolist())) == 1:
+                    t[i, j, 4] = t[i, j, 0]
+    return fwd, rev
+
+
+def translate_reads(reads) -> tuple[np.ndarray, np.ndarray]:
+    """Flat letters + offsets of the query block of a blastx run: for read s the contexts 6s..6s+5 = frames +1 +2 +3, -1 -2 -3
+    (util/sequence/translate.h:58-100), with every stop-to-stop stretch shorter than Config::min_orf_len X-ed out
+    (data/block/block.cpp:86-100, util/sequence/sequence.cpp:180-197).  Pass the result to block_image() and run the
+    context with query_contexts=6."""
+    fwd, rev = _codon_tables()
+    code = {c: i for i, c in enumerate("ACGTN")}
+    code.update({c: 4 for c in "MRWSYKVHDBX"})
+    seqs = []
+    for r in reads:
+        d = np.array([code[c] for c in r.upper()], dtype=np.int64)
+        L = len(d)
+        fr = [np.zeros(0, dtype=np.int8)] * 6
+        if L >= 3:
+            fr = []
+            for f in range(3):
+                n = (L - f) // 3
+                p = 3 * np.arange(n) + f
+                fr.append(fwd[d[p], d[p + 1], d[p + 2]])
+            for f in range(3):
+                n = (L - f) // 3
+                p = L - 3 - (3 * np.arange(n) + f)
+                fr.append(rev[d[p + 2], d[p + 1], d[p]])
+        l0 = len(fr[0])
+        min_len = 1 if l0 < 30 else 20 if l0 < 100 else 40
+        for v in fr:
+            v = v.copy()
+            stops = np.flatnonzero(v == 24).tolist()
+            b = 0
+            for e in stops + [len(v)]:
+                if e - b < min_len:
+                    v[b:e] = 23
+                b = e + 1
+            seqs.append(v)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(v) for v in seqs], out=off[1:])
+    return (np.concatenate(seqs).astype(np.int8) if seqs else np.zeros(0, dtype=np.int8)), off
+
+
+def fmt6_translated(matches: np.ndarray, read_lens, q_prefix: str = "r", d_prefix: str = "d") -> str:
+    """fmt6 for a query_contexts=6 run: dmnd_match.query is a context (6 * read + frame) and q_begin / q_end count letters of
+    that frame; the reference prints nucleotide coordinates on the read, high end first for the reverse strand
+    (TranslatedPosition::absolute_interval, basic/translated_position.h:121-127)."""
+    out = []
+    for m in matches:
+        s, f = divmod(int(m["query"]), 6)
+        b, e, L = 3 * int(m["q_begin"]) + f % 3, 3 * int(m["q_end"]) + f % 3, int(read_lens[s])
+        qs, qe = (b + 1, e) if f < 3 else (L - b, L - e + 1)
+        ev = "0.0" if m["evalue"] == 0.0 else "%.2e" % m["evalue"]
+        out.append("%s%d\t%s%d\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
+            q_prefix, s, d_prefix, m["target"], format_double(float(m["identities"]) * 100.0 / float(m["length"])),
+            m["length"], m["mismatches"], m["gap_openings"], qs, qe, m["t_begin"] + 1, m["t_end"],
             ev, format_double(float(m["bit_score"]))))
     return "\n".join(out) + ("\n" if out else "")

@@ -73,6 +73,105 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 	b.finish();
 }
 
+// ---- blastx: DNA queries, translated into their six reading frames (util/sequence/translate.h:58-100, basic/basic.cpp:86-139,
+// data/block/block.cpp:86-100).  The query block holds, for query s, the contexts 6s .. 6s+5: frames +1 +2 +3 of the read, then
+// -1 -2 -3 of its reverse complement; every stretch between two stop codons that is shorter than min_orf_len is X-ed out.
+struct DnaQueries {
+	std::vector<std::string> ids, titles;
+	std::vector<int32_t> len;  // nucleotides
+};
+
+int8_t encode_dna(char c) {  // nucleotide_traits (stats/stats.cpp:42): "ACGTN", everything in "MRWSYKVHDBX" reads as N
+	switch (toupper((unsigned char)c)) {
+	case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'N': return 4;
+	case 'M': case 'R': case 'W': case 'S': case 'Y': case 'K': case 'V': case 'H': case 'D': case 'B': case 'X': return 4;
+	default: throw std::runtime_error(std::string("Invalid character in sequence: '") + c + "'");
+	}
+}
+
+struct CodonTable {  // Translator::init(1): the standard code; a codon with N is X unless its first two bases fix the amino acid
+	int8_t fwd[5][5][5], rev[5][5][5];
+	CodonTable() {
+		static const char* code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+		static const unsigned idx[4] = { 2, 1, 3, 0 }, comp[4] = { 3, 2, 1, 0 };
+		for (unsigned i = 0; i < 5; ++i) for (unsigned j = 0; j < 5; ++j) for (unsigned k = 0; k < 5; ++k) {
+			if (i == 4 || j == 4 || k == 4) { fwd[i][j][k] = rev[i][j][k] = 23; continue; }
+			fwd[i][j][k] = encode(code[idx[i] * 16 + idx[j] * 4 + idx[k]]);
+			rev[i][j][k] = encode(code[idx[comp[i]] * 16 + idx[comp[j]] * 4 + idx[comp[k]]]);
+		}
+		for (unsigned i = 0; i < 4; ++i) for (unsigned j = 0; j < 4; ++j) {
+			if (std::count(fwd[i][j], fwd[i][j] + 4, fwd[i][j][0]) == 4) fwd[i][j][4] = fwd[i][j][0];
+			if (std::count(rev[i][j], rev[i][j] + 4, rev[i][j][0]) == 4) rev[i][j][4] = rev[i][j][0];
+		}
+	}
+};
+
+void push_translated(const std::vector<int8_t>& dna, SeqBlock& b) {
+	static const CodonTable ct;
+	const size_t L = dna.size();
+	std::vector<int8_t> fr[6];
+	if (L >= 3) {
+		for (int f = 0; f < 3; ++f) {
+			const size_t n = (L - (size_t)f) / 3;
+			fr[f].resize(n); fr[f + 3].resize(n);
+			for (size_t i = 0; i < n; ++i) {
+				const size_t p = 3 * i + (size_t)f;            // codon start on the forward strand
+				fr[f][i] = ct.fwd[dna[p]][dna[p + 1]][dna[p + 2]];
+				const size_t r = L - 3 - p;                    // the reverse strand's codon i of frame f, read back to front
+				fr[f + 3][i] = ct.rev[dna[r + 2]][dna[r + 1]][dna[r]];
+			}
+		}
+	}
+	const size_t l0 = fr[0].size();
+	const size_t min_len = l0 < 30 ? 1 : (l0 < 100 ? 20 : 40);  // Config::min_orf_len (basic/config.h:413-424), --min-orf not given
+	for (int f = 0; f < 6; ++f) {
+		std::vector<int8_t>& v = fr[f];
+		for (size_t begin = 0;;) {  // Util::Seq::find_orfs (util/sequence/sequence.cpp:180-197)
+			size_t it = begin;
+			while (it < v.size() && v[it] != 24) ++it;
+			if (it - begin < min_len) std::fill(v.begin() + (ptrdiff_t)begin, v.begin() + (ptrdiff_t)it, (int8_t)23);
+			if (it >= v.size()) break;
+			begin = it + 1;
+		}
+		b.letters.insert(b.letters.end(), v.begin(), v.end());
+		b.letters.push_back((int8_t)DMND_DELIMITER);
+		b.limits.push_back((int64_t)b.letters.size());
+	}
+}
+
+void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::string line;
+	std::vector<int8_t> dna;
+	bool open = false;
+	auto close_seq = [&] {
+		if (!open) return;
+		dq.len.push_back((int32_t)dna.size());
+		push_translated(dna, b);
+		dna.clear();
+		open = false;
+	};
+	while (std::getline(f, line)) {
+		if (!line.empty() && line.back() == '\r') line.pop_back();
+		if (line.empty()) continue;
+		if (line[0] == '>') {
+			close_seq();
+			size_t e = 1;
+			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;
+			dq.ids.push_back(line.substr(1, e - 1));
+			dq.titles.push_back(line.substr(1));
+			open = true;
+		}
+		else {
+			if (!open) throw std::runtime_error("FASTA format error: sequence data before the first header in " + path);
+			for (char c : line) dna.push_back(encode_dna(c));
+		}
+	}
+	close_seq();
+	b.finish();
+}
+
 // ---- DIAMOND database files (legacy/dmnd/dmnd.h:28-66, dmnd.cpp:50-120,224-234,319-327): 40-byte header, a size-prefixed second
 // header with a 128-bit hash, one record per sequence (0xff, letters with bit 7 = tantan soft mask, 0xff, title, 0), then the
 // position array {u64 offset, u32 length, u32 0} with a terminating entry.  Little endian.
@@ -213,7 +312,7 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 }
 
 [[noreturn]] void usage(const char* msg) {
-	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] [-c N] [-k N] [-e X] "
+	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] | dmnd-b200 blastx --fast -q READS.fna -d DB -o OUT [-p N] [-c N] [-k N] [-e X] "
 	                "[--comp-based-stats 0|1] [--masking 0|none|1|tantan] [--motif-masking 0|1] [-f 6] [--log]\n", msg);
 	exit(1);
 }
@@ -241,9 +340,11 @@ int main(int argc, char** argv) {
 			if (in.empty() || db.empty()) usage("makedb needs --in and -d");
 			return make_db(in, db, masking);
 		}
-		if (cmd != "blastp") usage("only blastp and makedb are implemented (blastx is a 'next' row, see DESIGN.md)");
+		if (cmd != "blastp" && cmd != "blastx") usage("only blastp, blastx and makedb are implemented");
+		const bool translated = cmd == "blastx";
 		dmnd_search_opts o;
 		dmnd_search_opts_default(&o);
+		if (translated) o.query_contexts = 6;
 		o.sensitivity = 1;  // like the reference: no sensitivity flag = Sensitivity::DEFAULT, --fast = Sensitivity::FAST
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
@@ -294,12 +395,17 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (translated && o.sensitivity != 0) usage("blastx is built for --fast only (pass --fast): the other modes treat translated frames of <= 85 letters differently in the seed stage");
+		if (translated && pairwise) usage("-f 0 is not implemented for blastx");
 		if (pairwise) o.want_transcript = 1;
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
-		read_fasta(qf, q);
+		DnaQueries dq;
+		if (translated) read_dna_fasta(qf, dq, q);
+		else read_fasta(qf, q);
+		const uint32_t nq_block = translated ? (uint32_t)dq.ids.size() * 6u : q.size();
 		if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
 		else read_fasta(df, r);
 		dmnd_params params;
@@ -307,7 +413,7 @@ int main(int argc, char** argv) {
 		dmnd_ctx* ctx = nullptr;
 		if (dmnd_create(0, &params, &ctx)) throw std::runtime_error(dmnd_last_error());
 		dmnd_result* res = nullptr;
-		if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), q.size(), r.letters.data(), r.letters.size(),
+		if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, r.letters.data(), r.letters.size(),
 		                r.limits.data(), r.size(), &o, &res))
 			throw std::runtime_error(dmnd_last_error());
 		size_t n = 0;
@@ -388,12 +494,20 @@ int main(int argc, char** argv) {
 			for (size_t fi = 0; fi < fields.size(); ++fi) {
 				const std::string& f = fields[fi];
 				if (fi) line += '\t';
-				if (f == "qseqid") line += q.ids[x.query];
+				if (f == "qseqid") line += translated ? dq.ids[x.query / 6] : q.ids[x.query];
 				else if (f == "sseqid") line += r.ids[x.target];
 				else if (f == "pident") { format_double((double)x.identities * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
 				else if (f == "length") line += std::to_string(x.length);
 				else if (f == "mismatch") line += std::to_string(x.mismatches);
 				else if (f == "gapopen") line += std::to_string(x.gap_openings);
+				else if (translated && (f == "qstart" || f == "qend")) {
+					// TranslatedPosition::absolute_interval (basic/translated_position.h:121-127): in-strand = 3 * translated + frame offset;
+					// a reverse-strand range is mirrored, and printed from its high end (output/blast_tab_format.cpp, query_source_range)
+					const int fr = (int)(x.query % 6), off = fr % 3, L = dq.len[x.query / 6];
+					const int b_in = 3 * x.q_begin + off, e_in = 3 * x.q_end + off;
+					if (fr < 3) line += std::to_string(f == "qstart" ? b_in + 1 : e_in);
+					else line += std::to_string(f == "qstart" ? L - b_in : L - e_in + 1);
+				}
 				else if (f == "qstart") line += std::to_string(x.q_begin + 1);
 				else if (f == "qend") line += std::to_string(x.q_end);
 				else if (f == "sstart") line += std::to_string(x.t_begin + 1);
@@ -403,7 +517,7 @@ int main(int argc, char** argv) {
 				else if (f == "score") line += std::to_string(x.score);
 				else if (f == "gaps") line += std::to_string(x.gaps);
 				else if (f == "nident") line += std::to_string(x.identities);
-				else if (f == "qlen") line += std::to_string(q.limits[x.query + 1] - q.limits[x.query] - 1);
+				else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[x.query / 6] : q.limits[x.query + 1] - q.limits[x.query] - 1);
 				else if (f == "slen") line += std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1);
 				else if (f == "cigar") {  // print_cigar, output/sam_format.cpp:67-83: match and substitution are both M
 					uint32_t run = 0; int op = -1;

@@ -182,10 +182,10 @@ struct List {  // trivially-copyable elements only
 	void clear() { n = 0; }
 };
 
-struct SeedHit { int i, j, score; dmnd_segment seg; uint8_t gf;  /* gf: the hit passes the gapped filter (modes that have one) */ bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
+struct SeedHit { int i, j, score; dmnd_segment seg; uint8_t gf;  /* gf: the hit passes the gapped filter (modes that have one) */ uint8_t frame;  /* query context of the hit (0 for blastp), align/load_hits.h:86 */ bool operator<(const SeedHit& x) const { const int d1 = i - j, d2 = x.i - x.j; return d1 < d2 || (d1 == d2 && j < x.j); } };
 struct TargetScore { uint32_t target; uint16_t score; bool operator<(const TargetScore& x) const { return score > x.score || (score == x.score && target < x.target); } };
 
-struct HspLite { int score; double evalue; int d_begin, d_end; };
+struct HspLite { int score; double evalue; int d_begin, d_end; uint32_t ctx;  /* query block id of the frame that aligned (= the query for blastp) */ };
 inline bool hsp_less(const HspLite& a, const HspLite& b) {  // basic/match.h:199-202 (query_source_range.begin_ is 0 in round 1)
 	return a.score > b.score || (a.score == b.score && a.d_begin < b.d_begin);
 }
@@ -278,6 +278,7 @@ struct Env {
 	bool gapped_filter = false;  // Extension::gapped_filter before the ungapped stage (align/extend.cpp:205-214)
 	int n_shapes = 1;   // shapes of the sensitivity mode (search/setup.cpp:80-304): one dmnd_search_shape per shape
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
+	uint32_t contexts = 1;  // align_mode.query_contexts: 6 = blastx, the query block holds the six frames of every query back to back
 	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
 	const int8_t* rseq(uint32_t t) const { const int8_t* p = r_patch ? r_patch->find(t) : nullptr; return p ? p : r_letters + r_limits[t]; }
 	const int64_t *q_limits, *r_limits;
@@ -294,8 +295,8 @@ struct Env {
 enum Phase : uint8_t { PH_ROUND1_PRODUCE, PH_ROUND1_CONSUME, PH_ROUND2_PRODUCE, PH_ROUND2_CONSUME, PH_DONE };
 
 struct QueryState {
-	uint32_t qid;
-	int qlen;
+	uint32_t qid;  // block id of the query's first context (the query itself for blastp)
+	int qlen;      // length of that context (query_seq[0].length() in the reference)
 	Phase phase;
 	bool new_hits_ev;
 	bool fused;
@@ -481,7 +482,7 @@ void Driver::load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, W
 			++ntg;
 		}
 		const uint16_t hs = (uint16_t)DMND_HIT_SCORE(*h);
-		tc.seed_hits.push_back({ h->seed_offset, hsp->site.j, (int)hs, hsp->s, hsp->gf });
+		tc.seed_hits.push_back({ h->seed_offset, hsp->site.j, (int)hs, hsp->s, hsp->gf, (uint8_t)(h->query - q.qid) });
 		score = std::max(score, hs);
 	}
 	if (target != UINT32_MAX) tc.target_scores.push_back({ ntg - 1, score });
@@ -514,7 +515,7 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	// round 1 can simply be kept: a query whose targets mostly survive culling (<= 64 targets, one ranking chunk, at most
 	// max_target_seqs = 25 culled away) sends its round-1 problems through the traceback kernel once and answers round 2
 	// from those results -- one device round trip instead of two, 13 instead of 9 + 13 lane-ops per surviving cell.
-	q.fused = e.fuse && target_count <= 64 && target_count <= q.chunk_size;
+	q.fused = e.fuse && e.contexts == 1 && target_count <= 64 && target_count <= q.chunk_size;
 	q.phase = PH_ROUND1_PRODUCE;
 }
 
@@ -526,8 +527,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	q.prob_target.clear();
 	std::vector<dmnd_dp_problem>& plist = q.fused ? tc.p2 : tc.p1;  // fused: straight into the traceback batch
 	q.prob_begin = plist.size();
-	const int8_t* query = e.qseq(q.qid);
-	const int band = band_for(q.qlen, e.band_slow);
+	const int band = band_for(q.qlen, e.band_slow);  // Extension::band(query_seq->length(), mode): the first context's length
 	const TargetScore* ts = tc.target_scores.data() + q.ts_off;
 	const uint32_t* hb = tc.hit_begin.data() + q.tgt_off;
 	const uint32_t* ids = tc.target_block_ids.data() + q.ts_off;
@@ -536,7 +536,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		const uint32_t block_id = ids[tix];
 		const int slen = e.tlen(block_id);
 		const int8_t* subject = e.rseq(block_id);
-		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0 }, false, 0 });
+		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0, q.qid }, false, 0 });
 		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
 		if (e.gapped_filter) {  // Extension::gapped_filter (align/gapped_filter.cpp:41-63): a target stays iff one of its hits passes
 			bool any = false;
@@ -544,40 +544,58 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 			if (!any) continue;
 		}
 		++tc.n_extended;
-		std::sort(tc.hits.begin(), tc.hits.end());
-		tc.segs.clear();
-		for (const SeedHit& h : tc.hits) {  // align/ungapped.cpp:81-91
-			if (!tc.segs.empty() && tc.segs.back().diag() == h.i - h.j && tc.segs.back().subject_end() >= h.j) continue;
-			// xdrop_ungapped(query, cbs, target, hit.i, hit.j) was evaluated for every hit on the device (dmnd_hits_xdrop)
-			const Segment d{ h.seg.i, h.seg.j, h.seg.len, h.seg.score };
-			if (d.score > 0) tc.segs.push_back(d);
-		}
-		if (tc.segs.empty()) continue;
-		stable_small_sort(tc.segs, [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
-		chain_segments(*e.sc, query, q.qlen, subject, slen, tc.segs, tc.chains);
-		stable_small_sort(tc.chains, [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
-		// add_dp_targets, align/gapped_score.cpp:107-180
-		int d0 = INT_MAX, d1 = INT_MIN;
-		auto emit = [&] {
-			plist.push_back(dmnd_dp_problem{ q.qid, block_id, d0, d1 });
-			q.prob_target.push(tc.arena, q.r1.n - 1);
-			tc.cells1 += (uint64_t)(d1 - d0) * (uint64_t)banded_cols(q.qlen, slen, d0, d1);
-		};
-		for (const Chain& h : tc.chains) {
-			const int b0 = std::max(h.d_min - band, -(slen - 1)), b1 = std::min(h.d_max + 1 + band, q.qlen);
-			bool merge = false;
-			if (d0 != INT_MAX) {
-				const int ib = std::max(d0, b0), ie = std::min(d1, b1);
-				const double overlap = ie > ib ? ie - ib : 0;
-				merge = overlap / (d1 - d0) > 0.0 || overlap / (b1 - b0) > 0.0;
+		// translated queries: a target with ONE seed hit skips the x-drop extension and chaining, its band is centred on the
+		// hit's diagonal (align/ungapped.cpp:76-80)
+		const bool single = e.contexts > 1 && tc.hits.size() == 1;
+		if (!single) std::sort(tc.hits.begin(), tc.hits.end());
+		for (uint32_t f = 0; f < e.contexts; ++f) {  // ungapped_stage + add_dp_targets, one frame after the other (ungapped.cpp:110-116, gapped_score.cpp:119)
+			const uint32_t ctx = q.qid + f;
+			tc.chains.clear();
+			int qlen_f = q.qlen;
+			if (single) {
+				if (tc.hits[0].frame != f) continue;
+				qlen_f = e.qlen(ctx);
+				Chain c; c.d_min = c.d_max = tc.hits[0].i - tc.hits[0].j; c.score = tc.hits[0].score;
+				tc.chains.push_back(c);
 			}
-			if (merge) { d0 = std::min(d0, b0); d1 = std::max(d1, b1); }
 			else {
-				if (d0 != INT_MAX) emit();
-				d0 = b0; d1 = b1;
+				tc.segs.clear();
+				for (const SeedHit& h : tc.hits) {  // align/ungapped.cpp:81-91
+					if (h.frame != f) continue;
+					if (!tc.segs.empty() && tc.segs.back().diag() == h.i - h.j && tc.segs.back().subject_end() >= h.j) continue;
+					// xdrop_ungapped(query, cbs, target, hit.i, hit.j) was evaluated for every hit on the device (dmnd_hits_xdrop)
+					const Segment d{ h.seg.i, h.seg.j, h.seg.len, h.seg.score };
+					if (d.score > 0) tc.segs.push_back(d);
+				}
+				if (tc.segs.empty()) continue;
+				if (e.contexts > 1) qlen_f = e.qlen(ctx);
+				stable_small_sort(tc.segs, [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
+				chain_segments(*e.sc, e.qseq(ctx), qlen_f, subject, slen, tc.segs, tc.chains);
+				stable_small_sort(tc.chains, [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
 			}
+			// add_dp_targets, align/gapped_score.cpp:107-180
+			int d0 = INT_MAX, d1 = INT_MIN;
+			auto emit = [&] {
+				plist.push_back(dmnd_dp_problem{ ctx, block_id, d0, d1 });
+				q.prob_target.push(tc.arena, q.r1.n - 1);
+				tc.cells1 += (uint64_t)(d1 - d0) * (uint64_t)banded_cols(qlen_f, slen, d0, d1);
+			};
+			for (const Chain& h : tc.chains) {
+				const int b0 = std::max(h.d_min - band, -(slen - 1)), b1 = std::min(h.d_max + 1 + band, qlen_f);
+				bool merge = false;
+				if (d0 != INT_MAX) {
+					const int ib = std::max(d0, b0), ie = std::min(d1, b1);
+					const double overlap = ie > ib ? ie - ib : 0;
+					merge = overlap / (d1 - d0) > 0.0 || overlap / (b1 - b0) > 0.0;
+				}
+				if (merge) { d0 = std::min(d0, b0); d1 = std::max(d1, b1); }
+				else {
+					if (d0 != INT_MAX) emit();
+					d0 = b0; d1 = b1;
+				}
+			}
+			if (!tc.chains.empty()) emit();
 		}
-		if (!tc.chains.empty()) emit();
 	}
 	q.prob_count = (uint32_t)(plist.size() - q.prob_begin);
 	if (q.fused) { tc.fused_r1 += q.prob_count; tc.fused_r1_wave += q.prob_count; }
@@ -596,12 +614,16 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 	for (uint32_t k = 0; k < q.prob_count; ++k) {
 		const int score = res[k].score;
 		Target& t = q.r1.p[q.prob_target.p[k]];
-		const double ev = e.sc->evalue(score, (unsigned)q.qlen, (unsigned)t.tlen);
+		const uint32_t ctx = probs[k].query;
+		const double ev = e.sc->evalue(score, (unsigned)(ctx == q.qid ? q.qlen : e.qlen(ctx)), (unsigned)t.tlen);
 		if (score > 0 && ev <= e.max_evalue) {  // banded_swipe.h:341-342, ScoreMatrix::report_cutoff
-			const HspLite h{ score, ev, probs[k].d_begin, probs[k].d_end };
-			if (!t.has_hsp || hsp_less(h, t.hsp)) { t.hsp = h; t.hsp_prob = k; }
+			const HspLite h{ score, ev, probs[k].d_begin, probs[k].d_end, ctx };
+			// Target::add_hit(list,it), target.h:104-112: a strictly higher score moves filter_score AND best_context to this HSP's
+			// frame (frames arrive in ascending order, as the reference's loop over the frames delivers them); inner_culling keeps
+			// the best HSP of best_context only (culling.cpp:58-67)
+			if (score > t.filter_score) { t.filter_evalue = ev; t.filter_score = score; t.hsp = h; t.hsp_prob = k; }
+			else if (t.has_hsp && ctx == t.hsp.ctx && hsp_less(h, t.hsp)) { t.hsp = h; t.hsp_prob = k; }
 			t.has_hsp = true;
-			if (score > t.filter_score) { t.filter_evalue = ev; t.filter_score = score; }  // Target::add_hit(list,it), target.h:104-112
 		}
 	}
 	// keep targets with hits (gapped_score.cpp:236-243)
@@ -656,9 +678,9 @@ void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
 	q.r2.reserve(tc.arena, q.aligned_targets.n);
 	for (const Target& tg : q.aligned_targets) {
 		if (tg.has_hsp) {
-			tc.p2.push_back(dmnd_dp_problem{ q.qid, tg.block_id, tg.hsp.d_begin, tg.hsp.d_end });
+			tc.p2.push_back(dmnd_dp_problem{ tg.hsp.ctx, tg.block_id, tg.hsp.d_begin, tg.hsp.d_end });
 			q.prob_target.push(tc.arena, q.r2.n);
-			tc.cells2 += (uint64_t)(tg.hsp.d_end - tg.hsp.d_begin) * (uint64_t)banded_cols(q.qlen, tg.tlen, tg.hsp.d_begin, tg.hsp.d_end);
+			tc.cells2 += (uint64_t)(tg.hsp.d_end - tg.hsp.d_begin) * (uint64_t)banded_cols(tg.hsp.ctx == q.qid ? q.qlen : env.qlen(tg.hsp.ctx), tg.tlen, tg.hsp.d_begin, tg.hsp.d_end);
 		}
 		Match m;
 		std::memset(&m, 0, sizeof m);
@@ -672,9 +694,9 @@ void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
 void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr, double known_evalue) {
 	// gapped_final.cpp:140-149; known_evalue >= 0: the e-value of (r.score, qlen, tlen) was already computed in round 1
 	const Env& e = env;
-	const double ev = known_evalue >= 0.0 ? known_evalue : e.sc->evalue(r.score, (unsigned)q.qlen, (unsigned)m.tlen);
+	const double ev = known_evalue >= 0.0 ? known_evalue : e.sc->evalue(r.score, (unsigned)(pr.query == q.qid ? q.qlen : e.qlen(pr.query)), (unsigned)m.tlen);
 	if (r.score > 0 && ev <= e.max_evalue) {
-		const HspLite h{ r.score, ev, pr.d_begin, pr.d_end };
+		const HspLite h{ r.score, ev, pr.d_begin, pr.d_end, pr.query };
 		if (!m.has_hsp || hsp_less(h, m.h)) {
 			m.h = h; m.r = r;
 			m.tr_off = 0; m.tr_len = 0;
@@ -876,6 +898,7 @@ void dmnd_search_opts_default(dmnd_search_opts* o) {
 	std::memset(o, 0, sizeof *o);
 	o->sensitivity = 0; o->threads = 8; o->index_chunks = 0; o->comp_based_stats = 1; o->max_target_seqs = 25;
 	o->max_evalue = 0.001; o->db_letters = 0; o->want_transcript = 0;
+	o->query_contexts = 1;
 	o->masking = 1; o->motif_masking = 1;  // the reference's defaults for blastp --fast (run/config.cpp:126-135, search/setup.cpp:43)
 }
 
@@ -1067,13 +1090,14 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	// ---- group by query (hits arrive grouped by ascending query id): boundaries found in parallel
 	t0 = Clock::now();
 	const int T = host_threads;
+	const uint32_t C = env.contexts;
 	std::vector<std::vector<size_t>> tl_bounds((size_t)T);
 	std::atomic<int> bad(0);
 	w.run([&](int t) {
 		auto& v = tl_bounds[(size_t)t];
 		v.clear();
 		for (size_t i = nh * (size_t)t / (size_t)T, en = nh * (size_t)(t + 1) / (size_t)T; i < en; ++i)
-			if (i == 0 || w.hv[i].query != w.hv[i - 1].query) {
+			if (i == 0 || w.hv[i].query / C != w.hv[i - 1].query / C) {  // one group per query = all its contexts (search/hit.h:71-78)
 				if (i > 0 && w.hv[i].query < w.hv[i - 1].query) bad = 1;
 				v.push_back(i);
 			}
@@ -1092,7 +1116,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		tc.reset();
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			QueryState& q = w.qs[k];
-			q.qid = w.hv[w.qstart[k]].query;
+			q.qid = w.hv[w.qstart[k]].query / C * C;
 			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; w.hs[x].gf = w.gfv[x]; }
 			d.load_hits(q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]);
 			d.start(q, tc);
@@ -1133,7 +1157,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 			const QueryState& q = w.qs[k];
 			for (const Match& m : q.matches) {
 				std::memset(o, 0, sizeof *o);
-				o->query = q.qid; o->target = m.target_block_id; o->score = m.h.score; o->evalue = m.h.evalue;
+				o->query = m.h.ctx; o->target = m.target_block_id; o->score = m.h.score; o->evalue = m.h.evalue;
 				o->bit_score = sc.bitscore(m.h.score);
 				o->q_begin = m.r.q_begin; o->q_end = m.r.q_end; o->t_begin = m.r.t_begin; o->t_end = m.r.t_end;
 				o->identities = m.r.identities; o->mismatches = m.r.mismatches; o->gap_openings = m.r.gap_openings;
@@ -1178,7 +1202,7 @@ struct LanePlan {
 	int host_threads = 1, nlanes = 1;
 	std::vector<uint32_t> cut;
 };
-static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits) {
+static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits, uint32_t contexts) {
 	LanePlan p;
 	p.host_threads = effective_cpus();
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) p.host_threads = std::max(1, std::atoi(ev));
@@ -1191,6 +1215,7 @@ static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits) {
 	for (int l = 1; l < p.nlanes; ++l) {
 		const int64_t want = q_limits[0] + (q_limits[nq] - q_limits[0]) * l / p.nlanes;
 		p.cut[(size_t)l] = (uint32_t)(std::lower_bound(q_limits, q_limits + nq + 1, want) - q_limits);
+		p.cut[(size_t)l] = p.cut[(size_t)l] / contexts * contexts;  // a query's contexts stay in one lane
 		p.cut[(size_t)l] = std::min(std::max(p.cut[(size_t)l], p.cut[(size_t)l - 1]), nq);
 	}
 	return p;
@@ -1219,7 +1244,13 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	int64_t ref_letters = 0;
 	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
-	const LanePlan plan = plan_lanes(nq, q_limits);
+	const uint32_t contexts = opts->query_contexts > 1 ? (uint32_t)opts->query_contexts : 1u;
+	if ((contexts != 1 && contexts != 6) || nq % contexts != 0 || (contexts > 1 && opts->sensitivity != 0)) {
+		dmnd_set_last_error("dmnd_blastp: query_contexts must be 1 or 6 with nq a multiple of it; translated queries are built for --fast only "
+		                    "(the window-filter modes switch to cutoff_table_short and a whole-query window for frames of <= 85 letters, search/stage2.h:41-63)");
+		return 1;
+	}
+	const LanePlan plan = plan_lanes(nq, q_limits, contexts);
 	const int host_threads = plan.host_threads, nlanes = plan.nlanes;
 	sh.ensure(host_threads, nlanes);
 
@@ -1229,7 +1260,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
-	e.mask_algo = mask_algo;
+	e.mask_algo = mask_algo; e.contexts = contexts;
 	{
 		const ModeTraits* mt = mode_traits(opts->sensitivity);
 		if (!mt) { dmnd_set_last_error("dmnd_blastp: bad sensitivity"); return 1; }
@@ -1317,7 +1348,7 @@ int dmnd_blastp(dmnd_ctx* ctx, const int8_t* q_letters, size_t q_raw_len, const 
 	// the reference block first (the index build needs it), then the query block range by range on the copy stream: lane 0
 	// starts as soon as ITS range is there, the other ranges travel while it already searches
 	if (dmnd_block_upload(ctx, r_letters, r_raw_len, r_limits, nr, &rb)) return 1;
-	const LanePlan plan = plan_lanes(nq, q_limits);
+	const LanePlan plan = plan_lanes(nq, q_limits, opts->query_contexts > 1 ? (uint32_t)opts->query_contexts : 1u);
 	if (dmnd_block_upload_ranges(ctx, q_letters, q_raw_len, q_limits, nq, plan.cut.data(), plan.nlanes, &qb)) { dmnd_block_free(ctx, rb); return 1; }
 	prof.lap("e2e: block uploads (queries in flight)");
 	const int rc = blastp_impl(ctx, qb, rb, q_letters, q_limits, nq, r_letters, r_limits, nr, opts, mask_bits(opts), out);

@@ -286,6 +286,88 @@ def repeat_workload(seed: int, n_db: int = 1500, n_q: int = 400):
     return {"q_letters": np.concatenate(qs).astype(np.int8), "q_off": qo, "db_letters": dbl, "db_off": off, "src": None}
 
 
+# ---- blastx: DNA reads over a protein database ------------------------------------------------------------------------------
+_CODE = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"  # standard code, TCAG order
+_CODONS = {}
+for _i, _a in enumerate(_CODE):
+    _CODONS.setdefault(_a, []).append("TCAG"[_i >> 4] + "TCAG"[(_i >> 2) & 3] + "TCAG"[_i & 3])
+
+
+def _revcomp(s: str) -> str:
+    return s[::-1].translate(str.maketrans("ACGTNR", "TGCANY"))
+
+
+def reads_workload(seed: int, n_db: int = 1500, n_q: int = 500):
+    """DNA queries for blastx: back-translated, mutated windows of database proteins on either strand with random flanks;
+    plus frame-shifted reads (one target hit in two frames), chimeras of two proteins, reads with N / IUPAC codes, trinucleotide
+    repeats (tantan masks a translated frame), reads without a homolog, reads shorter than a codon, and a few gene-length
+    queries.  The database carries mutated paralogs of its first 200 proteins (41 of the first five) so that a read has several targets."""
+    rng = np.random.default_rng(seed)
+    dbl, dbo = make_db(n_db, rng)
+    seqs = [dbl[dbo[i]:dbo[i + 1]] for i in range(n_db)]
+    for i in list(range(200)) + [j % 5 for j in range(200)]:  # one paralog each, 40 more of the first five (culling at 25 targets)
+        c = seqs[i].copy()
+        sub = rng.random(len(c)) < rng.uniform(0.05, 0.3)
+        c[sub] = draw_letters(rng, int(sub.sum()))
+        seqs.append(c)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in seqs], out=off[1:])
+    dbl = np.concatenate(seqs).astype(np.int8)
+
+    def rand_dna(n):
+        return "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+
+    def coding(max_aa):
+        u = rng.random()
+        sid = int(rng.integers(0, 5)) if u < 0.1 else int(rng.integers(0, 200)) if u < 0.6 else int(rng.integers(0, len(seqs)))
+        p = seqs[sid]
+        L = int(min(len(p), rng.integers(12, max_aa)))
+        st = int(rng.integers(0, len(p) - L + 1))
+        w = p[st:st + L].copy()
+        sub = rng.random(L) < rng.uniform(0.03, 0.35)
+        w[sub] = draw_letters(rng, int(sub.sum()))
+        return "".join(_CODONS[ALPHABET[a]][int(rng.integers(0, len(_CODONS[ALPHABET[a]])))] for a in w)
+
+    reads = []
+    for k in range(n_q):
+        if k % 29 == 0:
+            r = rand_dna(int(rng.integers(30, 400)))
+        elif k % 31 == 1:
+            r = rand_dna(int(rng.integers(1, 6)))  # shorter than two codons: (nearly) empty frames
+        else:
+            r = coding(600 if k % 7 == 0 else 110)
+            if k % 11 == 2 and len(r) > 60:  # frame shift in the middle
+                m = len(r) // 2
+                r = r[:m] + rand_dna(int(rng.integers(1, 3))) + r[m:]
+            if k % 13 == 3:  # chimera, second part possibly on the other strand
+                r2 = coding(110)
+                r = r + rand_dna(int(rng.integers(0, 9))) + (_revcomp(r2) if rng.random() < 0.5 else r2)
+            if k % 23 == 4:
+                r = r + "GCA" * 30
+            r = rand_dna(int(rng.integers(0, 40))) + r + rand_dna(int(rng.integers(0, 40)))
+            if k % 10 == 3:
+                r = list(r)
+                for x in rng.integers(0, len(r), 3):
+                    r[int(x)] = "N"
+                r = "".join(r)
+            if k % 19 == 4:
+                x = int(rng.integers(0, len(r)))
+                r = r[:x] + "R" + r[x + 1:]
+            if rng.random() < 0.5:
+                r = _revcomp(r)
+        reads.append(r)
+    return {"dna": reads, "db_letters": dbl, "db_off": off}
+
+
+def write_dna_fasta(path: str, reads, prefix: str = "r") -> None:
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">%s%d\n%s\n" % (prefix, i, r))
+
+
+BX_WORKLOADS = {"bx": (reads_workload, dict(seed=55))}  # goldens: tests/golden/bx.x0.tsv (blastx --fast, default flags)
+
+
 WORKLOADS = {
     # name: (factory, kwargs)  -- the committed golden fixtures under tests/golden/ are keyed by these names
     "c1": (workload, dict(n_q=1000, n_db=10000, seed=1)),

@@ -258,6 +258,10 @@ typedef struct dmnd_search_opts {
 	int32_t want_transcript;   /* 1 = keep edit transcripts (fmt 0) */
 	int32_t masking;           /* --masking: 1 = tantan (reference default), 0 = none */
 	int32_t motif_masking;     /* --motif-masking: 1 = soft-mask abundant motifs (reference default for --fast), 0 = off */
+	int32_t query_contexts;    /* 1 = blastp; 6 = blastx (align_mode.query_contexts, basic/basic.cpp:42-47): the query block holds the six
+	                              translated frames of every DNA query as consecutive sequences (context id = 6 * query + frame,
+	                              data/block/block.cpp:86-100), nq is a multiple of 6, dmnd_match.query is the CONTEXT that aligned and
+	                              q_begin / q_end are positions in that frame's translation.  0 is read as 1.  --fast only. */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

@@ -15,6 +15,8 @@ For every workload W and parity-ladder level L:
     F0 = L2 in the BLAST pairwise format (-f 0): .txt
     T2 = L2 (--fast, default flags) with the transcript-bearing output fields: cigar, btop, qseq_gapped, sseq_gapped -- pins the
          traceback (and the masked letters the reference prints) byte for byte
+    X0 / XT = `blastx --fast` with default flags on the DNA reads of synth.BX_WORKLOADS (12 default fields / + the transcript
+         fields, qlen, slen): six translated frames per read, DNA coordinates, frame-aware culling
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -66,5 +68,25 @@ def main():
                 print(name, lvl, sum(1 for _ in open(out)), cn)
 
 
+def main_blastx():
+    for name in synth.BX_WORKLOADS:
+        f, kw = synth.BX_WORKLOADS[name]
+        w = f(**kw)
+        with tempfile.TemporaryDirectory() as td:
+            q, d = os.path.join(td, "q.fna"), os.path.join(td, "d.faa")
+            synth.write_dna_fasta(q, w["dna"])
+            synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+            for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"])):
+                out = os.path.join(HERE, f"{name}.{lvl}.tsv")
+                if os.path.exists(out) and "--missing" in sys.argv:
+                    continue
+                r = subprocess.run([REF, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
+                log = r.stderr + r.stdout
+                cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
+                json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)
+                print(name, lvl, sum(1 for _ in open(out)), cn)
+
+
 if __name__ == "__main__":
     main()
+    main_blastx()

@@ -1,0 +1,99 @@
+"""blastx: DNA queries translated into six frames per read, searched with the unchanged K layer, extended
+per frame with the reference's frame-aware target logic (align/ungapped.cpp:76-116, gapped_score.cpp:107-246, culling.cpp:58-67)
+and reported in nucleotide coordinates.  Goldens: tests/golden/bx.x0 / bx.xt = the unmodified reference, `blastx --fast`,
+default flags (tantan + motif masking of the translated frames, Hauser CBS), on synth.BX_WORKLOADS.  CPU only: the host
+pipeline over the oracle's K layer."""
+import json, os, subprocess
+import numpy as np
+import pytest
+from conftest import GOLDEN, REF_BIN, ROOT
+
+CLI = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+XT_FIELDS = "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped score qlen slen".split()
+
+
+def _bx():
+    from diamond_b200 import synth
+    f, kw = synth.BX_WORKLOADS["bx"]
+    return f(**kw)
+
+
+def _files(w, tmp_path):
+    from diamond_b200 import synth
+    q, d = str(tmp_path / "q.fna"), str(tmp_path / "d.faa")
+    synth.write_dna_fasta(q, w["dna"])
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    return q, d
+
+
+@pytest.mark.parametrize("lanes", ["1", "3"])
+def test_blastx_library_matches_reference_golden(oracle_lib, lanes, monkeypatch):
+    """Through the C ABI: query block = api.translate_reads (six contexts per read), opts.query_contexts = 6."""
+    from diamond_b200 import api
+    monkeypatch.setenv("DMND_LANES", lanes)
+    w = _bx()
+    ql, qo = api.translate_reads(w["dna"])
+    assert len(qo) - 1 == 6 * len(w["dna"])
+    q_raw, q_lim = api.block_image(ql, qo)
+    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+    g = api.Context(lib=oracle_lib, masking=1, motif_masking=1, query_contexts=6)
+    m, _, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    assert api.fmt6_translated(m, [len(r) for r in w["dna"]]) == open(os.path.join(GOLDEN, "bx.x0.tsv")).read()
+    gold = json.load(open(os.path.join(GOLDEN, "bx.x0.counters.json")))
+    keys = ("seeds_hit", "seed_hits", "tentative_matches3") if lanes == "1" else ("seed_hits", "tentative_matches3")  # (a seed shared by two lanes counts in both)
+    assert {k: st["seed"][k] for k in keys} == {k: gold[k] for k in keys}
+    assert st["targets"] == gold["targets"] and st["targets_extended"] == gold["targets_extended"]
+    frames = np.bincount(m["query"] % 6, minlength=6)
+    assert frames.min() > 0  # every frame of either strand produced alignments
+    per_read = {}
+    for x in m:
+        per_read.setdefault(int(x["query"]) // 6, set()).add(int(x["query"]) % 6)
+    assert any(len(v) > 1 for v in per_read.values())  # chimeric / frame-shifted reads: one read reports targets in several frames
+
+
+def test_blastx_cli_default_fields(oracle_lib, tmp_path):
+    q, d = _files(_bx(), tmp_path)
+    o = str(tmp_path / "o.tsv")
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, "bx.x0.tsv")).read()
+
+
+def test_blastx_cli_transcript_fields(oracle_lib, tmp_path):
+    """cigar / btop / gapped sequences of the translated frame (masked letters included), score, qlen in nucleotides."""
+    q, d = _files(_bx(), tmp_path)
+    o = str(tmp_path / "o.tsv")
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + XT_FIELDS + ["-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, "bx.xt.tsv")).read()
+
+
+def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
+    from diamond_b200 import api
+    q, d = _files(_bx(), tmp_path)
+    r = subprocess.run([CLI, "blastx", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # default sensitivity
+    assert r.returncode != 0 and "--fast" in r.stderr
+    r = subprocess.run([CLI, "blastx", "--fast", "-f", "0", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0
+    # the library: contexts other than 1 / 6, nq not a multiple, or a window-filter mode
+    raw, lim = api.block_image(np.zeros(40, dtype=np.int8), np.array([0, 10, 20, 30, 40], dtype=np.int64))
+    g = api.Context(lib=oracle_lib, query_contexts=6)
+    with pytest.raises(api.DmndError):
+        g.blastp(raw, lim, raw, lim)  # 4 sequences
+    g.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN) or not os.path.exists("/root/reference/src/test/SRR14011045_1.fna.gz"), reason="needs the reference build and its test data")
+def test_live_reference_nanopore_reads(oracle_lib, tmp_path):
+    """The reference's own blastx test input (src/test/SRR14011045_1.fna.gz against nr_10k.faa, CMakeLists.txt:544): 200 nanopore
+    reads of 0.3-4 kb full of frame shifts, run here with --fast and the transcript fields."""
+    import gzip
+    q = str(tmp_path / "nano.fna")
+    open(q, "wb").write(gzip.open("/root/reference/src/test/SRR14011045_1.fna.gz").read())
+    d = "/root/reference/src/test/nr_10k.faa"
+    ours, ref = str(tmp_path / "o.tsv"), str(tmp_path / "r.tsv")
+    subprocess.run([REF_BIN, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + XT_FIELDS + ["-o", ref, "-p", "8", "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + XT_FIELDS + ["-o", ours, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(ours).read() == open(ref).read() and sum(1 for _ in open(ref)) > 400
