@@ -32,7 +32,8 @@ class Params(C.Structure):
                 ("gapped_filter_diag_score", C.c_int32), ("gapped_filter_window", C.c_int32),
                 ("background_scores_f32", C.c_float * 20),
                 ("tantan_lr", C.c_float * 1024), ("tantan_d", C.c_float * 50), ("tantan_b2b", C.c_float), ("tantan_f2f", C.c_float),
-                ("tantan_p_repeat_end", C.c_float), ("tantan_p_mask", C.c_float), ("max_motif_len", C.c_int32)]
+                ("tantan_p_repeat_end", C.c_float), ("tantan_p_mask", C.c_float), ("max_motif_len", C.c_int32),
+                ("query_contexts", C.c_int32), ("ungapped_cutoff_short", C.c_int32 * 32)]
 
 
 class Hit(C.Structure):
@@ -95,7 +96,7 @@ SEGMENT_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("len", "<i4"), ("score", 
 PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"), ("d_end", "<i4")])
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
-SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
+SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
            "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",

@@ -133,6 +133,7 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s) {
 const char* dmnd_last_error(void) { return g_err.c_str(); }
 void dmnd_set_last_error(const char* m) { g_err = m ? m : ""; }
 const char* dmnd_backend(void) { return "cuda-sm100a"; }
+const dmnd_params* dmnd_ctx_params(const dmnd_ctx* ctx) { return &ctx->params; }
 
 int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	int ndev = 0;
@@ -175,6 +176,7 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	std::memcpy(d.background_scores_f32, params->background_scores_f32, sizeof d.background_scores_f32);
 	std::memcpy(d.ungapped_cutoff, params->ungapped_cutoff, sizeof d.ungapped_cutoff);
 	d.short_query_ungapped_cutoff = params->short_query_ungapped_cutoff; d.short_query_max_len = params->short_query_max_len;
+	d.query_contexts = params->query_contexts > 1 ? params->query_contexts : 1; std::memcpy(d.ungapped_cutoff_short, params->ungapped_cutoff_short, sizeof d.ungapped_cutoff_short);
 	std::memcpy(d.gapped_cutoff1, params->gapped_cutoff1, sizeof d.gapped_cutoff1); std::memcpy(d.gapped_cutoff2, params->gapped_cutoff2, sizeof d.gapped_cutoff2);
 	d.gapped_filter_diag_score = params->gapped_filter_diag_score; d.gapped_filter_window = params->gapped_filter_window;
 	std::memcpy(d.tantan_lr, params->tantan_lr, sizeof d.tantan_lr);

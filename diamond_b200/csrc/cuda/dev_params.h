@@ -21,6 +21,7 @@ struct DevParams {
 	double lnfact[DMND_MAX_WEIGHT + 1];
 	float background_scores_f32[20];
 	int32_t ungapped_cutoff[32], short_query_ungapped_cutoff, short_query_max_len;  // stage-2 ungapped window filter (0 tables: skipped)
+	int32_t query_contexts, ungapped_cutoff_short[32];  // blastx: 6 frames per query; frames of <= 85 letters (search/stage2.h:41-63)
 	int16_t gapped_cutoff1[32][32], gapped_cutoff2[32][32];  // gapped filter (align/gapped_filter.cpp): CutoffTable2D at e-values 2000 / gapped_filter_evalue
 	int32_t gapped_filter_diag_score, gapped_filter_window;
 	// tantan (masking/tantan.cpp:121-214): likelihood ratios [a*32+b], per-offset repeat start probabilities, transition constants

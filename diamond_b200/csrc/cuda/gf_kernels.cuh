@@ -82,12 +82,20 @@ static __global__ void __launch_bounds__(128) gapped_filter_kernel(const int8_t*
 	const int8_t *qs = q_letters + qo, *cb = q_bias + qo, *ss = r_letters + ro;
 	const int hi = hit.seed_offset, hj = (int)((int64_t)sloc - ro);
 	int* diag = s_diag[(threadIdx.x >> 5) & 3];
-	const int bq = 32 - __clz((unsigned)qlen), bs = 32 - __clz((unsigned)slen);
+	// the cutoffs are read at query_profile->length() = the length of the query's FIRST context, whatever frame the hit lies in;
+	// translated queries shorter than MIN_STAGE2_QLEN = 100 pass after the first scan (align/gapped_filter.cpp:44-55)
+	const bool translated = P->query_contexts > 1;
+	const uint32_t q0 = translated ? hit.query / (uint32_t)P->query_contexts * (uint32_t)P->query_contexts : hit.query;
+	const int qlen0 = translated ? (int)(q_limits[q0 + 1] - q_limits[q0] - 1) : qlen;
+	const int bq = 32 - __clz((unsigned)qlen0), bs = 32 - __clz((unsigned)slen);
 	bool ok = false;
 	const int f1 = gf_scan_align<64>(s_score, diag, P, qs, cb, qlen, ss, slen, hi, hj, 100, lane);
-	if (f1 > (int)P->gapped_cutoff1[bq][bs]) {  // warp-uniform (f1 is broadcast)
-		const int f2 = gf_scan_align<128>(s_score, diag, P, qs, cb, qlen, ss, slen, hi, hj, P->gapped_filter_window, lane);
-		ok = f2 > (int)P->gapped_cutoff2[bq][bs];
+	if (qlen0 > 0 && f1 > (int)P->gapped_cutoff1[bq][bs]) {  // warp-uniform (f1 is broadcast)
+		if (translated && qlen0 < 100) ok = true;
+		else {
+			const int f2 = gf_scan_align<128>(s_score, diag, P, qs, cb, qlen, ss, slen, hi, hj, P->gapped_filter_window, lane);
+			ok = f2 > (int)P->gapped_cutoff2[bq][bs];
+		}
 	}
 	if (lane == 0) pass[w] = ok ? 1 : 0;
 }

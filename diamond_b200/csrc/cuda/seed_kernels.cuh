@@ -315,8 +315,10 @@ __device__ __forceinline__ void stage2_tail(const int8_t* __restrict__ q_letters
 	uint32_t a = 0, b = nq;
 	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)q_limits[mid] <= (uint64_t)e.qloc) a = mid; else b = mid; }
 	const int seed_offset = (int)((int64_t)e.qloc - q_limits[a]);
-	// search/stage2.h:92-103
-	const int window = x.P->ungapped_window;
+	// search/stage2.h:92-103; ungapped_window(query_len), :58-63: a translated frame of <= 85 letters is scored over its whole length
+	const int query_len = (int)(q_limits[a + 1] - q_limits[a] - 1);
+	const bool short_frame = x.P->query_contexts > 1 && query_len <= 85;
+	const int window = short_frame ? query_len : x.P->ungapped_window;
 	int cb, ce;
 	clip(qp - window, 2 * window, window, cb, ce);
 	const int window_left = window - cb, window_clipped = ce - cb;
@@ -326,8 +328,8 @@ __device__ __forceinline__ void stage2_tail(const int8_t* __restrict__ q_letters
 		// ungapped_cutoff (search/stage2.h:41-57) and the window score: scalar ungapped_window (dp/ungapped_align.cpp:244-257) for
 		// calls with < 4 subjects, the int8 kernel (dp/ungapped_simd.cpp:32-88) otherwise -- its biased saturating lanes differ
 		// from the scalar loop only by capping the result at 255
-		const int query_len = (int)(q_limits[a + 1] - q_limits[a] - 1);
-		const int cutoff = query_len <= x.P->short_query_max_len ? x.P->short_query_ungapped_cutoff : x.P->ungapped_cutoff[32 - __clz((unsigned)query_len)];
+		const int cutoff = query_len <= x.P->short_query_max_len ? x.P->short_query_ungapped_cutoff
+			: (short_frame ? x.P->ungapped_cutoff_short : x.P->ungapped_cutoff)[32 - __clz((unsigned)query_len)];
 		const int8_t* sw = sp - window_left;
 		int st = 0, best = 0;
 		for (int t = 0; t < window_clipped; ++t) {

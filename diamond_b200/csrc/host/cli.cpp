@@ -312,7 +312,7 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 }
 
 [[noreturn]] void usage(const char* msg) {
-	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] | dmnd-b200 blastx --fast -q READS.fna -d DB -o OUT [-p N] [-c N] [-k N] [-e X] "
+	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] | dmnd-b200 blastx [--fast ...] -q READS.fna -d DB -o OUT [-p N] [-c N] [-k N] [-e X] "
 	                "[--comp-based-stats 0|1] [--masking 0|none|1|tantan] [--motif-masking 0|1] [-f 6] [--log]\n", msg);
 	exit(1);
 }
@@ -395,7 +395,6 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
-		if (translated && o.sensitivity != 0) usage("blastx is built for --fast only (pass --fast): the other modes treat translated frames of <= 85 letters differently in the seed stage");
 		if (translated && pairwise) usage("-f 0 is not implemented for blastx");
 		if (pairwise) o.want_transcript = 1;
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT

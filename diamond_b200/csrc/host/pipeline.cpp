@@ -538,7 +538,7 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 		const int8_t* subject = e.rseq(block_id);
 		q.r1.push(tc.arena, Target{ block_id, slen, 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0, q.qid }, false, 0 });
 		tc.hits.assign(tc.seed_hits.begin() + hb[tix], tc.seed_hits.begin() + hb[tix + 1]);
-		if (e.gapped_filter) {  // Extension::gapped_filter (align/gapped_filter.cpp:41-63): a target stays iff one of its hits passes
+		if (e.gapped_filter && !(e.contexts > 1 && q.qlen < 85)) {  // Extension::gapped_filter (align/gapped_filter.cpp:41-63): a target stays iff one of its hits passes; translated queries whose first frame is < GAPPED_FILTER_MIN_QLEN = 85 skip it (align/extend.cpp:197-206)
 			bool any = false;
 			for (const SeedHit& h : tc.hits) any |= h.gf != 0;
 			if (!any) continue;
@@ -862,7 +862,7 @@ extern "C" {
 // (align/extend.cpp:86).  The shape codes are the reference's (spaced-seed patterns are data of the method, like BLOSUM62).
 struct ModeTraits {
 	int n_shapes; const char* const* codes;
-	int min_identities; double ungapped_evalue, gapped_filter_evalue; int index_chunks; double seed_cut;
+	int min_identities; double ungapped_evalue, ungapped_evalue_short, gapped_filter_evalue; int index_chunks; double seed_cut;
 	bool motif_masking, band_slow; double ranking_letters;
 };
 static const ModeTraits* mode_traits(int sensitivity) {
@@ -881,14 +881,14 @@ static const ModeTraits* mode_traits(int sensitivity) {
 		"1010001010010011", "1010010001010101", "1010010100010011", "1010010101001001", "1010100000101011", "1010100011000101", "1011000010001011", "1100010000111001",
 		"1100010010001011", "1100100001001011", "1100100100100011", "1100110000001101", "1101000100010011", "1101000110000101", "1110000001010011", "1110100000010101" };
 	static const ModeTraits t[7] = {
-		//  shapes        minid ug_ev     gf_ev chunks seed_cut motif  slow   ranking letters
-		{ 1, fast,  11, 0.0,      0.0, 4, 0.9, true,  false, 2e9 },
-		{ 2, dflt,  11, 10000.0,  0.0, 4, 0.8, true,  false, 2e9 },
-		{ 8, mid,   11, 10000.0,  0.0, 4, 1.0, true,  false, 2e9 },
-		{ 16, sens, 11, 10000.0,  1.0, 4, 1.0, true,  false, 2e9 },
-		{ 16, sens, 11, 10000.0,  1.0, 4, 1.0, false, true,  2e9 },   // MORE_SENSITIVE: the shapes of SENSITIVE, no motif masking, BANDED_SLOW
-		{ 14, very,  9, 100000.0, 1.0, 1, 1.0, false, true,  800e6 },
-		{ 64, ultra, 9, 300000.0, 1.0, 1, 1.0, false, true,  800e6 },
+		//  shapes        minid ug_ev     ug_ev_s  gf_ev chunks seed_cut motif  slow   ranking letters
+		{ 1, fast,  11, 0.0,      0.0,     0.0, 4, 0.9, true,  false, 2e9 },
+		{ 2, dflt,  11, 10000.0,  10000.0, 0.0, 4, 0.8, true,  false, 2e9 },
+		{ 8, mid,   11, 10000.0,  10000.0, 0.0, 4, 1.0, true,  false, 2e9 },
+		{ 16, sens, 11, 10000.0,  10000.0, 1.0, 4, 1.0, true,  false, 2e9 },
+		{ 16, sens, 11, 10000.0,  10000.0, 1.0, 4, 1.0, false, true,  2e9 },   // MORE_SENSITIVE: the shapes of SENSITIVE, no motif masking, BANDED_SLOW
+		{ 14, very,  9, 100000.0, 30000.0, 1.0, 1, 1.0, false, true,  800e6 },
+		{ 64, ultra, 9, 300000.0, 30000.0, 1.0, 1, 1.0, false, true,  800e6 },
 	};
 	return sensitivity >= 0 && sensitivity <= 6 ? &t[sensitivity] : nullptr;
 }
@@ -945,6 +945,10 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 	if (p->ungapped_evalue > 0.0)
 		for (int b = 1; b <= 31; ++b)  // CutoffTable: rawscore(bitscore_norm(evalue, 2^(b-1))), stats/score_matrix.h:133-151
 			p->ungapped_cutoff[b] = sc.rawscore(-std::log(p->ungapped_evalue / 1e9 / (double)(1u << (b - 1))) / std::log(2.0));
+	p->query_contexts = o->query_contexts > 1 ? o->query_contexts : 1;
+	if (mt->ungapped_evalue_short > 0.0)  // cfg.cutoff_table_short (search/setup.cpp:375), read for translated frames of 61..85 letters
+		for (int b = 1; b <= 31; ++b)
+			p->ungapped_cutoff_short[b] = sc.rawscore(-std::log(mt->ungapped_evalue_short / 1e9 / (double)(1u << (b - 1))) / std::log(2.0));
 	p->gapped_filter_evalue = mt->gapped_filter_evalue;
 	p->gapped_filter_window = 200;
 	p->gapped_filter_diag_score = sc.rawscore(12.0);
@@ -1245,9 +1249,12 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	for (uint32_t i = 0; i < nr; ++i) ref_letters += r_limits[i + 1] - r_limits[i] - 1;
 	sc.db_letters = opts->db_letters ? (double)opts->db_letters : (double)ref_letters;
 	const uint32_t contexts = opts->query_contexts > 1 ? (uint32_t)opts->query_contexts : 1u;
-	if ((contexts != 1 && contexts != 6) || nq % contexts != 0 || (contexts > 1 && opts->sensitivity != 0)) {
-		dmnd_set_last_error("dmnd_blastp: query_contexts must be 1 or 6 with nq a multiple of it; translated queries are built for --fast only "
-		                    "(the window-filter modes switch to cutoff_table_short and a whole-query window for frames of <= 85 letters, search/stage2.h:41-63)");
+	if ((contexts != 1 && contexts != 6) || nq % contexts != 0) {
+		dmnd_set_last_error("dmnd_blastp: query_contexts must be 1 or 6 with nq a multiple of it");
+		return 1;
+	}
+	if ((uint32_t)std::max(dmnd_ctx_params(ctx)->query_contexts, 1) != contexts) {
+		dmnd_set_last_error("dmnd_blastp: the context was created for another query_contexts (dmnd_params_init copies it from the options)");
 		return 1;
 	}
 	const LanePlan plan = plan_lanes(nq, q_limits, contexts);

@@ -74,6 +74,12 @@ typedef struct dmnd_params {
 	float tantan_d[50];               /* d[49] = b2f0, d[i] = d[i+1] * growth (tantan.cpp:136-142) */
 	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
 	int32_t max_motif_len;            /* config.max_motif_len = 30 (basic/config.cpp:602) */
+	/* translated queries (blastx): the three places where the K layer asks align_mode.query_translated */
+	int32_t query_contexts;           /* 1, or 6: the query block holds six frames per query; a frame of <= 85 letters then takes the stage-2
+	                                     window over its whole length and ungapped_cutoff_short (search/stage2.h:41-63), and the gapped filter
+	                                     reads its cutoffs at the length of the query's FIRST frame and stops after its first scan when that is
+	                                     < 100 (align/gapped_filter.cpp:44-55) */
+	int32_t ungapped_cutoff_short[32]; /* CutoffTable(traits.ungapped_evalue_short), search/setup.cpp:345,375 */
 } dmnd_params;
 
 /* Search::Hit (search/hit.h:30-48) as a fixed 16-byte record. */
@@ -128,6 +134,8 @@ const char* dmnd_last_error(void);
 void dmnd_set_last_error(const char* msg);
 /* "cuda-sm100a" for the product library, "oracle-cpu" for the test stand-in under oracle/. */
 const char* dmnd_backend(void);
+/* The parameters a context was created with (dmnd_blastp checks that its options describe the same kind of query block). */
+const dmnd_params* dmnd_ctx_params(const dmnd_ctx* ctx);
 
 /* ---- K layer ---------------------------------------------------------------------------------------------- */
 int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out);
@@ -261,7 +269,8 @@ typedef struct dmnd_search_opts {
 	int32_t query_contexts;    /* 1 = blastp; 6 = blastx (align_mode.query_contexts, basic/basic.cpp:42-47): the query block holds the six
 	                              translated frames of every DNA query as consecutive sequences (context id = 6 * query + frame,
 	                              data/block/block.cpp:86-100), nq is a multiple of 6, dmnd_match.query is the CONTEXT that aligned and
-	                              q_begin / q_end are positions in that frame's translation.  0 is read as 1.  --fast only. */
+	                              q_begin / q_end are positions in that frame's translation.  0 is read as 1.  dmnd_params_init copies it
+	                              into dmnd_params.query_contexts: create the context from the same options. */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

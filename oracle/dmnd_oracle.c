@@ -39,6 +39,8 @@ static char g_err[512];
 const char* dmnd_last_error(void) { return g_err; }
 void dmnd_set_last_error(const char* m) { snprintf(g_err, sizeof g_err, "%s", m); }
 const char* dmnd_backend(void) { return "oracle-cpu"; }
+struct dmnd_ctx;
+const dmnd_params* dmnd_ctx_params(const dmnd_ctx* ctx);
 static int fail(const char* m) { snprintf(g_err, sizeof g_err, "%s", m); return 1; }
 
 struct dmnd_block {
@@ -56,6 +58,7 @@ struct dmnd_ctx {
 	uint32_t m_minlen[DMND_MAX_SHAPES + 1], m_suffix[DMND_MAX_SHAPES + 1];
 };
 struct dmnd_hits { dmnd_hit* h; size_t n; };
+const dmnd_params* dmnd_ctx_params(const dmnd_ctx* ctx) { return &ctx->p; }
 /* letters hard-masked by the calling thread's last dmnd_block_mask (lanes share one oracle context but run on their own threads) */
 static __thread uint64_t* t_mask_pos; static __thread size_t t_mask_n, t_mask_cap;
 
@@ -598,7 +601,6 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
 	const uint32_t parts_total = (uint32_t)1 << p->seedp_bits;
 	const uint32_t nchunks = (uint32_t)p->index_chunks < parts_total ? (uint32_t)p->index_chunks : parts_total;
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
-	const int window = p->ungapped_window;
 	if (query->soft) motif_seed_mask(p, query, sid, q_begin, q_end);
 	for (uint32_t chunk = 0; chunk < nchunks; ++chunk) {
 		const uint32_t bsel = chunk < prem ? chunk : prem;
@@ -637,17 +639,20 @@ int dmnd_search_shape_range(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* 
 					const int8_t* qp = query->letters + qe[a].loc;
 					const uint32_t qid = seq_of(query, qe[a].loc);
 					const int seed_offset = (int)((int64_t)qe[a].loc - query->limits[qid]);
-					/* search/stage2.h:92-103 */
+					/* search/stage2.h:92-103; ungapped_window(query_len) :58-63: a translated frame of <= 85 letters uses its whole length */
+					const int query_len = (int)(query->limits[qid + 1] - query->limits[qid] - 1);
+					const int short_frame = p->query_contexts > 1 && query_len <= 85;
+					const int window = short_frame ? query_len : p->ungapped_window;
 					const int8_t *cb, *ce;
 					clip(qp - window, window * 2, window, &cb, &ce);
 					const int window_left = (int)(qp - cb), window_clipped = (int)(ce - cb);
 					const int interval_mod = p->left_most_interval > 0 ? seed_offset % p->left_most_interval : window_left;
 					const int overhang = window_left - interval_mod > 0 ? window_left - interval_mod : 0;
-					/* search/stage2.h:41-57 ungapped_cutoff (blastp: no translated-query branch) */
-					const int query_len = (int)(query->limits[qid + 1] - query->limits[qid] - 1);
+					/* search/stage2.h:41-57 ungapped_cutoff */
 					int score_cutoff = 0;
 					if (p->ungapped_evalue != 0.0) {
 						if (query_len <= p->short_query_max_len) score_cutoff = p->short_query_ungapped_cutoff;
+						else if (short_frame) score_cutoff = p->ungapped_cutoff_short[32 - __builtin_clz((uint32_t)query_len)];
 						else score_cutoff = p->ungapped_cutoff[32 - __builtin_clz((uint32_t)query_len)];
 					}
 					/* search/hamming/kernel.h:61-74: the key's subject locations are visited in tiles of config.tile_size = 1024;
@@ -809,11 +814,16 @@ int dmnd_hits_gapped_filter(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_b
 		const int qlen = (int)(query->limits[hit->query + 1] - query->limits[hit->query] - 1), slen = (int)(ref->limits[t + 1] - ref->limits[t] - 1);
 		const int hi = hit->seed_offset, hj = (int)((int64_t)sloc - ref->limits[t]);
 		pass[k] = 0;
-		/* align/gapped_filter.cpp:44-63 (blastp: no translated-query shortcut) */
+		/* align/gapped_filter.cpp:44-63; `qlen` there is query_profile->length(), the length of the query's FIRST context, whatever
+		 * frame the hit lies in; translated queries shorter than MIN_STAGE2_QLEN = 100 pass after the first scan */
+		const int translated = p->query_contexts > 1;
+		const uint32_t q0 = translated ? hit->query / (uint32_t)p->query_contexts * (uint32_t)p->query_contexts : hit->query;
+		const int qlen0 = (int)(query->limits[q0 + 1] - query->limits[q0] - 1);
 		const int f1 = gf_one(p, qs, cb, qlen, ss, slen, hi, hj, 64, 100);
-		if (f1 > p->gapped_cutoff1[bit_len(qlen)][bit_len(slen)]) {
+		if (qlen0 > 0 && f1 > p->gapped_cutoff1[bit_len(qlen0)][bit_len(slen)]) {
+			if (translated && qlen0 < 100) { pass[k] = 1; continue; }
 			const int f2 = gf_one(p, qs, cb, qlen, ss, slen, hi, hj, 128, p->gapped_filter_window);
-			if (f2 > p->gapped_cutoff2[bit_len(qlen)][bit_len(slen)]) pass[k] = 1;
+			if (f2 > p->gapped_cutoff2[bit_len(qlen0)][bit_len(slen)]) pass[k] = 1;
 		}
 	}
 	return 0;

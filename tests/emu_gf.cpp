@@ -25,6 +25,7 @@ int main(int argc, char** argv) {
 	std::vector<int64_t> qlim = slurp<int64_t>(dir + "/q.i64"), rlim = slurp<int64_t>(dir + "/r.i64");
 	const uint32_t nq = (uint32_t)qlim.size() - 1, nr = (uint32_t)rlim.size() - 1;
 	dmnd_search_opts o; dmnd_search_opts_default(&o); o.sensitivity = 3;
+	if (argc > 3) o.query_contexts = atoi(argv[3]);  // 6: translated frames (cutoffs at the first frame's length, one scan for short queries)
 	dmnd_params hp; if (dmnd_params_init(&o, &hp)) { fprintf(stderr, "%s\n", dmnd_last_error()); return 2; }
 	dmnd_ctx* ctx; if (dmnd_create(0, &hp, &ctx)) return 2;
 	dmnd_block *qb, *rb;
@@ -49,6 +50,7 @@ int main(int argc, char** argv) {
 		memcpy(P.score, hp.score, 1024); P.gap_open = hp.gap_open; P.gap_extend = hp.gap_extend;
 		memcpy(P.gapped_cutoff1, hp.gapped_cutoff1, sizeof P.gapped_cutoff1); memcpy(P.gapped_cutoff2, hp.gapped_cutoff2, sizeof P.gapped_cutoff2);
 		P.gapped_filter_diag_score = hp.gapped_filter_diag_score; P.gapped_filter_window = hp.gapped_filter_window;
+		P.query_contexts = hp.query_contexts > 1 ? hp.query_contexts : 1;
 		std::vector<uint8_t> got(n + 8, 7);
 		emu::launch((unsigned)((n + 3) / 4), 128, [&] { gapped_filter_kernel(ql.data(), bias.data(), qlim.data(), rraw.data(), rlim.data(), nr, hits.data(), n, &P, got.data()); });
 		size_t bad = 0;

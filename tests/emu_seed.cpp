@@ -32,6 +32,7 @@ static void fill_dev_params(const dmnd_params& hp, DevParams& d) {
 	d.index_chunks = hp.index_chunks; d.left_most_interval = hp.left_most_interval; d.ungapped_window = hp.ungapped_window; d.gap_open = hp.gap_open; d.gap_extend = hp.gap_extend;
 	d.seed_cut = hp.seed_cut;
 	memcpy(d.ungapped_cutoff, hp.ungapped_cutoff, sizeof d.ungapped_cutoff); d.short_query_ungapped_cutoff = hp.short_query_ungapped_cutoff; d.short_query_max_len = hp.short_query_max_len;
+	d.query_contexts = hp.query_contexts > 1 ? hp.query_contexts : 1; memcpy(d.ungapped_cutoff_short, hp.ungapped_cutoff_short, sizeof d.ungapped_cutoff_short);
 	unsigned long long pw = 1; for (int i = 0; i < hp.shape_weight; ++i) pw *= (unsigned long long)hp.reduction_size;
 	int bits = 0; for (unsigned long long x = pw - 1; x > 0; x >>= 1) ++bits;
 	d.seed_bits = bits;
@@ -137,6 +138,7 @@ int main(int argc, char** argv) {
 	const std::string dir = argv[1];
 	dmnd_search_opts o; dmnd_search_opts_default(&o); o.sensitivity = atoi(argv[2]);
 	const int masking = atoi(argv[3]);
+	if (argc > 4) o.query_contexts = atoi(argv[4]);  // 6: the query block holds translated frames (blastx)
 	Blk q, r;
 	q.letters = slurp<int8_t>(dir + "/q.i8"); q.limits = slurp<int64_t>(dir + "/q.i64"); r.letters = slurp<int8_t>(dir + "/r.i8"); r.limits = slurp<int64_t>(dir + "/r.i64");
 	q.raw_len = q.letters.size(); r.raw_len = r.letters.size(); q.nseq = (uint32_t)q.limits.size() - 1; r.nseq = (uint32_t)r.limits.size() - 1;

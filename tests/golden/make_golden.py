@@ -17,6 +17,8 @@ For every workload W and parity-ladder level L:
          traceback (and the masked letters the reference prints) byte for byte
     X0 / XT = `blastx --fast` with default flags on the DNA reads of synth.BX_WORKLOADS (12 default fields / + the transcript
          fields, qlen, slen): six translated frames per read, DNA coordinates, frame-aware culling
+    X1 / X3 / X5 = blastx at the default sensitivity / --sensitive / --very-sensitive (whole-frame stage-2 window and the gapped filter's
+         exceptions for short translated queries; cutoff_table_short differs from cutoff_table only in X5)
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -76,11 +78,12 @@ def main_blastx():
             q, d = os.path.join(td, "q.fna"), os.path.join(td, "d.faa")
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
-            for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"])):
+            for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", [])):
                 out = os.path.join(HERE, f"{name}.{lvl}.tsv")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                r = subprocess.run([REF, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
+                mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
+                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)

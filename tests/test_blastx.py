@@ -69,11 +69,31 @@ def test_blastx_cli_transcript_fields(oracle_lib, tmp_path):
     assert open(o).read() == open(os.path.join(GOLDEN, "bx.xt.tsv")).read()
 
 
+@pytest.mark.parametrize("lvl,flags", [("x1", []), ("x3", ["--sensitive"]), ("x5", ["--very-sensitive"])])
+def test_blastx_modes_above_fast(oracle_lib, tmp_path, lvl, flags):
+    """No flag = the default sensitivity, as most users run `diamond blastx`: translated frames of <= 85 letters take the
+    stage-2 window over their whole length (search/stage2.h:58-63), --sensitive and above add the gapped filter with its
+    exceptions for short translated queries (align/extend.cpp:197-206, gapped_filter.cpp:44-55), --very-sensitive reads
+    cutoff_table_short for frames of 61..85 letters."""
+    q, d = _files(_bx(), tmp_path)
+    o = str(tmp_path / "o.tsv")
+    r = subprocess.run([CLI, "blastx"] + flags + ["-q", q, "-d", d, "-o", o, "-p", "8", "--log"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, f"bx.{lvl}.tsv")).read()
+    gold = json.load(open(os.path.join(GOLDEN, f"bx.{lvl}.counters.json")))
+    import re
+    got = {k: int(re.search(p, r.stderr).group(1)) for k, p in (("tentative_matches2", r"Hits \(filter stage 2\) = (\d+)"), ("tentative_matches3", r"Hits \(filter stage 3\) = (\d+)"),
+                                                                  ("targets", r"Target hits \(stage 0\) = (\d+)"), ("targets_extended", r"Target hits \(stage 3\) = (\d+)"))}
+    assert got == {k: gold[k] for k in got}
+    if lvl != "x1":
+        assert gold["targets_extended"] < gold["targets"]  # the gapped filter removed targets
+
+
 def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
     from diamond_b200 import api
     q, d = _files(_bx(), tmp_path)
-    r = subprocess.run([CLI, "blastx", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # default sensitivity
-    assert r.returncode != 0 and "--fast" in r.stderr
+    r = subprocess.run([CLI, "blastx", "--fast", "--min-orf", "5", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "unsupported option" in r.stderr
     r = subprocess.run([CLI, "blastx", "--fast", "-f", "0", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode != 0
     # the library: contexts other than 1 / 6, nq not a multiple, or a window-filter mode

@@ -16,3 +16,21 @@ def test_seed_stage_emulation_matches_oracle_default_sensitivity(oracle_lib, tmp
                     "-L" + os.path.join(ROOT, "oracle", "_build"), "-ldmnd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")], check=True)
     r = subprocess.run([exe, str(tmp_path), "1", "1"], capture_output=True, text=True)
     assert r.returncode == 0 and "shapes=2 " in r.stdout and "fails=0 " in r.stdout, r.stdout + r.stderr
+
+
+def test_seed_stage_emulation_translated_frames(oracle_lib, tmp_path):
+    """blastx at the default sensitivity: frames of <= 85 letters take the whole-frame window (search/stage2.h:58-63) in the
+    stage-2 kernel; the query block = six translated contexts of the first reads of the `bx` workload."""
+    from diamond_b200 import api, synth
+    f, kw = synth.BX_WORKLOADS["bx"]
+    w = f(**kw)
+    ql, qo = api.translate_reads(w["dna"][:150])
+    q_raw, q_lim = api.block_image(ql, qo)
+    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+    assert ((qo[1:] - qo[:-1]) <= 85).mean() > 0.5 and ((qo[1:] - qo[:-1]) > 85).any()
+    q_raw.tofile(str(tmp_path / "q.i8")); q_lim.tofile(str(tmp_path / "q.i64")); r_raw.tofile(str(tmp_path / "r.i8")); r_lim.tofile(str(tmp_path / "r.i64"))
+    exe = str(tmp_path / "emu_seed")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "emu_seed.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "oracle", "_build"), "-ldmnd_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")], check=True)
+    r = subprocess.run([exe, str(tmp_path), "1", "1", "6"], capture_output=True, text=True)
+    assert r.returncode == 0 and "shapes=2 " in r.stdout and "fails=0 " in r.stdout, r.stdout + r.stderr
