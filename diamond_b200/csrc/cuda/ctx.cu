@@ -466,6 +466,31 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
 	return 0;
 }
 
+int dmnd_debug_block_soft(dmnd_ctx* ctx, const dmnd_block* b, uint8_t* out, size_t raw_len) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len != b->raw_len) { set_error("dmnd_debug_block_soft: length mismatch"); return 1; }
+	std::vector<uint32_t> bits(raw_len / 32 + 1);
+	DMND_CUDA_CHECK(cudaMemcpyAsync(bits.data(), b->soft, bits.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
+	for (size_t p = 0; p < raw_len; ++p) out[p] = b->has_soft ? (uint8_t)((bits[p >> 5] >> (p & 31)) & 1u) : 0;
+	return 0;
+}
+
+int dmnd_debug_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, uint64_t* keys, uint32_t* locs, size_t cap, size_t* n) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (sid < 0 || sid >= ctx->params.n_shapes) { set_error("dmnd_debug_ref_index: bad shape id"); return 1; }
+	dmnd_cuda::RefIndex& ix = ctx->own_index;
+	if (dmnd_cuda::build_ref_index(ctx, ref, sid, ix)) return 1;
+	*n = (size_t)ix.nref;
+	if (cap < *n) { set_error("dmnd_debug_ref_index: buffer too small"); return 1; }
+	if (*n) {
+		DMND_CUDA_CHECK(cudaMemcpyAsync(keys, ix.keys.p, *n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		DMND_CUDA_CHECK(cudaMemcpyAsync(locs, ix.locs.p, *n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
+	}
+	return 0;
+}
+
 static int clear_range(dmnd_ctx* ctx, dmnd_block* b, size_t begin, size_t end) {
 	if (end <= begin) return 0;
 	const size_t threads = (end - (begin / 16) * 16 + 15) / 16;

@@ -182,6 +182,14 @@ void* dmnd_host_alloc(dmnd_ctx* ctx, size_t bytes);
 void dmnd_host_free(dmnd_ctx* ctx, void* p);
 /* Reads back the block's letters (query letters carry SEED_MASK bits set by dmnd_search_shape). */
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
+/* ---- diagnostics: intermediate state of the seed stage for tests and tools/seed_stage_diag.py (not on the path) ----
+ * dmnd_debug_block_soft: the block's soft-masking table after dmnd_block_mask(MOTIF) (Block::soft_mask, data/block/block.cpp:162-178),
+ *   one byte per letter of the block image, 1 = inside an abundant motif.
+ * dmnd_debug_ref_index: the reference side of the seed join for shape sid as the search reads it: *n (key, location) records in
+ *   index order -- keys ascending; inside a key the locations ascend in the modes with the stage-2 window filter (their order decides
+ *   which survivors share a window_ungapped_best call).  The key is an implementation detail (equal keys <=> equal seeds). */
+int dmnd_debug_block_soft(dmnd_ctx* ctx, const dmnd_block* b, uint8_t* out, size_t raw_len);
+int dmnd_debug_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, uint64_t* keys, uint32_t* locs, size_t cap, size_t* n);
 /* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
 int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
 int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end);

@@ -582,6 +582,17 @@ int dmnd_oracle_block_soft(const dmnd_block* b, uint8_t* out, size_t raw_len) {
 	if (b->soft) memcpy(out, b->soft, raw_len); else memset(out, 0, raw_len);
 	return 0;
 }
+int dmnd_debug_block_soft(dmnd_ctx* ctx, const dmnd_block* b, uint8_t* out, size_t raw_len) { (void)ctx; return dmnd_oracle_block_soft(b, out, raw_len); }
+/* every seed of the block for shape sid, sorted by (seed, location): what the reference's seed arrays hold (key = the packed seed) */
+int dmnd_debug_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, uint64_t* keys, uint32_t* locs, size_t cap, size_t* n) {
+	if (sid < 0 || sid >= ctx->p.n_shapes) return fail("dmnd_debug_ref_index: bad shape id");
+	entry* e;
+	*n = enum_seeds(&ctx->p, sid, ref, 0, (uint32_t)1 << ctx->p.seedp_bits, 0, ref->nseq, &e);
+	if (cap < *n) { free(e); return fail("dmnd_debug_ref_index: buffer too small"); }
+	for (size_t k = 0; k < *n; ++k) { keys[k] = e[k].seed; locs[k] = (uint32_t)e[k].loc; }
+	free(e);
+	return 0;
+}
 int dmnd_oracle_motif_seed_mask(dmnd_ctx* ctx, dmnd_block* b, int sid, uint32_t q_begin, uint32_t q_end) {
 	if (b->soft) motif_seed_mask(&ctx->p, b, sid, q_begin, q_end);
 	return 0;
