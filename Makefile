@@ -35,7 +35,7 @@ diamond_b200/libdmnd_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
 
 diamond_b200/bin/dmnd-b200: $(HOST)/cli.cpp diamond_b200/libdmnd_b200.so
 	@mkdir -p $(dir $@)
-	$(CXX) $(CXXFLAGS) $< -o $@ -Ldiamond_b200 -ldmnd_b200 -Wl,-rpath,'$$ORIGIN/..'
+	$(CXX) $(CXXFLAGS) $< -o $@ -Ldiamond_b200 -ldmnd_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
 
 $(OBJ)/oracle/dmnd_oracle.o: oracle/dmnd_oracle.c include/dmnd_b200.h $(HOST)/motif_table.h
 	@mkdir -p $(dir $@)
@@ -44,7 +44,7 @@ oracle/_build/libdmnd_oracle.so: $(HOST_OBJ) $(OBJ)/oracle/dmnd_oracle.o
 	@mkdir -p $(dir $@)
 	$(CXX) -shared -pthread -o $@ $^ -lm
 oracle/_build/dmnd-oracle-cli: $(HOST)/cli.cpp oracle/_build/libdmnd_oracle.so
-	$(CXX) $(CXXFLAGS) $< -o $@ -Loracle/_build -ldmnd_oracle -Wl,-rpath,'$$ORIGIN'
+	$(CXX) $(CXXFLAGS) $< -o $@ -Loracle/_build -ldmnd_oracle -lz -Wl,-rpath,'$$ORIGIN'
 
 ref:
 	$(MAKE) -C oracle/ref_build -j$$(nproc)

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <sstream>
+#include <zlib.h>
 #include <iterator>
 #include <utility>
 #include <stdexcept>
@@ -27,6 +29,21 @@ struct SeqBlock {
 	uint32_t size() const { return (uint32_t)ids.size(); }
 };
 
+// Whole input file as text; gzip-compressed files are inflated, anything else is read as it is (gzread is transparent), like the
+// reference's input layer (util/io/compressed_stream.cpp) for .gz queries and databases in FASTA format.
+std::string slurp_text(const std::string& path) {
+	gzFile g = gzopen(path.c_str(), "rb");
+	if (!g) throw std::runtime_error("Error opening file " + path);
+	std::string out;
+	char buf[1 << 16];
+	int n;
+	while ((n = gzread(g, buf, sizeof buf)) > 0) out.append(buf, (size_t)n);
+	const bool bad = n < 0;
+	gzclose(g);
+	if (bad) throw std::runtime_error("Error reading file " + path);
+	return out;
+}
+
 int8_t encode(char c) {  // basic/value.cpp:26-41 with amino_acid_traits (stats/stats.cpp:41): "UO-" -> mask
 	static int8_t table[256];
 	static bool init = false;
@@ -43,8 +60,7 @@ int8_t encode(char c) {  // basic/value.cpp:26-41 with amino_acid_traits (stats/
 }
 
 void read_fasta(const std::string& path, SeqBlock& b) {
-	std::ifstream f(path, std::ios::binary);
-	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::istringstream f(slurp_text(path));
 	std::string line;
 	bool open = false;
 	auto close_seq = [&] {
@@ -140,8 +156,7 @@ void push_translated(const std::vector<int8_t>& dna, SeqBlock& b) {
 }
 
 void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b) {
-	std::ifstream f(path, std::ios::binary);
-	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::istringstream f(slurp_text(path));
 	std::string line;
 	std::vector<int8_t> dna;
 	bool open = false;
@@ -152,9 +167,38 @@ void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b) {
 		dna.clear();
 		open = false;
 	};
+	bool fastq = false, first = true;
 	while (std::getline(f, line)) {
 		if (!line.empty() && line.back() == '\r') line.pop_back();
 		if (line.empty()) continue;
+		if (first) { fastq = line[0] == '@'; first = false; }
+		if (fastq) {  // FASTQ: @title, sequence line(s), +, quality line(s); the qualities are not used on this path
+			if (line[0] != '@') throw std::runtime_error("FASTQ format error: missing @ in " + path);
+			close_seq();
+			size_t e = 1;
+			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;
+			dq.ids.push_back(line.substr(1, e - 1));
+			dq.titles.push_back(line.substr(1));
+			open = true;
+			// FastqTokenizer::read_record (data/fasta/parser.h:238-270): sequence lines up to the '+' line, then quality lines until they
+			// are as long as the sequence
+			std::string l2;
+			size_t len = 0, qlen = 0;
+			for (;;) {
+				if (!std::getline(f, l2)) throw std::runtime_error("Malformed FASTQ record in " + path);
+				if (!l2.empty() && l2.back() == '\r') l2.pop_back();
+				if (l2.empty()) throw std::runtime_error("Malformed FASTQ record in " + path);
+				if (l2[0] == '+') break;
+				len += l2.size();
+				for (char c : l2) dna.push_back(encode_dna(c));
+			}
+			while (std::getline(f, l2)) {
+				if (!l2.empty() && l2.back() == '\r') l2.pop_back();
+				qlen += l2.size();
+				if (qlen >= len) break;
+			}
+			continue;
+		}
 		if (line[0] == '>') {
 			close_seq();
 			size_t e = 1;
@@ -349,10 +393,13 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false;
+		bool pairwise = false, paf = false;
 		for (int i = 2; i < argc; ++i) {
-			const std::string a = argv[i];
-			auto val = [&]() -> const char* { if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
+			std::string a = argv[i];
+			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
+			const char* attached = nullptr;
+			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdo", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
+			auto val = [&]() -> const char* { if (attached) return attached; if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
 			if (a == "-q" || a == "--query") qf = val();
 			else if (a == "-d" || a == "--db") df = val();
 			else if (a == "-o" || a == "--out") of = val();
@@ -379,7 +426,8 @@ int main(int argc, char** argv) {
 			else if (a == "-f" || a == "--outfmt") {  // -f 6 [field ...]  (output/blast_tab_format.cpp:41-118; the 12 default fields + the transcript fields)
 				const std::string fmt = val();
 				if (fmt == "0") { pairwise = true; continue; }
-				if (fmt != "6") usage("only -f 6 [fields] and -f 0 are implemented");
+				if (fmt == "paf" || fmt == "103") { paf = true; continue; }
+				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0 and -f paf are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -390,13 +438,18 @@ int main(int argc, char** argv) {
 					fields.push_back(f);
 				}
 			}
+			else if (a == "--query-parallel-limit") val();  // a threading knob of the reference's extension stage: no effect on the result (its own goldens agree)
+			else if (a == "--algo") {  // 0 / double-indexed is what this path implements; 1 / query-indexed is the reference's other join order over the same
+				const std::string v = val();  // seeds, defined to give the same alignments (src/test: diamond-test-blastp-query-indexed.out == ...-more-sensitive.out)
+				if (v != "0" && v != "1" && v != "double-indexed" && v != "query-indexed") usage("--algo must be 0, 1, double-indexed or query-indexed");
+			}
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (translated && pairwise) usage("-f 0 is not implemented for blastx");
-		if (pairwise) o.want_transcript = 1;
+		if (pairwise || paf) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
@@ -432,6 +485,39 @@ int main(int argc, char** argv) {
 		if (!out) throw std::runtime_error("Error opening file " + of);
 		char buf[32];
 		std::string line;
+		if (paf) {
+			// PAFFormat (output/paf_format.cpp:24-68): one line per match, 0-based closed coordinates; queries without a match are
+			// reported too when the extension stage saw them, i.e. when they had seed hits (Output::Flags::DEFAULT_REPORT_UNALIGNED, align/align.cpp:167-181), in query order
+			const uint32_t nsrc = translated ? (uint32_t)dq.ids.size() : q.size();
+			size_t i = 0, nu = 0, u = 0;
+			const uint32_t* unal = dmnd_result_unaligned(res, &nu);  // queries with seed hits and no alignment; queries without seed hits print nothing
+			for (uint32_t s = 0; s < nsrc; ++s) {
+				const std::string& qid = translated ? dq.ids[s] : q.ids[s];
+				const size_t i0 = i;
+				while (i < n && (translated ? m[i].query / 6 : m[i].query) == s) ++i;
+				line.clear();
+				while (u < nu && (translated ? unal[u] / 6 : unal[u]) < s) ++u;
+				if (i == i0 && u < nu && (translated ? unal[u] / 6 : unal[u]) == s) line = qid + "\t4\t*\t0\t255\t*\t*\t0\t0\t*\t*\n";
+				for (size_t k = i0; k < i; ++k) {
+					const dmnd_match& x = m[k];
+					int64_t qlen = q.limits[x.query + 1] - q.limits[x.query] - 1, qb = x.q_begin, qe = x.q_end;
+					char strand = '+';
+					if (translated) {  // query_source_range: TranslatedPosition::absolute_interval (basic/translated_position.h:121-127)
+						const int fr = (int)(x.query % 6), off = fr % 3;
+						qlen = dq.len[s];
+						const int64_t b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + off;
+						if (fr < 3) { qb = b_in; qe = e_in; } else { qb = qlen - e_in; qe = qlen - b_in; strand = '-'; }
+					}
+					line += qid + "\t" + std::to_string(qlen) + "\t" + std::to_string(qb) + "\t" + std::to_string(qe - 1) + "\t" + strand + "\t" + r.ids[x.target] + "\t"
+						+ std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1) + "\t" + std::to_string(x.t_begin) + "\t" + std::to_string(x.t_end - 1) + "\t"
+						+ std::to_string(x.identities) + "\t" + std::to_string(x.length) + "\t255\tAS:i:" + std::to_string((uint32_t)x.bit_score) + "\tZR:i:" + std::to_string(x.score) + "\tZE:f:";
+					if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; }
+					line += '\n';
+				}
+				fwrite(line.data(), 1, line.size(), out);
+			}
+			n = 0;
+		}
 		if (pairwise) {
 			// PairwiseFormat (output/blast_pairwise_format.cpp:24-101): header once, an intro per aligned query, one record per match in
 			// 60-column blocks; numbers go through TextBuffer::print(i, width), which keeps only `width` characters (util/text_buffer.h:248-254)

@@ -284,7 +284,8 @@ struct Env {
 	const int64_t *q_limits, *r_limits;
 	uint32_t nq, nr;
 	int64_t ref_letters;
-	int max_target_seqs;
+	int max_target_seqs;  // cfg.max_target_seqs: -k, or "all" (INT_MAX) for -k 0 (output/output_format.cpp:236-245)
+	int outer_limit;      // config.max_target_seqs_ as given (0 for -k 0): the bound of extend()'s outer loop (align/extend.cpp:336)
 	double max_evalue;
 	bool hauser, want_transcript;
 	bool fuse;  // see Driver::start
@@ -326,11 +327,12 @@ struct ThreadCtx {
 	std::vector<Chain> chains;
 	std::vector<int8_t> cbs;
 	std::vector<Target> tmp_targets;
+	std::vector<uint32_t> unaligned;  // queries of this thread that had seed hits but no alignment
 	uint64_t cells1 = 0, cells2 = 0, n_targets = 0, n_matches = 0, n_aligned = 0, n_extended = 0;
 	uint64_t fused_r1 = 0, fused_r2 = 0, fused_r1_wave = 0;  // fused queries: round-1 problems traced, round-2 problems answered from them
 	void reset() {
 		arena.reset(); seed_hits.clear(); hit_begin.clear(); target_block_ids.clear(); target_scores.clear();
-		p1.clear(); p2.clear(); trbuf.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = n_extended = 0; fused_r1 = fused_r2 = fused_r1_wave = 0;
+		p1.clear(); p2.clear(); trbuf.clear(); unaligned.clear(); cells1 = cells2 = n_targets = n_matches = n_aligned = n_extended = 0; fused_r1 = fused_r2 = fused_r1_wave = 0;
 	}
 };
 
@@ -750,7 +752,7 @@ void Driver::consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* 
 void Driver::finish_outer(QueryState& q) {
 	// outer do-while of extend(), align/extend.cpp:336, then the final culling (:341)
 	const Env& e = env;
-	if ((int64_t)q.matches.n < e.max_target_seqs && q.i0 < (int64_t)q.n_targets && q.new_hits_ev) { q.phase = PH_ROUND1_PRODUCE; return; }
+	if ((int64_t)q.matches.n < e.outer_limit && q.i0 < (int64_t)q.n_targets && q.new_hits_ev) { q.phase = PH_ROUND1_PRODUCE; return; }
 	std::sort(q.matches.begin(), q.matches.end(), Match::cmp_evalue);
 	q.matches.n = (uint32_t)(output_range(q.matches.begin(), q.matches.end(), e.max_target_seqs) - q.matches.begin());
 	q.phase = PH_DONE;
@@ -834,6 +836,7 @@ struct dmnd_result {
 	RawBuf<uint8_t> transcripts;
 	dmnd_run_stats stats;
 	std::vector<uint64_t> masked[2];  // hard-masked letters of the query / reference block (dmnd_blastp with masking)
+	std::vector<uint32_t> unaligned;  // queries (first context) with seed hits and no alignment, ascending
 };
 // dmnd_result_free parks up to two results here; the next call reuses their (already touched) memory.
 struct ResultPool {
@@ -995,6 +998,7 @@ struct LaneOut {
 	RawBuf<dmnd_match>* matches = nullptr;  // the result's buffers (one lane) or the lane workspace's (several)
 	RawBuf<uint8_t>* transcripts = nullptr;
 	dmnd_run_stats stats;
+	std::vector<uint32_t> unaligned;
 	std::string error;
 	int rc = 0;
 };
@@ -1141,6 +1145,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
 			tc.n_matches += w.qs[k].matches.n;
 			if (w.qs[k].matches.n) ++tc.n_aligned;
+			else tc.unaligned.push_back(w.qs[k].qid);
 		}
 	});
 	for (int t = 0; t < T; ++t) {
@@ -1150,6 +1155,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		d.stats.cells_round1 += w.tc[(size_t)t].cells1; d.stats.cells_round2 += w.tc[(size_t)t].cells2;
 		d.stats.dp_problems_round2 += w.tc[(size_t)t].fused_r2; d.stats.dp_problems_fused += w.tc[(size_t)t].fused_r1;
 		d.stats.targets_extended += w.tc[(size_t)t].n_extended;
+		lo.unaligned.insert(lo.unaligned.end(), w.tc[(size_t)t].unaligned.begin(), w.tc[(size_t)t].unaligned.end());  // threads own ascending query ranges
 	}
 	lo.matches->resize(moff[(size_t)T]);
 	lo.transcripts->resize(troff[(size_t)T]);
@@ -1242,7 +1248,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	struct PoolReturn { void operator()(dmnd_result* r) const { result_pool().give(r); } };
 	std::unique_ptr<dmnd_result, PoolReturn> res(result_pool().take());
 	res->matches.resize(0); res->transcripts.resize(0);
-	res->masked[0].clear(); res->masked[1].clear();
+	res->masked[0].clear(); res->masked[1].clear(); res->unaligned.clear();
 	std::memset(&res->stats, 0, sizeof res->stats);
 	Scoring sc;
 	int64_t ref_letters = 0;
@@ -1264,7 +1270,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	Env e;
 	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
 	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
-	e.max_target_seqs = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
+	e.max_target_seqs = opts->max_target_seqs == 0 ? INT_MAX : opts->max_target_seqs; e.outer_limit = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
@@ -1332,6 +1338,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		});
 		for (int l = 0; l < nlanes; ++l) add_stats(res->stats, lo[(size_t)l].stats);
 	}
+	for (int l = 0; l < nlanes; ++l) res->unaligned.insert(res->unaligned.end(), lo[(size_t)l].unaligned.begin(), lo[(size_t)l].unaligned.end());
 	if (mask_algo) {  // lanes cover ascending query ranges and report ascending offsets: concatenation is sorted
 		for (int l = 0; l < nlanes; ++l) res->masked[0].insert(res->masked[0].end(), sh.lanes[(size_t)l]->mask_pos.begin(), sh.lanes[(size_t)l]->mask_pos.end());
 		res->masked[1] = sh.r_mask_pos;
@@ -1373,6 +1380,7 @@ const uint64_t* dmnd_result_masked_positions(const dmnd_result* r, int side, siz
 	*n = v.size();
 	return v.data();
 }
+const uint32_t* dmnd_result_unaligned(const dmnd_result* r, size_t* n) { *n = r->unaligned.size(); return r->unaligned.data(); }
 void dmnd_result_free(dmnd_result* r) { if (r) result_pool().give(r); }
 
 }  // extern "C"

@@ -268,7 +268,7 @@ typedef struct dmnd_search_opts {
 	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
 	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
 	int32_t comp_based_stats;  /* 0 or 1 (Hauser) */
-	int32_t max_target_seqs;   /* -k, default 25 */
+	int32_t max_target_seqs;   /* -k, default 25; 0 = report all targets (as the reference reads -k 0) */
 	double max_evalue;         /* -e, default 0.001 */
 	uint64_t db_letters;       /* 0 = letters of the reference block */
 	int32_t want_transcript;   /* 1 = keep edit transcripts (fmt 0) */
@@ -332,6 +332,10 @@ const dmnd_run_stats* dmnd_result_stats(const dmnd_result* r);
  * qseq_gapped, ...: output/blast_tab_format.cpp:365-398, align/output.cpp:80-90); a caller that formats those patches its copy
  * with these.  Empty for dmnd_blastp_resident (the caller masked the blocks itself). */
 const uint64_t* dmnd_result_masked_positions(const dmnd_result* r, int side, size_t* n);
+/* Queries (block id of their first context) that had seed hits but ended without an alignment, ascending: the queries the reference's
+ * output stage still visits (align/align.cpp:167-181, align/output.cpp:32-54) and formats with DEFAULT_REPORT_UNALIGNED (PAF, SAM) or
+ * --unal 1 report as unaligned.  Queries without any seed hit are not listed, as the reference does not report them either. */
+const uint32_t* dmnd_result_unaligned(const dmnd_result* r, size_t* n);
 void dmnd_result_free(dmnd_result* r);
 
 #ifdef __cplusplus

@@ -1,0 +1,75 @@
+"""The reference's OWN regression tests (CMakeLists.txt:534-583, src/test/test.cmake: `diamond ARGS -o NAME.out` must equal the
+committed src/test/NAME.out byte for byte) replayed through this repository's CLI over the oracle-linked host pipeline: every
+case whose options the path implements.  These are the reference's known-answer vectors for the path: real proteins
+(data.faa: 300 sequences; nr_10k.faa), its nanopore reads for blastx (FASTQ and gzipped FASTA), all sensitivity modes from the
+default to --ultra-sensitive, -k / -e / --comp-based-stats 0, the pairwise format.  The command lines are taken from the
+reference's CMakeLists.txt at run time, not retyped here.  CPU only; skipped where /root/reference is absent (the GPU box)."""
+import os, re, shlex, subprocess
+import pytest
+from conftest import REF_BIN, ROOT, workload_blocks
+
+REF = "/root/reference"
+TD = os.path.join(REF, "src", "test")
+CLI = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+# the cases this path covers; the others need options outside it (taxonomy, BLAST databases, DAA, --top, --max-hsps 0, matrix
+# adjustment (--comp-based-stats 2-4), other matrices, PAF, -b block splitting, --global-ranking, linclust / realign / view)
+CASES = ["blastp", "blastp-mid-sens", "blastp-f0", "blastx-nanopore", "blastx-nanopore-fna",
+         "diamond-test-blastp-default", "diamond-test-blastp-multithreaded", "diamond-test-blastp-more-sensitive",
+         "diamond-test-blastp-very-sensitive", "diamond-test-blastp-ultra-sensitive", "diamond-test-blastp-target-parallel",
+         "diamond-test-blastp-query-indexed", "diamond-test-blastp-comp-based-stats-0", "diamond-test-blastp-target-seqs",
+         "diamond-test-blastp-evalue", "diamond-test-blastp-pairwise-format", "diamond-test-blastp-paf-format"]
+
+
+def ctest_commands():
+    """{test name: argument list} from the reference's CMakeLists.txt (add_test(... -DNAME=x "-DARGS=...") and add_diamond_test(x "..."))."""
+    txt = open(os.path.join(REF, "CMakeLists.txt")).read()
+    cmds = {}
+    for m in re.finditer(r'-DNAME=(\S+) "-DARGS=([^"]*)"', txt):
+        cmds[m.group(1)] = m.group(2)
+    for m in re.finditer(r'add_diamond_test\((\S+) "([^"]*)"\)', txt):
+        cmds[m.group(1)] = m.group(2)
+    return {k: shlex.split(v.replace("${TD}", TD)) for k, v in cmds.items()}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "CMakeLists.txt")), reason="needs /root/reference (its test inputs and expected outputs)")
+@pytest.mark.parametrize("name", CASES)
+def test_reference_ctest_case(oracle_lib, name, tmp_path):
+    args = ctest_commands()[name]
+    out = str(tmp_path / (name + ".out"))
+    r = subprocess.run([CLI] + args + ["-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, " ".join(args) + "\n" + r.stderr
+    want = open(os.path.join(TD, name + ".out"), "rb").read()
+    assert open(out, "rb").read() == want, " ".join(args)
+    assert len(want) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")
+@pytest.mark.parametrize("mode", ["blastp", "blastx"])
+def test_paf_reports_unaligned_queries_like_the_reference(oracle_lib, mode, tmp_path):
+    """PAF (Output::Flags::DEFAULT_REPORT_UNALIGNED): a query that had seed hits but no alignment gets the "4 *" record, a query
+    without seed hits gets nothing (align/align.cpp:167-181, align/output.cpp:32-54) -- dmnd_result_unaligned.  A strict e-value
+    makes many such queries; blastx adds the '-' strand and nucleotide coordinates."""
+    from diamond_b200 import synth
+    d = str(tmp_path / "d.faa")
+    if mode == "blastp":
+        w, *_ = workload_blocks("edge")
+        q = str(tmp_path / "q.faa")
+        synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+        flags = ["--fast", "-e", "1e-40"]
+    else:
+        f, kw = synth.BX_WORKLOADS["bx"]
+        w = f(**kw)
+        q = str(tmp_path / "q.fna")
+        synth.write_dna_fasta(q, w["dna"])
+        flags = ["-e", "1e-30"]
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    ours, ref = str(tmp_path / "o.paf"), str(tmp_path / "r.paf")
+    subprocess.run([REF_BIN, mode] + flags + ["-q", q, "-d", d, "-f", "paf", "-o", ref, "-p", "8", "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, mode] + flags + ["-q", q, "-d", d, "-f", "paf", "-o", ours, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(ours).read()
+    assert got == open(ref).read()
+    lines = got.splitlines()
+    assert sum(l.split("\t")[1:3] == ["4", "*"] for l in lines) > 50 and sum(l.split("\t")[4] == "+" for l in lines) > 20
+    if mode == "blastx":
+        assert sum(l.split("\t")[4] == "-" for l in lines) > 20
