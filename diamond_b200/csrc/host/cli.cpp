@@ -393,7 +393,7 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false;
+		bool pairwise = false, paf = false, k_set = false, top_set = false;
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
@@ -411,8 +411,9 @@ int main(int argc, char** argv) {
 			else if (a == "--ultra-sensitive") o.sensitivity = 6;
 			else if (a == "-p" || a == "--threads") o.threads = atoi(val());
 			else if (a == "-c" || a == "--index-chunks") o.index_chunks = atoi(val());
-			else if (a == "-k" || a == "--max-target-seqs") o.max_target_seqs = atoi(val());
+			else if (a == "-k" || a == "--max-target-seqs") { o.max_target_seqs = atoi(val()); k_set = true; }
 			else if (a == "-e" || a == "--evalue") o.max_evalue = atof(val());
+			else if (a == "--top") { o.top_percent = atof(val()); top_set = true; if (o.top_percent < 0.0 || o.top_percent > 100.0) usage("Allowed value range for --top is between 0.0 and 100.0"); }
 			else if (a == "--comp-based-stats") o.comp_based_stats = atoi(val());
 			else if (a == "--masking") {  // masking/masking.cpp:42-48: 0/none, 1/tantan (seg is not part of this build)
 				const std::string v = val();
@@ -448,6 +449,7 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (translated && pairwise) usage("-f 0 is not implemented for blastx");
 		if (pairwise || paf) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT

@@ -192,6 +192,7 @@ inline bool hsp_less(const HspLite& a, const HspLite& b) {  // basic/match.h:199
 struct Target {  // align/target.h:83-144 after inner_culling (max_hsps == 1): only the best HSP is kept
 	uint32_t block_id; int tlen; int filter_score; double filter_evalue; HspLite hsp; bool has_hsp;
 	uint32_t hsp_prob;  // fused queries: index (within the query's problem slice) of the problem that produced `hsp`
+	static bool comp_score(const Target& t, const Target& u) { return t.filter_score > u.filter_score || (t.filter_score == u.filter_score && t.block_id < u.block_id); }  // align/target.h:128-130
 	static bool comp_evalue(const Target& t, const Target& u) {
 		return t.filter_evalue < u.filter_evalue || (t.filter_evalue == u.filter_evalue && (t.filter_score > u.filter_score || (t.filter_score == u.filter_score && t.block_id < u.block_id)));
 	}
@@ -199,21 +200,11 @@ struct Target {  // align/target.h:83-144 after inner_culling (max_hsps == 1): o
 struct Match {  // align/extend.h:36-70
 	uint32_t target_block_id; int tlen; int filter_score; double filter_evalue; bool has_hsp; HspLite h; dmnd_dp_result r;
 	uint64_t tr_off; uint32_t tr_len;  // into the owner thread's transcript buffer
+	static bool cmp_score(const Match& m, const Match& n) { return m.filter_score > n.filter_score || (m.filter_score == n.filter_score && m.target_block_id < n.target_block_id); }  // align/extend.h:50-52
 	static bool cmp_evalue(const Match& m, const Match& n) {
 		return m.filter_evalue < n.filter_evalue || (m.filter_evalue == n.filter_evalue && (m.filter_score > n.filter_score || (m.filter_score == n.filter_score && m.target_block_id < n.target_block_id)));
 	}
 };
-
-template<typename It>
-It output_range(It begin, It end, int64_t max_target_seqs) {  // align/culling.cpp:90-109 (no --top)
-	if (end <= begin) return begin;
-	It i = begin;
-	if (i->filter_evalue == DBL_MAX) return begin;
-	i += std::min<ptrdiff_t>((ptrdiff_t)max_target_seqs, end - begin);
-	while (--i > begin && i->filter_evalue == DBL_MAX);
-	++i;
-	return i;
-}
 
 int band_for(int len, bool slow) {  // Extension::band, align/gapped_score.cpp:41-72
 	if (!slow) {  // Mode::BANDED_FAST
@@ -285,6 +276,7 @@ struct Env {
 	uint32_t nq, nr;
 	int64_t ref_letters;
 	int max_target_seqs;  // cfg.max_target_seqs: -k, or "all" (INT_MAX) for -k 0 (output/output_format.cpp:236-245)
+	double top = -1.0;    // --top (config.toppercent): >= 0 = report the targets within this percentage of the best bit score; -1 = not given
 	int outer_limit;      // config.max_target_seqs_ as given (0 for -k 0): the bound of extend()'s outer loop (align/extend.cpp:336)
 	double max_evalue;
 	bool hauser, want_transcript;
@@ -292,6 +284,22 @@ struct Env {
 	int qlen(uint32_t q) const { return (int)(q_limits[q + 1] - q_limits[q] - 1); }
 	int tlen(uint32_t t) const { return (int)(r_limits[t + 1] - r_limits[t] - 1); }
 };
+
+template<typename It>
+It output_range(It begin, It end, const Env& e) {  // align/culling.cpp:90-109
+	if (end <= begin) return begin;
+	It i = begin;
+	if (i->filter_evalue == DBL_MAX) return begin;
+	if (e.top >= 0.0) {  // --top: everything within `top` percent of the best bit score
+		const double cutoff = std::max((1.0 - e.top / 100.0) * e.sc->bitscore(begin->filter_score), 1.0);
+		while (i < end && e.sc->bitscore(i->filter_score) >= cutoff) ++i;
+		return i;
+	}
+	i += std::min<ptrdiff_t>((ptrdiff_t)e.max_target_seqs, end - begin);
+	while (--i > begin && i->filter_evalue == DBL_MAX);
+	++i;
+	return i;
+}
 
 enum Phase : uint8_t { PH_ROUND1_PRODUCE, PH_ROUND1_CONSUME, PH_ROUND2_PRODUCE, PH_ROUND2_CONSUME, PH_DONE };
 
@@ -504,12 +512,12 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	if (target_count == 0) { q.phase = PH_DONE; return; }
 	const int64_t block_mult = std::max<int64_t>((int64_t)std::round((double)e.ref_letters / e.ranking_letters), 1);
 	const int64_t mm = ((int64_t)e.max_target_seqs + 31) / 32 * 32;  // make_multiple(max_target_seqs, 32)
-	q.chunk_size = std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;
+	q.chunk_size = e.top >= 0.0 ? 128 * block_mult : std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;  // ranking_chunk_size, align/extend.cpp:79-92
 	TargetScore* ts = tc.target_scores.data() + q.ts_off;
 	if (q.chunk_size < target_count) std::sort(ts, ts + target_count);
 	q.i0 = 0;
 	q.i1 = std::min<int64_t>(q.chunk_size, target_count);
-	if ((q.i1 - q.i0) < e.max_target_seqs)
+	if (e.top < 0.0 && (q.i1 - q.i0) < e.max_target_seqs)
 		while (q.i1 < target_count && e.sc->evalue(ts[q.i1].score, (unsigned)q.qlen, 50) <= e.max_evalue)
 			q.i1 += std::min<int64_t>(16, target_count - q.i1);
 	// Fused rounds: round 2 re-evaluates, with traceback, exactly the (query, target, band) problem of round 1 that gave
@@ -604,9 +612,9 @@ void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
 	q.phase = PH_ROUND1_CONSUME;
 }
 
-static void culling_targets(List<Target>& targets, bool sort_only, int max_target_seqs) {  // align/culling.cpp:187-191
-	std::sort(targets.begin(), targets.end(), Target::comp_evalue);
-	if (!sort_only) targets.n = (uint32_t)(output_range(targets.begin(), targets.end(), max_target_seqs) - targets.begin());
+static void culling_targets(List<Target>& targets, bool sort_only, const Env& e) {  // align/culling.cpp:92-94,187-191
+	if (e.top >= 0.0) std::sort(targets.begin(), targets.end(), Target::comp_score); else std::sort(targets.begin(), targets.end(), Target::comp_evalue);
+	if (!sort_only) targets.n = (uint32_t)(output_range(targets.begin(), targets.end(), e) - targets.begin());
 }
 
 void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res) {
@@ -642,13 +650,15 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		// append_hits, align/culling.cpp:111-141 (with_culling = first_round_culling = true)
 		if (v.empty()) new_hits = false;
 		else {
-			new_hits = (int64_t)q.aligned_targets.n < e.max_target_seqs;
+			new_hits = e.top < 0.0 && (int64_t)q.aligned_targets.n < e.max_target_seqs;
 			bool append = new_hits;
-			culling_targets(q.aligned_targets, append, e.max_target_seqs);
+			culling_targets(q.aligned_targets, append, e);
 			double min_evalue = DBL_MAX;
-			for (const Target& t : v) min_evalue = std::min(min_evalue, t.filter_evalue);
-			Target* range_end = output_range(q.aligned_targets.begin(), q.aligned_targets.end(), e.max_target_seqs);
-			if (q.aligned_targets.n == 0 || min_evalue <= (range_end - 1)->filter_evalue) { append = true; new_hits = true; }
+			int max_score = 0;
+			for (const Target& t : v) { min_evalue = std::min(min_evalue, t.filter_evalue); max_score = std::max(max_score, t.filter_score); }
+			Target* range_end = output_range(q.aligned_targets.begin(), q.aligned_targets.end(), e);
+			if (q.aligned_targets.n == 0 || (e.top < 0.0 && min_evalue <= (range_end - 1)->filter_evalue)
+			    || (e.top >= 0.0 && max_score >= (int)((1.0 - e.top / 100.0) * (range_end - 1)->filter_score))) { append = true; new_hits = true; }  // top_cutoff_score<int>, basic/config.h:452-455
 			if (append) for (const Target& t : v) q.aligned_targets.push(tc.arena, t);
 		}
 	}
@@ -667,7 +677,7 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		terminate = !new_hits && (q.previous_tail_score == 0 || double(tscore) / (double)q.previous_tail_score <= 0.95 || e.sc->bitscore(tscore) < 25.0);
 	}
 	if (q.i0 < n_targets && !terminate) { q.phase = PH_ROUND1_PRODUCE; return; }
-	culling_targets(q.aligned_targets, false, e.max_target_seqs);  // extend.cpp:331
+	culling_targets(q.aligned_targets, false, e);  // extend.cpp:331
 	if (q.aligned_targets.n == 0) finish_outer(q);  // round 2 over nothing returns no matches
 	else q.phase = PH_ROUND2_PRODUCE;
 }
@@ -714,8 +724,8 @@ void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dm
 void Driver::finish_round2(QueryState& q, ThreadCtx& tc) {
 	const Env& e = env;
 	for (Match& m : q.r2) if (m.has_hsp) { m.filter_evalue = m.h.evalue; m.filter_score = m.h.score; }  // Match::inner_culling
-	std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
-	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e.max_target_seqs) - q.r2.begin());
+	if (e.top >= 0.0) std::sort(q.r2.begin(), q.r2.end(), Match::cmp_score); else std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
+	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e) - q.r2.begin());
 	for (const Match& m : q.r2) q.matches.push(tc.arena, m);
 	q.r2.clear();
 	q.aligned_targets.clear();
@@ -752,9 +762,9 @@ void Driver::consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* 
 void Driver::finish_outer(QueryState& q) {
 	// outer do-while of extend(), align/extend.cpp:336, then the final culling (:341)
 	const Env& e = env;
-	if ((int64_t)q.matches.n < e.outer_limit && q.i0 < (int64_t)q.n_targets && q.new_hits_ev) { q.phase = PH_ROUND1_PRODUCE; return; }
-	std::sort(q.matches.begin(), q.matches.end(), Match::cmp_evalue);
-	q.matches.n = (uint32_t)(output_range(q.matches.begin(), q.matches.end(), e.max_target_seqs) - q.matches.begin());
+	if (e.top < 0.0 && (int64_t)q.matches.n < e.outer_limit && q.i0 < (int64_t)q.n_targets && q.new_hits_ev) { q.phase = PH_ROUND1_PRODUCE; return; }
+	if (e.top >= 0.0) std::sort(q.matches.begin(), q.matches.end(), Match::cmp_score); else std::sort(q.matches.begin(), q.matches.end(), Match::cmp_evalue);
+	q.matches.n = (uint32_t)(output_range(q.matches.begin(), q.matches.end(), e) - q.matches.begin());
 	q.phase = PH_DONE;
 }
 
@@ -901,7 +911,7 @@ void dmnd_search_opts_default(dmnd_search_opts* o) {
 	std::memset(o, 0, sizeof *o);
 	o->sensitivity = 0; o->threads = 8; o->index_chunks = 0; o->comp_based_stats = 1; o->max_target_seqs = 25;
 	o->max_evalue = 0.001; o->db_letters = 0; o->want_transcript = 0;
-	o->query_contexts = 1;
+	o->query_contexts = 1; o->top_percent = -1.0;
 	o->masking = 1; o->motif_masking = 1;  // the reference's defaults for blastp --fast (run/config.cpp:126-135, search/setup.cpp:43)
 }
 
@@ -1271,6 +1281,9 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.sc = &sc; e.q_letters = q_letters; e.r_letters = r_letters;
 	e.q_limits = q_limits; e.r_limits = r_limits; e.nq = nq; e.nr = nr; e.ref_letters = ref_letters;
 	e.max_target_seqs = opts->max_target_seqs == 0 ? INT_MAX : opts->max_target_seqs; e.outer_limit = opts->max_target_seqs; e.max_evalue = opts->max_evalue;
+	if (opts->top_percent > 100.0) { dmnd_set_last_error("dmnd_blastp: top_percent must lie in [0, 100] (negative = not given)"); return 1; }
+	if (opts->top_percent >= 0.0 && opts->top_percent < 100.0) e.top = opts->top_percent;
+	else if (opts->top_percent == 100.0) e.max_target_seqs = INT_MAX;  // output/output_format.cpp:233-240: --top 100 = every target, ranked by e-value
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;

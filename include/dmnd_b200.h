@@ -279,6 +279,8 @@ typedef struct dmnd_search_opts {
 	                              data/block/block.cpp:86-100), nq is a multiple of 6, dmnd_match.query is the CONTEXT that aligned and
 	                              q_begin / q_end are positions in that frame's translation.  0 is read as 1.  dmnd_params_init copies it
 	                              into dmnd_params.query_contexts: create the context from the same options. */
+	double top_percent;        /* --top: report the targets whose bit score lies within this percentage of the query's best one instead of the
+	                              best max_target_seqs (config.toppercent; align/culling.cpp:90-141, align/extend.cpp:79-92,336); negative = not given */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

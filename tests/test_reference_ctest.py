@@ -11,13 +11,13 @@ from conftest import REF_BIN, ROOT, workload_blocks
 REF = "/root/reference"
 TD = os.path.join(REF, "src", "test")
 CLI = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
-# the cases this path covers; the others need options outside it (taxonomy, BLAST databases, DAA, --top, --max-hsps 0, matrix
-# adjustment (--comp-based-stats 2-4), other matrices, PAF, -b block splitting, --global-ranking, linclust / realign / view)
+# the cases this path covers; the others need options outside it (taxonomy, BLAST databases, DAA, --max-hsps 0, matrix
+# adjustment (--comp-based-stats 2-4), other matrices, -b block splitting, --global-ranking, linclust / realign / view)
 CASES = ["blastp", "blastp-mid-sens", "blastp-f0", "blastx-nanopore", "blastx-nanopore-fna",
          "diamond-test-blastp-default", "diamond-test-blastp-multithreaded", "diamond-test-blastp-more-sensitive",
          "diamond-test-blastp-very-sensitive", "diamond-test-blastp-ultra-sensitive", "diamond-test-blastp-target-parallel",
          "diamond-test-blastp-query-indexed", "diamond-test-blastp-comp-based-stats-0", "diamond-test-blastp-target-seqs",
-         "diamond-test-blastp-evalue", "diamond-test-blastp-pairwise-format", "diamond-test-blastp-paf-format"]
+         "diamond-test-blastp-evalue", "diamond-test-blastp-pairwise-format", "diamond-test-blastp-paf-format", "diamond-test-blastp-top"]
 
 
 def ctest_commands():
@@ -73,3 +73,20 @@ def test_paf_reports_unaligned_queries_like_the_reference(oracle_lib, mode, tmp_
     assert sum(l.split("\t")[1:3] == ["4", "*"] for l in lines) > 50 and sum(l.split("\t")[4] == "+" for l in lines) > 20
     if mode == "blastx":
         assert sum(l.split("\t")[4] == "-" for l in lines) > 20
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")
+@pytest.mark.parametrize("top,mode", [("50", ["--fast"])])
+def test_top_percent_like_the_reference(oracle_lib, top, mode, tmp_path):
+    """--top on protein families (hundreds of targets per query, several ranking chunks): score-ordered culling, the bit-score
+    window, one pass of the outer loop (align/culling.cpp:90-141, align/extend.cpp:79-92,336); --top 100 = every target."""
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("fam2")
+    q, d, ours, ref = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv", "r.tsv"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    subprocess.run([REF_BIN, "blastp"] + mode + ["-q", q, "-d", d, "--top", top, "-o", ref, "-p", "8", "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, "blastp"] + mode + ["-q", q, "-d", d, "--top", top, "-o", ours, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(ours).read() == open(ref).read()
+    assert sum(1 for _ in open(ref)) > 10000
