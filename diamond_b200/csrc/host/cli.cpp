@@ -105,10 +105,32 @@ int8_t encode_dna(char c) {  // nucleotide_traits (stats/stats.cpp:42): "ACGTN",
 	}
 }
 
-struct CodonTable {  // Translator::init(1): the standard code; a codon with N is X unless its first two bases fix the amino acid
+struct TranslateOpts { int strand_mask = 63, min_orf = 0, gencode = 1; };  // --strand, --min-orf (0 = Config::min_orf_len's rule), --query-gencode
+
+// NCBI translation tables (the ids --query-gencode accepts, basic/basic.cpp:86-113), TCAG order; nullptr = no such table
+const char* genetic_code(int id) {
+	static const char* codes[27] = { nullptr,
+		"FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSS**VVVVAAAADDEEGGGG",
+		"FFLLSSSSYY**CCWWTTTTPPPPHHQQRRRRIIMMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		"FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSSSVVVVAAAADDEEGGGG", "FFLLSSSSYYQQCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		nullptr, nullptr,
+		"FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG", "FFLLSSSSYY**CCCWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		"FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "FFLLSSSSYY**CC*WLLLSPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		"FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSGGVVVVAAAADDEEGGGG", "FFLLSSSSYYY*CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG",
+		nullptr,
+		"FFLLSSSSYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		nullptr, nullptr, nullptr, nullptr,
+		"FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNNKSSSSVVVVAAAADDEEGGGG", "FFLLSS*SYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG",
+		"FF*LSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSSKVVVVAAAADDEEGGGG",
+		"FFLLSSSSYY**CCGWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "FFLLSSSSYY**CC*WLLLAPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG" };
+	return id >= 1 && id <= 26 ? codes[id] : nullptr;
+}
+
+struct CodonTable {  // Translator::init(id): a codon with N is X unless its first two bases fix the amino acid
 	int8_t fwd[5][5][5], rev[5][5][5];
-	CodonTable() {
-		static const char* code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+	explicit CodonTable(int id) {
+		const char* code = genetic_code(id);
+		if (!code) throw std::runtime_error("Invalid genetic code id.");
 		static const unsigned idx[4] = { 2, 1, 3, 0 }, comp[4] = { 3, 2, 1, 0 };
 		for (unsigned i = 0; i < 5; ++i) for (unsigned j = 0; j < 5; ++j) for (unsigned k = 0; k < 5; ++k) {
 			if (i == 4 || j == 4 || k == 4) { fwd[i][j][k] = rev[i][j][k] = 23; continue; }
@@ -122,8 +144,8 @@ struct CodonTable {  // Translator::init(1): the standard code; a codon with N i
 	}
 };
 
-void push_translated(const std::vector<int8_t>& dna, SeqBlock& b) {
-	static const CodonTable ct;
+void push_translated(const std::vector<int8_t>& dna, SeqBlock& b, const TranslateOpts& to) {
+	static const CodonTable ct(to.gencode);  // one table per run
 	const size_t L = dna.size();
 	std::vector<int8_t> fr[6];
 	if (L >= 3) {
@@ -139,10 +161,11 @@ void push_translated(const std::vector<int8_t>& dna, SeqBlock& b) {
 		}
 	}
 	const size_t l0 = fr[0].size();
-	const size_t min_len = l0 < 30 ? 1 : (l0 < 100 ? 20 : 40);  // Config::min_orf_len (basic/config.h:413-424), --min-orf not given
+	const size_t min_len = to.min_orf > 0 ? (size_t)to.min_orf : (l0 < 30 ? 1 : (l0 < 100 ? 20 : 40));  // Config::min_orf_len (basic/config.h:413-424)
 	for (int f = 0; f < 6; ++f) {
 		std::vector<int8_t>& v = fr[f];
-		for (size_t begin = 0;;) {  // Util::Seq::find_orfs (util/sequence/sequence.cpp:180-197)
+		if (!((to.strand_mask >> f) & 1)) std::fill(v.begin(), v.end(), (int8_t)23);  // a strand that is not searched: the frame stays, all X (block.cpp:95-96)
+		else for (size_t begin = 0;;) {  // Util::Seq::find_orfs (util/sequence/sequence.cpp:180-197)
 			size_t it = begin;
 			while (it < v.size() && v[it] != 24) ++it;
 			if (it - begin < min_len) std::fill(v.begin() + (ptrdiff_t)begin, v.begin() + (ptrdiff_t)it, (int8_t)23);
@@ -155,7 +178,7 @@ void push_translated(const std::vector<int8_t>& dna, SeqBlock& b) {
 	}
 }
 
-void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b) {
+void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b, const TranslateOpts& to) {
 	std::istringstream f(slurp_text(path));
 	std::string line;
 	std::vector<int8_t> dna;
@@ -163,7 +186,7 @@ void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b) {
 	auto close_seq = [&] {
 		if (!open) return;
 		dq.len.push_back((int32_t)dna.size());
-		push_translated(dna, b);
+		push_translated(dna, b, to);
 		dna.clear();
 		open = false;
 	};
@@ -393,7 +416,8 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false, k_set = false, top_set = false;
+		bool pairwise = false, paf = false, k_set = false, top_set = false, unal = false;
+		int strand_mask = 63, min_orf = 0, gencode = 1;
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
@@ -444,6 +468,13 @@ int main(int argc, char** argv) {
 				const std::string v = val();  // seeds, defined to give the same alignments (src/test: diamond-test-blastp-query-indexed.out == ...-more-sensitive.out)
 				if (v != "0" && v != "1" && v != "double-indexed" && v != "query-indexed") usage("--algo must be 0, 1, double-indexed or query-indexed");
 			}
+			else if (a == "--unal") { const std::string v = val(); if (v != "0" && v != "1") usage("--unal must be 0 or 1"); unal = v == "1"; }
+			else if (a == "--strand") {  // frame_mask(), data/sequence_file.cpp:286-294
+				const std::string v = val();
+				if (v == "both") strand_mask = 63; else if (v == "plus") strand_mask = 7; else if (v == "minus") strand_mask = 56; else usage("Invalid value for parameter --strand");
+			}
+			else if (a == "--min-orf" || a == "-l") { min_orf = atoi(val()); if (min_orf < 0) usage("--min-orf must not be negative"); }
+			else if (a == "--query-gencode") gencode = atoi(val());
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			else usage(("unsupported option " + a).c_str());
@@ -457,7 +488,8 @@ int main(int argc, char** argv) {
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
 		DnaQueries dq;
-		if (translated) read_dna_fasta(qf, dq, q);
+		if (!translated && (strand_mask != 63 || min_orf != 0 || gencode != 1)) usage("--strand, --min-orf and --query-gencode belong to blastx");
+		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode });
 		else read_fasta(qf, q);
 		const uint32_t nq_block = translated ? (uint32_t)dq.ids.size() * 6u : q.size();
 		if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
@@ -573,8 +605,29 @@ int main(int argc, char** argv) {
 			}
 			n = 0;  // nothing left for the tabular writer
 		}
+		size_t n_unal = 0, u_next = 0;
+		const uint32_t* unal_q = dmnd_result_unaligned(res, &n_unal);
+		const uint32_t ctxs = translated ? 6u : 1u;
+		auto unaligned_upto = [&](uint32_t src_end) {  // --unal 1: TabularFormat::print_query_intro (output/blast_tab_format.cpp:776-788) for the queries
+			if (!unal || pairwise || paf) return;      // [.., src_end) that had seed hits and no alignment, in query order
+			for (; u_next < n_unal && unal_q[u_next] / ctxs < src_end; ++u_next) {
+				const uint32_t sq = unal_q[u_next] / ctxs;
+				line.clear();
+				for (size_t fi = 0; fi < fields.size(); ++fi) {
+					const std::string& f = fields[fi];
+					if (fi) line += '\t';
+					if (f == "qseqid") line += translated ? dq.ids[sq] : q.ids[sq];
+					else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);
+					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") line += '*';
+					else line += "-1";
+				}
+				line += '\n';
+				fwrite(line.data(), 1, line.size(), out);
+			}
+		};
 		for (size_t i = 0; i < n; ++i) {
 			const dmnd_match& x = m[i];
+			unaligned_upto(x.query / ctxs);
 			const uint8_t* t = tr + x.transcript_off;
 			const int8_t* qs = q.letters.data() + q.limits[x.query];
 			line.clear();
@@ -641,6 +694,7 @@ int main(int argc, char** argv) {
 			line += '\n';
 			fwrite(line.data(), 1, line.size(), out);
 		}
+		unaligned_upto(UINT32_MAX);
 		fclose(out);
 		if (log) {
 			const dmnd_run_stats* s = dmnd_result_stats(res);

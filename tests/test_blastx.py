@@ -117,3 +117,24 @@ def test_live_reference_nanopore_reads(oracle_lib, tmp_path):
     r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-f", "6"] + XT_FIELDS + ["-o", ours, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(ours).read() == open(ref).read() and sum(1 for _ in open(ref)) > 400
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")
+@pytest.mark.parametrize("flags", [["--strand", "minus"], ["--strand", "plus", "--min-orf", "30"], ["--query-gencode", "4", "--min-orf", "1"],
+                                   ["--unal", "1", "-e", "1e-30"], ["--top", "10"], ["-k", "0", "-c", "1"]])
+def test_blastx_options_like_the_reference(oracle_lib, flags, tmp_path):
+    """Translation options (frames of a strand that is not searched stay in the block as X, data/block/block.cpp:95-96; --min-orf
+    overrides Config::min_orf_len; NCBI table 4 reads TGA as W), --unal 1 records in nucleotide terms, --top and -k 0: live
+    against the reference on the `bx` reads."""
+    q, d = _files(_bx(), tmp_path)
+    ours, ref = str(tmp_path / "o.tsv"), str(tmp_path / "r.tsv")
+    fields = ["-f", "6", "qseqid", "sseqid", "pident", "length", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "qlen", "btop"]
+    subprocess.run([REF_BIN, "blastx", "--fast", "-q", q, "-d", d, "-o", ref, "-p", "8", "--quiet"] + flags + fields, capture_output=True, check=True)
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-o", ours, "-p", "8"] + flags + fields, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(ours).read()
+    assert got == open(ref).read() and got.count("\n") > 300
+    if "--unal" in flags:
+        assert sum(l.split("\t")[1] == "*" for l in got.splitlines()) > 50
+    if flags[:2] == ["--strand", "minus"]:
+        assert all(int(l.split("\t")[4]) > int(l.split("\t")[5]) for l in got.splitlines())  # qstart > qend: reverse strand only
