@@ -481,7 +481,6 @@ int main(int argc, char** argv) {
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
-		if (translated && pairwise) usage("-f 0 is not implemented for blastx");
 		if (pairwise || paf) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
@@ -557,15 +556,28 @@ int main(int argc, char** argv) {
 			// 60-column blocks; numbers go through TextBuffer::print(i, width), which keeps only `width` characters (util/text_buffer.h:248-254)
 			const dmnd_params* pp = &params;
 			auto put_num = [&](unsigned v, unsigned width) { char nb[24]; snprintf(nb, sizeof nb, "%*u", (int)width, v); line.append(nb, width); };
-			line = "BLASTP 2.3.0+\n\n\n";
+			line = "BLASTP 2.3.0+\n\n\n";  // the same header for blastx (print_header, blast_pairwise_format.cpp:97-101)
 			fwrite(line.data(), 1, line.size(), out);
+			size_t nu = 0, u = 0;
+			const uint32_t* unal_ids = dmnd_result_unaligned(res, &nu);
+			const uint32_t cx = translated ? 6u : 1u;
+			auto intro = [&](uint32_t sq) {
+				return "Query= " + (translated ? dq.titles[sq] : q.titles[sq]) + "\n\nLength=" + std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1) + "\n\n";
+			};
+			auto no_hits_upto = [&](uint32_t src_end) {  // DEFAULT_REPORT_UNALIGNED: queries with seed hits and no alignment (print_query_intro :88-95)
+				for (; u < nu && unal_ids[u] / cx < src_end; ++u) {
+					line = intro(unal_ids[u] / cx) + "\n***** No hits found *****\n\n\n";
+					fwrite(line.data(), 1, line.size(), out);
+				}
+			};
 			for (size_t i = 0; i < n; ++i) {
 				const dmnd_match& x = m[i];
+				const uint32_t sq = x.query / cx;
+				no_hits_upto(sq);
 				const uint8_t* t = tr + x.transcript_off;
 				const int8_t* qs = q.letters.data() + q.limits[x.query];
 				line.clear();
-				if (i == 0 || m[i - 1].query != x.query)
-					line += "Query= " + q.titles[x.query] + "\n\nLength=" + std::to_string(q.limits[x.query + 1] - q.limits[x.query] - 1) + "\n\n";
+				if (i == 0 || m[i - 1].query / cx != sq) line += intro(sq);
 				line += ">";
 				{	// OutputFormat::print_title(out, title, true, true, " "): the titles of a merged record ("\x01" or " >" between them,
 					// util/sequence/sequence.cpp:38) joined by one blank
@@ -583,8 +595,17 @@ int main(int argc, char** argv) {
 				const unsigned len = (unsigned)x.length;
 				line += "\n Identities = " + std::to_string(x.identities) + "/" + std::to_string(len) + " (" + std::to_string((unsigned)x.identities * 100u / len) + "%), Positives = "
 					+ std::to_string(x.positives) + "/" + std::to_string(len) + " (" + std::to_string((unsigned)x.positives * 100u / len) + "%), Gaps = " + std::to_string(x.gaps) + "/"
-					+ std::to_string(len) + " (" + std::to_string((unsigned)x.gaps * 100u / len) + "%)\n\n";
-				const unsigned digits = (unsigned)std::max(std::ceil(std::log10((double)x.t_end)), std::ceil(std::log10((double)x.q_end)));
+					+ std::to_string(len) + " (" + std::to_string((unsigned)x.gaps * 100u / len) + "%)\n";
+				// translated queries: the frame, and query positions on the read (TranslatedPosition::absolute / oriented_position,
+				// blast_pairwise_format.cpp:41-58): a letter at frame position p sits at in-strand 3p + offset, mirrored on the reverse strand
+				const int fr = translated ? (int)(x.query % 6) : 0, off = fr % 3;
+				const int64_t L = translated ? dq.len[sq] : 0;
+				if (translated) line += " Frame = " + std::to_string(fr < 3 ? fr + 1 : 2 - fr) + "\n";
+				line += "\n";
+				auto qpos_first = [&](int p) -> int64_t { return !translated ? p + 1 : (fr < 3 ? 3 * (int64_t)p + off + 1 : L - 3 * (int64_t)p - off); };  // the line's first letter
+				auto qpos_end = [&](int p) -> int64_t { return !translated ? p : (fr < 3 ? 3 * (int64_t)p + off : L - 3 * (int64_t)p - off + 1); };       // after its last one (p = next position)
+				const int64_t q_src_end = !translated ? x.q_end : (fr < 3 ? 3 * (int64_t)x.q_end + off : L - (3 * (int64_t)x.q_begin + off));
+				const unsigned digits = (unsigned)std::max(std::ceil(std::log10((double)x.t_end)), std::ceil(std::log10((double)q_src_end)));
 				int qi = x.q_begin, si = x.t_begin;
 				for (uint32_t k0 = 0; k0 < x.transcript_len; k0 += 60) {
 					const uint32_t k1 = std::min<uint32_t>(k0 + 60, x.transcript_len);
@@ -597,12 +618,13 @@ int main(int argc, char** argv) {
 						else if (op == DMND_OP_INSERTION) { ql += alphabet[qs[qi] & 31]; sl += '-'; ml += ' '; ++qi; }
 						else { ql += '-'; sl += alphabet[sc]; ml += ' '; ++si; }
 					}
-					line += "Query  "; put_num((unsigned)q0 + 1, digits); line += "  " + ql + " " + std::to_string(qi) + "\n";
+					line += "Query  "; put_num((unsigned)qpos_first(q0), digits); line += "  " + ql + " " + std::to_string(qpos_end(qi)) + "\n";
 					line.append(digits + 9, ' '); line += ml + "\n";
 					line += "Sbjct  "; put_num((unsigned)s0 + 1, digits); line += "  " + sl + " " + std::to_string(si) + "\n\n";
 				}
 				fwrite(line.data(), 1, line.size(), out);
 			}
+			no_hits_upto(UINT32_MAX);
 			n = 0;  // nothing left for the tabular writer
 		}
 		size_t n_unal = 0, u_next = 0;

@@ -92,10 +92,10 @@ def test_blastx_modes_above_fast(oracle_lib, tmp_path, lvl, flags):
 def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
     from diamond_b200 import api
     q, d = _files(_bx(), tmp_path)
-    r = subprocess.run([CLI, "blastx", "--fast", "--min-orf", "5", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    r = subprocess.run([CLI, "blastx", "--fast", "--range-culling", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported option" in r.stderr
-    r = subprocess.run([CLI, "blastx", "--fast", "-f", "0", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
-    assert r.returncode != 0
+    r = subprocess.run([CLI, "blastx", "--fast", "-F", "15", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # frameshift alignment
+    assert r.returncode != 0 and "unsupported option" in r.stderr
     # the library: contexts other than 1 / 6, nq not a multiple, or a window-filter mode
     raw, lim = api.block_image(np.zeros(40, dtype=np.int8), np.array([0, 10, 20, 30, 40], dtype=np.int64))
     g = api.Context(lib=oracle_lib, query_contexts=6)
@@ -138,3 +138,33 @@ def test_blastx_options_like_the_reference(oracle_lib, flags, tmp_path):
         assert sum(l.split("\t")[1] == "*" for l in got.splitlines()) > 50
     if flags[:2] == ["--strand", "minus"]:
         assert all(int(l.split("\t")[4]) > int(l.split("\t")[5]) for l in got.splitlines())  # qstart > qend: reverse strand only
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")
+@pytest.mark.parametrize("mode", ["blastx", "blastp"])
+def test_pairwise_format_translated_and_unaligned(oracle_lib, mode, tmp_path):
+    """-f 0 for blastx (" Frame = n" / "-n", query numbering on the read, descending on the reverse strand) and the "No hits found"
+    records of queries that had seed hits but no alignment (strict e-value), live against the reference."""
+    from diamond_b200 import synth
+    from conftest import workload_blocks
+    d = str(tmp_path / "d.faa")
+    if mode == "blastx":
+        w = _bx()
+        q = str(tmp_path / "q.fna")
+        synth.write_dna_fasta(q, w["dna"])
+        flags = ["--fast", "-e", "1e-20"]
+    else:
+        w, *_ = workload_blocks("edge")
+        q = str(tmp_path / "q.faa")
+        synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+        flags = ["--fast", "-e", "1e-40"]
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    ours, ref = str(tmp_path / "o.txt"), str(tmp_path / "r.txt")
+    subprocess.run([REF_BIN, mode] + flags + ["-q", q, "-d", d, "-f", "0", "-o", ref, "-p", "8", "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, mode] + flags + ["-q", q, "-d", d, "-f", "0", "-o", ours, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(ours).read()
+    assert got == open(ref).read()
+    assert got.count("***** No hits found *****") > 20
+    if mode == "blastx":
+        assert got.count(" Frame = -") > 50 and sum(got.count(f" Frame = {k}\n") for k in (1, 2, 3)) > 50
