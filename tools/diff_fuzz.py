@@ -1,0 +1,81 @@
+"""Differential fuzz of the CLI (oracle-linked build by default) against the unmodified reference: random small workloads x random
+option combinations from the surface the path implements; every run must give byte-identical output.
+
+    python tools/diff_fuzz.py [--runs 40] [--seed 1] [--cli oracle/_build/dmnd-oracle-cli]
+
+Needs oracle/_ref/diamond (make ref).  Prints the failing command lines, exit code 1 if any."""
+import argparse, os, random, subprocess, sys, tempfile
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from diamond_b200 import synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "diamond")
+MODES = [["--fast"], [], ["--mid-sensitive"], ["--sensitive"], ["--more-sensitive"], ["--very-sensitive"]]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--runs", type=int, default=40)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cli", default=os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli"))
+    a = ap.parse_args()
+    rnd = random.Random(a.seed)
+    bad = 0
+    with tempfile.TemporaryDirectory() as td:
+        for run in range(a.runs):
+            seed = rnd.randrange(1 << 30)
+            translated = rnd.random() < 0.4
+            d = os.path.join(td, "d.faa")
+            if translated:
+                w = synth.reads_workload(seed, n_db=rnd.choice([300, 800]), n_q=rnd.choice([80, 200]))
+                q = os.path.join(td, "q.fna")
+                synth.write_dna_fasta(q, w["dna"])
+            else:
+                kind = rnd.choice(["edge", "rep", "fam", "plain"])
+                if kind == "edge":
+                    w = synth.edge_workload(seed, n_db=rnd.choice([300, 1000]), n_q=rnd.choice([60, 200]))
+                elif kind == "rep":
+                    w = synth.repeat_workload(seed, n_db=rnd.choice([300, 800]), n_q=rnd.choice([60, 150]))
+                elif kind == "fam":
+                    w = synth.family_workload(n_fam=2, fam_size=rnd.choice([40, 120]), n_q=30, seed=seed, member_div=(0.02, 0.2), query_div=(0.03, 0.4))
+                else:
+                    w = synth.workload(n_q=rnd.choice([50, 200]), n_db=rnd.choice([500, 2000]), seed=seed, threads=1)
+                q = os.path.join(td, "q.faa")
+                synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+            synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+            opts = list(rnd.choice(MODES))
+            opts += ["-p", str(rnd.choice([1, 4, 8]))]
+            if rnd.random() < 0.3: opts += ["-c", str(rnd.choice([1, 2, 4]))]
+            if rnd.random() < 0.3: opts += ["--masking", rnd.choice(["0", "1"])]
+            if rnd.random() < 0.2: opts += ["--motif-masking", rnd.choice(["0", "1"])]
+            if rnd.random() < 0.3: opts += ["--comp-based-stats", rnd.choice(["0", "1"])]
+            r = rnd.random()
+            if r < 0.25: opts += ["-k", str(rnd.choice([0, 1, 3, 50]))]
+            elif r < 0.45: opts += ["--top", str(rnd.choice([0, 5, 30, 100]))]
+            if rnd.random() < 0.3: opts += ["-e", rnd.choice(["10", "1e-10", "1e-30"])]
+            if translated:
+                if rnd.random() < 0.3: opts += ["--strand", rnd.choice(["plus", "minus"])]
+                if rnd.random() < 0.3: opts += ["--min-orf", str(rnd.choice([1, 10, 35]))]
+            fmt = rnd.choice(["6", "6", "6f", "0", "paf"])
+            if fmt == "6f":
+                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score"]
+                if rnd.random() < 0.5: opts += ["--unal", "1"]
+            elif fmt != "6":
+                opts += ["-f", fmt]
+            cmd = ["blastx" if translated else "blastp", "-q", q, "-d", d] + opts
+            ro, oo = os.path.join(td, "r.out"), os.path.join(td, "o.out")
+            r1 = subprocess.run([REF] + cmd + ["-o", ro, "--quiet"], capture_output=True, text=True)
+            r2 = subprocess.run([a.cli] + cmd + ["-o", oo], capture_output=True, text=True)
+            ok = r1.returncode == 0 and r2.returncode == 0 and open(ro, "rb").read() == open(oo, "rb").read()
+            n = sum(1 for _ in open(ro)) if r1.returncode == 0 else -1
+            print(("ok   " if ok else "DIFF ") + f"run {run} seed {seed} lines {n}: " + " ".join(cmd[:1] + opts), flush=True)
+            if not ok:
+                bad += 1
+                print("     ref rc", r1.returncode, r1.stderr[-200:], "| ours rc", r2.returncode, r2.stderr[-200:])
+    print(f"{a.runs - bad} of {a.runs} identical")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
