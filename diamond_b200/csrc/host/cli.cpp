@@ -416,7 +416,7 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false, k_set = false, top_set = false, unal = false;
+		bool pairwise = false, paf = false, sam = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
@@ -452,7 +452,8 @@ int main(int argc, char** argv) {
 				const std::string fmt = val();
 				if (fmt == "0") { pairwise = true; continue; }
 				if (fmt == "paf" || fmt == "103") { paf = true; continue; }
-				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0 and -f paf are implemented");
+				if (fmt == "sam" || fmt == "101") { sam = true; continue; }
+				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f sam and -f paf are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -481,7 +482,7 @@ int main(int argc, char** argv) {
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
-		if (pairwise || paf) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
+		if (pairwise || paf || sam) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
@@ -518,6 +519,72 @@ int main(int argc, char** argv) {
 		if (!out) throw std::runtime_error("Error opening file " + of);
 		char buf[32];
 		std::string line;
+		if (sam) {
+			// SamFormat (output/sam_format.cpp:30-148): header (the @PG line carries THIS program's command line), one record per match,
+			// the "4 *" record for queries that had seed hits but no alignment
+			line = "@HD\tVN:1.5\tSO:query\n@PG\tPN:DIAMOND\tVN:2.2.2\tCL:";
+			for (int ai = 0; ai < argc; ++ai) { if (ai) line += ' '; line += argv[ai]; }
+			const char* ms = translated ? "BlastX" : "BlastP";
+			line += std::string("\n@mm\t") + ms + "\n@CO\t" + ms + "-like alignments\n@CO\tReporting AS: bitScore, ZR: rawScore, ZE: expected, ZI: percent identity, ZL: reference length, ZF: frame, ZS: query start DNA coordinate\n";
+			fwrite(line.data(), 1, line.size(), out);
+			const uint32_t cx = translated ? 6u : 1u;
+			size_t nu = 0, u = 0;
+			const uint32_t* unal_ids = dmnd_result_unaligned(res, &nu);
+			auto unaligned_to = [&](uint32_t src_end) {
+				for (; u < nu && unal_ids[u] / cx < src_end; ++u) {
+					line = (translated ? dq.ids[unal_ids[u] / cx] : q.ids[unal_ids[u]]) + "\t4\t*\t0\t255\t*\t*\t0\t0\t*\t*\n";
+					fwrite(line.data(), 1, line.size(), out);
+				}
+			};
+			for (size_t i = 0; i < n; ++i) {
+				const dmnd_match& x = m[i];
+				const uint32_t sq = x.query / cx;
+				unaligned_to(sq);
+				const uint8_t* t = tr + x.transcript_off;
+				const int8_t* qs = q.letters.data() + q.limits[x.query];
+				line = (translated ? dq.ids[sq] : q.ids[sq]) + "\t0\t" + r.ids[x.target] + "\t" + std::to_string(x.t_begin + 1) + "\t255\t";
+				{	// print_cigar: match and substitution are M
+					uint32_t run = 0; int op = -1;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6, c = (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;
+						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID"[op]; } run = 1; op = c; }
+					}
+					if (run) { line += std::to_string(run); line += "MID"[op]; }
+				}
+				line += "\t*\t0\t0\t";
+				for (int p2 = x.q_begin; p2 < x.q_end; ++p2) line += alphabet[qs[p2] & 31];
+				const int fr = translated ? (int)(x.query % 6) : 0, off = fr % 3;
+				const int64_t b_in = 3 * (int64_t)x.q_begin + off;
+				const int64_t zs = !translated ? x.q_begin + 1 : (fr < 3 ? b_in + 1 : (int64_t)dq.len[sq] - b_in);
+				line += "\t*\tAS:i:" + std::to_string((uint32_t)x.bit_score) + "\tNM:i:" + std::to_string(x.length - x.identities) + "\tZL:i:" + std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1)
+					+ "\tZR:i:" + std::to_string(x.score) + "\tZE:f:";
+				if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; }
+				line += "\tZI:i:" + std::to_string(x.identities * 100 / x.length) + "\tZF:i:" + std::to_string(fr < 3 ? fr + 1 : -(off + 1)) + "\tZS:i:" + std::to_string(zs) + "\tMD:Z:";
+				{	// print_md (sam_format.cpp:30-64)
+					unsigned matches = 0, del = 0;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6;
+						if (o2 == DMND_OP_MATCH) { del = 0; ++matches; }
+						else if (o2 == DMND_OP_SUBSTITUTION) {
+							if (matches > 0) { line += std::to_string(matches); matches = 0; }
+							else if (del > 0) { line += '0'; del = 0; }
+							line += alphabet[t[k] & 63];
+						}
+						else if (o2 == DMND_OP_DELETION) {
+							if (matches > 0) { line += std::to_string(matches); matches = 0; }
+							if (del == 0) line += '^';
+							line += alphabet[t[k] & 63];
+							++del;
+						}
+					}
+					if (matches > 0) line += std::to_string(matches);
+				}
+				line += '\n';
+				fwrite(line.data(), 1, line.size(), out);
+			}
+			unaligned_to(UINT32_MAX);
+			n = 0;
+		}
 		if (paf) {
 			// PAFFormat (output/paf_format.cpp:24-68): one line per match, 0-based closed coordinates; queries without a match are
 			// reported too when the extension stage saw them, i.e. when they had seed hits (Output::Flags::DEFAULT_REPORT_UNALIGNED, align/align.cpp:167-181), in query order
@@ -631,7 +698,7 @@ int main(int argc, char** argv) {
 		const uint32_t* unal_q = dmnd_result_unaligned(res, &n_unal);
 		const uint32_t ctxs = translated ? 6u : 1u;
 		auto unaligned_upto = [&](uint32_t src_end) {  // --unal 1: TabularFormat::print_query_intro (output/blast_tab_format.cpp:776-788) for the queries
-			if (!unal || pairwise || paf) return;      // [.., src_end) that had seed hits and no alignment, in query order
+			if (!unal || pairwise || paf || sam) return;      // [.., src_end) that had seed hits and no alignment, in query order
 			for (; u_next < n_unal && unal_q[u_next] / ctxs < src_end; ++u_next) {
 				const uint32_t sq = unal_q[u_next] / ctxs;
 				line.clear();

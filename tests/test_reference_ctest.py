@@ -90,3 +90,32 @@ def test_top_percent_like_the_reference(oracle_lib, top, mode, tmp_path):
     assert r.returncode == 0, r.stderr
     assert open(ours).read() == open(ref).read()
     assert sum(1 for _ in open(ref)) > 10000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")
+@pytest.mark.parametrize("mode", ["blastp", "blastx"])
+def test_sam_format_like_the_reference(oracle_lib, mode, tmp_path):
+    """-f sam (output/sam_format.cpp): CIGAR, the aligned query letters, NM / ZI / ZF / ZS and the MD string from the edit transcript,
+    "4 *" records for queries with seed hits and no alignment.  Everything but the @PG header line (it quotes the program's own
+    command line) must equal the reference's file."""
+    from diamond_b200 import synth
+    d = str(tmp_path / "d.faa")
+    if mode == "blastp":
+        w, *_ = workload_blocks("edge")
+        q = str(tmp_path / "q.faa")
+        synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    else:
+        f, kw = synth.BX_WORKLOADS["bx"]
+        w = f(**kw)
+        q = str(tmp_path / "q.fna")
+        synth.write_dna_fasta(q, w["dna"])
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    ours, ref = str(tmp_path / "o.sam"), str(tmp_path / "r.sam")
+    flags = ["--fast", "-e", "1e-15", "-q", q, "-d", d, "-f", "sam", "-p", "8"]
+    subprocess.run([REF_BIN, mode] + flags + ["-o", ref, "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, mode] + flags + ["-o", ours], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = ([l for l in open(p) if not l.startswith("@PG")] for p in (ours, ref))
+    assert a == b and len(a) > 100
+    assert any("^" in l.split("MD:Z:")[1] for l in a if "MD:Z:" in l) or mode == "blastp"
+    assert sum(l.split("\t")[1:3] == ["4", "*"] for l in a) > 10
