@@ -457,7 +457,8 @@ int main(int argc, char** argv) {
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
-					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen" };
+					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen",
+					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand" };
 					bool ok = false;
 					for (const char* k : known) ok |= f == k;
 					if (!ok) usage(("unsupported output field " + f).c_str());
@@ -483,7 +484,7 @@ int main(int argc, char** argv) {
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (pairwise || paf || sam) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
-		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") o.want_transcript = 1;  // HspValues::TRANSCRIPT
+		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
@@ -707,7 +708,9 @@ int main(int argc, char** argv) {
 					if (fi) line += '\t';
 					if (f == "qseqid") line += translated ? dq.ids[sq] : q.ids[sq];
 					else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);
-					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped") line += '*';
+					else if (f == "qtitle") line += translated ? dq.titles[sq] : q.titles[sq];
+					else if (f == "qframe") line += '0';
+					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "stitle" || f == "qstrand") line += '*';
 					else line += "-1";
 				}
 				line += '\n';
@@ -744,6 +747,18 @@ int main(int argc, char** argv) {
 				else if (f == "evalue") { if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; } }
 				else if (f == "bitscore") { format_double(x.bit_score, buf, sizeof buf); line += buf; }
 				else if (f == "score") line += std::to_string(x.score);
+				else if (f == "qtitle") line += translated ? dq.titles[x.query / 6] : q.titles[x.query];
+				else if (f == "stitle") { const std::string& tt = r.titles[x.target]; line.append(tt, 0, std::min(tt.find('\x01'), tt.find(" >"))); }  // print_title(full titles, first one only: "\x01" or " >" separate merged records)
+				else if (f == "positive") line += std::to_string(x.positives);
+				else if (f == "ppos") { format_double((double)x.positives * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
+				else if (f == "qcovhsp") {  // query_source_range().length() * 100 / source length (basic/match.h): nucleotides for blastx
+					const double cov = translated ? (double)(3 * (x.q_end - x.q_begin)) * 100.0 / (double)dq.len[x.query / 6]
+					                              : (double)(x.q_end - x.q_begin) * 100.0 / (double)(q.limits[x.query + 1] - q.limits[x.query] - 1);
+					format_double(cov, buf, sizeof buf); line += buf;
+				}
+				else if (f == "scovhsp") { format_double((double)(x.t_end - x.t_begin) * 100.0 / (double)(r.limits[x.target + 1] - r.limits[x.target] - 1), buf, sizeof buf); line += buf; }
+				else if (f == "qframe") { const int fr = (int)(x.query % 6); line += std::to_string(translated ? (fr < 3 ? fr + 1 : 2 - fr) : 0); }
+				else if (f == "qstrand") line += (translated && x.query % 6 >= 3) ? '-' : '+';
 				else if (f == "gaps") line += std::to_string(x.gaps);
 				else if (f == "nident") line += std::to_string(x.identities);
 				else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[x.query / 6] : q.limits[x.query + 1] - q.limits[x.query] - 1);

@@ -119,3 +119,24 @@ def test_sam_format_like_the_reference(oracle_lib, mode, tmp_path):
     assert a == b and len(a) > 100
     assert any("^" in l.split("MD:Z:")[1] for l in a if "MD:Z:" in l) or mode == "blastp"
     assert sum(l.split("\t")[1:3] == ["4", "*"] for l in a) > 10
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN) or not os.path.exists(os.path.join(TD, "nr_300.faa")), reason="needs the reference build and its test data")
+@pytest.mark.parametrize("mode", ["blastp", "blastx"])
+def test_more_tabular_fields_like_the_reference(oracle_lib, mode, tmp_path):
+    """qtitle / stitle (first title of a merged record), positive / ppos, qcovhsp / scovhsp, qframe / qstrand, with --unal 1, on the
+    reference's real test data (nr_300 proteins / nanopore reads against nr_10k)."""
+    import gzip
+    fields = "qseqid qtitle sseqid stitle pident positive ppos qcovhsp scovhsp qframe qstrand length evalue".split()
+    if mode == "blastp":
+        q = os.path.join(TD, "nr_300.faa")
+    else:
+        q = str(tmp_path / "nano.fna")
+        open(q, "wb").write(gzip.open(os.path.join(TD, "SRR14011045_1.fna.gz")).read())
+    flags = ["--fast", "-q", q, "-d", os.path.join(TD, "nr_10k.faa"), "-p", "8", "--unal", "1", "-e", "1e-10", "-f", "6"] + fields
+    ours, ref = str(tmp_path / "o.tsv"), str(tmp_path / "r.tsv")
+    subprocess.run([REF_BIN, mode] + flags + ["-o", ref, "--quiet"], capture_output=True, check=True)
+    r = subprocess.run([CLI, mode] + flags + ["-o", ours], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(ours).read()
+    assert got == open(ref).read() and got.count("\n") > 300
