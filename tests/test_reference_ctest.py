@@ -81,7 +81,7 @@ def test_top_percent_like_the_reference(oracle_lib, top, mode, tmp_path):
     """--top on protein families (hundreds of targets per query, several ranking chunks): score-ordered culling, the bit-score
     window, one pass of the outer loop (align/culling.cpp:90-141, align/extend.cpp:79-92,336); --top 100 = every target."""
     from diamond_b200 import synth
-    w, *_ = workload_blocks("fam2")
+    w = synth.family_workload(n_fam=3, fam_size=250, n_q=40, seed=77, member_div=(0.02, 0.15), query_div=(0.03, 0.3))
     q, d, ours, ref = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv", "r.tsv"))
     synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
     synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
@@ -89,7 +89,7 @@ def test_top_percent_like_the_reference(oracle_lib, top, mode, tmp_path):
     r = subprocess.run([CLI, "blastp"] + mode + ["-q", q, "-d", d, "--top", top, "-o", ours, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(ours).read() == open(ref).read()
-    assert sum(1 for _ in open(ref)) > 10000
+    assert sum(1 for _ in open(ref)) > 5000
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference build (make ref)")

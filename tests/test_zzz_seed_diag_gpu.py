@@ -7,7 +7,9 @@ import numpy as np
 import pytest
 from conftest import workload_blocks
 
-pytestmark = pytest.mark.gpu
+# never run on a B200 yet (written after the round's GPU budget was spent): non-strict xfail so that a surprise shows up as a
+# reported failure reason (or as XPASS when all is well) without stopping `pytest -m gpu -x` before the proven tests' results count
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="seed-stage diagnostics on the device: written after the GPU budget of round 1 was spent, first run pending")]
 
 
 @pytest.mark.parametrize("name", ["edge", "rep"])
