@@ -263,8 +263,9 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {
-	int32_t sensitivity;       /* 0 = --fast, 1 = default, 2 = --mid-sensitive, 3 = --sensitive, 4 = --more-sensitive, 5 = --very-sensitive, 6 = --ultra-sensitive; 1: 2 shapes of weight 10, stage-2 ungapped window
-	                              filter; CPU oracle + host pipeline only so far: the CUDA library rejects it) */
+	int32_t sensitivity;       /* 0 = --fast, 1 = default, 2 = --mid-sensitive, 3 = --sensitive, 4 = --more-sensitive, 5 = --very-sensitive,
+	                              6 = --ultra-sensitive (search/setup.cpp:40-54).  Call dmnd_search_opts_default() first: a zeroed struct is
+	                              not the default (top_percent 0 means --top 0).  Device status of the modes above 0: see DESIGN.md 7. */
 	int32_t threads;           /* reference -p: fixes seedp_bits (search/setup.cpp:306-309); host worker threads */
 	int32_t index_chunks;      /* reference -c; 0 = mode default (4) */
 	int32_t comp_based_stats;  /* 0 or 1 (Hauser) */
