@@ -95,6 +95,7 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 struct DnaQueries {
 	std::vector<std::string> ids, titles;
 	std::vector<int32_t> len;  // nucleotides
+	std::vector<std::string> dna;  // the reads as the reference prints them (nucleotide_traits alphabet: everything but ACGT is N)
 };
 
 int8_t encode_dna(char c) {  // nucleotide_traits (stats/stats.cpp:42): "ACGTN", everything in "MRWSYKVHDBX" reads as N
@@ -186,6 +187,7 @@ void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b, const 
 	auto close_seq = [&] {
 		if (!open) return;
 		dq.len.push_back((int32_t)dna.size());
+		{ std::string t(dna.size(), 'N'); for (size_t k = 0; k < dna.size(); ++k) t[k] = "ACGTN"[dna[k]]; dq.dna.push_back(std::move(t)); }
 		push_translated(dna, b, to);
 		dna.clear();
 		open = false;
@@ -458,7 +460,7 @@ int main(int argc, char** argv) {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
 					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen",
-					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand" };
+					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq" };
 					bool ok = false;
 					for (const char* k : known) ok |= f == k;
 					if (!ok) usage(("unsupported output field " + f).c_str());
@@ -484,7 +486,7 @@ int main(int argc, char** argv) {
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (pairwise || paf || sam) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
-		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos") o.want_transcript = 1;  // HspValues::TRANSCRIPT
+		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
@@ -710,7 +712,7 @@ int main(int argc, char** argv) {
 					else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);
 					else if (f == "qtitle") line += translated ? dq.titles[sq] : q.titles[sq];
 					else if (f == "qframe") line += '0';
-					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "stitle" || f == "qstrand") line += '*';
+					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "stitle" || f == "qstrand" || f == "qseq" || f == "sseq") line += '*';
 					else line += "-1";
 				}
 				line += '\n';
@@ -747,6 +749,24 @@ int main(int argc, char** argv) {
 				else if (f == "evalue") { if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; } }
 				else if (f == "bitscore") { format_double(x.bit_score, buf, sizeof buf); line += buf; }
 				else if (f == "score") line += std::to_string(x.score);
+				else if (f == "qseq") {  // the aligned stretch of the SOURCE query: letters of the read (forward orientation) for blastx
+					if (!translated) for (int p2 = x.q_begin; p2 < x.q_end; ++p2) line += alphabet[qs[p2] & 31];
+					else {
+						const int fr = (int)(x.query % 6), off = fr % 3;
+						const int64_t L = dq.len[x.query / 6], b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + off;
+						const int64_t b = fr < 3 ? b_in : L - e_in, e = fr < 3 ? e_in : L - b_in;
+						line.append(dq.dna[x.query / 6], (size_t)b, (size_t)(e - b));
+					}
+				}
+				else if (f == "sseq") {  // the subject letters of the alignment (no gap characters)
+					int qi = x.q_begin;
+					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						const int o2 = t[k] >> 6;
+						if (o2 == DMND_OP_MATCH) line += alphabet[qs[qi] & 31];
+						else if (o2 != DMND_OP_INSERTION) line += alphabet[t[k] & 63];
+						if (o2 != DMND_OP_DELETION) ++qi;
+					}
+				}
 				else if (f == "qtitle") line += translated ? dq.titles[x.query / 6] : q.titles[x.query];
 				else if (f == "stitle") { const std::string& tt = r.titles[x.target]; line.append(tt, 0, std::min(tt.find('\x01'), tt.find(" >"))); }  // print_title(full titles, first one only: "\x01" or " >" separate merged records)
 				else if (f == "positive") line += std::to_string(x.positives);

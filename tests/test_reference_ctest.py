@@ -124,10 +124,10 @@ def test_sam_format_like_the_reference(oracle_lib, mode, tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF_BIN) or not os.path.exists(os.path.join(TD, "nr_300.faa")), reason="needs the reference build and its test data")
 @pytest.mark.parametrize("mode", ["blastp", "blastx"])
 def test_more_tabular_fields_like_the_reference(oracle_lib, mode, tmp_path):
-    """qtitle / stitle (first title of a merged record), positive / ppos, qcovhsp / scovhsp, qframe / qstrand, with --unal 1, on the
+    """qtitle / stitle (first title of a merged record), positive / ppos, qcovhsp / scovhsp, qframe / qstrand, qseq (the read's nucleotides for blastx) / sseq, with --unal 1, on the
     reference's real test data (nr_300 proteins / nanopore reads against nr_10k)."""
     import gzip
-    fields = "qseqid qtitle sseqid stitle pident positive ppos qcovhsp scovhsp qframe qstrand length evalue".split()
+    fields = "qseqid qtitle sseqid stitle pident positive ppos qcovhsp scovhsp qframe qstrand length evalue qseq sseq".split()
     if mode == "blastp":
         q = os.path.join(TD, "nr_300.faa")
     else:
