@@ -420,6 +420,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
+		bool header_simple = false;
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
@@ -471,6 +472,11 @@ int main(int argc, char** argv) {
 			else if (a == "--algo") {  // 0 / double-indexed is what this path implements; 1 / query-indexed is the reference's other join order over the same
 				const std::string v = val();  // seeds, defined to give the same alignments (src/test: diamond-test-blastp-query-indexed.out == ...-more-sensitive.out)
 				if (v != "0" && v != "1" && v != "double-indexed" && v != "query-indexed") usage("--algo must be 0, 1, double-indexed or query-indexed");
+			}
+			else if (a == "--header") {  // TabularFormat::header_format (output/blast_tab_format.cpp:627-641): 0 = none, simple = the field keys; the
+				std::string v = "verbose";  // verbose form (no value) quotes the invocation and the long field descriptions and is not built
+				if (i + 1 < argc && argv[i + 1][0] != '-') v = argv[++i];
+				if (v == "0") header_simple = false; else if (v == "simple") header_simple = true; else usage("--header: only 0 and simple are implemented");
 			}
 			else if (a == "--unal") { const std::string v = val(); if (v != "0" && v != "1") usage("--unal must be 0 or 1"); unal = v == "1"; }
 			else if (a == "--strand") {  // frame_mask(), data/sequence_file.cpp:286-294
@@ -696,6 +702,12 @@ int main(int argc, char** argv) {
 			}
 			no_hits_upto(UINT32_MAX);
 			n = 0;  // nothing left for the tabular writer
+		}
+		if (header_simple && !pairwise && !paf && !sam) {  // TabularFormat::output_header: the field keys, tab-separated
+			line.clear();
+			for (size_t fi = 0; fi < fields.size(); ++fi) { if (fi) line += '\t'; line += fields[fi]; }
+			line += '\n';
+			fwrite(line.data(), 1, line.size(), out);
 		}
 		size_t n_unal = 0, u_next = 0;
 		const uint32_t* unal_q = dmnd_result_unaligned(res, &n_unal);

@@ -133,7 +133,7 @@ def test_more_tabular_fields_like_the_reference(oracle_lib, mode, tmp_path):
     else:
         q = str(tmp_path / "nano.fna")
         open(q, "wb").write(gzip.open(os.path.join(TD, "SRR14011045_1.fna.gz")).read())
-    flags = ["--fast", "-q", q, "-d", os.path.join(TD, "nr_10k.faa"), "-p", "8", "--unal", "1", "-e", "1e-10", "-f", "6"] + fields
+    flags = ["--fast", "-q", q, "-d", os.path.join(TD, "nr_10k.faa"), "-p", "8", "--unal", "1", "--header", "simple", "-e", "1e-10", "-f", "6"] + fields
     ours, ref = str(tmp_path / "o.tsv"), str(tmp_path / "r.tsv")
     subprocess.run([REF_BIN, mode] + flags + ["-o", ref, "--quiet"], capture_output=True, check=True)
     r = subprocess.run([CLI, mode] + flags + ["-o", ours], capture_output=True, text=True)
