@@ -487,6 +487,11 @@ int main(int argc, char** argv) {
 			else if (a == "--query-gencode") gencode = atoi(val());
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
+			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
+			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
+			else if (a == "--matrix") { std::string v = val(); for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
+			else if (a == "--id" || a == "--approx-id" || a == "--query-cover" || a == "--subject-cover") { if (atof(val()) != 0.0) usage((a + ": only 0 (no filter) is implemented").c_str()); }
+			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
