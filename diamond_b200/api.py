@@ -97,7 +97,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
-           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
+           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_masked_positions", "dmnd_result_unaligned", "dmnd_result_free"]
@@ -121,6 +121,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_block_download_letters.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_debug_block_soft.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_debug_ref_index.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dmnd_debug_left_most.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]
     lib.dmnd_block_mask.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.dmnd_block_mask_fetch.argtypes = [vp, vp, C.c_size_t]
     lib.dmnd_hits_gapped_filter.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
@@ -264,6 +265,12 @@ class Context:
         keys, locs, n = np.empty(raw_len, dtype=np.uint64), np.empty(raw_len, dtype=np.uint32), C.c_size_t()
         self._check(self.lib.dmnd_debug_ref_index(self.ctx, rb, sid, keys.ctypes.data, locs.ctypes.data, raw_len, C.byref(n)))
         return keys[:n.value].copy(), locs[:n.value].copy()
+
+    def debug_left_most(self, qb, rb, sid: int, chunk: int, qloc: int, sloc: int) -> np.ndarray:
+        """Diagnostics: the left-most filter of one (query location, reference location) pair with its intermediates (30 words)."""
+        out = np.zeros(30, dtype=np.uint64)
+        self._check(self.lib.dmnd_debug_left_most(self.ctx, qb, rb, sid, chunk, qloc, sloc, out.ctypes.data))
+        return out
 
     def build_index(self, b, sid: int = 0):
         self._check(self.lib.dmnd_block_build_index(self.ctx, b, sid))

@@ -491,6 +491,12 @@ int dmnd_debug_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, uint64_t
 	return 0;
 }
 
+int dmnd_debug_left_most(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out30) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (sid < 0 || sid >= ctx->params.n_shapes || chunk < 0) { set_error("dmnd_debug_left_most: bad shape id / chunk"); return 1; }
+	return dmnd_cuda::debug_left_most_impl(ctx, query, ref, sid, chunk, qloc, sloc, out30);
+}
+
 static int clear_range(dmnd_ctx* ctx, dmnd_block* b, size_t begin, size_t end) {
 	if (end <= begin) return 0;
 	const size_t threads = (end - (begin / 16) * 16 + 15) / 16;

@@ -17,6 +17,8 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 
+
+
 namespace dmnd_cuda {
 
 int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* host, dmnd_hit_site* sites, size_t cap) {
@@ -267,6 +269,84 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		counters->masked_seeds = hc[7];
 	}
 	*out = h;
+	return 0;
+}
+
+
+// ---- diagnostics (tools/seed_stage_diag.py): the left-most filter of ONE (query loc, reference loc) pair with its intermediates,
+// evaluated on the device with the production device functions, on the block's current SEED_MASK state.
+__global__ void lm_debug_kernel(const int8_t* q_letters, const int64_t* q_limits, uint32_t nq, const int8_t* r_letters, uint32_t qloc, uint32_t sloc, LmCtx x, unsigned long long* out) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const int8_t *qp = q_letters + qloc, *sp = r_letters + sloc;
+	uint32_t a = 0, b = nq;
+	while (b - a > 1) { const uint32_t mid = a + (b - a) / 2; if ((uint64_t)q_limits[mid] <= (uint64_t)qloc) a = mid; else b = mid; }
+	const int seed_offset0 = (int)((int64_t)qloc - q_limits[a]);
+	const int window0 = x.P->ungapped_window;
+	int cb, ce;
+	clip(qp - window0, 2 * window0, window0, cb, ce);
+	const int window_left0 = window0 - cb, window_clipped = ce - cb;
+	const int8_t* qc = qp - window0 + cb;
+	const int interval_mod = x.P->left_most_interval > 0 ? seed_offset0 % x.P->left_most_interval : window_left0;
+	const int overhang = max(window_left0 - interval_mod, 0);
+	const int8_t* query = qc + overhang; const int query_len = window_clipped - overhang; const int8_t* subject = sp - window_left0 + overhang;
+	const int seed_offset = window_left0 - overhang, seed_len = x.P->shape_len[x.sid];
+	out[0] = left_most_filter(x, query, query_len, subject, seed_offset, seed_len) ? 1 : 0;
+	const DevParams* P = x.P;
+	int d = max(seed_offset - 16, 0), window_left = min(16, seed_offset);
+	const int8_t *q = query + d, *s = subject + d;
+	int window = min(query_len - d, window_left + 1 + 32);
+	clip(s, window, window_left, cb, ce);
+	window = ce; d = cb;
+	q += d; s += d; window_left -= d; window -= d;
+	uint64_t match_mask = 0, seed_bits = 0;
+	for (int k = 0; k < window && k < 64; ++k) {
+		if (P->map8[q[k] & 31] == P->map8b[s[k] & 31]) match_mask |= (uint64_t)1 << k;
+		if (q[k] & DMND_SEED_MASK) seed_bits |= (uint64_t)1 << k;
+	}
+	const uint64_t query_seed_mask = ~seed_bits;
+	const uint32_t len_left = (uint32_t)(window_left + seed_len - 1),
+		match_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & match_mask), query_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & query_seed_mask);
+	const uint32_t raw_left = matcher_hit(x.cur_matcher, x.cur_minlen, x.cur_suffix, match_mask_left, len_left);
+	const uint32_t left_hit = raw_left & query_mask_left;
+	const uint32_t len_right = (uint32_t)(window - window_left - 1), match_mask_right = (uint32_t)(match_mask >> (window_left + 1)), query_mask_right = (uint32_t)(query_seed_mask >> (window_left + 1));
+	const uint32_t right_hit = (x.chunked ? matcher_hit(x.cur_matcher, x.cur_minlen, x.cur_suffix, match_mask_right, len_right) : matcher_hit(x.prev_matcher, x.prev_minlen, x.prev_suffix, match_mask_right, len_right)) & query_mask_right;
+	out[1] = match_mask; out[2] = seed_bits; out[3] = ((uint64_t)raw_left << 32) | left_hit; out[4] = right_hit;
+	out[5] = ((uint64_t)(uint32_t)seed_offset << 32) | (uint32_t)window_left; out[6] = ((uint64_t)(uint32_t)window << 32) | len_left;
+	out[7] = left_hit ? (verify_hits(x, left_hit, q, s, true, match_mask_left) ? 1 : 0) : 2;
+	out[8] = right_hit ? (verify_hits(x, right_hit, q + window_left + 1, s + window_left + 1, false, match_mask_right) ? 1 : 0) : 2;
+	// every left candidate: position, verify_hit, fingerprint count, partition of the subject seed of the current shape
+	int n = 0;
+	for (int pos = 0; pos < 32 && n < 20; ++pos) {
+		if (!((left_hit >> pos) & 1u)) continue;
+		const uint32_t mm = match_mask_left >> pos;
+		uint64_t seed = 0; int valid = 1;
+		for (int k = 0; k < P->shape_weight; ++k) { const int l = s[pos + P->shape_pos[x.sid][k]] & 31; if (l == 23 || l == 31 || l == 24) valid = 0; seed = seed * (uint64_t)P->reduction_size + P->reduction[l]; }
+		const uint32_t part = (uint32_t)(seed & (((uint64_t)1 << P->seedp_bits) - 1));
+		out[9 + n] = ((uint64_t)pos << 56) | ((uint64_t)(verify_hit(x, q + pos, s + pos, true, mm) ? 1 : 0) << 48) | ((uint64_t)(((P->shape_mask[x.sid] & mm) == P->shape_mask[x.sid]) ? 1 : 0) << 40)
+			| ((uint64_t)valid << 36) | ((uint64_t)fingerprint_match(q + pos, s + pos) << 24) | part;
+		++n;
+	}
+	out[29] = (uint64_t)n;
+}
+
+int debug_left_most_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out30) {
+	const dmnd_params& hp = ctx->params;
+	const uint32_t parts_total = 1u << hp.seedp_bits;
+	const uint32_t nchunks = std::min<uint32_t>((uint32_t)hp.index_chunks, parts_total);
+	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
+	const uint32_t bsel = std::min((uint32_t)chunk, prem);
+	const uint32_t pb = bsel * (psize + 1) + ((uint32_t)chunk - bsel) * psize, pe = pb + ((uint32_t)chunk < prem ? psize + 1 : psize);
+	LmCtx x;
+	x.P = ctx->d_params; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
+	x.cur_matcher = ctx->d_matcher[sid + 1]; x.cur_minlen = ctx->matcher_minlen[sid + 1]; x.cur_suffix = ctx->matcher_suffix[sid + 1];
+	x.prev_matcher = ctx->d_matcher[sid]; x.prev_minlen = ctx->matcher_minlen[sid]; x.prev_suffix = ctx->matcher_suffix[sid];
+	if (ctx->b_counters.ensure(128 * sizeof(unsigned long long))) return 1;
+	unsigned long long* d = ctx->b_counters.as<unsigned long long>();
+	DMND_CUDA_CHECK(cudaMemsetAsync(d, 0, 30 * 8, ctx->stream));
+	lm_debug_kernel<<<1, 32, 0, ctx->stream>>>(query->letters, query->limits, query->nseq, ref->letters, qloc, sloc, x, d);
+	DMND_CUDA_CHECK(cudaGetLastError());
+	DMND_CUDA_CHECK(cudaMemcpyAsync(out30, d, 30 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
 	return 0;
 }
 

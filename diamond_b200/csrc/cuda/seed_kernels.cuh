@@ -274,7 +274,12 @@ __device__ __forceinline__ void clip(const int8_t* seq, int len, int anchor, int
 		}
 }
 // search/left_most.h:62-110
-__device__ bool left_most_filter(const LmCtx& x, const int8_t* query, int query_len, const int8_t* subject, int seed_offset, int seed_len) {
+// __noinline__ on purpose.  Inlined into stage2_window_kernel, ptxas 12.9 (sm_100a) produced code whose result depended on how the
+// lanes of a warp diverged in the verify loops: on the B200 the filter kept 2-5 of ~3 100 pairs that the same code drops when it
+// runs one thread per warp, differently from run to run, only with two or more shapes (candidates that skip the partition test and
+// go straight to the fingerprint).  As a real call -- or with fingerprint_match out of line -- the kernel is deterministic and
+// equal to the oracle (profiles/lm_variants_r2.txt: variants 1, 5, 6 against 0, 2, 7).
+__device__ __noinline__ bool left_most_filter(const LmCtx& x, const int8_t* query, int query_len, const int8_t* subject, int seed_offset, int seed_len) {
 	const DevParams* P = x.P;
 	int d = max(seed_offset - 16, 0), window_left = min(16, seed_offset);
 	const int8_t *q = query + d, *s = subject + d;

@@ -16,6 +16,7 @@
 // per cell (gap: cur==vgap / cur==hgap, open: vgap'==open / hgap'==open) and a second kernel walks them
 // (banded_swipe.h:127-187, banded_matrix.h:357-402, basic/hssp.cpp:260-290), one problem per thread.
 #include "ctx.cuh"
+#include "swipe16.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cstring>
@@ -24,40 +25,6 @@
 #include <chrono>
 
 namespace dmnd_cuda {
-
-struct ProbGeom {  // derived on the device from the problem + block limits
-	const int8_t *q, *cb, *t;
-	int qlen, tlen, d_begin, B, j0, cols;
-};
-
-struct SwipeArgs {
-	const int8_t *q_letters, *q_bias, *r_letters;
-	const int64_t *q_limits, *r_limits;
-	const dmnd_dp_problem* probs;
-	const uint32_t* order;  // problem indices of this launch, heaviest first
-	uint32_t n;
-	int32_t* score;         // [problem]
-	int32_t* end_cell;      // [problem][2] = (column, band row) of the end cell, traceback only
-	uint8_t* trace;         // traceback masks, wavefront-major nibbles: byte [(m * 32 + lane) * R/2 + k/2], see trace_store()
-	const uint64_t* trace_excl; // exclusive prefix of trace bytes over the ORDER sequence (global order position)
-	uint64_t trace_base;    // prefix value at the first position of the slice in flight
-	uint32_t order_pos0;    // global order position of order[0]
-	unsigned int* work;     // atomic work counter
-};
-
-__device__ __forceinline__ ProbGeom geom(const SwipeArgs& a, const dmnd_dp_problem& pr) {
-	ProbGeom g;
-	const int64_t qo = a.q_limits[pr.query], to = a.r_limits[pr.target];
-	g.qlen = (int)(a.q_limits[pr.query + 1] - qo - 1);
-	g.tlen = (int)(a.r_limits[pr.target + 1] - to - 1);
-	g.q = a.q_letters + qo; g.cb = a.q_bias + qo; g.t = a.r_letters + to;
-	g.d_begin = pr.d_begin;
-	g.B = pr.d_end - pr.d_begin;
-	const int i1 = max(pr.d_end - 1, 0);
-	g.j0 = i1 - (pr.d_end - 1);
-	g.cols = min(g.qlen - 1 - pr.d_begin, g.tlen - 1) + 1 - g.j0;  // dp/dp.h:47-52
-	return g;
-}
 
 // The four reference masks of one cell, written as ORDER tests on the inputs instead of equality tests on the max
 // results (all of e_in, f_in, open are >= 0 by the floor semantics, so the two forms are equivalent):
@@ -86,16 +53,6 @@ __device__ __forceinline__ void trace_store(uint8_t* p, const uint32_t* pk) {
 	else if (R == 16) *reinterpret_cast<uint2*>(p) = make_uint2(pk[0], pk[1]);
 	else *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
-// register tile per lane of the warp kernels (32 R >= B); bands beyond 1024 diagonals use the same trace layout with R = 64 / 128
-// and are evaluated by swipe_wide_kernel (one CTA per problem)
-#define DMND_MAX_BAND 4096
-__host__ __device__ __forceinline__ int tile_rows(int B) { return B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : B <= 2048 ? 64 : 128; }
-// nibble of cell (column c, band row r) in the wavefront-major layout
-__device__ __forceinline__ unsigned trace_nibble(const uint8_t* tr, int R, int c, int r) {
-	const int m = c + (r >> 1), lane = r / R, k = r - lane * R;
-	return (tr[((size_t)m * 32 + lane) * (R >> 1) + (k >> 1)] >> ((k & 1) * 4)) & 15u;
-}
-
 template<int R, bool TRACE>
 __global__ void __launch_bounds__(128) swipe_kernel(const SwipeArgs a, const DevParams* __restrict__ P) {
 	__shared__ int8_t s_score[1024];
@@ -374,92 +331,6 @@ __global__ void __launch_bounds__(128) swipe_prof_kernel(const SwipeArgs a, cons
 			if (lane == 0) a.score[pi] = best;
 		}
 	}
-}
-
-struct WalkArgs {
-	const int8_t *q_letters, *q_bias, *r_letters;
-	const int64_t *q_limits, *r_limits;
-	const dmnd_dp_problem* probs;
-	const uint32_t* order;
-	uint32_t n;
-	const int32_t* score;
-	const int32_t* end_cell;
-	const uint8_t* trace;
-	const uint64_t* trace_excl;
-	uint64_t trace_base;
-	uint32_t order_pos0;
-	dmnd_dp_result* res;
-	uint8_t* transcripts;           // may be null
-	const uint64_t* transcript_off; // [problem], capacity qlen + tlen each
-};
-
-__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevParams* __restrict__ P) {
-	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= a.n) return;
-	const uint32_t pi = a.order[w];
-	const dmnd_dp_problem pr = a.probs[pi];
-	SwipeArgs sa;
-	sa.q_letters = a.q_letters; sa.q_bias = a.q_bias; sa.r_letters = a.r_letters; sa.q_limits = a.q_limits; sa.r_limits = a.r_limits;
-	const ProbGeom g = geom(sa, pr);
-	dmnd_dp_result res;
-	res.score = a.score[pi];
-	res.q_begin = res.q_end = res.t_begin = res.t_end = 0;
-	res.identities = res.mismatches = res.gap_openings = res.length = res.gaps = res.positives = 0;
-	res.transcript_off = 0; res.transcript_len = 0; res.status = 0;
-	const int best = res.score;
-	if (best > 0) {
-		const uint8_t* tr = a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base);
-		const int R = tile_rows(g.B);
-		int c = a.end_cell[2 * (size_t)pi], r = a.end_cell[2 * (size_t)pi + 1];
-		int i = g.j0 + g.d_begin + c + r, j = g.j0 + c;
-		res.q_end = i + 1; res.t_end = j + 1;
-		uint8_t* out = a.transcripts ? a.transcripts + a.transcript_off[pi] : nullptr;
-		const uint32_t cap = (uint32_t)(g.qlen + g.tlen);
-		uint32_t n = 0;
-		int sc = 0;
-		const int gopen = P->gap_open, gext = P->gap_extend;
-		bool bad = false;
-		while (i >= 0 && j >= 0 && sc < best) {
-			if (c < 0 || r < 0 || r >= g.B) { bad = true; break; }
-			const unsigned nib = trace_nibble(tr, R, c, r);
-			if ((nib & 3) == 0) {
-				const int ql = g.q[i] & 31, sl = g.t[j] & 31;
-				const int m = P->score[(ql << 5) | sl];
-				sc += m + (int)g.cb[i];
-				if (ql == sl) { ++res.identities; ++res.positives; if (out && n < cap) out[n] = (uint8_t)(DMND_OP_MATCH << 6); }
-				else { ++res.mismatches; if (m > 0) ++res.positives; if (out && n < cap) out[n] = (uint8_t)((DMND_OP_SUBSTITUTION << 6) | sl); }
-				++n; ++res.length;
-				--i; --j; --c;
-			}
-			else if (nib & 1) {
-				int l = 0;
-				do { ++l; --i; --r; } while (r >= 0 && (trace_nibble(tr, R, c, r) & 4) == 0 && i > 0);
-				if (r < 0) { bad = true; break; }
-				++res.gap_openings; res.length += l; res.gaps += l;
-				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)(DMND_OP_INSERTION << 6); ++n; }
-				sc -= gopen + l * gext;
-			}
-			else {
-				int l = 0;
-				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && (trace_nibble(tr, R, c, r) & 8) == 0 && j > 0);
-				if (c < 0 || r >= g.B) { bad = true; break; }
-				++res.gap_openings; res.length += l; res.gaps += l;
-				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)((DMND_OP_DELETION << 6) | (g.t[j + l - k] & 31)); ++n; }
-				sc -= gopen + l * gext;
-			}
-		}
-		if (bad || sc != best) res.status = 2;  // "Traceback error." (banded_swipe.h:176-177)
-		res.q_begin = i + 1; res.t_begin = j + 1;
-		if (out) {
-			if (n > cap) res.status = 1;
-			else {
-				for (uint32_t x = 0, y = n; x + 1 < y; ++x, --y) { const uint8_t tmp = out[x]; out[x] = out[y - 1]; out[y - 1] = tmp; }
-				res.transcript_off = (uint32_t)a.transcript_off[pi];
-				res.transcript_len = n;
-			}
-		}
-	}
-	a.res[pi] = res;
 }
 
 static __global__ void fill_score_results(const int32_t* score, dmnd_dp_result* res, uint32_t n) {

@@ -190,6 +190,11 @@ int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* lett
  *   which survivors share a window_ungapped_best call).  The key is an implementation detail (equal keys <=> equal seeds). */
 int dmnd_debug_block_soft(dmnd_ctx* ctx, const dmnd_block* b, uint8_t* out, size_t raw_len);
 int dmnd_debug_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, uint64_t* keys, uint32_t* locs, size_t cap, size_t* n);
+/* dmnd_debug_left_most: the left-most filter (search/left_most.h:62-110) of one (query location, reference location) pair of shape sid in
+ *   index chunk `chunk`, on the block's current SEED_MASK state: out30[0] = pass, [1] match mask, [2] SEED_MASK bits of the window,
+ *   [3] matcher hits left (raw << 32 | masked), [4] right, [5..6] window geometry, [7..8] verify_hits left / right (2 = not evaluated),
+ *   [9..28] per left candidate: pos << 56 | verify_hit << 48 | current-shape match << 40 | valid << 36 | fingerprint << 24 | partition, [29] count. */
+int dmnd_debug_left_most(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out30);
 /* Clears the SEED_MASK bits (run/double_indexed.cpp:211-212). */
 int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b);
 int dmnd_block_clear_seed_mask_range(dmnd_ctx* ctx, dmnd_block* b, uint32_t q_begin, uint32_t q_end);

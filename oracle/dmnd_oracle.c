@@ -563,6 +563,59 @@ static void motif_seed_mask(const dmnd_params* p, dmnd_block* query, int sid, ui
 		}
 	}
 }
+/* Diagnostics twin of the device library's dmnd_debug_left_most (tools/seed_stage_diag.py): same out30 layout. */
+int dmnd_debug_left_most(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out) {
+	const dmnd_params* p = &ctx->p;
+	const uint32_t parts_total = 1u << p->seedp_bits;
+	const uint32_t nchunks = (uint32_t)p->index_chunks < parts_total ? (uint32_t)p->index_chunks : parts_total;
+	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks, bsel = (uint32_t)chunk < prem ? (uint32_t)chunk : prem;
+	const uint32_t pb = bsel * (psize + 1) + ((uint32_t)chunk - bsel) * psize, pe = pb + ((uint32_t)chunk < prem ? psize + 1 : psize);
+	lm_ctx x; x.c = ctx; x.sid = sid; x.chunked = p->index_chunks > 1; x.range_begin = pb; x.range_end = pe;
+	memset(out, 0, 30 * sizeof *out);
+	const int8_t *qp = query->letters + qloc, *sp = ref->letters + sloc;
+	const uint32_t qid = seq_of(query, qloc);
+	const int seed_offset0 = (int)((int64_t)qloc - query->limits[qid]);
+	const int window0 = p->ungapped_window;
+	const int8_t *cb, *ce;
+	clip(qp - window0, window0 * 2, window0, &cb, &ce);
+	const int window_left0 = (int)(qp - cb), window_clipped = (int)(ce - cb);
+	const int interval_mod = p->left_most_interval > 0 ? seed_offset0 % p->left_most_interval : window_left0;
+	const int overhang = window_left0 - interval_mod > 0 ? window_left0 - interval_mod : 0;
+	const int8_t *qry = cb + overhang, *subject = sp - window_left0 + overhang;
+	const int query_len = window_clipped - overhang, seed_offset = window_left0 - overhang, seed_len = p->shape_len[sid];
+	out[0] = (unsigned long long)left_most_filter(&x, qry, query_len, subject, seed_offset, seed_len);
+	int d = seed_offset - 16 > 0 ? seed_offset - 16 : 0, window_left = seed_offset < 16 ? seed_offset : 16;
+	const int8_t *q = qry + d, *s = subject + d;
+	int window = query_len - d;
+	if (window > window_left + 1 + 32) window = window_left + 1 + 32;
+	clip(s, window, window_left, &cb, &ce);
+	window -= (int)(s + window - ce);
+	d = (int)(cb - s);
+	q += d; s += d; window_left -= d; window -= d;
+	const uint64_t match_mask = reduced_match(p, q, s, window), seed_bits = seed_mask_bits(q, window), query_seed_mask = ~seed_bits;
+	const uint32_t len_left = (uint32_t)(window_left + seed_len - 1), match_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & match_mask),
+		query_mask_left = (uint32_t)((((uint64_t)1 << len_left) - 1) & query_seed_mask);
+	const uint32_t raw_left = matcher_hit(ctx, sid + 1, match_mask_left, len_left), left_hit = raw_left & query_mask_left;
+	const uint32_t len_right = (uint32_t)(window - window_left - 1), match_mask_right = (uint32_t)(match_mask >> (window_left + 1)), query_mask_right = (uint32_t)(query_seed_mask >> (window_left + 1));
+	const uint32_t right_hit = matcher_hit(ctx, x.chunked ? sid + 1 : sid, match_mask_right, len_right) & query_mask_right;
+	out[1] = match_mask; out[2] = seed_bits; out[3] = ((uint64_t)raw_left << 32) | left_hit; out[4] = right_hit;
+	out[5] = ((uint64_t)(uint32_t)seed_offset << 32) | (uint32_t)window_left; out[6] = ((uint64_t)(uint32_t)window << 32) | len_left;
+	out[7] = left_hit ? (unsigned long long)verify_hits(&x, left_hit, q, s, 1, match_mask_left) : 2;
+	out[8] = right_hit ? (unsigned long long)verify_hits(&x, right_hit, q + window_left + 1, s + window_left + 1, 0, match_mask_right) : 2;
+	int n = 0;
+	for (int pos = 0; pos < 32 && n < 20; ++pos) {
+		if (!((left_hit >> pos) & 1u)) continue;
+		const uint32_t mm = match_mask_left >> pos;
+		uint64_t seed = 0; int valid = 1;
+		for (int k = 0; k < p->shape_weight; ++k) { const int l = s[pos + p->shape_pos[sid][k]] & DMND_LETTER_MASK; if (l == 23 || l == 31 || l == 24) valid = 0; seed = seed * (uint64_t)p->reduction_size + p->reduction[l]; }
+		const uint32_t part = (uint32_t)(seed & (((uint64_t)1 << p->seedp_bits) - 1));
+		out[9 + n] = ((uint64_t)pos << 56) | ((uint64_t)verify_hit(&x, q + pos, s + pos, 1, mm) << 48) | ((uint64_t)((p->shape_mask[sid] & mm) == p->shape_mask[sid]) << 40)
+			| ((uint64_t)valid << 36) | ((uint64_t)fingerprint_match(q + pos, s + pos) << 24) | part;
+		++n;
+	}
+	out[29] = (unsigned long long)n;
+	return 0;
+}
 /* Test-only: tantan on every sequence of the block (letters are masked in place); out_ratio[i] = log2(Z / W_bg) of
  * sequence i as the device's forward kernel computes it (diamond_b200/csrc/cuda/mask_kernels.cuh: sequences with a ratio
  * below 3 skip the backward pass there), out_masked[i] = letters tantan masked in it.  tests/test_masking.py checks the

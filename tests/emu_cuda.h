@@ -21,6 +21,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 
@@ -176,3 +177,56 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift)
 template<typename T, typename U> static inline T atomicAdd(T* p, U v) { const T o = *p; *p = (T)(o + (T)v); return o; }
 template<typename T, typename U> static inline T atomicOr(T* p, U v) { const T o = *p; *p = (T)(o | (T)v); return o; }
 template<typename T, typename U> static inline T atomicAnd(T* p, U v) { const T o = *p; *p = (T)(o & (T)v); return o; }
+
+// ---- additions for the packed 16-bit banded SWIPE kernel (diamond_b200/csrc/cuda/swipe16.cuh) ----
+#define __align__(n)
+#define __restrict__
+template<typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+	const int slot = emu::warp_rendezvous(mask, emu_to_bits(v));
+	const unsigned lane = threadIdx.x & 31u, base = lane & ~(unsigned)(width - 1);
+	const T r = lane >= base + delta ? emu_bits_to<T>(emu::read_lane(lane - delta, slot)) : v;
+	emu::warp_rendezvous(mask, 0);
+	return r;
+}
+template<typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width) {
+	const int slot = emu::warp_rendezvous(mask, emu_to_bits(v));
+	const unsigned lane = threadIdx.x & 31u, base = lane & ~(unsigned)(width - 1), src = lane + delta;
+	const T r = src < base + (unsigned)width ? emu_bits_to<T>(emu::read_lane(src, slot)) : v;
+	emu::warp_rendezvous(mask, 0);
+	return r;
+}
+static inline bool __all_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) == mask; }
+static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
+template<typename T, typename U> static inline T atomicExch(T* p, U v) { const T o = *p; *p = (T)v; return o; }
+static inline short emu_lo(unsigned x) { return (short)(x & 0xffffu); }
+static inline short emu_hi(unsigned x) { return (short)(x >> 16); }
+static inline unsigned emu_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }  // wraps like the hardware
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) {
+	const int lo = (short)(emu_lo(a) + emu_lo(b)), hi = (short)(emu_hi(a) + emu_hi(b));
+	return emu_pack(lo > emu_lo(c) ? lo : emu_lo(c), hi > emu_hi(c) ? hi : emu_hi(c));
+}
+static inline unsigned __viaddmax_s16x2_relu(unsigned a, unsigned b, unsigned c) {
+	const unsigned r = __viaddmax_s16x2(a, b, c);
+	return emu_pack(emu_lo(r) > 0 ? emu_lo(r) : 0, emu_hi(r) > 0 ? emu_hi(r) : 0);
+}
+static inline unsigned __vimax_s16x2(unsigned a, unsigned b) { return emu_pack(emu_lo(a) > emu_lo(b) ? emu_lo(a) : emu_lo(b), emu_hi(a) > emu_hi(b) ? emu_hi(a) : emu_hi(b)); }
+static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) {
+	const unsigned r = __vimax_s16x2(a, b);
+	return emu_pack(emu_lo(r) > 0 ? emu_lo(r) : 0, emu_hi(r) > 0 ? emu_hi(r) : 0);
+}
+static inline unsigned __vminu2(unsigned a, unsigned b) {
+	const unsigned al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+	return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+}
+static inline unsigned __vimax3_u32(unsigned a, unsigned b, unsigned c) { const unsigned m = a > b ? a : b; return m > c ? m : c; }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
+	const uint64_t v = ((uint64_t)b << 32) | a;
+	unsigned r = 0;
+	for (int k = 0; k < 4; ++k) {
+		const unsigned sel = (s >> (4 * k)) & 0xfu;
+		unsigned byte = (unsigned)(v >> (8 * (sel & 7u))) & 0xffu;
+		if (sel & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;
+		r |= byte << (8 * k);
+	}
+	return r;
+}

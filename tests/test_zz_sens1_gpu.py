@@ -6,15 +6,10 @@ import numpy as np
 import pytest
 from conftest import GOLDEN, ROOT, workload_blocks
 
-# Status at the end of round 1 (B200 runs recorded in profiles/pytest_gpu_r1.txt):
-#  * dmnd_hits_gapped_filter (gapped_filter_kernel) matches the oracle on the device: test_gapped_filter_flags_match_oracle passed.
-#  * the seed stage of the modes above --fast does NOT yet: after ordering a key's locations (build_ref_index) the last run
-#    still failed test_search_shapes_match_oracle -- shape 1 returned 69 hits where the oracle (= the reference) has 65 on `edge`,
-#    and fam2 shape 0 differed as well.  The GPU budget of the round ended there.  Those tests, and the pipeline tests that
-#    depend on them, are non-strict xfail so that they keep running without hiding the rest of the suite; the same comparisons
-#    pass on the CPU against the oracle-linked pipeline (tests/test_sensitivity_default.py), which is what pins the modes.
+# History: in round 1 these failed on the B200 (2-5 hits of ~3 100 too many for shape 1, different from run to run) although the same
+# kernel source passed under the CPU emulation.  Round 2 traced it to the code ptxas generated for the left-most filter when it was
+# inlined into stage2_window_kernel (profiles/lm_variants_r2.txt); the filter is a real call now and the tests are ordinary tests.
 pytestmark = pytest.mark.gpu
-SEED_STAGE_OPEN = pytest.mark.xfail(strict=False, reason="seed stage of the modes above --fast differs from the oracle on the device (round 1, see header)")
 
 def sorted_hits(h):
     return np.sort(h, order=["query", "subject_score", "seed_offset"])
@@ -35,7 +30,6 @@ def hit_diff(ho, hg, r_lim):
     return f"hits: oracle {len(ho)} device {len(hg)}; only oracle {len(set(a) - set(b))}: {only_o}; only device {len(set(b) - set(a))}: {only_g}; other score {sum(a[k] != b[k] for k in set(a) & set(b))}: {other}"
 
 
-@SEED_STAGE_OPEN
 @pytest.mark.parametrize("name,masking", [("fam2", 0), ("rep", 1), ("edge", 1)])
 def test_search_shapes_match_oracle(oracle_lib, product_lib, name, masking):
     from diamond_b200 import api
@@ -62,7 +56,6 @@ def test_search_shapes_match_oracle(oracle_lib, product_lib, name, masking):
         assert (sc == 255).sum() > 100 and (sc > 255).sum() > 0
 
 
-@SEED_STAGE_OPEN
 @pytest.mark.parametrize("name", ["c1", "fam2", "edge", "long", "rep"])
 def test_blastp_default_sensitivity_matches_reference_golden(product_lib, name):
     from diamond_b200 import api
@@ -95,7 +88,6 @@ def test_gapped_filter_flags_match_oracle(oracle_lib, product_lib, name):
     assert 0 < res[1][1].sum() < len(res[1][1])
 
 
-@SEED_STAGE_OPEN
 @pytest.mark.parametrize("sens,level", [(2, "s2"), (3, "s3")])
 @pytest.mark.parametrize("name", ["c1", "edge", "rep"])
 def test_blastp_mid_sensitive_and_sensitive_match_reference_golden(product_lib, name, sens, level):
@@ -111,7 +103,6 @@ def test_blastp_mid_sensitive_and_sensitive_match_reference_golden(product_lib, 
     assert st["targets"] == cn["targets"] and st["dp_problems_round2"] == cn["targets_round2"]
 
 
-@SEED_STAGE_OPEN
 def test_cli_without_sensitivity_flag(product_lib, tmp_path):
     from diamond_b200 import synth
     w, *_ = workload_blocks("c1")

@@ -1,14 +1,11 @@
 """blastx on the device: the same kernels as blastp --fast over a query block of six translated contexts per
 read; what changes is host logic (frames per target, frame-aware culling, nucleotide coordinates).  Against the reference's
-goldens (tests/golden/bx.*).  NOT YET RUN ON A B200 (written after the round's GPU budget was spent): the CPU suite
-(tests/test_blastx.py) runs the identical host code over the oracle's K layer."""
+goldens (tests/golden/bx.*); the CPU suite (tests/test_blastx.py) runs the identical host code over the oracle's K layer."""
 import json, os, subprocess
 import pytest
 from conftest import GOLDEN, ROOT
 
-# never run on a B200 yet (written after the round's GPU budget was spent): non-strict xfail so that a surprise shows up as a
-# reported failure reason (or as XPASS when all is well) without stopping `pytest -m gpu -x` before the proven tests' results count
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="blastx on the device: written after the GPU budget of round 1 was spent, first run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def _bx():

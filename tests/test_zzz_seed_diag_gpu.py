@@ -2,14 +2,12 @@
 table of both blocks and, per shape of the default sensitivity, the reference-side index -- same locations, equal keys <=> equal
 seeds, locations ascending inside a key (what the stage-2 window filter's call sizes depend on).  These localise a difference
 that tests/test_zz_sens1_gpu.py only sees in the hits; tools/seed_stage_diag.py prints the same comparison for every stage.
-Written after the round's GPU budget was spent: NOT YET RUN ON A B200 (sorted last so that a surprise cannot hide proven tests)."""
+(Sorted last: diagnostics.)"""
 import numpy as np
 import pytest
 from conftest import workload_blocks
 
-# never run on a B200 yet (written after the round's GPU budget was spent): non-strict xfail so that a surprise shows up as a
-# reported failure reason (or as XPASS when all is well) without stopping `pytest -m gpu -x` before the proven tests' results count
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="seed-stage diagnostics on the device: written after the GPU budget of round 1 was spent, first run pending")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["edge", "rep"])
