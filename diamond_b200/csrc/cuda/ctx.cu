@@ -215,6 +215,7 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	}
 	c->h_pinned_cap = 1 << 16;
 	DMND_CUDA_CHECK(cudaMallocHost(&c->h_pinned, c->h_pinned_cap));
+	if (dmnd_cuda::s16_table_build(c)) return 1;
 	*out = c;
 	return 0;
 }
@@ -249,6 +250,7 @@ void dmnd_destroy(dmnd_ctx* c) {
 	c->b_hits_out.release();
 	c->own_index.release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
+	if (c->d_s16_table) cudaFree(c->d_s16_table);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_sync);

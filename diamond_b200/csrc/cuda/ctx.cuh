@@ -93,6 +93,10 @@ struct dmnd_ctx {
 	uint64_t mask_n = 0;  // letters hard-masked by the last dmnd_block_mask on this context (sorted offsets in b_mask_pos)
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
 	bool force_generic_dp = false;
+	bool force_int32_dp = false;     // the packed 16-bit kernel overflowed: this call runs on the int32 kernels
+	int8_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
+	bool s16_ok = false;
+	uint64_t dp_overflows = 0;       // calls repeated on the int32 kernels
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
 	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
 	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)
@@ -145,6 +149,7 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap);
 int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard);
 int block_mask_fetch_impl(dmnd_ctx* ctx, uint64_t* positions, size_t cap);
+int s16_table_build(dmnd_ctx* ctx);
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 

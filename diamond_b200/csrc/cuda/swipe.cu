@@ -575,54 +575,108 @@ __global__ void __launch_bounds__(WIDE_THREADS) swipe_wide_kernel(const SwipeArg
 	}
 }
 
-// ---- device-side preparation: geometry, register-tile bin, cost class, bucket histogram ------------------------------
+// ---- device-side preparation: geometry, launch group, order key, trace cost ---------------------------------------------
+// Launch groups: 0..7 = packed 16-bit kernel (swipe16.cuh), register tile R = 4, 8, 12, 16 x {short, long query};
+// 8..21 = int32 kernels, tile_rows() = 2..128 x {short, long query}; 22 = statistics passes.  Inside a group the problems are
+// ordered by macro steps, longest first: the four problems of a quarter-warp-per-problem warp run in lock step, so they should
+// be of one size, and the heaviest work starts first.
+constexpr int NG = 23, G_STATS = 22, G_LEGACY = 8;
 struct PrepOut {
-	uint8_t* key;        // [n] bucket = (bin * 2 + long) * 16 + cost class (heavy problems first inside a bucket group)
-	unsigned int* maxq;  // [256] longest query per bucket (sizes the shared-memory profile of the launch)
+	uint32_t* key;       // [n] group << 20 | (0xFFFFF - macro steps)
+	uint32_t* idx;       // [n] problem index (sort payload)
 	uint64_t* cost;      // [n] trace bytes (traceback) or cells (score only)
 	uint64_t* tslen;     // [n] qlen + tlen (transcript capacity)
-	unsigned int* hist;  // [256]
+	unsigned int* hist;  // [NG] problems per group
+	unsigned int* maxq;  // [NG] longest query per group (sizes the shared memory of the launch)
+	unsigned long long* cost_hist;  // [NG] trace bytes per group, [NG] = sum of tslen: the host derives group bases and totals without a second sync
 	unsigned int* flag;  // error flag
-	unsigned long long* cost_hist;  // [256] cost per bucket, [256] sum of tslen: the host derives group bases and totals without a second sync
 };
-__global__ void prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t n, const int64_t* __restrict__ ql, uint32_t nq,
-                            const int64_t* __restrict__ rl, uint32_t nr, int trace, PrepOut o) {
+__global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t n, const int64_t* __restrict__ ql, uint32_t nq,
+                                                    const int64_t* __restrict__ rl, uint32_t nr, int trace, int s16, PrepOut o) {
+	__shared__ unsigned int s_hist[NG], s_maxq[NG];
+	__shared__ unsigned long long s_cost[NG + 1];
+	for (int x = threadIdx.x; x <= NG; x += blockDim.x) { if (x < NG) { s_hist[x] = 0; s_maxq[x] = 0; } s_cost[x] = 0; }
+	__syncthreads();
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) return;
-	const dmnd_dp_problem p = probs[k];
-	if (p.query >= nq || p.target >= nr) { atomicMax(o.flag, 1u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
-	const int qlen = (int)(ql[p.query + 1] - ql[p.query] - 1), tlen = (int)(rl[p.target + 1] - rl[p.target] - 1);
-	const int B = p.d_end - p.d_begin;
-	const int i1 = max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
-	const int cols = min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
-	if (B > DMND_MAX_BAND) { atomicMax(o.flag, 2u); o.key[k] = 0; o.cost[k] = 0; o.tslen[k] = 0; return; }
-	const bool live = B > 0 && cols > 0;
-	const int R = tile_rows(B);
-	const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : R == 32 ? 4 : R == 64 ? 5 : 6;
-	const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
-	const int cls = 15 - min(15, (63 - __clzll(cells + 1)) >> 1);
-	const int lng = (qlen + 32 * R + 4) > 768 ? 1 : 0;
-	// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (bucket 240, no trace bytes)
-	const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
-	const uint8_t key = stats ? (uint8_t)240 : (uint8_t)((b * 2 + lng) * 16 + cls);
-	atomicMax(&o.maxq[key], (unsigned)qlen);
-	o.key[k] = key;
-	const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
-	o.cost[k] = stats ? 0ull : trace ? nmacro * 16ull * (unsigned long long)R : cells;
-	o.tslen[k] = (uint64_t)qlen + (uint64_t)tlen;
-	atomicAdd(&o.hist[key], 1u);
-	atomicAdd(&o.cost_hist[key], o.cost[k]);
-	atomicAdd(&o.cost_hist[256], (unsigned long long)qlen + (unsigned long long)tlen);
-}
-__global__ void scatter_kernel(const uint8_t* __restrict__ key, uint32_t n, const unsigned int* __restrict__ off, unsigned int* fill, uint32_t* order) {
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) return;
-	const unsigned b = key[k];
-	order[off[b] + atomicAdd(&fill[b], 1u)] = k;
+	if (k < n) {
+		const dmnd_dp_problem p = probs[k];
+		uint32_t key = 0; uint64_t cost = 0, tslen = 0;
+		if (p.query >= nq || p.target >= nr) atomicMax(o.flag, 1u);
+		else {
+			const int qlen = (int)(ql[p.query + 1] - ql[p.query] - 1), tlen = (int)(rl[p.target + 1] - rl[p.target] - 1);
+			const int B = p.d_end - p.d_begin;
+			const int i1 = max(p.d_end - 1, 0), j0 = i1 - (p.d_end - 1);
+			const int cols = min(qlen - 1 - p.d_begin, tlen - 1) + 1 - j0;
+			if (B > DMND_MAX_BAND) atomicMax(o.flag, 2u);
+			else {
+				const bool live = B > 0 && cols > 0;
+				const unsigned long long cells = live ? (unsigned long long)B * (unsigned long long)cols : 0ull;
+				const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
+				// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (no trace bytes)
+				const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
+				int g; unsigned long long step_bytes;
+				if (stats) { g = G_STATS; step_bytes = 0; }
+				else if (s16 && B <= S16_MAX_BAND && nmacro <= (unsigned long long)S16_MAX_MACRO && qlen <= 16000) {
+					const int R = s16_rows(B);
+					g = (R / 4 - 1) * 2 + ((qlen + 8 * R + 4) > 768 ? 1 : 0);
+					step_bytes = (unsigned long long)s16_step_bytes(R);
+				}
+				else {
+					const int R = tile_rows(B);
+					const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : R == 32 ? 4 : R == 64 ? 5 : 6;
+					g = G_LEGACY + b * 2 + ((qlen + 32 * R + 4) > 768 ? 1 : 0);
+					step_bytes = 16ull * (unsigned long long)R;
+				}
+				key = ((uint32_t)g << 20) | (0xFFFFFu - (uint32_t)min(nmacro, 0xFFFFFull));
+				cost = stats ? 0ull : trace ? nmacro * step_bytes : cells;
+				tslen = (uint64_t)qlen + (uint64_t)tlen;
+				atomicAdd(&s_hist[g], 1u);
+				atomicMax(&s_maxq[g], (unsigned)qlen);
+				atomicAdd(&s_cost[g], cost);
+				atomicAdd(&s_cost[NG], tslen);
+			}
+		}
+		o.key[k] = key; o.idx[k] = k; o.cost[k] = cost; o.tslen[k] = tslen;
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x <= NG; x += blockDim.x) {
+		if (x < NG && s_hist[x]) { atomicAdd(&o.hist[x], s_hist[x]); atomicMax(&o.maxq[x], s_maxq[x]); }
+		if (s_cost[x]) atomicAdd(&o.cost_hist[x], s_cost[x]);
+	}
 }
 __global__ void gather_cost_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ cost, uint32_t n, uint64_t* out) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < n) out[k] = cost[order[k]];
+}
+
+template<bool TRACE>
+static int launch_s16_bin(int R, const SwipeArgs& a, const DevParams* P, const S16Args& sa, int grid, int threads, size_t smem, cudaStream_t st) {
+#define DMND_LAUNCH_S16(RR)                                                                                             \
+	do {                                                                                                                 \
+		if (smem > 40 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe16_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		swipe16_kernel<RR, TRACE><<<grid, threads, smem, st>>>(a, P, sa);                                                \
+	} while (0)
+	switch (R) {
+	case 4: DMND_LAUNCH_S16(4); break;
+	case 8: DMND_LAUNCH_S16(8); break;
+	case 12: DMND_LAUNCH_S16(12); break;
+	default: DMND_LAUNCH_S16(16); break;
+	}
+#undef DMND_LAUNCH_S16
+	return 0;
+}
+
+int s16_table_build(dmnd_ctx* ctx) {
+	DMND_CUDA_CHECK(cudaMalloc(&ctx->d_s16_table, (size_t)S16_TABLE_BYTES + 16));
+	unsigned* d_bad = nullptr;
+	DMND_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(unsigned)));
+	DMND_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(unsigned)));
+	s16_table_kernel<<<(S16_TABLE_BYTES + 255) / 256, 256>>>(ctx->d_params, ctx->d_s16_table, d_bad);
+	unsigned bad = 1;
+	DMND_CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+	cudaFree(d_bad);
+	ctx->s16_ok = bad == 0;  // a matrix with S + bias outside int8 never takes the packed kernel
+	return 0;
 }
 
 int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
@@ -640,21 +694,26 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		tp = now;
 	};
 	static const int RS[7] = { 2, 4, 8, 16, 32, 64, 128 };
-	constexpr int NG = 14;  // launch groups g = bin * 2 + long-query flag; bucket 240 = statistics passes
 	const unsigned nb = (unsigned)((n + 255) / 256);
+	const bool force_generic = ctx->force_generic_dp || getenv("DMND_GENERIC_DP") != nullptr;
+	const bool use_s16 = ctx->s16_ok && !ctx->force_int32_dp && !force_generic && getenv("DMND_INT32_DP") == nullptr;
 	// ---- device buffers
+	size_t sort_tmp = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 25, st);
 	if (ctx->b_probs.ensure(n * sizeof(dmnd_dp_problem)) || ctx->b_order.ensure(n * sizeof(uint32_t)) || ctx->b_results.ensure(n * sizeof(dmnd_dp_result))
-	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 1280 * sizeof(unsigned int) + 8 + 258 * sizeof(unsigned long long))
-	    || ctx->b_prep.ensure(n * (1 + 8 + 8 + 8 + 8) + 64))
+	    || ctx->b_work.ensure(n * sizeof(int32_t) * 3 + 256 * sizeof(unsigned int) + 8 + 64 * sizeof(unsigned long long))
+	    || ctx->b_prep.ensure(n * (8 + 8 + 8 + 8 + 4 + 4 + 4) + 64) || ctx->b_cub.ensure(sort_tmp))
 		return 1;
 	int32_t* d_score = ctx->b_work.as<int32_t>();
 	int32_t* d_end = d_score + n;
-	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);  // [0..63] work counters, [64] error flag, [65] profile overflow, [256..511] hist, [512..767] offsets, [768..1023] fill, [1024..1279] max qlen
+	unsigned int* d_counters = (unsigned int*)(d_end + 2 * n);  // [0..63] work counters, [64] error flag, [65] overflow of the int8 profile, [66] overflow of the packed kernel, [96..] hist, [128..] max qlen
 	uint64_t* d_cost = ctx->b_prep.as<uint64_t>();
 	uint64_t* d_tslen = d_cost + n;
 	uint64_t* d_cum = d_tslen + n;    // exclusive prefix of cost in order sequence (n entries) -- reused as gather buffer
 	uint64_t* d_tsoff = d_cum + n;    // exclusive prefix of tslen in problem order
-	uint8_t* d_key = (uint8_t*)(d_tsoff + n);
+	uint32_t* d_key = (uint32_t*)(d_tsoff + n);
+	uint32_t* d_key2 = d_key + n;
+	uint32_t* d_idx = d_key2 + n;
 	{
 		PhaseTimer t(ctx, PH_H2D);
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_probs.p, problems, n * sizeof(dmnd_dp_problem), cudaMemcpyHostToDevice, st));
@@ -663,33 +722,28 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	}
 	lap("upload problems");
 	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 1280 * sizeof(unsigned int), st));
-	unsigned long long* d_cost_hist = (unsigned long long*)(((uintptr_t)(d_counters + 1280) + 7) & ~(uintptr_t)7);  // [0..255] cost per bucket, [256] sum of tslen
-	DMND_CUDA_CHECK(cudaMemsetAsync(d_cost_hist, 0, 258 * sizeof(unsigned long long), st));
-	PrepOut po{ d_key, d_counters + 1024, d_cost, d_tslen, d_counters + 256, d_counters + 64, d_cost_hist };
-	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, po);
-	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..255] hist, [256] flag, [512..767] offsets (upload), [1024..1279] max qlen
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 256, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 1024, d_counters + 1024, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 256, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-	uint64_t* hq = (uint64_t*)(hp + 1536);  // [0..255] cost per bucket, [256] sum of tslen, then [260..270] group bases
-	t_dp.mark_end();  // device time of the prep kernel; the host's binning decisions below are not device time
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, 257 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 256 * sizeof(unsigned int), st));
+	unsigned long long* d_cost_hist = (unsigned long long*)(((uintptr_t)(d_counters + 256) + 7) & ~(uintptr_t)7);  // [0..NG-1] cost per group, [NG] sum of tslen
+	DMND_CUDA_CHECK(cudaMemsetAsync(d_cost_hist, 0, 64 * sizeof(unsigned long long), st));
+	PrepOut po{ d_key, d_idx, d_cost, d_tslen, d_counters + 96, d_counters + 128, d_cost_hist, d_counters + 64 };
+	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, use_s16 ? 1 : 0, po);
+	DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, sort_tmp, d_key, d_key2, d_idx, ctx->b_order.as<uint32_t>(), n, 0, 25, st));
+	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..31] hist, [32..63] max qlen, [64] flag, [65] profile overflow, [66] packed-kernel overflow
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 96, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 32, d_counters + 128, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 64, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	uint64_t* hq = (uint64_t*)(hp + 128);  // [0..NG-1] cost per group, [NG] sum of tslen, then [32..] group bases
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, (NG + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	ctx->launches += 4;
+	t_dp.mark_end();  // device time of the preparation; the host's decisions below are not device time
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	t_dp.collect();
-	if (hp[256] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
-	if (hp[256] == 2) { set_error("dmnd_banded_swipe: band wider than 4096 diagonals is not supported by this build"); return 1; }
-	unsigned int off[257];
-	off[0] = 0;
-	for (int k = 0; k < 256; ++k) off[k + 1] = off[k] + hp[k];
-	// launch groups: g = bin * 2 + long-query flag; inside a group the buckets are ordered heavy -> light
+	if (hp[64] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
+	if (hp[64] == 2) { set_error("dmnd_banded_swipe: band wider than 4096 diagonals is not supported by this build"); return 1; }
 	size_t grp_begin[NG + 1];
-	for (int g = 0; g <= NG; ++g) grp_begin[g] = off[std::min(g * 16, 256)];
-	std::memcpy(hp + 512, off, 256 * sizeof(unsigned int));
+	grp_begin[0] = 0;
+	for (int g = 0; g < NG; ++g) grp_begin[g + 1] = grp_begin[g] + hp[g];
 	t_dp.restart();
-	DMND_CUDA_CHECK(cudaMemcpyAsync(d_counters + 512, hp + 512, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
-	scatter_kernel<<<nb, 256, 0, st>>>(d_key, (uint32_t)n, d_counters + 512, d_counters + 768, ctx->b_order.as<uint32_t>());
-	ctx->launches += 2;
 	lap("device prep");
 
 	SwipeArgs a;
@@ -697,30 +751,43 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	a.probs = ctx->b_probs.as<dmnd_dp_problem>();
 	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_excl = nullptr; a.trace_base = 0; a.order_pos0 = 0;
 	uint64_t ts_total = 0;
-	const bool force_generic = ctx->force_generic_dp || getenv("DMND_GENERIC_DP") != nullptr;
-	// one DP launch over order[pos, e) of group g: profile kernel when the profile fits shared memory, else the generic one
+	// one DP launch over order[pos, e) of group g
 	auto launch_dp = [&](int g, size_t pos, size_t e, bool tr_mode) -> int {
-		const int R = RS[g >> 1];
-		unsigned maxq = 0;
-		for (int k = 0; k < 16; ++k) maxq = std::max(maxq, hp[1024 + g * 16 + k]);
-		const int w4 = ((int)maxq + 32 * R + 4 + 3) & ~3;
-		const size_t per_warp = (size_t)27 * (size_t)w4;
-		const int warps = (int)std::min<size_t>(4, ((size_t)200 << 10) / per_warp);
+		const unsigned maxq = hp[32 + g];
 		a.order = ctx->b_order.as<uint32_t>() + pos; a.n = (uint32_t)(e - pos); a.order_pos0 = (uint32_t)pos;
-		if (R > 32) {  // bands beyond 1024 diagonals: one CTA per problem
-			if (tr_mode) swipe_wide_kernel<true><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
-			else swipe_wide_kernel<false><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
-		}
-		else if (force_generic || warps == 0) {
-			const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
-			if (tr_mode) launch_bin<true>(R, a, ctx->d_params, grid, st); else launch_bin<false>(R, a, ctx->d_params, grid, st);
+		int R = 0, warps = 0;
+		if (g < G_LEGACY) {  // packed 16-bit kernel: shared score table + the queries of 4 problems per warp as 16-bit codes
+			R = 4 * (g / 2 + 1);
+			const int qstride = ((int)maxq + 8 * R + 4 + 7) & ~7;
+			const size_t tab = (size_t)((S16_TABLE_BYTES + 15) & ~15), per_warp = (size_t)4 * (size_t)qstride * 2;
+			warps = (int)std::min<size_t>(4, (((size_t)200 << 10) - tab) / per_warp);
+			if (warps < 1) { set_error("dmnd_banded_swipe: query too long for the packed kernel"); return 1; }  // (prep_kernel routes those to the int32 kernels)
+			const size_t smem = tab + per_warp * (size_t)warps;
+			const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)220 << 10) / (smem + 2048)));
+			const int grid = (int)std::min<size_t>((e - pos + 4 * warps - 1) / (4 * warps), (size_t)ctx->sm_count * ctas_per_sm);
+			S16Args sa{ ctx->d_s16_table, qstride, d_counters + 66 };
+			if (tr_mode ? launch_s16_bin<true>(R, a, ctx->d_params, sa, grid, warps * 32, smem, st) : launch_s16_bin<false>(R, a, ctx->d_params, sa, grid, warps * 32, smem, st)) return 1;
 		}
 		else {
-			const size_t smem = per_warp * (size_t)warps;
-			const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)220 << 10) / (smem + 2048)));
-			const int grid = (int)std::min<size_t>((e - pos + warps - 1) / warps, (size_t)ctx->sm_count * ctas_per_sm);
-			ProfArgs pa{ w4, d_counters + 65 };
-			if (tr_mode ? launch_prof_bin<true>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st) : launch_prof_bin<false>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st)) return 1;
+			R = RS[(g - G_LEGACY) >> 1];
+			const int w4 = ((int)maxq + 32 * R + 4 + 3) & ~3;
+			const size_t per_warp = (size_t)27 * (size_t)w4;
+			warps = (int)std::min<size_t>(4, ((size_t)200 << 10) / per_warp);
+			if (R > 32) {  // bands beyond 1024 diagonals: one CTA per problem
+				if (tr_mode) swipe_wide_kernel<true><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
+				else swipe_wide_kernel<false><<<(unsigned)(e - pos), WIDE_THREADS, DMND_WIDE_SMEM, st>>>(a, ctx->d_params);
+			}
+			else if (force_generic || warps == 0) {
+				const int grid = (int)std::min<size_t>((e - pos + 3) / 4, (size_t)ctx->sm_count * 8);
+				if (tr_mode) launch_bin<true>(R, a, ctx->d_params, grid, st); else launch_bin<false>(R, a, ctx->d_params, grid, st);
+			}
+			else {
+				const size_t smem = per_warp * (size_t)warps;
+				const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)220 << 10) / (smem + 2048)));
+				const int grid = (int)std::min<size_t>((e - pos + warps - 1) / warps, (size_t)ctx->sm_count * ctas_per_sm);
+				ProfArgs pa{ w4, d_counters + 65 };
+				if (tr_mode ? launch_prof_bin<true>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st) : launch_prof_bin<false>(R, a, ctx->d_params, pa, grid, warps * 32, smem, st)) return 1;
+			}
 		}
 		++ctx->launches;
 		if (cudaError_t le = cudaGetLastError()) {
@@ -733,7 +800,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	};
 
 	if (!trace) {
-		for (int g = 0; g < NG; ++g) {
+		for (int g = 0; g < G_STATS; ++g) {
 			const size_t pos = grp_begin[g], e = grp_begin[g + 1];
 			if (e > pos) { a.work = d_counters + g; if (launch_dp(g, pos, e, false)) return 1; }
 		}
@@ -756,17 +823,13 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp2, d_tslen, d_tsoff, n, st));
 			++ctx->launches;
 		}
-		// group bases and totals come from the per-bucket cost histogram of the prep kernel (already on the host): the scans
+		// group bases and totals come from the per-group cost sums of the prep kernel (already on the host): the scans
 		// above stay on the device, no second synchronisation
-		uint64_t* gbase = hq + 260;  // [0..NG] trace bytes before group g
+		uint64_t* gbase = hq + 32;  // [0..NG] trace bytes before group g
 		gbase[0] = 0;
-		for (int g = 0; g < NG; ++g) {
-			uint64_t c = 0;
-			for (int k = 0; k < 16; ++k) c += hq[g * 16 + k];
-			gbase[g + 1] = gbase[g] + c;
-		}
-		const uint64_t trace_total = gbase[NG];  // (the statistics bucket 240 carries no trace)
-		ts_total = hq[256];
+		for (int g = 0; g < NG; ++g) gbase[g + 1] = gbase[g] + hq[g];
+		const uint64_t trace_total = gbase[NG];  // (the statistics group carries no trace)
+		ts_total = hq[NG];
 		if (transcripts && ts_total > transcript_cap) { set_error("dmnd_banded_swipe: transcript buffer too small (need sum(qlen+tlen))"); return 1; }
 		if (ts_total > 0xffffffffull) { set_error("dmnd_banded_swipe: transcript buffer exceeds 4 GiB in one call"); return 1; }
 		if (transcripts && ctx->b_tr.ensure(ts_total + 16)) return 1;
@@ -785,7 +848,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			excl[n] = trace_total;
 		}
 		lap("trace prefix");
-		for (int g = 0; g < NG; ++g) {
+		for (int g = 0; g < G_STATS; ++g) {
 			size_t pos = grp_begin[g];
 			const size_t gend = grp_begin[g + 1];
 			while (pos < gend) {
@@ -802,13 +865,14 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 64 * sizeof(unsigned int), st));
 				a.work = d_counters;
 				a.trace = ctx->b_trace.as<uint8_t>(); a.trace_excl = d_excl; a.trace_base = base;
-				if (RS[g >> 1] > 32) DMND_CUDA_CHECK(cudaMemsetAsync(ctx->b_trace.p, 0, (size_t)bytes, st));  // the wide kernel ORs nibbles in
+				if (g >= G_LEGACY && RS[(g - G_LEGACY) >> 1] > 32) DMND_CUDA_CHECK(cudaMemsetAsync(ctx->b_trace.p, 0, (size_t)bytes, st));  // the wide kernel ORs nibbles in
 				if (launch_dp(g, pos, e, true)) return 1;
 				WalkArgs wa;
 				wa.q_letters = a.q_letters; wa.q_bias = a.q_bias; wa.r_letters = a.r_letters; wa.q_limits = a.q_limits; wa.r_limits = a.r_limits;
 				wa.probs = a.probs; wa.order = a.order; wa.n = a.n; wa.score = d_score; wa.end_cell = d_end;
 				wa.trace = a.trace; wa.trace_excl = d_excl; wa.trace_base = a.trace_base; wa.order_pos0 = a.order_pos0;
 				wa.res = ctx->b_results.as<dmnd_dp_result>();
+				wa.s16 = g < G_LEGACY ? 1 : 0;
 				wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
 				wa.transcript_off = transcripts ? d_tsoff : nullptr;
 				walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
@@ -817,13 +881,13 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				pos = e;
 			}
 		}
-		if (hp[240]) {  // statistics passes, one CTA per problem
+		if (hp[G_STATS]) {  // statistics passes, one CTA per problem
 			StatsArgs sa;
 			sa.q_letters = a.q_letters; sa.q_bias = a.q_bias; sa.r_letters = a.r_letters; sa.q_limits = a.q_limits; sa.r_limits = a.r_limits;
-			sa.probs = a.probs; sa.order = ctx->b_order.as<uint32_t>() + off[240]; sa.n = hp[240];
+			sa.probs = a.probs; sa.order = ctx->b_order.as<uint32_t>() + grp_begin[G_STATS]; sa.n = hp[G_STATS];
 			sa.res = ctx->b_results.as<dmnd_dp_result>();
 			DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMND_STATS_SMEM));
-			swipe_stats_kernel<<<hp[240], WIDE_THREADS, DMND_STATS_SMEM, st>>>(sa, ctx->d_params);
+			swipe_stats_kernel<<<hp[G_STATS], WIDE_THREADS, DMND_STATS_SMEM, st>>>(sa, ctx->d_params);
 			++ctx->launches;
 			DMND_CUDA_CHECK(cudaGetLastError());
 		}
@@ -837,10 +901,19 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		t.stop();
 		ctx->d2h_bytes += n * sizeof(dmnd_dp_result) + ((trace && transcripts) ? ts_total : 0);
 	}
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 257, d_counters + 65, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 65, d_counters + 65, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	lap("download results");
-	if (hp[257] != 0 && !force_generic) {
+	if (hp[66] != 0 && use_s16) {
+		// a score near the int16 range or a Hauser bias outside the table: the reference's int16 -> int32 cascade
+		// (banded_swipe.h:337,347), here for the whole call on the exact int32 kernels
+		++ctx->dp_overflows;
+		ctx->force_int32_dp = true;
+		const int rc = banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+		ctx->force_int32_dp = false;
+		return rc;
+	}
+	if (hp[65] != 0 && !force_generic) {
 		// S + bias left the int8 range of the shared-memory profile somewhere: redo the whole call on the generic kernel
 		ctx->force_generic_dp = true;
 		const int rc = banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 	const unsigned nge2 = (0x10000u - ge) * 0x00010001u & 0xffffffffu;  // (-ge, -ge)
 	const unsigned selF = gl == 0 ? 0x54DDu : 0x5432u, selE = gl == S16_LANES - 1 ? 0xBB32u : 0x5432u;
 	const int lofs = gl * U;
+	const unsigned zero2 = P->zero;
 
 	for (;;) {
 		unsigned int w = 0;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 					const unsigned sc = __byte_perm((unsigned)s_lo, (unsigned)s_hi, 0x5410);
 					const unsigned e_in = E[j + 1], f_in = j > 0 ? F[j > 0 ? j - 1 : 0] : f_edge;
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
-					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], 0u);
+					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);
 					const unsigned e_new = __viaddmax_s16x2_relu(e_in, nge2, open), f_new = __viaddmax_s16x2_relu(f_in, nge2, open);
 					if (TRACE) {
 						// inverted masks: min(difference, 1) per half (h >= e_in, f_in and e_new, f_new >= open always hold)
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 						pk[j >> 2] += ((n0 + 2u * n1) + 4u * (n2 + 2u * n3)) << (4 * (j & 3));
 						best[j] = __vimax3_u32(best[j], h * MUL[j] + ckLo, (h & MSK[j]) | ckHi);
 					}
-					else best[j] = __vimax_s16x2(best[j], h);
+					else best[j] = __vmaxs2(best[j], h);
 					H[j] = h; E[j] = e_new; F[j] = f_new;
 				}
 			}
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 					const unsigned sc = __byte_perm((unsigned)s_lo, (unsigned)s_hi, 0x5410);
 					const unsigned e_in = j + 1 < NP ? E[j + 1 < NP ? j + 1 : 0] : e_edge, f_in = F[j - 1];
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
-					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], 0u);
+					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);
 					const unsigned e_new = __viaddmax_s16x2_relu(e_in, nge2, open), f_new = __viaddmax_s16x2_relu(f_in, nge2, open);
 					if (TRACE) {
 						const unsigned n0 = __vminu2(h - f_in, 0x00010001u), n1 = __vminu2(h - e_in, 0x00010001u);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 						pk[j >> 2] += ((n0 + 2u * n1) + 4u * (n2 + 2u * n3)) << (4 * (j & 3));
 						best[j] = __vimax3_u32(best[j], h * MUL[j] + ckLo, (h & MSK[j]) | ckHi);
 					}
-					else best[j] = __vimax_s16x2(best[j], h);
+					else best[j] = __vmaxs2(best[j], h);
 					H[j] = h; E[j] = e_new; F[j] = f_new;
 				}
 			}

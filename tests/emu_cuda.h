@@ -209,9 +209,9 @@ static inline unsigned __viaddmax_s16x2_relu(unsigned a, unsigned b, unsigned c)
 	const unsigned r = __viaddmax_s16x2(a, b, c);
 	return emu_pack(emu_lo(r) > 0 ? emu_lo(r) : 0, emu_hi(r) > 0 ? emu_hi(r) : 0);
 }
-static inline unsigned __vimax_s16x2(unsigned a, unsigned b) { return emu_pack(emu_lo(a) > emu_lo(b) ? emu_lo(a) : emu_lo(b), emu_hi(a) > emu_hi(b) ? emu_hi(a) : emu_hi(b)); }
+static inline unsigned __vmaxs2(unsigned a, unsigned b) { return emu_pack(emu_lo(a) > emu_lo(b) ? emu_lo(a) : emu_lo(b), emu_hi(a) > emu_hi(b) ? emu_hi(a) : emu_hi(b)); }
 static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) {
-	const unsigned r = __vimax_s16x2(a, b);
+	const unsigned r = __vmaxs2(a, b);
 	return emu_pack(emu_lo(r) > 0 ? emu_lo(r) : 0, emu_hi(r) > 0 ? emu_hi(r) : 0);
 }
 static inline unsigned __vminu2(unsigned a, unsigned b) {
