@@ -57,7 +57,7 @@ class DpResult(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("seed_ms", "dp_score_ms", "dp_trace_ms", "h2d_ms", "d2h_ms")] + \
-               [(n, C.c_uint64) for n in ("launches", "h2d_bytes", "d2h_bytes")]
+               [(n, C.c_uint64) for n in ("launches", "h2d_bytes", "d2h_bytes", "dp_cells_score", "dp_cells_trace", "dp_cells_padded", "dp_overflow_reruns")]
 
 
 class SearchOpts(C.Structure):
@@ -99,7 +99,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
            "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
-           "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
+           "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_measure_int_peak_packed", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_masked_positions", "dmnd_result_unaligned", "dmnd_result_free"]
 
 
@@ -148,6 +148,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_banded_swipe.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
     lib.dmnd_timing_fetch.argtypes = [vp, C.POINTER(Timing), C.c_int]
     lib.dmnd_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.dmnd_measure_int_peak_packed.argtypes = [vp, C.POINTER(C.c_double)]
     lib.dmnd_search_opts_default.argtypes = [C.POINTER(SearchOpts)]
     lib.dmnd_search_opts_default.restype = None
     lib.dmnd_params_init.argtypes = [C.POINTER(SearchOpts), C.POINTER(Params)]
@@ -323,10 +324,10 @@ class Context:
         self.lib.dmnd_timing_fetch(self.ctx, C.byref(t), int(reset))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
 
-    def int_peak(self) -> float:
-        """Measured DPX issue rate in T lane-instructions / s (roofline denominator of the DP kernels)."""
+    def int_peak(self, packed: bool = False) -> float:
+        """Measured DPX issue rate in T lane-instructions / s (roofline denominator of the DP kernels); packed = VIADDMNMX.S16x2."""
         v = C.c_double()
-        self._check(self.lib.dmnd_measure_int_peak(self.ctx, C.byref(v)))
+        self._check((self.lib.dmnd_measure_int_peak_packed if packed else self.lib.dmnd_measure_int_peak)(self.ctx, C.byref(v)))
         return v.value / 1e12
 
     # ---- P layer

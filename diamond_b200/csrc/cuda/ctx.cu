@@ -98,14 +98,16 @@ static __global__ void __launch_bounds__(128) hauser_kernel(const int8_t* __rest
 	}
 }
 
-// Issue-rate micro-benchmark: 8 independent chains of VIADDMNMX per thread, enough warps to fill every SMSP.
+// Issue-rate micro-benchmark: 8 independent chains of one DPX instruction per thread, enough warps to fill every SMSP.
+// PACKED = false: VIADDMNMX (one 32-bit cell per lane), true: VIADDMNMX.S16x2 (two 16-bit cells per lane, swipe16.cuh).
+template<bool PACKED>
 static __global__ void __launch_bounds__(256) int_peak_kernel(int* out, int iters, int b) {
 	int a[8];
 #pragma unroll
 	for (int k = 0; k < 8; ++k) a[k] = threadIdx.x + k;
 	for (int i = 0; i < iters; ++i) {
 #pragma unroll
-		for (int k = 0; k < 8; ++k) a[k] = __viaddmax_s32(a[k], b, k - i);
+		for (int k = 0; k < 8; ++k) a[k] = PACKED ? (int)__viaddmax_s16x2((unsigned)a[k], (unsigned)b, (unsigned)(k - i)) : __viaddmax_s32(a[k], b, k - i);
 	}
 	int s = 0;
 #pragma unroll
@@ -115,13 +117,15 @@ static __global__ void __launch_bounds__(256) int_peak_kernel(int* out, int iter
 
 extern "C" {
 
-int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s) {
+static int measure_peak(dmnd_ctx* ctx, bool packed, double* lane_instr_per_s) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 15;
 	if (ctx->b_work.ensure((size_t)blocks * threads * sizeof(int))) return 1;
-	int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), 1024, -1);  // warm-up
+	if (packed) int_peak_kernel<true><<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), 1024, -1);  // warm-up
+	else int_peak_kernel<false><<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), 1024, -1);
 	cudaEventRecord(ctx->ev_a, ctx->stream);
-	int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), iters, -1);
+	if (packed) int_peak_kernel<true><<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), iters, -1);
+	else int_peak_kernel<false><<<blocks, threads, 0, ctx->stream>>>(ctx->b_work.as<int>(), iters, -1);
 	cudaEventRecord(ctx->ev_b, ctx->stream);
 	DMND_CUDA_CHECK(cudaEventSynchronize(ctx->ev_b));
 	float ms = 0;
@@ -129,6 +133,8 @@ int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s) {
 	*lane_instr_per_s = (double)blocks * threads * (double)iters * 8.0 / (ms * 1e-3);
 	return 0;
 }
+int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s) { return measure_peak(ctx, false, lane_instr_per_s); }
+int dmnd_measure_int_peak_packed(dmnd_ctx* ctx, double* lane_instr_per_s) { return measure_peak(ctx, true, lane_instr_per_s); }
 
 const char* dmnd_last_error(void) { return g_err.c_str(); }
 void dmnd_set_last_error(const char* m) { g_err = m ? m : ""; }
@@ -571,9 +577,11 @@ int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int flags) {
 		out->seed_ms += c->phase_ms[PH_SEED]; out->dp_score_ms += c->phase_ms[PH_DP_SCORE]; out->dp_trace_ms += c->phase_ms[PH_DP_TRACE];
 		out->h2d_ms += c->phase_ms[PH_H2D]; out->d2h_ms += c->phase_ms[PH_D2H];
 		out->launches += c->launches; out->h2d_bytes += c->h2d_bytes; out->d2h_bytes += c->d2h_bytes;
+		out->dp_cells_score += c->dp_cells_score; out->dp_cells_trace += c->dp_cells_trace; out->dp_cells_padded += c->dp_cells_padded; out->dp_overflow_reruns += c->dp_overflows;
 		if (flags & DMND_TIMING_RESET) {
 			for (double& x : c->phase_ms) x = 0;
 			c->launches = 0; c->h2d_bytes = 0; c->d2h_bytes = 0;
+			c->dp_cells_score = c->dp_cells_trace = c->dp_cells_padded = 0; c->dp_overflows = 0;
 		}
 	};
 	take(ctx);

@@ -97,6 +97,7 @@ struct dmnd_ctx {
 	int8_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
 	bool s16_ok = false;
 	uint64_t dp_overflows = 0;       // calls repeated on the int32 kernels
+	uint64_t dp_cells_score = 0, dp_cells_trace = 0, dp_cells_padded = 0;  // cells of the problems LAUNCHED (score-only / traceback kernels) and what the register tiles evaluate for them
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
 	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
 	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)

@@ -588,14 +588,15 @@ struct PrepOut {
 	uint64_t* tslen;     // [n] qlen + tlen (transcript capacity)
 	unsigned int* hist;  // [NG] problems per group
 	unsigned int* maxq;  // [NG] longest query per group (sizes the shared memory of the launch)
-	unsigned long long* cost_hist;  // [NG] trace bytes per group, [NG] = sum of tslen: the host derives group bases and totals without a second sync
+	unsigned long long* cost_hist;  // [NG] trace bytes per group, [NG] = sum of tslen: the host derives group bases and totals without a second sync;
+	                                // [NG + 1] algorithmic cells of the call, [NG + 2] cells the kernels evaluate incl. the padding of the register tiles
 	unsigned int* flag;  // error flag
 };
 __global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __restrict__ probs, uint32_t n, const int64_t* __restrict__ ql, uint32_t nq,
                                                     const int64_t* __restrict__ rl, uint32_t nr, int trace, int s16, PrepOut o) {
 	__shared__ unsigned int s_hist[NG], s_maxq[NG];
-	__shared__ unsigned long long s_cost[NG + 1];
-	for (int x = threadIdx.x; x <= NG; x += blockDim.x) { if (x < NG) { s_hist[x] = 0; s_maxq[x] = 0; } s_cost[x] = 0; }
+	__shared__ unsigned long long s_cost[NG + 3];
+	for (int x = threadIdx.x; x < NG + 3; x += blockDim.x) { if (x < NG) { s_hist[x] = 0; s_maxq[x] = 0; } s_cost[x] = 0; }
 	__syncthreads();
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < n) {
@@ -614,18 +615,18 @@ __global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __rest
 				const unsigned long long nmacro = live ? (unsigned long long)((2 * (cols - 1) + B + 1) >> 1) : 0ull;
 				// trace == 2: no transcript is wanted, so problems above max_swipe_dp take the statistics passes (no trace bytes)
 				const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
-				int g; unsigned long long step_bytes;
+				int g; unsigned long long step_bytes, rows = (unsigned long long)B;
 				if (stats) { g = G_STATS; step_bytes = 0; }
 				else if (s16 && B <= S16_MAX_BAND && nmacro <= (unsigned long long)S16_MAX_MACRO && qlen <= 16000) {
 					const int R = s16_rows(B);
 					g = (R / 4 - 1) * 2 + ((qlen + 8 * R + 4) > 768 ? 1 : 0);
-					step_bytes = (unsigned long long)s16_step_bytes(R);
+					step_bytes = (unsigned long long)s16_step_bytes(R); rows = (unsigned long long)(S16_LANES * R);
 				}
 				else {
 					const int R = tile_rows(B);
 					const int b = R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : R == 16 ? 3 : R == 32 ? 4 : R == 64 ? 5 : 6;
 					g = G_LEGACY + b * 2 + ((qlen + 32 * R + 4) > 768 ? 1 : 0);
-					step_bytes = 16ull * (unsigned long long)R;
+					step_bytes = 16ull * (unsigned long long)R; rows = 32ull * (unsigned long long)R;
 				}
 				key = ((uint32_t)g << 20) | (0xFFFFFu - (uint32_t)min(nmacro, 0xFFFFFull));
 				cost = stats ? 0ull : trace ? nmacro * step_bytes : cells;
@@ -634,12 +635,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __rest
 				atomicMax(&s_maxq[g], (unsigned)qlen);
 				atomicAdd(&s_cost[g], cost);
 				atomicAdd(&s_cost[NG], tslen);
+				atomicAdd(&s_cost[NG + 1], cells);
+				atomicAdd(&s_cost[NG + 2], nmacro * rows);
 			}
 		}
 		o.key[k] = key; o.idx[k] = k; o.cost[k] = cost; o.tslen[k] = tslen;
 	}
 	__syncthreads();
-	for (int x = threadIdx.x; x <= NG; x += blockDim.x) {
+	for (int x = threadIdx.x; x < NG + 3; x += blockDim.x) {
 		if (x < NG && s_hist[x]) { atomicAdd(&o.hist[x], s_hist[x]); atomicMax(&o.maxq[x], s_maxq[x]); }
 		if (s_cost[x]) atomicAdd(&o.cost_hist[x], s_cost[x]);
 	}
@@ -733,13 +736,15 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 32, d_counters + 128, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp + 64, d_counters + 64, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	uint64_t* hq = (uint64_t*)(hp + 128);  // [0..NG-1] cost per group, [NG] sum of tslen, then [32..] group bases
-	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, (NG + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	DMND_CUDA_CHECK(cudaMemcpyAsync(hq, d_cost_hist, (NG + 3) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 	ctx->launches += 4;
 	t_dp.mark_end();  // device time of the preparation; the host's decisions below are not device time
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	t_dp.collect();
 	if (hp[64] == 1) { set_error("dmnd_banded_swipe: sequence index out of range"); return 1; }
 	if (hp[64] == 2) { set_error("dmnd_banded_swipe: band wider than 4096 diagonals is not supported by this build"); return 1; }
+	(trace ? ctx->dp_cells_trace : ctx->dp_cells_score) += hq[NG + 1];
+	ctx->dp_cells_padded += hq[NG + 2];
 	size_t grp_begin[NG + 1];
 	grp_begin[0] = 0;
 	for (int g = 0; g < NG; ++g) grp_begin[g + 1] = grp_begin[g] + hp[g];

@@ -259,12 +259,18 @@ typedef struct dmnd_timing {
 	double seed_ms, dp_score_ms, dp_trace_ms, h2d_ms, d2h_ms;
 	uint64_t launches;
 	uint64_t h2d_bytes, d2h_bytes;
+	uint64_t dp_cells_score, dp_cells_trace; /* algorithmic cells (band x cols) of the problems the score-only / traceback kernels were LAUNCHED on:
+	                                            a fused query's problems are evaluated once, by the traceback kernel */
+	uint64_t dp_cells_padded;                /* cells those kernels evaluate incl. the padding of their register tiles and wavefront */
+	uint64_t dp_overflow_reruns;             /* dmnd_banded_swipe calls repeated on the int32 kernels (int16 range / bias table left) */
 } dmnd_timing;
 enum { DMND_TIMING_RESET = 1, DMND_TIMING_THIS_CONTEXT = 2 /* do not add the lanes */ };
 int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int flags);
 /* Roofline denominator for the DP kernels: measured issue rate (lane-instructions / s, whole GPU) of the three-input
  * integer DPX instructions (VIADDMNMX / VIMNMX3) the recurrence is built from.  Runs a ~20 ms micro-benchmark. */
 int dmnd_measure_int_peak(dmnd_ctx* ctx, double* lane_instr_per_s);
+/* Same for the packed form VIADDMNMX.S16x2 (two 16-bit cells per lane and instruction) the 16-bit kernel is built from. */
+int dmnd_measure_int_peak_packed(dmnd_ctx* ctx, double* lane_instr_per_s);
 
 /* ---- P layer ---------------------------------------------------------------------------------------------- */
 typedef struct dmnd_search_opts {

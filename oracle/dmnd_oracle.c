@@ -372,6 +372,7 @@ int dmnd_block_clear_seed_mask(dmnd_ctx* ctx, dmnd_block* b) {
 	return 0;
 }
 int dmnd_measure_int_peak(dmnd_ctx* ctx, double* v) { (void)ctx; *v = 0; return fail("oracle: no device to measure"); }
+int dmnd_measure_int_peak_packed(dmnd_ctx* ctx, double* v) { (void)ctx; *v = 0; return fail("oracle: no device to measure"); }
 int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int reset) {
 	(void)ctx; (void)reset;
 	memset(out, 0, sizeof *out);
