@@ -1,28 +1,45 @@
 #!/usr/bin/env python
-"""bench.py -- GCUPS of the blastp --fast hot path (BASELINE.json metric) on N B200s of one node.
+"""bench.py -- GCUPS of the seed-and-extend hot path (BASELINE.json metric) on N B200s of one node.
 
-  python bench.py --gpus N --steps K --warmup W            our arm (CUDA library behind the C ABI)
-  python bench.py --impl reference --gpus N --steps K ...  the UNMODIFIED reference (oracle/_ref/diamond) on host cores
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4]   our arm (CUDA library behind the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...               the UNMODIFIED reference (oracle/_ref/diamond) on host cores
 
-One "step" = one full pass of the hot path (seed search stages 0-2, extension rounds 1+2, culling) over one batch of
-synthetic queries against the resident reference block.  Workload at N=1 = BASELINE.json configs[1]: 1 M synthetic
-queries (len <= 300) x 100 k-protein DB, blastp --fast; at N>1 every rank processes its own 1 M-query block against the
-same DB (query sharding, no data-path collective; the packed reference block is NCCL-broadcast once) -> "weak".
+One "step" = one full pass of the hot path (masked blocks -> seed search stages 0-2 -> extension rounds 1+2 -> culling) over
+one batch of synthetic queries against the resident reference block.  Configurations (BASELINE.json `configs`):
+  c2 (default, the configuration the metric is quoted on): blastp --fast, 1 M queries (len <= 300) x 100 k-protein DB
+  c3: blastx --fast, 100 k DNA reads of 150 nt (six translated frames each) x 100 k-protein DB
+  c4: blastp --sensitive, 1 M queries x 500 k-protein DB (16 shapes, gapped filter)
+At N > 1 every rank processes its own query block against the same DB (query sharding, no data-path collective; the packed
+reference block is NCCL-broadcast once) -> "weak".
 GCUPS numerator = algorithmic DP cells = sum over every banded DP problem of rounds 1 and 2 of band x cols
 (dp/dp.h:121-124); it is a property of the workload (the DP target list is parity-checked against the reference).
 `value` times steps with both blocks already resident in HBM; `e2e` times dmnd_blastp() with pinned HOST buffers
-(block upload, problem lists, hit/result downloads inside).  Inputs (242 MB + 30 MB) exceed the 126 MB L2.
+(block upload, masking, problem lists, hit/result downloads inside).  Inputs exceed the 126 MB L2.
 Flags: the reference's DEFAULTS (tantan masking of both blocks, motif soft masking, Hauser composition bias) on both arms.
 Masking belongs to loading a block (run/double_indexed.cpp:122-127, :737-741): resident blocks are masked when they are
 made resident (outside the `value` region, like the upload); `e2e` and the reference arm mask inside the timed region.
-`--masking 0` runs both arms on the parity-ladder rung without masking (--masking 0 --motif-masking 0).
+
+Reference arm: the stock CLI on the SAME configuration (all queries of rank 0's block, FASTA in, fmt 6 out, whole process wall
+time), `-p` = the fastest of the thread counts tried on a 100 k-query sample; one process run per step, at most --ref-steps steps
+(a full run takes ~10 s).  The cell count of the configuration comes from profiles/workload_cells.json (written by our arm on an
+earlier run, `--emit-cells`): the reference process never loads the CUDA library.
 """
 import argparse, json, os, subprocess, sys, tempfile, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "diamond")
+CELLS_JSON = os.path.join(ROOT, "profiles", "workload_cells.json")
 NO_MASKING = ["--masking", "0", "--motif-masking", "0"]  # parity-ladder rung L1; [] = the reference's default flags
+
+CONFIGS = {
+    "c2": dict(kind="blastp", sens=0, flag="--fast", queries=1_000_000, db=100_000, seed=2, label="BASELINE configs[1]",
+               what="blastp --fast, {q} synthetic queries (len<=300) per GPU x {d}-protein DB"),
+    "c3": dict(kind="blastx", sens=0, flag="--fast", queries=100_000, db=100_000, seed=3, label="BASELINE configs[2]",
+               what="blastx --fast, {q} synthetic DNA reads (150 nt, six frames) per GPU x {d}-protein DB"),
+    "c4": dict(kind="blastp", sens=3, flag="--sensitive", queries=1_000_000, db=500_000, seed=4, label="BASELINE configs[3]",
+               what="blastp --sensitive, {q} synthetic queries (len<=300) per GPU x {d}-protein DB"),
+}
 
 
 def parse():
@@ -31,13 +48,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=1_000_000, help="queries per GPU")
-    ap.add_argument("--db", type=int, default=100_000)
-    ap.add_argument("--sample", type=int, default=100_000, help="queries of the bounded CPU-baseline sample")
-    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--queries", type=int, default=None, help="queries (reads) per GPU; default: the configuration's")
+    ap.add_argument("--db", type=int, default=None)
+    ap.add_argument("--sample", type=int, default=100_000, help="queries of the bounded CPU-baseline sample of our arm")
+    ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-steps", type=int, default=2, help="reference arm: at most this many timed full-configuration runs (and one warm-up)")
+    ap.add_argument("--emit-cells", default=None, help="comma list of reference thread counts: write the configuration's cell counts to gpurun_out/workload_cells.json and exit")
     ap.add_argument("--masking", type=int, default=1, choices=[0, 1], help="1 = reference default flags (tantan + motif masking), 0 = --masking 0 --motif-masking 0 on both arms")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.queries = a.queries or c["queries"]; a.db = a.db or c["db"]; a.seed = c["seed"] if a.seed is None else a.seed
+    return a
 
 
 class ClockSampler:
@@ -94,42 +117,83 @@ def effective_cpus():
     return n
 
 
-def make_workload(args, rank):
+def make_workload(args, rank, n=None):
+    """The rank's synthetic blocks.  Returns a dict: q_raw/q_lim/r_raw/r_lim (block images), ctx (Context keyword arguments), and
+    what the reference arm needs to write its FASTA files."""
     from diamond_b200 import api, synth
-    w = synth.workload(args.queries, args.db, args.seed, q_stream=rank)
-    q_raw, q_lim = api.block_image(w["q_letters"], w["q_off"])
+    c = CONFIGS[args.config]
+    n = n or args.queries
+    if c["kind"] == "blastx":
+        w = synth.c3_workload(args.queries, args.db, args.seed, q_stream=rank)
+        codes = w["dna_codes"][:n]
+        ql, qo = api.translate_codes(codes)
+        q_raw, q_lim = api.block_image(ql, qo)
+        out = {"dna_codes": codes, "read_lens": [codes.shape[1]] * n, "ctx": dict(sensitivity=c["sens"], query_contexts=6)}
+    else:
+        w = synth.workload(args.queries, args.db, args.seed, q_stream=rank)
+        q_raw, q_lim = api.block_image(w["q_letters"][: w["q_off"][n]], w["q_off"][: n + 1])
+        out = {"q_letters": w["q_letters"][: w["q_off"][n]], "q_off": w["q_off"][: n + 1], "ctx": dict(sensitivity=c["sens"])}
     r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
-    return w, q_raw, q_lim, r_raw, r_lim
+    out.update(q_raw=q_raw, q_lim=q_lim, r_raw=r_raw, r_lim=r_lim, db_letters=w["db_letters"], db_off=w["db_off"], n=n)
+    return out
 
 
-def write_sample_fasta(w, n, td):
+def write_fasta(wl, n, td):
+    """First n queries of the workload + the whole DB as FASTA."""
     from diamond_b200 import synth
-    q, d = os.path.join(td, "q.faa"), os.path.join(td, "d.faa")
-    synth.write_fasta(q, w["q_letters"][: w["q_off"][n]], w["q_off"][: n + 1], "q")
-    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    d = os.path.join(td, "d.faa")
+    synth.write_fasta(d, wl["db_letters"], wl["db_off"], "d")
+    if "dna_codes" in wl:
+        q = os.path.join(td, "q.fna")
+        synth.write_dna_codes_fasta(q, wl["dna_codes"][:n])
+    else:
+        q = os.path.join(td, "q.faa")
+        synth.write_fasta(q, wl["q_letters"][: wl["q_off"][n]], wl["q_off"][: n + 1], "q")
     return q, d
 
 
-def run_reference(q, d, out, threads, masking=1):
+def run_reference(args, q, d, out, threads):
+    c = CONFIGS[args.config]
+    cmd = [REF_BIN, c["kind"], c["flag"], "-q", q, "-d", d, "-f", "6", "-o", out, "-p", str(threads), "--log"] + ([] if args.masking else NO_MASKING)
     t0 = time.perf_counter()
-    r = subprocess.run([REF_BIN, "blastp", "--fast", "-q", q, "-d", d, "-f", "6", "-o", out, "-p", str(threads), "--log"] + ([] if masking else NO_MASKING),
-                       capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError("reference failed: " + r.stderr[-400:])
-    return dt, r.stderr + r.stdout
+    return dt
 
 
-def sample_cells_and_tsv(args, w, threads, device):
-    """Algorithmic cell count (and fmt-6 text) of the bounded sample, from our pipeline -- the numerator both arms share."""
+def fmt6_of(wl, m):
     from diamond_b200 import api
-    n = min(args.sample, args.queries)
-    q_raw, q_lim = api.block_image(w["q_letters"][: w["q_off"][n]], w["q_off"][: n + 1])
-    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
-    ctx = api.Context(device=device, threads=threads, masking=args.masking, motif_masking=args.masking)
-    m, _, st = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
-    ctx.close()
-    return st["cells_round1"] + st["cells_round2"], api.fmt6(m), n
+    return api.fmt6_translated(m, wl["read_lens"]) if "dna_codes" in wl else api.fmt6(m)
+
+
+def cells_key(args, n, threads):
+    return f"{args.config}:q{n}:db{args.db}:seed{args.seed}:masking{args.masking}:p{threads}:stream0"
+
+
+def load_cells():
+    best = {}
+    for p in (CELLS_JSON, os.path.join(ROOT, "gpurun_out", "workload_cells.json")):
+        try:
+            best.update(json.load(open(p)))
+        except Exception:
+            pass
+    return best
+
+
+def lookup_cells(args, n, threads):
+    """(cells, note) of the first n queries of rank 0's block; the exact -p entry if there is one, else the entry of another thread
+    count of the same configuration (the cell count moves by < 0.1 % with seedp_bits)."""
+    tab = load_cells()
+    k = cells_key(args, n, threads)
+    if k in tab:
+        return tab[k], "cell count of this configuration from profiles/workload_cells.json (our arm, same -p)"
+    pre = k.split(":p")[0]
+    for kk, v in sorted(tab.items()):
+        if kk.startswith(pre + ":p"):
+            return v, f"cell count from profiles/workload_cells.json entry {kk} (no entry for -p {threads})"
+    return None, "no cached cell count for this configuration: run `python bench.py --emit-cells <threads>` on a GPU box first"
 
 
 def main():
@@ -140,49 +204,76 @@ def main():
                                    "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:])
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     ncpu = effective_cpus()
-    ref_threads = ncpu  # the reference arm uses every host thread; our seedp_bits must follow the same -p (setup.cpp:306-309)
-    config = {"workload": f"blastp --fast, {args.queries} synthetic queries (len<=300) per GPU x {args.db}-protein DB (BASELINE configs[1])",
+    ref_threads = ncpu  # seedp_bits follows -p (setup.cpp:306-309): both arms are run with the same value
+    c = CONFIGS[args.config]
+    config = {"workload": c["what"].format(q=args.queries, d=args.db) + f" ({c['label']})", "config": args.config,
               "queries_per_gpu": args.queries, "db_seqs": args.db, "parallelism": f"query-sharded x{world}", "seed": args.seed,
-              "flags": "--fast (reference defaults: tantan masking, motif masking, comp-based-stats 1) -k 25 -e 0.001" if args.masking else "--fast --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001",
+              "flags": f"{c['flag']} (reference defaults: tantan masking, motif masking, comp-based-stats 1) -k 25 -e 0.001" if args.masking else f"{c['flag']} --masking 0 --motif-masking 0 --comp-based-stats 1 -k 25 -e 0.001",
               "masking": "resident blocks are masked when made resident (block load); e2e and the reference arm mask inside the timed region" if args.masking else "off on both arms",
               "reference_threads": ref_threads, "visible_cpus": os.cpu_count(),
-              "l2": "inputs (242 MB queries + 30 MB reference per GPU) larger than the 126 MB L2"}
+              "l2": "inputs (query + reference blocks, 100+ MB per GPU) larger than the 126 MB L2"}
+    metric = f"GCUPS {c['kind']} {c['flag']}"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        import torch
-        w, *_ = make_workload(args, 0)
         if not os.path.exists(REF_BIN):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/diamond not present in the snapshot"}))
             return
-        cells, _, n = sample_cells_and_tsv(args, w, ref_threads, 0) if torch.cuda.is_available() else (None, None, min(args.sample, args.queries))
+        wl = make_workload(args, 0)
         with tempfile.TemporaryDirectory() as td:
-            q, d = write_sample_fasta(w, n, td)
+            # thread count: the fastest on a 100 k-query sample (more threads than the CFS quota make the reference slower)
+            ns = min(100_000, args.queries)
+            qs, d = write_fasta(wl, ns, td)
+            cands = sorted({ncpu, min(ncpu, 16), min(ncpu, 32), min(ncpu, 64)})
+            tried = {}
+            for p in cands:
+                tried[p] = min(run_reference(args, qs, d, os.path.join(td, "s.tsv"), p) for _ in range(2 if len(cands) > 1 else 1))
+            best_p = min(tried, key=tried.get)
+            q, d = write_fasta(wl, args.queries, td)
+            warm, steps = min(args.warmup, 1), max(1, min(args.steps, args.ref_steps))
             times = []
-            for s in range(args.warmup + args.steps):
-                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads, args.masking)
-                if s >= args.warmup:
+            for s in range(warm + steps):
+                dt = run_reference(args, q, d, os.path.join(td, "o.tsv"), best_p)
+                if s >= warm:
                     times.append(dt)
+        cells, note = lookup_cells(args, args.queries, best_p)
         T = sum(times)
         val = (cells * len(times) / T / 1e9) if cells else None
-        sample = f"first {n} queries of rank 0's block x full {args.db}-protein DB, one reference process per step (FASTA in, fmt 6 out), -p {ref_threads}"
-        print(json.dumps({"impl": "reference", "metric": "GCUPS blastp --fast", "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "int8/int16 saturating SIMD (AVX2)", "data": "synthetic", "config": dict(config, sample=sample),
-                          "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ref_threads, "kind": "reference", "sample": sample},
+        sample = (f"the full configuration: all {args.queries} queries of rank 0's block x {args.db}-protein DB, one reference process per step (FASTA in, fmt 6 out, "
+                  f"whole process wall time), -p {best_p} = fastest of {tried} s on a {ns}-query sample; {len(times)} timed run(s) after {warm} warm-up; {note}")
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": len(times),
+                          "warmup": warm, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "int8/int16 saturating SIMD (AVX2)", "data": "synthetic", "config": dict(config, reference_threads=best_p, sample=sample, same_config=True),
+                          "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": best_p, "kind": "reference", "sample": sample},
                           "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     import numpy as np
     import torch
     from diamond_b200 import api
+
+    if args.emit_cells:
+        # cell counts of rank 0's block for the given reference thread counts (seedp_bits follows -p), and of the 100 k sample
+        wl = make_workload(args, 0)
+        tab = load_cells()
+        for p in [int(x) for x in args.emit_cells.split(",")]:
+            ctx = api.Context(device=0, threads=p, masking=args.masking, motif_masking=args.masking, **wl["ctx"])
+            _, _, st = ctx.blastp(wl["q_raw"], wl["q_lim"], wl["r_raw"], wl["r_lim"])
+            ctx.close()
+            tab[cells_key(args, args.queries, p)] = st["cells_round1"] + st["cells_round2"]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(tab, open(os.path.join(ROOT, "gpurun_out", "workload_cells.json"), "w"), indent=1, sort_keys=True)
+        print(json.dumps(tab))
+        return
+
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ.setdefault("DMND_HOST_THREADS", str(max(1, ncpu // world)))
-    w, q_raw, q_lim, r_raw, r_lim = make_workload(args, rank)
+    wl = make_workload(args, rank)
+    q_raw, q_lim, r_raw, r_lim = wl["q_raw"], wl["q_lim"], wl["r_raw"], wl["r_lim"]
     if world > 1:
         # the packed reference block travels once over NVLink (NCCL broadcast from rank 0); every rank then adopts it
         from diamond_b200 import shard
@@ -192,7 +283,7 @@ def main():
     # pinned host copies for the e2e path
     q_pin = torch.from_numpy(q_raw).pin_memory().numpy()
     r_pin = torch.from_numpy(r_raw).pin_memory().numpy()
-    ctx = api.Context(device=local, threads=ref_threads, masking=args.masking, motif_masking=args.masking)
+    ctx = api.Context(device=local, threads=ref_threads, masking=args.masking, motif_masking=args.masking, **wl["ctx"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,8 +349,8 @@ def main():
     cells_all, cells_all_e2e = float(tot[0].item()), float(tot[1].item())
     value = cells_all * args.steps / (ms / 1e3) / 1e9
     e2e = cells_all_e2e * args.steps / (ms_e2e / 1e3) / 1e9
-    # kernel time for the roofline: query lanes overlap on the device, so their stream times cannot be added up; the DP
-    # kernels are timed in a separate pass with ONE lane (every kernel of the step serialised on one stream, same work)
+    # kernel time for the roofline: query lanes overlap on the device, so their stream times cannot be added up; the kernels
+    # are timed in a separate pass with ONE lane (every kernel of the step serialised on one stream, same work)
     lanes_env = os.environ.get("DMND_LANES")
     os.environ["DMND_LANES"] = "1"
     rsteps = max(1, min(args.steps, 2))
@@ -273,34 +364,78 @@ def main():
 
     out = None
     if rank == 0:
-        # roofline of the dominant kernels (banded SWIPE, both rounds): integer-ALU bound, see DESIGN.md
+        # ---- roofline of the dominant kernels (banded SWIPE): integer-ALU bound, see DESIGN.md 4.
+        # achieved = lane-ops of the recurrence on the ALGORITHMIC cells of the problems the kernels were LAUNCHED on (a fused query's
+        # problem is evaluated once, by the traceback kernel): 9 per score-only cell, 13 per traceback cell, divided by the
+        # event-timed DP time of the single-lane pass.  peak = 4 lane-ops x the live-measured issue rate of VIADDMNMX.S16x2 (two 16-bit
+        # cells per lane and instruction, two lane-ops each); frac_s32_peak = against 2 x the rate of the 32-bit form (round 1's figure).
         dp_ms = (tm1["dp_score_ms"] + tm1["dp_trace_ms"]) / rsteps
-        laneops = st["cells_round1"] * 9 + st["cells_round2"] * 13  # 9 lane-ops / score cell, +4 for the trace masks
-        # peak: every DPX instruction (VIADDMNMX / VIMNMX3) retires two of those lane-ops; its issue rate is measured live
-        peak = 2.0 * ctx.int_peak()
+        laneops = (9 * tm1["dp_cells_score"] + 13 * tm1["dp_cells_trace"]) / rsteps
+        launched = (tm1["dp_cells_score"] + tm1["dp_cells_trace"]) / rsteps
+        peak16, peak32 = 4.0 * ctx.int_peak(packed=True), 2.0 * ctx.int_peak()
         ach = laneops / (dp_ms / 1e3) / 1e12 if dp_ms > 0 else None
-        roofline = {"bound": "int-alu", "kernel": "swipe_kernel<R,*> (banded SWIPE rounds 1+2)", "achieved": ach, "peak": peak, "unit": "Tlaneop/s",
-                    "frac": (ach / peak) if (ach and peak) else None,
-                    # dram__bytes_read + dram__bytes_write of swipe_prof_kernel<4,1>, one launch over 200 k queries (ncu --set full,
-                    # profiles/ncu_summary_r1.txt); 1.70e9 of it is the algorithmic trace (16 R bytes per macro step and problem)
-                    "traffic": 1.825e9, "traffic_note": "ncu capture of the dominant launch at 200 k queries; the kernel is ALU-pipe bound (89.5 % busy), not HBM bound", "kernel_ms_per_step": dp_ms,
-                    "kernel_gcups": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None,
-                    "seed_stage_ms_per_step": tm1["seed_ms"] / rsteps, "timed": f"CUDA events on the library stream, {rsteps} single-lane step(s) after the timed region"}
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+        except Exception:
+            pass
+        roofline = {"bound": "int-alu", "kernel": "swipe16_kernel<R,TRACE> + walk_kernel (banded SWIPE, packed 16-bit DPX lanes; int32 kernels as overflow cascade)",
+                    "achieved": ach, "peak": peak16, "unit": "Tlaneop/s", "frac": (ach / peak16) if (ach and peak16) else None,
+                    "frac_s32_peak": (ach / peak32) if (ach and peak32) else None, "peak_s32": peak32,
+                    "traffic": ncu.get("swipe16_bytes_per_launch"), "traffic_note": ncu.get("note", "no ncu capture committed for this round yet"),
+                    "kernel_ms_per_step": dp_ms, "cells_launched_per_step": launched,
+                    "padding_factor": (tm1["dp_cells_padded"] / max(1, tm1["dp_cells_score"] + tm1["dp_cells_trace"])),
+                    "overflow_reruns": tm1["dp_overflow_reruns"],
+                    "kernel_gcups": launched / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None,
+                    "timed": f"CUDA events on the library stream, {rsteps} single-lane step(s) after the timed region"}
+        # ---- roofline of the seed stage: HBM bound by SURVEY 8d's byte model of the double-indexed join, per shape and block pair:
+        # 1 B per letter of both blocks + 36 B per seed entry (write, partition pass, join read) + 96 B of fingerprints per (q, s) pair
+        # + 98 B per stage-1 survivor (left-most windows) + 15 B per hit
+        sd = st["seed"]
+        nshapes = int(ctx.params.n_shapes)
+        letters = int(q_raw.size + r_raw.size)
+        seed_bytes = nshapes * letters * (1 + 36) + 96 * sd["seed_hits"] + 98 * sd["tentative_matches1"] + 15 * sd["tentative_matches3"]
+        seed_ms = tm1["seed_ms"] / rsteps
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 0)) or 6486.0
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6486.0, "fallback (B200_PROFILING.md)"
+        seed_ach = seed_bytes / (seed_ms / 1e3) / 1e9 if seed_ms > 0 else None
+        roofline_seed = {"bound": "hbm", "kernel": "seed stage (ref index build + probe + mask + stage 1/2 + x-drop + hit sort)", "achieved": seed_ach, "peak": hbm_peak,
+                         "peak_source": hbm_src, "unit": "GB/s", "frac": (seed_ach / hbm_peak) if seed_ach else None, "algorithmic_bytes_per_step": seed_bytes,
+                         "kernel_ms_per_step": seed_ms, "traffic": ncu.get("probe_bytes_per_launch"),
+                         "note": "the byte model is the REFERENCE algorithm's (materialised seed arrays); this implementation probes a Bloom filter + bucket directory "
+                                 "instead and is bound by issue rate / L2 sector reads (DESIGN.md 4), so frac understates nothing but is far from HBM speed"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
-            scells, tsv, n = sample_cells_and_tsv(args, w, ref_threads, local)
+            n = min(args.sample, args.queries)
+            ws = make_workload(args, rank, n)
+            sctx = api.Context(device=local, threads=ref_threads, masking=args.masking, motif_masking=args.masking, **ws["ctx"])
+            sm, _, sst = sctx.blastp(ws["q_raw"], ws["q_lim"], ws["r_raw"], ws["r_lim"])
+            sctx.close()
+            scells, tsv = sst["cells_round1"] + sst["cells_round2"], fmt6_of(ws, sm)
             with tempfile.TemporaryDirectory() as td:
-                q, d = write_sample_fasta(w, n, td)
-                dt, log = run_reference(q, d, os.path.join(td, "o.tsv"), ref_threads, args.masking)
+                q, d = write_fasta(ws, n, td)
+                dt = run_reference(args, q, d, os.path.join(td, "o.tsv"), ref_threads)
                 same = open(os.path.join(td, "o.tsv")).read() == tsv
             cpu = {"value": scells / dt / 1e9, "unit": "GCUPS", "cores": ref_threads, "kind": "reference",
                    "sample": f"first {n} queries x full DB, one reference run (FASTA in, fmt 6 out), wall {dt:.2f} s; fmt-6 identical to ours: {same}"}
-        out = {"metric": "GCUPS blastp --fast", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (exact; reference int8/int16 lane semantics)",
+        # the cell count of this configuration for the reference arm (which must not load the CUDA library)
+        try:
+            tab = load_cells()
+            tab[cells_key(args, args.queries, ref_threads)] = cells
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(tab, open(os.path.join(ROOT, "gpurun_out", "workload_cells.json"), "w"), indent=1, sort_keys=True)
+        except Exception:
+            pass
+        out = {"metric": metric, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "int16 (packed DPX lanes, exact: overflow cascades to the int32 kernels; reference int8/int16 lane semantics)",
                "data": "synthetic", "config": config, "clocks": clk,
                "e2e": {"value": e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": tm2["h2d_bytes"] // args.steps,
                        "d2h_bytes_per_step": tm2["d2h_bytes"] // args.steps},
-               "gpu_launches": int(tm["launches"]), "roofline": roofline, "cpu_baseline": cpu,
+               "gpu_launches": int(tm["launches"]), "roofline": roofline, "roofline_seed": roofline_seed, "cpu_baseline": cpu,
                "step_ms": {"resident": step_ms_res, "e2e": step_ms_e2e}, "masking_ms": mask_info,
                "breakdown_ms_per_step": {"seed_stage": st["seed_ms"], "host_bridge": st["host_bridge_ms"], "dp_round1": st["dp1_ms"], "dp_round2": st["dp2_ms"], "total": st["total_ms"]},
                "work": {"cells_per_gpu": cells, "dp_problems_round1": st["dp_problems_round1"], "dp_problems_round2": st["dp_problems_round2"], "dp_problems_fused": st["dp_problems_fused"],

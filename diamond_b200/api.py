@@ -466,6 +466,43 @@ def translate_reads(reads) -> tuple[np.ndarray, np.ndarray]:
     return (np.concatenate(seqs).astype(np.int8) if seqs else np.zeros(0, dtype=np.int8)), off
 
 
+def translate_codes(codes: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """translate_reads() for reads of ONE length given as an (n, L) array of nucleotide codes 0..3 (4 = N), vectorised: the same six
+    contexts per read in the same order, the same ORF masking (tests/test_blastx.py compares the two)."""
+    fwd, rev = _codon_tables()
+    d = np.asarray(codes, dtype=np.int64)
+    n, L = d.shape
+    frames = []
+    for f in range(3):
+        k = (L - f) // 3
+        p = 3 * np.arange(k) + f
+        frames.append(fwd[d[:, p], d[:, p + 1], d[:, p + 2]])
+    for f in range(3):
+        k = (L - f) // 3
+        p = L - 3 - (3 * np.arange(k) + f)
+        frames.append(rev[d[:, p + 2], d[:, p + 1], d[:, p]])
+    l0 = frames[0].shape[1]
+    min_len = 1 if l0 < 30 else 20 if l0 < 100 else 40
+    out = []
+    for v in frames:
+        v = v.copy()
+        k = v.shape[1]
+        if k and min_len > 1:
+            idx = np.arange(k)[None, :]
+            stop = v == 24
+            prev = np.maximum.accumulate(np.where(stop, idx, -1), axis=1)          # last stop at or before i
+            nxt = np.minimum.accumulate(np.where(stop, idx, k)[:, ::-1], axis=1)[:, ::-1]  # next stop at or after i
+            v[(~stop) & ((nxt - prev - 1) < min_len)] = 23
+        out.append(v)
+    lens = np.array([v.shape[1] for v in out], dtype=np.int64)
+    width = int(lens.sum())
+    flat = np.concatenate(out, axis=1).reshape(-1).astype(np.int8)  # per read: frame 0 | frame 1 | ... | frame 5
+    off = np.zeros(6 * n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(np.tile(lens, n))
+    assert off[-1] == n * width
+    return flat, off
+
+
 def fmt6_translated(matches: np.ndarray, read_lens, q_prefix: str = "r", d_prefix: str = "d") -> str:
     """fmt6 for a query_contexts=6 run: dmnd_match.query is a context (6 * read + frame) and q_begin / q_end count letters of
     that frame; the reference prints nucleotide coordinates on the read, high end first for the reverse strand

@@ -365,6 +365,56 @@ def write_dna_fasta(path: str, reads, prefix: str = "r") -> None:
             f.write(">%s%d\n%s\n" % (prefix, i, r))
 
 
+def c3_workload(n_reads: int, n_db: int, seed: int, read_len: int = 150, q_stream: int = 0):
+    """BASELINE configs[2]: reads of `read_len` nt = a window of read_len / 3 residues of a database protein, substituted with a
+    per-read rate U(0.1, 0.6), back-translated with uniform codon choice, on either strand.  Vectorised (10^5 reads in a second):
+    returns the reads as an (n, read_len) array of nucleotide codes 0..3 = ACGT next to the database."""
+    rng = np.random.default_rng(seed)
+    dbl, dbo = make_db(n_db, rng)
+    rq = np.random.default_rng([seed, 1 + q_stream])
+    naa = read_len // 3
+    lens = np.diff(dbo)
+    src = rq.integers(0, n_db, n_reads)
+    while True:  # proteins shorter than the window are redrawn
+        bad = lens[src] < naa
+        if not bad.any():
+            break
+        src[bad] = rq.integers(0, n_db, int(bad.sum()))
+    st = (rq.random(n_reads) * (lens[src] - naa + 1)).astype(np.int64)
+    aa = dbl[(dbo[src] + st)[:, None] + np.arange(naa)[None, :]].astype(np.int64)
+    rate = rq.uniform(0.1, 0.6, n_reads)
+    sub = rq.random((n_reads, naa)) < rate[:, None]
+    aa[sub] = draw_letters(rq, int(sub.sum()))
+    # codon table: for amino acid a, its codons as rows of nucleotide codes; uniform choice
+    code = {c: i for i, c in enumerate("ACGT")}
+    ncod = np.array([len(_CODONS[ALPHABET[a]]) for a in range(20)], dtype=np.int64)
+    tab = np.zeros((20, int(ncod.max()), 3), dtype=np.uint8)
+    for a in range(20):
+        for k, cod in enumerate(_CODONS[ALPHABET[a]]):
+            tab[a, k] = [code[x] for x in cod]
+    pick = (rq.random((n_reads, naa)) * ncod[aa]).astype(np.int64)
+    dna = tab[aa, pick].reshape(n_reads, naa * 3)
+    if dna.shape[1] < read_len:
+        dna = np.concatenate([dna, rq.integers(0, 4, (n_reads, read_len - dna.shape[1]), dtype=np.uint8)], axis=1)
+    rev = rq.random(n_reads) < 0.5
+    dna[rev] = (3 - dna[rev])[:, ::-1]  # reverse complement: A<->T, C<->G with codes ACGT = 0123
+    return {"dna_codes": np.ascontiguousarray(dna), "db_letters": dbl, "db_off": dbo, "src": src}
+
+
+def write_dna_codes_fasta(path: str, codes: np.ndarray, prefix: str = "r") -> None:
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    text = lut[codes]
+    with open(path, "wb") as f:
+        chunks = []
+        for i in range(codes.shape[0]):
+            chunks.append(b">%s%d\n" % (prefix.encode(), i))
+            chunks.append(text[i].tobytes())
+            chunks.append(b"\n")
+            if len(chunks) >= 30000:
+                f.write(b"".join(chunks)); chunks = []
+        f.write(b"".join(chunks))
+
+
 BX_WORKLOADS = {"bx": (reads_workload, dict(seed=55))}  # goldens: tests/golden/bx.x0.tsv (blastx --fast, default flags)
 
 

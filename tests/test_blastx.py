@@ -168,3 +168,14 @@ def test_pairwise_format_translated_and_unaligned(oracle_lib, mode, tmp_path):
     assert got.count("***** No hits found *****") > 20
     if mode == "blastx":
         assert got.count(" Frame = -") > 50 and sum(got.count(f" Frame = {k}\n") for k in (1, 2, 3)) > 50
+
+
+def test_vectorised_translation_equals_per_read_translation():
+    """api.translate_codes (bench.py --config c3: 10^5 reads of one length) against api.translate_reads, incl. the ORF masking."""
+    import numpy as np
+    from diamond_b200 import api, synth
+    w = synth.c3_workload(1500, 2000, 3)
+    reads = ["".join("ACGT"[x] for x in row) for row in w["dna_codes"]]
+    a, b = api.translate_reads(reads), api.translate_codes(w["dna_codes"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (b[0] == 23).any() and (b[0] == 24).any()
