@@ -89,6 +89,7 @@ MATCH_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), (
                         ("reserved", "<u4")])
 assert MATCH_DTYPE.itemsize == C.sizeof(Match), (MATCH_DTYPE.itemsize, C.sizeof(Match))
 HIT_DTYPE = np.dtype([("query", "<u4"), ("seed_offset", "<i4"), ("subject_score", "<u8")])
+CHAIN_QUERY_DTYPE = np.dtype([("query", "<u4"), ("n_targets", "<u4"), ("n_problems", "<u4"), ("first", "<u4"), ("n_hits", "<u4"), ("flags", "<u4")])
 RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("score", "q_begin", "q_end", "t_begin", "t_end", "identities", "mismatches",
                                                "gap_openings", "length", "gaps", "positives")] +
                         [("transcript_off", "<u4"), ("transcript_len", "<u4"), ("status", "<i4")])
@@ -97,7 +98,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
-           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter",
+           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter", "dmnd_hits_chain", "dmnd_hits_chain_fetch", "dmnd_banded_swipe_chained",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_measure_int_peak_packed", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_masked_positions", "dmnd_result_unaligned", "dmnd_result_free"]
@@ -124,6 +125,9 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_debug_left_most.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]
     lib.dmnd_block_mask.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.dmnd_block_mask_fetch.argtypes = [vp, vp, C.c_size_t]
+    lib.dmnd_hits_chain.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.dmnd_hits_chain_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.dmnd_banded_swipe_chained.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
     lib.dmnd_hits_gapped_filter.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
     lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
     lib.dmnd_block_build_index.argtypes = [vp, vp, C.c_int]
@@ -310,6 +314,26 @@ class Context:
         if gapped_filter:
             return hits, cnd, gf
         return (hits, cnd) if xdrop is None else (hits, cnd, segs)
+
+    def hits_chain(self, qb, rb, sid: int = 0, xdrop: int = 0, band_slow: bool = False, max_targets: int = 64, align: bool = False):
+        """dmnd_search_shape + dmnd_hits_chain (+ dmnd_banded_swipe_chained with traceback when `align`): per-query records, the DP
+        problem list, the hits / segments / sites of the DMND_CHAIN_HOST queries, and the counts."""
+        h = C.c_void_p()
+        cn = StageCounters()
+        self._check(self.lib.dmnd_search_shape(self.ctx, qb, rb, sid, C.byref(h), C.byref(cn)))
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.dmnd_hits_chain(self.ctx, qb, rb, h, xdrop, int(band_slow), max_targets, out))
+        self.lib.dmnd_hits_free(self.ctx, h)
+        nq, npairs, nprob, nhh = (int(x) for x in out)
+        q = np.zeros(nq, dtype=CHAIN_QUERY_DTYPE); pr = np.zeros(nprob, dtype=PROBLEM_DTYPE)
+        hh = np.zeros(nhh, dtype=HIT_DTYPE); hs = np.zeros(nhh, dtype=SEGMENT_DTYPE); ht = np.zeros(nhh, dtype=np.dtype([("target", "<u4"), ("j", "<i4")]))
+        self._check(self.lib.dmnd_hits_chain_fetch(self.ctx, q.ctypes.data, pr.ctypes.data, hh.ctypes.data, hs.ctypes.data, ht.ctypes.data))
+        res = None
+        if align:
+            res = np.zeros(nprob, dtype=RESULT_DTYPE)
+            if nprob:
+                self._check(self.lib.dmnd_banded_swipe_chained(self.ctx, qb, rb, nprob, 1, res.ctypes.data, None, 0))
+        return {"queries": q, "problems": pr, "host_hits": hh, "host_segs": hs, "host_sites": ht, "n_pairs": npairs, "results": res}
 
     def banded_swipe(self, qb, rb, problems: np.ndarray, traceback: bool, transcript_cap: int = 0):
         problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)

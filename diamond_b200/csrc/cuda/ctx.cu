@@ -568,7 +568,22 @@ void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h) {
 int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
-	return banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+	return banded_swipe_impl(ctx, query, ref, problems, nullptr, n, mode, results, transcripts, transcript_cap);
+}
+
+int dmnd_hits_chain(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, int band_slow, int max_targets, dmnd_chain_out* out) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (ctx->params.query_contexts > 1) { set_error("dmnd_hits_chain: one query context only"); return 1; }
+	return hits_chain_impl(ctx, query, ref, h, raw_xdrop, band_slow, max_targets, out);
+}
+int dmnd_hits_chain_fetch(dmnd_ctx* ctx, dmnd_chain_query* queries, dmnd_dp_problem* problems, dmnd_hit* hits, dmnd_segment* segs, dmnd_hit_site* sites) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	return hits_chain_fetch_impl(ctx, queries, problems, hits, segs, sites);
+}
+int dmnd_banded_swipe_chained(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (n != ctx->chain_counts[1]) { set_error("dmnd_banded_swipe_chained: n is not the problem count of the last dmnd_hits_chain"); return 1; }
+	return banded_swipe_impl(ctx, query, ref, nullptr, ctx->chain_probs, n, mode, results, transcripts, transcript_cap);
 }
 
 int dmnd_timing_fetch(dmnd_ctx* ctx, dmnd_timing* out, int flags) {

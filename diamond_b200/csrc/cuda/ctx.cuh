@@ -100,6 +100,9 @@ struct dmnd_ctx {
 	uint64_t dp_cells_score = 0, dp_cells_trace = 0, dp_cells_padded = 0;  // cells of the problems LAUNCHED (score-only / traceback kernels) and what the register tiles evaluate for them
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
 	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
+	dmnd_cuda::DevBuf b_chain_probs;  // dmnd_hits_chain: the DP problems of the device-chained queries (read in place by dmnd_banded_swipe_chained)
+	dmnd_chain_query* chain_q = nullptr; dmnd_dp_problem* chain_probs = nullptr; dmnd_hit* chain_fb_hits = nullptr; dmnd_segment* chain_fb_segs = nullptr; dmnd_hit_site* chain_fb_sites = nullptr;
+	size_t chain_counts[3] = {};
 	dmnd_cuda::DevBuf b_hits_out;  // hit arena handed out by dmnd_search_shape (one live dmnd_hits per context)
 	struct FreeBlock { int8_t *letters, *bias; int64_t* limits; uint32_t* soft; size_t cap_bytes, cap_seqs; dmnd_cuda::RefIndex idx; };
 	std::vector<FreeBlock> block_pool;  // device memory of freed blocks, reused by dmnd_block_upload
@@ -150,8 +153,11 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap);
 int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard);
 int block_mask_fetch_impl(dmnd_ctx* ctx, uint64_t* positions, size_t cap);
+int launch_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* d_segs, dmnd_hit_site* d_sites);
+int hits_chain_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, int band_slow, int max_targets, dmnd_chain_out* out);
+int hits_chain_fetch_impl(dmnd_ctx* ctx, dmnd_chain_query* queries, dmnd_dp_problem* problems, dmnd_hit* hits, dmnd_segment* segs, dmnd_hit_site* sites);
 int s16_table_build(dmnd_ctx* ctx);
-int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
+int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, const dmnd_dp_problem* d_problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 
 }  // namespace dmnd_cuda

@@ -38,6 +38,15 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 	return 0;
 }
 
+// xdrop_kernel on the context's stream, results left on the device (dmnd_hits_chain, chain.cu)
+int launch_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* d_segs, dmnd_hit_site* d_sites) {
+	xdrop_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, ctx->stream>>>(query->letters, query->bias, query->limits, ref->letters, ref->limits, ref->nseq,
+		h->d, h->n, ctx->d_params, raw_xdrop, d_segs, d_sites);
+	++ctx->launches;
+	DMND_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
 int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap) {
 	if (cap < h->n) { set_error("dmnd_hits_gapped_filter: buffer too small"); return 1; }
 	if (ctx->params.gapped_filter_evalue <= 0.0) { set_error("dmnd_hits_gapped_filter: this sensitivity mode has no gapped filter"); return 1; }

@@ -682,7 +682,8 @@ int s16_table_build(dmnd_ctx* ctx) {
 	return 0;
 }
 
-int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n, int mode,
+// `d_problems` != nullptr: the problem list is already on the device (dmnd_hits_chain) and `problems` is ignored
+int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, const dmnd_dp_problem* d_problems, size_t n, int mode,
                       dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
 	if (n == 0) return 0;
 	if (n > 0xfffffff0ull) { set_error("dmnd_banded_swipe: too many problems in one call"); return 1; }
@@ -717,19 +718,20 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	uint32_t* d_key = (uint32_t*)(d_tsoff + n);
 	uint32_t* d_key2 = d_key + n;
 	uint32_t* d_idx = d_key2 + n;
-	{
+	if (!d_problems) {
 		PhaseTimer t(ctx, PH_H2D);
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->b_probs.p, problems, n * sizeof(dmnd_dp_problem), cudaMemcpyHostToDevice, st));
 		t.stop();
 		ctx->h2d_bytes += n * sizeof(dmnd_dp_problem);
 	}
+	const dmnd_dp_problem* dev_probs = d_problems ? d_problems : ctx->b_probs.as<dmnd_dp_problem>();
 	lap("upload problems");
 	PhaseTimer t_dp(ctx, trace ? PH_DP_TRACE : PH_DP_SCORE);
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 256 * sizeof(unsigned int), st));
 	unsigned long long* d_cost_hist = (unsigned long long*)(((uintptr_t)(d_counters + 256) + 7) & ~(uintptr_t)7);  // [0..NG-1] cost per group, [NG] sum of tslen
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cost_hist, 0, 64 * sizeof(unsigned long long), st));
 	PrepOut po{ d_key, d_idx, d_cost, d_tslen, d_counters + 96, d_counters + 128, d_cost_hist, d_counters + 64 };
-	prep_kernel<<<nb, 256, 0, st>>>(ctx->b_probs.as<dmnd_dp_problem>(), (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, use_s16 ? 1 : 0, po);
+	prep_kernel<<<nb, 256, 0, st>>>(dev_probs, (uint32_t)n, query->limits, query->nseq, ref->limits, ref->nseq, trace ? (transcripts ? 1 : 2) : 0, use_s16 ? 1 : 0, po);
 	DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, sort_tmp, d_key, d_key2, d_idx, ctx->b_order.as<uint32_t>(), n, 0, 25, st));
 	unsigned int* hp = (unsigned int*)ctx->h_pinned;  // [0..31] hist, [32..63] max qlen, [64] flag, [65] profile overflow, [66] packed-kernel overflow
 	DMND_CUDA_CHECK(cudaMemcpyAsync(hp, d_counters + 96, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -753,7 +755,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 
 	SwipeArgs a;
 	a.q_letters = query->letters; a.q_bias = query->bias; a.r_letters = ref->letters; a.q_limits = query->limits; a.r_limits = ref->limits;
-	a.probs = ctx->b_probs.as<dmnd_dp_problem>();
+	a.probs = dev_probs;
 	a.score = d_score; a.end_cell = d_end; a.trace = nullptr; a.trace_excl = nullptr; a.trace_base = 0; a.order_pos0 = 0;
 	uint64_t ts_total = 0;
 	// one DP launch over order[pos, e) of group g
@@ -914,14 +916,14 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		// (banded_swipe.h:337,347), here for the whole call on the exact int32 kernels
 		++ctx->dp_overflows;
 		ctx->force_int32_dp = true;
-		const int rc = banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+		const int rc = banded_swipe_impl(ctx, query, ref, problems, d_problems, n, mode, results, transcripts, transcript_cap);
 		ctx->force_int32_dp = false;
 		return rc;
 	}
 	if (hp[65] != 0 && !force_generic) {
 		// S + bias left the int8 range of the shared-memory profile somewhere: redo the whole call on the generic kernel
 		ctx->force_generic_dp = true;
-		const int rc = banded_swipe_impl(ctx, query, ref, problems, n, mode, results, transcripts, transcript_cap);
+		const int rc = banded_swipe_impl(ctx, query, ref, problems, d_problems, n, mode, results, transcripts, transcript_cap);
 		ctx->force_generic_dp = false;
 		return rc;
 	}

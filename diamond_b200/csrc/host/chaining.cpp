@@ -12,6 +12,7 @@
 //   chaining/greedy_align.cpp:426-497      merge_score / merge / merge_hsps / Chaining::run
 // The anchor (max_diag) bookkeeping of the reference is not carried: it only feeds the opt-in anchored SWIPE.
 #include "chaining.h"
+#include "../../../include/dmnd_b200.h"
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -434,3 +435,43 @@ void chain_segments(const Scoring& sc, const int8_t* query, int qlen, const int8
 }
 
 }  // namespace dmnd
+
+// C wrapper of the per-(query, target) bridge -- hits -> segments -> chains -> merged bands (pipeline.cpp: produce_round1) -- for the
+// TEST-ONLY oracle library's dmnd_hits_chain and for tests: the device code (cuda/chain_kernels.cuh) must return the same bands.
+extern "C" int dmnd_host_chain_pair(const int32_t* hit_i, const int32_t* hit_j, const dmnd_segment* hit_seg, int nh, const int8_t* query, int qlen,
+                                    const int8_t* subject, int slen, int band, int32_t* d0_out, int32_t* d1_out, int cap) {
+	using namespace dmnd;
+	static const Scoring sc;
+	struct H { int i, j; dmnd_segment s; };
+	std::vector<H> hh((size_t)nh);
+	for (int k = 0; k < nh; ++k) hh[(size_t)k] = H{ hit_i[k], hit_j[k], hit_seg[k] };
+	std::sort(hh.begin(), hh.end(), [](const H& x, const H& y) { const int a = x.i - x.j, b = y.i - y.j; return a < b || (a == b && x.j < y.j); });
+	std::vector<Segment> segs;
+	for (const H& h : hh) {  // align/ungapped.cpp:81-91
+		if (!segs.empty() && segs.back().diag() == h.i - h.j && segs.back().subject_end() >= h.j) continue;
+		if (h.s.score > 0) segs.push_back(Segment{ h.s.i, h.s.j, h.s.len, h.s.score });
+	}
+	if (segs.empty()) return 0;
+	std::stable_sort(segs.begin(), segs.end(), [](const Segment& x, const Segment& y) { return x.diag() < y.diag() || (x.diag() == y.diag() && x.j < y.j); });
+	std::vector<Chain> chains;
+	chain_segments(sc, query, qlen, subject, slen, segs, chains);
+	std::stable_sort(chains.begin(), chains.end(), [](const Chain& x, const Chain& y) { return x.d_min < y.d_min; });
+	int np = 0, d0 = INT_MAX, d1 = INT_MIN;
+	auto emit = [&]() -> bool { if (np >= cap) return false; d0_out[np] = d0; d1_out[np] = d1; ++np; return true; };
+	for (const Chain& h : chains) {  // add_dp_targets, align/gapped_score.cpp:107-180
+		const int b0 = std::max(h.d_min - band, -(slen - 1)), b1 = std::min(h.d_max + 1 + band, qlen);
+		bool merge = false;
+		if (d0 != INT_MAX) {
+			const int ib = std::max(d0, b0), ie = std::min(d1, b1);
+			const double overlap = ie > ib ? ie - ib : 0;
+			merge = overlap / (d1 - d0) > 0.0 || overlap / (b1 - b0) > 0.0;
+		}
+		if (merge) { d0 = std::min(d0, b0); d1 = std::max(d1, b1); }
+		else {
+			if (d0 != INT_MAX && !emit()) return -1;
+			d0 = b0; d1 = b1;
+		}
+	}
+	if (!chains.empty() && !emit()) return -1;
+	return np;
+}

@@ -309,6 +309,7 @@ struct QueryState {
 	Phase phase;
 	bool new_hits_ev;
 	bool fused;
+	bool bridged;  // its round-1 problems came from dmnd_hits_chain (no SeedHitList on the host)
 	// SeedHitList (align/target.h:160-165): slices of the owner thread's flat arrays
 	uint32_t sh_off, tgt_off, n_targets;  // hit_begin[tgt_off + k] (n_targets + 1 entries), block ids / scores [ts_off..]
 	uint32_t ts_off;
@@ -407,8 +408,9 @@ struct Workspace {
 	std::vector<HitSeg> hs;
 	std::vector<size_t> qstart;
 	std::vector<QueryState> qs;
-	HostBuf<dmnd_dp_problem> p1, p2;
-	HostBuf<dmnd_dp_result> res1, res2;
+	HostBuf<dmnd_dp_problem> p1, p2, cprobs;  // cprobs / cres / cq: dmnd_hits_chain's problem list, its results, its per-query records
+	HostBuf<dmnd_dp_result> res1, res2, cres;
+	HostBuf<dmnd_chain_query> cq;
 	HostBuf<uint8_t> tr;
 	RawBuf<dmnd_match> out_matches;   // lane output when several lanes run (copied into the result afterwards)
 	RawBuf<uint8_t> out_transcripts;
@@ -445,6 +447,7 @@ struct Driver {
 
 	void load_hits(QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end);
 	void start(QueryState& q, ThreadCtx& tc);
+	void start_bridged(QueryState& q, ThreadCtx& tc, const dmnd_chain_query& cq, const dmnd_dp_problem* probs);
 	void produce_round1(QueryState& q, ThreadCtx& tc);
 	void produce_round2(QueryState& q, ThreadCtx& tc);
 	void consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
@@ -504,6 +507,7 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	// align/extend.cpp:346-387 then :226-258
 	const Env& e = env;
 	q.qlen = e.qlen(q.qid);
+	q.bridged = false;
 	q.new_hits_ev = false; q.tail_score = q.previous_tail_score = 0;
 	q.aligned_targets = {}; q.r1 = {}; q.matches = {}; q.r2 = {}; q.prob_target = {};
 	q.prob_begin = 0; q.prob_count = 0;
@@ -527,6 +531,38 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	// from those results -- one device round trip instead of two, 13 instead of 9 + 13 lane-ops per surviving cell.
 	q.fused = e.fuse && e.contexts == 1 && target_count <= 64 && target_count <= q.chunk_size;
 	q.phase = PH_ROUND1_PRODUCE;
+}
+
+// A query whose round-1 problem list was produced on the device (dmnd_hits_chain): the state start() + produce_round1() would
+// have left for a fused query, minus the SeedHitList.  Targets without a problem are not listed: consume_round1 drops them anyway.
+void Driver::start_bridged(QueryState& q, ThreadCtx& tc, const dmnd_chain_query& cq, const dmnd_dp_problem* probs) {
+	const Env& e = env;
+	q.qid = cq.query;
+	q.qlen = e.qlen(q.qid);
+	q.bridged = true; q.fused = true;
+	q.new_hits_ev = false; q.tail_score = q.previous_tail_score = 0;
+	q.aligned_targets = {}; q.r1 = {}; q.matches = {}; q.r2 = {}; q.prob_target = {};
+	q.sh_off = q.tgt_off = q.ts_off = 0;
+	q.n_targets = cq.n_targets;
+	q.prob_begin = 0; q.prob_count = cq.n_problems;
+	tc.n_targets += cq.n_targets; tc.n_extended += cq.n_targets;
+	const int64_t block_mult = std::max<int64_t>((int64_t)std::round((double)e.ref_letters / e.ranking_letters), 1);
+	const int64_t mm = ((int64_t)e.max_target_seqs + 31) / 32 * 32;
+	q.chunk_size = e.top >= 0.0 ? 128 * block_mult : std::max<int64_t>(128, std::min<int64_t>(mm, 400)) * block_mult;
+	q.i0 = 0; q.i1 = q.n_targets;  // one ranking chunk (n_targets <= 64 < chunk_size)
+	q.r1.reserve(tc.arena, cq.n_problems);
+	uint32_t last = UINT32_MAX;
+	for (uint32_t k = 0; k < cq.n_problems; ++k) {
+		const dmnd_dp_problem& pr = probs[k];
+		if (pr.target != last) {
+			q.r1.push(tc.arena, Target{ pr.target, e.tlen(pr.target), 0, DBL_MAX, HspLite{ 0, 0.0, 0, 0, q.qid }, false, 0 });
+			last = pr.target;
+		}
+		q.prob_target.push(tc.arena, q.r1.n - 1);
+		tc.cells1 += (uint64_t)(pr.d_end - pr.d_begin) * (uint64_t)banded_cols(q.qlen, e.tlen(pr.target), pr.d_begin, pr.d_end);
+	}
+	tc.fused_r1 += cq.n_problems;
+	q.phase = PH_ROUND1_CONSUME;
 }
 
 void Driver::produce_round1(QueryState& q, ThreadCtx& tc) {
@@ -670,7 +706,7 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 	q.i0 = q.i1;
 	q.i1 += std::min<int64_t>(q.chunk_size, n_targets - q.i1);
 	q.previous_tail_score = q.tail_score;
-	if (new_hits) q.tail_score = ts[q.i1 - 1].score;
+	if (new_hits && !q.bridged) q.tail_score = ts[q.i1 - 1].score;  // (a bridged query has one ranking chunk: the tail score is never read)
 	bool terminate = false;
 	if (q.i0 < n_targets) {  // ranking_terminate, align/extend.cpp:111-119
 		const int tscore = ts[q.i1 - 1].score;
@@ -1053,11 +1089,32 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	seed_turn.wait_for(lane);
 	const int n_shapes = env.n_shapes;
 	size_t nh = 0;
+	// The bridge from hits to DP problems runs on the device (dmnd_hits_chain) for single-shape blastp without a gapped filter:
+	// the hits never come to the host, the round-1 problem list of every query with <= 64 targets is produced and aligned in HBM,
+	// and only queries with ranking chunks (or pairs beyond the device code's capacities) take the host code below.
+	const bool bridge = n_shapes == 1 && env.fuse && env.contexts == 1 && !env.gapped_filter && getenv("DMND_HOST_BRIDGE") == nullptr;
+	dmnd_chain_out co;
+	std::memset(&co, 0, sizeof co);
 	if (n_shapes == 1) {
 		const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
 		seed_turn.pass(lane);
 		if (seed_rc) return 1;
 		prof.lap("search_shape");
+		if (bridge) {
+			d.stats.hits = dmnd_hits_count(hits);
+			d.stats.seed_ms = ms_since(t0);
+			t0 = Clock::now();
+			if (dmnd_hits_chain(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, env.band_slow ? 1 : 0, 64, &co)) { dmnd_hits_free(ctx, hits); return 1; }
+			dmnd_hits_free(ctx, hits);
+			nh = (size_t)co.n_host_hits;
+			if (w.cq.resize(ctx, (size_t)co.n_queries) || w.cprobs.resize(ctx, (size_t)co.n_problems) || w.cres.resize(ctx, (size_t)co.n_problems)
+			    || w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh))
+				return 1;
+			if (dmnd_hits_chain_fetch(ctx, w.cq.data(), w.cprobs.data(), w.hv.data(), w.segv.data(), w.sitev.data())) return 1;
+			d.stats.host_bridge_ms += ms_since(t0);
+			prof.lap("hits_chain (device bridge)");
+		}
+		else {
 		nh = dmnd_hits_count(hits);
 		if (w.hv.resize(ctx, nh) || w.segv.resize(ctx, nh) || w.sitev.resize(ctx, nh)) { dmnd_hits_free(ctx, hits); return 1; }
 		if (nh && dmnd_hits_download(ctx, hits, w.hv.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
@@ -1065,6 +1122,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		// ... together with the sequence and local position of every hit (what load_hits would otherwise search for)
 		if (nh && dmnd_hits_xdrop_sites(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, w.segv.data(), w.sitev.data(), nh)) { dmnd_hits_free(ctx, hits); return 1; }
 		dmnd_hits_free(ctx, hits);
+		}
 	}
 	else {
 		// run_ref_chunk's loop over the shapes (run/double_indexed.cpp:185-214): SEED_MASK bits set by one shape stay visible
@@ -1102,13 +1160,63 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	if (n_shapes == 1) w.gfv.assign(nh, 1);
 	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
-	d.stats.seed_ms = ms_since(t0);
-	d.stats.hits = nh;
-
-	// ---- group by query (hits arrive grouped by ascending query id): boundaries found in parallel
-	t0 = Clock::now();
+	if (!bridge) { d.stats.seed_ms = ms_since(t0); d.stats.hits = nh; }
 	const int T = host_threads;
 	const uint32_t C = env.contexts;
+
+	if (bridge) {
+		// ---- the device-chained problem list is aligned where it lies; the host then only scores and culls (consume_fused)
+		t0 = Clock::now();
+		const size_t np = (size_t)co.n_problems, nqh = (size_t)co.n_queries;
+		uint8_t* trp = nullptr;
+		size_t cap = 0;
+		if (np && env.want_transcript) {
+			std::vector<size_t> part((size_t)T, 0);
+			w.run([&](int t) {
+				size_t c = 0;
+				for (size_t k = np * (size_t)t / (size_t)T, en = np * (size_t)(t + 1) / (size_t)T; k < en; ++k) c += (size_t)env.qlen(w.cprobs[k].query) + (size_t)env.tlen(w.cprobs[k].target);
+				part[(size_t)t] = c;
+			});
+			for (size_t c : part) cap += c;
+			if (w.tr.resize(ctx, cap)) return 1;
+			trp = w.tr.data();
+		}
+		if (np && dmnd_banded_swipe_chained(ctx, qb, rb, np, DMND_DP_TRACEBACK, w.cres.data(), trp, cap)) return 1;
+		d.stats.dp2_ms += ms_since(t0);
+		d.stats.dp_problems_round1 += np;
+		prof.lap("banded_swipe (chained list)");
+		t0 = Clock::now();
+		d.nq_hit = nqh;
+		w.qs.resize(nqh);
+		w.hs.resize(nh);
+		std::atomic<int> bad(0);
+		w.run([&](int t) {
+			ThreadCtx& tc = w.tc[(size_t)t];
+			tc.reset();
+			for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
+				QueryState& q = w.qs[k];
+				const dmnd_chain_query& cq = w.cq[k];
+				if (k > 0 && cq.query <= w.cq[k - 1].query) bad = 1;
+				if (cq.flags & DMND_CHAIN_HOST) {
+					q.qid = cq.query;
+					for (size_t x = cq.first; x < (size_t)cq.first + cq.n_hits; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; w.hs[x].gf = 1; }
+					d.load_hits(q, tc, w.hs.data() + cq.first, w.hs.data() + cq.first + cq.n_hits);
+					d.start(q, tc);
+				}
+				else {
+					d.start_bridged(q, tc, cq, w.cprobs.data() + cq.first);
+					d.consume_fused(q, tc, w.cprobs.data() + cq.first, w.cres.data() + cq.first, trp);
+				}
+			}
+		});
+		if (bad) { dmnd_set_last_error("dmnd_blastp: dmnd_hits_chain records not in ascending query order"); return 1; }
+		for (const ThreadCtx& tc : w.tc) d.stats.targets += tc.n_targets;
+		d.stats.host_bridge_ms += ms_since(t0);
+		prof.lap("consume chained queries (parallel)");
+	}
+	else {
+	// ---- group by query (hits arrive grouped by ascending query id): boundaries found in parallel
+	t0 = Clock::now();
 	std::vector<std::vector<size_t>> tl_bounds((size_t)T);
 	std::atomic<int> bad(0);
 	w.run([&](int t) {
@@ -1143,6 +1251,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	for (const ThreadCtx& tc : w.tc) d.stats.targets += tc.n_targets;
 	d.stats.host_bridge_ms += ms_since(t0);
 	prof.lap("load_hits (parallel)");
+	}
 
 	if (d.run_waves()) return 1;
 	prof.lap("run_waves");

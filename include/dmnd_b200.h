@@ -248,6 +248,33 @@ int dmnd_hits_gapped_filter(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_b
 int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t cap);
 void dmnd_hits_free(dmnd_ctx* ctx, dmnd_hits* h);
 
+/* ---- the host bridge on the device: hits -> DP problems without leaving HBM ------------------------------------------------
+ * dmnd_hits_chain replaces, for every query of `h`, load_hits (align/load_hits.h:44-122: hits grouped by target), the ungapped
+ * stage (align/ungapped.cpp:62-118: x-drop segment of every hit, covered hits skipped), Chaining::run (chaining/greedy_align.cpp:
+ * 482-497) and add_dp_targets (align/gapped_score.cpp:107-180: band = chain diagonals +- Extension::band(query length), overlapping
+ * bands merged): one record per query that has hits, ascending query ids, and the queries' banded DP problems in (query, target,
+ * band) order -- exactly the round-1 problem list of a query whose targets fit one ranking chunk.  Queries with more than
+ * `max_targets` targets (ranking chunks, align/extend.cpp:79-119) or with a (query, target) pair beyond the implementation's fixed
+ * capacities carry DMND_CHAIN_HOST and no problems: their hits, segments and sites are returned instead (dmnd_hits_chain_fetch) and
+ * the caller runs the reference's per-query logic on them.  The problem list stays on the device: dmnd_banded_swipe_chained aligns
+ * it in place.  Single query context only (blastp).  `band_slow`: Extension::Mode::BANDED_SLOW band table. */
+typedef struct dmnd_chain_query {
+	uint32_t query, n_targets, n_problems;
+	uint32_t first;   /* index of the query's first DP problem, or (DMND_CHAIN_HOST) of its first hit in the host-path arrays */
+	uint32_t n_hits, flags;
+} dmnd_chain_query;
+enum { DMND_CHAIN_HOST = 1 };
+typedef struct dmnd_chain_out { uint64_t n_queries, n_pairs, n_problems, n_host_hits; } dmnd_chain_out;
+int dmnd_hits_chain(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, int band_slow,
+                    int max_targets, dmnd_chain_out* out);
+/* Copies the last dmnd_hits_chain's records to the host: `queries` [n_queries], `problems` [n_problems], and the hits / segments /
+ * sites [n_host_hits] of the DMND_CHAIN_HOST queries (grouped by query, a query's hits ordered by target). */
+int dmnd_hits_chain_fetch(dmnd_ctx* ctx, dmnd_chain_query* queries, dmnd_dp_problem* problems, dmnd_hit* hits, dmnd_segment* segs,
+                          dmnd_hit_site* sites);
+/* dmnd_banded_swipe over the problem list the last dmnd_hits_chain left on the device (n = its n_problems), results in list order. */
+int dmnd_banded_swipe_chained(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, size_t n, int mode, dmnd_dp_result* results,
+                              uint8_t* transcripts, size_t transcript_cap);
+
 /* Banded affine-gap local alignment of n problems.  `transcripts` may be NULL (no edit transcript wanted). */
 int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems,
                       size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);

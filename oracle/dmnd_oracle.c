@@ -564,6 +564,97 @@ static void motif_seed_mask(const dmnd_params* p, dmnd_block* query, int sid, ui
 		}
 	}
 }
+/* ---- dmnd_hits_chain (test twin of cuda/chain.cu): the same records from the host code of diamond_b200/csrc/host (load_hits order,
+ * segment filter, chaining.cpp, band merge) through dmnd_host_chain_pair.  No fixed capacities: only queries with more than
+ * max_targets targets carry DMND_CHAIN_HOST. */
+int dmnd_host_chain_pair(const int32_t* hit_i, const int32_t* hit_j, const dmnd_segment* hit_seg, int nh, const int8_t* query, int qlen,
+                         const int8_t* subject, int slen, int band, int32_t* d0_out, int32_t* d1_out, int cap);
+typedef struct { dmnd_chain_query* q; size_t nq; dmnd_dp_problem* probs; size_t np, pcap; dmnd_hit* fh; dmnd_segment* fs; dmnd_hit_site* ft; size_t nf, fcap; } chain_state;
+static __thread chain_state t_chain;
+static const dmnd_hit* g_sort_hits; static const dmnd_hit_site* g_sort_sites;
+static __thread const dmnd_hit* t_sort_hits; static __thread const dmnd_hit_site* t_sort_sites;
+static int cmp_chain_idx(const void* a, const void* b) {
+	const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+	const dmnd_hit *hx = t_sort_hits + x, *hy = t_sort_hits + y;
+	if (hx->query != hy->query) return hx->query < hy->query ? -1 : 1;
+	if (t_sort_sites[x].target != t_sort_sites[y].target) return t_sort_sites[x].target < t_sort_sites[y].target ? -1 : 1;
+	return x < y ? -1 : (x > y);
+}
+static int chain_band_for(int len, int slow) {
+	if (!slow) return len < 50 ? 12 : len < 100 ? 16 : len < 250 ? 30 : len < 350 ? 40 : 64;
+	return len < 50 ? 15 : len < 100 ? 20 : len < 150 ? 30 : len < 200 ? 50 : len < 250 ? 60 : len < 350 ? 100 : len < 500 ? 120 : 150;
+}
+int dmnd_hits_chain(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, int band_slow, int max_targets, dmnd_chain_out* out) {
+	(void)g_sort_hits; (void)g_sort_sites;
+	memset(out, 0, sizeof *out);
+	chain_state* c = &t_chain;
+	c->nq = c->np = c->nf = 0;
+	const size_t n = h->n;
+	if (n == 0) return 0;
+	dmnd_segment* segs = (dmnd_segment*)malloc(n * sizeof *segs);
+	dmnd_hit_site* sites = (dmnd_hit_site*)malloc(n * sizeof *sites);
+	uint32_t* idx = (uint32_t*)malloc(n * sizeof *idx);
+	if (dmnd_hits_xdrop_sites(ctx, query, ref, h, raw_xdrop, segs, sites, n)) { free(segs); free(sites); free(idx); return 1; }
+	for (size_t k = 0; k < n; ++k) idx[k] = (uint32_t)k;
+	t_sort_hits = h->h; t_sort_sites = sites;
+	qsort(idx, n, sizeof *idx, cmp_chain_idx);
+	free(c->q); c->q = (dmnd_chain_query*)malloc(n * sizeof *c->q);
+	if (c->fcap < n) { free(c->fh); free(c->fs); free(c->ft); c->fh = (dmnd_hit*)malloc(n * sizeof *c->fh); c->fs = (dmnd_segment*)malloc(n * sizeof *c->fs); c->ft = (dmnd_hit_site*)malloc(n * sizeof *c->ft); c->fcap = n; }
+	size_t npairs = 0;
+	int32_t *hi = (int32_t*)malloc(n * sizeof *hi), *hj = (int32_t*)malloc(n * sizeof *hj);
+	dmnd_segment* hs = (dmnd_segment*)malloc(n * sizeof *hs);
+	for (size_t qb = 0; qb < n;) {
+		const uint32_t qid = h->h[idx[qb]].query;
+		size_t qe = qb;
+		uint32_t ntg = 0, last = 0xffffffffu;
+		while (qe < n && h->h[idx[qe]].query == qid) { if (sites[idx[qe]].target != last) { ++ntg; last = sites[idx[qe]].target; } ++qe; }
+		npairs += ntg;
+		dmnd_chain_query q; memset(&q, 0, sizeof q);
+		q.query = qid; q.n_targets = ntg; q.n_hits = (uint32_t)(qe - qb);
+		if ((int)ntg > max_targets) {
+			q.flags = DMND_CHAIN_HOST; q.first = (uint32_t)c->nf;
+			for (size_t k = qb; k < qe; ++k) { c->fh[c->nf] = h->h[idx[k]]; c->fs[c->nf] = segs[idx[k]]; c->ft[c->nf] = sites[idx[k]]; ++c->nf; }
+		}
+		else {
+			q.first = (uint32_t)c->np;
+			const int64_t qo = query->limits[qid];
+			const int qlen = (int)(query->limits[qid + 1] - qo - 1);
+			for (size_t pb = qb; pb < qe;) {
+				const uint32_t tg = sites[idx[pb]].target;
+				size_t pe = pb;
+				int nh = 0;
+				while (pe < qe && sites[idx[pe]].target == tg) { hi[nh] = h->h[idx[pe]].seed_offset; hj[nh] = sites[idx[pe]].j; hs[nh] = segs[idx[pe]]; ++nh; ++pe; }
+				const int64_t to = ref->limits[tg];
+				const int slen = (int)(ref->limits[tg + 1] - to - 1);
+				int32_t d0[64], d1[64];
+				const int np = dmnd_host_chain_pair(hi, hj, hs, nh, query->letters + qo, qlen, ref->letters + to, slen, chain_band_for(qlen, band_slow), d0, d1, 64);
+				if (np < 0) { free(segs); free(sites); free(idx); free(hi); free(hj); free(hs); return fail("dmnd_hits_chain: more than 64 bands for one target"); }
+				if (c->np + (size_t)np > c->pcap) { c->pcap = (c->np + (size_t)np) * 2 + 1024; c->probs = (dmnd_dp_problem*)realloc(c->probs, c->pcap * sizeof *c->probs); }
+				for (int k = 0; k < np; ++k) { dmnd_dp_problem pr; pr.query = qid; pr.target = tg; pr.d_begin = d0[k]; pr.d_end = d1[k]; c->probs[c->np++] = pr; }
+				q.n_problems += (uint32_t)np;
+				pb = pe;
+			}
+		}
+		c->q[c->nq++] = q;
+		qb = qe;
+	}
+	free(segs); free(sites); free(idx); free(hi); free(hj); free(hs);
+	out->n_queries = c->nq; out->n_pairs = npairs; out->n_problems = c->np; out->n_host_hits = c->nf;
+	return 0;
+}
+int dmnd_hits_chain_fetch(dmnd_ctx* ctx, dmnd_chain_query* queries, dmnd_dp_problem* problems, dmnd_hit* hits, dmnd_segment* segs, dmnd_hit_site* sites) {
+	(void)ctx;
+	const chain_state* c = &t_chain;
+	if (c->nq) memcpy(queries, c->q, c->nq * sizeof *queries);
+	if (c->np) memcpy(problems, c->probs, c->np * sizeof *problems);
+	if (c->nf) { memcpy(hits, c->fh, c->nf * sizeof *hits); memcpy(segs, c->fs, c->nf * sizeof *segs); memcpy(sites, c->ft, c->nf * sizeof *sites); }
+	return 0;
+}
+int dmnd_banded_swipe_chained(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap) {
+	if (n != t_chain.np) return fail("dmnd_banded_swipe_chained: n is not the problem count of the last dmnd_hits_chain");
+	return dmnd_banded_swipe(ctx, query, ref, t_chain.probs, n, mode, results, transcripts, transcript_cap);
+}
+
 /* Diagnostics twin of the device library's dmnd_debug_left_most (tools/seed_stage_diag.py): same out30 layout. */
 int dmnd_debug_left_most(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out) {
 	const dmnd_params* p = &ctx->p;
