@@ -311,6 +311,7 @@ int dmnd_block_upload(dmnd_ctx* ctx, const int8_t* letters, size_t raw_len, cons
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, ctx->stream));
 	DMND_CUDA_CHECK(cudaMemsetAsync(b->soft, 0, b->cap_bytes / 8 + 16, ctx->stream));
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	ctx->h2d_bytes += raw_len + sizeof(int64_t) * ((size_t)nseq + 1);
 	*out = b;
 	return 0;
@@ -374,6 +375,7 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 	if (bias) { DMND_CUDA_CHECK(cudaMemcpyAsync(b->bias, bias, raw_len, cudaMemcpyHostToDevice, ctx->stream)); ctx->h2d_bytes += raw_len; }
 	else DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, raw_len, ctx->stream));
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	return 0;
 }
 
@@ -383,6 +385,7 @@ int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid) {
 	PhaseTimer t(ctx, PH_SEED);
 	const int rc = build_ref_index(ctx, b, sid, b->idx);
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	return rc;
 }
 
@@ -401,6 +404,7 @@ int dmnd_block_compute_bias_range(dmnd_ctx* ctx, dmnd_block* b, int mode, uint32
 		DMND_CUDA_CHECK(cudaGetLastError());
 	}
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	return 0;
 }
 
@@ -555,6 +559,7 @@ int dmnd_hits_download(dmnd_ctx* ctx, const dmnd_hits* h, dmnd_hit* host, size_t
 	PhaseTimer t(ctx, PH_D2H);
 	DMND_CUDA_CHECK(cudaMemcpyAsync(host, h->d, h->n * sizeof(dmnd_hit), cudaMemcpyDeviceToHost, ctx->stream));
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	ctx->d2h_bytes += h->n * sizeof(dmnd_hit);
 	return 0;
 }

@@ -34,6 +34,7 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 	DMND_CUDA_CHECK(cudaMemcpyAsync(host, ctx->b_pairs.p, h->n * sizeof(dmnd_segment), cudaMemcpyDeviceToHost, ctx->stream));
 	if (sites) DMND_CUDA_CHECK(cudaMemcpyAsync(sites, d_sites, h->n * sizeof(dmnd_hit_site), cudaMemcpyDeviceToHost, ctx->stream));
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the caller's buffers are complete on return whether or not the timer synchronises
 	ctx->d2h_bytes += h->n * (sizeof(dmnd_segment) + (sites ? sizeof(dmnd_hit_site) : 0));
 	return 0;
 }
@@ -59,6 +60,7 @@ int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_b
 	DMND_CUDA_CHECK(cudaGetLastError());
 	DMND_CUDA_CHECK(cudaMemcpyAsync(pass, ctx->b_pairs.p, h->n, cudaMemcpyDeviceToHost, ctx->stream));
 	t.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
 	ctx->d2h_bytes += h->n;
 	return 0;
 }
@@ -268,6 +270,7 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	unsigned long long hc[16];
 	DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
 	timer.stop();
+	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	std::memcpy(hc, ctx->h_pinned, sizeof hc);
 	if (counters) {
 		counters->seeds_hit = hc[0];

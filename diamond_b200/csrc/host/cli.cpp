@@ -261,18 +261,32 @@ void read_dmnd(const std::string& path, SeqBlock& b) {
 	auto u32 = [&](size_t o) { uint32_t v; std::memcpy(&v, d.data() + o, 4); return v; };
 	if (d.size() < 96 || u64(0) != DMND_MAGIC) throw std::runtime_error("Database file is not a DIAMOND database.");
 	if (u32(12) < 2 || u32(12) > 3) throw std::runtime_error("Database was built with an unsupported database format version.");
-	const uint64_t nseq = u64(16), pos_off = u64(32);
-	if (pos_off + 16 * (nseq + 1) > d.size()) throw std::runtime_error("Database file is truncated.");
+	const uint64_t nseq = u64(16), pos_off = u64(32), size = d.size();
+	// header fields are untrusted: every bound is checked without arithmetic that could wrap
+	if (pos_off < 96 || pos_off > size || (size - pos_off) / 16 < 1 || nseq > (size - pos_off) / 16 - 1) throw std::runtime_error("Database file is truncated.");
+	size_t total = 0;
+	for (uint64_t i = 0; i < nseq; ++i) total += (size_t)u32(pos_off + 16 * i + 8) + 1;
+	if (total > size) throw std::runtime_error("Database file format error.");
+	b.letters.reserve(b.letters.size() + total);
 	for (uint64_t i = 0; i < nseq; ++i) {
 		const uint64_t pos = u64(pos_off + 16 * i), len = u32(pos_off + 16 * i + 8);
-		if (pos + len + 2 > pos_off || (unsigned char)d[pos] != 0xff || (unsigned char)d[pos + 1 + len] != 0xff) throw std::runtime_error("Database file format error.");
-		for (uint64_t k = 0; k < len; ++k) b.letters.push_back((int8_t)(d[pos + 1 + k] & 0x7f));  // the soft-mask bit is recomputed by the pipeline (same algorithm)
+		// record = 0xff, len letters, 0xff, title, NUL -- all of it before the position array
+		if (pos < 96 || pos >= pos_off || len > pos_off - pos || pos_off - pos - len < 3 || (unsigned char)d[pos] != 0xff || (unsigned char)d[pos + 1 + len] != 0xff)
+			throw std::runtime_error("Database file format error.");
+		const size_t at = b.letters.size();
+		b.letters.resize(at + len);
+		const char* src = d.data() + pos + 1;
+		for (uint64_t k = 0; k < len; ++k) b.letters[at + k] = (int8_t)(src[k] & 0x7f);  // the soft-mask bit is recomputed by the pipeline (same algorithm)
 		b.letters.push_back((int8_t)DMND_DELIMITER);
 		b.limits.push_back((int64_t)b.letters.size());
 		const char* title = d.data() + pos + 2 + len;
-		b.titles.emplace_back(title);
+		const size_t room = (size_t)(pos_off - (pos + 2 + len));
+		const void* nul = std::memchr(title, 0, room);
+		if (!nul) throw std::runtime_error("Database file format error.");
+		const size_t tlen = (size_t)((const char*)nul - title);
+		b.titles.emplace_back(title, tlen);
 		size_t e = 0;
-		while (title[e] && !strchr(" \t\x01", title[e])) ++e;
+		while (e < tlen && !strchr(" \t\x01", title[e])) ++e;
 		b.ids.emplace_back(title, e);
 	}
 	b.finish();

@@ -102,16 +102,23 @@ public:
 			busy_ = true;
 			waiting_.erase(std::find(waiting_.begin(), waiting_.end(), prio));
 		}
-		if (n_ == 1) f(0);
+		// exceptions (std::bad_alloc from a growing list is the realistic one) are caught per thread, the first is rethrown here after
+		// every worker has finished with `f` and the turn has been handed on -- a throw must neither leave workers inside the
+		// caller's std::function nor the other lanes blocked on the turn
+		std::exception_ptr first;
+		auto guarded = [&](int t) { try { f(t); } catch (...) { std::lock_guard<std::mutex> l(err_m_); if (!first) first = std::current_exception(); } };
+		const std::function<void(int)> g(guarded);
+		if (n_ == 1) g(0);
 		else {
-			{ std::lock_guard<std::mutex> l(m_); fn_ = &f; pending_ = n_ - 1; ++gen_; }
+			{ std::lock_guard<std::mutex> l(m_); fn_ = &g; pending_ = n_ - 1; ++gen_; }
 			cv_.notify_all();
-			f(0);
+			g(0);
 			std::unique_lock<std::mutex> l(m_);
 			done_.wait(l, [this] { return pending_ == 0; });
 		}
 		{ std::lock_guard<std::mutex> l(turn_m_); busy_ = false; }
 		turn_cv_.notify_all();
+		if (first) std::rethrow_exception(first);
 	}
 private:
 	void loop(int t) {
@@ -131,7 +138,7 @@ private:
 	}
 	int n_;
 	std::vector<std::thread> th_;
-	std::mutex m_, turn_m_;
+	std::mutex m_, turn_m_, err_m_;
 	std::condition_variable cv_, done_, turn_cv_;
 	std::vector<int> waiting_;
 	bool busy_ = false;
@@ -1056,6 +1063,13 @@ struct SeedTurn {
 	std::mutex m;
 	std::condition_variable cv;
 	int turn = 0;
+	// A lane masks its own query range in place before it searches, and the 48-byte fingerprints of a lane's LAST sequence read into
+	// the first letters of the next lane's range (search/hamming/finger_print.h:59-96 crosses sequence borders): lane k may only
+	// search once lane k + 1 has finished masking, as the reference masks the whole block before any search
+	// (run/double_indexed.cpp:737-741).  masked[l] is set when lane l's masking is on the device and complete (or was not asked for).
+	std::vector<char> masked;
+	void set_masked(int lane) { { std::lock_guard<std::mutex> l(m); if ((size_t)lane < masked.size()) masked[(size_t)lane] = 1; } cv.notify_all(); }
+	void wait_masked(int lane) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return (size_t)lane >= masked.size() || masked[(size_t)lane]; }); }
 	void wait_for(int lane) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return turn >= lane; }); }
 	void pass(int lane) { { std::lock_guard<std::mutex> l(m); turn = std::max(turn, lane + 1); } cv.notify_all(); }
 };
@@ -1085,7 +1099,9 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		if (!prep_rc && n_hard) prep_rc = dmnd_block_mask_fetch(ctx, w.mask_pos.data(), w.mask_pos.size());
 		if (!prep_rc) { w.q_patch.build(env.q_letters, env.q_limits, env.nq, q_begin, q_end, w.mask_pos.data(), w.mask_pos.size()); d.env.q_patch = &w.q_patch; }
 	}
+	seed_turn.set_masked(lane);  // (dmnd_block_mask returns when the range is masked on the device; also set on failure so nobody waits forever)
 	prep_rc = prep_rc || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
+	seed_turn.wait_masked(lane + 1);
 	seed_turn.wait_for(lane);
 	const int n_shapes = env.n_shapes;
 	size_t nh = 0;
@@ -1425,13 +1441,14 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	for (int l = 1; l < nlanes; ++l)
 		if (dmnd_ctx_lane(ctx, l - 1, &lctx[(size_t)l])) return 1;
 	SeedTurn seed_turn;
+	seed_turn.masked.assign((size_t)nlanes, 0);
 	auto body = [&](int l) {
 		LaneOut& o = lo[(size_t)l];
 		try {
 			o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn);
 			if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
 		}
-		catch (const std::exception& ex) { o.rc = 1; o.error = std::string("dmnd_blastp: ") + ex.what(); seed_turn.pass(l); }
+		catch (const std::exception& ex) { o.rc = 1; o.error = std::string("dmnd_blastp: ") + ex.what(); seed_turn.set_masked(l); seed_turn.pass(l); }
 	};
 	std::vector<std::thread> th;
 	for (int l = 1; l < nlanes; ++l) th.emplace_back(body, l);
