@@ -14,7 +14,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -pthread -Wall -Wextra
 
 HOST_SRC := pipeline.cpp chaining.cpp scoring.cpp
-CUDA_SRC := ctx.cu swipe.cu seed.cu mask.cu chain.cu
+CUDA_SRC := ctx.cu swipe.cu seed.cu mask.cu chain.cu comm.cu
 HOST_OBJ := $(patsubst %.cpp,$(OBJ)/host/%.o,$(HOST_SRC))
 CUDA_OBJ := $(patsubst %.cu,$(OBJ)/cuda/%.o,$(CUDA_SRC))
 

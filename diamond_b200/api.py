@@ -98,7 +98,7 @@ PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
-           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter", "dmnd_hits_chain", "dmnd_hits_chain_fetch", "dmnd_banded_swipe_chained",
+           "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter", "dmnd_comm_unique_id", "dmnd_comm_init", "dmnd_comm_destroy", "dmnd_block_broadcast", "dmnd_block_alloc_empty", "dmnd_block_geometry", "dmnd_block_download_limits", "dmnd_hits_chain", "dmnd_hits_chain_fetch", "dmnd_banded_swipe_chained",
            "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_measure_int_peak_packed", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_masked_positions", "dmnd_result_unaligned", "dmnd_result_free"]
@@ -125,6 +125,14 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_debug_left_most.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]
     lib.dmnd_block_mask.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.dmnd_block_mask_fetch.argtypes = [vp, vp, C.c_size_t]
+    lib.dmnd_comm_unique_id.argtypes = [vp]
+    lib.dmnd_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.dmnd_comm_destroy.argtypes = [vp]
+    lib.dmnd_comm_destroy.restype = None
+    lib.dmnd_block_broadcast.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
+    lib.dmnd_block_alloc_empty.argtypes = [vp, C.c_size_t, C.c_uint32, C.POINTER(vp)]
+    lib.dmnd_block_geometry.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    lib.dmnd_block_download_limits.argtypes = [vp, vp, vp, C.c_size_t]
     lib.dmnd_hits_chain.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dmnd_hits_chain_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dmnd_banded_swipe_chained.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
@@ -314,6 +322,25 @@ class Context:
         if gapped_filter:
             return hits, cnd, gf
         return (hits, cnd) if xdrop is None else (hits, cnd, segs)
+
+    # ---- multi-GPU: NCCL broadcast of the resident reference block (csrc/cuda/comm.cu)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.dmnd_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        self._check(self.lib.dmnd_comm_init(self.ctx, rank, nranks, C.create_string_buffer(unique_id, 128)))
+
+    def block_broadcast(self, root: int, block=None):
+        """Every rank calls it; the root passes its resident block.  Returns (block, raw_len, limits) on every rank."""
+        out = C.c_void_p()
+        self._check(self.lib.dmnd_block_broadcast(self.ctx, root, block, C.byref(out)))
+        raw_len, nseq = C.c_size_t(), C.c_uint32()
+        self.lib.dmnd_block_geometry(out, C.byref(raw_len), C.byref(nseq))
+        limits = np.empty(nseq.value + 1, dtype=np.int64)
+        self._check(self.lib.dmnd_block_download_limits(self.ctx, out, limits.ctypes.data, limits.size))
+        return out, raw_len.value, limits
 
     def hits_chain(self, qb, rb, sid: int = 0, xdrop: int = 0, band_slow: bool = False, max_targets: int = 64, align: bool = False):
         """dmnd_search_shape + dmnd_hits_chain (+ dmnd_banded_swipe_chained with traceback when `align`): per-query records, the DP

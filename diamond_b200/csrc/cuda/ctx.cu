@@ -257,6 +257,7 @@ void dmnd_destroy(dmnd_ctx* c) {
 	c->own_index.release();
 	for (int k = 0; k <= c->params.n_shapes; ++k) if (c->d_matcher[k]) cudaFree(c->d_matcher[k]);
 	if (c->d_s16_table) cudaFree(c->d_s16_table);
+	dmnd_comm_destroy(c);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_sync);
@@ -296,6 +297,31 @@ static int block_alloc(dmnd_ctx* ctx, size_t raw_len, const int64_t* limits, uin
 		}
 	}
 	*out = b; *padded_out = padded;
+	return 0;
+}
+
+int dmnd_block_geometry(const dmnd_block* b, size_t* raw_len, uint32_t* nseq) { *raw_len = b->raw_len; *nseq = b->nseq; return 0; }
+int dmnd_block_download_limits(dmnd_ctx* ctx, const dmnd_block* b, int64_t* limits, size_t count) {
+	(void)ctx;
+	if (count != (size_t)b->nseq + 1) { set_error("dmnd_block_download_limits: count must be nseq + 1"); return 1; }
+	std::memcpy(limits, b->h_limits.data(), count * sizeof(int64_t));
+	return 0;
+}
+
+// A block of the given geometry with nothing in it yet (dmnd_block_broadcast fills it from another rank): delimiters, zero bias, empty soft table.
+int dmnd_block_alloc_empty(dmnd_ctx* ctx, size_t raw_len, uint32_t nseq, dmnd_block** out) {
+	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (raw_len < 2 * DMND_PERIMETER_PADDING) { set_error("dmnd_block_alloc_empty: not a block image"); return 1; }
+	std::vector<int64_t> lim((size_t)nseq + 1, (int64_t)DMND_PERIMETER_PADDING);
+	lim[nseq] = (int64_t)(raw_len - DMND_PERIMETER_PADDING);  // placeholder limits that pass block_alloc's shape check; overwritten by the broadcast
+	dmnd_block* b = nullptr;
+	size_t padded = 0;
+	if (block_alloc(ctx, raw_len, lim.data(), nseq, "dmnd_block_alloc_empty", &b, &padded)) return 1;
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->letters, DMND_DELIMITER, padded + 64, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->bias, 0, padded + 64, ctx->stream));
+	DMND_CUDA_CHECK(cudaMemsetAsync(b->soft, 0, b->cap_bytes / 8 + 16, ctx->stream));
+	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));
+	*out = b;
 	return 0;
 }
 
@@ -382,8 +408,13 @@ int dmnd_block_set_bias(dmnd_ctx* ctx, dmnd_block* b, const int8_t* bias, size_t
 int dmnd_block_build_index(dmnd_ctx* ctx, dmnd_block* b, int sid) {
 	DMND_CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (sid < 0 || sid >= ctx->params.n_shapes) { set_error("dmnd_block_build_index: bad shape id"); return 1; }
+	// FNV-1a over the parameters: an index is only reused by contexts with the same shapes / reduction / mode
+	uint64_t ph = 1469598103934665603ull;
+	for (size_t k = 0; k < sizeof ctx->params; ++k) { ph ^= ((const unsigned char*)&ctx->params)[k]; ph *= 1099511628211ull; }
+	if (b->idx.valid && b->idx.sid == sid && b->idx.content_epoch == b->content_epoch && b->idx.params_hash == ph) return 0;  // resident block, unchanged: keep the index
 	PhaseTimer t(ctx, PH_SEED);
 	const int rc = build_ref_index(ctx, b, sid, b->idx);
+	b->idx.content_epoch = b->content_epoch; b->idx.params_hash = ph;
 	t.stop();
 	DMND_CUDA_CHECK(stream_wait(ctx, ctx->stream));  // the copy is complete on return, independent of the timer
 	return rc;

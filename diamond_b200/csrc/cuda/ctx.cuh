@@ -52,6 +52,7 @@ struct RefIndex {
 	int sid = -1, shift = 0;
 	uint32_t bloom_blocks = 0;
 	bool valid = false;
+	uint64_t content_epoch = 0, params_hash = 0;  // what the index was built from: the block's content epoch and the context's parameters
 	void release() { keys.release(); locs.release(); bucket.release(); bloom.release(); valid = false; }
 };
 }  // namespace dmnd_cuda
@@ -66,6 +67,7 @@ struct dmnd_block {
 	bool has_soft = false;      // dmnd_block_mask(MOTIF) has run: dmnd_search_shape reads `soft`
 	size_t raw_len = 0;
 	uint32_t nseq = 0;
+	uint64_t content_epoch = 1;     // bumped whenever letters or the soft table change (dmnd_block_mask): a cached index of an older epoch is rebuilt
 	std::vector<int64_t> h_limits;  // host copy (problem binning needs lengths)
 	std::vector<cudaEvent_t> range_ready;  // dmnd_block_upload_ranges: one event per uploaded sequence range
 	std::vector<uint32_t> range_cuts;      // [nranges + 1] sequence boundaries of those ranges
@@ -92,6 +94,7 @@ struct dmnd_ctx {
 	dmnd_cuda::DevBuf b_mask_pb, b_mask_scale, b_mask_pos, b_mask_pos2, b_mask_cov, b_mask_flag, b_mask_seqs, b_mask_zinv, b_mask_need;  // dmnd_block_mask scratch
 	uint64_t mask_n = 0;  // letters hard-masked by the last dmnd_block_mask on this context (sorted offsets in b_mask_pos)
 	std::vector<uint64_t> h_excl;  // host copy of the trace prefix (slicing)
+	void* comm = nullptr; int comm_rank = 0, comm_size = 1;  // NCCL communicator of dmnd_comm_init (comm.cu)
 	bool force_generic_dp = false;
 	bool force_int32_dp = false;     // the packed 16-bit kernel overflowed: this call runs on the int32 kernels
 	int8_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
@@ -153,6 +156,9 @@ int hits_xdrop_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* re
 int hits_gapped_filter_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, uint8_t* pass, size_t cap);
 int block_mask_impl(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, uint32_t s_end, uint64_t* n_hard);
 int block_mask_fetch_impl(dmnd_ctx* ctx, uint64_t* positions, size_t cap);
+}  // namespace dmnd_cuda
+extern "C" int dmnd_block_alloc_empty(dmnd_ctx* ctx, size_t raw_len, uint32_t nseq, dmnd_block** out);
+namespace dmnd_cuda {
 int launch_xdrop(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, dmnd_segment* d_segs, dmnd_hit_site* d_sites);
 int hits_chain_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_hits* h, int raw_xdrop, int band_slow, int max_targets, dmnd_chain_out* out);
 int hits_chain_fetch_impl(dmnd_ctx* ctx, dmnd_chain_query* queries, dmnd_dp_problem* problems, dmnd_hit* hits, dmnd_segment* segs, dmnd_hit_site* sites);

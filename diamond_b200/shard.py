@@ -48,6 +48,28 @@ def broadcast_reference(r_raw, r_limits, dist, device=None):
     return t.cpu().numpy().view(np.int8), l.cpu().numpy()
 
 
+def broadcast_reference_block(ctx, dist, device, block=None, root: int = 0):
+    """The resident reference block of rank `root` on every rank, sent device to device by the library's own NCCL broadcast
+    (dmnd_block_broadcast, csrc/cuda/comm.cu): masking, soft table and bias travel with the letters, nothing bounces through the
+    host.  torch.distributed only carries the 128-byte NCCL unique id.  Returns (block, raw_len, limits)."""
+    import os, torch
+    if "DMND_NCCL_LIB" not in os.environ:  # the NCCL torch was built with (the system one may be older)
+        try:
+            import nvidia.nccl
+            cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["DMND_NCCL_LIB"] = cand
+        except Exception:
+            pass
+    rank = dist.get_rank()
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == root:
+        uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(uid, root)
+    ctx.comm_init(rank, dist.get_world_size(), bytes(uid.cpu().numpy().tobytes()))
+    return ctx.block_broadcast(root, block if rank == root else None)
+
+
 def gather_matches(matches: np.ndarray, query_offset: int, dist):
     """All ranks' match records on rank 0, query ids re-based to the unsharded block, in rank (= query) order."""
     m = matches.copy()

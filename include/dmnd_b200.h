@@ -182,6 +182,21 @@ void* dmnd_host_alloc(dmnd_ctx* ctx, size_t bytes);
 void dmnd_host_free(dmnd_ctx* ctx, void* p);
 /* Reads back the block's letters (query letters carry SEED_MASK bits set by dmnd_search_shape). */
 int dmnd_block_download_letters(dmnd_ctx* ctx, const dmnd_block* b, int8_t* letters, size_t raw_len);
+/* ---- multi-GPU: one process per GPU, queries sharded, the packed reference block broadcast once over NVLink ------
+ * The 128-byte NCCL unique id is created on one rank (dmnd_comm_unique_id) and handed to every rank by the caller's own means
+ * (torch.distributed, MPI, a file); dmnd_comm_init joins the communicator.  dmnd_block_broadcast sends the root's RESIDENT block --
+ * letters as they are (masked if the root masked them), limits, soft-masking table, bias -- straight into a new block on every other
+ * rank (device to device, no host bounce); the root gets its own block back in *out.  This is the only collective of the path. */
+int dmnd_comm_unique_id(void* out128);
+int dmnd_comm_init(dmnd_ctx* ctx, int rank, int nranks, const void* unique_id128);
+void dmnd_comm_destroy(dmnd_ctx* ctx);
+int dmnd_block_broadcast(dmnd_ctx* ctx, int root, dmnd_block* src_on_root, dmnd_block** out);
+/* An empty block of the given geometry (what dmnd_block_broadcast allocates on the receiving ranks). */
+int dmnd_block_alloc_empty(dmnd_ctx* ctx, size_t raw_len, uint32_t nseq, dmnd_block** out);
+/* Geometry and limits of a resident block (a rank that received its reference block by broadcast reads them back from here). */
+int dmnd_block_geometry(const dmnd_block* b, size_t* raw_len, uint32_t* nseq);
+int dmnd_block_download_limits(dmnd_ctx* ctx, const dmnd_block* b, int64_t* limits, size_t count);
+
 /* ---- diagnostics: intermediate state of the seed stage for tests and tools/seed_stage_diag.py (not on the path) ----
  * dmnd_debug_block_soft: the block's soft-masking table after dmnd_block_mask(MOTIF) (Block::soft_mask, data/block/block.cpp:162-178),
  *   one byte per letter of the block image, 1 = inside an abundant motif.

@@ -655,6 +655,20 @@ int dmnd_banded_swipe_chained(dmnd_ctx* ctx, const dmnd_block* query, const dmnd
 	return dmnd_banded_swipe(ctx, query, ref, t_chain.probs, n, mode, results, transcripts, transcript_cap);
 }
 
+/* multi-GPU entry points: nothing to broadcast on a CPU (the sharding logic is tested with gloo through diamond_b200/shard.py) */
+int dmnd_comm_unique_id(void* out128) { (void)out128; return fail("oracle: no NCCL on the CPU"); }
+int dmnd_comm_init(dmnd_ctx* ctx, int rank, int nranks, const void* id) { (void)ctx; (void)rank; (void)nranks; (void)id; return fail("oracle: no NCCL on the CPU"); }
+void dmnd_comm_destroy(dmnd_ctx* ctx) { (void)ctx; }
+int dmnd_block_broadcast(dmnd_ctx* ctx, int root, dmnd_block* src, dmnd_block** out) { (void)ctx; (void)root; (void)src; (void)out; return fail("oracle: no NCCL on the CPU"); }
+int dmnd_block_alloc_empty(dmnd_ctx* ctx, size_t raw_len, uint32_t nseq, dmnd_block** out) { (void)ctx; (void)raw_len; (void)nseq; (void)out; return fail("oracle: not implemented"); }
+int dmnd_block_geometry(const dmnd_block* b, size_t* raw_len, uint32_t* nseq) { *raw_len = b->raw_len; *nseq = b->nseq; return 0; }
+int dmnd_block_download_limits(dmnd_ctx* ctx, const dmnd_block* b, int64_t* limits, size_t count) {
+	(void)ctx;
+	if (count != (size_t)b->nseq + 1) return fail("dmnd_block_download_limits: count must be nseq + 1");
+	memcpy(limits, b->limits, count * sizeof *limits);
+	return 0;
+}
+
 /* Diagnostics twin of the device library's dmnd_debug_left_most (tools/seed_stage_diag.py): same out30 layout. */
 int dmnd_debug_left_most(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, int sid, int chunk, uint32_t qloc, uint32_t sloc, unsigned long long* out) {
 	const dmnd_params* p = &ctx->p;
