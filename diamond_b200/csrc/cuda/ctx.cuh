@@ -36,6 +36,19 @@ struct DevBuf {
 		cap = want;
 		return 0;
 	}
+	// grow and keep the first `keep` bytes (device-to-device copy; cudaFree synchronises, so the copy is complete before the old buffer goes)
+	int ensure_keep(size_t bytes, size_t keep) {
+		if (bytes <= cap) return 0;
+		void* old = p;
+		const size_t want = bytes + bytes / 2 + 256;
+		void* np = nullptr;
+		cudaError_t e = cudaMalloc(&np, want);
+		if (e != cudaSuccess) { set_error(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); return 1; }
+		if (old && keep) cudaMemcpy(np, old, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice);
+		if (old) cudaFree(old);
+		p = np; cap = want;
+		return 0;
+	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 	template<typename T> T* as() const { return (T*)p; }
 };
@@ -97,12 +110,13 @@ struct dmnd_ctx {
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1;  // NCCL communicator of dmnd_comm_init (comm.cu)
 	bool force_generic_dp = false;
 	bool force_int32_dp = false;     // the packed 16-bit kernel overflowed: this call runs on the int32 kernels
-	int8_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
+	int16_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
 	bool s16_ok = false;
 	uint64_t dp_overflows = 0;       // calls repeated on the int32 kernels
 	uint64_t dp_cells_score = 0, dp_cells_trace = 0, dp_cells_padded = 0;  // cells of the problems LAUNCHED (score-only / traceback kernels) and what the register tiles evaluate for them
 	std::vector<dmnd_ctx*> lanes;  // owned lane contexts (dmnd_ctx_lane)
 	dmnd_cuda::RefIndex own_index;  // private reference index when the block carries none
+	const dmnd_block* own_index_block = nullptr;  // ... and the block it was built from (own_index.content_epoch = that block's epoch)
 	dmnd_cuda::DevBuf b_chain_probs;  // dmnd_hits_chain: the DP problems of the device-chained queries (read in place by dmnd_banded_swipe_chained)
 	dmnd_chain_query* chain_q = nullptr; dmnd_dp_problem* chain_probs = nullptr; dmnd_hit* chain_fb_hits = nullptr; dmnd_segment* chain_fb_segs = nullptr; dmnd_hit_site* chain_fb_sites = nullptr;
 	size_t chain_counts[3] = {};

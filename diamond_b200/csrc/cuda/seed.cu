@@ -141,7 +141,9 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	return 0;
 }
 
-int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
+// One query range [q_begin, q_end): its hits, grouped by query, are APPENDED to the context's hit arena after the `out_offset` hits of the
+// ranges before it (ascending ranges keep the whole list grouped by ascending query).
+static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, size_t out_offset, size_t* n_out, dmnd_stage_counters* counters) {
 	const dmnd_params& hp = ctx->params;
 	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
 	if (sid < 0 || sid >= hp.n_shapes) { set_error("dmnd_search_shape: bad shape id"); return 1; }
@@ -159,8 +161,12 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	// ---- reference index: the block's own (dmnd_block_build_index, shared by all lanes) or a private one built now
 	RefIndex& own = ctx->own_index;
 	const RefIndex* ixp = &ref->idx;
-	if (!(ref->idx.valid && ref->idx.sid == sid)) {
-		if (build_ref_index(ctx, ref, sid, own)) return 1;
+	if (!(ref->idx.valid && ref->idx.sid == sid && ref->idx.content_epoch == ref->content_epoch)) {
+		// the context's private index: rebuilt unless it already holds this shape of this block (the slices of one call share it)
+		if (!(own.valid && own.sid == sid && ctx->own_index_block == ref && own.content_epoch == ref->content_epoch)) {
+			if (build_ref_index(ctx, ref, sid, own)) return 1;
+			own.content_epoch = ref->content_epoch; ctx->own_index_block = ref;
+		}
 		ixp = &own;
 	}
 	const RefIndex& ix = *ixp;
@@ -250,11 +256,10 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	}
 
 	// ---- group hits by query (stable order inside a query is not required)
-	dmnd_hits* h = new dmnd_hits();
-	h->n = hits_total;
+	*n_out = hits_total;
 	if (hits_total) {
-		if (ctx->b_hits_out.ensure(hits_total * sizeof(dmnd_hit))) return 1;
-		h->d = ctx->b_hits_out.as<dmnd_hit>();
+		if (ctx->b_hits_out.ensure_keep((out_offset + hits_total) * sizeof(dmnd_hit), out_offset * sizeof(dmnd_hit))) return 1;
+		dmnd_hit* const h_d = ctx->b_hits_out.as<dmnd_hit>() + out_offset;
 		if (ctx->b_keys.ensure(hits_total * 4) || ctx->b_vals.ensure(hits_total * 4)) return 1;
 		uint32_t* k_in = ctx->b_keys.as<uint32_t>();
 		uint32_t* k_out = ctx->b_vals.as<uint32_t>();
@@ -262,9 +267,9 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		size_t tmp = 0;
 		int end_bit = 1;
 		while (((uint64_t)1 << end_bit) < (uint64_t)query->nseq) ++end_bit;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h->d, hits_total, 0, end_bit, st);
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h_d, hits_total, 0, end_bit, st);
 		if (ctx->b_cub.ensure(tmp)) return 1;
-		DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h->d, hits_total, 0, end_bit, st));
+		DMND_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->b_cub.p, tmp, k_in, k_out, ctx->b_hits.as<dmnd_hit>(), h_d, hits_total, 0, end_bit, st));
 		ctx->launches += 4;
 	}
 	unsigned long long hc[16];
@@ -273,13 +278,42 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 	DMND_CUDA_CHECK(stream_wait(ctx, st));
 	std::memcpy(hc, ctx->h_pinned, sizeof hc);
 	if (counters) {
-		counters->seeds_hit = hc[0];
-		counters->seed_hits = seed_hits_total;
-		counters->tentative_matches1 = hc[2];
-		counters->tentative_matches2 = hp.ungapped_evalue == 0.0 ? hc[2] : hc[8];
-		counters->tentative_matches3 = hits_total;
-		counters->masked_seeds = hc[7];
+		counters->seeds_hit += hc[0];
+		counters->seed_hits += seed_hits_total;
+		counters->tentative_matches1 += hc[2];
+		counters->tentative_matches2 += hp.ungapped_evalue == 0.0 ? hc[2] : hc[8];
+		counters->tentative_matches3 += hits_total;
+		counters->masked_seeds += hc[7];
 	}
+	return 0;
+}
+
+// Search::search_shape for the query range [q_begin, q_end).  Shapes of low weight match at (nearly) every query position, so the
+// entry and pair lists of a whole block would take tens of GB (C4: 3*10^8 positions x 16 shapes of weight 8): the range is cut at
+// sequence boundaries into slices of at most DMND_SEED_SLICE letters (default 4*10^7 for weights below 10, one slice otherwise).
+// Queries are independent of each other in every stage (SEED_MASK bits and left-most windows stay inside a sequence), so the
+// slices' hit lists, concatenated in range order, are the hits of the unsliced search.  "Seeds hit" / "masked seeds" count a key
+// once per slice it occurs in (a diagnostic counter only; the hit-level counters are exact).
+int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
+	dmnd_stage_counters cn;
+	std::memset(&cn, 0, sizeof cn);
+	size_t slice = ctx->params.shape_weight >= 10 ? (size_t)-1 : (size_t)40000000;
+	if (const char* ev = getenv("DMND_SEED_SLICE")) slice = std::max<size_t>(1024, strtoull(ev, nullptr, 10));
+	size_t total = 0;
+	uint32_t b = q_begin;
+	do {
+		uint32_t e = b;
+		const size_t p0 = (size_t)query->h_limits[b];
+		while (e < q_end && ((size_t)query->h_limits[e + 1] - p0 <= slice || e == b)) ++e;
+		size_t n = 0;
+		if (search_slice(ctx, query, ref, sid, b, e, total, &n, &cn)) return 1;
+		total += n;
+		b = e;
+	} while (b < q_end);
+	dmnd_hits* h = new dmnd_hits();
+	h->n = total;
+	h->d = total ? ctx->b_hits_out.as<dmnd_hit>() : nullptr;
+	if (counters) *counters = cn;
 	*out = h;
 	return 0;
 }

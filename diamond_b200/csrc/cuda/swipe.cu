@@ -674,7 +674,7 @@ int s16_table_build(dmnd_ctx* ctx) {
 	unsigned* d_bad = nullptr;
 	DMND_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(unsigned)));
 	DMND_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(unsigned)));
-	s16_table_kernel<<<(S16_TABLE_BYTES + 255) / 256, 256>>>(ctx->d_params, ctx->d_s16_table, d_bad);
+	s16_table_kernel<<<(S16_TABLE_ENTRIES + 255) / 256, 256>>>(ctx->d_params, ctx->d_s16_table, d_bad);
 	unsigned bad = 1;
 	DMND_CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
 	cudaFree(d_bad);

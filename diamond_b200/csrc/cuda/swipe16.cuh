@@ -68,8 +68,9 @@ __device__ __forceinline__ ProbGeom geom(const SwipeArgs& a, const dmnd_dp_probl
 // ---- the shared score table ------------------------------------------------------------------------------------------
 constexpr int S16_NBIAS = 32, S16_BIAS_MIN = -16;
 constexpr int S16_HALO_CODE = 32 * S16_NBIAS;          // column of -128
-constexpr int S16_TW = 32 * S16_NBIAS + 4;             // row stride in bytes (multiple of 4)
-constexpr int S16_TABLE_BYTES = 27 * S16_TW;
+constexpr int S16_TW = 32 * S16_NBIAS + 4;             // row stride in entries
+constexpr int S16_TABLE_ENTRIES = 27 * S16_TW;
+constexpr int S16_TABLE_BYTES = 2 * S16_TABLE_ENTRIES; // int16 entries: LDS.U16 + one IMAD packs two cells' scores (an int8 table needs a PRMT on the ALU pipe)
 constexpr int S16_LANES = 8;                           // lanes per problem
 constexpr int S16_MAX_BAND = 128;
 constexpr int S16_MAX_MACRO = 32000;                   // macro steps representable in the 16-bit column key
@@ -80,9 +81,9 @@ __host__ __device__ __forceinline__ int s16_step_bytes(int R) { return 4 * R; }
 
 // Fills the table from the 32 x 32 score matrix (stats/score_matrix.h:35-44 layout).  Returns false through *ok when an entry
 // leaves int8 (then the packed kernel must not be used with this matrix).
-__global__ void s16_table_kernel(const DevParams* __restrict__ P, int8_t* table, unsigned* bad) {
+__global__ void s16_table_kernel(const DevParams* __restrict__ P, int16_t* table, unsigned* bad) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= S16_TABLE_BYTES) return;
+	if (idx >= S16_TABLE_ENTRIES) return;
 	const int t = idx / S16_TW, c = idx - t * S16_TW;
 	int v = -128;
 	if (t < 26 && c < S16_HALO_CODE) {
@@ -92,11 +93,11 @@ __global__ void s16_table_kernel(const DevParams* __restrict__ P, int8_t* table,
 		if (sc == -128) v = -128;  // letter codes outside the alphabet (stats/score_matrix.h:35-44) never occur inside a sequence
 		else if (v > 127 || v < -127) { atomicExch(bad, 1u); v = max(min(v, 127), -127); }
 	}
-	table[idx] = (int8_t)v;
+	table[idx] = (int16_t)v;
 }
 
 struct S16Args {
-	const int8_t* table;     // S16_TABLE_BYTES, global
+	const int16_t* table;    // S16_TABLE_ENTRIES, global
 	int qstride;             // uint16 elements per problem slot in shared memory, >= max(qlen) + 8 R + 4 of the launch
 	unsigned int* overflow;  // raised when the call has to be repeated on the int32 kernels
 };
@@ -113,6 +114,15 @@ __device__ __forceinline__ unsigned s16_trace_nibble(const uint8_t* tr, int R, i
 	return (~(v >> ((p & 1) * 4))) & 15u;
 }
 
+// one 16-bit table entry, zero-extended, from a shared-memory byte address (tests/emu_cuda.h maps the address back to its arena)
+#ifndef DMND_S16_LDS
+__device__ __forceinline__ unsigned s16_lds(unsigned addr) {
+	unsigned short v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return (unsigned)v;
+}
+#endif
+
 template<int R, bool TRACE>
 __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const DevParams* __restrict__ P, const S16Args sa) {
 	DMND_DYN_SMEM(smem16);
@@ -122,12 +132,13 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		const uint4* src = reinterpret_cast<const uint4*>(sa.table);
 		uint4* dst = reinterpret_cast<uint4*>(smem16);
 		for (int i = threadIdx.x; i < S16_TABLE_BYTES / 16; i += blockDim.x) dst[i] = src[i];
-		for (int i = (S16_TABLE_BYTES / 16) * 16 + threadIdx.x; i < S16_TABLE_BYTES; i += blockDim.x) smem16[i] = sa.table[i];
+		for (int i = (S16_TABLE_BYTES / 16) * 16 + threadIdx.x; i < S16_TABLE_BYTES; i += blockDim.x) smem16[i] = reinterpret_cast<const int8_t*>(sa.table)[i];
 	}
 	__syncthreads();
 	const unsigned FULLM = 0xffffffffu;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, gl = lane & 7;
-	const int8_t* tab = smem16;
+	const unsigned tab = (unsigned)__cvta_generic_to_shared(smem16);  // byte address of the table in shared memory
+	const unsigned one = P->one, k65536 = P->k65536;
 	uint16_t* qc = reinterpret_cast<uint16_t*>(smem16 + ((S16_TABLE_BYTES + 15) & ~15)) + (size_t)(warp * 4 + sub) * sa.qstride;
 	const unsigned go2 = (unsigned)(P->gap_open + P->gap_extend) * 0x00010001u, ge = (unsigned)P->gap_extend;
 	const unsigned nge2 = (0x10000u - ge) * 0x00010001u & 0xffffffffu;  // (-ge, -ge)
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 					if ((unsigned)b >= (unsigned)S16_NBIAS) ok = false;
 					code = (g.q[i] & 31) * S16_NBIAS + min(max(b, 0), S16_NBIAS - 1);
 				}
-				qc[idx] = (uint16_t)code;
+				qc[idx] = (uint16_t)(2 * code);  // byte offset inside a table row
 			}
 		}
 		if (!__all_sync(FULLM, ok) && lane == 0) atomicExch(sa.overflow, 1u);
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		unsigned H[NP], E[NP], F[NP], best[NP];
 #pragma unroll
 		for (int j = 0; j < NP; ++j) { H[j] = 0; E[j] = 0; F[j] = 0; best[j] = 0; }
-		auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return min((int)(g.t[jj] & 31), 26) * S16_TW; };
+		auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return (int)tab + min((int)(g.t[jj] & 31), 26) * (2 * S16_TW); };  // byte address of the letter's row
 		int trow[U];
 		unsigned qreg[U + 1];
 		int I0 = ibase + m_lo + lofs + HALO;  // code index of row u = 0 (even k); odd k reads one further
@@ -198,9 +209,9 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		}
 		else {
 #pragma unroll
-			for (int u = 0; u < U; ++u) trow[u] = 26 * S16_TW;
+			for (int u = 0; u < U; ++u) trow[u] = (int)tab + 26 * (2 * S16_TW);
 #pragma unroll
-			for (int v = 0; v <= U; ++v) qreg[v] = S16_HALO_CODE;
+			for (int v = 0; v <= U; ++v) qreg[v] = 2 * S16_HALO_CODE;
 			I0 = 0;
 		}
 		uint8_t* tr = (TRACE && live) ? a.trace + (a.trace_excl[a.order_pos0 + slot] - a.trace_base) : nullptr;
@@ -209,8 +220,8 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		int m = m_lo;
 		for (int it = 0; it < trip; ++it) {
 			const bool active = m < m_hi;
-			int tnext = 26 * S16_TW;
-			unsigned qnext = S16_HALO_CODE;
+			int tnext = (int)tab + 26 * (2 * S16_TW);
+			unsigned qnext = 2 * S16_HALO_CODE;
 			if (active) { tnext = trow_of(g.j0 + m + 1 - lofs); qnext = qc[I0 + U + 1]; }
 			unsigned pk[NW];
 #pragma unroll
@@ -222,8 +233,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 				for (int j = 0; j < NP; j += 2) {
 					const int ul = j >> 1, uh = ul + R / 4;
-					const int s_lo = (int)tab[trow[ul] + (int)qreg[ul]], s_hi = (int)tab[trow[uh] + (int)qreg[uh]];
-					const unsigned sc = __byte_perm((unsigned)s_lo, (unsigned)s_hi, 0x5410);
+					const unsigned sc = s16_lds((unsigned)trow[uh] * one + qreg[uh]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul]);
 					const unsigned e_in = E[j + 1], f_in = j > 0 ? F[j > 0 ? j - 1 : 0] : f_edge;
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
 					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);
@@ -246,8 +256,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 				for (int j = 1; j < NP; j += 2) {
 					const int ul = j >> 1, uh = ul + R / 4;
-					const int s_lo = (int)tab[trow[ul] + (int)qreg[ul + 1]], s_hi = (int)tab[trow[uh] + (int)qreg[uh + 1]];
-					const unsigned sc = __byte_perm((unsigned)s_lo, (unsigned)s_hi, 0x5410);
+					const unsigned sc = s16_lds((unsigned)trow[uh] * one + qreg[uh + 1]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul + 1]);
 					const unsigned e_in = j + 1 < NP ? E[j + 1 < NP ? j + 1 : 0] : e_edge, f_in = F[j - 1];
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
 					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);

@@ -1351,8 +1351,9 @@ static LanePlan plan_lanes(uint32_t nq, const int64_t* q_limits, uint32_t contex
 	LanePlan p;
 	p.host_threads = effective_cpus();
 	if (const char* ev = std::getenv("DMND_HOST_THREADS")) p.host_threads = std::max(1, std::atoi(ev));
-	// staggered query lanes (see SeedTurn): small inputs gain nothing, 3 lanes measured best at 10^6 queries on 16 host CPUs
-	p.nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(3u, std::max<uint32_t>(2u, nq / 300000u));
+	// staggered query lanes (see SeedTurn): small inputs gain nothing; with the host bridge on the device 4 lanes measured best at 10^6
+	// queries on 16 host CPUs (profiles/lane_sweep_r2.txt: 3 / 4 / 6 / 8 lanes = 64.5 / 49.4 / 58.2 / 67.6 ms per step)
+	p.nlanes = nq < 40000u ? 1 : (int)std::min<uint32_t>(4u, std::max<uint32_t>(2u, nq / 250000u));
 	if (const char* ev = std::getenv("DMND_LANES")) p.nlanes = std::max(1, std::min(8, std::atoi(ev)));
 	p.nlanes = (int)std::min<uint32_t>((uint32_t)p.nlanes, std::max<uint32_t>(nq, 1));
 	p.cut.assign((size_t)p.nlanes + 1, nq);

@@ -4,7 +4,13 @@
 // Random problems with real neighbouring sequences on both sides, Hauser-like biases, masked letters, corner bands, every
 // register tile (R = 4, 8, 12, 16) and warps whose four problems differ in size.
 // usage: emu_swipe16 SEED MAXQ MAXBAND PROBLEMS [TRACE=1]
-#define DMND_DYN_SMEM(name) static int8_t name[1 << 18]
+#include <cstdint>
+#include <cstring>
+static int8_t g_emu_smem[1 << 18];  // the CTA's dynamic shared memory (blocks run one after the other)
+#define DMND_DYN_SMEM(name) int8_t* name = g_emu_smem
+#define __cvta_generic_to_shared(p) ((size_t)((const int8_t*)(p) - g_emu_smem))
+#define DMND_S16_LDS
+static inline unsigned s16_lds(unsigned addr) { uint16_t v; memcpy(&v, g_emu_smem + addr, 2); return v; }
 #include "emu_cuda.h"
 #include "../diamond_b200/csrc/cuda/swipe16.cuh"
 #include <algorithm>
@@ -25,7 +31,7 @@ int main(int argc, char** argv) {
 	dmnd_search_opts o; dmnd_search_opts_default(&o);
 	dmnd_params hp; dmnd_params_init(&o, &hp);
 	static DevParams P; memset(&P, 0, sizeof P);
-	memcpy(P.score, hp.score, 1024); P.gap_open = hp.gap_open; P.gap_extend = hp.gap_extend;
+	memcpy(P.score, hp.score, 1024); P.gap_open = hp.gap_open; P.gap_extend = hp.gap_extend; P.one = 1; P.k65536 = 65536;
 	dmnd_ctx* ctx; if (dmnd_create(0, &hp, &ctx)) return 2;
 	std::mt19937 rng((unsigned)seed);
 	// ---- blocks: nprob queries and nprob targets, real letters around every sequence
@@ -65,9 +71,9 @@ int main(int argc, char** argv) {
 	std::vector<uint8_t> want_ts(tcap + 16);
 	if (dmnd_banded_swipe(ctx, bq, bt, probs.data(), (size_t)nprob, trace ? 1 : 0, want.data(), trace ? want_ts.data() : nullptr, trace ? want_ts.size() : 0)) { printf("oracle: %s\n", dmnd_last_error()); return 2; }
 	// ---- the kernel under emulation: group by register tile, order by macro steps (as prep_kernel + the device sort do)
-	std::vector<int8_t> table((size_t)S16_TABLE_BYTES);
+	std::vector<int16_t> table((size_t)S16_TABLE_ENTRIES);
 	unsigned bad = 0;
-	emu::launch((S16_TABLE_BYTES + 255) / 256, 256, [&] { s16_table_kernel(&P, table.data(), &bad); });
+	emu::launch((S16_TABLE_ENTRIES + 255) / 256, 256, [&] { s16_table_kernel(&P, table.data(), &bad); });
 	if (bad) { printf("table out of int8\n"); return 2; }
 	std::vector<int32_t> score((size_t)nprob, -1), endc((size_t)nprob * 2, -1);
 	std::vector<dmnd_dp_result> got((size_t)nprob);

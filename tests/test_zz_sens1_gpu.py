@@ -113,3 +113,30 @@ def test_cli_without_sensitivity_flag(product_lib, tmp_path):
     r = subprocess.run([cli, "blastp", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, "c1.s1.tsv")).read()
+
+
+@pytest.mark.parametrize("sens", [0, 1, 3])
+def test_sliced_search_equals_unsliced(product_lib, sens, monkeypatch):
+    """dmnd_search_shape cuts a query range into slices of DMND_SEED_SLICE letters (bounded entry / pair lists for the low-weight shapes
+    of the sensitive modes); the concatenated hit lists must be the unsliced search's, hit for hit, and stay grouped by query."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("rep")
+    res = []
+    for slice_letters in (None, "3000"):
+        if slice_letters:
+            monkeypatch.setenv("DMND_SEED_SLICE", slice_letters)
+        else:
+            monkeypatch.setenv("DMND_SEED_SLICE", "1000000000")
+        c = api.Context(product_lib, threads=8, sensitivity=sens)
+        qb, rb = c.upload(q_raw, q_lim), c.upload(r_raw, r_lim)
+        c.mask_block(qb, 5, 0, len(q_lim) - 1); c.mask_block(rb, 5, 0, len(r_lim) - 1)
+        out = []
+        for sid in range(min(c.params.n_shapes, 3)):
+            hits, cn = c.search_shape(qb, rb, sid)
+            assert np.all(np.diff(hits["query"].astype(np.int64)) >= 0), "hits not grouped by ascending query"
+            out.append((sorted_hits(hits), {k: cn[k] for k in ("seed_hits", "tentative_matches1", "tentative_matches2", "tentative_matches3")}, c.download_letters(qb, q_raw.size)))
+        res.append(out)
+        c.free_block(qb); c.free_block(rb); c.close()
+    for (h0, c0, l0), (h1, c1, l1) in zip(*res):
+        assert c0 == c1 and np.array_equal(h0, h1) and np.array_equal(l0, l1)
+    assert len(res[0][0][0]) > 0
