@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __rest
 					step_bytes = 16ull * (unsigned long long)R; rows = 32ull * (unsigned long long)R;
 				}
 				key = ((uint32_t)g << 20) | (0xFFFFFu - (uint32_t)min(nmacro, 0xFFFFFull));
-				cost = stats ? 0ull : trace ? nmacro * step_bytes : cells;
+				cost = stats ? 0ull : trace ? (g < G_LEGACY ? s16_trace_bytes((int)(step_bytes / 4), nmacro) : nmacro * step_bytes) : cells;
 				tslen = (uint64_t)qlen + (uint64_t)tlen;
 				atomicAdd(&s_hist[g], 1u);
 				atomicMax(&s_maxq[g], (unsigned)qlen);
@@ -765,7 +765,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		int R = 0, warps = 0;
 		if (g < G_LEGACY) {  // packed 16-bit kernel: shared score table + the queries of 4 problems per warp as 16-bit codes
 			R = 4 * (g / 2 + 1);
-			const int qstride = ((int)maxq + 8 * R + 4 + 7) & ~7;
+			const int qstride = ((int)maxq + 8 * R + 4 + S16_TILE + 7) & ~7;
 			const size_t tab = (size_t)((S16_TABLE_BYTES + 15) & ~15), per_warp = (size_t)4 * (size_t)qstride * 2;
 			warps = (int)std::min<size_t>(4, (((size_t)200 << 10) - tab) / per_warp);
 			if (warps < 1) { set_error("dmnd_banded_swipe: query too long for the packed kernel"); return 1; }  // (prep_kernel routes those to the int32 kernels)
@@ -882,7 +882,16 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 				wa.s16 = g < G_LEGACY ? 1 : 0;
 				wa.transcripts = transcripts ? ctx->b_tr.as<uint8_t>() : nullptr;
 				wa.transcript_off = transcripts ? d_tsoff : nullptr;
-				walk_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(wa, ctx->d_params);
+				{
+					const unsigned wg = (unsigned)((a.n + 127) / 128);
+					switch (g < G_LEGACY ? 4 * (g / 2 + 1) : 0) {
+					case 4: walk16_kernel<4><<<wg, 128, 0, st>>>(wa, ctx->d_params); break;
+					case 8: walk16_kernel<8><<<wg, 128, 0, st>>>(wa, ctx->d_params); break;
+					case 12: walk16_kernel<12><<<wg, 128, 0, st>>>(wa, ctx->d_params); break;
+					case 16: walk16_kernel<16><<<wg, 128, 0, st>>>(wa, ctx->d_params); break;
+					default: walk_kernel<<<wg, 128, 0, st>>>(wa, ctx->d_params); break;
+					}
+				}
 				++ctx->launches;
 				DMND_CUDA_CHECK(cudaGetLastError());
 				pos = e;

@@ -73,11 +73,14 @@ constexpr int S16_TABLE_ENTRIES = 27 * S16_TW;
 constexpr int S16_TABLE_BYTES = 2 * S16_TABLE_ENTRIES; // int16 entries: LDS.U16 + one IMAD packs two cells' scores (an int8 table needs a PRMT on the ALU pipe)
 constexpr int S16_LANES = 8;                           // lanes per problem
 constexpr int S16_MAX_BAND = 128;
+constexpr int S16_TILE = 8;                            // macro steps per trace tile
 constexpr int S16_MAX_MACRO = 32000;                   // macro steps representable in the 16-bit column key
 __host__ __device__ __forceinline__ int s16_rows(int B) { return B <= 32 ? 4 : B <= 64 ? 8 : B <= 96 ? 12 : 16; }
 // trace bytes of one macro step of one problem: 8 lanes x R/2 bytes, laid out as R/8 regions of 8 x 4 bytes (the full words
 // of the lanes) followed by one region of 8 x 2 bytes when R % 8 == 4
 __host__ __device__ __forceinline__ int s16_step_bytes(int R) { return 4 * R; }
+// trace bytes of a problem: whole tiles
+__host__ __device__ __forceinline__ unsigned long long s16_trace_bytes(int R, unsigned long long nmacro) { return (nmacro + S16_TILE - 1) / S16_TILE * (unsigned long long)(S16_TILE * 4 * R); }
 
 // Fills the table from the 32 x 32 score matrix (stats/score_matrix.h:35-44 layout).  Returns false through *ok when an entry
 // leaves int8 (then the packed kernel must not be used with this matrix).
@@ -102,15 +105,16 @@ struct S16Args {
 	unsigned int* overflow;  // raised when the call has to be repeated on the int32 kernels
 };
 
-// nibble (4 trace bits, stored inverted) of cell (column c, band row r)
+// nibble (4 trace bits, stored inverted) of cell (column c, band row r): tiles of S16_TILE macro steps; inside a tile every lane's
+// S16_TILE steps of one word are adjacent (R / 8 regions of 8 lanes x 32 bytes, then one of 8 x 16 bytes when R % 8 == 4)
 __device__ __forceinline__ unsigned s16_trace_nibble(const uint8_t* tr, int R, int c, int r) {
 	const int m = c + (r >> 1), lane = r / R, k = r - lane * R, half = R >> 1;
 	const int hi = k >= half ? 1 : 0, j = k - hi * half, w = j >> 2, p = j & 3;
-	const uint8_t* blk = tr + (size_t)m * (size_t)(4 * R);
-	const int full = R >> 3;
+	const uint8_t* tb = tr + (size_t)(m / S16_TILE) * (size_t)(S16_TILE * 4 * R);
+	const int t = m & (S16_TILE - 1), full = R >> 3;
 	unsigned v;
-	if (w < full) v = blk[w * 32 + lane * 4 + hi * 2 + (p >> 1)];
-	else v = blk[full * 32 + lane * 2 + hi];
+	if (w < full) v = tb[w * (S16_LANES * 4 * S16_TILE) + lane * (4 * S16_TILE) + t * 4 + hi * 2 + (p >> 1)];
+	else v = tb[full * (S16_LANES * 4 * S16_TILE) + lane * (2 * S16_TILE) + t * 2 + hi];
 	return (~(v >> ((p & 1) * 4))) & 15u;
 }
 
@@ -126,7 +130,7 @@ __device__ __forceinline__ unsigned s16_lds(unsigned addr) {
 template<int R, bool TRACE>
 __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const DevParams* __restrict__ P, const S16Args sa) {
 	DMND_DYN_SMEM(smem16);
-	constexpr int NP = R / 2, U = R / 2, HALO = S16_LANES * R / 2, NW = (NP + 3) / 4, FULL = R / 8;
+	constexpr int NP = R / 2, U = R / 2, HALO = S16_LANES * R / 2 + S16_TILE, NW = (NP + 3) / 4, FULL = R / 8;  // (the halo covers the steps before m_lo of the first trace tile)
 	static_assert(R % 4 == 0 && R >= 4 && R <= 16, "rows per lane");
 	{  // table: global -> shared, once per CTA
 		const uint4* src = reinterpret_cast<const uint4*>(sa.table);
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		__syncwarp();
 		bool ok = true;
 		if (live) {
-			const int W = g.qlen + 8 * R + 4;
+			const int W = g.qlen + 8 * R + 4 + S16_TILE;
 			for (int idx = gl; idx < W; idx += S16_LANES) {
 				const int i = idx - HALO;
 				int code = S16_HALO_CODE;
@@ -179,8 +183,9 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		// ---- geometry of the wavefront
 		const int ibase = g.j0 + g.d_begin;
 		const int nsteps = 2 * (g.cols - 1) + g.B, nmacro = live ? (nsteps + 1) >> 1 : 0;
-		const int m_lo = live ? max(0, -ibase - HALO) : 0, m_hi = live ? min(nmacro, g.qlen - ibase) : 0;
-		int trip = max(m_hi - m_lo, 0);
+		const int m_lo = live ? max(0, -ibase - (HALO - S16_TILE)) : 0, m_hi = live ? min(nmacro, g.qlen - ibase) : 0;
+		const int m0 = m_lo & ~(S16_TILE - 1);  // the wavefront starts at a trace-tile boundary; the steps before m_lo only see the halo (all state stays 0)
+		int trip = max((m_hi - m0 + S16_TILE - 1) / S16_TILE, 0);  // tiles
 #pragma unroll
 		for (int o = 8; o < 32; o <<= 1) trip = max(trip, __shfl_xor_sync(FULLM, trip, o));
 		// per pair: gap-open constant (32767 for a row below the band: its H never opens a gap, so E of the first dead row stays
@@ -200,10 +205,10 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return (int)tab + min((int)(g.t[jj] & 31), 26) * (2 * S16_TW); };  // byte address of the letter's row
 		int trow[U];
 		unsigned qreg[U + 1];
-		int I0 = ibase + m_lo + lofs + HALO;  // code index of row u = 0 (even k); odd k reads one further
+		int I0 = ibase + m0 + lofs + HALO;  // code index of row u = 0 (even k); odd k reads one further
 		if (live) {
 #pragma unroll
-			for (int u = 0; u < U; ++u) trow[u] = trow_of(g.j0 + m_lo - lofs - u);
+			for (int u = 0; u < U; ++u) trow[u] = trow_of(g.j0 + m0 - lofs - u);
 #pragma unroll
 			for (int v = 0; v <= U; ++v) qreg[v] = qc[I0 + v];
 		}
@@ -216,9 +221,13 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		}
 		uint8_t* tr = (TRACE && live) ? a.trace + (a.trace_excl[a.order_pos0 + slot] - a.trace_base) : nullptr;
 		// column keys of the macro step: key = score << 16 | ck, ck larger for the earlier column, hi row beats lo row on a tie
-		unsigned ckLo = 2u * (unsigned)(S16_MAX_MACRO + 64 - m_lo), ckHi = ckLo + (unsigned)(R / 2 + 1);
-		int m = m_lo;
+		unsigned ckLo = 2u * (unsigned)(S16_MAX_MACRO + 64 - m0), ckHi = ckLo + (unsigned)(R / 2 + 1);
+		int m = m0;
 		for (int it = 0; it < trip; ++it) {
+		const int mt = m;  // first step of the tile
+		unsigned buf[S16_TILE][NW];
+#pragma unroll
+		for (int ts = 0; ts < S16_TILE; ++ts) {
 			const bool active = m < m_hi;
 			int tnext = (int)tab + 26 * (2 * S16_TW);
 			unsigned qnext = 2 * S16_HALO_CODE;
@@ -271,11 +280,9 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 					H[j] = h; E[j] = e_new; F[j] = f_new;
 				}
 			}
-			if (TRACE && active) {
-				uint8_t* blk = tr + (size_t)m * (size_t)(4 * R);
+			if (TRACE) {
 #pragma unroll
-				for (int x = 0; x < FULL; ++x) *reinterpret_cast<uint32_t*>(blk + x * 32 + gl * 4) = pk[x];
-				if (R % 8 == 4) *reinterpret_cast<uint16_t*>(blk + FULL * 32 + gl * 2) = (uint16_t)__byte_perm(pk[NW - 1], 0u, 0x4420);
+				for (int x = 0; x < NW; ++x) buf[ts][x] = pk[x];
 			}
 #pragma unroll
 			for (int u = U - 1; u > 0; --u) trow[u] = trow[u - 1];
@@ -285,6 +292,23 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 			qreg[U] = qnext;
 			if (active) { ++I0; ++m; }
 			ckLo -= 2u; ckHi -= 2u;
+		}
+		// ---- the tile's trace: every lane writes its 8 steps as one 32-byte (full words) / 16-byte (half pieces) run, so that the
+		// traceback walk, which mostly moves along a diagonal = one lane word per macro step, finds 8 consecutive steps in one sector
+		if (TRACE && mt < m_hi) {
+			uint8_t* tb = tr + (size_t)(mt / S16_TILE) * (size_t)(S16_TILE * 4 * R);
+#pragma unroll
+			for (int x = 0; x < FULL; ++x) {
+				uint4* dst = reinterpret_cast<uint4*>(tb + x * (S16_LANES * 4 * S16_TILE) + gl * (4 * S16_TILE));
+				dst[0] = make_uint4(buf[0][x], buf[1][x], buf[2][x], buf[3][x]);
+				dst[1] = make_uint4(buf[4][x], buf[5][x], buf[6][x], buf[7][x]);
+			}
+			if (R % 8 == 4) {  // the last word holds two pairs: bytes 0 and 2 -> one 16-bit piece per step
+				uint4* dst = reinterpret_cast<uint4*>(tb + FULL * (S16_LANES * 4 * S16_TILE) + gl * (2 * S16_TILE));
+				dst[0] = make_uint4(__byte_perm(buf[0][NW - 1], buf[1][NW - 1], 0x6420), __byte_perm(buf[2][NW - 1], buf[3][NW - 1], 0x6420),
+				                    __byte_perm(buf[4][NW - 1], buf[5][NW - 1], 0x6420), __byte_perm(buf[6][NW - 1], buf[7][NW - 1], 0x6420));
+			}
+		}
 		}
 		// ---- end cell of the problem
 		if (TRACE) {
@@ -355,7 +379,10 @@ struct WalkArgs {
 	const uint64_t* transcript_off; // [problem], capacity qlen + tlen each
 };
 
-__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevParams* __restrict__ P) {
+// S16R > 0: the launch's problems were evaluated by swipe16_kernel<S16R, true> (the register tile is a compile-time constant: the
+// nibble address needs no division); S16R = 0: layout chosen per problem at run time (int32 kernels, and the CPU emulation's entry)
+template<int S16R>
+__device__ __forceinline__ void walk_body(const WalkArgs& a, const DevParams* __restrict__ P) {
 	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= a.n) return;
 	const uint32_t pi = a.order[w];
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 	const int best = res.score;
 	if (best > 0) {
 		const uint8_t* tr = a.trace + (a.trace_excl[a.order_pos0 + w] - a.trace_base);
-		const int R = a.s16 ? s16_rows(g.B) : tile_rows(g.B);
+		const int R = S16R ? S16R : (a.s16 ? s16_rows(g.B) : tile_rows(g.B));
 		int c = a.end_cell[2 * (size_t)pi], r = a.end_cell[2 * (size_t)pi + 1];
 		int i = g.j0 + g.d_begin + c + r, j = g.j0 + c;
 		res.q_end = i + 1; res.t_end = j + 1;
@@ -383,7 +410,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 		bool bad = false;
 		while (i >= 0 && j >= 0 && sc < best) {
 			if (c < 0 || r < 0 || r >= g.B) { bad = true; break; }
-			const unsigned nib = (a.s16 ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r));
+			const unsigned nib = ((S16R || a.s16) ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r));
 			if ((nib & 3) == 0) {
 				const int ql = g.q[i] & 31, sl = g.t[j] & 31;
 				const int m = P->score[(ql << 5) | sl];
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 			}
 			else if (nib & 1) {
 				int l = 0;
-				do { ++l; --i; --r; } while (r >= 0 && ((a.s16 ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r)) & 4) == 0 && i > 0);
+				do { ++l; --i; --r; } while (r >= 0 && (((S16R || a.s16) ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r)) & 4) == 0 && i > 0);
 				if (r < 0) { bad = true; break; }
 				++res.gap_openings; res.length += l; res.gaps += l;
 				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)(DMND_OP_INSERTION << 6); ++n; }
@@ -403,7 +430,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 			}
 			else {
 				int l = 0;
-				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && ((a.s16 ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r)) & 8) == 0 && j > 0);
+				do { ++l; --j; --c; ++r; } while (c >= 0 && r < g.B && (((S16R || a.s16) ? s16_trace_nibble(tr, R, c, r) : trace_nibble(tr, R, c, r)) & 8) == 0 && j > 0);
 				if (c < 0 || r >= g.B) { bad = true; break; }
 				++res.gap_openings; res.length += l; res.gaps += l;
 				for (int k = 0; k < l; ++k) { if (out && n < cap) out[n] = (uint8_t)((DMND_OP_DELETION << 6) | (g.t[j + l - k] & 31)); ++n; }
@@ -423,6 +450,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevPa
 	}
 	a.res[pi] = res;
 }
+__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a, const DevParams* __restrict__ P) { walk_body<0>(a, P); }
+template<int S16R> __global__ void __launch_bounds__(128) walk16_kernel(const WalkArgs a, const DevParams* __restrict__ P) { walk_body<S16R>(a, P); }
 
 
 }  // namespace dmnd_cuda

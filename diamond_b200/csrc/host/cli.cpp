@@ -24,6 +24,7 @@ struct SeqBlock {
 	std::vector<int8_t> letters;
 	std::vector<int64_t> limits;
 	std::vector<std::string> ids, titles;  // id = title up to the first blank (Util::Seq::id_delimiters)
+	std::vector<uint64_t> rec_begin;       // FASTA input: byte offset of every record's '>' in the (inflated) file, then the file size: block cuts (-b)
 	SeqBlock() : letters(DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER) { limits.push_back(DMND_PERIMETER_PADDING); }
 	void finish() { letters.insert(letters.end(), DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER); }
 	uint32_t size() const { return (uint32_t)ids.size(); }
@@ -60,9 +61,11 @@ int8_t encode(char c) {  // basic/value.cpp:26-41 with amino_acid_traits (stats/
 }
 
 void read_fasta(const std::string& path, SeqBlock& b) {
-	std::istringstream f(slurp_text(path));
+	const std::string text = slurp_text(path);
+	std::istringstream f(text);
 	std::string line;
 	bool open = false;
+	uint64_t line_begin = 0;
 	auto close_seq = [&] {
 		if (!open) return;
 		b.letters.push_back((int8_t)DMND_DELIMITER);
@@ -70,10 +73,13 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 		open = false;
 	};
 	while (std::getline(f, line)) {
+		const uint64_t this_line = line_begin;
+		line_begin += line.size() + 1;
 		if (!line.empty() && line.back() == '\r') line.pop_back();
 		if (line.empty()) continue;
 		if (line[0] == '>') {
 			close_seq();
+			b.rec_begin.push_back(this_line);
 			size_t e = 1;
 			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;  // Util::Seq::id_delimiters
 			b.ids.push_back(line.substr(1, e - 1));
@@ -86,6 +92,7 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 		}
 	}
 	close_seq();
+	b.rec_begin.push_back((uint64_t)text.size());
 	b.finish();
 }
 
@@ -435,11 +442,12 @@ int main(int argc, char** argv) {
 		bool pairwise = false, paf = false, sam = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		bool header_simple = false;
+		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
 			const char* attached = nullptr;
-			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdo", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
+			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdob", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
 			auto val = [&]() -> const char* { if (attached) return attached; if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
 			if (a == "-q" || a == "--query") qf = val();
 			else if (a == "-d" || a == "--db") df = val();
@@ -452,6 +460,7 @@ int main(int argc, char** argv) {
 			else if (a == "--ultra-sensitive") o.sensitivity = 6;
 			else if (a == "-p" || a == "--threads") o.threads = atoi(val());
 			else if (a == "-c" || a == "--index-chunks") o.index_chunks = atoi(val());
+			else if (a == "-b" || a == "--block-size") { block_size = atof(val()); if (!(block_size > 0.0)) usage("--block-size must be positive"); }
 			else if (a == "-k" || a == "--max-target-seqs") { o.max_target_seqs = atoi(val()); k_set = true; }
 			else if (a == "-e" || a == "--evalue") o.max_evalue = atof(val());
 			else if (a == "--top") { o.top_percent = atof(val()); top_set = true; if (o.top_percent < 0.0 || o.top_percent > 100.0) usage("Allowed value range for --top is between 0.0 and 100.0"); }
@@ -526,22 +535,127 @@ int main(int argc, char** argv) {
 		if (dmnd_params_init(&o, &params)) throw std::runtime_error(dmnd_last_error());
 		dmnd_ctx* ctx = nullptr;
 		if (dmnd_create(0, &params, &ctx)) throw std::runtime_error(dmnd_last_error());
-		dmnd_result* res = nullptr;
-		if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, r.letters.data(), r.letters.size(),
-		                r.limits.data(), r.size(), &o, &res))
-			throw std::runtime_error(dmnd_last_error());
+		// ---- reference blocks (run/double_indexed.cpp:218-244): a database beyond the block size is searched block by block with the
+		// e-values of the WHOLE database, and the per-block results are joined per query (output/join_blocks.cpp).  Block cuts follow the
+		// reference's loaders: a .dmnd database by letters (SequenceFile::load_twopass, data/sequence_file.cpp:214-240: sequences are
+		// added while the block holds fewer than block-size letters), a FASTA database by bytes of the file (load_parallel :104-189 with
+		// FastaFile::raw_chunk: records up to the first record boundary at or after block-size bytes).
+		if (block_size == 0.0) block_size = o.sensitivity >= 5 ? 0.4 : 2.0;
+		const uint64_t max_letters = (uint64_t)(block_size * 1e9);
+		std::vector<uint32_t> cuts{ 0 };
+		{
+			const uint32_t nr = r.size();
+			uint32_t f = 0;
+			while (f < nr) {
+				uint32_t e = f;
+				if (!r.rec_begin.empty()) { while (e < nr && r.rec_begin[e] - r.rec_begin[f] < max_letters) ++e; }
+				else { uint64_t letters = 0; while (e < nr && letters < max_letters) { letters += (uint64_t)(r.limits[e + 1] - r.limits[e] - 1); ++e; } }
+				cuts.push_back(e);
+				f = e;
+			}
+			if (cuts.size() == 1) cuts.push_back(0);
+		}
+		const size_t nblocks = cuts.size() - 1;
+		uint64_t db_letters = 0;
+		for (uint32_t i = 0; i < r.size(); ++i) db_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
+		std::vector<dmnd_result*> results(nblocks, nullptr);
+		for (size_t bk = 0; bk < nblocks; ++bk) {
+			if (nblocks == 1) {
+				if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, r.letters.data(), r.letters.size(), r.limits.data(), r.size(), &o, &results[0]))
+					throw std::runtime_error(dmnd_last_error());
+				break;
+			}
+			const uint32_t f = cuts[bk], e = cuts[bk + 1];
+			const int64_t a = r.limits[f], z = r.limits[e];
+			std::vector<int8_t> bl((size_t)DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER);
+			bl.insert(bl.end(), r.letters.begin() + a, r.letters.begin() + z);
+			bl.insert(bl.end(), (size_t)DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER);
+			std::vector<int64_t> lim((size_t)(e - f) + 1);
+			for (uint32_t k = f; k <= e; ++k) lim[k - f] = r.limits[k] - a + DMND_PERIMETER_PADDING;
+			dmnd_search_opts ob = o;
+			ob.db_letters = db_letters;
+			if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, bl.data(), bl.size(), lim.data(), e - f, &ob, &results[bk]))
+				throw std::runtime_error(dmnd_last_error());
+		}
+		dmnd_result* res = results[0];
 		size_t n = 0;
 		const dmnd_match* m = dmnd_result_matches(res, &n);
 		size_t ntr = 0;
 		const uint8_t* tr = dmnd_result_transcripts(res, &ntr);
 		if (fields.empty()) fields = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore" };
 		// sequence-bearing fields print the MASKED letters, as the reference does (its blocks are masked in place)
-		for (int side = 0; side < 2; ++side) {
-			size_t nm = 0;
-			const uint64_t* mp = dmnd_result_masked_positions(res, side, &nm);
-			std::vector<int8_t>& l = side ? r.letters : q.letters;
-			for (size_t k = 0; k < nm; ++k) l[(size_t)mp[k]] = 23;
+		for (size_t bk = 0; bk < nblocks; ++bk)
+			for (int side = 0; side < 2; ++side) {
+				size_t nm = 0;
+				const uint64_t* mp = dmnd_result_masked_positions(results[bk], side, &nm);
+				std::vector<int8_t>& l = side ? r.letters : q.letters;
+				const int64_t shift = (side && nblocks > 1) ? r.limits[cuts[bk]] - DMND_PERIMETER_PADDING : 0;  // block image position -> position in the whole database image
+				for (size_t k = 0; k < nm; ++k) l[(size_t)((int64_t)mp[k] + shift)] = 23;
+			}
+		// join_blocks (output/join_blocks.cpp:120-265): per query a merge of the blocks' match lists, best e-value first (then score, then
+		// database order -- JoinRecord::cmp_evalue; by score with --top), cut by GlobalCulling (output/target_culling.h:39-90): the first
+		// target always, then max_target_seqs targets, or the targets within --top percent of the best bit score
+		std::vector<dmnd_match> joined;
+		std::vector<uint8_t> joined_tr;
+		std::vector<uint32_t> joined_unal;
+		if (nblocks > 1) {
+			struct Cur { const dmnd_match* m; size_t n, i; const uint8_t* tr; uint32_t first; };
+			std::vector<Cur> cur(nblocks);
+			for (size_t bk = 0; bk < nblocks; ++bk) { cur[bk].m = dmnd_result_matches(results[bk], &cur[bk].n); cur[bk].i = 0; size_t x = 0; cur[bk].tr = dmnd_result_transcripts(results[bk], &x); cur[bk].first = cuts[bk]; }
+			const uint32_t cx = translated ? 6u : 1u;
+			const bool by_score = top_set;
+			auto before = [&](const dmnd_match& a, uint32_t oa, const dmnd_match& b, uint32_t ob) {  // a comes out of the heap before b
+				if (!by_score && a.evalue != b.evalue) return a.evalue < b.evalue;
+				if (a.score != b.score) return a.score > b.score;
+				return oa < ob;
+			};
+			for (;;) {
+				uint32_t src = UINT32_MAX;
+				for (const Cur& c : cur) if (c.i < c.n) src = std::min(src, c.m[c.i].query / cx);
+				if (src == UINT32_MAX) break;
+				std::vector<size_t> end(nblocks);
+				for (size_t bk = 0; bk < nblocks; ++bk) { size_t e = cur[bk].i; while (e < cur[bk].n && cur[bk].m[e].query / cx == src) ++e; end[bk] = e; }
+				int64_t n_targets = 0;
+				double top_bits = 0.0;
+				for (;;) {
+					size_t best = nblocks;
+					for (size_t bk = 0; bk < nblocks; ++bk) {
+						if (cur[bk].i >= end[bk]) continue;
+						if (best == nblocks || before(cur[bk].m[cur[bk].i], cur[bk].first + cur[bk].m[cur[bk].i].target, cur[best].m[cur[best].i], cur[best].first + cur[best].m[cur[best].i].target)) best = bk;
+					}
+					if (best == nblocks) break;
+					const dmnd_match& x = cur[best].m[cur[best].i];
+					if (n_targets > 0) {  // GlobalCulling::cull
+						if (top_set) { if ((1.0 - x.bit_score / top_bits) * 100.0 > o.top_percent) break; }
+						else if (n_targets >= (int64_t)(o.max_target_seqs == 0 ? INT32_MAX : o.max_target_seqs)) break;
+					}
+					else top_bits = x.bit_score;
+					dmnd_match y = x;
+					y.target += cur[best].first;
+					y.transcript_off = joined_tr.size();
+					if (x.transcript_len) joined_tr.insert(joined_tr.end(), cur[best].tr + x.transcript_off, cur[best].tr + x.transcript_off + x.transcript_len);
+					joined.push_back(y);
+					++n_targets;
+					++cur[best].i;
+				}
+				for (size_t bk = 0; bk < nblocks; ++bk) cur[bk].i = end[bk];
+			}
+			// queries with seed hits in some block and no alignment in any
+			std::vector<uint32_t> all;
+			for (size_t bk = 0; bk < nblocks; ++bk) { size_t nu = 0; const uint32_t* u = dmnd_result_unaligned(results[bk], &nu); all.insert(all.end(), u, u + nu); }
+			std::sort(all.begin(), all.end());
+			all.erase(std::unique(all.begin(), all.end()), all.end());
+			size_t ji = 0;
+			for (uint32_t qid : all) {
+				while (ji < joined.size() && joined[ji].query / cx < qid / cx) ++ji;
+				if (!(ji < joined.size() && joined[ji].query / cx == qid / cx)) joined_unal.push_back(qid);
+			}
+			m = joined.data(); n = joined.size(); tr = joined_tr.data();
 		}
+		auto result_unaligned = [&](size_t* nu) -> const uint32_t* {
+			if (nblocks > 1) { *nu = joined_unal.size(); return joined_unal.data(); }
+			return dmnd_result_unaligned(res, nu);
+		};
 		static const char* alphabet = "ARNDCQEGHILKMFPSTWYVBJZX*_";
 		FILE* out = fopen(of.c_str(), "wb");
 		if (!out) throw std::runtime_error("Error opening file " + of);
@@ -557,7 +671,7 @@ int main(int argc, char** argv) {
 			fwrite(line.data(), 1, line.size(), out);
 			const uint32_t cx = translated ? 6u : 1u;
 			size_t nu = 0, u = 0;
-			const uint32_t* unal_ids = dmnd_result_unaligned(res, &nu);
+			const uint32_t* unal_ids = result_unaligned(&nu);
 			auto unaligned_to = [&](uint32_t src_end) {
 				for (; u < nu && unal_ids[u] / cx < src_end; ++u) {
 					line = (translated ? dq.ids[unal_ids[u] / cx] : q.ids[unal_ids[u]]) + "\t4\t*\t0\t255\t*\t*\t0\t0\t*\t*\n";
@@ -618,7 +732,7 @@ int main(int argc, char** argv) {
 			// reported too when the extension stage saw them, i.e. when they had seed hits (Output::Flags::DEFAULT_REPORT_UNALIGNED, align/align.cpp:167-181), in query order
 			const uint32_t nsrc = translated ? (uint32_t)dq.ids.size() : q.size();
 			size_t i = 0, nu = 0, u = 0;
-			const uint32_t* unal = dmnd_result_unaligned(res, &nu);  // queries with seed hits and no alignment; queries without seed hits print nothing
+			const uint32_t* unal = result_unaligned(&nu);  // queries with seed hits and no alignment; queries without seed hits print nothing
 			for (uint32_t s = 0; s < nsrc; ++s) {
 				const std::string& qid = translated ? dq.ids[s] : q.ids[s];
 				const size_t i0 = i;
@@ -654,7 +768,7 @@ int main(int argc, char** argv) {
 			line = "BLASTP 2.3.0+\n\n\n";  // the same header for blastx (print_header, blast_pairwise_format.cpp:97-101)
 			fwrite(line.data(), 1, line.size(), out);
 			size_t nu = 0, u = 0;
-			const uint32_t* unal_ids = dmnd_result_unaligned(res, &nu);
+			const uint32_t* unal_ids = result_unaligned(&nu);
 			const uint32_t cx = translated ? 6u : 1u;
 			auto intro = [&](uint32_t sq) {
 				return "Query= " + (translated ? dq.titles[sq] : q.titles[sq]) + "\n\nLength=" + std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1) + "\n\n";
@@ -729,7 +843,7 @@ int main(int argc, char** argv) {
 			fwrite(line.data(), 1, line.size(), out);
 		}
 		size_t n_unal = 0, u_next = 0;
-		const uint32_t* unal_q = dmnd_result_unaligned(res, &n_unal);
+		const uint32_t* unal_q = result_unaligned(&n_unal);
 		const uint32_t ctxs = translated ? 6u : 1u;
 		auto unaligned_upto = [&](uint32_t src_end) {  // --unal 1: TabularFormat::print_query_intro (output/blast_tab_format.cpp:776-788) for the queries
 			if (!unal || pairwise || paf || sam) return;      // [.., src_end) that had seed hits and no alignment, in query order
@@ -866,7 +980,7 @@ int main(int argc, char** argv) {
 			fprintf(stderr, "Time seed/bridge/dp1/dp2/total (ms) = %.2f / %.2f / %.2f / %.2f / %.2f\n", s->seed_ms, s->host_bridge_ms, s->dp1_ms, s->dp2_ms, s->total_ms);
 			fprintf(stderr, "%llu queries aligned.\n", (unsigned long long)s->queries_aligned);
 		}
-		dmnd_result_free(res);
+		for (dmnd_result* rr : results) dmnd_result_free(rr);
 		dmnd_destroy(ctx);
 		return 0;
 	}

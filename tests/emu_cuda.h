@@ -167,6 +167,7 @@ static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{ x, y, z, w }; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }

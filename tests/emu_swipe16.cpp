@@ -100,14 +100,14 @@ int main(int argc, char** argv) {
 		std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return nmacro[x] > nmacro[y]; });
 		if (order.size() > 8) std::swap(order[1], order[order.size() - 1]);
 		std::vector<uint64_t> excl(order.size() + 1, 0);
-		for (size_t k = 0; k < order.size(); ++k) excl[k + 1] = excl[k] + (uint64_t)nmacro[order[k]] * (uint64_t)s16_step_bytes(R);
+		for (size_t k = 0; k < order.size(); ++k) excl[k + 1] = excl[k] + s16_trace_bytes(R, (unsigned long long)nmacro[order[k]]);
 		std::vector<uint8_t> tr((size_t)excl.back() + 64, 0xA5);
 		unsigned work = 0;
 		SwipeArgs a;
 		a.q_letters = qb.data(); a.q_bias = bias.data(); a.r_letters = tb.data(); a.q_limits = qlim.data(); a.r_limits = tlim.data();
 		a.probs = probs.data(); a.order = order.data(); a.n = (uint32_t)order.size(); a.score = score.data(); a.end_cell = endc.data();
 		a.trace = tr.data(); a.trace_excl = excl.data(); a.trace_base = 0; a.order_pos0 = 0; a.work = &work;
-		S16Args sa; sa.table = table.data(); sa.qstride = (maxqlen + 8 * R + 4 + 7) & ~7; sa.overflow = &overflow;
+		S16Args sa; sa.table = table.data(); sa.qstride = (maxqlen + 8 * R + 4 + S16_TILE + 7) & ~7; sa.overflow = &overflow;
 		if (R == 4) run_group<4>(a, &P, sa, trace); else if (R == 8) run_group<8>(a, &P, sa, trace); else if (R == 12) run_group<12>(a, &P, sa, trace); else run_group<16>(a, &P, sa, trace);
 		if (trace) {
 			WalkArgs wa;

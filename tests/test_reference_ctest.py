@@ -12,12 +12,13 @@ REF = "/root/reference"
 TD = os.path.join(REF, "src", "test")
 CLI = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
 # the cases this path covers; the others need options outside it (taxonomy, BLAST databases, DAA, --max-hsps 0, matrix
-# adjustment (--comp-based-stats 2-4), other matrices, -b block splitting, --global-ranking, linclust / realign / view)
+# adjustment (--comp-based-stats 2-4), other matrices, --global-ranking, linclust / realign / view)
 CASES = ["blastp", "blastp-mid-sens", "blastp-f0", "blastx-nanopore", "blastx-nanopore-fna",
          "diamond-test-blastp-default", "diamond-test-blastp-multithreaded", "diamond-test-blastp-more-sensitive",
          "diamond-test-blastp-very-sensitive", "diamond-test-blastp-ultra-sensitive", "diamond-test-blastp-target-parallel",
          "diamond-test-blastp-query-indexed", "diamond-test-blastp-comp-based-stats-0", "diamond-test-blastp-target-seqs",
-         "diamond-test-blastp-evalue", "diamond-test-blastp-pairwise-format", "diamond-test-blastp-paf-format", "diamond-test-blastp-top"]
+         "diamond-test-blastp-evalue", "diamond-test-blastp-pairwise-format", "diamond-test-blastp-paf-format", "diamond-test-blastp-top",
+         "blastp-blocked", "diamond-test-blastp-blocked"]  # -b: reference blocks + join_blocks
 
 
 def ctest_commands():
@@ -140,3 +141,21 @@ def test_more_tabular_fields_like_the_reference(oracle_lib, mode, tmp_path):
     assert r.returncode == 0, r.stderr
     got = open(ours).read()
     assert got == open(ref).read() and got.count("\n") > 300
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(TD)), reason="needs the reference build and its test inputs")
+@pytest.mark.parametrize("extra", [["-c1", "-b0.00002"], ["--fast", "-b0.00003", "--top", "10"], ["-b0.00005", "-k", "3", "-f", "6", "qseqid", "sseqid", "evalue", "bitscore", "cigar"]])
+def test_blocked_dmnd_database_matches_reference(oracle_lib, extra, tmp_path):
+    """Reference blocks of a .dmnd database are cut by LETTERS (SequenceFile::load_twopass), FASTA databases by file bytes (the two
+    ctest cases above): our -b on a DIAMOND database file against the reference binary, incl. --top (join by score) and transcripts
+    carried through the join."""
+    db = str(tmp_path / "db")
+    subprocess.run([REF_BIN, "makedb", "--in", os.path.join(TD, "data.faa"), "-d", db, "--quiet"], check=True, capture_output=True)
+    outs = []
+    for exe in (REF_BIN, CLI):
+        out = str(tmp_path / (os.path.basename(exe) + ".out"))
+        r = subprocess.run([exe, "blastp", "-q", os.path.join(TD, "data.faa"), "-d", db + (".dmnd" if exe == CLI else ""), "-p4", "-o", out] + extra + (["--quiet"] if exe == REF_BIN else []),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] and len(outs[0]) > 1000
