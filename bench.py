@@ -79,13 +79,18 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        """Row count now: the timed region's samples are the rows between two marks (the sampler process is started BEFORE the warm-up:
+        its NVML initialisation stalls kernel launches for ~100 ms and must not fall into the timed region)."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for l in self.rows:
+        for l in self.rows[first:last]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -345,14 +350,16 @@ def main():
         r_res = ctx.download_letters(rb, r_raw.size)
     step_res = lambda: ctx.blastp_resident(qb, rb, q_res, q_lim, r_res, r_lim)
     step_e2e = lambda: ctx.blastp(q_pin, q_lim, r_pin, r_lim)
-    for _ in range(args.warmup):
-        step_res()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step_res()
+    c0 = clocks.mark()
     ms, (m, _, st), tm = timed(step_res, args.steps)
     step_ms_res = list(step_ms)
-    clk = clocks.stop() if rank == 0 else None
+    c1 = clocks.mark()
+    clk = clocks.stop(max(c0 - 1, 0), c1 + 1) if rank == 0 else None
     for _ in range(min(args.warmup, 2)):  # the e2e path has its own first-call allocations (block pool, staging)
         step_e2e()
     ms_e2e, (m2, _, st2), tm2 = timed(step_e2e, args.steps)

@@ -211,11 +211,25 @@ __global__ void mask_kernel(int8_t* q_letters, const DevParams* __restrict__ P, 
 	pairs[i] = np;
 }
 
+// search/hamming/finger_print.h:180-215: equal letters (bits 0..4) among the 48 positions [-16, 32) around both seeds.  Both windows
+// are read as thirteen aligned 32-bit words each and shifted into place (funnel shift by the byte misalignment), compared four
+// letters at a time: (x + 0x7f7f7f7f) & 0x80808080 has one bit per UNEQUAL letter (x = masked XOR, every byte <= 0x1f: no carries).
+// The aligned reads touch at most 3 bytes before q - 16 and after q + 32: inside the block image's padding / allocation slack.
 __device__ __forceinline__ unsigned fingerprint_match(const int8_t* q, const int8_t* s) {
-	unsigned n = 0;
-#pragma unroll 8
-	for (int k = -16; k < 32; ++k) n += ((q[k] ^ s[k]) & 31) == 0;
-	return n;
+	const uintptr_t qa = (uintptr_t)(q - 16), sa = (uintptr_t)(s - 16);
+	const uint32_t* __restrict__ qw = reinterpret_cast<const uint32_t*>(qa & ~(uintptr_t)3);
+	const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+	const unsigned qsh = (unsigned)(qa & 3) * 8u, ssh = (unsigned)(sa & 3) * 8u;
+	uint32_t qp = qw[0], sp = sw[0];
+	unsigned diff = 0;
+#pragma unroll
+	for (int k = 0; k < 12; ++k) {
+		const uint32_t qn = qw[k + 1], sn = sw[k + 1];
+		const uint32_t x = (__funnelshift_r(qp, qn, qsh) ^ __funnelshift_r(sp, sn, ssh)) & 0x1f1f1f1fu;
+		diff += (unsigned)__popc((x + 0x7f7f7f7fu) & 0x80808080u);
+		qp = qn; sp = sn;
+	}
+	return 48u - diff;
 }
 
 struct LmCtx {
