@@ -212,12 +212,20 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 	const uint32_t nchunks = std::min<uint32_t>((uint32_t)hp.index_chunks, parts_total);
 	if (nchunks > 64) { set_error("dmnd_search_shape: more than 64 index chunks are not supported"); return 1; }
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
-	if (ctx->b_pairs.ensure((nent + 2) * 8 * 2)) return 1;
+	// per entry: pairs in this chunk, their exclusive prefix, the rank among the chunk's active entries; then the active list itself
+	if (ctx->b_pairs.ensure((nent + 2) * (8 + 8 + 4 + 4 + 8) + 64)) return 1;
 	uint64_t* d_pairs = ctx->b_pairs.as<uint64_t>();
 	uint64_t* d_pair_off = d_pairs + nent + 1;
-	size_t scan_tmp = 0;
+	uint64_t* d_act_off = d_pair_off + nent + 1;
+	uint32_t* d_rank = reinterpret_cast<uint32_t*>(d_act_off + nent + 2);
+	uint32_t* d_act = d_rank + nent + 2;
+	uint32_t* d_nact = reinterpret_cast<uint32_t*>(d_cnt + 15);
+	struct HasPairs { __host__ __device__ uint32_t operator()(const uint64_t& v) const { return v > 0 ? 1u : 0u; } };
+	cub::TransformInputIterator<uint32_t, HasPairs, const uint64_t*> flag_it(d_pairs, HasPairs());
+	size_t scan_tmp = 0, scan_tmp2 = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st);
-	if (ctx->b_cub.ensure(scan_tmp)) return 1;
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp2, flag_it, d_rank, (size_t)nent + 1, st);
+	if (ctx->b_cub.ensure(std::max(scan_tmp, scan_tmp2))) return 1;
 	size_t hits_total = 0;
 	uint64_t seed_hits_total = 0;
 	for (uint32_t chunk = 0; chunk < nchunks && nent > 0; ++chunk) {
@@ -226,8 +234,10 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_pairs + nent, 0, 8, st));
 		mask_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(query->letters, P, sid, d_entries, (size_t)nent, pb, pe, d_pairs, d_key_seen, d_cnt);
 		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st));
-		ctx->launches += 3;
-		// no host round trip inside the chunk loop: the chunk's pair total stays on the device (stage12 reads it, a copy goes
+		DMND_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, scan_tmp2, flag_it, d_rank, (size_t)nent + 1, st));
+		active_scatter_kernel<<<(unsigned)((nent + 1 + 255) / 256), 256, 0, st>>>(d_pairs, d_pair_off, d_rank, (size_t)nent, d_act, d_act_off, d_nact);
+		ctx->launches += 6;
+		// no host round trip inside the chunk loop: the chunk's pair total stays on the device (the stage kernels read it, a copy goes
 		// to the counters), the grid covers the bound over all chunks and surplus CTAs leave at once
 		DMND_CUDA_CHECK(cudaMemcpyAsync(d_cnt + 16 + chunk, d_pair_off + nent, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
 		if (pairs_bound == 0) continue;
@@ -235,13 +245,13 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 		x.P = P; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
 		x.cur_matcher = ctx->d_matcher[sid + 1]; x.cur_minlen = ctx->matcher_minlen[sid + 1]; x.cur_suffix = ctx->matcher_suffix[sid + 1];
 		x.prev_matcher = ctx->d_matcher[sid]; x.prev_minlen = ctx->matcher_minlen[sid]; x.prev_suffix = ctx->matcher_suffix[sid];
+		const PairLookup L{ d_act, d_act_off, d_nact };
+		const unsigned grid = (unsigned)((pairs_bound + STAGE_CTA - 1) / STAGE_CTA);
 		if (hp.ungapped_evalue == 0.0)
-			stage12_kernel<<<(unsigned)((pairs_bound + 127) / 128), 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent,
-				d_pair_off, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+			stage12_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
 		else {
-			const unsigned grid = (unsigned)((pairs_bound + 127) / 128);
-			stage1_flags_kernel<<<grid, 128, 0, st>>>(query->letters, ref->letters, d_entries, (size_t)nent, d_pair_off, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(), d_cnt);
-			stage2_window_kernel<<<grid, 128, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, (size_t)nent, d_pair_off, d_locs,
+			stage1_flags_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, ref->letters, d_entries, L, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(), d_cnt);
+			stage2_window_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs,
 				ctx->b_keys2.as<uint32_t>(), x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
 			++ctx->launches;
 		}

@@ -370,21 +370,54 @@ __device__ __forceinline__ void stage2_tail(const int8_t* __restrict__ q_letters
 	hits[idx] = h;
 }
 
+// ---- which (entry, k) is pair `pid` of the chunk?  The chunk's ACTIVE entries (those that contribute pairs: right partition range,
+// seed not masked) are listed in act[] with the running pair count act_off[] (act_off[nact] = pairs of the chunk).  One binary search
+// per CTA finds the entry of the CTA's first pair; the CTA's 128 pairs lie in at most 128 further active entries (each has >= 1 pair),
+// whose offsets go to shared memory, and every thread finishes with a 7-step search there.  (A per-pair binary search over ALL
+// entries -- 28 dependent L2 reads where every query position has a partner, as in the sensitive modes -- was most of those modes' time.)
+struct PairLookup { const uint32_t* act; const uint64_t* act_off; const uint32_t* nact; };
+constexpr int STAGE_CTA = 128;
+__device__ __forceinline__ bool locate_pair(const PairLookup& L, uint64_t* s_off, uint32_t* s_first, uint64_t& pid, size_t& entry, uint32_t& k) {
+	const uint32_t nact = *L.nact;
+	const uint64_t total = L.act_off[nact], pid0 = (uint64_t)blockIdx.x * STAGE_CTA;
+	pid = pid0 + threadIdx.x;
+	if (pid0 >= total) return false;  // the whole CTA is beyond the chunk's pairs (the grid covers a bound over all chunks)
+	if (threadIdx.x == 0) {
+		uint32_t lo = 0, hi = nact;
+		while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (L.act_off[mid] <= pid0) lo = mid; else hi = mid; }
+		*s_first = lo;
+	}
+	__syncthreads();
+	const uint32_t first = *s_first;
+	for (int t = threadIdx.x; t <= STAGE_CTA; t += STAGE_CTA) s_off[t] = L.act_off[min(first + (uint32_t)t, nact)];
+	__syncthreads();
+	if (pid >= total) return false;
+	int lo = 0, hi = STAGE_CTA + 1;
+	while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= pid) lo = mid; else hi = mid; }
+	entry = (size_t)L.act[first + (uint32_t)lo];
+	k = (uint32_t)(pid - s_off[lo]);
+	return true;
+}
+// rank[] = exclusive count of active entries before i (scan of pairs[i] > 0): the scatter builds act / act_off from it
+__global__ void active_scatter_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rank, size_t n,
+                                      uint32_t* act, uint64_t* act_off, uint32_t* nact) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	if (i == n) { const uint32_t na = rank[n]; *nact = na; act_off[na] = pair_off[n]; return; }
+	if (pairs[i] > 0) { act[rank[i]] = (uint32_t)i; act_off[rank[i]] = pair_off[i]; }
+}
+
 // Chunk pass 2 (modes without the ungapped window filter, --fast): one thread per (query loc, reference loc) pair of the
 // chunk's surviving keys.
-__global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
-                               const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
-                               const uint64_t* __restrict__ pair_off /* exclusive scan, n_entries + 1: pair_off[n_entries] = pairs of this chunk */,
+__global__ void __launch_bounds__(STAGE_CTA) stage12_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                               const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, PairLookup L,
                                const uint32_t* __restrict__ ref_locs, LmCtx x, dmnd_hit* hits, unsigned long long* hit_count,
                                unsigned long long* counters) {
-	// the grid is sized from an upper bound known on the host (pairs over all chunks): the chunk's own total stays on the device
-	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (pid >= pair_off[n_entries]) return;
-	// entry = last e with pair_off[e] <= pid
-	size_t lo = 0, hi = n_entries;
-	while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+	__shared__ uint64_t s_off[STAGE_CTA + 1];
+	__shared__ uint32_t s_first;
+	uint64_t pid; size_t lo; uint32_t k;
+	if (!locate_pair(L, s_off, &s_first, pid, lo, k)) return;
 	const Entry e = entries[lo];
-	const uint32_t k = (uint32_t)(pid - pair_off[lo]);
 	const uint32_t sloc = ref_locs[e.lo + k];
 	if (fingerprint_match(q_letters + e.qloc, r_letters + sloc) < (unsigned)x.P->hamming_id) return;
 	atomicAdd(&counters[2], 1ull);
@@ -396,16 +429,16 @@ __global__ void stage12_kernel(const int8_t* __restrict__ q_letters, const int64
 // the size of a survivor's call decides which window kernel scores it.  Pass A writes one survivor bit per pair (one ballot
 // word per warp, the grid covers the bound so every word is written); pass B counts the survivors of the pair's tile in that
 // bitmap to find the size of its call.
-__global__ void stage1_flags_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
-                                    const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ ref_locs, unsigned hamming_id, uint32_t* flags,
+__global__ void __launch_bounds__(STAGE_CTA) stage1_flags_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries,
+                                    PairLookup L, const uint32_t* __restrict__ ref_locs, unsigned hamming_id, uint32_t* flags,
                                     unsigned long long* counters) {
-	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ uint64_t s_off[STAGE_CTA + 1];
+	__shared__ uint32_t s_first;
+	uint64_t pid; size_t lo; uint32_t k;
 	bool pass = false;
-	if (pid < pair_off[n_entries]) {
-		size_t lo = 0, hi = n_entries;
-		while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+	if (locate_pair(L, s_off, &s_first, pid, lo, k)) {
 		const Entry e = entries[lo];
-		const uint32_t sloc = ref_locs[e.lo + (uint32_t)(pid - pair_off[lo])];
+		const uint32_t sloc = ref_locs[e.lo + k];
 		pass = fingerprint_match(q_letters + e.qloc, r_letters + sloc) >= hamming_id;
 	}
 	const unsigned word = __ballot_sync(0xffffffffu, pass);
@@ -425,17 +458,16 @@ __device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits
 	}
 	return n;
 }
-__global__ void stage2_window_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
-                                     const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, size_t n_entries,
-                                     const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
+__global__ void __launch_bounds__(STAGE_CTA) stage2_window_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                                     const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, PairLookup L,
+                                     const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
                                      dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
-	const uint64_t pid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (pid >= pair_off[n_entries] || !((flags[pid >> 5] >> (pid & 31)) & 1u)) return;
-	size_t lo = 0, hi = n_entries;
-	while (hi - lo > 1) { const size_t mid = lo + (hi - lo) / 2; if (pair_off[mid] <= pid) lo = mid; else hi = mid; }
+	__shared__ uint64_t s_off[STAGE_CTA + 1];
+	__shared__ uint32_t s_first;
+	uint64_t pid; size_t lo; uint32_t k;
+	if (!locate_pair(L, s_off, &s_first, pid, lo, k) || !((flags[pid >> 5] >> (pid & 31)) & 1u)) return;
 	const Entry e = entries[lo];
-	const uint64_t first = pair_off[lo];
-	const uint32_t k = (uint32_t)(pid - first);
+	const uint64_t first = pid - k;
 	const uint32_t tile_begin = k & ~1023u, tile_end = min(tile_begin + 1024u, e.cnt);
 	const unsigned rank = count_bits(flags, first + tile_begin, pid), total = count_bits(flags, first + tile_begin, first + tile_end);
 	const int batch_size = (int)min(32u, total - (rank & ~31u));

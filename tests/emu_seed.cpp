@@ -98,7 +98,9 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 	std::vector<uint32_t> key_seen(((size_t)ix.nref + 31) / 32 + 1, 0), flags((size_t)pairs_bound / 32 + 8, 0xdeadbeefu);
 	const uint32_t parts_total = 1u << hp.seedp_bits, nchunks = std::min<uint32_t>((uint32_t)hp.index_chunks, parts_total);
 	const uint32_t psize = parts_total / nchunks, prem = parts_total % nchunks;
-	std::vector<uint64_t> pairs((size_t)nent + 1), pair_off((size_t)nent + 1);
+	std::vector<uint64_t> pairs((size_t)nent + 1), pair_off((size_t)nent + 1), act_off((size_t)nent + 2);
+	std::vector<uint32_t> rank((size_t)nent + 2), act((size_t)nent + 2);
+	uint32_t nact = 0;
 	uint64_t seed_hits_total = 0;
 	for (uint32_t chunk = 0; chunk < nchunks && nent > 0; ++chunk) {
 		const uint32_t bsel = std::min(chunk, prem);
@@ -107,18 +109,21 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 		emu::launch((unsigned)((nent + 255) / 256), 256, [&] { mask_kernel(query.letters.data(), &P, sid, entries.data(), (size_t)nent, pb, pe, pairs.data(), key_seen.data(), cnt); });
 		uint64_t run = 0;
 		for (size_t i = 0; i <= (size_t)nent; ++i) { pair_off[i] = run; run += pairs[i]; }  // cub::DeviceScan::ExclusiveSum
+		{ uint32_t r = 0; for (size_t i = 0; i <= (size_t)nent; ++i) { rank[i] = r; r += pairs[i] > 0 ? 1u : 0u; } }  // ... and the scan of (pairs > 0)
+		emu::launch((unsigned)((nent + 1 + 255) / 256), 256, [&] { active_scatter_kernel(pairs.data(), pair_off.data(), rank.data(), (size_t)nent, act.data(), act_off.data(), &nact); });
 		seed_hits_total += pair_off[(size_t)nent];
 		if (pairs_bound == 0) continue;
 		LmCtx x;
 		x.P = &P; x.sid = sid; x.chunked = hp.index_chunks > 1; x.range_begin = pb; x.range_end = pe;
 		x.cur_matcher = M.t[sid + 1].data(); x.cur_minlen = M.minlen[sid + 1]; x.cur_suffix = M.suffix[sid + 1];
 		x.prev_matcher = M.t[sid].data(); x.prev_minlen = M.minlen[sid]; x.prev_suffix = M.suffix[sid];
-		const unsigned grid = (unsigned)((pairs_bound + 127) / 128);
+		const PairLookup L{ act.data(), act_off.data(), &nact };
+		const unsigned grid = (unsigned)((pairs_bound + STAGE_CTA - 1) / STAGE_CTA);
 		if (hp.ungapped_evalue == 0.0)
-			emu::launch(grid, 128, [&] { stage12_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), (size_t)nent, pair_off.data(), ix.locs.data(), x, dh.data(), cnt + 6, cnt); });
+			emu::launch(grid, STAGE_CTA, [&] { stage12_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), x, dh.data(), cnt + 6, cnt); });
 		else {
-			emu::launch(grid, 128, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), (size_t)nent, pair_off.data(), ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), cnt); });
-			emu::launch(grid, 128, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), (size_t)nent, pair_off.data(), ix.locs.data(), flags.data(), x,
+			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), cnt); });
+			emu::launch(grid, STAGE_CTA, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
 				dh.data(), cnt + 6, cnt); });
 		}
 	}
