@@ -201,12 +201,25 @@ def lookup_cells(args, n, threads):
     return None, "no cached cell count for this configuration: run `python bench.py --emit-cells <threads>` on a GPU box first"
 
 
+_result_fd = None
+
+
+def emit(obj):
+    """stdout carries exactly ONE line, the JSON result: fd 1 is pointed at stderr for the run (NCCL's version banner and child
+    processes print there) and the result goes to the saved descriptor."""
+    os.write(_result_fd if _result_fd is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    global _result_fd
     args = parse()
     if args.gpus > 1 and "RANK" not in os.environ:
         # launched plainly with --gpus N: re-launch as one rank per GPU (what the driver does itself with torch.distributed.run)
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                                    "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:])
+    sys.stdout.flush()
+    _result_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     ncpu = effective_cpus()
     ref_threads = ncpu  # seedp_bits follows -p (setup.cpp:306-309): both arms are run with the same value
@@ -223,7 +236,7 @@ def main():
         if rank != 0:
             return
         if not os.path.exists(REF_BIN):
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/diamond not present in the snapshot"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/diamond not present in the snapshot"})
             return
         wl = make_workload(args, 0)
         with tempfile.TemporaryDirectory() as td:
@@ -247,7 +260,7 @@ def main():
         val = (cells * len(times) / T / 1e9) if cells else None
         sample = (f"the full configuration: all {args.queries} queries of rank 0's block x {args.db}-protein DB, one reference process per step (FASTA in, fmt 6 out, "
                   f"whole process wall time), -p {best_p} = fastest of {tried} s on a {ns}-query sample; {len(times)} timed run(s) after {warm} warm-up; {note}")
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": len(times),
+        emit(({"impl": "reference", "metric": metric, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": len(times),
                           "warmup": warm, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "int8/int16 saturating SIMD (AVX2)", "data": "synthetic", "config": dict(config, reference_threads=best_p, sample=sample, same_config=True),
                           "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": best_p, "kind": "reference", "sample": sample},
@@ -269,7 +282,7 @@ def main():
             tab[cells_key(args, args.queries, p)] = st["cells_round1"] + st["cells_round2"]
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(tab, open(os.path.join(ROOT, "gpurun_out", "workload_cells.json"), "w"), indent=1, sort_keys=True)
-        print(json.dumps(tab))
+        emit(tab)
         return
 
     torch.cuda.set_device(local)
@@ -464,7 +477,7 @@ def main():
                         "note": "cells = sum band x cols over the reference's round-1 and round-2 problem lists (dp/dp.h:121-124): a property of the workload, "
                                 "the same for both arms; fused queries evaluate a surviving problem's matrix once (with traceback) instead of twice",
                         "alignments": int(len(m)), "hits": st["hits"]}}
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

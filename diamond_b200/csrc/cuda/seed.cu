@@ -143,6 +143,8 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 
 // One query range [q_begin, q_end): its hits, grouped by query, are APPENDED to the context's hit arena after the `out_offset` hits of the
 // ranges before it (ascending ranges keep the whole list grouped by ascending query).
+struct HasPairs { __host__ __device__ uint32_t operator()(const uint64_t& v) const { return v > 0 ? 1u : 0u; } };
+
 static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, size_t out_offset, size_t* n_out, dmnd_stage_counters* counters) {
 	const dmnd_params& hp = ctx->params;
 	if (query->raw_len >= 0xffffffffull || ref->raw_len >= 0xffffffffull) { set_error("dmnd_search_shape: blocks of 4 G letters or more are not supported"); return 1; }
@@ -220,7 +222,6 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 	uint32_t* d_rank = reinterpret_cast<uint32_t*>(d_act_off + nent + 2);
 	uint32_t* d_act = d_rank + nent + 2;
 	uint32_t* d_nact = reinterpret_cast<uint32_t*>(d_cnt + 15);
-	struct HasPairs { __host__ __device__ uint32_t operator()(const uint64_t& v) const { return v > 0 ? 1u : 0u; } };
 	cub::TransformInputIterator<uint32_t, HasPairs, const uint64_t*> flag_it(d_pairs, HasPairs());
 	size_t scan_tmp = 0, scan_tmp2 = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, d_pairs, d_pair_off, (size_t)nent + 1, st);
