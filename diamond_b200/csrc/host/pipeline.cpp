@@ -45,12 +45,14 @@ using Clock = std::chrono::steady_clock;
 static double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
 
 // DMND_PROFILE=1: wall-clock of the host phases on stderr (development aid)
+static Clock::time_point g_prof_epoch = Clock::now();  // start of the current dmnd_blastp call (timestamps of the laps)
 struct Prof {
 	bool on = std::getenv("DMND_PROFILE") != nullptr;
+	int lane = -1;
 	Clock::time_point t = Clock::now();
 	void lap(const char* what) {
 		if (!on) return;
-		std::fprintf(stderr, "[dmnd profile] %-34s %8.2f ms\n", what, ms_since(t));
+		std::fprintf(stderr, "[dmnd profile] lane %2d %-34s %8.2f ms  (ends at %8.2f)\n", lane, what, ms_since(t), ms_since(g_prof_epoch));
 		t = Clock::now();
 	}
 };
@@ -1102,7 +1104,10 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	seed_turn.set_masked(lane);  // (dmnd_block_mask returns when the range is masked on the device; also set on failure so nobody waits forever)
 	prep_rc = prep_rc || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
 	seed_turn.wait_masked(lane + 1);
+	prof.lane = lane;
+	prof.lap("wait, mask, bias");
 	seed_turn.wait_for(lane);
+	prof.lap("wait for the seed turn");
 	const int n_shapes = env.n_shapes;
 	size_t nh = 0;
 	// The bridge from hits to DP problems runs on the device (dmnd_hits_chain) for single-shape blastp without a gapped filter:
@@ -1430,6 +1435,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 
 	// (the per-position composition bias of the queries is computed on the device by each lane for its own range)
 	// reference side of the seed join, once per call, shared by the lanes (the reference rebuilds it per run as well)
+	g_prof_epoch = Clock::now();
 	if (dmnd_block_build_index(ctx, const_cast<dmnd_block*>(rb), 0)) return 1;
 
 	const std::vector<uint32_t>& cut = plan.cut;
