@@ -14,7 +14,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -ffp-contract=off -fPIC -pthread -Wall -Wextra
 
 HOST_SRC := pipeline.cpp chaining.cpp scoring.cpp
-CUDA_SRC := ctx.cu swipe.cu seed.cu mask.cu chain.cu comm.cu
+CUDA_SRC := ctx.cu swipe.cu seed.cu mask.cu chain.cu comm.cu fs.cu
 HOST_OBJ := $(patsubst %.cpp,$(OBJ)/host/%.o,$(HOST_SRC))
 CUDA_OBJ := $(patsubst %.cu,$(OBJ)/cuda/%.o,$(CUDA_SRC))
 
@@ -23,10 +23,10 @@ lib: diamond_b200/libdmnd_b200.so
 cli: diamond_b200/bin/dmnd-b200
 oracle: oracle/_build/libdmnd_oracle.so oracle/_build/dmnd-oracle-cli
 
-$(OBJ)/host/%.o: $(HOST)/%.cpp $(wildcard $(HOST)/*.h) include/dmnd_b200.h
+$(OBJ)/host/%.o: $(HOST)/%.cpp $(wildcard $(HOST)/*.h) $(wildcard $(HOST)/*.inc) include/dmnd_b200.h
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
-$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh $(CUDA)/dev_params.h $(CUDA)/mask_kernels.cuh $(CUDA)/gf_kernels.cuh $(CUDA)/seed_kernels.cuh $(CUDA)/swipe16.cuh $(CUDA)/chain_kernels.cuh include/dmnd_b200.h $(HOST)/motif_table.h
+$(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh $(CUDA)/dev_params.h $(CUDA)/mask_kernels.cuh $(CUDA)/gf_kernels.cuh $(CUDA)/seed_kernels.cuh $(CUDA)/swipe16.cuh $(CUDA)/chain_kernels.cuh $(CUDA)/fs_kernels.cuh include/dmnd_b200.h $(HOST)/motif_table.h
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/cuda/$*.ptxas.log || (cat $(OBJ)/cuda/$*.ptxas.log; false)
 

@@ -63,7 +63,8 @@ class Timing(C.Structure):
 class SearchOpts(C.Structure):
     _fields_ = [("sensitivity", C.c_int32), ("threads", C.c_int32), ("index_chunks", C.c_int32),
                 ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
-                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32), ("query_contexts", C.c_int32), ("top_percent", C.c_double)]
+                ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32), ("query_contexts", C.c_int32), ("top_percent", C.c_double),
+                ("frame_shift", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class Match(C.Structure):
@@ -95,11 +96,14 @@ RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("score", "q_begin", "q_end", "t_be
                         [("transcript_off", "<u4"), ("transcript_len", "<u4"), ("status", "<i4")])
 SEGMENT_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("len", "<i4"), ("score", "<i4")])
 PROBLEM_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("d_begin", "<i4"), ("d_end", "<i4")])
+FS_RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("score", "q_begin", "q_end", "frame_begin", "frame_end", "t_begin", "t_end", "identities", "mismatches",
+                                                  "gap_openings", "length", "gaps", "positives")] +
+                           [("transcript_off", "<u4"), ("transcript_len", "<u4"), ("status", "<i4")])  # dmnd_fs_result
 
 # every symbol include/dmnd_b200.h declares (tests/test_abi.py checks the product library exports them all)
 SYMBOLS = ["dmnd_last_error", "dmnd_set_last_error", "dmnd_backend", "dmnd_ctx_params", "dmnd_create", "dmnd_destroy", "dmnd_ctx_lane", "dmnd_block_upload",
            "dmnd_block_upload_ranges", "dmnd_block_range_wait", "dmnd_block_compute_bias_range", "dmnd_block_free", "dmnd_block_set_bias", "dmnd_block_download_letters", "dmnd_debug_block_soft", "dmnd_debug_ref_index", "dmnd_debug_left_most", "dmnd_block_build_index", "dmnd_block_compute_bias", "dmnd_block_download_bias", "dmnd_block_download_bias_async", "dmnd_copy_wait", "dmnd_host_alloc", "dmnd_host_free", "dmnd_hits_xdrop", "dmnd_hits_xdrop_sites", "dmnd_block_clear_seed_mask", "dmnd_block_clear_seed_mask_range", "dmnd_block_mask", "dmnd_block_mask_fetch", "dmnd_hits_gapped_filter", "dmnd_comm_unique_id", "dmnd_comm_init", "dmnd_comm_destroy", "dmnd_block_broadcast", "dmnd_block_alloc_empty", "dmnd_block_geometry", "dmnd_block_download_limits", "dmnd_hits_chain", "dmnd_hits_chain_fetch", "dmnd_banded_swipe_chained",
-           "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe",
+           "dmnd_search_shape", "dmnd_search_shape_range", "dmnd_hits_count", "dmnd_hits_download", "dmnd_hits_free", "dmnd_banded_swipe", "dmnd_banded_3frame_swipe",
            "dmnd_timing_fetch", "dmnd_measure_int_peak", "dmnd_measure_int_peak_packed", "dmnd_search_opts_default", "dmnd_mode_motif_masking", "dmnd_params_init", "dmnd_blastp", "dmnd_blastp_resident",
            "dmnd_result_matches", "dmnd_result_transcripts", "dmnd_result_stats", "dmnd_result_masked_positions", "dmnd_result_unaligned", "dmnd_result_free"]
 
@@ -136,6 +140,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dmnd_hits_chain.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.dmnd_hits_chain_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.dmnd_banded_swipe_chained.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t]
+    lib.dmnd_banded_3frame_swipe.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t]
     lib.dmnd_hits_gapped_filter.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
     lib.dmnd_block_clear_seed_mask.argtypes = [vp, vp]
     lib.dmnd_block_build_index.argtypes = [vp, vp, C.c_int]
@@ -205,7 +210,7 @@ class Context:
 
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
                  comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
-                 masking: int = 0, motif_masking: int = 0, sensitivity: int = 0, query_contexts: int = 1):
+                 masking: int = 0, motif_masking: int = 0, sensitivity: int = 0, query_contexts: int = 1, frame_shift: int = 0):
         """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
         wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
         default to the reference's own defaults (1, 1)."""
@@ -222,6 +227,7 @@ class Context:
         self.opts.masking = int(masking)
         self.opts.motif_masking = int(motif_masking)
         self.opts.query_contexts = int(query_contexts)  # 6 = blastx: six translated frames per query in the query block
+        self.opts.frame_shift = int(frame_shift)        # blastx -F: frameshift alignment mode (needs query_contexts = 6)
         self.params = Params()
         self._check(self.lib.dmnd_params_init(C.byref(self.opts), C.byref(self.params)))
         self.ctx = C.c_void_p()
@@ -370,6 +376,15 @@ class Context:
                                                res.ctypes.data, tr.ctypes.data if tr is not None else None, transcript_cap))
         return res, tr
 
+    def banded_3frame_swipe(self, qb, rb, problems: np.ndarray, frame_shift: int, traceback: bool, transcript_cap: int = 0):
+        """dmnd_banded_3frame_swipe: problems[k].query = block id of the strand's first frame (6 q or 6 q + 3)."""
+        problems = np.ascontiguousarray(problems, dtype=PROBLEM_DTYPE)
+        res = np.zeros(len(problems), dtype=FS_RESULT_DTYPE)
+        tr = np.zeros(transcript_cap, dtype=np.uint8) if transcript_cap else None
+        self._check(self.lib.dmnd_banded_3frame_swipe(self.ctx, qb, rb, problems.ctypes.data, len(problems), int(frame_shift), 1 if traceback else 0,
+                                                      res.ctypes.data, tr.ctypes.data if tr is not None else None, transcript_cap))
+        return res, tr
+
     def timing(self, reset: bool = False) -> dict:
         t = Timing()
         self.lib.dmnd_timing_fetch(self.ctx, C.byref(t), int(reset))
@@ -478,11 +493,11 @@ def _codon_tables():
     return fwd, rev
 
 
-def translate_reads(reads) -> tuple[np.ndarray, np.ndarray]:
+def translate_reads(reads, frame_shift: int = 0) -> tuple[np.ndarray, np.ndarray]:
     """Flat letters + offsets of the query block of a blastx run: for read s the contexts 6s..6s+5 = frames +1 +2 +3, -1 -2 -3
     (util/sequence/translate.h:58-100), with every stop-to-stop stretch shorter than Config::min_orf_len X-ed out
     (data/block/block.cpp:86-100, util/sequence/sequence.cpp:180-197).  Pass the result to block_image() and run the
-    context with query_contexts=6."""
+    context with query_contexts=6.  frame_shift != 0 (blastx -F): no ORF masking (Config::min_orf_len returns 1, basic/config.h:413-416)."""
     fwd, rev = _codon_tables()
     code = {c: i for i, c in enumerate("ACGTN")}
     code.update({c: 4 for c in "MRWSYKVHDBX"})
@@ -502,7 +517,7 @@ def translate_reads(reads) -> tuple[np.ndarray, np.ndarray]:
                 p = L - 3 - (3 * np.arange(n) + f)
                 fr.append(rev[d[p + 2], d[p + 1], d[p]])
         l0 = len(fr[0])
-        min_len = 1 if l0 < 30 else 20 if l0 < 100 else 40
+        min_len = 1 if (l0 < 30 or frame_shift) else 20 if l0 < 100 else 40
         for v in fr:
             v = v.copy()
             stops = np.flatnonzero(v == 24).tolist()
@@ -561,7 +576,8 @@ def fmt6_translated(matches: np.ndarray, read_lens, q_prefix: str = "r", d_prefi
     out = []
     for m in matches:
         s, f = divmod(int(m["query"]), 6)
-        b, e, L = 3 * int(m["q_begin"]) + f % 3, 3 * int(m["q_end"]) + f % 3, int(read_lens[s])
+        fe = int(m["reserved"]) - 1 if int(m["reserved"]) else f  # frameshift mode: the frame the alignment ENDS in (Hsp::set_end, basic/hssp.cpp:208-217)
+        b, e, L = 3 * int(m["q_begin"]) + f % 3, 3 * int(m["q_end"]) + fe % 3, int(read_lens[s])
         qs, qe = (b + 1, e) if f < 3 else (L - b, L - e + 1)
         ev = "0.0" if m["evalue"] == 0.0 else "%.2e" % m["evalue"]
         out.append("%s%d\t%s%d\t%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (

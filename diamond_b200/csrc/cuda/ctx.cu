@@ -168,7 +168,7 @@ int dmnd_create(int device, const dmnd_params* params, dmnd_ctx** out) {
 	DMND_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
 	DevParams& d = c->h_dev_params;
 	std::memset(&d, 0, sizeof d);
-	d.one = 1; d.k65536 = 65536;
+	d.one = 1; d.k65536 = 65536; d.neg2 = 0x80008000u;
 	std::memcpy(d.score, params->score, 1024);
 	std::memcpy(d.reduction, params->reduction, 32);
 	std::memcpy(d.map8, params->map8, 32);

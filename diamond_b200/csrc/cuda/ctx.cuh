@@ -110,7 +110,7 @@ struct dmnd_ctx {
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1;  // NCCL communicator of dmnd_comm_init (comm.cu)
 	bool force_generic_dp = false;
 	bool force_int32_dp = false;     // the packed 16-bit kernel overflowed: this call runs on the int32 kernels
-	int16_t* d_s16_table = nullptr;   // shared score table of swipe16_kernel (swipe16.cuh), built once per context
+	uint8_t* d_s16_table = nullptr;   // global image of the score table of swipe16_kernel (swipe16.cuh), built once per context
 	bool s16_ok = false;
 	uint64_t dp_overflows = 0;       // calls repeated on the int32 kernels
 	uint64_t dp_cells_score = 0, dp_cells_trace = 0, dp_cells_padded = 0;  // cells of the problems LAUNCHED (score-only / traceback kernels) and what the register tiles evaluate for them

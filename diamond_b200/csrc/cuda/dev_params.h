@@ -30,6 +30,7 @@ struct DevParams {
 	float tantan_b2b, tantan_f2f, tantan_p_repeat_end, tantan_p_mask;
 	int32_t max_motif_len;
 	uint32_t one, k65536;  // 1 and 65536 as run-time values: products with them are IMADs (FMA pipe) where a constant would become an ALU-pipe add / shift / PRMT (swipe16.cuh)
+	uint32_t neg2;  // 0x80008000 = (-32768, -32768): third operand of the packed bias add of swipe16.cuh (max with it is the identity)
 	uint32_t zero;  // always 0: read into a register where ptxas would otherwise materialise a packed 0 with an extra PRMT per use (swipe16.cuh)
 };
 

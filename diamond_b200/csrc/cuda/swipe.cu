@@ -670,7 +670,7 @@ static int launch_s16_bin(int R, const SwipeArgs& a, const DevParams* P, const S
 }
 
 int s16_table_build(dmnd_ctx* ctx) {
-	DMND_CUDA_CHECK(cudaMalloc(&ctx->d_s16_table, (size_t)S16_TABLE_BYTES + 16));
+	DMND_CUDA_CHECK(cudaMalloc(&ctx->d_s16_table, (size_t)S16_TABLE_ENTRIES + 16));
 	unsigned* d_bad = nullptr;
 	DMND_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(unsigned)));
 	DMND_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(unsigned)));
@@ -766,7 +766,7 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 		if (g < G_LEGACY) {  // packed 16-bit kernel: shared score table + the queries of 4 problems per warp as 16-bit codes
 			R = 4 * (g / 2 + 1);
 			const int qstride = ((int)maxq + 8 * R + 4 + S16_TILE + 7) & ~7;
-			const size_t tab = (size_t)((S16_TABLE_BYTES + 15) & ~15), per_warp = (size_t)4 * (size_t)qstride * 2;
+			const size_t tab = (size_t)((S16_TABLE_BYTES + 15) & ~15), per_warp = (size_t)4 * (size_t)qstride * 4;  // per problem: bias pairs (2 bytes) + codes (16 bit)
 			warps = (int)std::min<size_t>(4, (((size_t)200 << 10) - tab) / per_warp);
 			if (warps < 1) { set_error("dmnd_banded_swipe: query too long for the packed kernel"); return 1; }  // (prep_kernel routes those to the int32 kernels)
 			const size_t smem = tab + per_warp * (size_t)warps;

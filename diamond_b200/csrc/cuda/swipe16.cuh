@@ -12,15 +12,20 @@
 // with the shuffled pair of the adjacent lane.
 //
 // Scores.  Instead of a per-problem score profile (27 x query length bytes, which limited residency to ~20 problems per SM)
-// the CTA holds ONE table in shared memory, T[t][q * 32 + (bias + 16)] = S[t][q] + bias for the 26 target letters, all 32
-// query letter codes and Hauser biases -16..15 (row 26 and the last column are -128: delimiter / outside the query), and
-// each problem only its query as 16-bit table columns ("codes").  A lane keeps the R/2 + 1 codes and R/2 target rows it
-// needs in registers and shifts them by one per macro step: one LDS.S8 per cell, address = row register + code register.
+// the CTA holds ONE table in shared memory: the 27 x 32 matrix S[t][q] + 128 as bytes (row 26 and the query codes >= 26 are 0 =
+// score -128: delimiter / outside the sequence), REPLICATED PER LANE -- entry e = t * 32 + q of lane l lives in byte e & 3 of
+// word (e >> 2) * 32 + l, i.e. in bank l -- so the 32 lanes of a warp, which look up unrelated (t, q) pairs, never meet in a bank
+// (the 55 KB table with the bias folded in that this replaces ran at 3.8 wavefronts per request and kept the shared-memory pipe
+// 87 % busy: profiles/ncu_swipe16_r2b.txt).  A problem keeps its query as byte offsets into a table row ("codes", 16 bit) and its
+// composition bias as packed pairs (bias[i] - 128 | bias[i + R/4] - 128 << 16: the two rows of a register pair are R/4 query
+// positions apart; stored as two bytes, expanded when a lane loads one), so one LDS.U8 per cell + one IMAD packs the two scores of a pair and one VIADDMNMX.S16x2 adds both biases and
+// removes both offsets.  A lane keeps the R/2 + 1 codes, R/4 + 1 bias pairs and R/2 target rows it needs in registers and shifts
+// them by one per macro step.
 //
 // Results are the reference's: H, hgap, vgap floored at 0 (saturating lanes, score_vector_int16.h), trace masks per cell
 // (banded_matrix.h:313-445), end cell = first column of the maximum, then the last row (banded_swipe.h:312-328).  A score
-// that reaches 32767 - 255, a bias outside -16..15 or a table entry outside int8 raises the overflow flag and the caller
-// repeats the call on the exact int32 kernels of swipe.cu -- the reference's int16 -> int32 cascade (banded_swipe.h:337).
+// that reaches 32767 - 255 raises the overflow flag and the caller repeats the call on the exact int32 kernels of swipe.cu --
+// the reference's int16 -> int32 cascade (banded_swipe.h:337).
 #pragma once
 #include "dev_params.h"
 
@@ -66,11 +71,12 @@ __device__ __forceinline__ ProbGeom geom(const SwipeArgs& a, const dmnd_dp_probl
 }
 
 // ---- the shared score table ------------------------------------------------------------------------------------------
-constexpr int S16_NBIAS = 32, S16_BIAS_MIN = -16;
-constexpr int S16_HALO_CODE = 32 * S16_NBIAS;          // column of -128
-constexpr int S16_TW = 32 * S16_NBIAS + 4;             // row stride in entries
-constexpr int S16_TABLE_ENTRIES = 27 * S16_TW;
-constexpr int S16_TABLE_BYTES = 2 * S16_TABLE_ENTRIES; // int16 entries: LDS.U16 + one IMAD packs two cells' scores (an int8 table needs a PRMT on the ALU pipe)
+constexpr int S16_TABLE_ENTRIES = 27 * 32;             // global image: S[t][q] + 128, one byte per entry
+constexpr int S16_TROW = 8 * 32 * 4;                   // bytes of one target-letter row of the lane-replicated table in shared memory
+constexpr int S16_TABLE_BYTES = 27 * S16_TROW;
+constexpr int S16_HALO_Q = 31;                         // query code of a position outside the query (entry 0 = score -128)
+constexpr unsigned S16_HALO_BB = 0xFF80FF80u;          // bias pair of such positions: (0 - 128, 0 - 128)
+__host__ __device__ __forceinline__ int s16_qoff(int q) { return (q >> 2) * 128 + (q & 3); }  // byte offset of query code q inside a table row (+ 4 * lane)
 constexpr int S16_LANES = 8;                           // lanes per problem
 constexpr int S16_MAX_BAND = 128;
 constexpr int S16_TILE = 8;                            // macro steps per trace tile
@@ -82,25 +88,20 @@ __host__ __device__ __forceinline__ int s16_step_bytes(int R) { return 4 * R; }
 // trace bytes of a problem: whole tiles
 __host__ __device__ __forceinline__ unsigned long long s16_trace_bytes(int R, unsigned long long nmacro) { return (nmacro + S16_TILE - 1) / S16_TILE * (unsigned long long)(S16_TILE * 4 * R); }
 
-// Fills the table from the 32 x 32 score matrix (stats/score_matrix.h:35-44 layout).  Returns false through *ok when an entry
-// leaves int8 (then the packed kernel must not be used with this matrix).
-__global__ void s16_table_kernel(const DevParams* __restrict__ P, int16_t* table, unsigned* bad) {
+// Fills the global image of the table from the 32 x 32 score matrix (stats/score_matrix.h:35-44 layout): entry t * 32 + q =
+// S[t][q] + 128 for letters inside the alphabet, 0 (= score -128) elsewhere.  *bad stays 0 (kept for the caller's check).
+__global__ void s16_table_kernel(const DevParams* __restrict__ P, uint8_t* table, unsigned* bad) {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= S16_TABLE_ENTRIES) return;
-	const int t = idx / S16_TW, c = idx - t * S16_TW;
-	int v = -128;
-	if (t < 26 && c < S16_HALO_CODE) {
-		const int ql = c / S16_NBIAS, b = c - ql * S16_NBIAS + S16_BIAS_MIN;
-		const int sc = (int)P->score[(t << 5) | ql];
-		v = sc + b;
-		if (sc == -128) v = -128;  // letter codes outside the alphabet (stats/score_matrix.h:35-44) never occur inside a sequence
-		else if (v > 127 || v < -127) { atomicExch(bad, 1u); v = max(min(v, 127), -127); }
-	}
-	table[idx] = (int16_t)v;
+	const int t = idx >> 5, ql = idx & 31;
+	int v = 0;
+	if (t < 26 && ql < 26) v = (int)P->score[(t << 5) | ql] + 128;
+	if (v < 0 || v > 255) { atomicExch(bad, 1u); v = 0; }
+	table[idx] = (uint8_t)v;
 }
 
 struct S16Args {
-	const int16_t* table;    // S16_TABLE_ENTRIES, global
+	const uint8_t* table;    // S16_TABLE_ENTRIES bytes, global
 	int qstride;             // uint16 elements per problem slot in shared memory, >= max(qlen) + 8 R + 4 of the launch
 	unsigned int* overflow;  // raised when the call has to be repeated on the int32 kernels
 };
@@ -118,32 +119,37 @@ __device__ __forceinline__ unsigned s16_trace_nibble(const uint8_t* tr, int R, i
 	return (~(v >> ((p & 1) * 4))) & 15u;
 }
 
-// one 16-bit table entry, zero-extended, from a shared-memory byte address (tests/emu_cuda.h maps the address back to its arena)
+// one table entry (a byte), zero-extended, from a shared-memory byte address (tests/emu_cuda.h maps the address back to its arena)
 #ifndef DMND_S16_LDS
 __device__ __forceinline__ unsigned s16_lds(unsigned addr) {
-	unsigned short v;
-	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-	return (unsigned)v;
+	unsigned v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
 }
 #endif
 
 template<int R, bool TRACE>
 __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const DevParams* __restrict__ P, const S16Args sa) {
 	DMND_DYN_SMEM(smem16);
-	constexpr int NP = R / 2, U = R / 2, HALO = S16_LANES * R / 2 + S16_TILE, NW = (NP + 3) / 4, FULL = R / 8;  // (the halo covers the steps before m_lo of the first trace tile)
+	constexpr int NP = R / 2, U = R / 2, NB = R / 4, HALO = S16_LANES * R / 2 + S16_TILE, NW = (NP + 3) / 4, FULL = R / 8;  // (the halo covers the steps before m_lo of the first trace tile)
 	static_assert(R % 4 == 0 && R >= 4 && R <= 16, "rows per lane");
-	{  // table: global -> shared, once per CTA
-		const uint4* src = reinterpret_cast<const uint4*>(sa.table);
-		uint4* dst = reinterpret_cast<uint4*>(smem16);
-		for (int i = threadIdx.x; i < S16_TABLE_BYTES / 16; i += blockDim.x) dst[i] = src[i];
-		for (int i = (S16_TABLE_BYTES / 16) * 16 + threadIdx.x; i < S16_TABLE_BYTES; i += blockDim.x) smem16[i] = reinterpret_cast<const int8_t*>(sa.table)[i];
+	{  // table: global -> shared, once per CTA; word (e >> 2) * 32 + l holds the entries 4 (e >> 2) .. + 3 for lane l
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(sa.table);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(smem16);
+		for (int i = threadIdx.x; i < S16_TABLE_BYTES / 4; i += blockDim.x) dst[i] = src[i >> 5];
 	}
 	__syncthreads();
 	const unsigned FULLM = 0xffffffffu;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, gl = lane & 7;
 	const unsigned tab = (unsigned)__cvta_generic_to_shared(smem16);  // byte address of the table in shared memory
 	const unsigned one = P->one, k65536 = P->k65536;
-	uint16_t* qc = reinterpret_cast<uint16_t*>(smem16 + ((S16_TABLE_BYTES + 15) & ~15)) + (size_t)(warp * 4 + sub) * sa.qstride;
+	// per problem slot: qstride bias pairs (two bytes: bias[i] + 128, bias[i + R/4] + 128), then qstride codes (16 bit)
+	uint16_t* bbs = reinterpret_cast<uint16_t*>(smem16 + ((S16_TABLE_BYTES + 15) & ~15) + (size_t)(warp * 4 + sub) * (size_t)sa.qstride * 4);
+	uint16_t* qc = bbs + sa.qstride;
+	// a stored pair (u0 | u1 << 8) becomes the packed operand (u0 - 256 | (u1 - 256) << 16) = (bias - 128, bias' - 128): one PRMT spreads the bytes,
+	// one OR sets the two high bytes
+	auto bb_expand = [](unsigned v) { return __byte_perm(v, 0u, 0x4140u) | 0xFF00FF00u; };
+	const unsigned neg2 = P->neg2;  // (-32768, -32768): the no-op third operand of the packed bias add (a run-time value keeps it a register operand)
 	const unsigned go2 = (unsigned)(P->gap_open + P->gap_extend) * 0x00010001u, ge = (unsigned)P->gap_extend;
 	const unsigned nge2 = (0x10000u - ge) * 0x00010001u & 0xffffffffu;  // (-ge, -ge)
 	const unsigned selF = gl == 0 ? 0x54DDu : 0x5432u, selE = gl == S16_LANES - 1 ? 0xBB32u : 0x5432u;
@@ -162,23 +168,19 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		ProbGeom g = geom(a, pr);
 		if (!have) { g.B = 0; g.cols = 0; }
 		const bool live = g.B > 0 && g.cols > 0;
-		// ---- the query as table columns
+		// ---- the query as table columns and bias pairs
 		__syncwarp();
-		bool ok = true;
 		if (live) {
 			const int W = g.qlen + 8 * R + 4 + S16_TILE;
 			for (int idx = gl; idx < W; idx += S16_LANES) {
-				const int i = idx - HALO;
-				int code = S16_HALO_CODE;
-				if (i >= 0 && i < g.qlen) {
-					const int b = (int)g.cb[i] - S16_BIAS_MIN;
-					if ((unsigned)b >= (unsigned)S16_NBIAS) ok = false;
-					code = (g.q[i] & 31) * S16_NBIAS + min(max(b, 0), S16_NBIAS - 1);
-				}
-				qc[idx] = (uint16_t)(2 * code);  // byte offset inside a table row
+				const int i = idx - HALO, i2 = i + NB;
+				int code = s16_qoff(S16_HALO_Q), b0 = 0, b1 = 0;
+				if (i >= 0 && i < g.qlen) { code = s16_qoff(g.q[i] & 31); b0 = (int)g.cb[i]; }
+				if (i2 >= 0 && i2 < g.qlen) b1 = (int)g.cb[i2];
+				qc[idx] = (uint16_t)code;  // byte offset inside a table row
+				bbs[idx] = (uint16_t)((unsigned)(b0 + 128) | ((unsigned)(b1 + 128) << 8));
 			}
 		}
-		if (!__all_sync(FULLM, ok) && lane == 0) atomicExch(sa.overflow, 1u);
 		__syncwarp();
 		// ---- geometry of the wavefront
 		const int ibase = g.j0 + g.d_begin;
@@ -202,21 +204,25 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 		unsigned H[NP], E[NP], F[NP], best[NP];
 #pragma unroll
 		for (int j = 0; j < NP; ++j) { H[j] = 0; E[j] = 0; F[j] = 0; best[j] = 0; }
-		auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return (int)tab + min((int)(g.t[jj] & 31), 26) * (2 * S16_TW); };  // byte address of the letter's row
+		auto trow_of = [&](int j) { const int jj = min(max(j, -1), g.tlen); return (int)tab + 4 * lane + min((int)(g.t[jj] & 31), 26) * S16_TROW; };  // byte address of the letter's row in this lane's bank
 		int trow[U];
-		unsigned qreg[U + 1];
+		unsigned qreg[U + 1], bbreg[NB + 1];
 		int I0 = ibase + m0 + lofs + HALO;  // code index of row u = 0 (even k); odd k reads one further
 		if (live) {
 #pragma unroll
 			for (int u = 0; u < U; ++u) trow[u] = trow_of(g.j0 + m0 - lofs - u);
 #pragma unroll
 			for (int v = 0; v <= U; ++v) qreg[v] = qc[I0 + v];
+#pragma unroll
+			for (int v = 0; v <= NB; ++v) bbreg[v] = bb_expand(bbs[I0 + v]);
 		}
 		else {
 #pragma unroll
-			for (int u = 0; u < U; ++u) trow[u] = (int)tab + 26 * (2 * S16_TW);
+			for (int u = 0; u < U; ++u) trow[u] = (int)tab + 4 * lane + 26 * S16_TROW;
 #pragma unroll
-			for (int v = 0; v <= U; ++v) qreg[v] = 2 * S16_HALO_CODE;
+			for (int v = 0; v <= U; ++v) qreg[v] = (unsigned)s16_qoff(S16_HALO_Q);
+#pragma unroll
+			for (int v = 0; v <= NB; ++v) bbreg[v] = S16_HALO_BB;
 			I0 = 0;
 		}
 		uint8_t* tr = (TRACE && live) ? a.trace + (a.trace_excl[a.order_pos0 + slot] - a.trace_base) : nullptr;
@@ -229,9 +235,9 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 		for (int ts = 0; ts < S16_TILE; ++ts) {
 			const bool active = m < m_hi;
-			int tnext = (int)tab + 26 * (2 * S16_TW);
-			unsigned qnext = 2 * S16_HALO_CODE;
-			if (active) { tnext = trow_of(g.j0 + m + 1 - lofs); qnext = qc[I0 + U + 1]; }
+			int tnext = (int)tab + 4 * lane + 26 * S16_TROW;
+			unsigned qnext = (unsigned)s16_qoff(S16_HALO_Q), bbnext = S16_HALO_BB;
+			if (active) { tnext = trow_of(g.j0 + m + 1 - lofs); qnext = qc[I0 + U + 1]; bbnext = bb_expand(bbs[I0 + NB + 1]); }
 			unsigned pk[NW];
 #pragma unroll
 			for (int x = 0; x < NW; ++x) pk[x] = 0;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 				for (int j = 0; j < NP; j += 2) {
 					const int ul = j >> 1, uh = ul + R / 4;
-					const unsigned sc = s16_lds((unsigned)trow[uh] * one + qreg[uh]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul]);
+					const unsigned sc = __viaddmax_s16x2(s16_lds((unsigned)trow[uh] * one + qreg[uh]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul]), bbreg[ul], neg2);
 					const unsigned e_in = E[j + 1], f_in = j > 0 ? F[j > 0 ? j - 1 : 0] : f_edge;
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
 					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 				for (int j = 1; j < NP; j += 2) {
 					const int ul = j >> 1, uh = ul + R / 4;
-					const unsigned sc = s16_lds((unsigned)trow[uh] * one + qreg[uh + 1]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul + 1]);
+					const unsigned sc = __viaddmax_s16x2(s16_lds((unsigned)trow[uh] * one + qreg[uh + 1]) * k65536 + s16_lds((unsigned)trow[ul] * one + qreg[ul + 1]), bbreg[ul + 1], neg2);
 					const unsigned e_in = j + 1 < NP ? E[j + 1 < NP ? j + 1 : 0] : e_edge, f_in = F[j - 1];
 					const unsigned h = __vimax_s16x2_relu(__viaddmax_s16x2(H[j], sc, e_in), f_in);
 					const unsigned open = __viaddmax_s16x2_relu(h, GO2[j], zero2);
@@ -290,6 +296,9 @@ __global__ void __launch_bounds__(128) swipe16_kernel(const SwipeArgs a, const D
 #pragma unroll
 			for (int v = 0; v < U; ++v) qreg[v] = qreg[v + 1];
 			qreg[U] = qnext;
+#pragma unroll
+			for (int v = 0; v < NB; ++v) bbreg[v] = bbreg[v + 1];
+			bbreg[NB] = bbnext;
 			if (active) { ++I0; ++m; }
 			ckLo -= 2u; ckHi -= 2u;
 		}

@@ -113,7 +113,7 @@ int8_t encode_dna(char c) {  // nucleotide_traits (stats/stats.cpp:42): "ACGTN",
 	}
 }
 
-struct TranslateOpts { int strand_mask = 63, min_orf = 0, gencode = 1; };  // --strand, --min-orf (0 = Config::min_orf_len's rule), --query-gencode
+struct TranslateOpts { int strand_mask = 63, min_orf = 0, gencode = 1, frame_shift = 0; };  // --strand, --min-orf (0 = Config::min_orf_len's rule), --query-gencode, -F
 
 // NCBI translation tables (the ids --query-gencode accepts, basic/basic.cpp:86-113), TCAG order; nullptr = no such table
 const char* genetic_code(int id) {
@@ -169,7 +169,7 @@ void push_translated(const std::vector<int8_t>& dna, SeqBlock& b, const Translat
 		}
 	}
 	const size_t l0 = fr[0].size();
-	const size_t min_len = to.min_orf > 0 ? (size_t)to.min_orf : (l0 < 30 ? 1 : (l0 < 100 ? 20 : 40));  // Config::min_orf_len (basic/config.h:413-424)
+	const size_t min_len = to.min_orf > 0 ? (size_t)to.min_orf : ((l0 < 30 || to.frame_shift != 0) ? 1 : (l0 < 100 ? 20 : 40));  // Config::min_orf_len (basic/config.h:413-424): no ORF masking in frameshift mode
 	for (int f = 0; f < 6; ++f) {
 		std::vector<int8_t>& v = fr[f];
 		if (!((to.strand_mask >> f) & 1)) std::fill(v.begin(), v.end(), (int8_t)23);  // a strand that is not searched: the frame stays, all X (block.cpp:95-96)
@@ -447,7 +447,7 @@ int main(int argc, char** argv) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
 			const char* attached = nullptr;
-			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdob", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
+			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdobF", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
 			auto val = [&]() -> const char* { if (attached) return attached; if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
 			if (a == "-q" || a == "--query") qf = val();
 			else if (a == "-d" || a == "--db") df = val();
@@ -508,6 +508,7 @@ int main(int argc, char** argv) {
 			}
 			else if (a == "--min-orf" || a == "-l") { min_orf = atoi(val()); if (min_orf < 0) usage("--min-orf must not be negative"); }
 			else if (a == "--query-gencode") gencode = atoi(val());
+			else if (a == "-F" || a == "--frameshift") { o.frame_shift = atoi(val()); if (o.frame_shift <= 0) usage("--frameshift needs a positive penalty (the reference's usual value is 15)"); }
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
@@ -526,7 +527,14 @@ int main(int argc, char** argv) {
 		SeqBlock q, r;
 		DnaQueries dq;
 		if (!translated && (strand_mask != 63 || min_orf != 0 || gencode != 1)) usage("--strand, --min-orf and --query-gencode belong to blastx");
-		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode });
+		if (o.frame_shift && !translated) usage("Frameshift alignments are only supported for translated searches.");  // basic/config.cpp:822-823
+		const bool fshift = o.frame_shift != 0;
+		if (fshift) {
+			o.want_transcript = 1;  // output/output_format.cpp:256-257
+			if (paf || sam || block_size != 0.0) usage("--frameshift: -f sam, -f paf and -b are not implemented in this mode");
+			for (const std::string& f : fields) if (f == "qseq" || f == "sseq" || f == "qcovhsp" || f == "positive" || f == "ppos") usage(("--frameshift: output field " + f + " is not implemented in this mode").c_str());
+		}
+		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode, o.frame_shift });
 		else read_fasta(qf, q);
 		const uint32_t nq_block = translated ? (uint32_t)dq.ids.size() * 6u : q.size();
 		if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
@@ -652,11 +660,41 @@ int main(int argc, char** argv) {
 			}
 			m = joined.data(); n = joined.size(); tr = joined_tr.data();
 		}
+		// frameshift mode: the legacy pipeline visits EVERY query, also those without a seed hit (align/align.cpp:120-130,168-172), so every
+		// query without an alignment is reported by the formats that report unaligned queries
+		std::vector<uint32_t> fs_unal;
+		if (fshift) {
+			size_t mi = 0;
+			for (uint32_t sq = 0; sq < (uint32_t)dq.ids.size(); ++sq) {
+				while (mi < n && m[mi].query / 6 < sq) ++mi;
+				if (!(mi < n && m[mi].query / 6 == sq)) fs_unal.push_back(6 * sq);
+			}
+		}
 		auto result_unaligned = [&](size_t* nu) -> const uint32_t* {
+			if (fshift) { *nu = fs_unal.size(); return fs_unal.data(); }
 			if (nblocks > 1) { *nu = joined_unal.size(); return joined_unal.data(); }
 			return dmnd_result_unaligned(res, nu);
 		};
 		static const char* alphabet = "ARNDCQEGHILKMFPSTWYVBJZX*_";
+		// Hsp::Iterator (basic/match.h:105-161) over a transcript: qat[k] = the query letter transcript byte k consumes (match, substitution,
+		// insertion), -1 / -2 for a forward / reverse frameshift byte (the query position moves one nucleotide on / back: the frame of the
+		// letters after it changes, TranslatedPosition::shift_forward / shift_back), 0 for a deletion.  qcur = position after byte k:
+		// codon index * 3 + frame offset inside the strand (TranslatedPosition::in_strand).  Without frameshift bytes this is qs[qi++].
+		std::vector<int> qat, qcur;
+		auto walk_query = [&](const dmnd_match& x, const uint8_t* t) {
+			qat.assign(x.transcript_len, 0); qcur.assign((size_t)x.transcript_len + 1, 0);
+			const uint32_t c0 = x.query - (translated ? x.query % 3 : 0);  // first frame of the strand
+			int off = translated ? (int)(x.query % 3) : 0, pos = x.q_begin;
+			qcur[0] = 3 * pos + off;
+			for (uint32_t k = 0; k < x.transcript_len; ++k) {
+				const uint8_t b = t[k];
+				if (b == DMND_TR_FRAMESHIFT_FWD) { qat[k] = -1; if (++off == 3) { off = 0; ++pos; } }
+				else if (b == DMND_TR_FRAMESHIFT_REV) { qat[k] = -2; if (--off < 0) { off = 2; --pos; } }
+				else if ((b >> 6) != DMND_OP_DELETION) { qat[k] = q.letters[(size_t)q.limits[c0 + (uint32_t)off] + (size_t)pos] & 31; ++pos; }
+				qcur[k + 1] = 3 * pos + off;
+			}
+		};
+		auto end_frame = [&](const dmnd_match& x) -> int { return x.reserved ? (int)x.reserved - 1 : (int)(x.query % 6); };  // frame the alignment ends in
 		FILE* out = fopen(of.c_str(), "wb");
 		if (!out) throw std::runtime_error("Error opening file " + of);
 		char buf[32];
@@ -813,21 +851,28 @@ int main(int argc, char** argv) {
 				line += "\n";
 				auto qpos_first = [&](int p) -> int64_t { return !translated ? p + 1 : (fr < 3 ? 3 * (int64_t)p + off + 1 : L - 3 * (int64_t)p - off); };  // the line's first letter
 				auto qpos_end = [&](int p) -> int64_t { return !translated ? p : (fr < 3 ? 3 * (int64_t)p + off : L - 3 * (int64_t)p - off + 1); };       // after its last one (p = next position)
-				const int64_t q_src_end = !translated ? x.q_end : (fr < 3 ? 3 * (int64_t)x.q_end + off : L - (3 * (int64_t)x.q_begin + off));
+				const int64_t q_src_end = !translated ? x.q_end : (fr < 3 ? 3 * (int64_t)x.q_end + end_frame(x) % 3 : L - (3 * (int64_t)x.q_begin + off));
 				const unsigned digits = (unsigned)std::max(std::ceil(std::log10((double)x.t_end)), std::ceil(std::log10((double)q_src_end)));
-				int qi = x.q_begin, si = x.t_begin;
+				(void)qpos_first; (void)qpos_end; (void)qs;
+				walk_query(x, t);
+				// line numbers from the in-strand position (3 * codon + frame offset): first letter TranslatedPosition::absolute + 1, after the
+				// last one oriented_position(in_strand - 1) + 1 (blast_pairwise_format.cpp:54-63)
+				auto in_first = [&](int in) -> int64_t { return !translated ? in / 3 + 1 : (fr < 3 ? (int64_t)in + 1 : L - in); };
+				auto in_end = [&](int in) -> int64_t { return !translated ? in / 3 : (fr < 3 ? (int64_t)in : L - in + 1); };
+				int si = x.t_begin;
 				for (uint32_t k0 = 0; k0 < x.transcript_len; k0 += 60) {
 					const uint32_t k1 = std::min<uint32_t>(k0 + 60, x.transcript_len);
 					std::string ql, ml, sl;
-					const int q0 = qi, s0 = si;
+					const int s0 = si;
 					for (uint32_t k = k0; k < k1; ++k) {
 						const int op = t[k] >> 6, sc = t[k] & 63;
-						if (op == DMND_OP_MATCH) { const char c = alphabet[qs[qi] & 31]; ql += c; ml += c; sl += c; ++qi; ++si; }
-						else if (op == DMND_OP_SUBSTITUTION) { const int a = qs[qi] & 31; ql += alphabet[a]; sl += alphabet[sc]; ml += pp->score[a * 32 + sc] > 0 ? '+' : ' '; ++qi; ++si; }
-						else if (op == DMND_OP_INSERTION) { ql += alphabet[qs[qi] & 31]; sl += '-'; ml += ' '; ++qi; }
+						if (qat[k] < 0) { ql += qat[k] == -1 ? '\\' : '/'; sl += '-'; ml += ' '; }
+						else if (op == DMND_OP_MATCH) { const char c = alphabet[qat[k]]; ql += c; ml += c; sl += c; ++si; }
+						else if (op == DMND_OP_SUBSTITUTION) { const int a = qat[k]; ql += alphabet[a]; sl += alphabet[sc]; ml += pp->score[a * 32 + sc] > 0 ? '+' : ' '; ++si; }
+						else if (op == DMND_OP_INSERTION) { ql += alphabet[qat[k]]; sl += '-'; ml += ' '; }
 						else { ql += '-'; sl += alphabet[sc]; ml += ' '; ++si; }
 					}
-					line += "Query  "; put_num((unsigned)qpos_first(q0), digits); line += "  " + ql + " " + std::to_string(qpos_end(qi)) + "\n";
+					line += "Query  "; put_num((unsigned)in_first(qcur[k0]), digits); line += "  " + ql + " " + std::to_string(in_end(qcur[k1])) + "\n";
 					line.append(digits + 9, ' '); line += ml + "\n";
 					line += "Sbjct  "; put_num((unsigned)s0 + 1, digits); line += "  " + sl + " " + std::to_string(si) + "\n\n";
 				}
@@ -883,7 +928,7 @@ int main(int argc, char** argv) {
 					// TranslatedPosition::absolute_interval (basic/translated_position.h:121-127): in-strand = 3 * translated + frame offset;
 					// a reverse-strand range is mirrored, and printed from its high end (output/blast_tab_format.cpp, query_source_range)
 					const int fr = (int)(x.query % 6), off = fr % 3, L = dq.len[x.query / 6];
-					const int b_in = 3 * x.q_begin + off, e_in = 3 * x.q_end + off;
+					const int b_in = 3 * x.q_begin + off, e_in = 3 * x.q_end + end_frame(x) % 3;  // Hsp::set_begin / set_end (basic/hssp.cpp:197-217): begin and end in their own frames
 					if (fr < 3) line += std::to_string(f == "qstart" ? b_in + 1 : e_in);
 					else line += std::to_string(f == "qstart" ? L - b_in : L - e_in + 1);
 				}
@@ -928,34 +973,36 @@ int main(int argc, char** argv) {
 				else if (f == "nident") line += std::to_string(x.identities);
 				else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[x.query / 6] : q.limits[x.query + 1] - q.limits[x.query] - 1);
 				else if (f == "slen") line += std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1);
-				else if (f == "cigar") {  // print_cigar, output/sam_format.cpp:67-83: match and substitution are both M
+				else if (f == "cigar") {  // print_cigar, output/sam_format.cpp:67-83: match and substitution are both M, frameshifts \ and /
 					uint32_t run = 0; int op = -1;
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
-						const int o2 = t[k] >> 6, c = (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;
-						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID"[op]; } run = 1; op = c; }
+						const int o2 = t[k] >> 6, c = t[k] == DMND_TR_FRAMESHIFT_FWD ? 3 : t[k] == DMND_TR_FRAMESHIFT_REV ? 4 : (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;
+						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID\\/"[op]; } run = 1; op = c; }
 					}
-					if (run) { line += std::to_string(run); line += "MID"[op]; }
+					if (run) { line += std::to_string(run); line += "MID\\/"[op]; }
 				}
 				else if (f == "btop") {  // output/blast_tab_format.cpp:365-398
-					uint32_t nm = 0; int qi = x.q_begin;
+					uint32_t nm = 0;
+					walk_query(x, t);
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
 						const int o2 = t[k] >> 6;
-						if (o2 == DMND_OP_MATCH) { ++nm; ++qi; continue; }
+						if (o2 == DMND_OP_MATCH) { ++nm; continue; }
 						if (nm) { line += std::to_string(nm); nm = 0; }
-						if (o2 == DMND_OP_SUBSTITUTION) { line += alphabet[qs[qi++] & 31]; line += alphabet[t[k] & 63]; }
-						else if (o2 == DMND_OP_INSERTION) { line += alphabet[qs[qi++] & 31]; line += '-'; }
+						if (qat[k] < 0) { line += qat[k] == -1 ? '\\' : '/'; line += '-'; }
+						else if (o2 == DMND_OP_SUBSTITUTION) { line += alphabet[qat[k]]; line += alphabet[t[k] & 63]; }
+						else if (o2 == DMND_OP_INSERTION) { line += alphabet[qat[k]]; line += '-'; }
 						else { line += '-'; line += alphabet[t[k] & 63]; }
 					}
 					if (nm) line += std::to_string(nm);
 				}
 				else if (f == "qseq_gapped" || f == "sseq_gapped") {
 					const bool query_side = f[0] == 'q';
-					int qi = x.q_begin;
+					walk_query(x, t);
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
 						const int o2 = t[k] >> 6;
-						const char qc = (o2 == DMND_OP_DELETION) ? '-' : alphabet[qs[qi] & 31];
-						const char sc = (o2 == DMND_OP_INSERTION) ? '-' : (o2 == DMND_OP_MATCH ? alphabet[qs[qi] & 31] : alphabet[t[k] & 63]);
-						if (o2 != DMND_OP_DELETION) ++qi;
+						if (qat[k] < 0) { line += query_side ? (qat[k] == -1 ? '\\' : '/') : '-'; continue; }  // HspContext::Iterator::query_char / subject_char
+						const char qc = (o2 == DMND_OP_DELETION) ? '-' : alphabet[qat[k]];
+						const char sc = (o2 == DMND_OP_INSERTION) ? '-' : (o2 == DMND_OP_MATCH ? alphabet[qat[k]] : alphabet[t[k] & 63]);
 						line += query_side ? qc : sc;
 					}
 				}

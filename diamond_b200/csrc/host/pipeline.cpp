@@ -209,6 +209,7 @@ struct Target {  // align/target.h:83-144 after inner_culling (max_hsps == 1): o
 struct Match {  // align/extend.h:36-70
 	uint32_t target_block_id; int tlen; int filter_score; double filter_evalue; bool has_hsp; HspLite h; dmnd_dp_result r;
 	uint64_t tr_off; uint32_t tr_len;  // into the owner thread's transcript buffer
+	uint32_t end_frame;                // frameshift mode: 1 + context offset (0..5) of the frame the alignment ends in; 0 otherwise
 	static bool cmp_score(const Match& m, const Match& n) { return m.filter_score > n.filter_score || (m.filter_score == n.filter_score && m.target_block_id < n.target_block_id); }  // align/extend.h:50-52
 	static bool cmp_evalue(const Match& m, const Match& n) {
 		return m.filter_evalue < n.filter_evalue || (m.filter_evalue == n.filter_evalue && (m.filter_score > n.filter_score || (m.filter_score == n.filter_score && m.target_block_id < n.target_block_id)));
@@ -279,6 +280,7 @@ struct Env {
 	int n_shapes = 1;   // shapes of the sensitivity mode (search/setup.cpp:80-304): one dmnd_search_shape per shape
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
 	uint32_t contexts = 1;  // align_mode.query_contexts: 6 = blastx, the query block holds the six frames of every query back to back
+	int frame_shift = 0;    // config.frame_shift: > 0 = frameshift alignment mode, the legacy extension pipeline (align/align.cpp:168-172)
 	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
 	const int8_t* rseq(uint32_t t) const { const int8_t* p = r_patch ? r_patch->find(t) : nullptr; return p ? p : r_letters + r_limits[t]; }
 	const int64_t *q_limits, *r_limits;
@@ -466,6 +468,13 @@ struct Driver {
 	void finish_round2(QueryState& q, ThreadCtx& tc);
 	void finish_outer(QueryState& q);
 	int run_waves();
+	// frameshift alignment mode (legacy.inc)
+	std::vector<struct LegacyQuery> lq;
+	void legacy_init(size_t k, QueryState& q, ThreadCtx& tc, Workspace::HitSeg* begin, Workspace::HitSeg* end);
+	void legacy_produce(LegacyQuery& L, const QueryState& q, ThreadCtx& tc, bool score_only);
+	void legacy_consume_scores(LegacyQuery& L, const QueryState& q, const dmnd_fs_result* res);
+	void legacy_consume_trace(LegacyQuery& L, QueryState& q, ThreadCtx& tc, const dmnd_fs_result* res, const uint8_t* tr);
+	int run_legacy();
 };
 
 // std::stable_sort without its temporary-buffer allocation for the short lists that dominate (insertion sort is stable)
@@ -883,6 +892,8 @@ int Driver::run_waves() {
 	return 0;
 }
 
+#include "legacy.inc"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1113,7 +1124,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	// The bridge from hits to DP problems runs on the device (dmnd_hits_chain) for single-shape blastp without a gapped filter:
 	// the hits never come to the host, the round-1 problem list of every query with <= 64 targets is produced and aligned in HBM,
 	// and only queries with ranking chunks (or pairs beyond the device code's capacities) take the host code below.
-	const bool bridge = n_shapes == 1 && env.fuse && env.contexts == 1 && !env.gapped_filter && getenv("DMND_HOST_BRIDGE") == nullptr;
+	const bool bridge = n_shapes == 1 && env.fuse && env.contexts == 1 && !env.gapped_filter && !env.frame_shift && getenv("DMND_HOST_BRIDGE") == nullptr;
 	dmnd_chain_out co;
 	std::memset(&co, 0, sizeof co);
 	if (n_shapes == 1) {
@@ -1257,6 +1268,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	d.nq_hit = nqh;
 	w.qs.resize(nqh);
 	w.hs.resize(nh);
+	if (env.frame_shift) { d.lq.clear(); d.lq.resize(nqh); }
 	prof.lap("group queries");
 	w.run([&](int t) {
 		ThreadCtx& tc = w.tc[(size_t)t];
@@ -1265,6 +1277,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 			QueryState& q = w.qs[k];
 			q.qid = w.hv[w.qstart[k]].query / C * C;
 			for (size_t x = w.qstart[k]; x < w.qstart[k + 1]; ++x) { w.hs[x].h = w.hv[x]; w.hs[x].s = w.segv[x]; w.hs[x].site = w.sitev[x]; w.hs[x].gf = w.gfv[x]; }
+			if (env.frame_shift) { d.legacy_init(k, q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]); continue; }
 			d.load_hits(q, tc, w.hs.data() + w.qstart[k], w.hs.data() + w.qstart[k + 1]);
 			d.start(q, tc);
 		}
@@ -1274,7 +1287,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	prof.lap("load_hits (parallel)");
 	}
 
-	if (d.run_waves()) return 1;
+	if (env.frame_shift ? d.run_legacy() : d.run_waves()) return 1;
 	prof.lap("run_waves");
 
 	// ---- emit: per-thread counts -> offsets -> parallel fill (matches grouped by ascending query)
@@ -1313,6 +1326,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 				o->identities = m.r.identities; o->mismatches = m.r.mismatches; o->gap_openings = m.r.gap_openings;
 				o->length = m.r.length; o->gaps = m.r.gaps; o->positives = m.r.positives;
 				o->transcript_off = troff[(size_t)t] + m.tr_off; o->transcript_len = m.tr_len;
+				o->reserved = m.end_frame;
 				++o;
 			}
 		}
@@ -1416,12 +1430,20 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	if (opts->top_percent >= 0.0 && opts->top_percent < 100.0) e.top = opts->top_percent;
 	else if (opts->top_percent == 100.0) e.max_target_seqs = INT_MAX;  // output/output_format.cpp:233-240: --top 100 = every target, ranked by e-value
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
+	e.frame_shift = opts->frame_shift;
+	if (e.frame_shift < 0 || (e.frame_shift > 0 && contexts != 6)) { dmnd_set_last_error("dmnd_blastp: frame_shift needs translated queries (query_contexts = 6) and a positive penalty"); return 1; }
+	if (e.frame_shift) {
+		// the legacy pipeline extends without composition bias (align/legacy/query_mapper.cpp:131: xdrop_ungapped(.., nullptr, ..);
+		// banded_3frame_swipe takes no bias at all) and always keeps the transcript (output/output_format.cpp:256-257)
+		e.hauser = false; e.want_transcript = true;
+	}
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
 	{
 		const ModeTraits* mt = mode_traits(opts->sensitivity);
 		if (!mt) { dmnd_set_last_error("dmnd_blastp: bad sensitivity"); return 1; }
 		e.n_shapes = mt->n_shapes; e.gapped_filter = mt->gapped_filter_evalue > 0.0; e.band_slow = mt->band_slow; e.ranking_letters = mt->ranking_letters;
+		if (e.frame_shift) e.gapped_filter = false;  // Extension::gapped_filter belongs to Extension::extend, which frameshift mode does not run
 	}
 	if (mask_algo) {
 		// "Masking reference" (run/double_indexed.cpp:122-127) and the reference block's motif table, before its seed index

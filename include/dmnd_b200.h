@@ -294,6 +294,31 @@ int dmnd_banded_swipe_chained(dmnd_ctx* ctx, const dmnd_block* query, const dmnd
 int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems,
                       size_t n, int mode, dmnd_dp_result* results, uint8_t* transcripts, size_t transcript_cap);
 
+/* ---- frameshift alignment (blastx -F): 3-frame banded DP ------------------------------------------------------------------
+ * banded_3frame_swipe (dp/swipe/banded_3frame_swipe.cpp:392-520, cell update dp/swipe/swipe.h:57-83): one DP over the three reading
+ * frames of one strand of a DNA query against a protein target.  problems[k].query = block id of the strand's first frame (6q for
+ * the forward strand, 6q + 3 for the reverse strand; the next two sequences of the query block are its frames +1 and +2),
+ * d_begin / d_end = band of translated diagonals (i - j, i = codon index).  Cell (codon start x = 3i + f, column j):
+ *   H = max(0, H(x-3, j-1) + s, H(x-4, j-1) + s - F, H(x-2, j-1) + s - F, hgap from (x, j-1), vgap from (x-3, j)),
+ * F = frame_shift, no composition bias (the reference's legacy pipeline passes none).  DMND_DP_SCORE_ONLY fills `score` only
+ * (the caller passes the band its int16 SIMD batch would have had, see host/legacy.cpp); DMND_DP_TRACEBACK keeps the score
+ * matrix and walks it back exactly as the reference does (:338-390, TracebackIterator :152-250), incl. its gap search order.
+ * Transcript bytes as dmnd_banded_swipe, plus DMND_TR_FRAMESHIFT_FWD / _REV (op_frameshift_forward / _reverse; in forward
+ * order such a byte precedes the match column that was reached through the shift). */
+typedef struct dmnd_fs_result {
+	int32_t score;
+	int32_t q_begin, q_end;          /* Hsp::query_range: codon indices, q_begin in frame_begin, q_end in frame_end */
+	int32_t frame_begin, frame_end;  /* frame offsets 0..2 inside the strand (Hsp::set_begin / set_end, basic/hssp.cpp:197-217) */
+	int32_t t_begin, t_end;
+	int32_t identities, mismatches, gap_openings, length, gaps, positives; /* Hsp::push_match / push_gap, basic/hssp.cpp:260-290 */
+	uint32_t transcript_off, transcript_len;
+	int32_t status;                  /* 0 ok; 1 = transcript buffer too small; 2 = "Traceback error" of the reference */
+} dmnd_fs_result;
+#define DMND_TR_FRAMESHIFT_FWD 0x41 /* '\' in the reference's pairwise and btop output */
+#define DMND_TR_FRAMESHIFT_REV 0x42 /* '/' */
+int dmnd_banded_3frame_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n,
+                             int frame_shift, int mode, dmnd_fs_result* results, uint8_t* transcripts, size_t transcript_cap);
+
 /* Device time (ms) spent in the library's own kernels since the last reset, and the number of kernel launches: filled
  * from CUDA events recorded on the context's stream.  A root context reports itself plus its lanes; lanes run
  * concurrently, so their stream times overlap (a serial kernel time needs a single-lane run). */
@@ -335,6 +360,13 @@ typedef struct dmnd_search_opts {
 	                              into dmnd_params.query_contexts: create the context from the same options. */
 	double top_percent;        /* --top: report the targets whose bit score lies within this percentage of the query's best one instead of the
 	                              best max_target_seqs (config.toppercent; align/culling.cpp:90-141, align/extend.cpp:79-92,336); negative = not given */
+	int32_t frame_shift;       /* blastx -F: frame shift penalty (config.frame_shift, 15 when given as 0 in long-read mode); > 0 selects the reference's
+	                              frameshift alignment mode: the legacy extension pipeline (align/align.cpp:168-172, align/legacy/) -- ungapped
+	                              ranking, 3-frame banded DP over seed-hit bands (dmnd_banded_3frame_swipe), no composition bias.  Needs
+	                              query_contexts == 6.  dmnd_match then reports the frame the alignment BEGINS in (query), codon positions in the
+	                              begin / end frames (q_begin, q_end) and the END frame in `reserved` (1 + context offset 0..5); transcripts are
+	                              always kept and may hold DMND_TR_FRAMESHIFT_* bytes.  0 = off */
+	int32_t reserved0;
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

@@ -1196,3 +1196,143 @@ int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 	}
 	return 0;
 }
+
+/* ---- frameshift alignment: banded_3frame_swipe<int32_t, ...> for ONE target (dp/swipe/banded_3frame_swipe.cpp:392-520) ----------
+ * Buffers as the reference keeps them: Banded3FrameSwipeTracebackMatrix (:118-296) = one column of 3*band + 1 scores per target
+ * letter (+ a zero column in front), band index p = 3 * (i - i0(column)) + frame, the last entry of a column stays 0; hgap_ of
+ * 3*band + 3 entries, read at p + 3 and written at p.  The score-only matrix (:43-115) overwrites one column in place and yields
+ * the same cell values (every value is read before its slot is rewritten), so both modes run this one function.  Cell update:
+ * dp/swipe/swipe.h:57-83 on int32_t (saturate = max with 0).  Entries the reference never writes (rows before the query start
+ * other than the three that set_zero clears, rows past the query end) are uninitialised memory there; they are 0 here. */
+static int fs_swipe_one(const dmnd_ctx* ctx, const int8_t* const q[3], const int ql[3], int dna_len, const int8_t* t, int tlen,
+                        int d_begin, int d_end, int F, int mode, dmnd_fs_result* res, uint8_t* tr, size_t tr_cap, size_t* tr_used) {
+	const dmnd_params* p = &ctx->p;
+	memset(res, 0, sizeof *res);
+	const int band = d_end - d_begin, B3 = band * 3, W = B3 + 1;
+	const int i1s = imax(d_end - 1, 0), i0s = i1s + 1 - band, pos0 = i1s - (d_end - 1); /* :410-421, TargetIterator (target_iterator.h:68-92) */
+	const int qlen = ql[0];
+	if (band <= 0 || qlen <= 0 || tlen - pos0 <= 0) return 0;
+	const int ncol = tlen - pos0;
+	int* S = (int*)calloc((size_t)W * ((size_t)ncol + 1), sizeof(int));
+	int* hgap = (int*)calloc((size_t)B3 + 3, sizeof(int));
+	if (!S || !hgap) { free(S); free(hgap); return fail("oracle: out of memory (3-frame swipe)"); }
+	const int go = p->gap_open + p->gap_extend, ge = p->gap_extend;
+	int best = 0, max_col = 0;
+	for (int j = 0, i0 = i0s, i1 = i1s; j < ncol; ++j, ++i0, ++i1) {
+		const int i0_ = imax(i0, 0), i1_ = imin(i1, qlen - 1);
+		if (i0_ > i1_) break;
+		const int* old = S + (size_t)j * W;
+		int* cur = S + (size_t)(j + 1) * W;
+		int pidx = (i0_ - i0) * 3;
+		if (pidx > 0) cur[pidx - 1] = cur[pidx - 2] = cur[pidx - 3] = 0; /* ColumnIterator::set_zero */
+		const int tl = t[pos0 + j] & DMND_LETTER_MASK;
+		int vg[3] = { 0, 0, 0 }, col_best = 0;
+		int sm4 = 0, sm3 = old[pidx], sm2 = old[pidx + 1];
+		int stop = 0;
+		for (int i = i0_; i <= i1_ && !stop; ++i)
+			for (int f = 0; f < 3; ++f) {
+				if (f > 0 && i >= ql[f]) { stop = 1; break; } /* :469,477: `break` leaves the row loop */
+				int hg = hgap[pidx + 3];
+				const int sc = p->score[(q[f][i] & DMND_LETTER_MASK) * 32 + tl];
+				int c = sm3 + sc;
+				const int fs = sc - F;
+				c = imax(c, sm4 + fs); c = imax(c, sm2 + fs);
+				c = imax(imax(c, vg[f]), hg);
+				c = imax(c, 0);
+				col_best = imax(col_best, c);
+				vg[f] -= ge; hg -= ge;
+				const int open = c - go;
+				vg[f] = imax(vg[f], open); hg = imax(hg, open);
+				hgap[pidx] = hg; cur[pidx] = c;
+				++pidx;
+				sm4 = sm3; sm3 = sm2; sm2 = old[pidx + 1 <= B3 ? pidx + 1 : B3];
+			}
+		if (col_best > best) { best = col_best; max_col = j; }
+	}
+	res->score = best;
+	if (mode != DMND_DP_TRACEBACK || best <= 0) { free(S); free(hgap); return 0; }
+	/* traceback(): :338-390, dp.traceback :257-267 */
+	const long total = (long)W * ((long)ncol + 1);
+#define SV(x) (((x) >= 0 && (x) < total) ? S[(x)] : 0)
+	const int col = max_col + 1, i0c = i0s + max_col;
+	long idx = -1;
+	for (int x = imax(-i0c, 0) * 3, xe = imin(B3, dna_len - 2 - i0c * 3); x < xe; ++x)
+		if (S[(size_t)col * W + x] == best) { idx = (long)col * W + x; break; }
+	if (idx < 0) { free(S); free(hgap); res->status = 2; return 0; }
+	int fr = (int)((idx - (long)col * W) % 3), i = i0c + (int)((idx - (long)col * W) / 3), j = pos0 + max_col;
+	res->q_end = i + 1; res->t_end = j + 1; res->frame_end = fr;
+	size_t n = 0, base = *tr_used;
+	int overflow = 0, err = 0;
+#define PUSHB(b) do { if (tr) { if (base + n < tr_cap) tr[base + n] = (uint8_t)(b); else overflow = 1; } ++n; } while (0)
+#define PUSH_MATCH() do { if (qa == sa) { PUSHB(DMND_OP_MATCH << 6); ++res->identities; ++res->positives; } \
+		else { PUSHB((DMND_OP_SUBSTITUTION << 6) | sa); ++res->mismatches; if (m > 0) ++res->positives; } ++res->length; } while (0)
+	while (SV(idx) > 0 && !err) {
+		if (i < 0 || j < 0 || i >= ql[fr]) { err = 1; break; }
+		const int qa = q[fr][i] & DMND_LETTER_MASK, sa = t[j] & DMND_LETTER_MASK;
+		const int m = p->score[qa * 32 + sa], sc = SV(idx);
+		if (sc == SV(idx - W) + m) { PUSH_MATCH(); idx -= W; --i; --j; }
+		else if (sc == SV(idx - (W + 1)) + m - F) { /* walk_forward_shift :180-191 */
+			PUSH_MATCH(); PUSHB(DMND_TR_FRAMESHIFT_FWD);
+			idx -= W + 1; --i; --j; --fr;
+			if (fr == -1) { fr = 2; --i; }
+		}
+		else if (sc == SV(idx - (W - 1)) + m - F) { /* walk_reverse_shift :192-203 */
+			PUSH_MATCH(); PUSHB(DMND_TR_FRAMESHIFT_REV);
+			idx -= W - 1; --i; --j; ++fr;
+			if (fr == 3) { fr = 0; ++i; }
+		}
+		else { /* walk_gap(d_begin, d_end) :204-244 */
+			const int i0g = imax(d_begin + j, 0), j0g = imax(i - d_end, -1);
+			const long hstep = B3 - 2;
+			long h = idx - hstep, h0 = idx - (long)(j - j0g) * hstep, v = idx - 3, v0 = idx - (long)(i - i0g + 1) * 3;
+			int g = go, l = 1, found = 0;
+			while (v > v0 && h > h0) {
+				if (sc + g == SV(h)) { found = 2; break; }
+				else if (sc + g == SV(v)) { found = 1; break; }
+				h -= hstep; v -= 3; ++l; g += ge;
+			}
+			if (!found) while (v > v0) { if (sc + g == SV(v)) { found = 1; break; } v -= 3; ++l; g += ge; }
+			if (!found) while (h > h0) { if (sc + g == SV(h)) { found = 2; break; } h -= hstep; ++l; g += ge; }
+			if (!found) { err = 1; break; }
+			++res->gap_openings; res->length += l; res->gaps += l; /* Hsp::push_gap */
+			if (found == 1) { idx = v; i -= l; for (int k = 0; k < l; ++k) PUSHB(DMND_OP_INSERTION << 6); }
+			else { idx = h; j -= l; for (int k = 0; k < l; ++k) PUSHB((DMND_OP_DELETION << 6) | (t[j + l - k] & DMND_LETTER_MASK)); }
+		}
+	}
+#undef PUSH_MATCH
+#undef PUSHB
+#undef SV
+	free(S); free(hgap);
+	if (err) { res->status = 2; return 0; }
+	res->q_begin = i + 1; res->t_begin = j + 1; res->frame_begin = fr;
+	if (tr) {
+		if (overflow) res->status = 1;
+		else {
+			for (size_t a = 0, b = n; a + 1 < b; ++a, --b) { uint8_t x = tr[base + a]; tr[base + a] = tr[base + b - 1]; tr[base + b - 1] = x; }
+			res->transcript_off = (uint32_t)base; res->transcript_len = (uint32_t)n;
+			*tr_used = base + n;
+		}
+	}
+	return 0;
+}
+
+int dmnd_banded_3frame_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref, const dmnd_dp_problem* problems, size_t n,
+                             int frame_shift, int mode, dmnd_fs_result* results, uint8_t* transcripts, size_t transcript_cap) {
+	size_t used = 0;
+	for (size_t k = 0; k < n; ++k) {
+		const dmnd_dp_problem* pr = &problems[k];
+		if ((uint64_t)pr->query + 3 > query->nseq || pr->target >= ref->nseq) return fail("dmnd_banded_3frame_swipe: sequence index out of range");
+		const int8_t* q[3]; int ql[3];
+		for (int f = 0; f < 3; ++f) {
+			const int64_t o = query->limits[pr->query + f];
+			q[f] = query->letters + o; ql[f] = (int)(query->limits[pr->query + f + 1] - o - 1);
+		}
+		const int dna_len = ql[0] + ql[1] + ql[2] + 2; /* frame f holds (dna_len - f) / 3 codons (basic/translated_position.h:47-50) */
+		const int64_t to = ref->limits[pr->target];
+		const int tlen = (int)(ref->limits[pr->target + 1] - to - 1);
+		if (fs_swipe_one(ctx, q, ql, dna_len, ref->letters + to, tlen, pr->d_begin, pr->d_end, frame_shift, mode, &results[k], transcripts,
+		                 transcript_cap, &used))
+			return 1;
+	}
+	return 0;
+}

@@ -10,7 +10,7 @@ static int8_t g_emu_smem[1 << 18];  // the CTA's dynamic shared memory (blocks r
 #define DMND_DYN_SMEM(name) int8_t* name = g_emu_smem
 #define __cvta_generic_to_shared(p) ((size_t)((const int8_t*)(p) - g_emu_smem))
 #define DMND_S16_LDS
-static inline unsigned s16_lds(unsigned addr) { uint16_t v; memcpy(&v, g_emu_smem + addr, 2); return v; }
+static inline unsigned s16_lds(unsigned addr) { return (uint8_t)g_emu_smem[addr]; }
 #include "emu_cuda.h"
 #include "../diamond_b200/csrc/cuda/swipe16.cuh"
 #include <algorithm>
@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
 	dmnd_search_opts o; dmnd_search_opts_default(&o);
 	dmnd_params hp; dmnd_params_init(&o, &hp);
 	static DevParams P; memset(&P, 0, sizeof P);
-	memcpy(P.score, hp.score, 1024); P.gap_open = hp.gap_open; P.gap_extend = hp.gap_extend; P.one = 1; P.k65536 = 65536;
+	memcpy(P.score, hp.score, 1024); P.gap_open = hp.gap_open; P.gap_extend = hp.gap_extend; P.one = 1; P.k65536 = 65536; P.neg2 = 0x80008000u;
 	dmnd_ctx* ctx; if (dmnd_create(0, &hp, &ctx)) return 2;
 	std::mt19937 rng((unsigned)seed);
 	// ---- blocks: nprob queries and nprob targets, real letters around every sequence
@@ -71,7 +71,7 @@ int main(int argc, char** argv) {
 	std::vector<uint8_t> want_ts(tcap + 16);
 	if (dmnd_banded_swipe(ctx, bq, bt, probs.data(), (size_t)nprob, trace ? 1 : 0, want.data(), trace ? want_ts.data() : nullptr, trace ? want_ts.size() : 0)) { printf("oracle: %s\n", dmnd_last_error()); return 2; }
 	// ---- the kernel under emulation: group by register tile, order by macro steps (as prep_kernel + the device sort do)
-	std::vector<int16_t> table((size_t)S16_TABLE_ENTRIES);
+	std::vector<uint8_t> table((size_t)S16_TABLE_ENTRIES);
 	unsigned bad = 0;
 	emu::launch((S16_TABLE_ENTRIES + 255) / 256, 256, [&] { s16_table_kernel(&P, table.data(), &bad); });
 	if (bad) { printf("table out of int8\n"); return 2; }

@@ -19,6 +19,9 @@ For every workload W and parity-ladder level L:
          fields, qlen, slen): six translated frames per read, DNA coordinates, frame-aware culling
     X1 / X3 / X5 = blastx at the default sensitivity / --sensitive / --very-sensitive (whole-frame stage-2 window and the gapped filter's
          exceptions for short translated queries; cutoff_table_short differs from cutoff_table only in X5)
+    XF / XF0 / XF3 = blastx in frameshift alignment mode (-F 15: the legacy extension pipeline + the 3-frame banded DP): --fast with
+         the transcript fields (cigar / btop carry the \\ and / frameshift marks) + qframe, --fast in the pairwise format (.txt, with
+         the "No hits found" records of every unaligned read), --sensitive with the default fields
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -44,7 +47,7 @@ COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter st
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
             "targets_round2": r"Target hits \(stage 5\) = (\d+)", "seedp_bits": r"Seed partition bits = (\d+)",
-            "targets_extended": r"Target hits \(stage 3\) = (\d+)"}
+            "targets_extended": r"Target hits \(stage 3\) = (\d+)", "targets_stage2": r"Target hits \(stage 2\) = (\d+)"}
 
 
 def main():
@@ -78,12 +81,15 @@ def main_blastx():
             q, d = os.path.join(td, "q.fna"), os.path.join(td, "d.faa")
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
-            for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", [])):
-                out = os.path.join(HERE, f"{name}.{lvl}.tsv")
+            for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", []),
+                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", [])):
+                out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl != "xf0" else f"{name}.{lvl}.txt")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
-                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
+                mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"], "xf3": ["--sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
+                if lvl.startswith("xf"):
+                    mode = mode + ["-F", "15"]
+                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "0" if lvl == "xf0" else "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)

@@ -94,8 +94,8 @@ def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
     q, d = _files(_bx(), tmp_path)
     r = subprocess.run([CLI, "blastx", "--fast", "--range-culling", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported option" in r.stderr
-    r = subprocess.run([CLI, "blastx", "--fast", "-F", "15", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # frameshift alignment
-    assert r.returncode != 0 and "unsupported option" in r.stderr
+    r = subprocess.run([CLI, "blastx", "--fast", "-F", "15", "-f", "sam", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # frameshift alignment: tabular and pairwise only
+    assert r.returncode != 0 and "not implemented in this mode" in r.stderr
     # the library: contexts other than 1 / 6, nq not a multiple, or a window-filter mode
     raw, lim = api.block_image(np.zeros(40, dtype=np.int8), np.array([0, 10, 20, 30, 40], dtype=np.int64))
     g = api.Context(lib=oracle_lib, query_contexts=6)
@@ -179,3 +179,50 @@ def test_vectorised_translation_equals_per_read_translation():
     a, b = api.translate_reads(reads), api.translate_codes(w["dna_codes"])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert (b[0] == 23).any() and (b[0] == 24).any()
+
+
+# ---- frameshift alignment mode (blastx -F 15): the reference's legacy extension pipeline (align/legacy/*) over the 3-frame banded DP
+# (dp/swipe/banded_3frame_swipe.cpp); goldens bx.xf / bx.xf0 / bx.xf3 = the unmodified reference with -F 15
+XF_FIELDS = XT_FIELDS + ["qframe"]
+
+
+@pytest.mark.parametrize("lvl,flags,ext", [("xf", ["--fast", "-f", "6"] + XF_FIELDS, "tsv"), ("xf0", ["--fast", "-f", "0"], "txt"), ("xf3", ["--sensitive"], "tsv")])
+def test_blastx_frameshift_cli(oracle_lib, tmp_path, lvl, flags, ext):
+    """Transcripts with \\ and / frameshift marks (cigar, btop, gapped sequences), begin and end of an alignment in different frames,
+    the pairwise format with its "No hits found" record for EVERY unaligned read, and a many-shape mode (no gapped filter in the legacy pipeline)."""
+    q, d = _files(_bx(), tmp_path)
+    o = str(tmp_path / "o.out")
+    r = subprocess.run([CLI, "blastx"] + flags + ["-F", "15", "-q", q, "-d", d, "-o", o, "-p", "8", "--log"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, f"bx.{lvl}.{ext}")).read()
+    gold = json.load(open(os.path.join(GOLDEN, f"bx.{lvl}.counters.json")))
+    log = r.stderr + r.stdout
+    assert f"Target hits (stage 0) = {gold['targets']}" in log            # targets with a positive ungapped hit (QueryMapper::count_targets)
+    assert f"Target hits (stage 3) = {gold['targets_stage2']}" in log     # targets that enter the traceback DP (the reference's TARGET_HITS2)
+
+
+def test_blastx_frameshift_library(oracle_lib):
+    """Through the C ABI: frame_shift in dmnd_search_opts, the end frame of an alignment in dmnd_match.reserved."""
+    from diamond_b200 import api
+    w = _bx()
+    ql, qo = api.translate_reads(w["dna"], frame_shift=15)
+    q_raw, q_lim = api.block_image(ql, qo)
+    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+    g = api.Context(lib=oracle_lib, masking=1, motif_masking=1, query_contexts=6, frame_shift=15)
+    m, tr, st = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    gold = ["\t".join(l.split("\t")[:12]) for l in open(os.path.join(GOLDEN, "bx.xf.tsv")).read().splitlines()]
+    assert api.fmt6_translated(m, [len(r) for r in w["dna"]]).splitlines() == gold
+    shifted = sum(1 for x in m if int(x["reserved"]) - 1 != int(x["query"]) % 6)
+    assert shifted > 20 and (m["reserved"] > 0).all()  # alignments that end in another frame than they begin in
+    fs_bytes = np.isin(tr, [0x41, 0x42]).sum()
+    assert fs_bytes >= shifted
+
+
+def test_frameshift_needs_translated_queries(oracle_lib):
+    from diamond_b200 import api
+    with pytest.raises(api.DmndError):
+        g = api.Context(lib=oracle_lib, query_contexts=1, frame_shift=15)
+        w = _bx()
+        r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+        g.blastp(r_raw, r_lim, r_raw, r_lim)
