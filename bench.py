@@ -39,6 +39,10 @@ CONFIGS = {
                what="blastx --fast, {q} synthetic DNA reads (150 nt, six frames) per GPU x {d}-protein DB"),
     "c4": dict(kind="blastp", sens=3, flag="--sensitive", queries=1_000_000, db=500_000, seed=4, label="BASELINE configs[3]",
                what="blastp --sensitive, {q} synthetic queries (len<=300) per GPU x {d}-protein DB"),
+    # configs[4]: "very-sensitive with frameshift + traceback": frameshift alignment exists for translated searches only (basic/config.cpp:822-823), so
+    # the queries are DNA reads (600 nt, 70 % of them with a single-nucleotide insertion or deletion); every alignment is traced back in this mode
+    "c5": dict(kind="blastx", sens=5, flag="--very-sensitive", frame_shift=15, read_len=600, indel=0.7, queries=12_500, db=1_000_000, seed=5, label="BASELINE configs[4] (per-GPU share of its 8-GPU layout: 100 000 reads / 8)",
+               what="blastx --very-sensitive -F 15 (frameshift alignment, traceback), {q} synthetic DNA reads (600 nt, six frames) per GPU x {d}-protein DB"),
 }
 
 
@@ -129,11 +133,12 @@ def make_workload(args, rank, n=None):
     c = CONFIGS[args.config]
     n = n or args.queries
     if c["kind"] == "blastx":
-        w = synth.c3_workload(args.queries, args.db, args.seed, q_stream=rank)
+        fs = c.get("frame_shift", 0)
+        w = synth.c3_workload(args.queries, args.db, args.seed, read_len=c.get("read_len", 150), q_stream=rank, indel_rate=c.get("indel", 0.0))
         codes = w["dna_codes"][:n]
-        ql, qo = api.translate_codes(codes)
+        ql, qo = api.translate_codes(codes, frame_shift=fs)
         q_raw, q_lim = api.block_image(ql, qo)
-        out = {"dna_codes": codes, "read_lens": [codes.shape[1]] * n, "ctx": dict(sensitivity=c["sens"], query_contexts=6)}
+        out = {"dna_codes": codes, "read_lens": [codes.shape[1]] * n, "ctx": dict(sensitivity=c["sens"], query_contexts=6, frame_shift=fs)}
     else:
         w = synth.workload(args.queries, args.db, args.seed, q_stream=rank)
         q_raw, q_lim = api.block_image(w["q_letters"][: w["q_off"][n]], w["q_off"][: n + 1])
@@ -160,6 +165,8 @@ def write_fasta(wl, n, td):
 def run_reference(args, q, d, out, threads):
     c = CONFIGS[args.config]
     cmd = [REF_BIN, c["kind"], c["flag"], "-q", q, "-d", d, "-f", "6", "-o", out, "-p", str(threads), "--log"] + ([] if args.masking else NO_MASKING)
+    if c.get("frame_shift"):
+        cmd += ["-F", str(c["frame_shift"])]
     t0 = time.perf_counter()
     r = subprocess.run(cmd, capture_output=True, text=True)
     dt = time.perf_counter() - t0

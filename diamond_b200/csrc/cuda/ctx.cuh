@@ -60,13 +60,14 @@ enum Phase { PH_SEED = 0, PH_DP_SCORE, PH_DP_TRACE, PH_H2D, PH_D2H, PH_COUNT };
 namespace dmnd_cuda {
 // Seed index of a reference block for one shape: sorted 40-bit key mixes + locations, bucket directory, Bloom filter.
 struct RefIndex {
-	DevBuf keys, locs, bucket, bloom;
+	DevBuf keys, locs, bucket, bloom, bitmap;
 	unsigned long long nref = 0;
 	int sid = -1, shift = 0;
 	uint32_t bloom_blocks = 0;
+	uint32_t bitmap_mask = 0;  // bits of the first-level filter - 1
 	bool valid = false;
 	uint64_t content_epoch = 0, params_hash = 0;  // what the index was built from: the block's content epoch and the context's parameters
-	void release() { keys.release(); locs.release(); bucket.release(); bloom.release(); valid = false; }
+	void release() { keys.release(); locs.release(); bucket.release(); bloom.release(); bitmap.release(); valid = false; }
 };
 }  // namespace dmnd_cuda
 
@@ -99,7 +100,8 @@ struct dmnd_ctx {
 	uint8_t* d_matcher[DMND_MAX_SHAPES + 1] = {};  // PatternMatcher tables
 	uint32_t matcher_minlen[DMND_MAX_SHAPES + 1] = {}, matcher_suffix[DMND_MAX_SHAPES + 1] = {};
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
-	cudaEvent_t ev_copy = nullptr;
+	cudaEvent_t ev_copy = nullptr, ev_bias = nullptr;  // ev_bias: end of the last dmnd_block_compute_bias_range_async on copy_stream
+	bool bias_pending = false;
 	int sm_count = 148;
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;

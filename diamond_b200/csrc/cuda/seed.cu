@@ -12,6 +12,7 @@
 // Chunk order matters and is reproduced: SEED_MASK bits set while processing chunk k are visible to the left-most
 // filter of chunks >= k, and verify_hit compares seed partitions against the current chunk's range (left_most.h:32-41).
 #include "ctx.cuh"
+#include <cmath>
 #include "seed_kernels.cuh"
 #include "gf_kernels.cuh"
 #include <cub/cub.cuh>
@@ -135,7 +136,13 @@ int build_ref_index(dmnd_ctx* ctx, const dmnd_block* ref, int sid, RefIndex& ix)
 	while ((unsigned long long)bloom_blocks * 32ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
 	if (ix.bloom.ensure((size_t)bloom_blocks * 32)) return 1;
 	DMND_CUDA_CHECK(cudaMemsetAsync(ix.bloom.p, 0, (size_t)bloom_blocks * 32, st));
-	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, ix.bloom.as<uint32_t>(), bloom_blocks - 1); ++ctx->launches; }
+	// first-level bitmap: >= 4 bits per reference key
+	uint64_t bitmap_bits = (uint64_t)1 << 20;
+	while (bitmap_bits < 4ull * nref && bitmap_bits < ((uint64_t)1 << 31)) bitmap_bits <<= 1;
+	if (ix.bitmap.ensure((size_t)(bitmap_bits / 8))) return 1;
+	DMND_CUDA_CHECK(cudaMemsetAsync(ix.bitmap.p, 0, (size_t)(bitmap_bits / 8), st));
+	ix.bitmap_mask = (uint32_t)(bitmap_bits - 1);
+	if (nref) { bloom_build_kernel<<<(unsigned)((nref + 255) / 256), 256, 0, st>>>(d_keys, (size_t)nref, ix.bloom.as<uint32_t>(), bloom_blocks - 1, ix.bitmap.as<uint32_t>(), ix.bitmap_mask); ++ctx->launches; }
 	DMND_CUDA_CHECK(stream_wait(ctx, st));  // other lanes may use the index from their own streams
 	ix.nref = nref; ix.sid = sid; ix.shift = shift; ix.bloom_blocks = bloom_blocks; ix.valid = true;
 	return 0;
@@ -187,7 +194,7 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, query->has_soft ? query->soft : nullptr, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, query->has_soft ? query->soft : nullptr, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ix.bitmap.as<uint32_t>(), ix.bitmap_mask, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
 		++ctx->launches;
 		// entry count and the (q,s) pair bound of this pass (count + 1 == d_cnt + 6) in one round trip
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 5, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -308,7 +315,13 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
 	dmnd_stage_counters cn;
 	std::memset(&cn, 0, sizeof cn);
-	size_t slice = ctx->params.shape_weight >= 10 ? (size_t)-1 : (size_t)40000000;
+	// ... and fewer where the reference is large for the shape weight: a query position then meets ~ reference letters / 10^weight
+	// reference positions (x 3 for the skew of real seed frequencies), and the (q, s) pair buffers of a slice are held to ~2.5*10^8 pairs
+	size_t slice = (size_t)-1;
+	if (ctx->params.shape_weight < 10) {
+		const double per_pos = 3.0 * (double)ref->raw_len / std::pow((double)ctx->params.reduction_size, (double)ctx->params.shape_weight);
+		slice = (size_t)std::min(4e7, std::max(1e6, 2.5e8 / std::max(per_pos, 1.0)));
+	}
 	if (const char* ev = getenv("DMND_SEED_SLICE")) slice = std::max<size_t>(1024, strtoull(ev, nullptr, 10));
 	size_t total = 0;
 	uint32_t b = q_begin;

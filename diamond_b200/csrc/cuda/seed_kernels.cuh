@@ -57,10 +57,21 @@ __device__ __forceinline__ void bloom_slots(uint64_t key, uint32_t block_mask, u
 	block = (uint32_t)(h >> 40) & block_mask;
 	bits = (uint32_t)(h >> 8);  // four 8-bit positions inside the 256-bit block
 }
-__global__ void bloom_build_kernel(const uint64_t* __restrict__ keys, size_t n, uint32_t* bloom, uint32_t block_mask) {
+// First-level filter in front of the Bloom blocks: ONE bit per key in a table of >= 4 bits per reference key (16 MB for the 3*10^7
+// keys of a 100 k-protein block).  The 34 MB of Bloom blocks do not stay L2 resident beside the streamed query letters on a B200
+// (lines homed in the far L2 partition are cached twice: ncu showed 23 % of the Bloom sector reads going to DRAM, 4.3 GB per 10^6
+// queries for 0.25 GB of letters); the bitmap does, and it answers ~80 % of the query positions, so only one position in five
+// goes on to a Bloom block at all.
+__device__ __forceinline__ uint32_t bitmap_slot(uint64_t key, uint32_t mask) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 33) & mask; }
+__device__ __forceinline__ bool bitmap_test(const uint32_t* __restrict__ bitmap, uint32_t mask, uint64_t key) {
+	const uint32_t b = bitmap_slot(key, mask);
+	return (bitmap[b >> 5] >> (b & 31)) & 1u;
+}
+__global__ void bloom_build_kernel(const uint64_t* __restrict__ keys, size_t n, uint32_t* bloom, uint32_t block_mask, uint32_t* bitmap, uint32_t bitmap_mask) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	if (i > 0 && keys[i] == keys[i - 1]) return;  // sorted: one insert per distinct key
+	{ const uint32_t b = bitmap_slot(keys[i], bitmap_mask); atomicOr(&bitmap[b >> 5], 1u << (b & 31)); }
 	uint32_t block, bits;
 	bloom_slots(keys[i], block_mask, block, bits);
 	uint32_t* w = bloom + (size_t)block * 8;
@@ -99,11 +110,55 @@ struct ShapeArg {
 // Tile loader shared by the enumeration kernels: TILE consecutive letters (+ 32 halo) become "codes" in shared memory:
 // reduced class 0..9, 0x40 for MASK/STOP (reduction 23), 0x80 for the delimiter.  One global byte per letter, coalesced.
 #define SEED_TILE 1024
-__device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p0, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut) {
+#define SEED_RAW_BYTES (SEED_TILE + 32 + 32)  // the tile's letters + the longest seed window, widened to 16-byte boundaries on both sides
+// The tile's letters travel global -> shared as ONE bulk asynchronous copy (cp.async.bulk, the 1-D form of TMA; SASS UBLKCP): a
+// single thread arms an mbarrier with the byte count and issues the copy, the copy engine completes the barrier, every thread waits
+// on its phase.  Source and destination must be 16-byte aligned: the copy starts at p0 rounded down and ends at min(tile end,
+// p_end + 32) rounded up (positions >= p_end are never evaluated, so what lies behind that is not needed -- and not read: the last
+// tile of a block would otherwise reach past the block's padding).  Device builds only; the CPU emulation of this file
+// (tests/emu_seed.cpp) takes the plain loop below.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void bulk_load_letters(const int8_t* __restrict__ src16, unsigned bytes, uint8_t* s_raw, unsigned long long* mbar) {
+	const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar), dst = (unsigned)__cvta_generic_to_shared(s_raw);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src16), "r"(bytes), "r"(mb) : "memory");
+	}
+	unsigned done = 0;
+	while (!done)  // phase 0 of a barrier used once per CTA
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+}
+#endif
+__device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p0, size_t p_end, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut,
+                                               uint8_t* s_raw, unsigned long long* mbar) {
 	if (threadIdx.x < 32) {
 		const unsigned r = P->reduction[threadIdx.x];
 		s_lut[threadIdx.x] = threadIdx.x == DMND_DELIMITER ? 0x80 : (r == 23 ? 0x40 : (uint8_t)r);
 	}
+#if defined(__CUDA_ARCH__)
+	{
+		const size_t a0 = p0 & ~(size_t)15, need_end = min(p0 + SEED_TILE + 32, p_end + 32), a1 = (need_end + 15) & ~(size_t)15;
+		bulk_load_letters(letters + a0, (unsigned)(a1 - a0), s_raw, mbar);  // (contains the barrier that also publishes s_lut)
+		const int off = (int)(p0 - a0), have = (int)(a1 - p0);
+		if (soft) {
+			for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) {
+				const uint8_t c = x < have ? s_lut[s_raw[off + x] & 31] : (uint8_t)0x80;
+				s_code[x] = (x < have && soft_bit(soft, p0 + x) && !(c & 0x80)) ? (uint8_t)0x40 : c;
+			}
+		}
+		else
+			for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) s_code[x] = x < have ? s_lut[s_raw[off + x] & 31] : (uint8_t)0x80;
+		__syncthreads();
+		return;
+	}
+#else
+	(void)s_raw; (void)mbar; (void)p_end;
+#endif
 	__syncthreads();
 	if (soft) {  // soft-masked letters read as MASK_LETTER (class flag 0x40); they are never delimiters
 		for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) {
@@ -131,10 +186,12 @@ __device__ __forceinline__ bool seed_from_codes(const uint8_t* s_code, int o, co
 
 __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, const ShapeArg sh,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
-                             const uint32_t* __restrict__ bloom, uint32_t bloom_mask,
+                             const uint32_t* __restrict__ bloom, uint32_t bloom_mask, const uint32_t* __restrict__ bitmap, uint32_t bitmap_mask,
                              Entry* entries, unsigned long long* count, unsigned long long cap) {
 	__shared__ uint8_t s_code[SEED_TILE + 32];
 	__shared__ uint8_t s_lut[32];
+	__shared__ __align__(16) uint8_t s_raw[SEED_RAW_BYTES];
+	__shared__ __align__(8) unsigned long long s_mbar;
 	// matches of the tile are staged in shared memory: ONE pair of global atomics per CTA (returning atomics on a single
 	// hot address cost microseconds each and stalled every warp that found a match) and a coalesced copy-out
 	__shared__ Entry s_ent[SEED_TILE];
@@ -142,14 +199,14 @@ __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ l
 	__shared__ unsigned long long s_pairs, s_base;
 	const size_t p0 = p_begin + (size_t)blockIdx.x * SEED_TILE;
 	if (threadIdx.x == 0) { s_n = 0; s_pairs = 0; }
-	load_code_tile(letters, soft, p0, P, s_code, s_lut);
+	load_code_tile(letters, soft, p0, p_end, P, s_code, s_lut, s_raw, &s_mbar);
 	for (int it = 0; it < SEED_TILE / 256; ++it) {
 		const int o = it * 256 + threadIdx.x;
 		const size_t p = p0 + o;
 		uint64_t seed = 0;
 		bool ok = p < p_end && seed_from_codes(s_code, o, sh, seed);
 		uint64_t key = 0;
-		if (ok) { key = mix40(seed); ok = bloom_test(bloom, bloom_mask, key); }
+		if (ok) { key = mix40(seed); ok = bitmap_test(bitmap, bitmap_mask, key) && bloom_test(bloom, bloom_mask, key); }
 		if (ok) {
 			const uint32_t b = (uint32_t)(key >> shift);
 			uint32_t i = bucket[b];

@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const dmnd_dp_problem* __rest
 				const bool stats = trace == 2 && cells > (unsigned long long)DMND_MAX_SWIPE_DP;
 				int g; unsigned long long step_bytes, rows = (unsigned long long)B;
 				if (stats) { g = G_STATS; step_bytes = 0; }
-				else if (s16 && B <= S16_MAX_BAND && nmacro <= (unsigned long long)S16_MAX_MACRO && qlen <= 16000) {
+				else if (s16 && B <= S16_MAX_BAND && nmacro <= (unsigned long long)S16_MAX_MACRO && qlen <= S16_MAX_QLEN) {
 					const int R = s16_rows(B);
 					g = (R / 4 - 1) * 2 + ((qlen + 8 * R + 4) > 768 ? 1 : 0);
 					step_bytes = (unsigned long long)s16_step_bytes(R); rows = (unsigned long long)(S16_LANES * R);
@@ -770,7 +770,9 @@ int banded_swipe_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
 			warps = (int)std::min<size_t>(4, (((size_t)200 << 10) - tab) / per_warp);
 			if (warps < 1) { set_error("dmnd_banded_swipe: query too long for the packed kernel"); return 1; }  // (prep_kernel routes those to the int32 kernels)
 			const size_t smem = tab + per_warp * (size_t)warps;
-			const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)220 << 10) / (smem + 2048)));
+			// 227 KB of shared memory per SM, 1 KB reserved per CTA: the 27 KB table + 16 queries of <= 300 letters make 4 CTAs = 16 warps per SM
+			// (the register file holds exactly 16 warps of the 128-register kernels)
+			const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16 / warps, ((size_t)227 << 10) / (smem + 1024)));
 			const int grid = (int)std::min<size_t>((e - pos + 4 * warps - 1) / (4 * warps), (size_t)ctx->sm_count * ctas_per_sm);
 			S16Args sa{ ctx->d_s16_table, qstride, d_counters + 66 };
 			if (tr_mode ? launch_s16_bin<true>(R, a, ctx->d_params, sa, grid, warps * 32, smem, st) : launch_s16_bin<false>(R, a, ctx->d_params, sa, grid, warps * 32, smem, st)) return 1;

@@ -80,6 +80,7 @@ __host__ __device__ __forceinline__ int s16_qoff(int q) { return (q >> 2) * 128 
 constexpr int S16_LANES = 8;                           // lanes per problem
 constexpr int S16_MAX_BAND = 128;
 constexpr int S16_TILE = 8;                            // macro steps per trace tile
+constexpr int S16_MAX_QLEN = 10000;                     // longest query of the packed kernel: one warp's four problems (4 bytes per query position each) beside the table in shared memory
 constexpr int S16_MAX_MACRO = 32000;                   // macro steps representable in the 16-bit column key
 __host__ __device__ __forceinline__ int s16_rows(int B) { return B <= 32 ? 4 : B <= 64 ? 8 : B <= 96 ? 12 : 16; }
 // trace bytes of one macro step of one problem: 8 lanes x R/2 bytes, laid out as R/8 regions of 8 x 4 bytes (the full words

@@ -1113,7 +1113,9 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		if (!prep_rc) { w.q_patch.build(env.q_letters, env.q_limits, env.nq, q_begin, q_end, w.mask_pos.data(), w.mask_pos.size()); d.env.q_patch = &w.q_patch; }
 	}
 	seed_turn.set_masked(lane);  // (dmnd_block_mask returns when the range is masked on the device; also set on failure so nobody waits forever)
-	prep_rc = prep_rc || dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
+	// the composition bias of this range on the lane's second stream: the seed stage reads letters only, the first consumers (x-drop
+	// extension, DP) wait for it on the device (dmnd_block_bias_wait below)
+	prep_rc = prep_rc || dmnd_block_compute_bias_range_async(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
 	seed_turn.wait_masked(lane + 1);
 	prof.lane = lane;
 	prof.lap("wait, mask, bias");
@@ -1130,7 +1132,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	if (n_shapes == 1) {
 		const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
 		seed_turn.pass(lane);
-		if (seed_rc) return 1;
+		if (seed_rc || dmnd_block_bias_wait(ctx)) return 1;  // from here on the lane's stream reads the bias (x-drop extension, DP)
 		prof.lap("search_shape");
 		if (bridge) {
 			d.stats.hits = dmnd_hits_count(hits);
@@ -1160,7 +1162,7 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		// run_ref_chunk's loop over the shapes (run/double_indexed.cpp:185-214): SEED_MASK bits set by one shape stay visible
 		// to the next ones, the hits of all shapes feed one extension; every shape's hits arrive grouped by query and are merged
 		// into one query-grouped list (counting sort by query, stable)
-		int rc = prep_rc;
+		int rc = prep_rc || dmnd_block_bias_wait(ctx);  // (the x-drop extension and the gapped filter of every shape read the bias)
 		std::vector<dmnd_hit>& ah = w.acc_hits; std::vector<dmnd_segment>& as = w.acc_segs; std::vector<dmnd_hit_site>& at = w.acc_sites;
 		ah.clear(); as.clear(); at.clear(); w.acc_gf.clear();
 		for (int sid = 0; sid < n_shapes && !rc; ++sid) {

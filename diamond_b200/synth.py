@@ -365,7 +365,7 @@ def write_dna_fasta(path: str, reads, prefix: str = "r") -> None:
             f.write(">%s%d\n%s\n" % (prefix, i, r))
 
 
-def c3_workload(n_reads: int, n_db: int, seed: int, read_len: int = 150, q_stream: int = 0):
+def c3_workload(n_reads: int, n_db: int, seed: int, read_len: int = 150, q_stream: int = 0, indel_rate: float = 0.0):
     """BASELINE configs[2]: reads of `read_len` nt = a window of read_len / 3 residues of a database protein, substituted with a
     per-read rate U(0.1, 0.6), back-translated with uniform codon choice, on either strand.  Vectorised (10^5 reads in a second):
     returns the reads as an (n, read_len) array of nucleotide codes 0..3 = ACGT next to the database."""
@@ -396,6 +396,16 @@ def c3_workload(n_reads: int, n_db: int, seed: int, read_len: int = 150, q_strea
     dna = tab[aa, pick].reshape(n_reads, naa * 3)
     if dna.shape[1] < read_len:
         dna = np.concatenate([dna, rq.integers(0, 4, (n_reads, read_len - dna.shape[1]), dtype=np.uint8)], axis=1)
+    if indel_rate > 0.0:  # configs[4]: a single-nucleotide deletion or insertion inside the read (length kept) = one frameshift per affected read
+        hit = np.flatnonzero(rq.random(n_reads) < indel_rate)
+        pos = rq.integers(read_len // 4, 3 * read_len // 4, len(hit))
+        ins = rq.random(len(hit)) < 0.5
+        fill = rq.integers(0, 4, len(hit), dtype=np.uint8)
+        for r, p, i, b in zip(hit.tolist(), pos.tolist(), ins.tolist(), fill.tolist()):
+            if i:
+                dna[r, p + 1:] = dna[r, p:-1].copy(); dna[r, p] = b
+            else:
+                dna[r, p:-1] = dna[r, p + 1:].copy(); dna[r, -1] = b
     rev = rq.random(n_reads) < 0.5
     dna[rev] = (3 - dna[rev])[:, ::-1]  # reverse complement: A<->T, C<->G with codes ACGT = 0123
     return {"dna_codes": np.ascontiguousarray(dna), "db_letters": dbl, "db_off": dbo, "src": src}

@@ -53,7 +53,7 @@ static Matchers build_matchers(const dmnd_params& hp) {  // dmnd_create (ctx.cu)
 	return m;
 }
 
-struct Index { std::vector<uint64_t> keys; std::vector<uint32_t> locs, bucket, bloom; int shift; uint32_t bloom_blocks; unsigned long long nref; };
+struct Index { std::vector<uint64_t> keys; std::vector<uint32_t> locs, bucket, bloom, bitmap; int shift; uint32_t bloom_blocks, bitmap_mask; unsigned long long nref; };
 
 // build_ref_index (seed.cu)
 static void build_index(const Blk& ref, const DevParams& P, const dmnd_params& hp, int sid, Index& ix) {
@@ -75,7 +75,10 @@ static void build_index(const Blk& ref, const DevParams& P, const dmnd_params& h
 	uint32_t bloom_blocks = 1024;
 	while ((unsigned long long)bloom_blocks * 32ull < nref && bloom_blocks < (1u << 26)) bloom_blocks <<= 1;
 	ix.bloom.assign((size_t)bloom_blocks * 8, 0);
-	if (nref) emu::launch((unsigned)((nref + 255) / 256), 256, [&] { bloom_build_kernel(ix.keys.data(), (size_t)nref, ix.bloom.data(), bloom_blocks - 1); });
+	uint64_t bitmap_bits = (uint64_t)1 << 20;
+	while (bitmap_bits < 4ull * nref && bitmap_bits < ((uint64_t)1 << 31)) bitmap_bits <<= 1;
+	ix.bitmap.assign((size_t)(bitmap_bits / 32), 0); ix.bitmap_mask = (uint32_t)(bitmap_bits - 1);
+	if (nref) emu::launch((unsigned)((nref + 255) / 256), 256, [&] { bloom_build_kernel(ix.keys.data(), (size_t)nref, ix.bloom.data(), bloom_blocks - 1, ix.bitmap.data(), ix.bitmap_mask); });
 	ix.shift = shift; ix.bloom_blocks = bloom_blocks; ix.nref = nref;
 }
 
@@ -89,7 +92,7 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
 	std::vector<Entry> entries(ecap);
 	emu::launch((unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, [&] { probe_kernel(query.letters.data(), query.has_soft ? query.soft.data() : nullptr, qp_begin, qp_end, &P, sh, ix.keys.data(),
-		ix.bucket.data(), ix.shift, ix.bloom.data(), ix.bloom_blocks - 1, entries.data(), cnt + 5, ecap); });
+		ix.bucket.data(), ix.shift, ix.bloom.data(), ix.bloom_blocks - 1, ix.bitmap.data(), ix.bitmap_mask, entries.data(), cnt + 5, ecap); });
 	const unsigned long long nent = cnt[5], pairs_bound = cnt[6];
 	if (nent > ecap) { printf("FAIL entry capacity\n"); exit(1); }
 	if (query.has_soft && qpos > 0) emu::launch((unsigned)((qpos + 255) / 256), 256, [&] { motif_seedmask_kernel(query.letters.data(), query.soft.data(), qp_begin, qp_end, hp.shape_len[sid]); });
