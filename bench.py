@@ -293,6 +293,8 @@ def main():
         return
 
     torch.cuda.set_device(local)
+    from diamond_b200 import shard
+    numa_note = shard.pin_to_gpu_numa_node(local) if world > 1 else "one rank: not pinned"  # before the library starts its host threads
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -478,12 +480,12 @@ def main():
                "e2e": {"value": e2e, "unit": "GCUPS", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": tm2["h2d_bytes"] // args.steps,
                        "d2h_bytes_per_step": tm2["d2h_bytes"] // args.steps},
                "gpu_launches": int(tm["launches"]), "roofline": roofline, "roofline_seed": roofline_seed, "cpu_baseline": cpu,
-               "step_ms": {"resident": step_ms_res, "e2e": step_ms_e2e}, "masking_ms": mask_info, "reference_broadcast_ms": bcast_ms,
+               "step_ms": {"resident": step_ms_res, "e2e": step_ms_e2e}, "masking_ms": mask_info, "reference_broadcast_ms": bcast_ms, "host_pinning_rank0": numa_note,
                "breakdown_ms_per_step": {"seed_stage": st["seed_ms"], "host_bridge": st["host_bridge_ms"], "dp_round1": st["dp1_ms"], "dp_round2": st["dp2_ms"], "total": st["total_ms"]},
                "work": {"cells_per_gpu": cells, "dp_problems_round1": st["dp_problems_round1"], "dp_problems_round2": st["dp_problems_round2"], "dp_problems_fused": st["dp_problems_fused"],
                         "note": "cells = sum band x cols over the reference's round-1 and round-2 problem lists (dp/dp.h:121-124): a property of the workload, "
                                 "the same for both arms; fused queries evaluate a surviving problem's matrix once (with traceback) instead of twice",
-                        "alignments": int(len(m)), "hits": st["hits"]}}
+                        "alignments": int(len(m)), "hits": st["hits"], "seed_counters": {k: int(v) for k, v in st["seed"].items()}, "targets": st["targets"]}}
         emit(out)
     ctx.close()
     if world > 1:

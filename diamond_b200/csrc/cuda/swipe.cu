@@ -23,6 +23,7 @@
 #include <numeric>
 #include <cstdlib>
 #include <chrono>
+#include <mutex>
 
 namespace dmnd_cuda {
 
@@ -355,11 +356,26 @@ static void launch_bin(int R, const SwipeArgs& a, const DevParams* P, int grid, 
 	}
 }
 
+// The kernels with dynamic shared memory above the 48 KB default get the opt-in limit ONCE per kernel (the attribute is a property of
+// the function, shared by every lane thread of the process: setting it to each launch's own size let one lane lower it between another
+// lane's set and launch -> "invalid argument" when the lanes' longest queries differed)
+constexpr int DMND_SMEM_OPTIN = 227 * 1024;
+template<typename K> static cudaError_t smem_optin(K kernel) {
+	static std::mutex mtx;
+	static std::vector<const void*> done;  // (kernels of one signature share this instantiation: keyed by the function itself)
+	std::lock_guard<std::mutex> g(mtx);
+	const void* key = reinterpret_cast<const void*>(kernel);
+	if (std::find(done.begin(), done.end(), key) != done.end()) return cudaSuccess;
+	const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DMND_SMEM_OPTIN);
+	if (e == cudaSuccess) done.push_back(key);
+	return e;
+}
+
 template<bool TRACE>
 static int launch_prof_bin(int R, const SwipeArgs& a, const DevParams* P, const ProfArgs& pa, int grid, int threads, size_t smem, cudaStream_t st) {
 #define DMND_LAUNCH_PROF(RR)                                                                                            \
 	do {                                                                                                                 \
-		if (smem > 40 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe_prof_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* the 48 KB default covers static + dynamic */ \
+		if (smem > 40 * 1024) DMND_CUDA_CHECK(smem_optin(swipe_prof_kernel<RR, TRACE>)); /* the 48 KB default covers static + dynamic */ \
 		swipe_prof_kernel<RR, TRACE><<<grid, threads, smem, st>>>(a, P, pa);                                             \
 	} while (0)
 	switch (R) {
@@ -656,7 +672,7 @@ template<bool TRACE>
 static int launch_s16_bin(int R, const SwipeArgs& a, const DevParams* P, const S16Args& sa, int grid, int threads, size_t smem, cudaStream_t st) {
 #define DMND_LAUNCH_S16(RR)                                                                                             \
 	do {                                                                                                                 \
-		if (smem > 40 * 1024) DMND_CUDA_CHECK(cudaFuncSetAttribute(swipe16_kernel<RR, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		if (smem > 40 * 1024) DMND_CUDA_CHECK(smem_optin(swipe16_kernel<RR, TRACE>));                                     \
 		swipe16_kernel<RR, TRACE><<<grid, threads, smem, st>>>(a, P, sa);                                                \
 	} while (0)
 	switch (R) {

@@ -6,6 +6,33 @@ from __future__ import annotations
 import numpy as np
 
 
+def pin_to_gpu_numa_node(gpu_index: int) -> str:
+    """Restricts this process (and the host threads the library starts later) to the CPUs of the NUMA node the GPU hangs on: the
+    host side of a rank -- pinned staging buffers, the worker pool that scores and culls -- then stays next to its GPU's PCIe root.
+    On a two-socket 8-GPU box GPUs 4-7 sit on node 1; unpinned ranks of those GPUs ran their host work across the socket link.
+    Returns a short note for the bench record; does nothing (and says why) where the topology cannot be read."""
+    import os, subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        if not bus:
+            return "no pci bus id"
+        dom, rest = bus.split(":", 1)
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node").read())
+        if node < 0:
+            return "single NUMA node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} CPUs)"
+    except Exception as e:  # topology files missing in a container, nvidia-smi absent, ...
+        return f"not pinned ({type(e).__name__})"
+
+
 def query_ranges(q_limits: np.ndarray, parts: int):
     """Contiguous query-id ranges with ~equal letter counts (the reference's SequenceSet::partition,
     data/sequence_set.cpp:57-75, does the same for threads)."""
