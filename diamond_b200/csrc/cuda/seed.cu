@@ -194,7 +194,7 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 	for (; qpos > 0;) {
 		if (ctx->b_entries.ensure(ecap * sizeof(Entry))) return 1;
 		DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 5, 0, 2 * sizeof(unsigned long long), st));
-		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, query->has_soft ? query->soft : nullptr, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, ix.bitmap.as<uint32_t>(), ix.bitmap_mask, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap);
+		probe_kernel<<<(unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, 0, st>>>(query->letters, query->has_soft ? query->soft : nullptr, qp_begin, qp_end, P, shape_arg(hp, sid), d_keys, d_bucket, shift, d_bloom, bloom_blocks - 1, getenv("DMND_NO_BITMAP") ? nullptr : ix.bitmap.as<uint32_t>(), ix.bitmap_mask, ctx->b_entries.as<Entry>(), d_cnt + 5, ecap, getenv("DMND_NO_BULK") ? 0 : 1);
 		++ctx->launches;
 		// entry count and the (q,s) pair bound of this pass (count + 1 == d_cnt + 6) in one round trip
 		DMND_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, d_cnt + 5, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -210,7 +210,7 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 	}
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
 	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
-	if (hp.ungapped_evalue != 0.0 && ctx->b_keys2.ensure(((size_t)pairs_bound / 32 + 8) * 4)) return 1;  // stage-1 survivor bits
+	if (hp.ungapped_evalue != 0.0 && (ctx->b_keys2.ensure(((size_t)pairs_bound / 32 + 8) * 4) || ctx->b_surv.ensure(((size_t)pairs_bound + 32) * sizeof(Survivor)))) return 1;  // stage-1 survivor bits + list
 	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;
 	if (ctx->b_vals.ensure(bm_words * 4)) return 1;  // b_vals (unsorted reference locs) is dead after the sort
 	uint32_t* d_key_seen = ctx->b_vals.as<uint32_t>();
@@ -258,9 +258,11 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 		if (hp.ungapped_evalue == 0.0)
 			stage12_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs, x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
 		else {
-			stage1_flags_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, ref->letters, d_entries, L, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(), d_cnt);
-			stage2_window_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs,
-				ctx->b_keys2.as<uint32_t>(), x, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+			DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 9, 0, sizeof(unsigned long long), st));  // survivors of this chunk
+			stage1_flags_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, ref->letters, d_entries, L, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(),
+				ctx->b_surv.as<Survivor>(), d_cnt + 9, d_cnt);
+			stage2_window_kernel<<<(unsigned)std::min<unsigned long long>(grid, (unsigned long long)ctx->sm_count * 16), STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs,
+				ctx->b_keys2.as<uint32_t>(), x, ctx->b_surv.as<Survivor>(), d_cnt + 9, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
 			++ctx->launches;
 		}
 		++ctx->launches;

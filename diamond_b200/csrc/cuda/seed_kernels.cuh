@@ -135,13 +135,13 @@ __device__ __forceinline__ void bulk_load_letters(const int8_t* __restrict__ src
 }
 #endif
 __device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p0, size_t p_end, const DevParams* __restrict__ P, uint8_t* s_code, uint8_t* s_lut,
-                                               uint8_t* s_raw, unsigned long long* mbar) {
+                                               uint8_t* s_raw, unsigned long long* mbar, bool bulk) {
 	if (threadIdx.x < 32) {
 		const unsigned r = P->reduction[threadIdx.x];
 		s_lut[threadIdx.x] = threadIdx.x == DMND_DELIMITER ? 0x80 : (r == 23 ? 0x40 : (uint8_t)r);
 	}
 #if defined(__CUDA_ARCH__)
-	{
+	if (bulk) {
 		const size_t a0 = p0 & ~(size_t)15, need_end = min(p0 + SEED_TILE + 32, p_end + 32), a1 = (need_end + 15) & ~(size_t)15;
 		bulk_load_letters(letters + a0, (unsigned)(a1 - a0), s_raw, mbar);  // (contains the barrier that also publishes s_lut)
 		const int off = (int)(p0 - a0), have = (int)(a1 - p0);
@@ -156,9 +156,8 @@ __device__ __forceinline__ void load_code_tile(const int8_t* __restrict__ letter
 		__syncthreads();
 		return;
 	}
-#else
-	(void)s_raw; (void)mbar; (void)p_end;
 #endif
+	(void)s_raw; (void)mbar; (void)p_end; (void)bulk;
 	__syncthreads();
 	if (soft) {  // soft-masked letters read as MASK_LETTER (class flag 0x40); they are never delimiters
 		for (int x = threadIdx.x; x < SEED_TILE + 32; x += blockDim.x) {
@@ -187,7 +186,7 @@ __device__ __forceinline__ bool seed_from_codes(const uint8_t* s_code, int o, co
 __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ letters, const uint32_t* __restrict__ soft, size_t p_begin, size_t p_end, const DevParams* __restrict__ P, const ShapeArg sh,
                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ bucket, int shift,
                              const uint32_t* __restrict__ bloom, uint32_t bloom_mask, const uint32_t* __restrict__ bitmap, uint32_t bitmap_mask,
-                             Entry* entries, unsigned long long* count, unsigned long long cap) {
+                             Entry* entries, unsigned long long* count, unsigned long long cap, int bulk) {
 	__shared__ uint8_t s_code[SEED_TILE + 32];
 	__shared__ uint8_t s_lut[32];
 	__shared__ __align__(16) uint8_t s_raw[SEED_RAW_BYTES];
@@ -199,14 +198,14 @@ __global__ void __launch_bounds__(256) probe_kernel(const int8_t* __restrict__ l
 	__shared__ unsigned long long s_pairs, s_base;
 	const size_t p0 = p_begin + (size_t)blockIdx.x * SEED_TILE;
 	if (threadIdx.x == 0) { s_n = 0; s_pairs = 0; }
-	load_code_tile(letters, soft, p0, p_end, P, s_code, s_lut, s_raw, &s_mbar);
+	load_code_tile(letters, soft, p0, p_end, P, s_code, s_lut, s_raw, &s_mbar, bulk != 0);
 	for (int it = 0; it < SEED_TILE / 256; ++it) {
 		const int o = it * 256 + threadIdx.x;
 		const size_t p = p0 + o;
 		uint64_t seed = 0;
 		bool ok = p < p_end && seed_from_codes(s_code, o, sh, seed);
 		uint64_t key = 0;
-		if (ok) { key = mix40(seed); ok = bitmap_test(bitmap, bitmap_mask, key) && bloom_test(bloom, bloom_mask, key); }
+		if (ok) { key = mix40(seed); ok = (bitmap == nullptr || bitmap_test(bitmap, bitmap_mask, key)) && bloom_test(bloom, bloom_mask, key); }
 		if (ok) {
 			const uint32_t b = (uint32_t)(key >> shift);
 			uint32_t i = bucket[b];
@@ -484,11 +483,14 @@ __global__ void __launch_bounds__(STAGE_CTA) stage12_kernel(const int8_t* __rest
 // Modes WITH the ungapped window filter: the reference scores the stage-1 survivors of one query location in calls of up to 32
 // subjects (per 1024-subject tile of the key, ascending subject order: search/hamming/kernel.h:61-74, hit_field.h:44-57), and
 // the size of a survivor's call decides which window kernel scores it.  Pass A writes one survivor bit per pair (one ballot
-// word per warp, the grid covers the bound so every word is written); pass B counts the survivors of the pair's tile in that
-// bitmap to find the size of its call.
+// word per warp, the grid covers the bound so every word is written) AND appends the survivors (4-5 % of the pairs with the
+// low-weight shapes of the sensitive modes) to a compact list; pass B runs over that list only -- a grid over all pairs spent 40 %
+// of the --sensitive seed stage finding out that a thread's pair had not survived -- and counts the survivors of the pair's tile
+// in the bitmap to find the size of its call.
+struct Survivor { uint64_t pid; uint32_t entry, k; };
 __global__ void __launch_bounds__(STAGE_CTA) stage1_flags_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries,
                                     PairLookup L, const uint32_t* __restrict__ ref_locs, unsigned hamming_id, uint32_t* flags,
-                                    unsigned long long* counters) {
+                                    Survivor* surv, unsigned long long* surv_count, unsigned long long* counters) {
 	__shared__ uint64_t s_off[STAGE_CTA + 1];
 	__shared__ uint32_t s_first;
 	uint64_t pid; size_t lo; uint32_t k;
@@ -499,9 +501,15 @@ __global__ void __launch_bounds__(STAGE_CTA) stage1_flags_kernel(const int8_t* _
 		pass = fingerprint_match(q_letters + e.qloc, r_letters + sloc) >= hamming_id;
 	}
 	const unsigned word = __ballot_sync(0xffffffffu, pass);
-	if ((threadIdx.x & 31) == 0) {
+	const unsigned lane = threadIdx.x & 31;
+	unsigned long long base = 0;
+	if (lane == 0) {
 		flags[pid >> 5] = word;
-		if (word) atomicAdd(&counters[2], (unsigned long long)__popc(word));
+		if (word) { atomicAdd(&counters[2], (unsigned long long)__popc(word)); base = atomicAdd(surv_count, (unsigned long long)__popc(word)); }
+	}
+	if (word) {
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (pass) surv[base + __popc(word & ((1u << lane) - 1u))] = Survivor{ pid, (uint32_t)lo, k };
 	}
 }
 __device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits, uint64_t a, uint64_t b) {  // set bits in [a, b)
@@ -518,17 +526,21 @@ __device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits
 __global__ void __launch_bounds__(STAGE_CTA) stage2_window_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
                                      const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, PairLookup L,
                                      const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
+                                     const Survivor* __restrict__ surv, const unsigned long long* __restrict__ surv_count,
                                      dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
-	__shared__ uint64_t s_off[STAGE_CTA + 1];
-	__shared__ uint32_t s_first;
-	uint64_t pid; size_t lo; uint32_t k;
-	if (!locate_pair(L, s_off, &s_first, pid, lo, k) || !((flags[pid >> 5] >> (pid & 31)) & 1u)) return;
-	const Entry e = entries[lo];
-	const uint64_t first = pid - k;
-	const uint32_t tile_begin = k & ~1023u, tile_end = min(tile_begin + 1024u, e.cnt);
-	const unsigned rank = count_bits(flags, first + tile_begin, pid), total = count_bits(flags, first + tile_begin, first + tile_end);
-	const int batch_size = (int)min(32u, total - (rank & ~31u));
-	stage2_tail(q_letters, q_limits, nq, r_letters, e, ref_locs[e.lo + k], x, batch_size, hits, hit_count, counters);
+	(void)L;
+	const unsigned long long n = *surv_count;  // known on the device only: a fixed grid strides over the list
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+		const Survivor s = surv[i];
+		const uint64_t pid = s.pid;
+		const uint32_t k = s.k;
+		const Entry e = entries[s.entry];
+		const uint64_t first = pid - k;
+		const uint32_t tile_begin = k & ~1023u, tile_end = min(tile_begin + 1024u, e.cnt);
+		const unsigned rank = count_bits(flags, first + tile_begin, pid), total = count_bits(flags, first + tile_begin, first + tile_end);
+		const int batch_size = (int)min(32u, total - (rank & ~31u));
+		stage2_tail(q_letters, q_limits, nq, r_letters, e, ref_locs[e.lo + k], x, batch_size, hits, hit_count, counters);
+	}
 }
 
 __global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, uint32_t* keys) {

@@ -366,7 +366,10 @@ template<typename K> static cudaError_t smem_optin(K kernel) {
 	std::lock_guard<std::mutex> g(mtx);
 	const void* key = reinterpret_cast<const void*>(kernel);
 	if (std::find(done.begin(), done.end(), key) != done.end()) return cudaSuccess;
-	const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DMND_SMEM_OPTIN);
+	cudaFuncAttributes fa;
+	cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DMND_SMEM_OPTIN - (int)fa.sharedSizeBytes);  // the limit covers static + dynamic
 	if (e == cudaSuccess) done.push_back(key);
 	return e;
 }

@@ -1113,9 +1113,10 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		if (!prep_rc) { w.q_patch.build(env.q_letters, env.q_limits, env.nq, q_begin, q_end, w.mask_pos.data(), w.mask_pos.size()); d.env.q_patch = &w.q_patch; }
 	}
 	seed_turn.set_masked(lane);  // (dmnd_block_mask returns when the range is masked on the device; also set on failure so nobody waits forever)
-	// the composition bias of this range on the lane's second stream: the seed stage reads letters only, the first consumers (x-drop
-	// extension, DP) wait for it on the device (dmnd_block_bias_wait below)
-	prep_rc = prep_rc || dmnd_block_compute_bias_range_async(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end);
+	// the composition bias of this range.  DMND_ASYNC_BIAS=1 computes it on the lane's second stream beside the seed stage (which reads
+	// letters only; the first consumers wait on the device, dmnd_block_bias_wait below): it removes a 2 ms bubble at the start of a step
+	// but two of two B200 runs with it showed a 190 ms outlier step, so the synchronous form stays the default (profiles/ab_seed_r2.txt)
+	prep_rc = prep_rc || (getenv("DMND_ASYNC_BIAS") ? dmnd_block_compute_bias_range_async(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end) : dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end));
 	seed_turn.wait_masked(lane + 1);
 	prof.lane = lane;
 	prof.lap("wait, mask, bias");

@@ -92,7 +92,7 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 	size_t ecap = std::max<size_t>(1 << 20, qpos / 8);
 	std::vector<Entry> entries(ecap);
 	emu::launch((unsigned)((qpos + SEED_TILE - 1) / SEED_TILE), 256, [&] { probe_kernel(query.letters.data(), query.has_soft ? query.soft.data() : nullptr, qp_begin, qp_end, &P, sh, ix.keys.data(),
-		ix.bucket.data(), ix.shift, ix.bloom.data(), ix.bloom_blocks - 1, ix.bitmap.data(), ix.bitmap_mask, entries.data(), cnt + 5, ecap); });
+		ix.bucket.data(), ix.shift, ix.bloom.data(), ix.bloom_blocks - 1, ix.bitmap.data(), ix.bitmap_mask, entries.data(), cnt + 5, ecap, 1); });
 	const unsigned long long nent = cnt[5], pairs_bound = cnt[6];
 	if (nent > ecap) { printf("FAIL entry capacity\n"); exit(1); }
 	if (query.has_soft && qpos > 0) emu::launch((unsigned)((qpos + 255) / 256), 256, [&] { motif_seedmask_kernel(query.letters.data(), query.soft.data(), qp_begin, qp_end, hp.shape_len[sid]); });
@@ -125,9 +125,11 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 		if (hp.ungapped_evalue == 0.0)
 			emu::launch(grid, STAGE_CTA, [&] { stage12_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), x, dh.data(), cnt + 6, cnt); });
 		else {
-			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), cnt); });
-			emu::launch(grid, STAGE_CTA, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
-				dh.data(), cnt + 6, cnt); });
+			std::vector<Survivor> surv((size_t)pairs_bound + 32);
+			cnt[9] = 0;
+			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), surv.data(), cnt + 9, cnt); });
+			emu::launch(std::min(grid, 7u), STAGE_CTA, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
+				surv.data(), cnt + 9, dh.data(), cnt + 6, cnt); });
 		}
 	}
 	hits.assign(dh.begin(), dh.begin() + (ptrdiff_t)cnt[6]);
