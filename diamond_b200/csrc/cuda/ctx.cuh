@@ -106,6 +106,7 @@ struct dmnd_ctx {
 	// scratch
 	dmnd_cuda::DevBuf b_keys, b_keys2, b_vals, b_vals2, b_cub, b_bucket, b_entries, b_pairs, b_hits, b_hits2, b_counters;
 	dmnd_cuda::DevBuf b_surv;  // stage-1 survivors of one index chunk (seed.cu)
+	unsigned long long last_pairs_bound = 0;  // (q, s) pairs of the last search slice (sizes the next one)
 	dmnd_cuda::DevBuf b_probs, b_results, b_order, b_trace, b_trace_off, b_tr, b_work, b_prep, b_bloom;
 	dmnd_cuda::DevBuf b_mask_pb, b_mask_scale, b_mask_pos, b_mask_pos2, b_mask_cov, b_mask_flag, b_mask_seqs, b_mask_zinv, b_mask_need;  // dmnd_block_mask scratch
 	uint64_t mask_n = 0;  // letters hard-masked by the last dmnd_block_mask on this context (sorted offsets in b_mask_pos)

@@ -209,8 +209,12 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 		++ctx->launches;
 	}
 	DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(unsigned long long), st));
+	ctx->last_pairs_bound = pairs_bound;
 	if (ctx->b_hits.ensure((size_t)(pairs_bound + 1) * sizeof(dmnd_hit))) return 1;
-	if (hp.ungapped_evalue != 0.0 && (ctx->b_keys2.ensure(((size_t)pairs_bound / 32 + 8) * 4) || ctx->b_surv.ensure(((size_t)pairs_bound + 32) * sizeof(Survivor)))) return 1;  // stage-1 survivor bits + list
+	// stage-1 survivors of one chunk: 1.6 % of the pairs on the --sensitive bench workload; the list holds 1/8 of the slice's pairs and a
+	// chunk that overflows it is scored by the grid over all its pairs instead
+	const unsigned long long surv_cap = pairs_bound / 8 + (1ull << 20);
+	if (hp.ungapped_evalue != 0.0 && (ctx->b_keys2.ensure(((size_t)pairs_bound / 32 + 8) * 4) || ctx->b_surv.ensure((size_t)surv_cap * sizeof(Survivor)))) return 1;  // stage-1 survivor bits + list
 	const size_t bm_words = ((size_t)nref + 31) / 32 + 1;
 	if (ctx->b_vals.ensure(bm_words * 4)) return 1;  // b_vals (unsorted reference locs) is dead after the sort
 	uint32_t* d_key_seen = ctx->b_vals.as<uint32_t>();
@@ -260,9 +264,12 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 		else {
 			DMND_CUDA_CHECK(cudaMemsetAsync(d_cnt + 9, 0, sizeof(unsigned long long), st));  // survivors of this chunk
 			stage1_flags_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, ref->letters, d_entries, L, d_locs, (unsigned)hp.hamming_id, ctx->b_keys2.as<uint32_t>(),
-				ctx->b_surv.as<Survivor>(), d_cnt + 9, d_cnt);
+				ctx->b_surv.as<Survivor>(), d_cnt + 9, surv_cap, d_cnt);
 			stage2_window_kernel<<<(unsigned)std::min<unsigned long long>(grid, (unsigned long long)ctx->sm_count * 16), STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs,
-				ctx->b_keys2.as<uint32_t>(), x, ctx->b_surv.as<Survivor>(), d_cnt + 9, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+				ctx->b_keys2.as<uint32_t>(), x, ctx->b_surv.as<Survivor>(), d_cnt + 9, surv_cap, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);
+			stage2_window_full_kernel<<<grid, STAGE_CTA, 0, st>>>(query->letters, query->limits, query->nseq, ref->letters, d_entries, L, d_locs,
+				ctx->b_keys2.as<uint32_t>(), x, d_cnt + 9, surv_cap, ctx->b_hits.as<dmnd_hit>(), d_cnt + 6, d_cnt);  // leaves at once unless the list overflowed
+			++ctx->launches;
 			++ctx->launches;
 		}
 		++ctx->launches;
@@ -317,13 +324,13 @@ static int search_slice(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref,
 int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, int sid, uint32_t q_begin, uint32_t q_end, dmnd_hits** out, dmnd_stage_counters* counters) {
 	dmnd_stage_counters cn;
 	std::memset(&cn, 0, sizeof cn);
-	// ... and fewer where the reference is large for the shape weight: a query position then meets ~ reference letters / 10^weight
-	// reference positions (x 3 for the skew of real seed frequencies), and the (q, s) pair buffers of a slice are held to ~2.5*10^8 pairs
-	size_t slice = (size_t)-1;
-	if (ctx->params.shape_weight < 10) {
-		const double per_pos = 3.0 * (double)ref->raw_len / std::pow((double)ctx->params.reduction_size, (double)ctx->params.shape_weight);
-		slice = (size_t)std::min(4e7, std::max(1e6, 2.5e8 / std::max(per_pos, 1.0)));
-	}
+	// The (q, s) pair buffers of a slice (16 bytes per pair for the hits, 2 for the survivor list) are held to ~5*10^8 pairs: the first
+	// slice of a call is small (the pair density of real seed frequencies is 50-100 x what letters / 10^weight suggests: 292 pairs per
+	// query letter for --sensitive on 1.5*10^8 reference letters), every further slice is sized from the density measured so far
+	const bool adaptive = ctx->params.shape_weight < 10 && getenv("DMND_SEED_SLICE") == nullptr;
+	const double target_pairs = 5e8;
+	size_t slice = adaptive ? (size_t)2000000 : (size_t)-1;
+	double letters_done = 0.0, pairs_done = 0.0;
 	if (const char* ev = getenv("DMND_SEED_SLICE")) slice = std::max<size_t>(1024, strtoull(ev, nullptr, 10));
 	size_t total = 0;
 	uint32_t b = q_begin;
@@ -334,6 +341,10 @@ int search_shape_impl(dmnd_ctx* ctx, dmnd_block* query, const dmnd_block* ref, i
 		size_t n = 0;
 		if (search_slice(ctx, query, ref, sid, b, e, total, &n, &cn)) return 1;
 		total += n;
+		if (adaptive) {
+			letters_done += (double)((size_t)query->h_limits[e] - p0); pairs_done += (double)ctx->last_pairs_bound;
+			slice = (size_t)std::min(4e7, std::max(2e5, target_pairs * letters_done / std::max(pairs_done, 1.0)));
+		}
 		b = e;
 	} while (b < q_end);
 	dmnd_hits* h = new dmnd_hits();

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(STAGE_CTA) stage12_kernel(const int8_t* __rest
 struct Survivor { uint64_t pid; uint32_t entry, k; };
 __global__ void __launch_bounds__(STAGE_CTA) stage1_flags_kernel(const int8_t* __restrict__ q_letters, const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries,
                                     PairLookup L, const uint32_t* __restrict__ ref_locs, unsigned hamming_id, uint32_t* flags,
-                                    Survivor* surv, unsigned long long* surv_count, unsigned long long* counters) {
+                                    Survivor* surv, unsigned long long* surv_count, unsigned long long surv_cap, unsigned long long* counters) {
 	__shared__ uint64_t s_off[STAGE_CTA + 1];
 	__shared__ uint32_t s_first;
 	uint64_t pid; size_t lo; uint32_t k;
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(STAGE_CTA) stage1_flags_kernel(const int8_t* _
 	}
 	if (word) {
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (pass) surv[base + __popc(word & ((1u << lane) - 1u))] = Survivor{ pid, (uint32_t)lo, k };
+		if (pass && base + 32 <= surv_cap) surv[base + __popc(word & ((1u << lane) - 1u))] = Survivor{ pid, (uint32_t)lo, k };  // (a full list is detected by the count: the window pass then takes the grid over all pairs)
 	}
 }
 __device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits, uint64_t a, uint64_t b) {  // set bits in [a, b)
@@ -526,10 +526,11 @@ __device__ __forceinline__ unsigned count_bits(const uint32_t* __restrict__ bits
 __global__ void __launch_bounds__(STAGE_CTA) stage2_window_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
                                      const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, PairLookup L,
                                      const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
-                                     const Survivor* __restrict__ surv, const unsigned long long* __restrict__ surv_count,
+                                     const Survivor* __restrict__ surv, const unsigned long long* __restrict__ surv_count, unsigned long long surv_cap,
                                      dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
 	(void)L;
 	const unsigned long long n = *surv_count;  // known on the device only: a fixed grid strides over the list
+	if (n + 32 > surv_cap) return;             // the list overflowed (sized for 1/8 of the pairs): stage2_window_full_kernel does this chunk
 	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
 		const Survivor s = surv[i];
 		const uint64_t pid = s.pid;
@@ -541,6 +542,25 @@ __global__ void __launch_bounds__(STAGE_CTA) stage2_window_kernel(const int8_t* 
 		const int batch_size = (int)min(32u, total - (rank & ~31u));
 		stage2_tail(q_letters, q_limits, nq, r_letters, e, ref_locs[e.lo + k], x, batch_size, hits, hit_count, counters);
 	}
+}
+
+// the same pass as a grid over all pairs of the chunk: only when the survivor list overflowed
+__global__ void __launch_bounds__(STAGE_CTA) stage2_window_full_kernel(const int8_t* __restrict__ q_letters, const int64_t* __restrict__ q_limits, uint32_t nq,
+                                     const int8_t* __restrict__ r_letters, const Entry* __restrict__ entries, PairLookup L,
+                                     const uint32_t* __restrict__ ref_locs, const uint32_t* __restrict__ flags, LmCtx x,
+                                     const unsigned long long* __restrict__ surv_count, unsigned long long surv_cap,
+                                     dmnd_hit* hits, unsigned long long* hit_count, unsigned long long* counters) {
+	__shared__ uint64_t s_off[STAGE_CTA + 1];
+	__shared__ uint32_t s_first;
+	if (*surv_count + 32 <= surv_cap) return;
+	uint64_t pid; size_t lo; uint32_t k;
+	if (!locate_pair(L, s_off, &s_first, pid, lo, k) || !((flags[pid >> 5] >> (pid & 31)) & 1u)) return;
+	const Entry e = entries[lo];
+	const uint64_t first = pid - k;
+	const uint32_t tile_begin = k & ~1023u, tile_end = min(tile_begin + 1024u, e.cnt);
+	const unsigned rank = count_bits(flags, first + tile_begin, pid), total = count_bits(flags, first + tile_begin, first + tile_end);
+	const int batch_size = (int)min(32u, total - (rank & ~31u));
+	stage2_tail(q_letters, q_limits, nq, r_letters, e, ref_locs[e.lo + k], x, batch_size, hits, hit_count, counters);
 }
 
 __global__ void extract_query_kernel(const dmnd_hit* __restrict__ h, size_t n, uint32_t* keys) {

@@ -125,11 +125,15 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 		if (hp.ungapped_evalue == 0.0)
 			emu::launch(grid, STAGE_CTA, [&] { stage12_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), x, dh.data(), cnt + 6, cnt); });
 		else {
-			std::vector<Survivor> surv((size_t)pairs_bound + 32);
+			// every other chunk with a list that is too small: the window pass must then come from the grid over all pairs
+			const unsigned long long surv_cap = (chunk & 1) ? 40 : pairs_bound + 64;
+			std::vector<Survivor> surv((size_t)surv_cap);
 			cnt[9] = 0;
-			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), surv.data(), cnt + 9, cnt); });
+			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), surv.data(), cnt + 9, surv_cap, cnt); });
 			emu::launch(std::min(grid, 7u), STAGE_CTA, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
-				surv.data(), cnt + 9, dh.data(), cnt + 6, cnt); });
+				surv.data(), cnt + 9, surv_cap, dh.data(), cnt + 6, cnt); });
+			emu::launch(grid, STAGE_CTA, [&] { stage2_window_full_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
+				cnt + 9, surv_cap, dh.data(), cnt + 6, cnt); });
 		}
 	}
 	hits.assign(dh.begin(), dh.begin() + (ptrdiff_t)cnt[6]);
