@@ -120,12 +120,16 @@ static int fs_impl(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* ref
 		DMND_CUDA_CHECK(stream_wait(ctx, st));
 	}
 	else {
-		std::vector<int32_t> sc(n);
-		DMND_CUDA_CHECK(cudaMemcpyAsync(sc.data(), d_score, n * 4, cudaMemcpyDeviceToHost, st));
-		ctx->d2h_bytes += n * 4;
+		std::vector<int32_t> sc(2 * n);  // scores, then the first column that reaches each
+		DMND_CUDA_CHECK(cudaMemcpyAsync(sc.data(), d_score, 2 * n * 4, cudaMemcpyDeviceToHost, st));
+		ctx->d2h_bytes += 2 * n * 4;
 		timer.stop();
 		DMND_CUDA_CHECK(stream_wait(ctx, st));
-		for (size_t k = 0; k < n; ++k) { std::memset(&results[k], 0, sizeof results[k]); results[k].score = sc[k]; }
+		for (size_t k = 0; k < n; ++k) {
+			std::memset(&results[k], 0, sizeof results[k]);
+			results[k].score = sc[k];
+			if (sc[k] > 0) { const int i1 = std::max(problems[k].d_end - 1, 0); results[k].t_end = i1 - (problems[k].d_end - 1) + sc[n + k] + 1; }
+		}
 	}
 	return 0;
 }

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(128) fs_swipe_kernel(const FsArgs a, const Dev
 			const int ov = __shfl_xor_sync(FULL, bv, o), oc = __shfl_xor_sync(FULL, bc, o);
 			if (ov > bv || (ov == bv && ov > 0 && oc < bc)) { bv = ov; bc = oc; }
 		}
-		if (lane == 0) { a.score[pi] = bv; if (TRACE) a.max_col[pi] = bc; }
+		if (lane == 0) { a.score[pi] = bv; a.max_col[pi] = bc; }
 	}
 }
 

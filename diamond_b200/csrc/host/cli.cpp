@@ -441,7 +441,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false;
+		bool header_simple = false, long_reads = false;
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
@@ -508,6 +508,8 @@ int main(int argc, char** argv) {
 			}
 			else if (a == "--min-orf" || a == "-l") { min_orf = atoi(val()); if (min_orf < 0) usage("--min-orf must not be negative"); }
 			else if (a == "--query-gencode") gencode = atoi(val());
+			else if (a == "--range-culling") o.range_culling = 1;
+			else if (a == "--long-reads") long_reads = true;  // basic/config.cpp:679-686
 			else if (a == "-F" || a == "--frameshift") { o.frame_shift = atoi(val()); if (o.frame_shift <= 0) usage("--frameshift needs a positive penalty (the reference's usual value is 15)"); }
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
@@ -520,6 +522,12 @@ int main(int argc, char** argv) {
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
+		if (long_reads) {  // --long-reads = --range-culling --top 10 -F 15 (each only where not given)
+			o.range_culling = 1;
+			if (!top_set) { o.top_percent = 10.0; top_set = true; }
+			if (o.frame_shift == 0) o.frame_shift = 15;
+		}
+		if (o.range_culling && o.frame_shift == 0) usage("Query range culling is only supported in frameshift alignment mode (option -F).");  // basic/config.cpp:824-825
 		if (pairwise || paf || sam) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
@@ -662,12 +670,33 @@ int main(int argc, char** argv) {
 		}
 		// frameshift mode: the legacy pipeline visits EVERY query, also those without a seed hit (align/align.cpp:120-130,168-172), so every
 		// query without an alignment is reported by the formats that report unaligned queries
+		// -- but only inside a query BIN of the seed-hit buffer that holds at least one hit: align_queries loops over the bins
+		// (search/hit_buffer.cpp:149-188, one bin per load), a bin without hits starts no worker, and the unaligned records of its
+		// queries never appear.  Bins = SequenceSet::partition(query_bins, true, true) (data/sequence_set.cpp:57-75): query_bins =
+		// max(round(threads / 8), 16; 64 for --ultra-sensitive) runs of whole queries of >= ceil(letters / query_bins) letters.
 		std::vector<uint32_t> fs_unal;
 		if (fshift) {
+			const uint32_t nsrc = (uint32_t)dq.ids.size();
+			std::vector<uint8_t> has_hits(nsrc, 0);
+			for (size_t i = 0; i < n; ++i) has_hits[m[i].query / 6] = 1;
+			{ size_t nu = 0; const uint32_t* u = dmnd_result_unaligned(res, &nu); for (size_t i = 0; i < nu; ++i) has_hits[u[i] / 6] = 1; }
+			const unsigned n_part = std::max((unsigned)std::lround((double)o.threads / 8.0), o.sensitivity >= 6 ? 64u : 16u);
+			int64_t letters = 0;
+			for (uint32_t c = 0; c < 6 * nsrc; ++c) letters += q.limits[c + 1] - q.limits[c] - 1;
+			const int64_t per_bin = (letters + n_part - 1) / n_part;
+			std::vector<uint8_t> visited(nsrc, 0);
+			for (uint32_t sq = 0; sq < nsrc;) {
+				int64_t acc = 0;
+				const uint32_t b0 = sq;
+				while (sq < nsrc && acc < per_bin) { for (uint32_t c = 6 * sq; c < 6 * sq + 6; ++c) acc += q.limits[c + 1] - q.limits[c] - 1; ++sq; }
+				bool any = false;
+				for (uint32_t x = b0; x < sq; ++x) any |= has_hits[x] != 0;
+				if (any) std::fill(visited.begin() + b0, visited.begin() + sq, (uint8_t)1);
+			}
 			size_t mi = 0;
-			for (uint32_t sq = 0; sq < (uint32_t)dq.ids.size(); ++sq) {
+			for (uint32_t sq = 0; sq < nsrc; ++sq) {
 				while (mi < n && m[mi].query / 6 < sq) ++mi;
-				if (!(mi < n && m[mi].query / 6 == sq)) fs_unal.push_back(6 * sq);
+				if (!(mi < n && m[mi].query / 6 == sq) && visited[sq]) fs_unal.push_back(6 * sq);
 			}
 		}
 		auto result_unaligned = [&](size_t* nu) -> const uint32_t* {

@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cfloat>
 #include <climits>
+#include <map>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -281,6 +282,7 @@ struct Env {
 	int mask_algo = 0;  // DMND_MASK_* bits a lane applies to its own query range before searching (0: blocks arrive masked)
 	uint32_t contexts = 1;  // align_mode.query_contexts: 6 = blastx, the query block holds the six frames of every query back to back
 	int frame_shift = 0;    // config.frame_shift: > 0 = frameshift alignment mode, the legacy extension pipeline (align/align.cpp:168-172)
+	bool range_culling = false; double range_cover = 50.0;  // config.query_range_culling / query_range_cover (frameshift mode only, basic/config.cpp:824-825)
 	const int8_t* qseq(uint32_t q) const { const int8_t* p = q_patch ? q_patch->find(q) : nullptr; return p ? p : q_letters + q_limits[q]; }
 	const int8_t* rseq(uint32_t t) const { const int8_t* p = r_patch ? r_patch->find(t) : nullptr; return p ? p : r_letters + r_limits[t]; }
 	const int64_t *q_limits, *r_limits;
@@ -1435,6 +1437,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.hauser = opts->comp_based_stats == 1; e.want_transcript = opts->want_transcript != 0;
 	e.frame_shift = opts->frame_shift;
 	if (e.frame_shift < 0 || (e.frame_shift > 0 && contexts != 6)) { dmnd_set_last_error("dmnd_blastp: frame_shift needs translated queries (query_contexts = 6) and a positive penalty"); return 1; }
+	e.range_culling = opts->range_culling != 0;
+	if (e.range_culling && !e.frame_shift) { dmnd_set_last_error("dmnd_blastp: query range culling is only supported in frameshift alignment mode"); return 1; }  // basic/config.cpp:824-825
 	if (e.frame_shift) {
 		// the legacy pipeline extends without composition bias (align/legacy/query_mapper.cpp:131: xdrop_ungapped(.., nullptr, ..);
 		// banded_3frame_swipe takes no bias at all) and always keeps the transcript (output/output_format.cpp:256-257)

@@ -305,8 +305,9 @@ int dmnd_banded_swipe(dmnd_ctx* ctx, const dmnd_block* query, const dmnd_block* 
  * the forward strand, 6q + 3 for the reverse strand; the next two sequences of the query block are its frames +1 and +2),
  * d_begin / d_end = band of translated diagonals (i - j, i = codon index).  Cell (codon start x = 3i + f, column j):
  *   H = max(0, H(x-3, j-1) + s, H(x-4, j-1) + s - F, H(x-2, j-1) + s - F, hgap from (x, j-1), vgap from (x-3, j)),
- * F = frame_shift, no composition bias (the reference's legacy pipeline passes none).  DMND_DP_SCORE_ONLY fills `score` only
- * (the caller passes the band its int16 SIMD batch would have had, see host/legacy.cpp); DMND_DP_TRACEBACK keeps the score
+ * F = frame_shift, no composition bias (the reference's legacy pipeline passes none).  DMND_DP_SCORE_ONLY fills `score` and `t_end`
+ * (1 + the first target position whose column reaches the score: the reference's max_col; the caller passes the band its int16 SIMD
+ * batch would have had, see host/legacy.inc); DMND_DP_TRACEBACK keeps the score
  * matrix and walks it back exactly as the reference does (:338-390, TracebackIterator :152-250), incl. its gap search order.
  * Transcript bytes as dmnd_banded_swipe, plus DMND_TR_FRAMESHIFT_FWD / _REV (op_frameshift_forward / _reverse; in forward
  * order such a byte precedes the match column that was reached through the shift). */
@@ -371,7 +372,9 @@ typedef struct dmnd_search_opts {
 	                              query_contexts == 6.  dmnd_match then reports the frame the alignment BEGINS in (query), codon positions in the
 	                              begin / end frames (q_begin, q_end) and the END frame in `reserved` (1 + context offset 0..5); transcripts are
 	                              always kept and may hold DMND_TR_FRAMESHIFT_* bytes.  0 = off */
-	int32_t reserved0;
+	int32_t range_culling;     /* --range-culling (config.query_range_culling, frameshift mode only): targets are ranked and culled per query RANGE --
+	                              a target is dropped when half of the read range of its HSPs is already covered by better targets
+	                              (align/legacy/banded_swipe_pipeline.cpp:139-154, output/target_culling.h:110-160).  --long-reads = this + top 10 + -F 15 */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

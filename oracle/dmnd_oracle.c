@@ -1252,6 +1252,7 @@ static int fs_swipe_one(const dmnd_ctx* ctx, const int8_t* const q[3], const int
 		if (col_best > best) { best = col_best; max_col = j; }
 	}
 	res->score = best;
+	if (best > 0) res->t_end = pos0 + max_col + 1; /* score only: the first column that reaches the score (the reference's max_col, :495-498) */
 	if (mode != DMND_DP_TRACEBACK || best <= 0) { free(S); free(hgap); return 0; }
 	/* traceback(): :338-390, dp.traceback :257-267 */
 	const long total = (long)W * ((long)ncol + 1);

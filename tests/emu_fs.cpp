@@ -108,7 +108,11 @@ int main(int argc, char** argv) {
 	for (int i = 0; i < nprob; ++i) {
 		const dmnd_fs_result &ro = want[(size_t)i], &re = got[(size_t)i];
 		bool same;
-		if (!trace) same = ro.score == score[(size_t)i];
+		if (!trace) {  // score and the first column that reaches it (dmnd_fs_result.t_end of the score-only mode)
+			const dmnd_dp_problem& pr = probs[(size_t)i];
+			const int i1 = std::max(pr.d_end - 1, 0), pos0 = i1 - (pr.d_end - 1);
+			same = ro.score == score[(size_t)i] && (ro.score <= 0 || ro.t_end == pos0 + maxcol[(size_t)i] + 1);
+		}
 		else {
 			same = ro.score == re.score && ro.status == re.status && ro.q_begin == re.q_begin && ro.q_end == re.q_end && ro.frame_begin == re.frame_begin && ro.frame_end == re.frame_end
 				&& ro.t_begin == re.t_begin && ro.t_end == re.t_end && ro.identities == re.identities && ro.mismatches == re.mismatches && ro.gap_openings == re.gap_openings

@@ -22,6 +22,7 @@ For every workload W and parity-ladder level L:
     XF / XF0 / XF3 = blastx in frameshift alignment mode (-F 15: the legacy extension pipeline + the 3-frame banded DP): --fast with
          the transcript fields (cigar / btop carry the \\ and / frameshift marks) + qframe, --fast in the pairwise format (.txt, with
          the "No hits found" records of every unaligned read), --sensitive with the default fields
+    XL = blastx --long-reads (= --range-culling --top 10 -F 15, default sensitivity): targets ranked and culled per query range
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
 """
@@ -82,13 +83,15 @@ def main_blastx():
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", []),
-                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", [])):
+                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", [])):
                 out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl != "xf0" else f"{name}.{lvl}.txt")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
                 mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"], "xf3": ["--sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
                 if lvl.startswith("xf"):
                     mode = mode + ["-F", "15"]
+                if lvl == "xl":
+                    mode = ["--long-reads"]  # default sensitivity, --range-culling --top 10 -F 15
                 r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "0" if lvl == "xf0" else "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

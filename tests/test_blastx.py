@@ -186,13 +186,13 @@ def test_vectorised_translation_equals_per_read_translation():
 XF_FIELDS = XT_FIELDS + ["qframe"]
 
 
-@pytest.mark.parametrize("lvl,flags,ext", [("xf", ["--fast", "-f", "6"] + XF_FIELDS, "tsv"), ("xf0", ["--fast", "-f", "0"], "txt"), ("xf3", ["--sensitive"], "tsv")])
+@pytest.mark.parametrize("lvl,flags,ext", [("xf", ["--fast", "-f", "6"] + XF_FIELDS, "tsv"), ("xf0", ["--fast", "-f", "0"], "txt"), ("xf3", ["--sensitive"], "tsv"), ("xl", ["--long-reads"], "tsv")])
 def test_blastx_frameshift_cli(oracle_lib, tmp_path, lvl, flags, ext):
     """Transcripts with \\ and / frameshift marks (cigar, btop, gapped sequences), begin and end of an alignment in different frames,
     the pairwise format with its "No hits found" record for EVERY unaligned read, and a many-shape mode (no gapped filter in the legacy pipeline)."""
     q, d = _files(_bx(), tmp_path)
     o = str(tmp_path / "o.out")
-    r = subprocess.run([CLI, "blastx"] + flags + ["-F", "15", "-q", q, "-d", d, "-o", o, "-p", "8", "--log"], capture_output=True, text=True)
+    r = subprocess.run([CLI, "blastx"] + flags + ([] if lvl == "xl" else ["-F", "15"]) + ["-q", q, "-d", d, "-o", o, "-p", "8", "--log"], capture_output=True, text=True)  # xl: --long-reads = --range-culling --top 10 -F 15
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, f"bx.{lvl}.{ext}")).read()
     gold = json.load(open(os.path.join(GOLDEN, f"bx.{lvl}.counters.json")))

@@ -61,6 +61,9 @@ def test_frameshift_cli_matches_reference_golden(product_lib, tmp_path):
     r = subprocess.run([cli, "blastx", "--sensitive", "-F", "15", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(o).read() == open(os.path.join(GOLDEN, "bx.xf3.tsv")).read()
+    r = subprocess.run([cli, "blastx", "--long-reads", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)  # range culling: the score-only round's column feeds the read ranges
+    assert r.returncode == 0, r.stderr
+    assert open(o).read() == open(os.path.join(GOLDEN, "bx.xl.tsv")).read()
 
 
 @pytest.mark.parametrize("seed,maxdna,maxband", [(1, 600, 130), (2, 150, 40), (3, 4000, 900)])
@@ -123,9 +126,9 @@ def test_3frame_swipe_kernels_match_oracle(product_lib, oracle_lib, seed, maxdna
         qb, rb = g.upload(q_raw, q_lim), g.upload(r_raw, r_lim)
         so, _ = g.banded_3frame_swipe(qb, rb, pr, 15, False)
         tb, tr = g.banded_3frame_swipe(qb, rb, pr, 15, True, cap)
-        out[name] = (so["score"].copy(), tb.copy(), [bytes(tr[int(x["transcript_off"]):int(x["transcript_off"]) + int(x["transcript_len"])]) for x in tb])
+        out[name] = (so["score"].copy(), tb.copy(), [bytes(tr[int(x["transcript_off"]):int(x["transcript_off"]) + int(x["transcript_len"])]) for x in tb], so["t_end"].copy())
         g.close()
-    assert np.array_equal(out["gpu"][0], out["oracle"][0])
+    assert np.array_equal(out["gpu"][0], out["oracle"][0]) and np.array_equal(out["gpu"][3], out["oracle"][3])  # score-only: score and t_end (first column of the score)
     a, b = out["gpu"][1], out["oracle"][1]
     for k in ("score", "q_begin", "q_end", "frame_begin", "frame_end", "t_begin", "t_end", "identities", "mismatches", "gap_openings", "length", "gaps", "positives", "transcript_len", "status"):
         assert np.array_equal(a[k], b[k]), k

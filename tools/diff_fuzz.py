@@ -19,13 +19,15 @@ def main():
     ap.add_argument("--runs", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cli", default=os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli"))
+    ap.add_argument("--frameshift", type=float, default=None, help="probability of -F on a blastx run (default 0.35); 1 with --translated-only = frameshift runs only")
+    ap.add_argument("--translated-only", action="store_true")
     a = ap.parse_args()
     rnd = random.Random(a.seed)
     bad = 0
     with tempfile.TemporaryDirectory() as td:
         for run in range(a.runs):
             seed = rnd.randrange(1 << 30)
-            translated = rnd.random() < 0.4
+            translated = a.translated_only or rnd.random() < 0.4
             d = os.path.join(td, "d.faa")
             if translated:
                 w = synth.reads_workload(seed, n_db=rnd.choice([300, 800]), n_q=rnd.choice([80, 200]))
@@ -57,8 +59,18 @@ def main():
             if translated:
                 if rnd.random() < 0.3: opts += ["--strand", rnd.choice(["plus", "minus"])]
                 if rnd.random() < 0.3: opts += ["--min-orf", str(rnd.choice([1, 10, 35]))]
-            fmt = rnd.choice(["6", "6", "6f", "6g", "0", "paf", "sam"])
-            if fmt == "6f":
+            fshift = translated and rnd.random() < (a.frameshift if a.frameshift is not None else 0.35)  # blastx -F: the legacy pipeline + 3-frame DP
+            if fshift:
+                u = rnd.random()
+                if u < 0.25 and "--top" not in opts and "-k" not in opts: opts += ["--long-reads"]  # = --range-culling --top 10 -F 15
+                else:
+                    opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
+                    if u < 0.5: opts += ["--range-culling"]
+            fmt = rnd.choice(["6", "6", "6f", "0"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "0", "paf", "sam"])
+            if fmt == "6f" and fshift:
+                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident"]
+                if rnd.random() < 0.5: opts += ["--unal", "1"]
+            elif fmt == "6f":
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
             elif fmt == "6g":
