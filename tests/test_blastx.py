@@ -93,6 +93,8 @@ def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
     from diamond_b200 import api
     q, d = _files(_bx(), tmp_path)
     r = subprocess.run([CLI, "blastx", "--fast", "--range-culling", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "only supported in frameshift alignment mode" in r.stderr  # the reference's own rule (basic/config.cpp:824-825)
+    r = subprocess.run([CLI, "blastx", "--fast", "--taxon-k", "1", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported option" in r.stderr
     r = subprocess.run([CLI, "blastx", "--fast", "-F", "15", "-f", "sam", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # frameshift alignment: tabular and pairwise only
     assert r.returncode != 0 and "not implemented in this mode" in r.stderr
