@@ -1089,8 +1089,32 @@ struct SeedTurn {
 	void pass(int lane) { { std::lock_guard<std::mutex> l(m); turn = std::max(turn, lane + 1); } cv.notify_all(); }
 };
 
+// Block mode of the device-bridged path (one shape, one context, no gapped filter): the seed stage and dmnd_hits_chain run ONCE over the
+// whole query block (lane 0, after every lane has prepared -- waited for, masked, biased -- its own query range), then every lane takes the
+// queries of its range from the shared chain records: banded swipe on the lane's context (at most two calls in flight, in lane order) and the
+// host work beside the next lane's kernels.  A seed stage per lane cost 38 ms of wall time per 10^6 queries for 19 ms of kernels (the lanes'
+// seed kernels queue behind each other's DP); one seed stage over the block takes 15 ms.  DMND_PIPELINE_LANES=1 selects the per-lane form.
+struct BlockStage {
+	bool on = false;
+	int nlanes = 0;
+	std::mutex m;
+	std::condition_variable cv;
+	int prepped = 0;      // lanes whose query range is resident, masked and biased
+	int state = 0;        // 0 = chain records not there yet, 1 = published, -1 = failed
+	Workspace* root = nullptr;  // lane 0's workspace: cq / cprobs / hv / segv / sitev of the whole block
+	dmnd_chain_out co{};
+	int dp_started = 0, dp_done = 0;
+	void arrive() { { std::lock_guard<std::mutex> l(m); ++prepped; } cv.notify_all(); }
+	void wait_all_prepped() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return prepped >= nlanes || state < 0; }); }
+	void publish(int st) { { std::lock_guard<std::mutex> l(m); if (state == 0) state = st; } cv.notify_all(); }
+	int wait_published() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return state != 0; }); return state; }
+	void dp_begin(int lane) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return state < 0 || (dp_started >= lane && dp_done >= lane - 1); }); dp_started = std::max(dp_started, lane + 1); cv.notify_all(); }
+	void dp_end(int lane) { { std::lock_guard<std::mutex> l(m); dp_started = std::max(dp_started, lane + 1); dp_done = std::max(dp_done, lane + 1); } cv.notify_all(); }
+	void abort() { { std::lock_guard<std::mutex> l(m); state = -1; prepped = nlanes; dp_started = dp_done = nlanes; } cv.notify_all(); }
+};
+
 static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const Env& env, const Scoring& sc, uint32_t q_begin, uint32_t q_end,
-                    Workspace& w, int host_threads, LaneOut& lo, int lane, SeedTurn& seed_turn) {
+                    Workspace& w, int host_threads, LaneOut& lo, int lane, SeedTurn& seed_turn, BlockStage& bs) {
 	auto t_total = Clock::now();
 	Driver d;
 	d.ctx = ctx; d.qb = qb; d.rb = rb; d.ws = &w; d.T = host_threads; d.env = env;
@@ -1118,11 +1142,12 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	// the composition bias of this range.  DMND_ASYNC_BIAS=1 computes it on the lane's second stream beside the seed stage (which reads
 	// letters only; the first consumers wait on the device, dmnd_block_bias_wait below): it removes a 2 ms bubble at the start of a step
 	// but two of two B200 runs with it showed a 190 ms outlier step, so the synchronous form stays the default (profiles/ab_seed_r2.txt)
-	prep_rc = prep_rc || (getenv("DMND_ASYNC_BIAS") ? dmnd_block_compute_bias_range_async(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end) : dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end));
-	seed_turn.wait_masked(lane + 1);
+	// (block mode: lane 0 extends the hits of EVERY range, so each lane's bias must be complete when the lane reports in)
+	prep_rc = prep_rc || ((getenv("DMND_ASYNC_BIAS") && !bs.on) ? dmnd_block_compute_bias_range_async(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end) : dmnd_block_compute_bias_range(ctx, qb, env.hauser ? 1 : 0, q_begin, q_end));
+	if (!bs.on) seed_turn.wait_masked(lane + 1);  // (block mode: lane 0 searches the whole block after EVERY lane has prepared its range)
 	prof.lane = lane;
 	prof.lap("wait, mask, bias");
-	seed_turn.wait_for(lane);
+	if (!bs.on) seed_turn.wait_for(lane);
 	prof.lap("wait for the seed turn");
 	const int n_shapes = env.n_shapes;
 	size_t nh = 0;
@@ -1132,7 +1157,99 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	const bool bridge = n_shapes == 1 && env.fuse && env.contexts == 1 && !env.gapped_filter && !env.frame_shift && getenv("DMND_HOST_BRIDGE") == nullptr;
 	dmnd_chain_out co;
 	std::memset(&co, 0, sizeof co);
-	if (n_shapes == 1) {
+	// block mode: this lane's slice of the shared chain records -- queries [bk0, bk1) of bs.root->cq, their problems [bp0, bp1) of
+	// bs.root->cprobs, and (queries that take the host path) their hits [bh0, bh1) of bs.root->hv / segv / sitev
+	size_t bk0 = 0, bk1 = 0, bp0 = 0, bp1 = 0, bh0 = 0, bh1 = 0;
+	if (bs.on && bridge) {
+		struct DpGuard { BlockStage& b; int lane; bool armed = true; ~DpGuard() { if (armed) b.dp_end(lane); } } dp_guard{ bs, lane };  // a lane that leaves early must not block the DP order
+		bs.arrive();
+		if (lane == 0) {
+			Workspace& rw = w;
+			bs.root = &rw;
+			bs.wait_all_prepped();
+			int rc = prep_rc || bs.state < 0;
+			if (!rc) rc = dmnd_search_shape_range(ctx, qb, rb, 0, 0, env.nq, &hits, &d.stats.seed);
+			prof.lap("search_shape (whole block)");
+			if (!rc) {
+				d.stats.hits = dmnd_hits_count(hits);
+				d.stats.seed_ms = ms_since(t0);
+				t0 = Clock::now();
+				rc = dmnd_block_bias_wait(ctx) || dmnd_hits_chain(ctx, qb, rb, hits, sc.raw_ungapped_xdrop, env.band_slow ? 1 : 0, 64, &bs.co);
+				dmnd_hits_free(ctx, hits);
+				const size_t hn = (size_t)bs.co.n_host_hits;
+				rc = rc || rw.cq.resize(ctx, (size_t)bs.co.n_queries) || rw.cprobs.resize(ctx, (size_t)bs.co.n_problems) || rw.hv.resize(ctx, hn) || rw.segv.resize(ctx, hn) || rw.sitev.resize(ctx, hn);
+				rc = rc || dmnd_hits_chain_fetch(ctx, rw.cq.data(), rw.cprobs.data(), rw.hv.data(), rw.segv.data(), rw.sitev.data());
+				rc = rc || dmnd_block_clear_seed_mask_range(ctx, qb, 0, env.nq);  // run/double_indexed.cpp:211-212
+				d.stats.host_bridge_ms += ms_since(t0);
+				prof.lap("hits_chain (whole block)");
+			}
+			bs.publish(rc ? -1 : 1);
+			if (rc) return 1;
+		}
+		else if (bs.wait_published() < 0 || prep_rc) { if (!prep_rc) dmnd_set_last_error("dmnd_blastp: the block's seed stage failed (lane 0 carries the message)"); return 1; }
+		if (lane != 0 && dmnd_block_bias_wait(ctx)) return 1;
+		t0 = Clock::now();
+		const Workspace& rw = *bs.root;
+		co = bs.co;
+		const dmnd_chain_query* cqa = rw.cq.data();
+		const size_t nqa = (size_t)co.n_queries;
+		bk0 = (size_t)(std::lower_bound(cqa, cqa + nqa, q_begin, [](const dmnd_chain_query& c, uint32_t q) { return c.query < q; }) - cqa);
+		bk1 = (size_t)(std::lower_bound(cqa, cqa + nqa, q_end, [](const dmnd_chain_query& c, uint32_t q) { return c.query < q; }) - cqa);
+		bool pset = false, hset = false;
+		for (size_t k = bk0; k < bk1; ++k) {
+			const dmnd_chain_query& c = cqa[k];
+			if (c.flags & DMND_CHAIN_HOST) { if (!hset) { bh0 = c.first; hset = true; } bh1 = (size_t)c.first + c.n_hits; }
+			else if (c.n_problems) { if (!pset) { bp0 = c.first; pset = true; } bp1 = (size_t)c.first + c.n_problems; }
+		}
+		const size_t np = bp1 - bp0;
+		uint8_t* trp = nullptr;
+		size_t cap = 0;
+		if (np && env.want_transcript) {
+			for (size_t k = bp0; k < bp1; ++k) cap += (size_t)env.qlen(rw.cprobs[k].query) + (size_t)env.tlen(rw.cprobs[k].target);
+			if (w.tr.resize(ctx, cap)) return 1;
+			trp = w.tr.data();
+		}
+		if (w.cres.resize(ctx, np)) return 1;
+		d.stats.host_bridge_ms += ms_since(t0);
+		t0 = Clock::now();
+		bs.dp_begin(lane);
+		prof.lap("wait for the DP turn");
+		const int dp_rc = np ? dmnd_banded_swipe(ctx, qb, rb, rw.cprobs.data() + bp0, np, DMND_DP_TRACEBACK, w.cres.data(), trp, cap) : 0;
+		dp_guard.armed = false;
+		bs.dp_end(lane);
+		if (dp_rc) return 1;
+		d.stats.dp2_ms += ms_since(t0);
+		d.stats.dp_problems_round1 += np;
+		prof.lap("banded_swipe (lane's problems)");
+		t0 = Clock::now();
+		const size_t nqh = bk1 - bk0;
+		d.nq_hit = nqh;
+		w.qs.resize(nqh);
+		w.hs.resize(bh1 - bh0);
+		w.run([&](int t) {
+			ThreadCtx& tc = w.tc[(size_t)t];
+			tc.reset();
+			for (size_t k = d.block_begin(t), en = d.block_begin(t + 1); k < en; ++k) {
+				QueryState& q = w.qs[k];
+				const dmnd_chain_query& cq = cqa[bk0 + k];
+				if (cq.flags & DMND_CHAIN_HOST) {
+					q.qid = cq.query;
+					Workspace::HitSeg* hsb = w.hs.data() + ((size_t)cq.first - bh0);
+					for (size_t x = 0; x < cq.n_hits; ++x) { hsb[x].h = rw.hv[cq.first + x]; hsb[x].s = rw.segv[cq.first + x]; hsb[x].site = rw.sitev[cq.first + x]; hsb[x].gf = 1; }
+					d.load_hits(q, tc, hsb, hsb + cq.n_hits);
+					d.start(q, tc);
+				}
+				else {
+					d.start_bridged(q, tc, cq, rw.cprobs.data() + cq.first);
+					d.consume_fused(q, tc, rw.cprobs.data() + cq.first, w.cres.data() + ((size_t)cq.first - bp0), trp);
+				}
+			}
+		});
+		for (const ThreadCtx& tc : w.tc) d.stats.targets += tc.n_targets;
+		d.stats.host_bridge_ms += ms_since(t0);
+		prof.lap("consume chained queries (parallel)");
+	}
+	else if (n_shapes == 1) {
 		const int seed_rc = prep_rc ? 1 : dmnd_search_shape_range(ctx, qb, rb, 0, q_begin, q_end, &hits, &d.stats.seed);
 		seed_turn.pass(lane);
 		if (seed_rc || dmnd_block_bias_wait(ctx)) return 1;  // from here on the lane's stream reads the bias (x-drop extension, DP)
@@ -1194,14 +1311,16 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 		w.gfv.resize(nh);
 		for (size_t k = 0; k < nh; ++k) { const size_t o = off[(size_t)(ah[k].query - q_begin)]++; w.hv[o] = ah[k]; w.segv[o] = as[k]; w.sitev[o] = at[k]; w.gfv[o] = w.acc_gf[k]; }
 	}
+	const bool block_mode = bs.on && bridge;
 	if (n_shapes == 1) w.gfv.assign(nh, 1);
-	if (dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
+	if (!block_mode && dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
 	if (!bridge) { d.stats.seed_ms = ms_since(t0); d.stats.hits = nh; }
 	const int T = host_threads;
 	const uint32_t C = env.contexts;
 
-	if (bridge) {
+	if (block_mode) {}  // (its queries were consumed above)
+	else if (bridge) {
 		// ---- the device-chained problem list is aligned where it lies; the host then only scores and culls (consume_fused)
 		t0 = Clock::now();
 		const size_t np = (size_t)co.n_problems, nqh = (size_t)co.n_queries;
@@ -1478,13 +1597,17 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 		if (dmnd_ctx_lane(ctx, l - 1, &lctx[(size_t)l])) return 1;
 	SeedTurn seed_turn;
 	seed_turn.masked.assign((size_t)nlanes, 0);
+	BlockStage bs;
+	bs.nlanes = nlanes;
+	bs.on = nlanes > 1 && e.n_shapes == 1 && e.fuse && e.contexts == 1 && !e.gapped_filter && !e.frame_shift && std::getenv("DMND_HOST_BRIDGE") == nullptr
+	        && std::getenv("DMND_PIPELINE_LANES") == nullptr;
 	auto body = [&](int l) {
 		LaneOut& o = lo[(size_t)l];
 		try {
-			o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn);
+			o.rc = lane_run(lctx[(size_t)l], qb, rb, e, sc, cut[(size_t)l], cut[(size_t)l + 1], *sh.lanes[(size_t)l], host_threads, o, l, seed_turn, bs);
 			if (o.rc) o.error = dmnd_last_error();  // the error text is thread-local in the CUDA library
 		}
-		catch (const std::exception& ex) { o.rc = 1; o.error = std::string("dmnd_blastp: ") + ex.what(); seed_turn.set_masked(l); seed_turn.pass(l); }
+		catch (const std::exception& ex) { o.rc = 1; o.error = std::string("dmnd_blastp: ") + ex.what(); seed_turn.set_masked(l); seed_turn.pass(l); bs.abort(); }
 	};
 	std::vector<std::thread> th;
 	for (int l = 1; l < nlanes; ++l) th.emplace_back(body, l);
