@@ -1092,8 +1092,11 @@ struct SeedTurn {
 // Block mode of the device-bridged path (one shape, one context, no gapped filter): the seed stage and dmnd_hits_chain run ONCE over the
 // whole query block (lane 0, after every lane has prepared -- waited for, masked, biased -- its own query range), then every lane takes the
 // queries of its range from the shared chain records: banded swipe on the lane's context (at most two calls in flight, in lane order) and the
-// host work beside the next lane's kernels.  A seed stage per lane cost 38 ms of wall time per 10^6 queries for 19 ms of kernels (the lanes'
-// seed kernels queue behind each other's DP); one seed stage over the block takes 15 ms.  DMND_PIPELINE_LANES=1 selects the per-lane form.
+// host work beside the next lane's kernels.  The idea: a seed stage per lane costs 38 ms of wall time per 10^6 queries for 19 ms of kernels
+// (the lanes' seed kernels queue behind each other's DP), one seed stage over the block takes 15 ms.  Measured on a B200 (same box, 10 steps
+// each, profiles/ab_block_mode_r2.txt): 55.0 ms per resident step and 80.8 ms end to end against 50.2 / 75.3 ms for the per-lane pipeline --
+// the block's seed stage runs alone on the GPU, and what the lanes lose in queueing they win back in overlap.  Kept behind
+// DMND_PIPELINE_BLOCK=1 (results are identical: the CPU suite runs both forms); the per-lane pipeline is the default.
 struct BlockStage {
 	bool on = false;
 	int nlanes = 0;
@@ -1600,7 +1603,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	BlockStage bs;
 	bs.nlanes = nlanes;
 	bs.on = nlanes > 1 && e.n_shapes == 1 && e.fuse && e.contexts == 1 && !e.gapped_filter && !e.frame_shift && std::getenv("DMND_HOST_BRIDGE") == nullptr
-	        && std::getenv("DMND_PIPELINE_LANES") == nullptr;
+	        && std::getenv("DMND_PIPELINE_BLOCK") != nullptr;  // opt-in: measured slower than the per-lane pipeline (see BlockStage)
 	auto body = [&](int l) {
 		LaneOut& o = lo[(size_t)l];
 		try {
