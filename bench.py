@@ -397,9 +397,13 @@ def main():
     # are timed in a separate pass with ONE lane (every kernel of the step serialised on one stream, same work)
     lanes_env = os.environ.get("DMND_LANES")
     os.environ["DMND_LANES"] = "1"
-    rsteps = max(1, min(args.steps, 2))
+    # up to three single-lane steps, each timed on its own; the one with the least kernel time is reported (a step is deterministic work:
+    # anything above the minimum is a stall of the box -- sporadic 100-300 ms hiccups were seen on this pool -- not kernel time)
+    rpasses = max(1, min(args.steps, 3))
+    rsteps = 1
     step_res()
-    _, _, tm1 = timed(step_res, rsteps)
+    passes = [timed(step_res, 1)[2] for _ in range(rpasses)]
+    tm1 = min(passes, key=lambda t: t["dp_score_ms"] + t["dp_trace_ms"] + t["seed_ms"])
     if lanes_env is None:
         del os.environ["DMND_LANES"]
     else:
@@ -431,7 +435,7 @@ def main():
                     "padding_factor": (tm1["dp_cells_padded"] / max(1, tm1["dp_cells_score"] + tm1["dp_cells_trace"])),
                     "overflow_reruns": tm1["dp_overflow_reruns"],
                     "kernel_gcups": launched / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None,
-                    "timed": f"CUDA events on the library stream, {rsteps} single-lane step(s) after the timed region"}
+                    "timed": f"CUDA events on the library stream, the fastest of {rpasses} single-lane step(s) after the timed region"}
         # ---- roofline of the seed stage: HBM bound by SURVEY 8d's byte model of the double-indexed join, per shape and block pair:
         # 1 B per letter of both blocks + 36 B per seed entry (write, partition pass, join read) + 96 B of fingerprints per (q, s) pair
         # + 98 B per stage-1 survivor (left-most windows) + 15 B per hit
