@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the seed-and-extend hot path (BASELINE.json metric) on N B200s of one node.
 
-  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4]   our arm (CUDA library behind the C ABI)
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4|c5]   our arm (CUDA library behind the C ABI)
   python bench.py --impl reference --gpus N --steps K ...               the UNMODIFIED reference (oracle/_ref/diamond) on host cores
 
 One "step" = one full pass of the hot path (masked blocks -> seed search stages 0-2 -> extension rounds 1+2 -> culling) over
@@ -9,6 +9,8 @@ one batch of synthetic queries against the resident reference block.  Configurat
   c2 (default, the configuration the metric is quoted on): blastp --fast, 1 M queries (len <= 300) x 100 k-protein DB
   c3: blastx --fast, 100 k DNA reads of 150 nt (six translated frames each) x 100 k-protein DB
   c4: blastp --sensitive, 1 M queries x 500 k-protein DB (16 shapes, gapped filter)
+  c5: blastx --very-sensitive -F 15 (frameshift alignment: legacy pipeline + 3-frame banded DP, every alignment traced back), 12 500 reads of
+      600 nt with single-nucleotide indels (the per-GPU share of configs[4]'s 100 k queries on 8 GPUs) x 1 M-protein DB; cells = 3 x band x cols
 At N > 1 every rank processes its own query block against the same DB (query sharding, no data-path collective; the packed
 reference block is NCCL-broadcast once) -> "weak".
 GCUPS numerator = algorithmic DP cells = sum over every banded DP problem of rounds 1 and 2 of band x cols

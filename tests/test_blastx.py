@@ -228,3 +228,18 @@ def test_frameshift_needs_translated_queries(oracle_lib):
         w = _bx()
         r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
         g.blastp(r_raw, r_lim, r_raw, r_lim)
+
+
+def test_blastx_frameshift_lanes(oracle_lib, monkeypatch):
+    """The frameshift pipeline with three query lanes (each lane runs its own legacy rounds on its context): same output."""
+    from diamond_b200 import api
+    monkeypatch.setenv("DMND_LANES", "3")
+    w = _bx()
+    ql, qo = api.translate_reads(w["dna"], frame_shift=15)
+    q_raw, q_lim = api.block_image(ql, qo)
+    r_raw, r_lim = api.block_image(w["db_letters"], w["db_off"])
+    g = api.Context(lib=oracle_lib, masking=1, motif_masking=1, query_contexts=6, frame_shift=15)
+    m, _, _ = g.blastp(q_raw, q_lim, r_raw, r_lim)
+    g.close()
+    gold = ["\t".join(l.split("\t")[:12]) for l in open(os.path.join(GOLDEN, "bx.xf.tsv")).read().splitlines()]
+    assert api.fmt6_translated(m, [len(r) for r in w["dna"]]).splitlines() == gold
