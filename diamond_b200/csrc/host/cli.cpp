@@ -539,7 +539,8 @@ int main(int argc, char** argv) {
 		const bool fshift = o.frame_shift != 0;
 		if (fshift) {
 			o.want_transcript = 1;  // output/output_format.cpp:256-257
-			if (paf || sam || block_size != 0.0) usage("--frameshift: -f sam, -f paf and -b are not implemented in this mode");
+			if (paf || sam) usage("--frameshift: -f sam and -f paf are not implemented in this mode");
+			if (block_size != 0.0 && (o.range_culling || pairwise || unal)) usage("--frameshift with -b: only the tabular format without --unal and without --range-culling is implemented");
 			for (const std::string& f : fields) if (f == "qseq" || f == "sseq" || f == "qcovhsp" || f == "positive" || f == "ppos") usage(("--frameshift: output field " + f + " is not implemented in this mode").c_str());
 		}
 		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode, o.frame_shift });
@@ -665,6 +666,24 @@ int main(int argc, char** argv) {
 			for (uint32_t qid : all) {
 				while (ji < joined.size() && joined[ji].query / cx < qid / cx) ++ji;
 				if (!(ji < joined.size() && joined[ji].query / cx == qid / cx)) joined_unal.push_back(qid);
+			}
+			if (fshift) {
+				// Blocked runs of the legacy pipeline travel through IntermediateRecords, and the join re-derives the alignment statistics from
+				// the transcript (HspContext::parse, basic/hssp.cpp:52-100) instead of keeping the traceback's counters: `length` then counts
+				// the frameshift marks as columns, and a gap run is not interrupted by a mark
+				for (dmnd_match& y : joined) {
+					const uint8_t* t = joined_tr.data() + y.transcript_off;
+					y.length = y.identities = y.mismatches = y.gap_openings = y.gaps = 0;
+					unsigned d = 0;
+					for (uint32_t k = 0; k < y.transcript_len; ++k) {
+						++y.length;
+						if (t[k] == DMND_TR_FRAMESHIFT_FWD || t[k] == DMND_TR_FRAMESHIFT_REV) continue;
+						const int op = t[k] >> 6;
+						if (op == DMND_OP_MATCH) { ++y.identities; d = 0; }
+						else if (op == DMND_OP_SUBSTITUTION) { ++y.mismatches; d = 0; }
+						else { if (d == 0) ++y.gap_openings; ++d; ++y.gaps; }
+					}
+				}
 			}
 			m = joined.data(); n = joined.size(); tr = joined_tr.data();
 		}

@@ -243,3 +243,44 @@ def test_blastx_frameshift_lanes(oracle_lib, monkeypatch):
     g.close()
     gold = ["\t".join(l.split("\t")[:12]) for l in open(os.path.join(GOLDEN, "bx.xf.tsv")).read().splitlines()]
     assert api.fmt6_translated(m, [len(r) for r in w["dna"]]).splitlines() == gold
+
+
+def test_frameshift_repeated_calls_on_one_context(oracle_lib):
+    """The P layer keeps its per-query states between calls (no page faults in steady state): a second frameshift search on the same
+    context, over a different reference block, must not see the first one's match lists (regression: stale list pointers gave
+    later blocks of a -b run matches of the wrong queries)."""
+    from diamond_b200 import api
+    w = _bx()
+    ql, qo = api.translate_reads(w["dna"], frame_shift=15)
+    q_raw, q_lim = api.block_image(ql, qo)
+    nd = len(w["db_off"]) - 1
+    half = nd // 2
+    blocks = [api.block_image(w["db_letters"][: w["db_off"][half]], w["db_off"][: half + 1]),
+              api.block_image(w["db_letters"][w["db_off"][half]:], w["db_off"][half:] - w["db_off"][half])]
+    lens = [len(r) for r in w["dna"]]
+    outs = []
+    g = api.Context(lib=oracle_lib, masking=1, motif_masking=1, query_contexts=6, frame_shift=15)
+    for r_raw, r_lim in blocks + blocks[:1]:
+        m, _, _ = g.blastp(q_raw, q_lim, r_raw, r_lim)
+        outs.append(api.fmt6_translated(m, lens))
+    g.close()
+    assert outs[0] == outs[2] and outs[0] != outs[1]
+    for k, (r_raw, r_lim) in enumerate(blocks):  # each against a fresh context
+        f = api.Context(lib=oracle_lib, masking=1, motif_masking=1, query_contexts=6, frame_shift=15)
+        m, _, _ = f.blastp(q_raw, q_lim, r_raw, r_lim)
+        f.close()
+        assert api.fmt6_translated(m, lens) == outs[k]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference binary (make ref)")
+def test_frameshift_with_reference_blocks_matches_the_reference(oracle_lib, tmp_path):
+    """blastx -F 15 -b: per-block legacy runs joined per query; the reference re-derives the statistics of a joined record from its
+    transcript (HspContext::parse), so `length` counts the frameshift marks there -- compared live with the reference."""
+    q, d = _files(_bx(), tmp_path)
+    fields = "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop gaps nident qframe".split()
+    for flags in (["--fast", "-b0.0002"], ["--sensitive", "-b0.0001", "-k", "5", "-f", "6"] + fields):
+        o1, o2 = str(tmp_path / "ref.tsv"), str(tmp_path / "our.tsv")
+        subprocess.run([REF_BIN, "blastx", "-q", q, "-d", d, "-F", "15", "-p", "8", "--quiet", "-o", o1] + flags, check=True, capture_output=True)
+        r = subprocess.run([CLI, "blastx", "-q", q, "-d", d, "-F", "15", "-p", "8", "-o", o2] + flags, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(o1).read() == open(o2).read()
