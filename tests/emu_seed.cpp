@@ -132,6 +132,7 @@ static void search_shape(Blk& query, const Blk& ref, const DevParams& P, const d
 			emu::launch(grid, STAGE_CTA, [&] { stage1_flags_kernel(query.letters.data(), ref.letters.data(), entries.data(), L, ix.locs.data(), (unsigned)hp.hamming_id, flags.data(), surv.data(), cnt + 9, surv_cap, cnt); });
 			emu::launch(std::min(grid, 7u), STAGE_CTA, [&] { stage2_window_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
 				surv.data(), cnt + 9, surv_cap, dh.data(), cnt + 6, cnt); });
+			if (cnt[9] + 32 > surv_cap)  // (the library launches it unconditionally and the kernel leaves at once unless the list overflowed; the emulation saves the coroutines)
 			emu::launch(grid, STAGE_CTA, [&] { stage2_window_full_kernel(query.letters.data(), query.limits.data(), query.nseq, ref.letters.data(), entries.data(), L, ix.locs.data(), flags.data(), x,
 				cnt + 9, surv_cap, dh.data(), cnt + 6, cnt); });
 		}

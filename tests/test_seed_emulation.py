@@ -9,7 +9,9 @@ from conftest import ROOT, workload_blocks
 
 
 def test_seed_stage_emulation_matches_oracle_default_sensitivity(oracle_lib, tmp_path):
-    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("edge")
+    from diamond_b200 import api
+    w, q_raw, q_lim, _, _ = workload_blocks("edge")
+    r_raw, r_lim = api.block_image(w["db_letters"][:w["db_off"][800]], w["db_off"][:801])  # 800 of the 2 000 proteins: the emulation's cost is one coroutine per reference position
     q_raw.tofile(str(tmp_path / "q.i8")); q_lim.tofile(str(tmp_path / "q.i64")); r_raw.tofile(str(tmp_path / "r.i8")); r_lim.tofile(str(tmp_path / "r.i64"))
     exe = str(tmp_path / "emu_seed")
     subprocess.run(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "emu_seed.cpp"), "-o", exe,
