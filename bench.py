@@ -296,7 +296,13 @@ def main():
 
     torch.cuda.set_device(local)
     from diamond_b200 import shard
-    numa_note = shard.pin_to_gpu_numa_node(local) if world > 1 else "one rank: not pinned"  # before the library starts its host threads
+    bus = None
+    try:  # the CUDA device's own PCI address (torch >= 2.1 exposes it)
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        bus = None
+    numa_note = shard.pin_to_gpu_numa_node(local, bus) if world > 1 else "one rank: not pinned"  # before the library starts its host threads
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -6,18 +6,28 @@ from __future__ import annotations
 import numpy as np
 
 
-def pin_to_gpu_numa_node(gpu_index: int) -> str:
+def pin_to_gpu_numa_node(gpu_index: int, pci_bus_id: str | None = None) -> str:
     """Restricts this process (and the host threads the library starts later) to the CPUs of the NUMA node the GPU hangs on: the
     host side of a rank -- pinned staging buffers, the worker pool that scores and culls -- then stays next to its GPU's PCIe root.
     On a two-socket 8-GPU box GPUs 4-7 sit on node 1; unpinned ranks of those GPUs ran their host work across the socket link.
     Returns a short note for the bench record; does nothing (and says why) where the topology cannot be read."""
     import os, subprocess
     try:
-        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
-        if not bus:
-            return "no pci bus id"
-        dom, rest = bus.split(":", 1)
-        node = int(open(f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node").read())
+        # pci_bus_id ("0000:1b:00.0") of the CUDA device if the caller knows it (CUDA's device order need not be nvidia-smi's); else, or if
+        # sysfs does not know that address, ask nvidia-smi for the device of this index
+        node = None
+        for src in ("caller", "nvidia-smi"):
+            bus = pci_bus_id if src == "caller" else subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                                                     capture_output=True, text=True, timeout=20).stdout.strip()
+            if not bus:
+                continue
+            dom, rest = bus.split(":", 1)
+            path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read())
+                break
+        if node is None:
+            return "no NUMA information for the device"
         if node < 0:
             return "single NUMA node"
         cpus = set()
