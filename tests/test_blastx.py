@@ -284,3 +284,30 @@ def test_frameshift_with_reference_blocks_matches_the_reference(oracle_lib, tmp_
         r = subprocess.run([CLI, "blastx", "-q", q, "-d", d, "-F", "15", "-p", "8", "-o", o2] + flags, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(o1).read() == open(o2).read()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs the reference binary (make ref)")
+def test_frameshift_score_only_int16_overflow(oracle_lib, tmp_path):
+    """A 40 kb read against 32 near-identical 13 500-letter targets: more than -k targets, so the score-only round runs, and every score
+    (~79 000) saturates the reference's int16 SIMD lanes -- it repeats such a target alone, in its own band, in int32
+    (dp/swipe/banded_3frame_swipe.cpp:600-607); host/legacy.inc does the same.  Compared live with the reference."""
+    from diamond_b200 import synth
+    rng = np.random.default_rng(7)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    L = 13500
+    prot = rng.integers(0, 20, L)
+    q, d, o1, o2 = (str(tmp_path / x) for x in ("q.fna", "d.faa", "ref.tsv", "our.tsv"))
+    open(q, "w").write(">long\n" + "".join(synth._CODONS[aa[a]][0] for a in prot) + "\n")
+    with open(d, "w") as f:
+        for k in range(32):
+            p = prot.copy()
+            m = rng.random(L) < 0.002 * k
+            p[m] = rng.integers(0, 20, int(m.sum()))
+            f.write(f">t{k}\n" + "".join(aa[a] for a in p) + "\n")
+        for k in range(200):
+            f.write(f">r{k}\n" + "".join(aa[a] for a in rng.integers(0, 20, 300)) + "\n")
+    subprocess.run([REF_BIN, "blastx", "--fast", "-q", q, "-d", d, "-F", "15", "-p", "8", "--quiet", "-o", o1], check=True, capture_output=True)
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-F", "15", "-p", "8", "-o", o2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = open(o1).read()
+    assert open(o2).read() == ref and len(ref.splitlines()) == 25 and float(ref.splitlines()[0].split("\t")[11]) > 30000  # raw score ~ 79 000 > 65 535
