@@ -45,6 +45,27 @@ std::string slurp_text(const std::string& path) {
 	return out;
 }
 
+// Block::length_sorted (data/block/block.cpp:229-255): longest sequence first, ties by DESCENDING block id (std::greater on (length, id)).
+// The reference sorts the query and the reference block this way when min_length_ratio is set (run/double_indexed.cpp:112-115,727-731):
+// queries are then reported in this order, and the block ids that break ranking ties are the sorted ones.
+void length_sort(SeqBlock& b) {
+	const uint32_t n = b.size();
+	std::vector<std::pair<int64_t, uint32_t>> key(n);
+	for (uint32_t i = 0; i < n; ++i) key[i] = { b.limits[i + 1] - b.limits[i] - 1, i };
+	std::sort(key.begin(), key.end(), std::greater<std::pair<int64_t, uint32_t>>());
+	SeqBlock s;
+	s.letters.reserve(b.letters.size());
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t j = key[i].second;
+		s.letters.insert(s.letters.end(), b.letters.begin() + b.limits[j], b.letters.begin() + b.limits[j + 1]);  // the letters and their delimiter
+		s.limits.push_back((int64_t)s.letters.size());
+		s.ids.push_back(std::move(b.ids[j]));
+		if (!b.titles.empty()) s.titles.push_back(std::move(b.titles[j]));
+	}
+	s.finish();
+	b = std::move(s);
+}
+
 int8_t encode(char c) {  // basic/value.cpp:26-41 with amino_acid_traits (stats/stats.cpp:41): "UO-" -> mask
 	static int8_t table[256];
 	static bool init = false;
@@ -516,7 +537,10 @@ int main(int argc, char** argv) {
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
 			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
 			else if (a == "--matrix") { std::string v = val(); for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
-			else if (a == "--id" || a == "--approx-id" || a == "--query-cover" || a == "--subject-cover") { if (atof(val()) != 0.0) usage((a + ": only 0 (no filter) is implemented").c_str()); }
+			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
+			else if (a == "--query-cover") o.query_cover = atof(val());
+			else if (a == "--subject-cover") o.subject_cover = atof(val());
+			else if (a == "--approx-id") { if (atof(val()) != 0.0) usage("--approx-id: only 0 (no filter) is implemented"); }
 			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }
 			else usage(("unsupported option " + a).c_str());
 		}
@@ -573,6 +597,14 @@ int main(int argc, char** argv) {
 			if (cuts.size() == 1) cuts.push_back(0);
 		}
 		const size_t nblocks = cuts.size() - 1;
+		bool mutual = false;
+		if (!translated && o.query_cover >= 50.0 && o.query_cover == o.subject_cover) {  // min_length_ratio is set (run/config.cpp:156-159): both blocks are searched length-sorted
+			mutual = true;
+			length_sort(q);
+			if (nblocks == 1) length_sort(r);  // (more blocks: every block is sorted on its own when it is searched, below)
+		}
+		std::vector<std::vector<uint32_t>> bperm(nblocks);   // mutual coverage with several blocks: sorted block id -> id within the unsorted block
+		std::vector<std::vector<int64_t>> blimits(nblocks);  // ... and the limits of the sorted block image
 		uint64_t db_letters = 0;
 		for (uint32_t i = 0; i < r.size(); ++i) db_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
 		std::vector<dmnd_result*> results(nblocks, nullptr);
@@ -589,6 +621,21 @@ int main(int argc, char** argv) {
 			bl.insert(bl.end(), (size_t)DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER);
 			std::vector<int64_t> lim((size_t)(e - f) + 1);
 			for (uint32_t k = f; k <= e; ++k) lim[k - f] = r.limits[k] - a + DMND_PERIMETER_PADDING;
+			if (mutual) {  // Block::length_sorted of this reference block (run/double_indexed.cpp:112-115)
+				std::vector<std::pair<int64_t, uint32_t>> key((size_t)(e - f));
+				for (uint32_t k = 0; k < e - f; ++k) key[k] = { lim[k + 1] - lim[k] - 1, k };
+				std::sort(key.begin(), key.end(), std::greater<std::pair<int64_t, uint32_t>>());
+				std::vector<int8_t> sl((size_t)DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER);
+				std::vector<int64_t> slim{ (int64_t)DMND_PERIMETER_PADDING };
+				for (const auto& kv : key) {
+					sl.insert(sl.end(), bl.begin() + lim[kv.second], bl.begin() + lim[kv.second + 1]);
+					slim.push_back((int64_t)sl.size());
+					bperm[bk].push_back(kv.second);
+				}
+				sl.insert(sl.end(), (size_t)DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER);
+				bl.swap(sl); lim.swap(slim);
+				blimits[bk] = lim;
+			}
 			dmnd_search_opts ob = o;
 			ob.db_letters = db_letters;
 			if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, bl.data(), bl.size(), lim.data(), e - f, &ob, &results[bk]))
@@ -607,7 +654,15 @@ int main(int argc, char** argv) {
 				const uint64_t* mp = dmnd_result_masked_positions(results[bk], side, &nm);
 				std::vector<int8_t>& l = side ? r.letters : q.letters;
 				const int64_t shift = (side && nblocks > 1) ? r.limits[cuts[bk]] - DMND_PERIMETER_PADDING : 0;  // block image position -> position in the whole database image
-				for (size_t k = 0; k < nm; ++k) l[(size_t)((int64_t)mp[k] + shift)] = 23;
+				for (size_t k = 0; k < nm; ++k) {
+					int64_t pos = (int64_t)mp[k];
+					if (side && !bperm[bk].empty()) {  // position in the sorted block image -> the same letter in the unsorted one
+						const std::vector<int64_t>& sl = blimits[bk];
+						const size_t i = (size_t)(std::upper_bound(sl.begin(), sl.end(), pos) - sl.begin()) - 1;
+						pos = pos - sl[i] + (r.limits[cuts[bk] + bperm[bk][i]] - r.limits[cuts[bk]] + DMND_PERIMETER_PADDING);
+					}
+					l[(size_t)(pos + shift)] = 23;
+				}
 			}
 		// join_blocks (output/join_blocks.cpp:120-265): per query a merge of the blocks' match lists, best e-value first (then score, then
 		// database order -- JoinRecord::cmp_evalue; by score with --top), cut by GlobalCulling (output/target_culling.h:39-90): the first
@@ -621,6 +676,7 @@ int main(int argc, char** argv) {
 			for (size_t bk = 0; bk < nblocks; ++bk) { cur[bk].m = dmnd_result_matches(results[bk], &cur[bk].n); cur[bk].i = 0; size_t x = 0; cur[bk].tr = dmnd_result_transcripts(results[bk], &x); cur[bk].first = cuts[bk]; }
 			const uint32_t cx = translated ? 6u : 1u;
 			const bool by_score = top_set;
+			auto oid = [&](size_t bk, uint32_t t) { return cuts[bk] + (bperm[bk].empty() ? t : bperm[bk][t]); };  // database order of a block's target
 			auto before = [&](const dmnd_match& a, uint32_t oa, const dmnd_match& b, uint32_t ob) {  // a comes out of the heap before b
 				if (!by_score && a.evalue != b.evalue) return a.evalue < b.evalue;
 				if (a.score != b.score) return a.score > b.score;
@@ -638,7 +694,7 @@ int main(int argc, char** argv) {
 					size_t best = nblocks;
 					for (size_t bk = 0; bk < nblocks; ++bk) {
 						if (cur[bk].i >= end[bk]) continue;
-						if (best == nblocks || before(cur[bk].m[cur[bk].i], cur[bk].first + cur[bk].m[cur[bk].i].target, cur[best].m[cur[best].i], cur[best].first + cur[best].m[cur[best].i].target)) best = bk;
+						if (best == nblocks || before(cur[bk].m[cur[bk].i], oid(bk, cur[bk].m[cur[bk].i].target), cur[best].m[cur[best].i], oid(best, cur[best].m[cur[best].i].target))) best = bk;
 					}
 					if (best == nblocks) break;
 					const dmnd_match& x = cur[best].m[cur[best].i];
@@ -648,7 +704,7 @@ int main(int argc, char** argv) {
 					}
 					else top_bits = x.bit_score;
 					dmnd_match y = x;
-					y.target += cur[best].first;
+					y.target = oid(best, x.target);
 					y.transcript_off = joined_tr.size();
 					if (x.transcript_len) joined_tr.insert(joined_tr.end(), cur[best].tr + x.transcript_off, cur[best].tr + x.transcript_off + x.transcript_len);
 					joined.push_back(y);

@@ -294,6 +294,11 @@ struct Env {
 	double max_evalue;
 	bool hauser, want_transcript;
 	bool fuse;  // see Driver::start
+	// --id / --query-cover / --subject-cover (config.min_id, query_cover, subject_cover): with any of them set the reference only SORTS the
+	// targets after round 1 (first_round_culling = !have_filters || --top, align/extend.cpp:94-96,288) and runs round 2 in steps
+	double min_id = 0.0, query_cover = 0.0, subject_cover = 0.0;
+	bool have_filters = false, first_round_culling = true;
+	double min_length_ratio = 0.0;  // Search::Config::min_length_ratio (run/config.cpp:156-164)
 	int qlen(uint32_t q) const { return (int)(q_limits[q + 1] - q_limits[q] - 1); }
 	int tlen(uint32_t t) const { return (int)(r_limits[t + 1] - r_limits[t] - 1); }
 };
@@ -332,6 +337,7 @@ struct QueryState {
 	List<Target> aligned_targets, r1;
 	List<Match> matches, r2;
 	List<uint32_t> prob_target;  // per DP problem in flight: index into r1 / r2
+	uint32_t r2_it, r2_begin, r2_prev;  // round 2 in steps (filters): next target of aligned_targets, first match of this step, matches before the round
 	size_t prob_begin;           // offset in the owner thread's problem list of this wave
 	uint32_t prob_count;
 };
@@ -466,6 +472,7 @@ struct Driver {
 	void consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res);
 	void consume_round2(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
 	void consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* probs, const dmnd_dp_result* res, const uint8_t* tr);
+	bool filtered_out(const QueryState& q, const Match& m) const;
 	void take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dmnd_dp_problem& pr, const dmnd_dp_result& r, const uint8_t* tr, double known_evalue = -1.0);
 	void finish_round2(QueryState& q, ThreadCtx& tc);
 	void finish_outer(QueryState& q);
@@ -707,7 +714,7 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		if (v.empty()) new_hits = false;
 		else {
 			new_hits = e.top < 0.0 && (int64_t)q.aligned_targets.n < e.max_target_seqs;
-			bool append = new_hits;
+			bool append = !e.first_round_culling || new_hits;
 			culling_targets(q.aligned_targets, append, e);
 			double min_evalue = DBL_MAX;
 			int max_score = 0;
@@ -733,18 +740,26 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		terminate = !new_hits && (q.previous_tail_score == 0 || double(tscore) / (double)q.previous_tail_score <= 0.95 || e.sc->bitscore(tscore) < 25.0);
 	}
 	if (q.i0 < n_targets && !terminate) { q.phase = PH_ROUND1_PRODUCE; return; }
-	culling_targets(q.aligned_targets, false, e);  // extend.cpp:331
+	culling_targets(q.aligned_targets, !e.first_round_culling, e);  // extend.cpp:331
 	if (q.aligned_targets.n == 0) finish_outer(q);  // round 2 over nothing returns no matches
-	else q.phase = PH_ROUND2_PRODUCE;
+	else { q.phase = PH_ROUND2_PRODUCE; q.r2.clear(); q.r2_it = 0; q.r2_prev = q.matches.n; }
 }
 
 void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
-	// round-2 problems (gapped_final.cpp:64-78,118-124): one per kept HSP of every culled target
+	// round-2 problems (gapped_final.cpp:64-78,118-124): one per kept HSP of every culled target.  With filters and without --top the
+	// targets are taken in steps (:107-111): max(k - matches so far, 16) rounded up to a multiple of 16, until k matches passed the filters
+	const Env& e = env;
 	q.prob_begin = tc.p2.size();
 	q.prob_target.clear();
-	q.r2.clear();
-	q.r2.reserve(tc.arena, q.aligned_targets.n);
-	for (const Target& tg : q.aligned_targets) {
+	uint32_t step = q.aligned_targets.n - q.r2_it;
+	if (!e.first_round_culling && e.top < 0.0) {
+		const int64_t want = std::max<int64_t>((int64_t)e.max_target_seqs - (int64_t)q.r2.n, 16);
+		step = (uint32_t)std::min<int64_t>((want + 15) / 16 * 16, (int64_t)step);
+	}
+	q.r2.reserve(tc.arena, q.r2.n + step);
+	q.r2_begin = q.r2.n;
+	for (uint32_t k = q.r2_it; k < q.r2_it + step; ++k) {
+		const Target& tg = q.aligned_targets.p[k];
 		if (tg.has_hsp) {
 			tc.p2.push_back(dmnd_dp_problem{ tg.hsp.ctx, tg.block_id, tg.hsp.d_begin, tg.hsp.d_end });
 			q.prob_target.push(tc.arena, q.r2.n);
@@ -755,6 +770,7 @@ void Driver::produce_round2(QueryState& q, ThreadCtx& tc) {
 		m.target_block_id = tg.block_id; m.tlen = tg.tlen; m.filter_score = 0; m.filter_evalue = DBL_MAX; m.has_hsp = false;
 		q.r2.push(tc.arena, m);
 	}
+	q.r2_it += step;
 	q.prob_count = (uint32_t)(tc.p2.size() - q.prob_begin);
 	q.phase = PH_ROUND2_CONSUME;
 }
@@ -777,11 +793,27 @@ void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dm
 	}
 }
 
+bool Driver::filtered_out(const QueryState& q, const Match& m) const {
+	// filter_hsp, align/culling.cpp:144-170 (Hsp::id_percent / query_cover_percent / subject_cover_percent, basic/match.h:208-221); the
+	// query range is the HSP's range on the DNA read for translated queries: three letters per codon (basic/translated_position.h:120-135)
+	const Env& e = env;
+	const dmnd_dp_result& r = m.r;
+	const int source_query_len = e.contexts == 6 ? e.qlen(q.qid) + e.qlen(q.qid + 1) + e.qlen(q.qid + 2) + 2 : q.qlen;
+	const int q_range = (r.q_end - r.q_begin) * (e.contexts == 6 ? 3 : 1);
+	const double qcov = (double)q_range * 100 / (unsigned)source_query_len, tcov = (double)(r.t_end - r.t_begin) * 100 / (unsigned)m.tlen;
+	return (double)r.identities * 100.0 / (double)r.length < e.min_id || qcov < e.query_cover || tcov < e.subject_cover;
+}
+
 void Driver::finish_round2(QueryState& q, ThreadCtx& tc) {
 	const Env& e = env;
-	for (Match& m : q.r2) if (m.has_hsp) { m.filter_evalue = m.h.evalue; m.filter_score = m.h.score; }  // Match::inner_culling
+	for (Match* m = q.r2.begin() + q.r2_begin; m < q.r2.end(); ++m) {
+		if (m->has_hsp) { m->filter_evalue = m->h.evalue; m->filter_score = m->h.score; }  // Match::inner_culling
+		if (e.have_filters && m->has_hsp && filtered_out(q, *m)) { m->has_hsp = false; m->filter_evalue = DBL_MAX; m->filter_score = 0; }  // Match::apply_filters, culling.cpp:172-185
+	}
 	if (e.top >= 0.0) std::sort(q.r2.begin(), q.r2.end(), Match::cmp_score); else std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
 	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e) - q.r2.begin());
+	// the next step of the filtered schedule (gapped_final.cpp:156: it < targets.end() && goon())
+	if (q.r2_it < q.aligned_targets.n && (e.top >= 0.0 || (int64_t)q.r2.n + (int64_t)q.r2_prev < (int64_t)e.max_target_seqs)) { q.phase = PH_ROUND2_PRODUCE; return; }
 	for (const Match& m : q.r2) q.matches.push(tc.arena, m);
 	q.r2.clear();
 	q.aligned_targets.clear();
@@ -799,6 +831,7 @@ void Driver::consume_fused(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem* 
 	if (q.phase != PH_ROUND2_PRODUCE) return;  // nothing survived, or (never for a fused query) another ranking chunk
 	q.r2.clear();
 	q.r2.reserve(tc.arena, q.aligned_targets.n);
+	q.r2_begin = 0; q.r2_it = q.aligned_targets.n;  // (fused queries never run with filters: one step)
 	for (const Target& tg : q.aligned_targets) {
 		Match m;
 		std::memset(&m, 0, sizeof m);
@@ -1316,6 +1349,20 @@ static int lane_run(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, const E
 	}
 	const bool block_mode = bs.on && bridge;
 	if (n_shapes == 1) w.gfv.assign(nh, 1);
+	if (env.min_length_ratio > 0.0 && !bridge) {
+		// mutual-coverage seed stage (search/hamming/kernel_mutual_cov.h:28-52, chosen by stage1_dispatch when min_length_ratio > 0): over
+		// length-sorted blocks its two cursors admit exactly the (query, target) pairs with qlen / tlen >= mlr and tlen / qlen >= mlr.
+		// Every later step of the seed stage is per pair, so dropping the other pairs' hits here gives the same hit list.
+		const double mlr = env.min_length_ratio;
+		size_t o = 0;
+		for (size_t x = 0; x < nh; ++x) {
+			const int ql = env.qlen(w.hv[x].query), tl = env.tlen(w.sitev[x].target);
+			if ((double)ql / tl < mlr || (double)tl / ql < mlr) continue;
+			if (o != x) { w.hv[o] = w.hv[x]; w.segv[o] = w.segv[x]; w.sitev[o] = w.sitev[x]; w.gfv[o] = w.gfv[x]; }
+			++o;
+		}
+		nh = o;
+	}
 	if (!block_mode && dmnd_block_clear_seed_mask_range(ctx, qb, q_begin, q_end)) return 1;  // run/double_indexed.cpp:211-212
 	prof.lap("hits download");
 	if (!bridge) { d.stats.seed_ms = ms_since(t0); d.stats.hits = nh; }
@@ -1568,6 +1615,15 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	}
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
+	e.min_id = opts->min_id; e.query_cover = opts->query_cover; e.subject_cover = opts->subject_cover;
+	if (!(e.min_id >= 0.0 && e.min_id <= 100.0) || !(e.query_cover >= 0.0 && e.query_cover <= 100.0) || !(e.subject_cover >= 0.0 && e.subject_cover <= 100.0)) {
+		dmnd_set_last_error("dmnd_blastp: min_id, query_cover and subject_cover are percentages (0 = no filter)");
+		return 1;
+	}
+	e.have_filters = e.min_id > 0.0 || e.query_cover > 0.0 || e.subject_cover > 0.0;
+	e.first_round_culling = !e.have_filters || e.top >= 0.0;  // align/extend.cpp:288 (config.toppercent.present(): --top 100 counts, see below)
+	if (e.have_filters) e.fuse = false;  // fused rounds and the device bridge assume round 2 = the culled targets of round 1, in one step
+	if (e.query_cover >= 50.0 && e.query_cover == e.subject_cover && contexts == 1) e.min_length_ratio = std::max(e.query_cover / 100 - 0.05, 0.0);  // run/config.cpp:156-159
 	{
 		const ModeTraits* mt = mode_traits(opts->sensitivity);
 		if (!mt) { dmnd_set_last_error("dmnd_blastp: bad sensitivity"); return 1; }

@@ -375,6 +375,14 @@ typedef struct dmnd_search_opts {
 	int32_t range_culling;     /* --range-culling (config.query_range_culling, frameshift mode only): targets are ranked and culled per query RANGE --
 	                              a target is dropped when half of the read range of its HSPs is already covered by better targets
 	                              (align/legacy/banded_swipe_pipeline.cpp:139-154, output/target_culling.h:110-160).  --long-reads = this + top 10 + -F 15 */
+	double min_id;             /* --id: minimum identity percentage of a reported alignment (config.min_id), 0 = no filter */
+	double query_cover;        /* --query-cover: minimum percentage of the query (of the DNA read for translated searches) an alignment spans */
+	double subject_cover;      /* --subject-cover: the same for the target.  Any of the three filters switches the extension to the reference's
+	                              filtered schedule (align/extend.cpp:95,288: targets are only sorted, not culled, after round 1; round 2 runs in
+	                              steps of max_target_seqs targets with Match::apply_filters after each, align/gapped_final.cpp:107-158,
+	                              align/culling.cpp:144-184) -- without it a filter would merely thin out the best max_target_seqs targets.
+	                              Equal query and subject covers >= 50 in a protein search also set the reference's min_length_ratio
+	                              (run/config.cpp:156-159): seed hits between sequences whose length ratio lies below cover/100 - 0.05 are dropped */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

@@ -22,6 +22,12 @@ For every workload W and parity-ladder level L:
     XF / XF0 / XF3 = blastx in frameshift alignment mode (-F 15: the legacy extension pipeline + the 3-frame banded DP): --fast with
          the transcript fields (cigar / btop carry the \\ and / frameshift marks) + qframe, --fast in the pairwise format (.txt, with
          the "No hits found" records of every unaligned read), --sensitive with the default fields
+    I1 = --fast with the report filters --id 60 --query-cover 50: the extension's filtered schedule (targets only sorted after round 1,
+         round 2 in steps with Match::apply_filters, align/extend.cpp:288, align/gapped_final.cpp:107-158)
+    M1 = default sensitivity with --query-cover 70 --subject-cover 70: equal covers >= 50 set min_length_ratio = 0.65 -- length-sorted
+         blocks (queries are reported longest first) and the mutual-coverage seed stage (search/hamming/kernel_mutual_cov.h)
+    XI / XFI = blastx --fast --id 50 --query-cover 60 / blastx --fast -F 15 --id 50 --subject-cover 20 (the legacy pipeline's
+         Target::apply_filters, align/legacy/query_mapper.cpp:338-349)
     XL = blastx --long-reads (= --range-culling --top 10 -F 15, default sensitivity): targets ranked and culled per query range
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
@@ -39,11 +45,13 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "s1": [],
           "s2": [],
           "s3": [], "s4": [], "s5": [], "s6": [],
-          "t2": [], "f0": []}
+          "t2": [], "f0": [],
+          "i1": ["--id", "60", "--query-cover", "50"],
+          "m1": ["--query-cover", "70", "--subject-cover", "70"]}
 FORMAT = {"f0": "0"}  # BLAST pairwise (-f 0); everything else is tabular (-f 6)
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
-MODE = {"s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-ONLY = {"f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
+MODE = {"m1": [], "s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
+ONLY = {"i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -83,7 +91,7 @@ def main_blastx():
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", []),
-                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", [])):
+                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", []), ("xi", []), ("xfi", [])):
                 out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl != "xf0" else f"{name}.{lvl}.txt")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
@@ -92,6 +100,10 @@ def main_blastx():
                     mode = mode + ["-F", "15"]
                 if lvl == "xl":
                     mode = ["--long-reads"]  # default sensitivity, --range-culling --top 10 -F 15
+                if lvl == "xi":
+                    mode = mode + ["--id", "50", "--query-cover", "60"]
+                if lvl == "xfi":
+                    mode = mode + ["--id", "50", "--subject-cover", "20"]
                 r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "0" if lvl == "xf0" else "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

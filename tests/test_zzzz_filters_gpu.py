@@ -1,0 +1,21 @@
+"""Report filters (--id / --query-cover / --subject-cover) on the device: the files of tests/test_filters.py through the product CLI.
+The filtered schedule is host logic over the same kernels (score-only and traceback DP in more, smaller waves; the seed stage's hits
+thinned by the length ratio for equal covers), so the reference's goldens must come out byte for byte here as well.
+(Written after the round's GPU budget was spent: first device run = the round-end suite.)"""
+import os
+import pytest
+from conftest import GOLDEN, ROOT
+from test_filters import PROTEIN, TRANSLATED, run_protein, run_translated
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "diamond_b200", "bin", "dmnd-b200")
+
+
+@pytest.mark.parametrize("name,lvl,flags", PROTEIN)
+def test_filtered_protein_search_on_device(product_lib, name, lvl, flags, tmp_path):
+    assert run_protein(CLI, name, flags, tmp_path) == open(os.path.join(GOLDEN, f"{name}.{lvl}.tsv")).read()
+
+
+@pytest.mark.parametrize("lvl,flags", TRANSLATED)
+def test_filtered_translated_search_on_device(product_lib, lvl, flags, tmp_path):
+    assert run_translated(CLI, flags, tmp_path) == open(os.path.join(GOLDEN, f"bx.{lvl}.tsv")).read()

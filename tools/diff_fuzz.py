@@ -21,13 +21,15 @@ def main():
     ap.add_argument("--cli", default=os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli"))
     ap.add_argument("--frameshift", type=float, default=None, help="probability of -F on a blastx run (default 0.35); 1 with --translated-only = frameshift runs only")
     ap.add_argument("--translated-only", action="store_true")
+    ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
+    ap.add_argument("--protein-only", action="store_true")
     a = ap.parse_args()
     rnd = random.Random(a.seed)
     bad = 0
     with tempfile.TemporaryDirectory() as td:
         for run in range(a.runs):
             seed = rnd.randrange(1 << 30)
-            translated = a.translated_only or rnd.random() < 0.4
+            translated = not a.protein_only and (a.translated_only or rnd.random() < 0.4)
             d = os.path.join(td, "d.faa")
             if translated:
                 w = synth.reads_workload(seed, n_db=rnd.choice([300, 800]), n_q=rnd.choice([80, 200]))
@@ -56,6 +58,13 @@ def main():
             if r < 0.25: opts += ["-k", str(rnd.choice([0, 1, 3, 50]))]
             elif r < 0.45: opts += ["--top", str(rnd.choice([0, 5, 30, 100]))]
             if rnd.random() < 0.3: opts += ["-e", rnd.choice(["10", "1e-10", "1e-30"])]
+            if rnd.random() < a.filters:  # report filters: the extension's filtered schedule (align/extend.cpp:288, gapped_final.cpp:107-158)
+                u = rnd.random()
+                if u < 0.5 or rnd.random() < 0.3: opts += ["--id", str(rnd.choice([30, 50, 70, 90]))]
+                if u >= 0.3: opts += ["--query-cover", str(rnd.choice([20, 40, 60, 80, 95]))]
+                if u >= 0.6: opts += ["--subject-cover", str(rnd.choice([10, 30, 55, 70, 90]))]
+                if u >= 0.6 and rnd.random() < 0.5:  # equal covers >= 50: min_length_ratio, length-sorted blocks, the mutual-coverage seed stage (protein searches)
+                    opts[-1] = opts[-3] = str(rnd.choice([50, 60, 80, 90]))
             if translated:
                 if rnd.random() < 0.3: opts += ["--strand", rnd.choice(["plus", "minus"])]
                 if rnd.random() < 0.3: opts += ["--min-orf", str(rnd.choice([1, 10, 35]))]
