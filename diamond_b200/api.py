@@ -65,7 +65,7 @@ class SearchOpts(C.Structure):
                 ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
                 ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32), ("query_contexts", C.c_int32), ("top_percent", C.c_double),
                 ("frame_shift", C.c_int32), ("range_culling", C.c_int32),
-                ("min_id", C.c_double), ("query_cover", C.c_double), ("subject_cover", C.c_double)]
+                ("min_id", C.c_double), ("query_cover", C.c_double), ("subject_cover", C.c_double), ("min_bit_score", C.c_double)]
 
 
 class Match(C.Structure):
@@ -212,7 +212,7 @@ class Context:
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
                  comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
                  masking: int = 0, motif_masking: int = 0, sensitivity: int = 0, query_contexts: int = 1, frame_shift: int = 0, range_culling: int = 0, top_percent: float | None = None,
-                 min_id: float = 0.0, query_cover: float = 0.0, subject_cover: float = 0.0):
+                 min_id: float = 0.0, query_cover: float = 0.0, subject_cover: float = 0.0, min_bit_score: float = 0.0):
         """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
         wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
         default to the reference's own defaults (1, 1)."""
@@ -234,6 +234,7 @@ class Context:
         self.opts.min_id = float(min_id)                # --id / --query-cover / --subject-cover: report filters inside the extension
         self.opts.query_cover = float(query_cover)
         self.opts.subject_cover = float(subject_cover)
+        self.opts.min_bit_score = float(min_bit_score)  # --min-score: replaces the e-value bound
         if top_percent is not None:
             self.opts.top_percent = float(top_percent)  # --top
         self.params = Params()

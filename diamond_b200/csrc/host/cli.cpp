@@ -538,6 +538,7 @@ int main(int argc, char** argv) {
 			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
 			else if (a == "--matrix") { std::string v = val(); for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
+			else if (a == "--min-score") o.min_bit_score = atof(val());  // basic/config.cpp:299: overrides the e-value setting
 			else if (a == "--query-cover") o.query_cover = atof(val());
 			else if (a == "--subject-cover") o.subject_cover = atof(val());
 			else if (a == "--approx-id") { if (atof(val()) != 0.0) usage("--approx-id: only 0 (no filter) is implemented"); }

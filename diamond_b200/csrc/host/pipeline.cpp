@@ -292,6 +292,8 @@ struct Env {
 	double top = -1.0;    // --top (config.toppercent): >= 0 = report the targets within this percentage of the best bit score; -1 = not given
 	int outer_limit;      // config.max_target_seqs_ as given (0 for -k 0): the bound of extend()'s outer loop (align/extend.cpp:336)
 	double max_evalue;
+	double min_bit_score = 0.0;  // --min-score (config.min_bit_score): replaces the e-value bound of ScoreMatrix::report_cutoff (stats/score_matrix.cpp:234-239)
+	bool report_cutoff(int score, double evalue) const { return min_bit_score != 0.0 ? sc->bitscore(score) >= min_bit_score : evalue <= max_evalue; }
 	bool hauser, want_transcript;
 	bool fuse;  // see Driver::start
 	// --id / --query-cover / --subject-cover (config.min_id, query_cover, subject_cover): with any of them set the reference only SORTS the
@@ -548,7 +550,7 @@ void Driver::start(QueryState& q, ThreadCtx& tc) {
 	if (q.chunk_size < target_count) std::sort(ts, ts + target_count);
 	q.i0 = 0;
 	q.i1 = std::min<int64_t>(q.chunk_size, target_count);
-	if (e.top < 0.0 && (q.i1 - q.i0) < e.max_target_seqs)
+	if (e.top < 0.0 && e.min_bit_score == 0.0 && (q.i1 - q.i0) < e.max_target_seqs)  // align/extend.cpp:262
 		while (q.i1 < target_count && e.sc->evalue(ts[q.i1].score, (unsigned)q.qlen, 50) <= e.max_evalue)
 			q.i1 += std::min<int64_t>(16, target_count - q.i1);
 	// Fused rounds: round 2 re-evaluates, with traceback, exactly the (query, target, band) problem of round 1 that gave
@@ -689,7 +691,7 @@ void Driver::consume_round1(QueryState& q, ThreadCtx& tc, const dmnd_dp_problem*
 		Target& t = q.r1.p[q.prob_target.p[k]];
 		const uint32_t ctx = probs[k].query;
 		const double ev = e.sc->evalue(score, (unsigned)(ctx == q.qid ? q.qlen : e.qlen(ctx)), (unsigned)t.tlen);
-		if (score > 0 && ev <= e.max_evalue) {  // banded_swipe.h:341-342, ScoreMatrix::report_cutoff
+		if (score > 0 && e.report_cutoff(score, ev)) {  // banded_swipe.h:341-342, ScoreMatrix::report_cutoff
 			const HspLite h{ score, ev, probs[k].d_begin, probs[k].d_end, ctx };
 			// Target::add_hit(list,it), target.h:104-112: a strictly higher score moves filter_score AND best_context to this HSP's
 			// frame (frames arrive in ascending order, as the reference's loop over the frames delivers them); inner_culling keeps
@@ -779,7 +781,7 @@ void Driver::take_round2_result(QueryState& q, ThreadCtx& tc, Match& m, const dm
 	// gapped_final.cpp:140-149; known_evalue >= 0: the e-value of (r.score, qlen, tlen) was already computed in round 1
 	const Env& e = env;
 	const double ev = known_evalue >= 0.0 ? known_evalue : e.sc->evalue(r.score, (unsigned)(pr.query == q.qid ? q.qlen : e.qlen(pr.query)), (unsigned)m.tlen);
-	if (r.score > 0 && ev <= e.max_evalue) {
+	if (r.score > 0 && e.report_cutoff(r.score, ev)) {
 		const HspLite h{ r.score, ev, pr.d_begin, pr.d_end, pr.query };
 		if (!m.has_hsp || hsp_less(h, m.h)) {
 			m.h = h; m.r = r;
@@ -1615,6 +1617,9 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	}
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
+	e.min_bit_score = opts->min_bit_score;
+	if (!(e.min_bit_score >= 0.0)) { dmnd_set_last_error("dmnd_blastp: min_bit_score must not be negative (0 = the e-value bound applies)"); return 1; }
+	if (e.min_bit_score != 0.0) e.fuse = false;  // (the device bridge admits one ranking chunk of <= 64 targets: unaffected, but keep the tested host schedule)
 	e.min_id = opts->min_id; e.query_cover = opts->query_cover; e.subject_cover = opts->subject_cover;
 	if (!(e.min_id >= 0.0 && e.min_id <= 100.0) || !(e.query_cover >= 0.0 && e.query_cover <= 100.0) || !(e.subject_cover >= 0.0 && e.subject_cover <= 100.0)) {
 		dmnd_set_last_error("dmnd_blastp: min_id, query_cover and subject_cover are percentages (0 = no filter)");

@@ -383,6 +383,8 @@ typedef struct dmnd_search_opts {
 	                              align/culling.cpp:144-184) -- without it a filter would merely thin out the best max_target_seqs targets.
 	                              Equal query and subject covers >= 50 in a protein search also set the reference's min_length_ratio
 	                              (run/config.cpp:156-159): seed hits between sequences whose length ratio lies below cover/100 - 0.05 are dropped */
+	double min_bit_score;      /* --min-score: minimum bit score of a reported alignment; when set it REPLACES the e-value bound (ScoreMatrix::report_cutoff,
+	                              stats/score_matrix.cpp:234-239) and the ranking loop no longer widens its first chunk by e-value (align/extend.cpp:262) */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

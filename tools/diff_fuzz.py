@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--translated-only", action="store_true")
     ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
     ap.add_argument("--protein-only", action="store_true")
+    ap.add_argument("--coords-only", action="store_true", help="include field lists of coordinates only (known to differ in rare ties, see the comment at fmt 6c)")
+    ap.add_argument("--keep", default=None, help="directory that receives the inputs and both outputs of every differing run")
+    ap.add_argument("--min-score", type=float, default=0.1, help="probability of --min-score on a run")
     a = ap.parse_args()
     rnd = random.Random(a.seed)
     bad = 0
@@ -58,6 +61,7 @@ def main():
             if r < 0.25: opts += ["-k", str(rnd.choice([0, 1, 3, 50]))]
             elif r < 0.45: opts += ["--top", str(rnd.choice([0, 5, 30, 100]))]
             if rnd.random() < 0.3: opts += ["-e", rnd.choice(["10", "1e-10", "1e-30"])]
+            if rnd.random() < a.min_score: opts += ["--min-score", str(rnd.choice([20, 40, 60, 100, 250]))]  # overrides -e
             if rnd.random() < a.filters:  # report filters: the extension's filtered schedule (align/extend.cpp:288, gapped_final.cpp:107-158)
                 u = rnd.random()
                 if u < 0.5 or rnd.random() < 0.3: opts += ["--id", str(rnd.choice([30, 50, 70, 90]))]
@@ -75,7 +79,7 @@ def main():
                 else:
                     opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
                     if u < 0.5: opts += ["--range-culling"]
-            fmt = rnd.choice(["6", "6", "6f", "0"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "0", "paf", "sam"])
+            fmt = rnd.choice(["6", "6", "6f", "0"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "paf", "sam"])
             if fmt == "6f" and fshift:
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
@@ -85,6 +89,13 @@ def main():
             elif fmt == "6g":
                 opts += ["-f", "6", "qseqid", "qtitle", "sseqid", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq", "gaps", "nident", "qseq_gapped", "sseq_gapped"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
+            elif fmt == "6c":  # short field lists: score-only (the reference's round 2 then runs without coordinates) and statistics without a transcript.
+                # Lists of coordinates ONLY (qstart .. send, qcovhsp, scovhsp and nothing that needs the traceback) are left out unless --coords-only
+                # is given: the reference then takes begin coordinates from a reversed score-only pass (HspValues::COORDS, dp/swipe/swipe_wrapper.cpp:98-99,364-444),
+                # which among equally scoring alignments can pick another begin than its own traceback does; this build always traces back
+                lists = [["qseqid", "sseqid", "evalue", "bitscore", "score"], ["qseqid", "sseqid", "length", "pident", "evalue"], ["qseqid", "sseqid", "qlen", "slen", "nident", "mismatch", "qstart", "send"]]
+                if a.coords_only: lists += [["qseqid", "sseqid", "qstart", "qend", "sstart", "send", "evalue", "bitscore"], ["qseqid", "sseqid", "qlen", "slen", "qcovhsp", "scovhsp", "evalue"]]
+                opts += ["-f", "6"] + rnd.choice(lists)
             elif fmt != "6":
                 opts += ["-f", fmt]
             cmd = ["blastx" if translated else "blastp", "-q", q, "-d", d] + opts
@@ -98,6 +109,13 @@ def main():
             print(("ok   " if ok else "DIFF ") + f"run {run} seed {seed} lines {n}: " + " ".join(cmd[:1] + opts), flush=True)
             if not ok:
                 bad += 1
+                if a.keep:
+                    import shutil
+                    kd = os.path.join(a.keep, f"run{run}")
+                    os.makedirs(kd, exist_ok=True)
+                    for f in (q, d, ro, oo):
+                        if os.path.exists(f): shutil.copy(f, kd)
+                    open(os.path.join(kd, "cmd.txt"), "w").write(" ".join(cmd) + "\n")
                 print("     ref rc", r1.returncode, r1.stderr[-200:], "| ours rc", r2.returncode, r2.stderr[-200:])
     print(f"{a.runs - bad} of {a.runs} identical")
     sys.exit(1 if bad else 0)
