@@ -24,6 +24,7 @@ struct SeqBlock {
 	std::vector<int8_t> letters;
 	std::vector<int64_t> limits;
 	std::vector<std::string> ids, titles;  // id = title up to the first blank (Util::Seq::id_delimiters)
+	std::vector<uint32_t> oid;             // ordinal of every sequence in its file when the block was reordered (length_sort); empty = the block's own order
 	std::vector<uint64_t> rec_begin;       // FASTA input: byte offset of every record's '>' in the (inflated) file, then the file size: block cuts (-b)
 	SeqBlock() : letters(DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER) { limits.push_back(DMND_PERIMETER_PADDING); }
 	void finish() { letters.insert(letters.end(), DMND_PERIMETER_PADDING, (int8_t)DMND_DELIMITER); }
@@ -60,6 +61,7 @@ void length_sort(SeqBlock& b) {
 		s.letters.insert(s.letters.end(), b.letters.begin() + b.limits[j], b.letters.begin() + b.limits[j + 1]);  // the letters and their delimiter
 		s.limits.push_back((int64_t)s.letters.size());
 		s.ids.push_back(std::move(b.ids[j]));
+		s.oid.push_back(b.oid.empty() ? j : b.oid[j]);
 		if (!b.titles.empty()) s.titles.push_back(std::move(b.titles[j]));
 	}
 	s.finish();
@@ -231,7 +233,7 @@ void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b, const 
 			size_t e = 1;
 			while (e < line.size() && !strchr(" \t\x01", line[e])) ++e;
 			dq.ids.push_back(line.substr(1, e - 1));
-			dq.titles.push_back(line.substr(1));
+			dq.titles.push_back(line.substr(1) + "\n");  // the reference's FASTQ reader keeps a newline at the end of the title (data/fasta/parser.h:247): qtitle, -f 0 and -f 5 show it
 			open = true;
 			// FastqTokenizer::read_record (data/fasta/parser.h:238-270): sequence lines up to the '+' line, then quality lines until they
 			// are as long as the sequence
@@ -460,9 +462,10 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false, sam = false, k_set = false, top_set = false, unal = false;
+		bool pairwise = false, paf = false, sam = false, xml = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		bool header_simple = false, long_reads = false;
+		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
@@ -500,7 +503,8 @@ int main(int argc, char** argv) {
 				if (fmt == "0") { pairwise = true; continue; }
 				if (fmt == "paf" || fmt == "103") { paf = true; continue; }
 				if (fmt == "sam" || fmt == "101") { sam = true; continue; }
-				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f sam and -f paf are implemented");
+				if (fmt == "xml" || fmt == "5") { xml = true; continue; }
+				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f 5 (xml), -f sam and -f paf are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -536,7 +540,7 @@ int main(int argc, char** argv) {
 			else if (a == "--quiet") {}
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
 			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
-			else if (a == "--matrix") { std::string v = val(); for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
+			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
 			else if (a == "--min-score") o.min_bit_score = atof(val());  // basic/config.cpp:299: overrides the e-value setting
 			else if (a == "--query-cover") o.query_cover = atof(val());
@@ -553,7 +557,7 @@ int main(int argc, char** argv) {
 			if (o.frame_shift == 0) o.frame_shift = 15;
 		}
 		if (o.range_culling && o.frame_shift == 0) usage("Query range culling is only supported in frameshift alignment mode (option -F).");  // basic/config.cpp:824-825
-		if (pairwise || paf || sam) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
+		if (pairwise || paf || sam || xml) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
@@ -565,6 +569,7 @@ int main(int argc, char** argv) {
 		if (fshift) {
 			o.want_transcript = 1;  // output/output_format.cpp:256-257
 			if (paf || sam) usage("--frameshift: -f sam and -f paf are not implemented in this mode");
+			if (xml && block_size != 0.0) usage("--frameshift with -b: only the tabular format is implemented");
 			if (block_size != 0.0 && (o.range_culling || pairwise || unal)) usage("--frameshift with -b: only the tabular format without --unal and without --range-culling is implemented");
 			for (const std::string& f : fields) if (f == "qseq" || f == "sseq" || f == "qcovhsp" || f == "positive" || f == "ppos") usage(("--frameshift: output field " + f + " is not implemented in this mode").c_str());
 		}
@@ -714,15 +719,15 @@ int main(int argc, char** argv) {
 				}
 				for (size_t bk = 0; bk < nblocks; ++bk) cur[bk].i = end[bk];
 			}
-			// queries with seed hits in some block and no alignment in any
-			std::vector<uint32_t> all;
-			for (size_t bk = 0; bk < nblocks; ++bk) { size_t nu = 0; const uint32_t* u = dmnd_result_unaligned(results[bk], &nu); all.insert(all.end(), u, u + nu); }
-			std::sort(all.begin(), all.end());
-			all.erase(std::unique(all.begin(), all.end()), all.end());
-			size_t ji = 0;
-			for (uint32_t qid : all) {
-				while (ji < joined.size() && joined[ji].query / cx < qid / cx) ++ji;
-				if (!(ji < joined.size() && joined[ji].query / cx == qid / cx)) joined_unal.push_back(qid);
+			// a blocked run reports EVERY query without a joined record as unaligned (output/join_blocks.cpp:302-308,365-372: the join walks
+			// the query ids between two records and after the last one) -- not only those with seed hits, as a one-block run does
+			{
+				const uint32_t nsrc = translated ? (uint32_t)dq.ids.size() : q.size();
+				size_t ji = 0;
+				for (uint32_t sq = 0; sq < nsrc; ++sq) {
+					while (ji < joined.size() && joined[ji].query / cx < sq) ++ji;
+					if (!(ji < joined.size() && joined[ji].query / cx == sq)) joined_unal.push_back(sq * cx);
+				}
 			}
 			if (fshift) {
 				// Blocked runs of the legacy pipeline travel through IntermediateRecords, and the join re-derives the alignment statistics from
@@ -986,7 +991,141 @@ int main(int argc, char** argv) {
 			no_hits_upto(UINT32_MAX);
 			n = 0;  // nothing left for the tabular writer
 		}
-		if (header_simple && !pairwise && !paf && !sam) {  // TabularFormat::output_header: the field keys, tab-separated
+		if (xml) {
+			// XMLFormat (output/xml_format.cpp:31-176): the BLAST XML of NCBI's DTD -- a header naming the first query of the block, one <Iteration>
+			// per aligned query (and per query with seed hits and no alignment: DEFAULT_REPORT_UNALIGNED), one <Hit> per target with its HSP
+			// (coordinates on the read, unoriented, for translated queries), the aligned letters and BLAST's midline, and the footer without a final newline
+			const dmnd_params* pp = &params;
+			auto esc = [](const std::string& in, std::string& out_) {  // EscapeSequences::XML (util/util.cpp:80-86)
+				for (char c : in) {
+					if (c == '"') out_ += "&quot;"; else if (c == '\'') out_ += "&apos;"; else if (c == '<') out_ += "&lt;"; else if (c == '>') out_ += "&gt;"; else if (c == '&') out_ += "&amp;"; else out_ += c;
+				}
+			};
+			auto next_title = [](const std::string& t, size_t a, size_t* next) -> std::string {  // one title of a merged record: "\x01" or " >" ends it (FASTA_HEADER_SEP)
+				size_t e = a;
+				while (e < t.size() && t[e] != '\x01' && !(t[e] == ' ' && e + 1 < t.size() && t[e + 1] == '>')) ++e;
+				*next = e >= t.size() ? std::string::npos : (t[e] == '\x01' ? e + 1 : e + 2);
+				return t.substr(a, e - a);
+			};
+			auto accession = [](std::string t) {  // Util::Seq::get_accession (util/sequence/sequence.cpp:76-103): UniRef / gi| / xx| prefixes, |xx and .version suffixes go
+				size_t i;
+				if (t.compare(0, 6, "UniRef") == 0) t.erase(0, t.find('_') + 1);
+				else if ((i = t.find('|')) != std::string::npos) {
+					if (t.compare(0, 3, "gi|") == 0) { t.erase(0, t.find('|', i + 1) + 1); i = t.find('|'); }
+					t.erase(0, i + 1);
+					i = t.find('|');
+					if (i != std::string::npos) t.erase(i);
+				}
+				i = t.rfind('.');
+				if (i != std::string::npos) t.erase(i);
+				return t;
+			};
+			const uint32_t cx = translated ? 6u : 1u;
+			auto q_title = [&](uint32_t sq) -> const std::string& { return translated ? dq.titles[sq] : q.titles[sq]; };
+			auto q_len = [&](uint32_t sq) -> int64_t { return translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1; };
+			uint64_t all_letters = 0;
+			for (uint32_t i = 0; i < r.size(); ++i) all_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
+			{
+				size_t nx;
+				std::string e0, dbl;
+				const uint32_t n_src = translated ? (uint32_t)dq.ids.size() : q.size();
+				if (n_src) { std::string full; esc(q_title(0), full); e0 = full.substr(0, q_title(0).find('\x01')); }
+				(void)nx;
+				std::ostringstream ev;
+				ev << o.max_evalue;  // (a stringstream's default formatting of the double: 0.001, 1e-10, 10)
+				line = "<?xml version=\"1.0\"?>\n<!DOCTYPE BlastOutput PUBLIC \"-//NCBI//NCBI BlastOutput/EN\" \"http://www.ncbi.nlm.nih.gov/dtd/NCBI_BlastOutput.dtd\">\n<BlastOutput>\n"
+				       "  <BlastOutput_program>" + std::string(translated ? "blastx" : "blastp") + "</BlastOutput_program>\n  <BlastOutput_version>diamond 2.2.2</BlastOutput_version>\n"
+				       "  <BlastOutput_reference>Benjamin Buchfink, Xie Chao, and Daniel Huson (2015), &quot;Fast and sensitive protein alignment using DIAMOND&quot;, Nature Methods 12:59-60.</BlastOutput_reference>\n"
+				       "  <BlastOutput_db>" + df + "</BlastOutput_db>\n  <BlastOutput_query-ID>Query_1</BlastOutput_query-ID>\n  <BlastOutput_query-def>" + e0 + "</BlastOutput_query-def>\n"
+				       "  <BlastOutput_query-len>" + std::to_string(n_src ? q_len(0) : 0) + "</BlastOutput_query-len>\n  <BlastOutput_param>\n    <Parameters>\n      <Parameters_matrix>" + matrix_name + "</Parameters_matrix>\n"
+				       "      <Parameters_expect>" + ev.str() + "</Parameters_expect>\n      <Parameters_gap-open>11</Parameters_gap-open>\n      <Parameters_gap-extend>1</Parameters_gap-extend>\n"
+				       "      <Parameters_filter>F</Parameters_filter>\n    </Parameters>\n  </BlastOutput_param>\n<BlastOutput_iterations>\n";
+				if (n_src) fwrite(line.data(), 1, line.size(), out);  // (the header is printed by the first query block that has ids: none without queries)
+			}
+			auto intro = [&](uint32_t sq) {
+				const uint32_t oid = (!translated && !q.oid.empty()) ? q.oid[sq] : sq;
+				size_t nx;
+				std::string t;
+				esc(next_title(q_title(sq), 0, &nx), t);
+				return "<Iteration>\n  <Iteration_iter-num>" + std::to_string(oid + 1) + "</Iteration_iter-num>\n  <Iteration_query-ID>Query_" + std::to_string(oid + 1) + "</Iteration_query-ID>\n  <Iteration_query-def>"
+				       + t + "</Iteration_query-def>\n  <Iteration_query-len>" + std::to_string(q_len(sq)) + "</Iteration_query-len>\n<Iteration_hits>\n";
+			};
+			char kb[40], lb[40];
+			snprintf(kb, sizeof kb, "%lf", 0.041);  // ScoreMatrix::k() / lambda() of BLOSUM62 11/1 (TextBuffer::print_d)
+			snprintf(lb, sizeof lb, "%lf", 0.267);
+			const std::string epilog_tail = "</Iteration_hits>\n  <Iteration_stat>\n    <Statistics>\n      <Statistics_db-num>" + std::to_string(r.size()) + "</Statistics_db-num>\n      <Statistics_db-len>" + std::to_string(all_letters)
+			                                + "</Statistics_db-len>\n      <Statistics_hsp-len>0</Statistics_hsp-len>\n      <Statistics_eff-space>0</Statistics_eff-space>\n      <Statistics_kappa>" + kb
+			                                + "</Statistics_kappa>\n      <Statistics_lambda>" + lb + "</Statistics_lambda>\n      <Statistics_entropy>0</Statistics_entropy>\n    </Statistics>\n  </Iteration_stat>\n</Iteration>\n";
+			size_t nu = 0, u = 0;
+			const uint32_t* unal_ids = result_unaligned(&nu);
+			auto no_hits_upto = [&](uint32_t src_end) {
+				for (; u < nu && unal_ids[u] / cx < src_end; ++u) {
+					line = intro(unal_ids[u] / cx) + epilog_tail;
+					fwrite(line.data(), 1, line.size(), out);
+				}
+			};
+			uint32_t hit_num = 0;
+			for (size_t i = 0; i < n; ++i) {
+				const dmnd_match& x = m[i];
+				const uint32_t sq = x.query / cx;
+				const bool first = i == 0 || m[i - 1].query / cx != sq, last = i + 1 == n || m[i + 1].query / cx != sq;
+				line.clear();
+				if (first) { no_hits_upto(sq); line = intro(sq); hit_num = 0; }
+				const uint8_t* t = tr + x.transcript_off;
+				const std::string& tt = r.titles[x.target];
+				size_t d0 = 0;
+				while (d0 < tt.size() && !strchr(" \a\b\f\n\r\t\v\x01", tt[d0])) ++d0;  // Util::Seq::get_title_def: id | definition at the first id delimiter
+				const std::string id = tt.substr(0, d0), def = d0 >= tt.size() ? std::string() : tt.substr(d0 + 1);
+				if (hit_num > 0) line += "  </Hit_hsps>\n</Hit>\n";
+				line += "<Hit>\n  <Hit_num>" + std::to_string(hit_num + 1) + "</Hit_num>\n  <Hit_id>";
+				esc(id, line);
+				line += "</Hit_id>\n  <Hit_def>";
+				for (size_t a = 0, k = 0; a != std::string::npos; ++k) {  // OutputFormat::print_title(def, full, all, " &gt;")
+					size_t nx;
+					const std::string one = next_title(def, a, &nx);
+					if (k) line += " &gt;";
+					esc(one, line);
+					a = nx;
+				}
+				line += "</Hit_def>\n  <Hit_accession>";
+				esc(accession(id), line);
+				line += "</Hit_accession>\n  <Hit_len>" + std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1) + "</Hit_len>\n  <Hit_hsps>\n";
+				++hit_num;
+				format_double(x.bit_score, buf, sizeof buf);
+				line += "    <Hsp>\n      <Hsp_num>1</Hsp_num>\n      <Hsp_bit-score>" + std::string(buf) + "</Hsp_bit-score>\n      <Hsp_score>" + std::to_string(x.score) + "</Hsp_score>\n      <Hsp_evalue>";
+				if (x.evalue == 0.0) line += "0.0"; else { snprintf(buf, sizeof buf, "%.2e", x.evalue); line += buf; }
+				int64_t qf = x.q_begin, qt = x.q_end;  // query_source_range: [begin, end) on the query as given
+				int frame_tag = 0;
+				if (translated) {
+					const int fr = (int)(x.query % 6), off = fr % 3;
+					const int64_t L = dq.len[sq], b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + end_frame(x) % 3;
+					if (fr < 3) { qf = b_in; qt = e_in; } else { qf = L - e_in; qt = L - b_in; }
+					frame_tag = fr < 3 ? fr + 1 : 2 - fr;  // Hsp::blast_query_frame
+				}
+				line += "</Hsp_evalue>\n      <Hsp_query-from>" + std::to_string(qf + 1) + "</Hsp_query-from>\n      <Hsp_query-to>" + std::to_string(qt) + "</Hsp_query-to>\n      <Hsp_hit-from>" + std::to_string(x.t_begin + 1)
+				        + "</Hsp_hit-from>\n      <Hsp_hit-to>" + std::to_string(x.t_end) + "</Hsp_hit-to>\n      <Hsp_query-frame>" + std::to_string(frame_tag) + "</Hsp_query-frame>\n      <Hsp_hit-frame>0</Hsp_hit-frame>\n      <Hsp_identity>"
+				        + std::to_string(x.identities) + "</Hsp_identity>\n      <Hsp_positive>" + std::to_string(x.positives) + "</Hsp_positive>\n      <Hsp_gaps>" + std::to_string(x.gaps) + "</Hsp_gaps>\n      <Hsp_align-len>"
+				        + std::to_string(x.length) + "</Hsp_align-len>\n         <Hsp_qseq>";
+				walk_query(x, t);
+				std::string ql, ml, sl;
+				for (uint32_t k = 0; k < x.transcript_len; ++k) {
+					const int op = t[k] >> 6, sc = t[k] & 63;
+					if (qat[k] < 0) { ql += qat[k] == -1 ? '\\' : '/'; sl += '-'; ml += ' '; }
+					else if (op == DMND_OP_MATCH) { const char c = alphabet[qat[k]]; ql += c; ml += c; sl += c; }
+					else if (op == DMND_OP_SUBSTITUTION) { const int a = qat[k]; ql += alphabet[a]; sl += alphabet[sc]; ml += pp->score[a * 32 + sc] > 0 ? '+' : ' '; }
+					else if (op == DMND_OP_INSERTION) { ql += alphabet[qat[k]]; sl += '-'; ml += ' '; }
+					else { ql += '-'; sl += alphabet[sc]; ml += ' '; }
+				}
+				line += ql + "</Hsp_qseq>\n         <Hsp_hseq>" + sl + "</Hsp_hseq>\n      <Hsp_midline>" + ml + "</Hsp_midline>\n    </Hsp>\n";
+				if (last) line += "  </Hit_hsps>\n</Hit>\n" + epilog_tail;
+				fwrite(line.data(), 1, line.size(), out);
+			}
+			no_hits_upto(UINT32_MAX);
+			line = "</BlastOutput_iterations>\n</BlastOutput>";
+			fwrite(line.data(), 1, line.size(), out);
+			n = 0;
+		}
+		if (header_simple && !pairwise && !paf && !sam && !xml) {  // TabularFormat::output_header: the field keys, tab-separated
 			line.clear();
 			for (size_t fi = 0; fi < fields.size(); ++fi) { if (fi) line += '\t'; line += fields[fi]; }
 			line += '\n';
@@ -996,7 +1135,7 @@ int main(int argc, char** argv) {
 		const uint32_t* unal_q = result_unaligned(&n_unal);
 		const uint32_t ctxs = translated ? 6u : 1u;
 		auto unaligned_upto = [&](uint32_t src_end) {  // --unal 1: TabularFormat::print_query_intro (output/blast_tab_format.cpp:776-788) for the queries
-			if (!unal || pairwise || paf || sam) return;      // [.., src_end) that had seed hits and no alignment, in query order
+			if (!unal || pairwise || paf || sam || xml) return;      // [.., src_end) that had seed hits and no alignment, in query order
 			for (; u_next < n_unal && unal_q[u_next] / ctxs < src_end; ++u_next) {
 				const uint32_t sq = unal_q[u_next] / ctxs;
 				line.clear();

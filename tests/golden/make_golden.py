@@ -22,6 +22,10 @@ For every workload W and parity-ladder level L:
     XF / XF0 / XF3 = blastx in frameshift alignment mode (-F 15: the legacy extension pipeline + the 3-frame banded DP): --fast with
          the transcript fields (cigar / btop carry the \\ and / frameshift marks) + qframe, --fast in the pairwise format (.txt, with
          the "No hits found" records of every unaligned read), --sensitive with the default fields
+    F5 = L2 in the BLAST XML format (-f 5): .xml
+    B1 = --fast -b 0.00003 --unal 1 -k 3: several reference blocks joined per query (output/join_blocks.cpp); a blocked run reports EVERY query
+         without an alignment as unaligned, not only those with seed hits
+    XX = blastx --fast -k 1 -e 1e-20 in the BLAST XML format (read coordinates, query frame)
     I1 = --fast with the report filters --id 60 --query-cover 50: the extension's filtered schedule (targets only sorted after round 1,
          round 2 in steps with Match::apply_filters, align/extend.cpp:288, align/gapped_final.cpp:107-158)
     M1 = default sensitivity with --query-cover 70 --subject-cover 70: equal covers >= 50 set min_length_ratio = 0.65 -- length-sorted
@@ -46,12 +50,14 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "s2": [],
           "s3": [], "s4": [], "s5": [], "s6": [],
           "t2": [], "f0": [],
+          "f5": [], "b1": ["-b", "0.00003", "--unal", "1", "-k", "3"],
           "i1": ["--id", "60", "--query-cover", "50"],
           "m1": ["--query-cover", "70", "--subject-cover", "70"]}
-FORMAT = {"f0": "0"}  # BLAST pairwise (-f 0); everything else is tabular (-f 6)
+FORMAT = {"f0": "0", "f5": "5"}  # BLAST pairwise (-f 0), BLAST XML (-f 5); everything else is tabular (-f 6)
+EXT = {"f0": "txt", "f5": "xml"}
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
 MODE = {"m1": [], "s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-ONLY = {"i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
+ONLY = {"f5": ("edge",), "b1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -71,7 +77,7 @@ def main():
             for lvl, flags in LEVELS.items():
                 if lvl in ONLY and name not in ONLY[lvl]:
                     continue
-                out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl not in FORMAT else f"{name}.{lvl}.txt")
+                out = os.path.join(HERE, f"{name}.{lvl}.{EXT.get(lvl, 'tsv')}")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
                 r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", "8", "--log"] + flags,
@@ -91,8 +97,8 @@ def main_blastx():
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", []),
-                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", []), ("xi", []), ("xfi", [])):
-                out = os.path.join(HERE, f"{name}.{lvl}.tsv" if lvl != "xf0" else f"{name}.{lvl}.txt")
+                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", []), ("xi", []), ("xfi", []), ("xx", [])):
+                out = os.path.join(HERE, f"{name}.{lvl}." + {"xf0": "txt", "xx": "xml"}.get(lvl, "tsv"))
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
                 mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"], "xf3": ["--sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
@@ -100,11 +106,13 @@ def main_blastx():
                     mode = mode + ["-F", "15"]
                 if lvl == "xl":
                     mode = ["--long-reads"]  # default sensitivity, --range-culling --top 10 -F 15
+                if lvl == "xx":
+                    mode = mode + ["-k", "1", "-e", "1e-20"]
                 if lvl == "xi":
                     mode = mode + ["--id", "50", "--query-cover", "60"]
                 if lvl == "xfi":
                     mode = mode + ["--id", "50", "--subject-cover", "20"]
-                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", "0" if lvl == "xf0" else "6"] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
+                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", {"xf0": "0", "xx": "5"}.get(lvl, "6")] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)

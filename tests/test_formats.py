@@ -1,0 +1,64 @@
+"""BLAST XML (-f 5, output/xml_format.cpp:31-176) and the unaligned records of a blocked run (output/join_blocks.cpp:302-308,365-372), against
+files written by the unmodified reference (tests/golden/make_golden.py, levels F5, XX, B1)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, workload_blocks
+from test_filters import run_protein, run_translated
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CLI = os.path.join(ROOT, "oracle", "_build", "dmnd-oracle-cli")
+
+
+def check_xml_protein(cli, tmp_path):
+    out = run_protein(cli, "edge", ["--fast", "-f", "5"], tmp_path)
+    gold = open(os.path.join(GOLDEN, "edge.f5.xml")).read()
+    # the header quotes the -d argument as given: the golden was written for "<tmp>/d.faa"
+    strip = lambda s: "\n".join(l for l in s.split("\n") if "<BlastOutput_db>" not in l)
+    assert strip(out) == strip(gold)
+    assert not gold.endswith("\n")  # the footer has no final newline
+
+
+def check_xml_translated(cli, tmp_path):
+    out = run_translated(cli, ["--fast", "-f", "5", "-k", "1", "-e", "1e-20"], tmp_path)
+    gold = open(os.path.join(GOLDEN, "bx.xx.xml")).read()
+    strip = lambda s: "\n".join(l for l in s.split("\n") if "<BlastOutput_db>" not in l)
+    assert strip(out) == strip(gold)
+    assert "<Hsp_query-frame>-2</Hsp_query-frame>" in gold
+
+
+def check_blocked_unaligned(cli, tmp_path):
+    out = run_protein(cli, "rep", ["--fast", "-b", "0.00003", "--unal", "1", "-k", "3"], tmp_path)
+    gold = open(os.path.join(GOLDEN, "rep.b1.tsv")).read()
+    assert out == gold
+    assert sum(1 for l in gold.splitlines() if l.split("\t")[1] == "*") > 50  # every query without an alignment, seed hits or not
+
+
+def test_xml_protein(oracle_lib, tmp_path):
+    check_xml_protein(CLI, tmp_path)
+
+
+def test_xml_translated(oracle_lib, tmp_path):
+    check_xml_translated(CLI, tmp_path)
+
+
+def test_blocked_run_reports_every_unaligned_query(oracle_lib, tmp_path):
+    check_blocked_unaligned(CLI, tmp_path)
+
+
+def test_fastq_titles_keep_their_newline(oracle_lib, tmp_path):
+    """The reference's FASTQ reader appends a newline to the title (data/fasta/parser.h:247); qtitle shows it."""
+    from diamond_b200 import synth
+    f, kw = synth.BX_WORKLOADS["bx"]
+    w = f(**kw)
+    q, d, o = (str(tmp_path / x) for x in ("q.fastq", "d.faa", "o.tsv"))
+    with open(q, "w") as fh:
+        for i, s in enumerate(w["dna"][:40]):
+            fh.write(f"@r{i} read {i}\n{s}\n+\n{'I' * len(s)}\n")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    r = subprocess.run([CLI, "blastx", "--fast", "-q", q, "-d", d, "-o", o, "-f", "6", "qseqid", "qtitle", "sseqid", "-k", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(o).read().split("\n")
+    assert lines[0].startswith("r") and lines[0].split("\t")[1].startswith("r") and lines[1].startswith("\td")  # "id<TAB>title<NL><TAB>target"

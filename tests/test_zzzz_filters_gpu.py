@@ -19,3 +19,11 @@ def test_filtered_protein_search_on_device(product_lib, name, lvl, flags, tmp_pa
 @pytest.mark.parametrize("lvl,flags", TRANSLATED)
 def test_filtered_translated_search_on_device(product_lib, lvl, flags, tmp_path):
     assert run_translated(CLI, flags, tmp_path) == open(os.path.join(GOLDEN, f"bx.{lvl}.tsv")).read()
+
+
+# ---- BLAST XML and the blocked run's unaligned records through the product CLI (tests/test_formats.py holds the CPU twins)
+def test_xml_and_blocked_unaligned_on_device(product_lib, tmp_path):
+    from test_formats import check_blocked_unaligned, check_xml_protein, check_xml_translated
+    check_xml_protein(CLI, tmp_path)
+    check_xml_translated(CLI, tmp_path)
+    check_blocked_unaligned(CLI, tmp_path)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--translated-only", action="store_true")
     ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
     ap.add_argument("--protein-only", action="store_true")
+    ap.add_argument("--blocks", type=float, default=0.15, help="probability of -b (several reference blocks) on a run without -F")
     ap.add_argument("--coords-only", action="store_true", help="include field lists of coordinates only (known to differ in rare ties, see the comment at fmt 6c)")
     ap.add_argument("--keep", default=None, help="directory that receives the inputs and both outputs of every differing run")
     ap.add_argument("--min-score", type=float, default=0.1, help="probability of --min-score on a run")
@@ -79,7 +80,8 @@ def main():
                 else:
                     opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
                     if u < 0.5: opts += ["--range-culling"]
-            fmt = rnd.choice(["6", "6", "6f", "0"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "paf", "sam"])
+            if not fshift and rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
+            fmt = rnd.choice(["6", "6", "6f", "0", "5"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam"])
             if fmt == "6f" and fshift:
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
