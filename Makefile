@@ -33,7 +33,7 @@ $(OBJ)/cuda/%.o: $(CUDA)/%.cu $(CUDA)/ctx.cuh $(CUDA)/dev_params.h $(CUDA)/mask_
 diamond_b200/libdmnd_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt
 
-diamond_b200/bin/dmnd-b200: $(HOST)/cli.cpp diamond_b200/libdmnd_b200.so
+diamond_b200/bin/dmnd-b200: $(HOST)/cli.cpp $(HOST)/range_cover.h diamond_b200/libdmnd_b200.so
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) $< -o $@ -Ldiamond_b200 -ldmnd_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
 
@@ -43,7 +43,7 @@ $(OBJ)/oracle/dmnd_oracle.o: oracle/dmnd_oracle.c include/dmnd_b200.h $(HOST)/mo
 oracle/_build/libdmnd_oracle.so: $(HOST_OBJ) $(OBJ)/oracle/dmnd_oracle.o
 	@mkdir -p $(dir $@)
 	$(CXX) -shared -pthread -o $@ $^ -lm
-oracle/_build/dmnd-oracle-cli: $(HOST)/cli.cpp oracle/_build/libdmnd_oracle.so
+oracle/_build/dmnd-oracle-cli: $(HOST)/cli.cpp $(HOST)/range_cover.h oracle/_build/libdmnd_oracle.so
 	$(CXX) $(CXXFLAGS) $< -o $@ -Loracle/_build -ldmnd_oracle -lz -Wl,-rpath,'$$ORIGIN'
 
 ref:

@@ -17,6 +17,7 @@
 #include <string>
 #include <algorithm>
 #include "../../../include/dmnd_b200.h"
+#include "range_cover.h"
 
 namespace {
 
@@ -568,10 +569,6 @@ int main(int argc, char** argv) {
 		const bool fshift = o.frame_shift != 0;
 		if (fshift) {
 			o.want_transcript = 1;  // output/output_format.cpp:256-257
-			if (paf || sam) usage("--frameshift: -f sam and -f paf are not implemented in this mode");
-			if (xml && block_size != 0.0) usage("--frameshift with -b: only the tabular format is implemented");
-			if (block_size != 0.0 && (o.range_culling || pairwise || unal)) usage("--frameshift with -b: only the tabular format without --unal and without --range-culling is implemented");
-			for (const std::string& f : fields) if (f == "qseq" || f == "sseq" || f == "qcovhsp" || f == "positive" || f == "ppos") usage(("--frameshift: output field " + f + " is not implemented in this mode").c_str());
 		}
 		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode, o.frame_shift });
 		else read_fasta(qf, q);
@@ -696,6 +693,9 @@ int main(int argc, char** argv) {
 				for (size_t bk = 0; bk < nblocks; ++bk) { size_t e = cur[bk].i; while (e < cur[bk].n && cur[bk].m[e].query / cx == src) ++e; end[bk] = e; }
 				int64_t n_targets = 0;
 				double top_bits = 0.0;
+				// --range-culling: the join culls per query range as the extension did (RangeCulling::cull / add over the records' absolute_query_range,
+				// output/target_culling.h:132-160): a record whose read range is >= 50 % covered by records already reported is skipped, never final
+				RangeCover part(top_set ? 0 : (o.max_target_seqs == 0 ? INT64_MAX : (int64_t)o.max_target_seqs));
 				for (;;) {
 					size_t best = nblocks;
 					for (size_t bk = 0; bk < nblocks; ++bk) {
@@ -704,6 +704,21 @@ int main(int argc, char** argv) {
 					}
 					if (best == nblocks) break;
 					const dmnd_match& x = cur[best].m[cur[best].i];
+					if (o.range_culling) {
+						const int fr = (int)(x.query % 6), off = fr % 3, ef = x.reserved ? ((int)x.reserved - 1) % 3 : off;
+						const int L = dq.len[x.query / 6], b_in = 3 * x.q_begin + off, e_in = 3 * x.q_end + ef;
+						const int rb = fr < 3 ? b_in : L - e_in, re = fr < 3 ? e_in : L - b_in;
+						const int c = top_set ? part.covered_max(rb, re, int((double)x.score / (1.0 - o.top_percent / 100.0))) : part.covered_full(rb, re);
+						++cur[best].i;
+						if (!((double)c / (double)(re - rb) * 100.0 < 50.0)) continue;  // config.query_range_cover
+						part.insert(rb, re, x.score);
+						dmnd_match y = x;
+						y.target = oid(best, x.target);
+						y.transcript_off = joined_tr.size();
+						if (x.transcript_len) joined_tr.insert(joined_tr.end(), cur[best].tr + x.transcript_off, cur[best].tr + x.transcript_off + x.transcript_len);
+						joined.push_back(y);
+						continue;
+					}
 					if (n_targets > 0) {  // GlobalCulling::cull
 						if (top_set) { if ((1.0 - x.bit_score / top_bits) * 100.0 > o.top_percent) break; }
 						else if (n_targets >= (int64_t)(o.max_target_seqs == 0 ? INT32_MAX : o.max_target_seqs)) break;
@@ -781,8 +796,8 @@ int main(int argc, char** argv) {
 			}
 		}
 		auto result_unaligned = [&](size_t* nu) -> const uint32_t* {
+			if (nblocks > 1) { *nu = joined_unal.size(); return joined_unal.data(); }  // (a blocked run: the join's rule, frameshift mode or not)
 			if (fshift) { *nu = fs_unal.size(); return fs_unal.data(); }
-			if (nblocks > 1) { *nu = joined_unal.size(); return joined_unal.data(); }
 			return dmnd_result_unaligned(res, nu);
 		};
 		static const char* alphabet = "ARNDCQEGHILKMFPSTWYVBJZX*_";
@@ -836,13 +851,17 @@ int main(int argc, char** argv) {
 				{	// print_cigar: match and substitution are M
 					uint32_t run = 0; int op = -1;
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
-						const int o2 = t[k] >> 6, c = (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;
-						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID"[op]; } run = 1; op = c; }
+						const int o2 = t[k] >> 6;
+						const int c = t[k] == DMND_TR_FRAMESHIFT_FWD ? 3 : t[k] == DMND_TR_FRAMESHIFT_REV ? 4 : (o2 == DMND_OP_INSERTION) ? 1 : (o2 == DMND_OP_DELETION) ? 2 : 0;  // frameshifts: \ and /
+						if (c == op) ++run; else { if (run) { line += std::to_string(run); line += "MID\\/"[op]; } run = 1; op = c; }
 					}
-					if (run) { line += std::to_string(run); line += "MID"[op]; }
+					if (run) { line += std::to_string(run); line += "MID\\/"[op]; }
 				}
 				line += "\t*\t0\t0\t";
-				for (int p2 = x.q_begin; p2 < x.q_end; ++p2) line += alphabet[qs[p2] & 31];
+				// SEQ = query_range().length() letters of the frame the alignment BEGINS in (sam_format.cpp:114).  After a forward frameshift the range can
+				// end one codon past that frame: the reference then prints the block's delimiter through alphabet[31], one of the bytes BEHIND its
+				// 26-letter alphabet literal -- 'Y' in the binary gcc builds from its sources here (the "MRWSYKVHDBX" literal follows); mirrored as such
+				for (int p2 = x.q_begin; p2 < x.q_end; ++p2) line += (qs[p2] & 31) == DMND_DELIMITER ? 'Y' : alphabet[qs[p2] & 31];
 				const int fr = translated ? (int)(x.query % 6) : 0, off = fr % 3;
 				const int64_t b_in = 3 * (int64_t)x.q_begin + off;
 				const int64_t zs = !translated ? x.q_begin + 1 : (fr < 3 ? b_in + 1 : (int64_t)dq.len[sq] - b_in);
@@ -895,7 +914,7 @@ int main(int argc, char** argv) {
 					if (translated) {  // query_source_range: TranslatedPosition::absolute_interval (basic/translated_position.h:121-127)
 						const int fr = (int)(x.query % 6), off = fr % 3;
 						qlen = dq.len[s];
-						const int64_t b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + off;
+						const int64_t b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + end_frame(x) % 3;  // (after a frameshift the end lies in its own frame)
 						if (fr < 3) { qb = b_in; qe = e_in; } else { qb = qlen - e_in; qe = qlen - b_in; strand = '-'; }
 					}
 					line += qid + "\t" + std::to_string(qlen) + "\t" + std::to_string(qb) + "\t" + std::to_string(qe - 1) + "\t" + strand + "\t" + r.ids[x.target] + "\t"
@@ -1187,18 +1206,23 @@ int main(int argc, char** argv) {
 					if (!translated) for (int p2 = x.q_begin; p2 < x.q_end; ++p2) line += alphabet[qs[p2] & 31];
 					else {
 						const int fr = (int)(x.query % 6), off = fr % 3;
-						const int64_t L = dq.len[x.query / 6], b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + off;
+						const int64_t L = dq.len[x.query / 6], b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + end_frame(x) % 3;  // (the end lies in its own frame after a frameshift)
 						const int64_t b = fr < 3 ? b_in : L - e_in, e = fr < 3 ? e_in : L - b_in;
 						line.append(dq.dna[x.query / 6], (size_t)b, (size_t)(e - b));
 					}
 				}
 				else if (f == "sseq") {  // the subject letters of the alignment (no gap characters)
-					int qi = x.q_begin;
+					walk_query(x, t);  // (a match byte stands for the query letter it consumes; frameshift bytes consume nucleotides, no subject letter)
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
+						if (qat[k] < 0) {  // HspContext::Iterator::subject() of a frameshift operation falls through to query(): the query letter at the
+							// position before the shift (basic/match.h:325-334) -- the reference's sseq carries that letter, so does this one
+							const uint32_t c0 = x.query - x.query % 3;
+							line += alphabet[q.letters[(size_t)q.limits[c0 + (uint32_t)(qcur[k] % 3)] + (size_t)(qcur[k] / 3)] & 31];
+							continue;
+						}
 						const int o2 = t[k] >> 6;
-						if (o2 == DMND_OP_MATCH) line += alphabet[qs[qi] & 31];
+						if (o2 == DMND_OP_MATCH) line += alphabet[qat[k]];
 						else if (o2 != DMND_OP_INSERTION) line += alphabet[t[k] & 63];
-						if (o2 != DMND_OP_DELETION) ++qi;
 					}
 				}
 				else if (f == "qtitle") line += translated ? dq.titles[x.query / 6] : q.titles[x.query];
@@ -1206,7 +1230,7 @@ int main(int argc, char** argv) {
 				else if (f == "positive") line += std::to_string(x.positives);
 				else if (f == "ppos") { format_double((double)x.positives * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
 				else if (f == "qcovhsp") {  // query_source_range().length() * 100 / source length (basic/match.h): nucleotides for blastx
-					const double cov = translated ? (double)(3 * (x.q_end - x.q_begin)) * 100.0 / (double)dq.len[x.query / 6]
+					const double cov = translated ? (double)(3 * (x.q_end - x.q_begin) + end_frame(x) % 3 - (int)(x.query % 3)) * 100.0 / (double)dq.len[x.query / 6]
 					                              : (double)(x.q_end - x.q_begin) * 100.0 / (double)(q.limits[x.query + 1] - q.limits[x.query] - 1);
 					format_double(cov, buf, sizeof buf); line += buf;
 				}

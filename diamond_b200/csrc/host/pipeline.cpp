@@ -37,6 +37,7 @@
 #include <vector>
 #include "../../../include/dmnd_b200.h"
 #include "chaining.h"
+#include "range_cover.h"
 #include "scoring.h"
 
 namespace {

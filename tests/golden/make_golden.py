@@ -32,6 +32,9 @@ For every workload W and parity-ladder level L:
          blocks (queries are reported longest first) and the mutual-coverage seed stage (search/hamming/kernel_mutual_cov.h)
     XI / XFI = blastx --fast --id 50 --query-cover 60 / blastx --fast -F 15 --id 50 --subject-cover 20 (the legacy pipeline's
          Target::apply_filters, align/legacy/query_mapper.cpp:338-349)
+    XFP / XFS = blastx --fast -F 15 in the PAF format / in the SAM format (-k 1 -e 1e-20; frameshift operations in the CIGAR, the @PG line
+         quotes the reference's own command line and is skipped by the tests)
+    XLB = blastx --long-reads -b 0.0002: several reference blocks, the join culling per query range
     XL = blastx --long-reads (= --range-culling --top 10 -F 15, default sensitivity): targets ranked and culled per query range
 it writes  W.L.tsv  (fmt 6, byte-exact)  and  W.L.counters.json  (the --log stage counters, basic/basic.cpp:186-211).
 The reference is always run with -p 8 (seedp_bits = 8) and default -c (4 index chunks): its output depends on both.
@@ -97,8 +100,8 @@ def main_blastx():
             synth.write_dna_fasta(q, w["dna"])
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             for lvl, fields in (("x0", []), ("xt", FIELDS["t2"] + ["score", "qlen", "slen"]), ("x1", []), ("x3", []), ("x5", []),
-                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", []), ("xi", []), ("xfi", []), ("xx", [])):
-                out = os.path.join(HERE, f"{name}.{lvl}." + {"xf0": "txt", "xx": "xml"}.get(lvl, "tsv"))
+                                ("xf", FIELDS["t2"] + ["score", "qlen", "slen", "qframe"]), ("xf0", []), ("xf3", []), ("xl", []), ("xi", []), ("xfi", []), ("xx", []), ("xfp", []), ("xfs", []), ("xlb", [])):
+                out = os.path.join(HERE, f"{name}.{lvl}." + {"xf0": "txt", "xx": "xml", "xfp": "paf", "xfs": "sam"}.get(lvl, "tsv"))
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
                 mode = {"x1": [], "x3": ["--sensitive"], "x5": ["--very-sensitive"], "xf3": ["--sensitive"]}.get(lvl, ["--fast"])  # x1 = no flag: the default sensitivity
@@ -106,13 +109,17 @@ def main_blastx():
                     mode = mode + ["-F", "15"]
                 if lvl == "xl":
                     mode = ["--long-reads"]  # default sensitivity, --range-culling --top 10 -F 15
+                if lvl == "xfs":
+                    mode = mode + ["-k", "1", "-e", "1e-20"]
+                if lvl == "xlb":
+                    mode = ["--long-reads", "-b", "0.0002"]
                 if lvl == "xx":
                     mode = mode + ["-k", "1", "-e", "1e-20"]
                 if lvl == "xi":
                     mode = mode + ["--id", "50", "--query-cover", "60"]
                 if lvl == "xfi":
                     mode = mode + ["--id", "50", "--subject-cover", "20"]
-                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", {"xf0": "0", "xx": "5"}.get(lvl, "6")] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
+                r = subprocess.run([REF, "blastx"] + mode + ["-q", q, "-d", d, "-f", {"xf0": "0", "xx": "5", "xfp": "paf", "xfs": "sam"}.get(lvl, "6")] + fields + ["-o", out, "-p", "8", "--log"], capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)

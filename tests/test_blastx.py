@@ -96,8 +96,8 @@ def test_blastx_rejects_what_it_does_not_implement(oracle_lib, tmp_path):
     assert r.returncode != 0 and "only supported in frameshift alignment mode" in r.stderr  # the reference's own rule (basic/config.cpp:824-825)
     r = subprocess.run([CLI, "blastx", "--fast", "--taxon-k", "1", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode != 0 and "unsupported option" in r.stderr
-    r = subprocess.run([CLI, "blastx", "--fast", "-F", "15", "-f", "sam", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)  # frameshift alignment: tabular and pairwise only
-    assert r.returncode != 0 and "not implemented in this mode" in r.stderr
+    r = subprocess.run([CLI, "blastx", "--fast", "--max-hsps", "3", "-q", q, "-d", d, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "only 1 is implemented" in r.stderr
     # the library: contexts other than 1 / 6, nq not a multiple, or a window-filter mode
     raw, lim = api.block_image(np.zeros(40, dtype=np.int8), np.array([0, 10, 20, 30, 40], dtype=np.int64))
     g = api.Context(lib=oracle_lib, query_contexts=6)

@@ -62,3 +62,22 @@ def test_fastq_titles_keep_their_newline(oracle_lib, tmp_path):
     assert r.returncode == 0, r.stderr
     lines = open(o).read().split("\n")
     assert lines[0].startswith("r") and lines[0].split("\t")[1].startswith("r") and lines[1].startswith("\td")  # "id<TAB>title<NL><TAB>target"
+
+
+FRAMESHIFT_FORMATS = [("xfp", "paf", ["--fast", "-F", "15", "-f", "paf"]), ("xfs", "sam", ["--fast", "-F", "15", "-f", "sam", "-k", "1", "-e", "1e-20"]), ("xlb", "tsv", ["--long-reads", "-b", "0.0002"])]
+
+
+def check_frameshift_format(cli, lvl, ext, flags, tmp_path):
+    """Frameshift mode in the PAF and SAM formats (read coordinates of an alignment whose end lies in another frame; frameshift operations in the
+    CIGAR) and --long-reads over several reference blocks (the join's culling per query range): the reference's files."""
+    out = run_translated(cli, flags, tmp_path)
+    gold = open(os.path.join(GOLDEN, f"bx.{lvl}.{ext}")).read()
+    drop_pg = lambda s: [l for l in s.split("\n") if not l.startswith("@PG")]  # SAM quotes the program's own command line there
+    assert drop_pg(out) == drop_pg(gold)
+    if lvl == "xfs":
+        assert any("\\" in l.split("\t")[5] or "/" in l.split("\t")[5] for l in gold.splitlines() if not l.startswith("@"))
+
+
+@pytest.mark.parametrize("lvl,ext,flags", FRAMESHIFT_FORMATS)
+def test_frameshift_formats(oracle_lib, lvl, ext, flags, tmp_path):
+    check_frameshift_format(CLI, lvl, ext, flags, tmp_path)

@@ -27,3 +27,9 @@ def test_xml_and_blocked_unaligned_on_device(product_lib, tmp_path):
     check_xml_protein(CLI, tmp_path)
     check_xml_translated(CLI, tmp_path)
     check_blocked_unaligned(CLI, tmp_path)
+
+
+def test_frameshift_formats_on_device(product_lib, tmp_path):
+    from test_formats import FRAMESHIFT_FORMATS, check_frameshift_format
+    for lvl, ext, flags in FRAMESHIFT_FORMATS:
+        check_frameshift_format(CLI, lvl, ext, flags, tmp_path)

@@ -80,10 +80,10 @@ def main():
                 else:
                     opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
                     if u < 0.5: opts += ["--range-culling"]
-            if not fshift and rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
-            fmt = rnd.choice(["6", "6", "6f", "0", "5"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam"])
+            if rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
+            fmt = rnd.choice(["6", "6", "6f", "0", "5", "sam", "paf"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam"])
             if fmt == "6f" and fshift:
-                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident"]
+                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident", "qseq", "sseq", "qcovhsp", "scovhsp", "positive", "ppos", "qstrand", "qtitle", "stitle"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
             elif fmt == "6f":
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score"]
