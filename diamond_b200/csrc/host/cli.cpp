@@ -126,6 +126,7 @@ void read_fasta(const std::string& path, SeqBlock& b) {
 struct DnaQueries {
 	std::vector<std::string> ids, titles;
 	std::vector<int32_t> len;  // nucleotides
+	std::vector<std::string> qual; // FASTQ quality strings (empty for FASTA input): the qqual / full_qqual fields
 	std::vector<std::string> dna;  // the reads as the reference prints them (nucleotide_traits alphabet: everything but ACGT is N)
 };
 
@@ -248,11 +249,15 @@ void read_dna_fasta(const std::string& path, DnaQueries& dq, SeqBlock& b, const 
 				len += l2.size();
 				for (char c : l2) dna.push_back(encode_dna(c));
 			}
+			std::string qual;
 			while (std::getline(f, l2)) {
 				if (!l2.empty() && l2.back() == '\r') l2.pop_back();
 				qlen += l2.size();
+				qual += l2;
 				if (qlen >= len) break;
 			}
+			dq.qual.resize(dq.ids.size());
+			dq.qual.back() = std::move(qual);
 			continue;
 		}
 		if (line[0] == '>') {
@@ -510,7 +515,8 @@ int main(int argc, char** argv) {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
 					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen",
-					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq" };
+					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq",
+					                               "sallseqid", "salltitles", "full_sseq", "full_qseq", "qnum", "snum", "hspnum", "qseq_translated", "normalized_nident", "qqual", "full_qqual" };
 					bool ok = false;
 					for (const char* k : known) ok |= f == k;
 					if (!ok) usage(("unsupported output field " + f).c_str());
@@ -559,7 +565,8 @@ int main(int argc, char** argv) {
 		}
 		if (o.range_culling && o.frame_shift == 0) usage("Query range culling is only supported in frameshift alignment mode (option -F).");  // basic/config.cpp:824-825
 		if (pairwise || paf || sam || xml) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
-		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq") o.want_transcript = 1;  // HspValues::TRANSCRIPT
+		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq" || f == "qseq_translated") o.want_transcript = 1;  // HspValues::TRANSCRIPT
+		for (const std::string& f : fields) if (f == "qseq_translated" && !translated) usage("Output field only supported for translated search.");  // output/blast_tab_format.cpp:685-686
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
 		if (o.comp_based_stats != 0 && o.comp_based_stats != 1) usage("--comp-based-stats must be 0 or 1");
 		SeqBlock q, r;
@@ -650,6 +657,10 @@ int main(int argc, char** argv) {
 		size_t ntr = 0;
 		const uint8_t* tr = dmnd_result_transcripts(res, &ntr);
 		if (fields.empty()) fields = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore" };
+		// (full_sseq prints the target as loaded -- the reference keeps an unmasked copy of the block for it -- while a protein query's full_qseq shows
+		// its masked letters like every other sequence field: a copy of the reference letters is taken before the masked ones are patched in)
+		std::vector<int8_t> r_unmasked;
+		for (const std::string& f : fields) if (f == "full_sseq") r_unmasked = r.letters;
 		// sequence-bearing fields print the MASKED letters, as the reference does (its blocks are masked in place)
 		for (size_t bk = 0; bk < nblocks; ++bk)
 			for (int side = 0; side < 2; ++side) {
@@ -678,7 +689,8 @@ int main(int argc, char** argv) {
 			std::vector<Cur> cur(nblocks);
 			for (size_t bk = 0; bk < nblocks; ++bk) { cur[bk].m = dmnd_result_matches(results[bk], &cur[bk].n); cur[bk].i = 0; size_t x = 0; cur[bk].tr = dmnd_result_transcripts(results[bk], &x); cur[bk].first = cuts[bk]; }
 			const uint32_t cx = translated ? 6u : 1u;
-			const bool by_score = top_set;
+			const bool top_on = top_set && o.top_percent != 100.0;  // --top 100 unsets toppercent: every target, ranked by e-value (output/output_format.cpp:236-239)
+			const bool by_score = top_on;
 			auto oid = [&](size_t bk, uint32_t t) { return cuts[bk] + (bperm[bk].empty() ? t : bperm[bk][t]); };  // database order of a block's target
 			auto before = [&](const dmnd_match& a, uint32_t oa, const dmnd_match& b, uint32_t ob) {  // a comes out of the heap before b
 				if (!by_score && a.evalue != b.evalue) return a.evalue < b.evalue;
@@ -695,7 +707,7 @@ int main(int argc, char** argv) {
 				double top_bits = 0.0;
 				// --range-culling: the join culls per query range as the extension did (RangeCulling::cull / add over the records' absolute_query_range,
 				// output/target_culling.h:132-160): a record whose read range is >= 50 % covered by records already reported is skipped, never final
-				RangeCover part(top_set ? 0 : (o.max_target_seqs == 0 ? INT64_MAX : (int64_t)o.max_target_seqs));
+				RangeCover part(top_on ? 0 : ((o.max_target_seqs == 0 || top_set) ? INT64_MAX : (int64_t)o.max_target_seqs));
 				for (;;) {
 					size_t best = nblocks;
 					for (size_t bk = 0; bk < nblocks; ++bk) {
@@ -708,7 +720,7 @@ int main(int argc, char** argv) {
 						const int fr = (int)(x.query % 6), off = fr % 3, ef = x.reserved ? ((int)x.reserved - 1) % 3 : off;
 						const int L = dq.len[x.query / 6], b_in = 3 * x.q_begin + off, e_in = 3 * x.q_end + ef;
 						const int rb = fr < 3 ? b_in : L - e_in, re = fr < 3 ? e_in : L - b_in;
-						const int c = top_set ? part.covered_max(rb, re, int((double)x.score / (1.0 - o.top_percent / 100.0))) : part.covered_full(rb, re);
+						const int c = top_on ? part.covered_max(rb, re, int((double)x.score / (1.0 - o.top_percent / 100.0))) : part.covered_full(rb, re);
 						++cur[best].i;
 						if (!((double)c / (double)(re - rb) * 100.0 < 50.0)) continue;  // config.query_range_cover
 						part.insert(rb, re, x.score);
@@ -720,8 +732,8 @@ int main(int argc, char** argv) {
 						continue;
 					}
 					if (n_targets > 0) {  // GlobalCulling::cull
-						if (top_set) { if ((1.0 - x.bit_score / top_bits) * 100.0 > o.top_percent) break; }
-						else if (n_targets >= (int64_t)(o.max_target_seqs == 0 ? INT32_MAX : o.max_target_seqs)) break;
+						if (top_on) { if ((1.0 - x.bit_score / top_bits) * 100.0 > o.top_percent) break; }
+						else if (n_targets >= (int64_t)((o.max_target_seqs == 0 || top_set) ? INT32_MAX : o.max_target_seqs)) break;
 					}
 					else top_bits = x.bit_score;
 					dmnd_match y = x;
@@ -1165,6 +1177,10 @@ int main(int argc, char** argv) {
 					else if (f == "qlen") line += std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);
 					else if (f == "qtitle") line += translated ? dq.titles[sq] : q.titles[sq];
 					else if (f == "qframe") line += '0';
+					else if (f == "hspnum" || f == "normalized_nident") throw std::runtime_error("Invalid output field: " + f);  // no unaligned form in the reference either (make_invalid_intro_handler, blast_tab_format.cpp:119-124)
+					else if (f == "full_qseq") { if (translated) line += dq.dna[sq]; else for (int64_t p2 = q.limits[sq]; p2 < q.limits[sq + 1] - 1; ++p2) line += alphabet[q.letters[(size_t)p2] & 31]; }
+					else if (f == "full_qqual") line += (translated && sq < dq.qual.size() && !dq.qual[sq].empty()) ? dq.qual[sq] : std::string("*");
+					else if (f == "sallseqid" || f == "salltitles" || f == "full_sseq" || f == "qqual" || f == "qseq_translated") line += '*';
 					else if (f == "sseqid" || f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "stitle" || f == "qstrand" || f == "qseq" || f == "sseq") line += '*';
 					else line += "-1";
 				}
@@ -1227,6 +1243,41 @@ int main(int argc, char** argv) {
 				}
 				else if (f == "qtitle") line += translated ? dq.titles[x.query / 6] : q.titles[x.query];
 				else if (f == "stitle") { const std::string& tt = r.titles[x.target]; line.append(tt, 0, std::min(tt.find('\x01'), tt.find(" >"))); }  // print_title(full titles, first one only: "\x01" or " >" separate merged records)
+				else if (f == "sallseqid" || f == "salltitles") {  // print_title over every title of a merged record ("\x01" or " >" between them): ids joined by ';', titles by "<>"
+					const std::string& tt = r.titles[x.target];
+					const bool ids_only = f == "sallseqid";
+					for (size_t a = 0, k = 0; a <= tt.size(); ++k) {
+						size_t e = a;
+						while (e < tt.size() && tt[e] != '\x01' && !(tt[e] == ' ' && e + 1 < tt.size() && tt[e + 1] == '>')) ++e;
+						if (k) line += ids_only ? ";" : "<>";
+						size_t ie = e;
+						if (ids_only) { ie = a; while (ie < e && !strchr(" \a\b\f\n\r\t\v", tt[ie])) ++ie; }
+						line.append(tt, a, ie - a);
+						if (e >= tt.size()) break;
+						a = tt[e] == '\x01' ? e + 1 : e + 2;
+					}
+				}
+				else if (f == "full_sseq") for (int64_t p2 = r.limits[x.target]; p2 < r.limits[x.target + 1] - 1; ++p2) line += alphabet[r_unmasked[(size_t)p2] & 31];  // the target as loaded (Output::Flags::TARGET_SEQS keeps the unmasked block, run/double_indexed.cpp:118-120)
+				else if (f == "full_qseq") { if (translated) line += dq.dna[x.query / 6]; else for (int64_t p2 = q.limits[x.query]; p2 < q.limits[x.query + 1] - 1; ++p2) line += alphabet[q.letters[(size_t)p2] & 31]; }
+				else if (f == "qnum") line += std::to_string(translated ? x.query / 6 : (q.oid.empty() ? x.query : q.oid[x.query]));
+				else if (f == "snum") line += std::to_string(r.oid.empty() ? x.target : r.oid[x.target]);
+				else if (f == "hspnum") line += '0';
+				else if (f == "normalized_nident") { snprintf(buf, sizeof buf, "%lf", (double)x.identities / (double)std::max<int64_t>(q.limits[x.query + 1] - q.limits[x.query] - 1, r.limits[x.target + 1] - r.limits[x.target] - 1)); line += buf; }
+				else if (f == "qseq_translated") {  // the aligned letters of the frame; in frameshift mode the query letters the transcript consumes (blast_tab_format.cpp:565-576)
+					walk_query(x, t);
+					for (uint32_t k = 0; k < x.transcript_len; ++k) if (qat[k] >= 0 && (t[k] >> 6) != DMND_OP_DELETION) line += alphabet[qat[k]];
+				}
+				else if (f == "qqual" || f == "full_qqual") {
+					const uint32_t sq = x.query / 6;
+					if (!translated || sq >= dq.qual.size() || dq.qual[sq].empty()) line += '*';
+					else if (f == "full_qqual") line += dq.qual[sq];
+					else {
+						const int fr = (int)(x.query % 6), off = fr % 3;
+						const int64_t L = dq.len[sq], b_in = 3 * (int64_t)x.q_begin + off, e_in = 3 * (int64_t)x.q_end + end_frame(x) % 3;
+						const int64_t b = fr < 3 ? b_in : L - e_in, e = fr < 3 ? e_in : L - b_in;
+						line.append(dq.qual[sq], (size_t)b, (size_t)(e - b));
+					}
+				}
 				else if (f == "positive") line += std::to_string(x.positives);
 				else if (f == "ppos") { format_double((double)x.positives * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
 				else if (f == "qcovhsp") {  // query_source_range().length() * 100 / source length (basic/match.h): nucleotides for blastx

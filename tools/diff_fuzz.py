@@ -83,13 +83,13 @@ def main():
             if rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
             fmt = rnd.choice(["6", "6", "6f", "0", "5", "sam", "paf"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam"])
             if fmt == "6f" and fshift:
-                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident", "qseq", "sseq", "qcovhsp", "scovhsp", "positive", "ppos", "qstrand", "qtitle", "stitle"]
+                opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident", "qseq", "sseq", "qcovhsp", "scovhsp", "positive", "ppos", "qstrand", "qtitle", "stitle", "sallseqid", "salltitles", "qnum", "snum", "qseq_translated", "full_qseq", "qqual"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
             elif fmt == "6f":
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
             elif fmt == "6g":
-                opts += ["-f", "6", "qseqid", "qtitle", "sseqid", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq", "gaps", "nident", "qseq_gapped", "sseq_gapped"]
+                opts += ["-f", "6", "qseqid", "qtitle", "sseqid", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq", "gaps", "nident", "qseq_gapped", "sseq_gapped", "sallseqid", "salltitles", "full_sseq", "full_qseq", "qnum", "snum", "full_qqual"] + (["qseq_translated"] if translated else [])
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
             elif fmt == "6c":  # short field lists: score-only (the reference's round 2 then runs without coordinates) and statistics without a transcript.
                 # Lists of coordinates ONLY (qstart .. send, qcovhsp, scovhsp and nothing that needs the traceback) are left out unless --coords-only
