@@ -468,7 +468,7 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false, sam = false, xml = false, k_set = false, top_set = false, unal = false;
+		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		bool header_simple = false, long_reads = false;
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
@@ -510,7 +510,8 @@ int main(int argc, char** argv) {
 				if (fmt == "paf" || fmt == "103") { paf = true; continue; }
 				if (fmt == "sam" || fmt == "101") { sam = true; continue; }
 				if (fmt == "xml" || fmt == "5") { xml = true; continue; }
-				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f 5 (xml), -f sam and -f paf are implemented");
+				if (fmt == "daa" || fmt == "100") { daa = true; continue; }
+				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f 5 (xml), -f 100 (daa), -f sam and -f paf are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -557,6 +558,7 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (daa && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (long_reads) {  // --long-reads = --range-culling --top 10 -F 15 (each only where not given)
 			o.range_culling = 1;
@@ -564,7 +566,7 @@ int main(int argc, char** argv) {
 			if (o.frame_shift == 0) o.frame_shift = 15;
 		}
 		if (o.range_culling && o.frame_shift == 0) usage("Query range culling is only supported in frameshift alignment mode (option -F).");  // basic/config.cpp:824-825
-		if (pairwise || paf || sam || xml) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
+		if (pairwise || paf || sam || xml || daa) o.want_transcript = 1;  // both formats ask for HspValues::TRANSCRIPT (output/output_format.h:205-216)
 		for (const std::string& f : fields) if (f == "cigar" || f == "btop" || f == "qseq_gapped" || f == "sseq_gapped" || f == "positive" || f == "ppos" || f == "sseq" || f == "qseq_translated") o.want_transcript = 1;  // HspValues::TRANSCRIPT
 		for (const std::string& f : fields) if (f == "qseq_translated" && !translated) usage("Output field only supported for translated search.");  // output/blast_tab_format.cpp:685-686
 		if (!motif_set) o.motif_masking = dmnd_mode_motif_masking(o.sensitivity);  // the mode's default (traits.motif_masking, search/setup.cpp:322-325)
@@ -1022,6 +1024,110 @@ int main(int argc, char** argv) {
 			no_hits_upto(UINT32_MAX);
 			n = 0;  // nothing left for the tabular writer
 		}
+		if (daa) {
+			// DIAMOND alignment archive (legacy/daa/daa_file.h:31-97, daa_write.cpp:29-112, output/output.h:33-55, basic/packed_sequence.h,
+			// basic/packed_transcript.h): two headers, one record per aligned query (length, id, the packed query -- 5 bits per residue, 2 or 3 per
+			// nucleotide -- and its matches: dictionary id of the target, flag byte, score / oriented query begin / subject begin in 1, 2 or 4
+			// bytes, the packed transcript), a zero, then the dictionary: target ids and lengths in order of first use.  The reference
+			// numbers the dictionary in the order its threads reach the targets; this writer's order is that of a one-thread run (-p 1).
+			if (nblocks > 1) throw std::runtime_error("-f 100 (DAA) is implemented for a database of one block");
+			struct Header2 {
+				uint64_t diamond_build, db_seqs, db_seqs_used, db_letters, flags, query_records;
+				int32_t mode, gap_open, gap_extend, reward, penalty, reserved1, reserved2, reserved3;
+				double k, lambda, evalue, reserved5;
+				char score_matrix[16];
+				uint64_t block_size[256];
+				char block_type[256];
+			} h2;
+			std::memset(&h2, 0, sizeof h2);
+			const uint64_t h1[2] = { 0x3c0e53476d3ee36bull, 1 };
+			std::string body;
+			auto put = [&](const void* p2, size_t nb) { body.append((const char*)p2, nb); };
+			auto put_packed = [&](uint32_t v) { if (v <= 0xFFu) { const uint8_t b = (uint8_t)v; put(&b, 1); } else if (v <= 0xFFFFu) { const uint16_t b = (uint16_t)v; put(&b, 2); } else put(&v, 4); };
+			auto len_flag = [](uint32_t v) -> unsigned { return v <= 0xFFu ? 0u : v <= 0xFFFFu ? 1u : 2u; };
+			std::vector<uint32_t> dict_of(r.size(), UINT32_MAX), dict;
+			const uint32_t cx = translated ? 6u : 1u;
+			uint64_t n_queries = 0;
+			size_t rec_pos = 0;
+			for (size_t i = 0; i < n; ++i) {
+				const dmnd_match& x = m[i];
+				const uint32_t sq = x.query / cx;
+				if (i == 0 || m[i - 1].query / cx != sq) {
+					rec_pos = body.size();
+					const uint32_t zero = 0, qlen = (uint32_t)(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);
+					put(&zero, 4); put(&qlen, 4);
+					const std::string& id = translated ? dq.ids[sq] : q.ids[sq];
+					put(id.c_str(), id.size() + 1);
+					bool has_n = false;
+					if (translated) for (char c : dq.dna[sq]) has_n |= c == 'N';
+					const uint8_t fl = has_n ? 1 : 0;
+					put(&fl, 1);
+					const unsigned bits = translated ? (has_n ? 3u : 2u) : 5u;
+					unsigned acc = 0, nb = 0;
+					for (uint32_t p2 = 0; p2 < qlen; ++p2) {
+						const unsigned v = translated ? (unsigned)(strchr("ACGTN", dq.dna[sq][p2]) - "ACGTN") : (unsigned)(q.letters[(size_t)q.limits[sq] + p2] & 31);
+						acc |= v << nb; nb += bits;
+						if (nb >= 8) { const uint8_t b = (uint8_t)(acc & 0xFF); put(&b, 1); nb -= 8; acc >>= 8; }
+					}
+					if (nb > 0) { const uint8_t b = (uint8_t)(acc & 0xFF); put(&b, 1); }
+					++n_queries;
+				}
+				if (dict_of[x.target] == UINT32_MAX) { dict_of[x.target] = (uint32_t)dict.size(); dict.push_back(x.target); }
+				int64_t qb = x.q_begin;  // Hsp::oriented_range().begin_: 0-based, on the read for translated queries (a reverse-strand alignment begins at its high end)
+				unsigned rev = 0;
+				if (translated) {
+					const int fr = (int)(x.query % 6), off = fr % 3;
+					const int64_t b_in = 3 * (int64_t)x.q_begin + off;
+					qb = fr < 3 ? b_in : (int64_t)dq.len[sq] - b_in - 1;
+					rev = fr < 3 ? 0u : 1u;
+				}
+				const uint8_t flag = (uint8_t)(len_flag((uint32_t)x.score) | (len_flag((uint32_t)qb) << 2) | (len_flag((uint32_t)x.t_begin) << 4) | (rev << 6));
+				put(&dict_of[x.target], 4); put(&flag, 1);
+				put_packed((uint32_t)x.score); put_packed((uint32_t)qb); put_packed((uint32_t)x.t_begin);
+				// PackedTranscript as the traceback leaves it (basic/hssp.cpp:260-290, banded_swipe.h:160-182): a match is one byte with count 1, a
+				// deletion / substitution one byte with its subject letter, a frameshift a substitution by letter 26 (reverse) or 27 (forward);
+				// an insertion gap of n columns is pushed as counts of 63, ..., 63, n mod 63 while walking back from the alignment's end, and the
+				// whole transcript is reversed afterwards: the remainder byte comes first
+				const uint8_t* t = tr + x.transcript_off;
+				for (uint32_t k = 0; k < x.transcript_len;) {
+					const uint8_t b = t[k];
+					uint8_t c;
+					if (b == DMND_TR_FRAMESHIFT_FWD || b == DMND_TR_FRAMESHIFT_REV) c = (uint8_t)((3u << 6) | (b == DMND_TR_FRAMESHIFT_FWD ? 27u : 26u));
+					else if ((b >> 6) == DMND_OP_DELETION || (b >> 6) == DMND_OP_SUBSTITUTION) c = b;
+					else if ((b >> 6) == DMND_OP_MATCH) c = 1u;
+					else {
+						uint32_t e = k;
+						while (e < x.transcript_len && t[e] != DMND_TR_FRAMESHIFT_FWD && t[e] != DMND_TR_FRAMESHIFT_REV && (t[e] >> 6) == DMND_OP_INSERTION) ++e;
+						const uint32_t run = e - k;
+						if (run % 63u) { c = (uint8_t)((1u << 6) | (run % 63u)); put(&c, 1); }
+						for (uint32_t f63 = run / 63u; f63; --f63) { c = (uint8_t)((1u << 6) | 63u); put(&c, 1); }
+						k = e;
+						continue;
+					}
+					put(&c, 1);
+					++k;
+				}
+				const uint8_t term = 0;
+				put(&term, 1);
+				if (i + 1 == n || m[i + 1].query / cx != sq) { const uint32_t sz = (uint32_t)(body.size() - rec_pos - 4); std::memcpy(&body[rec_pos], &sz, 4); }
+			}
+			{ const uint32_t zero = 0; put(&zero, 4); }
+			h2.block_size[0] = body.size();
+			uint64_t names = 0;
+			for (uint32_t tgt : dict) { put(r.ids[tgt].c_str(), r.ids[tgt].size() + 1); names += r.ids[tgt].size() + 1; }
+			for (uint32_t tgt : dict) { const uint32_t l = (uint32_t)(r.limits[tgt + 1] - r.limits[tgt] - 1); put(&l, 4); }
+			uint64_t all_letters = 0;
+			for (uint32_t i = 0; i < r.size(); ++i) all_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
+			h2.diamond_build = 182; h2.db_seqs = r.size(); h2.db_seqs_used = dict.size(); h2.db_letters = all_letters; h2.query_records = n_queries;
+			h2.mode = translated ? 3 : 2; h2.gap_open = 11; h2.gap_extend = 1; h2.k = 0.041; h2.lambda = 0.267; h2.evalue = o.max_evalue;
+			{ std::string mn = matrix_name; for (char& c : mn) c = (char)tolower((unsigned char)c); strncpy(h2.score_matrix, mn.c_str(), sizeof h2.score_matrix - 1); }
+			h2.block_size[1] = names; h2.block_size[2] = dict.size() * sizeof(uint32_t);
+			h2.block_type[0] = 1; h2.block_type[1] = 2; h2.block_type[2] = 3;
+			fwrite(h1, 1, sizeof h1, out);
+			fwrite(&h2, 1, sizeof h2, out);
+			fwrite(body.data(), 1, body.size(), out);
+			n = 0;
+		}
 		if (xml) {
 			// XMLFormat (output/xml_format.cpp:31-176): the BLAST XML of NCBI's DTD -- a header naming the first query of the block, one <Iteration>
 			// per aligned query (and per query with seed hits and no alignment: DEFAULT_REPORT_UNALIGNED), one <Hit> per target with its HSP
@@ -1156,7 +1262,7 @@ int main(int argc, char** argv) {
 			fwrite(line.data(), 1, line.size(), out);
 			n = 0;
 		}
-		if (header_simple && !pairwise && !paf && !sam && !xml) {  // TabularFormat::output_header: the field keys, tab-separated
+		if (header_simple && !pairwise && !paf && !sam && !xml && !daa) {  // TabularFormat::output_header: the field keys, tab-separated
 			line.clear();
 			for (size_t fi = 0; fi < fields.size(); ++fi) { if (fi) line += '\t'; line += fields[fi]; }
 			line += '\n';
@@ -1166,7 +1272,7 @@ int main(int argc, char** argv) {
 		const uint32_t* unal_q = result_unaligned(&n_unal);
 		const uint32_t ctxs = translated ? 6u : 1u;
 		auto unaligned_upto = [&](uint32_t src_end) {  // --unal 1: TabularFormat::print_query_intro (output/blast_tab_format.cpp:776-788) for the queries
-			if (!unal || pairwise || paf || sam || xml) return;      // [.., src_end) that had seed hits and no alignment, in query order
+			if (!unal || pairwise || paf || sam || xml || daa) return;      // [.., src_end) that had seed hits and no alignment, in query order
 			for (; u_next < n_unal && unal_q[u_next] / ctxs < src_end; ++u_next) {
 				const uint32_t sq = unal_q[u_next] / ctxs;
 				line.clear();

@@ -23,6 +23,7 @@ For every workload W and parity-ladder level L:
          the transcript fields (cigar / btop carry the \\ and / frameshift marks) + qframe, --fast in the pairwise format (.txt, with
          the "No hits found" records of every unaligned read), --sensitive with the default fields
     F5 = L2 in the BLAST XML format (-f 5): .xml
+    D1 = --fast -k 2 -p 1 in the DAA format (-f 100): .daa, the binary alignment archive (headers, packed queries and transcripts, target dictionary)
     B1 = --fast -b 0.00003 --unal 1 -k 3: several reference blocks joined per query (output/join_blocks.cpp); a blocked run reports EVERY query
          without an alignment as unaligned, not only those with seed hits
     XX = blastx --fast -k 1 -e 1e-20 in the BLAST XML format (read coordinates, query frame)
@@ -53,14 +54,15 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "s2": [],
           "s3": [], "s4": [], "s5": [], "s6": [],
           "t2": [], "f0": [],
-          "f5": [], "b1": ["-b", "0.00003", "--unal", "1", "-k", "3"],
+          "f5": [], "b1": ["-b", "0.00003", "--unal", "1", "-k", "3"], "d1": ["-k", "2"],
           "i1": ["--id", "60", "--query-cover", "50"],
           "m1": ["--query-cover", "70", "--subject-cover", "70"]}
-FORMAT = {"f0": "0", "f5": "5"}  # BLAST pairwise (-f 0), BLAST XML (-f 5); everything else is tabular (-f 6)
-EXT = {"f0": "txt", "f5": "xml"}
+FORMAT = {"f0": "0", "f5": "5", "d1": "100"}  # BLAST pairwise (-f 0), BLAST XML (-f 5); everything else is tabular (-f 6)
+EXT = {"f0": "txt", "f5": "xml", "d1": "daa"}
+THREADS = {"d1": "1"}  # the reference numbers the DAA's target dictionary in the order its threads reach the targets: one thread = one order
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
 MODE = {"m1": [], "s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-ONLY = {"f5": ("edge",), "b1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
+ONLY = {"f5": ("edge",), "b1": ("rep",), "d1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -83,12 +85,12 @@ def main():
                 out = os.path.join(HERE, f"{name}.{lvl}.{EXT.get(lvl, 'tsv')}")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", "8", "--log"] + flags,
+                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", THREADS.get(lvl, "8"), "--log"] + flags,
                                    capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)
-                print(name, lvl, sum(1 for _ in open(out)), cn)
+                print(name, lvl, sum(1 for _ in open(out, "rb")), cn)
 
 
 def main_blastx():
@@ -123,7 +125,7 @@ def main_blastx():
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}
                 json.dump(cn, open(os.path.join(HERE, f"{name}.{lvl}.counters.json"), "w"), indent=1, sort_keys=True)
-                print(name, lvl, sum(1 for _ in open(out)), cn)
+                print(name, lvl, sum(1 for _ in open(out, "rb")), cn)
 
 
 if __name__ == "__main__":

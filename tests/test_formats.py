@@ -81,3 +81,24 @@ def check_frameshift_format(cli, lvl, ext, flags, tmp_path):
 @pytest.mark.parametrize("lvl,ext,flags", FRAMESHIFT_FORMATS)
 def test_frameshift_formats(oracle_lib, lvl, ext, flags, tmp_path):
     check_frameshift_format(CLI, lvl, ext, flags, tmp_path)
+
+
+def check_daa(cli, tmp_path):
+    """-f 100: the DIAMOND alignment archive, byte for byte (one thread: the dictionary order of the reference depends on its threads)."""
+    import struct
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("rep")
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    r = subprocess.run([cli, "blastp", "--fast", "-k", "2", "-f", "100", "-q", q, "-d", d, "-o", o, "-p", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(o + ".daa", "rb").read()  # the extension is appended, as the reference does
+    gold = open(os.path.join(GOLDEN, "rep.d1.daa"), "rb").read()
+    assert got == gold
+    magic, version = struct.unpack("<QQ", gold[:16])
+    assert magic == 0x3c0e53476d3ee36b and version == 1
+
+
+def test_daa(oracle_lib, tmp_path):
+    check_daa(CLI, tmp_path)

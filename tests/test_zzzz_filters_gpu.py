@@ -23,10 +23,11 @@ def test_filtered_translated_search_on_device(product_lib, lvl, flags, tmp_path)
 
 # ---- BLAST XML and the blocked run's unaligned records through the product CLI (tests/test_formats.py holds the CPU twins)
 def test_xml_and_blocked_unaligned_on_device(product_lib, tmp_path):
-    from test_formats import check_blocked_unaligned, check_xml_protein, check_xml_translated
+    from test_formats import check_blocked_unaligned, check_daa, check_xml_protein, check_xml_translated
     check_xml_protein(CLI, tmp_path)
     check_xml_translated(CLI, tmp_path)
     check_blocked_unaligned(CLI, tmp_path)
+    check_daa(CLI, tmp_path)
 
 
 def test_frameshift_formats_on_device(product_lib, tmp_path):

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--translated-only", action="store_true")
     ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
     ap.add_argument("--protein-only", action="store_true")
+    ap.add_argument("--format", default=None, help="use this output format on every run (6, 6f, 6g, 6c, 0, 5, 100, sam, paf)")
     ap.add_argument("--blocks", type=float, default=0.15, help="probability of -b (several reference blocks) on a run without -F")
     ap.add_argument("--coords-only", action="store_true", help="include field lists of coordinates only (known to differ in rare ties, see the comment at fmt 6c)")
     ap.add_argument("--keep", default=None, help="directory that receives the inputs and both outputs of every differing run")
@@ -81,7 +82,8 @@ def main():
                     opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
                     if u < 0.5: opts += ["--range-culling"]
             if rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
-            fmt = rnd.choice(["6", "6", "6f", "0", "5", "sam", "paf"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam"])
+            fmt = rnd.choice(["6", "6", "6f", "0", "5", "sam", "paf", "100"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam", "100"])
+            if a.format: fmt = a.format
             if fmt == "6f" and fshift:
                 opts += ["-f", "6", "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore", "cigar", "btop", "qlen", "slen", "score", "qframe", "qseq_gapped", "sseq_gapped", "gaps", "nident", "qseq", "sseq", "qcovhsp", "scovhsp", "positive", "ppos", "qstrand", "qtitle", "stitle", "sallseqid", "salltitles", "qnum", "snum", "qseq_translated", "full_qseq", "qqual"]
                 if rnd.random() < 0.5: opts += ["--unal", "1"]
@@ -98,16 +100,21 @@ def main():
                 lists = [["qseqid", "sseqid", "evalue", "bitscore", "score"], ["qseqid", "sseqid", "length", "pident", "evalue"], ["qseqid", "sseqid", "qlen", "slen", "nident", "mismatch", "qstart", "send"]]
                 if a.coords_only: lists += [["qseqid", "sseqid", "qstart", "qend", "sstart", "send", "evalue", "bitscore"], ["qseqid", "sseqid", "qlen", "slen", "qcovhsp", "scovhsp", "evalue"]]
                 opts += ["-f", "6"] + rnd.choice(lists)
+            elif fmt == "100":  # DAA: one block, and one thread -- the reference numbers its target dictionary in the order its threads reach the targets
+                if "-b" in opts: del opts[opts.index("-b"):opts.index("-b") + 2]
+                opts[opts.index("-p") + 1] = "1"
+                opts += ["-f", "100"]
             elif fmt != "6":
                 opts += ["-f", fmt]
             cmd = ["blastx" if translated else "blastp", "-q", q, "-d", d] + opts
-            ro, oo = os.path.join(td, "r.out"), os.path.join(td, "o.out")
+            ext = ".daa" if fmt == "100" else ".out"  # (both programs append .daa to the name of a DAA file that lacks it)
+            ro, oo = os.path.join(td, "r" + ext), os.path.join(td, "o" + ext)
             r1 = subprocess.run([REF] + cmd + ["-o", ro, "--quiet"], capture_output=True, text=True)
             r2 = subprocess.run([a.cli] + cmd + ["-o", oo], capture_output=True, text=True)
             def content(path):  # a SAM file quotes the program's own command line in its @PG line
                 return [l for l in open(path, "rb") if not l.startswith(b"@PG")]
             ok = r1.returncode == 0 and r2.returncode == 0 and content(ro) == content(oo)
-            n = sum(1 for _ in open(ro)) if r1.returncode == 0 else -1
+            n = sum(1 for _ in open(ro, "rb")) if r1.returncode == 0 else -1
             print(("ok   " if ok else "DIFF ") + f"run {run} seed {seed} lines {n}: " + " ".join(cmd[:1] + opts), flush=True)
             if not ok:
                 bad += 1
