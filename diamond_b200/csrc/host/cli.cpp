@@ -10,6 +10,7 @@
 #include <sstream>
 #include <zlib.h>
 #include <iterator>
+#include <unordered_map>
 #include <utility>
 #include <stdexcept>
 #include <string>
@@ -50,11 +51,13 @@ std::string slurp_text(const std::string& path) {
 // Block::length_sorted (data/block/block.cpp:229-255): longest sequence first, ties by DESCENDING block id (std::greater on (length, id)).
 // The reference sorts the query and the reference block this way when min_length_ratio is set (run/double_indexed.cpp:112-115,727-731):
 // queries are then reported in this order, and the block ids that break ranking ties are the sorted ones.
-void length_sort(SeqBlock& b) {
+// `chunks` (optional): first sequence of every query block the reference would load (ascending, starting with 0): each is sorted on its own.
+void length_sort(SeqBlock& b, const std::vector<uint32_t>* chunks = nullptr) {
 	const uint32_t n = b.size();
 	std::vector<std::pair<int64_t, uint32_t>> key(n);
 	for (uint32_t i = 0; i < n; ++i) key[i] = { b.limits[i + 1] - b.limits[i] - 1, i };
-	std::sort(key.begin(), key.end(), std::greater<std::pair<int64_t, uint32_t>>());
+	if (!chunks) std::sort(key.begin(), key.end(), std::greater<std::pair<int64_t, uint32_t>>());
+	else for (size_t c = 0; c + 1 < chunks->size(); ++c) std::sort(key.begin() + (*chunks)[c], key.begin() + (*chunks)[c + 1], std::greater<std::pair<int64_t, uint32_t>>());
 	SeqBlock s;
 	s.letters.reserve(b.letters.size());
 	for (uint32_t i = 0; i < n; ++i) {
@@ -470,7 +473,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false, long_reads = false;
+		bool header_simple = false, long_reads = false, no_self_hits = false;
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
@@ -550,6 +553,7 @@ int main(int argc, char** argv) {
 			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
 			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
+			else if (a == "--no-self-hits") no_self_hits = true;  // basic/config.cpp:312
 			else if (a == "--min-score") o.min_bit_score = atof(val());  // basic/config.cpp:299: overrides the e-value setting
 			else if (a == "--query-cover") o.query_cover = atof(val());
 			else if (a == "--subject-cover") o.subject_cover = atof(val());
@@ -574,6 +578,7 @@ int main(int argc, char** argv) {
 		SeqBlock q, r;
 		DnaQueries dq;
 		if (!translated && (strand_mask != 63 || min_orf != 0 || gencode != 1)) usage("--strand, --min-orf and --query-gencode belong to blastx");
+		if (no_self_hits && translated) usage("--no-self-hits option is not supported in blastx mode.");  // basic/config.cpp:677-678
 		if (o.frame_shift && !translated) usage("Frameshift alignments are only supported for translated searches.");  // basic/config.cpp:822-823
 		const bool fshift = o.frame_shift != 0;
 		if (fshift) {
@@ -595,33 +600,63 @@ int main(int argc, char** argv) {
 		// FastaFile::raw_chunk: records up to the first record boundary at or after block-size bytes).
 		if (block_size == 0.0) block_size = o.sensitivity >= 5 ? 0.4 : 2.0;
 		const uint64_t max_letters = (uint64_t)(block_size * 1e9);
-		std::vector<uint32_t> cuts{ 0 };
-		{
-			const uint32_t nr = r.size();
+		auto block_cuts = [&](const SeqBlock& b) {
+			std::vector<uint32_t> c{ 0 };
+			const uint32_t nb = b.size();
 			uint32_t f = 0;
-			while (f < nr) {
+			while (f < nb) {
 				uint32_t e = f;
-				if (!r.rec_begin.empty()) { while (e < nr && r.rec_begin[e] - r.rec_begin[f] < max_letters) ++e; }
-				else { uint64_t letters = 0; while (e < nr && letters < max_letters) { letters += (uint64_t)(r.limits[e + 1] - r.limits[e] - 1); ++e; } }
-				cuts.push_back(e);
+				if (!b.rec_begin.empty()) { while (e < nb && b.rec_begin[e] - b.rec_begin[f] < max_letters) ++e; }
+				else { uint64_t letters = 0; while (e < nb && letters < max_letters) { letters += (uint64_t)(b.limits[e + 1] - b.limits[e] - 1); ++e; } }
+				c.push_back(e);
 				f = e;
 			}
-			if (cuts.size() == 1) cuts.push_back(0);
-		}
+			if (c.size() == 1) c.push_back(0);
+			return c;
+		};
+		const std::vector<uint32_t> cuts = block_cuts(r);
 		const size_t nblocks = cuts.size() - 1;
 		bool mutual = false;
 		if (!translated && o.query_cover >= 50.0 && o.query_cover == o.subject_cover) {  // min_length_ratio is set (run/config.cpp:156-159): both blocks are searched length-sorted
 			mutual = true;
-			length_sort(q);
+			// (the query file is loaded in blocks of the same size, each sorted on its own: only a block size below the query file's shows it)
+			const std::vector<uint32_t> qcuts = block_cuts(q);
+			length_sort(q, qcuts.size() > 2 ? &qcuts : nullptr);
 			if (nblocks == 1) length_sort(r);  // (more blocks: every block is sorted on its own when it is searched, below)
 		}
 		std::vector<std::vector<uint32_t>> bperm(nblocks);   // mutual coverage with several blocks: sorted block id -> id within the unsorted block
 		std::vector<std::vector<int64_t>> blimits(nblocks);  // ... and the limits of the sorted block image
 		uint64_t db_letters = 0;
 		for (uint32_t i = 0; i < r.size(); ++i) db_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
+		// --no-self-hits: an alignment of a query with the target of the same title and the same letters is not reported (filter_hsp,
+		// align/culling.cpp:166-168).  Titles live here, so the pairs are found here: self_of[target] = the query it is a copy of
+		std::vector<uint32_t> self_of, self_targets;
+		if (no_self_hits) {
+			std::unordered_map<std::string, std::vector<uint32_t>> by_title;
+			for (uint32_t i = 0; i < q.size(); ++i) by_title[q.titles[i]].push_back(i);
+			self_of.assign(r.size(), UINT32_MAX);
+			for (uint32_t t2 = 0; t2 < r.size(); ++t2) {
+				auto it = by_title.find(r.titles[t2]);
+				if (it == by_title.end()) continue;
+				const int64_t tl = r.limits[t2 + 1] - r.limits[t2];
+				for (uint32_t qi : it->second)
+					if (q.limits[qi + 1] - q.limits[qi] == tl && std::equal(r.letters.begin() + r.limits[t2], r.letters.begin() + r.limits[t2 + 1], q.letters.begin() + q.limits[qi],
+					                                                       [](int8_t a2, int8_t b2) { return (a2 & 31) == (b2 & 31); })) { self_of[t2] = qi; break; }
+			}
+		}
+		auto self_for_block = [&](size_t bk) -> const uint32_t* {  // the block's own target numbers (its sort order, if it was length-sorted)
+			if (!no_self_hits) return nullptr;
+			self_targets.assign(q.size(), UINT32_MAX);
+			for (uint32_t tl = 0; tl < cuts[bk + 1] - cuts[bk]; ++tl) {
+				const uint32_t g = cuts[bk] + (bperm[bk].empty() ? tl : bperm[bk][tl]);
+				if (self_of[g] != UINT32_MAX) self_targets[self_of[g]] = tl;
+			}
+			return self_targets.data();
+		};
 		std::vector<dmnd_result*> results(nblocks, nullptr);
 		for (size_t bk = 0; bk < nblocks; ++bk) {
 			if (nblocks == 1) {
+				o.self_targets = self_for_block(0);
 				if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, r.letters.data(), r.letters.size(), r.limits.data(), r.size(), &o, &results[0]))
 					throw std::runtime_error(dmnd_last_error());
 				break;
@@ -650,6 +685,7 @@ int main(int argc, char** argv) {
 			}
 			dmnd_search_opts ob = o;
 			ob.db_letters = db_letters;
+			ob.self_targets = self_for_block(bk);
 			if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, bl.data(), bl.size(), lim.data(), e - f, &ob, &results[bk]))
 				throw std::runtime_error(dmnd_last_error());
 		}

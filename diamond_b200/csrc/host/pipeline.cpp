@@ -302,6 +302,7 @@ struct Env {
 	double min_id = 0.0, query_cover = 0.0, subject_cover = 0.0;
 	bool have_filters = false, first_round_culling = true;
 	double min_length_ratio = 0.0;  // Search::Config::min_length_ratio (run/config.cpp:156-164)
+	const uint32_t* self_targets = nullptr;  // --no-self-hits: per query (source query for translated searches) the target whose HSP Match::apply_filters removes
 	int qlen(uint32_t q) const { return (int)(q_limits[q + 1] - q_limits[q] - 1); }
 	int tlen(uint32_t t) const { return (int)(r_limits[t + 1] - r_limits[t] - 1); }
 };
@@ -811,7 +812,7 @@ void Driver::finish_round2(QueryState& q, ThreadCtx& tc) {
 	const Env& e = env;
 	for (Match* m = q.r2.begin() + q.r2_begin; m < q.r2.end(); ++m) {
 		if (m->has_hsp) { m->filter_evalue = m->h.evalue; m->filter_score = m->h.score; }  // Match::inner_culling
-		if (e.have_filters && m->has_hsp && filtered_out(q, *m)) { m->has_hsp = false; m->filter_evalue = DBL_MAX; m->filter_score = 0; }  // Match::apply_filters, culling.cpp:172-185
+		if (m->has_hsp && ((e.have_filters && filtered_out(q, *m)) || (e.self_targets && e.self_targets[q.qid / e.contexts] == m->target_block_id))) { m->has_hsp = false; m->filter_evalue = DBL_MAX; m->filter_score = 0; }  // Match::apply_filters, culling.cpp:172-185
 	}
 	if (e.top >= 0.0) std::sort(q.r2.begin(), q.r2.end(), Match::cmp_score); else std::sort(q.r2.begin(), q.r2.end(), Match::cmp_evalue);  // culling(r, cfg), culling.cpp:199-202
 	q.r2.n = (uint32_t)(output_range(q.r2.begin(), q.r2.end(), e) - q.r2.begin());
@@ -1618,6 +1619,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	}
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
+	e.self_targets = opts->self_targets;
 	e.min_bit_score = opts->min_bit_score;
 	if (!(e.min_bit_score >= 0.0)) { dmnd_set_last_error("dmnd_blastp: min_bit_score must not be negative (0 = the e-value bound applies)"); return 1; }
 	if (e.min_bit_score != 0.0) e.fuse = false;  // (the device bridge admits one ranking chunk of <= 64 targets: unaffected, but keep the tested host schedule)

@@ -385,6 +385,10 @@ typedef struct dmnd_search_opts {
 	                              (run/config.cpp:156-159): seed hits between sequences whose length ratio lies below cover/100 - 0.05 are dropped */
 	double min_bit_score;      /* --min-score: minimum bit score of a reported alignment; when set it REPLACES the e-value bound (ScoreMatrix::report_cutoff,
 	                              stats/score_matrix.cpp:234-239) and the ranking loop no longer widens its first chunk by e-value (align/extend.cpp:262) */
+	const uint32_t* self_targets; /* --no-self-hits: NULL, or one entry per query (per DNA query for translated searches): the reference sequence whose alignment with
+	                              this query is not reported (UINT32_MAX = none).  The reference drops an HSP when query and target have the same title and the same
+	                              letters (filter_hsp, align/culling.cpp:166-168, part of Match::apply_filters after round 2); titles live with the caller, so the
+	                              caller names the pairs.  Unlike the other filters this one does not change the extension's schedule (align/extend.cpp:94-96) */
 } dmnd_search_opts;
 
 typedef struct dmnd_match {

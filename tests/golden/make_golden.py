@@ -27,6 +27,8 @@ For every workload W and parity-ladder level L:
     B1 = --fast -b 0.00003 --unal 1 -k 3: several reference blocks joined per query (output/join_blocks.cpp); a blocked run reports EVERY query
          without an alignment as unaligned, not only those with seed hits
     XX = blastx --fast -k 1 -e 1e-20 in the BLAST XML format (read coordinates, query frame)
+    N1 = --fast --no-self-hits -k 3, the database searched against itself: the alignment of a sequence with its own copy is dropped after
+         round 2 (filter_hsp, align/culling.cpp:166-168), so two of the three best targets remain
     I1 = --fast with the report filters --id 60 --query-cover 50: the extension's filtered schedule (targets only sorted after round 1,
          round 2 in steps with Match::apply_filters, align/extend.cpp:288, align/gapped_final.cpp:107-158)
     M1 = default sensitivity with --query-cover 70 --subject-cover 70: equal covers >= 50 set min_length_ratio = 0.65 -- length-sorted
@@ -55,6 +57,7 @@ LEVELS = {"l0": ["--masking", "0", "--motif-masking", "0", "--comp-based-stats",
           "s3": [], "s4": [], "s5": [], "s6": [],
           "t2": [], "f0": [],
           "f5": [], "b1": ["-b", "0.00003", "--unal", "1", "-k", "3"], "d1": ["-k", "2"],
+          "n1": ["--no-self-hits", "-k", "3"],
           "i1": ["--id", "60", "--query-cover", "50"],
           "m1": ["--query-cover", "70", "--subject-cover", "70"]}
 FORMAT = {"f0": "0", "f5": "5", "d1": "100"}  # BLAST pairwise (-f 0), BLAST XML (-f 5); everything else is tabular (-f 6)
@@ -62,7 +65,8 @@ EXT = {"f0": "txt", "f5": "xml", "d1": "daa"}
 THREADS = {"d1": "1"}  # the reference numbers the DAA's target dictionary in the order its threads reach the targets: one thread = one order
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
 MODE = {"m1": [], "s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-ONLY = {"f5": ("edge",), "b1": ("rep",), "d1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
+SELF = ("n1",)  # levels that search the database against itself
+ONLY = {"n1": ("fam2",), "f5": ("edge",), "b1": ("rep",), "d1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
             "tentative_matches3": r"Hits \(filter stage 3\) = (\d+)", "targets": r"Target hits \(stage 0\) = (\d+)",
@@ -85,7 +89,7 @@ def main():
                 out = os.path.join(HERE, f"{name}.{lvl}.{EXT.get(lvl, 'tsv')}")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", THREADS.get(lvl, "8"), "--log"] + flags,
+                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", d if lvl in SELF else q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", THREADS.get(lvl, "8"), "--log"] + flags,
                                    capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

@@ -91,3 +91,19 @@ def test_filter_options_are_checked(oracle_lib):
     with pytest.raises(api.DmndError, match="percentages"):
         ctx.blastp(q_raw, q_lim, r_raw, r_lim)
     ctx.close()
+
+
+def check_no_self_hits(cli, tmp_path):
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("fam2")
+    d, o = (str(tmp_path / x) for x in ("d.faa", "o.tsv"))
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    r = subprocess.run([cli, "blastp", "--fast", "--no-self-hits", "-k", "3", "-q", d, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gold = open(os.path.join(GOLDEN, "fam2.n1.tsv")).read()
+    assert open(o).read() == gold
+    assert not any(l.split("\t")[0] == l.split("\t")[1] for l in gold.splitlines())
+
+
+def test_no_self_hits(oracle_lib, tmp_path):
+    check_no_self_hits(CLI, tmp_path)

@@ -34,3 +34,8 @@ def test_frameshift_formats_on_device(product_lib, tmp_path):
     from test_formats import FRAMESHIFT_FORMATS, check_frameshift_format
     for lvl, ext, flags in FRAMESHIFT_FORMATS:
         check_frameshift_format(CLI, lvl, ext, flags, tmp_path)
+
+
+def test_no_self_hits_on_device(product_lib, tmp_path):
+    from test_filters import check_no_self_hits
+    check_no_self_hits(CLI, tmp_path)
