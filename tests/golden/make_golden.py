@@ -27,7 +27,7 @@ For every workload W and parity-ladder level L:
     B1 = --fast -b 0.00003 --unal 1 -k 3: several reference blocks joined per query (output/join_blocks.cpp); a blocked run reports EVERY query
          without an alignment as unaligned, not only those with seed hits
     XX = blastx --fast -k 1 -e 1e-20 in the BLAST XML format (read coordinates, query frame)
-    N1 = --fast --no-self-hits -k 3, the database searched against itself: the alignment of a sequence with its own copy is dropped after
+    N1 = --fast --no-self-hits -k 3, the first 150 database sequences as queries (same titles): the alignment of a sequence with its own copy is dropped after
          round 2 (filter_hsp, align/culling.cpp:166-168), so two of the three best targets remain
     I1 = --fast with the report filters --id 60 --query-cover 50: the extension's filtered schedule (targets only sorted after round 1,
          round 2 in steps with Match::apply_filters, align/extend.cpp:288, align/gapped_final.cpp:107-158)
@@ -65,7 +65,7 @@ EXT = {"f0": "txt", "f5": "xml", "d1": "daa"}
 THREADS = {"d1": "1"}  # the reference numbers the DAA's target dictionary in the order its threads reach the targets: one thread = one order
 FIELDS = {"t2": "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped".split()}
 MODE = {"m1": [], "s1": [], "s2": ["--mid-sensitive"], "s3": ["--sensitive"], "s4": ["--more-sensitive"], "s5": ["--very-sensitive"], "s6": ["--ultra-sensitive"]}
-SELF = ("n1",)  # levels that search the database against itself
+SELF = ("n1",)  # levels whose queries are copies of database sequences (same titles)
 ONLY = {"n1": ("fam2",), "f5": ("edge",), "b1": ("rep",), "d1": ("rep",), "i1": ("c1", "fam2", "edge"), "m1": ("fam2", "edge"), "f0": ("edge", "long"), "t2": ("c1", "edge", "long", "rep"), "s4": ("c1", "edge", "rep"), "s5": ("c1", "edge", "rep"), "s6": ("c1", "edge", "rep")}  # the many-shape modes: small workloads only  # every other level runs --fast
 COUNTERS = {"seeds_hit": r"Seeds hit\s+= (\d+)", "seed_hits": r"Hits \(filter stage 0\) = (\d+)",
             "tentative_matches1": r"Hits \(filter stage 1\) = (\d+)", "tentative_matches2": r"Hits \(filter stage 2\) = (\d+)",
@@ -83,13 +83,15 @@ def main():
             q, d = os.path.join(td, "q.faa"), os.path.join(td, "d.faa")
             synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+            qs = os.path.join(td, "qs.faa")  # SELF levels: the first 150 database sequences, under their database titles, as the queries
+            synth.write_fasta(qs, w["db_letters"][:w["db_off"][150]], w["db_off"][:151], "d")
             for lvl, flags in LEVELS.items():
                 if lvl in ONLY and name not in ONLY[lvl]:
                     continue
                 out = os.path.join(HERE, f"{name}.{lvl}.{EXT.get(lvl, 'tsv')}")
                 if os.path.exists(out) and "--missing" in sys.argv:
                     continue
-                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", d if lvl in SELF else q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", THREADS.get(lvl, "8"), "--log"] + flags,
+                r = subprocess.run([REF, "blastp"] + MODE.get(lvl, ["--fast"]) + ["-q", qs if lvl in SELF else q, "-d", d, "-f", FORMAT.get(lvl, "6")] + FIELDS.get(lvl, []) + ["-o", out, "-p", THREADS.get(lvl, "8"), "--log"] + flags,
                                    capture_output=True, text=True, check=True)
                 log = r.stderr + r.stdout
                 cn = {k: int(re.search(p, log).group(1)) for k, p in COUNTERS.items()}

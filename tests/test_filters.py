@@ -96,9 +96,10 @@ def test_filter_options_are_checked(oracle_lib):
 def check_no_self_hits(cli, tmp_path):
     from diamond_b200 import synth
     w, *_ = workload_blocks("fam2")
-    d, o = (str(tmp_path / x) for x in ("d.faa", "o.tsv"))
+    q, d, o = (str(tmp_path / x) for x in ("qs.faa", "d.faa", "o.tsv"))
     synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
-    r = subprocess.run([cli, "blastp", "--fast", "--no-self-hits", "-k", "3", "-q", d, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
+    synth.write_fasta(q, w["db_letters"][:w["db_off"][150]], w["db_off"][:151], "d")  # the first 150 database sequences under their database titles
+    r = subprocess.run([cli, "blastp", "--fast", "--no-self-hits", "-k", "3", "-q", q, "-d", d, "-o", o, "-p", "8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     gold = open(os.path.join(GOLDEN, "fam2.n1.tsv")).read()
     assert open(o).read() == gold
