@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--translated-only", action="store_true")
     ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
     ap.add_argument("--protein-only", action="store_true")
+    ap.add_argument("--dmnd", type=float, default=0.15, help="probability that the database is a .dmnd file made by the reference")
     ap.add_argument("--all-vs-all", type=float, default=0.08, help="probability that a protein run searches the database against itself (70 %% of those with --no-self-hits)")
     ap.add_argument("--format", default=None, help="use this output format on every run (6, 6f, 6g, 6c, 0, 5, 100, sam, paf)")
     ap.add_argument("--blocks", type=float, default=0.15, help="probability of -b (several reference blocks) on a run without -F")
@@ -55,7 +56,11 @@ def main():
                 synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
             opts = list(rnd.choice(MODES))
-            if not translated and rnd.random() < a.all_vs_all:  # the database against itself, with and without --no-self-hits
+            if rnd.random() < a.dmnd:  # a DIAMOND database file instead of FASTA (blocks are then cut by letters, titles come from the file)
+                subprocess.run([REF, "makedb", "--in", d, "-d", os.path.join(td, "db"), "--quiet"], check=True, capture_output=True)
+                d = os.path.join(td, "db.dmnd")
+            if rnd.random() < 0.15: opts += ["--header", "simple"]
+            if not translated and d.endswith(".faa") and rnd.random() < a.all_vs_all:  # the database against itself, with and without --no-self-hits
                 q = d
                 if rnd.random() < 0.7: opts += ["--no-self-hits"]
             opts += ["-p", str(rnd.choice([1, 4, 8]))]
