@@ -520,7 +520,7 @@ int main(int argc, char** argv) {
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
 					                               "cigar", "btop", "qseq_gapped", "sseq_gapped", "score", "gaps", "nident", "qlen", "slen",
 					                               "qtitle", "stitle", "positive", "ppos", "qcovhsp", "scovhsp", "qframe", "qstrand", "qseq", "sseq",
-					                               "sallseqid", "salltitles", "full_sseq", "full_qseq", "qnum", "snum", "hspnum", "qseq_translated", "normalized_nident", "qqual", "full_qqual" };
+					                               "sallseqid", "salltitles", "full_sseq", "full_qseq", "qnum", "snum", "hspnum", "qseq_translated", "normalized_nident", "qqual", "full_qqual", "approx_pident" };
 					bool ok = false;
 					for (const char* k : known) ok |= f == k;
 					if (!ok) usage(("unsupported output field " + f).c_str());
@@ -557,7 +557,7 @@ int main(int argc, char** argv) {
 			else if (a == "--min-score") o.min_bit_score = atof(val());  // basic/config.cpp:299: overrides the e-value setting
 			else if (a == "--query-cover") o.query_cover = atof(val());
 			else if (a == "--subject-cover") o.subject_cover = atof(val());
-			else if (a == "--approx-id") { if (atof(val()) != 0.0) usage("--approx-id: only 0 (no filter) is implemented"); }
+			else if (a == "--approx-id") o.approx_min_id = atof(val());
 			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }
 			else usage(("unsupported option " + a).c_str());
 		}
@@ -1404,6 +1404,14 @@ int main(int argc, char** argv) {
 				else if (f == "qnum") line += std::to_string(translated ? x.query / 6 : (q.oid.empty() ? x.query : q.oid[x.query]));
 				else if (f == "snum") line += std::to_string(r.oid.empty() ? x.target : r.oid[x.target]);
 				else if (f == "hspnum") line += '0';
+				else if (f == "approx_pident") {  // Hsp::approx_id_percent (basic/hssp.cpp:381-392): 100 for identical stretches, else Stats::approx_id of the score per column
+					const int ql = x.q_end - x.q_begin, tl = x.t_end - x.t_begin;
+					bool identical = ql == tl;
+					for (int k2 = 0; identical && k2 < ql; ++k2) identical = (qs[x.q_begin + k2] & 31) == (r.letters[(size_t)r.limits[x.target] + (size_t)(x.t_begin + k2)] & 31);
+					const int mx = std::max(ql, tl);
+					format_double(fshift ? 0.0 /* the 3-frame DP leaves Hsp::approx_id at 0 */ : identical || mx == 0 ? 100.0 : std::min(std::max(std::fma((double)x.score / mx, 16.56, 11.41), 0.0), 100.0), buf, sizeof buf);
+					line += buf;
+				}
 				else if (f == "normalized_nident") { snprintf(buf, sizeof buf, "%lf", (double)x.identities / (double)std::max<int64_t>(q.limits[x.query + 1] - q.limits[x.query] - 1, r.limits[x.target + 1] - r.limits[x.target] - 1)); line += buf; }
 				else if (f == "qseq_translated") {  // the aligned letters of the frame; in frameshift mode the query letters the transcript consumes (blast_tab_format.cpp:565-576)
 					walk_query(x, t);

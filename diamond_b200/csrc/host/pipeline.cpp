@@ -299,7 +299,7 @@ struct Env {
 	bool fuse;  // see Driver::start
 	// --id / --query-cover / --subject-cover (config.min_id, query_cover, subject_cover): with any of them set the reference only SORTS the
 	// targets after round 1 (first_round_culling = !have_filters || --top, align/extend.cpp:94-96,288) and runs round 2 in steps
-	double min_id = 0.0, query_cover = 0.0, subject_cover = 0.0;
+	double min_id = 0.0, query_cover = 0.0, subject_cover = 0.0, approx_min_id = 0.0;
 	bool have_filters = false, first_round_culling = true;
 	double min_length_ratio = 0.0;  // Search::Config::min_length_ratio (run/config.cpp:156-164)
 	const uint32_t* self_targets = nullptr;  // --no-self-hits: per query (source query for translated searches) the target whose HSP Match::apply_filters removes
@@ -805,6 +805,15 @@ bool Driver::filtered_out(const QueryState& q, const Match& m) const {
 	const int source_query_len = e.contexts == 6 ? e.qlen(q.qid) + e.qlen(q.qid + 1) + e.qlen(q.qid + 2) + 2 : q.qlen;
 	const int q_range = (r.q_end - r.q_begin) * (e.contexts == 6 ? 3 : 1);
 	const double qcov = (double)q_range * 100 / (unsigned)source_query_len, tcov = (double)(r.t_end - r.t_begin) * 100 / (unsigned)m.tlen;
+	if (e.approx_min_id > 0.0) {  // hsp.approx_id (banded_swipe.h:185): 100 for identical stretches, else the linear estimate from score per column
+		const int ql = r.q_end - r.q_begin, tl = r.t_end - r.t_begin;
+		const int8_t *qs = e.qseq(m.h.ctx) + r.q_begin, *ts = e.rseq(m.target_block_id) + r.t_begin;
+		bool identical = ql == tl;
+		for (int i = 0; identical && i < ql; ++i) identical = (qs[i] & 31) == (ts[i] & 31);
+		const int mx = std::max(ql, tl);
+		const double approx = identical ? 100.0 : (mx == 0 ? 100.0 : std::min(std::max(std::fma((double)r.score / mx, 16.56, 11.41), 0.0), 100.0));
+		if (approx < e.approx_min_id) return true;
+	}
 	return (double)r.identities * 100.0 / (double)r.length < e.min_id || qcov < e.query_cover || tcov < e.subject_cover;
 }
 
@@ -1037,7 +1046,7 @@ int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* p) {
 			if (*c == '1') { p->shape_pos[s][w++] = len; p->shape_mask[s] |= 1u << len; }
 		p->shape_len[s] = len; p->shape_weight = w;
 	}
-	p->hamming_id = mt->min_identities;
+	p->hamming_id = std::max(mt->min_identities, o->approx_min_id >= 90.0 ? 30 : o->approx_min_id >= 50.0 ? 20 : 0);  // hamming_id_cutoff(config.approx_min_id), search/setup.cpp:70-79,343
 	p->index_chunks = o->index_chunks > 0 ? o->index_chunks : mt->index_chunks;
 	{  // seedp_bits, search/setup.cpp:306-309
 		auto bit_length = [](int64_t x) { int n = 0; while (x > 0) { ++n; x >>= 1; } return n; };
@@ -1623,12 +1632,13 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.min_bit_score = opts->min_bit_score;
 	if (!(e.min_bit_score >= 0.0)) { dmnd_set_last_error("dmnd_blastp: min_bit_score must not be negative (0 = the e-value bound applies)"); return 1; }
 	if (e.min_bit_score != 0.0) e.fuse = false;  // (the device bridge admits one ranking chunk of <= 64 targets: unaffected, but keep the tested host schedule)
-	e.min_id = opts->min_id; e.query_cover = opts->query_cover; e.subject_cover = opts->subject_cover;
-	if (!(e.min_id >= 0.0 && e.min_id <= 100.0) || !(e.query_cover >= 0.0 && e.query_cover <= 100.0) || !(e.subject_cover >= 0.0 && e.subject_cover <= 100.0)) {
+	e.min_id = opts->min_id; e.query_cover = opts->query_cover; e.subject_cover = opts->subject_cover; e.approx_min_id = opts->approx_min_id;
+	if (e.approx_min_id != 0.0 && e.min_id != 0.0) { dmnd_set_last_error("Incompatible options: --approx-id, --id."); return 1; }  // run/config.cpp:168-169
+	if (!(e.min_id >= 0.0 && e.min_id <= 100.0) || !(e.query_cover >= 0.0 && e.query_cover <= 100.0) || !(e.subject_cover >= 0.0 && e.subject_cover <= 100.0) || !(e.approx_min_id >= 0.0 && e.approx_min_id <= 100.0)) {
 		dmnd_set_last_error("dmnd_blastp: min_id, query_cover and subject_cover are percentages (0 = no filter)");
 		return 1;
 	}
-	e.have_filters = e.min_id > 0.0 || e.query_cover > 0.0 || e.subject_cover > 0.0;
+	e.have_filters = e.min_id > 0.0 || e.query_cover > 0.0 || e.subject_cover > 0.0 || e.approx_min_id > 0.0;
 	e.first_round_culling = !e.have_filters || e.top >= 0.0;  // align/extend.cpp:288 (config.toppercent.present(): --top 100 counts, see below)
 	if (e.have_filters) e.fuse = false;  // fused rounds and the device bridge assume round 2 = the culled targets of round 1, in one step
 	if (e.query_cover >= 50.0 && e.query_cover == e.subject_cover && contexts == 1) e.min_length_ratio = std::max(e.query_cover / 100 - 0.05, 0.0);  // run/config.cpp:156-159

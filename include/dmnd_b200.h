@@ -385,6 +385,10 @@ typedef struct dmnd_search_opts {
 	                              (run/config.cpp:156-159): seed hits between sequences whose length ratio lies below cover/100 - 0.05 are dropped */
 	double min_bit_score;      /* --min-score: minimum bit score of a reported alignment; when set it REPLACES the e-value bound (ScoreMatrix::report_cutoff,
 	                              stats/score_matrix.cpp:234-239) and the ranking loop no longer widens its first chunk by e-value (align/extend.cpp:262) */
+	double approx_min_id;      /* --approx-id: minimum APPROXIMATE identity percentage, min(max(16.56 * score / max(query range, target range) + 11.41, 0), 100),
+	                              100 for an alignment of identical stretches (Stats::approx_id, stats/stats.cpp:113-118; Hsp::approx_id_percent,
+	                              basic/hssp.cpp:381-392).  A report filter like min_id; 50 / 90 and above also raise the Hamming cutoff of seed stage 1 to
+	                              20 / 30 identities (search/setup.cpp:70-79,343: dmnd_params_init copies that into dmnd_params.hamming_id) */
 	const uint32_t* self_targets; /* --no-self-hits: NULL, or one entry per query (per DNA query for translated searches): the reference sequence whose alignment with
 	                              this query is not reported (UINT32_MAX = none).  The reference drops an HSP when query and target have the same title and the same
 	                              letters (filter_hsp, align/culling.cpp:166-168, part of Match::apply_filters after round 2); titles live with the caller, so the

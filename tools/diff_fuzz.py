@@ -75,7 +75,7 @@ def main():
             if rnd.random() < a.min_score: opts += ["--min-score", str(rnd.choice([20, 40, 60, 100, 250]))]  # overrides -e
             if rnd.random() < a.filters:  # report filters: the extension's filtered schedule (align/extend.cpp:288, gapped_final.cpp:107-158)
                 u = rnd.random()
-                if u < 0.5 or rnd.random() < 0.3: opts += ["--id", str(rnd.choice([30, 50, 70, 90]))]
+                if u < 0.5 or rnd.random() < 0.3: opts += [rnd.choice(["--id", "--id", "--approx-id"]), str(rnd.choice([30, 50, 70, 90]))]  # (--approx-id >= 50 / 90 also raises the seed stage's Hamming cutoff)
                 if u >= 0.3: opts += ["--query-cover", str(rnd.choice([20, 40, 60, 80, 95]))]
                 if u >= 0.6: opts += ["--subject-cover", str(rnd.choice([10, 30, 55, 70, 90]))]
                 if u >= 0.6 and rnd.random() < 0.5:  # equal covers >= 50: min_length_ratio, length-sorted blocks, the mutual-coverage seed stage (protein searches)
