@@ -344,7 +344,7 @@ int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, ui
 			tantan_one(&ctx->p, b->letters + b->limits[i], (int)(b->limits[i + 1] - b->limits[i] - 1), (uint64_t)b->limits[i], NULL);
 	if (t_mask_n) qsort(t_mask_pos, t_mask_n, sizeof(uint64_t), cmp_u64);
 	if (algo & DMND_MASK_MOTIF) {
-		b->soft = b->soft_buf;
+		__atomic_store_n(&b->soft, b->soft_buf, __ATOMIC_RELAXED); /* (query lanes mask their own ranges of one block concurrently: same value from every lane) */
 		for (uint32_t i = s_begin; i < s_end; ++i) {
 			const int len = (int)(b->limits[i + 1] - b->limits[i] - 1);
 			memset(b->soft + b->limits[i], 0, (size_t)len);
