@@ -347,8 +347,8 @@ int dmnd_block_mask(dmnd_ctx* ctx, dmnd_block* b, int algo, uint32_t s_begin, ui
 		__atomic_store_n(&b->soft, b->soft_buf, __ATOMIC_RELAXED); /* (query lanes mask their own ranges of one block concurrently: same value from every lane) */
 		for (uint32_t i = s_begin; i < s_end; ++i) {
 			const int len = (int)(b->limits[i + 1] - b->limits[i] - 1);
-			memset(b->soft + b->limits[i], 0, (size_t)len);
-			motifs_one(&ctx->p, b->letters + b->limits[i], len, b->soft + b->limits[i]);
+			memset(b->soft_buf + b->limits[i], 0, (size_t)len);
+			motifs_one(&ctx->p, b->letters + b->limits[i], len, b->soft_buf + b->limits[i]);
 		}
 	}
 	if (n_hard) *n_hard = t_mask_n;
