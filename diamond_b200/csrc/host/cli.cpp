@@ -473,7 +473,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false, long_reads = false, no_self_hits = false;
+		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false;
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
@@ -550,7 +550,7 @@ int main(int argc, char** argv) {
 			else if (a == "--log") log = true;
 			else if (a == "--quiet") {}
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
-			else if (a == "--compress") { if (std::string(val()) != "0") usage("--compress: only 0 is implemented"); }
+			else if (a == "--compress") { const std::string v = val(); if (v == "1") gz_out = true; else if (v != "0") usage("--compress: 0 (none) and 1 (gzip) are implemented"); }
 			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
 			else if (a == "--no-self-hits") no_self_hits = true;  // basic/config.cpp:312
@@ -562,6 +562,7 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (daa && gz_out) usage("Compression is not supported for DAA format.");  // basic/config.cpp:726-727
 		if (daa && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (long_reads) {  // --long-reads = --range-culling --top 10 -F 15 (each only where not given)
@@ -1481,6 +1482,19 @@ int main(int argc, char** argv) {
 		}
 		unaligned_upto(UINT32_MAX);
 		fclose(out);
+		if (gz_out) {  // --compress 1: the output as a gzip file, ".gz" appended to its name (basic/config.cpp:770-771)
+			const std::string gzname = (of.size() >= 3 && of.compare(of.size() - 3, 3, ".gz") == 0) ? of : of + ".gz";
+			std::ifstream in(of, std::ios::binary);
+			std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+			in.close();
+			const std::string tmp = gzname + ".tmp";
+			gzFile g = gzopen(tmp.c_str(), "wb");
+			if (!g) throw std::runtime_error("Error opening file " + gzname);
+			for (size_t off = 0; off < data.size();) { const unsigned chunk = (unsigned)std::min<size_t>(data.size() - off, 1u << 30); if (gzwrite(g, data.data() + off, chunk) != (int)chunk) { gzclose(g); throw std::runtime_error("Error writing file " + gzname); } off += chunk; }
+			gzclose(g);
+			std::remove(of.c_str());
+			std::rename(tmp.c_str(), gzname.c_str());
+		}
 		if (log) {
 			const dmnd_run_stats* s = dmnd_result_stats(res);
 			fprintf(stderr, "Seed partition bits = %d\n", params.seedp_bits);
