@@ -427,6 +427,149 @@ int make_db(const std::string& in, std::string out_path, bool masking) {
 	return 0;
 }
 
+
+// ---- DIAMOND alignment archive (legacy/daa/daa_file.h:31-97): the second header as it lies in the file
+struct DaaHeader2 {
+	uint64_t diamond_build, db_seqs, db_seqs_used, db_letters, flags, query_records;
+	int32_t mode, gap_open, gap_extend, reward, penalty, reserved1, reserved2, reserved3;
+	double k, lambda, evalue, reserved5;
+	char score_matrix[16];
+	uint64_t block_size[256];
+	char block_type[256];
+};
+constexpr uint64_t DAA_MAGIC = 0x3c0e53476d3ee36bull;
+
+// `view`: a DAA file back into the structures the writers print from (legacy/daa/daa_record.cpp:30-107, view.cpp): queries (unpacked, DNA
+// reads translated into their six frames), the target dictionary as a reference block without letters, one dmnd_match per stored
+// alignment with the statistics re-derived from its transcript the way HspContext::parse does (basic/hssp.cpp:52-100: a frameshift
+// mark counts as a column), e-value and bit score recomputed from the raw score and the database size in the header.
+void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries& dq, SeqBlock& r, std::vector<dmnd_match>& matches, std::vector<uint8_t>& transcripts,
+              DaaHeader2& h2, const int8_t* score32) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) throw std::runtime_error("Error opening file " + path);
+	std::string d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	uint64_t h1[2];
+	if (d.size() < sizeof h1 + sizeof h2) throw std::runtime_error("Input file is not a DAA file.");
+	std::memcpy(h1, d.data(), sizeof h1);
+	if (h1[0] != DAA_MAGIC) throw std::runtime_error("Input file is not a DAA file.");
+	if (h1[1] > 1) throw std::runtime_error("DAA version requires later version of DIAMOND.");
+	std::memcpy(&h2, d.data() + sizeof h1, sizeof h2);
+	if (h2.block_size[0] == 0) throw std::runtime_error("Invalid DAA file. DIAMOND run has probably not completed successfully.");
+	if (h2.mode != 2 && h2.mode != 3) throw std::runtime_error("view: only blastp and blastx archives are implemented");
+	*translated = h2.mode == 3;
+	const size_t base = sizeof h1 + sizeof h2;
+	// the dictionary: names, then lengths
+	size_t p = base + (size_t)h2.block_size[0];
+	for (uint64_t i = 0; i < h2.db_seqs_used; ++i) {
+		const size_t e = d.find('\0', p);
+		if (e == std::string::npos) throw std::runtime_error("Invalid DAA file (target names).");
+		r.ids.push_back(d.substr(p, e - p));
+		r.titles.push_back(r.ids.back());
+		p = e + 1;
+	}
+	if (p + 4 * h2.db_seqs_used > d.size()) throw std::runtime_error("Invalid DAA file (target lengths).");
+	for (uint64_t i = 0; i < h2.db_seqs_used; ++i) {
+		uint32_t l; std::memcpy(&l, d.data() + p + 4 * i, 4);
+		r.letters.insert(r.letters.end(), (size_t)l, (int8_t)23);  // (the archive does not hold the targets: their letters come out of the transcripts)
+		r.letters.push_back((int8_t)DMND_DELIMITER);
+		r.limits.push_back((int64_t)r.letters.size());
+	}
+	r.finish();
+	const TranslateOpts to{ 63, 0, 1, 1 };  // (the reference's view translates the stored read as it is: no ORF masking)
+	auto rd = [&](size_t& at, unsigned code) -> uint32_t {  // read_packed: 1, 2 or 4 bytes
+		uint32_t v = 0;
+		const size_t nb = code == 0 ? 1 : code == 1 ? 2 : 4;
+		if (at + nb > d.size()) throw std::runtime_error("Invalid DAA file (record).");
+		std::memcpy(&v, d.data() + at, nb);
+		at += nb;
+		return v;
+	};
+	p = base;
+	for (uint32_t qi = 0;; ++qi) {
+		uint32_t size; std::memcpy(&size, d.data() + p, 4);
+		if (size == 0) break;
+		const size_t rec_end = p + 4 + size;
+		if (rec_end > base + h2.block_size[0]) throw std::runtime_error("Invalid DAA file (query record).");
+		size_t at = p + 4;
+		uint32_t qlen; std::memcpy(&qlen, d.data() + at, 4); at += 4;
+		const size_t ne = d.find('\0', at);
+		const std::string name = d.substr(at, ne - at);
+		at = ne + 1;
+		const bool has_n = (d[at++] & 1) != 0;
+		const unsigned bits = *translated ? (has_n ? 3u : 2u) : 5u;
+		std::vector<int8_t> seq(qlen);
+		{
+			unsigned acc = 0, nb = 0; uint32_t l = 0;
+			const size_t nbytes = ((size_t)qlen * bits + 7) / 8;
+			for (size_t b = 0; b < nbytes; ++b) {
+				acc |= (unsigned)(uint8_t)d[at + b] << nb; nb += 8;
+				while (nb >= bits && l < qlen) { seq[l++] = (int8_t)(acc & ((1u << bits) - 1)); nb -= bits; acc >>= bits; }
+			}
+			at += nbytes;
+		}
+		if (*translated) {
+			dq.ids.push_back(name); dq.titles.push_back(name); dq.len.push_back((int32_t)qlen);
+			std::string t(qlen, 'N'); for (uint32_t k = 0; k < qlen; ++k) t[k] = "ACGTN"[seq[k] > 4 ? 4 : seq[k]];
+			dq.dna.push_back(std::move(t));
+			push_translated(seq, q, to);
+		}
+		else {
+			q.ids.push_back(name); q.titles.push_back(name);
+			q.letters.insert(q.letters.end(), seq.begin(), seq.end());
+			q.letters.push_back((int8_t)DMND_DELIMITER);
+			q.limits.push_back((int64_t)q.letters.size());
+		}
+		while (at < rec_end) {
+			dmnd_match x;
+			std::memset(&x, 0, sizeof x);
+			uint32_t dict; std::memcpy(&dict, d.data() + at, 4); at += 4;
+			const uint8_t flag = (uint8_t)d[at++];
+			x.target = dict;
+			x.score = (int32_t)rd(at, flag & 3u);
+			const uint32_t qb = rd(at, (flag >> 2) & 3u);
+			x.t_begin = (int32_t)rd(at, (flag >> 4) & 3u);
+			int frame = 0, off = 0, pos = (int)qb;
+			if (*translated) {  // IntermediateRecord::frame (output/output_format.cpp:79-84): the oriented begin on the read gives strand and frame
+				const int in_strand = (flag & 64) ? (int)qlen - 1 - (int)qb : (int)qb;
+				off = in_strand % 3; frame = ((flag & 64) ? 3 : 0) + off; pos = in_strand / 3;
+			}
+			x.query = *translated ? 6u * qi + (uint32_t)frame : qi;
+			x.q_begin = pos;
+			x.transcript_off = transcripts.size();
+			const uint32_t c0 = *translated ? 6u * qi + (uint32_t)(frame / 3 * 3) : qi;
+			int tpos = x.t_begin;
+			unsigned gap_run = 0;
+			bool shifted = false;
+			for (;; ++at) {
+				if (at >= rec_end) throw std::runtime_error("Invalid DAA file (transcript).");
+				const uint8_t c = (uint8_t)d[at];
+				if (c == 0) { ++at; break; }
+				const unsigned op = c >> 6, val = c & 63u;
+				auto qletter = [&]() -> int { return q.letters[(size_t)q.limits[c0 + (uint32_t)off] + (size_t)pos] & 31; };
+				if (op == 0) for (unsigned k = 0; k < val; ++k) { transcripts.push_back(0x00); ++x.identities; ++x.positives; ++x.length; ++pos; ++tpos; gap_run = 0; }
+				else if (op == 1) for (unsigned k = 0; k < val; ++k) { transcripts.push_back(0x40); if (gap_run++ == 0) ++x.gap_openings; ++x.gaps; ++x.length; ++pos; }
+				else if (op == 2) { transcripts.push_back(c); if (gap_run++ == 0) ++x.gap_openings; ++x.gaps; ++x.length; ++tpos; }
+				else if (val == 26 || val == 27) {  // frameshift: a column of its own for parse(), the frame of the following letters changes
+					transcripts.push_back(val == 27 ? (uint8_t)DMND_TR_FRAMESHIFT_FWD : (uint8_t)DMND_TR_FRAMESHIFT_REV);
+					++x.length; shifted = true;
+					if (val == 27) { if (++off == 3) { off = 0; ++pos; } } else { if (--off < 0) { off = 2; --pos; } }
+				}
+				else { transcripts.push_back(c); ++x.mismatches; ++x.length; if (score32[qletter() * 32 + (int)val] > 0) ++x.positives; ++pos; ++tpos; gap_run = 0; }
+			}
+			x.transcript_len = (uint32_t)(transcripts.size() - x.transcript_off);
+			x.q_end = pos; x.t_end = tpos;
+			if (*translated && shifted) x.reserved = 1u + (uint32_t)(frame / 3 * 3 + off);
+			const uint32_t tlen = (uint32_t)(r.limits[dict + 1] - r.limits[dict] - 1);
+			const uint32_t c_first = *translated ? 6u * qi : qi;  // (the reference's view takes the length of the FIRST frame, daa_record.cpp:84 -- a search takes the aligned frame's)
+			const uint32_t ql = (uint32_t)(q.limits[c_first + 1] - q.limits[c_first] - 1);
+			dmnd_alignment_stats(x.score, ql, tlen, h2.db_letters, &x.evalue, &x.bit_score);
+			matches.push_back(x);
+		}
+		p = rec_end;
+	}
+	q.finish();
+}
+
 int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 	if (x >= 100.0) return snprintf(p, n, "%lli", (long long)std::floor(x));
 	const long long i = std::llround(x * 10.0);
@@ -462,8 +605,20 @@ int main(int argc, char** argv) {
 			if (in.empty() || db.empty()) usage("makedb needs --in and -d");
 			return make_db(in, db, masking);
 		}
-		if (cmd != "blastp" && cmd != "blastx") usage("only blastp, blastx and makedb are implemented");
-		const bool translated = cmd == "blastx";
+		if (cmd != "blastp" && cmd != "blastx" && cmd != "view") usage("only blastp, blastx, view and makedb are implemented");
+		const bool view_mode = cmd == "view";  // diamond view -a FILE.daa -o OUT [-f ...]: the stored alignments through the same writers
+		std::string daa_in;
+		bool translated = cmd == "blastx";
+		if (view_mode) {  // the archive's header says whether its queries are reads (the options below depend on it)
+			for (int i = 2; i + 1 < argc; ++i) if (!strcmp(argv[i], "-a") || !strcmp(argv[i], "--daa")) daa_in = argv[i + 1];
+			if (daa_in.empty()) usage("view needs -a FILE.daa");
+			if (!std::ifstream(daa_in) && std::ifstream(daa_in + ".daa")) daa_in += ".daa";  // auto_append_extension_if_exists
+			std::ifstream hf(daa_in, std::ios::binary);
+			uint64_t h1[2] = { 0, 0 };
+			DaaHeader2 hh;
+			if (!hf.read((char*)h1, sizeof h1) || !hf.read((char*)&hh, sizeof hh) || h1[0] != DAA_MAGIC) usage("Input file is not a DAA file.");
+			translated = hh.mode == 3;
+		}
 		dmnd_search_opts o;
 		dmnd_search_opts_default(&o);
 		if (translated) o.query_contexts = 6;
@@ -480,9 +635,10 @@ int main(int argc, char** argv) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
 			const char* attached = nullptr;
-			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdobF", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
+			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdobFa", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
 			auto val = [&]() -> const char* { if (attached) return attached; if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
-			if (a == "-q" || a == "--query") qf = val();
+			if (view_mode && (a == "-a" || a == "--daa")) val();
+			else if (a == "-q" || a == "--query") qf = val();
 			else if (a == "-d" || a == "--db") df = val();
 			else if (a == "-o" || a == "--out") of = val();
 			else if (a == "--fast") o.sensitivity = 0;
@@ -561,7 +717,13 @@ int main(int argc, char** argv) {
 			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }
 			else usage(("unsupported option " + a).c_str());
 		}
-		if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		if (view_mode) {
+			if (of.empty()) usage("view needs -o");
+			if (daa) usage("view: the output format is one of 0, 5, 6, sam, paf");
+			if (o.min_id != 0.0 || o.query_cover != 0.0 || o.subject_cover != 0.0 || o.approx_min_id != 0.0 || o.min_bit_score != 0.0 || unal || block_size != 0.0 || o.frame_shift || no_self_hits)
+				usage("view prints the stored alignments: search options do not apply");
+		}
+		else if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (daa && gz_out) usage("Compression is not supported for DAA format.");  // basic/config.cpp:726-727
 		if (daa && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
@@ -585,15 +747,21 @@ int main(int argc, char** argv) {
 		if (fshift) {
 			o.want_transcript = 1;  // output/output_format.cpp:256-257
 		}
-		if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode, o.frame_shift });
-		else read_fasta(qf, q);
-		const uint32_t nq_block = translated ? (uint32_t)dq.ids.size() * 6u : q.size();
-		if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
-		else read_fasta(df, r);
 		dmnd_params params;
 		if (dmnd_params_init(&o, &params)) throw std::runtime_error(dmnd_last_error());
+		std::vector<dmnd_match> view_matches;
+		std::vector<uint8_t> view_transcripts;
+		DaaHeader2 view_header;
+		if (view_mode) load_daa(daa_in, &translated, q, dq, r, view_matches, view_transcripts, view_header, params.score);
+		else {
+			if (translated) read_dna_fasta(qf, dq, q, TranslateOpts{ strand_mask, min_orf, gencode, o.frame_shift });
+			else read_fasta(qf, q);
+			if (is_dmnd(df) || (!std::ifstream(df) && is_dmnd(df + ".dmnd"))) read_dmnd(is_dmnd(df) ? df : df + ".dmnd", r);  // -d takes a DIAMOND database or a FASTA file, like the reference
+			else read_fasta(df, r);
+		}
+		const uint32_t nq_block = translated ? (uint32_t)dq.ids.size() * 6u : q.size();
 		dmnd_ctx* ctx = nullptr;
-		if (dmnd_create(0, &params, &ctx)) throw std::runtime_error(dmnd_last_error());
+		if (!view_mode && dmnd_create(0, &params, &ctx)) throw std::runtime_error(dmnd_last_error());
 		// ---- reference blocks (run/double_indexed.cpp:218-244): a database beyond the block size is searched block by block with the
 		// e-values of the WHOLE database, and the per-block results are joined per query (output/join_blocks.cpp).  Block cuts follow the
 		// reference's loaders: a .dmnd database by letters (SequenceFile::load_twopass, data/sequence_file.cpp:214-240: sequences are
@@ -655,7 +823,7 @@ int main(int argc, char** argv) {
 			return self_targets.data();
 		};
 		std::vector<dmnd_result*> results(nblocks, nullptr);
-		for (size_t bk = 0; bk < nblocks; ++bk) {
+		for (size_t bk = 0; bk < nblocks && !view_mode; ++bk) {
 			if (nblocks == 1) {
 				o.self_targets = self_for_block(0);
 				if (dmnd_blastp(ctx, q.letters.data(), q.letters.size(), q.limits.data(), nq_block, r.letters.data(), r.letters.size(), r.limits.data(), r.size(), &o, &results[0]))
@@ -691,17 +859,17 @@ int main(int argc, char** argv) {
 				throw std::runtime_error(dmnd_last_error());
 		}
 		dmnd_result* res = results[0];
-		size_t n = 0;
-		const dmnd_match* m = dmnd_result_matches(res, &n);
+		size_t n = view_matches.size();
+		const dmnd_match* m = view_mode ? view_matches.data() : dmnd_result_matches(res, &n);
 		size_t ntr = 0;
-		const uint8_t* tr = dmnd_result_transcripts(res, &ntr);
+		const uint8_t* tr = view_mode ? view_transcripts.data() : dmnd_result_transcripts(res, &ntr);
 		if (fields.empty()) fields = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore" };
 		// (full_sseq prints the target as loaded -- the reference keeps an unmasked copy of the block for it -- while a protein query's full_qseq shows
 		// its masked letters like every other sequence field: a copy of the reference letters is taken before the masked ones are patched in)
 		std::vector<int8_t> r_unmasked;
 		for (const std::string& f : fields) if (f == "full_sseq") r_unmasked = r.letters;
 		// sequence-bearing fields print the MASKED letters, as the reference does (its blocks are masked in place)
-		for (size_t bk = 0; bk < nblocks; ++bk)
+		for (size_t bk = 0; bk < nblocks && !view_mode; ++bk)
 			for (int side = 0; side < 2; ++side) {
 				size_t nm = 0;
 				const uint64_t* mp = dmnd_result_masked_positions(results[bk], side, &nm);
@@ -847,6 +1015,7 @@ int main(int argc, char** argv) {
 			}
 		}
 		auto result_unaligned = [&](size_t* nu) -> const uint32_t* {
+			if (view_mode) { *nu = 0; return nullptr; }  // (an archive holds aligned queries only)
 			if (nblocks > 1) { *nu = joined_unal.size(); return joined_unal.data(); }  // (a blocked run: the join's rule, frameshift mode or not)
 			if (fshift) { *nu = fs_unal.size(); return fs_unal.data(); }
 			return dmnd_result_unaligned(res, nu);
@@ -1227,7 +1396,7 @@ int main(int argc, char** argv) {
 			char kb[40], lb[40];
 			snprintf(kb, sizeof kb, "%lf", 0.041);  // ScoreMatrix::k() / lambda() of BLOSUM62 11/1 (TextBuffer::print_d)
 			snprintf(lb, sizeof lb, "%lf", 0.267);
-			const std::string epilog_tail = "</Iteration_hits>\n  <Iteration_stat>\n    <Statistics>\n      <Statistics_db-num>" + std::to_string(r.size()) + "</Statistics_db-num>\n      <Statistics_db-len>" + std::to_string(all_letters)
+			const std::string epilog_tail = "</Iteration_hits>\n  <Iteration_stat>\n    <Statistics>\n      <Statistics_db-num>" + std::to_string(view_mode ? view_header.db_seqs : (uint64_t)r.size()) + "</Statistics_db-num>\n      <Statistics_db-len>" + std::to_string(view_mode ? view_header.db_letters : all_letters)
 			                                + "</Statistics_db-len>\n      <Statistics_hsp-len>0</Statistics_hsp-len>\n      <Statistics_eff-space>0</Statistics_eff-space>\n      <Statistics_kappa>" + kb
 			                                + "</Statistics_kappa>\n      <Statistics_lambda>" + lb + "</Statistics_lambda>\n      <Statistics_entropy>0</Statistics_entropy>\n    </Statistics>\n  </Iteration_stat>\n</Iteration>\n";
 			size_t nu = 0, u = 0;
@@ -1495,7 +1664,7 @@ int main(int argc, char** argv) {
 			std::remove(of.c_str());
 			std::rename(tmp.c_str(), gzname.c_str());
 		}
-		if (log) {
+		if (log && !view_mode) {
 			const dmnd_run_stats* s = dmnd_result_stats(res);
 			fprintf(stderr, "Seed partition bits = %d\n", params.seedp_bits);
 			fprintf(stderr, "Seeds hit             = %llu\n", (unsigned long long)s->seed.seeds_hit);

@@ -1009,6 +1009,13 @@ static const ModeTraits* mode_traits(int sensitivity) {
 	};
 	return sensitivity >= 0 && sensitivity <= 6 ? &t[sensitivity] : nullptr;
 }
+extern "C" int dmnd_alignment_stats(int32_t raw_score, uint32_t query_len, uint32_t target_len, uint64_t db_letters, double* evalue, double* bit_score) {
+	Scoring sc;
+	sc.db_letters = (double)db_letters;
+	if (evalue) *evalue = sc.evalue(raw_score, query_len, target_len);
+	if (bit_score) *bit_score = sc.bitscore(raw_score);
+	return 0;
+}
 extern "C" int dmnd_mode_motif_masking(int sensitivity) { const ModeTraits* t = mode_traits(sensitivity); return t ? (int)t->motif_masking : -1; }
 
 void dmnd_search_opts_default(dmnd_search_opts* o) {

@@ -424,6 +424,10 @@ typedef struct dmnd_result dmnd_result;
 void dmnd_search_opts_default(dmnd_search_opts* o);
 /* The sensitivity mode's default for --motif-masking (SensitivityTraits::motif_masking, search/setup.cpp:40-54): 1, 0, or -1 for a bad mode. */
 int dmnd_mode_motif_masking(int sensitivity);
+/* E-value and bit score of a raw alignment score under the path's scoring system (BLOSUM62 11/1, ScoreMatrix::evalue / bitscore,
+ * stats/score_matrix.cpp:217-254 with the ALP area correction) for a database of db_letters letters: what a reader of stored alignments
+ * (`view` over a DAA file) needs to print the columns the search computed. */
+int dmnd_alignment_stats(int32_t raw_score, uint32_t query_len, uint32_t target_len, uint64_t db_letters, double* evalue, double* bit_score);
 /* Fills a dmnd_params for BLOSUM62 11/1 and the given options (host restatement of setup_search). */
 int dmnd_params_init(const dmnd_search_opts* o, dmnd_params* out);
 /* One (query block, reference block) pass of blastp: seed search, extension rounds, culling.

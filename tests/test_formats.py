@@ -102,3 +102,23 @@ def check_daa(cli, tmp_path):
 
 def test_daa(oracle_lib, tmp_path):
     check_daa(CLI, tmp_path)
+
+
+def check_view(cli, tmp_path):
+    """`view`: the reference's archive (golden D1) read back and printed -- for a protein search exactly what the search itself prints, in the
+    tabular format with the transcript fields and in the pairwise format (legacy/daa/daa_record.cpp:30-86, view.cpp)."""
+    fields = "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore cigar btop qseq_gapped sseq_gapped positive score".split()
+    for fmt in (["-f", "6"] + fields, ["-f", "0"]):
+        direct = run_protein(cli, "rep", ["--fast", "-k", "2"] + fmt, tmp_path)
+        o = str(tmp_path / "view.out")
+        r = subprocess.run([cli, "view", "-a", os.path.join(GOLDEN, "rep.d1.daa"), "-o", o] + fmt, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        viewed = open(o).read()
+        if fmt[1] == "0":  # (an archive holds aligned queries only: the search's "No hits found" records are not in it)
+            assert "***** No hits found *****" not in viewed and viewed.count("Query= ") <= direct.count("Query= ")
+            direct = "".join(b for b in __import__("re").split(r"(?=Query= )", direct) if "No hits found" not in b)
+        assert viewed == direct
+
+
+def test_view(oracle_lib, tmp_path):
+    check_view(CLI, tmp_path)
