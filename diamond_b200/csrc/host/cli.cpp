@@ -493,6 +493,7 @@ void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries
 		size_t at = p + 4;
 		uint32_t qlen; std::memcpy(&qlen, d.data() + at, 4); at += 4;
 		const size_t ne = d.find('\0', at);
+		if (ne == std::string::npos || ne >= rec_end) throw std::runtime_error("Invalid DAA file (query name).");
 		const std::string name = d.substr(at, ne - at);
 		at = ne + 1;
 		const bool has_n = (d[at++] & 1) != 0;
@@ -501,12 +502,14 @@ void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries
 		{
 			unsigned acc = 0, nb = 0; uint32_t l = 0;
 			const size_t nbytes = ((size_t)qlen * bits + 7) / 8;
+			if (at + nbytes > rec_end) throw std::runtime_error("Invalid DAA file (query sequence).");
 			for (size_t b = 0; b < nbytes; ++b) {
 				acc |= (unsigned)(uint8_t)d[at + b] << nb; nb += 8;
 				while (nb >= bits && l < qlen) { seq[l++] = (int8_t)(acc & ((1u << bits) - 1)); nb -= bits; acc >>= bits; }
 			}
 			at += nbytes;
 		}
+		for (int8_t& c : seq) if (*translated ? c > 4 : c > 25) c = *translated ? 4 : 23;  // (a damaged file: keep the letters inside their alphabet)
 		if (*translated) {
 			dq.ids.push_back(name); dq.titles.push_back(name); dq.len.push_back((int32_t)qlen);
 			std::string t(qlen, 'N'); for (uint32_t k = 0; k < qlen; ++k) t[k] = "ACGTN"[seq[k] > 4 ? 4 : seq[k]];
@@ -523,6 +526,7 @@ void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries
 			dmnd_match x;
 			std::memset(&x, 0, sizeof x);
 			uint32_t dict; std::memcpy(&dict, d.data() + at, 4); at += 4;
+			if (at + 5 > rec_end || dict >= r.size()) throw std::runtime_error("Invalid DAA file (match record).");
 			const uint8_t flag = (uint8_t)d[at++];
 			x.target = dict;
 			x.score = (int32_t)rd(at, flag & 3u);
@@ -545,9 +549,14 @@ void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries
 				const uint8_t c = (uint8_t)d[at];
 				if (c == 0) { ++at; break; }
 				const unsigned op = c >> 6, val = c & 63u;
-				auto qletter = [&]() -> int { return q.letters[(size_t)q.limits[c0 + (uint32_t)off] + (size_t)pos] & 31; };
-				if (op == 0) for (unsigned k = 0; k < val; ++k) { transcripts.push_back(0x00); ++x.identities; ++x.positives; ++x.length; ++pos; ++tpos; gap_run = 0; }
-				else if (op == 1) for (unsigned k = 0; k < val; ++k) { transcripts.push_back(0x40); if (gap_run++ == 0) ++x.gap_openings; ++x.gaps; ++x.length; ++pos; }
+				if ((op == 2 && val > 25) || (op == 3 && val > 27)) throw std::runtime_error("Invalid DAA file (transcript letter).");
+				auto qletter = [&]() -> int {
+					const int64_t fl = q.limits[c0 + (uint32_t)off + 1] - q.limits[c0 + (uint32_t)off] - 1;
+					if (pos < 0 || pos >= fl) throw std::runtime_error("Invalid DAA file (alignment outside its query).");
+					return q.letters[(size_t)q.limits[c0 + (uint32_t)off] + (size_t)pos] & 31;
+				};
+				if (op == 0) for (unsigned k = 0; k < val; ++k) { qletter(); transcripts.push_back(0x00); ++x.identities; ++x.positives; ++x.length; ++pos; ++tpos; gap_run = 0; }
+				else if (op == 1) for (unsigned k = 0; k < val; ++k) { qletter(); transcripts.push_back(0x40); if (gap_run++ == 0) ++x.gap_openings; ++x.gaps; ++x.length; ++pos; }
 				else if (op == 2) { transcripts.push_back(c); if (gap_run++ == 0) ++x.gap_openings; ++x.gaps; ++x.length; ++tpos; }
 				else if (val == 26 || val == 27) {  // frameshift: a column of its own for parse(), the frame of the following letters changes
 					transcripts.push_back(val == 27 ? (uint8_t)DMND_TR_FRAMESHIFT_FWD : (uint8_t)DMND_TR_FRAMESHIFT_REV);
@@ -558,6 +567,10 @@ void load_daa(const std::string& path, bool* translated, SeqBlock& q, DnaQueries
 			}
 			x.transcript_len = (uint32_t)(transcripts.size() - x.transcript_off);
 			x.q_end = pos; x.t_end = tpos;
+			{
+				const int64_t fl = q.limits[c0 + (uint32_t)off + 1] - q.limits[c0 + (uint32_t)off] - 1, bl = q.limits[x.query + 1] - q.limits[x.query] - 1;
+				if (x.q_begin < 0 || x.q_begin > bl || pos < 0 || pos > fl + 1 || tpos > r.limits[dict + 1] - r.limits[dict] - 1) throw std::runtime_error("Invalid DAA file (alignment outside its sequences).");
+			}
 			if (*translated && shifted) x.reserved = 1u + (uint32_t)(frame / 3 * 3 + off);
 			const uint32_t tlen = (uint32_t)(r.limits[dict + 1] - r.limits[dict] - 1);
 			const uint32_t c_first = *translated ? 6u * qi : qi;  // (the reference's view takes the length of the FIRST frame, daa_record.cpp:84 -- a search takes the aligned frame's)
