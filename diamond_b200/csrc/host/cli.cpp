@@ -641,14 +641,14 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false;
+		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false;
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
 			std::string a = argv[i];
 			// a short option with its value attached (-p4, -c1, -k0, -f0, -e10000), as the reference's parser accepts it
 			const char* attached = nullptr;
-			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdobFa", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
+			if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("pckefqdobFat", a[1])) { attached = argv[i] + 2; a = a.substr(0, 2); }
 			auto val = [&]() -> const char* { if (attached) return attached; if (i + 1 >= argc) usage(("missing value for " + a).c_str()); return argv[++i]; };
 			if (view_mode && (a == "-a" || a == "--daa")) val();
 			else if (a == "-q" || a == "--query") qf = val();
@@ -717,7 +717,9 @@ int main(int argc, char** argv) {
 			else if (a == "--long-reads") long_reads = true;  // basic/config.cpp:679-686
 			else if (a == "-F" || a == "--frameshift") { o.frame_shift = atoi(val()); if (o.frame_shift <= 0) usage("--frameshift needs a positive penalty (the reference's usual value is 15)"); }
 			else if (a == "--log") log = true;
-			else if (a == "--quiet") {}
+			else if (a == "--quiet" || a == "--verbose" || a == "-v" || a == "--ignore-warnings") {}
+			else if (a == "--tmpdir" || a == "-t" || a == "--parallel-tmpdir") val();  // (no temporary files on this path: hits and per-block results stay in memory)
+			else if (a == "--no-auto-append") no_auto_append = true;  // basic/config.cpp:765
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
 			else if (a == "--compress") { const std::string v = val(); if (v == "1") gz_out = true; else if (v != "0") usage("--compress: 0 (none) and 1 (gzip) are implemented"); }
 			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
@@ -738,7 +740,7 @@ int main(int argc, char** argv) {
 		}
 		else if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
 		if (daa && gz_out) usage("Compression is not supported for DAA format.");  // basic/config.cpp:726-727
-		if (daa && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
+		if (daa && !no_auto_append && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
 		if (long_reads) {  // --long-reads = --range-culling --top 10 -F 15 (each only where not given)
 			o.range_culling = 1;
@@ -1665,7 +1667,7 @@ int main(int argc, char** argv) {
 		unaligned_upto(UINT32_MAX);
 		fclose(out);
 		if (gz_out) {  // --compress 1: the output as a gzip file, ".gz" appended to its name (basic/config.cpp:770-771)
-			const std::string gzname = (of.size() >= 3 && of.compare(of.size() - 3, 3, ".gz") == 0) ? of : of + ".gz";
+			const std::string gzname = (no_auto_append || (of.size() >= 3 && of.compare(of.size() - 3, 3, ".gz") == 0)) ? of : of + ".gz";
 			std::ifstream in(of, std::ios::binary);
 			std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
 			in.close();
