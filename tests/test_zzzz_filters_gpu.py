@@ -39,3 +39,9 @@ def test_frameshift_formats_on_device(product_lib, tmp_path):
 def test_no_self_hits_on_device(product_lib, tmp_path):
     from test_filters import check_no_self_hits
     check_no_self_hits(CLI, tmp_path)
+
+
+def test_view_on_device_build(product_lib, tmp_path):
+    """`view` needs no GPU, but the product CLI and library must carry it (dmnd_alignment_stats) like the test stand-in does."""
+    from test_formats import check_view
+    check_view(CLI, tmp_path)
