@@ -36,7 +36,7 @@ struct SeqBlock {
 // Whole input file as text; gzip-compressed files are inflated, anything else is read as it is (gzread is transparent), like the
 // reference's input layer (util/io/compressed_stream.cpp) for .gz queries and databases in FASTA format.
 std::string slurp_text(const std::string& path) {
-	gzFile g = gzopen(path.c_str(), "rb");
+	gzFile g = path.empty() ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");  // no file name = standard input, as the reference reads its queries then
 	if (!g) throw std::runtime_error("Error opening file " + path);
 	std::string out;
 	char buf[1 << 16];
@@ -733,12 +733,12 @@ int main(int argc, char** argv) {
 			else usage(("unsupported option " + a).c_str());
 		}
 		if (view_mode) {
-			if (of.empty()) usage("view needs -o");
 			if (daa) usage("view: the output format is one of 0, 5, 6, sam, paf");
 			if (o.min_id != 0.0 || o.query_cover != 0.0 || o.subject_cover != 0.0 || o.approx_min_id != 0.0 || o.min_bit_score != 0.0 || unal || block_size != 0.0 || o.frame_shift || no_self_hits)
 				usage("view prints the stored alignments: search options do not apply");
 		}
-		else if (qf.empty() || df.empty() || of.empty()) usage("-q, -d and -o are required");
+		else if (df.empty()) usage("-d is required");  // (no -q: the queries come from standard input; no -o: the output goes to standard output)
+		if (of.empty() && (daa || gz_out)) usage("-f 100 and --compress need an output file (-o)");
 		if (daa && gz_out) usage("Compression is not supported for DAA format.");  // basic/config.cpp:726-727
 		if (daa && !no_auto_append && (of.size() < 4 || of.compare(of.size() - 4, 4, ".daa") != 0)) of += ".daa";  // auto_append_extension, basic/config.cpp:725-730
 		if (k_set && top_set) usage("--top and --max-target-seqs are mutually exclusive.");  // basic/config.cpp:674-675
@@ -1055,7 +1055,7 @@ int main(int argc, char** argv) {
 			}
 		};
 		auto end_frame = [&](const dmnd_match& x) -> int { return x.reserved ? (int)x.reserved - 1 : (int)(x.query % 6); };  // frame the alignment ends in
-		FILE* out = fopen(of.c_str(), "wb");
+		FILE* out = of.empty() ? stdout : fopen(of.c_str(), "wb");
 		if (!out) throw std::runtime_error("Error opening file " + of);
 		char buf[32];
 		std::string line;
@@ -1665,7 +1665,7 @@ int main(int argc, char** argv) {
 			fwrite(line.data(), 1, line.size(), out);
 		}
 		unaligned_upto(UINT32_MAX);
-		fclose(out);
+		if (out == stdout) fflush(out); else fclose(out);
 		if (gz_out) {  // --compress 1: the output as a gzip file, ".gz" appended to its name (basic/config.cpp:770-771)
 			const std::string gzname = (no_auto_append || (of.size() >= 3 && of.compare(of.size() - 3, 3, ".gz") == 0)) ? of : of + ".gz";
 			std::ifstream in(of, std::ios::binary);
