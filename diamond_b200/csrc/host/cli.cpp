@@ -590,8 +590,12 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 }
 
 [[noreturn]] void usage(const char* msg) {
-	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB | dmnd-b200 blastp -q QUERY.faa -d DB[.dmnd|.faa] -o OUT [--fast] [-p N] | dmnd-b200 blastx [--fast ...] -q READS.fna -d DB -o OUT [-p N] [-c N] [-k N] [-e X] "
-	                "[--comp-based-stats 0|1] [--masking 0|none|1|tantan] [--motif-masking 0|1] [-f 6] [--log]\n", msg);
+	fprintf(stderr, "Error: %s\nusage: dmnd-b200 makedb --in DB.faa -d DB\n"
+	                "       dmnd-b200 blastp|blastx -d DB[.dmnd|.faa] [-q QUERIES] [-o OUT] [--fast|--mid-sensitive|--sensitive|--more-sensitive|--very-sensitive|--ultra-sensitive]\n"
+	                "                [-p N] [-c N] [-b G] [-k N | --top P] [-e X | --min-score B] [--id P | --approx-id P] [--query-cover P] [--subject-cover P] [--no-self-hits]\n"
+	                "                [--comp-based-stats 0|1] [--masking 0|1] [--motif-masking 0|1] [-F 15 [--range-culling] | --long-reads] [--strand both|plus|minus] [--min-orf N] [--query-gencode N]\n"
+	                "                [-f 6 [fields] [--unal 0|1] [--header simple] | -f 0 | -f 5 | -f 100 | -f sam | -f paf] [--compress 0|1] [--log]\n"
+	                "       dmnd-b200 view -a FILE.daa [-o OUT] [-f ...]\n", msg);
 	exit(1);
 }
 
@@ -729,6 +733,8 @@ int main(int argc, char** argv) {
 			else if (a == "--query-cover") o.query_cover = atof(val());
 			else if (a == "--subject-cover") o.subject_cover = atof(val());
 			else if (a == "--approx-id") o.approx_min_id = atof(val());
+			else if (a == "--gapopen") { if (atoi(val()) != 11) usage("--gapopen: only 11 (BLOSUM62's default, with --gapextend 1) is implemented"); }
+			else if (a == "--gapextend") { if (atoi(val()) != 1) usage("--gapextend: only 1 (with --gapopen 11) is implemented"); }
 			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }
 			else usage(("unsupported option " + a).c_str());
 		}
