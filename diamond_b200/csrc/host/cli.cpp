@@ -622,6 +622,22 @@ int main(int argc, char** argv) {
 			if (in.empty() || db.empty()) usage("makedb needs --in and -d");
 			return make_db(in, db, masking);
 		}
+		if (cmd == "dbinfo") {  // diamond dbinfo -d DB: the header of a DIAMOND database (legacy/dmnd/dmnd.h:28-66)
+			std::string db;
+			for (int i = 2; i < argc; ++i) { const std::string a = argv[i]; if ((a == "-d" || a == "--db") && i + 1 < argc) db = argv[++i]; else if (a != "--quiet") usage(("unsupported option " + a).c_str()); }
+			if (db.empty()) usage("dbinfo needs -d");
+			if (!is_dmnd(db) && is_dmnd(db + ".dmnd")) db += ".dmnd";
+			std::ifstream f(db, std::ios::binary);
+			unsigned char h[40];
+			uint64_t magic = 0, seqs = 0, letters = 0;
+			uint32_t build = 0, version = 0;
+			if (!f.read((char*)h, sizeof h)) throw std::runtime_error("Database file is not a DIAMOND database.");
+			std::memcpy(&magic, h, 8); std::memcpy(&build, h + 8, 4); std::memcpy(&version, h + 12, 4); std::memcpy(&seqs, h + 16, 8); std::memcpy(&letters, h + 24, 8);
+			if (magic != DMND_MAGIC) throw std::runtime_error("Database file is not a DIAMOND database.");
+			printf("%23s  %s\n%23s  %u\n%23s  %u\n%23s  %llu\n%23s  %llu\n", "Database type", "Diamond database", "Database format version", version, "Diamond build", build,
+			       "Sequences", (unsigned long long)seqs, "Letters", (unsigned long long)letters);
+			return 0;
+		}
 		if (cmd != "blastp" && cmd != "blastx" && cmd != "view") usage("only blastp, blastx, view and makedb are implemented");
 		const bool view_mode = cmd == "view";  // diamond view -a FILE.daa -o OUT [-f ...]: the stored alignments through the same writers
 		std::string daa_in;
