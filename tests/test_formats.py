@@ -122,3 +122,25 @@ def check_view(cli, tmp_path):
 
 def test_view(oracle_lib, tmp_path):
     check_view(CLI, tmp_path)
+
+
+def test_stdio_compress_dbinfo(oracle_lib, tmp_path):
+    """Queries from standard input, output to standard output, --compress 1 (gzip, ".gz" appended), dbinfo."""
+    import gzip
+    from diamond_b200 import synth
+    w, *_ = workload_blocks("edge")
+    q, d, o = (str(tmp_path / x) for x in ("q.faa", "d.faa", "o.tsv"))
+    synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
+    synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+    gold = open(os.path.join(GOLDEN, "edge.l2.tsv")).read()
+    r = subprocess.run([CLI, "blastp", "--fast", "-d", d, "-p", "8"], input=open(q, "rb").read(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.decode() == gold
+    r = subprocess.run([CLI, "blastp", "--fast", "-q", q, "-d", d, "-o", o, "-p", "8", "--compress", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not os.path.exists(o) and gzip.open(o + ".gz", "rt").read() == gold
+    db = str(tmp_path / "db")
+    assert subprocess.run([CLI, "makedb", "--in", d, "-d", db], capture_output=True).returncode == 0
+    r = subprocess.run([CLI, "dbinfo", "-d", db], capture_output=True, text=True)
+    n_letters = int(w["db_off"][-1])
+    assert r.returncode == 0 and f"Sequences  {len(w['db_off']) - 1}\n" in r.stdout and f"Letters  {n_letters}\n" in r.stdout and "Database format version  3" in r.stdout
