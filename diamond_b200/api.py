@@ -212,7 +212,8 @@ class Context:
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, threads: int = 8, index_chunks: int = 0,
                  comp_based_stats: int = 1, max_target_seqs: int = 25, max_evalue: float = 1e-3, want_transcript: bool = False,
                  masking: int = 0, motif_masking: int = 0, sensitivity: int = 0, query_contexts: int = 1, frame_shift: int = 0, range_culling: int = 0, top_percent: float | None = None,
-                 min_id: float = 0.0, query_cover: float = 0.0, subject_cover: float = 0.0, min_bit_score: float = 0.0):
+                 min_id: float = 0.0, query_cover: float = 0.0, subject_cover: float = 0.0, min_bit_score: float = 0.0, approx_min_id: float = 0.0,
+                 self_targets: np.ndarray | None = None):
         """masking / motif_masking: the reference's --masking (1 = tantan) and --motif-masking.  This test-harness
         wrapper defaults to the parity-ladder rungs without masking; dmnd_search_opts_default() and the CLI
         default to the reference's own defaults (1, 1)."""
@@ -235,6 +236,9 @@ class Context:
         self.opts.query_cover = float(query_cover)
         self.opts.subject_cover = float(subject_cover)
         self.opts.min_bit_score = float(min_bit_score)  # --min-score: replaces the e-value bound
+        self.opts.approx_min_id = float(approx_min_id)  # --approx-id
+        self._self_targets = None if self_targets is None else np.ascontiguousarray(self_targets, dtype=np.uint32)  # --no-self-hits: per query the target to suppress (0xFFFFFFFF = none)
+        self.opts.self_targets = None if self._self_targets is None else self._self_targets.ctypes.data
         if top_percent is not None:
             self.opts.top_percent = float(top_percent)  # --top
         self.params = Params()

@@ -108,3 +108,22 @@ def check_no_self_hits(cli, tmp_path):
 
 def test_no_self_hits(oracle_lib, tmp_path):
     check_no_self_hits(CLI, tmp_path)
+
+
+def test_library_self_targets_and_min_score(oracle_lib):
+    """dmnd_search_opts.self_targets / min_bit_score through the Python mirror: the N1 golden from the library call, and a bit-score bound that
+    keeps exactly the lines of the unfiltered golden at or above it (--min-score replaces the e-value bound; nothing else moves at -k 25 here)."""
+    from diamond_b200 import api
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("fam2")
+    n = 150
+    qs_raw, qs_lim = api.block_image(w["db_letters"][:w["db_off"][n]], w["db_off"][:n + 1])
+    ctx = api.Context(oracle_lib, masking=1, motif_masking=1, max_target_seqs=3, self_targets=np.arange(n, dtype=np.uint32))
+    m, _, _ = ctx.blastp(qs_raw, qs_lim, r_raw, r_lim)
+    ctx.close()
+    assert api.fmt6(m, q_prefix="d") == open(os.path.join(GOLDEN, "fam2.n1.tsv")).read()
+    w, q_raw, q_lim, r_raw, r_lim = workload_blocks("edge")
+    ctx = api.Context(oracle_lib, masking=1, motif_masking=1, min_bit_score=100.0)
+    m, _, _ = ctx.blastp(q_raw, q_lim, r_raw, r_lim)
+    ctx.close()
+    gold = [l for l in open(os.path.join(GOLDEN, "edge.l2.tsv")).read().splitlines() if float(l.split("\t")[11]) >= 100.0]
+    assert api.fmt6(m).splitlines() == gold
