@@ -749,6 +749,10 @@ int main(int argc, char** argv) {
 			else if (a == "--query-cover") o.query_cover = atof(val());
 			else if (a == "--subject-cover") o.subject_cover = atof(val());
 			else if (a == "--approx-id") o.approx_min_id = atof(val());
+			else if (a == "--ext") {  // search/setup.cpp:377-384
+				const std::string v = val();
+				if (v == "banded-fast") o.ext_mode = 1; else if (v == "banded-slow") o.ext_mode = 2; else usage("--ext: banded-fast and banded-slow are implemented (full, global and none are not on this path)");
+			}
 			else if (a == "--gapopen") { if (atoi(val()) != 11) usage("--gapopen: only 11 (BLOSUM62's default, with --gapextend 1) is implemented"); }
 			else if (a == "--gapextend") { if (atoi(val()) != 1) usage("--gapextend: only 1 (with --gapopen 11) is implemented"); }
 			else if (a == "--max-hsps") { if (std::string(val()) != "1") usage("--max-hsps: only 1 is implemented"); }

@@ -1635,6 +1635,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	}
 	e.fuse = std::getenv("DMND_NO_FUSE") == nullptr;
 	e.mask_algo = mask_algo; e.contexts = contexts;
+	if (opts->ext_mode < 0 || opts->ext_mode > 2) { dmnd_set_last_error("dmnd_blastp: ext_mode is 0 (mode default), 1 (banded-fast) or 2 (banded-slow)"); return 1; }
 	e.self_targets = opts->self_targets;
 	e.min_bit_score = opts->min_bit_score;
 	if (!(e.min_bit_score >= 0.0)) { dmnd_set_last_error("dmnd_blastp: min_bit_score must not be negative (0 = the e-value bound applies)"); return 1; }
@@ -1652,7 +1653,7 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	{
 		const ModeTraits* mt = mode_traits(opts->sensitivity);
 		if (!mt) { dmnd_set_last_error("dmnd_blastp: bad sensitivity"); return 1; }
-		e.n_shapes = mt->n_shapes; e.gapped_filter = mt->gapped_filter_evalue > 0.0; e.band_slow = mt->band_slow; e.ranking_letters = mt->ranking_letters;
+		e.n_shapes = mt->n_shapes; e.gapped_filter = mt->gapped_filter_evalue > 0.0; e.band_slow = opts->ext_mode == 0 ? mt->band_slow : opts->ext_mode == 2; e.ranking_letters = mt->ranking_letters;  // --ext (search/setup.cpp:377-384)
 		if (e.frame_shift) e.gapped_filter = false;  // Extension::gapped_filter belongs to Extension::extend, which frameshift mode does not run
 	}
 	if (mask_algo) {

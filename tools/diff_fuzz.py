@@ -60,6 +60,7 @@ def main():
                 subprocess.run([REF, "makedb", "--in", d, "-d", os.path.join(td, "db"), "--quiet"], check=True, capture_output=True)
                 d = os.path.join(td, "db.dmnd")
             if rnd.random() < 0.15: opts += ["--header", "simple"]
+            if rnd.random() < 0.1: opts += ["--ext", rnd.choice(["banded-fast", "banded-slow"])]
             if not translated and d.endswith(".faa") and rnd.random() < a.all_vs_all:  # the database against itself, with and without --no-self-hits
                 q = d
                 if rnd.random() < 0.7: opts += ["--no-self-hits"]
