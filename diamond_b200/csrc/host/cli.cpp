@@ -661,7 +661,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false;
+		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false, salltitles = false, sallseqid = false;
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
@@ -744,6 +744,8 @@ int main(int argc, char** argv) {
 			else if (a == "--compress") { const std::string v = val(); if (v == "1") gz_out = true; else if (v != "0") usage("--compress: 0 (none) and 1 (gzip) are implemented"); }
 			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
+			else if (a == "--salltitles") salltitles = true;  // SAM reference names and DAA dictionary entries carry every full title (basic/config.cpp; sam_format.cpp:100, daa_record.cpp:27)
+			else if (a == "--sallseqid") sallseqid = true;   // DAA dictionary entries carry every sequence id of a merged record
 			else if (a == "--no-self-hits") no_self_hits = true;  // basic/config.cpp:312
 			else if (a == "--min-score") o.min_bit_score = atof(val());  // basic/config.cpp:299: overrides the e-value setting
 			else if (a == "--query-cover") o.query_cover = atof(val());
@@ -1061,6 +1063,21 @@ int main(int argc, char** argv) {
 			if (fshift) { *nu = fs_unal.size(); return fs_unal.data(); }
 			return dmnd_result_unaligned(res, nu);
 		};
+		// every title of a merged record ("\x01" or " >" between them, util/sequence/sequence.cpp:38), whole or cut to its id, joined by `sep` (OutputFormat::print_title)
+		auto all_titles = [](const std::string& tt, bool ids_only, const char* sep) {
+			std::string out_;
+			for (size_t a = 0, k = 0; a <= tt.size(); ++k) {
+				size_t e = a;
+				while (e < tt.size() && tt[e] != '\x01' && !(tt[e] == ' ' && e + 1 < tt.size() && tt[e + 1] == '>')) ++e;
+				if (k) out_ += sep;
+				size_t ie = e;
+				if (ids_only) { ie = a; while (ie < e && !strchr(" \a\b\f\n\r\t\v", tt[ie])) ++ie; }
+				out_.append(tt, a, ie - a);
+				if (e >= tt.size()) break;
+				a = tt[e] == '\x01' ? e + 1 : e + 2;
+			}
+			return out_;
+		};
 		static const char* alphabet = "ARNDCQEGHILKMFPSTWYVBJZX*_";
 		// Hsp::Iterator (basic/match.h:105-161) over a transcript: qat[k] = the query letter transcript byte k consumes (match, substitution,
 		// insertion), -1 / -2 for a forward / reverse frameshift byte (the query position moves one nucleotide on / back: the frame of the
@@ -1108,7 +1125,7 @@ int main(int argc, char** argv) {
 				unaligned_to(sq);
 				const uint8_t* t = tr + x.transcript_off;
 				const int8_t* qs = q.letters.data() + q.limits[x.query];
-				line = (translated ? dq.ids[sq] : q.ids[sq]) + "\t0\t" + r.ids[x.target] + "\t" + std::to_string(x.t_begin + 1) + "\t255\t";
+				line = (translated ? dq.ids[sq] : q.ids[sq]) + "\t0\t" + (salltitles ? all_titles(r.titles[x.target], false, "<>") : r.ids[x.target]) + "\t" + std::to_string(x.t_begin + 1) + "\t255\t";
 				{	// print_cigar: match and substitution are M
 					uint32_t run = 0; int op = -1;
 					for (uint32_t k = 0; k < x.transcript_len; ++k) {
@@ -1361,7 +1378,10 @@ int main(int argc, char** argv) {
 			{ const uint32_t zero = 0; put(&zero, 4); }
 			h2.block_size[0] = body.size();
 			uint64_t names = 0;
-			for (uint32_t tgt : dict) { put(r.ids[tgt].c_str(), r.ids[tgt].size() + 1); names += r.ids[tgt].size() + 1; }
+			for (uint32_t tgt : dict) {  // Block::dict_id (data/block/block.cpp:138-150): the full title, all sequence ids ("\x01" between them) or the first id
+				const std::string nm = salltitles ? r.titles[tgt] : sallseqid ? all_titles(r.titles[tgt], true, "\x01") : r.ids[tgt];
+				put(nm.c_str(), nm.size() + 1); names += nm.size() + 1;
+			}
 			for (uint32_t tgt : dict) { const uint32_t l = (uint32_t)(r.limits[tgt + 1] - r.limits[tgt] - 1); put(&l, 4); }
 			uint64_t all_letters = 0;
 			for (uint32_t i = 0; i < r.size(); ++i) all_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
