@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--translated-only", action="store_true")
     ap.add_argument("--filters", type=float, default=0.25, help="probability of --id / --query-cover / --subject-cover on a run")
     ap.add_argument("--protein-only", action="store_true")
+    ap.add_argument("--titles", type=float, default=0.3, help="probability of descriptive / merged sequence titles in both files")
     ap.add_argument("--dmnd", type=float, default=0.15, help="probability that the database is a .dmnd file made by the reference")
     ap.add_argument("--all-vs-all", type=float, default=0.08, help="probability that a protein run searches the database against itself (70 %% of those with --no-self-hits)")
     ap.add_argument("--format", default=None, help="use this output format on every run (6, 6f, 6g, 6c, 0, 5, 100, sam, paf)")
@@ -55,7 +56,18 @@ def main():
                 q = os.path.join(td, "q.faa")
                 synth.write_fasta(q, w["q_letters"], w["q_off"], "q")
             synth.write_fasta(d, w["db_letters"], w["db_off"], "d")
+            if rnd.random() < a.titles:  # descriptive titles, some of them merged records (" >" between the titles), and characters XML has to escape
+                for path in (q, d):
+                    out, k = [], 0
+                    for l in open(path).read().split("\n"):
+                        if l.startswith(">"):
+                            k += 1
+                            if k % 3 == 0: l += " first <desc> & 'quoted' >alt%d second \"desc\"" % k
+                            elif k % 3 == 1: l += " only desc|with.pipe"
+                        out.append(l)
+                    open(path, "w").write("\n".join(out))
             opts = list(rnd.choice(MODES))
+            if rnd.random() < 0.1: opts += [rnd.choice(["--salltitles", "--sallseqid"])]
             if rnd.random() < a.dmnd:  # a DIAMOND database file instead of FASTA (blocks are then cut by letters, titles come from the file)
                 subprocess.run([REF, "makedb", "--in", d, "-d", os.path.join(td, "db"), "--quiet"], check=True, capture_output=True)
                 d = os.path.join(td, "db.dmnd")
