@@ -43,6 +43,14 @@ def main():
                 w = synth.reads_workload(seed, n_db=rnd.choice([300, 800]), n_q=rnd.choice([80, 200]))
                 q = os.path.join(td, "q.fna")
                 synth.write_dna_fasta(q, w["dna"])
+                if rnd.random() < 0.15:  # the same reads as FASTQ (titles then end in a newline, as the reference's FASTQ reader leaves them)
+                    recs = open(q).read().split(">")[1:]
+                    q = os.path.join(td, "q.fastq")
+                    with open(q, "w") as fh:
+                        for rec in recs:
+                            name, _, seq = rec.partition("\n")
+                            seq = seq.replace("\n", "")
+                            if seq: fh.write("@%s\n%s\n+\n%s\n" % (name, seq, "".join(chr(33 + (7 * i) % 40) for i in range(len(seq)))))
             else:
                 kind = rnd.choice(["edge", "rep", "fam", "plain"])
                 if kind == "edge":
@@ -93,6 +101,7 @@ def main():
                 if u >= 0.6: opts += ["--subject-cover", str(rnd.choice([10, 30, 55, 70, 90]))]
                 if u >= 0.6 and rnd.random() < 0.5:  # equal covers >= 50: min_length_ratio, length-sorted blocks, the mutual-coverage seed stage (protein searches)
                     opts[-1] = opts[-3] = str(rnd.choice([50, 60, 80, 90]))
+            if translated and rnd.random() < 0.15: opts += ["--query-gencode", str(rnd.choice([1, 2, 4, 11, 25]))]
             if translated:
                 if rnd.random() < 0.3: opts += ["--strand", rnd.choice(["plus", "minus"])]
                 if rnd.random() < 0.3: opts += ["--min-orf", str(rnd.choice([1, 10, 35]))]
@@ -128,6 +137,10 @@ def main():
                 opts += ["-f", "100"]
             elif fmt != "6":
                 opts += ["-f", fmt]
+            if rnd.random() < 0.1 and not q.endswith(".gz") and not q.endswith(".fastq") and q != d:  # gzip-compressed FASTA queries (the reference built here loads NO query from a gzip-compressed FASTQ file; this CLI reads it)
+                import gzip, shutil
+                with open(q, "rb") as fi, gzip.open(q + ".gz", "wb") as fo: shutil.copyfileobj(fi, fo)
+                q += ".gz"
             cmd = ["blastx" if translated else "blastp", "-q", q, "-d", d] + opts
             ext = ".daa" if fmt == "100" else ".out"  # (both programs append .daa to the name of a DAA file that lacks it)
             ro, oo = os.path.join(td, "r" + ext), os.path.join(td, "o" + ext)
