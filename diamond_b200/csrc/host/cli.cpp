@@ -662,6 +662,7 @@ int main(int argc, char** argv) {
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false, salltitles = false, sallseqid = false;
+		uint64_t daa_build = 182;  // Const::build_version of the reference release this path follows
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
 		for (int i = 2; i < argc; ++i) {
@@ -739,6 +740,7 @@ int main(int argc, char** argv) {
 			else if (a == "--log") log = true;
 			else if (a == "--quiet" || a == "--verbose" || a == "-v" || a == "--ignore-warnings") {}
 			else if (a == "--tmpdir" || a == "-t" || a == "--parallel-tmpdir") val();  // (no temporary files on this path: hits and per-block results stay in memory)
+			else if (a == "--daa-build-version") daa_build = (uint64_t)atoll(val());  // config.daa_build_version: the build number a DAA header quotes (daa_file.h:45)
 			else if (a == "--no-auto-append") no_auto_append = true;  // basic/config.cpp:765
 			// options that wrappers (e.g. the Galaxy tool) always spell out: accepted at their default value only, anything else is refused
 			else if (a == "--compress") { const std::string v = val(); if (v == "1") gz_out = true; else if (v != "0") usage("--compress: 0 (none) and 1 (gzip) are implemented"); }
@@ -1385,7 +1387,7 @@ int main(int argc, char** argv) {
 			for (uint32_t tgt : dict) { const uint32_t l = (uint32_t)(r.limits[tgt + 1] - r.limits[tgt] - 1); put(&l, 4); }
 			uint64_t all_letters = 0;
 			for (uint32_t i = 0; i < r.size(); ++i) all_letters += (uint64_t)(r.limits[i + 1] - r.limits[i] - 1);
-			h2.diamond_build = 182; h2.db_seqs = r.size(); h2.db_seqs_used = dict.size(); h2.db_letters = all_letters; h2.query_records = n_queries;
+			h2.diamond_build = daa_build; h2.db_seqs = r.size(); h2.db_seqs_used = dict.size(); h2.db_letters = all_letters; h2.query_records = n_queries;
 			h2.mode = translated ? 3 : 2; h2.gap_open = 11; h2.gap_extend = 1; h2.k = 0.041; h2.lambda = 0.267; h2.evalue = o.max_evalue;
 			{ std::string mn = matrix_name; for (char& c : mn) c = (char)tolower((unsigned char)c); strncpy(h2.score_matrix, mn.c_str(), sizeof h2.score_matrix - 1); }
 			h2.block_size[1] = names; h2.block_size[2] = dict.size() * sizeof(uint32_t);
