@@ -661,7 +661,7 @@ int main(int argc, char** argv) {
 		std::vector<std::string> fields;
 		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
-		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false, salltitles = false, sallseqid = false;
+		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false, salltitles = false, sallseqid = false, xml_blord = false, no_parse_seqids = false, sam_qlen = false;
 		uint64_t daa_build = 182;  // Const::build_version of the reference release this path follows
 		std::string matrix_name = "blosum62";  // config.matrix as given (the XML header quotes it)
 		double block_size = 0.0;  // -b: reference block size in 10^9 letters (0 = the mode's default: 2.0, 0.4 from --very-sensitive on; run/double_indexed.cpp:792-795)
@@ -746,6 +746,9 @@ int main(int argc, char** argv) {
 			else if (a == "--compress") { const std::string v = val(); if (v == "1") gz_out = true; else if (v != "0") usage("--compress: 0 (none) and 1 (gzip) are implemented"); }
 			else if (a == "--matrix") { std::string v = val(); matrix_name = v; for (char& c : v) c = (char)toupper((unsigned char)c); if (v != "BLOSUM62") usage("--matrix: only BLOSUM62 (gap penalties 11/1) is implemented"); }
 			else if (a == "--id") o.min_id = atof(val());  // basic/config.cpp:263,300-301: report filters, applied inside the extension (align/culling.cpp:144-184)
+			else if (a == "--xml-blord-format") xml_blord = true;  // XML: <Hit_id>gnl|BL_ORD_ID|ordinal</Hit_id>, the whole title line in Hit_def (xml_format.cpp:44-49)
+			else if (a == "--no-parse-seqids") no_parse_seqids = true;  // XML: Hit_accession = the id as it is (xml_format.cpp:60)
+			else if (a == "--sam-query-len") sam_qlen = true;  // SAM: a ZQ:i:<query length> field (sam_format.cpp:136-137)
 			else if (a == "--salltitles") salltitles = true;  // SAM reference names and DAA dictionary entries carry every full title (basic/config.cpp; sam_format.cpp:100, daa_record.cpp:27)
 			else if (a == "--sallseqid") sallseqid = true;   // DAA dictionary entries carry every sequence id of a merged record
 			else if (a == "--no-self-hits") no_self_hits = true;  // basic/config.cpp:312
@@ -1168,6 +1171,7 @@ int main(int argc, char** argv) {
 					}
 					if (matches > 0) line += std::to_string(matches);
 				}
+				if (sam_qlen) line += "\tZQ:i:" + std::to_string(translated ? (int64_t)dq.len[sq] : q.limits[sq + 1] - q.limits[sq] - 1);  // r.query.source().length()
 				line += '\n';
 				fwrite(line.data(), 1, line.size(), out);
 			}
@@ -1484,17 +1488,18 @@ int main(int argc, char** argv) {
 				const std::string id = tt.substr(0, d0), def = d0 >= tt.size() ? std::string() : tt.substr(d0 + 1);
 				if (hit_num > 0) line += "  </Hit_hsps>\n</Hit>\n";
 				line += "<Hit>\n  <Hit_num>" + std::to_string(hit_num + 1) + "</Hit_num>\n  <Hit_id>";
-				esc(id, line);
+				if (xml_blord) line += "gnl|BL_ORD_ID|" + std::to_string(r.oid.empty() ? x.target : r.oid[x.target]); else esc(id, line);
 				line += "</Hit_id>\n  <Hit_def>";
+				const std::string& defs = xml_blord ? tt : def;  // --xml-blord-format: the whole title line
 				for (size_t a = 0, k = 0; a != std::string::npos; ++k) {  // OutputFormat::print_title(def, full, all, " &gt;")
 					size_t nx;
-					const std::string one = next_title(def, a, &nx);
+					const std::string one = next_title(defs, a, &nx);
 					if (k) line += " &gt;";
 					esc(one, line);
 					a = nx;
 				}
 				line += "</Hit_def>\n  <Hit_accession>";
-				esc(accession(id), line);
+				esc(no_parse_seqids ? id : accession(id), line);
 				line += "</Hit_accession>\n  <Hit_len>" + std::to_string(r.limits[x.target + 1] - r.limits[x.target] - 1) + "</Hit_len>\n  <Hit_hsps>\n";
 				++hit_num;
 				format_double(x.bit_score, buf, sizeof buf);

@@ -137,6 +137,8 @@ def main():
                 opts += ["-f", "100"]
             elif fmt != "6":
                 opts += ["-f", fmt]
+                if fmt == "5" and rnd.random() < 0.3: opts += [rnd.choice(["--xml-blord-format", "--no-parse-seqids"])]
+                if fmt == "sam" and rnd.random() < 0.3: opts += ["--sam-query-len"]
             if rnd.random() < 0.1 and not q.endswith(".gz") and not q.endswith(".fastq") and q != d:  # gzip-compressed FASTA queries (the reference built here loads NO query from a gzip-compressed FASTQ file; this CLI reads it)
                 import gzip, shutil
                 with open(q, "rb") as fi, gzip.open(q + ".gz", "wb") as fo: shutil.copyfileobj(fi, fo)
