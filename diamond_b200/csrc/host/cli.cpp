@@ -659,7 +659,7 @@ int main(int argc, char** argv) {
 		std::string qf, df, of;
 		bool log = false, motif_set = false;
 		std::vector<std::string> fields;
-		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, k_set = false, top_set = false, unal = false;
+		bool pairwise = false, paf = false, sam = false, xml = false, daa = false, json = false, k_set = false, top_set = false, unal = false;
 		int strand_mask = 63, min_orf = 0, gencode = 1;
 		bool header_simple = false, long_reads = false, no_self_hits = false, gz_out = false, no_auto_append = false, salltitles = false, sallseqid = false, xml_blord = false, no_parse_seqids = false, sam_qlen = false;
 		uint64_t daa_build = 182;  // Const::build_version of the reference release this path follows
@@ -704,7 +704,8 @@ int main(int argc, char** argv) {
 				if (fmt == "sam" || fmt == "101") { sam = true; continue; }
 				if (fmt == "xml" || fmt == "5") { xml = true; continue; }
 				if (fmt == "daa" || fmt == "100") { daa = true; continue; }
-				if (fmt != "6" && fmt != "tab") usage("only -f 6 [fields], -f 0, -f 5 (xml), -f 100 (daa), -f sam and -f paf are implemented");
+				if (fmt == "json-flat" || fmt == "104") json = true;  // the tabular fields as a JSON array of flat objects (TabularFormat(true), blast_tab_format.cpp:740-773,823-834)
+				if (fmt != "6" && fmt != "tab" && !json) usage("only -f 6 [fields], -f 0, -f 5 (xml), -f 100 (daa), -f sam and -f paf are implemented");
 				while (i + 1 < argc && argv[i + 1][0] != '-') {
 					const std::string f = argv[++i];
 					static const char* known[] = { "qseqid", "sseqid", "pident", "length", "mismatch", "gapopen", "qstart", "qend", "sstart", "send", "evalue", "bitscore",
@@ -1542,6 +1543,7 @@ int main(int argc, char** argv) {
 			line += '\n';
 			fwrite(line.data(), 1, line.size(), out);
 		}
+		if (json && !pairwise && !paf && !sam && !xml && !daa) fwrite("[", 1, 1, out);
 		size_t n_unal = 0, u_next = 0;
 		const uint32_t* unal_q = result_unaligned(&n_unal);
 		const uint32_t ctxs = translated ? 6u : 1u;
@@ -1576,7 +1578,13 @@ int main(int argc, char** argv) {
 			line.clear();
 			for (size_t fi = 0; fi < fields.size(); ++fi) {
 				const std::string& f = fields[fi];
-				if (fi) line += '\t';
+				// json-flat: "key":value lines, strings quoted, the arrays (sallseqid, salltitles) bracketed with every element quoted
+				const bool j_arr = json && (f == "sallseqid" || f == "salltitles");
+				const bool j_str = json && (f == "qseqid" || f == "sseqid" || f == "qseq" || f == "sseq" || f == "btop" || f == "stitle" || f == "qtitle" || f == "full_sseq" || f == "qqual" || f == "full_qqual"
+				                            || f == "full_qseq" || f == "qseq_gapped" || f == "sseq_gapped" || f == "qstrand" || f == "cigar" || f == "qseq_translated");
+				if (json) { line += "\t\"" + f + "\":"; if (j_str) line += '"'; if (j_arr) line += "[\""; }
+				else if (fi) line += '\t';
+				const size_t value_at = line.size();
 				if (f == "qseqid") line += translated ? dq.ids[x.query / 6] : q.ids[x.query];
 				else if (f == "sseqid") line += r.ids[x.target];
 				else if (f == "pident") { format_double((double)x.identities * 100.0 / (double)x.length, buf, sizeof buf); line += buf; }
@@ -1629,7 +1637,7 @@ int main(int argc, char** argv) {
 					for (size_t a = 0, k = 0; a <= tt.size(); ++k) {
 						size_t e = a;
 						while (e < tt.size() && tt[e] != '\x01' && !(tt[e] == ' ' && e + 1 < tt.size() && tt[e + 1] == '>')) ++e;
-						if (k) line += ids_only ? ";" : "<>";
+						if (k) line += json ? "\",\"" : ids_only ? ";" : "<>";
 						size_t ie = e;
 						if (ids_only) { ie = a; while (ie < e && !strchr(" \a\b\f\n\r\t\v", tt[ie])) ++ie; }
 						line.append(tt, a, ie - a);
@@ -1713,11 +1721,15 @@ int main(int argc, char** argv) {
 						line += query_side ? qc : sc;
 					}
 				}
+				(void)value_at;
+				if (json) { if (j_str) line += '"'; if (j_arr) line += "\"]"; line += fi + 1 < fields.size() ? ",\n" : "\n"; }
 			}
-			line += '\n';
+			if (json) line = std::string(i ? "," : "") + "\n\t{\n" + line + "\t}";  // (a comma between the records of one query, the query separator between queries: one after every record but the last)
+			else line += '\n';
 			fwrite(line.data(), 1, line.size(), out);
 		}
 		unaligned_upto(UINT32_MAX);
+		if (json) fwrite("\n]", 1, 2, out);
 		if (out == stdout) fflush(out); else fclose(out);
 		if (gz_out) {  // --compress 1: the output as a gzip file, ".gz" appended to its name (basic/config.cpp:770-771)
 			const std::string gzname = (no_auto_append || (of.size() >= 3 && of.compare(of.size() - 3, 3, ".gz") == 0)) ? of : of + ".gz";

@@ -144,3 +144,16 @@ def test_stdio_compress_dbinfo(oracle_lib, tmp_path):
     r = subprocess.run([CLI, "dbinfo", "-d", db], capture_output=True, text=True)
     n_letters = int(w["db_off"][-1])
     assert r.returncode == 0 and f"Sequences  {len(w['db_off']) - 1}\n" in r.stdout and f"Letters  {n_letters}\n" in r.stdout and "Database format version  3" in r.stdout
+
+
+def test_json_flat(oracle_lib, tmp_path):
+    """-f 104 / json-flat: the tabular fields as an array of flat objects.  Same values as the tabular golden, and -- unlike the reference's
+    file, which loses the comma between two records wherever one of its query bins ends (a new OutputWriter starts "first", output/output.h:97-110)
+    -- always valid JSON."""
+    import json
+    out = run_protein(CLI, "edge", ["--fast", "-f", "104"], tmp_path)
+    recs = json.loads(out)
+    gold = [l.split("\t") for l in open(os.path.join(GOLDEN, "edge.l2.tsv")).read().splitlines()]
+    assert len(recs) == len(gold) and list(recs[0].keys()) == "qseqid sseqid pident length mismatch gapopen qstart qend sstart send evalue bitscore".split()
+    values = [[v.strip('"') for v in __import__("re").findall(r'^\t"[a-z_]+":(.*?),?$', blk, flags=8)] for blk in out.split("\n\t{\n")[1:]]
+    assert values == gold
