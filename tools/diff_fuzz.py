@@ -139,7 +139,7 @@ def main():
                 opts += ["-f", fmt]
                 if fmt == "5" and rnd.random() < 0.3: opts += [rnd.choice(["--xml-blord-format", "--no-parse-seqids"])]
                 if fmt == "sam" and rnd.random() < 0.3: opts += ["--sam-query-len"]
-            if rnd.random() < 0.1 and not q.endswith(".gz") and not q.endswith(".fastq") and q != d:  # gzip-compressed FASTA queries (the reference built here loads NO query from a gzip-compressed FASTQ file; this CLI reads it)
+            if rnd.random() < 0.1 and not q.endswith(".gz") and not q.endswith(".fastq") and q != d and "qqual" not in opts and "full_qqual" not in opts:  # (with a quality field the reference loads nothing from a .gz file either)  # gzip-compressed FASTA queries (the reference built here loads NO query from a gzip-compressed FASTQ file; this CLI reads it)
                 import gzip, shutil
                 with open(q, "rb") as fi, gzip.open(q + ".gz", "wb") as fo: shutil.copyfileobj(fi, fo)
                 q += ".gz"
