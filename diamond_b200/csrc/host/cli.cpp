@@ -594,8 +594,8 @@ int format_double(double x, char* p, size_t n) {  // util/string/string.h:87-92
 	                "       dmnd-b200 blastp|blastx -d DB[.dmnd|.faa] [-q QUERIES] [-o OUT] [--fast|--mid-sensitive|--sensitive|--more-sensitive|--very-sensitive|--ultra-sensitive]\n"
 	                "                [-p N] [-c N] [-b G] [-k N | --top P] [-e X | --min-score B] [--id P | --approx-id P] [--query-cover P] [--subject-cover P] [--no-self-hits]\n"
 	                "                [--comp-based-stats 0|1] [--masking 0|1] [--motif-masking 0|1] [-F 15 [--range-culling] | --long-reads] [--strand both|plus|minus] [--min-orf N] [--query-gencode N]\n"
-	                "                [-f 6 [fields] [--unal 0|1] [--header simple] | -f 0 | -f 5 | -f 100 | -f sam | -f paf] [--compress 0|1] [--log]\n"
-	                "       dmnd-b200 view -a FILE.daa [-o OUT] [-f ...]\n", msg);
+	                "                [-f 6|104 [fields] [--unal 0|1] [--header simple] | -f 0 | -f 5 | -f 100 | -f sam | -f paf] [--salltitles|--sallseqid] [--ext banded-fast|banded-slow] [--compress 0|1] [--log]\n"
+	                "       dmnd-b200 view -a FILE.daa [-o OUT] [-f ...]\n       dmnd-b200 dbinfo -d DB\n", msg);
 	exit(1);
 }
 
