@@ -65,7 +65,7 @@ class SearchOpts(C.Structure):
                 ("comp_based_stats", C.c_int32), ("max_target_seqs", C.c_int32), ("max_evalue", C.c_double),
                 ("db_letters", C.c_uint64), ("want_transcript", C.c_int32), ("masking", C.c_int32), ("motif_masking", C.c_int32), ("query_contexts", C.c_int32), ("top_percent", C.c_double),
                 ("frame_shift", C.c_int32), ("range_culling", C.c_int32),
-                ("min_id", C.c_double), ("query_cover", C.c_double), ("subject_cover", C.c_double), ("min_bit_score", C.c_double), ("approx_min_id", C.c_double), ("self_targets", C.c_void_p), ("ext_mode", C.c_int32)]
+                ("min_id", C.c_double), ("query_cover", C.c_double), ("subject_cover", C.c_double), ("min_bit_score", C.c_double), ("approx_min_id", C.c_double), ("self_targets", C.c_void_p), ("range_cover", C.c_double), ("ext_mode", C.c_int32)]
 
 
 class Match(C.Structure):

@@ -736,6 +736,7 @@ int main(int argc, char** argv) {
 			else if (a == "--min-orf" || a == "-l") { min_orf = atoi(val()); if (min_orf < 0) usage("--min-orf must not be negative"); }
 			else if (a == "--query-gencode") gencode = atoi(val());
 			else if (a == "--range-culling") o.range_culling = 1;
+			else if (a == "--range-cover") o.range_cover = atof(val());  // config.query_range_cover (default 50)
 			else if (a == "--long-reads") long_reads = true;  // basic/config.cpp:679-686
 			else if (a == "-F" || a == "--frameshift") { o.frame_shift = atoi(val()); if (o.frame_shift <= 0) usage("--frameshift needs a positive penalty (the reference's usual value is 15)"); }
 			else if (a == "--log") log = true;
@@ -978,7 +979,7 @@ int main(int argc, char** argv) {
 						const int rb = fr < 3 ? b_in : L - e_in, re = fr < 3 ? e_in : L - b_in;
 						const int c = top_on ? part.covered_max(rb, re, int((double)x.score / (1.0 - o.top_percent / 100.0))) : part.covered_full(rb, re);
 						++cur[best].i;
-						if (!((double)c / (double)(re - rb) * 100.0 < 50.0)) continue;  // config.query_range_cover
+						if (!((double)c / (double)(re - rb) * 100.0 < (o.range_cover > 0.0 ? o.range_cover : 50.0))) continue;  // config.query_range_cover
 						part.insert(rb, re, x.score);
 						dmnd_match y = x;
 						y.target = oid(best, x.target);

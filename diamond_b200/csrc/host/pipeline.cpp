@@ -1627,6 +1627,8 @@ static int blastp_impl(dmnd_ctx* ctx, dmnd_block* qb, const dmnd_block* rb, cons
 	e.frame_shift = opts->frame_shift;
 	if (e.frame_shift < 0 || (e.frame_shift > 0 && contexts != 6)) { dmnd_set_last_error("dmnd_blastp: frame_shift needs translated queries (query_contexts = 6) and a positive penalty"); return 1; }
 	e.range_culling = opts->range_culling != 0;
+	if (opts->range_cover < 0.0 || opts->range_cover > 100.0) { dmnd_set_last_error("dmnd_blastp: range_cover is a percentage (0 = the default, 50)"); return 1; }
+	if (opts->range_cover > 0.0) e.range_cover = opts->range_cover;
 	if (e.range_culling && !e.frame_shift) { dmnd_set_last_error("dmnd_blastp: query range culling is only supported in frameshift alignment mode"); return 1; }  // basic/config.cpp:824-825
 	if (e.frame_shift) {
 		// the legacy pipeline extends without composition bias (align/legacy/query_mapper.cpp:131: xdrop_ungapped(.., nullptr, ..);

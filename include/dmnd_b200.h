@@ -393,6 +393,8 @@ typedef struct dmnd_search_opts {
 	                              this query is not reported (UINT32_MAX = none).  The reference drops an HSP when query and target have the same title and the same
 	                              letters (filter_hsp, align/culling.cpp:166-168, part of Match::apply_filters after round 2); titles live with the caller, so the
 	                              caller names the pairs.  Unlike the other filters this one does not change the extension's schedule (align/extend.cpp:94-96) */
+	double range_cover;        /* --range-cover: with range_culling, the percentage of a target's query range that better targets must cover before it is dropped
+	                              (config.query_range_cover, default 50); 0 = the default */
 	int32_t ext_mode;          /* --ext: 0 = the sensitivity mode's own extension mode (align/extend.cpp:62-75), 1 = banded-fast, 2 = banded-slow (the band table of
 	                              Extension::band, align/gapped_score.cpp:41-72); the reference's full / global / none modes are not on this path */
 } dmnd_search_opts;

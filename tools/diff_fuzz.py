@@ -111,7 +111,9 @@ def main():
                 if u < 0.25 and "--top" not in opts and "-k" not in opts: opts += ["--long-reads"]  # = --range-culling --top 10 -F 15
                 else:
                     opts += ["-F", str(rnd.choice([15, 15, 10, 20]))]
-                    if u < 0.5: opts += ["--range-culling"]
+                    if u < 0.5:
+                        opts += ["--range-culling"]
+                        if rnd.random() < 0.3: opts += ["--range-cover", str(rnd.choice([20, 35, 80]))]
             if rnd.random() < a.blocks: opts += ["-b", rnd.choice(["0.00005", "0.0001", "0.0003"])]  # reference blocks + join_blocks
             fmt = rnd.choice(["6", "6", "6f", "0", "5", "sam", "paf", "100"]) if fshift else rnd.choice(["6", "6", "6f", "6g", "6c", "0", "5", "paf", "sam", "100"])
             if a.format: fmt = a.format
