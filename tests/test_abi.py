@@ -58,3 +58,21 @@ def test_ctypes_structs_have_the_c_sizes(tmp_path):
     want = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     got = [C.sizeof(t) for t in (api.Params, api.SearchOpts, api.RunStats, api.Match, api.Hit, api.DpResult, api.Timing)]
     assert got == want
+
+
+def test_search_opts_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of dmnd_search_opts (diamond_b200/api.py) against the C header, field by field: a stale mirror makes the library read
+    garbage options (it happened once this round).  gcc prints sizeof and every offsetof; ctypes must agree."""
+    import ctypes as C
+    import subprocess
+    from diamond_b200 import api
+    names = [n for n, _ in api.SearchOpts._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dmnd_b200.h"\nint main(void) { printf("%zu\\n", sizeof(dmnd_search_opts));\n'
+                   + "".join('printf("%s %%zu\\n", offsetof(dmnd_search_opts, %s));\n' % (n, n) for n in names) + "return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert int(out[0]) == C.sizeof(api.SearchOpts)
+    for line, n in zip(out[1:], names):
+        assert line == f"{n} {getattr(api.SearchOpts, n).offset}"
