@@ -76,3 +76,20 @@ def test_search_opts_layout_matches_the_header(tmp_path):
     assert int(out[0]) == C.sizeof(api.SearchOpts)
     for line, n in zip(out[1:], names):
         assert line == f"{n} {getattr(api.SearchOpts, n).offset}"
+
+
+def test_every_struct_mirror_has_the_header_size(tmp_path):
+    """sizeof of every C struct the Python mirror restates (ctypes Structures and numpy record dtypes)."""
+    import ctypes as C
+    import subprocess
+    from diamond_b200 import api
+    pairs = {"dmnd_params": C.sizeof(api.Params), "dmnd_hit": C.sizeof(api.Hit), "dmnd_stage_counters": C.sizeof(api.StageCounters), "dmnd_dp_problem": C.sizeof(api.DpProblem),
+             "dmnd_dp_result": C.sizeof(api.DpResult), "dmnd_timing": C.sizeof(api.Timing), "dmnd_match": C.sizeof(api.Match), "dmnd_run_stats": C.sizeof(api.RunStats),
+             "dmnd_fs_result": api.FS_RESULT_DTYPE.itemsize}
+    assert api.MATCH_DTYPE.itemsize == C.sizeof(api.Match)
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "dmnd_b200.h"\nint main(void) {\n' + "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in pairs) + "return 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert {k: int(v) for k, v in got.items()} == pairs
